@@ -1,0 +1,343 @@
+"""Oracle: flux-form advection, Centered(order=2) and WENO(order=5).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Restates src/Advection/:
+  reconstruction_coefficients.jl:49-64,87-89,122-152   stencil_coefficients / calc_reconstruction_stencil
+  centered_reconstruction.jl:5-55, centered_advective_fluxes.jl:15-33
+  upwind_biased_reconstruction.jl, upwind_biased_advective_fluxes.jl:21-121
+  weno_reconstruction.jl:77-93, weno_interpolants.jl:71-83,117-137,169-174,204-216,261-266,290-338,409-437,500
+  topologically_conditional_interpolation.jl:46-52,75-120
+  momentum_advection_operators.jl:46-83, tracer_advection_operators.jl:30-34
+  src/Utils/newton_div.jl:8-23
+"""
+from fractions import Fraction
+
+import numpy as np
+
+from .operators import O, dC, dF, sh
+
+_err = dict(over="ignore", invalid="ignore", divide="ignore")
+
+
+# ---------------------------------------------------------------------------------
+# Coefficients
+# ---------------------------------------------------------------------------------
+def _round(FT, frac):
+    return FT(float(frac)) if FT is np.float64 else np.float32(float(frac))
+
+
+def stencil_coefficients(FT, r, order):
+    """reconstruction_coefficients.jl:49-64 on a uniform grid (xr = xi = 1:100, i = 50):
+    xr[i] - xi[i-(r-q+1)] = r-q+1 and xi[i-(r-m+1)] - xi[i-(r-l+1)] = m-l.
+    The first order-1 coefficients are rounded to FT, the last is 1 - sum(others) in FT arithmetic."""
+    FT = np.dtype(FT).type
+    coeffs = []
+    for j in range(order):
+        c = Fraction(0)
+        for m in range(j + 1, order + 1):
+            num = Fraction(0)
+            for l in range(order + 1):
+                if l == m:
+                    continue
+                p = Fraction(1)
+                for q in range(order + 1):
+                    if q != m and q != l:
+                        p *= (r - q + 1)
+                num += p
+            den = Fraction(1)
+            for l in range(order + 1):
+                if l != m:
+                    den *= (m - l)
+            c += num / den
+        coeffs.append(c)
+    rounded = [_round(FT, c) for c in coeffs[:-1]]
+    s = FT(0)
+    for c in rounded:          # Base.sum of a short Vector: left-to-right
+        s = FT(s + c)
+    return tuple(rounded) + (FT(FT(1) - s),)
+
+
+def centered_coefficients(FT, buffer):
+    """uniform_reconstruction_coefficients(FT, Val(:symmetric), buffer) :87
+    returned in *stencil order* ψ[i-buffer] ... ψ[i+buffer-1] as used by calc_reconstruction_stencil:122-152
+    (coefficient of the idx-th stencil point is coeff[order - idx + 1])."""
+    order = 2 * buffer
+    c = stencil_coefficients(FT, buffer - 1, order)
+    return tuple(c[order - idx] for idx in range(1, order + 1))
+
+
+class Centered:
+    def __init__(self, FT=np.float64, order=2):
+        assert order in (2, 4)
+        self.FT = np.dtype(FT).type
+        self.buffer = order // 2
+        self.coeffs = centered_coefficients(self.FT, self.buffer)
+        self.buffer_scheme = Centered(FT, order - 2) if order > 2 else None
+        self.kind = "centered"
+
+
+class UpwindBiased1:
+    """UpwindBiased(order=1): buffer 1, symmetric part = Centered(2)"""
+
+    def __init__(self, FT=np.float64):
+        self.FT = np.dtype(FT).type
+        self.buffer = 1
+        self.advecting_velocity_scheme = Centered(FT, 2)
+        self.buffer_scheme = None
+        self.kind = "upwind1"
+
+
+class WENO:
+    """WENO{N,FT,Float32}: order 5 (buffer 3) or 3 (buffer 2).  weno_reconstruction.jl:77-93"""
+
+    # smoothness_coefficients weno_interpolants.jl:169-174
+    SMOOTH = {2: ((1, -2, 1), (1, -2, 1)),
+              3: ((10, -31, 11, 25, -19, 4), (4, -13, 5, 13, -13, 4), (4, -19, 11, 25, -31, 10))}
+    CSTAR = {2: (Fraction(2, 3), Fraction(1, 3)),
+             3: (Fraction(3, 10), Fraction(3, 5), Fraction(1, 10))}
+
+    def __init__(self, FT=np.float64, order=5):
+        assert order in (3, 5)
+        self.FT = np.dtype(FT).type
+        self.buffer = (order + 1) // 2
+        self.kind = "weno"
+        self.advecting_velocity_scheme = Centered(FT, order - 1)
+        self.buffer_scheme = WENO(FT, order - 2) if order > 3 else UpwindBiased1(FT)
+        B = self.buffer
+        self.coeff_p = tuple(stencil_coefficients(self.FT, r, B) for r in range(B))   # :117-118
+        self.cstar = tuple(_round(self.FT, c) for c in self.CSTAR[B])                # :78-83
+        self.smooth = tuple(tuple(self.FT(c) for c in row) for row in self.SMOOTH[B])
+        self.eps = self.FT(np.float32(1e-8))                                          # ϵ = 1f-8 :71
+
+
+def newton_div(FT, a, b):
+    """newton_div(Float32, a, b::FT)   src/Utils/newton_div.jl:8-23"""
+    if FT is np.float32:
+        return a * (np.float32(1) / b)                    # :23  a * inv_fast(b)
+    inv_b = (np.float32(1) / b.astype(np.float32)).astype(np.float64)
+    x = a * inv_b
+    # x = fma(fma(x, -b, a), inv_b, x): emulate the two fused ops in extended precision
+    r = (a.astype(np.longdouble) - x.astype(np.longdouble) * b.astype(np.longdouble)).astype(np.float64)
+    x = (r.astype(np.longdouble) * inv_b.astype(np.longdouble) + x.astype(np.longdouble)).astype(np.float64)
+    return x
+
+
+def _weno_value(sch, S, left):
+    """biased_interpolate for WENO{B}: S = (ψ[i-B], …, ψ[i+B-1]); ``left`` boolean array (bias(ũ) isa LeftBias).
+    weno_interpolants.jl:432-437 (stencils), :204-216,261 (β), :308-309 (τ), :290-297 (α), :332-338 (ω), :500."""
+    B, FT = sch.buffer, sch.FT
+    # sub-stencils r = 0..B-1 : Left (S[B-r .. 2B-1-r]) ; Right (S[B+r], S[B+r-1], …)  (1-based in the source)
+    stencils = []
+    for r in range(B):
+        L = [S[B - 1 - r + j] for j in range(B)]
+        R = [S[B + r - j] for j in range(B)]
+        stencils.append([np.where(left, L[j], R[j]) for j in range(B)])
+    betas = []
+    for r in range(B):
+        psi, C = stencils[r], sch.smooth[r]
+        beta, c = None, 0
+        for s in range(B - 1):
+            inner = None
+            for i in range(s, B):
+                term = C[c + i - s] * psi[i]
+                inner = term if inner is None else inner + term
+            c += B - s
+            term = psi[s] * inner
+            beta = term if beta is None else beta + term
+        beta = beta + psi[B - 1] * psi[B - 1] * C[c]
+        betas.append(beta)
+    tau = np.abs(betas[0] - betas[B - 1])
+    alphas = []
+    for r in range(B):
+        q = newton_div(FT, tau, betas[r] + sch.eps)
+        alphas.append(sch.cstar[r] * (FT(1) + q * q))
+    ssum = alphas[0]
+    for r in range(1, B):
+        ssum = ssum + alphas[r]
+    rs = FT(1) / ssum
+    out = None
+    for r in range(B):
+        w = alphas[r] * rs
+        p = None
+        for j in range(B):                               # sum(coeff .* ψ): left to right
+            t = sch.coeff_p[r][j] * stencils[r][j]
+            p = t if p is None else p + t
+        t = w * p
+        out = t if out is None else out + t
+    return out
+
+
+def _centered_value(sch, S):
+    """symmetric_interpolate for Centered{B}: S = (ψ[i-B], …, ψ[i+B-1])"""
+    out = None
+    for c, s in zip(sch.coeffs, S):
+        t = c * s
+        out = t if out is None else out + t
+    return out
+
+
+def _inside(ctx, d, o, lo, hi):
+    idx = ctx.index(d, o)
+    return (idx >= lo) & (idx <= hi)
+
+
+def symmetric_face(ctx, scheme, q, d):
+    """_symmetric_interpolate_ξᶠ(i,j,k, grid, scheme, q): face-type symmetric interpolation with the
+    boundary fallback chain of topologically_conditional_interpolation.jl:46-52,99-120."""
+    g = ctx.g
+
+    def at(o, sch):
+        if sch.kind != "centered":
+            inner = sch.advecting_velocity_scheme
+        else:
+            inner = sch
+        Bc = inner.buffer
+        S = [q(sh(o, d, n)) for n in range(-Bc, Bc)]
+        val = _centered_value(inner, S)
+        if g.bounded(d) and sch.buffer > 1:
+            R, N = sch.buffer, g.N[d]
+            ok = _inside(ctx, d, o, R + 1, N + 1 - R)       # outside_symmetric_haloᶠ
+            return np.where(ok, val, at(o, sch.buffer_scheme))
+        return val
+
+    if g.flat(d):
+        return q                                            # flat_advective_fluxes / identity
+    def run(o):
+        with np.errstate(**_err):
+            return at(o, scheme)
+    return run
+
+
+def symmetric_center(ctx, scheme, q, d):
+    """_symmetric_interpolate_ξᶜ(i) = face-type at i+1 with the centre-type bounds check"""
+    g = ctx.g
+
+    def at(o, sch):
+        inner = sch.advecting_velocity_scheme if sch.kind != "centered" else sch
+        Bc = inner.buffer
+        o1 = sh(o, d, 1)
+        S = [q(sh(o1, d, n)) for n in range(-Bc, Bc)]
+        val = _centered_value(inner, S)
+        if g.bounded(d) and sch.buffer > 1:
+            R, N = sch.buffer, g.N[d]
+            ok = _inside(ctx, d, o, R, N + 1 - R)           # outside_symmetric_haloᶜ
+            return np.where(ok, val, at(o, sch.buffer_scheme))
+        return val
+
+    if g.flat(d):
+        return q
+    def run(o):
+        with np.errstate(**_err):
+            return at(o, scheme)
+    return run
+
+
+def _biased(ctx, scheme, q, d, left_q, center_type):
+    """_biased_interpolate_ξᶠ / ξᶜ with boundary fallback WENO5 -> WENO3 -> Upwind1."""
+    g = ctx.g
+
+    def at(o, sch, left):
+        oo = sh(o, d, 1) if center_type else o
+        if sch.kind == "upwind1":
+            # calc_reconstruction_stencil(FT, 1, :left/:right): 1*ψ[i-1] (left), 1*ψ[i] (right)
+            return np.where(left, q(sh(oo, d, -1)), q(oo))
+        if sch.kind == "centered":
+            B = sch.buffer
+            return _centered_value(sch, [q(sh(oo, d, n)) for n in range(-B, B)])
+        B = sch.buffer
+        S = [q(sh(oo, d, n)) for n in range(-B, B)]
+        val = _weno_value(sch, S, left)
+        if g.bounded(d):
+            R, N = B, g.N[d]
+            if center_type:   # outside_biased_haloᶜ
+                lo, hi = max(R, R - 1), min(N + 1 - (R - 1), N + 1 - R)
+            else:             # outside_biased_haloᶠ
+                lo, hi = max(R + 1, R), min(N + 1 - (R - 1), N + 1 - R)
+            ok = _inside(ctx, d, o, lo, hi)
+            return np.where(ok, val, at(o, sch.buffer_scheme, left))
+        return val
+
+    def run(o):
+        with np.errstate(**_err):
+            return at(o, scheme, left_q(o))
+    return run
+
+
+def biased_face(ctx, scheme, q, d, left_q):
+    return _biased(ctx, scheme, q, d, left_q, False)
+
+
+def biased_center(ctx, scheme, q, d, left_q):
+    return _biased(ctx, scheme, q, d, left_q, True)
+
+
+# ---------------------------------------------------------------------------------
+# Advective fluxes and flux divergences
+# ---------------------------------------------------------------------------------
+def _zero_q(ctx):
+    return lambda o: ctx.zeros()
+
+
+def momentum_flux(ctx, scheme, U, comp, d, psi_f):
+    """advective_momentum_flux_{U,V,W}{u,v,w}: flux of velocity component ``comp`` (0,1,2) carried
+    in direction ``d`` by U[d].  Returns a quantity.  Flux location: centre-type in d if d == comp
+    (ccc), otherwise face-type in both d and comp."""
+    g, FT = ctx.g, ctx.FT
+    if g.flat(d):
+        return _zero_q(ctx)                                  # flat_advective_fluxes.jl:13-29
+    adv = ctx.field(U[d])
+    psi = ctx.field(psi_f)
+    A = g.A[d]
+    if scheme.kind == "centered":
+        # centered_advective_fluxes.jl:15-27 :  A * sym(U) * sym(ψ)
+        if d == comp:
+            ut = symmetric_center(ctx, scheme, adv, d)
+            pt = symmetric_center(ctx, scheme, psi, d)
+        else:
+            ut = symmetric_face(ctx, scheme, adv, comp)      # interpolate advecting velocity along comp
+            pt = symmetric_face(ctx, scheme, psi, d)         # interpolate advected along d
+        return lambda o: A * ut(o) * pt(o)
+    # upwind_biased_advective_fluxes.jl:23-93 :  ũ = sym(A*U) ; ψᴿ = biased(ψ; bias(ũ)) ; ũ*ψᴿ
+    aq = lambda o: A * adv(o)
+    if d == comp:
+        ut = symmetric_center(ctx, scheme, aq, d)
+        pt = biased_center(ctx, scheme, psi, d, lambda o: ut(o) > 0)
+    else:
+        ut = symmetric_face(ctx, scheme, aq, comp)
+        pt = biased_face(ctx, scheme, psi, d, lambda o: ut(o) > 0)
+    return lambda o: ut(o) * pt(o)
+
+
+def div_momentum(ctx, scheme, U, comp):
+    """div_𝐯u / div_𝐯v / div_𝐯w   momentum_advection_operators.jl:46-83"""
+    g = ctx.g
+    total = None
+    for d in range(3):
+        F = momentum_flux(ctx, scheme, U, comp, d, U[comp])
+        term = (dF(ctx, F, d) if d == comp else dC(ctx, F, d))(O)
+        total = term if total is None else total + term
+    return g.rV * total
+
+
+def tracer_flux(ctx, scheme, U, c_f, d):
+    """advective_tracer_flux_{x,y,z}"""
+    g = ctx.g
+    if g.flat(d):
+        return _zero_q(ctx)
+    u = ctx.field(U[d])
+    c = ctx.field(c_f)
+    A = g.A[d]
+    if scheme.kind == "centered":
+        ct = symmetric_face(ctx, scheme, c, d)
+        return lambda o: (A * u(o)) * ct(o)                  # Ax_q(U) * sym(c)  :31-33
+    ct = biased_face(ctx, scheme, c, d, lambda o: u(o) > 0)
+    return lambda o: A * u(o) * ct(o)                        # Ax * ũ * cᴿ  :99-121
+
+
+def div_tracer(ctx, scheme, U, c_f):
+    """div_Uc   tracer_advection_operators.jl:30-34"""
+    g = ctx.g
+    total = None
+    for d in range(3):
+        term = dC(ctx, tracer_flux(ctx, scheme, U, c_f, d), d)(O)
+        total = term if total is None else total + term
+    return g.rV * total

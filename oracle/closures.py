@@ -1,0 +1,317 @@
+"""Oracle: turbulence closures (ScalarDiffusivity, AnisotropicMinimumDissipation), buoyancy, Coriolis.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Restates
+  src/TurbulenceClosures/closure_kernel_operators.jl:22-48
+  src/TurbulenceClosures/abstract_scalar_diffusivity_closure.jl:189-204,240-242,310-332
+  src/TurbulenceClosures/velocity_tracer_gradients.jl:6-46,126-250
+  src/TurbulenceClosures/turbulence_closure_implementations/scalar_diffusivity.jl:195-198
+  src/TurbulenceClosures/turbulence_closure_implementations/anisotropic_minimum_dissipation.jl:154-351
+  src/BuoyancyFormulations/linear_equation_of_state.jl:72-80, buoyancy_tracer.jl:12, g_dot_b.jl:2-4
+  src/Coriolis/f_plane.jl:50-52, src/Operators/interpolation_operators.jl:119-131, src/Grids/inactive_node.jl
+"""
+import numpy as np
+
+from .operators import O, dC, dF, ddC, ddF, iC, iF, sh
+
+
+class ScalarDiffusivity:
+    def __init__(self, nu=0.0, kappa=0.0):
+        self.nu, self.kappa = nu, kappa       # kappa: number or dict tracer->number
+        self.kind = "scalar"
+
+    def kappa_for(self, name):
+        return self.kappa[name] if isinstance(self.kappa, dict) else self.kappa
+
+
+class AnisotropicMinimumDissipation:
+    def __init__(self, C=1.0 / 3.0, Cnu=None, Ckappa=None):
+        self.Cnu = C if Cnu is None else Cnu
+        self.Ckappa = C if Ckappa is None else Ckappa
+        self.kind = "amd"
+
+    def Ckappa_for(self, name):
+        return self.Ckappa[name] if isinstance(self.Ckappa, dict) else self.Ckappa
+
+
+# ---------------------------------------------------------------------------------
+# Viscosity / diffusivity "extractors"   abstract_scalar_diffusivity_closure.jl:310-332
+# ---------------------------------------------------------------------------------
+def _nu_at(ctx, nu, loc):
+    """nu: number or quantity of a ccc field; loc in {'ccc','ffc','fcf','cff'}"""
+    if not callable(nu):
+        v = ctx.FT(nu)
+        return lambda o: v
+    q = nu
+    # ℑxyᶠᶠᵃ = ℑyᶠ(ℑxᶠ(·)), ℑxzᶠᵃᶠ = ℑzᶠ(ℑxᶠ(·)), ℑyzᵃᶠᶠ = ℑzᶠ(ℑyᶠ(·))  (interpolation_operators.jl:45-56):
+    # the lower dimension is the inner operator.
+    for d in [d for d in range(3) if loc[d] == "f"]:
+        q = iF(ctx, q, d)
+    return q
+
+
+def _kappa_at(ctx, kappa, d):
+    if not callable(kappa):
+        v = ctx.FT(kappa)
+        return lambda o: v
+    return iF(ctx, kappa, d)
+
+
+def _strain_offdiag(ctx, U, a, b):
+    """Σ_ab (a != b) at the location that is Face in a and b:  0.5 (∂b u_a + ∂a u_b)
+    velocity_tracer_gradients.jl:31-42"""
+    h = ctx.FT(0.5)
+    lo, hi = (a, b) if a < b else (b, a)
+    # source order: Σ12 = 0.5(∂y u + ∂x v); Σ13 = 0.5(∂z u + ∂x w); Σ23 = 0.5(∂z v + ∂y w)
+    first = ddF(ctx, ctx.field(U[lo]), hi)
+    second = ddF(ctx, ctx.field(U[hi]), lo)
+    return lambda o: h * (first(o) + second(o))
+
+
+def div_tau(ctx, closure_nu, U, comp):
+    """∂ⱼ τ_{comp,j}   closure_kernel_operators.jl:22-41 with τ = -2 ν Σ  (:189-204)"""
+    g, FT = ctx.g, ctx.FT
+    total = None
+    two = FT(2)
+    for d in range(3):
+        if d == comp:
+            loc = "ccc"
+            sig = ddC(ctx, ctx.field(U[comp]), comp)               # Σ_aa = ∂a u_a at ccc
+        else:
+            l = ["c", "c", "c"]
+            l[d] = "f"
+            l[comp] = "f"
+            loc = "".join(l)
+            sig = _strain_offdiag(ctx, U, comp, d)
+        nu = _nu_at(ctx, closure_nu, loc)
+        A = g.A[d]
+        flux = (lambda nu, sig, A: (lambda o: A * (-two * (nu(o) * sig(o)))))(nu, sig, A)
+        term = (dF(ctx, flux, d) if d == comp else dC(ctx, flux, d))(O)
+        total = term if total is None else total + term
+    return g.rV * total
+
+
+def div_q(ctx, kappa, c_f):
+    """∇·q_c   closure_kernel_operators.jl:43-48 with q = -κ ∂c (:240-242)"""
+    g = ctx.g
+    c = ctx.field(c_f)
+    total = None
+    for d in range(3):
+        kap = _kappa_at(ctx, kappa, d)
+        grad = ddF(ctx, c, d)
+        A = g.A[d]
+        flux = (lambda kap, grad, A: (lambda o: A * (-(kap(o) * grad(o)))))(kap, grad, A)
+        term = dC(ctx, flux, d)(O)
+        total = term if total is None else total + term
+    return g.rV * total
+
+
+# ---------------------------------------------------------------------------------
+# AMD   anisotropic_minimum_dissipation.jl:154-351 ; velocity_tracer_gradients.jl:126-250
+# ---------------------------------------------------------------------------------
+def _sq(q):
+    return lambda o: q(o) ** 2
+
+
+def _mul(a, b):
+    return lambda o: a(o) * b(o)
+
+
+class _AMD:
+    def __init__(self, ctx, U):
+        g, FT = ctx.g, ctx.FT
+        self.ctx = ctx
+        u, v, w = (ctx.field(f) for f in U)
+        Dfx, Dfy, Dfz = FT(2) * g.dx, FT(2) * g.dy, FT(2) * g.dz      # Δᶠ = 2Δ (:224-226)
+        self.Df = (Dfx, Dfy, Dfz)
+        # normalised gradients (velocity_tracer_gradients.jl:126-154)
+        self.dxu = ddC(ctx, u, 0)
+        self.dyv = ddC(ctx, v, 1)
+        self.dzw = ddC(ctx, w, 2)
+        rxy, ryx = FT(Dfx / Dfy), FT(Dfy / Dfx)
+        rxz, rzx = FT(Dfx / Dfz), FT(Dfz / Dfx)
+        ryz, rzy = FT(Dfy / Dfz), FT(Dfz / Dfy)
+        _dxv, _dyu = ddF(ctx, v, 0), ddF(ctx, u, 1)
+        _dxw, _dzu = ddF(ctx, w, 0), ddF(ctx, u, 2)
+        _dyw, _dzv = ddF(ctx, w, 1), ddF(ctx, v, 2)
+        self.dxv = lambda o: rxy * _dxv(o)       # ffc
+        self.dyu = lambda o: ryx * _dyu(o)       # ffc
+        self.dxw = lambda o: rxz * _dxw(o)       # fcf
+        self.dzu = lambda o: rzx * _dzu(o)       # fcf
+        self.dyw = lambda o: ryz * _dyw(o)       # cff
+        self.dzv = lambda o: rzy * _dzv(o)       # cff
+        h = FT(0.5)
+        self.S12 = lambda o: h * (self.dyu(o) + self.dxv(o))
+        self.S13 = lambda o: h * (self.dzu(o) + self.dxw(o))
+        self.S23 = lambda o: h * (self.dzv(o) + self.dyw(o))
+
+    # ℑxyᶜᶜᵃ = ℑyᶜ(ℑxᶜ(·)),  ℑxzᶜᵃᶜ = ℑzᶜ(ℑxᶜ(·)),  ℑyzᵃᶜᶜ = ℑzᶜ(ℑyᶜ(·))  (interpolation_operators.jl:45-56)
+    def Ixy(self, q):
+        return iC(self.ctx, iC(self.ctx, q, 0), 1)
+
+    def Ixz(self, q):
+        return iC(self.ctx, iC(self.ctx, q, 0), 2)
+
+    def Iyz(self, q):
+        return iC(self.ctx, iC(self.ctx, q, 1), 2)
+
+    def q_trace(self):
+        """norm_tr_∇uᶜᶜᶜ  :285-306"""
+        t = self.dxu(O) ** 2
+        t = t + self.dyv(O) ** 2
+        t = t + self.dzw(O) ** 2
+        t = t + self.Ixy(_sq(self.dxv))(O)
+        t = t + self.Ixy(_sq(self.dyu))(O)
+        t = t + self.Ixz(_sq(self.dxw))(O)
+        t = t + self.Ixz(_sq(self.dzu))(O)
+        t = t + self.Iyz(_sq(self.dyw))(O)
+        t = t + self.Iyz(_sq(self.dzv))(O)
+        return t
+
+    def r_term(self):
+        """norm_uᵢₐ_uⱼₐ_Σᵢⱼᶜᶜᶜ  :240-279 (S11 = dxu, S22 = dyv, S33 = dzw)"""
+        FT = self.ctx.FT
+        two = FT(2)
+        S11, S22, S33 = self.dxu(O), self.dyv(O), self.dzw(O)
+        Ixy, Ixz, Iyz = self.Ixy, self.Ixz, self.Iyz
+        t1 = S11 * self.dxu(O) ** 2
+        t1 = t1 + S22 * Ixy(_sq(self.dxv))(O)
+        t1 = t1 + S33 * Ixz(_sq(self.dxw))(O)
+        t1 = t1 + two * self.dxu(O) * Ixy(_mul(self.dxv, self.S12))(O)
+        t1 = t1 + two * self.dxu(O) * Ixz(_mul(self.dxw, self.S13))(O)
+        t1 = t1 + two * Ixy(self.dxv)(O) * Ixz(self.dxw)(O) * Iyz(self.S23)(O)
+
+        t2 = S11 * Ixy(_sq(self.dyu))(O)
+        t2 = t2 + S22 * self.dyv(O) ** 2
+        t2 = t2 + S33 * Iyz(_sq(self.dyw))(O)
+        t2 = t2 + two * self.dyv(O) * Ixy(_mul(self.dyu, self.S12))(O)
+        t2 = t2 + two * Ixy(self.dyu)(O) * Iyz(self.dyw)(O) * Ixz(self.S13)(O)
+        t2 = t2 + two * self.dyv(O) * Iyz(_mul(self.dyw, self.S23))(O)
+
+        t3 = S11 * Ixz(_sq(self.dzu))(O)
+        t3 = t3 + S22 * Iyz(_sq(self.dzv))(O)
+        t3 = t3 + S33 * self.dzw(O) ** 2
+        t3 = t3 + two * Ixz(self.dzu)(O) * Iyz(self.dzv)(O) * Ixy(self.S12)(O)
+        t3 = t3 + two * self.dzw(O) * Ixz(_mul(self.dzu, self.S13))(O)
+        t3 = t3 + two * self.dzw(O) * Iyz(_mul(self.dzv, self.S23))(O)
+        return t1 + t2 + t3
+
+    def delta2(self):
+        FT = self.ctx.FT
+        Dfx, Dfy, Dfz = self.Df
+        return FT(3) / (FT(1) / Dfx ** 2 + FT(1) / Dfy ** 2 + FT(1) / Dfz ** 2)
+
+    def tracer_terms(self, c_f):
+        ctx = self.ctx
+        c = ctx.field(c_f)
+        Dfx, Dfy, Dfz = self.Df
+        _cx, _cy, _cz = ddF(ctx, c, 0), ddF(ctx, c, 1), ddF(ctx, c, 2)
+        cx = lambda o: Dfx * _cx(o)
+        cy = lambda o: Dfy * _cy(o)
+        cz = lambda o: Dfz * _cz(o)
+        Ix = lambda q: iC(ctx, q, 0)
+        Iy = lambda q: iC(ctx, q, 1)
+        Iz = lambda q: iC(ctx, q, 2)
+        sigma = Ix(_sq(cx))(O) + Iy(_sq(cy))(O) + Iz(_sq(cz))(O)          # norm_θᵢ²ᶜᶜᶜ :349-351
+        Ixy, Ixz, Iyz = self.Ixy, self.Ixz, self.Iyz
+        a = self.dxu(O) * Ix(_sq(cx))(O)
+        a = a + Ixy(self.dxv)(O) * Ix(cx)(O) * Iy(cy)(O)
+        a = a + Ixz(self.dxw)(O) * Ix(cx)(O) * Iz(cz)(O)
+        b = Ixy(self.dyu)(O) * Iy(cy)(O) * Ix(cx)(O)
+        b = b + self.dyv(O) * Iy(_sq(cy))(O)
+        b = b + Ixz(self.dyw)(O) * Iy(cy)(O) * Iz(cz)(O)       # sic: ℑxzᶜᵃᶜ on norm_∂y_w (:336)
+        cc = Ixz(self.dzu)(O) * Iz(cz)(O) * Ix(cx)(O)
+        cc = cc + Iyz(self.dzv)(O) * Iz(cz)(O) * Iy(cy)(O)
+        cc = cc + self.dzw(O) * Iz(_sq(cz))(O)
+        return sigma, a + b + cc
+
+
+def compute_amd(ctx, closure, U, tracers, nu_e, kappa_e):
+    """_compute_AMD_viscosity! / _compute_AMD_diffusivity!  :154-197 over the window of ctx (interior)."""
+    g, FT = ctx.g, ctx.FT
+    amd = _AMD(ctx, U)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = amd.q_trace()
+        r = amd.r_term()
+        d2 = amd.delta2()
+        Cb_zeta = FT(0) / (FT(2) * g.dz)
+        nu = -FT(closure.Cnu) * d2 * (r - Cb_zeta) / q
+        nu = np.where(q == 0, FT(0), nu)
+        nu_e.interior[...] = np.maximum(FT(0), nu)
+        for name, c in tracers.items():
+            sigma, theta = amd.tracer_terms(c)
+            kap = -FT(closure.Ckappa_for(name)) * d2 * theta / sigma
+            kap = np.where(sigma == 0, FT(0), kap)
+            kappa_e[name].interior[...] = np.maximum(FT(0), kap)
+
+
+# ---------------------------------------------------------------------------------
+# Buoyancy
+# ---------------------------------------------------------------------------------
+class SeawaterBuoyancy:
+    """SeawaterBuoyancy with LinearEquationOfState: b = g (α T - β S)"""
+
+    def __init__(self, g=9.80665, alpha=1.67e-4, beta=7.8e-4):
+        self.g, self.alpha, self.beta = g, alpha, beta
+        self.kind = "seawater"
+        self.required = ("T", "S")
+
+
+class BuoyancyTracer:
+    def __init__(self):
+        self.kind = "tracer"
+        self.required = ("b",)
+
+
+def buoyancy_q(ctx, buoyancy, tracers):
+    FT = ctx.FT
+    if buoyancy.kind == "tracer":
+        return ctx.field(tracers["b"])
+    T, S = ctx.field(tracers["T"]), ctx.field(tracers["S"])
+    gg, al, be = FT(buoyancy.g), FT(buoyancy.alpha), FT(buoyancy.beta)
+    return lambda o: gg * (al * T(o) - be * S(o))
+
+
+# ---------------------------------------------------------------------------------
+# Coriolis: FPlane with active-weighted interpolation
+# ---------------------------------------------------------------------------------
+def _inactive_cell(ctx, o):
+    g = ctx.g
+    bad = np.zeros((1, 1, 1), dtype=bool)
+    for d in range(3):
+        if g.bounded(d):
+            idx = ctx.index(d, o)
+            bad = bad | (idx < 1) | (idx > g.N[d])
+    return bad
+
+
+def _peripheral(ctx, o, loc):
+    """peripheral_node for loc with exactly one Face (inactive_node.jl:152-158)"""
+    res = _inactive_cell(ctx, o)
+    for d in range(3):
+        if loc[d] == "f":
+            res = res | _inactive_cell(ctx, sh(o, d, -1))
+    return res
+
+
+def fplane_x(ctx, f, U):
+    """x_f_cross_U = -f * active_weighted_ℑxyᶠᶜᶜ(v)   f_plane.jl:50"""
+    FT = ctx.FT
+    v = ctx.field(U[1])
+    num = iC(ctx, iF(ctx, v, 0), 1)(O)                      # ℑxyᶠᶜᵃ = ℑyᶜ(ℑxᶠ(v))
+    act = lambda o: (~_peripheral(ctx, o, "cfc")).astype(FT) * np.ones(ctx.shape, FT)
+    nodes = iC(ctx, iF(ctx, act, 0), 1)(O)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        val = np.where(nodes == 0, FT(0), num / nodes)
+    return -FT(f) * val
+
+
+def fplane_y(ctx, f, U):
+    """y_f_cross_U = +f * active_weighted_ℑxyᶜᶠᶜ(u)   f_plane.jl:51"""
+    FT = ctx.FT
+    u = ctx.field(U[0])
+    num = iF(ctx, iC(ctx, u, 0), 1)(O)                      # ℑxyᶜᶠᵃ = ℑyᶠ(ℑxᶜ(u))
+    act = lambda o: (~_peripheral(ctx, o, "fcc")).astype(FT) * np.ones(ctx.shape, FT)
+    nodes = iF(ctx, iC(ctx, act, 0), 1)(O)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        val = np.where(nodes == 0, FT(0), num / nodes)
+    return FT(f) * val
