@@ -1,0 +1,162 @@
+/*
+ * oceananigans_b200.h — C ABI of liboceananigans_b200.so
+ *
+ * A B200-native (sm_100a) implementation of ONE path of Oceananigans.jl v0.100.5: the
+ * NonhydrostaticModel time step on a regular RectilinearGrid.  The reference has no FFI; its seam
+ * is Julia multiple dispatch on the architecture type (ext/OceananigansCUDAExt.jl:37-138).  Every
+ * entry point below names the reference method (file:line under /root/reference) it stands in for;
+ * INTEGRATION.md shows the Julia `ccall` binding for each one.
+ *
+ * Conventions
+ *  - plain C symbols, opaque handle, every call returns 0 on success or a negative oc_status;
+ *    oc_last_error() returns the message of the last failure on the calling thread.
+ *  - unsupported configurations are ERRORS at oc_model_create, never fallbacks (mirrors the
+ *    ArgumentErrors of nonhydrostatic_model.jl:141-169).  There is no CPU path in this library.
+ *  - the library owns all device memory.  Host buffers are dense, x fastest ("parent" layout of
+ *    src/Grids/new_data.jl:15-73): interior buffers are Nx'×Ny'×Nz' with N' = N (+1 for a Face
+ *    location in a Bounded dimension); parent buffers add the halos (N' + 2H; Flat: N=1, H=0).
+ *  - one caller thread per model; work is asynchronous on the model's stream; oc_sync() waits.
+ */
+#ifndef OCEANANIGANS_B200_H
+#define OCEANANIGANS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OC_ABI_VERSION 1
+#define OC_MAX_TRACERS 8
+#define OC_MAX_FIELDS (3 + OC_MAX_TRACERS)
+
+typedef enum { OC_OK = 0, OC_ERR_INVALID = -1, OC_ERR_UNSUPPORTED = -2, OC_ERR_CUDA = -3, OC_ERR_STATE = -4 } oc_status;
+
+typedef enum { OC_F64 = 0, OC_F32 = 1 } oc_float_type;
+typedef enum { OC_PERIODIC = 0, OC_BOUNDED = 1, OC_FLAT = 2 } oc_topology;          /* src/Grids/Grids.jl:68-104 */
+typedef enum { OC_CENTERED2 = 0, OC_WENO5 = 1 } oc_advection;                        /* Centered(order=2), WENO(order=5) */
+typedef enum { OC_RK3 = 0, OC_AB2 = 1 } oc_timestepper;                              /* src/TimeSteppers */
+typedef enum { OC_BUOYANCY_NONE = 0, OC_BUOYANCY_TRACER = 1, OC_BUOYANCY_SEAWATER_LINEAR = 2 } oc_buoyancy;
+
+/* boundary_condition.jl:8,83-110.  OC_BC_DEFAULT resolves by topology and location
+ * (field_boundary_conditions.jl:15-60): Periodic -> periodic, Bounded+Center -> Flux(nothing),
+ * Bounded+Face -> Open(nothing) i.e. impenetrable, Flat -> none. */
+typedef enum { OC_BC_DEFAULT = 0, OC_BC_PERIODIC = 1, OC_BC_FLUX = 2, OC_BC_VALUE = 3, OC_BC_GRADIENT = 4,
+               OC_BC_OPEN = 5, OC_BC_NONE = 6 } oc_bc_kind;
+typedef struct { int32_t kind; int32_t has_value; double value; } oc_bc;             /* scalar-valued BCs only */
+enum { OC_WEST = 0, OC_EAST = 1, OC_SOUTH = 2, OC_NORTH = 3, OC_BOTTOM = 4, OC_TOP = 5 };
+
+/* Field identifiers.  Prognostic fields first, in the order of prognostic_fields(model). */
+enum { OC_FIELD_U = 0, OC_FIELD_V = 1, OC_FIELD_W = 2, OC_FIELD_TRACER0 = 3,
+       OC_FIELD_PNHS = 32, OC_FIELD_PHY = 33, OC_FIELD_NU_E = 34, OC_FIELD_KAPPA_E0 = 40,
+       OC_FIELD_GN0 = 64 /* + prognostic index */, OC_FIELD_GM0 = 96 /* + prognostic index */ };
+
+/* The plain-data description of `NonhydrostaticModel(; grid, advection, closure, tracers, buoyancy,
+ * coriolis, timestepper, boundary_conditions)` (nonhydrostatic_model.jl:115-244). */
+typedef struct {
+    int32_t abi_version;          /* OC_ABI_VERSION */
+    int32_t float_type;           /* oc_float_type: eltype(grid) */
+    int32_t N[3];                 /* grid size; 1 in Flat dimensions */
+    int32_t H[3];                 /* halo size; 0 in Flat dimensions (already inflated, :184,248-262) */
+    int32_t topology[3];          /* oc_topology */
+    double  delta[3];             /* Δx, Δy, Δz as the reference computed them (FT value widened); 1 for Flat */
+    double  extent[3];            /* Lx, Ly, Lz (for poisson_eigenvalues.jl:8-31) */
+    int32_t advection;            /* oc_advection */
+    int32_t timestepper;          /* oc_timestepper */
+    double  ab2_chi;              /* quasi_adams_bashforth_2.jl:39 (default 0.1) */
+    int32_t n_tracers;
+    int32_t has_scalar_diffusivity; double nu; double kappa[OC_MAX_TRACERS];        /* ScalarDiffusivity(ν, κ) */
+    int32_t has_amd; double amd_Cnu; double amd_Ckappa[OC_MAX_TRACERS];             /* AnisotropicMinimumDissipation */
+    int32_t buoyancy;             /* oc_buoyancy */
+    double  gravity, thermal_expansion, haline_contraction;                         /* SeawaterBuoyancy + LinearEquationOfState */
+    int32_t tracer_T, tracer_S, tracer_b;  /* tracer indices used by the buoyancy model (-1 if unused) */
+    int32_t has_coriolis; double coriolis_f;                                        /* FPlane(f) */
+    oc_bc   bcs[OC_MAX_FIELDS][6];         /* per prognostic field × side */
+    int32_t device;               /* CUDA device ordinal */
+    int32_t reserved[7];
+} oc_config;
+
+typedef struct oc_model oc_model;
+
+typedef struct {
+    int32_t location[3];          /* 0 = Center, 1 = Face */
+    int32_t interior_size[3];     /* N' */
+    int32_t parent_size[3];       /* N' + 2H */
+    void*   device_ptr;           /* borrowed: element (i,j,k)=(1,1,1) of the field in the INTERNAL padded layout */
+    int64_t stride_y, stride_z;   /* internal strides in elements (stride_x = 1) */
+} oc_field_info;
+
+typedef struct { double time; int64_t iteration; int32_t stage; double last_dt, last_stage_dt; } oc_clock;
+
+/* ---- life cycle ----  NonhydrostaticModel(...) constructor hooks: nonhydrostatic_pressure_solver
+ * (NonhydrostaticModels.jl:35-40), new_data/zeros(arch,…) (src/Grids/new_data.jl:68-73) */
+const char* oc_last_error(void);
+int  oc_abi_version(void);
+void oc_config_init(oc_config* cfg);                                   /* defaults of the reference constructors */
+int  oc_model_create(const oc_config* cfg, oc_model** out);
+int  oc_model_destroy(oc_model* m);
+int  oc_sync(oc_model* m);                                             /* sync_device! ext/OceananigansCUDAExt.jl:136-138 */
+
+/* ---- data movement ----  set!(u::Field, a::Array) src/Fields/set!.jl:101-121 ; Array(interior(f)) / Array(parent(f));
+ * on_architecture(CPU(), ·) ext/OceananigansCUDAExt.jl:66-76 */
+int  oc_field_info_get(oc_model* m, int field, oc_field_info* info);
+int  oc_upload_interior(oc_model* m, int field, const void* host, size_t nbytes);
+int  oc_download_interior(oc_model* m, int field, void* host, size_t nbytes);
+int  oc_upload_parent(oc_model* m, int field, const void* host, size_t nbytes);
+int  oc_download_parent(oc_model* m, int field, void* host, size_t nbytes);
+
+/* ---- staged entry points (the methods time_step! calls; used by parity tests and mid-step callbacks) ---- */
+/* fill_halo_regions!(fields...; fill_open_bcs)  src/BoundaryConditions/fill_halo_regions.jl:25-36; `fields` lists field ids */
+int  oc_fill_halo_regions(oc_model* m, const int* fields, int nfields, int fill_open_bcs);
+/* update_state!(model; compute_tendencies)  update_nonhydrostatic_model_state.jl:20-56 */
+int  oc_update_state(oc_model* m, int compute_tendencies);
+/* compute_tendencies!(model)  compute_nonhydrostatic_tendencies.jl:18-46 (Gⁿ, without flux-BC terms) */
+int  oc_compute_tendencies(oc_model* m);
+/* compute_flux_bc_tendencies!  :170-184 */
+int  oc_compute_flux_bc_tendencies(oc_model* m);
+/* rk3_substep!(model, Δt, γ, ζ)  runge_kutta_3.jl:179-203 ; stage = 1, 2, 3 selects (γ, ζ) */
+int  oc_rk3_substep(oc_model* m, double dt, int stage);
+/* ab2_step!(model, Δt) with χ  quasi_adams_bashforth_2.jl:127-154 */
+int  oc_ab2_step(oc_model* m, double dt, double chi);
+/* cache_previous_tendencies!  store_tendencies.jl:12-22 */
+int  oc_cache_previous_tendencies(oc_model* m);
+/* compute_pressure_correction!(model, Δt)  pressure_correction.jl:8-20 (halo fill of U with open BCs,
+ * source term, FFT solve, halo fill of pNHS) */
+int  oc_compute_pressure_correction(oc_model* m, double dt);
+/* make_pressure_correction!(model, Δt)  pressure_correction.jl:40-53 */
+int  oc_make_pressure_correction(oc_model* m, double dt);
+/* solve!(ϕ, ::FFTBasedPoissonSolver, b)  fft_based_poisson_solver.jl:95-125 : host rhs (Nx×Ny×Nz, model FT) -> host ϕ */
+int  oc_poisson_solve(oc_model* m, const void* rhs_host, void* phi_host, size_t nbytes);
+
+/* ---- the hot path ---- */
+/* set!(model; ...) tail: fill halos, update_state!, projection with Δt = 1, update_state!  set_nonhydrostatic_model.jl:44-57 */
+int  oc_set_finalize(oc_model* m, int enforce_incompressibility);
+/* time_step!(model::AbstractModel{<:RungeKutta3TimeStepper}, Δt)  runge_kutta_3.jl:93-170 — fused schedule */
+int  oc_time_step_rk3(oc_model* m, double dt);
+/* time_step!(model::AbstractModel{<:QuasiAdamsBashforth2TimeStepper}, Δt; euler)  quasi_adams_bashforth_2.jl:74-114 */
+int  oc_time_step_ab2(oc_model* m, double dt, int euler);
+int  oc_get_clock(oc_model* m, oc_clock* clock);
+int  oc_set_clock(oc_model* m, const oc_clock* clock);                 /* Checkpointer pickup: checkpointer.jl:202-228 */
+
+/* ---- measurement ---- */
+/* Per-kernel-class device timing with CUDA events on the model's stream.  Classes: */
+enum { OC_TIMER_TENDENCY = 0, OC_TIMER_HALO = 1, OC_TIMER_POISSON_RHS = 2, OC_TIMER_FFT = 3, OC_TIMER_POISSON_MID = 4,
+       OC_TIMER_PROJECTION = 5, OC_TIMER_AUX = 6, OC_TIMER_SUBSTEP = 7, OC_TIMER_COUNT = 8 };
+int  oc_timers_enable(oc_model* m, int enable);
+int  oc_timers_reset(oc_model* m);
+int  oc_timers_get(oc_model* m, double* ms /*[OC_TIMER_COUNT]*/, int64_t* launches /*[OC_TIMER_COUNT]*/);
+/* CUDA-event stopwatch on the model's stream (bench.py times K steps with it); stop synchronises the stream. */
+int  oc_stopwatch_start(oc_model* m);
+int  oc_stopwatch_stop(oc_model* m, double* elapsed_ms);
+/* page-locked host buffers for fast oc_upload_* / oc_download_* (cf. unified_array / device_copy_to!
+ * ext/OceananigansCUDAExt.jl:89-100) */
+int  oc_host_alloc(void** ptr, size_t nbytes);
+int  oc_host_free(void* ptr);
+int64_t oc_launch_count(oc_model* m);                                   /* kernels launched by this library so far */
+int  oc_device_bytes(oc_model* m, int64_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCEANANIGANS_B200_H */

@@ -1,0 +1,541 @@
+"""Host-side mirror of the reference API for the NonhydrostaticModel path.
+
+Julia is not available in the build image, so the host layer above the C ABI is Python; it mirrors the
+reference's names, argument meaning and error behaviour (``!`` becomes a trailing underscore):
+
+    RectilinearGrid(arch, FT; size, extent | x,y,z, topology, halo)   src/Grids/rectilinear_grid.jl:264-291
+    NonhydrostaticModel(; grid, advection, closure, tracers, buoyancy, coriolis, timestepper,
+                        boundary_conditions)                          src/Models/NonhydrostaticModels/nonhydrostatic_model.jl:115-244
+    set_(model; u=…, T=…)            set!         set_nonhydrostatic_model.jl:33-60
+    time_step_(model, Δt)            time_step!   src/TimeSteppers/runge_kutta_3.jl:93, quasi_adams_bashforth_2.jl:74
+    Simulation(model; Δt, stop_iteration, stop_time), run_(sim)      src/Simulations/run.jl:92-176
+    update_state_, compute_tendencies_, fill_halo_regions_, …        staged entry points
+
+The Julia glue with the identical mapping is in julia/OceananigansB200Ext.jl and INTEGRATION.md.
+All numerics run in liboceananigans_b200.so (CUDA, sm_100a); nothing here computes on the CPU.
+"""
+import ctypes as C
+import math
+from fractions import Fraction
+
+import numpy as np
+
+from . import _lib as L
+
+__all__ = [
+    "B200", "Periodic", "Bounded", "Flat", "Center", "Face", "RectilinearGrid",
+    "Centered", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation",
+    "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "FPlane",
+    "FluxBoundaryCondition", "ValueBoundaryCondition", "GradientBoundaryCondition", "OpenBoundaryCondition",
+    "FieldBoundaryConditions", "NonhydrostaticModel", "Field", "set_", "time_step_", "update_state_",
+    "compute_tendencies_", "compute_flux_bc_tendencies_", "rk3_substep_", "ab2_step_", "cache_previous_tendencies_",
+    "compute_pressure_correction_", "make_pressure_correction_", "fill_halo_regions_", "solve_poisson",
+    "interior", "parent", "Simulation", "run_", "Clock", "OceananigansB200Error",
+]
+
+OceananigansB200Error = L.OceananigansB200Error
+
+
+class B200:
+    """Architecture tag: `struct B200 <: AbstractSerialArchitecture` (cf. GPU(), src/Architectures.jl:44-46)."""
+
+    def __init__(self, device=0):
+        self.device = device
+
+
+class _Topo:
+    def __init__(self, name, code):
+        self.name, self.code = name, code
+
+    def __repr__(self):
+        return self.name
+
+
+Periodic, Bounded, Flat = _Topo("Periodic", L.OC_PERIODIC), _Topo("Bounded", L.OC_BOUNDED), _Topo("Flat", L.OC_FLAT)
+Center, Face = "Center", "Face"
+
+
+def _tuple(x, n=None):
+    if x is None:
+        return None
+    t = tuple(x) if isinstance(x, (tuple, list)) else (x,)
+    return t
+
+
+class RectilinearGrid:
+    """Regular RectilinearGrid.  `size`, `extent`/`x,y,z`, `halo` list only the non-Flat dimensions."""
+
+    def __init__(self, architecture=None, FT=np.float64, *, size, extent=None, x=None, y=None, z=None,
+                 topology=(Periodic, Periodic, Bounded), halo=None):
+        if isinstance(architecture, type) or (architecture is not None and not isinstance(architecture, B200)):
+            # RectilinearGrid(FT; ...) form
+            FT, architecture = architecture, None
+        self.architecture = architecture or B200()
+        self.FT = np.dtype(FT).type
+        if self.FT not in (np.float32, np.float64):
+            raise ValueError("eltype(grid) must be Float32 or Float64")
+        self.topology = tuple(topology)
+        nonflat = [d for d in range(3) if self.topology[d] is not Flat]
+        size = _tuple(size)
+        if len(size) != len(nonflat):
+            raise ValueError(f"size={size} must have {len(nonflat)} elements for topology {self.topology}")  # input_validation.jl
+        bounds = [None] * 3
+        if extent is not None:
+            extent = _tuple(extent)
+            if len(extent) != len(nonflat):
+                raise ValueError("extent must list the non-Flat dimensions")
+            for n, d in enumerate(nonflat):
+                bounds[d] = (0.0, float(extent[n])) if d < 2 else (-float(extent[n]), 0.0)
+        else:
+            for d, b in enumerate((x, y, z)):
+                if b is not None:
+                    if callable(b) or len(b) != 2:
+                        raise NotImplementedError("stretched coordinates are out of scope (FourierTridiagonalPoissonSolver path)")
+                    bounds[d] = (float(b[0]), float(b[1]))
+        halo = _tuple(halo)
+        N, H, Lx, D, x0 = [1, 1, 1], [0, 0, 0], [1.0] * 3, [1.0] * 3, [0.0] * 3
+        for n, d in enumerate(nonflat):
+            if bounds[d] is None:
+                raise ValueError("missing domain extent for a non-Flat dimension")
+            N[d] = int(size[n])
+            H[d] = int(halo[n]) if halo is not None else min(3, N[d])            # input_validation.jl:71-77
+            a, b = bounds[d]
+            if not b > a:
+                raise ValueError("domain end must be larger than its start")
+            delta = (Fraction(b) - Fraction(a)) / N[d]                          # grid_generation.jl:105-110
+            D[d] = float(self.FT(float(delta)))
+            Lx[d] = float(self.FT(float(Fraction(b) - Fraction(a))))
+            x0[d] = a
+        self.N, self.H, self.L, self.D, self.x0 = tuple(N), tuple(H), tuple(Lx), tuple(D), tuple(x0)
+        self.Nx, self.Ny, self.Nz = self.N
+        self.Hx, self.Hy, self.Hz = self.H
+        self.Lx, self.Ly, self.Lz = self.L
+        self.dx, self.dy, self.dz = self.D
+
+    def with_halo(self, halo):
+        g = RectilinearGrid.__new__(RectilinearGrid)
+        g.__dict__.update(self.__dict__)
+        g.H = tuple(0 if self.topology[d] is Flat else int(halo[d]) for d in range(3))
+        g.Hx, g.Hy, g.Hz = g.H
+        return g
+
+    def nodes(self, d, loc):
+        n = self.N[d] + (1 if (loc == Face and self.topology[d] is Bounded) else 0)
+        return self.x0[d] + (np.arange(n) + (0.5 if loc == Center else 0.0)) * self.D[d]
+
+    def __repr__(self):
+        return f"RectilinearGrid{{{self.FT.__name__}}}(size={self.N}, halo={self.H}, topology={self.topology})"
+
+
+# ------------------------------------------------------------------------------------------ physics descriptors
+class Centered:
+    def __init__(self, FT=np.float64, order=2):
+        if order != 2:
+            raise NotImplementedError("Centered: only order=2 is implemented on B200 (other orders: SURVEY §8f)")
+        self.order, self.buffer, self.code = 2, 1, L.OC_CENTERED2
+
+
+class WENO:
+    def __init__(self, FT=np.float64, order=5, bounds=None):
+        if order != 5 or bounds is not None:
+            raise NotImplementedError("WENO: only order=5 without bounds is implemented on B200")
+        self.order, self.buffer, self.code = 5, 3, L.OC_WENO5
+
+
+class ScalarDiffusivity:
+    def __init__(self, FT=np.float64, nu=0.0, kappa=0.0, **kw):
+        self.nu = kw.get("ν", nu)
+        self.kappa = kw.get("κ", kappa)
+        if callable(self.nu) or callable(self.kappa):
+            raise NotImplementedError("function-valued diffusivities are out of scope")
+
+
+class AnisotropicMinimumDissipation:
+    def __init__(self, FT=np.float64, C=1.0 / 3.0, Cnu=None, Ckappa=None, Cb=None):
+        if Cb is not None:
+            raise NotImplementedError("AMD buoyancy modification (Cb) is out of scope")
+        self.Cnu = C if Cnu is None else Cnu
+        self.Ckappa = C if Ckappa is None else Ckappa
+
+
+class LinearEquationOfState:
+    def __init__(self, FT=np.float64, thermal_expansion=1.67e-4, haline_contraction=7.8e-4):
+        self.thermal_expansion, self.haline_contraction = thermal_expansion, haline_contraction
+
+
+class SeawaterBuoyancy:
+    def __init__(self, FT=np.float64, gravitational_acceleration=9.80665, equation_of_state=None,
+                 constant_temperature=None, constant_salinity=None):
+        if constant_temperature is not None or constant_salinity is not None:
+            raise NotImplementedError("constant_temperature / constant_salinity are out of scope")
+        self.g = gravitational_acceleration
+        self.eos = equation_of_state or LinearEquationOfState()
+        if not isinstance(self.eos, LinearEquationOfState):
+            raise NotImplementedError("only LinearEquationOfState (TEOS-10 coefficients are not in the reference tree)")
+        self.required = ("T", "S")
+
+
+class BuoyancyTracer:
+    required = ("b",)
+
+
+class FPlane:
+    def __init__(self, FT=np.float64, f=None):
+        if f is None:
+            raise ValueError("FPlane needs f")
+        self.f = f
+
+
+class _BC:
+    def __init__(self, kind, value):
+        if callable(value) or (value is not None and not np.isscalar(value)):
+            raise NotImplementedError("only scalar-valued boundary conditions are implemented (arrays/functions: next)")
+        self.kind, self.value = kind, value
+
+
+def FluxBoundaryCondition(value):
+    return _BC(L.OC_BC_FLUX, value)
+
+
+def ValueBoundaryCondition(value):
+    return _BC(L.OC_BC_VALUE, value)
+
+
+def GradientBoundaryCondition(value):
+    return _BC(L.OC_BC_GRADIENT, value)
+
+
+def OpenBoundaryCondition(value=None):
+    return _BC(L.OC_BC_OPEN, value)
+
+
+_SIDES = ("west", "east", "south", "north", "bottom", "top")
+
+
+class FieldBoundaryConditions:
+    def __init__(self, **sides):
+        for k in sides:
+            if k not in _SIDES:
+                raise ValueError(f"unknown side {k}")
+        self.sides = sides
+
+
+class Clock:
+    def __init__(self, model):
+        self._m = model
+
+    def _get(self):
+        c = L.oc_clock()
+        self._m._lib.check(self._m._lib.oc_get_clock(self._m._h, C.byref(c)))
+        return c
+
+    time = property(lambda s: s._get().time)
+    iteration = property(lambda s: s._get().iteration)
+    stage = property(lambda s: s._get().stage)
+    last_Δt = property(lambda s: s._get().last_dt)
+    last_dt = property(lambda s: s._get().last_dt)
+    last_stage_Δt = property(lambda s: s._get().last_stage_dt)
+
+
+class Field:
+    """A handle to a device field.  `interior(f)` / `parent(f)` return host copies (numpy, indexed [i, j, k])."""
+
+    def __init__(self, model, fid, name):
+        self.model, self.id, self.name = model, fid, name
+
+    def info(self):
+        info = L.oc_field_info()
+        self.model._lib.check(self.model._lib.oc_field_info_get(self.model._h, self.id, C.byref(info)))
+        return info
+
+    @property
+    def location(self):
+        return tuple(Face if x else Center for x in self.info().location)
+
+    def _download(self, parent_):
+        info = self.info()
+        shape = tuple(info.parent_size if parent_ else info.interior_size)
+        a = np.empty(shape, dtype=self.model.grid.FT, order="F")
+        fn = self.model._lib.oc_download_parent if parent_ else self.model._lib.oc_download_interior
+        self.model._lib.check(fn(self.model._h, self.id, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return a
+
+    def interior(self):
+        return self._download(False)
+
+    def parent(self):
+        return self._download(True)
+
+    def set(self, value):
+        """set!(field, array | number | f(x, y, z))   src/Fields/set!.jl:34-121"""
+        g = self.model.grid
+        info = self.info()
+        shape = tuple(info.interior_size)
+        if callable(value):
+            locs = [Face if x else Center for x in info.location]
+            nodes = [g.nodes(d, locs[d]) if g.topology[d] is not Flat else np.zeros(1) for d in range(3)]
+            X = np.meshgrid(*nodes, indexing="ij")
+            args = [A for d, A in enumerate(X) if g.topology[d] is not Flat]
+            value = np.broadcast_to(np.asarray(value(*args), dtype=np.float64), X[0].shape)
+        if np.isscalar(value):
+            a = np.full(shape, value, dtype=g.FT, order="F")
+        else:
+            a = np.asarray(value)
+            if a.size != int(np.prod(shape)):
+                raise ValueError(f"cannot set {self.name} of size {shape} from an array of shape {a.shape}")   # set!.jl:105-112
+            a = np.asfortranarray(a.reshape(shape).astype(g.FT))
+        self.model._lib.check(self.model._lib.oc_upload_interior(self.model._h, self.id, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def set_parent(self, a):
+        info = self.info()
+        a = np.asfortranarray(np.asarray(a).reshape(tuple(info.parent_size)).astype(self.model.grid.FT))
+        self.model._lib.check(self.model._lib.oc_upload_parent(self.model._h, self.id, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+
+def interior(f):
+    return f.interior()
+
+
+def parent(f):
+    return f.parent()
+
+
+class _NT(dict):
+    """NamedTuple-like: attribute and key access"""
+    __getattr__ = dict.__getitem__
+
+
+class NonhydrostaticModel:
+    def __init__(self, *, grid, advection=None, closure=None, tracers=(), buoyancy=None, coriolis=None,
+                 timestepper="RungeKutta3", boundary_conditions=None, forcing=None, stokes_drift=None,
+                 background_fields=None, biogeochemistry=None, particles=None, library=None):
+        for name, val in (("forcing", forcing), ("stokes_drift", stokes_drift), ("background_fields", background_fields),
+                          ("biogeochemistry", biogeochemistry), ("particles", particles)):
+            if val:
+                raise NotImplementedError(f"{name} is out of scope of the B200 path (Julia closures / other subsystems)")
+        self._lib = library if library is not None else L.load()
+        tracers = (tracers,) if isinstance(tracers, str) else tuple(tracers)
+        if len(tracers) > L.OC_MAX_TRACERS:
+            raise ValueError("too many tracers")
+        advection = advection if advection is not None else Centered()
+        closures = () if closure is None else (tuple(closure) if isinstance(closure, (tuple, list)) else (closure,))
+        # inflate_grid_halo_size   nonhydrostatic_model.jl:184,248-262
+        need = advection.buffer
+        for c in closures:
+            need = max(need, 2 if isinstance(c, AnisotropicMinimumDissipation) else 1)
+        H = tuple(max(grid.H[d], need) if grid.topology[d] is not Flat else 0 for d in range(3))
+        if H != grid.H:
+            grid = grid.with_halo(H)
+        self.grid, self.advection, self.closure, self.buoyancy, self.coriolis = grid, advection, closure, buoyancy, coriolis
+        self.timestepper_name = {"RungeKutta3": "RungeKutta3", "QuasiAdamsBashforth2": "QuasiAdamsBashforth2"}.get(timestepper)
+        if self.timestepper_name is None:
+            raise ValueError(f"unknown timestepper {timestepper}")
+        cfg = L.oc_config()
+        self._lib.oc_config_init(C.byref(cfg))
+        cfg.float_type = L.OC_F64 if grid.FT is np.float64 else L.OC_F32
+        for d in range(3):
+            cfg.N[d], cfg.H[d], cfg.topology[d] = grid.N[d], grid.H[d], grid.topology[d].code
+            cfg.delta[d], cfg.extent[d] = grid.D[d], grid.L[d]
+        cfg.advection = advection.code
+        cfg.timestepper = L.OC_RK3 if timestepper == "RungeKutta3" else L.OC_AB2
+        cfg.n_tracers = len(tracers)
+        sd = [c for c in closures if isinstance(c, ScalarDiffusivity)]
+        amd = [c for c in closures if isinstance(c, AnisotropicMinimumDissipation)]
+        if len(sd) > 1 or len(amd) > 1 or len(sd) + len(amd) != len(closures):
+            raise NotImplementedError("closure must be ScalarDiffusivity, AnisotropicMinimumDissipation or a 2-tuple of them")
+        pick = lambda v, n: float(v[n]) if isinstance(v, dict) else float(v)
+        if sd:
+            cfg.has_scalar_diffusivity, cfg.nu = 1, float(sd[0].nu)
+            for t, n in enumerate(tracers):
+                cfg.kappa[t] = pick(sd[0].kappa, n)
+        if amd:
+            cfg.has_amd, cfg.amd_Cnu = 1, float(amd[0].Cnu)
+            for t, n in enumerate(tracers):
+                cfg.amd_Ckappa[t] = pick(amd[0].Ckappa, n)
+        if buoyancy is not None:
+            for n in buoyancy.required:
+                if n not in tracers:
+                    raise ValueError(f"buoyancy model requires tracer {n}")         # validate_buoyancy
+            if isinstance(buoyancy, SeawaterBuoyancy):
+                cfg.buoyancy = L.OC_BUOYANCY_SEAWATER_LINEAR
+                cfg.gravity, cfg.thermal_expansion, cfg.haline_contraction = buoyancy.g, buoyancy.eos.thermal_expansion, buoyancy.eos.haline_contraction
+                cfg.tracer_T, cfg.tracer_S = tracers.index("T"), tracers.index("S")
+            elif isinstance(buoyancy, BuoyancyTracer):
+                cfg.buoyancy, cfg.tracer_b = L.OC_BUOYANCY_TRACER, tracers.index("b")
+            else:
+                raise NotImplementedError("unsupported buoyancy model")
+        if coriolis is not None:
+            if not isinstance(coriolis, FPlane):
+                raise NotImplementedError("only FPlane Coriolis")
+            cfg.has_coriolis, cfg.coriolis_f = 1, float(coriolis.f)
+        names = ("u", "v", "w") + tracers
+        bcs = boundary_conditions or {}
+        for k in bcs:
+            if k not in names:
+                raise ValueError(f"boundary_conditions given for unknown field {k}")
+        for f, n in enumerate(names):
+            fb = bcs.get(n)
+            if fb is None:
+                continue
+            for s, side in enumerate(_SIDES):
+                bc = fb.sides.get(side)
+                if bc is not None:
+                    cfg.bcs[f][s].kind = bc.kind
+                    cfg.bcs[f][s].has_value = 0 if bc.value is None else 1
+                    cfg.bcs[f][s].value = 0.0 if bc.value is None else float(bc.value)
+        cfg.device = grid.architecture.device
+        self._cfg = cfg
+        h = C.c_void_p()
+        self._lib.check(self._lib.oc_model_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.tracer_names = tracers
+        self.velocities = _NT(u=Field(self, 0, "u"), v=Field(self, 1, "v"), w=Field(self, 2, "w"))
+        self.tracers = _NT({n: Field(self, 3 + t, n) for t, n in enumerate(tracers)})
+        self.pressures = _NT(pNHS=Field(self, L.OC_FIELD_PNHS, "pNHS"),
+                             pHY=Field(self, L.OC_FIELD_PHY, "pHY′") if buoyancy is not None else None)
+        self.diffusivity_fields = None
+        if amd:
+            self.diffusivity_fields = _NT(nu_e=Field(self, L.OC_FIELD_NU_E, "νₑ"),
+                                          kappa_e=_NT({n: Field(self, L.OC_FIELD_KAPPA_E0 + t, "κₑ." + n) for t, n in enumerate(tracers)}))
+        self.fields = _NT({**self.velocities, **self.tracers})
+        self.timestepper = _NT(Gn=_NT({n: Field(self, L.OC_FIELD_GN0 + f, "Gⁿ." + n) for f, n in enumerate(names)}),
+                               Gm=_NT({n: Field(self, L.OC_FIELD_GM0 + f, "G⁻." + n) for f, n in enumerate(names)}))
+        self.clock = Clock(self)
+        # constructor tail: update_state!(model; compute_tendencies=false)   nonhydrostatic_model.jl:241
+        self._lib.check(self._lib.oc_update_state(self._h, 0))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.oc_model_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # measurement helpers
+    def sync(self):
+        self._lib.check(self._lib.oc_sync(self._h))
+
+    def launch_count(self):
+        return int(self._lib.oc_launch_count(self._h))
+
+    def device_bytes(self):
+        b = C.c_int64()
+        self._lib.check(self._lib.oc_device_bytes(self._h, C.byref(b)))
+        return b.value
+
+    def timers(self, enable=None, reset=False):
+        if enable is not None:
+            self._lib.check(self._lib.oc_timers_enable(self._h, 1 if enable else 0))
+        if reset:
+            self._lib.check(self._lib.oc_timers_reset(self._h))
+            return None
+        ms = (C.c_double * 8)()
+        n = (C.c_int64 * 8)()
+        self._lib.check(self._lib.oc_timers_get(self._h, ms, n))
+        return {name: (ms[i], n[i]) for i, name in enumerate(L.OC_TIMER_NAMES)}
+
+
+# ------------------------------------------------------------------------------------------ model methods
+def set_(model, enforce_incompressibility=True, **kwargs):
+    """set!(model; enforce_incompressibility=true, kwargs...)"""
+    for name, value in kwargs.items():
+        if name not in model.fields:
+            raise ValueError(f"name {name} not found in model.velocities or model.tracers.")   # set_nonhydrostatic_model.jl:41
+        model.fields[name].set(value)
+    model._lib.check(model._lib.oc_set_finalize(model._h, 1 if enforce_incompressibility else 0))
+
+
+def time_step_(model, dt, euler=False, callbacks=()):
+    """time_step!(model, Δt; callbacks=[], euler=false)"""
+    if callbacks:
+        raise NotImplementedError("mid-step callbacks need the staged entry points; use update_state_/… directly")
+    if model.timestepper_name == "RungeKutta3":
+        model._lib.check(model._lib.oc_time_step_rk3(model._h, float(dt)))
+    else:
+        model._lib.check(model._lib.oc_time_step_ab2(model._h, float(dt), 1 if euler else 0))
+
+
+def update_state_(model, compute_tendencies=True):
+    model._lib.check(model._lib.oc_update_state(model._h, 1 if compute_tendencies else 0))
+
+
+def compute_tendencies_(model):
+    model._lib.check(model._lib.oc_compute_tendencies(model._h))
+
+
+def compute_flux_bc_tendencies_(model):
+    model._lib.check(model._lib.oc_compute_flux_bc_tendencies(model._h))
+
+
+def rk3_substep_(model, dt, stage):
+    model._lib.check(model._lib.oc_rk3_substep(model._h, float(dt), int(stage)))
+
+
+def ab2_step_(model, dt, chi=0.1):
+    model._lib.check(model._lib.oc_ab2_step(model._h, float(dt), float(chi)))
+
+
+def cache_previous_tendencies_(model):
+    model._lib.check(model._lib.oc_cache_previous_tendencies(model._h))
+
+
+def compute_pressure_correction_(model, dt):
+    model._lib.check(model._lib.oc_compute_pressure_correction(model._h, float(dt)))
+
+
+def make_pressure_correction_(model, dt):
+    model._lib.check(model._lib.oc_make_pressure_correction(model._h, float(dt)))
+
+
+def fill_halo_regions_(fields, fill_open_bcs=True):
+    """fill_halo_regions!(field | fields)"""
+    fields = [fields] if isinstance(fields, Field) else list(fields)
+    model = fields[0].model
+    ids = (C.c_int * len(fields))(*[f.id for f in fields])
+    model._lib.check(model._lib.oc_fill_halo_regions(model._h, ids, len(fields), 1 if fill_open_bcs else 0))
+
+
+def solve_poisson(model, rhs):
+    """solve!(ϕ, model.pressure_solver, rhs) for a host right-hand side of shape (Nx, Ny, Nz)"""
+    g = model.grid
+    a = np.asfortranarray(np.asarray(rhs).reshape(g.N).astype(g.FT))
+    out = np.empty(g.N, dtype=g.FT, order="F")
+    model._lib.check(model._lib.oc_poisson_solve(model._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), a.nbytes))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ Simulation
+class Simulation:
+    """Simulation(model; Δt, stop_iteration=Inf, stop_time=Inf)   src/Simulations/simulation.jl"""
+
+    def __init__(self, model, Δt=None, dt=None, stop_iteration=math.inf, stop_time=math.inf, align_time_step=True):
+        self.model = model
+        self.Δt = Δt if Δt is not None else dt
+        if self.Δt is None:
+            raise ValueError("Simulation needs Δt")
+        self.stop_iteration, self.stop_time, self.align_time_step = stop_iteration, stop_time, align_time_step
+        self.callbacks = {}
+        self.running = False
+
+    def add_callback(self, name, fn, every=1):
+        self.callbacks[name] = (fn, every)
+
+
+def run_(sim):
+    """run!(simulation)  src/Simulations/run.jl:92-176 — time_step!(sim) until a stop criterion fires."""
+    model = sim.model
+    sim.running = True
+    while sim.running:
+        clk = model.clock._get()
+        if clk.iteration >= sim.stop_iteration or clk.time >= sim.stop_time:
+            break
+        dt = sim.Δt
+        if sim.align_time_step and math.isfinite(sim.stop_time):       # aligned_time_step  run.jl:41-57
+            dt = min(dt, sim.stop_time - clk.time)
+        time_step_(model, dt)
+        it = clk.iteration + 1
+        for fn, every in sim.callbacks.values():
+            if it % every == 0:
+                fn(sim)
+    sim.running = False

@@ -1,0 +1,117 @@
+// oc_advection.h — point reconstructions for flux-form advection: Centered(order=2/4), WENO(order=5)
+// with its WENO(order=3) -> UpwindBiased(order=1) boundary chain.
+//
+// Replaces (paths under /root/reference/src/Advection): centered_reconstruction.jl:47-55,
+// upwind_biased_reconstruction.jl:57-86, weno_interpolants.jl:71-83,117-137,169-174,204-216,261-266,
+// 290-338,409-437,500, reconstruction_coefficients.jl:122-152, topologically_conditional_interpolation.jl
+// :46-52,99-120.  All functions take a pointer `p` to ψ at the FACE index (ψ[i] in the reference's
+// notation; ψ[i+n] = p[n*s]) and work for global or shared memory alike.
+#pragma once
+#include "oc_common.h"
+
+namespace oc {
+
+// ---- symmetric (advecting-velocity) interpolation: Σ c_n · (a·q[i+n]) --------------------------------
+// Centered(order=2):  0.5 q[i-1] + 0.5 q[i]      (centered_reconstruction.jl:47-49, coefficients (1/2, 1/2))
+template <class FT>
+OC_HD FT sym2(const FT* p, int s, FT a) {
+    return FT(0.5) * (a * p[-s]) + FT(0.5) * (a * p[0]);
+}
+// Centered(order=4):  c0 q[i-2] + c1 q[i-1] + c2 q[i] + c3 q[i+1], summed left to right (@muladd)
+template <class FT>
+OC_HD FT sym4(const AdvCoef<FT>& C, const FT* p, int s, FT a) {
+    FT r = C.c4[0] * (a * p[-2 * s]);
+    r = r + C.c4[1] * (a * p[-s]);
+    r = r + C.c4[2] * (a * p[0]);
+    r = r + C.c4[3] * (a * p[s]);
+    return r;
+}
+
+// ---- WENO building blocks -----------------------------------------------------------------------------
+// β for WENO{3}: ψ1(C1ψ1 + C2ψ2 + C3ψ3) + ψ2(C4ψ2 + C5ψ3) + ψ3ψ3C6     weno_interpolants.jl:204-216,261
+template <class FT>
+OC_HD FT beta3(FT a, FT b, FT c, FT C1, FT C2, FT C3, FT C4, FT C5, FT C6) {
+    return a * (C1 * a + C2 * b + C3 * c) + b * (C4 * b + C5 * c) + c * c * C6;
+}
+
+// WENO(order=5) biased reconstruction at the face.  q0..q4 is the 5-point upwind-ordered stencil:
+//   LeftBias : (ψ[i-3], ψ[i-2], ψ[i-1], ψ[i],   ψ[i+1])
+//   RightBias: (ψ[i+2], ψ[i+1], ψ[i],   ψ[i-1], ψ[i-2])
+// so that S0 = (q2,q3,q4), S1 = (q1,q2,q3), S2 = (q0,q1,q2) for both biases (weno_interpolants.jl:435-437).
+template <class FT>
+OC_HD FT weno5_value(const AdvCoef<FT>& C, FT q0, FT q1, FT q2, FT q3, FT q4) {
+    // smoothness_coefficients :172-174
+    FT b0 = beta3<FT>(q2, q3, q4, FT(10), FT(-31), FT(11), FT(25), FT(-19), FT(4));
+    FT b1 = beta3<FT>(q1, q2, q3, FT(4), FT(-13), FT(5), FT(13), FT(-13), FT(4));
+    FT b2 = beta3<FT>(q0, q1, q2, FT(4), FT(-19), FT(11), FT(25), FT(-31), FT(10));
+    FT tau = oc_abs<FT>(b0 - b2);                                   // :309
+    FT r0 = newton_div(tau, b0 + C.eps);                            // :293
+    FT r1 = newton_div(tau, b1 + C.eps);
+    FT r2 = newton_div(tau, b2 + C.eps);
+    FT a0 = C.w5c[0] * (FT(1) + r0 * r0);
+    FT a1 = C.w5c[1] * (FT(1) + r1 * r1);
+    FT a2 = C.w5c[2] * (FT(1) + r2 * r2);
+    FT rs = FT(1) / (a0 + a1 + a2);                                 // :336
+    FT p0 = C.w5p[0][0] * q2 + C.w5p[0][1] * q3 + C.w5p[0][2] * q4; // biased_p :136-137
+    FT p1 = C.w5p[1][0] * q1 + C.w5p[1][1] * q2 + C.w5p[1][2] * q3;
+    FT p2 = C.w5p[2][0] * q0 + C.w5p[2][1] * q1 + C.w5p[2][2] * q2;
+    return (a0 * rs) * p0 + (a1 * rs) * p1 + (a2 * rs) * p2;        // :500
+}
+
+// WENO(order=3): q0..q2 upwind ordered: Left (ψ[i-2], ψ[i-1], ψ[i]); Right (ψ[i+1], ψ[i], ψ[i-1]);
+// S0 = (q1,q2), S1 = (q0,q1)   (:432-433); β = ψ1(ψ1 - 2ψ2) + ψ2ψ2   (:169-170)
+template <class FT>
+OC_HD FT weno3_value(const AdvCoef<FT>& C, FT q0, FT q1, FT q2) {
+    FT b0 = q1 * (FT(1) * q1 + FT(-2) * q2) + q2 * q2 * FT(1);
+    FT b1 = q0 * (FT(1) * q0 + FT(-2) * q1) + q1 * q1 * FT(1);
+    FT tau = oc_abs<FT>(b0 - b1);                                   // :308
+    FT r0 = newton_div(tau, b0 + C.eps);
+    FT r1 = newton_div(tau, b1 + C.eps);
+    FT a0 = C.w3c[0] * (FT(1) + r0 * r0);
+    FT a1 = C.w3c[1] * (FT(1) + r1 * r1);
+    FT rs = FT(1) / (a0 + a1);
+    FT p0 = C.w3p[0][0] * q1 + C.w3p[0][1] * q2;
+    FT p1 = C.w3p[1][0] * q0 + C.w3p[1][1] * q1;
+    return (a0 * rs) * p0 + (a1 * rs) * p1;
+}
+
+// Order selector near walls of a Bounded dimension, in terms of the 0-based FACE index f of the stencil
+// (topologically_conditional_interpolation.jl:46-52 with required_halo_size = 3 and 2):
+//   face-type  : high order iff 3 <= f <= N-3 ; mid order iff 2 <= f <= N-2
+//   centre-type: (evaluated at face f = c+1)  high iff 3 <= f <= N-2 ; mid iff 2 <= f <= N-1
+struct OrderWindow {
+    int lo_hi, hi_hi, lo_mid, hi_mid;
+};
+OC_HD OrderWindow order_window(bool bounded, bool centre_type, int N) {
+    OrderWindow w;
+    if (!bounded) {
+        w.lo_hi = -(1 << 30); w.hi_hi = (1 << 30); w.lo_mid = w.lo_hi; w.hi_mid = w.hi_hi;
+    } else if (centre_type) {
+        w.lo_hi = 3; w.hi_hi = N - 2; w.lo_mid = 2; w.hi_mid = N - 1;
+    } else {
+        w.lo_hi = 3; w.hi_hi = N - 3; w.lo_mid = 2; w.hi_mid = N - 2;
+    }
+    return w;
+}
+
+// _biased_interpolate for the WENO(order=5) scheme at face index f (pointer p at ψ[f], stride s).
+template <class FT>
+OC_HD FT weno5_biased(const AdvCoef<FT>& C, const FT* p, int s, bool left, int f, const OrderWindow& w) {
+    if (f >= w.lo_hi && f <= w.hi_hi) {
+        int o0 = left ? -3 * s : 2 * s, ds = left ? s : -s;
+        return weno5_value<FT>(C, p[o0], p[o0 + ds], p[o0 + 2 * ds], p[o0 + 3 * ds], p[o0 + 4 * ds]);
+    } else if (f >= w.lo_mid && f <= w.hi_mid) {
+        int o0 = left ? -2 * s : s, ds = left ? s : -s;
+        return weno3_value<FT>(C, p[o0], p[o0 + ds], p[o0 + 2 * ds]);
+    }
+    return left ? p[-s] : p[0];                                      // UpwindBiased(order=1)
+}
+
+// _symmetric_interpolate for the WENO(order=5) scheme (Centered(4) -> Centered(2) near walls) of a·q
+template <class FT>
+OC_HD FT weno5_symmetric(const AdvCoef<FT>& C, const FT* p, int s, FT a, int f, const OrderWindow& w) {
+    if (f >= w.lo_hi && f <= w.hi_hi) return sym4<FT>(C, p, s, a);
+    return sym2<FT>(p, s, a);
+}
+
+}  // namespace oc

@@ -1,0 +1,79 @@
+// oc_common.h — geometry, coefficient tables and small helpers shared by all kernels.
+//
+// Internal field layout: every 3-D field of a model shares ONE geometry.  A field
+// pointer `p` addresses interior element (0,0,0) (reference index (1,1,1)); element (i,j,k) is
+// p[i + j*sy + k*sz].  Rows are padded so that p and every row start are 128-byte aligned; halos
+// (H planes each side, +1 plane for the extra Face point of Bounded dimensions) surround the interior.
+// Flat dimensions are stored as Periodic with N = 1 and H = 3 (all planes equal), which makes every
+// difference zero and every interpolation the identity, exactly as src/Operators/*.jl define for Flat.
+#pragma once
+#include "oc_exec.h"
+
+namespace oc {
+
+template <class FT>
+struct Geom {
+    int N[3];        // interior size
+    int H[3];        // internal halo size
+    int bounded[3];  // 1 = Bounded topology
+    int flat[3];     // 1 = Flat (stored as periodic N=1)
+    int sy, sz;      // strides in elements (sx = 1)
+    FT d[3];         // Δx, Δy, Δz
+    FT rd[3];        // 1/Δ           reciprocal_metric_operators.jl:7
+    FT A[3];         // Ax=Δy·Δz, Ay=Δx·Δz, Az=Δx·Δy   spacings_and_areas_and_volumes.jl:309-333
+    FT V, rV;        // V = Az·Δz, 1/V                  :376, reciprocal_metric_operators.jl:13
+    OC_HD int st(int dim) const { return dim == 0 ? 1 : (dim == 1 ? sy : sz); }
+    OC_HD int idx(int i, int j, int k) const { return i + j * sy + k * sz; }
+};
+
+// Reconstruction coefficients, computed on the host exactly like the reference
+// (reconstruction_coefficients.jl:49-64: rationals rounded to FT, the last one is 1 - sum(others)).
+template <class FT>
+struct AdvCoef {
+    FT c4[4];        // Centered(order=4) in stencil order ψ[i-2..i+1]
+    FT w5p[3][3];    // WENO{3} coeff_p(r)   weno_interpolants.jl:117-118
+    FT w5c[3];       // C★ = 3/10, 3/5, 1/10  :81-83
+    FT w3p[2][2];    // WENO{2} coeff_p(r)
+    FT w3c[2];       // C★ = 2/3, 1/3         :78-79
+    FT eps;          // ϵ = 1f-8 widened      :71
+};
+
+template <class FT>
+OC_HD FT oc_abs(FT x) { return x < FT(0) ? -x : x; }
+
+template <class FT>
+OC_HD FT oc_max(FT a, FT b) { return a > b ? a : b; }
+
+OC_HD double oc_fma(double a, double b, double c) {
+#ifdef OC_HOSTSIM
+    return std::fma(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+
+// newton_div(Float32, a, b)   src/Utils/newton_div.jl:8-23
+OC_HD double newton_div(double a, double b) {
+    float bl = (float)b;
+#ifdef OC_HOSTSIM
+    float inv = 1.0f / bl;
+#else
+#ifdef __CUDA_ARCH__
+    float inv = __frcp_rn(bl);
+#else
+    float inv = 1.0f / bl;
+#endif
+#endif
+    double invd = (double)inv;
+    double x = a * invd;
+    return oc_fma(oc_fma(x, -b, a), invd, x);
+}
+OC_HD float newton_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return a * __frcp_rn(b);
+#else
+    return a * (1.0f / b);
+#endif
+}
+
+}  // namespace oc

@@ -1,0 +1,127 @@
+// oc_halo.h — ONE fused halo-fill launch for any set of fields and all six sides.
+//
+// Replaces fill_halo_regions! and its ~3 launches per field (src/BoundaryConditions/fill_halo_regions.jl
+// :25-108, fill_halo_regions_periodic.jl:5-32, _flux.jl:9-27, _value_gradient.jl:7-119, _open.jl:2-14) and
+// the ordering rule of boundary_condition_ordering.jl:113-128 (non-periodic sides first, periodic sides
+// afterwards over the whole parent extent so that corners receive periodic images of BC halos).
+//
+// Because every halo value is ultimately a function of ONE interior cell, the ordered multi-pass fill
+// collapses to a single pass: for a halo cell P, wrap its periodic coordinates into the interior; if the
+// result Q lies in the first halo plane of exactly one Bounded dimension (and inside 1:N in the other
+// Bounded dimensions) apply that side's BC formula to the adjacent interior cell; halo planes 2..H of
+// Bounded sides, and Bounded×Bounded corners, are never written — exactly like the reference.  Open
+// (impenetrable) BCs set the wall-normal velocity ON the boundary face (index 1 and N+1).
+#pragma once
+#include "oc_common.h"
+
+namespace oc {
+
+enum { HALO_MAX_FIELDS = 24, HALO_MAX_BOXES = HALO_MAX_FIELDS * 9 };
+
+// one side of one field, after default resolution
+struct SideBC {
+    int kind;      // oc_bc_kind: 1 periodic, 2 flux, 3 value, 4 gradient, 5 open, 6 none
+    double value;
+};
+
+template <class FT>
+struct HaloField {
+    FT* p;
+    int face[3];       // location: 1 = Face
+    SideBC bc[6];
+};
+
+struct HaloBox {
+    int field;
+    int lo[3];
+    int n[3];
+    int first_block;   // prefix sum of blocks
+};
+
+template <class FT>
+struct HaloKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    int nfields, nboxes;
+    int fill_open;
+    HaloField<FT> f[HALO_MAX_FIELDS];
+    const HaloBox* boxes;      // device array [nboxes]
+
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        // locate the box of this block (boxes are few: linear scan from the back)
+        int bi = nboxes - 1;
+        while (bi > 0 && boxes[bi].first_block > b.x) --bi;
+        const HaloBox bx = boxes[bi];
+        long long cell = (long long)(b.x - bx.first_block) * nt + tid;
+        long long ncell = (long long)bx.n[0] * bx.n[1] * bx.n[2];
+        if (cell >= ncell) return;
+        int P[3];
+        P[0] = bx.lo[0] + (int)(cell % bx.n[0]);
+        P[1] = bx.lo[1] + (int)((cell / bx.n[0]) % bx.n[1]);
+        P[2] = bx.lo[2] + (int)(cell / ((long long)bx.n[0] * bx.n[1]));
+        const HaloField<FT>& fld = f[bx.field];
+
+        int Q[3];
+        int bc_dim = -1, bc_side = 0, nbc = 0;
+        bool wall = false;
+        FT wall_value = FT(0);
+        bool moved = false;
+        for (int d = 0; d < 3; ++d) {
+            int idx = P[d], N = g.N[d];
+            if (!g.bounded[d]) {                       // Periodic (and Flat stored as periodic)
+                int q = idx % N;
+                if (q < 0) q += N;
+                if (q != idx) moved = true;
+                Q[d] = q;
+            } else if (fld.face[d]) {                  // wall-normal velocity: interior points 0..N
+                if (idx < 0 || idx > N) return;        // never filled (field_boundary_conditions.jl:15-25: Open only)
+                Q[d] = idx;
+                if (idx == 0 || idx == N) {
+                    const SideBC& s = fld.bc[2 * d + (idx == 0 ? 0 : 1)];
+                    if (s.kind == 5 && fill_open) { wall = true; wall_value = FT(s.value); }
+                }
+            } else {                                   // Center-located in a Bounded dimension
+                if (idx >= 0 && idx < N) Q[d] = idx;
+                else if (idx == -1) { Q[d] = 0; bc_dim = d; bc_side = 0; ++nbc; }
+                else if (idx == N) { Q[d] = N - 1; bc_dim = d; bc_side = 1; ++nbc; }
+                else return;                           // halo planes 2..H are never written
+            }
+        }
+        if (nbc > 1) return;                           // Bounded×Bounded corners are never written
+        if (nbc == 1 || wall) {
+            // non-periodic fills cover the interior tangential range 1:N of the other dimensions only
+            // (fill_halo_regions.jl:119-128); periodic coordinates were wrapped above.
+            for (int d = 0; d < 3; ++d)
+                if (g.bounded[d] && d != bc_dim && !(wall && fld.face[d] && (P[d] == 0 || P[d] == g.N[d]) && nbc == 0)) {
+                    if (P[d] < 0 || P[d] >= g.N[d]) return;
+                }
+        }
+        if (nbc == 0 && !wall && !moved) return;       // a plain interior cell: nothing to do
+        FT* p = fld.p;
+        int dst = g.idx(P[0], P[1], P[2]);
+        if (wall && nbc == 0) { p[dst] = wall_value; return; }
+        FT cI = p[g.idx(Q[0], Q[1], Q[2])];
+        if (nbc == 1) {
+            const SideBC& s = fld.bc[2 * bc_dim + bc_side];
+            FT delta = g.d[bc_dim];
+            if (s.kind == 2) {
+                // Flux: c[0] = c[1], c[N+1] = c[N]                            fill_halo_regions_flux.jl:9-27
+            } else if (s.kind == 4) {
+                FT grad = FT(s.value);                                       // _value_gradient.jl:9-10
+                cI = cI + grad * (bc_side == 0 ? -delta : delta);
+            } else if (s.kind == 3) {
+                FT val = FT(s.value);                                        // :12-13
+                if (bc_side == 0) { FT grad = (cI - val) / (delta / FT(2)); cI = cI + grad * (-delta); }
+                else { FT grad = (val - cI) / (delta / FT(2)); cI = cI + grad * delta; }
+            } else {
+                return;                                                      // none
+            }
+        }
+        p[dst] = cI;
+    }
+};
+
+}  // namespace oc

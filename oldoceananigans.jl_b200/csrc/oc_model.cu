@@ -1,0 +1,924 @@
+// oc_model.cu — Model<FT> implementation and the extern "C" entry points of include/oceananigans_b200.h.
+#include "oc_model.h"
+
+#include <algorithm>
+#include <map>
+
+namespace oc {
+
+// ---------------------------------------------------------------------------------------------------------
+// coefficients (host).  stencil_coefficients on a uniform grid, exact rationals rounded to FT, last one
+// 1 - sum(others)   (src/Advection/reconstruction_coefficients.jl:49-64)
+// ---------------------------------------------------------------------------------------------------------
+struct Rat {
+    long long n, d;
+};
+static long long gcdll(long long a, long long b) { a = a < 0 ? -a : a; b = b < 0 ? -b : b; while (b) { long long t = a % b; a = b; b = t; } return a ? a : 1; }
+static Rat rnorm(Rat r) { long long g = gcdll(r.n, r.d); r.n /= g; r.d /= g; if (r.d < 0) { r.n = -r.n; r.d = -r.d; } return r; }
+static Rat radd(Rat a, Rat b) { return rnorm(Rat{a.n * b.d + b.n * a.d, a.d * b.d}); }
+
+template <class FT>
+static void stencil_coefficients(int r, int order, FT* out) {
+    std::vector<Rat> c(order);
+    for (int j = 0; j < order; ++j) {
+        Rat acc{0, 1};
+        for (int m = j + 1; m <= order; ++m) {
+            long long num = 0;
+            for (int l = 0; l <= order; ++l) {
+                if (l == m) continue;
+                long long p = 1;
+                for (int q = 0; q <= order; ++q)
+                    if (q != m && q != l) p *= (r - q + 1);
+                num += p;
+            }
+            long long den = 1;
+            for (int l = 0; l <= order; ++l)
+                if (l != m) den *= (m - l);
+            acc = radd(acc, rnorm(Rat{num, den}));
+        }
+        c[j] = acc;
+    }
+    FT s = FT(0);
+    for (int j = 0; j < order - 1; ++j) {
+        out[j] = (FT)((long double)c[j].n / (long double)c[j].d);
+        s = s + out[j];
+    }
+    out[order - 1] = FT(1) - s;
+}
+
+template <class FT>
+static AdvCoef<FT> make_coefficients() {
+    AdvCoef<FT> C;
+    FT c4[4];
+    stencil_coefficients<FT>(1, 4, c4);                    // Centered(order=4): buffer 2 -> r = buffer-1
+    for (int idx = 1; idx <= 4; ++idx) C.c4[idx - 1] = c4[4 - idx];   // calc_reconstruction_stencil: coeff[order-idx+1]
+    for (int r = 0; r < 3; ++r) stencil_coefficients<FT>(r, 3, C.w5p[r]);
+    for (int r = 0; r < 2; ++r) stencil_coefficients<FT>(r, 2, C.w3p[r]);
+    C.w5c[0] = (FT)(3.0L / 10.0L); C.w5c[1] = (FT)(3.0L / 5.0L); C.w5c[2] = (FT)(1.0L / 10.0L);
+    C.w3c[0] = (FT)(2.0L / 3.0L); C.w3c[1] = (FT)(1.0L / 3.0L);
+    C.eps = (FT)1e-8f;
+    return C;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+Model<FT>::Model(const oc_config& c) : cfg_(c) {
+    if (c.abi_version != OC_ABI_VERSION) throw Error(OC_ERR_INVALID, "oc_config.abi_version mismatch");
+    if (c.n_tracers < 0 || c.n_tracers > OC_MAX_TRACERS) throw Error(OC_ERR_INVALID, "n_tracers out of range");
+    if (c.advection != OC_CENTERED2 && c.advection != OC_WENO5) throw Error(OC_ERR_UNSUPPORTED, "advection scheme: only Centered(order=2) and WENO(order=5)");
+    if (c.timestepper != OC_RK3 && c.timestepper != OC_AB2) throw Error(OC_ERR_UNSUPPORTED, "timestepper: only RungeKutta3 and QuasiAdamsBashforth2");
+    F_ = 3 + c.n_tracers;
+    int need = c.advection == OC_WENO5 ? 3 : 1;
+    if (c.has_amd) need = std::max(need, 2);
+    for (int d = 0; d < 3; ++d) {
+        const int t = c.topology[d];
+        if (t != OC_PERIODIC && t != OC_BOUNDED && t != OC_FLAT) throw Error(OC_ERR_INVALID, "bad topology");
+        if (c.N[d] < 1) throw Error(OC_ERR_INVALID, "grid size must be >= 1");
+        if (t == OC_FLAT) {
+            if (c.N[d] != 1 || c.H[d] != 0) throw Error(OC_ERR_INVALID, "Flat dimensions must have N = 1 and H = 0");
+        } else {
+            if (c.H[d] < need) throw Error(OC_ERR_INVALID, "halo too small for the advection scheme / closure (inflate_grid_halo_size)");
+            if (c.H[d] > 8) throw Error(OC_ERR_UNSUPPORTED, "halo larger than 8");
+            if (c.N[d] < c.H[d]) throw Error(OC_ERR_UNSUPPORTED, "N < H in a non-Flat dimension (adapt_advection_order lowering is not implemented)");
+            if (!(c.delta[d] > 0)) throw Error(OC_ERR_INVALID, "grid spacing must be positive");
+        }
+        Hcfg_[d] = c.H[d];
+        g_.N[d] = c.N[d];
+        g_.H[d] = t == OC_FLAT ? 3 : c.H[d];
+        g_.bounded[d] = t == OC_BOUNDED;
+        g_.flat[d] = t == OC_FLAT;
+        g_.d[d] = t == OC_FLAT ? FT(1) : (FT)c.delta[d];
+        g_.rd[d] = FT(1) / g_.d[d];
+    }
+    if (c.has_amd && (g_.flat[0] || g_.flat[1] || g_.flat[2])) throw Error(OC_ERR_UNSUPPORTED, "AnisotropicMinimumDissipation on a grid with Flat dimensions");
+    if (c.buoyancy == OC_BUOYANCY_SEAWATER_LINEAR && (c.tracer_T < 0 || c.tracer_S < 0 || c.tracer_T >= c.n_tracers || c.tracer_S >= c.n_tracers))
+        throw Error(OC_ERR_INVALID, "SeawaterBuoyancy needs tracers T and S");
+    if (c.buoyancy == OC_BUOYANCY_TRACER && (c.tracer_b < 0 || c.tracer_b >= c.n_tracers)) throw Error(OC_ERR_INVALID, "BuoyancyTracer needs tracer b");
+    g_.A[0] = g_.d[1] * g_.d[2];
+    g_.A[1] = g_.d[0] * g_.d[2];
+    g_.A[2] = g_.d[0] * g_.d[1];
+    g_.V = g_.A[2] * g_.d[2];
+    g_.rV = FT(1) / g_.V;
+    const int pad = 128 / (int)sizeof(FT);
+    g_.sy = ((pad + g_.N[0] + g_.H[0] + 1 + pad - 1) / pad) * pad;
+    const int rows = g_.N[1] + 2 * g_.H[1] + 1, planes = g_.N[2] + 2 * g_.H[2] + 1;
+    g_.sz = g_.sy * rows;
+    field_elems_ = (size_t)g_.sz * planes;
+    if (field_elems_ >= ((size_t)1 << 31)) throw Error(OC_ERR_UNSUPPORTED, "field larger than 2^31 elements");
+    origin_off_ = pad + (long long)g_.H[1] * g_.sy + (long long)g_.H[2] * g_.sz;
+    C_ = make_coefficients<FT>();
+    gamma_[0] = (FT)(8.0L / 15.0L); gamma_[1] = (FT)(5.0L / 12.0L); gamma_[2] = (FT)(3.0L / 4.0L);   // runge_kutta_3.jl:69-78
+    zeta_[0] = FT(0); zeta_[1] = (FT)(-17.0L / 60.0L); zeta_[2] = (FT)(-5.0L / 12.0L);
+#ifndef OC_HOSTSIM
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    cuda_check(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+#endif
+    const int locs[4][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
+    for (int f = 0; f < F_; ++f) {
+        const int* loc = locs[f < 3 ? f : 3];
+        FieldRec a = alloc_field(loc), b = alloc_field(loc);
+        resolve_bcs(a, c.bcs[f]);
+        resolve_bcs(b, c.bcs[f]);
+        state_.push_back(a);
+        next_.push_back(b);
+        FieldRec gn = alloc_field(loc), gm = alloc_field(loc);
+        resolve_bcs(gn, nullptr);
+        resolve_bcs(gm, nullptr);
+        Gn_.push_back(gn);
+        Gm_.push_back(gm);
+    }
+    pNHS_ = alloc_field(locs[3]);
+    resolve_bcs(pNHS_, nullptr);
+    has_pHY_ = c.buoyancy != OC_BUOYANCY_NONE;          // nonhydrostatic_model.jl:147-153
+    if (has_pHY_) { pHY_ = alloc_field(locs[3]); resolve_bcs(pHY_, nullptr); }
+    has_amd_ = c.has_amd != 0;
+    if (has_amd_) {
+        nu_e_ = alloc_field(locs[3]);
+        resolve_bcs(nu_e_, nullptr);
+        for (int t = 0; t < c.n_tracers; ++t) { kappa_e_.push_back(alloc_field(locs[3])); resolve_bcs(kappa_e_.back(), nullptr); }
+    }
+    // pressure solver
+    std::string err = fft_.init(g_.N, g_.bounded, stream_);
+    if (!err.empty()) throw Error(OC_ERR_CUDA, err);
+    fftbuf_ = (FT*)dev_alloc(fft_.buffer_bytes);
+    device_bytes += (int64_t)fft_.buffer_bytes + (int64_t)fft_.work_bytes;
+    for (int d = 0; d < 3; ++d) {
+        const int N = g_.N[d];
+        std::vector<double> lam(N, 0.0);
+        const double L = c.topology[d] == OC_FLAT ? 1.0 : c.extent[d];
+        for (int i = 0; i < N; ++i) {                    // poisson_eigenvalues.jl:8-31 (Float64)
+            if (c.topology[d] == OC_PERIODIC) lam[i] = std::pow(2.0 * std::sin(i * M_PI / N) / (L / N), 2);
+            else if (c.topology[d] == OC_BOUNDED) lam[i] = std::pow(2.0 * std::sin(i * M_PI / (2.0 * N)) / (L / N), 2);
+        }
+        lam_[d] = (double*)dev_alloc(sizeof(double) * N);
+        dev_upload(lam_[d], lam.data(), sizeof(double) * N, stream_);
+        if (g_.bounded[d]) {
+            std::vector<Cd> tw(N);
+            for (int k = 0; k < N; ++k) { double a = -M_PI * k / (2.0 * N); tw[k] = Cd{std::cos(a), std::sin(a)}; }
+            tw_[d] = (Cd*)dev_alloc(sizeof(Cd) * N);
+            dev_upload(tw_[d], tw.data(), sizeof(Cd) * N, stream_);
+        }
+    }
+    boxes_dev_ = nullptr;
+    for (int i = 0; i < OC_TIMER_COUNT; ++i) { timer_ms_[i] = 0; timer_n_[i] = 0; }
+    sync();
+}
+
+template <class FT>
+Model<FT>::~Model() {
+    auto fr = [](FieldRec& f) { dev_free(f.base); };
+    for (auto& f : state_) fr(f);
+    for (auto& f : next_) fr(f);
+    for (auto& f : Gn_) fr(f);
+    for (auto& f : Gm_) fr(f);
+    fr(pNHS_); fr(pHY_); fr(nu_e_);
+    for (auto& f : kappa_e_) fr(f);
+    dev_free(fftbuf_);
+    for (int d = 0; d < 3; ++d) { dev_free(lam_[d]); dev_free(tw_[d]); }
+    for (auto& kv : halo_cache_) dev_free(kv.second.boxes);
+#ifndef OC_HOSTSIM
+    for (void* e : event_pool_) cudaEventDestroy((cudaEvent_t)e);
+    for (auto& r : timer_recs_) { cudaEventDestroy((cudaEvent_t)r.e0); cudaEventDestroy((cudaEvent_t)r.e1); }
+    if (sw0_) { cudaEventDestroy((cudaEvent_t)sw0_); cudaEventDestroy((cudaEvent_t)sw1_); }
+    if (stream_) cudaStreamDestroy(stream_);
+#endif
+}
+
+template <class FT>
+typename Model<FT>::FieldRec Model<FT>::alloc_field(const int face[3]) {
+    FieldRec f;
+    f.base = (FT*)dev_alloc(sizeof(FT) * field_elems_);
+    f.p = f.base + origin_off_;
+    for (int d = 0; d < 3; ++d) f.face[d] = face[d];
+    device_bytes += (int64_t)(sizeof(FT) * field_elems_);
+    return f;
+}
+
+// field_boundary_conditions.jl:15-60 defaults + user overrides
+template <class FT>
+void Model<FT>::resolve_bcs(FieldRec& f, const oc_bc* user) {
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s) {
+            SideBC r;
+            r.value = 0.0;
+            const int t = cfg_.topology[d];
+            int kind = user ? user[2 * d + s].kind : OC_BC_DEFAULT;
+            if (t == OC_PERIODIC) {
+                if (kind != OC_BC_DEFAULT && kind != OC_BC_PERIODIC) throw Error(OC_ERR_INVALID, "non-periodic boundary condition in a Periodic dimension");
+                r.kind = OC_BC_PERIODIC;
+            } else if (t == OC_FLAT) {
+                r.kind = OC_BC_NONE;
+            } else {
+                if (kind == OC_BC_DEFAULT) kind = f.face[d] ? OC_BC_OPEN : OC_BC_FLUX;
+                if (kind == OC_BC_PERIODIC) throw Error(OC_ERR_INVALID, "periodic boundary condition in a Bounded dimension");
+                if (f.face[d] && kind != OC_BC_OPEN) throw Error(OC_ERR_UNSUPPORTED, "wall-normal velocity supports only Open (impenetrable) boundary conditions");
+                if (!f.face[d] && kind == OC_BC_OPEN) throw Error(OC_ERR_INVALID, "Open boundary condition on a field that is not wall-normal");
+                r.kind = kind;
+                if (user && user[2 * d + s].has_value) r.value = user[2 * d + s].value;
+            }
+            f.bc[2 * d + s] = r;
+        }
+}
+
+template <class FT>
+void Model<FT>::sync() {
+#ifndef OC_HOSTSIM
+    cuda_check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");
+#endif
+}
+
+template <class FT>
+typename Model<FT>::FieldRec& Model<FT>::lookup(int field) {
+    if (field >= 0 && field < F_) return state_[field];
+    if (field == OC_FIELD_PNHS) return pNHS_;
+    if (field == OC_FIELD_PHY && has_pHY_) return pHY_;
+    if (field == OC_FIELD_NU_E && has_amd_) return nu_e_;
+    if (field >= OC_FIELD_KAPPA_E0 && field < OC_FIELD_KAPPA_E0 + (int)kappa_e_.size()) return kappa_e_[field - OC_FIELD_KAPPA_E0];
+    if (field >= OC_FIELD_GN0 && field < OC_FIELD_GN0 + F_) return Gn_[field - OC_FIELD_GN0];
+    if (field >= OC_FIELD_GM0 && field < OC_FIELD_GM0 + F_) return Gm_[field - OC_FIELD_GM0];
+    throw Error(OC_ERR_INVALID, "unknown field id " + std::to_string(field));
+}
+
+template <class FT>
+void Model<FT>::field_info(int field, oc_field_info* info) {
+    if ((field == OC_FIELD_PHY || field == OC_FIELD_NU_E || (field >= OC_FIELD_KAPPA_E0 && field < OC_FIELD_GN0)) && !aux_valid_) aux();
+    if (field >= OC_FIELD_GN0 && field < OC_FIELD_GN0 + F_) compute_tendencies_if_stale();
+    FieldRec& f = lookup(field);
+    for (int d = 0; d < 3; ++d) {
+        info->location[d] = f.face[d];
+        info->interior_size[d] = g_.N[d] + ((f.face[d] && g_.bounded[d]) ? 1 : 0);
+        info->parent_size[d] = info->interior_size[d] + 2 * Hcfg_[d];
+    }
+    info->device_ptr = f.p;
+    info->stride_y = g_.sy;
+    info->stride_z = g_.sz;
+}
+
+template <class FT>
+void Model<FT>::transfer(int field, void* host, size_t nbytes, bool parent, bool upload) {
+    oc_field_info info;
+    field_info(field, &info);
+    FieldRec& f = lookup(field);
+    int ext[3], lo[3];
+    size_t n = 1;
+    for (int d = 0; d < 3; ++d) {
+        ext[d] = parent ? info.parent_size[d] : info.interior_size[d];
+        lo[d] = parent ? -Hcfg_[d] : 0;
+        n *= (size_t)ext[d];
+    }
+    if (n * sizeof(FT) != nbytes) throw Error(OC_ERR_INVALID, "host buffer size mismatch: expected " + std::to_string(n * sizeof(FT)) + " bytes");
+    FT* origin = f.p + lo[0] + (long long)lo[1] * g_.sy + (long long)lo[2] * g_.sz;
+    dev_copy_box(origin, sizeof(FT), g_.sy, g_.sz, host, ext, upload, stream_);
+    if (upload) {
+        // Flat dimensions are stored as periodic N=1: refresh their (internal) halo copies
+        if (g_.flat[0] || g_.flat[1] || g_.flat[2]) { std::vector<FieldRec*> one{&f}; halo(one, false); }
+        if (field < F_) { tend_valid_ = false; aux_valid_ = false; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// timers
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+void Model<FT>::begin_timer(int cls) {
+#ifndef OC_HOSTSIM
+    if (!timing_) return;
+    auto get = [&]() -> void* {
+        if (!event_pool_.empty()) { void* e = event_pool_.back(); event_pool_.pop_back(); return e; }
+        cudaEvent_t e;
+        cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+        return (void*)e;
+    };
+    TimerRec r{cls, get(), get()};
+    cuda_check(cudaEventRecord((cudaEvent_t)r.e0, stream_), "cudaEventRecord");
+    timer_recs_.push_back(r);
+#else
+    (void)cls;
+#endif
+}
+template <class FT>
+void Model<FT>::end_timer() {
+#ifndef OC_HOSTSIM
+    if (!timing_) return;
+    cuda_check(cudaEventRecord((cudaEvent_t)timer_recs_.back().e1, stream_), "cudaEventRecord");
+#endif
+}
+template <class FT>
+void Model<FT>::collect_timers() {
+#ifndef OC_HOSTSIM
+    sync();
+    for (auto& r : timer_recs_) {
+        float ms = 0;
+        cuda_check(cudaEventElapsedTime(&ms, (cudaEvent_t)r.e0, (cudaEvent_t)r.e1), "cudaEventElapsedTime");
+        timer_ms_[r.cls] += ms;
+        timer_n_[r.cls] += 1;
+        event_pool_.push_back(r.e0);
+        event_pool_.push_back(r.e1);
+    }
+    timer_recs_.clear();
+#endif
+}
+template <class FT>
+void Model<FT>::timers_reset() {
+    collect_timers();
+    for (int i = 0; i < OC_TIMER_COUNT; ++i) { timer_ms_[i] = 0; timer_n_[i] = 0; }
+}
+template <class FT>
+void Model<FT>::timers_get(double* ms, int64_t* n) {
+    collect_timers();
+    for (int i = 0; i < OC_TIMER_COUNT; ++i) { ms[i] = timer_ms_[i]; n[i] = timer_n_[i]; }
+}
+
+template <class FT>
+void Model<FT>::stopwatch_start() {
+#ifndef OC_HOSTSIM
+    if (!sw0_) {
+        cudaEvent_t a, b;
+        cuda_check(cudaEventCreate(&a), "cudaEventCreate");
+        cuda_check(cudaEventCreate(&b), "cudaEventCreate");
+        sw0_ = a; sw1_ = b;
+    }
+    cuda_check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");
+    cuda_check(cudaEventRecord((cudaEvent_t)sw0_, stream_), "cudaEventRecord");
+#endif
+}
+template <class FT>
+double Model<FT>::stopwatch_stop() {
+#ifndef OC_HOSTSIM
+    if (!sw0_) throw Error(OC_ERR_STATE, "stopwatch not started");
+    cuda_check(cudaEventRecord((cudaEvent_t)sw1_, stream_), "cudaEventRecord");
+    cuda_check(cudaEventSynchronize((cudaEvent_t)sw1_), "cudaEventSynchronize");
+    float ms = 0;
+    cuda_check(cudaEventElapsedTime(&ms, (cudaEvent_t)sw0_, (cudaEvent_t)sw1_), "cudaEventElapsedTime");
+    return ms;
+#else
+    return 0.0;
+#endif
+}
+
+template <class FT>
+template <class K>
+void Model<FT>::go(const K& k, Dim3 grid, size_t smem, int cls) {
+    begin_timer(cls);
+    cudaError_t e = launch(k, grid, smem, stream_);
+    end_timer();
+#ifndef OC_HOSTSIM
+    cuda_check(e, "kernel launch");
+#else
+    (void)e;
+#endif
+    ++launches;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// halo fill: one launch for any list of fields
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open) {
+    if (fields.empty()) return;
+    if ((int)fields.size() > HALO_MAX_FIELDS) throw Error(OC_ERR_INVALID, "too many fields in one halo fill");
+    std::string key;
+    for (FieldRec* f : fields) key += (char)('0' + f->face[0] + 2 * f->face[1] + 4 * f->face[2]);
+    auto it = halo_cache_.find(key);
+    if (it == halo_cache_.end()) {
+        std::vector<HaloBox> boxes;
+        int nb = 0;
+        auto add = [&](int fi, int lo0, int n0, int lo1, int n1, int lo2, int n2) {
+            if (n0 <= 0 || n1 <= 0 || n2 <= 0) return;
+            HaloBox b;
+            b.field = fi;
+            b.lo[0] = lo0; b.lo[1] = lo1; b.lo[2] = lo2;
+            b.n[0] = n0; b.n[1] = n1; b.n[2] = n2;
+            b.first_block = nb;
+            long long cells = (long long)n0 * n1 * n2;
+            nb += (int)((cells + HaloKernel<FT>::THREADS - 1) / HaloKernel<FT>::THREADS);
+            boxes.push_back(b);
+        };
+        const int* N = g_.N;
+        const int* H = g_.H;
+        for (int fi = 0; fi < (int)fields.size(); ++fi) {
+            const int X0 = -H[0], XN = N[0] + 2 * H[0] + 1, Y0 = -H[1], YN = N[1] + 2 * H[1] + 1;
+            add(fi, X0, XN, Y0, YN, -H[2], H[2]);                  // bottom slab
+            add(fi, X0, XN, Y0, YN, N[2], H[2] + 1);               // top slab (incl. the extra Face plane)
+            add(fi, X0, XN, -H[1], H[1], 0, N[2]);                 // south
+            add(fi, X0, XN, N[1], H[1] + 1, 0, N[2]);              // north
+            add(fi, -H[0], H[0], 0, N[1], 0, N[2]);                // west
+            add(fi, N[0], H[0] + 1, 0, N[1], 0, N[2]);             // east
+            for (int d = 0; d < 3; ++d)                            // lower wall plane of a wall-normal velocity
+                if (fields[fi]->face[d] && g_.bounded[d]) {
+                    int lo[3] = {0, 0, 0}, n[3] = {N[0], N[1], N[2]};
+                    n[d] = 1;
+                    add(fi, lo[0], n[0], lo[1], n[1], lo[2], n[2]);
+                }
+        }
+        HaloCache hc;
+        hc.nboxes = (int)boxes.size();
+        hc.nblocks = nb;
+        hc.boxes = (HaloBox*)dev_alloc(sizeof(HaloBox) * boxes.size());
+        dev_upload(hc.boxes, boxes.data(), sizeof(HaloBox) * boxes.size(), stream_);
+        sync();
+        it = halo_cache_.emplace(key, hc).first;
+    }
+    HaloKernel<FT> k;
+    k.g = g_;
+    k.nfields = (int)fields.size();
+    k.nboxes = it->second.nboxes;
+    k.fill_open = fill_open ? 1 : 0;
+    k.boxes = it->second.boxes;
+    for (int fi = 0; fi < (int)fields.size(); ++fi) {
+        k.f[fi].p = fields[fi]->p;
+        for (int d = 0; d < 3; ++d) k.f[fi].face[d] = fields[fi]->face[d];
+        for (int s = 0; s < 6; ++s) k.f[fi].bc[s] = fields[fi]->bc[s];
+    }
+    Dim3 grid;
+    grid.x = it->second.nblocks;
+    go(k, grid, 0, OC_TIMER_HALO);
+}
+
+template <class FT>
+void Model<FT>::fill_halo_regions(const int* fields, int n, int fill_open) {
+    std::vector<FieldRec*> list;
+    for (int i = 0; i < n; ++i) list.push_back(&lookup(fields[i]));
+    halo(list, fill_open != 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// auxiliary fields: AMD diffusivities (+ their halos), hydrostatic pressure   (compute_auxiliaries! :58-69)
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+void Model<FT>::aux() {
+    if (has_amd_) {
+        AmdKernel<FT> k;
+        k.g = g_;
+        k.u = state_[0].p; k.v = state_[1].p; k.w = state_[2].p;
+        k.nu_e = nu_e_.p;
+        k.Cnu = (FT)cfg_.amd_Cnu;
+        k.ntr = cfg_.n_tracers;
+        for (int t = 0; t < cfg_.n_tracers; ++t) { k.c[t] = state_[3 + t].p; k.kappa_e[t] = kappa_e_[t].p; k.Ckappa[t] = (FT)cfg_.amd_Ckappa[t]; }
+        go(k, grid_xyz(AmdKernel<FT>::THREADS), 0, OC_TIMER_AUX);
+        std::vector<FieldRec*> list{&nu_e_};
+        for (auto& f : kappa_e_) list.push_back(&f);
+        halo(list, true);
+    }
+    if (has_pHY_ && !g_.flat[2]) {
+        HydrostaticPressureKernel<FT> k;
+        k.g = g_;
+        k.pHY = pHY_.p;
+        k.buoyancy = cfg_.buoyancy;
+        if (cfg_.buoyancy == OC_BUOYANCY_TRACER) { k.bT = state_[3 + cfg_.tracer_b].p; k.bS = nullptr; }
+        else { k.bT = state_[3 + cfg_.tracer_T].p; k.bS = state_[3 + cfg_.tracer_S].p; }
+        k.grav = (FT)cfg_.gravity; k.alpha = (FT)cfg_.thermal_expansion; k.beta = (FT)cfg_.haline_contraction;
+        k.ilo = g_.flat[0] ? 0 : -1; k.ni = g_.flat[0] ? g_.N[0] : g_.N[0] + 2;
+        k.jlo = g_.flat[1] ? 0 : -1; k.nj = g_.flat[1] ? g_.N[1] : g_.N[1] + 2;
+        Dim3 grid;
+        grid.x = (k.ni + HydrostaticPressureKernel<FT>::THREADS - 1) / HydrostaticPressureKernel<FT>::THREADS;
+        grid.y = k.nj;
+        go(k, grid, 0, OC_TIMER_AUX);
+    }
+    aux_valid_ = true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tendencies (+ fused substep)
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+template <int KIND>
+void Model<FT>::launch_tendency(int fidx, TendencyArgs<FT>& a) {
+    (void)fidx;
+    Dim3 grid;
+    constexpr int TX = 32, TY = 8, TZ = 8;
+    grid.x = (g_.N[0] + TX - 1) / TX;
+    grid.y = (g_.N[1] + TY - 1) / TY;
+    grid.z = (g_.N[2] + TZ - 1) / TZ;
+    if (cfg_.advection == OC_WENO5) {
+        TendencyKernel<FT, 1, KIND, TX, TY, TZ> k;
+        k.a = a;
+        go(k, grid, k.SMEM, OC_TIMER_TENDENCY);
+    } else {
+        TendencyKernel<FT, 0, KIND, TX, TY, TZ> k;
+        k.a = a;
+        go(k, grid, k.SMEM, OC_TIMER_TENDENCY);
+    }
+}
+
+template <class FT>
+void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state) {
+    if (!aux_valid_) aux();
+    for (int f = 0; f < F_; ++f) {
+        TendencyArgs<FT> a;
+        memset(&a, 0, sizeof(a));
+        a.g = g_;
+        a.C = C_;
+        for (int d = 0; d < 3; ++d) a.U[d] = state_[d].p;
+        a.c = f >= 3 ? state_[f].p : nullptr;
+        a.pHY = (has_pHY_ && !g_.flat[2]) ? pHY_.p : nullptr;
+        a.bT = a.bS = nullptr;
+        a.buoyancy = 0;     // the w-equation gets no buoyancy term when pHY′ exists (always, when buoyancy != nothing)
+        a.nu_e = (has_amd_ && f < 3) ? nu_e_.p : nullptr;
+        a.kappa_e = (has_amd_ && f >= 3) ? kappa_e_[f - 3].p : nullptr;
+        a.Gm = Gm_[f].p;
+        a.Gn = Gn_[f].p;
+        a.Ucur = state_[f].p;
+        a.Unew = next_[f].p;
+        a.has_scalar = cfg_.has_scalar_diffusivity;
+        a.nu = (FT)cfg_.nu;
+        a.kappa = f >= 3 ? (FT)cfg_.kappa[f - 3] : FT(0);
+        a.grav = (FT)cfg_.gravity; a.alpha = (FT)cfg_.thermal_expansion; a.beta = (FT)cfg_.haline_contraction;
+        a.has_coriolis = cfg_.has_coriolis;
+        a.f = (FT)cfg_.coriolis_f;
+        for (int s = 0; s < 6; ++s) {
+            const SideBC& bc = state_[f].bc[s];
+            const oc_bc& ub = cfg_.bcs[f][s];
+            a.fbc.on[s] = (bc.kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX && ub.has_value) ? 1 : 0;
+            a.fbc.val[s] = (FT)bc.value;
+        }
+        a.add_flux_bcs = add_flux_bcs ? 1 : 0;
+        a.mode = mode;
+        a.dt = (FT)dt;
+        a.ab2_euler = euler ? 1 : 0;
+        if (mode == STEP_RK3_FIRST) { a.ca = (FT)dt * gamma_[0]; a.cb = FT(0); }
+        else if (mode == STEP_RK3) { a.ca = gamma_[stage - 1]; a.cb = zeta_[stage - 1]; }
+        else if (mode == STEP_AB2) { a.ca = FT(1.5) + (FT)chi; a.cb = FT(0.5) + (FT)chi; }
+        if (f == 0) launch_tendency<KIND_U>(f, a);
+        else if (f == 1) launch_tendency<KIND_V>(f, a);
+        else if (f == 2) launch_tendency<KIND_W>(f, a);
+        else launch_tendency<KIND_C>(f, a);
+    }
+    if (swap_state && mode != STEP_NONE)
+        for (int f = 0; f < F_; ++f) std::swap(state_[f].p, next_[f].p), std::swap(state_[f].base, next_[f].base);
+}
+
+template <class FT>
+void Model<FT>::compute_tendencies_if_stale() {
+    if (tend_valid_) return;
+    for (int f = 0; f < F_; ++f) std::swap(Gn_[f].p, Gm_[f].p), std::swap(Gn_[f].base, Gm_[f].base);   // cache, then recompute
+    tendencies(STEP_NONE, 0.0, 1, 0.0, false, false, false);
+    tend_valid_ = true;
+}
+
+template <class FT>
+void Model<FT>::compute_tendencies() {
+    tendencies(STEP_NONE, 0.0, 1, 0.0, false, false, false);
+    tend_valid_ = true;
+}
+
+template <class FT>
+void Model<FT>::update_state(int compute_tend) {
+    std::vector<FieldRec*> list;
+    for (auto& f : state_) list.push_back(&f);
+    halo(list, false);                                   // fill_open_bcs = false   update_nonhydrostatic_model_state.jl:34
+    aux();
+    if (compute_tend) compute_tendencies();
+}
+
+template <class FT>
+void Model<FT>::compute_flux_bc_tendencies() {
+    for (int f = 0; f < F_; ++f) {
+        FluxBCKernel<FT> k;
+        k.g = g_;
+        k.Gn = Gn_[f].p;
+        bool any = false;
+        for (int s = 0; s < 6; ++s) {
+            const oc_bc& ub = cfg_.bcs[f][s];
+            k.fbc.on[s] = (state_[f].bc[s].kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX && ub.has_value) ? 1 : 0;
+            k.fbc.val[s] = (FT)state_[f].bc[s].value;
+            any = any || k.fbc.on[s];
+        }
+        if (any) go(k, grid_xyz(256), 0, OC_TIMER_SUBSTEP);
+    }
+}
+
+template <class FT>
+void Model<FT>::rk3_substep(double dt, int stage) {
+    if (stage < 1 || stage > 3) throw Error(OC_ERR_INVALID, "RK3 stage must be 1, 2 or 3");
+    for (int f = 0; f < F_; ++f) {
+        SubstepKernel<FT> k;
+        k.g = g_;
+        k.U = state_[f].p; k.Gn = Gn_[f].p; k.Gm = Gm_[f].p;
+        k.comp = f < 3 ? f : -1;
+        k.dt = (FT)dt;
+        k.ab2_euler = 0;
+        if (stage == 1) { k.mode = STEP_RK3_FIRST; k.ca = (FT)dt * gamma_[0]; k.cb = FT(0); }
+        else { k.mode = STEP_RK3; k.ca = gamma_[stage - 1]; k.cb = zeta_[stage - 1]; }
+        go(k, grid_xyz(256), 0, OC_TIMER_SUBSTEP);
+    }
+    tend_valid_ = false;
+    aux_valid_ = false;
+}
+
+template <class FT>
+void Model<FT>::ab2_step(double dt, double chi) {
+    for (int f = 0; f < F_; ++f) {
+        SubstepKernel<FT> k;
+        k.g = g_;
+        k.U = state_[f].p; k.Gn = Gn_[f].p; k.Gm = Gm_[f].p;
+        k.comp = f < 3 ? f : -1;
+        k.mode = STEP_AB2;
+        k.dt = (FT)dt;
+        k.ca = FT(1.5) + (FT)chi; k.cb = FT(0.5) + (FT)chi;
+        k.ab2_euler = ((FT)chi == FT(-0.5)) ? 1 : 0;
+        go(k, grid_xyz(256), 0, OC_TIMER_SUBSTEP);
+    }
+    tend_valid_ = false;
+    aux_valid_ = false;
+}
+
+template <class FT>
+void Model<FT>::cache_previous_tendencies() {
+    for (int f = 0; f < F_; ++f) {
+        CopyKernel<FT> k;
+        k.g = g_;
+        k.dst = Gm_[f].p; k.src = Gn_[f].p;
+        go(k, grid_xyz(256), 0, OC_TIMER_SUBSTEP);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pressure
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+void Model<FT>::run_fft_solve() {
+    begin_timer(OC_TIMER_FFT);
+    std::string e = fft_.forward(fftbuf_);
+    end_timer();
+    if (!e.empty()) throw Error(OC_ERR_CUDA, e);
+    PoissonMidKernel<FT> k;
+    k.L = fft_.L;
+    k.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_);
+    for (int d = 0; d < 3; ++d) { k.lam[d] = lam_[d]; k.tw[d] = tw_[d]; }
+    k.nrep[0] = g_.bounded[0] ? g_.N[0] / 2 + 1 : fft_.L.nxc;
+    k.nrep[1] = g_.bounded[1] ? g_.N[1] / 2 + 1 : g_.N[1];
+    k.nrep[2] = g_.bounded[2] ? g_.N[2] / 2 + 1 : g_.N[2];
+    k.norm = 1.0 / ((double)g_.N[0] * g_.N[1] * g_.N[2]);
+    Dim3 grid;
+    grid.x = (k.nrep[0] + PoissonMidKernel<FT>::THREADS - 1) / PoissonMidKernel<FT>::THREADS;
+    grid.y = k.nrep[1];
+    grid.z = k.nrep[2];
+    go(k, grid, 0, OC_TIMER_POISSON_MID);
+    begin_timer(OC_TIMER_FFT);
+    e = fft_.inverse(fftbuf_);
+    end_timer();
+    if (!e.empty()) throw Error(OC_ERR_CUDA, e);
+}
+
+template <class FT>
+void Model<FT>::pressure_solve_from_state() {
+    PoissonRhsKernel<FT> k;
+    k.g = g_;
+    k.L = fft_.L;
+    k.u = state_[0].p; k.v = state_[1].p; k.w = state_[2].p;
+    k.buf = fftbuf_;
+    go(k, grid_xyz(256), 0, OC_TIMER_POISSON_RHS);
+    run_fft_solve();
+}
+
+template <class FT>
+void Model<FT>::projection(double dt) {
+    ProjectionKernel<FT> k;
+    k.g = g_;
+    k.L = fft_.L;
+    k.buf = fftbuf_;
+    k.u = state_[0].p; k.v = state_[1].p; k.w = state_[2].p;
+    k.pNHS = pNHS_.p;
+    k.dt_plus = std::max((double)std::numeric_limits<FT>::epsilon(), dt);
+    go(k, grid_xyz(256), 0, OC_TIMER_PROJECTION);
+}
+
+template <class FT>
+void Model<FT>::compute_pressure_correction(double dt) {
+    (void)dt;
+    std::vector<FieldRec*> vel{&state_[0], &state_[1], &state_[2]};
+    halo(vel, true);
+    pressure_solve_from_state();
+    PoissonUnpackKernel<FT> k;
+    k.g = g_;
+    k.L = fft_.L;
+    k.buf = fftbuf_;
+    k.field = pNHS_.p;
+    k.dense = nullptr;
+    go(k, grid_xyz(256), 0, OC_TIMER_PROJECTION);
+    std::vector<FieldRec*> p{&pNHS_};
+    halo(p, true);
+}
+
+template <class FT>
+void Model<FT>::make_pressure_correction(double dt) {
+    GradSubKernel<FT> k;
+    k.g = g_;
+    k.u = state_[0].p; k.v = state_[1].p; k.w = state_[2].p;
+    k.p = pNHS_.p;
+    k.dt_plus = 1.0;
+    go(k, grid_xyz(256), 0, OC_TIMER_PROJECTION);
+    ScaleKernel<FT> s;
+    s.g = g_;
+    s.p = pNHS_.p;
+    s.dt_plus = std::max((double)std::numeric_limits<FT>::epsilon(), dt);
+    go(s, grid_xyz(256), 0, OC_TIMER_PROJECTION);
+    tend_valid_ = false;
+    aux_valid_ = false;
+}
+
+template <class FT>
+void Model<FT>::poisson_solve(const void* rhs, void* phi, size_t nbytes) {
+    size_t n = (size_t)g_.N[0] * g_.N[1] * g_.N[2];
+    if (nbytes != n * sizeof(FT)) throw Error(OC_ERR_INVALID, "poisson_solve: buffer size mismatch");
+    FT* dense = (FT*)dev_alloc(nbytes);
+    dev_upload(dense, rhs, nbytes, stream_);
+    PoissonLoadKernel<FT> l;
+    l.L = fft_.L;
+    l.rhs = dense;
+    l.buf = fftbuf_;
+    go(l, grid_xyz(256), 0, OC_TIMER_POISSON_RHS);
+    run_fft_solve();
+    PoissonUnpackKernel<FT> k;
+    k.g = g_;
+    k.L = fft_.L;
+    k.buf = fftbuf_;
+    k.field = nullptr;
+    k.dense = dense;
+    go(k, grid_xyz(256), 0, OC_TIMER_PROJECTION);
+    dev_download(phi, dense, nbytes, stream_);
+    dev_free(dense);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// hot path
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+void Model<FT>::set_finalize(int enforce) {
+    std::vector<FieldRec*> all;
+    for (auto& f : state_) all.push_back(&f);
+    halo(all, true);                                     // set!: fill_halo_regions!(ϕ) per field (open BCs included)
+    aux_valid_ = false;
+    tend_valid_ = false;
+    if (enforce) {
+        pressure_solve_from_state();                     // Δt = 1   set_nonhydrostatic_model.jl:52-56
+        projection(1.0);
+        halo(all, false);
+    }
+}
+
+// One fused stage: [aux] -> tendency+substep per field -> halo(U, open) -> Poisson -> projection -> halo(all)
+template <class FT>
+void Model<FT>::stage(int mode, double dt, int stage_no, double stage_dt, double chi, bool euler) {
+    if (!tend_valid_)                                    // Gⁿ holds the previous evaluation: it becomes G⁻ (cache by swap)
+        for (int f = 0; f < F_; ++f) std::swap(Gn_[f].p, Gm_[f].p), std::swap(Gn_[f].base, Gm_[f].base);
+    tendencies(mode, dt, stage_no, chi, euler, true, true);
+    tend_valid_ = false;
+    aux_valid_ = false;
+    std::vector<FieldRec*> vel{&state_[0], &state_[1], &state_[2]};
+    halo(vel, true);
+    pressure_solve_from_state();
+    projection(stage_dt);
+    std::vector<FieldRec*> all;
+    for (auto& f : state_) all.push_back(&f);
+    halo(all, false);
+}
+
+template <class FT>
+void Model<FT>::time_step_rk3(double dt) {
+    if (cfg_.timestepper != OC_RK3) throw Error(OC_ERR_STATE, "model was created with another time stepper");
+    // stage_Δt(Δt, γ, ζ) = Δt (γ + ζ) with γ, ζ in FT   runge_kutta_3.jl:107-109,176-177
+    const double dt1 = dt * (double)gamma_[0];
+    const double dt2 = dt * (double)(FT)(gamma_[1] + zeta_[1]);
+    const double dt3 = dt * (double)(FT)(gamma_[2] + zeta_[2]);
+    const double tn1 = clock.time + dt;
+    stage(STEP_RK3_FIRST, dt, 1, dt1, 0.0, false);
+    clock.time += dt1; clock.stage += 1; clock.last_stage_dt = dt1;
+    stage(STEP_RK3, dt, 2, dt2, 0.0, false);
+    clock.time += dt2; clock.stage += 1; clock.last_stage_dt = dt2;
+    stage(STEP_RK3, dt, 3, dt3, 0.0, false);
+    const double corrected = tn1 - clock.time;           // :148-161
+    clock.time += dt3;
+    clock.iteration += 1;
+    clock.stage = 1;
+    clock.last_dt = dt;
+    clock.last_stage_dt = corrected;
+}
+
+template <class FT>
+void Model<FT>::time_step_ab2(double dt, int euler_in) {
+    if (cfg_.timestepper != OC_AB2) throw Error(OC_ERR_STATE, "model was created with another time stepper");
+    const bool euler = euler_in || (dt != clock.last_dt);            // quasi_adams_bashforth_2.jl:88
+    const double chi = euler ? -0.5 : cfg_.ab2_chi;
+    stage(STEP_AB2, dt, 1, dt, chi, euler);
+    clock.time += dt;
+    clock.iteration += 1;
+    clock.stage = 1;
+    clock.last_dt = dt;
+    clock.last_stage_dt = dt;
+}
+
+template class Model<double>;
+template class Model<float>;
+
+}  // namespace oc
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+struct oc_model {
+    std::unique_ptr<oc::ModelBase> impl;
+};
+
+static thread_local std::string g_last_error;
+
+template <class Fn>
+static int guarded(Fn&& fn) {
+    try {
+        fn();
+        return OC_OK;
+    } catch (const oc::Error& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return OC_ERR_INVALID;
+    }
+}
+#define OC_REQUIRE(m) if (!(m) || !(m)->impl) { g_last_error = "null model handle"; return OC_ERR_INVALID; }
+
+extern "C" {
+
+const char* oc_last_error(void) { return g_last_error.c_str(); }
+int oc_abi_version(void) { return OC_ABI_VERSION; }
+
+void oc_config_init(oc_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->abi_version = OC_ABI_VERSION;
+    c->float_type = OC_F64;
+    for (int d = 0; d < 3; ++d) { c->N[d] = 1; c->H[d] = 0; c->topology[d] = OC_FLAT; c->delta[d] = 1.0; c->extent[d] = 1.0; }
+    c->advection = OC_CENTERED2;
+    c->timestepper = OC_RK3;
+    c->ab2_chi = 0.1;
+    c->gravity = 9.80665;                 // Oceananigans.defaults.gravitational_acceleration
+    c->thermal_expansion = 1.67e-4;       // LinearEquationOfState defaults   linear_equation_of_state.jl:39-40
+    c->haline_contraction = 7.8e-4;
+    c->tracer_T = c->tracer_S = c->tracer_b = -1;
+    c->amd_Cnu = 1.0 / 3.0;
+    for (int t = 0; t < OC_MAX_TRACERS; ++t) c->amd_Ckappa[t] = 1.0 / 3.0;
+}
+
+int oc_model_create(const oc_config* cfg, oc_model** out) {
+    if (!cfg || !out) { g_last_error = "null argument"; return OC_ERR_INVALID; }
+    *out = nullptr;
+    return guarded([&] {
+        std::unique_ptr<oc_model> m(new oc_model);
+        if (cfg->float_type == OC_F64) m->impl.reset(new oc::Model<double>(*cfg));
+        else if (cfg->float_type == OC_F32) m->impl.reset(new oc::Model<float>(*cfg));
+        else throw oc::Error(OC_ERR_INVALID, "float_type must be OC_F64 or OC_F32");
+        *out = m.release();
+    });
+}
+int oc_model_destroy(oc_model* m) {
+    if (!m) return OC_OK;
+    return guarded([&] { delete m; });
+}
+int oc_sync(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->sync(); }); }
+int oc_field_info_get(oc_model* m, int field, oc_field_info* info) { OC_REQUIRE(m); return guarded([&] { m->impl->field_info(field, info); }); }
+int oc_upload_interior(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, const_cast<void*>(host), nbytes, false, true); }); }
+int oc_download_interior(oc_model* m, int field, void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, host, nbytes, false, false); }); }
+int oc_upload_parent(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, const_cast<void*>(host), nbytes, true, true); }); }
+int oc_download_parent(oc_model* m, int field, void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, host, nbytes, true, false); }); }
+int oc_fill_halo_regions(oc_model* m, const int* fields, int nfields, int fill_open_bcs) { OC_REQUIRE(m); return guarded([&] { m->impl->fill_halo_regions(fields, nfields, fill_open_bcs); }); }
+int oc_update_state(oc_model* m, int compute_tendencies) { OC_REQUIRE(m); return guarded([&] { m->impl->update_state(compute_tendencies); }); }
+int oc_compute_tendencies(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->compute_tendencies(); }); }
+int oc_compute_flux_bc_tendencies(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->compute_flux_bc_tendencies(); }); }
+int oc_rk3_substep(oc_model* m, double dt, int stage) { OC_REQUIRE(m); return guarded([&] { m->impl->rk3_substep(dt, stage); }); }
+int oc_ab2_step(oc_model* m, double dt, double chi) { OC_REQUIRE(m); return guarded([&] { m->impl->ab2_step(dt, chi); }); }
+int oc_cache_previous_tendencies(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->cache_previous_tendencies(); }); }
+int oc_compute_pressure_correction(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&] { m->impl->compute_pressure_correction(dt); }); }
+int oc_make_pressure_correction(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&] { m->impl->make_pressure_correction(dt); }); }
+int oc_poisson_solve(oc_model* m, const void* rhs, void* phi, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->poisson_solve(rhs, phi, nbytes); }); }
+int oc_set_finalize(oc_model* m, int enforce) { OC_REQUIRE(m); return guarded([&] { m->impl->set_finalize(enforce); }); }
+int oc_time_step_rk3(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&] { m->impl->time_step_rk3(dt); }); }
+int oc_time_step_ab2(oc_model* m, double dt, int euler) { OC_REQUIRE(m); return guarded([&] { m->impl->time_step_ab2(dt, euler); }); }
+int oc_get_clock(oc_model* m, oc_clock* c) { OC_REQUIRE(m); *c = m->impl->clock; return OC_OK; }
+int oc_set_clock(oc_model* m, const oc_clock* c) { OC_REQUIRE(m); m->impl->clock = *c; return OC_OK; }
+int oc_timers_enable(oc_model* m, int enable) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_enable(enable); }); }
+int oc_timers_reset(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_reset(); }); }
+int oc_timers_get(oc_model* m, double* ms, int64_t* n) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_get(ms, n); }); }
+int oc_stopwatch_start(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->stopwatch_start(); }); }
+int oc_stopwatch_stop(oc_model* m, double* ms) { OC_REQUIRE(m); return guarded([&] { *ms = m->impl->stopwatch_stop(); }); }
+int oc_host_alloc(void** ptr, size_t nbytes) {
+    return guarded([&] {
+#ifndef OC_HOSTSIM
+        oc::cuda_check(cudaHostAlloc(ptr, nbytes, cudaHostAllocDefault), "cudaHostAlloc");
+#else
+        *ptr = malloc(nbytes);
+#endif
+    });
+}
+int oc_host_free(void* ptr) {
+    return guarded([&] {
+#ifndef OC_HOSTSIM
+        oc::cuda_check(cudaFreeHost(ptr), "cudaFreeHost");
+#else
+        free(ptr);
+#endif
+    });
+}
+int64_t oc_launch_count(oc_model* m) { return (m && m->impl) ? m->impl->launches : -1; }
+int oc_device_bytes(oc_model* m, int64_t* bytes) { OC_REQUIRE(m); *bytes = m->impl->device_bytes; return OC_OK; }
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+// oc_model.h — the model object behind the C ABI: device memory, launch sequencing, time stepping.
+//
+// Host-side orchestration that replaces time_step! (src/TimeSteppers/runge_kutta_3.jl:93-170,
+// quasi_adams_bashforth_2.jl:74-120), update_state! (src/Models/NonhydrostaticModels/
+// update_nonhydrostatic_model_state.jl:20-69), compute_pressure_correction!/make_pressure_correction!
+// (pressure_correction.jl:8-53) and set!'s projection (set_nonhydrostatic_model.jl:44-57).
+#pragma once
+#include <cmath>
+#include <limits>
+#include <map>
+#include <memory>
+#include <stdexcept>
+
+#include "../../include/oceananigans_b200.h"
+#include "oc_aux.h"
+#include "oc_fft.h"
+#include "oc_halo.h"
+#include "oc_tendency.h"
+
+namespace oc {
+
+// ---------------------------------------------------------------------------------------------------------
+// device memory shims (product: CUDA runtime; OC_HOSTSIM: host heap, tests only)
+// ---------------------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#ifndef OC_HOSTSIM
+inline void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw Error(OC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+inline void* dev_alloc(size_t bytes) {
+    void* p = nullptr;
+    cuda_check(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc");
+    cuda_check(cudaMemset(p, 0, bytes), "cudaMemset");
+    return p;
+}
+inline void dev_free(void* p) { if (p) cudaFree(p); }
+inline void dev_upload(void* d, const void* h, size_t bytes, Stream s) {
+    cuda_check(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
+}
+inline void dev_download(void* h, const void* d, size_t bytes, Stream s) {
+    cuda_check(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+    cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+}
+// box copy between a dense host array (x fastest, extents ext) and a strided device field
+inline void dev_copy_box(void* dev_origin, size_t elem, long long sy, long long sz, void* host, const int ext[3], bool to_device, Stream s) {
+    if (ext[0] <= 0 || ext[1] <= 0 || ext[2] <= 0) return;
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    // device side: pitch = sy elements, slice = sz elements  =>  rows per slice = sz / sy (exact by construction)
+    cudaPitchedPtr dptr = make_cudaPitchedPtr(dev_origin, (size_t)sy * elem, (size_t)sy * elem, (size_t)(sz / sy));
+    cudaPitchedPtr hptr = make_cudaPitchedPtr(host, (size_t)ext[0] * elem, (size_t)ext[0] * elem, (size_t)ext[1]);
+    p.extent = make_cudaExtent((size_t)ext[0] * elem, (size_t)ext[1], (size_t)ext[2]);
+    if (to_device) { p.srcPtr = hptr; p.dstPtr = dptr; p.kind = cudaMemcpyHostToDevice; }
+    else { p.srcPtr = dptr; p.dstPtr = hptr; p.kind = cudaMemcpyDeviceToHost; }
+    cuda_check(cudaMemcpy3DAsync(&p, s), "cudaMemcpy3DAsync");
+    cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+}
+#else
+inline void* dev_alloc(size_t bytes) { void* p = calloc(bytes ? bytes : 1, 1); if (!p) throw Error(OC_ERR_CUDA, "calloc"); return p; }
+inline void dev_free(void* p) { free(p); }
+inline void dev_upload(void* d, const void* h, size_t bytes, Stream) { memcpy(d, h, bytes); }
+inline void dev_download(void* h, const void* d, size_t bytes, Stream) { memcpy(h, d, bytes); }
+inline void dev_copy_box(void* dev_origin, size_t elem, long long sy, long long sz, void* host, const int ext[3], bool to_device, Stream) {
+    for (int k = 0; k < ext[2]; ++k)
+        for (int j = 0; j < ext[1]; ++j) {
+            char* d = (char*)dev_origin + (size_t)(j * sy + k * sz) * elem;
+            char* h = (char*)host + ((size_t)j + (size_t)ext[1] * k) * ext[0] * elem;
+            if (to_device) memcpy(d, h, (size_t)ext[0] * elem); else memcpy(h, d, (size_t)ext[0] * elem);
+        }
+}
+#endif
+
+struct ModelBase {
+    virtual ~ModelBase() {}
+    virtual void sync() = 0;
+    virtual void field_info(int field, oc_field_info* info) = 0;
+    virtual void transfer(int field, void* host, size_t nbytes, bool parent, bool upload) = 0;
+    virtual void fill_halo_regions(const int* fields, int n, int fill_open) = 0;
+    virtual void update_state(int compute_tendencies) = 0;
+    virtual void compute_tendencies() = 0;
+    virtual void compute_flux_bc_tendencies() = 0;
+    virtual void rk3_substep(double dt, int stage) = 0;
+    virtual void ab2_step(double dt, double chi) = 0;
+    virtual void cache_previous_tendencies() = 0;
+    virtual void compute_pressure_correction(double dt) = 0;
+    virtual void make_pressure_correction(double dt) = 0;
+    virtual void poisson_solve(const void* rhs, void* phi, size_t nbytes) = 0;
+    virtual void set_finalize(int enforce) = 0;
+    virtual void time_step_rk3(double dt) = 0;
+    virtual void time_step_ab2(double dt, int euler) = 0;
+    virtual void timers_enable(int on) = 0;
+    virtual void timers_reset() = 0;
+    virtual void timers_get(double* ms, int64_t* n) = 0;
+    virtual void stopwatch_start() = 0;
+    virtual double stopwatch_stop() = 0;
+    oc_clock clock{0.0, 0, 1, INFINITY, INFINITY};
+    int64_t launches = 0;
+    int64_t device_bytes = 0;
+};
+
+template <class FT>
+class Model : public ModelBase {
+public:
+    explicit Model(const oc_config& c);
+    ~Model() override;
+    void sync() override;
+    void field_info(int field, oc_field_info* info) override;
+    void transfer(int field, void* host, size_t nbytes, bool parent, bool upload) override;
+    void fill_halo_regions(const int* fields, int n, int fill_open) override;
+    void update_state(int compute_tendencies) override;
+    void compute_tendencies() override;
+    void compute_flux_bc_tendencies() override;
+    void rk3_substep(double dt, int stage) override;
+    void ab2_step(double dt, double chi) override;
+    void cache_previous_tendencies() override;
+    void compute_pressure_correction(double dt) override;
+    void make_pressure_correction(double dt) override;
+    void poisson_solve(const void* rhs, void* phi, size_t nbytes) override;
+    void set_finalize(int enforce) override;
+    void time_step_rk3(double dt) override;
+    void time_step_ab2(double dt, int euler) override;
+    void timers_enable(int on) override { timing_ = on != 0; }
+    void timers_reset() override;
+    void timers_get(double* ms, int64_t* n) override;
+    void stopwatch_start() override;
+    double stopwatch_stop() override;
+
+private:
+    struct FieldRec {
+        FT* base = nullptr;   // allocation
+        FT* p = nullptr;      // interior origin
+        int face[3] = {0, 0, 0};
+        SideBC bc[6];
+    };
+    oc_config cfg_;
+    Geom<FT> g_{};
+    AdvCoef<FT> C_{};
+    int F_ = 3;                       // prognostic fields
+    int Hcfg_[3];
+    size_t field_elems_ = 0;
+    long long origin_off_ = 0;
+    std::vector<FieldRec> state_, next_, Gn_, Gm_;
+    FieldRec pNHS_, pHY_, nu_e_;
+    std::vector<FieldRec> kappa_e_;
+    bool has_pHY_ = false, has_amd_ = false;
+    bool tend_valid_ = false;     // Gⁿ == G(current state)
+    bool aux_valid_ = false;      // pHY′, νₑ, κₑ computed from the current state
+    struct HaloCache { HaloBox* boxes; int nboxes; int nblocks; };
+    std::map<std::string, HaloCache> halo_cache_;
+    Fft3<FT> fft_;
+    FT* fftbuf_ = nullptr;
+    double* lam_[3] = {nullptr, nullptr, nullptr};
+    Cd* tw_[3] = {nullptr, nullptr, nullptr};
+    HaloBox* boxes_dev_ = nullptr;
+    Stream stream_ = 0;
+    FT gamma_[3], zeta_[3];
+    // timers
+    bool timing_ = false;
+    struct TimerRec { int cls; void* e0; void* e1; };
+    std::vector<TimerRec> timer_recs_;
+    std::vector<void*> event_pool_;
+    double timer_ms_[OC_TIMER_COUNT];
+    int64_t timer_n_[OC_TIMER_COUNT];
+    void* sw0_ = nullptr;
+    void* sw1_ = nullptr;
+
+    FieldRec alloc_field(const int face[3]);
+    FieldRec& lookup(int field);
+    void resolve_bcs(FieldRec& f, const oc_bc* user);
+    void halo(const std::vector<FieldRec*>& fields, bool fill_open);
+    void aux();
+    void compute_tendencies_if_stale();
+    void tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state);
+    template <int KIND> void launch_tendency(int fidx, TendencyArgs<FT>& a);
+    void pressure_solve_from_state();
+    void run_fft_solve();
+    void projection(double dt);
+    void stage(int mode, double dt, int stage_no, double stage_dt, double chi, bool euler);
+    void begin_timer(int cls);
+    void end_timer();
+    void collect_timers();
+    template <class K> void go(const K& k, Dim3 grid, size_t smem, int cls);
+    Dim3 grid_xyz(int threads) const { Dim3 d; d.x = (g_.N[0] + threads - 1) / threads; d.y = g_.N[1]; d.z = g_.N[2]; return d; }
+};
+
+}  // namespace oc

@@ -1,0 +1,298 @@
+// oc_poisson.h — kernels around the FFTs of the pressure solve.
+//
+// Replaces, for FFTBasedPoissonSolver (src/Solvers/fft_based_poisson_solver.jl:95-137):
+//   _compute_source_term!            src/Models/NonhydrostaticModels/solve_for_pressure.jl:12-18
+//   permute_*/unpermute_* + copyto! + twiddle broadcasts (Makhoul DCT)   src/Solvers/index_permutations.jl:38-90,
+//                                                                       discrete_transforms.jl:108-176
+//   ϕc = -b/(λx+λy+λz) ; ϕc[1,1,1] = 0                                 fft_based_poisson_solver.jl:110,115
+//   copy_real_component! + _make_pressure_correction! + pNHS ./= Δt     :122-137, pressure_correction.jl:31-53
+//
+// Scheme (validated against scipy's DCT-II/III in tests/test_transform_math.py):
+//   rhs kernel   : div(u*,v*,w*) written at the Makhoul-permuted position in every Bounded dimension
+//                  (v[n] = x[2n], v[N-1-n] = x[2n+1]); real-to-complex layout when x is not Bounded.
+//   forward FFT  : ONE multi-dimensional FFT over all non-trivial dimensions (cuFFT).
+//   mid kernel   : per reflection orbit {k, N-k} of each Bounded dimension, in registers:
+//                  X[k] = ω_k V[k] + conj(ω_k) V[N-k]   (ω_k = exp(-iπk/2N); DCT-II, FFTW REDFT10 scaling)
+//                  Φ = -X / (λx+λy+λz), Φ[0,0,0] = 0, times 1/(Nx·Ny·Nz)
+//                  W[k] = ½ conj(ω_k) (Φ[k] - i Φ[N-k]),  Φ[N] := 0   (DCT-III · 1/2N folded in)
+//   inverse FFT  : ONE multi-dimensional inverse FFT.
+//   projection   : reads ϕ = Δt·p at un-permuted positions, U -= ∇ϕ, pNHS = ϕ/Δt — no separate
+//                  copy-real / halo-fill / scale passes.
+#pragma once
+#include "oc_common.h"
+
+namespace oc {
+
+template <class FT>
+struct Cplx {
+    FT x, y;
+};
+
+struct Cd {
+    double x, y;
+};
+OC_HD Cd cmul(Cd a, Cd b) { return Cd{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+OC_HD Cd cconj(Cd a) { return Cd{a.x, -a.y}; }
+OC_HD Cd cadd(Cd a, Cd b) { return Cd{a.x + b.x, a.y + b.y}; }
+
+// Layout of the transform buffer.
+struct SpectralLayout {
+    int N[3];          // physical sizes
+    int bounded[3];
+    int r2c;           // 1: real rows padded to 2*(Nx/2+1) reals, complex rows Nx/2+1; 0: full complex, Nx per row
+    int nxc;           // complex row length
+    int nxr;           // real row length in reals (r2c) — for c2c the real value sits at 2*i
+    OC_HD long long real_index(int i, int j, int k) const {
+        return r2c ? ((long long)i + (long long)nxr * (j + (long long)N[1] * k))
+                   : 2 * ((long long)i + (long long)N[0] * (j + (long long)N[1] * k));
+    }
+    OC_HD long long cplx_index(int i, int j, int k) const { return (long long)i + (long long)nxc * (j + (long long)N[1] * k); }
+};
+
+// Makhoul permutation: x[z] goes to position z/2 (z even) or N-1-(z-1)/2 (z odd)   index_permutations.jl:18-36
+OC_HD int makhoul(int z, int N, int bounded) {
+    if (!bounded) return z;
+    return (z & 1) ? N - 1 - (z >> 1) : (z >> 1);
+}
+
+template <class FT>
+struct PoissonRhsKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    SpectralLayout L;
+    const FT* u;
+    const FT* v;
+    const FT* w;
+    FT* buf;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int i = b.x * nt + tid, j = b.y, k = b.z;
+        if (i >= g.N[0]) return;
+        int o = g.idx(i, j, k);
+        // divᶜᶜᶜ = V⁻¹ (δxᶜ(Ax u) + δyᶜ(Ay v) + δzᶜ(Az w))      divergence_operators.jl:16-19
+        FT dx = g.flat[0] ? FT(0) : g.A[0] * u[o + 1] - g.A[0] * u[o];
+        FT dy = g.flat[1] ? FT(0) : g.A[1] * v[o + g.sy] - g.A[1] * v[o];
+        FT dz = g.flat[2] ? FT(0) : g.A[2] * w[o + g.sz] - g.A[2] * w[o];
+        FT div = g.rV * (dx + dy + dz);
+        long long r = L.real_index(makhoul(i, L.N[0], L.bounded[0]), makhoul(j, L.N[1], L.bounded[1]),
+                                   makhoul(k, L.N[2], L.bounded[2]));
+        buf[r] = div;
+        if (!L.r2c) buf[r + 1] = FT(0);
+    }
+};
+
+// Host rhs (dense Nx×Ny×Nz) -> buffer, for the stand-alone solve!(ϕ, solver, b) entry point.
+template <class FT>
+struct PoissonLoadKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    SpectralLayout L;
+    const FT* rhs;
+    FT* buf;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int i = b.x * nt + tid, j = b.y, k = b.z;
+        if (i >= L.N[0]) return;
+        long long r = L.real_index(makhoul(i, L.N[0], L.bounded[0]), makhoul(j, L.N[1], L.bounded[1]),
+                                   makhoul(k, L.N[2], L.bounded[2]));
+        buf[r] = rhs[(long long)i + (long long)L.N[0] * (j + (long long)L.N[1] * k)];
+        if (!L.r2c) buf[r + 1] = FT(0);
+    }
+};
+
+template <class FT>
+struct PoissonMidKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = 1;
+    SpectralLayout L;
+    Cplx<FT>* spec;
+    const double* lam[3];      // eigenvalues, Float64   poisson_eigenvalues.jl:8-31
+    const Cd* tw[3];           // ω_k = exp(-iπk/2N) for Bounded dims (nullptr otherwise)
+    int nrep[3];               // number of orbit representatives per dim
+    double norm;               // 1/(Nx Ny Nz)
+
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int rx = b.x * nt + tid, ry = b.y, rz = b.z;
+        if (rx >= nrep[0]) return;
+        // orbit members per dim: index a and its reflection (N - a) % N (only for Bounded dims)
+        int idx[3][2];
+        int rep[3] = {rx, ry, rz};
+        int np[3];
+        for (int d = 0; d < 3; ++d) {
+            idx[d][0] = rep[d];
+            if (L.bounded[d]) { idx[d][1] = (L.N[d] - rep[d]) % L.N[d]; np[d] = 2; }
+            else { idx[d][1] = rep[d]; np[d] = 1; }
+        }
+        Cd v[2][2][2];
+        for (int c = 0; c < 2; ++c)
+            for (int bb = 0; bb < 2; ++bb)
+                for (int aa = 0; aa < 2; ++aa) {
+                    if (aa < np[0] && bb < np[1] && c < np[2]) {
+                        Cplx<FT> e = spec[L.cplx_index(idx[0][aa], idx[1][bb], idx[2][c])];
+                        v[c][bb][aa] = Cd{(double)e.x, (double)e.y};
+                    } else {
+                        v[c][bb][aa] = Cd{0.0, 0.0};
+                    }
+                }
+        // forward post-twiddle along every Bounded dim: X[k] = ω_k V[k] + conj(ω_k) V[N-k]
+        for (int d = 0; d < 3; ++d) {
+            if (!L.bounded[d]) continue;
+            Cd w0 = tw[d][idx[d][0]], w1 = tw[d][idx[d][1]];
+            for (int p = 0; p < 2; ++p)
+                for (int q = 0; q < 2; ++q) {
+                    Cd* e0 = d == 0 ? &v[p][q][0] : (d == 1 ? &v[p][0][q] : &v[0][p][q]);
+                    Cd* e1 = d == 0 ? &v[p][q][1] : (d == 1 ? &v[p][1][q] : &v[1][p][q]);
+                    Cd a0 = *e0, a1 = *e1;
+                    *e0 = cadd(cmul(w0, a0), cmul(cconj(w0), a1));
+                    *e1 = cadd(cmul(w1, a1), cmul(cconj(w1), a0));
+                }
+        }
+        // eigenvalue divide
+        for (int c = 0; c < np[2]; ++c)
+            for (int bb = 0; bb < np[1]; ++bb)
+                for (int aa = 0; aa < np[0]; ++aa) {
+                    int kx = idx[0][aa], ky = idx[1][bb], kz = idx[2][c];
+                    double l = lam[0][kx] + lam[1][ky] + lam[2][kz];
+                    Cd e = v[c][bb][aa];
+                    if (kx == 0 && ky == 0 && kz == 0) e = Cd{0.0, 0.0};
+                    else { double s = -norm / l; e.x *= s; e.y *= s; }
+                    v[c][bb][aa] = e;
+                }
+        // inverse pre-twiddle: W[k] = ½ conj(ω_k) (Φ[k] - i Φ[N-k]), Φ[N] := 0
+        for (int d = 0; d < 3; ++d) {
+            if (!L.bounded[d]) continue;
+            Cd w0 = tw[d][idx[d][0]], w1 = tw[d][idx[d][1]];
+            bool z0 = idx[d][0] == 0, z1 = idx[d][1] == 0;
+            for (int p = 0; p < 2; ++p)
+                for (int q = 0; q < 2; ++q) {
+                    Cd* e0 = d == 0 ? &v[p][q][0] : (d == 1 ? &v[p][0][q] : &v[0][p][q]);
+                    Cd* e1 = d == 0 ? &v[p][q][1] : (d == 1 ? &v[p][1][q] : &v[1][p][q]);
+                    Cd a0 = *e0, a1 = *e1;
+                    Cd r0 = z0 ? Cd{0.0, 0.0} : a1;     // Φ[N - k0]
+                    Cd r1 = z1 ? Cd{0.0, 0.0} : a0;     // Φ[N - k1]
+                    // (a - i r) = (a.x + r.y, a.y - r.x)
+                    Cd t0 = Cd{a0.x + r0.y, a0.y - r0.x}, t1 = Cd{a1.x + r1.y, a1.y - r1.x};
+                    Cd h0 = cmul(cconj(w0), t0), h1 = cmul(cconj(w1), t1);
+                    *e0 = Cd{0.5 * h0.x, 0.5 * h0.y};
+                    *e1 = Cd{0.5 * h1.x, 0.5 * h1.y};
+                }
+        }
+        for (int c = 0; c < np[2]; ++c)
+            for (int bb = 0; bb < np[1]; ++bb)
+                for (int aa = 0; aa < np[0]; ++aa) {
+                    Cd e = v[c][bb][aa];
+                    spec[L.cplx_index(idx[0][aa], idx[1][bb], idx[2][c])] = Cplx<FT>{(FT)e.x, (FT)e.y};
+                }
+    }
+};
+
+// ϕ at logical cell (i,j,k) from the transform buffer; i = -1 / N handled by the caller
+template <class FT>
+OC_HD FT phi_at(const SpectralLayout& L, const FT* buf, int i, int j, int k) {
+    return buf[L.real_index(makhoul(i, L.N[0], L.bounded[0]), makhoul(j, L.N[1], L.bounded[1]),
+                            makhoul(k, L.N[2], L.bounded[2]))];
+}
+
+// Fused projection: U -= ∇ϕ over 1:N (gradient across a wall is 0 by the no-flux halo of ϕ), pNHS = ϕ/Δt
+template <class FT>
+struct ProjectionKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    SpectralLayout L;
+    const FT* buf;
+    FT* u;
+    FT* v;
+    FT* w;
+    FT* pNHS;
+    double dt_plus;       // max(eps(FT), Δt)
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int i = b.x * nt + tid, j = b.y, k = b.z;
+        if (i >= g.N[0]) return;
+        int o = g.idx(i, j, k);
+        FT p0 = phi_at<FT>(L, buf, i, j, k);
+        if (!g.flat[0]) {
+            FT pm = (i > 0) ? phi_at<FT>(L, buf, i - 1, j, k) : (g.bounded[0] ? p0 : phi_at<FT>(L, buf, g.N[0] - 1, j, k));
+            u[o] = u[o] - (p0 - pm) * g.rd[0];
+        }
+        if (!g.flat[1]) {
+            FT pm = (j > 0) ? phi_at<FT>(L, buf, i, j - 1, k) : (g.bounded[1] ? p0 : phi_at<FT>(L, buf, i, g.N[1] - 1, k));
+            v[o] = v[o] - (p0 - pm) * g.rd[1];
+        }
+        if (!g.flat[2]) {
+            FT pm = (k > 0) ? phi_at<FT>(L, buf, i, j, k - 1) : (g.bounded[2] ? p0 : phi_at<FT>(L, buf, i, j, g.N[2] - 1));
+            w[o] = w[o] - (p0 - pm) * g.rd[2];
+        }
+        pNHS[o] = (FT)((double)p0 / dt_plus);
+    }
+};
+
+// Staged API: buffer -> field interior (copy_real_component!), and host output for solve!
+template <class FT>
+struct PoissonUnpackKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    SpectralLayout L;
+    const FT* buf;
+    FT* field;      // halo'd field or nullptr
+    FT* dense;      // dense Nx×Ny×Nz or nullptr
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int i = b.x * nt + tid, j = b.y, k = b.z;
+        if (i >= L.N[0]) return;
+        FT p0 = phi_at<FT>(L, buf, i, j, k);
+        if (field) field[g.idx(i, j, k)] = p0;
+        if (dense) dense[(long long)i + (long long)L.N[0] * (j + (long long)L.N[1] * k)] = p0;
+    }
+};
+
+// Staged API: _make_pressure_correction! from the halo-filled pNHS field, then pNHS ./= Δt (interior only)
+template <class FT>
+struct GradSubKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    FT* u;
+    FT* v;
+    FT* w;
+    FT* p;
+    double dt_plus;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int i = b.x * nt + tid, j = b.y, k = b.z;
+        if (i >= g.N[0]) return;
+        int o = g.idx(i, j, k);
+        FT p0 = p[o];
+        if (!g.flat[0]) u[o] = u[o] - (p0 - p[o - 1]) * g.rd[0];
+        if (!g.flat[1]) v[o] = v[o] - (p0 - p[o - g.sy]) * g.rd[1];
+        if (!g.flat[2]) w[o] = w[o] - (p0 - p[o - g.sz]) * g.rd[2];
+    }
+};
+template <class FT>
+struct ScaleKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    FT* p;
+    double dt_plus;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int i = b.x * nt + tid, j = b.y, k = b.z;
+        if (i >= g.N[0]) return;
+        int o = g.idx(i, j, k);
+        p[o] = (FT)((double)p[o] / dt_plus);
+    }
+};
+
+}  // namespace oc

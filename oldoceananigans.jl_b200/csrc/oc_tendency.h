@@ -1,0 +1,374 @@
+// oc_tendency.h — fused tendency (+ RK3/AB2 substep) kernel for one prognostic field.
+//
+// Replaces compute_Gu!/Gv!/Gw!/Gc! (src/Models/NonhydrostaticModels/compute_nonhydrostatic_tendencies.jl
+// :138-163 -> nonhydrostatic_tendency_kernel_functions.jl:70-298), compute_flux_bc_tendencies!
+// (compute_flux_bcs.jl:116-163), rk3_substep_field! (src/TimeSteppers/runge_kutta_3.jl:212-226),
+// ab2_step_field! (quasi_adams_bashforth_2.jl:162-175) and _cache_field_tendencies!
+// (store_tendencies.jl:6-9, by pointer swap) with ONE launch per field.
+//
+// Design: a CTA owns a TX×TY×TZ tile of cells.  Phase 0 evaluates every face flux of
+// the tile ONCE (advective + closure flux, (TX+1)·TY·TZ + TX·(TY+1)·TZ + TX·TY·(TZ+1) faces) into
+// shared memory — the reference evaluates both faces of every cell in every thread, i.e. each face
+// twice.  Phase 1 forms the flux divergence per cell, adds Coriolis / hydrostatic-pressure / buoyancy /
+// flux-BC terms, writes Gⁿ and the substepped state U* (state is double-buffered: read Uⁿ, write U*).
+#pragma once
+#include "oc_advection.h"
+
+namespace oc {
+
+enum FieldKind { KIND_U = 0, KIND_V = 1, KIND_W = 2, KIND_C = 3 };
+enum SubstepMode { STEP_NONE = 0, STEP_RK3_FIRST = 1, STEP_RK3 = 2, STEP_AB2 = 3 };
+
+template <class FT>
+struct FluxBC {          // compute_flux_bcs.jl: G[1] += J·A/V ; G[N] -= J·A/V
+    int on[6];
+    FT val[6];
+};
+
+template <class FT>
+struct TendencyArgs {
+    Geom<FT> g;
+    AdvCoef<FT> C;
+    const FT* U[3];      // current state u, v, w
+    const FT* c;         // tracer being stepped (KIND_C) else nullptr
+    const FT* pHY;       // hydrostatic pressure anomaly or nullptr
+    const FT* bT;        // buoyancy sources for the w-equation when pHY′ is absent (nullptr otherwise)
+    const FT* bS;
+    const FT* nu_e;      // AMD eddy viscosity (ccc) or nullptr
+    const FT* kappa_e;   // AMD eddy diffusivity of this tracer or nullptr
+    const FT* Gm;        // G⁻ of this field (read) or nullptr
+    FT* Gn;              // Gⁿ of this field (written)
+    const FT* Ucur;      // this field, current state (same as U[kind] or c)
+    FT* Unew;            // this field, next state (STEP_* != NONE)
+    int has_scalar;      // ScalarDiffusivity present
+    FT nu, kappa;        // its ν and this tracer's κ
+    int buoyancy;        // 0 none, 1 tracer b (bT), 2 seawater linear (bT = T, bS = S)
+    FT grav, alpha, beta;
+    int has_coriolis;
+    FT f;
+    FluxBC<FT> fbc;      // flux boundary conditions of this field
+    int add_flux_bcs;
+    int mode;            // SubstepMode
+    FT dt, ca, cb;       // RK3_FIRST: U + (dt·γ)·G with ca = dt·γ ; RK3: U + dt(ca·G + cb·G⁻) ; AB2: ca = 1.5+χ, cb = 0.5+χ
+    int ab2_euler;
+};
+
+template <class FT, int ADV, int KIND, int TX_, int TY_, int TZ_>
+struct TendencyKernel {
+    static constexpr int PHASES = 2;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int TX = TX_, TY = TY_, TZ = TZ_;
+    static constexpr int NFX = (TX + 1) * TY * TZ, NFY = TX * (TY + 1) * TZ, NFZ = TX * TY * (TZ + 1);
+    static constexpr size_t SMEM = sizeof(FT) * (size_t)(NFX + NFY + NFZ);
+    static constexpr int COMP = KIND == KIND_C ? -1 : KIND;
+
+    TendencyArgs<FT> a;
+
+    // ---- closure fluxes -------------------------------------------------------------------------------
+    // ν at the location that is Face in dims (d1,d2) (d1 < d2): ℑ_{d2}ᶠ(ℑ_{d1}ᶠ νₑ)  interpolation_operators.jl:45-56
+    OC_HD FT nu_ff(int o, int d1, int d2) const {
+        const Geom<FT>& g = a.g;
+        int s1 = g.st(d1), s2 = g.st(d2);
+        const FT* n = a.nu_e + o;
+        return FT(0.5) * (FT(0.5) * (n[-s1 - s2] + n[-s2]) + FT(0.5) * (n[-s1] + n[0]));
+    }
+
+    // viscous flux A_d · τ_{comp,d} at flux index o   (closure_kernel_operators.jl:22-41;
+    // abstract_scalar_diffusivity_closure.jl:189-204; velocity_tracer_gradients.jl:25-42)
+    OC_HD FT viscous_flux(int o, int d) const {
+        const Geom<FT>& g = a.g;
+        FT sig;
+        if (d == COMP) {
+            const FT* u = a.U[d] + o;
+            sig = (u[g.st(d)] - u[0]) * g.rd[d];                                  // Σ_dd at ccc
+        } else {
+            int lo = d < COMP ? d : COMP, hi = d < COMP ? COMP : d;
+            const FT* ul = a.U[lo] + o;
+            const FT* uh = a.U[hi] + o;
+            FT dl = (ul[0] - ul[-g.st(hi)]) * g.rd[hi];                           // ∂_hi u_lo
+            FT dh = (uh[0] - uh[-g.st(lo)]) * g.rd[lo];                           // ∂_lo u_hi
+            sig = FT(0.5) * (dl + dh);
+        }
+        FT flux = FT(0);
+        if (a.has_scalar) flux = g.A[d] * (FT(-2) * (a.nu * sig));
+        if (a.nu_e) {
+            FT nu;
+            if (d == COMP) nu = a.nu_e[o];
+            else nu = nu_ff(o, d < COMP ? d : COMP, d < COMP ? COMP : d);
+            FT f2 = g.A[d] * (FT(-2) * (nu * sig));
+            flux = a.has_scalar ? flux + f2 : f2;
+        }
+        return flux;
+    }
+
+    // diffusive tracer flux A_d · q_d at face index o   (:43-48, :240-242, κ at faces :327-330)
+    OC_HD FT diffusive_flux(int o, int d) const {
+        const Geom<FT>& g = a.g;
+        int s = g.st(d);
+        const FT* c = a.c + o;
+        FT grad = (c[0] - c[-s]) * g.rd[d];
+        FT flux = FT(0);
+        if (a.has_scalar) flux = g.A[d] * (-(a.kappa * grad));
+        if (a.kappa_e) {
+            FT kap = FT(0.5) * (a.kappa_e[o - s] + a.kappa_e[o]);
+            FT f2 = g.A[d] * (-(kap * grad));
+            flux = a.has_scalar ? flux + f2 : f2;
+        }
+        return flux;
+    }
+
+    // ---- advective fluxes -----------------------------------------------------------------------------
+    // Flux of this field through the faces normal to d, at flux index (i,j,k): for momentum component
+    // COMP the flux is centre-type in d when d == COMP (located at ccc) and face-type otherwise.
+    OC_HD FT advective_flux(int i, int j, int k, int d) const {
+        const Geom<FT>& g = a.g;
+        if (g.flat[d]) return FT(0);                                               // flat_advective_fluxes.jl:13-29
+        int o = g.idx(i, j, k);
+        int sd = g.st(d);
+        int id = d == 0 ? i : (d == 1 ? j : k);
+        FT A = g.A[d];
+        if (KIND == KIND_C) {
+            FT u = a.U[d][o];
+            const FT* c = a.c + o;
+            if (ADV == 0) {
+                return (A * u) * (FT(0.5) * c[-sd] + FT(0.5) * c[0]);              // centered_advective_fluxes.jl:31-33
+            } else {
+                OrderWindow w = order_window(g.bounded[d] != 0, false, g.N[d]);
+                FT cr = weno5_biased<FT>(a.C, c, sd, u > FT(0), id, w);            // upwind_biased_advective_fluxes.jl:99-121
+                return A * u * cr;
+            }
+        } else {
+            const FT* psi = a.U[COMP < 0 ? 0 : COMP] + o;
+            const FT* adv = a.U[d] + o;
+            if (d == COMP) {
+                // centre-type: evaluate the face-type stencils at face id+1
+                if (ADV == 0) {
+                    FT ut = FT(0.5) * adv[0] + FT(0.5) * adv[sd];
+                    FT pt = FT(0.5) * psi[0] + FT(0.5) * psi[sd];
+                    return A * ut * pt;                                            // centered_advective_fluxes.jl:15,22,27
+                } else {
+                    OrderWindow w = order_window(g.bounded[d] != 0, true, g.N[d]);
+                    FT ut = weno5_symmetric<FT>(a.C, adv + sd, sd, A, id + 1, w);
+                    FT pr = weno5_biased<FT>(a.C, psi + sd, sd, ut > FT(0), id + 1, w);
+                    return ut * pr;                                                // upwind_biased_advective_fluxes.jl:23-29
+                }
+            } else {
+                int cc = COMP < 0 ? 0 : COMP;
+                int sc = g.st(cc);
+                int ic = cc == 0 ? i : (cc == 1 ? j : k);
+                if (ADV == 0) {
+                    FT ut = g.flat[cc] ? adv[0] : (FT(0.5) * adv[-sc] + FT(0.5) * adv[0]);
+                    FT pt = FT(0.5) * psi[-sd] + FT(0.5) * psi[0];
+                    return A * ut * pt;                                            // :16-26
+                } else {
+                    OrderWindow wc = order_window(g.bounded[cc] != 0, false, g.N[cc]);
+                    OrderWindow wd = order_window(g.bounded[d] != 0, false, g.N[d]);
+                    FT ut = g.flat[cc] ? A * adv[0] : weno5_symmetric<FT>(a.C, adv, sc, A, ic, wc);
+                    FT pr = weno5_biased<FT>(a.C, psi, sd, ut > FT(0), id, wd);
+                    return ut * pr;                                                // :31-93
+                }
+            }
+        }
+    }
+
+    OC_HD FT total_flux(int i, int j, int k, int d) const {
+        FT F = advective_flux(i, j, k, d);
+        if (a.has_scalar || a.nu_e || a.kappa_e) {
+            if (!a.g.flat[d]) {
+                int o = a.g.idx(i, j, k);
+                F = F + (KIND == KIND_C ? diffusive_flux(o, d) : viscous_flux(o, d));
+            }
+        }
+        return F;
+    }
+
+    // buoyancy_perturbationᶜᶜᶜ  (linear_equation_of_state.jl:72-74, buoyancy_tracer.jl:12)
+    OC_HD FT buoyancy_at(int o) const {
+        if (a.buoyancy == 1) return a.bT[o];
+        return a.grav * (a.alpha * a.bT[o] - a.beta * a.bS[o]);
+    }
+
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char* smem) const {
+        const Geom<FT>& g = a.g;
+        FT* fx = reinterpret_cast<FT*>(smem);
+        FT* fy = fx + NFX;
+        FT* fz = fy + NFY;
+        const int i0 = b.x * TX, j0 = b.y * TY, k0 = b.z * TZ;
+        const int shx = COMP == 0 ? -1 : 0, shy = COMP == 1 ? -1 : 0, shz = COMP == 2 ? -1 : 0;
+        if (PHASE == 0) {
+            for (int n = tid; n < NFX; n += nt) {
+                int s = n % (TX + 1), jj = (n / (TX + 1)) % TY, kk = n / ((TX + 1) * TY);
+                int j = j0 + jj, k = k0 + kk;
+                FT F = FT(0);
+                if (j < g.N[1] && k < g.N[2] && i0 + s <= g.N[0]) F = total_flux(i0 + s + shx, j, k, 0);
+                fx[n] = F;
+            }
+            for (int n = tid; n < NFY; n += nt) {
+                int ii = n % TX, s = (n / TX) % (TY + 1), kk = n / (TX * (TY + 1));
+                int i = i0 + ii, k = k0 + kk;
+                FT F = FT(0);
+                if (i < g.N[0] && k < g.N[2] && j0 + s <= g.N[1]) F = total_flux(i, j0 + s + shy, k, 1);
+                fy[n] = F;
+            }
+            for (int n = tid; n < NFZ; n += nt) {
+                int ii = n % TX, jj = (n / TX) % TY, s = n / (TX * TY);
+                int i = i0 + ii, j = j0 + jj;
+                FT F = FT(0);
+                if (i < g.N[0] && j < g.N[1] && k0 + s <= g.N[2]) F = total_flux(i, j, k0 + s + shz, 2);
+                fz[n] = F;
+            }
+        } else {
+            for (int n = tid; n < TX * TY * TZ; n += nt) {
+                int ii = n % TX, jj = (n / TX) % TY, kk = n / (TX * TY);
+                int i = i0 + ii, j = j0 + jj, k = k0 + kk;
+                if (i >= g.N[0] || j >= g.N[1] || k >= g.N[2]) continue;
+                int o = g.idx(i, j, k);
+                FT u0 = a.Ucur[o];
+                // exclude_periphery: wall faces of a Face-located field in a Bounded dimension are not stepped
+                // (src/Utils/kernel_launching.jl:145-146)
+                bool wall = false;
+                if (COMP >= 0) {
+                    int ic = COMP == 0 ? i : (COMP == 1 ? j : k);
+                    wall = g.bounded[COMP] && ic == 0 && g.N[COMP] > 1;
+                }
+                if (wall) {
+                    if (a.mode != STEP_NONE) a.Unew[o] = u0;
+                    continue;
+                }
+                FT dFx = fx[(kk * TY + jj) * (TX + 1) + ii + 1] - fx[(kk * TY + jj) * (TX + 1) + ii];
+                FT dFy = fy[(kk * (TY + 1) + jj + 1) * TX + ii] - fy[(kk * (TY + 1) + jj) * TX + ii];
+                FT dFz = fz[((kk + 1) * TY + jj) * TX + ii] - fz[(kk * TY + jj) * TX + ii];
+                FT G = -(g.rV * (dFx + dFy + dFz));
+                if (KIND == KIND_W && a.buoyancy && !a.pHY && !g.flat[2]) {
+                    // maybe_z_dot_g_bᶜᶜᶠ: only without the hydrostatic split (nonhydrostatic_tendency_kernel_functions.jl:168-170)
+                    G = G + FT(0.5) * (buoyancy_at(o - g.sz) + buoyancy_at(o));
+                }
+                if ((KIND == KIND_U || KIND == KIND_V) && a.has_coriolis) {
+                    // FPlane: x_f_cross_U = -f·ℑxyᶠᶜᶜ(v)/active ; y_f_cross_U = +f·ℑxyᶜᶠᶜ(u)/active   f_plane.jl:50-52
+                    FT num, cnt;
+                    if (KIND == KIND_U) {
+                        const FT* v = a.U[1] + o;
+                        num = FT(0.5) * (FT(0.5) * (v[-1] + v[0]) + FT(0.5) * (v[g.sy - 1] + v[g.sy]));
+                        // v-nodes (i-1,j),(i,j),(i-1,j+1),(i,j+1): active iff not on/outside a wall (inactive_node.jl:152-158)
+                        int ax0 = !(g.bounded[0] && (i - 1 < 0)), ax1 = 1;
+                        int ay0 = !(g.bounded[1] && (j < 1)), ay1 = !(g.bounded[1] && (j + 1 > g.N[1] - 1));
+                        cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
+                        FT val = cnt == FT(0) ? FT(0) : num / cnt;
+                        G = G - (-a.f * val);
+                    } else {
+                        const FT* u = a.U[0] + o;
+                        num = FT(0.5) * (FT(0.5) * (u[-g.sy] + u[-g.sy + 1]) + FT(0.5) * (u[0] + u[1]));
+                        // u-nodes (i,j-1),(i+1,j-1),(i,j),(i+1,j)
+                        int ax0 = !(g.bounded[0] && (i < 1)), ax1 = !(g.bounded[0] && (i + 1 > g.N[0] - 1));
+                        int ay0 = !(g.bounded[1] && (j - 1 < 0)), ay1 = 1;
+                        cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
+                        FT val = cnt == FT(0) ? FT(0) : num / cnt;
+                        G = G - (a.f * val);
+                    }
+                }
+                if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) {
+                    // hydrostatic_pressure_gradient_x/y = ∂xᶠᶜᶜ / ∂yᶜᶠᶜ pHY′
+                    int s = KIND == KIND_U ? 1 : g.sy;
+                    if (!g.flat[KIND]) G = G - (a.pHY[o] - a.pHY[o - s]) * g.rd[KIND];
+                }
+                if (a.add_flux_bcs) {
+                    // compute_flux_bcs.jl:126-163 — G[1] += J·A/V ; G[N] -= J·A/V
+                    int ijk[3] = {i, j, k};
+                    for (int d = 0; d < 3; ++d) {
+                        if (a.fbc.on[2 * d] && ijk[d] == 0) G = G + a.fbc.val[2 * d] * g.A[d] / g.V;
+                        if (a.fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) G = G - a.fbc.val[2 * d + 1] * g.A[d] / g.V;
+                    }
+                }
+                a.Gn[o] = G;
+                if (a.mode == STEP_RK3_FIRST) {
+                    a.Unew[o] = u0 + a.ca * G;
+                } else if (a.mode == STEP_RK3) {
+                    a.Unew[o] = u0 + a.dt * (a.ca * G + a.cb * a.Gm[o]);
+                } else if (a.mode == STEP_AB2) {
+                    FT Gu = a.ab2_euler ? a.ca * G : a.ca * G - a.cb * a.Gm[o];
+                    a.Unew[o] = u0 + a.dt * Gu;
+                }
+            }
+        }
+    }
+};
+
+// Stand-alone substep (the staged API: rk3_substep! / ab2_step! on already computed Gⁿ, G⁻), in place.
+template <class FT>
+struct SubstepKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    FT* U;
+    const FT* Gn;
+    const FT* Gm;
+    int comp;          // 0,1,2 velocity component or -1
+    int mode;
+    FT dt, ca, cb;
+    int ab2_euler;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int i = b.x * nt + tid, j = b.y, k = b.z;
+        if (i >= g.N[0]) return;
+        if (comp >= 0) {
+            int ic = comp == 0 ? i : (comp == 1 ? j : k);
+            if (g.bounded[comp] && ic == 0 && g.N[comp] > 1) return;
+        }
+        int o = g.idx(i, j, k);
+        FT G = Gn[o];
+        if (mode == STEP_RK3_FIRST) U[o] = U[o] + ca * G;
+        else if (mode == STEP_RK3) U[o] = U[o] + dt * (ca * G + cb * Gm[o]);
+        else if (mode == STEP_AB2) {
+            FT Gu = ab2_euler ? ca * G : ca * G - cb * Gm[o];
+            U[o] = U[o] + dt * Gu;
+        }
+    }
+};
+
+// Adds flux-BC contributions to an existing Gⁿ (staged API compute_flux_bc_tendencies!)
+template <class FT>
+struct FluxBCKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    FT* Gn;
+    FluxBC<FT> fbc;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int i = b.x * nt + tid, j = b.y, k = b.z;
+        if (i >= g.N[0]) return;
+        int ijk[3] = {i, j, k};
+        int o = g.idx(i, j, k);
+        FT G = Gn[o];
+        bool touched = false;
+        for (int d = 0; d < 3; ++d) {
+            if (fbc.on[2 * d] && ijk[d] == 0) { G = G + fbc.val[2 * d] * g.A[d] / g.V; touched = true; }
+            if (fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) { G = G - fbc.val[2 * d + 1] * g.A[d] / g.V; touched = true; }
+        }
+        if (touched) Gn[o] = G;
+    }
+};
+
+// Copy interior (cache_previous_tendencies! for the staged API)
+template <class FT>
+struct CopyKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    FT* dst;
+    const FT* src;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int i = b.x * nt + tid, j = b.y, k = b.z;
+        if (i >= g.N[0]) return;
+        int o = g.idx(i, j, k);
+        dst[o] = src[o];
+    }
+};
+
+}  // namespace oc

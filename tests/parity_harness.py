@@ -1,0 +1,125 @@
+"""Shared parity harness: builds the same model in the product host API (oceananigans_b200) and in the CPU oracle,
+feeds identical seeded initial conditions and compares after each step.
+
+Used by tests/test_gpu_parity.py (-m gpu: the CUDA library, through the C ABI) and tests/test_hostsim_parity.py
+(CPU: the host-simulation build of the same kernel sources, injected explicitly — see tests/hostsim/README.md).
+Tolerances are the north_star's: relative L∞ ≤ 1e-11 (Float64) / ≤ 1e-4 (Float32) for u, v, w, p and tracers.
+"""
+import numpy as np
+
+import oceananigans_b200 as ob
+import oracle
+from oracle import advection as adv
+from oracle import closures as clo
+from oracle.grid import BC
+
+TOPO = {"P": ob.Periodic, "B": ob.Bounded, "F": ob.Flat}
+EXTENT = (1.0, 1.5, 2.0)
+TOL = {np.float64: 1e-11, np.float32: 1e-4}
+
+
+def build_pair(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
+               bcs=False, library=None, extent=EXTENT):
+    nonflat = [d for d in range(3) if topo[d] != "F"]
+    size = tuple(N[d] for d in nonflat)
+    ext = tuple(extent[d] for d in nonflat)
+    grid = ob.RectilinearGrid(FT, size=size, extent=ext, topology=tuple(TOPO[c] for c in topo))
+    a = ob.Centered() if scheme == "centered" else ob.WENO()
+    tr = ("T", "S") if buoy == "seawater" else (("b",) if buoy == "tracer" else (("c",) if buoy == "passive" else ()))
+    bo = ob.SeawaterBuoyancy() if buoy == "seawater" else (ob.BuoyancyTracer() if buoy == "tracer" else None)
+    obo = clo.SeawaterBuoyancy() if buoy == "seawater" else (clo.BuoyancyTracer() if buoy == "tracer" else None)
+    cl = {"scalar": ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), "amd": ob.AnisotropicMinimumDissipation(), "none": None,
+          "both": (ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), ob.AnisotropicMinimumDissipation())}[closure]
+    ocl = {"scalar": clo.ScalarDiffusivity(1e-3, 2e-3), "amd": clo.AnisotropicMinimumDissipation(), "none": None,
+           "both": (clo.ScalarDiffusivity(1e-3, 2e-3), clo.AnisotropicMinimumDissipation())}[closure]
+    bc_b = bc_o = None
+    if bcs:
+        # the BC kinds of test/regression_tests/ocean_large_eddy_simulation_regression_test.jl:19-37
+        t0 = tr[0]
+        bc_b = {"u": ob.FieldBoundaryConditions(top=ob.FluxBoundaryCondition(-2e-3)),
+                t0: ob.FieldBoundaryConditions(top=ob.FluxBoundaryCondition(5e-3), bottom=ob.GradientBoundaryCondition(0.05)),
+                "v": ob.FieldBoundaryConditions(bottom=ob.ValueBoundaryCondition(0.1))}
+        bc_o = {"u": {"top": BC("flux", -2e-3)}, t0: {"top": BC("flux", 5e-3), "bottom": BC("gradient", 0.05)},
+                "v": {"bottom": BC("value", 0.1)}}
+    m = ob.NonhydrostaticModel(grid=grid, advection=a, tracers=tr, buoyancy=bo, closure=cl, timestepper=ts,
+                               coriolis=ob.FPlane(f=f) if f else None, boundary_conditions=bc_b, library=library)
+    og = oracle.Grid(FT, size=size, extent=ext, topology=tuple(topo))
+    oa = adv.Centered(FT, 2) if scheme == "centered" else adv.WENO(FT, 5)
+    om = oracle.OracleModel(og, advection=oa, tracers=tr, buoyancy=obo, closure=ocl, timestepper=ts, coriolis_f=f,
+                            boundary_conditions=bc_o)
+    return m, om
+
+
+def initial_conditions(om, seed=1234, smooth=False):
+    """SURVEY §8d synthetic inputs: rng(1234); u,v,w ~ U(-1,1); T = 20 + 0.01 N(0,1); S = 35 + 0.01 N(0,1)."""
+    rng = np.random.default_rng(seed)
+    ic = {}
+    for name in ("u", "v", "w"):
+        ic[name] = rng.uniform(-1, 1, om.fields[name].interior.shape)
+    base = {"T": 20.0, "S": 35.0, "b": 0.0, "c": 1.0}
+    for n in om.tracers:
+        ic[n] = base.get(n, 0.0) + 0.01 * rng.standard_normal(om.fields[n].interior.shape)
+    return ic
+
+
+def rel_linf(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), np.finfo(np.float64).tiny))
+
+
+def compare(m, om, parent_too=True):
+    """max relative L∞ error over u, v, w, tracers (interior [+ parent incl. halos]) and p (interior)."""
+    worst = {}
+    for name in om.fields:
+        worst[name] = rel_linf(m.fields[name].interior(), om.fields[name].interior)
+        if parent_too:
+            worst[name + ".parent"] = rel_linf(m.fields[name].parent(), om.fields[name].data)
+    worst["p"] = rel_linf(m.pressures.pNHS.interior(), om.pNHS.interior)
+    return worst
+
+
+def run_case(steps=(1, 10), dt=None, **kw):
+    """returns {step: {field: rel error}}"""
+    m, om = build_pair(**kw)
+    ic = initial_conditions(om)
+    ob.set_(m, **ic)
+    om.set(**ic)
+    if dt is None:
+        dt = 0.1 * float(min(om.grid.D[d] for d in range(3) if not om.grid.flat(d)))
+    out = {0: compare(m, om)}
+    for s in range(1, max(steps) + 1):
+        ob.time_step_(m, dt)
+        om.time_step(dt)
+        if s in steps:
+            out[s] = compare(m, om)
+    return out, m, om
+
+
+# (id, kwargs) — small cases the oracle finishes in seconds
+CASES = [
+    ("C2-like PPP centered", dict(N=(16, 12, 8), topo="PPP", scheme="centered", closure="none", buoy="none")),
+    ("C3-like PPP weno TS", dict(N=(16, 12, 8), topo="PPP", scheme="weno")),
+    ("C3-like F32", dict(N=(16, 12, 8), topo="PPP", scheme="weno", FT=np.float32)),
+    ("C4-like PPB weno amd fplane bcs", dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True)),
+    ("C1-like PPF weno 2D", dict(N=(16, 12, 1), topo="PPF", scheme="weno", closure="none", buoy="none")),
+    ("PPB centered scalar", dict(N=(16, 12, 8), topo="PPB", scheme="centered")),
+    ("PBB weno", dict(N=(16, 12, 8), topo="PBB", scheme="weno")),
+    ("BBB weno amd", dict(N=(16, 12, 8), topo="BBB", scheme="weno", closure="amd", f=1e-2)),
+    ("BPP centered", dict(N=(16, 12, 8), topo="BPP", scheme="centered")),
+    ("PFB weno tracer-b fplane", dict(N=(16, 1, 12), topo="PFB", scheme="weno", buoy="tracer", f=0.2)),
+    ("PPB weno AB2", dict(N=(16, 12, 8), topo="PPB", scheme="weno", ts="QuasiAdamsBashforth2")),
+    ("PPB centered both closures bcs F32", dict(N=(16, 12, 8), topo="PPB", scheme="centered", closure="both", bcs=True, FT=np.float32)),
+    ("odd sizes PPB", dict(N=(13, 9, 7), topo="PPB", scheme="weno")),
+    ("tile-crossing 40x36x33 PPB", dict(N=(40, 36, 33), topo="PPB", scheme="weno")),
+]
+
+
+def check_case(kw, library=None, steps=(1, 10)):
+    FT = kw.get("FT", np.float64)
+    if max(kw["N"]) > 32:
+        steps = (1, 2)
+    out, m, om = run_case(steps=steps, library=library, **kw)
+    tol = TOL[FT]
+    for s, errs in out.items():
+        for name, e in errs.items():
+            assert e <= tol, f"step {s} field {name}: rel L-inf {e:.3e} > {tol:g}"
+    return out

@@ -1,0 +1,57 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/oceananigans_b200.h declares; the host
+layer rejects out-of-scope configurations loudly (no fallbacks)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "oceananigans_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(oc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_bound_in_python():
+    from oceananigans_b200 import _lib
+    assert set(_declared_symbols()) == set(_lib.SYMBOLS)
+
+
+def test_cuda_library_loads_and_exports_every_symbol():
+    import __graft_entry__ as ge
+    from oceananigans_b200 import _lib
+    if not os.path.exists(ge.LIB):
+        ge.build()
+    lib = _lib.Library(ge.LIB)           # resolves every symbol, checks the ABI version
+    assert lib.oc_abi_version() == _lib.OC_ABI_VERSION
+    import ctypes as C
+    for name in _declared_symbols():
+        assert hasattr(lib.dll, name), name
+    cfg = _lib.oc_config()
+    lib.oc_config_init(C.byref(cfg))     # pure host call; no compute without a GPU
+    assert cfg.abi_version == 1 and cfg.ab2_chi == 0.1 and abs(cfg.gravity - 9.80665) < 1e-15
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from oceananigans_b200 import _lib
+    with pytest.raises(_lib.OceananigansB200Error, match="no CPU fallback"):
+        _lib.Library(str(tmp_path / "nope.so"))
+
+
+def test_out_of_scope_configurations_are_errors():
+    import oceananigans_b200 as ob
+    with pytest.raises(NotImplementedError):
+        ob.WENO(order=7)
+    with pytest.raises(NotImplementedError):
+        ob.Centered(order=4)
+    with pytest.raises(NotImplementedError):
+        ob.RectilinearGrid(np.float64, size=(4, 4, 4), x=(0, 1), y=(0, 1), z=[0, 0.1, 0.3, 0.6, 1.0])
+    with pytest.raises(ValueError):
+        ob.RectilinearGrid(np.float64, size=(4, 4), extent=(1, 1, 1))
+    g = ob.RectilinearGrid(np.float32, size=(4, 4, 4), extent=(1, 1, 1))
+    assert g.H == (3, 3, 3) and g.FT is np.float32
+    assert abs(g.dz - np.float32(0.25)) == 0

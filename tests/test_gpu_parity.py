@@ -1,0 +1,118 @@
+"""GPU parity tests (`-m gpu`): the CUDA library, through the C ABI, against the CPU oracle on identical seeded
+inputs after 1 and 10 time steps — relative L∞ ≤ 1e-11 (Float64) / ≤ 1e-4 (Float32) for u, v, w, p and tracers,
+interior AND parent arrays (halo indexing).  Full-size configurations are checked through size-independent
+properties (incompressibility, tracer conservation, agreement of the staged and fused paths)."""
+import numpy as np
+import pytest
+
+import parity_harness as ph
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import oceananigans_b200 as ob_
+    from oceananigans_b200 import _lib
+    lib = _lib.load()                    # raises if the CUDA library is missing
+    assert lib.path.endswith("liboceananigans_b200.so")
+    return ob_
+
+
+@pytest.mark.parametrize("name,kw", ph.CASES, ids=[c[0] for c in ph.CASES])
+def test_cuda_matches_oracle(ob, name, kw):
+    ph.check_case(kw, library=None, steps=(1, 10))
+
+
+def test_poisson_all_topologies(ob):
+    """divergence_free_poisson_solution: test/test_poisson_solvers.jl:58-98 through solve!"""
+    import oracle
+    rng = np.random.default_rng(7)
+    for FT, tol in ((np.float64, 1e-12), (np.float32, 2e-5)):
+        for topo in ["PPP", "PPB", "PBP", "BPP", "PBB", "BBP", "BPB", "BBB"]:
+            for N in [(7, 7, 7), (16, 16, 16), (11, 16, 11), (1, 16, 16), (16, 1, 16), (16, 16, 1)]:
+                grid = ob.RectilinearGrid(FT, size=N, extent=(1, 1, 1), topology=tuple(ph.TOPO[c] for c in topo))
+                m = ob.NonhydrostaticModel(grid=grid)
+                om = oracle.OracleModel(oracle.Grid(FT, size=N, extent=(1, 1, 1), topology=tuple(topo)))
+                rhs = rng.standard_normal(N)
+                rhs -= rhs.mean()
+                a, b = ob.solve_poisson(m, rhs), om.solve_poisson(rhs.astype(FT))
+                assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1.0), (FT, topo, N)
+
+
+def test_two_dimensional_topologies(ob):
+    """test/test_poisson_solvers.jl:66-67 two_dimensional_topologies, through a full time step"""
+    for topo in ["PPF", "PBF", "BBF", "PFB", "FPB", "FBB"]:
+        N = tuple(1 if c == "F" else n for c, n in zip(topo, (12, 10, 8)))
+        ph.check_case(dict(N=N, topo=topo, scheme="weno", closure="scalar", buoy="passive"), steps=(1, 3))
+
+
+def test_staged_entry_points_match_fused_step(ob):
+    kw = dict(N=(24, 20, 16), topo="PPB", scheme="weno", closure="amd", bcs=True, f=1e-2)
+    m1, om = ph.build_pair(**kw)
+    m2, _ = ph.build_pair(**kw)
+    ic = ph.initial_conditions(om)
+    ob.set_(m1, **ic)
+    ob.set_(m2, **ic)
+    dt = 0.005
+    ob.time_step_(m1, dt)
+    g, z = [8 / 15, 5 / 12, 3 / 4], [0.0, -17 / 60, -5 / 12]
+    ob.update_state_(m2, True)
+    for s in (1, 2, 3):
+        ob.compute_flux_bc_tendencies_(m2)
+        ob.rk3_substep_(m2, dt, s)
+        sdt = dt * (g[s - 1] + z[s - 1])
+        ob.compute_pressure_correction_(m2, sdt)
+        ob.make_pressure_correction_(m2, sdt)
+        if s < 3:
+            ob.cache_previous_tendencies_(m2)
+        ob.update_state_(m2, True)
+    for n in m1.fields:
+        assert ph.rel_linf(m1.fields[n].interior(), m2.fields[n].interior()) < 1e-12, n
+
+
+def _divergence(m):
+    g = m.grid
+    u, v, w = (m.velocities[n].parent().astype(np.float64) for n in "uvw")
+    H = g.H
+    sl = lambda a, d, s: a[tuple(slice(H[e] + (s if e == d else 0), H[e] + g.N[e] + (s if e == d else 0)) for e in range(3))]
+    return (sl(u, 0, 1) - sl(u, 0, 0)) / g.dx + (sl(v, 1, 1) - sl(v, 1, 0)) / g.dy + (sl(w, 2, 1) - sl(w, 2, 0)) / g.dz
+
+
+@pytest.mark.parametrize("FT,atol", [(np.float64, 1e-9), (np.float32, 5e-2)])
+def test_full_size_c2_incompressible_and_bounded(ob, FT, atol):
+    """BASELINE config C2 (256³ triply periodic, Centered) at full size: ∇·U ≈ 0 after steps
+    (test/test_time_stepping.jl:124-158 property), energy does not grow without forcing."""
+    N = 256
+    grid = ob.RectilinearGrid(FT, size=(N, N, N), extent=(1, 1, 1), topology=(ob.Periodic,) * 3)
+    m = ob.NonhydrostaticModel(grid=grid, advection=ob.Centered())
+    rng = np.random.default_rng(1234)
+    ob.set_(m, u=rng.uniform(-1, 1, (N, N, N)), v=rng.uniform(-1, 1, (N, N, N)), w=rng.uniform(-1, 1, (N, N, N)))
+    e0 = sum(float((m.velocities[n].interior().astype(np.float64) ** 2).mean()) for n in "uvw")
+    for _ in range(3):
+        ob.time_step_(m, 0.1 / N)
+    div = _divergence(m)
+    scale = N * 1.0            # |u|/Δx
+    assert np.abs(div).max() <= atol * scale
+    e1 = sum(float((m.velocities[n].interior().astype(np.float64) ** 2).mean()) for n in "uvw")
+    assert np.isfinite(e1) and e1 <= e0 * 1.01
+
+
+def test_full_size_c3_tracer_conservation(ob):
+    """BASELINE config C3 at 256×256×128 (the 512³ case is the bench workload): WENO-5, T/S, SeawaterBuoyancy,
+    ScalarDiffusivity; flux-form advection conserves ⟨T⟩, ⟨S⟩ in a periodic box; ∇·U ≈ 0."""
+    N = (256, 256, 128)
+    grid = ob.RectilinearGrid(np.float64, size=N, extent=(1, 1, 0.5), topology=(ob.Periodic,) * 3)
+    m = ob.NonhydrostaticModel(grid=grid, advection=ob.WENO(), tracers=("T", "S"), buoyancy=ob.SeawaterBuoyancy(),
+                               closure=ob.ScalarDiffusivity(nu=1e-5, kappa=1e-5))
+    rng = np.random.default_rng(1234)
+    ic = {n: rng.uniform(-1, 1, N) for n in "uvw"}
+    ic["T"] = 20 + 0.01 * rng.standard_normal(N)
+    ic["S"] = 35 + 0.01 * rng.standard_normal(N)
+    ob.set_(m, **ic)
+    T0, S0 = m.tracers.T.interior().mean(), m.tracers.S.interior().mean()
+    for _ in range(2):
+        ob.time_step_(m, 0.1 / 256)
+    assert abs(m.tracers.T.interior().mean() - T0) < 1e-11 * 20
+    assert abs(m.tracers.S.interior().mean() - S0) < 1e-11 * 35
+    assert np.abs(_divergence(m)).max() < 1e-9 * 256
