@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py — cell-updates/s per full time step of the NonhydrostaticModel hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c3f32|c4|c1] [--impl ours|reference]
+
+One "step" is one full `time_step!(model, Δt)` (RK3: three stages, each tendency+substep, halo fills, FFT
+pressure solve and projection) over one synthetic, seeded initial state.
+
+  value        whole-job cell-updates/s with the state resident in HBM (CUDA events on the library's stream)
+  e2e          the same metric through the host API with HOST buffers: every step uploads the prognostic
+               fields from pinned host memory (set!), steps, and downloads u, v, w, tracers and p (interior)
+  roofline     the dominant kernel class (fused tendency+substep launches): algorithmic bytes / CUDA-event time
+               against MEASURED_PEAKS.json's HBM copy bandwidth; `step` = whole-step algorithmic bytes
+                / step time against the same peak
+  cpu_baseline the oracle (NumPy port of the reference algorithm; oracle/) timed on this host on a bounded sample
+
+`--impl reference` times the CPU restatement of the reference (the Julia reference cannot run here: no julia
+binary) on the same physics at a bounded size.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "cell-updates/sec per full RK3 step"
+
+# name -> description of the BASELINE.json configuration
+WORKLOADS = {
+    "c1": dict(N=(128, 128, 1), topo="PPF", FT="f64", adv="weno", tracers=(), buoy=None, closure=None, F=3, b=0, a=0,
+               label="C1 128^2 (P,P,Flat) WENO-5 F64"),
+    "c2": dict(N=(256, 256, 256), topo="PPP", FT="f64", adv="centered", tracers=(), buoy=None, closure=None, F=3, b=0, a=0,
+               label="C2 256^3 (P,P,P) Centered-2 F64 no tracers"),
+    "c3": dict(N=(512, 512, 512), topo="PPP", FT="f64", adv="weno", tracers=("T", "S"), buoy="seawater", closure="scalar",
+               F=5, b=1, a=0, label="C3 512^3 (P,P,P) WENO-5 T,S SeawaterBuoyancy ScalarDiffusivity F64"),
+    "c3f32": dict(N=(512, 512, 512), topo="PPP", FT="f32", adv="weno", tracers=("T", "S"), buoy="seawater", closure="scalar",
+                  F=5, b=1, a=0, label="C3 512^3 (P,P,P) WENO-5 T,S SeawaterBuoyancy ScalarDiffusivity F32"),
+    "c4": dict(N=(512, 512, 256), topo="PPB", FT="f64", adv="weno", tracers=("T", "S"), buoy="seawater", closure="amd",
+               F=5, b=1, a=1, label="C4 512^2x256 (P,P,B) WENO-5 AMD FPlane flux BCs F64"),
+}
+
+
+def reals_per_cell_step(w):
+    """10F + 3b + 9b + 3a(1+Nt) + 3a(4+2Nt) + 57 (2-D: Poisson 7 + projection 5 per stage)."""
+    F, b, a = w["F"], w["b"], w["a"]
+    Nt = F - 3
+    if w["N"][2] == 1:
+        return 10 * F + 3 * (7 + 5)
+    return 10 * F + 3 * b + 9 * b + 3 * a * (1 + Nt) + 3 * a * (4 + 2 * Nt) + 57
+
+
+def tendency_reals_per_cell_step(w):
+    """K1 of SURVEY.md §8d summed over the 3 stages: read F + b + a(1+Nt) (+F G⁻ for s>1), write F (+F Gⁿ for s<3)."""
+    F, b, a = w["F"], w["b"], w["a"]
+    Nt = F - 3
+    return 3 * (2 * F + b + a * (1 + Nt)) + 2 * F + 2 * F
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- model construction
+def build_model(w, device, rank=0):
+    import oceananigans_b200 as ob
+    FT = np.float64 if w["FT"] == "f64" else np.float32
+    topo = {"P": ob.Periodic, "B": ob.Bounded, "F": ob.Flat}
+    nonflat = [d for d in range(3) if w["topo"][d] != "F"]
+    size = tuple(w["N"][d] for d in nonflat)
+    if w is WORKLOADS["c4"] or w.get("closure") == "amd":
+        extent = tuple(float(w["N"][d]) for d in nonflat)                      # Δ = 1 m
+    elif w["topo"] == "PPF":
+        extent = (2 * np.pi, 2 * np.pi)
+    else:
+        extent = tuple(1.0 for _ in nonflat)
+    grid = ob.RectilinearGrid(ob.B200(device), FT, size=size, extent=extent, topology=tuple(topo[c] for c in w["topo"]))
+    adv = ob.WENO() if w["adv"] == "weno" else ob.Centered()
+    kw = dict(grid=grid, advection=adv, tracers=w["tracers"])
+    if w["buoy"] == "seawater":
+        if w["closure"] == "amd":
+            kw["buoyancy"] = ob.SeawaterBuoyancy(equation_of_state=ob.LinearEquationOfState(thermal_expansion=2e-4, haline_contraction=8e-4))
+        else:
+            kw["buoyancy"] = ob.SeawaterBuoyancy()
+    if w["closure"] == "scalar":
+        kw["closure"] = ob.ScalarDiffusivity(nu=1e-5, kappa=1e-5)
+    elif w["closure"] == "amd":
+        kw["closure"] = ob.AnisotropicMinimumDissipation()
+        kw["coriolis"] = ob.FPlane(f=1e-4)
+        kw["boundary_conditions"] = {      # test/regression_tests/ocean_large_eddy_simulation_regression_test.jl:19-37
+            "u": ob.FieldBoundaryConditions(top=ob.FluxBoundaryCondition(-2e-5)),
+            "T": ob.FieldBoundaryConditions(top=ob.FluxBoundaryCondition(5e-5), bottom=ob.GradientBoundaryCondition(0.005)),
+            "S": ob.FieldBoundaryConditions(top=ob.FluxBoundaryCondition(5e-8)),
+        }
+    model = ob.NonhydrostaticModel(**kw)
+    return ob, model
+
+
+def synthetic_ic(w, model, seed=1234):
+    """rng(1234); u,v,w ~ U(-1,1); T = 20 + 0.01 N(0,1); S = 35 + 0.01 N(0,1) (C4: LES-like profile)."""
+    rng = np.random.default_rng(seed)
+    FT = model.grid.FT
+    ic = {}
+    for n in ("u", "v", "w"):
+        shape = tuple(model.fields[n].info().interior_size)
+        if w["closure"] == "amd":
+            ic[n] = (1e-3 * rng.standard_normal(shape, dtype=np.float32)).astype(FT)
+        else:
+            ic[n] = rng.uniform(-1, 1, shape).astype(FT) if FT is np.float64 else (2 * rng.random(shape, dtype=np.float32) - 1)
+    for n in w["tracers"]:
+        shape = tuple(model.fields[n].info().interior_size)
+        base = {"T": 20.0, "S": 35.0}.get(n, 0.0)
+        ic[n] = (base + 0.01 * rng.standard_normal(shape, dtype=np.float32)).astype(FT)
+    return ic
+
+
+def default_dt(w):
+    if w["closure"] == "amd":
+        return 1.0
+    if w["topo"] == "PPF":
+        return 0.01
+    return 0.1 / w["N"][0]
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = WORKLOADS[args.workload]
+    ob, model = build_model(w, local, rank)
+    lib, h = model._lib, model._h
+    ic = synthetic_ic(w, model, seed=1234 + rank)
+    ob.set_(model, **ic)
+    names = ("u", "v", "w") + tuple(w["tracers"])
+    dt = default_dt(w)
+    cells = int(np.prod(w["N"]))
+    itemsize = 8 if w["FT"] == "f64" else 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        model.sync()
+
+    # warm-up
+    for _ in range(args.warmup):
+        ob.time_step_(model, dt)
+    barrier()
+    launches0 = model.launch_count()
+    model.timers(enable=True)
+    model.timers(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = C.c_double()
+    barrier()
+    lib.check(lib.oc_stopwatch_start(h))
+    for _ in range(args.steps):
+        ob.time_step_(model, dt)
+    lib.check(lib.oc_stopwatch_stop(h, C.byref(ms)))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    elapsed_ms = ms.value
+    timers = model.timers()
+    model.timers(enable=False)
+    launches = model.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * cells / (ms_per_step * 1e-3)
+
+    # sanity: the state must still be finite (a NaN run is not a measurement)
+    umax = float(np.abs(model.velocities.u.interior()).max())
+    if not np.isfinite(umax):
+        raise SystemExit("state became non-finite during the benchmark")
+
+    # ---- e2e: host buffers in, host buffers out, every step -------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        bufs = {}
+        for n in names + ("pNHS",):
+            f = model.pressures.pNHS if n == "pNHS" else model.fields[n]
+            shape = tuple(f.info().interior_size)
+            nbytes = int(np.prod(shape)) * itemsize
+            p = C.c_void_p()
+            lib.check(lib.oc_host_alloc(C.byref(p), nbytes))
+            arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double if itemsize == 8 else C.c_float)), shape=(nbytes // itemsize,))
+            bufs[n] = (p, nbytes, arr, f)
+        for n in names:                      # host copy of the current state = the step's input
+            p, nbytes, arr, f = bufs[n]
+            lib.check(lib.oc_download_interior(h, f.id, p, nbytes))
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        h2d = sum(bufs[n][1] for n in names)
+        d2h = sum(bufs[n][1] for n in names + ("pNHS",))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            for n in names:                  # set!(model; u=…, v=…, …) from pinned host memory
+                p, nbytes, arr, f = bufs[n]
+                lib.check(lib.oc_upload_interior(h, f.id, p, nbytes))
+            lib.check(lib.oc_set_finalize(h, 0))
+            ob.time_step_(model, dt)
+            for n in names + ("pNHS",):      # Array(interior(field))
+                p, nbytes, arr, f = bufs[n]
+                lib.check(lib.oc_download_interior(h, f.id, p, nbytes))
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": world * cells / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "what": "per step: upload u,v,w,tracers from pinned host (set!), time_step!, download u,v,w,tracers,pNHS"}
+        for n in bufs:
+            lib.oc_host_free(bufs[n][0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    tend_ms, tend_n = timers["tendency"]
+    tend_bytes_step = cells * tendency_reals_per_cell_step(w) * itemsize
+    launches_per_step = tend_n / args.steps if args.steps else 0
+    bytes_per_launch = tend_bytes_step / launches_per_step if launches_per_step else 0
+    avg_launch_ms = tend_ms / tend_n if tend_n else float("nan")
+    achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if tend_n else 0.0
+    step_bytes = cells * reals_per_cell_step(w) * itemsize
+    step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": w["FT"], "data": "synthetic (seeded rng 1234, SURVEY.md 8d)",
+        "config": {"workload": w["label"], "grid": list(w["N"]), "topology": w["topo"], "timestepper": "RungeKutta3", "dt": dt,
+                   "cells_per_gpu": cells, "l2_policy": "working set (>25 GB at 512^3) far exceeds the 126 MB L2; no flush needed"
+                   if cells >= 256 ** 3 else "working set may fit L2 (launch-latency configuration)"},
+        "roofline": {"bound": "hbm", "kernel": "TendencyKernel (fused tendency + RK3 substep, one launch per prognostic field)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "avg_launch_ms": avg_launch_ms, "launches_per_step": launches_per_step,
+                     "step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
+                              "reals_per_cell_step": reals_per_cell_step(w)}},
+        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()},
+        "kernel_launches_per_step": {k: v[1] / args.steps for k, v in timers.items()},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "e2e": e2e,
+        "device_bytes": model.device_bytes(),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline(w, args.cpu_size)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs
+def oracle_model(w, N):
+    import oracle
+    from oracle import advection as adv, closures as clo
+    from oracle.grid import BC
+    FT = np.float64 if w["FT"] == "f64" else np.float32
+    nonflat = [d for d in range(3) if w["topo"][d] != "F"]
+    size = tuple(N[d] for d in nonflat)
+    extent = tuple(float(N[d]) for d in nonflat) if w["closure"] == "amd" else tuple(1.0 for _ in nonflat)
+    og = oracle.Grid(FT, size=size, extent=extent, topology=tuple(w["topo"]))
+    kw = dict(advection=adv.WENO(FT, 5) if w["adv"] == "weno" else adv.Centered(FT, 2), tracers=w["tracers"])
+    if w["buoy"] == "seawater":
+        kw["buoyancy"] = clo.SeawaterBuoyancy()
+    if w["closure"] == "scalar":
+        kw["closure"] = clo.ScalarDiffusivity(1e-5, 1e-5)
+    elif w["closure"] == "amd":
+        kw["closure"] = clo.AnisotropicMinimumDissipation()
+        kw["coriolis_f"] = 1e-4
+        kw["boundary_conditions"] = {"u": {"top": BC("flux", -2e-5)}, "T": {"top": BC("flux", 5e-5), "bottom": BC("gradient", 0.005)},
+                                     "S": {"top": BC("flux", 5e-8)}}
+    om = oracle.OracleModel(og, **kw)
+    rng = np.random.default_rng(1234)
+    ic = {n: rng.uniform(-1, 1, om.fields[n].interior.shape) for n in ("u", "v", "w")}
+    for n in w["tracers"]:
+        ic[n] = {"T": 20.0, "S": 35.0}.get(n, 0.0) + 0.01 * rng.standard_normal(om.fields[n].interior.shape)
+    om.set(**ic)
+    return om
+
+
+def cpu_sample_size(w, n):
+    return tuple(1 if w["N"][d] == 1 else min(w["N"][d], n) for d in range(3))
+
+
+def cpu_baseline(w, n):
+    """The oracle (NumPy port of the reference algorithm) on a bounded sample of the same physics."""
+    N = cpu_sample_size(w, n)
+    om = oracle_model(w, N)
+    dt = default_dt(w) * w["N"][0] / N[0] if w["closure"] != "amd" else 1.0
+    om.time_step(dt)                       # warm-up (imports, FFT plans)
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        om.time_step(dt)
+        steps += 1
+        if time.perf_counter() - t0 > 10.0 or steps >= 20:
+            break
+    s = (time.perf_counter() - t0) / steps
+    return {"value": int(np.prod(N)) / s, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+            "sample": f"{steps} RK3 step(s) of the same physics at {N[0]}x{N[1]}x{N[2]} ({s:.2f} s/step), NumPy oracle, 1 thread; "
+                      "the Julia reference cannot run here (no julia binary)"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference's algorithm (oracle/) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    N = cpu_sample_size(w, args.cpu_size)
+    om = oracle_model(w, N)
+    dt = default_dt(w) * w["N"][0] / N[0] if w["closure"] != "amd" else 1.0
+    for _ in range(min(args.warmup, 1)):
+        om.time_step(dt)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        om.time_step(dt)
+    s = (time.perf_counter() - t0) / steps
+    v = int(np.prod(N)) / s
+    sample = (f"{steps} RK3 step(s) at {N[0]}x{N[1]}x{N[2]} (bounded sample of {w['label']}), NumPy oracle port, 1 thread; "
+              "Julia reference not runnable here")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": w["FT"], "data": "synthetic (seeded rng 1234)", "config": {"workload": w["label"], "sample_grid": list(N)},
+        "cpu_baseline": {"value": v, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-size", type=int, default=48, help="edge of the bounded CPU sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
