@@ -80,7 +80,7 @@ OC_HD FT weno3_value(const AdvCoef<FT>& C, FT q0, FT q1, FT q2) {
 //   face-type  : high order iff 3 <= f <= N-3 ; mid order iff 2 <= f <= N-2
 //   centre-type: (evaluated at face f = c+1)  high iff 3 <= f <= N-2 ; mid iff 2 <= f <= N-1
 struct OrderWindow {
-    int lo_hi, hi_hi, lo_mid, hi_mid;
+    int lo_hi = 0, hi_hi = 0, lo_mid = 0, hi_mid = 0;
 };
 OC_HD OrderWindow order_window(bool bounded, bool centre_type, int N) {
     OrderWindow w;

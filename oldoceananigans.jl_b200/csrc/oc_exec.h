@@ -74,6 +74,41 @@ inline cudaError_t launch(const K& k, Dim3 grid, size_t smem_bytes, Stream strea
     kernel_entry<K><<<dim3(grid.x, grid.y, grid.z), K::THREADS, smem_bytes, stream>>>(k);
     return cudaGetLastError();
 }
+
+// ---- iterated kernels (z-marching) -------------------------------------------------------------------------
+// A marching kernel is a POD functor with
+//     OC_DEV void begin0(b, tid, smem) const;            // mbarrier init
+//     OC_DEV void begin1(b, tid, smem) const;            // prologue loads
+//     OC_HD  int  iterations(b) const;                   // number of plane iterations of this block
+//     template <int PHASE> OC_DEV void step(b, tid, smem, it) const;   // PHASE 0, 1 separated by __syncthreads()
+template <class K>
+__global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) march_entry(const __grid_constant__ K k) {
+    extern __shared__ __align__(128) char smem[];
+    Block b{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z};
+    const int tid = (int)threadIdx.x;
+    k.begin0(b, tid, smem);
+    __syncthreads();
+    k.begin1(b, tid, smem);
+    const int n = k.iterations(b);
+    for (int it = 0; it < n; ++it) {
+        k.template step<0>(b, tid, smem, it);
+        __syncthreads();
+        k.template step<1>(b, tid, smem, it);
+    }
+}
+
+template <class K>
+inline cudaError_t launch_march(const K& k, Dim3 grid, size_t smem_bytes, Stream stream) {
+    if (grid.x <= 0 || grid.y <= 0 || grid.z <= 0) return cudaSuccess;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(march_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    march_entry<K><<<dim3(grid.x, grid.y, grid.z), K::THREADS, smem_bytes, stream>>>(k);
+    return cudaGetLastError();
+}
 #else
 typedef void* Stream;
 typedef int cudaError_t;
@@ -97,6 +132,26 @@ inline cudaError_t launch(const K& k, Dim3 grid, size_t smem_bytes, Stream) {
                 if constexpr (K::PHASES > 1) hostsim_phase<K, 1>(k, b, sm);
                 if constexpr (K::PHASES > 2) hostsim_phase<K, 2>(k, b, sm);
                 if constexpr (K::PHASES > 3) hostsim_phase<K, 3>(k, b, sm);
+            }
+    return cudaSuccess;
+}
+
+template <class K>
+inline cudaError_t launch_march(const K& k, Dim3 grid, size_t smem_bytes, Stream) {
+    std::vector<char> smem(smem_bytes + 128);
+    char* sm = smem.data();
+    sm += (128 - ((uintptr_t)sm & 127)) & 127;
+    for (int bz = 0; bz < grid.z; ++bz)
+        for (int by = 0; by < grid.y; ++by)
+            for (int bx = 0; bx < grid.x; ++bx) {
+                Block b{bx, by, bz};
+                for (int tid = 0; tid < K::THREADS; ++tid) k.begin0(b, tid, sm);
+                for (int tid = 0; tid < K::THREADS; ++tid) k.begin1(b, tid, sm);
+                const int n = k.iterations(b);
+                for (int it = 0; it < n; ++it) {
+                    for (int tid = 0; tid < K::THREADS; ++tid) k.template step<0>(b, tid, sm, it);
+                    for (int tid = 0; tid < K::THREADS; ++tid) k.template step<1>(b, tid, sm, it);
+                }
             }
     return cudaSuccess;
 }

@@ -1,0 +1,592 @@
+// oc_march.h — z-marching, TMA-staged fused tendency (+ RK3/AB2 substep) kernel for one prognostic field.
+//
+// Replaces the same reference functions as oc_tendency.h (compute_Gu!/Gv!/Gw!/Gc!, compute_flux_bc_tendencies!,
+// rk3_substep_field!, ab2_step_field!, _cache_field_tendencies!; see the citations there) for grids without
+// Flat dimensions.  oc_tendency.h stays the general kernel (Flat dimensions, tiny grids).
+//
+// Design.  A CTA owns a TX×TY column of cells and marches through a chunk of z-levels.
+//  * Every stencil operand comes from shared memory.  Per field the CTA keeps a RING of x–y planes (with the
+//    halo the stencils need) that one elected thread fills with TMA (cp.async.bulk.tensor.3d → mbarrier
+//    complete_tx), PF = 3 planes ahead of the level being computed: the advected field needs levels
+//    k-2 … k+3 (WENO-5 in z), advecting velocities 1 to 4 levels.  HBM sees each plane once; halo overlap between
+//    neighbouring CTAs is served by L2.
+//  * Per level: phase 0 evaluates every face flux of the level once — (TX+1)·TY x-faces, TX·(TY+1) y-faces and the
+//    TX·TY upper z-faces (the lower z-face flux is the previous level's upper one and is carried in shared memory) —
+//    __syncthreads — phase 1 forms the flux divergence, adds Coriolis / hydrostatic pressure gradient / flux-BC
+//    terms, writes Gⁿ and the substepped field (coalesced stores) and issues the TMA loads three levels ahead.
+//    One __syncthreads per level; flux buffers are double (x, y) / triple (z) buffered.
+#pragma once
+#include "oc_tendency.h"
+
+#ifndef OC_HOSTSIM
+#include <cuda.h>
+#endif
+
+namespace oc {
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA source descriptor and primitives.  Product build: CUtensorMap + PTX.  OC_HOSTSIM (tests only): plain copies.
+// ---------------------------------------------------------------------------------------------------------
+#ifndef OC_HOSTSIM
+template <class FT>
+struct alignas(64) TileSrc {
+    CUtensorMap map;
+};
+
+OC_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+OC_DEV void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+OC_DEV void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+OC_DEV void mbar_expect(uint64_t* bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+OC_DEV void mbar_wait(uint64_t* bar, int parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+OC_DEV void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+template <class FT>
+OC_DEV void tile_issue(void* dst, const TileSrc<FT>* src, int c0, int c1, int c2, uint64_t* bar, int, int) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)(uintptr_t)&src->map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+#else
+template <class FT>
+struct TileSrc {
+    const FT* base;
+    int dim[3];
+    long long stride[3];
+};
+inline void mbar_init(uint64_t*, int) {}
+inline void mbar_fence_init() {}
+inline void mbar_expect(uint64_t*, int) {}
+inline void mbar_wait(uint64_t*, int) {}
+inline void proxy_fence_async() {}
+template <class FT>
+inline void tile_issue(void* dst, const TileSrc<FT>* src, int c0, int c1, int c2, uint64_t*, int bx, int by) {
+    FT* d = (FT*)dst;
+    for (int j = 0; j < by; ++j)
+        for (int i = 0; i < bx; ++i) {
+            int x = c0 + i, y = c1 + j, z = c2;
+            bool in = x >= 0 && x < src->dim[0] && y >= 0 && y < src->dim[1] && z >= 0 && z < src->dim[2];
+            d[j * bx + i] = in ? src->base[x * src->stride[0] + y * src->stride[1] + z * src->stride[2]] : FT(0);   // OOB fill = 0, like TMA
+        }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// rings
+// ---------------------------------------------------------------------------------------------------------
+template <int XO_, int BX_, int YO_, int BY_, int LO_, int HI_, int D_>
+struct RingSpec {
+    static constexpr int XO = XO_, BX = BX_, YO = YO_, BY = BY_, LO = LO_, HI = HI_, D = D_;
+    static constexpr int LIVE = HI_ - LO_ + 1;
+};
+
+template <class FT, class RS>
+struct Ring {
+    static constexpr int BOX_BYTES = RS::BX * RS::BY * (int)sizeof(FT);
+    static constexpr int SLOT_BYTES = ((BOX_BYTES + 127) / 128) * 128;
+    static constexpr int SLOT = SLOT_BYTES / (int)sizeof(FT);
+    static constexpr int BYTES = SLOT_BYTES * RS::D;
+    FT* s;
+    static constexpr bool POW2 = (RS::D & (RS::D - 1)) == 0;
+    OC_HD static int slot_of(int lev) { return POW2 ? ((lev + 64 * RS::D) & (RS::D - 1)) : ((lev + 64 * RS::D) % RS::D); }
+    OC_HD FT operator()(int ii, int jj, int lev) const { return s[slot_of(lev) * SLOT + (jj - RS::YO) * RS::BX + (ii - RS::XO)]; }
+    OC_HD FT* slot(int lev) const { return s + slot_of(lev) * SLOT; }
+};
+
+// Loads for iteration it + PF are issued in phase 1 of iteration it; they overwrite the slot of level
+// k + PF + HI - D, which must not be read any more: D >= LIVE + PF - 1 for rings read only in phase 0,
+// D >= LIVE + PF for rings whose lowest level is also read in phase 1.
+enum { MARCH_PF = 3, MARCH_NBAR = 4 };
+
+// Which planes each kernel stages.  `FIELD` names the global field: -1 = the stepped field itself (ψ or c), 0/1/2 = u/v/w.
+// E = elements per 16 bytes; box x-origins are kept multiples of E (16-byte aligned box rows).
+template <int KIND, int TX, int TY, int E>
+struct MarchSpec;
+template <int TX, int TY, int E>
+struct MarchSpec<KIND_C, TX, TY, E> {
+    static constexpr int NR = 4;
+    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 8>;   // c: WENO-5 radius in x, y, z
+    using R1 = RingSpec<0, TX + 4, 0, TY, 0, 0, 3>;          // u at the x-faces of level k
+    using R2 = RingSpec<0, TX, 0, TY + 1, 0, 0, 3>;          // v at the y-faces
+    using R3 = RingSpec<0, TX, 0, TY, 1, 1, 3>;              // w at the upper z-face (level k+1)
+    static constexpr int F1 = 0, F2 = 1, F3 = 2;
+};
+template <int TX, int TY, int E>
+struct MarchSpec<KIND_U, TX, TY, E> {
+    static constexpr int NR = 3;
+    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 8>;   // u
+    using R1 = RingSpec<-E, TX + 2 * E, 0, TY + 1, 0, 0, 4>;     // v[i-2..i+1, j0..j0+TY] (Centered-4 along x, Coriolis, τ12); D = 4: also read in phase 1
+    using R2 = RingSpec<-E, TX + 2 * E, 0, TY, 1, 1, 3>;         // w[i-2..i+1] at level k+1
+    using R3 = RingSpec<0, 4, 0, 1, 0, 0, 1>;
+    static constexpr int F1 = 1, F2 = 2, F3 = -2;
+};
+template <int TX, int TY, int E>
+struct MarchSpec<KIND_V, TX, TY, E> {
+    static constexpr int NR = 3;
+    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 8>;   // v
+    using R1 = RingSpec<0, TX + 4, -2, TY + 3, 0, 0, 4>;     // u[i0..i0+TX, j-2..j+1]; D = 4: also read in phase 1 (Coriolis)
+    using R2 = RingSpec<0, TX, -2, TY + 3, 1, 1, 3>;         // w[j-2..j+1] at level k+1
+    using R3 = RingSpec<0, 4, 0, 1, 0, 0, 1>;
+    static constexpr int F1 = 0, F2 = 2, F3 = -2;
+};
+template <int TX, int TY, int E>
+struct MarchSpec<KIND_W, TX, TY, E> {
+    static constexpr int NR = 3;
+    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 8>;   // w
+    using R1 = RingSpec<0, TX + 4, 0, TY, -2, 1, 6>;         // u[k-2..k+1] at the x-faces (Centered-4 along z)
+    using R2 = RingSpec<0, TX, 0, TY + 1, -2, 1, 6>;         // v[k-2..k+1] at the y-faces
+    using R3 = RingSpec<0, 4, 0, 1, 0, 0, 1>;
+    static constexpr int F1 = 0, F2 = 1, F3 = -2;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// compile-time reconstruction coefficients: exact rationals rounded to FT, the last one of each set is
+// 1 - sum(others) in FT arithmetic (src/Advection/reconstruction_coefficients.jl:49-64).  p/q with small integers is
+// correctly rounded by FT(p)/FT(q).  Model<FT> checks this table against make_coefficients() at construction.
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+struct AdvConst {
+    static constexpr FT p00 = FT(1) / FT(3), p01 = FT(5) / FT(6), p02 = FT(1) - (p00 + p01);      // WENO{3} coeff_p(r = 0)
+    static constexpr FT p10 = FT(-1) / FT(6), p11 = FT(5) / FT(6), p12 = FT(1) - (p10 + p11);     // r = 1
+    static constexpr FT p20 = FT(1) / FT(3), p21 = FT(-7) / FT(6), p22 = FT(1) - (p20 + p21);     // r = 2
+    static constexpr FT c50 = FT(3) / FT(10), c51 = FT(3) / FT(5), c52 = FT(1) / FT(10);          // C★
+    static constexpr FT q00 = FT(1) / FT(2), q01 = FT(1) - q00;                                   // WENO{2} coeff_p
+    static constexpr FT q10 = FT(-1) / FT(2), q11 = FT(1) - q10;
+    static constexpr FT c30 = FT(2) / FT(3), c31 = FT(1) / FT(3);
+    static constexpr FT k0 = FT(-1) / FT(12), k1 = FT(7) / FT(12), k2 = FT(7) / FT(12), k3 = FT(1) - ((k0 + k1) + k2);
+    static constexpr FT c40 = k3, c41 = k2, c42 = k1, c43 = k0;                                   // Centered(4), stencil order ψ[i-2..i+1]
+    static constexpr FT eps = (FT)1e-8f;
+};
+
+// newton_div(Float32, a, b) with the GPU meaning of Base.FastMath.inv_fast: the approximate reciprocal (MUFU.RCP)
+// (src/Utils/newton_div.jl:8-23)
+OC_HD float rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+OC_HD double newton_div_fast(double a, double b) {
+    double invd = (double)rcp_fast((float)b);
+    double x = a * invd;
+    return oc_fma(oc_fma(x, -b, a), invd, x);
+}
+OC_HD float newton_div_fast(float a, float b) { return a * rcp_fast(b); }
+
+template <class FT>
+OC_HD FT weno5_value_c(FT q0, FT q1, FT q2, FT q3, FT q4) {
+    using K = AdvConst<FT>;
+    FT b0 = beta3<FT>(q2, q3, q4, FT(10), FT(-31), FT(11), FT(25), FT(-19), FT(4));
+    FT b1 = beta3<FT>(q1, q2, q3, FT(4), FT(-13), FT(5), FT(13), FT(-13), FT(4));
+    FT b2 = beta3<FT>(q0, q1, q2, FT(4), FT(-19), FT(11), FT(25), FT(-31), FT(10));
+    FT tau = oc_abs<FT>(b0 - b2);
+    FT r0 = newton_div_fast(tau, b0 + K::eps);
+    FT r1 = newton_div_fast(tau, b1 + K::eps);
+    FT r2 = newton_div_fast(tau, b2 + K::eps);
+    FT a0 = K::c50 * (FT(1) + r0 * r0);
+    FT a1 = K::c51 * (FT(1) + r1 * r1);
+    FT a2 = K::c52 * (FT(1) + r2 * r2);
+    FT rs = FT(1) / (a0 + a1 + a2);
+    FT p0 = K::p00 * q2 + K::p01 * q3 + K::p02 * q4;
+    FT p1 = K::p10 * q1 + K::p11 * q2 + K::p12 * q3;
+    FT p2 = K::p20 * q0 + K::p21 * q1 + K::p22 * q2;
+    return (a0 * rs) * p0 + (a1 * rs) * p1 + (a2 * rs) * p2;
+}
+template <class FT>
+OC_HD FT weno3_value_c(FT q0, FT q1, FT q2) {
+    using K = AdvConst<FT>;
+    FT b0 = q1 * (FT(1) * q1 + FT(-2) * q2) + q2 * q2 * FT(1);
+    FT b1 = q0 * (FT(1) * q0 + FT(-2) * q1) + q1 * q1 * FT(1);
+    FT tau = oc_abs<FT>(b0 - b1);
+    FT r0 = newton_div_fast(tau, b0 + K::eps);
+    FT r1 = newton_div_fast(tau, b1 + K::eps);
+    FT a0 = K::c30 * (FT(1) + r0 * r0);
+    FT a1 = K::c31 * (FT(1) + r1 * r1);
+    FT rs = FT(1) / (a0 + a1);
+    FT p0 = K::q00 * q1 + K::q01 * q2;
+    FT p1 = K::q10 * q0 + K::q11 * q1;
+    return (a0 * rs) * p0 + (a1 * rs) * p1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// reconstructions on ring accessors (same arithmetic, in the same order, as oc_advection.h)
+// ---------------------------------------------------------------------------------------------------------
+template <int DIR, class FT, class A>
+OC_HD FT rd(const A& a, int ii, int jj, int lev, int n) {
+    if (DIR == 0) return a(ii + n, jj, lev);
+    if (DIR == 1) return a(ii, jj + n, lev);
+    return a(ii, jj, lev + n);
+}
+
+// _biased_interpolate (WENO(order=5) chain) at face (ii,jj,lev) along DIR; f = global face index along DIR.
+// WIN = false: the dimension is not Bounded — always the high-order branch, no window logic.
+template <int DIR, bool WIN, class FT, class A>
+OC_HD FT t_weno5_biased(const A& a, int ii, int jj, int lev, bool left, int f, const OrderWindow& w) {
+    if (!WIN || (f >= w.lo_hi && f <= w.hi_hi)) {
+        FT m3 = rd<DIR, FT>(a, ii, jj, lev, -3), m2 = rd<DIR, FT>(a, ii, jj, lev, -2), m1 = rd<DIR, FT>(a, ii, jj, lev, -1);
+        FT p0 = rd<DIR, FT>(a, ii, jj, lev, 0), p1 = rd<DIR, FT>(a, ii, jj, lev, 1), p2 = rd<DIR, FT>(a, ii, jj, lev, 2);
+        return weno5_value_c<FT>(left ? m3 : p2, left ? m2 : p1, left ? m1 : p0, left ? p0 : m1, left ? p1 : m2);
+    } else if (f >= w.lo_mid && f <= w.hi_mid) {
+        FT m2 = rd<DIR, FT>(a, ii, jj, lev, -2), m1 = rd<DIR, FT>(a, ii, jj, lev, -1);
+        FT p0 = rd<DIR, FT>(a, ii, jj, lev, 0), p1 = rd<DIR, FT>(a, ii, jj, lev, 1);
+        return weno3_value_c<FT>(left ? m2 : p1, left ? m1 : p0, left ? p0 : m1);
+    }
+    return left ? rd<DIR, FT>(a, ii, jj, lev, -1) : rd<DIR, FT>(a, ii, jj, lev, 0);
+}
+
+// _symmetric_interpolate of A·q (Centered(4) → Centered(2) near walls)
+template <int DIR, bool WIN, class FT, class A>
+OC_HD FT t_weno5_symmetric(const A& a, int ii, int jj, int lev, FT area, int f, const OrderWindow& w) {
+    using K = AdvConst<FT>;
+    if (!WIN || (f >= w.lo_hi && f <= w.hi_hi)) {
+        FT r = K::c40 * (area * rd<DIR, FT>(a, ii, jj, lev, -2));
+        r = r + K::c41 * (area * rd<DIR, FT>(a, ii, jj, lev, -1));
+        r = r + K::c42 * (area * rd<DIR, FT>(a, ii, jj, lev, 0));
+        r = r + K::c43 * (area * rd<DIR, FT>(a, ii, jj, lev, 1));
+        return r;
+    }
+    return FT(0.5) * (area * rd<DIR, FT>(a, ii, jj, lev, -1)) + FT(0.5) * (area * rd<DIR, FT>(a, ii, jj, lev, 0));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel.  BND = 0: no Bounded dimension (all wall logic compiled out); 1: generic.
+//              CLO = 0: constant ν, κ (possibly 0: no closure); 1: generic (AMD eddy fields, closure tuples).
+// One thread per y-face: THREADS = TX·(TY+1); the x-faces and z-faces map onto the same threads so that every
+// warp evaluates at most three fluxes per level (no tail warps in front of the barrier).
+// ---------------------------------------------------------------------------------------------------------
+template <class FT, int ADV, int KIND, int BND, int CLO>
+struct MarchKernel {
+    static constexpr int TX = 32, TY = 8;
+    static constexpr int THREADS = TX * (TY + 1);
+    static constexpr int MIN_BLOCKS = 3;
+    static constexpr int COMP = KIND == KIND_C ? -1 : KIND;
+    static constexpr bool WIN = BND != 0;
+    using SP = MarchSpec<KIND, TX, TY, 16 / (int)sizeof(FT)>;
+    using G0 = Ring<FT, typename SP::R0>;
+    using G1 = Ring<FT, typename SP::R1>;
+    using G2 = Ring<FT, typename SP::R2>;
+    using G3 = Ring<FT, typename SP::R3>;
+    static constexpr int NR = SP::NR;
+    static constexpr int NFX = (TX + 1) * TY, NFY = TX * (TY + 1), NFZ = TX * TY;
+    static constexpr int NFXP = ((NFX + 15) / 16) * 16, NFYP = ((NFY + 15) / 16) * 16;
+    // shared-memory map (bytes)
+    static constexpr size_t OFF_BAR = 0;
+    static constexpr size_t OFF_R0 = 128;
+    static constexpr size_t OFF_R1 = OFF_R0 + G0::BYTES;
+    static constexpr size_t OFF_R2 = OFF_R1 + G1::BYTES;
+    static constexpr size_t OFF_R3 = OFF_R2 + G2::BYTES;
+    static constexpr size_t OFF_FX = OFF_R3 + (NR > 3 ? G3::BYTES : 0);
+    static constexpr size_t OFF_FY = OFF_FX + sizeof(FT) * 2 * NFXP;
+    static constexpr size_t OFF_FZ = OFF_FY + sizeof(FT) * 2 * NFYP;
+    static constexpr size_t SMEM = OFF_FZ + sizeof(FT) * 3 * NFZ;
+    static constexpr int LEVEL_BYTES = G0::BOX_BYTES + G1::BOX_BYTES + G2::BOX_BYTES + (NR > 3 ? G3::BOX_BYTES : 0);
+    static constexpr int FIRST_BYTES = G0::BOX_BYTES * SP::R0::LIVE + G1::BOX_BYTES * SP::R1::LIVE + G2::BOX_BYTES * SP::R2::LIVE +
+                                       (NR > 3 ? G3::BOX_BYTES * SP::R3::LIVE : 0);
+
+    TendencyArgs<FT> a;
+    TileSrc<FT> src[4];   // staged fields, ring order
+    int xpad;             // TMA coordinate of interior index i = 0 (j = 0 ↔ H[1], k = 0 ↔ H[2])
+    int KC;               // z-levels per chunk (grid.z chunks)
+
+    OC_HD int k_begin(const Block& b) const { return b.z * KC; }
+    OC_HD int k_end(const Block& b) const { int e = (b.z + 1) * KC; return e < a.g.N[2] ? e : a.g.N[2]; }
+    OC_HD int iterations(const Block& b) const { return k_end(b) - k_begin(b) + 1; }   // + the z-flux-only pre-iteration
+
+    OC_HD G0 r0(char* smem) const { return G0{reinterpret_cast<FT*>(smem + OFF_R0)}; }
+    OC_HD G1 r1(char* smem) const { return G1{reinterpret_cast<FT*>(smem + OFF_R1)}; }
+    OC_HD G2 r2(char* smem) const { return G2{reinterpret_cast<FT*>(smem + OFF_R2)}; }
+    OC_HD G3 r3(char* smem) const { return G3{reinterpret_cast<FT*>(smem + OFF_R3)}; }
+
+    // ---- loads -----------------------------------------------------------------------------------------------
+    template <class G, class RS>
+    OC_DEV void issue_level(const G& ring, const TileSrc<FT>* s, int i0, int j0, int lev, uint64_t* bar) const {
+        tile_issue<FT>(ring.slot(lev), s, i0 + RS::XO + xpad, j0 + RS::YO + a.g.H[1], lev + a.g.H[2], bar, RS::BX, RS::BY);
+    }
+    // the new level every ring needs for the iteration at level k
+    OC_DEV void issue_iteration(char* smem, int i0, int j0, int k, uint64_t* bar) const {
+        issue_level<G0, typename SP::R0>(r0(smem), &src[0], i0, j0, k + SP::R0::HI, bar);
+        issue_level<G1, typename SP::R1>(r1(smem), &src[1], i0, j0, k + SP::R1::HI, bar);
+        issue_level<G2, typename SP::R2>(r2(smem), &src[2], i0, j0, k + SP::R2::HI, bar);
+        if (NR > 3) issue_level<G3, typename SP::R3>(r3(smem), &src[3], i0, j0, k + SP::R3::HI, bar);
+    }
+
+    OC_DEV void begin0(const Block&, int tid, char* smem) const {
+        if (tid == 0) {
+            uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+            for (int n = 0; n < MARCH_NBAR; ++n) mbar_init(bar + n, 1);
+            mbar_fence_init();
+        }
+    }
+    OC_DEV void begin1(const Block& b, int tid, char* smem) const {
+        if (tid != 0) return;
+        uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+        const int i0 = b.x * TX, j0 = b.y * TY, kf = k_begin(b) - 1, n = iterations(b);
+        // iteration 0 (level kf): every live level of every ring
+        mbar_expect(bar, FIRST_BYTES);
+        for (int l = SP::R0::LO; l < SP::R0::HI; ++l) issue_level<G0, typename SP::R0>(r0(smem), &src[0], i0, j0, kf + l, bar);
+        for (int l = SP::R1::LO; l < SP::R1::HI; ++l) issue_level<G1, typename SP::R1>(r1(smem), &src[1], i0, j0, kf + l, bar);
+        for (int l = SP::R2::LO; l < SP::R2::HI; ++l) issue_level<G2, typename SP::R2>(r2(smem), &src[2], i0, j0, kf + l, bar);
+        if (NR > 3)
+            for (int l = SP::R3::LO; l < SP::R3::HI; ++l) issue_level<G3, typename SP::R3>(r3(smem), &src[3], i0, j0, kf + l, bar);
+        issue_iteration(smem, i0, j0, kf, bar);
+        for (int it = 1; it < MARCH_PF && it < n; ++it) {
+            mbar_expect(bar + (it % MARCH_NBAR), LEVEL_BYTES);
+            issue_iteration(smem, i0, j0, kf + it, bar + (it % MARCH_NBAR));
+        }
+    }
+
+    // ---- closure fluxes (mirror of TendencyKernel::viscous_flux / diffusive_flux) ---------------------------------
+    // velocity component C at tile-local (ii,jj) and level lev, displaced by n along direction DIR
+    template <int C, int DIR>
+    OC_HD FT vel(char* smem, int ii, int jj, int lev, int n) const {
+        if (C == COMP) return rd<DIR, FT>(r0(smem), ii, jj, lev, n);
+        if (C == SP::F1) return rd<DIR, FT>(r1(smem), ii, jj, lev, n);
+        return rd<DIR, FT>(r2(smem), ii, jj, lev, n);
+    }
+
+    OC_HD FT nu_ff(int o, int d1, int d2) const {
+        const Geom<FT>& g = a.g;
+        int s1 = g.st(d1), s2 = g.st(d2);
+        const FT* n = a.nu_e + o;
+        return FT(0.5) * (FT(0.5) * (n[-s1 - s2] + n[-s2]) + FT(0.5) * (n[-s1] + n[0]));
+    }
+
+    template <int D>
+    OC_HD FT viscous_flux(char* smem, int ii, int jj, int lev, int i, int j) const {
+        const Geom<FT>& g = a.g;
+        FT sig;
+        if (D == COMP) {
+            sig = (vel<COMP, D>(smem, ii, jj, lev, 1) - vel<COMP, D>(smem, ii, jj, lev, 0)) * g.rd[D];
+        } else {
+            constexpr int lo = D < COMP ? D : COMP, hi = D < COMP ? COMP : D;
+            FT dl = (vel<lo, hi>(smem, ii, jj, lev, 0) - vel<lo, hi>(smem, ii, jj, lev, -1)) * g.rd[hi];
+            FT dh = (vel<hi, lo>(smem, ii, jj, lev, 0) - vel<hi, lo>(smem, ii, jj, lev, -1)) * g.rd[lo];
+            sig = FT(0.5) * (dl + dh);
+        }
+        if (CLO == 0) return g.A[D] * (FT(-2) * (a.nu * sig));
+        FT flux = FT(0);
+        if (a.has_scalar) flux = g.A[D] * (FT(-2) * (a.nu * sig));
+        if (a.nu_e) {
+            const int o = g.idx(i, j, lev);
+            FT nu;
+            if (D == COMP) nu = a.nu_e[o];
+            else nu = nu_ff(o, D < COMP ? D : COMP, D < COMP ? COMP : D);
+            FT f2 = g.A[D] * (FT(-2) * (nu * sig));
+            flux = a.has_scalar ? flux + f2 : f2;
+        }
+        return flux;
+    }
+
+    template <int D>
+    OC_HD FT diffusive_flux(char* smem, int ii, int jj, int lev, int i, int j) const {
+        const Geom<FT>& g = a.g;
+        G0 c = r0(smem);
+        FT grad = (rd<D, FT>(c, ii, jj, lev, 0) - rd<D, FT>(c, ii, jj, lev, -1)) * g.rd[D];
+        if (CLO == 0) return g.A[D] * (-(a.kappa * grad));
+        FT flux = FT(0);
+        if (a.has_scalar) flux = g.A[D] * (-(a.kappa * grad));
+        if (a.kappa_e) {
+            const int o = g.idx(i, j, lev);
+            int s = g.st(D);
+            FT kap = FT(0.5) * (a.kappa_e[o - s] + a.kappa_e[o]);
+            FT f2 = g.A[D] * (-(kap * grad));
+            flux = a.has_scalar ? flux + f2 : f2;
+        }
+        return flux;
+    }
+
+    // ---- advective flux through the faces normal to D at flux index (ii, jj, lev); id = global index along D, ic along COMP
+    template <int D>
+    OC_HD FT advective_flux(char* smem, int ii, int jj, int lev, int id, int ic) const {
+        const Geom<FT>& g = a.g;
+        const FT A = g.A[D];
+        if (KIND == KIND_C) {
+            FT u = D == 0 ? r1(smem)(ii, jj, lev) : (D == 1 ? r2(smem)(ii, jj, lev) : r3(smem)(ii, jj, lev));
+            G0 c = r0(smem);
+            if (ADV == 0) {
+                return (A * u) * (FT(0.5) * rd<D, FT>(c, ii, jj, lev, -1) + FT(0.5) * rd<D, FT>(c, ii, jj, lev, 0));
+            } else {
+                OrderWindow w;
+                if (WIN) w = order_window(g.bounded[D] != 0, false, g.N[D]);
+                FT cr = t_weno5_biased<D, WIN, FT>(c, ii, jj, lev, u > FT(0), id, w);
+                return A * u * cr;
+            }
+        } else {
+            constexpr int CC = COMP < 0 ? 0 : COMP;
+            G0 psi = r0(smem);
+            if (D == CC) {
+                // centre-type: the face-type stencils evaluated at face id+1
+                if (ADV == 0) {
+                    FT ut = FT(0.5) * rd<D, FT>(psi, ii, jj, lev, 0) + FT(0.5) * rd<D, FT>(psi, ii, jj, lev, 1);
+                    return A * ut * ut;
+                } else {
+                    OrderWindow w;
+                    if (WIN) w = order_window(g.bounded[D] != 0, true, g.N[D]);
+                    const int i1 = ii + (D == 0), j1 = jj + (D == 1), l1 = lev + (D == 2);
+                    FT ut = t_weno5_symmetric<D, WIN, FT>(psi, i1, j1, l1, A, id + 1, w);
+                    FT pr = t_weno5_biased<D, WIN, FT>(psi, i1, j1, l1, ut > FT(0), id + 1, w);
+                    return ut * pr;
+                }
+            } else {
+                // face-type: advecting velocity U[D] interpolated along CC, ψ reconstructed along D
+                if (ADV == 0) {
+                    FT ut = FT(0.5) * vel<D, CC>(smem, ii, jj, lev, -1) + FT(0.5) * vel<D, CC>(smem, ii, jj, lev, 0);
+                    FT pt = FT(0.5) * rd<D, FT>(psi, ii, jj, lev, -1) + FT(0.5) * rd<D, FT>(psi, ii, jj, lev, 0);
+                    return A * ut * pt;
+                } else {
+                    OrderWindow wc, wd;
+                    if (WIN) { wc = order_window(g.bounded[CC] != 0, false, g.N[CC]); wd = order_window(g.bounded[D] != 0, false, g.N[D]); }
+                    FT ut;
+                    if (D == SP::F1) ut = t_weno5_symmetric<CC, WIN, FT>(r1(smem), ii, jj, lev, A, ic, wc);
+                    else ut = t_weno5_symmetric<CC, WIN, FT>(r2(smem), ii, jj, lev, A, ic, wc);
+                    FT pr = t_weno5_biased<D, WIN, FT>(psi, ii, jj, lev, ut > FT(0), id, wd);
+                    return ut * pr;
+                }
+            }
+        }
+    }
+
+    // i, j, k: global flux index; (ii, jj): the same, tile-local
+    template <int D>
+    OC_HD FT total_flux(char* smem, int ii, int jj, int i, int j, int k) const {
+        const int id = D == 0 ? i : (D == 1 ? j : k);
+        const int ic = COMP == 0 ? i : (COMP == 1 ? j : k);
+        FT F = advective_flux<D>(smem, ii, jj, k, id, ic);
+        if (CLO == 0 || a.has_scalar || a.nu_e || a.kappa_e) {
+            if constexpr (KIND == KIND_C) F = F + diffusive_flux<D>(smem, ii, jj, k, i, j);
+            else F = F + viscous_flux<D>(smem, ii, jj, k, i, j);
+        }
+        return F;
+    }
+
+    // ---- one level ---------------------------------------------------------------------------------------------------
+    template <int PHASE>
+    OC_DEV void step(const Block& b, int tid, char* smem, int it) const {
+        const Geom<FT>& g = a.g;
+        const int i0 = b.x * TX, j0 = b.y * TY;
+        const int k = k_begin(b) - 1 + it;                   // level of this iteration (it = 0: z-flux only)
+        constexpr int shx = COMP == 0 ? -1 : 0, shy = COMP == 1 ? -1 : 0, shz = COMP == 2 ? -1 : 0;
+        FT* fx = reinterpret_cast<FT*>(smem + OFF_FX) + (it & 1) * NFXP;
+        FT* fy = reinterpret_cast<FT*>(smem + OFF_FY) + (it & 1) * NFYP;
+        FT* fzs = reinterpret_cast<FT*>(smem + OFF_FZ);
+        FT* fz_up = fzs + (it % 3) * NFZ;
+        const FT* fz_lo = fzs + ((it + 2) % 3) * NFZ;
+        uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+        const int lane = tid & (TX - 1), row = tid / TX;     // row = 0 … TY
+        if (PHASE == 0) {
+            mbar_wait(bar + (it % MARCH_NBAR), (it / MARCH_NBAR) & 1);
+            if (it > 0) {
+                {   // y-face (lane, row)
+                    FT F = FT(0);
+                    if (i0 + lane < g.N[0] && j0 + row <= g.N[1]) F = total_flux<1>(smem, lane, row + shy, i0 + lane, j0 + row + shy, k);
+                    fy[row * TX + lane] = F;
+                }
+                // x-faces: rows 0 … TY-1 take faces s = 0 … TX-1; the last warp takes the TY faces s = TX
+                const int s = row < TY ? lane : TX, jj = row < TY ? row : lane;
+                if (row < TY || lane < TY) {
+                    FT F = FT(0);
+                    if (j0 + jj < g.N[1] && i0 + s <= g.N[0]) F = total_flux<0>(smem, s + shx, jj, i0 + s + shx, j0 + jj, k);
+                    fx[jj * (TX + 1) + s] = F;
+                }
+            }
+            if (row < TY) {   // upper z-face of cell (lane, row)
+                FT F = FT(0);
+                if (i0 + lane < g.N[0] && j0 + row < g.N[1] && k + 1 <= g.N[2]) F = total_flux<2>(smem, lane, row, i0 + lane, j0 + row, k + 1 + shz);
+                fz_up[row * TX + lane] = F;
+            }
+        } else {
+            // loads three levels ahead: the slots they overwrite were last read before the __syncthreads above
+            if (tid == 0) {
+                const int nit = it + MARCH_PF;
+                if (nit < iterations(b)) {
+                    proxy_fence_async();
+                    mbar_expect(bar + (nit % MARCH_NBAR), LEVEL_BYTES);
+                    issue_iteration(smem, i0, j0, k + MARCH_PF, bar + (nit % MARCH_NBAR));
+                }
+            }
+            if (it == 0 || row >= TY) return;
+            const int ii = lane, jj = row, n = row * TX + lane;
+            const int i = i0 + ii, j = j0 + jj;
+            if (i >= g.N[0] || j >= g.N[1]) return;
+            const int o = g.idx(i, j, k);
+            const FT u0 = r0(smem)(ii, jj, k);
+            if (WIN && COMP >= 0) {
+                // exclude_periphery: the wall face of a wall-normal velocity is not stepped (kernel_launching.jl:145-146)
+                const int ic = COMP == 0 ? i : (COMP == 1 ? j : k);
+                if (g.bounded[COMP < 0 ? 0 : COMP] && ic == 0 && g.N[COMP < 0 ? 0 : COMP] > 1) {
+                    if (a.mode != STEP_NONE) a.Unew[o] = u0;
+                    return;
+                }
+            }
+            const FT dFx = fx[jj * (TX + 1) + ii + 1] - fx[jj * (TX + 1) + ii];
+            const FT dFy = fy[(jj + 1) * TX + ii] - fy[jj * TX + ii];
+            const FT dFz = fz_up[n] - fz_lo[n];
+            FT G = -(g.rV * (dFx + dFy + dFz));
+            if ((KIND == KIND_U || KIND == KIND_V) && a.has_coriolis) {
+                // FPlane (f_plane.jl:50-52); the other horizontal component is ring 1
+                G1 q = r1(smem);
+                FT num, cnt = FT(1);
+                if (KIND == KIND_U) {
+                    num = FT(0.5) * (FT(0.5) * (q(ii - 1, jj, k) + q(ii, jj, k)) + FT(0.5) * (q(ii - 1, jj + 1, k) + q(ii, jj + 1, k)));
+                    if (WIN) {
+                        int ax0 = !(g.bounded[0] && (i - 1 < 0)), ax1 = 1;
+                        int ay0 = !(g.bounded[1] && (j < 1)), ay1 = !(g.bounded[1] && (j + 1 > g.N[1] - 1));
+                        cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
+                    }
+                    FT val = cnt == FT(0) ? FT(0) : num / cnt;
+                    G = G - (-a.f * val);
+                } else {
+                    num = FT(0.5) * (FT(0.5) * (q(ii, jj - 1, k) + q(ii + 1, jj - 1, k)) + FT(0.5) * (q(ii, jj, k) + q(ii + 1, jj, k)));
+                    if (WIN) {
+                        int ax0 = !(g.bounded[0] && (i < 1)), ax1 = !(g.bounded[0] && (i + 1 > g.N[0] - 1));
+                        int ay0 = !(g.bounded[1] && (j - 1 < 0)), ay1 = 1;
+                        cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
+                    }
+                    FT val = cnt == FT(0) ? FT(0) : num / cnt;
+                    G = G - (a.f * val);
+                }
+            }
+            if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) {
+                const int s = KIND == KIND_U ? 1 : g.sy;
+                G = G - (a.pHY[o] - a.pHY[o - s]) * g.rd[KIND == KIND_U ? 0 : 1];
+            }
+            if (WIN && a.add_flux_bcs) {
+                const int ijk[3] = {i, j, k};
+                for (int d = 0; d < 3; ++d) {
+                    if (a.fbc.on[2 * d] && ijk[d] == 0) G = G + a.fbc.val[2 * d] * g.A[d] / g.V;
+                    if (a.fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) G = G - a.fbc.val[2 * d + 1] * g.A[d] / g.V;
+                }
+            }
+            a.Gn[o] = G;
+            if (a.mode == STEP_RK3_FIRST) {
+                a.Unew[o] = u0 + a.ca * G;
+            } else if (a.mode == STEP_RK3) {
+                a.Unew[o] = u0 + a.dt * (a.ca * G + a.cb * a.Gm[o]);
+            } else if (a.mode == STEP_AB2) {
+                FT Gu = a.ab2_euler ? a.ca * G : a.ca * G - a.cb * a.Gm[o];
+                a.Unew[o] = u0 + a.dt * Gu;
+            }
+        }
+    }
+};
+
+}  // namespace oc

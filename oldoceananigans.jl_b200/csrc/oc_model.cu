@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <map>
+#include <type_traits>
 
 namespace oc {
 
@@ -84,7 +85,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         }
         Hcfg_[d] = c.H[d];
         g_.N[d] = c.N[d];
-        g_.H[d] = t == OC_FLAT ? 3 : c.H[d];
+        g_.H[d] = t == OC_FLAT ? 3 : std::max(3, c.H[d]);   // internal halo >= 3 (TMA boxes); the API halo is Hcfg_
         g_.bounded[d] = t == OC_BOUNDED;
         g_.flat[d] = t == OC_FLAT;
         g_.d[d] = t == OC_FLAT ? FT(1) : (FT)c.delta[d];
@@ -106,7 +107,19 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     field_elems_ = (size_t)g_.sz * planes;
     if (field_elems_ >= ((size_t)1 << 31)) throw Error(OC_ERR_UNSUPPORTED, "field larger than 2^31 elements");
     origin_off_ = pad + (long long)g_.H[1] * g_.sy + (long long)g_.H[2] * g_.sz;
+    xpad_ = pad;
+    march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]);
     C_ = make_coefficients<FT>();
+    {   // the compile-time table of oc_march.h must be the very same numbers
+        using K = AdvConst<FT>;
+        const FT tab[] = {K::p00, K::p01, K::p02, K::p10, K::p11, K::p12, K::p20, K::p21, K::p22, K::c50, K::c51, K::c52,
+                          K::q00, K::q01, K::q10, K::q11, K::c30, K::c31, K::c40, K::c41, K::c42, K::c43, K::eps};
+        const FT ref[] = {C_.w5p[0][0], C_.w5p[0][1], C_.w5p[0][2], C_.w5p[1][0], C_.w5p[1][1], C_.w5p[1][2], C_.w5p[2][0], C_.w5p[2][1],
+                          C_.w5p[2][2], C_.w5c[0], C_.w5c[1], C_.w5c[2], C_.w3p[0][0], C_.w3p[0][1], C_.w3p[1][0], C_.w3p[1][1],
+                          C_.w3c[0], C_.w3c[1], C_.c4[0], C_.c4[1], C_.c4[2], C_.c4[3], C_.eps};
+        for (size_t n = 0; n < sizeof(tab) / sizeof(tab[0]); ++n)
+            if (tab[n] != ref[n]) throw Error(OC_ERR_STATE, "internal: compile-time reconstruction coefficient " + std::to_string(n) + " differs from the reference derivation");
+    }
     gamma_[0] = (FT)(8.0L / 15.0L); gamma_[1] = (FT)(5.0L / 12.0L); gamma_[2] = (FT)(3.0L / 4.0L);   // runge_kutta_3.jl:69-78
     zeta_[0] = FT(0); zeta_[1] = (FT)(-17.0L / 60.0L); zeta_[2] = (FT)(-5.0L / 12.0L);
 #ifndef OC_HOSTSIM
@@ -501,6 +514,103 @@ void Model<FT>::launch_tendency(int fidx, TendencyArgs<FT>& a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// z-marching TMA kernel (oc_march.h)
+// ---------------------------------------------------------------------------------------------------------
+#ifndef OC_HOSTSIM
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cuda_check(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q), "cudaGetDriverEntryPoint");
+        if (q != cudaDriverEntryPointSuccess || !p) throw Error(OC_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+#endif
+
+// TMA descriptor of a whole field allocation (x fastest; rows sy, planes sz) with a bx × by × 1 box
+template <class FT>
+TileSrc<FT> Model<FT>::tile_src(const FT* base, int bx, int by) {
+    const int rows = g_.sz / g_.sy, planes = (int)(field_elems_ / (size_t)g_.sz);
+#ifndef OC_HOSTSIM
+    auto key = std::make_tuple((const void*)base, bx, by);
+    auto it = tmap_cache_.find(key);
+    if (it != tmap_cache_.end()) return it->second;
+    TileSrc<FT> t;
+    cuuint64_t dims[3] = {(cuuint64_t)g_.sy, (cuuint64_t)rows, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)g_.sy * sizeof(FT), (cuuint64_t)g_.sz * sizeof(FT)};
+    cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode_tiled_fn()(&t.map, sizeof(FT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                                   (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(OC_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    tmap_cache_.emplace(key, t);
+    return t;
+#else
+    (void)bx; (void)by;
+    TileSrc<FT> t;
+    t.base = base;
+    t.dim[0] = g_.sy; t.dim[1] = rows; t.dim[2] = planes;
+    t.stride[0] = 1; t.stride[1] = g_.sy; t.stride[2] = g_.sz;
+    return t;
+#endif
+}
+
+template <class FT>
+template <int KIND>
+void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
+    auto run = [&](auto k) {
+        using K = decltype(k);
+        using SP = typename K::SP;
+        constexpr int TX = K::TX, TY = K::TY;
+        k.a = a;
+        k.xpad = xpad_;
+        const FT* self = state_[fidx].base;
+        auto vel_base = [&](int c) -> const FT* { return state_[c].base; };
+        k.src[0] = tile_src(self, SP::R0::BX, SP::R0::BY);
+        k.src[1] = tile_src(vel_base(SP::F1), SP::R1::BX, SP::R1::BY);
+        k.src[2] = tile_src(vel_base(SP::F2), SP::R2::BX, SP::R2::BY);
+        if (SP::NR > 3) k.src[3] = tile_src(vel_base(SP::F3 < 0 ? 0 : SP::F3), SP::R3::BX, SP::R3::BY);
+        else k.src[3] = k.src[0];
+        Dim3 grid;
+        grid.x = (g_.N[0] + TX - 1) / TX;
+        grid.y = (g_.N[1] + TY - 1) / TY;
+        // z chunks: enough CTAs to fill the machine several times over, but chunks of at least 16 levels
+        const int tiles = grid.x * grid.y;
+        int zch = (148 * 8 + tiles - 1) / tiles;
+        zch = std::max(1, std::min(zch, (g_.N[2] + 15) / 16));
+        k.KC = (g_.N[2] + zch - 1) / zch;
+        grid.z = (g_.N[2] + k.KC - 1) / k.KC;
+        begin_timer(OC_TIMER_TENDENCY);
+        cudaError_t e = launch_march(k, grid, K::SMEM, stream_);
+        end_timer();
+#ifndef OC_HOSTSIM
+        cuda_check(e, "march kernel launch");
+#else
+        (void)e;
+#endif
+        ++launches;
+    };
+    const bool bnd = g_.bounded[0] || g_.bounded[1] || g_.bounded[2];
+    const bool gen = has_amd_;
+    auto pick = [&](auto adv) {
+        constexpr int ADV = decltype(adv)::value;
+        if (!bnd && !gen) run(MarchKernel<FT, ADV, KIND, 0, 0>{});
+        else if (!bnd) run(MarchKernel<FT, ADV, KIND, 0, 1>{});
+        else if (!gen) run(MarchKernel<FT, ADV, KIND, 1, 0>{});
+        else run(MarchKernel<FT, ADV, KIND, 1, 1>{});
+    };
+    if (cfg_.advection == OC_WENO5) pick(std::integral_constant<int, 1>{});
+    else pick(std::integral_constant<int, 0>{});
+}
+
 template <class FT>
 void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state) {
     if (!aux_valid_) aux();
@@ -539,7 +649,12 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
         if (mode == STEP_RK3_FIRST) { a.ca = (FT)dt * gamma_[0]; a.cb = FT(0); }
         else if (mode == STEP_RK3) { a.ca = gamma_[stage - 1]; a.cb = zeta_[stage - 1]; }
         else if (mode == STEP_AB2) { a.ca = FT(1.5) + (FT)chi; a.cb = FT(0.5) + (FT)chi; }
-        if (f == 0) launch_tendency<KIND_U>(f, a);
+        if (march_ok_) {
+            if (f == 0) launch_march_tendency<KIND_U>(f, a);
+            else if (f == 1) launch_march_tendency<KIND_V>(f, a);
+            else if (f == 2) launch_march_tendency<KIND_W>(f, a);
+            else launch_march_tendency<KIND_C>(f, a);
+        } else if (f == 0) launch_tendency<KIND_U>(f, a);
         else if (f == 1) launch_tendency<KIND_V>(f, a);
         else if (f == 2) launch_tendency<KIND_W>(f, a);
         else launch_tendency<KIND_C>(f, a);
@@ -642,6 +757,18 @@ void Model<FT>::run_fft_solve() {
     std::string e = fft_.forward(fftbuf_);
     end_timer();
     if (!e.empty()) throw Error(OC_ERR_CUDA, e);
+    if (!g_.bounded[0] && !g_.bounded[1] && !g_.bounded[2]) {
+        PoissonDivideKernel<FT> k;
+        k.L = fft_.L;
+        k.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_);
+        for (int d = 0; d < 3; ++d) k.lam[d] = lam_[d];
+        k.norm = 1.0 / ((double)g_.N[0] * g_.N[1] * g_.N[2]);
+        k.chunk = 2048;
+        Dim3 grid;
+        grid.x = (fft_.L.nxc * g_.N[1] + k.chunk - 1) / k.chunk;
+        grid.y = g_.N[2];
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+    } else {
     PoissonMidKernel<FT> k;
     k.L = fft_.L;
     k.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_);
@@ -655,6 +782,7 @@ void Model<FT>::run_fft_solve() {
     grid.y = k.nrep[1];
     grid.z = k.nrep[2];
     go(k, grid, 0, OC_TIMER_POISSON_MID);
+    }
     begin_timer(OC_TIMER_FFT);
     e = fft_.inverse(fftbuf_);
     end_timer();

@@ -9,12 +9,14 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <tuple>
 #include <stdexcept>
 
 #include "../../include/oceananigans_b200.h"
 #include "oc_aux.h"
 #include "oc_fft.h"
 #include "oc_halo.h"
+#include "oc_march.h"
 #include "oc_tendency.h"
 
 namespace oc {
@@ -35,6 +37,8 @@ inline void* dev_alloc(size_t bytes) {
     void* p = nullptr;
     cuda_check(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc");
     cuda_check(cudaMemset(p, 0, bytes), "cudaMemset");
+    // the memset runs on the legacy default stream, which is NOT ordered with the model's non-blocking stream
+    cuda_check(cudaStreamSynchronize(cudaStreamLegacy), "cudaStreamSynchronize(legacy)");
     return p;
 }
 inline void dev_free(void* p) { if (p) cudaFree(p); }
@@ -176,6 +180,13 @@ private:
     void compute_tendencies_if_stale();
     void tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state);
     template <int KIND> void launch_tendency(int fidx, TendencyArgs<FT>& a);
+    template <int KIND> void launch_march_tendency(int fidx, TendencyArgs<FT>& a);
+    TileSrc<FT> tile_src(const FT* base, int bx, int by);
+    int xpad_ = 0;
+    bool march_ok_ = false;       // no Flat dimension: the z-marching TMA kernel applies
+#ifndef OC_HOSTSIM
+    std::map<std::tuple<const void*, int, int>, TileSrc<FT>> tmap_cache_;
+#endif
     void pressure_solve_from_state();
     void run_fft_solve();
     void projection(double dt);

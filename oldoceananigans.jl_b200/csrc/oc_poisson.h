@@ -191,6 +191,36 @@ struct PoissonMidKernel {
     }
 };
 
+// No Bounded dimension (plain DFTs): Φ = -X / (λx+λy+λz) / (Nx·Ny·Nz), Φ[0,0,0] = 0 — a pure streaming pass
+// (fft_based_poisson_solver.jl:110,115).  A block owns `chunk` consecutive spectral elements of one k-plane.
+template <class FT>
+struct PoissonDivideKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    SpectralLayout L;
+    Cplx<FT>* spec;
+    const double* lam[3];
+    double norm;
+    int chunk;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const int k = b.y;
+        const int plane = L.nxc * L.N[1];
+        const int n1 = (b.x + 1) * chunk < plane ? (b.x + 1) * chunk : plane;
+        const double lz = lam[2][k];
+        Cplx<FT>* row = spec + (long long)plane * k;
+        for (int n = b.x * chunk + tid; n < n1; n += nt) {
+            const int j = n / L.nxc, i = n - j * L.nxc;
+            const double l = lam[0][i] + lam[1][j] + lz;
+            Cplx<FT> e = row[n];
+            double s = -norm / l;
+            if (i == 0 && j == 0 && k == 0) s = 0.0;
+            row[n] = Cplx<FT>{(FT)((double)e.x * s), (FT)((double)e.y * s)};
+        }
+    }
+};
+
 // ϕ at logical cell (i,j,k) from the transform buffer; i = -1 / N handled by the caller
 template <class FT>
 OC_HD FT phi_at(const SpectralLayout& L, const FT* buf, int i, int j, int k) {
