@@ -107,6 +107,8 @@ struct Ring {
     OC_HD static int slot_of(int lev) { return POW2 ? ((lev + 64 * RS::D) & (RS::D - 1)) : ((lev + 64 * RS::D) % RS::D); }
     OC_HD FT operator()(int ii, int jj, int lev) const { return s[slot_of(lev) * SLOT + (jj - RS::YO) * RS::BX + (ii - RS::XO)]; }
     OC_HD FT* slot(int lev) const { return s + slot_of(lev) * SLOT; }
+    OC_HD const FT* ptr(int ii, int jj, int lev) const { return s + slot_of(lev) * SLOT + (jj - RS::YO) * RS::BX + (ii - RS::XO); }
+    static constexpr int STRIDE_Y = RS::BX;
 };
 
 // Loads for iteration it + PF are issued in phase 1 of iteration it; they overwrite the slot of level
@@ -192,25 +194,52 @@ OC_HD double newton_div_fast(double a, double b) {
 }
 OC_HD float newton_div_fast(float a, float b) { return a * rcp_fast(b); }
 
+OC_HD float oc_fmaf(float a, float b, float c) {
+#ifdef OC_HOSTSIM
+    return std::fma(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+OC_HD double fmaT(double a, double b, double c) { return oc_fma(a, b, c); }
+OC_HD float fmaT(float a, float b, float c) { return oc_fmaf(a, b, c); }
+
+// 1/x for x >= 1 (a sum of WENO α's): Float32 reciprocal + one Newton step (relative error ~1e-14 in Float64)
+OC_HD double rcp_newton(double x) {
+    double r = (double)rcp_fast((float)x);
+    return oc_fma(r, oc_fma(-x, r, 1.0), r);
+}
+OC_HD float rcp_newton(float x) { return rcp_fast(x); }
+
+// WENO(order=5) value from the upwind-ordered stencil q0..q4 (weno_interpolants.jl:172-174,204-216,261,290-337,500).
+// Algebraically the reference's formula, arranged to minimise FP64 instructions:
+//   β_r = ψ1(C1ψ1+C2ψ2+C3ψ3)+ψ2(C4ψ2+C5ψ3)+C6ψ3² = 13/4 (second difference)² + 3/4 (one-sided first difference)²;
+//   everything is carried divided by 3/4 (ε too), which leaves τ/(β+ε) unchanged;
+//   Σ ω_r p_r = q2 + Σ C★_r w_r (p_r - q2) / Σ C★_r w_r  with  w_r = 1 + (τ/(β_r+ε))²  (the coeff_p(r) sum to 1).
 template <class FT>
 OC_HD FT weno5_value_c(FT q0, FT q1, FT q2, FT q3, FT q4) {
     using K = AdvConst<FT>;
-    FT b0 = beta3<FT>(q2, q3, q4, FT(10), FT(-31), FT(11), FT(25), FT(-19), FT(4));
-    FT b1 = beta3<FT>(q1, q2, q3, FT(4), FT(-13), FT(5), FT(13), FT(-13), FT(4));
-    FT b2 = beta3<FT>(q0, q1, q2, FT(4), FT(-19), FT(11), FT(25), FT(-31), FT(10));
-    FT tau = oc_abs<FT>(b0 - b2);
-    FT r0 = newton_div_fast(tau, b0 + K::eps);
-    FT r1 = newton_div_fast(tau, b1 + K::eps);
-    FT r2 = newton_div_fast(tau, b2 + K::eps);
-    FT a0 = K::c50 * (FT(1) + r0 * r0);
-    FT a1 = K::c51 * (FT(1) + r1 * r1);
-    FT a2 = K::c52 * (FT(1) + r2 * r2);
-    FT rs = FT(1) / (a0 + a1 + a2);
-    FT p0 = K::p00 * q2 + K::p01 * q3 + K::p02 * q4;
-    FT p1 = K::p10 * q1 + K::p11 * q2 + K::p12 * q3;
-    FT p2 = K::p20 * q0 + K::p21 * q1 + K::p22 * q2;
-    return (a0 * rs) * p0 + (a1 * rs) * p1 + (a2 * rs) * p2;
+    constexpr FT c133 = FT(13) / FT(3);
+    constexpr FT epss = K::eps * (FT(4) / FT(3));
+    const FT e1 = q1 - q0, e2 = q2 - q1, e3 = q3 - q2, e4 = q4 - q3;
+    const FT d0 = e4 - e3, d1 = e3 - e2, d2 = e2 - e1;
+    const FT g0 = fmaT(FT(-3), e3, e4), g1 = e2 + e3, g2 = fmaT(FT(3), e2, -e1);
+    const FT b0 = fmaT(c133 * d0, d0, fmaT(g0, g0, epss));
+    const FT b1 = fmaT(c133 * d1, d1, fmaT(g1, g1, epss));
+    const FT b2 = fmaT(c133 * d2, d2, fmaT(g2, g2, epss));
+    const FT tau = oc_abs<FT>(b0 - b2);
+    const FT r0 = newton_div_fast(tau, b0), r1 = newton_div_fast(tau, b1), r2 = newton_div_fast(tau, b2);
+    const FT w0 = fmaT(r0, r0, FT(1)), w1 = fmaT(r1, r1, FT(1)), w2 = fmaT(r2, r2, FT(1));
+    const FT den = fmaT(K::c52, w2, fmaT(K::c51, w1, K::c50 * w0));
+    // C★_r (p_r - q2) in terms of the differences
+    constexpr FT a03 = K::c50 * (FT(2) / FT(3)), a04 = K::c50 * (FT(-1) / FT(6));
+    constexpr FT a12 = K::c51 * (FT(1) / FT(6)), a13 = K::c51 * (FT(1) / FT(3));
+    constexpr FT a22 = K::c52 * (FT(5) / FT(6)), a21 = K::c52 * (FT(-1) / FT(3));
+    const FT t0 = fmaT(a04, e4, a03 * e3), t1 = fmaT(a13, e3, a12 * e2), t2 = fmaT(a21, e1, a22 * e2);
+    const FT num = fmaT(w2, t2, fmaT(w1, t1, w0 * t0));
+    return fmaT(num, rcp_newton(den), q2);
 }
+
 template <class FT>
 OC_HD FT weno3_value_c(FT q0, FT q1, FT q2) {
     using K = AdvConst<FT>;
@@ -242,6 +271,14 @@ OC_HD FT rd(const A& a, int ii, int jj, int lev, int n) {
 template <int DIR, bool WIN, class FT, class A>
 OC_HD FT t_weno5_biased(const A& a, int ii, int jj, int lev, bool left, int f, const OrderWindow& w) {
     if (!WIN || (f >= w.lo_hi && f <= w.hi_hi)) {
+        if (DIR < 2) {
+            // in-plane: pick the upwind stencil by address (5 loads) instead of loading 6 values and selecting
+            const int st = DIR == 0 ? 1 : A::STRIDE_Y;
+            const FT* c = a.ptr(ii, jj, lev);
+            const FT* ctr = left ? c - st : c;
+            const int sg = left ? st : -st;
+            return weno5_value_c<FT>(ctr[-2 * sg], ctr[-sg], ctr[0], ctr[sg], ctr[2 * sg]);
+        }
         FT m3 = rd<DIR, FT>(a, ii, jj, lev, -3), m2 = rd<DIR, FT>(a, ii, jj, lev, -2), m1 = rd<DIR, FT>(a, ii, jj, lev, -1);
         FT p0 = rd<DIR, FT>(a, ii, jj, lev, 0), p1 = rd<DIR, FT>(a, ii, jj, lev, 1), p2 = rd<DIR, FT>(a, ii, jj, lev, 2);
         return weno5_value_c<FT>(left ? m3 : p2, left ? m2 : p1, left ? m1 : p0, left ? p0 : m1, left ? p1 : m2);
