@@ -78,22 +78,24 @@ inline cudaError_t launch(const K& k, Dim3 grid, size_t smem_bytes, Stream strea
 // ---- iterated kernels (z-marching) -------------------------------------------------------------------------
 // A marching kernel is a POD functor with
 //     OC_DEV void begin0(b, tid, smem) const;            // mbarrier init
-//     OC_DEV void begin1(b, tid, smem) const;            // prologue loads
+//     OC_DEV void begin1(b, tid, smem, State&) const;    // prologue loads, per-thread marching state
 //     OC_HD  int  iterations(b) const;                   // number of plane iterations of this block
-//     template <int PHASE> OC_DEV void step(b, tid, smem, it) const;   // PHASE 0, 1 separated by __syncthreads()
+//     template <int PHASE> OC_DEV void step(b, tid, smem, it, State&) const;   // PHASE 0, 1 separated by __syncthreads()
 template <class K>
 __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) march_entry(const __grid_constant__ K k) {
     extern __shared__ __align__(128) char smem[];
     Block b{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z};
     const int tid = (int)threadIdx.x;
+    typename K::State st;
     k.begin0(b, tid, smem);
     __syncthreads();
-    k.begin1(b, tid, smem);
+    k.begin1(b, tid, smem, st);
     const int n = k.iterations(b);
+#pragma unroll 1
     for (int it = 0; it < n; ++it) {
-        k.template step<0>(b, tid, smem, it);
+        k.template step<0>(b, tid, smem, it, st);
         __syncthreads();
-        k.template step<1>(b, tid, smem, it);
+        k.template step<1>(b, tid, smem, it, st);
     }
 }
 
@@ -145,12 +147,13 @@ inline cudaError_t launch_march(const K& k, Dim3 grid, size_t smem_bytes, Stream
         for (int by = 0; by < grid.y; ++by)
             for (int bx = 0; bx < grid.x; ++bx) {
                 Block b{bx, by, bz};
+                std::vector<typename K::State> st(K::THREADS);
                 for (int tid = 0; tid < K::THREADS; ++tid) k.begin0(b, tid, sm);
-                for (int tid = 0; tid < K::THREADS; ++tid) k.begin1(b, tid, sm);
+                for (int tid = 0; tid < K::THREADS; ++tid) k.begin1(b, tid, sm, st[tid]);
                 const int n = k.iterations(b);
                 for (int it = 0; it < n; ++it) {
-                    for (int tid = 0; tid < K::THREADS; ++tid) k.template step<0>(b, tid, sm, it);
-                    for (int tid = 0; tid < K::THREADS; ++tid) k.template step<1>(b, tid, sm, it);
+                    for (int tid = 0; tid < K::THREADS; ++tid) k.template step<0>(b, tid, sm, it, st[tid]);
+                    for (int tid = 0; tid < K::THREADS; ++tid) k.template step<1>(b, tid, sm, it, st[tid]);
                 }
             }
     return cudaSuccess;

@@ -102,13 +102,27 @@ struct Ring {
     static constexpr int SLOT_BYTES = ((BOX_BYTES + 127) / 128) * 128;
     static constexpr int SLOT = SLOT_BYTES / (int)sizeof(FT);
     static constexpr int BYTES = SLOT_BYTES * RS::D;
-    FT* s;
     static constexpr bool POW2 = (RS::D & (RS::D - 1)) == 0;
-    OC_HD static int slot_of(int lev) { return POW2 ? ((lev + 64 * RS::D) & (RS::D - 1)) : ((lev + 64 * RS::D) % RS::D); }
-    OC_HD FT operator()(int ii, int jj, int lev) const { return s[slot_of(lev) * SLOT + (jj - RS::YO) * RS::BX + (ii - RS::XO)]; }
-    OC_HD FT* slot(int lev) const { return s + slot_of(lev) * SLOT; }
-    OC_HD const FT* ptr(int ii, int jj, int lev) const { return s + slot_of(lev) * SLOT + (jj - RS::YO) * RS::BX + (ii - RS::XO); }
     static constexpr int STRIDE_Y = RS::BX;
+    FT* s;
+    int k;        // the level of the current iteration
+    int sk;       // its ring slot (carried and advanced by the marching loop: no per-access modulo)
+    OC_HD static int slot_of(int lev) { return POW2 ? ((lev + 64 * RS::D) & (RS::D - 1)) : ((lev + 64 * RS::D) % RS::D); }
+    // slot of level lev = k + c, |c| < D (c folds to a constant after inlining)
+    OC_HD int slot_rel(int lev) const {
+        int t = sk + (lev - k);
+        if (POW2) return t & (RS::D - 1);
+        t = t < 0 ? t + RS::D : t;
+        return t >= RS::D ? t - RS::D : t;
+    }
+    OC_HD FT operator()(int ii, int jj, int lev) const { return s[slot_rel(lev) * SLOT + (jj - RS::YO) * RS::BX + (ii - RS::XO)]; }
+    OC_HD const FT* ptr(int ii, int jj, int lev) const { return s + slot_rel(lev) * SLOT + (jj - RS::YO) * RS::BX + (ii - RS::XO); }
+    OC_HD FT* slot(int lev) const { return s + slot_of(lev) * SLOT; }     // absolute (TMA issue, one thread)
+    OC_HD static int next_slot(int sk) { return sk + 1 == RS::D ? 0 : sk + 1; }
+};
+
+struct MarchState {
+    int sk[4];    // ring slot of the current level, per ring
 };
 
 // Loads for iteration it + PF are issued in phase 1 of iteration it; they overwrite the slot of level
@@ -211,11 +225,49 @@ OC_HD double rcp_newton(double x) {
 }
 OC_HD float rcp_newton(float x) { return rcp_fast(x); }
 
+// 1/x in Float64 for any normal x > 0: MUFU.RCP64H seed + the cubic-then-quadratic refinement CUDA's own division uses
+// (error ~ seed^6).  No Float32 round trip, so no exponent-range limit.
+OC_HD double rcp_full(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(e, r, r);
+#else
+    return 1.0 / x;
+#endif
+}
+
+OC_HD double absT(double x) {
+#ifdef OC_HOSTSIM
+    return std::fabs(x);
+#else
+    return fabs(x);
+#endif
+}
+OC_HD float absT(float x) {
+#ifdef OC_HOSTSIM
+    return std::fabs(x);
+#else
+    return fabsf(x);
+#endif
+}
+
+OC_HD double rcp_den(double x) { return rcp_full(x); }
+OC_HD float rcp_den(float x) { return rcp_fast(x); }
+
 // WENO(order=5) value from the upwind-ordered stencil q0..q4 (weno_interpolants.jl:172-174,204-216,261,290-337,500).
 // Algebraically the reference's formula, arranged to minimise FP64 instructions:
 //   β_r = ψ1(C1ψ1+C2ψ2+C3ψ3)+ψ2(C4ψ2+C5ψ3)+C6ψ3² = 13/4 (second difference)² + 3/4 (one-sided first difference)²;
 //   everything is carried divided by 3/4 (ε too), which leaves τ/(β+ε) unchanged;
-//   Σ ω_r p_r = q2 + Σ C★_r w_r (p_r - q2) / Σ C★_r w_r  with  w_r = 1 + (τ/(β_r+ε))²  (the coeff_p(r) sum to 1).
+//   Σ ω_r p_r = q2 + Σ C★_r w_r (p_r - q2) / Σ C★_r w_r  with  w_r = 1 + (τ/(β_r+ε))²  (the coeff_p(r) sum to 1);
+//   numerator and denominator both carry a factor 60, which makes every constant a small integer
+//   (C★ = 3/10, 3/5, 1/10; C★_r (p_r - q2) = (12 e3 - 3 e4, 6 e2 + 12 e3, 5 e2 - 2 e1) / 60).
+// Float64: the three weights are formed without divisions, w_r ∝ (b_r² + τ²)·(b_s b_t)² (one common factor
+// (b0 b1 b2)² cancels in the ratio), leaving ONE reciprocal per face.  Float32 keeps newton_div (a single MUFU.RCP).
 template <class FT>
 OC_HD FT weno5_value_c(FT q0, FT q1, FT q2, FT q3, FT q4) {
     using K = AdvConst<FT>;
@@ -227,17 +279,23 @@ OC_HD FT weno5_value_c(FT q0, FT q1, FT q2, FT q3, FT q4) {
     const FT b0 = fmaT(c133 * d0, d0, fmaT(g0, g0, epss));
     const FT b1 = fmaT(c133 * d1, d1, fmaT(g1, g1, epss));
     const FT b2 = fmaT(c133 * d2, d2, fmaT(g2, g2, epss));
-    const FT tau = oc_abs<FT>(b0 - b2);
-    const FT r0 = newton_div_fast(tau, b0), r1 = newton_div_fast(tau, b1), r2 = newton_div_fast(tau, b2);
-    const FT w0 = fmaT(r0, r0, FT(1)), w1 = fmaT(r1, r1, FT(1)), w2 = fmaT(r2, r2, FT(1));
-    const FT den = fmaT(K::c52, w2, fmaT(K::c51, w1, K::c50 * w0));
-    // C★_r (p_r - q2) in terms of the differences
-    constexpr FT a03 = K::c50 * (FT(2) / FT(3)), a04 = K::c50 * (FT(-1) / FT(6));
-    constexpr FT a12 = K::c51 * (FT(1) / FT(6)), a13 = K::c51 * (FT(1) / FT(3));
-    constexpr FT a22 = K::c52 * (FT(5) / FT(6)), a21 = K::c52 * (FT(-1) / FT(3));
-    const FT t0 = fmaT(a04, e4, a03 * e3), t1 = fmaT(a13, e3, a12 * e2), t2 = fmaT(a21, e1, a22 * e2);
-    const FT num = fmaT(w2, t2, fmaT(w1, t1, w0 * t0));
-    return fmaT(num, rcp_newton(den), q2);
+    const FT tau = b0 - b2;                                  // only τ² is used
+    FT w0, w1, w2;
+    if (sizeof(FT) == 8) {
+        const FT t2 = tau * tau;
+        const FT m01 = b0 * b1, m02 = b0 * b2, m12 = b1 * b2;
+        w0 = fmaT(b0, b0, t2) * (m12 * m12);
+        w1 = fmaT(b1, b1, t2) * (m02 * m02);
+        w2 = fmaT(b2, b2, t2) * (m01 * m01);
+    } else {
+        const FT at = absT(tau);
+        const FT r0 = newton_div_fast(at, b0), r1 = newton_div_fast(at, b1), r2 = newton_div_fast(at, b2);
+        w0 = fmaT(r0, r0, FT(1)); w1 = fmaT(r1, r1, FT(1)); w2 = fmaT(r2, r2, FT(1));
+    }
+    const FT den = fmaT(FT(6), w2, fmaT(FT(36), w1, FT(18) * w0));
+    const FT t0 = fmaT(FT(-3), e4, FT(12) * e3), t1 = fmaT(FT(12), e3, FT(6) * e2), t2n = fmaT(FT(-2), e1, FT(5) * e2);
+    const FT num = fmaT(w2, t2n, fmaT(w1, t1, w0 * t0));
+    return fmaT(num, rcp_den(den), q2);
 }
 
 template <class FT>
@@ -245,7 +303,7 @@ OC_HD FT weno3_value_c(FT q0, FT q1, FT q2) {
     using K = AdvConst<FT>;
     FT b0 = q1 * (FT(1) * q1 + FT(-2) * q2) + q2 * q2 * FT(1);
     FT b1 = q0 * (FT(1) * q0 + FT(-2) * q1) + q1 * q1 * FT(1);
-    FT tau = oc_abs<FT>(b0 - b1);
+    FT tau = absT(b0 - b1);
     FT r0 = newton_div_fast(tau, b0 + K::eps);
     FT r1 = newton_div_fast(tau, b1 + K::eps);
     FT a0 = K::c30 * (FT(1) + r0 * r0);
@@ -293,13 +351,11 @@ OC_HD FT t_weno5_biased(const A& a, int ii, int jj, int lev, bool left, int f, c
 // _symmetric_interpolate of A·q (Centered(4) → Centered(2) near walls)
 template <int DIR, bool WIN, class FT, class A>
 OC_HD FT t_weno5_symmetric(const A& a, int ii, int jj, int lev, FT area, int f, const OrderWindow& w) {
-    using K = AdvConst<FT>;
     if (!WIN || (f >= w.lo_hi && f <= w.hi_hi)) {
-        FT r = K::c40 * (area * rd<DIR, FT>(a, ii, jj, lev, -2));
-        r = r + K::c41 * (area * rd<DIR, FT>(a, ii, jj, lev, -1));
-        r = r + K::c42 * (area * rd<DIR, FT>(a, ii, jj, lev, 0));
-        r = r + K::c43 * (area * rd<DIR, FT>(a, ii, jj, lev, 1));
-        return r;
+        // Centered(4): (-1, 7, 7, -1)/12
+        const FT in = rd<DIR, FT>(a, ii, jj, lev, -1) + rd<DIR, FT>(a, ii, jj, lev, 0);
+        const FT out = rd<DIR, FT>(a, ii, jj, lev, -2) + rd<DIR, FT>(a, ii, jj, lev, 1);
+        return (area * (FT(1) / FT(12))) * fmaT(FT(7), in, -out);
     }
     return FT(0.5) * (area * rd<DIR, FT>(a, ii, jj, lev, -1)) + FT(0.5) * (area * rd<DIR, FT>(a, ii, jj, lev, 0));
 }
@@ -310,11 +366,11 @@ OC_HD FT t_weno5_symmetric(const A& a, int ii, int jj, int lev, FT area, int f, 
 // One thread per y-face: THREADS = TX·(TY+1); the x-faces and z-faces map onto the same threads so that every
 // warp evaluates at most three fluxes per level (no tail warps in front of the barrier).
 // ---------------------------------------------------------------------------------------------------------
-template <class FT, int ADV, int KIND, int BND, int CLO>
+template <class FT, int ADV, int KIND, int BND, int CLO, int TY_ = 8>
 struct MarchKernel {
-    static constexpr int TX = 32, TY = 8;
+    static constexpr int TX = 32, TY = TY_;
     static constexpr int THREADS = TX * (TY + 1);
-    static constexpr int MIN_BLOCKS = 3;
+    static constexpr int MIN_BLOCKS = TY_ == 8 ? 3 : 5;
     static constexpr int COMP = KIND == KIND_C ? -1 : KIND;
     static constexpr bool WIN = BND != 0;
     using SP = MarchSpec<KIND, TX, TY, 16 / (int)sizeof(FT)>;
@@ -348,10 +404,17 @@ struct MarchKernel {
     OC_HD int k_end(const Block& b) const { int e = (b.z + 1) * KC; return e < a.g.N[2] ? e : a.g.N[2]; }
     OC_HD int iterations(const Block& b) const { return k_end(b) - k_begin(b) + 1; }   // + the z-flux-only pre-iteration
 
-    OC_HD G0 r0(char* smem) const { return G0{reinterpret_cast<FT*>(smem + OFF_R0)}; }
-    OC_HD G1 r1(char* smem) const { return G1{reinterpret_cast<FT*>(smem + OFF_R1)}; }
-    OC_HD G2 r2(char* smem) const { return G2{reinterpret_cast<FT*>(smem + OFF_R2)}; }
-    OC_HD G3 r3(char* smem) const { return G3{reinterpret_cast<FT*>(smem + OFF_R3)}; }
+    // ring views for the iteration at level kk with slot state st (`Ctx` bundles what the flux functions need)
+    struct Ctx {
+        char* smem;
+        int k;
+        MarchState st;
+    };
+    OC_HD G0 r0(const Ctx& c) const { return G0{reinterpret_cast<FT*>(c.smem + OFF_R0), c.k, c.st.sk[0]}; }
+    OC_HD G1 r1(const Ctx& c) const { return G1{reinterpret_cast<FT*>(c.smem + OFF_R1), c.k, c.st.sk[1]}; }
+    OC_HD G2 r2(const Ctx& c) const { return G2{reinterpret_cast<FT*>(c.smem + OFF_R2), c.k, c.st.sk[2]}; }
+    OC_HD G3 r3(const Ctx& c) const { return G3{reinterpret_cast<FT*>(c.smem + OFF_R3), c.k, c.st.sk[3]}; }
+    OC_HD Ctx raw(char* smem) const { return Ctx{smem, 0, MarchState{{0, 0, 0, 0}}}; }
 
     // ---- loads -----------------------------------------------------------------------------------------------
     template <class G, class RS>
@@ -360,10 +423,11 @@ struct MarchKernel {
     }
     // the new level every ring needs for the iteration at level k
     OC_DEV void issue_iteration(char* smem, int i0, int j0, int k, uint64_t* bar) const {
-        issue_level<G0, typename SP::R0>(r0(smem), &src[0], i0, j0, k + SP::R0::HI, bar);
-        issue_level<G1, typename SP::R1>(r1(smem), &src[1], i0, j0, k + SP::R1::HI, bar);
-        issue_level<G2, typename SP::R2>(r2(smem), &src[2], i0, j0, k + SP::R2::HI, bar);
-        if (NR > 3) issue_level<G3, typename SP::R3>(r3(smem), &src[3], i0, j0, k + SP::R3::HI, bar);
+        const Ctx c = raw(smem);
+        issue_level<G0, typename SP::R0>(r0(c), &src[0], i0, j0, k + SP::R0::HI, bar);
+        issue_level<G1, typename SP::R1>(r1(c), &src[1], i0, j0, k + SP::R1::HI, bar);
+        issue_level<G2, typename SP::R2>(r2(c), &src[2], i0, j0, k + SP::R2::HI, bar);
+        if (NR > 3) issue_level<G3, typename SP::R3>(r3(c), &src[3], i0, j0, k + SP::R3::HI, bar);
     }
 
     OC_DEV void begin0(const Block&, int tid, char* smem) const {
@@ -373,17 +437,23 @@ struct MarchKernel {
             mbar_fence_init();
         }
     }
-    OC_DEV void begin1(const Block& b, int tid, char* smem) const {
+    typedef MarchState State;
+    OC_DEV void begin1(const Block& b, int tid, char* smem, MarchState& st) const {
+        {   // ring slots of the first level (kf = k_begin - 1)
+            const int kf0 = k_begin(b) - 1;
+            st.sk[0] = G0::slot_of(kf0); st.sk[1] = G1::slot_of(kf0); st.sk[2] = G2::slot_of(kf0); st.sk[3] = G3::slot_of(kf0);
+        }
         if (tid != 0) return;
         uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
         const int i0 = b.x * TX, j0 = b.y * TY, kf = k_begin(b) - 1, n = iterations(b);
         // iteration 0 (level kf): every live level of every ring
         mbar_expect(bar, FIRST_BYTES);
-        for (int l = SP::R0::LO; l < SP::R0::HI; ++l) issue_level<G0, typename SP::R0>(r0(smem), &src[0], i0, j0, kf + l, bar);
-        for (int l = SP::R1::LO; l < SP::R1::HI; ++l) issue_level<G1, typename SP::R1>(r1(smem), &src[1], i0, j0, kf + l, bar);
-        for (int l = SP::R2::LO; l < SP::R2::HI; ++l) issue_level<G2, typename SP::R2>(r2(smem), &src[2], i0, j0, kf + l, bar);
+        const Ctx c = raw(smem);
+        for (int l = SP::R0::LO; l < SP::R0::HI; ++l) issue_level<G0, typename SP::R0>(r0(c), &src[0], i0, j0, kf + l, bar);
+        for (int l = SP::R1::LO; l < SP::R1::HI; ++l) issue_level<G1, typename SP::R1>(r1(c), &src[1], i0, j0, kf + l, bar);
+        for (int l = SP::R2::LO; l < SP::R2::HI; ++l) issue_level<G2, typename SP::R2>(r2(c), &src[2], i0, j0, kf + l, bar);
         if (NR > 3)
-            for (int l = SP::R3::LO; l < SP::R3::HI; ++l) issue_level<G3, typename SP::R3>(r3(smem), &src[3], i0, j0, kf + l, bar);
+            for (int l = SP::R3::LO; l < SP::R3::HI; ++l) issue_level<G3, typename SP::R3>(r3(c), &src[3], i0, j0, kf + l, bar);
         issue_iteration(smem, i0, j0, kf, bar);
         for (int it = 1; it < MARCH_PF && it < n; ++it) {
             mbar_expect(bar + (it % MARCH_NBAR), LEVEL_BYTES);
@@ -394,7 +464,7 @@ struct MarchKernel {
     // ---- closure fluxes (mirror of TendencyKernel::viscous_flux / diffusive_flux) ---------------------------------
     // velocity component C at tile-local (ii,jj) and level lev, displaced by n along direction DIR
     template <int C, int DIR>
-    OC_HD FT vel(char* smem, int ii, int jj, int lev, int n) const {
+    OC_HD FT vel(const Ctx& smem, int ii, int jj, int lev, int n) const {
         if (C == COMP) return rd<DIR, FT>(r0(smem), ii, jj, lev, n);
         if (C == SP::F1) return rd<DIR, FT>(r1(smem), ii, jj, lev, n);
         return rd<DIR, FT>(r2(smem), ii, jj, lev, n);
@@ -408,7 +478,7 @@ struct MarchKernel {
     }
 
     template <int D>
-    OC_HD FT viscous_flux(char* smem, int ii, int jj, int lev, int i, int j) const {
+    OC_HD FT viscous_flux(const Ctx& smem, int ii, int jj, int lev, int i, int j) const {
         const Geom<FT>& g = a.g;
         FT sig;
         if (D == COMP) {
@@ -419,7 +489,7 @@ struct MarchKernel {
             FT dh = (vel<hi, lo>(smem, ii, jj, lev, 0) - vel<hi, lo>(smem, ii, jj, lev, -1)) * g.rd[lo];
             sig = FT(0.5) * (dl + dh);
         }
-        if (CLO == 0) return g.A[D] * (FT(-2) * (a.nu * sig));
+        if (CLO == 0) return (FT(-2) * a.nu * g.A[D]) * sig;
         FT flux = FT(0);
         if (a.has_scalar) flux = g.A[D] * (FT(-2) * (a.nu * sig));
         if (a.nu_e) {
@@ -434,11 +504,11 @@ struct MarchKernel {
     }
 
     template <int D>
-    OC_HD FT diffusive_flux(char* smem, int ii, int jj, int lev, int i, int j) const {
+    OC_HD FT diffusive_flux(const Ctx& smem, int ii, int jj, int lev, int i, int j) const {
         const Geom<FT>& g = a.g;
         G0 c = r0(smem);
         FT grad = (rd<D, FT>(c, ii, jj, lev, 0) - rd<D, FT>(c, ii, jj, lev, -1)) * g.rd[D];
-        if (CLO == 0) return g.A[D] * (-(a.kappa * grad));
+        if (CLO == 0) return -(a.kappa * g.A[D]) * grad;
         FT flux = FT(0);
         if (a.has_scalar) flux = g.A[D] * (-(a.kappa * grad));
         if (a.kappa_e) {
@@ -453,7 +523,7 @@ struct MarchKernel {
 
     // ---- advective flux through the faces normal to D at flux index (ii, jj, lev); id = global index along D, ic along COMP
     template <int D>
-    OC_HD FT advective_flux(char* smem, int ii, int jj, int lev, int id, int ic) const {
+    OC_HD FT advective_flux(const Ctx& smem, int ii, int jj, int lev, int id, int ic) const {
         const Geom<FT>& g = a.g;
         const FT A = g.A[D];
         if (KIND == KIND_C) {
@@ -504,7 +574,7 @@ struct MarchKernel {
 
     // i, j, k: global flux index; (ii, jj): the same, tile-local
     template <int D>
-    OC_HD FT total_flux(char* smem, int ii, int jj, int i, int j, int k) const {
+    OC_HD FT total_flux(const Ctx& smem, int ii, int jj, int i, int j, int k) const {
         const int id = D == 0 ? i : (D == 1 ? j : k);
         const int ic = COMP == 0 ? i : (COMP == 1 ? j : k);
         FT F = advective_flux<D>(smem, ii, jj, k, id, ic);
@@ -517,10 +587,12 @@ struct MarchKernel {
 
     // ---- one level ---------------------------------------------------------------------------------------------------
     template <int PHASE>
-    OC_DEV void step(const Block& b, int tid, char* smem, int it) const {
+    OC_DEV void step(const Block& b, int tid, char* smem_raw, int it, MarchState& st) const {
         const Geom<FT>& g = a.g;
+        char* smem = smem_raw;
         const int i0 = b.x * TX, j0 = b.y * TY;
         const int k = k_begin(b) - 1 + it;                   // level of this iteration (it = 0: z-flux only)
+        const Ctx cx{smem_raw, k, st};
         constexpr int shx = COMP == 0 ? -1 : 0, shy = COMP == 1 ? -1 : 0, shz = COMP == 2 ? -1 : 0;
         FT* fx = reinterpret_cast<FT*>(smem + OFF_FX) + (it & 1) * NFXP;
         FT* fy = reinterpret_cast<FT*>(smem + OFF_FY) + (it & 1) * NFYP;
@@ -532,25 +604,32 @@ struct MarchKernel {
         if (PHASE == 0) {
             mbar_wait(bar + (it % MARCH_NBAR), (it / MARCH_NBAR) & 1);
             if (it > 0) {
-                {   // y-face (lane, row)
+                {   // y-face (lane, row).  CLO == 0: every operand is in shared memory, so out-of-range faces of partial
+                    // tiles are evaluated too (on zero-filled / neighbouring data) and discarded — no divergent branch
+                    const bool ok = i0 + lane < g.N[0] && j0 + row <= g.N[1];
                     FT F = FT(0);
-                    if (i0 + lane < g.N[0] && j0 + row <= g.N[1]) F = total_flux<1>(smem, lane, row + shy, i0 + lane, j0 + row + shy, k);
-                    fy[row * TX + lane] = F;
+                    if (CLO == 0 || ok) F = total_flux<1>(cx, lane, row + shy, i0 + lane, j0 + row + shy, k);
+                    fy[row * TX + lane] = ok ? F : FT(0);
                 }
                 // x-faces: rows 0 … TY-1 take faces s = 0 … TX-1; the last warp takes the TY faces s = TX
                 const int s = row < TY ? lane : TX, jj = row < TY ? row : lane;
                 if (row < TY || lane < TY) {
+                    const bool ok = j0 + jj < g.N[1] && i0 + s <= g.N[0];
                     FT F = FT(0);
-                    if (j0 + jj < g.N[1] && i0 + s <= g.N[0]) F = total_flux<0>(smem, s + shx, jj, i0 + s + shx, j0 + jj, k);
-                    fx[jj * (TX + 1) + s] = F;
+                    if (CLO == 0 || ok) F = total_flux<0>(cx, s + shx, jj, i0 + s + shx, j0 + jj, k);
+                    fx[jj * (TX + 1) + s] = ok ? F : FT(0);
                 }
             }
             if (row < TY) {   // upper z-face of cell (lane, row)
+                const bool ok = i0 + lane < g.N[0] && j0 + row < g.N[1] && k + 1 <= g.N[2];
                 FT F = FT(0);
-                if (i0 + lane < g.N[0] && j0 + row < g.N[1] && k + 1 <= g.N[2]) F = total_flux<2>(smem, lane, row, i0 + lane, j0 + row, k + 1 + shz);
-                fz_up[row * TX + lane] = F;
+                if (CLO == 0 || ok) F = total_flux<2>(cx, lane, row, i0 + lane, j0 + row, k + 1 + shz);
+                fz_up[row * TX + lane] = ok ? F : FT(0);
             }
         } else {
+            // advance the ring slots for the next level (cx keeps this level's)
+            st.sk[0] = G0::next_slot(st.sk[0]); st.sk[1] = G1::next_slot(st.sk[1]);
+            st.sk[2] = G2::next_slot(st.sk[2]); st.sk[3] = G3::next_slot(st.sk[3]);
             // loads three levels ahead: the slots they overwrite were last read before the __syncthreads above
             if (tid == 0) {
                 const int nit = it + MARCH_PF;
@@ -565,7 +644,7 @@ struct MarchKernel {
             const int i = i0 + ii, j = j0 + jj;
             if (i >= g.N[0] || j >= g.N[1]) return;
             const int o = g.idx(i, j, k);
-            const FT u0 = r0(smem)(ii, jj, k);
+            const FT u0 = r0(cx)(ii, jj, k);
             if (WIN && COMP >= 0) {
                 // exclude_periphery: the wall face of a wall-normal velocity is not stepped (kernel_launching.jl:145-146)
                 const int ic = COMP == 0 ? i : (COMP == 1 ? j : k);
@@ -580,7 +659,7 @@ struct MarchKernel {
             FT G = -(g.rV * (dFx + dFy + dFz));
             if ((KIND == KIND_U || KIND == KIND_V) && a.has_coriolis) {
                 // FPlane (f_plane.jl:50-52); the other horizontal component is ring 1
-                G1 q = r1(smem);
+                G1 q = r1(cx);
                 FT num, cnt = FT(1);
                 if (KIND == KIND_U) {
                     num = FT(0.5) * (FT(0.5) * (q(ii - 1, jj, k) + q(ii, jj, k)) + FT(0.5) * (q(ii - 1, jj + 1, k) + q(ii, jj + 1, k)));

@@ -600,9 +600,11 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
     };
     const bool bnd = g_.bounded[0] || g_.bounded[1] || g_.bounded[2];
     const bool gen = has_amd_;
+    static const int ty_env = getenv("OC_MARCH_TY") ? atoi(getenv("OC_MARCH_TY")) : 8;
     auto pick = [&](auto adv) {
         constexpr int ADV = decltype(adv)::value;
-        if (!bnd && !gen) run(MarchKernel<FT, ADV, KIND, 0, 0>{});
+        if (!bnd && !gen && ty_env == 4) run(MarchKernel<FT, ADV, KIND, 0, 0, 4>{});
+        else if (!bnd && !gen) run(MarchKernel<FT, ADV, KIND, 0, 0>{});
         else if (!bnd) run(MarchKernel<FT, ADV, KIND, 0, 1>{});
         else if (!gen) run(MarchKernel<FT, ADV, KIND, 1, 0>{});
         else run(MarchKernel<FT, ADV, KIND, 1, 1>{});
