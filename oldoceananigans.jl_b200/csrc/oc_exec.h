@@ -80,7 +80,8 @@ inline cudaError_t launch(const K& k, Dim3 grid, size_t smem_bytes, Stream strea
 //     OC_DEV void begin0(b, tid, smem) const;            // mbarrier init
 //     OC_DEV void begin1(b, tid, smem, State&) const;    // prologue loads, per-thread marching state
 //     OC_HD  int  iterations(b) const;                   // number of plane iterations of this block
-//     template <int PHASE> OC_DEV void step(b, tid, smem, it, State&) const;   // PHASE 0, 1 separated by __syncthreads()
+//     template <int PHASE> OC_DEV void step(b, tid, smem, it, State&) const;   // PHASE 0, 1, 2 for it = 0 … iterations()
+//     OC_DEV void sync_wait(smem, it) / sync_arrive(smem, it) const;            // split (arrive / wait) block barrier
 template <class K>
 __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) march_entry(const __grid_constant__ K k) {
     extern __shared__ __align__(128) char smem[];
@@ -92,10 +93,12 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) march_entry(const _
     k.begin1(b, tid, smem, st);
     const int n = k.iterations(b);
 #pragma unroll 1
-    for (int it = 0; it < n; ++it) {
+    for (int it = 0; it <= n; ++it) {
         k.template step<0>(b, tid, smem, it, st);
-        __syncthreads();
+        if (it >= 1) k.sync_wait(smem, it - 1);          // split barrier: every thread has arrived for iteration it-1
         k.template step<1>(b, tid, smem, it, st);
+        k.template step<2>(b, tid, smem, it, st);
+        if (it < n) k.sync_arrive(smem, it);
     }
 }
 
@@ -151,9 +154,10 @@ inline cudaError_t launch_march(const K& k, Dim3 grid, size_t smem_bytes, Stream
                 for (int tid = 0; tid < K::THREADS; ++tid) k.begin0(b, tid, sm);
                 for (int tid = 0; tid < K::THREADS; ++tid) k.begin1(b, tid, sm, st[tid]);
                 const int n = k.iterations(b);
-                for (int it = 0; it < n; ++it) {
+                for (int it = 0; it <= n; ++it) {
                     for (int tid = 0; tid < K::THREADS; ++tid) k.template step<0>(b, tid, sm, it, st[tid]);
                     for (int tid = 0; tid < K::THREADS; ++tid) k.template step<1>(b, tid, sm, it, st[tid]);
+                    for (int tid = 0; tid < K::THREADS; ++tid) k.template step<2>(b, tid, sm, it, st[tid]);
                 }
             }
     return cudaSuccess;

@@ -57,6 +57,7 @@ OC_DEV void mbar_wait(uint64_t* bar, int parity) {
         : "memory");
 }
 OC_DEV void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+OC_DEV void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 template <class FT>
 OC_DEV void tile_issue(void* dst, const TileSrc<FT>* src, int c0, int c1, int c2, uint64_t* bar, int, int) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -75,6 +76,7 @@ inline void mbar_fence_init() {}
 inline void mbar_expect(uint64_t*, int) {}
 inline void mbar_wait(uint64_t*, int) {}
 inline void proxy_fence_async() {}
+inline void mbar_arrive(uint64_t*) {}
 template <class FT>
 inline void tile_issue(void* dst, const TileSrc<FT>* src, int c0, int c1, int c2, uint64_t*, int bx, int by) {
     FT* d = (FT*)dst;
@@ -110,6 +112,9 @@ struct Ring {
     OC_HD static int slot_of(int lev) { return POW2 ? ((lev + 64 * RS::D) & (RS::D - 1)) : ((lev + 64 * RS::D) % RS::D); }
     // slot of level lev = k + c, |c| < D (c folds to a constant after inlining)
     OC_HD int slot_rel(int lev) const {
+#if defined(__CUDA_ARCH__)
+        __builtin_assume(sk >= 0 && sk < RS::D);     // lets (lev - k) == 0 fold to sk
+#endif
         int t = sk + (lev - k);
         if (POW2) return t & (RS::D - 1);
         t = t < 0 ? t + RS::D : t;
@@ -121,14 +126,20 @@ struct Ring {
     OC_HD static int next_slot(int sk) { return sk + 1 == RS::D ? 0 : sk + 1; }
 };
 
-struct MarchState {
+struct MarchSlots {
     int sk[4];    // ring slot of the current level, per ring
+};
+template <class FT>
+struct MarchStateT {
+    MarchSlots sl;
+    FT fz_prev;   // this thread's upper z-face flux of the previous level (= lower flux of the current one)
+    FT dfz;       // δz of the z-face fluxes of the level whose divergence is formed next
 };
 
 // Loads for iteration it + PF are issued in phase 1 of iteration it; they overwrite the slot of level
 // k + PF + HI - D, which must not be read any more: D >= LIVE + PF - 1 for rings read only in phase 0,
 // D >= LIVE + PF for rings whose lowest level is also read in phase 1.
-enum { MARCH_PF = 3, MARCH_NBAR = 4 };
+enum { MARCH_PF = 2, MARCH_NBAR = 4, MARCH_NSYNC = 4 };
 
 // Which planes each kernel stages.  `FIELD` names the global field: -1 = the stepped field itself (ψ or c), 0/1/2 = u/v/w.
 // E = elements per 16 bytes; box x-origins are kept multiples of E (16-byte aligned box rows).
@@ -388,9 +399,8 @@ struct MarchKernel {
     static constexpr size_t OFF_R2 = OFF_R1 + G1::BYTES;
     static constexpr size_t OFF_R3 = OFF_R2 + G2::BYTES;
     static constexpr size_t OFF_FX = OFF_R3 + (NR > 3 ? G3::BYTES : 0);
-    static constexpr size_t OFF_FY = OFF_FX + sizeof(FT) * 2 * NFXP;
-    static constexpr size_t OFF_FZ = OFF_FY + sizeof(FT) * 2 * NFYP;
-    static constexpr size_t SMEM = OFF_FZ + sizeof(FT) * 3 * NFZ;
+    static constexpr size_t OFF_FY = OFF_FX + sizeof(FT) * MARCH_NSYNC * NFXP;
+    static constexpr size_t SMEM = OFF_FY + sizeof(FT) * MARCH_NSYNC * NFYP;
     static constexpr int LEVEL_BYTES = G0::BOX_BYTES + G1::BOX_BYTES + G2::BOX_BYTES + (NR > 3 ? G3::BOX_BYTES : 0);
     static constexpr int FIRST_BYTES = G0::BOX_BYTES * SP::R0::LIVE + G1::BOX_BYTES * SP::R1::LIVE + G2::BOX_BYTES * SP::R2::LIVE +
                                        (NR > 3 ? G3::BOX_BYTES * SP::R3::LIVE : 0);
@@ -408,13 +418,13 @@ struct MarchKernel {
     struct Ctx {
         char* smem;
         int k;
-        MarchState st;
+        MarchSlots st;
     };
     OC_HD G0 r0(const Ctx& c) const { return G0{reinterpret_cast<FT*>(c.smem + OFF_R0), c.k, c.st.sk[0]}; }
     OC_HD G1 r1(const Ctx& c) const { return G1{reinterpret_cast<FT*>(c.smem + OFF_R1), c.k, c.st.sk[1]}; }
     OC_HD G2 r2(const Ctx& c) const { return G2{reinterpret_cast<FT*>(c.smem + OFF_R2), c.k, c.st.sk[2]}; }
     OC_HD G3 r3(const Ctx& c) const { return G3{reinterpret_cast<FT*>(c.smem + OFF_R3), c.k, c.st.sk[3]}; }
-    OC_HD Ctx raw(char* smem) const { return Ctx{smem, 0, MarchState{{0, 0, 0, 0}}}; }
+    OC_HD Ctx raw(char* smem) const { return Ctx{smem, 0, MarchSlots{{0, 0, 0, 0}}}; }
 
     // ---- loads -----------------------------------------------------------------------------------------------
     template <class G, class RS>
@@ -434,11 +444,14 @@ struct MarchKernel {
         if (tid == 0) {
             uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
             for (int n = 0; n < MARCH_NBAR; ++n) mbar_init(bar + n, 1);
+            for (int n = 0; n < MARCH_NSYNC; ++n) mbar_init(bar + MARCH_NBAR + n, THREADS);
             mbar_fence_init();
         }
     }
-    typedef MarchState State;
-    OC_DEV void begin1(const Block& b, int tid, char* smem, MarchState& st) const {
+    typedef MarchStateT<FT> State;
+    OC_DEV void begin1(const Block& b, int tid, char* smem, State& stt) const {
+        MarchSlots& st = stt.sl;
+        stt.fz_prev = FT(0); stt.dfz = FT(0);
         {   // ring slots of the first level (kf = k_begin - 1)
             const int kf0 = k_begin(b) - 1;
             st.sk[0] = G0::slot_of(kf0); st.sk[1] = G1::slot_of(kf0); st.sk[2] = G2::slot_of(kf0); st.sk[3] = G3::slot_of(kf0);
@@ -585,69 +598,88 @@ struct MarchKernel {
         return F;
     }
 
-    // ---- one level ---------------------------------------------------------------------------------------------------
+    // ---- one level, software-pipelined ----------------------------------------------------------------------------------
+    // The marching loop (oc_exec.h: march_entry) runs, for it = 0 … n:
+    //     step<0>(it)   wait for the TMA data of level k(it); x- and y-face fluxes of the level -> stage it % 4
+    //     -- wait until every thread has ARRIVED for iteration it-1 (split mbarrier: nobody blocks at the arrive) --
+    //     step<1>(it)   thread 0 issues the loads of iteration it+2; divergence / substep / stores of level k(it-1)
+    //     step<2>(it)   upper z-face flux of level k(it) (kept in registers: the same thread owns the cell above and below)
+    //     -- arrive for iteration it --
+    // so a warp only stalls when another warp is a whole level behind.  Hazards: flux stage it % 4 is rewritten in
+    // step<0>(it+4), which is only reached after the wait for iteration it+2, i.e. after every thread finished
+    // step<1>(it+1) (the last reader).  Ring slots: the loads issued in step<1>(it) overwrite levels that were last read in
+    // iteration it-1 (see MarchSpec), whose arrivals have all been observed.
+    OC_HD uint64_t* sync_bar(char* smem, int it) const { return reinterpret_cast<uint64_t*>(smem + OFF_BAR) + MARCH_NBAR + (it % MARCH_NSYNC); }
+    OC_HD static int sync_parity(int it) { return (it / MARCH_NSYNC) & 1; }
+
+    OC_DEV void sync_wait(char* smem, int it) const { mbar_wait(sync_bar(smem, it), sync_parity(it)); }
+    OC_DEV void sync_arrive(char* smem, int it) const { mbar_arrive(sync_bar(smem, it)); }
+
     template <int PHASE>
-    OC_DEV void step(const Block& b, int tid, char* smem_raw, int it, MarchState& st) const {
+    OC_DEV void step(const Block& b, int tid, char* smem, int it, State& stt) const {
         const Geom<FT>& g = a.g;
-        char* smem = smem_raw;
         const int i0 = b.x * TX, j0 = b.y * TY;
+        const int nit = iterations(b);
         const int k = k_begin(b) - 1 + it;                   // level of this iteration (it = 0: z-flux only)
-        const Ctx cx{smem_raw, k, st};
+        const Ctx cx{smem, k, stt.sl};
         constexpr int shx = COMP == 0 ? -1 : 0, shy = COMP == 1 ? -1 : 0, shz = COMP == 2 ? -1 : 0;
-        FT* fx = reinterpret_cast<FT*>(smem + OFF_FX) + (it & 1) * NFXP;
-        FT* fy = reinterpret_cast<FT*>(smem + OFF_FY) + (it & 1) * NFYP;
-        FT* fzs = reinterpret_cast<FT*>(smem + OFF_FZ);
-        FT* fz_up = fzs + (it % 3) * NFZ;
-        const FT* fz_lo = fzs + ((it + 2) % 3) * NFZ;
         uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
         const int lane = tid & (TX - 1), row = tid / TX;     // row = 0 … TY
         if (PHASE == 0) {
+            if (it >= nit) return;
             mbar_wait(bar + (it % MARCH_NBAR), (it / MARCH_NBAR) & 1);
-            if (it > 0) {
-                {   // y-face (lane, row).  CLO == 0: every operand is in shared memory, so out-of-range faces of partial
-                    // tiles are evaluated too (on zero-filled / neighbouring data) and discarded — no divergent branch
-                    const bool ok = i0 + lane < g.N[0] && j0 + row <= g.N[1];
-                    FT F = FT(0);
-                    if (CLO == 0 || ok) F = total_flux<1>(cx, lane, row + shy, i0 + lane, j0 + row + shy, k);
-                    fy[row * TX + lane] = ok ? F : FT(0);
-                }
-                // x-faces: rows 0 … TY-1 take faces s = 0 … TX-1; the last warp takes the TY faces s = TX
-                const int s = row < TY ? lane : TX, jj = row < TY ? row : lane;
-                if (row < TY || lane < TY) {
-                    const bool ok = j0 + jj < g.N[1] && i0 + s <= g.N[0];
-                    FT F = FT(0);
-                    if (CLO == 0 || ok) F = total_flux<0>(cx, s + shx, jj, i0 + s + shx, j0 + jj, k);
-                    fx[jj * (TX + 1) + s] = ok ? F : FT(0);
-                }
+            if (it == 0) return;
+            FT* fx = reinterpret_cast<FT*>(smem + OFF_FX) + (it % MARCH_NSYNC) * NFXP;
+            FT* fy = reinterpret_cast<FT*>(smem + OFF_FY) + (it % MARCH_NSYNC) * NFYP;
+            {   // y-face (lane, row).  CLO == 0: every operand is in shared memory, so out-of-range faces of partial
+                // tiles are evaluated too (on zero-filled / neighbouring data) and discarded — no divergent branch
+                const bool ok = i0 + lane < g.N[0] && j0 + row <= g.N[1];
+                FT F = FT(0);
+                if (CLO == 0 || ok) F = total_flux<1>(cx, lane, row + shy, i0 + lane, j0 + row + shy, k);
+                fy[row * TX + lane] = (CLO == 0 || ok) ? F : FT(0);     // faces outside the grid are never consumed
             }
+            // x-faces: rows 0 … TY-1 take faces s = 0 … TX-1; the last warp takes the TY faces s = TX
+            const int s = row < TY ? lane : TX, jj = row < TY ? row : lane;
+            if (row < TY || lane < TY) {
+                const bool ok = j0 + jj < g.N[1] && i0 + s <= g.N[0];
+                FT F = FT(0);
+                if (CLO == 0 || ok) F = total_flux<0>(cx, s + shx, jj, i0 + s + shx, j0 + jj, k);
+                fx[jj * (TX + 1) + s] = (CLO == 0 || ok) ? F : FT(0);
+            }
+        } else if (PHASE == 2) {
+            if (it >= nit) return;
             if (row < TY) {   // upper z-face of cell (lane, row)
                 const bool ok = i0 + lane < g.N[0] && j0 + row < g.N[1] && k + 1 <= g.N[2];
                 FT F = FT(0);
                 if (CLO == 0 || ok) F = total_flux<2>(cx, lane, row, i0 + lane, j0 + row, k + 1 + shz);
-                fz_up[row * TX + lane] = ok ? F : FT(0);
+                F = (CLO == 0 || ok) ? F : FT(0);
+                stt.dfz = F - stt.fz_prev;
+                stt.fz_prev = F;
             }
+            // advance the ring slots to the next level
+            stt.sl.sk[0] = G0::next_slot(stt.sl.sk[0]); stt.sl.sk[1] = G1::next_slot(stt.sl.sk[1]);
+            stt.sl.sk[2] = G2::next_slot(stt.sl.sk[2]); stt.sl.sk[3] = G3::next_slot(stt.sl.sk[3]);
         } else {
-            // advance the ring slots for the next level (cx keeps this level's)
-            st.sk[0] = G0::next_slot(st.sk[0]); st.sk[1] = G1::next_slot(st.sk[1]);
-            st.sk[2] = G2::next_slot(st.sk[2]); st.sk[3] = G3::next_slot(st.sk[3]);
-            // loads three levels ahead: the slots they overwrite were last read before the __syncthreads above
             if (tid == 0) {
-                const int nit = it + MARCH_PF;
-                if (nit < iterations(b)) {
+                const int lit = it + MARCH_PF;
+                if (lit < nit) {
                     proxy_fence_async();
-                    mbar_expect(bar + (nit % MARCH_NBAR), LEVEL_BYTES);
-                    issue_iteration(smem, i0, j0, k + MARCH_PF, bar + (nit % MARCH_NBAR));
+                    mbar_expect(bar + (lit % MARCH_NBAR), LEVEL_BYTES);
+                    issue_iteration(smem, i0, j0, k + MARCH_PF, bar + (lit % MARCH_NBAR));
                 }
             }
-            if (it == 0 || row >= TY) return;
-            const int ii = lane, jj = row, n = row * TX + lane;
+            if (it < 2 || row >= TY) return;                 // levels start at iteration 1; their divergence is formed one iteration later
+            const int kc = k - 1;                            // the level being finished
+            const FT* fx = reinterpret_cast<const FT*>(smem + OFF_FX) + ((it - 1) % MARCH_NSYNC) * NFXP;
+            const FT* fy = reinterpret_cast<const FT*>(smem + OFF_FY) + ((it - 1) % MARCH_NSYNC) * NFYP;
+            const int ii = lane, jj = row;
             const int i = i0 + ii, j = j0 + jj;
             if (i >= g.N[0] || j >= g.N[1]) return;
-            const int o = g.idx(i, j, k);
-            const FT u0 = r0(cx)(ii, jj, k);
+            const int o = g.idx(i, j, kc);
+            const FT u0 = r0(cx)(ii, jj, kc);
             if (WIN && COMP >= 0) {
                 // exclude_periphery: the wall face of a wall-normal velocity is not stepped (kernel_launching.jl:145-146)
-                const int ic = COMP == 0 ? i : (COMP == 1 ? j : k);
+                const int ic = COMP == 0 ? i : (COMP == 1 ? j : kc);
                 if (g.bounded[COMP < 0 ? 0 : COMP] && ic == 0 && g.N[COMP < 0 ? 0 : COMP] > 1) {
                     if (a.mode != STEP_NONE) a.Unew[o] = u0;
                     return;
@@ -655,14 +687,14 @@ struct MarchKernel {
             }
             const FT dFx = fx[jj * (TX + 1) + ii + 1] - fx[jj * (TX + 1) + ii];
             const FT dFy = fy[(jj + 1) * TX + ii] - fy[jj * TX + ii];
-            const FT dFz = fz_up[n] - fz_lo[n];
+            const FT dFz = stt.dfz;
             FT G = -(g.rV * (dFx + dFy + dFz));
             if ((KIND == KIND_U || KIND == KIND_V) && a.has_coriolis) {
                 // FPlane (f_plane.jl:50-52); the other horizontal component is ring 1
                 G1 q = r1(cx);
                 FT num, cnt = FT(1);
                 if (KIND == KIND_U) {
-                    num = FT(0.5) * (FT(0.5) * (q(ii - 1, jj, k) + q(ii, jj, k)) + FT(0.5) * (q(ii - 1, jj + 1, k) + q(ii, jj + 1, k)));
+                    num = FT(0.5) * (FT(0.5) * (q(ii - 1, jj, kc) + q(ii, jj, kc)) + FT(0.5) * (q(ii - 1, jj + 1, kc) + q(ii, jj + 1, kc)));
                     if (WIN) {
                         int ax0 = !(g.bounded[0] && (i - 1 < 0)), ax1 = 1;
                         int ay0 = !(g.bounded[1] && (j < 1)), ay1 = !(g.bounded[1] && (j + 1 > g.N[1] - 1));
@@ -671,7 +703,7 @@ struct MarchKernel {
                     FT val = cnt == FT(0) ? FT(0) : num / cnt;
                     G = G - (-a.f * val);
                 } else {
-                    num = FT(0.5) * (FT(0.5) * (q(ii, jj - 1, k) + q(ii + 1, jj - 1, k)) + FT(0.5) * (q(ii, jj, k) + q(ii + 1, jj, k)));
+                    num = FT(0.5) * (FT(0.5) * (q(ii, jj - 1, kc) + q(ii + 1, jj - 1, kc)) + FT(0.5) * (q(ii, jj, kc) + q(ii + 1, jj, kc)));
                     if (WIN) {
                         int ax0 = !(g.bounded[0] && (i < 1)), ax1 = !(g.bounded[0] && (i + 1 > g.N[0] - 1));
                         int ay0 = !(g.bounded[1] && (j - 1 < 0)), ay1 = 1;
@@ -682,11 +714,11 @@ struct MarchKernel {
                 }
             }
             if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) {
-                const int s = KIND == KIND_U ? 1 : g.sy;
-                G = G - (a.pHY[o] - a.pHY[o - s]) * g.rd[KIND == KIND_U ? 0 : 1];
+                const int sp = KIND == KIND_U ? 1 : g.sy;
+                G = G - (a.pHY[o] - a.pHY[o - sp]) * g.rd[KIND == KIND_U ? 0 : 1];
             }
             if (WIN && a.add_flux_bcs) {
-                const int ijk[3] = {i, j, k};
+                const int ijk[3] = {i, j, kc};
                 for (int d = 0; d < 3; ++d) {
                     if (a.fbc.on[2 * d] && ijk[d] == 0) G = G + a.fbc.val[2 * d] * g.A[d] / g.V;
                     if (a.fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) G = G - a.fbc.val[2 * d + 1] * g.A[d] / g.V;
