@@ -1,0 +1,224 @@
+# OceananigansB200Ext.jl — Julia glue between Oceananigans.jl (v0.100.5) and liboceananigans_b200.so.
+#
+# STATUS: written against the reference sources under /root/reference but NOT executed — the build image has no `julia`
+# binary (SURVEY.md §0).  The Python host layer (oldoceananigans.jl_b200/api.py) implements the same mapping and is what the
+# test-suite runs.  Every `ccall` below binds one symbol of include/oceananigans_b200.h; the struct layouts mirror that header
+# field by field (checked for the Python twin by tests/test_cabi.py::test_struct_layouts_match_header).
+#
+# Design: `B200 <: AbstractSerialArchitecture` keeps a HOST mirror of every field (plain `Array`s, so every host-side feature of
+# Oceananigans — output writers, diagnostics, checkpointer, `interior(field)` — keeps working unchanged) and a DEVICE twin of the
+# model that owns the state between `fetch!` calls.  The methods the time-stepper calls are overloaded for models on `B200`, so
+# no KernelAbstractions kernel is ever launched for them (cf. ext/OceananigansCUDAExt.jl:37-138, which plays the same role for
+# CUDA.jl).  There is no fallback: an unsupported configuration throws at model construction.
+module OceananigansB200Ext
+
+using Oceananigans
+using Oceananigans.Architectures: AbstractSerialArchitecture
+using Oceananigans.Grids: RectilinearGrid, Periodic, Bounded, Flat, topology, halo_size
+using Oceananigans.Fields: interior
+using Oceananigans.TimeSteppers: RungeKutta3TimeStepper, QuasiAdamsBashforth2TimeStepper
+using Oceananigans.Models.NonhydrostaticModels: NonhydrostaticModel
+using Oceananigans.Advection: Centered, WENO
+using Oceananigans.TurbulenceClosures: ScalarDiffusivity, AnisotropicMinimumDissipation
+using Oceananigans.BuoyancyFormulations: SeawaterBuoyancy, BuoyancyTracer, LinearEquationOfState, BuoyancyForce
+using Oceananigans.Coriolis: FPlane
+using Oceananigans.BoundaryConditions: BoundaryCondition, Flux, Value, Gradient, Open, Periodic as PeriodicBC
+
+import Oceananigans.Architectures as AC
+import Oceananigans.TimeSteppers: time_step!, update_state!
+import Oceananigans.Fields: set!
+
+const LIB = get(ENV, "OCEANANIGANS_B200_LIB", "liboceananigans_b200.so")
+
+# ---- architecture ----------------------------------------------------------------------------------------------------------
+"`B200(device=0)`: the B200-native architecture.  Host arrays are `Array`s (the mirror); the device twin lives in the library."
+struct B200 <: AbstractSerialArchitecture
+    device::Int32
+end
+B200() = B200(0)
+AC.array_type(::B200) = Array                       # src/Architectures.jl:59-66
+AC.architecture(::B200) = B200()
+AC.on_architecture(::B200, a::Array) = a            # ext/OceananigansCUDAExt.jl:66-76
+AC.on_architecture(::B200, a::Number) = a
+AC.device!(a::B200, i) = nothing
+Base.summary(::B200) = "B200"
+
+# ---- C structs (include/oceananigans_b200.h) -----------------------------------------------------------------------------------
+const OC_MAX_TRACERS = 8
+const OC_MAX_FIELDS = 3 + OC_MAX_TRACERS
+
+struct OcBC
+    kind::Int32; has_value::Int32; value::Float64
+end
+
+mutable struct OcConfig               # `oc_config`, same field order; NTuple for C arrays
+    abi_version::Int32; float_type::Int32
+    N::NTuple{3,Int32}; H::NTuple{3,Int32}; topology::NTuple{3,Int32}
+    delta::NTuple{3,Float64}; extent::NTuple{3,Float64}
+    advection::Int32; timestepper::Int32; ab2_chi::Float64
+    n_tracers::Int32
+    has_scalar_diffusivity::Int32; nu::Float64; kappa::NTuple{OC_MAX_TRACERS,Float64}
+    has_amd::Int32; amd_Cnu::Float64; amd_Ckappa::NTuple{OC_MAX_TRACERS,Float64}
+    buoyancy::Int32; gravity::Float64; thermal_expansion::Float64; haline_contraction::Float64
+    tracer_T::Int32; tracer_S::Int32; tracer_b::Int32
+    has_coriolis::Int32; coriolis_f::Float64
+    bcs::NTuple{OC_MAX_FIELDS,NTuple{6,OcBC}}
+    device::Int32; reserved::NTuple{7,Int32}
+    OcConfig() = new()
+end
+
+struct OcClock
+    time::Float64; iteration::Int64; stage::Int32; last_dt::Float64; last_stage_dt::Float64
+end
+
+check(status) = status == 0 || error("liboceananigans_b200: ", unsafe_string(ccall((:oc_last_error, LIB), Cstring, ())))
+
+# ---- the device twin ----------------------------------------------------------------------------------------------------------
+mutable struct DeviceModel
+    handle::Ptr{Cvoid}
+    function DeviceModel(cfg::OcConfig)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:oc_model_create, LIB), Cint, (Ref{OcConfig}, Ref{Ptr{Cvoid}}), cfg, h))     # oc_model_create
+        dm = new(h[])
+        finalizer(d -> ccall((:oc_model_destroy, LIB), Cint, (Ptr{Cvoid},), d.handle), dm)       # oc_model_destroy
+        return dm
+    end
+end
+
+const TWINS = WeakKeyDict{Any,DeviceModel}()
+
+topo_code(::Type{Periodic}) = Int32(0); topo_code(::Type{Bounded}) = Int32(1); topo_code(::Type{Flat}) = Int32(2)
+
+bc_record(bc::BoundaryCondition{<:Flux, Nothing}) = OcBC(2, 0, 0.0)
+bc_record(bc::BoundaryCondition{<:Flux, <:Number}) = OcBC(2, 1, bc.condition)
+bc_record(bc::BoundaryCondition{<:Value, <:Number}) = OcBC(3, 1, bc.condition)
+bc_record(bc::BoundaryCondition{<:Gradient, <:Number}) = OcBC(4, 1, bc.condition)
+bc_record(bc::BoundaryCondition{<:Open, Nothing}) = OcBC(5, 0, 0.0)
+bc_record(bc::BoundaryCondition{<:PeriodicBC}) = OcBC(1, 0, 0.0)
+bc_record(::Nothing) = OcBC(6, 0, 0.0)
+bc_record(bc) = throw(ArgumentError("B200: boundary condition $bc is out of scope (functions / arrays / mixed)"))
+
+"Translate `NonhydrostaticModel(; grid, advection, closure, tracers, buoyancy, coriolis, timestepper)` into `oc_config`."
+function config(model::NonhydrostaticModel)
+    grid = model.grid
+    grid isa RectilinearGrid || throw(ArgumentError("B200: only RectilinearGrid"))
+    FT = eltype(grid)
+    cfg = OcConfig()
+    ccall((:oc_config_init, LIB), Cvoid, (Ref{OcConfig},), cfg)                                   # oc_config_init
+    cfg.float_type = FT == Float64 ? 0 : 1
+    TX, TY, TZ = topology(grid)
+    cfg.topology = (topo_code(TX), topo_code(TY), topo_code(TZ))
+    cfg.N = Int32.((grid.Nx, grid.Ny, grid.Nz)); cfg.H = Int32.(halo_size(grid))
+    grid.Δxᶜᵃᵃ isa Number && grid.Δyᵃᶜᵃ isa Number && grid.z.Δᵃᵃᶜ isa Number ||
+        throw(ArgumentError("B200: stretched grids are out of scope (FourierTridiagonalPoissonSolver path)"))
+    cfg.delta = Float64.((grid.Δxᶜᵃᵃ, grid.Δyᵃᶜᵃ, grid.z.Δᵃᵃᶜ)); cfg.extent = Float64.((grid.Lx, grid.Ly, grid.Lz))
+    adv = model.advection.momentum
+    cfg.advection = adv isa Centered && Oceananigans.Advection.required_halo_size_x(adv) == 1 ? 0 :
+                    adv isa WENO && Oceananigans.Advection.required_halo_size_x(adv) == 3 ? 1 :
+                    throw(ArgumentError("B200: advection must be Centered(order=2) or WENO(order=5)"))
+    cfg.timestepper = model.timestepper isa RungeKutta3TimeStepper ? 0 :
+                      model.timestepper isa QuasiAdamsBashforth2TimeStepper ? 1 : throw(ArgumentError("B200: unsupported time stepper"))
+    model.timestepper isa QuasiAdamsBashforth2TimeStepper && (cfg.ab2_chi = model.timestepper.χ)
+    names = keys(model.tracers); cfg.n_tracers = length(names)
+    closures = model.closure isa Tuple ? model.closure : (model.closure,)
+    for c in closures
+        c === nothing && continue
+        if c isa ScalarDiffusivity
+            cfg.has_scalar_diffusivity = 1; cfg.nu = c.ν
+            cfg.kappa = ntuple(t -> t <= length(names) ? Float64(c.κ[t]) : 0.0, OC_MAX_TRACERS)
+        elseif c isa AnisotropicMinimumDissipation
+            c.Cb === nothing || throw(ArgumentError("B200: AMD buoyancy modification is out of scope"))
+            cfg.has_amd = 1; cfg.amd_Cnu = c.Cν
+            cfg.amd_Ckappa = ntuple(t -> t <= length(names) ? Float64(c.Cκ[t]) : 0.0, OC_MAX_TRACERS)
+        else
+            throw(ArgumentError("B200: closure $(summary(c)) is out of scope"))
+        end
+    end
+    b = model.buoyancy isa BuoyancyForce ? model.buoyancy.formulation : model.buoyancy
+    if b isa SeawaterBuoyancy
+        eos = b.equation_of_state; eos isa LinearEquationOfState || throw(ArgumentError("B200: only LinearEquationOfState"))
+        cfg.buoyancy = 2; cfg.gravity = b.gravitational_acceleration
+        cfg.thermal_expansion = eos.thermal_expansion; cfg.haline_contraction = eos.haline_contraction
+        cfg.tracer_T = findfirst(==(:T), names) - 1; cfg.tracer_S = findfirst(==(:S), names) - 1
+    elseif b isa BuoyancyTracer
+        cfg.buoyancy = 1; cfg.tracer_b = findfirst(==(:b), names) - 1
+    elseif b !== nothing
+        throw(ArgumentError("B200: unsupported buoyancy formulation"))
+    end
+    if model.coriolis isa FPlane
+        cfg.has_coriolis = 1; cfg.coriolis_f = model.coriolis.f
+    elseif model.coriolis !== nothing
+        throw(ArgumentError("B200: only FPlane"))
+    end
+    fields = (model.velocities..., model.tracers...)
+    cfg.bcs = ntuple(OC_MAX_FIELDS) do f
+        f > length(fields) && return ntuple(_ -> OcBC(0, 0, 0.0), 6)
+        bcs = fields[f].boundary_conditions
+        map(bc_record, (bcs.west, bcs.east, bcs.south, bcs.north, bcs.bottom, bcs.top))
+    end
+    cfg.device = AC.architecture(grid).device
+    return cfg
+end
+
+twin(model) = get!(() -> DeviceModel(config(model)), TWINS, model)
+
+prognostic(model) = (model.velocities..., model.tracers...)
+
+"Host mirror -> device (set!(u::Field, a::Array), src/Fields/set!.jl:101-121)."
+function push!(model)
+    dm = twin(model)
+    for (f, field) in enumerate(prognostic(model))
+        a = Array(interior(field))
+        GC.@preserve a check(ccall((:oc_upload_interior, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t), dm.handle, f - 1, a, sizeof(a)))
+    end
+end
+
+"Device -> host mirror: prognostic fields (parent arrays, halos included), pNHS, and the clock."
+function fetch!(model)
+    dm = twin(model)
+    ids = (collect(0:length(prognostic(model))-1)..., 32)
+    for (id, field) in zip(ids, (prognostic(model)..., model.pressures.pNHS))
+        p = parent(field)
+        GC.@preserve p check(ccall((:oc_download_parent, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t), dm.handle, id, p, sizeof(p)))
+    end
+    clk = Ref{OcClock}()
+    check(ccall((:oc_get_clock, LIB), Cint, (Ptr{Cvoid}, Ref{OcClock}), dm.handle, clk))
+    c = model.clock
+    c.time = clk[].time; c.iteration = clk[].iteration; c.stage = clk[].stage; c.last_Δt = clk[].last_dt; c.last_stage_Δt = clk[].last_stage_dt
+    return nothing
+end
+
+const B200Model = NonhydrostaticModel{<:Any, <:Any, <:B200}
+
+# set!(model; u=…, v=…, T=…)  src/Models/NonhydrostaticModels/set_nonhydrostatic_model.jl:33-60
+function set!(model::B200Model; enforce_incompressibility=true, kwargs...)
+    for (name, value) in kwargs
+        set!(getproperty(name in keys(model.velocities) ? model.velocities : model.tracers, name), value)   # host mirror (CPU path of set!)
+    end
+    push!(model)
+    check(ccall((:oc_set_finalize, LIB), Cint, (Ptr{Cvoid}, Cint), twin(model).handle, enforce_incompressibility))
+    fetch!(model)
+    return nothing
+end
+
+# time_step!(model, Δt)  src/TimeSteppers/runge_kutta_3.jl:93, quasi_adams_bashforth_2.jl:74
+function time_step!(model::NonhydrostaticModel{<:RungeKutta3TimeStepper, <:Any, <:B200}, Δt; callbacks=[])
+    isempty(callbacks) || throw(ArgumentError("B200: mid-step callbacks need the staged entry points (oc_update_state, …)"))
+    check(ccall((:oc_time_step_rk3, LIB), Cint, (Ptr{Cvoid}, Cdouble), twin(model).handle, Δt))
+    clk = Ref{OcClock}(); check(ccall((:oc_get_clock, LIB), Cint, (Ptr{Cvoid}, Ref{OcClock}), twin(model).handle, clk))
+    model.clock.time = clk[].time; model.clock.iteration = clk[].iteration; model.clock.last_Δt = clk[].last_dt
+    return nothing
+end
+function time_step!(model::NonhydrostaticModel{<:QuasiAdamsBashforth2TimeStepper, <:Any, <:B200}, Δt; callbacks=[], euler=false)
+    isempty(callbacks) || throw(ArgumentError("B200: mid-step callbacks need the staged entry points"))
+    check(ccall((:oc_time_step_ab2, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cint), twin(model).handle, Δt, euler))
+    clk = Ref{OcClock}(); check(ccall((:oc_get_clock, LIB), Cint, (Ptr{Cvoid}, Ref{OcClock}), twin(model).handle, clk))
+    model.clock.time = clk[].time; model.clock.iteration = clk[].iteration; model.clock.last_Δt = clk[].last_dt
+    return nothing
+end
+
+# update_state!(model, callbacks; compute_tendencies)  update_nonhydrostatic_model_state.jl:20
+update_state!(model::B200Model, callbacks=[]; compute_tendencies=true) =
+    check(ccall((:oc_update_state, LIB), Cint, (Ptr{Cvoid}, Cint), twin(model).handle, compute_tendencies))
+
+end # module

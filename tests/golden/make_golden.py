@@ -1,0 +1,56 @@
+"""Generates tests/golden/*.npz from the CPU oracle (oracle/), the restatement of the reference algorithm.
+
+    python tests/golden/make_golden.py
+
+The Julia reference cannot run in the build image (no julia binary) and its own regression files are downloaded at
+test time (test/data_dependencies.jl:17-38), so these vectors freeze the ORACLE's output: they guard the oracle against
+drift (tests/test_golden.py, CPU) and give the CUDA path (-m gpu) and the host simulation a fixed target.
+Each file holds the seeded initial condition (after set!'s projection) and u, v, w, p, tracers after 1 and 3 steps.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GOLDEN_CASES = {
+    "ppp_weno_ts_f64": dict(N=(12, 10, 8), topo="PPP", scheme="weno"),
+    "ppb_weno_amd_fplane_bcs_f64": dict(N=(12, 10, 8), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True),
+    "ppp_centered_f64": dict(N=(12, 10, 8), topo="PPP", scheme="centered", closure="none", buoy="none"),
+    "ppf_weno_2d_f64": dict(N=(12, 10, 1), topo="PPF", scheme="weno", closure="none", buoy="none"),
+    "ppb_weno_ab2_f64": dict(N=(12, 10, 8), topo="PPB", scheme="weno", ts="QuasiAdamsBashforth2"),
+    "ppp_weno_ts_f32": dict(N=(12, 10, 8), topo="PPP", scheme="weno", FT=np.float32),
+}
+STEPS = (1, 3)
+
+
+
+
+def main():
+    import oracle
+    from oracle import advection as adv, closures as clo
+    import parity_harness as ph
+    for name, kw in GOLDEN_CASES.items():
+        om = ph.build_oracle(**kw)
+        ic = ph.initial_conditions(om)
+        om.set(**ic)
+        dt = 0.1 * float(min(om.grid.D[d] for d in range(3) if not om.grid.flat(d)))
+        out = {"dt": np.float64(dt)}
+        for n, a in ic.items():
+            out["ic_" + n] = a
+        for s in range(1, max(STEPS) + 1):
+            om.time_step(dt)
+            if s in STEPS:
+                for n in om.fields:
+                    out[f"s{s}_{n}"] = om.fields[n].interior.copy()
+                out[f"s{s}_p"] = om.pNHS.interior.copy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print("wrote", name, {k: v.shape for k, v in out.items() if k.startswith("s1_")})
+
+
+if __name__ == "__main__":
+    main()

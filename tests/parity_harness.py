@@ -18,36 +18,52 @@ EXTENT = (1.0, 1.5, 2.0)
 TOL = {np.float64: 1e-11, np.float32: 1e-4}
 
 
-def build_pair(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
-               bcs=False, library=None, extent=EXTENT):
+def _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent):
     nonflat = [d for d in range(3) if topo[d] != "F"]
     size = tuple(N[d] for d in nonflat)
     ext = tuple(extent[d] for d in nonflat)
-    grid = ob.RectilinearGrid(FT, size=size, extent=ext, topology=tuple(TOPO[c] for c in topo))
-    a = ob.Centered() if scheme == "centered" else ob.WENO()
     tr = ("T", "S") if buoy == "seawater" else (("b",) if buoy == "tracer" else (("c",) if buoy == "passive" else ()))
-    bo = ob.SeawaterBuoyancy() if buoy == "seawater" else (ob.BuoyancyTracer() if buoy == "tracer" else None)
+    return size, ext, tr
+
+
+def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
+                 bcs=False, extent=EXTENT, **_):
+    size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
     obo = clo.SeawaterBuoyancy() if buoy == "seawater" else (clo.BuoyancyTracer() if buoy == "tracer" else None)
-    cl = {"scalar": ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), "amd": ob.AnisotropicMinimumDissipation(), "none": None,
-          "both": (ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), ob.AnisotropicMinimumDissipation())}[closure]
     ocl = {"scalar": clo.ScalarDiffusivity(1e-3, 2e-3), "amd": clo.AnisotropicMinimumDissipation(), "none": None,
            "both": (clo.ScalarDiffusivity(1e-3, 2e-3), clo.AnisotropicMinimumDissipation())}[closure]
-    bc_b = bc_o = None
+    bc_o = None
+    if bcs:
+        t0 = tr[0]
+        bc_o = {"u": {"top": BC("flux", -2e-3)}, t0: {"top": BC("flux", 5e-3), "bottom": BC("gradient", 0.05)},
+                "v": {"bottom": BC("value", 0.1)}}
+    og = oracle.Grid(FT, size=size, extent=ext, topology=tuple(topo))
+    oa = adv.Centered(FT, 2) if scheme == "centered" else adv.WENO(FT, 5)
+    return oracle.OracleModel(og, advection=oa, tracers=tr, buoyancy=obo, closure=ocl, timestepper=ts, coriolis_f=f,
+                              boundary_conditions=bc_o)
+
+
+def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
+                  bcs=False, library=None, extent=EXTENT):
+    size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
+    grid = ob.RectilinearGrid(FT, size=size, extent=ext, topology=tuple(TOPO[c] for c in topo))
+    a = ob.Centered() if scheme == "centered" else ob.WENO()
+    bo = ob.SeawaterBuoyancy() if buoy == "seawater" else (ob.BuoyancyTracer() if buoy == "tracer" else None)
+    cl = {"scalar": ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), "amd": ob.AnisotropicMinimumDissipation(), "none": None,
+          "both": (ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), ob.AnisotropicMinimumDissipation())}[closure]
+    bc_b = None
     if bcs:
         # the BC kinds of test/regression_tests/ocean_large_eddy_simulation_regression_test.jl:19-37
         t0 = tr[0]
         bc_b = {"u": ob.FieldBoundaryConditions(top=ob.FluxBoundaryCondition(-2e-3)),
                 t0: ob.FieldBoundaryConditions(top=ob.FluxBoundaryCondition(5e-3), bottom=ob.GradientBoundaryCondition(0.05)),
                 "v": ob.FieldBoundaryConditions(bottom=ob.ValueBoundaryCondition(0.1))}
-        bc_o = {"u": {"top": BC("flux", -2e-3)}, t0: {"top": BC("flux", 5e-3), "bottom": BC("gradient", 0.05)},
-                "v": {"bottom": BC("value", 0.1)}}
-    m = ob.NonhydrostaticModel(grid=grid, advection=a, tracers=tr, buoyancy=bo, closure=cl, timestepper=ts,
-                               coriolis=ob.FPlane(f=f) if f else None, boundary_conditions=bc_b, library=library)
-    og = oracle.Grid(FT, size=size, extent=ext, topology=tuple(topo))
-    oa = adv.Centered(FT, 2) if scheme == "centered" else adv.WENO(FT, 5)
-    om = oracle.OracleModel(og, advection=oa, tracers=tr, buoyancy=obo, closure=ocl, timestepper=ts, coriolis_f=f,
-                            boundary_conditions=bc_o)
-    return m, om
+    return ob.NonhydrostaticModel(grid=grid, advection=a, tracers=tr, buoyancy=bo, closure=cl, timestepper=ts,
+                                  coriolis=ob.FPlane(f=f) if f else None, boundary_conditions=bc_b, library=library)
+
+
+def build_pair(library=None, **kw):
+    return build_product(library=library, **kw), build_oracle(**kw)
 
 
 def initial_conditions(om, seed=1234, smooth=False):

@@ -55,3 +55,27 @@ def test_out_of_scope_configurations_are_errors():
     g = ob.RectilinearGrid(np.float32, size=(4, 4, 4), extent=(1, 1, 1))
     assert g.H == (3, 3, 3) and g.FT is np.float32
     assert abs(g.dz - np.float32(0.25)) == 0
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every C-ABI struct, printed by a C program compiled against include/oceananigans_b200.h with gcc,
+    equal the ctypes (and therefore the Julia `struct`) layouts."""
+    import ctypes as C
+    import subprocess
+    from oceananigans_b200 import _lib
+    structs = {"oc_config": _lib.oc_config, "oc_field_info": _lib.oc_field_info, "oc_clock": _lib.oc_clock, "oc_bc": _lib.oc_bc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {']
+    for name, st in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for fname, _ in st._fields_:
+            lines.append(f'  printf("{name}.{fname} %zu\\n", offsetof({name}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for name, st in structs.items():
+        assert int(out[name]) == C.sizeof(st), name
+        for fname, _ in st._fields_:
+            assert int(out[f"{name}.{fname}"]) == getattr(st, fname).offset, (name, fname)

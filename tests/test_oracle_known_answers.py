@@ -368,3 +368,49 @@ def test_flux_bc_budget():
             m.time_step(dt)
         mean = m.tracers["c"].interior.mean()
         assert np.isclose(mean, sign * flux * m.clock.time / 0.75, rtol=1e-10)
+
+
+def test_weno_beta_conditioning():
+    """DESIGN.md §2 numerical note.  The reference's expanded smoothness indicators (weno_interpolants.jl:204-216) cancel
+    catastrophically for fields with a large mean (S ≈ 35 ± 0.01): evaluated in Float64 (the oracle does exactly that) one
+    reconstruction carries ~1e-11 relative round-off, while the algebraically identical difference form used by the CUDA
+    kernel (13/4 (second difference)² + 3/4 (one-sided difference)²) is accurate to ~1e-14.  This bounds how closely ANY two
+    Float64 evaluations of the reference formula can agree on T and S, and explains the ~1e-12 GPU–oracle gap there."""
+    from oracle import advection as adv
+    rng = np.random.default_rng(0)
+    n = 20000
+    S = [35 + 0.01 * rng.standard_normal(n) for _ in range(6)]
+    sch = adv.WENO(np.float64, 5)
+    val = adv._weno_value(sch, S, np.ones(n, bool))
+    L = np.longdouble
+    q = [s.astype(L) for s in S[:5]]
+
+    def beta(a, b, c, C):
+        return a * (C[0] * a + C[1] * b + C[2] * c) + b * (C[3] * b + C[4] * c) + c * c * C[5]
+
+    b0 = beta(q[2], q[3], q[4], (10, -31, 11, 25, -19, 4))
+    b1 = beta(q[1], q[2], q[3], (4, -13, 5, 13, -13, 4))
+    b2 = beta(q[0], q[1], q[2], (4, -19, 11, 25, -31, 10))
+    eps = L(np.float32(1e-8))
+    tau = abs(b0 - b2)
+    a = [L(3) / 10 * (1 + (tau / (b0 + eps)) ** 2), L(3) / 5 * (1 + (tau / (b1 + eps)) ** 2), L(1) / 10 * (1 + (tau / (b2 + eps)) ** 2)]
+    p0 = q[2] / 3 + q[3] * 5 / 6 - q[4] / 6
+    p1 = -q[1] / 6 + q[2] * 5 / 6 + q[3] / 3
+    p2 = q[0] / 3 - q[1] * 7 / 6 + q[2] * 11 / 6
+    truth = (a[0] * p0 + a[1] * p1 + a[2] * p2) / (a[0] + a[1] + a[2])
+    err_expanded = float(np.abs(val - truth).max() / 35)
+    # the kernel's arrangement (csrc/oc_march.h: weno5_value_c), in Float64
+    q = S[:5]
+    e1, e2, e3, e4 = q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3]
+    d0, d1, d2 = e4 - e3, e3 - e2, e2 - e1
+    g0, g1, g2 = e4 - 3 * e3, e2 + e3, 3 * e2 - e1
+    es = float(np.float32(1e-8)) * 4 / 3
+    B0, B1, B2 = 13 / 3 * d0 * d0 + g0 * g0 + es, 13 / 3 * d1 * d1 + g1 * g1 + es, 13 / 3 * d2 * d2 + g2 * g2 + es
+    t2 = (B0 - B2) ** 2
+    w0, w1, w2 = (B0 * B0 + t2) * (B1 * B2) ** 2, (B1 * B1 + t2) * (B0 * B2) ** 2, (B2 * B2 + t2) * (B0 * B1) ** 2
+    den = 6 * w2 + 36 * w1 + 18 * w0
+    num = w2 * (5 * e2 - 2 * e1) + w1 * (12 * e3 + 6 * e2) + w0 * (12 * e3 - 3 * e4)
+    mine = q[2] + num / den
+    err_diff = float(np.abs(mine - truth).max() / 35)
+    assert err_diff < 1e-13                 # the kernel's form is accurate
+    assert 1e-13 < err_expanded < 1e-9      # the reference's form loses ~5 digits more on such data
