@@ -126,19 +126,32 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- model construction
-def build_model(w, device, rank=0):
+def global_size(w, world):
+    """Weak scaling: 2^27 cells per GPU for the 512^3 workloads; 8 GPUs = BASELINE's 1024^3 (slab-decomposed in y)."""
+    if world == 1:
+        return tuple(w["N"])
+    if w["topo"] != "PPP" or w["N"] != (512, 512, 512):
+        raise SystemExit("multi-GPU runs: the triply periodic 512^3-per-GPU workloads (c3, c3f32)")
+    return {2: (1024, 512, 512), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}[world]
+
+
+def build_model(w, device, rank=0, world=1):
     import oceananigans_b200 as ob
     FT = np.float64 if w["FT"] == "f64" else np.float32
     topo = {"P": ob.Periodic, "B": ob.Bounded, "F": ob.Flat}
     nonflat = [d for d in range(3) if w["topo"][d] != "F"]
-    size = tuple(w["N"][d] for d in nonflat)
+    gsize = global_size(w, world)
+    size = tuple(gsize[d] for d in nonflat)
     if w is WORKLOADS["c4"] or w.get("closure") == "amd":
         extent = tuple(float(w["N"][d]) for d in nonflat)                      # Δ = 1 m (SURVEY §8d C4)
     elif w["topo"] == "PPF":
         extent = (2 * np.pi, 2 * np.pi)
     else:
         extent = tuple(1.0 for _ in nonflat)
-    grid = ob.RectilinearGrid(ob.B200(device), FT, size=size, extent=extent, topology=tuple(topo[c] for c in w["topo"]))
+    arch = ob.B200(device) if world == 1 else ob.Distributed(ob.B200(device), partition=ob.Partition(1, world), rank=rank, nranks=world)
+    if world > 1:
+        extent = tuple(gsize[d] / 512.0 for d in nonflat)          # same Δ as the single-GPU workload
+    grid = ob.RectilinearGrid(arch, FT, size=size, extent=extent, topology=tuple(topo[c] for c in w["topo"]))
     adv = ob.WENO() if w["adv"] == "weno" else ob.Centered()
     kw = dict(grid=grid, advection=adv, tracers=w["tracers"])
     if w["buoy"] == "seawater":
@@ -202,13 +215,14 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = WORKLOADS[args.workload]
-    ob, model = build_model(w, local, rank)
+    ob, model = build_model(w, local, rank, world)
     lib, h = model._lib, model._h
     ic = synthetic_ic(w, model, seed=1234 + rank)
     ob.set_(model, **ic)
     names = ("u", "v", "w") + tuple(w["tracers"])
     dt = default_dt(w)
-    cells = int(np.prod(w["N"]))
+    gsz = global_size(w, world)
+    cells = int(np.prod(gsz)) // world                      # cells per GPU
     itemsize = 8 if w["FT"] == "f64" else 4
 
     def barrier():
@@ -309,7 +323,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": w["FT"], "data": "synthetic (seeded rng 1234, SURVEY.md 8d)",
-        "config": {"workload": w["label"], "grid": list(w["N"]), "topology": w["topo"], "timestepper": "RungeKutta3", "dt": dt,
+        "config": {"workload": w["label"] if world == 1 else w["label"].replace("512^3", "x".join(map(str, gsz)) + " (slab-y over %d GPUs)" % world),
+                   "grid": list(gsz), "topology": w["topo"], "timestepper": "RungeKutta3", "dt": dt,
                    "cells_per_gpu": cells, "l2_policy": "working set (>25 GB at 512^3) far exceeds the 126 MB L2; no flush needed"
                    if cells >= 256 ** 3 else "working set may fit L2 (launch-latency configuration)"},
         "roofline": {"bound": "hbm", "kernel": "TendencyKernel (fused tendency + RK3 substep, one launch per prognostic field)",

@@ -74,7 +74,10 @@ typedef struct {
     int32_t has_coriolis; double coriolis_f;                                        /* FPlane(f) */
     oc_bc   bcs[OC_MAX_FIELDS][6];         /* per prognostic field × side */
     int32_t device;               /* CUDA device ordinal */
-    int32_t reserved[7];
+    /* Distributed(arch; partition = Partition(1, R)): slab decomposition in y (distributed_architectures.jl:242-302).
+     * N[1] is the LOCAL size, extent[1] the GLOBAL extent; dist_nranks <= 1 means a serial model. */
+    int32_t dist_rank, dist_nranks;
+    int32_t reserved[5];
 } oc_config;
 
 typedef struct oc_model oc_model;
@@ -139,10 +142,24 @@ int  oc_time_step_ab2(oc_model* m, double dt, int euler);
 int  oc_get_clock(oc_model* m, oc_clock* clock);
 int  oc_set_clock(oc_model* m, const oc_clock* clock);                 /* Checkpointer pickup: checkpointer.jl:202-228 */
 
+/* ---- multi-GPU: one process per GPU, slab decomposition in y ----
+ * Replaces Distributed(...) + fill_halo_regions! on distributed fields (src/DistributedComputations/halo_communication.jl:87-333)
+ * and DistributedFFTBasedPoissonSolver (distributed_fft_based_poisson_solver.jl:92-188).  Create the model with
+ * cfg.dist_rank / cfg.dist_nranks set, then attach a transport before the first halo fill:
+ *   oc_dist_unique_id   rank 0 makes the 128-byte NCCL id; the host layer broadcasts it (MPI.bcast / torch.distributed)
+ *   oc_dist_attach_nccl ncclCommInitRank inside the library; halo exchange and FFT transposes are grouped ncclSend/ncclRecv
+ *   oc_dist_attach_host TEST-ONLY (host simulation build): transfers go through a host callback so that the decomposition logic
+ *                       can be exercised by world_size-2 gloo tests on CPU; the CUDA library returns OC_ERR_UNSUPPORTED. */
+typedef int (*oc_exchange_fn)(void* user, int nmsg, const int* send_peers, const int* recv_peers, const int* tags,
+                              void* const* send_ptrs, const size_t* send_bytes, void* const* recv_ptrs, const size_t* recv_bytes);
+int  oc_dist_unique_id(void* id128);
+int  oc_dist_attach_nccl(oc_model* m, const void* id128);
+int  oc_dist_attach_host(oc_model* m, oc_exchange_fn fn, void* user);
+
 /* ---- measurement ---- */
 /* Per-kernel-class device timing with CUDA events on the model's stream.  Classes: */
 enum { OC_TIMER_TENDENCY = 0, OC_TIMER_HALO = 1, OC_TIMER_POISSON_RHS = 2, OC_TIMER_FFT = 3, OC_TIMER_POISSON_MID = 4,
-       OC_TIMER_PROJECTION = 5, OC_TIMER_AUX = 6, OC_TIMER_SUBSTEP = 7, OC_TIMER_COUNT = 8 };
+       OC_TIMER_PROJECTION = 5, OC_TIMER_AUX = 6, OC_TIMER_SUBSTEP = 7, OC_TIMER_COMM = 8, OC_TIMER_COUNT = 9 };
 int  oc_timers_enable(oc_model* m, int enable);
 int  oc_timers_reset(oc_model* m);
 int  oc_timers_get(oc_model* m, double* ms /*[OC_TIMER_COUNT]*/, int64_t* launches /*[OC_TIMER_COUNT]*/);

@@ -10,7 +10,7 @@ import os
 OC_ABI_VERSION = 1
 OC_MAX_TRACERS = 8
 OC_MAX_FIELDS = 3 + OC_MAX_TRACERS
-OC_TIMER_NAMES = ("tendency", "halo", "poisson_rhs", "fft", "poisson_mid", "projection", "aux", "substep")
+OC_TIMER_NAMES = ("tendency", "halo", "poisson_rhs", "fft", "poisson_mid", "projection", "aux", "substep", "comm")
 
 # enums
 OC_F64, OC_F32 = 0, 1
@@ -40,7 +40,7 @@ class oc_config(C.Structure):
         ("tracer_T", C.c_int32), ("tracer_S", C.c_int32), ("tracer_b", C.c_int32),
         ("has_coriolis", C.c_int32), ("coriolis_f", C.c_double),
         ("bcs", (oc_bc * 6) * OC_MAX_FIELDS),
-        ("device", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("device", C.c_int32), ("dist_rank", C.c_int32), ("dist_nranks", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -53,6 +53,9 @@ class oc_clock(C.Structure):
     _fields_ = [("time", C.c_double), ("iteration", C.c_int64), ("stage", C.c_int32),
                 ("last_dt", C.c_double), ("last_stage_dt", C.c_double)]
 
+
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                          C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
 
 # every symbol include/oceananigans_b200.h declares: name -> (restype, argtypes)
 _M = C.c_void_p
@@ -83,6 +86,9 @@ SYMBOLS = {
     "oc_time_step_ab2": (C.c_int, [_M, C.c_double, C.c_int]),
     "oc_get_clock": (C.c_int, [_M, C.POINTER(oc_clock)]),
     "oc_set_clock": (C.c_int, [_M, C.POINTER(oc_clock)]),
+    "oc_dist_unique_id": (C.c_int, [C.c_void_p]),
+    "oc_dist_attach_nccl": (C.c_int, [_M, C.c_void_p]),
+    "oc_dist_attach_host": (C.c_int, [_M, C.c_void_p, C.c_void_p]),
     "oc_timers_enable": (C.c_int, [_M, C.c_int]),
     "oc_timers_reset": (C.c_int, [_M]),
     "oc_timers_get": (C.c_int, [_M, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -23,7 +23,7 @@ import numpy as np
 from . import _lib as L
 
 __all__ = [
-    "B200", "Periodic", "Bounded", "Flat", "Center", "Face", "RectilinearGrid",
+    "B200", "Distributed", "Partition", "Periodic", "Bounded", "Flat", "Center", "Face", "RectilinearGrid",
     "Centered", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation",
     "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "FPlane",
     "FluxBoundaryCondition", "ValueBoundaryCondition", "GradientBoundaryCondition", "OpenBoundaryCondition",
@@ -41,6 +41,38 @@ class B200:
 
     def __init__(self, device=0):
         self.device = device
+
+
+class Partition:
+    """Partition(x, y, z): ranks per dimension (src/DistributedComputations/distributed_architectures.jl:14-18).
+    The B200 path implements the slab decomposition Partition(1, R)."""
+
+    def __init__(self, x=1, y=1, z=1):
+        if x != 1 or z != 1:
+            raise NotImplementedError("only slab decompositions in y, Partition(1, R), are implemented (z is never partitioned in "
+                                      "the reference either; pencil decompositions: next)")
+        self.x, self.y, self.z = int(x), int(y), int(z)
+
+
+class Distributed:
+    """Distributed(B200(device); partition=Partition(1, R)): one process per GPU
+    (src/DistributedComputations/distributed_architectures.jl:242-302).  rank / nranks default to torch.distributed's.
+    `exchange` is the TEST-ONLY host transport of the host simulation (a Python callable, see tests/dist_worker.py); the
+    CUDA library communicates with NCCL over NVLink."""
+
+    def __init__(self, child_architecture=None, partition=None, rank=None, nranks=None, exchange=None):
+        self.child = child_architecture or B200()
+        self.device = self.child.device
+        if rank is None or nranks is None:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise ValueError("Distributed needs rank/nranks or an initialised torch.distributed process group")
+            rank, nranks = dist.get_rank(), dist.get_world_size()
+        self.rank, self.nranks = int(rank), int(nranks)
+        self.partition = partition or Partition(1, self.nranks)
+        if self.partition.y != self.nranks:
+            raise ValueError("partition does not match the number of ranks")
+        self.exchange = exchange
 
 
 class _Topo:
@@ -67,7 +99,7 @@ class RectilinearGrid:
 
     def __init__(self, architecture=None, FT=np.float64, *, size, extent=None, x=None, y=None, z=None,
                  topology=(Periodic, Periodic, Bounded), halo=None):
-        if isinstance(architecture, type) or (architecture is not None and not isinstance(architecture, B200)):
+        if isinstance(architecture, type) or (architecture is not None and not isinstance(architecture, (B200, Distributed))):
             # RectilinearGrid(FT; ...) form
             FT, architecture = architecture, None
         self.architecture = architecture or B200()
@@ -274,6 +306,9 @@ class Field:
         if callable(value):
             locs = [Face if x else Center for x in info.location]
             nodes = [g.nodes(d, locs[d]) if g.topology[d] is not Flat else np.zeros(1) for d in range(3)]
+            if self.model.distributed:      # this rank's rows
+                nyl, r = info.interior_size[1], g.architecture.rank
+                nodes[1] = nodes[1][r * nyl:(r + 1) * nyl]
             X = np.meshgrid(*nodes, indexing="ij")
             args = [A for d, A in enumerate(X) if g.topology[d] is not Flat]
             value = np.broadcast_to(np.asarray(value(*args), dtype=np.float64), X[0].shape)
@@ -336,6 +371,14 @@ class NonhydrostaticModel:
         for d in range(3):
             cfg.N[d], cfg.H[d], cfg.topology[d] = grid.N[d], grid.H[d], grid.topology[d].code
             cfg.delta[d], cfg.extent[d] = grid.D[d], grid.L[d]
+        arch = grid.architecture
+        self.distributed = isinstance(arch, Distributed) and arch.nranks > 1
+        if self.distributed:
+            # local grid of this rank: Ny / R rows (distributed_grids.jl:75-126); the spacing and the global extent stay
+            if grid.N[1] % arch.nranks != 0:
+                raise ValueError("Ny must be divisible by the number of ranks")
+            cfg.N[1] = grid.N[1] // arch.nranks
+            cfg.dist_rank, cfg.dist_nranks = arch.rank, arch.nranks
         cfg.advection = advection.code
         cfg.timestepper = L.OC_RK3 if timestepper == "RungeKutta3" else L.OC_AB2
         cfg.n_tracers = len(tracers)
@@ -388,6 +431,8 @@ class NonhydrostaticModel:
         h = C.c_void_p()
         self._lib.check(self._lib.oc_model_create(C.byref(cfg), C.byref(h)))
         self._h = h
+        if self.distributed:
+            self._attach_transport(arch)
         self.tracer_names = tracers
         self.velocities = _NT(u=Field(self, 0, "u"), v=Field(self, 1, "v"), w=Field(self, 2, "w"))
         self.tracers = _NT({n: Field(self, 3 + t, n) for t, n in enumerate(tracers)})
@@ -403,6 +448,31 @@ class NonhydrostaticModel:
         self.clock = Clock(self)
         # constructor tail: update_state!(model; compute_tendencies=false)   nonhydrostatic_model.jl:241
         self._lib.check(self._lib.oc_update_state(self._h, 0))
+
+    def _attach_transport(self, arch):
+        if arch.exchange is not None:
+            fn = arch.exchange
+
+            def trampoline(user, n, sp, rp, tg, sptr, sb, rptr, rb):
+                try:
+                    return int(fn([(sp[i], rp[i], tg[i], sptr[i], sb[i], rptr[i], rb[i]) for i in range(n)]) or 0)
+                except Exception as e:          # never unwind through C
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            self._exchange_cb = L.EXCHANGE_FN(trampoline)      # keep alive
+            self._lib.check(self._lib.oc_dist_attach_host(self._h, C.cast(self._exchange_cb, C.c_void_p), None))
+            return
+        import torch
+        import torch.distributed as dist
+        ident = (C.c_uint8 * 128)()
+        if arch.rank == 0:
+            self._lib.check(self._lib.oc_dist_unique_id(ident))
+        backend = dist.get_backend()
+        t = torch.tensor(list(ident), dtype=torch.uint8, device="cuda" if backend == "nccl" else "cpu")
+        dist.broadcast(t, src=0)
+        ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+        self._lib.check(self._lib.oc_dist_attach_nccl(self._h, ident))
 
     def __del__(self):
         try:
@@ -430,8 +500,8 @@ class NonhydrostaticModel:
         if reset:
             self._lib.check(self._lib.oc_timers_reset(self._h))
             return None
-        ms = (C.c_double * 8)()
-        n = (C.c_int64 * 8)()
+        ms = (C.c_double * len(L.OC_TIMER_NAMES))()
+        n = (C.c_int64 * len(L.OC_TIMER_NAMES))()
         self._lib.check(self._lib.oc_timers_get(self._h, ms, n))
         return {name: (ms[i], n[i]) for i, name in enumerate(L.OC_TIMER_NAMES)}
 

@@ -1,0 +1,336 @@
+// oc_dist.h — slab (y) domain decomposition over R GPUs: halo exchange and the transposed distributed FFT.
+//
+// Replaces, for Partition(1, R) on a RectilinearGrid that is Periodic in y (src/DistributedComputations):
+//   halo_communication.jl:87-333 + communication_buffers.jl:30-135  fill_halo_regions! with MPI Isend/Irecv of packed y-halos
+//   distributed_transpose.jl:25-191 + transposable_field.jl:49-105   pack -> Alltoallv -> unpack transposes
+//   distributed_fft_based_poisson_solver.jl:92-188                   FFT(z,x local) -> transpose -> FFT(y) -> divide -> back
+// One process per GPU; NCCL (dlopen'ed: libnccl.so.2 — no link-time dependency for single-GPU users) carries both patterns
+// as grouped ncclSend/ncclRecv.  A host-callback transport exists for the TEST-ONLY host simulation (world_size-2 gloo tests).
+//
+// Layouts.  Local spectral buffer (as on one GPU): complex (nxc, Ny_l, Nz), x fastest — the z-chunk destined to rank d is
+// CONTIGUOUS, so the forward all-to-all needs no pack.  Received blocks land in `stage` as [s][zl][yl][x]; TransposeUnpack
+// turns them into T = (y fastest, x, zl) through a shared-memory tile so that both sides are coalesced and the y-FFT is a
+// contiguous batched 1-D transform.  The way back mirrors it.
+#pragma once
+#include "oc_halo.h"
+#include "oc_poisson.h"
+
+#ifndef OC_HOSTSIM
+#include <cufft.h>
+#include <dlfcn.h>
+#endif
+
+namespace oc {
+
+struct Msg {
+    int send_peer, recv_peer, tag;     // messages between one pair of ranks are matched in posting order (tag: host transport)
+    void* send;
+    size_t send_bytes;
+    void* recv;
+    size_t recv_bytes;
+};
+
+// oc_exchange_fn of include/oceananigans_b200.h: perform all transfers, return 0 on success
+typedef int (*HostExchangeFn)(void*, int, const int*, const int*, const int*, void* const*, const size_t*, void* const*, const size_t*);
+
+struct Transport {
+    virtual ~Transport() {}
+    virtual std::string exchange(const std::vector<Msg>& msgs, Stream stream) = 0;
+};
+
+struct HostTransport : Transport {
+    HostExchangeFn fn;
+    void* user;
+    HostTransport(HostExchangeFn f, void* u) : fn(f), user(u) {}
+    std::string exchange(const std::vector<Msg>& msgs, Stream) override {
+        std::vector<int> sp, rp, tg;
+        std::vector<void*> sptr, rptr;
+        std::vector<size_t> sb, rb;
+        for (const Msg& m : msgs) {
+            sp.push_back(m.send_peer); rp.push_back(m.recv_peer); tg.push_back(m.tag);
+            sptr.push_back(m.send); sb.push_back(m.send_bytes); rptr.push_back(m.recv); rb.push_back(m.recv_bytes);
+        }
+        int rc = fn(user, (int)msgs.size(), sp.data(), rp.data(), tg.data(), sptr.data(), sb.data(), rptr.data(), rb.data());
+        return rc == 0 ? "" : "host exchange callback failed with code " + std::to_string(rc);
+    }
+};
+
+#ifndef OC_HOSTSIM
+// The handful of NCCL entry points, resolved at run time.
+struct NcclApi {
+    typedef struct ncclComm* comm_t;
+    struct UniqueId { char internal[128]; };
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(comm_t*, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string load() {
+        if (GetUniqueId) return "";
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return std::string("cannot load libnccl.so.2: ") + dlerror();
+#define OC_NCCL_SYM(field, name) *(void**)(&field) = dlsym(h, name); if (!field) return std::string("libnccl lacks ") + name;
+        OC_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+        OC_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        OC_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        OC_NCCL_SYM(Send, "ncclSend")
+        OC_NCCL_SYM(Recv, "ncclRecv")
+        OC_NCCL_SYM(GroupStart, "ncclGroupStart")
+        OC_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+        OC_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef OC_NCCL_SYM
+        return "";
+    }
+};
+inline NcclApi& nccl_api() { static NcclApi api; return api; }
+
+struct NcclTransport : Transport {
+    NcclApi::comm_t comm = nullptr;
+    std::string init(int rank, int nranks, const void* id128) {
+        std::string e = nccl_api().load();
+        if (!e.empty()) return e;
+        NcclApi::UniqueId id;
+        memcpy(id.internal, id128, 128);
+        int rc = nccl_api().CommInitRank(&comm, nranks, id, rank);
+        if (rc != 0) return std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(rc);
+        return "";
+    }
+    ~NcclTransport() override { if (comm) nccl_api().CommDestroy(comm); }
+    std::string exchange(const std::vector<Msg>& msgs, Stream stream) override {
+        NcclApi& n = nccl_api();
+        int rc = n.GroupStart();
+        for (const Msg& m : msgs) {
+            if (rc == 0 && m.recv_bytes) rc = n.Recv(m.recv, m.recv_bytes, /*ncclChar*/ 0, m.recv_peer, comm, stream);
+            if (rc == 0 && m.send_bytes) rc = n.Send(m.send, m.send_bytes, 0, m.send_peer, comm, stream);
+        }
+        int rc2 = n.GroupEnd();
+        if (rc == 0) rc = rc2;
+        return rc == 0 ? "" : std::string("NCCL send/recv: ") + n.GetErrorString(rc);
+    }
+};
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// y-halo pack / unpack: all fields, both sides, one launch.  A slab is H rows × the whole x pitch × every plane.
+// buffer layout: [side][field][plane][row][x]
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+struct HaloPackKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    int nfields, planes, rows;     // rows = halo width exchanged
+    int unpack;                    // 0: interior edge rows -> buffer ; 1: buffer -> halo rows
+    FT* base[HALO_MAX_FIELDS];     // allocation bases
+    FT* buf;                       // [2][nfields][planes][rows][sy]
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const long long per_side = (long long)nfields * planes * rows * g.sy;
+        long long n = (long long)b.x * nt + tid;
+        if (n >= 2 * per_side) return;
+        const int side = (int)(n / per_side);
+        long long r = n - side * per_side;
+        const int x = (int)(r % g.sy); r /= g.sy;
+        const int row = (int)(r % rows); r /= rows;
+        const int pl = (int)(r % planes);
+        const int f = (int)(r / planes);
+        // allocation row index of interior row j is j + H[1]
+        int jrow;
+        if (!unpack) jrow = side == 0 ? g.H[1] + row : g.H[1] + g.N[1] - rows + row;          // low edge / high edge interior rows
+        else jrow = side == 0 ? g.H[1] - rows + row : g.H[1] + g.N[1] + row;                   // low halo / high halo rows
+        FT* p = base[f] + (long long)pl * g.sz + (long long)jrow * g.sy + x;
+        if (!unpack) buf[n] = *p; else *p = buf[n];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// transposes between stage = [s][zl][yl][x] (x fastest) and T = [zl][x][y] (y fastest), y = s·Ny_l + yl.  32×32 tiles.
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+struct TransposeKernel {
+    static constexpr int PHASES = 2;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr size_t SMEM = sizeof(Cplx<FT>) * 32 * 33;
+    int nxc, nyl, nzl, R;
+    int to_T;                  // 1: stage -> T ; 0: T -> stage
+    Cplx<FT>* stage;
+    Cplx<FT>* T;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char* smem) const {
+        Cplx<FT>* tile = reinterpret_cast<Cplx<FT>*>(smem);
+        const int ny = nyl * R;
+        const int x0 = b.x * 32, y0 = b.y * 32, zl = b.z;
+        const int tx = tid & 31, ty = tid >> 5;        // 32 × 8
+        if ((PHASE == 0) == (to_T != 0)) {
+            // touch the stage side (x contiguous): PHASE 0 reads it when to_T, PHASE 1 writes it when !to_T
+            for (int r = ty; r < 32; r += 8) {
+                const int x = x0 + tx, y = y0 + r;
+                if (x < nxc && y < ny) {
+                    const int s = y / nyl, yl = y - s * nyl;
+                    Cplx<FT>* p = stage + ((((long long)s * nzl + zl) * nyl + yl) * nxc + x);
+                    if (to_T) tile[r * 33 + tx] = *p; else *p = tile[r * 33 + tx];
+                }
+            }
+        } else {
+            // touch the T side (y contiguous)
+            for (int r = ty; r < 32; r += 8) {
+                const int x = x0 + r, y = y0 + tx;
+                if (x < nxc && y < ny) {
+                    Cplx<FT>* p = T + (((long long)zl * nxc + x) * ny + y);
+                    if (to_T) *p = tile[tx * 33 + r]; else tile[tx * 33 + r] = *p;
+                }
+            }
+        }
+    }
+};
+
+// spectral divide in the transposed layout T = [zl][x][y]: global kz = rank·nzl + zl
+template <class FT>
+struct PoissonDivideTKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    int nxc, ny, nzl, kz0;
+    Cplx<FT>* T;
+    const double* lam[3];      // λx[nxc…], λy[ny] (GLOBAL y), λz[Nz] (global z)
+    double norm;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const int y = b.x * nt + tid, x = b.y, zl = b.z;
+        if (y >= ny) return;
+        const int kz = kz0 + zl;
+        const double l = lam[0][x] + lam[1][y] + lam[2][kz];
+        Cplx<FT>* p = T + (((long long)zl * nxc + x) * ny + y);
+        Cplx<FT> e = *p;
+        double s = -norm / l;
+        if (x == 0 && y == 0 && kz == 0) s = 0.0;
+        *p = Cplx<FT>{(FT)((double)e.x * s), (FT)((double)e.y * s)};
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// local transforms of the distributed solve: 2-D (z, x) real-to-complex batched over y, and 1-D y complex.
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+class DistFft {
+public:
+    int Nx = 0, Nyl = 0, Nz = 0, R = 1, nxc = 0, nxr = 0, Ny = 0, Nzl = 0;
+    size_t work_bytes = 0;
+
+    std::string init(int nx, int nyl, int nz, int r, Stream stream) {
+        Nx = nx; Nyl = nyl; Nz = nz; R = r;
+        nxc = Nx / 2 + 1; nxr = 2 * nxc; Ny = Nyl * R; Nzl = Nz / R;
+#ifndef OC_HOSTSIM
+        const bool dbl = sizeof(FT) == 8;
+        size_t w[3] = {0, 0, 0};
+        for (cufftHandle* h : {&fwd_, &inv_, &y_}) {
+            if (cufftCreate(h) != CUFFT_SUCCESS) return "cufftCreate failed";
+            cufftSetAutoAllocation(*h, 0);
+        }
+        int n2[2] = {Nz, Nx};
+        int rembed[2] = {Nz, nxr * Nyl}, cembed[2] = {Nz, nxc * Nyl};
+        if (cufftMakePlanMany(fwd_, 2, n2, rembed, 1, nxr, cembed, 1, nxc, dbl ? CUFFT_D2Z : CUFFT_R2C, Nyl, &w[0]) != CUFFT_SUCCESS)
+            return "cufftMakePlanMany(zx forward) failed";
+        if (cufftMakePlanMany(inv_, 2, n2, cembed, 1, nxc, rembed, 1, nxr, dbl ? CUFFT_Z2D : CUFFT_C2R, Nyl, &w[1]) != CUFFT_SUCCESS)
+            return "cufftMakePlanMany(zx inverse) failed";
+        int n1[1] = {Ny};
+        if (cufftMakePlanMany(y_, 1, n1, nullptr, 1, Ny, nullptr, 1, Ny, dbl ? CUFFT_Z2Z : CUFFT_C2C, nxc * Nzl, &w[2]) != CUFFT_SUCCESS)
+            return "cufftMakePlanMany(y) failed";
+        work_bytes = std::max(w[0], std::max(w[1], w[2]));
+        if (work_bytes) {
+            if (cudaMalloc(&work_, work_bytes) != cudaSuccess) return "cudaMalloc(cuFFT work area) failed";
+            for (cufftHandle h : {fwd_, inv_, y_}) cufftSetWorkArea(h, work_);
+        }
+        for (cufftHandle h : {fwd_, inv_, y_}) cufftSetStream(h, stream);
+        planned_ = true;
+#else
+        (void)stream;
+#endif
+        return "";
+    }
+    ~DistFft() {
+#ifndef OC_HOSTSIM
+        if (planned_) { cufftDestroy(fwd_); cufftDestroy(inv_); cufftDestroy(y_); }
+        if (work_) cudaFree(work_);
+#endif
+    }
+
+#ifndef OC_HOSTSIM
+    std::string zx(void* buf, bool fwd) {
+        cufftResult r;
+        if (sizeof(FT) == 8) r = fwd ? cufftExecD2Z(fwd_, (cufftDoubleReal*)buf, (cufftDoubleComplex*)buf) : cufftExecZ2D(inv_, (cufftDoubleComplex*)buf, (cufftDoubleReal*)buf);
+        else r = fwd ? cufftExecR2C(fwd_, (cufftReal*)buf, (cufftComplex*)buf) : cufftExecC2R(inv_, (cufftComplex*)buf, (cufftReal*)buf);
+        return r == CUFFT_SUCCESS ? "" : "cuFFT zx exec failed with code " + std::to_string((int)r);
+    }
+    std::string y(void* T, bool fwd) {
+        cufftResult r;
+        if (sizeof(FT) == 8) r = cufftExecZ2Z(y_, (cufftDoubleComplex*)T, (cufftDoubleComplex*)T, fwd ? CUFFT_FORWARD : CUFFT_INVERSE);
+        else r = cufftExecC2C(y_, (cufftComplex*)T, (cufftComplex*)T, fwd ? CUFFT_FORWARD : CUFFT_INVERSE);
+        return r == CUFFT_SUCCESS ? "" : "cuFFT y exec failed with code " + std::to_string((int)r);
+    }
+#else
+    // naive DFTs (test-only)
+    static void dft(std::vector<Cd>& line, bool fwd) {
+        const int n = (int)line.size();
+        std::vector<Cd> out(n);
+        const double sgn = fwd ? -1.0 : 1.0;
+        for (int q = 0; q < n; ++q) {
+            Cd s{0, 0};
+            for (int m = 0; m < n; ++m) {
+                double ang = sgn * 2.0 * M_PI * (double)((long long)q * m % n) / n;
+                s = cadd(s, cmul(line[m], Cd{std::cos(ang), std::sin(ang)}));
+            }
+            out[q] = s;
+        }
+        line = out;
+    }
+    std::string zx(void* bufv, bool fwd) {
+        FT* buf = (FT*)bufv;
+        for (int j = 0; j < Nyl; ++j) {
+            std::vector<Cd> full((size_t)Nx * Nz);
+            auto at = [&](int i, int k) -> Cd& { return full[(size_t)i + (size_t)Nx * k]; };
+            if (fwd) {
+                for (int k = 0; k < Nz; ++k) for (int i = 0; i < Nx; ++i) at(i, k) = Cd{(double)buf[i + (long long)nxr * (j + (long long)Nyl * k)], 0.0};
+            } else {
+                for (int k = 0; k < Nz; ++k) for (int i = 0; i < Nx; ++i) {
+                    if (i < nxc) { long long c = i + (long long)nxc * (j + (long long)Nyl * k); at(i, k) = Cd{(double)buf[2 * c], (double)buf[2 * c + 1]}; }
+                    else { long long c = (Nx - i) + (long long)nxc * (j + (long long)Nyl * ((Nz - k) % Nz)); at(i, k) = Cd{(double)buf[2 * c], -(double)buf[2 * c + 1]}; }
+                }
+            }
+            for (int k = 0; k < Nz; ++k) { std::vector<Cd> l(Nx); for (int i = 0; i < Nx; ++i) l[i] = at(i, k); dft(l, fwd); for (int i = 0; i < Nx; ++i) at(i, k) = l[i]; }
+            for (int i = 0; i < Nx; ++i) { std::vector<Cd> l(Nz); for (int k = 0; k < Nz; ++k) l[k] = at(i, k); dft(l, fwd); for (int k = 0; k < Nz; ++k) at(i, k) = l[k]; }
+            if (fwd) {
+                for (int k = 0; k < Nz; ++k) for (int i = 0; i < nxc; ++i) { long long c = i + (long long)nxc * (j + (long long)Nyl * k); buf[2 * c] = (FT)at(i, k).x; buf[2 * c + 1] = (FT)at(i, k).y; }
+            } else {
+                for (int k = 0; k < Nz; ++k) for (int i = 0; i < Nx; ++i) buf[i + (long long)nxr * (j + (long long)Nyl * k)] = (FT)at(i, k).x;
+            }
+        }
+        return "";
+    }
+    std::string y(void* Tv, bool fwd) {
+        FT* T = (FT*)Tv;
+        for (long long b = 0; b < (long long)nxc * Nzl; ++b) {
+            std::vector<Cd> l(Ny);
+            for (int y = 0; y < Ny; ++y) l[y] = Cd{(double)T[2 * (b * Ny + y)], (double)T[2 * (b * Ny + y) + 1]};
+            dft(l, fwd);
+            for (int y = 0; y < Ny; ++y) { T[2 * (b * Ny + y)] = (FT)l[y].x; T[2 * (b * Ny + y) + 1] = (FT)l[y].y; }
+        }
+        return "";
+    }
+#endif
+
+private:
+#ifndef OC_HOSTSIM
+    cufftHandle fwd_ = 0, inv_ = 0, y_ = 0;
+    void* work_ = nullptr;
+    bool planned_ = false;
+#endif
+};
+
+}  // namespace oc

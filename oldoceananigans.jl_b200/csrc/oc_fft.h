@@ -21,7 +21,7 @@ public:
     size_t buffer_bytes = 0;
     size_t work_bytes = 0;
 
-    std::string init(const int N[3], const int bounded[3], Stream stream) {
+    std::string init(const int N[3], const int bounded[3], Stream stream, bool plan = true) {
         for (int d = 0; d < 3; ++d) { L.N[d] = N[d]; L.bounded[d] = bounded[d]; }
         L.r2c = (!bounded[0] && N[0] > 1) ? 1 : 0;
         L.nxc = L.r2c ? N[0] / 2 + 1 : N[0];
@@ -30,6 +30,7 @@ public:
         rank_ = 0;
         for (int d = 2; d >= 0; --d)
             if (N[d] > 1) dims_[rank_++] = N[d];      // slowest first
+        if (!plan) { rank_ = 0; return ""; }
 #ifndef OC_HOSTSIM
         if (rank_ == 0) return "";
         const bool dbl = sizeof(FT) == 8;

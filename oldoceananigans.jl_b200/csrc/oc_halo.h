@@ -46,6 +46,7 @@ struct HaloKernel {
     Geom<FT> g;
     int nfields, nboxes;
     int fill_open;
+    int skip[3];               // 1: halos of this (periodic) dimension are filled by neighbour exchange, not here (oc_dist.h)
     HaloField<FT> f[HALO_MAX_FIELDS];
     const HaloBox* boxes;      // device array [nboxes]
 
@@ -72,6 +73,7 @@ struct HaloKernel {
         for (int d = 0; d < 3; ++d) {
             int idx = P[d], N = g.N[d];
             if (!g.bounded[d]) {                       // Periodic (and Flat stored as periodic)
+                if (skip[d] && (idx < 0 || idx >= N)) return;
                 int q = idx % N;
                 if (q < 0) q += N;
                 if (q != idx) moved = true;

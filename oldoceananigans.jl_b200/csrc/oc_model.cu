@@ -150,13 +150,34 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         resolve_bcs(nu_e_, nullptr);
         for (int t = 0; t < c.n_tracers; ++t) { kappa_e_.push_back(alloc_field(locs[3])); resolve_bcs(kappa_e_.back(), nullptr); }
     }
+    // slab decomposition in y (Distributed(arch; partition = Partition(1, R)))
+    dist_ = c.dist_nranks > 1;
+    if (dist_) {
+        rank_ = c.dist_rank; R_ = c.dist_nranks;
+        if (rank_ < 0 || rank_ >= R_) throw Error(OC_ERR_INVALID, "dist_rank out of range");
+        for (int d = 0; d < 3; ++d)
+            if (c.topology[d] != OC_PERIODIC) throw Error(OC_ERR_UNSUPPORTED, "distributed models: only (Periodic, Periodic, Periodic) grids in this round (Bounded x/z: next)");
+        if (g_.N[2] % R_ != 0) throw Error(OC_ERR_INVALID, "distributed FFT: Nz must be divisible by the number of ranks (distributed_fft_based_poisson_solver.jl:211-229)");
+        if (g_.N[1] < g_.H[1]) throw Error(OC_ERR_INVALID, "distributed models: local Ny smaller than the halo");
+    }
     // pressure solver
-    std::string err = fft_.init(g_.N, g_.bounded, stream_);
+    std::string err = fft_.init(g_.N, g_.bounded, stream_, !dist_);
     if (!err.empty()) throw Error(OC_ERR_CUDA, err);
     fftbuf_ = (FT*)dev_alloc(fft_.buffer_bytes);
     device_bytes += (int64_t)fft_.buffer_bytes + (int64_t)fft_.work_bytes;
+    if (dist_) {
+        err = dfft_.init(g_.N[0], g_.N[1], g_.N[2], R_, stream_);
+        if (!err.empty()) throw Error(OC_ERR_CUDA, err);
+        distT_ = (FT*)dev_alloc(fft_.buffer_bytes);
+        diststage_ = (FT*)dev_alloc(fft_.buffer_bytes);
+        const int planes = (int)(field_elems_ / (size_t)g_.sz);
+        halo_buf_elems_ = (size_t)2 * F_ * planes * g_.H[1] * g_.sy;
+        halo_send_ = (FT*)dev_alloc(sizeof(FT) * halo_buf_elems_);
+        halo_recv_ = (FT*)dev_alloc(sizeof(FT) * halo_buf_elems_);
+        device_bytes += (int64_t)(2 * fft_.buffer_bytes + dfft_.work_bytes + 2 * sizeof(FT) * halo_buf_elems_);
+    }
     for (int d = 0; d < 3; ++d) {
-        const int N = g_.N[d];
+        const int N = (d == 1 && dist_) ? g_.N[d] * R_ : g_.N[d];       // eigenvalues are global arrays (distributed_fft_based_poisson_solver.jl:106-112)
         std::vector<double> lam(N, 0.0);
         const double L = c.topology[d] == OC_FLAT ? 1.0 : c.extent[d];
         for (int i = 0; i < N; ++i) {                    // poisson_eigenvalues.jl:8-31 (Float64)
@@ -187,6 +208,7 @@ Model<FT>::~Model() {
     fr(pNHS_); fr(pHY_); fr(nu_e_);
     for (auto& f : kappa_e_) fr(f);
     dev_free(fftbuf_);
+    dev_free(distT_); dev_free(diststage_); dev_free(halo_send_); dev_free(halo_recv_);
     for (int d = 0; d < 3; ++d) { dev_free(lam_[d]); dev_free(tw_[d]); }
     for (auto& kv : halo_cache_) dev_free(kv.second.boxes);
 #ifndef OC_HOSTSIM
@@ -437,6 +459,7 @@ void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open) {
     k.nfields = (int)fields.size();
     k.nboxes = it->second.nboxes;
     k.fill_open = fill_open ? 1 : 0;
+    k.skip[0] = 0; k.skip[1] = dist_ ? 1 : 0; k.skip[2] = 0;
     k.boxes = it->second.boxes;
     for (int fi = 0; fi < (int)fields.size(); ++fi) {
         k.f[fi].p = fields[fi]->p;
@@ -446,6 +469,95 @@ void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open) {
     Dim3 grid;
     grid.x = it->second.nblocks;
     go(k, grid, 0, OC_TIMER_HALO);
+    if (dist_) exchange_y(fields);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// distributed: y-halo exchange with the two slab neighbours (halo_communication.jl:87-333)
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+void Model<FT>::dist_attach(Transport* t) {
+    if (!dist_) { delete t; throw Error(OC_ERR_STATE, "the model was not created with dist_nranks > 1"); }
+    transport_.reset(t);
+}
+
+template <class FT>
+void Model<FT>::exchange_y(const std::vector<FieldRec*>& fields) {
+    if (!transport_) throw Error(OC_ERR_STATE, "distributed model without a transport: call oc_dist_attach_nccl first");
+    const int nf = (int)fields.size();
+    if (nf > F_) throw Error(OC_ERR_INVALID, "halo exchange of more fields than the exchange buffers hold");
+    const int planes = (int)(field_elems_ / (size_t)g_.sz);
+    HaloPackKernel<FT> k;
+    k.g = g_;
+    k.nfields = nf; k.planes = planes; k.rows = g_.H[1];
+    for (int f = 0; f < nf; ++f) k.base[f] = fields[f]->base;
+    const size_t per_side = (size_t)nf * planes * g_.H[1] * g_.sy;
+    Dim3 grid;
+    grid.x = (int)((2 * per_side + 255) / 256);
+    k.unpack = 0; k.buf = halo_send_;
+    go(k, grid, 0, OC_TIMER_COMM);
+    const int prev = (rank_ + R_ - 1) % R_, next = (rank_ + 1) % R_;
+    // low-edge rows go to prev (they are its high halo); high-edge rows go to next (its low halo).  Posting order: for R = 2 the
+    // peer's first send (its low edge) must meet my first receive (my high halo).
+    std::vector<Msg> msgs;
+    msgs.push_back(Msg{prev, next, 0, halo_send_, per_side * sizeof(FT), halo_recv_ + per_side, per_side * sizeof(FT)});
+    msgs.push_back(Msg{next, prev, 1, halo_send_ + per_side, per_side * sizeof(FT), halo_recv_, per_side * sizeof(FT)});
+    begin_timer(OC_TIMER_COMM);
+    std::string e = transport_->exchange(msgs, stream_);
+    end_timer();
+    if (!e.empty()) throw Error(OC_ERR_CUDA, e);
+    k.unpack = 1; k.buf = halo_recv_;
+    go(k, grid, 0, OC_TIMER_COMM);
+}
+
+// all-to-all of the R equal chunks of a spectral buffer (distributed_transpose.jl:185-191)
+template <class FT>
+void Model<FT>::all_to_all(FT* send, FT* recv) {
+    const size_t chunk = fft_.buffer_bytes / R_;
+    std::vector<Msg> msgs;
+    for (int d = 1; d < R_; ++d) {
+        const int to = (rank_ + d) % R_, from = (rank_ + R_ - d) % R_;
+        msgs.push_back(Msg{to, from, 2 + d, (char*)send + chunk * to, chunk, (char*)recv + chunk * from, chunk});
+    }
+    begin_timer(OC_TIMER_COMM);
+#ifndef OC_HOSTSIM
+    cuda_check(cudaMemcpyAsync((char*)recv + chunk * rank_, (char*)send + chunk * rank_, chunk, cudaMemcpyDeviceToDevice, stream_), "cudaMemcpyAsync D2D");
+#else
+    memcpy((char*)recv + chunk * rank_, (char*)send + chunk * rank_, chunk);
+#endif
+    std::string e = transport_ ? transport_->exchange(msgs, stream_) : std::string("distributed model without a transport");
+    end_timer();
+    if (!e.empty()) throw Error(OC_ERR_CUDA, e);
+}
+
+// FFT(z,x) local -> transpose -> FFT(y) -> divide -> FFT⁻¹(y) -> transpose back -> FFT⁻¹(z,x)
+// (distributed_fft_based_poisson_solver.jl:141-178)
+template <class FT>
+void Model<FT>::run_fft_solve_dist() {
+    auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
+    begin_timer(OC_TIMER_FFT); std::string e = dfft_.zx(fftbuf_, true); end_timer(); chk(e);
+    all_to_all(fftbuf_, diststage_);
+    TransposeKernel<FT> t;
+    t.nxc = dfft_.nxc; t.nyl = g_.N[1]; t.nzl = dfft_.Nzl; t.R = R_;
+    t.stage = reinterpret_cast<Cplx<FT>*>(diststage_); t.T = reinterpret_cast<Cplx<FT>*>(distT_);
+    Dim3 tg;
+    tg.x = (dfft_.nxc + 31) / 32; tg.y = (dfft_.Ny + 31) / 32; tg.z = dfft_.Nzl;
+    t.to_T = 1;
+    go(t, tg, TransposeKernel<FT>::SMEM, OC_TIMER_POISSON_MID);
+    begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, true); end_timer(); chk(e);
+    PoissonDivideTKernel<FT> k;
+    k.nxc = dfft_.nxc; k.ny = dfft_.Ny; k.nzl = dfft_.Nzl; k.kz0 = rank_ * dfft_.Nzl;
+    k.T = reinterpret_cast<Cplx<FT>*>(distT_);
+    for (int d = 0; d < 3; ++d) k.lam[d] = lam_[d];
+    k.norm = 1.0 / ((double)g_.N[0] * dfft_.Ny * g_.N[2]);
+    Dim3 grid;
+    grid.x = (dfft_.Ny + 255) / 256; grid.y = dfft_.nxc; grid.z = dfft_.Nzl;
+    go(k, grid, 0, OC_TIMER_POISSON_MID);
+    begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, false); end_timer(); chk(e);
+    t.to_T = 0;
+    go(t, tg, TransposeKernel<FT>::SMEM, OC_TIMER_POISSON_MID);
+    all_to_all(diststage_, fftbuf_);
+    begin_timer(OC_TIMER_FFT); e = dfft_.zx(fftbuf_, false); end_timer(); chk(e);
 }
 
 template <class FT>
@@ -755,6 +867,7 @@ void Model<FT>::cache_previous_tendencies() {
 // ---------------------------------------------------------------------------------------------------------
 template <class FT>
 void Model<FT>::run_fft_solve() {
+    if (dist_) { run_fft_solve_dist(); return; }
     begin_timer(OC_TIMER_FFT);
     std::string e = fft_.forward(fftbuf_);
     end_timer();
@@ -804,6 +917,16 @@ void Model<FT>::pressure_solve_from_state() {
 
 template <class FT>
 void Model<FT>::projection(double dt) {
+    if (dist_) {
+        // the gradient across the slab boundary needs the neighbour's ϕ: unpack into pNHS, exchange its halo, then correct
+        PoissonUnpackKernel<FT> u;
+        u.g = g_; u.L = fft_.L; u.buf = fftbuf_; u.field = pNHS_.p; u.dense = nullptr;
+        go(u, grid_xyz(256), 0, OC_TIMER_PROJECTION);
+        std::vector<FieldRec*> p{&pNHS_};
+        halo(p, true);
+        make_pressure_correction(dt);
+        return;
+    }
     ProjectionKernel<FT> k;
     k.g = g_;
     k.L = fft_.L;
@@ -1025,6 +1148,48 @@ int oc_time_step_rk3(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&]
 int oc_time_step_ab2(oc_model* m, double dt, int euler) { OC_REQUIRE(m); return guarded([&] { m->impl->time_step_ab2(dt, euler); }); }
 int oc_get_clock(oc_model* m, oc_clock* c) { OC_REQUIRE(m); *c = m->impl->clock; return OC_OK; }
 int oc_set_clock(oc_model* m, const oc_clock* c) { OC_REQUIRE(m); m->impl->clock = *c; return OC_OK; }
+int oc_dist_unique_id(void* id128) {
+    if (!id128) { g_last_error = "null argument"; return OC_ERR_INVALID; }
+    return guarded([&] {
+#ifndef OC_HOSTSIM
+        std::string e = oc::nccl_api().load();
+        if (!e.empty()) throw oc::Error(OC_ERR_CUDA, e);
+        oc::NcclApi::UniqueId id;
+        int rc = oc::nccl_api().GetUniqueId(&id);
+        if (rc != 0) throw oc::Error(OC_ERR_CUDA, std::string("ncclGetUniqueId: ") + oc::nccl_api().GetErrorString(rc));
+        memcpy(id128, id.internal, 128);
+#else
+        memset(id128, 0, 128);
+#endif
+    });
+}
+int oc_dist_attach_nccl(oc_model* m, const void* id128) {
+    OC_REQUIRE(m);
+    return guarded([&] {
+#ifndef OC_HOSTSIM
+        if (!id128) throw oc::Error(OC_ERR_INVALID, "null NCCL id");
+        std::unique_ptr<oc::NcclTransport> t(new oc::NcclTransport);
+        std::string e = t->init(m->impl->dist_rank(), m->impl->dist_nranks(), id128);
+        if (!e.empty()) throw oc::Error(OC_ERR_CUDA, e);
+        m->impl->dist_attach(t.release());
+#else
+        (void)id128;
+        throw oc::Error(OC_ERR_UNSUPPORTED, "the host simulation has no NCCL transport (use oc_dist_attach_host)");
+#endif
+    });
+}
+int oc_dist_attach_host(oc_model* m, oc_exchange_fn fn, void* user) {
+    OC_REQUIRE(m);
+    return guarded([&] {
+#ifdef OC_HOSTSIM
+        if (!fn) throw oc::Error(OC_ERR_INVALID, "null exchange callback");
+        m->impl->dist_attach(new oc::HostTransport(fn, user));
+#else
+        (void)fn; (void)user;
+        throw oc::Error(OC_ERR_UNSUPPORTED, "the host-callback transport is a test facility of the host simulation build; use oc_dist_attach_nccl");
+#endif
+    });
+}
 int oc_timers_enable(oc_model* m, int enable) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_enable(enable); }); }
 int oc_timers_reset(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_reset(); }); }
 int oc_timers_get(oc_model* m, double* ms, int64_t* n) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_get(ms, n); }); }

@@ -14,6 +14,7 @@
 
 #include "../../include/oceananigans_b200.h"
 #include "oc_aux.h"
+#include "oc_dist.h"
 #include "oc_fft.h"
 #include "oc_halo.h"
 #include "oc_march.h"
@@ -96,6 +97,9 @@ struct ModelBase {
     virtual void set_finalize(int enforce) = 0;
     virtual void time_step_rk3(double dt) = 0;
     virtual void time_step_ab2(double dt, int euler) = 0;
+    virtual void dist_attach(Transport* t) = 0;
+    virtual int dist_rank() const = 0;
+    virtual int dist_nranks() const = 0;
     virtual void timers_enable(int on) = 0;
     virtual void timers_reset() = 0;
     virtual void timers_get(double* ms, int64_t* n) = 0;
@@ -127,6 +131,9 @@ public:
     void set_finalize(int enforce) override;
     void time_step_rk3(double dt) override;
     void time_step_ab2(double dt, int euler) override;
+    void dist_attach(Transport* t) override;
+    int dist_rank() const override { return rank_; }
+    int dist_nranks() const override { return R_; }
     void timers_enable(int on) override { timing_ = on != 0; }
     void timers_reset() override;
     void timers_get(double* ms, int64_t* n) override;
@@ -182,6 +189,19 @@ private:
     template <int KIND> void launch_tendency(int fidx, TendencyArgs<FT>& a);
     template <int KIND> void launch_march_tendency(int fidx, TendencyArgs<FT>& a);
     TileSrc<FT> tile_src(const FT* base, int bx, int by);
+    // slab decomposition in y (oc_dist.h)
+    bool dist_ = false;
+    int rank_ = 0, R_ = 1;
+    std::unique_ptr<Transport> transport_;
+    DistFft<FT> dfft_;
+    FT* distT_ = nullptr;          // transposed spectral buffer (y fastest)
+    FT* diststage_ = nullptr;      // all-to-all staging
+    FT* halo_send_ = nullptr;
+    FT* halo_recv_ = nullptr;
+    size_t halo_buf_elems_ = 0;
+    void exchange_y(const std::vector<FieldRec*>& fields);
+    void all_to_all(FT* send, FT* recv);
+    void run_fft_solve_dist();
     int xpad_ = 0;
     bool march_ok_ = false;       // no Flat dimension: the z-marching TMA kernel applies
 #ifndef OC_HOSTSIM

@@ -1,0 +1,83 @@
+"""One rank of the CPU multi-process test of the slab-decomposed path (launched by tests/test_distributed.py).
+
+Each rank builds the host simulation of the kernels with Distributed(partition=Partition(1, R)) and a gloo transport
+(torch.distributed isend/irecv on the library's buffers), steps the model, and compares its slab with the single-domain oracle.
+Usage: python tests/dist_worker.py <case-json>   with RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT in the environment."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def gloo_exchange(msgs):
+    """oc_exchange_fn: (send_peer, recv_peer, tag, send_ptr, send_bytes, recv_ptr, recv_bytes) per message."""
+    reqs, keep = [], []
+    for sp, rp, tag, sptr, sb, rptr, rb in msgs:
+        r = torch.frombuffer((C.c_char * rb).from_address(rptr), dtype=torch.uint8)
+        keep.append(r)
+        reqs.append(dist.irecv(r, src=rp, tag=tag))
+    for sp, rp, tag, sptr, sb, rptr, rb in msgs:
+        s = torch.frombuffer((C.c_char * sb).from_address(sptr), dtype=torch.uint8)
+        keep.append(s)
+        reqs.append(dist.isend(s, dst=sp, tag=tag))
+    for q in reqs:
+        q.wait()
+    return 0
+
+
+def main():
+    kw = json.loads(sys.argv[1])
+    steps = kw.pop("steps", 2)
+    FT = np.float32 if kw.pop("f32", False) else np.float64
+    nccl = os.environ.get("OC_DIST_BACKEND", "gloo") == "nccl"      # -m gpu variant: the CUDA library, NCCL over NVLink
+    if nccl:
+        torch.cuda.set_device(int(os.environ["RANK"]))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["RANK"])))
+    else:
+        dist.init_process_group("gloo")
+    rank, R = dist.get_rank(), dist.get_world_size()
+    import oceananigans_b200 as ob
+    from oceananigans_b200 import _lib
+    import parity_harness as ph
+    import __graft_entry__ as ge
+    lib = None if nccl else _lib.Library(ge.HOSTSIM)
+    N, topo = tuple(kw["N"]), kw["topo"]
+    arch = ob.Distributed(ob.B200(rank if nccl else 0), partition=ob.Partition(1, R), rank=rank, nranks=R,
+                          exchange=None if nccl else gloo_exchange)
+    grid = ob.RectilinearGrid(arch, FT, size=N, extent=ph.EXTENT, topology=tuple(ph.TOPO[c] for c in topo))
+    scheme = kw.get("scheme", "weno")
+    model = ob.NonhydrostaticModel(grid=grid, advection=ob.WENO() if scheme == "weno" else ob.Centered(), tracers=("T", "S"),
+                                   buoyancy=ob.SeawaterBuoyancy(), closure=ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3),
+                                   coriolis=ob.FPlane(f=kw["f"]) if kw.get("f") else None, library=lib)
+    om = ph.build_oracle(N=N, topo=topo, scheme=scheme, FT=FT, f=kw.get("f"))
+    ic = ph.initial_conditions(om)
+    nyl = N[1] // R
+    sl = slice(rank * nyl, (rank + 1) * nyl)
+    ob.set_(model, **{n: a[:, sl, :] for n, a in ic.items()})
+    om.set(**ic)
+    dt = 0.1 * float(min(om.grid.D))
+    worst = 0.0
+    for s in range(steps + 1):
+        if s:
+            ob.time_step_(model, dt)
+            om.time_step(dt)
+        for n in om.fields:
+            worst = max(worst, ph.rel_linf(model.fields[n].interior(), om.fields[n].interior[:, sl, :]) * (np.abs(om.fields[n].interior[:, sl, :]).max() / np.abs(om.fields[n].interior).max()))
+        worst = max(worst, float(np.abs(model.pressures.pNHS.interior() - om.pNHS.interior[:, sl, :]).max() / np.abs(om.pNHS.interior).max()))
+    t = torch.tensor([worst], dtype=torch.float64, device="cuda" if nccl else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"worst": float(t.item()), "ranks": R, "steps": steps}))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

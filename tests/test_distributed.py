@@ -1,0 +1,80 @@
+"""The N > 1 path on CPU: world_size-2 (and 4) gloo processes, each running the host simulation of the kernels on its y-slab
+with the same decomposition / pack / exchange / transposed-FFT logic the CUDA library uses with NCCL.  The slabs must agree
+with the single-domain oracle to the north_star tolerance (cf. test/test_distributed_poisson_solvers.jl:70-89 and
+test/test_distributed_models.jl:334-407,518-536 of the reference, which also run 4 ranks on one node)."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def run_ranks(R, case, timeout=600, backend="gloo"):
+    import __graft_entry__ as ge
+    if backend == "gloo" and not os.path.exists(ge.HOSTSIM):
+        ge.build()
+    port = _free_port()
+    procs = []
+    for r in range(R):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(R), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1",
+                   OC_DIST_BACKEND=backend)
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), json.dumps(case)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=timeout) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-3000:]
+    return json.loads(outs[0][0].strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("R,case", [
+    (2, dict(N=(16, 12, 8), topo="PPP", scheme="weno", steps=2)),
+    (2, dict(N=(16, 12, 8), topo="PPP", scheme="centered", f=1e-2, steps=2)),
+    (4, dict(N=(12, 16, 8), topo="PPP", scheme="weno", steps=1)),
+    (2, dict(N=(16, 12, 8), topo="PPP", scheme="weno", steps=2, f32=True)),
+])
+def test_slab_decomposition_matches_single_domain_oracle(R, case):
+    res = run_ranks(R, dict(case))
+    tol = 1e-4 if case.get("f32") else 1e-11
+    assert res["ranks"] == R and res["worst"] <= tol, res
+
+
+def test_distributed_rejects_unsupported_configurations():
+    import oceananigans_b200 as ob
+    with pytest.raises(NotImplementedError):
+        ob.Partition(2, 2)
+    with pytest.raises(ValueError):
+        ob.Distributed(ob.B200(0), partition=ob.Partition(1, 3), rank=0, nranks=2)
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,case", [
+    (2, dict(N=(64, 48, 32), topo="PPP", scheme="weno", steps=2)),
+    (2, dict(N=(40, 24, 16), topo="PPP", scheme="centered", f=1e-2, steps=3)),
+])
+def test_nccl_slab_decomposition_matches_oracle(R, case):
+    """The CUDA library on R GPUs of one box (NCCL halo exchange + transposed distributed FFT) against the oracle."""
+    if _gpu_count() < R:
+        pytest.skip(f"needs {R} GPUs")
+    res = run_ranks(R, dict(case), backend="nccl")
+    assert res["ranks"] == R and res["worst"] <= 1e-11, res
