@@ -87,6 +87,10 @@ OC_HD FT interp1c(const F& fn, int o, int s) {
     return FT(0.5) * (fn(o) + fn(o + s));
 }
 
+// 4-point interpolation of values already evaluated at the corners {o, o+s1, o+s2, o+s1+s2} — the arithmetic of interp2c
+template <class FT>
+OC_HD FT interp4(const FT* f) { return FT(0.5) * (FT(0.5) * (f[0] + f[1]) + FT(0.5) * (f[2] + f[3])); }
+
 template <class FT>
 struct AmdKernel {
     static constexpr int PHASES = 1;
@@ -103,6 +107,9 @@ struct AmdKernel {
     FT* kappa_e[8];
     FT Ckappa[8];
 
+    // Every normalised gradient is evaluated ONCE at the four corners its interpolations need (24 evaluations per cell);
+    // all 30 terms of AMD are then products of those — same operands, same order of operations as the reference's
+    // nested ℑ(…) calls (anisotropic_minimum_dissipation.jl:240-351).
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
         int i = b.x * nt + tid, j = b.y, k = b.z;
@@ -113,74 +120,97 @@ struct AmdKernel {
         FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = FT(2) * g.d[2];
         FT delta2 = FT(3) / (FT(1) / (fx * fx) + FT(1) / (fy * fy) + FT(1) / (fz * fz));   // :166,190
         auto sq = [](FT x) { return x * x; };
-        // interpolated products
-        auto Ixy = [&](auto fn) { return interp2c<FT>(fn, o, sx, sy); };
-        auto Ixz = [&](auto fn) { return interp2c<FT>(fn, o, sx, sz); };
-        auto Iyz = [&](auto fn) { return interp2c<FT>(fn, o, sy, sz); };
-        FT dxu = P.dxu(o), dyv = P.dyv(o), dzw = P.dzw(o);
-        FT Ixy_dxv2 = Ixy([&](int q) { return sq(P.dxv(q)); });
-        FT Ixy_dyu2 = Ixy([&](int q) { return sq(P.dyu(q)); });
-        FT Ixz_dxw2 = Ixz([&](int q) { return sq(P.dxw(q)); });
-        FT Ixz_dzu2 = Ixz([&](int q) { return sq(P.dzu(q)); });
-        FT Iyz_dyw2 = Iyz([&](int q) { return sq(P.dyw(q)); });
-        FT Iyz_dzv2 = Iyz([&](int q) { return sq(P.dzv(q)); });
+        const int cxy[4] = {o, o + sx, o + sy, o + sx + sy};
+        const int cxz[4] = {o, o + sx, o + sz, o + sx + sz};
+        const int cyz[4] = {o, o + sy, o + sz, o + sy + sz};
+        FT dxv[4], dyu[4], dxw[4], dzu[4], dyw[4], dzv[4], t[4];
+        for (int n = 0; n < 4; ++n) {
+            dxv[n] = P.dxv(cxy[n]); dyu[n] = P.dyu(cxy[n]);
+            dxw[n] = P.dxw(cxz[n]); dzu[n] = P.dzu(cxz[n]);
+            dyw[n] = P.dyw(cyz[n]); dzv[n] = P.dzv(cyz[n]);
+        }
+        const FT dxu = P.dxu(o), dyv = P.dyv(o), dzw = P.dzw(o);
+        for (int n = 0; n < 4; ++n) t[n] = sq(dxv[n]);
+        const FT Ixy_dxv2 = interp4<FT>(t);
+        for (int n = 0; n < 4; ++n) t[n] = sq(dyu[n]);
+        const FT Ixy_dyu2 = interp4<FT>(t);
+        for (int n = 0; n < 4; ++n) t[n] = sq(dxw[n]);
+        const FT Ixz_dxw2 = interp4<FT>(t);
+        for (int n = 0; n < 4; ++n) t[n] = sq(dzu[n]);
+        const FT Ixz_dzu2 = interp4<FT>(t);
+        for (int n = 0; n < 4; ++n) t[n] = sq(dyw[n]);
+        const FT Iyz_dyw2 = interp4<FT>(t);
+        for (int n = 0; n < 4; ++n) t[n] = sq(dzv[n]);
+        const FT Iyz_dzv2 = interp4<FT>(t);
+        const FT Ixy_dxv = interp4<FT>(dxv), Ixy_dyu = interp4<FT>(dyu);
+        const FT Ixz_dxw = interp4<FT>(dxw), Ixz_dzu = interp4<FT>(dzu);
+        const FT Iyz_dyw = interp4<FT>(dyw), Iyz_dzv = interp4<FT>(dzv);
         // norm_tr_∇uᶜᶜᶜ :285-306
         FT q = sq(dxu) + sq(dyv) + sq(dzw) + Ixy_dxv2 + Ixy_dyu2 + Ixz_dxw2 + Ixz_dzu2 + Iyz_dyw2 + Iyz_dzv2;
         FT nu = FT(0);
         if (q != FT(0)) {
             // norm_uᵢₐ_uⱼₐ_Σᵢⱼᶜᶜᶜ :240-279
-            FT Ixy_dxv = Ixy([&](int p) { return P.dxv(p); });
-            FT Ixy_dyu = Ixy([&](int p) { return P.dyu(p); });
-            FT Ixz_dxw = Ixz([&](int p) { return P.dxw(p); });
-            FT Ixz_dzu = Ixz([&](int p) { return P.dzu(p); });
-            FT Iyz_dyw = Iyz([&](int p) { return P.dyw(p); });
-            FT Iyz_dzv = Iyz([&](int p) { return P.dzv(p); });
-            FT Ixy_S12 = Ixy([&](int p) { return P.S12(p); });
-            FT Ixz_S13 = Ixz([&](int p) { return P.S13(p); });
-            FT Iyz_S23 = Iyz([&](int p) { return P.S23(p); });
+            FT S12[4], S13[4], S23[4];
+            for (int n = 0; n < 4; ++n) {
+                S12[n] = FT(0.5) * (dyu[n] + dxv[n]);
+                S13[n] = FT(0.5) * (dzu[n] + dxw[n]);
+                S23[n] = FT(0.5) * (dzv[n] + dyw[n]);
+            }
+            const FT Ixy_S12 = interp4<FT>(S12), Ixz_S13 = interp4<FT>(S13), Iyz_S23 = interp4<FT>(S23);
+            for (int n = 0; n < 4; ++n) t[n] = dxv[n] * S12[n];
+            const FT Ixy_dxvS12 = interp4<FT>(t);
+            for (int n = 0; n < 4; ++n) t[n] = dxw[n] * S13[n];
+            const FT Ixz_dxwS13 = interp4<FT>(t);
+            for (int n = 0; n < 4; ++n) t[n] = dyu[n] * S12[n];
+            const FT Ixy_dyuS12 = interp4<FT>(t);
+            for (int n = 0; n < 4; ++n) t[n] = dyw[n] * S23[n];
+            const FT Iyz_dywS23 = interp4<FT>(t);
+            for (int n = 0; n < 4; ++n) t[n] = dzu[n] * S13[n];
+            const FT Ixz_dzuS13 = interp4<FT>(t);
+            for (int n = 0; n < 4; ++n) t[n] = dzv[n] * S23[n];
+            const FT Iyz_dzvS23 = interp4<FT>(t);
             FT t1 = dxu * sq(dxu) + dyv * Ixy_dxv2 + dzw * Ixz_dxw2
-                  + FT(2) * dxu * Ixy([&](int p) { return P.dxv(p) * P.S12(p); })
-                  + FT(2) * dxu * Ixz([&](int p) { return P.dxw(p) * P.S13(p); })
+                  + FT(2) * dxu * Ixy_dxvS12
+                  + FT(2) * dxu * Ixz_dxwS13
                   + FT(2) * Ixy_dxv * Ixz_dxw * Iyz_S23;
             FT t2 = dxu * Ixy_dyu2 + dyv * sq(dyv) + dzw * Iyz_dyw2
-                  + FT(2) * dyv * Ixy([&](int p) { return P.dyu(p) * P.S12(p); })
+                  + FT(2) * dyv * Ixy_dyuS12
                   + FT(2) * Ixy_dyu * Iyz_dyw * Ixz_S13
-                  + FT(2) * dyv * Iyz([&](int p) { return P.dyw(p) * P.S23(p); });
+                  + FT(2) * dyv * Iyz_dywS23;
             FT t3 = dxu * Ixz_dzu2 + dyv * Iyz_dzv2 + dzw * sq(dzw)
                   + FT(2) * Ixz_dzu * Iyz_dzv * Ixy_S12
-                  + FT(2) * dzw * Ixz([&](int p) { return P.dzu(p) * P.S13(p); })
-                  + FT(2) * dzw * Iyz([&](int p) { return P.dzv(p) * P.S23(p); });
+                  + FT(2) * dzw * Ixz_dzuS13
+                  + FT(2) * dzw * Iyz_dzvS23;
             FT r = t1 + t2 + t3;
             FT Cb_zeta = FT(0) / fz;                                                       // Cb = nothing :281
             nu = -Cnu * delta2 * (r - Cb_zeta) / q;                                        // :168
         }
         nu_e[o] = oc_max<FT>(FT(0), nu);
-        for (int t = 0; t < ntr; ++t) {
-            const FT* cc = c[t];
+        if (ntr == 0) return;
+        // ℑxzᶜᵃᶜ(norm_∂y_w) — sic, :336 — needs ∂y w at the xz corners
+        for (int n = 0; n < 4; ++n) t[n] = P.dyw(cxz[n]);
+        const FT Ixz_dyw = interp4<FT>(t);
+        for (int tr = 0; tr < ntr; ++tr) {
+            const FT* cc = c[tr];
             auto cx = [&](int p) { return fx * ((cc[p] - cc[p - sx]) * g.rd[0]); };       // norm_∂x_c at fcc
             auto cy = [&](int p) { return fy * ((cc[p] - cc[p - sy]) * g.rd[1]); };
             auto cz = [&](int p) { return fz * ((cc[p] - cc[p - sz]) * g.rd[2]); };
-            FT Ix_cx2 = interp1c<FT>([&](int p) { return sq(cx(p)); }, o, sx);
-            FT Iy_cy2 = interp1c<FT>([&](int p) { return sq(cy(p)); }, o, sy);
-            FT Iz_cz2 = interp1c<FT>([&](int p) { return sq(cz(p)); }, o, sz);
+            const FT cx0 = cx(o), cx1 = cx(o + sx), cy0 = cy(o), cy1 = cy(o + sy), cz0 = cz(o), cz1 = cz(o + sz);
+            FT Ix_cx2 = FT(0.5) * (sq(cx0) + sq(cx1));
+            FT Iy_cy2 = FT(0.5) * (sq(cy0) + sq(cy1));
+            FT Iz_cz2 = FT(0.5) * (sq(cz0) + sq(cz1));
             FT sigma = Ix_cx2 + Iy_cy2 + Iz_cz2;                                           // norm_θᵢ²ᶜᶜᶜ :349-351
             FT kap = FT(0);
             if (sigma != FT(0)) {
-                FT Ix_cx = interp1c<FT>(cx, o, sx), Iy_cy = interp1c<FT>(cy, o, sy), Iz_cz = interp1c<FT>(cz, o, sz);
-                FT Ixy_dxv = Ixy([&](int p) { return P.dxv(p); });
-                FT Ixy_dyu = Ixy([&](int p) { return P.dyu(p); });
-                FT Ixz_dxw = Ixz([&](int p) { return P.dxw(p); });
-                FT Ixz_dzu = Ixz([&](int p) { return P.dzu(p); });
-                FT Ixz_dyw = Ixz([&](int p) { return P.dyw(p); });                         // sic: ℑxzᶜᵃᶜ(norm_∂y_w) :336
-                FT Iyz_dzv = Iyz([&](int p) { return P.dzv(p); });
+                FT Ix_cx = FT(0.5) * (cx0 + cx1), Iy_cy = FT(0.5) * (cy0 + cy1), Iz_cz = FT(0.5) * (cz0 + cz1);
                 // norm_uᵢⱼ_cⱼ_cᵢᶜᶜᶜ :322-347
                 FT a1 = dxu * Ix_cx2 + Ixy_dxv * Ix_cx * Iy_cy + Ixz_dxw * Ix_cx * Iz_cz;
                 FT a2 = Ixy_dyu * Iy_cy * Ix_cx + dyv * Iy_cy2 + Ixz_dyw * Iy_cy * Iz_cz;
                 FT a3 = Ixz_dzu * Iz_cz * Ix_cx + Iyz_dzv * Iz_cz * Iy_cy + dzw * Iz_cz2;
                 FT theta = a1 + a2 + a3;
-                kap = -Ckappa[t] * delta2 * theta / sigma;                                 // :191
+                kap = -Ckappa[tr] * delta2 * theta / sigma;                                // :191
             }
-            kappa_e[t][o] = oc_max<FT>(FT(0), kap);
+            kappa_e[tr][o] = oc_max<FT>(FT(0), kap);
         }
     }
 };

@@ -917,15 +917,24 @@ void Model<FT>::pressure_solve_from_state() {
 
 template <class FT>
 void Model<FT>::projection(double dt) {
+    const FT* prev_row = nullptr;
     if (dist_) {
-        // the gradient across the slab boundary needs the neighbour's ϕ: unpack into pNHS, exchange its halo, then correct
-        PoissonUnpackKernel<FT> u;
-        u.g = g_; u.L = fft_.L; u.buf = fftbuf_; u.field = pNHS_.p; u.dense = nullptr;
-        go(u, grid_xyz(256), 0, OC_TIMER_PROJECTION);
-        std::vector<FieldRec*> p{&pNHS_};
-        halo(p, true);
-        make_pressure_correction(dt);
-        return;
+        // the pressure gradient at the first local row needs the y-neighbour's last row of ϕ: one dense (Nx, Nz) message
+        // (the reference fills all of pNHS's halos, halo_communication.jl:87-187; only this row is ever read)
+        const size_t n = (size_t)g_.N[0] * g_.N[2];
+        if (2 * n > halo_buf_elems_) throw Error(OC_ERR_STATE, "internal: exchange buffer too small for the ϕ row");
+        PhiRowKernel<FT> r;
+        r.L = fft_.L; r.buf = fftbuf_; r.row = halo_send_;
+        Dim3 rg;
+        rg.x = (g_.N[0] + 255) / 256; rg.y = g_.N[2];
+        go(r, rg, 0, OC_TIMER_COMM);
+        const int prev = (rank_ + R_ - 1) % R_, next = (rank_ + 1) % R_;
+        std::vector<Msg> msgs{Msg{next, prev, 1, halo_send_, n * sizeof(FT), halo_recv_, n * sizeof(FT)}};
+        begin_timer(OC_TIMER_COMM);
+        std::string e = transport_ ? transport_->exchange(msgs, stream_) : std::string("distributed model without a transport");
+        end_timer();
+        if (!e.empty()) throw Error(OC_ERR_CUDA, e);
+        prev_row = halo_recv_;
     }
     ProjectionKernel<FT> k;
     k.g = g_;
@@ -933,6 +942,7 @@ void Model<FT>::projection(double dt) {
     k.buf = fftbuf_;
     k.u = state_[0].p; k.v = state_[1].p; k.w = state_[2].p;
     k.pNHS = pNHS_.p;
+    k.prev_row = prev_row;
     k.dt_plus = std::max((double)std::numeric_limits<FT>::epsilon(), dt);
     go(k, grid_xyz(256), 0, OC_TIMER_PROJECTION);
 }

@@ -242,6 +242,7 @@ struct ProjectionKernel {
     FT* w;
     FT* pNHS;
     double dt_plus;       // max(eps(FT), Δt)
+    const FT* prev_row;   // slab decomposition: ϕ of the y-neighbour's last row, dense (Nx, Nz); nullptr on one GPU
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
         int i = b.x * nt + tid, j = b.y, k = b.z;
@@ -253,7 +254,8 @@ struct ProjectionKernel {
             u[o] = u[o] - (p0 - pm) * g.rd[0];
         }
         if (!g.flat[1]) {
-            FT pm = (j > 0) ? phi_at<FT>(L, buf, i, j - 1, k) : (g.bounded[1] ? p0 : phi_at<FT>(L, buf, i, g.N[1] - 1, k));
+            FT pm = (j > 0) ? phi_at<FT>(L, buf, i, j - 1, k)
+                            : (prev_row ? prev_row[i + (long long)g.N[0] * k] : (g.bounded[1] ? p0 : phi_at<FT>(L, buf, i, g.N[1] - 1, k)));
             v[o] = v[o] - (p0 - pm) * g.rd[1];
         }
         if (!g.flat[2]) {
@@ -261,6 +263,23 @@ struct ProjectionKernel {
             w[o] = w[o] - (p0 - pm) * g.rd[2];
         }
         pNHS[o] = (FT)((double)p0 / dt_plus);
+    }
+};
+
+// slab decomposition: the last local row of ϕ, dense (Nx, Nz), for the y-neighbour's pressure gradient at its first row
+template <class FT>
+struct PhiRowKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    SpectralLayout L;
+    const FT* buf;
+    FT* row;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int i = b.x * nt + tid, k = b.y;
+        if (i >= L.N[0]) return;
+        row[i + (long long)L.N[0] * k] = phi_at<FT>(L, buf, i, L.N[1] - 1, k);
     }
 };
 
