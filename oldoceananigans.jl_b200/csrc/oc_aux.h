@@ -36,6 +36,7 @@ struct HydrostaticPressureKernel {
         int o = g.idx(i, j, Nz);                       // k = Nz (reference index Nz+1): the halo/periodic image above the top
         FT bup = b_at(o);
         FT p = FT(0);
+#pragma unroll 8
         for (int k = Nz - 1; k >= 0; --k) {
             o -= g.sz;
             FT bk = b_at(o);

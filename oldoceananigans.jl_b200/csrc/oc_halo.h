@@ -56,13 +56,16 @@ struct HaloKernel {
         int bi = nboxes - 1;
         while (bi > 0 && boxes[bi].first_block > b.x) --bi;
         const HaloBox bx = boxes[bi];
-        long long cell = (long long)(b.x - bx.first_block) * nt + tid;
-        long long ncell = (long long)bx.n[0] * bx.n[1] * bx.n[2];
+        // boxes are halo slabs: far fewer than 2^31 cells each (checked on the host), so 32-bit index arithmetic
+        const unsigned cell = (unsigned)(b.x - bx.first_block) * (unsigned)nt + (unsigned)tid;
+        const unsigned ncell = (unsigned)bx.n[0] * (unsigned)bx.n[1] * (unsigned)bx.n[2];
         if (cell >= ncell) return;
         int P[3];
-        P[0] = bx.lo[0] + (int)(cell % bx.n[0]);
-        P[1] = bx.lo[1] + (int)((cell / bx.n[0]) % bx.n[1]);
-        P[2] = bx.lo[2] + (int)(cell / ((long long)bx.n[0] * bx.n[1]));
+        const unsigned row = cell / (unsigned)bx.n[0];
+        P[0] = bx.lo[0] + (int)(cell - row * (unsigned)bx.n[0]);
+        const unsigned pl = row / (unsigned)bx.n[1];
+        P[1] = bx.lo[1] + (int)(row - pl * (unsigned)bx.n[1]);
+        P[2] = bx.lo[2] + (int)pl;
         const HaloField<FT>& fld = f[bx.field];
 
         int Q[3];

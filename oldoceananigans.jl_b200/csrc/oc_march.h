@@ -44,13 +44,20 @@ OC_DEV void mbar_fence_init() {
 OC_DEV void mbar_expect(uint64_t* bar, int bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Potentially-blocking wait.  A lost TMA transaction or a protocol bug would otherwise hang the GPU until the watchdog: after
+// ~2^26 failed polls (seconds) the kernel traps, which the host sees as a launch failure instead of a hang.
 OC_DEV void mbar_wait(uint64_t* bar, int parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
+        ".reg .u32 cnt;\n\t"
+        "mov.u32 cnt, 0;\n\t"
         "WAIT_LOOP:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
         "@P1 bra WAIT_DONE;\n\t"
+        "add.u32 cnt, cnt, 1;\n\t"
+        "setp.gt.u32 P1, cnt, 0x4000000;\n\t"
+        "@P1 trap;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity)

@@ -426,6 +426,7 @@ void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open) {
             b.n[0] = n0; b.n[1] = n1; b.n[2] = n2;
             b.first_block = nb;
             long long cells = (long long)n0 * n1 * n2;
+            if (cells >= (1LL << 31)) throw Error(OC_ERR_UNSUPPORTED, "halo slab with 2^31 or more cells");
             nb += (int)((cells + HaloKernel<FT>::THREADS - 1) / HaloKernel<FT>::THREADS);
             boxes.push_back(b);
         };
@@ -882,6 +883,17 @@ void Model<FT>::run_fft_solve() {
         Dim3 grid;
         grid.x = (fft_.L.nxc * g_.N[1] + k.chunk - 1) / k.chunk;
         grid.y = g_.N[2];
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+    } else if (!g_.bounded[0] && !g_.bounded[1] && g_.bounded[2]) {
+        PoissonMidZKernel<FT> k;
+        k.L = fft_.L;
+        k.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_);
+        for (int d = 0; d < 3; ++d) k.lam[d] = lam_[d];
+        k.twz = tw_[2];
+        k.norm = 1.0 / ((double)g_.N[0] * g_.N[1] * g_.N[2]);
+        Dim3 grid;
+        grid.x = (fft_.L.nxc * g_.N[1] + 255) / 256;
+        grid.y = g_.N[2] / 2 + 1;
         go(k, grid, 0, OC_TIMER_POISSON_MID);
     } else {
     PoissonMidKernel<FT> k;

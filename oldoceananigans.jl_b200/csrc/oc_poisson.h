@@ -221,6 +221,50 @@ struct PoissonDivideKernel {
     }
 };
 
+// The common LES topology (Periodic, Periodic, Bounded): only z carries a DCT.  One thread per (x, y) and reflection orbit
+// {kz, Nz-kz}; same operations, in the same order, as PoissonMidKernel restricted to d = 2 — but a pure streaming pass
+// (coalesced 16-byte complex loads along x, no local arrays).
+template <class FT>
+struct PoissonMidZKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    SpectralLayout L;
+    Cplx<FT>* spec;
+    const double* lam[3];
+    const Cd* twz;
+    double norm;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const int plane = L.nxc * L.N[1];
+        const int n = b.x * nt + tid;
+        if (n >= plane) return;
+        const int j = n / L.nxc, i = n - j * L.nxc;
+        const int k0 = b.y, k1 = (L.N[2] - k0) % L.N[2];
+        Cplx<FT>* p0 = spec + (long long)plane * k0 + n;
+        Cplx<FT>* p1 = spec + (long long)plane * k1 + n;
+        const Cplx<FT> s0 = *p0, s1 = *p1;
+        Cd a0{(double)s0.x, (double)s0.y}, a1{(double)s1.x, (double)s1.y};
+        const Cd w0 = twz[k0], w1 = twz[k1];
+        // forward post-twiddle: X[k] = ω_k V[k] + conj(ω_k) V[N-k]
+        Cd e0 = cadd(cmul(w0, a0), cmul(cconj(w0), a1));
+        Cd e1 = cadd(cmul(w1, a1), cmul(cconj(w1), a0));
+        // eigenvalue divide
+        const double lxy = lam[0][i] + lam[1][j];
+        if (i == 0 && j == 0 && k0 == 0) e0 = Cd{0.0, 0.0};
+        else { const double sc = -norm / (lxy + lam[2][k0]); e0.x *= sc; e0.y *= sc; }
+        if (i == 0 && j == 0 && k1 == 0) e1 = Cd{0.0, 0.0};
+        else { const double sc = -norm / (lxy + lam[2][k1]); e1.x *= sc; e1.y *= sc; }
+        // inverse pre-twiddle: W[k] = ½ conj(ω_k) (Φ[k] - i Φ[N-k]), Φ[N] := 0
+        const Cd r0 = k0 == 0 ? Cd{0.0, 0.0} : e1;
+        const Cd r1 = k1 == 0 ? Cd{0.0, 0.0} : e0;
+        const Cd t0{e0.x + r0.y, e0.y - r0.x}, t1{e1.x + r1.y, e1.y - r1.x};
+        const Cd h0 = cmul(cconj(w0), t0), h1 = cmul(cconj(w1), t1);
+        *p0 = Cplx<FT>{(FT)(0.5 * h0.x), (FT)(0.5 * h0.y)};
+        *p1 = Cplx<FT>{(FT)(0.5 * h1.x), (FT)(0.5 * h1.y)};
+    }
+};
+
 // ϕ at logical cell (i,j,k) from the transform buffer; i = -1 / N handled by the caller
 template <class FT>
 OC_HD FT phi_at(const SpectralLayout& L, const FT* buf, int i, int j, int k) {
