@@ -105,11 +105,11 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) march_entry(const _
 template <class K>
 inline cudaError_t launch_march(const K& k, Dim3 grid, size_t smem_bytes, Stream stream) {
     if (grid.x <= 0 || grid.y <= 0 || grid.z <= 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
+    static size_t configured = 0;
+    if (configured < smem_bytes) {
         cudaError_t e = cudaFuncSetAttribute(march_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured = smem_bytes;
     }
     march_entry<K><<<dim3(grid.x, grid.y, grid.z), K::THREADS, smem_bytes, stream>>>(k);
     return cudaGetLastError();

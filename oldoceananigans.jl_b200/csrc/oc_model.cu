@@ -124,7 +124,19 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     zeta_[0] = FT(0); zeta_[1] = (FT)(-17.0L / 60.0L); zeta_[2] = (FT)(-5.0L / 12.0L);
 #ifndef OC_HOSTSIM
     cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
-    cuda_check(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    {
+        int lo = 0, hi = 0;
+        cuda_check(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
+        cuda_check(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, hi), "cudaStreamCreate");     // solve + communication first
+        cuda_check(cudaStreamCreateWithPriority(&stream2_, cudaStreamNonBlocking, lo), "cudaStreamCreate");
+    }
+    {
+        cudaEvent_t a, b;
+        cuda_check(cudaEventCreateWithFlags(&a, cudaEventDisableTiming), "cudaEventCreate");
+        cuda_check(cudaEventCreateWithFlags(&b, cudaEventDisableTiming), "cudaEventCreate");
+        ev_fork_ = a; ev_join_ = b;
+    }
+    launch_stream_ = stream_;
 #endif
     const int locs[4][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
     for (int f = 0; f < F_; ++f) {
@@ -215,6 +227,8 @@ Model<FT>::~Model() {
     for (void* e : event_pool_) cudaEventDestroy((cudaEvent_t)e);
     for (auto& r : timer_recs_) { cudaEventDestroy((cudaEvent_t)r.e0); cudaEventDestroy((cudaEvent_t)r.e1); }
     if (sw0_) { cudaEventDestroy((cudaEvent_t)sw0_); cudaEventDestroy((cudaEvent_t)sw1_); }
+    if (ev_fork_) { cudaEventDestroy((cudaEvent_t)ev_fork_); cudaEventDestroy((cudaEvent_t)ev_join_); }
+    if (stream2_) cudaStreamDestroy(stream2_);
     if (stream_) cudaStreamDestroy(stream_);
 #endif
 }
@@ -258,8 +272,31 @@ void Model<FT>::resolve_bcs(FieldRec& f, const oc_bc* user) {
 template <class FT>
 void Model<FT>::sync() {
 #ifndef OC_HOSTSIM
+    join_tracers();
     cuda_check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");
 #endif
+}
+
+// The tracer tendency kernels of a stage only read the OLD velocities and their own tracer, and the pressure solve only touches
+// the NEW velocities: they run concurrently on two streams (FP64-bound stencils overlap the HBM-bound FFT passes and, on several
+// GPUs, the NCCL transposes).  fork: stream2 waits for everything issued so far; join: stream_ waits for the tracer kernels.
+template <class FT>
+void Model<FT>::fork_tracers() {
+#ifndef OC_HOSTSIM
+    cuda_check(cudaEventRecord((cudaEvent_t)ev_fork_, stream_), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(stream2_, (cudaEvent_t)ev_fork_, 0), "cudaStreamWaitEvent");
+    launch_stream_ = stream2_;
+#endif
+    tracers_in_flight_ = true;
+}
+template <class FT>
+void Model<FT>::join_tracers() {
+    if (!tracers_in_flight_) return;
+#ifndef OC_HOSTSIM
+    cuda_check(cudaEventRecord((cudaEvent_t)ev_join_, stream2_), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_join_, 0), "cudaStreamWaitEvent");
+#endif
+    tracers_in_flight_ = false;
 }
 
 template <class FT>
@@ -325,7 +362,7 @@ void Model<FT>::begin_timer(int cls) {
         return (void*)e;
     };
     TimerRec r{cls, get(), get()};
-    cuda_check(cudaEventRecord((cudaEvent_t)r.e0, stream_), "cudaEventRecord");
+    cuda_check(cudaEventRecord((cudaEvent_t)r.e0, launch_stream_), "cudaEventRecord");
     timer_recs_.push_back(r);
 #else
     (void)cls;
@@ -335,7 +372,7 @@ template <class FT>
 void Model<FT>::end_timer() {
 #ifndef OC_HOSTSIM
     if (!timing_) return;
-    cuda_check(cudaEventRecord((cudaEvent_t)timer_recs_.back().e1, stream_), "cudaEventRecord");
+    cuda_check(cudaEventRecord((cudaEvent_t)timer_recs_.back().e1, launch_stream_), "cudaEventRecord");
 #endif
 }
 template <class FT>
@@ -395,7 +432,7 @@ template <class FT>
 template <class K>
 void Model<FT>::go(const K& k, Dim3 grid, size_t smem, int cls) {
     begin_timer(cls);
-    cudaError_t e = launch(k, grid, smem, stream_);
+    cudaError_t e = launch(k, grid, smem, launch_stream_);
     end_timer();
 #ifndef OC_HOSTSIM
     cuda_check(e, "kernel launch");
@@ -702,7 +739,11 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
         k.KC = (g_.N[2] + zch - 1) / zch;
         grid.z = (g_.N[2] + k.KC - 1) / k.KC;
         begin_timer(OC_TIMER_TENDENCY);
-        cudaError_t e = launch_march(k, grid, K::SMEM, stream_);
+        // Kernels that overlap the pressure solve (stream2) leave a third of every SM free — two CTAs per SM instead of three, by
+        // asking for more shared memory than they use — so that the FFT passes and the NCCL kernels can be co-resident.
+        size_t smem = K::SMEM;
+        if (launch_stream_ != stream_ && smem < 80 * 1024) smem = 80 * 1024;
+        cudaError_t e = launch_march(k, grid, smem, launch_stream_);
         end_timer();
 #ifndef OC_HOSTSIM
         cuda_check(e, "march kernel launch");
@@ -727,9 +768,16 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
 }
 
 template <class FT>
-void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state) {
+void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state, bool defer_tracer_join) {
+    join_tracers();
     if (!aux_valid_) aux();
+    // Measured (profiles/): on one GPU the co-residency costs the tracer kernels more than the overlap wins (69.4 vs 67.5 ms);
+    // across GPUs it hides part of the NCCL transposes (77.1 vs 79.4 ms at 2 GPUs) — so it is on for distributed models only.
+    static const char* ov_env = getenv("OC_OVERLAP");
+    const bool want = ov_env ? atoi(ov_env) != 0 : dist_;
+    const bool overlap = defer_tracer_join && F_ > 3 && march_ok_ && want;
     for (int f = 0; f < F_; ++f) {
+        if (f == 3 && overlap) fork_tracers();
         TendencyArgs<FT> a;
         memset(&a, 0, sizeof(a));
         a.g = g_;
@@ -774,6 +822,7 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
         else if (f == 2) launch_tendency<KIND_W>(f, a);
         else launch_tendency<KIND_C>(f, a);
     }
+    launch_stream_ = stream_;
     if (swap_state && mode != STEP_NONE)
         for (int f = 0; f < F_; ++f) std::swap(state_[f].p, next_[f].p), std::swap(state_[f].base, next_[f].base);
 }
@@ -1038,13 +1087,14 @@ template <class FT>
 void Model<FT>::stage(int mode, double dt, int stage_no, double stage_dt, double chi, bool euler) {
     if (!tend_valid_)                                    // Gⁿ holds the previous evaluation: it becomes G⁻ (cache by swap)
         for (int f = 0; f < F_; ++f) std::swap(Gn_[f].p, Gm_[f].p), std::swap(Gn_[f].base, Gm_[f].base);
-    tendencies(mode, dt, stage_no, chi, euler, true, true);
+    tendencies(mode, dt, stage_no, chi, euler, true, true, /*defer_tracer_join=*/true);
     tend_valid_ = false;
     aux_valid_ = false;
     std::vector<FieldRec*> vel{&state_[0], &state_[1], &state_[2]};
     halo(vel, true);
     pressure_solve_from_state();
     projection(stage_dt);
+    join_tracers();                                      // the tracer substeps (stream2) before their halos are filled
     std::vector<FieldRec*> all;
     for (auto& f : state_) all.push_back(&f);
     halo(all, false);

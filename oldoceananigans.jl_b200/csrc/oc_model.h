@@ -168,6 +168,13 @@ private:
     Cd* tw_[3] = {nullptr, nullptr, nullptr};
     HaloBox* boxes_dev_ = nullptr;
     Stream stream_ = 0;
+    Stream stream2_ = 0;          // tracer tendencies run here, concurrently with the pressure solve on stream_
+    Stream launch_stream_ = 0;    // the stream kernel launches and timer events currently go to
+    void* ev_fork_ = nullptr;
+    void* ev_join_ = nullptr;
+    bool tracers_in_flight_ = false;
+    void fork_tracers();
+    void join_tracers();
     FT gamma_[3], zeta_[3];
     // timers
     bool timing_ = false;
@@ -185,7 +192,7 @@ private:
     void halo(const std::vector<FieldRec*>& fields, bool fill_open);
     void aux();
     void compute_tendencies_if_stale();
-    void tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state);
+    void tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state, bool defer_tracer_join = false);
     template <int KIND> void launch_tendency(int fidx, TendencyArgs<FT>& a);
     template <int KIND> void launch_march_tendency(int fidx, TendencyArgs<FT>& a);
     TileSrc<FT> tile_src(const FT* base, int bx, int by);
