@@ -243,17 +243,20 @@ OC_HD double rcp_newton(double x) {
 }
 OC_HD float rcp_newton(float x) { return rcp_fast(x); }
 
-// 1/x in Float64 for any normal x > 0: MUFU.RCP64H seed + the cubic-then-quadratic refinement CUDA's own division uses
-// (error ~ seed^6).  No Float32 round trip, so no exponent-range limit.
+// 1/x in Float64 for any normal x > 0: MUFU.RCP64H seed (≥ 20 good bits, measured through the parity tests) + one cubic
+// refinement step (error ~ seed³ ≲ 1e-18·…; the value only needs ~1e-14).  No Float32 round trip, so no exponent-range limit.
 OC_HD double rcp_full(double x) {
 #if defined(__CUDA_ARCH__)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     double e = fma(-x, r, 1.0);
-    e = fma(e, e, e);
+    e = fma(e, e, e);                 // r (1 + e + e²): cubic convergence, error ~ seed³
     r = fma(r, e, r);
+#ifdef OC_RCP_FULL
     e = fma(-x, r, 1.0);
-    return fma(e, r, r);
+    r = fma(e, r, r);
+#endif
+    return r;
 #else
     return 1.0 / x;
 #endif
@@ -528,7 +531,7 @@ struct MarchKernel {
         const Geom<FT>& g = a.g;
         G0 c = r0(smem);
         FT grad = (rd<D, FT>(c, ii, jj, lev, 0) - rd<D, FT>(c, ii, jj, lev, -1)) * g.rd[D];
-        if (CLO == 0) return -(a.kappa * g.A[D]) * grad;
+        if (CLO == 0) return -(a.kappa * g.A[D]) * grad;   // (folded with the advective part in total_flux for CLO == 0)
         FT flux = FT(0);
         if (a.has_scalar) flux = g.A[D] * (-(a.kappa * grad));
         if (a.kappa_e) {
@@ -598,6 +601,12 @@ struct MarchKernel {
         const int id = D == 0 ? i : (D == 1 ? j : k);
         const int ic = COMP == 0 ? i : (COMP == 1 ? j : k);
         FT F = advective_flux<D>(smem, ii, jj, k, id, ic);
+        if (CLO == 0 && KIND == KIND_C) {
+            // constant κ: F - (κ A / Δ)(c[0] - c[-1]) with the constant folded (one subtraction and one FMA)
+            G0 c = r0(smem);
+            const FT dc = rd<D, FT>(c, ii, jj, k, 0) - rd<D, FT>(c, ii, jj, k, -1);
+            return fmaT(-(a.kappa * a.g.A[D] * a.g.rd[D]), dc, F);
+        }
         if (CLO == 0 || a.has_scalar || a.nu_e || a.kappa_e) {
             if constexpr (KIND == KIND_C) F = F + diffusive_flux<D>(smem, ii, jj, k, i, j);
             else F = F + viscous_flux<D>(smem, ii, jj, k, i, j);
