@@ -142,6 +142,13 @@ int  oc_time_step_ab2(oc_model* m, double dt, int euler);
 int  oc_get_clock(oc_model* m, oc_clock* clock);
 int  oc_set_clock(oc_model* m, const oc_clock* clock);                 /* Checkpointer pickup: checkpointer.jl:202-228 */
 
+/* ---- on-device step diagnostics (one reduction pass, a 40-byte device-to-host copy) ----
+ * cell_advection_timescale(grid, velocities)  src/Advection/cell_advection_timescale.jl:13-34  (TimeStepWizard,
+ * src/Simulations/time_step_wizard.jl:101-115); maximum(abs, u|v|w) for progress messages; hasnan(u)  src/Diagnostics/nan_checker.jl.
+ * Distributed models return the LOCAL values: reduce them across ranks as the reference does (all_reduce(min, …)). */
+typedef struct { double cell_advection_timescale; double max_abs_u, max_abs_v, max_abs_w; int32_t has_nan; int32_t pad; } oc_diagnostics;
+int  oc_compute_diagnostics(oc_model* m, oc_diagnostics* out);
+
 /* ---- multi-GPU: one process per GPU, slab decomposition in y ----
  * Replaces Distributed(...) + fill_halo_regions! on distributed fields (src/DistributedComputations/halo_communication.jl:87-333)
  * and DistributedFFTBasedPoissonSolver (distributed_fft_based_poisson_solver.jl:92-188).  Create the model with

@@ -49,6 +49,11 @@ class oc_field_info(C.Structure):
                 ("device_ptr", C.c_void_p), ("stride_y", C.c_int64), ("stride_z", C.c_int64)]
 
 
+class oc_diagnostics(C.Structure):
+    _fields_ = [("cell_advection_timescale", C.c_double), ("max_abs_u", C.c_double), ("max_abs_v", C.c_double),
+                ("max_abs_w", C.c_double), ("has_nan", C.c_int32), ("pad", C.c_int32)]
+
+
 class oc_clock(C.Structure):
     _fields_ = [("time", C.c_double), ("iteration", C.c_int64), ("stage", C.c_int32),
                 ("last_dt", C.c_double), ("last_stage_dt", C.c_double)]
@@ -86,6 +91,7 @@ SYMBOLS = {
     "oc_time_step_ab2": (C.c_int, [_M, C.c_double, C.c_int]),
     "oc_get_clock": (C.c_int, [_M, C.POINTER(oc_clock)]),
     "oc_set_clock": (C.c_int, [_M, C.POINTER(oc_clock)]),
+    "oc_compute_diagnostics": (C.c_int, [_M, C.POINTER(oc_diagnostics)]),
     "oc_dist_unique_id": (C.c_int, [C.c_void_p]),
     "oc_dist_attach_nccl": (C.c_int, [_M, C.c_void_p]),
     "oc_dist_attach_host": (C.c_int, [_M, C.c_void_p, C.c_void_p]),

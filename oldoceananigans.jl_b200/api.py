@@ -31,6 +31,7 @@ __all__ = [
     "compute_tendencies_", "compute_flux_bc_tendencies_", "rk3_substep_", "ab2_step_", "cache_previous_tendencies_",
     "compute_pressure_correction_", "make_pressure_correction_", "fill_halo_regions_", "solve_poisson",
     "interior", "parent", "Simulation", "run_", "Clock", "OceananigansB200Error",
+    "cell_advection_timescale", "hasnan", "step_diagnostics", "TimeStepWizard",
 ]
 
 OceananigansB200Error = L.OceananigansB200Error
@@ -573,6 +574,60 @@ def solve_poisson(model, rhs):
     out = np.empty(g.N, dtype=g.FT, order="F")
     model._lib.check(model._lib.oc_poisson_solve(model._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), a.nbytes))
     return out
+
+
+# ------------------------------------------------------------------------------------------ diagnostics
+def step_diagnostics(model):
+    """One on-device reduction pass: (cell_advection_timescale, max|u|, max|v|, max|w|, hasnan(u)); distributed models reduce across
+    ranks (all_reduce(min / max), src/Simulations/time_step_wizard.jl:112)."""
+    d = L.oc_diagnostics()
+    model._lib.check(model._lib.oc_compute_diagnostics(model._h, C.byref(d)))
+    out = dict(cell_advection_timescale=d.cell_advection_timescale, max_abs_u=d.max_abs_u, max_abs_v=d.max_abs_v,
+               max_abs_w=d.max_abs_w, has_nan=bool(d.has_nan))
+    if getattr(model, "distributed", False):
+        import torch
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            t = torch.tensor([-out["cell_advection_timescale"], out["max_abs_u"], out["max_abs_v"], out["max_abs_w"],
+                              float(out["has_nan"])], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t = t.cpu().tolist()
+            out = dict(cell_advection_timescale=-t[0], max_abs_u=t[1], max_abs_v=t[2], max_abs_w=t[3], has_nan=bool(t[4]))
+    return out
+
+
+def cell_advection_timescale(model):
+    """cell_advection_timescale(model)   src/Advection/cell_advection_timescale.jl:13-34"""
+    return step_diagnostics(model)["cell_advection_timescale"]
+
+
+def hasnan(model):
+    """hasnan(model) = hasnan(first(fields(model)))   src/Diagnostics/nan_checker.jl"""
+    return step_diagnostics(model)["has_nan"]
+
+
+class TimeStepWizard:
+    """TimeStepWizard(cfl=0.2, max_change=1.1, min_change=0.5, max_Δt=Inf, min_Δt=0)   src/Simulations/time_step_wizard.jl:65-116
+    (advective CFL only: the diffusive timescale is out of scope)."""
+
+    def __init__(self, cfl=0.2, max_change=1.1, min_change=0.5, max_Δt=math.inf, min_Δt=0.0, max_dt=None, min_dt=None):
+        if min_change >= 1:
+            raise ValueError(f"min_change must be < 1. You provided min_change = {min_change}.")
+        if max_change <= 1:
+            raise ValueError(f"max_change must be > 1. You provided max_change = {max_change}.")
+        self.cfl, self.max_change, self.min_change = cfl, max_change, min_change
+        self.max_dt = max_Δt if max_dt is None else max_dt
+        self.min_dt = min_Δt if min_dt is None else min_dt
+
+    def new_time_step(self, old_dt, model):
+        new_dt = self.cfl * cell_advection_timescale(model)
+        new_dt = min(self.max_change * old_dt, new_dt)
+        new_dt = max(self.min_change * old_dt, new_dt)
+        return min(max(new_dt, self.min_dt), self.max_dt)
+
+    def __call__(self, simulation):
+        simulation.Δt = self.new_time_step(simulation.Δt, simulation.model)
 
 
 # ------------------------------------------------------------------------------------------ Simulation

@@ -59,9 +59,9 @@ struct AmdPoint {
     const FT* v;
     const FT* w;
     FT rxy, ryx, rxz, rzx, ryz, rzy;   // Δᶠa/Δᶠb with Δᶠ = 2Δ   (:224-226)
-    OC_HD AmdPoint(const Geom<FT>& g_, const FT* u_, const FT* v_, const FT* w_) : g(g_), u(u_), v(v_), w(w_) {
-        FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = FT(2) * g.d[2];
-        rxy = fx / fy; ryx = fy / fx; rxz = fx / fz; rzx = fz / fx; ryz = fy / fz; rzy = fz / fy;
+    // the six filter-width ratios are loop invariants with divisions: formed once on the host (AmdConsts), same FT arithmetic
+    OC_HD AmdPoint(const Geom<FT>& g_, const FT* u_, const FT* v_, const FT* w_, const FT* r) : g(g_), u(u_), v(v_), w(w_) {
+        rxy = r[0]; ryx = r[1]; rxz = r[2]; rzx = r[3]; ryz = r[4]; rzy = r[5];
     }
     // normalised gradients at their natural locations (velocity_tracer_gradients.jl:126-154); o = linear index
     OC_HD FT dxu(int o) const { return (u[o + 1] - u[o]) * g.rd[0]; }                       // ccc
@@ -95,7 +95,7 @@ OC_HD FT interp4(const FT* f) { return FT(0.5) * (FT(0.5) * (f[0] + f[1]) + FT(0
 template <class FT>
 struct AmdKernel {
     static constexpr int PHASES = 1;
-    static constexpr int THREADS = 128;
+    static constexpr int THREADS = 256;      // 32 (x) × 8 (y) cells per CTA: the 27-point neighbourhoods share L1 lines in x AND y
     static constexpr int MIN_BLOCKS = 1;
     Geom<FT> g;
     const FT* u;
@@ -107,19 +107,26 @@ struct AmdKernel {
     const FT* c[8];
     FT* kappa_e[8];
     FT Ckappa[8];
+    FT ratios[6];      // Δᶠa/Δᶠb   (:224-226)
+    FT delta2;         // δ² = 3 / (1/Δᶠx² + 1/Δᶠy² + 1/Δᶠz²)   (:166,190)
+    void set_consts() {
+        FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = FT(2) * g.d[2];
+        ratios[0] = fx / fy; ratios[1] = fy / fx; ratios[2] = fx / fz; ratios[3] = fz / fx; ratios[4] = fy / fz; ratios[5] = fz / fy;
+        delta2 = FT(3) / (FT(1) / (fx * fx) + FT(1) / (fy * fy) + FT(1) / (fz * fz));
+    }
 
     // Every normalised gradient is evaluated ONCE at the four corners its interpolations need (24 evaluations per cell);
     // all 30 terms of AMD are then products of those — same operands, same order of operations as the reference's
     // nested ℑ(…) calls (anisotropic_minimum_dissipation.jl:240-351).
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
-        int i = b.x * nt + tid, j = b.y, k = b.z;
-        if (i >= g.N[0]) return;
+        (void)nt;
+        int i = b.x * 32 + (tid & 31), j = b.y * 8 + (tid >> 5), k = b.z;
+        if (i >= g.N[0] || j >= g.N[1]) return;
         const int o = g.idx(i, j, k);
         const int sx = 1, sy = g.sy, sz = g.sz;
-        AmdPoint<FT> P(g, u, v, w);
-        FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = FT(2) * g.d[2];
-        FT delta2 = FT(3) / (FT(1) / (fx * fx) + FT(1) / (fy * fy) + FT(1) / (fz * fz));   // :166,190
+        AmdPoint<FT> P(g, u, v, w, ratios);
+        const FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = FT(2) * g.d[2];
         auto sq = [](FT x) { return x * x; };
         const int cxy[4] = {o, o + sx, o + sy, o + sx + sy};
         const int cxz[4] = {o, o + sx, o + sz, o + sx + sz};
@@ -212,6 +219,71 @@ struct AmdKernel {
                 kap = -Ckappa[tr] * delta2 * theta / sigma;                                // :191
             }
             kappa_e[tr][o] = oc_max<FT>(FT(0), kap);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// On-device step diagnostics: cell_advection_timescale (src/Advection/cell_advection_timescale.jl:13-34,
+// the TimeStepWizard's reduction, src/Simulations/time_step_wizard.jl:101-115), max|u|, max|v|, max|w| (progress messages) and
+// the NaNChecker's hasnan(u) (src/Diagnostics/nan_checker.jl) in ONE pass — instead of full-field device-to-host copies.
+// All reduced quantities are non-negative doubles, so their bit patterns order like unsigned integers.
+// out[0] = min timescale, out[1..3] = max |u|,|v|,|w|, out[4] = NaN flag.
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+struct DiagnosticsKernel {
+    static constexpr int PHASES = 2;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr size_t SMEM = sizeof(double) * 5 * THREADS;
+    Geom<FT> g;
+    const FT* u;
+    const FT* v;
+    const FT* w;
+    unsigned long long* out;
+    OC_HD static unsigned long long bits(double x) { unsigned long long b; memcpy(&b, &x, 8); return b; }
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char* smem) const {
+        double* sh = reinterpret_cast<double*>(smem);
+        if (PHASE == 0) {
+            double tmin = 1.0e300, mu = 0.0, mv = 0.0, mw = 0.0, nan = 0.0;
+            const int j = b.y, k = b.z;
+            for (int i = b.x * nt + tid; i < g.N[0]; i += nt * 1) {
+                const int o = g.idx(i, j, k);
+                const FT uu = u[o], vv = v[o], ww = w[o];
+                const FT au = oc_abs<FT>(uu), av = oc_abs<FT>(vv), aw = oc_abs<FT>(ww);
+                FT inv = (g.flat[0] ? FT(0) : au * g.rd[0]) + (g.flat[1] ? FT(0) : av * g.rd[1]) + (g.flat[2] ? FT(0) : aw * g.rd[2]);
+                double tau = (double)(FT(1) / inv);
+                if (tau < tmin) tmin = tau;             // NaN compares false: a NaN cell does not enter the minimum, it raises the flag
+                if ((double)au > mu) mu = au;
+                if ((double)av > mv) mv = av;
+                if ((double)aw > mw) mw = aw;
+                if (uu != uu) nan = 1.0;
+            }
+            sh[tid] = tmin; sh[nt + tid] = mu; sh[2 * nt + tid] = mv; sh[3 * nt + tid] = mw; sh[4 * nt + tid] = nan;
+        } else {
+            if (tid != 0) return;
+            double tmin = 1.0e300, mu = 0.0, mv = 0.0, mw = 0.0, nan = 0.0;
+            for (int t = 0; t < nt; ++t) {
+                if (sh[t] < tmin) tmin = sh[t];
+                if (sh[nt + t] > mu) mu = sh[nt + t];
+                if (sh[2 * nt + t] > mv) mv = sh[2 * nt + t];
+                if (sh[3 * nt + t] > mw) mw = sh[3 * nt + t];
+                if (sh[4 * nt + t] > nan) nan = sh[4 * nt + t];
+            }
+#ifndef OC_HOSTSIM
+            atomicMin(out + 0, bits(tmin));
+            atomicMax(out + 1, bits(mu));
+            atomicMax(out + 2, bits(mv));
+            atomicMax(out + 3, bits(mw));
+            if (nan > 0.0) atomicMax(out + 4, 1ull);
+#else
+            if (bits(tmin) < out[0]) out[0] = bits(tmin);
+            if (bits(mu) > out[1]) out[1] = bits(mu);
+            if (bits(mv) > out[2]) out[2] = bits(mv);
+            if (bits(mw) > out[3]) out[3] = bits(mw);
+            if (nan > 0.0) out[4] = 1ull;
+#endif
         }
     }
 };

@@ -382,7 +382,7 @@ OC_HD FT t_weno5_symmetric(const A& a, int ii, int jj, int lev, FT area, int f, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// the kernel.  BND = 0: no Bounded dimension (all wall logic compiled out); 1: generic.
+// the kernel.  BND = bit mask of possibly-Bounded dimensions: 0 (none: all wall logic compiled out), 4 (z only), 7 (generic).
 //              CLO = 0: constant ν, κ (possibly 0: no closure); 1: generic (AMD eddy fields, closure tuples).
 // One thread per y-face: THREADS = TX·(TY+1); the x-faces and z-faces map onto the same threads so that every
 // warp evaluates at most three fluxes per level (no tail warps in front of the barrier).
@@ -393,7 +393,9 @@ struct MarchKernel {
     static constexpr int THREADS = TX * (TY + 1);
     static constexpr int MIN_BLOCKS = TY_ == 8 ? 3 : 5;
     static constexpr int COMP = KIND == KIND_C ? -1 : KIND;
-    static constexpr bool WIN = BND != 0;
+    static constexpr bool WIN = BND != 0;                 // any wall logic at all
+    // BND is a bit mask of the dimensions that MAY be Bounded (7 = generic): order-reduction windows exist only there
+    template <int D> static constexpr bool WINV = ((BND >> D) & 1) != 0;
     using SP = MarchSpec<KIND, TX, TY, 16 / (int)sizeof(FT)>;
     using G0 = Ring<FT, typename SP::R0>;
     using G1 = Ring<FT, typename SP::R1>;
@@ -556,8 +558,8 @@ struct MarchKernel {
                 return (A * u) * (FT(0.5) * rd<D, FT>(c, ii, jj, lev, -1) + FT(0.5) * rd<D, FT>(c, ii, jj, lev, 0));
             } else {
                 OrderWindow w;
-                if (WIN) w = order_window(g.bounded[D] != 0, false, g.N[D]);
-                FT cr = t_weno5_biased<D, WIN, FT>(c, ii, jj, lev, u > FT(0), id, w);
+                if (WINV<D>) w = order_window(g.bounded[D] != 0, false, g.N[D]);
+                FT cr = t_weno5_biased<D, WINV<D>, FT>(c, ii, jj, lev, u > FT(0), id, w);
                 return A * u * cr;
             }
         } else {
@@ -570,10 +572,10 @@ struct MarchKernel {
                     return A * ut * ut;
                 } else {
                     OrderWindow w;
-                    if (WIN) w = order_window(g.bounded[D] != 0, true, g.N[D]);
+                    if (WINV<D>) w = order_window(g.bounded[D] != 0, true, g.N[D]);
                     const int i1 = ii + (D == 0), j1 = jj + (D == 1), l1 = lev + (D == 2);
-                    FT ut = t_weno5_symmetric<D, WIN, FT>(psi, i1, j1, l1, A, id + 1, w);
-                    FT pr = t_weno5_biased<D, WIN, FT>(psi, i1, j1, l1, ut > FT(0), id + 1, w);
+                    FT ut = t_weno5_symmetric<D, WINV<D>, FT>(psi, i1, j1, l1, A, id + 1, w);
+                    FT pr = t_weno5_biased<D, WINV<D>, FT>(psi, i1, j1, l1, ut > FT(0), id + 1, w);
                     return ut * pr;
                 }
             } else {
@@ -584,11 +586,12 @@ struct MarchKernel {
                     return A * ut * pt;
                 } else {
                     OrderWindow wc, wd;
-                    if (WIN) { wc = order_window(g.bounded[CC] != 0, false, g.N[CC]); wd = order_window(g.bounded[D] != 0, false, g.N[D]); }
+                    if (WINV<CC>) wc = order_window(g.bounded[CC] != 0, false, g.N[CC]);
+                    if (WINV<D>) wd = order_window(g.bounded[D] != 0, false, g.N[D]);
                     FT ut;
-                    if (D == SP::F1) ut = t_weno5_symmetric<CC, WIN, FT>(r1(smem), ii, jj, lev, A, ic, wc);
-                    else ut = t_weno5_symmetric<CC, WIN, FT>(r2(smem), ii, jj, lev, A, ic, wc);
-                    FT pr = t_weno5_biased<D, WIN, FT>(psi, ii, jj, lev, ut > FT(0), id, wd);
+                    if (D == SP::F1) ut = t_weno5_symmetric<CC, WINV<CC>, FT>(r1(smem), ii, jj, lev, A, ic, wc);
+                    else ut = t_weno5_symmetric<CC, WINV<CC>, FT>(r2(smem), ii, jj, lev, A, ic, wc);
+                    FT pr = t_weno5_biased<D, WINV<D>, FT>(psi, ii, jj, lev, ut > FT(0), id, wd);
                     return ut * pr;
                 }
             }

@@ -220,6 +220,7 @@ Model<FT>::~Model() {
     fr(pNHS_); fr(pHY_); fr(nu_e_);
     for (auto& f : kappa_e_) fr(f);
     dev_free(fftbuf_);
+    dev_free(diag_dev_);
     dev_free(distT_); dev_free(diststage_); dev_free(halo_send_); dev_free(halo_recv_);
     for (int d = 0; d < 3; ++d) { dev_free(lam_[d]); dev_free(tw_[d]); }
     for (auto& kv : halo_cache_) dev_free(kv.second.boxes);
@@ -618,7 +619,10 @@ void Model<FT>::aux() {
         k.Cnu = (FT)cfg_.amd_Cnu;
         k.ntr = cfg_.n_tracers;
         for (int t = 0; t < cfg_.n_tracers; ++t) { k.c[t] = state_[3 + t].p; k.kappa_e[t] = kappa_e_[t].p; k.Ckappa[t] = (FT)cfg_.amd_Ckappa[t]; }
-        go(k, grid_xyz(AmdKernel<FT>::THREADS), 0, OC_TIMER_AUX);
+        k.set_consts();
+        Dim3 ag;
+        ag.x = (g_.N[0] + 31) / 32; ag.y = (g_.N[1] + 7) / 8; ag.z = g_.N[2];
+        go(k, ag, 0, OC_TIMER_AUX);
         std::vector<FieldRec*> list{&nu_e_};
         for (auto& f : kappa_e_) list.push_back(&f);
         halo(list, true);
@@ -754,14 +758,15 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
     };
     const bool bnd = g_.bounded[0] || g_.bounded[1] || g_.bounded[2];
     const bool gen = has_amd_;
-    static const int ty_env = getenv("OC_MARCH_TY") ? atoi(getenv("OC_MARCH_TY")) : 8;
     auto pick = [&](auto adv) {
         constexpr int ADV = decltype(adv)::value;
-        if (!bnd && !gen && ty_env == 4) run(MarchKernel<FT, ADV, KIND, 0, 0, 4>{});
-        else if (!bnd && !gen) run(MarchKernel<FT, ADV, KIND, 0, 0>{});
+        const bool zonly = !g_.bounded[0] && !g_.bounded[1] && g_.bounded[2];     // the LES topology (Periodic, Periodic, Bounded)
+        if (!bnd && !gen) run(MarchKernel<FT, ADV, KIND, 0, 0>{});
         else if (!bnd) run(MarchKernel<FT, ADV, KIND, 0, 1>{});
-        else if (!gen) run(MarchKernel<FT, ADV, KIND, 1, 0>{});
-        else run(MarchKernel<FT, ADV, KIND, 1, 1>{});
+        else if (zonly && !gen) run(MarchKernel<FT, ADV, KIND, 4, 0>{});
+        else if (zonly) run(MarchKernel<FT, ADV, KIND, 4, 1>{});
+        else if (!gen) run(MarchKernel<FT, ADV, KIND, 7, 0>{});
+        else run(MarchKernel<FT, ADV, KIND, 7, 1>{});
     };
     if (cfg_.advection == OC_WENO5) pick(std::integral_constant<int, 1>{});
     else pick(std::integral_constant<int, 0>{});
@@ -1043,6 +1048,31 @@ void Model<FT>::make_pressure_correction(double dt) {
 }
 
 template <class FT>
+void Model<FT>::diagnostics(oc_diagnostics* out) {
+    join_tracers();
+    if (!diag_dev_) diag_dev_ = (unsigned long long*)dev_alloc(sizeof(unsigned long long) * 5);
+    const double big = 1.0e300;
+    unsigned long long init[5] = {0, 0, 0, 0, 0};
+    memcpy(&init[0], &big, 8);
+    dev_upload(diag_dev_, init, sizeof(init), stream_);
+    DiagnosticsKernel<FT> k;
+    k.g = g_;
+    k.u = state_[0].p; k.v = state_[1].p; k.w = state_[2].p;
+    k.out = diag_dev_;
+    Dim3 grid;
+    grid.x = 1; grid.y = g_.N[1]; grid.z = g_.N[2];
+    go(k, grid, DiagnosticsKernel<FT>::SMEM, OC_TIMER_AUX);
+    unsigned long long res[5];
+    dev_download(res, diag_dev_, sizeof(res), stream_);
+    double d[4];
+    memcpy(d, res, sizeof(d));
+    out->cell_advection_timescale = d[0] >= big ? INFINITY : d[0];
+    out->max_abs_u = d[1]; out->max_abs_v = d[2]; out->max_abs_w = d[3];
+    out->has_nan = res[4] ? 1 : 0;
+    out->pad = 0;
+}
+
+template <class FT>
 void Model<FT>::poisson_solve(const void* rhs, void* phi, size_t nbytes) {
     size_t n = (size_t)g_.N[0] * g_.N[1] * g_.N[2];
     if (nbytes != n * sizeof(FT)) throw Error(OC_ERR_INVALID, "poisson_solve: buffer size mismatch");
@@ -1220,6 +1250,7 @@ int oc_time_step_rk3(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&]
 int oc_time_step_ab2(oc_model* m, double dt, int euler) { OC_REQUIRE(m); return guarded([&] { m->impl->time_step_ab2(dt, euler); }); }
 int oc_get_clock(oc_model* m, oc_clock* c) { OC_REQUIRE(m); *c = m->impl->clock; return OC_OK; }
 int oc_set_clock(oc_model* m, const oc_clock* c) { OC_REQUIRE(m); m->impl->clock = *c; return OC_OK; }
+int oc_compute_diagnostics(oc_model* m, oc_diagnostics* out) { OC_REQUIRE(m); return guarded([&] { m->impl->diagnostics(out); }); }
 int oc_dist_unique_id(void* id128) {
     if (!id128) { g_last_error = "null argument"; return OC_ERR_INVALID; }
     return guarded([&] {

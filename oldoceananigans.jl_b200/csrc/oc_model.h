@@ -97,6 +97,7 @@ struct ModelBase {
     virtual void set_finalize(int enforce) = 0;
     virtual void time_step_rk3(double dt) = 0;
     virtual void time_step_ab2(double dt, int euler) = 0;
+    virtual void diagnostics(oc_diagnostics* out) = 0;
     virtual void dist_attach(Transport* t) = 0;
     virtual int dist_rank() const = 0;
     virtual int dist_nranks() const = 0;
@@ -131,6 +132,7 @@ public:
     void set_finalize(int enforce) override;
     void time_step_rk3(double dt) override;
     void time_step_ab2(double dt, int euler) override;
+    void diagnostics(oc_diagnostics* out) override;
     void dist_attach(Transport* t) override;
     int dist_rank() const override { return rank_; }
     int dist_nranks() const override { return R_; }
@@ -167,6 +169,7 @@ private:
     double* lam_[3] = {nullptr, nullptr, nullptr};
     Cd* tw_[3] = {nullptr, nullptr, nullptr};
     HaloBox* boxes_dev_ = nullptr;
+    unsigned long long* diag_dev_ = nullptr;
     Stream stream_ = 0;
     Stream stream2_ = 0;          // tracer tendencies run here, concurrently with the pressure solve on stream_
     Stream launch_stream_ = 0;    // the stream kernel launches and timer events currently go to
