@@ -271,7 +271,7 @@ struct DiagnosticsKernel {
                 if (sh[3 * nt + t] > mw) mw = sh[3 * nt + t];
                 if (sh[4 * nt + t] > nan) nan = sh[4 * nt + t];
             }
-#ifndef OC_HOSTSIM
+#if defined(__CUDA_ARCH__)
             atomicMin(out + 0, bits(tmin));
             atomicMax(out + 1, bits(mu));
             atomicMax(out + 2, bits(mv));
