@@ -33,6 +33,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "cell-updates/sec per full RK3 step"
+# measured DRAM traffic per MarchKernel launch (bytes), from one `ncu --set full` capture per workload (profiles/)
+NCU_TRAFFIC = {"c3": 6.53e9}
 
 # name -> description of the BASELINE.json configuration
 WORKLOADS = {
@@ -328,7 +330,8 @@ def run_ours(args):
                    "cells_per_gpu": cells, "l2_policy": "working set (>25 GB at 512^3) far exceeds the 126 MB L2; no flush needed"
                    if cells >= 256 ** 3 else "working set may fit L2 (launch-latency configuration)"},
         "roofline": {"bound": "hbm", "kernel": "TendencyKernel (fused tendency + RK3 substep, one launch per prognostic field)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(args.workload if world == 1 else None),
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 5 first-stage launches in profiles/r01d_ncu_march_c3_summary.txt (ncu --set full)" if (world == 1 and args.workload in NCU_TRAFFIC) else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                      "avg_launch_ms": avg_launch_ms, "launches_per_step": launches_per_step,
                      "step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
