@@ -143,10 +143,10 @@ struct MarchStateT {
     FT dfz;       // δz of the z-face fluxes of the level whose divergence is formed next
 };
 
-// Loads for iteration it + PF are issued in phase 1 of iteration it; they overwrite the slot of level
-// k + PF + HI - D, which must not be read any more: D >= LIVE + PF - 1 for rings read only in phase 0,
-// D >= LIVE + PF for rings whose lowest level is also read in phase 1.
-enum { MARCH_PF = 2, MARCH_NBAR = 4, MARCH_NSYNC = 4 };
+// Loads for iteration it + PF are issued in step<1>(it), after every thread has finished iteration it-1; they overwrite the
+// slot of level k + PF + HI - D, which must lie below everything iteration it still reads: D >= LIVE + PF, and one more for a
+// ring whose level k-1 is read by the divergence phase of iteration it (the Coriolis operand of the u / v kernels).
+enum { MARCH_NBAR = 4, MARCH_NSYNC = 4 };     // the prefetch distance PF (levels) is per kernel kind: MarchSpec<…>::PF
 
 // Which planes each kernel stages.  `FIELD` names the global field: -1 = the stepped field itself (ψ or c), 0/1/2 = u/v/w.
 // E = elements per 16 bytes; box x-origins are kept multiples of E (16-byte aligned box rows).
@@ -154,6 +154,7 @@ template <int KIND, int TX, int TY, int E>
 struct MarchSpec;
 template <int TX, int TY, int E>
 struct MarchSpec<KIND_C, TX, TY, E> {
+    static constexpr int PF = 2;
     static constexpr int NR = 4;
     using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 8>;   // c: WENO-5 radius in x, y, z
     using R1 = RingSpec<0, TX + 4, 0, TY, 0, 0, 3>;          // u at the x-faces of level k
@@ -163,6 +164,7 @@ struct MarchSpec<KIND_C, TX, TY, E> {
 };
 template <int TX, int TY, int E>
 struct MarchSpec<KIND_U, TX, TY, E> {
+    static constexpr int PF = 2;
     static constexpr int NR = 3;
     using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 8>;   // u
     using R1 = RingSpec<-E, TX + 2 * E, 0, TY + 1, 0, 0, 4>;     // v[i-2..i+1, j0..j0+TY] (Centered-4 along x, Coriolis, τ12); D = 4: also read in phase 1
@@ -172,6 +174,7 @@ struct MarchSpec<KIND_U, TX, TY, E> {
 };
 template <int TX, int TY, int E>
 struct MarchSpec<KIND_V, TX, TY, E> {
+    static constexpr int PF = 2;
     static constexpr int NR = 3;
     using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 8>;   // v
     using R1 = RingSpec<0, TX + 4, -2, TY + 3, 0, 0, 4>;     // u[i0..i0+TX, j-2..j+1]; D = 4: also read in phase 1 (Coriolis)
@@ -181,10 +184,12 @@ struct MarchSpec<KIND_V, TX, TY, E> {
 };
 template <int TX, int TY, int E>
 struct MarchSpec<KIND_W, TX, TY, E> {
+    // PF = 1: with three 4-to-6-level rings the w kernel would otherwise fit only two CTAs per SM (measured 3.5 vs 3.0 ms)
+    static constexpr int PF = 1;
     static constexpr int NR = 3;
-    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 8>;   // w
-    using R1 = RingSpec<0, TX + 4, 0, TY, -2, 1, 6>;         // u[k-2..k+1] at the x-faces (Centered-4 along z)
-    using R2 = RingSpec<0, TX, 0, TY + 1, -2, 1, 6>;         // v[k-2..k+1] at the y-faces
+    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 7>;   // w
+    using R1 = RingSpec<0, TX + 4, 0, TY, -2, 1, 5>;         // u[k-2..k+1] at the x-faces (Centered-4 along z)
+    using R2 = RingSpec<0, TX, 0, TY + 1, -2, 1, 5>;         // v[k-2..k+1] at the y-faces
     using R3 = RingSpec<0, 4, 0, 1, 0, 0, 1>;
     static constexpr int F1 = 0, F2 = 1, F3 = -2;
 };
@@ -480,7 +485,7 @@ struct MarchKernel {
         if (NR > 3)
             for (int l = SP::R3::LO; l < SP::R3::HI; ++l) issue_level<G3, typename SP::R3>(r3(c), &src[3], i0, j0, kf + l, bar);
         issue_iteration(smem, i0, j0, kf, bar);
-        for (int it = 1; it < MARCH_PF && it < n; ++it) {
+        for (int it = 1; it < SP::PF && it < n; ++it) {
             mbar_expect(bar + (it % MARCH_NBAR), LEVEL_BYTES);
             issue_iteration(smem, i0, j0, kf + it, bar + (it % MARCH_NBAR));
         }
@@ -689,11 +694,11 @@ struct MarchKernel {
             stt.sl.sk[2] = G2::next_slot(stt.sl.sk[2]); stt.sl.sk[3] = G3::next_slot(stt.sl.sk[3]);
         } else {
             if (tid == 0) {
-                const int lit = it + MARCH_PF;
+                const int lit = it + SP::PF;
                 if (lit < nit) {
                     proxy_fence_async();
                     mbar_expect(bar + (lit % MARCH_NBAR), LEVEL_BYTES);
-                    issue_iteration(smem, i0, j0, k + MARCH_PF, bar + (lit % MARCH_NBAR));
+                    issue_iteration(smem, i0, j0, k + SP::PF, bar + (lit % MARCH_NBAR));
                 }
             }
             if (it < 2 || row >= TY) return;                 // levels start at iteration 1; their divergence is formed one iteration later
