@@ -158,6 +158,7 @@ struct TransposeKernel {
     static constexpr int MIN_BLOCKS = 1;
     static constexpr size_t SMEM = sizeof(Cplx<FT>) * 32 * 33;
     int nxc, nyl, nzl, R;
+    int zl0;                   // first local z-level of this launch (grid.z levels from there): sub-chunk pipelining
     int to_T;                  // 1: stage -> T ; 0: T -> stage
     Cplx<FT>* stage;
     Cplx<FT>* T;
@@ -165,7 +166,7 @@ struct TransposeKernel {
     OC_HD void run(const Block& b, int tid, int nt, char* smem) const {
         Cplx<FT>* tile = reinterpret_cast<Cplx<FT>*>(smem);
         const int ny = nyl * R;
-        const int x0 = b.x * 32, y0 = b.y * 32, zl = b.z;
+        const int x0 = b.x * 32, y0 = b.y * 32, zl = zl0 + b.z;
         const int tx = tid & 31, ty = tid >> 5;        // 32 × 8
         if ((PHASE == 0) == (to_T != 0)) {
             // touch the stage side (x contiguous): PHASE 0 reads it when to_T, PHASE 1 writes it when !to_T
@@ -197,12 +198,13 @@ struct PoissonDivideTKernel {
     static constexpr int THREADS = 256;
     static constexpr int MIN_BLOCKS = 1;
     int nxc, ny, nzl, kz0;
+    int zl0;
     Cplx<FT>* T;
     const double* lam[3];      // λx[nxc…], λy[ny] (GLOBAL y), λz[Nz] (global z)
     double norm;
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
-        const int y = b.x * nt + tid, x = b.y, zl = b.z;
+        const int y = b.x * nt + tid, x = b.y, zl = zl0 + b.z;
         if (y >= ny) return;
         const int kz = kz0 + zl;
         const double l = lam[0][x] + lam[1][y] + lam[2][kz];
@@ -223,9 +225,11 @@ public:
     int Nx = 0, Nyl = 0, Nz = 0, R = 1, nxc = 0, nxr = 0, Ny = 0, Nzl = 0;
     size_t work_bytes = 0;
 
-    std::string init(int nx, int nyl, int nz, int r, Stream stream) {
+    int C = 1;                 // the y stage runs in C sub-chunks of Nzl / C levels (pipelined against the all-to-alls)
+    std::string init(int nx, int nyl, int nz, int r, Stream stream, Stream ystream) {
         Nx = nx; Nyl = nyl; Nz = nz; R = r;
         nxc = Nx / 2 + 1; nxr = 2 * nxc; Ny = Nyl * R; Nzl = Nz / R;
+        C = Nzl % 4 == 0 ? 4 : (Nzl % 2 == 0 ? 2 : 1);
 #ifndef OC_HOSTSIM
         const bool dbl = sizeof(FT) == 8;
         size_t w[3] = {0, 0, 0};
@@ -240,17 +244,17 @@ public:
         if (cufftMakePlanMany(inv_, 2, n2, cembed, 1, nxc, rembed, 1, nxr, dbl ? CUFFT_Z2D : CUFFT_C2R, Nyl, &w[1]) != CUFFT_SUCCESS)
             return "cufftMakePlanMany(zx inverse) failed";
         int n1[1] = {Ny};
-        if (cufftMakePlanMany(y_, 1, n1, nullptr, 1, Ny, nullptr, 1, Ny, dbl ? CUFFT_Z2Z : CUFFT_C2C, nxc * Nzl, &w[2]) != CUFFT_SUCCESS)
+        if (cufftMakePlanMany(y_, 1, n1, nullptr, 1, Ny, nullptr, 1, Ny, dbl ? CUFFT_Z2Z : CUFFT_C2C, nxc * (Nzl / C), &w[2]) != CUFFT_SUCCESS)
             return "cufftMakePlanMany(y) failed";
         work_bytes = std::max(w[0], std::max(w[1], w[2]));
         if (work_bytes) {
             if (cudaMalloc(&work_, work_bytes) != cudaSuccess) return "cudaMalloc(cuFFT work area) failed";
             for (cufftHandle h : {fwd_, inv_, y_}) cufftSetWorkArea(h, work_);
         }
-        for (cufftHandle h : {fwd_, inv_, y_}) cufftSetStream(h, stream);
+        cufftSetStream(fwd_, stream); cufftSetStream(inv_, stream); cufftSetStream(y_, ystream);
         planned_ = true;
 #else
-        (void)stream;
+        (void)stream; (void)ystream;
 #endif
         return "";
     }
@@ -268,7 +272,9 @@ public:
         else r = fwd ? cufftExecR2C(fwd_, (cufftReal*)buf, (cufftComplex*)buf) : cufftExecC2R(inv_, (cufftComplex*)buf, (cufftReal*)buf);
         return r == CUFFT_SUCCESS ? "" : "cuFFT zx exec failed with code " + std::to_string((int)r);
     }
-    std::string y(void* T, bool fwd) {
+    // the y transforms of sub-chunk c (levels c·Nzl/C … of T)
+    std::string y(void* Tbase, bool fwd, int c) {
+        char* T = (char*)Tbase + (size_t)c * (Nzl / C) * nxc * Ny * 2 * sizeof(FT);
         cufftResult r;
         if (sizeof(FT) == 8) r = cufftExecZ2Z(y_, (cufftDoubleComplex*)T, (cufftDoubleComplex*)T, fwd ? CUFFT_FORWARD : CUFFT_INVERSE);
         else r = cufftExecC2C(y_, (cufftComplex*)T, (cufftComplex*)T, fwd ? CUFFT_FORWARD : CUFFT_INVERSE);
@@ -313,9 +319,9 @@ public:
         }
         return "";
     }
-    std::string y(void* Tv, bool fwd) {
-        FT* T = (FT*)Tv;
-        for (long long b = 0; b < (long long)nxc * Nzl; ++b) {
+    std::string y(void* Tv, bool fwd, int c) {
+        FT* T = (FT*)Tv + (size_t)c * (Nzl / C) * nxc * Ny * 2;
+        for (long long b = 0; b < (long long)nxc * (Nzl / C); ++b) {
             std::vector<Cd> l(Ny);
             for (int y = 0; y < Ny; ++y) l[y] = Cd{(double)T[2 * (b * Ny + y)], (double)T[2 * (b * Ny + y) + 1]};
             dft(l, fwd);

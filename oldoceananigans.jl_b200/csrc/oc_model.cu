@@ -178,7 +178,18 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     fftbuf_ = (FT*)dev_alloc(fft_.buffer_bytes);
     device_bytes += (int64_t)fft_.buffer_bytes + (int64_t)fft_.work_bytes;
     if (dist_) {
-        err = dfft_.init(g_.N[0], g_.N[1], g_.N[2], R_, stream_);
+#ifndef OC_HOSTSIM
+        cuda_check(cudaStreamCreateWithFlags(&stream3_, cudaStreamNonBlocking), "cudaStreamCreate");
+#endif
+        err = dfft_.init(g_.N[0], g_.N[1], g_.N[2], R_, stream_, stream3_);
+#ifndef OC_HOSTSIM
+        for (int c = 0; c < dfft_.C; ++c) {
+            cudaEvent_t a, b;
+            cuda_check(cudaEventCreateWithFlags(&a, cudaEventDisableTiming), "cudaEventCreate");
+            cuda_check(cudaEventCreateWithFlags(&b, cudaEventDisableTiming), "cudaEventCreate");
+            ev_a2a_.push_back(a); ev_mid_.push_back(b);
+        }
+#endif
         if (!err.empty()) throw Error(OC_ERR_CUDA, err);
         distT_ = (FT*)dev_alloc(fft_.buffer_bytes);
         diststage_ = (FT*)dev_alloc(fft_.buffer_bytes);
@@ -229,6 +240,9 @@ Model<FT>::~Model() {
     for (auto& r : timer_recs_) { cudaEventDestroy((cudaEvent_t)r.e0); cudaEventDestroy((cudaEvent_t)r.e1); }
     if (sw0_) { cudaEventDestroy((cudaEvent_t)sw0_); cudaEventDestroy((cudaEvent_t)sw1_); }
     if (ev_fork_) { cudaEventDestroy((cudaEvent_t)ev_fork_); cudaEventDestroy((cudaEvent_t)ev_join_); }
+    for (void* e : ev_a2a_) cudaEventDestroy((cudaEvent_t)e);
+    for (void* e : ev_mid_) cudaEventDestroy((cudaEvent_t)e);
+    if (stream3_) cudaStreamDestroy(stream3_);
     if (stream2_) cudaStreamDestroy(stream2_);
     if (stream_) cudaStreamDestroy(stream_);
 #endif
@@ -549,20 +563,20 @@ void Model<FT>::exchange_y(const std::vector<FieldRec*>& fields) {
     go(k, grid, 0, OC_TIMER_COMM);
 }
 
-// all-to-all of the R equal chunks of a spectral buffer (distributed_transpose.jl:185-191)
+// all-to-all of sub-chunk c (of C) of the R equal chunks of a spectral buffer (distributed_transpose.jl:185-191)
 template <class FT>
-void Model<FT>::all_to_all(FT* send, FT* recv) {
-    const size_t chunk = fft_.buffer_bytes / R_;
+void Model<FT>::all_to_all(FT* send, FT* recv, int c, int C) {
+    const size_t chunk = fft_.buffer_bytes / R_, sub = chunk / C, off = sub * c;
     std::vector<Msg> msgs;
     for (int d = 1; d < R_; ++d) {
         const int to = (rank_ + d) % R_, from = (rank_ + R_ - d) % R_;
-        msgs.push_back(Msg{to, from, 2 + d, (char*)send + chunk * to, chunk, (char*)recv + chunk * from, chunk});
+        msgs.push_back(Msg{to, from, 2 + d + 16 * c, (char*)send + chunk * to + off, sub, (char*)recv + chunk * from + off, sub});
     }
     begin_timer(OC_TIMER_COMM);
 #ifndef OC_HOSTSIM
-    cuda_check(cudaMemcpyAsync((char*)recv + chunk * rank_, (char*)send + chunk * rank_, chunk, cudaMemcpyDeviceToDevice, stream_), "cudaMemcpyAsync D2D");
+    cuda_check(cudaMemcpyAsync((char*)recv + chunk * rank_ + off, (char*)send + chunk * rank_ + off, sub, cudaMemcpyDeviceToDevice, stream_), "cudaMemcpyAsync D2D");
 #else
-    memcpy((char*)recv + chunk * rank_, (char*)send + chunk * rank_, chunk);
+    memcpy((char*)recv + chunk * rank_ + off, (char*)send + chunk * rank_ + off, sub);
 #endif
     std::string e = transport_ ? transport_->exchange(msgs, stream_) : std::string("distributed model without a transport");
     end_timer();
@@ -570,32 +584,51 @@ void Model<FT>::all_to_all(FT* send, FT* recv) {
 }
 
 // FFT(z,x) local -> transpose -> FFT(y) -> divide -> FFT⁻¹(y) -> transpose back -> FFT⁻¹(z,x)
-// (distributed_fft_based_poisson_solver.jl:141-178)
+// (distributed_fft_based_poisson_solver.jl:141-178).  The y stage is independent per local z-level, so it runs in C sub-chunks
+// on a second stream: the all-to-all of sub-chunk c+1 (NCCL, stream_) overlaps the transposes / y-FFTs / divide of sub-chunk c,
+// and the way back starts as soon as a sub-chunk is finished.  (The reference does not overlap transposes with FFTs.)
 template <class FT>
 void Model<FT>::run_fft_solve_dist() {
     auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
+    const int C = dfft_.C, nz = dfft_.Nzl / C;
     begin_timer(OC_TIMER_FFT); std::string e = dfft_.zx(fftbuf_, true); end_timer(); chk(e);
-    all_to_all(fftbuf_, diststage_);
-    TransposeKernel<FT> t;
-    t.nxc = dfft_.nxc; t.nyl = g_.N[1]; t.nzl = dfft_.Nzl; t.R = R_;
-    t.stage = reinterpret_cast<Cplx<FT>*>(diststage_); t.T = reinterpret_cast<Cplx<FT>*>(distT_);
-    Dim3 tg;
-    tg.x = (dfft_.nxc + 31) / 32; tg.y = (dfft_.Ny + 31) / 32; tg.z = dfft_.Nzl;
-    t.to_T = 1;
-    go(t, tg, TransposeKernel<FT>::SMEM, OC_TIMER_POISSON_MID);
-    begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, true); end_timer(); chk(e);
-    PoissonDivideTKernel<FT> k;
-    k.nxc = dfft_.nxc; k.ny = dfft_.Ny; k.nzl = dfft_.Nzl; k.kz0 = rank_ * dfft_.Nzl;
-    k.T = reinterpret_cast<Cplx<FT>*>(distT_);
-    for (int d = 0; d < 3; ++d) k.lam[d] = lam_[d];
-    k.norm = 1.0 / ((double)g_.N[0] * dfft_.Ny * g_.N[2]);
-    Dim3 grid;
-    grid.x = (dfft_.Ny + 255) / 256; grid.y = dfft_.nxc; grid.z = dfft_.Nzl;
-    go(k, grid, 0, OC_TIMER_POISSON_MID);
-    begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, false); end_timer(); chk(e);
-    t.to_T = 0;
-    go(t, tg, TransposeKernel<FT>::SMEM, OC_TIMER_POISSON_MID);
-    all_to_all(diststage_, fftbuf_);
+    for (int c = 0; c < C; ++c) {
+        all_to_all(fftbuf_, diststage_, c, C);
+#ifndef OC_HOSTSIM
+        cuda_check(cudaEventRecord((cudaEvent_t)ev_a2a_[c], stream_), "cudaEventRecord");
+#endif
+    }
+    for (int c = 0; c < C; ++c) {
+#ifndef OC_HOSTSIM
+        cuda_check(cudaStreamWaitEvent(stream3_, (cudaEvent_t)ev_a2a_[c], 0), "cudaStreamWaitEvent");
+        launch_stream_ = stream3_;
+#endif
+        TransposeKernel<FT> t;
+        t.nxc = dfft_.nxc; t.nyl = g_.N[1]; t.nzl = dfft_.Nzl; t.R = R_; t.zl0 = c * nz;
+        t.stage = reinterpret_cast<Cplx<FT>*>(diststage_); t.T = reinterpret_cast<Cplx<FT>*>(distT_);
+        Dim3 tg;
+        tg.x = (dfft_.nxc + 31) / 32; tg.y = (dfft_.Ny + 31) / 32; tg.z = nz;
+        t.to_T = 1;
+        go(t, tg, TransposeKernel<FT>::SMEM, OC_TIMER_POISSON_MID);
+        begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, true, c); end_timer(); chk(e);
+        PoissonDivideTKernel<FT> k;
+        k.nxc = dfft_.nxc; k.ny = dfft_.Ny; k.nzl = dfft_.Nzl; k.kz0 = rank_ * dfft_.Nzl; k.zl0 = c * nz;
+        k.T = reinterpret_cast<Cplx<FT>*>(distT_);
+        for (int d = 0; d < 3; ++d) k.lam[d] = lam_[d];
+        k.norm = 1.0 / ((double)g_.N[0] * dfft_.Ny * g_.N[2]);
+        Dim3 grid;
+        grid.x = (dfft_.Ny + 255) / 256; grid.y = dfft_.nxc; grid.z = nz;
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+        begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, false, c); end_timer(); chk(e);
+        t.to_T = 0;
+        go(t, tg, TransposeKernel<FT>::SMEM, OC_TIMER_POISSON_MID);
+#ifndef OC_HOSTSIM
+        cuda_check(cudaEventRecord((cudaEvent_t)ev_mid_[c], stream3_), "cudaEventRecord");
+        launch_stream_ = stream_;
+        cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_mid_[c], 0), "cudaStreamWaitEvent");
+#endif
+        all_to_all(diststage_, fftbuf_, c, C);
+    }
     begin_timer(OC_TIMER_FFT); e = dfft_.zx(fftbuf_, false); end_timer(); chk(e);
 }
 

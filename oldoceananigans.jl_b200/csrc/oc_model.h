@@ -210,7 +210,9 @@ private:
     FT* halo_recv_ = nullptr;
     size_t halo_buf_elems_ = 0;
     void exchange_y(const std::vector<FieldRec*>& fields);
-    void all_to_all(FT* send, FT* recv);
+    void all_to_all(FT* send, FT* recv, int c, int C);
+    Stream stream3_ = 0;          // the y stage of the distributed solve (pipelined against the all-to-alls on stream_)
+    std::vector<void*> ev_a2a_, ev_mid_;
     void run_fft_solve_dist();
     int xpad_ = 0;
     bool march_ok_ = false;       // no Flat dimension: the z-marching TMA kernel applies
