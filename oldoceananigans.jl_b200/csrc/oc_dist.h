@@ -191,6 +191,47 @@ struct TransposeKernel {
     }
 };
 
+// Bounded z in a slab (y) decomposition: z is local in the first stage, so the Makhoul twiddles of the DCT are applied on the
+// local layout (complex (nxc, Ny_l, Nz), x fastest) right after the forward (z, x) FFT / right before the inverse one — the
+// forward and inverse halves of PoissonMidZKernel, separated by the transposed y stage.
+//   forward : X[k] = ω_k V[k] + conj(ω_k) V[N-k]                 (DCT-II, FFTW REDFT10 scaling)
+//   inverse : W[k] = ½ conj(ω_k) (Φ[k] - i Φ[N-k]),  Φ[N] := 0   (DCT-III with its 1/2N folded in)
+template <class FT>
+struct ZTwiddleKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    int plane, Nz;             // plane = nxc · Ny_l
+    int inverse;
+    Cplx<FT>* spec;
+    const Cd* twz;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const int n = b.x * nt + tid;
+        if (n >= plane) return;
+        const int k0 = b.y, k1 = (Nz - k0) % Nz;
+        Cplx<FT>* p0 = spec + (long long)plane * k0 + n;
+        Cplx<FT>* p1 = spec + (long long)plane * k1 + n;
+        const Cplx<FT> s0 = *p0, s1 = *p1;
+        const Cd a0{(double)s0.x, (double)s0.y}, a1{(double)s1.x, (double)s1.y};
+        const Cd w0 = twz[k0], w1 = twz[k1];
+        Cd e0, e1;
+        if (!inverse) {
+            e0 = cadd(cmul(w0, a0), cmul(cconj(w0), a1));
+            e1 = cadd(cmul(w1, a1), cmul(cconj(w1), a0));
+        } else {
+            const Cd r0 = k0 == 0 ? Cd{0.0, 0.0} : a1;
+            const Cd r1 = k1 == 0 ? Cd{0.0, 0.0} : a0;
+            const Cd t0{a0.x + r0.y, a0.y - r0.x}, t1{a1.x + r1.y, a1.y - r1.x};
+            const Cd h0 = cmul(cconj(w0), t0), h1 = cmul(cconj(w1), t1);
+            e0 = Cd{0.5 * h0.x, 0.5 * h0.y};
+            e1 = Cd{0.5 * h1.x, 0.5 * h1.y};
+        }
+        *p0 = Cplx<FT>{(FT)e0.x, (FT)e0.y};
+        *p1 = Cplx<FT>{(FT)e1.x, (FT)e1.y};
+    }
+};
+
 // spectral divide in the transposed layout T = [zl][x][y]: global kz = rank·nzl + zl
 template <class FT>
 struct PoissonDivideTKernel {

@@ -167,8 +167,8 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     if (dist_) {
         rank_ = c.dist_rank; R_ = c.dist_nranks;
         if (rank_ < 0 || rank_ >= R_) throw Error(OC_ERR_INVALID, "dist_rank out of range");
-        for (int d = 0; d < 3; ++d)
-            if (c.topology[d] != OC_PERIODIC) throw Error(OC_ERR_UNSUPPORTED, "distributed models: only (Periodic, Periodic, Periodic) grids in this round (Bounded x/z: next)");
+        if (c.topology[0] != OC_PERIODIC || c.topology[1] != OC_PERIODIC || c.topology[2] == OC_FLAT)
+            throw Error(OC_ERR_UNSUPPORTED, "distributed models: (Periodic, Periodic, Periodic | Bounded) grids (Bounded x / y and Flat dimensions: next)");
         if (g_.N[2] % R_ != 0) throw Error(OC_ERR_INVALID, "distributed FFT: Nz must be divisible by the number of ranks (distributed_fft_based_poisson_solver.jl:211-229)");
         if (g_.N[1] < g_.H[1]) throw Error(OC_ERR_INVALID, "distributed models: local Ny smaller than the halo");
     }
@@ -592,6 +592,14 @@ void Model<FT>::run_fft_solve_dist() {
     auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
     const int C = dfft_.C, nz = dfft_.Nzl / C;
     begin_timer(OC_TIMER_FFT); std::string e = dfft_.zx(fftbuf_, true); end_timer(); chk(e);
+    ZTwiddleKernel<FT> zt;
+    Dim3 zg;
+    if (g_.bounded[2]) {      // DCT-II post-twiddle while z is still local
+        zt.plane = dfft_.nxc * g_.N[1]; zt.Nz = g_.N[2]; zt.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_); zt.twz = tw_[2];
+        zg.x = (zt.plane + 255) / 256; zg.y = g_.N[2] / 2 + 1;
+        zt.inverse = 0;
+        go(zt, zg, 0, OC_TIMER_POISSON_MID);
+    }
     for (int c = 0; c < C; ++c) {
         all_to_all(fftbuf_, diststage_, c, C);
 #ifndef OC_HOSTSIM
@@ -628,6 +636,10 @@ void Model<FT>::run_fft_solve_dist() {
         cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_mid_[c], 0), "cudaStreamWaitEvent");
 #endif
         all_to_all(diststage_, fftbuf_, c, C);
+    }
+    if (g_.bounded[2]) {      // DCT-III pre-twiddle, z local again
+        zt.inverse = 1;
+        go(zt, zg, 0, OC_TIMER_POISSON_MID);
     }
     begin_timer(OC_TIMER_FFT); e = dfft_.zx(fftbuf_, false); end_timer(); chk(e);
 }

@@ -52,12 +52,11 @@ def main():
     N, topo = tuple(kw["N"]), kw["topo"]
     arch = ob.Distributed(ob.B200(rank if nccl else 0), partition=ob.Partition(1, R), rank=rank, nranks=R,
                           exchange=None if nccl else gloo_exchange)
-    grid = ob.RectilinearGrid(arch, FT, size=N, extent=ph.EXTENT, topology=tuple(ph.TOPO[c] for c in topo))
     scheme = kw.get("scheme", "weno")
-    model = ob.NonhydrostaticModel(grid=grid, advection=ob.WENO() if scheme == "weno" else ob.Centered(), tracers=("T", "S"),
-                                   buoyancy=ob.SeawaterBuoyancy(), closure=ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3),
-                                   coriolis=ob.FPlane(f=kw["f"]) if kw.get("f") else None, library=lib)
-    om = ph.build_oracle(N=N, topo=topo, scheme=scheme, FT=FT, f=kw.get("f"))
+    case = dict(N=N, topo=topo, scheme=scheme, FT=FT, f=kw.get("f"), closure=kw.get("closure", "scalar"), bcs=kw.get("bcs", False),
+                ts=kw.get("ts", "RungeKutta3"))
+    model = ph.build_product(library=lib, arch=arch, **case)
+    om = ph.build_oracle(**case)
     ic = ph.initial_conditions(om)
     nyl = N[1] // R
     sl = slice(rank * nyl, (rank + 1) * nyl)

@@ -44,9 +44,10 @@ def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closur
 
 
 def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
-                  bcs=False, library=None, extent=EXTENT):
+                  bcs=False, library=None, extent=EXTENT, arch=None):
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
-    grid = ob.RectilinearGrid(FT, size=size, extent=ext, topology=tuple(TOPO[c] for c in topo))
+    grid = ob.RectilinearGrid(arch if arch is not None else FT, FT, size=size, extent=ext, topology=tuple(TOPO[c] for c in topo)) \
+        if arch is not None else ob.RectilinearGrid(FT, size=size, extent=ext, topology=tuple(TOPO[c] for c in topo))
     a = ob.Centered() if scheme == "centered" else ob.WENO()
     bo = ob.SeawaterBuoyancy() if buoy == "seawater" else (ob.BuoyancyTracer() if buoy == "tracer" else None)
     cl = {"scalar": ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), "amd": ob.AnisotropicMinimumDissipation(), "none": None,

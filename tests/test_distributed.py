@@ -44,6 +44,9 @@ def run_ranks(R, case, timeout=600, backend="gloo"):
     (2, dict(N=(16, 12, 8), topo="PPP", scheme="centered", f=1e-2, steps=2)),
     (4, dict(N=(12, 16, 8), topo="PPP", scheme="weno", steps=1)),
     (2, dict(N=(16, 12, 8), topo="PPP", scheme="weno", steps=2, f32=True)),
+    # the LES topology: Bounded z (DCT twiddles around the transposed stage), AMD, FPlane, flux / gradient / value BCs
+    (2, dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, steps=2)),
+    (2, dict(N=(12, 8, 6), topo="PPB", scheme="centered", steps=2, ts="QuasiAdamsBashforth2")),
 ])
 def test_slab_decomposition_matches_single_domain_oracle(R, case):
     res = run_ranks(R, dict(case))
@@ -71,6 +74,7 @@ def _gpu_count():
 @pytest.mark.parametrize("R,case", [
     (2, dict(N=(64, 48, 32), topo="PPP", scheme="weno", steps=2)),
     (2, dict(N=(40, 24, 16), topo="PPP", scheme="centered", f=1e-2, steps=3)),
+    (2, dict(N=(48, 32, 16), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, steps=2)),
 ])
 def test_nccl_slab_decomposition_matches_oracle(R, case):
     """The CUDA library on R GPUs of one box (NCCL halo exchange + transposed distributed FFT) against the oracle."""
