@@ -35,6 +35,8 @@ if ROOT not in sys.path:
 METRIC = "cell-updates/sec per full RK3 step"
 # measured DRAM traffic per MarchKernel launch (bytes), from one `ncu --set full` capture per workload (profiles/)
 NCU_TRAFFIC = {"c3": 6.53e9}
+# FP64 instructions executed per cell per MarchKernel launch (ncu source page, profiles/r01d_ncu_march_c3_summary.txt)
+NCU_FP64_PER_CELL = {"c3": 196.0}
 
 # name -> description of the BASELINE.json configuration
 WORKLOADS = {
@@ -336,6 +338,14 @@ def run_ours(args):
                      "avg_launch_ms": avg_launch_ms, "launches_per_step": launches_per_step,
                      "step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
                               "reals_per_cell_step": reals_per_cell_step(w)}},
+        # WENO-5 in Float64 is bound by the FP64 pipe, not by HBM: FP64 warp-instructions issued per second by the
+        # MarchKernel launches against B200's 64 FP64 lanes / clk / SM (148 SMs at the sampled SM clock)
+        "fp64_pipe": ({"fp64_instr_per_cell_per_launch": NCU_FP64_PER_CELL[args.workload],
+                       "achieved_lane_ops_per_s": NCU_FP64_PER_CELL[args.workload] * cells / (avg_launch_ms * 1e-3),
+                       "peak_lane_ops_per_s": 64 * 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6,
+                       "frac": NCU_FP64_PER_CELL[args.workload] * cells / (avg_launch_ms * 1e-3) / (64 * 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
+                       "source": "instruction count from the ncu source page; time from this run's CUDA events"}
+                      if (world == 1 and args.workload in NCU_FP64_PER_CELL and tend_n) else None),
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()},
         "kernel_launches_per_step": {k: v[1] / args.steps for k, v in timers.items()},
         "gpu_launches": int(launches),

@@ -96,7 +96,7 @@ template <class FT>
 struct AmdKernel {
     static constexpr int PHASES = 1;
     static constexpr int THREADS = 256;      // 32 (x) × 8 (y) cells per CTA: the 27-point neighbourhoods share L1 lines in x AND y
-    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int MIN_BLOCKS = 3;     // cap registers at 80: the kernel is latency-bound at the 110 it would otherwise take
     Geom<FT> g;
     const FT* u;
     const FT* v;
