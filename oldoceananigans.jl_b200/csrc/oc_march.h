@@ -146,50 +146,50 @@ struct MarchStateT {
 // Loads for iteration it + PF are issued in step<1>(it), after every thread has finished iteration it-1; they overwrite the
 // slot of level k + PF + HI - D, which must lie below everything iteration it still reads: D >= LIVE + PF, and one more for a
 // ring whose level k-1 is read by the divergence phase of iteration it (the Coriolis operand of the u / v kernels).
-enum { MARCH_NBAR = 4, MARCH_NSYNC = 4 };     // the prefetch distance PF (levels) is per kernel kind: MarchSpec<…>::PF
+enum { MARCH_NBAR = 4 };     // data barriers; the prefetch distance PF and the number of flux stages NSYNC are per kernel
 
 // Which planes each kernel stages.  `FIELD` names the global field: -1 = the stepped field itself (ψ or c), 0/1/2 = u/v/w.
 // E = elements per 16 bytes; box x-origins are kept multiples of E (16-byte aligned box rows).
-template <int KIND, int TX, int TY, int E>
+// PF = prefetch distance in levels; ring depth D = LIVE + PF (one more for a ring whose level k-1 is read by the divergence phase).
+template <int KIND, int TX, int TY, int E, int PF_>
 struct MarchSpec;
-template <int TX, int TY, int E>
-struct MarchSpec<KIND_C, TX, TY, E> {
-    static constexpr int PF = 2;
+template <int TX, int TY, int E, int PF_>
+struct MarchSpec<KIND_C, TX, TY, E, PF_> {
+    static constexpr int PF = PF_;
     static constexpr int NR = 4;
-    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 8>;   // c: WENO-5 radius in x, y, z
-    using R1 = RingSpec<0, TX + 4, 0, TY, 0, 0, 3>;          // u at the x-faces of level k
-    using R2 = RingSpec<0, TX, 0, TY + 1, 0, 0, 3>;          // v at the y-faces
-    using R3 = RingSpec<0, TX, 0, TY, 1, 1, 3>;              // w at the upper z-face (level k+1)
+    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 6 + PF>;   // c: WENO-5 radius in x, y, z
+    using R1 = RingSpec<0, TX + 4, 0, TY, 0, 0, 1 + PF>;          // u at the x-faces of level k
+    using R2 = RingSpec<0, TX, 0, TY + 1, 0, 0, 1 + PF>;          // v at the y-faces
+    using R3 = RingSpec<0, TX, 0, TY, 1, 1, 1 + PF>;              // w at the upper z-face (level k+1)
     static constexpr int F1 = 0, F2 = 1, F3 = 2;
 };
-template <int TX, int TY, int E>
-struct MarchSpec<KIND_U, TX, TY, E> {
-    static constexpr int PF = 2;
+template <int TX, int TY, int E, int PF_>
+struct MarchSpec<KIND_U, TX, TY, E, PF_> {
+    static constexpr int PF = PF_;
     static constexpr int NR = 3;
-    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 8>;   // u
-    using R1 = RingSpec<-E, TX + 2 * E, 0, TY + 1, 0, 0, 4>;     // v[i-2..i+1, j0..j0+TY] (Centered-4 along x, Coriolis, τ12); D = 4: also read in phase 1
-    using R2 = RingSpec<-E, TX + 2 * E, 0, TY, 1, 1, 3>;         // w[i-2..i+1] at level k+1
+    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 6 + PF>;       // u
+    using R1 = RingSpec<-E, TX + 2 * E, 0, TY + 1, 0, 0, 2 + PF>;     // v[i-2..i+1, j0..j0+TY] (Centered-4 along x, Coriolis, τ12); +1: level k-1 is read by the divergence phase
+    using R2 = RingSpec<-E, TX + 2 * E, 0, TY, 1, 1, 1 + PF>;         // w[i-2..i+1] at level k+1
     using R3 = RingSpec<0, 4, 0, 1, 0, 0, 1>;
     static constexpr int F1 = 1, F2 = 2, F3 = -2;
 };
-template <int TX, int TY, int E>
-struct MarchSpec<KIND_V, TX, TY, E> {
-    static constexpr int PF = 2;
+template <int TX, int TY, int E, int PF_>
+struct MarchSpec<KIND_V, TX, TY, E, PF_> {
+    static constexpr int PF = PF_;
     static constexpr int NR = 3;
-    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 8>;   // v
-    using R1 = RingSpec<0, TX + 4, -2, TY + 3, 0, 0, 4>;     // u[i0..i0+TX, j-2..j+1]; D = 4: also read in phase 1 (Coriolis)
-    using R2 = RingSpec<0, TX, -2, TY + 3, 1, 1, 3>;         // w[j-2..j+1] at level k+1
+    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 6 + PF>;   // v
+    using R1 = RingSpec<0, TX + 4, -2, TY + 3, 0, 0, 2 + PF>;     // u[i0..i0+TX, j-2..j+1]; +1: also read by the divergence phase (Coriolis)
+    using R2 = RingSpec<0, TX, -2, TY + 3, 1, 1, 1 + PF>;         // w[j-2..j+1] at level k+1
     using R3 = RingSpec<0, 4, 0, 1, 0, 0, 1>;
     static constexpr int F1 = 0, F2 = 2, F3 = -2;
 };
-template <int TX, int TY, int E>
-struct MarchSpec<KIND_W, TX, TY, E> {
-    // PF = 1: with three 4-to-6-level rings the w kernel would otherwise fit only two CTAs per SM (measured 3.5 vs 3.0 ms)
-    static constexpr int PF = 1;
+template <int TX, int TY, int E, int PF_>
+struct MarchSpec<KIND_W, TX, TY, E, PF_> {
+    static constexpr int PF = PF_;
     static constexpr int NR = 3;
-    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 7>;   // w
-    using R1 = RingSpec<0, TX + 4, 0, TY, -2, 1, 5>;         // u[k-2..k+1] at the x-faces (Centered-4 along z)
-    using R2 = RingSpec<0, TX, 0, TY + 1, -2, 1, 5>;         // v[k-2..k+1] at the y-faces
+    using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 6 + PF>;   // w
+    using R1 = RingSpec<0, TX + 4, 0, TY, -2, 1, 4 + PF>;         // u[k-2..k+1] at the x-faces (Centered-4 along z)
+    using R2 = RingSpec<0, TX, 0, TY + 1, -2, 1, 4 + PF>;         // v[k-2..k+1] at the y-faces
     using R3 = RingSpec<0, 4, 0, 1, 0, 0, 1>;
     static constexpr int F1 = 0, F2 = 1, F3 = -2;
 };
@@ -396,12 +396,16 @@ template <class FT, int ADV, int KIND, int BND, int CLO, int TY_ = 8>
 struct MarchKernel {
     static constexpr int TX = 32, TY = TY_;
     static constexpr int THREADS = TX * (TY + 1);
-    static constexpr int MIN_BLOCKS = TY_ == 8 ? 3 : 5;
+    // 32×8 tiles: three 288-thread CTAs per SM (the w kernel needs PF = 1 for that: with PF = 2 its three 4-to-6-level rings
+    // fit only two, measured 3.5 vs 3.0 ms).  32×16 tiles: two 544-thread CTAs per SM, PF = 1, three flux stages.
+    static constexpr int MIN_BLOCKS = TY_ == 8 ? 3 : 2;
+    static constexpr int PFK = TY_ == 8 ? (KIND == KIND_W ? 1 : 2) : 1;
+    static constexpr int NSYNC = TY_ == 8 ? 4 : 3;
     static constexpr int COMP = KIND == KIND_C ? -1 : KIND;
     static constexpr bool WIN = BND != 0;                 // any wall logic at all
     // BND is a bit mask of the dimensions that MAY be Bounded (7 = generic): order-reduction windows exist only there
     template <int D> static constexpr bool WINV = ((BND >> D) & 1) != 0;
-    using SP = MarchSpec<KIND, TX, TY, 16 / (int)sizeof(FT)>;
+    using SP = MarchSpec<KIND, TX, TY, 16 / (int)sizeof(FT), PFK>;
     using G0 = Ring<FT, typename SP::R0>;
     using G1 = Ring<FT, typename SP::R1>;
     using G2 = Ring<FT, typename SP::R2>;
@@ -416,8 +420,8 @@ struct MarchKernel {
     static constexpr size_t OFF_R2 = OFF_R1 + G1::BYTES;
     static constexpr size_t OFF_R3 = OFF_R2 + G2::BYTES;
     static constexpr size_t OFF_FX = OFF_R3 + (NR > 3 ? G3::BYTES : 0);
-    static constexpr size_t OFF_FY = OFF_FX + sizeof(FT) * MARCH_NSYNC * NFXP;
-    static constexpr size_t SMEM = OFF_FY + sizeof(FT) * MARCH_NSYNC * NFYP;
+    static constexpr size_t OFF_FY = OFF_FX + sizeof(FT) * NSYNC * NFXP;
+    static constexpr size_t SMEM = OFF_FY + sizeof(FT) * NSYNC * NFYP;
     static constexpr int LEVEL_BYTES = G0::BOX_BYTES + G1::BOX_BYTES + G2::BOX_BYTES + (NR > 3 ? G3::BOX_BYTES : 0);
     static constexpr int FIRST_BYTES = G0::BOX_BYTES * SP::R0::LIVE + G1::BOX_BYTES * SP::R1::LIVE + G2::BOX_BYTES * SP::R2::LIVE +
                                        (NR > 3 ? G3::BOX_BYTES * SP::R3::LIVE : 0);
@@ -461,7 +465,7 @@ struct MarchKernel {
         if (tid == 0) {
             uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
             for (int n = 0; n < MARCH_NBAR; ++n) mbar_init(bar + n, 1);
-            for (int n = 0; n < MARCH_NSYNC; ++n) mbar_init(bar + MARCH_NBAR + n, THREADS / 32);   // one arrival per warp
+            for (int n = 0; n < NSYNC; ++n) mbar_init(bar + MARCH_NBAR + n, THREADS / 32);   // one arrival per warp
             mbar_fence_init();
         }
     }
@@ -633,8 +637,8 @@ struct MarchKernel {
     // step<0>(it+4), which is only reached after the wait for iteration it+2, i.e. after every thread finished
     // step<1>(it+1) (the last reader).  Ring slots: the loads issued in step<1>(it) overwrite levels that were last read in
     // iteration it-1 (see MarchSpec), whose arrivals have all been observed.
-    OC_HD uint64_t* sync_bar(char* smem, int it) const { return reinterpret_cast<uint64_t*>(smem + OFF_BAR) + MARCH_NBAR + (it % MARCH_NSYNC); }
-    OC_HD static int sync_parity(int it) { return (it / MARCH_NSYNC) & 1; }
+    OC_HD uint64_t* sync_bar(char* smem, int it) const { return reinterpret_cast<uint64_t*>(smem + OFF_BAR) + MARCH_NBAR + (it % NSYNC); }
+    OC_HD static int sync_parity(int it) { return (it / NSYNC) & 1; }
 
     OC_DEV void sync_wait(char* smem, int it) const { mbar_wait(sync_bar(smem, it), sync_parity(it)); }
     // one arrival per warp (after __syncwarp, so the elected lane's release covers the whole warp's flux stores): every arrival
@@ -662,8 +666,8 @@ struct MarchKernel {
             if (it >= nit) return;
             mbar_wait(bar + (it % MARCH_NBAR), (it / MARCH_NBAR) & 1);
             if (it == 0) return;
-            FT* fx = reinterpret_cast<FT*>(smem + OFF_FX) + (it % MARCH_NSYNC) * NFXP;
-            FT* fy = reinterpret_cast<FT*>(smem + OFF_FY) + (it % MARCH_NSYNC) * NFYP;
+            FT* fx = reinterpret_cast<FT*>(smem + OFF_FX) + (it % NSYNC) * NFXP;
+            FT* fy = reinterpret_cast<FT*>(smem + OFF_FY) + (it % NSYNC) * NFYP;
             {   // y-face (lane, row).  CLO == 0: every operand is in shared memory, so out-of-range faces of partial
                 // tiles are evaluated too (on zero-filled / neighbouring data) and discarded — no divergent branch
                 const bool ok = i0 + lane < g.N[0] && j0 + row <= g.N[1];
@@ -703,8 +707,8 @@ struct MarchKernel {
             }
             if (it < 2 || row >= TY) return;                 // levels start at iteration 1; their divergence is formed one iteration later
             const int kc = k - 1;                            // the level being finished
-            const FT* fx = reinterpret_cast<const FT*>(smem + OFF_FX) + ((it - 1) % MARCH_NSYNC) * NFXP;
-            const FT* fy = reinterpret_cast<const FT*>(smem + OFF_FY) + ((it - 1) % MARCH_NSYNC) * NFYP;
+            const FT* fx = reinterpret_cast<const FT*>(smem + OFF_FX) + ((it - 1) % NSYNC) * NFXP;
+            const FT* fy = reinterpret_cast<const FT*>(smem + OFF_FY) + ((it - 1) % NSYNC) * NFYP;
             const int ii = lane, jj = row;
             const int i = i0 + ii, j = j0 + jj;
             if (i >= g.N[0] || j >= g.N[1]) return;

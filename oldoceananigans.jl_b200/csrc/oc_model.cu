@@ -803,6 +803,8 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
     };
     const bool bnd = g_.bounded[0] || g_.bounded[1] || g_.bounded[2];
     const bool gen = has_amd_;
+    // (A 32×16-tile variant — MarchKernel<…, 16>: two 544-thread CTAs per SM, 34 warps, 50 registers — was measured slower,
+    //  48.3 vs 45.4 ms per step at 512³: the kernel is bound by the FP64 pipe and dependent-issue latency, not by warp count.)
     auto pick = [&](auto adv) {
         constexpr int ADV = decltype(adv)::value;
         const bool zonly = !g_.bounded[0] && !g_.bounded[1] && g_.bounded[2];     // the LES topology (Periodic, Periodic, Bounded)
