@@ -2,7 +2,8 @@
  * oceananigans_b200.h — C ABI of liboceananigans_b200.so
  *
  * A B200-native (sm_100a) implementation of ONE path of Oceananigans.jl v0.100.5: the
- * NonhydrostaticModel time step on a regular RectilinearGrid.  The reference has no FFI; its seam
+ * NonhydrostaticModel time step on a RectilinearGrid (regular, or vertically stretched with the
+ * FourierTridiagonalPoissonSolver).  The reference has no FFI; its seam
  * is Julia multiple dispatch on the architecture type (ext/OceananigansCUDAExt.jl:37-138).  Every
  * entry point below names the reference method (file:line under /root/reference) it stands in for;
  * INTEGRATION.md shows the Julia `ccall` binding for each one.
@@ -27,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OC_ABI_VERSION 1
+#define OC_ABI_VERSION 2
 #define OC_MAX_TRACERS 8
 #define OC_MAX_FIELDS (3 + OC_MAX_TRACERS)
 
@@ -77,7 +78,14 @@ typedef struct {
     /* Distributed(arch; partition = Partition(1, R)): slab decomposition in y (distributed_architectures.jl:242-302).
      * N[1] is the LOCAL size, extent[1] the GLOBAL extent; dist_nranks <= 1 means a serial model. */
     int32_t dist_rank, dist_nranks;
-    int32_t reserved[5];
+    /* Vertically stretched grid: RectilinearGrid(…; z = faces::AbstractVector)  (rectilinear_grid.jl:264-291,
+     * grid_generation.jl:33-94).  z_stretched = 1: z_faces points to N[2]+1 increasing face positions (FT values widened to
+     * double; host memory, read during oc_model_create only); topology[2] must be Bounded; delta[2] is ignored and
+     * extent[2] = z_faces[N] - z_faces[0].  The pressure solver is then the FourierTridiagonalPoissonSolver
+     * (src/Solvers/fourier_tridiagonal_poisson_solver.jl:74-131; NonhydrostaticModels.jl:35-40). */
+    int32_t z_stretched;
+    const double* z_faces;
+    int32_t reserved[2];
 } oc_config;
 
 typedef struct oc_model oc_model;
@@ -129,7 +137,9 @@ int  oc_cache_previous_tendencies(oc_model* m);
 int  oc_compute_pressure_correction(oc_model* m, double dt);
 /* make_pressure_correction!(model, Δt)  pressure_correction.jl:40-53 */
 int  oc_make_pressure_correction(oc_model* m, double dt);
-/* solve!(ϕ, ::FFTBasedPoissonSolver, b)  fft_based_poisson_solver.jl:95-125 : host rhs (Nx×Ny×Nz, model FT) -> host ϕ */
+/* solve!(ϕ, ::FFTBasedPoissonSolver, b)  fft_based_poisson_solver.jl:95-125 : host rhs (Nx×Ny×Nz, model FT) -> host ϕ;
+ * on a stretched grid solve!(ϕ, ::FourierTridiagonalPoissonSolver, b)  fourier_tridiagonal_poisson_solver.jl:204-246
+ * (b is multiplied by Δzᶜᶜᶜ inside, like set_source_term!; the volume mean of ϕ is removed) */
 int  oc_poisson_solve(oc_model* m, const void* rhs_host, void* phi_host, size_t nbytes);
 
 /* ---- the hot path ---- */

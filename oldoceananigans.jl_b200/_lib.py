@@ -7,7 +7,7 @@ C ABI of the host-simulation build (tests/hostsim) — the package itself never 
 import ctypes as C
 import os
 
-OC_ABI_VERSION = 1
+OC_ABI_VERSION = 2
 OC_MAX_TRACERS = 8
 OC_MAX_FIELDS = 3 + OC_MAX_TRACERS
 OC_TIMER_NAMES = ("tendency", "halo", "poisson_rhs", "fft", "poisson_mid", "projection", "aux", "substep", "comm")
@@ -40,7 +40,8 @@ class oc_config(C.Structure):
         ("tracer_T", C.c_int32), ("tracer_S", C.c_int32), ("tracer_b", C.c_int32),
         ("has_coriolis", C.c_int32), ("coriolis_f", C.c_double),
         ("bcs", (oc_bc * 6) * OC_MAX_FIELDS),
-        ("device", C.c_int32), ("dist_rank", C.c_int32), ("dist_nranks", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("device", C.c_int32), ("dist_rank", C.c_int32), ("dist_nranks", C.c_int32),
+        ("z_stretched", C.c_int32), ("z_faces", C.POINTER(C.c_double)), ("reserved", C.c_int32 * 2),
     ]
 
 

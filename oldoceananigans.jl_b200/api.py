@@ -96,7 +96,10 @@ def _tuple(x, n=None):
 
 
 class RectilinearGrid:
-    """Regular RectilinearGrid.  `size`, `extent`/`x,y,z`, `halo` list only the non-Flat dimensions."""
+    """RectilinearGrid, regular or vertically stretched.  `size`, `extent`/`x,y,z`, `halo` list only the non-Flat dimensions.
+    `z` may be a 2-tuple (interval, regular spacing), or a vector of Nz+1 increasing faces / a function of the face index
+    (variably spaced Bounded z: rectilinear_grid.jl:264-291, grid_generation.jl:33-94), which selects the
+    FourierTridiagonalPoissonSolver.  Stretched x or y are out of scope."""
 
     def __init__(self, architecture=None, FT=np.float64, *, size, extent=None, x=None, y=None, z=None,
                  topology=(Periodic, Periodic, Bounded), halo=None):
@@ -122,9 +125,24 @@ class RectilinearGrid:
         else:
             for d, b in enumerate((x, y, z)):
                 if b is not None:
-                    if callable(b) or len(b) != 2:
-                        raise NotImplementedError("stretched coordinates are out of scope (FourierTridiagonalPoissonSolver path)")
+                    if callable(b) or not isinstance(b, tuple) or len(b) != 2:
+                        if d < 2:
+                            raise NotImplementedError("stretched x / y coordinates are out of scope (only z can be variably spaced)")
+                        continue                                     # stretched z: handled below
                     bounds[d] = (float(b[0]), float(b[1]))
+        self.z_faces = None
+        if extent is None and z is not None and (callable(z) or not isinstance(z, tuple) or len(z) != 2):
+            if self.topology[2] is not Bounded:
+                raise ValueError("a variably spaced z needs the Bounded topology")      # fourier_tridiagonal_poisson_solver.jl:86-90
+            nz = int(size[nonflat.index(2)])
+            zf = [z(i) for i in range(1, nz + 2)] if callable(z) else list(z)
+            if len(zf) != nz + 1:
+                raise ValueError("z must list Nz+1 faces")
+            zf = np.asarray(zf, dtype=self.FT)                      # interior_face_nodes = zeros(FT, N+1)
+            if not np.all(np.diff(zf) > 0):
+                raise ValueError("The elements of z must be increasing!")              # grid_generation.jl:45-48
+            self.z_faces = np.ascontiguousarray(zf.astype(np.float64))
+            bounds[2] = (float(zf[0]), float(zf[-1]))
         halo = _tuple(halo)
         N, H, Lx, D, x0 = [1, 1, 1], [0, 0, 0], [1.0] * 3, [1.0] * 3, [0.0] * 3
         for n, d in enumerate(nonflat):
@@ -144,6 +162,11 @@ class RectilinearGrid:
         self.Hx, self.Hy, self.Hz = self.H
         self.Lx, self.Ly, self.Lz = self.L
         self.dx, self.dy, self.dz = self.D
+        if self.z_faces is not None:
+            self.L = (self.L[0], self.L[1], float(self.FT(self.FT(self.z_faces[-1]) - self.FT(self.z_faces[0]))))
+            self.Lz = self.L[2]
+            self.D = (self.D[0], self.D[1], float("nan"))          # no constant Δz
+            self.dz = None
 
     def with_halo(self, halo):
         g = RectilinearGrid.__new__(RectilinearGrid)
@@ -154,6 +177,9 @@ class RectilinearGrid:
 
     def nodes(self, d, loc):
         n = self.N[d] + (1 if (loc == Face and self.topology[d] is Bounded) else 0)
+        if d == 2 and self.z_faces is not None:
+            zf = self.z_faces.astype(self.FT)
+            return (zf if loc == Face else ((zf[1:] + zf[:-1]) / self.FT(2))).astype(np.float64)[:n]
         return self.x0[d] + (np.arange(n) + (0.5 if loc == Center else 0.0)) * self.D[d]
 
     def __repr__(self):
@@ -372,6 +398,11 @@ class NonhydrostaticModel:
         for d in range(3):
             cfg.N[d], cfg.H[d], cfg.topology[d] = grid.N[d], grid.H[d], grid.topology[d].code
             cfg.delta[d], cfg.extent[d] = grid.D[d], grid.L[d]
+        if grid.z_faces is not None:
+            self._z_faces = grid.z_faces                            # keep the buffer alive across oc_model_create
+            cfg.z_stretched = 1
+            cfg.z_faces = self._z_faces.ctypes.data_as(C.POINTER(C.c_double))
+            cfg.delta[2] = 0.0
         arch = grid.architecture
         self.distributed = isinstance(arch, Distributed) and arch.nranks > 1
         if self.distributed:

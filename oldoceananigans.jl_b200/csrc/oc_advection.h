@@ -27,6 +27,21 @@ OC_HD FT sym4(const AdvCoef<FT>& C, const FT* p, int s, FT a) {
     return r;
 }
 
+// The same along z on a vertically stretched grid: the area belongs to the advecting velocity's own point, a_n = h·Δzᶜ[k+n]
+// (Ax_qᶠᶜᶜ / Ay_qᶜᶠᶜ inside ℑzᵃᵃᶠ, upwind_biased_advective_fluxes.jl:79-91); dz points at Δzᶜ of level k.
+template <class FT>
+OC_HD FT sym2z(const FT* p, int s, FT h, const FT* dz) {
+    return FT(0.5) * ((h * dz[-1]) * p[-s]) + FT(0.5) * ((h * dz[0]) * p[0]);
+}
+template <class FT>
+OC_HD FT sym4z(const AdvCoef<FT>& C, const FT* p, int s, FT h, const FT* dz) {
+    FT r = C.c4[0] * ((h * dz[-2]) * p[-2 * s]);
+    r = r + C.c4[1] * ((h * dz[-1]) * p[-s]);
+    r = r + C.c4[2] * ((h * dz[0]) * p[0]);
+    r = r + C.c4[3] * ((h * dz[1]) * p[s]);
+    return r;
+}
+
 // ---- WENO building blocks -----------------------------------------------------------------------------
 // β for WENO{3}: ψ1(C1ψ1 + C2ψ2 + C3ψ3) + ψ2(C4ψ2 + C5ψ3) + ψ3ψ3C6     weno_interpolants.jl:204-216,261
 template <class FT>
@@ -112,6 +127,11 @@ template <class FT>
 OC_HD FT weno5_symmetric(const AdvCoef<FT>& C, const FT* p, int s, FT a, int f, const OrderWindow& w) {
     if (f >= w.lo_hi && f <= w.hi_hi) return sym4<FT>(C, p, s, a);
     return sym2<FT>(p, s, a);
+}
+template <class FT>
+OC_HD FT weno5_symmetric_z(const AdvCoef<FT>& C, const FT* p, int s, FT h, const FT* dz, int f, const OrderWindow& w) {
+    if (f >= w.lo_hi && f <= w.hi_hi) return sym4z<FT>(C, p, s, h, dz);
+    return sym2z<FT>(p, s, h, dz);
 }
 
 }  // namespace oc

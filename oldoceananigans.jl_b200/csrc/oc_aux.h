@@ -41,7 +41,8 @@ struct HydrostaticPressureKernel {
             o -= g.sz;
             FT bk = b_at(o);
             FT bf = FT(0.5) * (bk + bup);              // z_dot_g_bᶜᶜᶠ(k+1) = ℑzᵃᵃᶠ b   g_dot_b.jl:4
-            p = (k == Nz - 1) ? -bf * g.d[2] : p - bf * g.d[2];
+            const FT dzf = g.dz_at(true, k + 1);       // Δzᶜᶜᶠ of the face above cell k   update_hydrostatic_pressure.jl:15-19
+            p = (k == Nz - 1) ? -bf * dzf : p - bf * dzf;
             pHY[o] = p;
             bup = bk;
         }
@@ -58,24 +59,38 @@ struct AmdPoint {
     const FT* u;
     const FT* v;
     const FT* w;
-    FT rxy, ryx, rxz, rzx, ryz, rzy;   // Δᶠa/Δᶠb with Δᶠ = 2Δ   (:224-226)
-    // the six filter-width ratios are loop invariants with divisions: formed once on the host (AmdConsts), same FT arithmetic
-    OC_HD AmdPoint(const Geom<FT>& g_, const FT* u_, const FT* v_, const FT* w_, const FT* r) : g(g_), u(u_), v(v_), w(w_) {
-        rxy = r[0]; ryx = r[1]; rxz = r[2]; rzx = r[3]; ryz = r[4]; rzy = r[5];
+    FT rxy, ryx;                       // Δᶠa/Δᶠb with Δᶠ = 2Δ   (:224-226)
+    // ratios with Δᶠz and the z-derivative metrics at the cell's level [0] and the level above [1]: every Δᶠz_{loc}(i,j,k′) is
+    // 2·Δzᶜᶜᶜ(k′) at the INDEX k′ of the evaluation point (:228-234), ∂z at fcf / cff uses Δz⁻¹ᶠ(k′), ∂z w at ccc Δz⁻¹ᶜ(k)
+    FT rxz[2], rzx[2], ryz[2], rzy[2], rdzf[2], fz[2], rdzc;
+    // the filter-width ratios are loop invariants with divisions: on a regular grid formed once on the host (set_consts), same FT
+    // arithmetic; on a stretched grid formed here from the level tables
+    OC_HD AmdPoint(const Geom<FT>& g_, const FT* u_, const FT* v_, const FT* w_, const FT* r, int k) : g(g_), u(u_), v(v_), w(w_) {
+        rxy = r[0]; ryx = r[1];
+        if (!g.stretched()) {
+            for (int n = 0; n < 2; ++n) { rxz[n] = r[2]; rzx[n] = r[3]; ryz[n] = r[4]; rzy[n] = r[5]; rdzf[n] = g.rd[2]; fz[n] = FT(2) * g.d[2]; }
+            rdzc = g.rd[2];
+        } else {
+            const FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1];
+            for (int n = 0; n < 2; ++n) {
+                fz[n] = FT(2) * g.dzc[k + n];
+                rxz[n] = fx / fz[n]; rzx[n] = fz[n] / fx; ryz[n] = fy / fz[n]; rzy[n] = fz[n] / fy;
+                rdzf[n] = g.rdzf[k + n];
+            }
+            rdzc = g.rdzc[k];
+        }
     }
-    // normalised gradients at their natural locations (velocity_tracer_gradients.jl:126-154); o = linear index
+    // normalised gradients at their natural locations (velocity_tracer_gradients.jl:126-154); o = linear index,
+    // up = 0: the point is on the cell's level, 1: on the level above
     OC_HD FT dxu(int o) const { return (u[o + 1] - u[o]) * g.rd[0]; }                       // ccc
     OC_HD FT dyv(int o) const { return (v[o + g.sy] - v[o]) * g.rd[1]; }                    // ccc
-    OC_HD FT dzw(int o) const { return (w[o + g.sz] - w[o]) * g.rd[2]; }                    // ccc
+    OC_HD FT dzw(int o) const { return (w[o + g.sz] - w[o]) * rdzc; }                       // ccc
     OC_HD FT dxv(int o) const { return rxy * ((v[o] - v[o - 1]) * g.rd[0]); }               // ffc
     OC_HD FT dyu(int o) const { return ryx * ((u[o] - u[o - g.sy]) * g.rd[1]); }            // ffc
-    OC_HD FT dxw(int o) const { return rxz * ((w[o] - w[o - 1]) * g.rd[0]); }               // fcf
-    OC_HD FT dzu(int o) const { return rzx * ((u[o] - u[o - g.sz]) * g.rd[2]); }            // fcf
-    OC_HD FT dyw(int o) const { return ryz * ((w[o] - w[o - g.sy]) * g.rd[1]); }            // cff
-    OC_HD FT dzv(int o) const { return rzy * ((v[o] - v[o - g.sz]) * g.rd[2]); }            // cff
-    OC_HD FT S12(int o) const { return FT(0.5) * (dyu(o) + dxv(o)); }
-    OC_HD FT S13(int o) const { return FT(0.5) * (dzu(o) + dxw(o)); }
-    OC_HD FT S23(int o) const { return FT(0.5) * (dzv(o) + dyw(o)); }
+    OC_HD FT dxw(int o, int up) const { return rxz[up] * ((w[o] - w[o - 1]) * g.rd[0]); }       // fcf
+    OC_HD FT dzu(int o, int up) const { return rzx[up] * ((u[o] - u[o - g.sz]) * rdzf[up]); }   // fcf
+    OC_HD FT dyw(int o, int up) const { return ryz[up] * ((w[o] - w[o - g.sy]) * g.rd[1]); }    // cff
+    OC_HD FT dzv(int o, int up) const { return rzy[up] * ((v[o] - v[o - g.sz]) * rdzf[up]); }   // cff
 };
 
 // ℑ of a functor F(o) from (Face,Face) in dims (d1<d2) to centre: ℑ_{d2}ᶜ(ℑ_{d1}ᶜ F)   interpolation_operators.jl:45-56
@@ -125,8 +140,9 @@ struct AmdKernel {
         if (i >= g.N[0] || j >= g.N[1]) return;
         const int o = g.idx(i, j, k);
         const int sx = 1, sy = g.sy, sz = g.sz;
-        AmdPoint<FT> P(g, u, v, w, ratios);
-        const FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = FT(2) * g.d[2];
+        AmdPoint<FT> P(g, u, v, w, ratios, k);
+        const FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = P.fz[0];
+        const FT d2 = g.stretched() ? FT(3) / (FT(1) / (fx * fx) + FT(1) / (fy * fy) + FT(1) / (fz * fz)) : delta2;   // δ² (:166,190)
         auto sq = [](FT x) { return x * x; };
         const int cxy[4] = {o, o + sx, o + sy, o + sx + sy};
         const int cxz[4] = {o, o + sx, o + sz, o + sx + sz};
@@ -134,8 +150,8 @@ struct AmdKernel {
         FT dxv[4], dyu[4], dxw[4], dzu[4], dyw[4], dzv[4], t[4];
         for (int n = 0; n < 4; ++n) {
             dxv[n] = P.dxv(cxy[n]); dyu[n] = P.dyu(cxy[n]);
-            dxw[n] = P.dxw(cxz[n]); dzu[n] = P.dzu(cxz[n]);
-            dyw[n] = P.dyw(cyz[n]); dzv[n] = P.dzv(cyz[n]);
+            dxw[n] = P.dxw(cxz[n], n >> 1); dzu[n] = P.dzu(cxz[n], n >> 1);     // corners 2, 3 are on the level above
+            dyw[n] = P.dyw(cyz[n], n >> 1); dzv[n] = P.dzv(cyz[n], n >> 1);
         }
         const FT dxu = P.dxu(o), dyv = P.dyv(o), dzw = P.dzw(o);
         for (int n = 0; n < 4; ++n) t[n] = sq(dxv[n]);
@@ -191,19 +207,19 @@ struct AmdKernel {
                   + FT(2) * dzw * Iyz_dzvS23;
             FT r = t1 + t2 + t3;
             FT Cb_zeta = FT(0) / fz;                                                       // Cb = nothing :281
-            nu = -Cnu * delta2 * (r - Cb_zeta) / q;                                        // :168
+            nu = -Cnu * d2 * (r - Cb_zeta) / q;                                            // :168
         }
         nu_e[o] = oc_max<FT>(FT(0), nu);
         if (ntr == 0) return;
         // ℑxzᶜᵃᶜ(norm_∂y_w) — sic, :336 — needs ∂y w at the xz corners
-        for (int n = 0; n < 4; ++n) t[n] = P.dyw(cxz[n]);
+        for (int n = 0; n < 4; ++n) t[n] = P.dyw(cxz[n], n >> 1);
         const FT Ixz_dyw = interp4<FT>(t);
         for (int tr = 0; tr < ntr; ++tr) {
             const FT* cc = c[tr];
             auto cx = [&](int p) { return fx * ((cc[p] - cc[p - sx]) * g.rd[0]); };       // norm_∂x_c at fcc
             auto cy = [&](int p) { return fy * ((cc[p] - cc[p - sy]) * g.rd[1]); };
-            auto cz = [&](int p) { return fz * ((cc[p] - cc[p - sz]) * g.rd[2]); };
-            const FT cx0 = cx(o), cx1 = cx(o + sx), cy0 = cy(o), cy1 = cy(o + sy), cz0 = cz(o), cz1 = cz(o + sz);
+            auto cz = [&](int p, int up) { return P.fz[up] * ((cc[p] - cc[p - sz]) * P.rdzf[up]); };   // norm_∂z_c at ccf
+            const FT cx0 = cx(o), cx1 = cx(o + sx), cy0 = cy(o), cy1 = cy(o + sy), cz0 = cz(o, 0), cz1 = cz(o + sz, 1);
             FT Ix_cx2 = FT(0.5) * (sq(cx0) + sq(cx1));
             FT Iy_cy2 = FT(0.5) * (sq(cy0) + sq(cy1));
             FT Iz_cz2 = FT(0.5) * (sq(cz0) + sq(cz1));
@@ -216,7 +232,7 @@ struct AmdKernel {
                 FT a2 = Ixy_dyu * Iy_cy * Ix_cx + dyv * Iy_cy2 + Ixz_dyw * Iy_cy * Iz_cz;
                 FT a3 = Ixz_dzu * Iz_cz * Ix_cx + Iyz_dzv * Iz_cz * Iy_cy + dzw * Iz_cz2;
                 FT theta = a1 + a2 + a3;
-                kap = -Ckappa[tr] * delta2 * theta / sigma;                                // :191
+                kap = -Ckappa[tr] * d2 * theta / sigma;                                    // :191
             }
             kappa_e[tr][o] = oc_max<FT>(FT(0), kap);
         }
@@ -252,7 +268,7 @@ struct DiagnosticsKernel {
                 const int o = g.idx(i, j, k);
                 const FT uu = u[o], vv = v[o], ww = w[o];
                 const FT au = oc_abs<FT>(uu), av = oc_abs<FT>(vv), aw = oc_abs<FT>(ww);
-                FT inv = (g.flat[0] ? FT(0) : au * g.rd[0]) + (g.flat[1] ? FT(0) : av * g.rd[1]) + (g.flat[2] ? FT(0) : aw * g.rd[2]);
+                FT inv = (g.flat[0] ? FT(0) : au * g.rd[0]) + (g.flat[1] ? FT(0) : av * g.rd[1]) + (g.flat[2] ? FT(0) : aw * g.rdz_at(true, k));   // Δz⁻¹ᶜᶜᶠ
                 double tau = (double)(FT(1) / inv);
                 if (tau < tmin) tmin = tau;             // NaN compares false: a NaN cell does not enter the minimum, it raises the flag
                 if ((double)au > mu) mu = au;

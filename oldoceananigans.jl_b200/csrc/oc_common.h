@@ -22,8 +22,29 @@ struct Geom {
     FT rd[3];        // 1/Δ           reciprocal_metric_operators.jl:7
     FT A[3];         // Ax=Δy·Δz, Ay=Δx·Δz, Az=Δx·Δy   spacings_and_areas_and_volumes.jl:309-333
     FT V, rV;        // V = Az·Δz, 1/V                  :376, reciprocal_metric_operators.jl:13
+    // Vertically stretched grid (z Bounded, variably spaced; x and y stay regular): level tables, indexable with the
+    // 0-based level k = -(H[2]+1) … N[2]+H[2]+1 (reference index k+1).  nullptr on regular grids, where d[2], rd[2], A[], V, rV
+    // are the (constant) metrics.  dzc = Δzᵃᵃᶜ, dzf = Δzᵃᵃᶠ (grid_generation.jl:33-94), rdzc / rdzf = their reciprocals
+    // (reciprocal_metric_operators.jl:7), rVc / rVf = 1/(Az·Δz) at Center / Face levels (:13).
+    const FT* dzc;
+    const FT* dzf;
+    const FT* rdzc;
+    const FT* rdzf;
+    const FT* rVc;
+    const FT* rVf;
     OC_HD int st(int dim) const { return dim == 0 ? 1 : (dim == 1 ? sy : sz); }
     OC_HD int idx(int i, int j, int k) const { return i + j * sy + k * sz; }
+    OC_HD bool stretched() const { return dzc != nullptr; }
+    // metrics at level k for a point whose z-location is Face (zf = true) or Center
+    OC_HD FT dz_at(bool zf, int k) const { return dzc ? (zf ? dzf[k] : dzc[k]) : d[2]; }
+    OC_HD FT rdz_at(bool zf, int k) const { return dzc ? (zf ? rdzf[k] : rdzc[k]) : rd[2]; }
+    OC_HD FT rV_at(bool zf, int k) const { return dzc ? (zf ? rVf[k] : rVc[k]) : rV; }
+    // Ax = Δy·Δz, Ay = Δx·Δz, Az = Δx·Δy   (spacings_and_areas_and_volumes.jl:309-333)
+    OC_HD FT area_at(int dim, bool zf, int k) const {
+        if (dim == 2 || !dzc) return A[dim];
+        return d[dim == 0 ? 1 : 0] * (zf ? dzf[k] : dzc[k]);
+    }
+    OC_HD FT vol_at(bool zf, int k) const { return dzc ? A[2] * (zf ? dzf[k] : dzc[k]) : V; }
 };
 
 // Reconstruction coefficients, computed on the host exactly like the reference

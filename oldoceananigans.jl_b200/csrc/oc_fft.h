@@ -21,14 +21,18 @@ public:
     size_t buffer_bytes = 0;
     size_t work_bytes = 0;
 
-    std::string init(const int N[3], const int bounded[3], Stream stream, bool plan = true) {
+    // zbatch: z is not transformed (FourierTridiagonalPoissonSolver on a stretched grid: plan_transforms(grid, storage,
+    // planner_flag, tridiagonal_dim), fourier_tridiagonal_poisson_solver.jl:107) — batched (y, x) transforms, one per level
+    std::string init(const int N[3], const int bounded[3], Stream stream, bool plan = true, bool zbatch = false) {
         for (int d = 0; d < 3; ++d) { L.N[d] = N[d]; L.bounded[d] = bounded[d]; }
+        zbatch_ = zbatch;
+        if (zbatch) L.bounded[2] = 0;                 // no Makhoul permutation, no twiddles along z
         L.r2c = (!bounded[0] && N[0] > 1) ? 1 : 0;
         L.nxc = L.r2c ? N[0] / 2 + 1 : N[0];
         L.nxr = 2 * L.nxc;
         buffer_bytes = sizeof(FT) * 2 * (size_t)L.nxc * N[1] * N[2];
         rank_ = 0;
-        for (int d = 2; d >= 0; --d)
+        for (int d = zbatch ? 1 : 2; d >= 0; --d)
             if (N[d] > 1) dims_[rank_++] = N[d];      // slowest first
         if (!plan) { rank_ = 0; return ""; }
 #ifndef OC_HOSTSIM
@@ -40,11 +44,24 @@ public:
         if (cufftCreate(&fwd_) != CUFFT_SUCCESS || cufftCreate(&inv_) != CUFFT_SUCCESS) return "cufftCreate failed";
         cufftSetAutoAllocation(fwd_, 0);
         cufftSetAutoAllocation(inv_, 0);
+        if (zbatch) {
+            // explicit in-place layouts: rows of nxr reals / nxc complex numbers, Ny rows per level, levels contiguous
+            int remb[2], cemb[2];
+            if (rank_ == 2) { remb[0] = N[1]; remb[1] = L.r2c ? L.nxr : N[0]; cemb[0] = N[1]; cemb[1] = L.nxc; }
+            else if (N[0] > 1) { remb[0] = L.r2c ? L.nxr : N[0]; cemb[0] = L.nxc; }
+            else { remb[0] = N[1]; cemb[0] = N[1]; }
+            const int rdist = (L.r2c ? L.nxr : N[0]) * N[1], cdist = L.nxc * N[1];
+            if (cufftMakePlanMany(fwd_, rank_, dims_, remb, 1, rdist, cemb, 1, cdist, fwd, N[2], &wf) != CUFFT_SUCCESS)
+                return "cufftMakePlanMany(forward, batched over z) failed";
+            if (cufftMakePlanMany(inv_, rank_, dims_, cemb, 1, cdist, remb, 1, rdist, inv, N[2], &wi) != CUFFT_SUCCESS)
+                return "cufftMakePlanMany(inverse, batched over z) failed";
+        } else {
         if (cufftMakePlanMany(fwd_, rank_, dims_, nullptr, 1, 0, nullptr, 1, 0, fwd, 1, &wf) != CUFFT_SUCCESS)
             return "cufftMakePlanMany(forward) failed";
         if (L.r2c || true) {
             if (cufftMakePlanMany(inv_, rank_, dims_, nullptr, 1, 0, nullptr, 1, 0, inv, 1, &wi) != CUFFT_SUCCESS)
                 return "cufftMakePlanMany(inverse) failed";
+        }
         }
         work_bytes = wf > wi ? wf : wi;
         if (work_bytes) {
@@ -73,6 +90,7 @@ public:
 private:
     int rank_ = 0;
     int dims_[3] = {1, 1, 1};
+    bool zbatch_ = false;
 #ifndef OC_HOSTSIM
     cufftHandle fwd_ = 0, inv_ = 0;
     void* work_ = nullptr;
@@ -111,7 +129,7 @@ private:
                     long long c = L.cplx_index(i, j, k);
                     at(i, j, k) = Cd{(double)buf[2 * c], (double)buf[2 * c + 1]};
                 } else {   // Hermitian partner
-                    long long c = L.cplx_index(Nx - i, (Ny - j) % Ny, (Nz - k) % Nz);
+                    long long c = L.cplx_index(Nx - i, (Ny - j) % Ny, zbatch_ ? k : (Nz - k) % Nz);
                     at(i, j, k) = Cd{(double)buf[2 * c], -(double)buf[2 * c + 1]};
                 }
             }
@@ -119,7 +137,7 @@ private:
         const double sgn = fwd ? -1.0 : 1.0;
         const int n[3] = {Nx, Ny, Nz};
         for (int d = 0; d < 3; ++d) {
-            if (n[d] == 1) continue;
+            if (n[d] == 1 || (d == 2 && zbatch_)) continue;
             std::vector<Cd> line(n[d]), out(n[d]);
             int o1 = (d + 1) % 3, o2 = (d + 2) % 3;
             for (int a = 0; a < n[o1]; ++a) for (int bq = 0; bq < n[o2]; ++bq) {

@@ -111,7 +111,8 @@ struct HaloKernel {
         FT cI = p[g.idx(Q[0], Q[1], Q[2])];
         if (nbc == 1) {
             const SideBC& s = fld.bc[2 * bc_dim + bc_side];
-            FT delta = g.d[bc_dim];
+            // Δ between the interior and the halo point, at the boundary face (fill_halo_regions_value_gradient.jl:44,60)
+            FT delta = bc_dim == 2 ? g.dz_at(true, bc_side == 0 ? 0 : g.N[2]) : g.d[bc_dim];
             if (s.kind == 2) {
                 // Flux: c[0] = c[1], c[N+1] = c[N]                            fill_halo_regions_flux.jl:9-27
             } else if (s.kind == 4) {

@@ -386,6 +386,21 @@ OC_HD FT t_weno5_symmetric(const A& a, int ii, int jj, int lev, FT area, int f, 
     return FT(0.5) * (area * rd<DIR, FT>(a, ii, jj, lev, -1)) + FT(0.5) * (area * rd<DIR, FT>(a, ii, jj, lev, 0));
 }
 
+// The same along z on a vertically stretched grid: a_n = h·Δzᶜ[lev+n] belongs to the advecting velocity's own point
+// (Ax_qᶠᶜᶜ / Ay_qᶜᶠᶜ inside ℑzᵃᵃᶠ: upwind_biased_advective_fluxes.jl:79-91); dz points at Δzᶜ of level lev.
+template <bool WIN, class FT, class A>
+OC_HD FT t_weno5_symmetric_z(const A& a, int ii, int jj, int lev, FT h, const FT* dz, int f, const OrderWindow& w) {
+    using K = AdvConst<FT>;
+    if (!WIN || (f >= w.lo_hi && f <= w.hi_hi)) {
+        FT r = K::c40 * ((h * dz[-2]) * a(ii, jj, lev - 2));
+        r = r + K::c41 * ((h * dz[-1]) * a(ii, jj, lev - 1));
+        r = r + K::c42 * ((h * dz[0]) * a(ii, jj, lev));
+        r = r + K::c43 * ((h * dz[1]) * a(ii, jj, lev + 1));
+        return r;
+    }
+    return FT(0.5) * ((h * dz[-1]) * a(ii, jj, lev - 1)) + FT(0.5) * ((h * dz[0]) * a(ii, jj, lev));
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the kernel.  BND = bit mask of possibly-Bounded dimensions: 0 (none: all wall logic compiled out), 4 (z only), 7 (generic).
 //              CLO = 0: constant ν, κ (possibly 0: no closure); 1: generic (AMD eddy fields, closure tuples).
@@ -446,6 +461,14 @@ struct MarchKernel {
     OC_HD G2 r2(const Ctx& c) const { return G2{reinterpret_cast<FT*>(c.smem + OFF_R2), c.k, c.st.sk[2]}; }
     OC_HD G3 r3(const Ctx& c) const { return G3{reinterpret_cast<FT*>(c.smem + OFF_R3), c.k, c.st.sk[3]}; }
     OC_HD Ctx raw(char* smem) const { return Ctx{smem, 0, MarchSlots{{0, 0, 0, 0}}}; }
+
+    // ---- metrics.  Only a Bounded z can be stretched, so the level tables exist only in kernels with wall logic in z;
+    // everywhere else these fold to the constants of the regular grid.  zf: the point is Face-located in z.
+    static constexpr bool ZS = WINV<2>;
+    OC_HD FT m_area(int D, bool zf, int lev) const { return ZS ? a.g.area_at(D, zf, lev) : a.g.A[D]; }
+    OC_HD FT m_rdz(bool zf, int lev) const { return ZS ? a.g.rdz_at(zf, lev) : a.g.rd[2]; }
+    OC_HD FT m_rV(bool zf, int lev) const { return ZS ? a.g.rV_at(zf, lev) : a.g.rV; }
+    OC_HD FT m_vol(bool zf, int lev) const { return ZS ? a.g.vol_at(zf, lev) : a.g.V; }
 
     // ---- loads -----------------------------------------------------------------------------------------------
     template <class G, class RS>
@@ -516,22 +539,23 @@ struct MarchKernel {
         const Geom<FT>& g = a.g;
         FT sig;
         if (D == COMP) {
-            sig = (vel<COMP, D>(smem, ii, jj, lev, 1) - vel<COMP, D>(smem, ii, jj, lev, 0)) * g.rd[D];
+            sig = (vel<COMP, D>(smem, ii, jj, lev, 1) - vel<COMP, D>(smem, ii, jj, lev, 0)) * (D == 2 ? m_rdz(false, lev) : g.rd[D]);
         } else {
             constexpr int lo = D < COMP ? D : COMP, hi = D < COMP ? COMP : D;
-            FT dl = (vel<lo, hi>(smem, ii, jj, lev, 0) - vel<lo, hi>(smem, ii, jj, lev, -1)) * g.rd[hi];
+            FT dl = (vel<lo, hi>(smem, ii, jj, lev, 0) - vel<lo, hi>(smem, ii, jj, lev, -1)) * (hi == 2 ? m_rdz(true, lev) : g.rd[hi]);
             FT dh = (vel<hi, lo>(smem, ii, jj, lev, 0) - vel<hi, lo>(smem, ii, jj, lev, -1)) * g.rd[lo];
             sig = FT(0.5) * (dl + dh);
         }
-        if (CLO == 0) return (FT(-2) * a.nu * g.A[D]) * sig;
+        const FT AD = m_area(D, COMP == 2, lev);
+        if (CLO == 0) return (FT(-2) * a.nu * AD) * sig;
         FT flux = FT(0);
-        if (a.has_scalar) flux = g.A[D] * (FT(-2) * (a.nu * sig));
+        if (a.has_scalar) flux = AD * (FT(-2) * (a.nu * sig));
         if (a.nu_e) {
             const int o = g.idx(i, j, lev);
             FT nu;
             if (D == COMP) nu = a.nu_e[o];
             else nu = nu_ff(o, D < COMP ? D : COMP, D < COMP ? COMP : D);
-            FT f2 = g.A[D] * (FT(-2) * (nu * sig));
+            FT f2 = AD * (FT(-2) * (nu * sig));
             flux = a.has_scalar ? flux + f2 : f2;
         }
         return flux;
@@ -541,15 +565,16 @@ struct MarchKernel {
     OC_HD FT diffusive_flux(const Ctx& smem, int ii, int jj, int lev, int i, int j) const {
         const Geom<FT>& g = a.g;
         G0 c = r0(smem);
-        FT grad = (rd<D, FT>(c, ii, jj, lev, 0) - rd<D, FT>(c, ii, jj, lev, -1)) * g.rd[D];
-        if (CLO == 0) return -(a.kappa * g.A[D]) * grad;   // (folded with the advective part in total_flux for CLO == 0)
+        FT grad = (rd<D, FT>(c, ii, jj, lev, 0) - rd<D, FT>(c, ii, jj, lev, -1)) * (D == 2 ? m_rdz(true, lev) : g.rd[D]);
+        const FT AD = m_area(D, false, lev);
+        if (CLO == 0) return -(a.kappa * AD) * grad;   // (folded with the advective part in total_flux for CLO == 0)
         FT flux = FT(0);
-        if (a.has_scalar) flux = g.A[D] * (-(a.kappa * grad));
+        if (a.has_scalar) flux = AD * (-(a.kappa * grad));
         if (a.kappa_e) {
             const int o = g.idx(i, j, lev);
             int s = g.st(D);
             FT kap = FT(0.5) * (a.kappa_e[o - s] + a.kappa_e[o]);
-            FT f2 = g.A[D] * (-(kap * grad));
+            FT f2 = AD * (-(kap * grad));
             flux = a.has_scalar ? flux + f2 : f2;
         }
         return flux;
@@ -559,7 +584,9 @@ struct MarchKernel {
     template <int D>
     OC_HD FT advective_flux(const Ctx& smem, int ii, int jj, int lev, int id, int ic) const {
         const Geom<FT>& g = a.g;
-        const FT A = g.A[D];
+        // Centered: the area at the flux point; upwind schemes: the area of the advecting velocity's own point (they differ only
+        // for the x / y fluxes of w on a stretched grid, which take the per-level areas inside the z interpolation below)
+        const FT A = m_area(D, COMP == 2 && ADV == 0, lev);
         if (KIND == KIND_C) {
             FT u = D == 0 ? r1(smem)(ii, jj, lev) : (D == 1 ? r2(smem)(ii, jj, lev) : r3(smem)(ii, jj, lev));
             G0 c = r0(smem);
@@ -598,7 +625,11 @@ struct MarchKernel {
                     if (WINV<CC>) wc = order_window(g.bounded[CC] != 0, false, g.N[CC]);
                     if (WINV<D>) wd = order_window(g.bounded[D] != 0, false, g.N[D]);
                     FT ut;
-                    if (D == SP::F1) ut = t_weno5_symmetric<CC, WINV<CC>, FT>(r1(smem), ii, jj, lev, A, ic, wc);
+                    if (ZS && CC == 2 && g.stretched()) {
+                        const FT h = g.d[D == 0 ? 1 : 0];
+                        if (D == SP::F1) ut = t_weno5_symmetric_z<WINV<CC>, FT>(r1(smem), ii, jj, lev, h, g.dzc + lev, ic, wc);
+                        else ut = t_weno5_symmetric_z<WINV<CC>, FT>(r2(smem), ii, jj, lev, h, g.dzc + lev, ic, wc);
+                    } else if (D == SP::F1) ut = t_weno5_symmetric<CC, WINV<CC>, FT>(r1(smem), ii, jj, lev, A, ic, wc);
                     else ut = t_weno5_symmetric<CC, WINV<CC>, FT>(r2(smem), ii, jj, lev, A, ic, wc);
                     FT pr = t_weno5_biased<D, WINV<D>, FT>(psi, ii, jj, lev, ut > FT(0), id, wd);
                     return ut * pr;
@@ -617,7 +648,7 @@ struct MarchKernel {
             // constant κ: F - (κ A / Δ)(c[0] - c[-1]) with the constant folded (one subtraction and one FMA)
             G0 c = r0(smem);
             const FT dc = rd<D, FT>(c, ii, jj, k, 0) - rd<D, FT>(c, ii, jj, k, -1);
-            return fmaT(-(a.kappa * a.g.A[D] * a.g.rd[D]), dc, F);
+            return fmaT(-(a.kappa * m_area(D, false, k) * (D == 2 ? m_rdz(true, k) : a.g.rd[D])), dc, F);
         }
         if (CLO == 0 || a.has_scalar || a.nu_e || a.kappa_e) {
             if constexpr (KIND == KIND_C) F = F + diffusive_flux<D>(smem, ii, jj, k, i, j);
@@ -725,7 +756,7 @@ struct MarchKernel {
             const FT dFx = fx[jj * (TX + 1) + ii + 1] - fx[jj * (TX + 1) + ii];
             const FT dFy = fy[(jj + 1) * TX + ii] - fy[jj * TX + ii];
             const FT dFz = stt.dfz;
-            FT G = -(g.rV * (dFx + dFy + dFz));
+            FT G = -(m_rV(COMP == 2, kc) * (dFx + dFy + dFz));
             if ((KIND == KIND_U || KIND == KIND_V) && a.has_coriolis) {
                 // FPlane (f_plane.jl:50-52); the other horizontal component is ring 1
                 G1 q = r1(cx);
@@ -757,8 +788,9 @@ struct MarchKernel {
             if (WIN && a.add_flux_bcs) {
                 const int ijk[3] = {i, j, kc};
                 for (int d = 0; d < 3; ++d) {
-                    if (a.fbc.on[2 * d] && ijk[d] == 0) G = G + a.fbc.val[2 * d] * g.A[d] / g.V;
-                    if (a.fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) G = G - a.fbc.val[2 * d + 1] * g.A[d] / g.V;
+                    const FT Ad = m_area(d, COMP == 2, kc), Vd = m_vol(COMP == 2, kc);
+                    if (a.fbc.on[2 * d] && ijk[d] == 0) G = G + a.fbc.val[2 * d] * Ad / Vd;
+                    if (a.fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) G = G - a.fbc.val[2 * d + 1] * Ad / Vd;
                 }
             }
             a.Gn[o] = G;

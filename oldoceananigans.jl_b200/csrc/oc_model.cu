@@ -69,6 +69,16 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     if (c.advection != OC_CENTERED2 && c.advection != OC_WENO5) throw Error(OC_ERR_UNSUPPORTED, "advection scheme: only Centered(order=2) and WENO(order=5)");
     if (c.timestepper != OC_RK3 && c.timestepper != OC_AB2) throw Error(OC_ERR_UNSUPPORTED, "timestepper: only RungeKutta3 and QuasiAdamsBashforth2");
     F_ = 3 + c.n_tracers;
+    stretched_ = c.z_stretched != 0;
+    if (stretched_) {
+        // only a Bounded direction can be the tridiagonal one (fourier_tridiagonal_poisson_solver.jl:86-90)
+        if (c.topology[2] != OC_BOUNDED) throw Error(OC_ERR_INVALID, "a stretched z needs the Bounded topology (FourierTridiagonalPoissonSolver)");
+        if (!c.z_faces) throw Error(OC_ERR_INVALID, "z_stretched without z_faces");
+        if (c.N[2] < 2) throw Error(OC_ERR_UNSUPPORTED, "stretched z with fewer than 2 levels");
+        for (int k = 0; k < c.N[2]; ++k)
+            if (!((FT)c.z_faces[k + 1] > (FT)c.z_faces[k])) throw Error(OC_ERR_INVALID, "The elements of z must be increasing!");
+        if (c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "distributed models on vertically stretched grids (DistributedFourierTridiagonalPoissonSolver: next)");
+    }
     int need = c.advection == OC_WENO5 ? 3 : 1;
     if (c.has_amd) need = std::max(need, 2);
     for (int d = 0; d < 3; ++d) {
@@ -81,7 +91,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
             if (c.H[d] < need) throw Error(OC_ERR_INVALID, "halo too small for the advection scheme / closure (inflate_grid_halo_size)");
             if (c.H[d] > 8) throw Error(OC_ERR_UNSUPPORTED, "halo larger than 8");
             if (c.N[d] < c.H[d]) throw Error(OC_ERR_UNSUPPORTED, "N < H in a non-Flat dimension (adapt_advection_order lowering is not implemented)");
-            if (!(c.delta[d] > 0)) throw Error(OC_ERR_INVALID, "grid spacing must be positive");
+            if (!(stretched_ && d == 2) && !(c.delta[d] > 0)) throw Error(OC_ERR_INVALID, "grid spacing must be positive");
         }
         Hcfg_[d] = c.H[d];
         g_.N[d] = c.N[d];
@@ -95,6 +105,10 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     if (c.buoyancy == OC_BUOYANCY_SEAWATER_LINEAR && (c.tracer_T < 0 || c.tracer_S < 0 || c.tracer_T >= c.n_tracers || c.tracer_S >= c.n_tracers))
         throw Error(OC_ERR_INVALID, "SeawaterBuoyancy needs tracers T and S");
     if (c.buoyancy == OC_BUOYANCY_TRACER && (c.tracer_b < 0 || c.tracer_b >= c.n_tracers)) throw Error(OC_ERR_INVALID, "BuoyancyTracer needs tracer b");
+    if (stretched_) {     // the constant z metrics do not exist: poison them so that a kernel that forgot the level tables shows up
+        g_.d[2] = std::numeric_limits<FT>::quiet_NaN();
+        g_.rd[2] = g_.d[2];
+    }
     g_.A[0] = g_.d[1] * g_.d[2];
     g_.A[1] = g_.d[0] * g_.d[2];
     g_.A[2] = g_.d[0] * g_.d[1];
@@ -109,6 +123,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     origin_off_ = pad + (long long)g_.H[1] * g_.sy + (long long)g_.H[2] * g_.sz;
     xpad_ = pad;
     march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]);
+    g_.dzc = g_.dzf = g_.rdzc = g_.rdzf = g_.rVc = g_.rVf = nullptr;
     C_ = make_coefficients<FT>();
     {   // the compile-time table of oc_march.h must be the very same numbers
         using K = AdvConst<FT>;
@@ -172,8 +187,10 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         if (g_.N[2] % R_ != 0) throw Error(OC_ERR_INVALID, "distributed FFT: Nz must be divisible by the number of ranks (distributed_fft_based_poisson_solver.jl:211-229)");
         if (g_.N[1] < g_.H[1]) throw Error(OC_ERR_INVALID, "distributed models: local Ny smaller than the halo");
     }
+    if (stretched_) build_z_tables(c.z_faces);
+    cfg_.z_faces = nullptr;                              // borrowed host pointer: not kept
     // pressure solver
-    std::string err = fft_.init(g_.N, g_.bounded, stream_, !dist_);
+    std::string err = fft_.init(g_.N, g_.bounded, stream_, !dist_, stretched_);
     if (!err.empty()) throw Error(OC_ERR_CUDA, err);
     fftbuf_ = (FT*)dev_alloc(fft_.buffer_bytes);
     device_bytes += (int64_t)fft_.buffer_bytes + (int64_t)fft_.work_bytes;
@@ -218,7 +235,64 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     }
     boxes_dev_ = nullptr;
     for (int i = 0; i < OC_TIMER_COUNT; ++i) { timer_ms_[i] = 0; timer_n_[i] = 0; }
+    if (stretched_) {
+        // FourierTridiagonalPoissonSolver(grid): the Thomas factors of every horizontal wavenumber's column
+        const size_t n = (size_t)fft_.L.nxc * g_.N[1] * g_.N[2];
+        tri_R_ = (FT*)dev_alloc(sizeof(FT) * n);
+        tri_T_ = (FT*)dev_alloc(sizeof(FT) * n);
+        device_bytes += (int64_t)(2 * sizeof(FT) * n);
+        TridiagSetupKernel<FT> k;
+        k.L = fft_.L;
+        k.lam[0] = lam_[0]; k.lam[1] = lam_[1];
+        k.dzc = g_.dzc; k.rdzf = g_.rdzf;
+        k.R = tri_R_; k.T = tri_T_;
+        k.eps10 = 10.0 * (double)std::numeric_limits<FT>::epsilon();
+        Dim3 grid;
+        grid.x = (fft_.L.nxc + TridiagSetupKernel<FT>::THREADS - 1) / TridiagSetupKernel<FT>::THREADS;
+        grid.y = g_.N[1];
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+    }
     sync();
+}
+
+// generate_coordinate for a Bounded, variably spaced coordinate (src/Grids/grid_generation.jl:33-94), in FT arithmetic:
+// halo faces continue with the first / last interior spacing, centres are face averages, Δzᶜ[k] = F[k+1] - F[k],
+// Δzᶠ[k] = C[k] - C[k-1].  Tables cover the 0-based levels -(H+1) … N+H+1 (the reference's cover a subset of that range with
+// the same values: every halo spacing equals the edge spacing).
+template <class FT>
+void Model<FT>::build_z_tables(const double* faces) {
+    const int N = g_.N[2], H = g_.H[2] + 1;
+    const int nt = N + 2 * H + 1;                       // levels -H … N+H
+    std::vector<FT> F(nt + 1), Cc(nt + 1);
+    // faces: level k <-> F[k + H]; interior faces 0 … N
+    for (int k = 0; k <= N; ++k) F[k + H] = (FT)faces[k];
+    const FT dlo = F[H + 1] - F[H], dhi = F[H + N] - F[H + N - 1];
+    for (int m = 1; m <= H; ++m) {                      // F₋[i] = c¹ - sum(Δᶠ₋[i:H]) : m equal terms summed left to right
+        FT slo = FT(0), shi = FT(0);
+        for (int q = 0; q < m; ++q) { slo = slo + dlo; shi = shi + dhi; }
+        F[H - m] = F[H] - slo;
+        F[H + N + m] = F[H + N] + shi;
+    }
+    // one more face above so that the centre of the topmost level exists
+    { FT shi = FT(0); for (int q = 0; q < H + 1; ++q) shi = shi + dhi; F[nt] = F[H + N] + shi; }
+    for (int n = 0; n < nt; ++n) Cc[n] = (F[n + 1] + F[n]) / FT(2);
+    std::vector<FT> tab(6 * (size_t)nt);
+    FT* dzc = tab.data(); FT* dzf = dzc + nt; FT* rdzc = dzf + nt; FT* rdzf = rdzc + nt; FT* rVc = rdzf + nt; FT* rVf = rVc + nt;
+    for (int n = 0; n < nt; ++n) {
+        dzc[n] = F[n + 1] - F[n];
+        dzf[n] = n > 0 ? Cc[n] - Cc[n - 1] : Cc[1] - Cc[0];
+        rdzc[n] = FT(1) / dzc[n];
+        rdzf[n] = FT(1) / dzf[n];
+        rVc[n] = FT(1) / (g_.A[2] * dzc[n]);             // V = Az·Δz ; V⁻¹ = 1/V
+        rVf[n] = FT(1) / (g_.A[2] * dzf[n]);
+    }
+    ztab_ = (FT*)dev_alloc(sizeof(FT) * tab.size());
+    dev_upload(ztab_, tab.data(), sizeof(FT) * tab.size(), stream_);
+#ifndef OC_HOSTSIM
+    cuda_check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");     // `tab` is a stack-owned staging buffer
+#endif
+    device_bytes += (int64_t)(sizeof(FT) * tab.size());
+    g_.dzc = ztab_ + H; g_.dzf = g_.dzc + nt; g_.rdzc = g_.dzf + nt; g_.rdzf = g_.rdzc + nt; g_.rVc = g_.rdzf + nt; g_.rVf = g_.rVc + nt;
 }
 
 template <class FT>
@@ -231,6 +305,7 @@ Model<FT>::~Model() {
     fr(pNHS_); fr(pHY_); fr(nu_e_);
     for (auto& f : kappa_e_) fr(f);
     dev_free(fftbuf_);
+    dev_free(ztab_); dev_free(tri_R_); dev_free(tri_T_);
     dev_free(diag_dev_);
     dev_free(distT_); dev_free(diststage_); dev_free(halo_send_); dev_free(halo_recv_);
     for (int d = 0; d < 3; ++d) { dev_free(lam_[d]); dev_free(tw_[d]); }
@@ -908,6 +983,7 @@ void Model<FT>::compute_flux_bc_tendencies() {
         FluxBCKernel<FT> k;
         k.g = g_;
         k.Gn = Gn_[f].p;
+        k.zface = f == 2 ? 1 : 0;
         bool any = false;
         for (int s = 0; s < 6; ++s) {
             const oc_bc& ub = cfg_.bcs[f][s];
@@ -974,7 +1050,21 @@ void Model<FT>::run_fft_solve() {
     std::string e = fft_.forward(fftbuf_);
     end_timer();
     if (!e.empty()) throw Error(OC_ERR_CUDA, e);
-    if (!g_.bounded[0] && !g_.bounded[1] && !g_.bounded[2]) {
+    if (stretched_) {
+        // solve!(ϕ, ::BatchedTridiagonalSolver, rhs) + ϕ .-= mean(ϕ)   fourier_tridiagonal_poisson_solver.jl:213-226
+        TridiagSolveKernel<FT> k;
+        k.L = fft_.L;
+        k.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_);
+        k.R = tri_R_; k.T = tri_T_; k.rdzf = g_.rdzf;
+        k.tw[0] = tw_[0]; k.tw[1] = tw_[1];
+        k.nrep[0] = g_.bounded[0] ? g_.N[0] / 2 + 1 : fft_.L.nxc;
+        k.nrep[1] = g_.bounded[1] ? g_.N[1] / 2 + 1 : g_.N[1];
+        k.norm = 1.0 / ((double)g_.N[0] * g_.N[1]);
+        Dim3 grid;
+        grid.x = (k.nrep[0] + TridiagSolveKernel<FT>::THREADS - 1) / TridiagSolveKernel<FT>::THREADS;
+        grid.y = k.nrep[1];
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+    } else if (!g_.bounded[0] && !g_.bounded[1] && !g_.bounded[2]) {
         PoissonDivideKernel<FT> k;
         k.L = fft_.L;
         k.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_);
@@ -1129,6 +1219,7 @@ void Model<FT>::poisson_solve(const void* rhs, void* phi, size_t nbytes) {
     l.L = fft_.L;
     l.rhs = dense;
     l.buf = fftbuf_;
+    l.dzc = stretched_ ? g_.dzc : nullptr;
     go(l, grid_xyz(256), 0, OC_TIMER_POISSON_RHS);
     run_fft_solve();
     PoissonUnpackKernel<FT> k;
@@ -1259,6 +1350,8 @@ void oc_config_init(oc_config* c) {
     c->tracer_T = c->tracer_S = c->tracer_b = -1;
     c->amd_Cnu = 1.0 / 3.0;
     for (int t = 0; t < OC_MAX_TRACERS; ++t) c->amd_Ckappa[t] = 1.0 / 3.0;
+    c->z_stretched = 0;
+    c->z_faces = nullptr;
 }
 
 int oc_model_create(const oc_config* cfg, oc_model** out) {

@@ -216,6 +216,12 @@ private:
     void run_fft_solve_dist();
     int xpad_ = 0;
     bool march_ok_ = false;       // no Flat dimension: the z-marching TMA kernel applies
+    // vertically stretched grid: level tables (Geom::dzc …) and the FourierTridiagonalPoissonSolver's elimination factors
+    bool stretched_ = false;
+    FT* ztab_ = nullptr;          // six tables of N[2] + 2 H[2] + 3 levels
+    FT* tri_R_ = nullptr;
+    FT* tri_T_ = nullptr;
+    void build_z_tables(const double* faces);
 #ifndef OC_HOSTSIM
     std::map<std::tuple<const void*, int, int>, TileSrc<FT>> tmap_cache_;
 #endif

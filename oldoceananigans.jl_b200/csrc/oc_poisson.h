@@ -72,10 +72,14 @@ struct PoissonRhsKernel {
         if (i >= g.N[0]) return;
         int o = g.idx(i, j, k);
         // divᶜᶜᶜ = V⁻¹ (δxᶜ(Ax u) + δyᶜ(Ay v) + δzᶜ(Az w))      divergence_operators.jl:16-19
-        FT dx = g.flat[0] ? FT(0) : g.A[0] * u[o + 1] - g.A[0] * u[o];
-        FT dy = g.flat[1] ? FT(0) : g.A[1] * v[o + g.sy] - g.A[1] * v[o];
+        const FT Ax = g.area_at(0, false, k), Ay = g.area_at(1, false, k);
+        FT dx = g.flat[0] ? FT(0) : Ax * u[o + 1] - Ax * u[o];
+        FT dy = g.flat[1] ? FT(0) : Ay * v[o + g.sy] - Ay * v[o];
         FT dz = g.flat[2] ? FT(0) : g.A[2] * w[o + g.sz] - g.A[2] * w[o];
-        FT div = g.rV * (dx + dy + dz);
+        FT div = g.rV_at(false, k) * (dx + dy + dz);
+        // stretched grid: the tridiagonal system is the Poisson equation times Δzᶜᶜᶜ
+        // (_fourier_tridiagonal_source_term!, solve_for_pressure.jl:36-42); z is not transformed (L.bounded[2] = 0)
+        if (g.stretched()) div = g.dzc[k] * div;
         long long r = L.real_index(makhoul(i, L.N[0], L.bounded[0]), makhoul(j, L.N[1], L.bounded[1]),
                                    makhoul(k, L.N[2], L.bounded[2]));
         buf[r] = div;
@@ -92,13 +96,15 @@ struct PoissonLoadKernel {
     SpectralLayout L;
     const FT* rhs;
     FT* buf;
+    const FT* dzc;     // stretched grid: set_source_term! multiplies by Δzᶜᶜᶜ (fourier_tridiagonal_poisson_solver.jl:239-246); else nullptr
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
         int i = b.x * nt + tid, j = b.y, k = b.z;
         if (i >= L.N[0]) return;
         long long r = L.real_index(makhoul(i, L.N[0], L.bounded[0]), makhoul(j, L.N[1], L.bounded[1]),
                                    makhoul(k, L.N[2], L.bounded[2]));
-        buf[r] = rhs[(long long)i + (long long)L.N[0] * (j + (long long)L.N[1] * k)];
+        FT val = rhs[(long long)i + (long long)L.N[0] * (j + (long long)L.N[1] * k)];
+        buf[r] = dzc ? val * dzc[k] : val;
         if (!L.r2c) buf[r + 1] = FT(0);
     }
 };
@@ -265,6 +271,185 @@ struct PoissonMidZKernel {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// FourierTridiagonalPoissonSolver for a vertically stretched grid (src/Solvers/fourier_tridiagonal_poisson_solver.jl:74-246,
+// batched_tridiagonal_solver.jl:220-243): transforms in x and y only; per horizontal wavenumber the system
+//     ϕ[k-1]/Δzᶠ[k] + D[k] ϕ[k] + ϕ[k+1]/Δzᶠ[k+1] = Δzᶜ[k] b̂[k],   D[k] = -(1/Δzᶠ[k+1] + 1/Δzᶠ[k]) - Δzᶜ[k](λx+λy)
+// (homogeneous Neumann: the missing neighbour's term dropped at k = 1, Nz) is solved with the Thomas algorithm.  The matrix
+// depends only on the grid, so the elimination factors are tabulated once: R[k] = 1/β_k and T[k] = c_{k-1}/β_{k-1} with
+// β_1 = D[1], β_k = D[k] - a_{k-1} T[k] (a = c = 1/Δzᶠ[k+1]).  A pivot that is not "definitely diagonally dominant"
+// (|β| ≤ 10 eps, :232) gets R = 0, and so does the last pivot of the singular (λx = λy = 0) column: its free constant is fixed by
+// removing the volume mean of ϕ (:222-226), which lives entirely in that column.
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+struct TridiagSetupKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = 1;
+    SpectralLayout L;
+    const double* lam[2];
+    const FT* dzc;
+    const FT* rdzf;
+    FT* R;
+    FT* T;
+    double eps10;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const int i = b.x * nt + tid, j = b.y;
+        if (i >= L.nxc) return;
+        const int Nz = L.N[2];
+        const double l = lam[0][i] + lam[1][j];
+        const long long plane = (long long)L.nxc * L.N[1];
+        long long c = L.cplx_index(i, j, 0);
+        double beta = 0.0;
+        for (int k = 0; k < Nz; ++k, c += plane) {
+            // compute_main_diagonal! (HomogeneousZFormulation) :172-185 — FT reciprocals, Float64 eigenvalue term, stored as FT
+            FT off;
+            if (k == 0) off = -rdzf[1];
+            else if (k == Nz - 1) off = -rdzf[Nz - 1];
+            else off = -(rdzf[k + 1] + rdzf[k]);
+            const double D = (double)(FT)((double)off - (double)dzc[k] * l);
+            double t = 0.0;
+            if (k > 0) {
+                const double a = (double)rdzf[k];            // lower_diagonal[k-1] = upper_diagonal[k-1] = 1/Δzᶠ[k]  :198-202
+                t = a / beta;
+                beta = D - a * t;
+            } else {
+                beta = D;
+            }
+            double r = (beta > eps10 || beta < -eps10) ? 1.0 / beta : 0.0;
+            if (i == 0 && j == 0 && k == Nz - 1) r = 0.0;
+            R[c] = (FT)r;
+            T[c] = (FT)t;
+        }
+    }
+};
+
+template <class FT>
+struct TridiagSolveKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 64;
+    static constexpr int MIN_BLOCKS = 1;
+    SpectralLayout L;
+    Cplx<FT>* spec;
+    const FT* R;
+    const FT* T;
+    const FT* rdzf;
+    const Cd* tw[2];           // ω_k = exp(-iπk/2N) for Bounded x / y (nullptr otherwise)
+    int nrep[2];
+    double norm;               // 1/(Nx·Ny): cuFFT's inverse is un-normalised; the DCT-III's 1/2N is the ½ of the pre-twiddle times 1/N
+
+    // forward post-twiddle of the 2×2 orbit along every Bounded horizontal dimension (see PoissonMidKernel)
+    OC_HD void twiddle_fwd(Cd v[2][2], const int idx[2][2]) const {
+        for (int d = 0; d < 2; ++d) {
+            if (!L.bounded[d]) continue;
+            const Cd w0 = tw[d][idx[d][0]], w1 = tw[d][idx[d][1]];
+            for (int q = 0; q < 2; ++q) {
+                Cd* e0 = d == 0 ? &v[q][0] : &v[0][q];
+                Cd* e1 = d == 0 ? &v[q][1] : &v[1][q];
+                const Cd a0 = *e0, a1 = *e1;
+                *e0 = cadd(cmul(w0, a0), cmul(cconj(w0), a1));
+                *e1 = cadd(cmul(w1, a1), cmul(cconj(w1), a0));
+            }
+        }
+    }
+    OC_HD void twiddle_inv(Cd v[2][2], const int idx[2][2]) const {
+        for (int d = 0; d < 2; ++d) {
+            if (!L.bounded[d]) continue;
+            const Cd w0 = tw[d][idx[d][0]], w1 = tw[d][idx[d][1]];
+            const bool z0 = idx[d][0] == 0, z1 = idx[d][1] == 0;
+            for (int q = 0; q < 2; ++q) {
+                Cd* e0 = d == 0 ? &v[q][0] : &v[0][q];
+                Cd* e1 = d == 0 ? &v[q][1] : &v[1][q];
+                const Cd a0 = *e0, a1 = *e1;
+                const Cd r0 = z0 ? Cd{0.0, 0.0} : a1, r1 = z1 ? Cd{0.0, 0.0} : a0;
+                const Cd t0{a0.x + r0.y, a0.y - r0.x}, t1{a1.x + r1.y, a1.y - r1.x};
+                const Cd h0 = cmul(cconj(w0), t0), h1 = cmul(cconj(w1), t1);
+                *e0 = Cd{0.5 * h0.x, 0.5 * h0.y};
+                *e1 = Cd{0.5 * h1.x, 0.5 * h1.y};
+            }
+        }
+    }
+
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const int rx = b.x * nt + tid, ry = b.y;
+        if (rx >= nrep[0]) return;
+        const int Nz = L.N[2];
+        const int rep[2] = {rx, ry};
+        int idx[2][2], np[2];
+        for (int d = 0; d < 2; ++d) {
+            idx[d][0] = rep[d];
+            if (L.bounded[d]) { idx[d][1] = (L.N[d] - rep[d]) % L.N[d]; np[d] = 2; }
+            else { idx[d][1] = rep[d]; np[d] = 1; }
+        }
+        const long long plane = (long long)L.nxc * L.N[1];
+        long long col[2][2];
+        for (int bb = 0; bb < 2; ++bb)
+            for (int aa = 0; aa < 2; ++aa) col[bb][aa] = L.cplx_index(idx[0][aa], idx[1][bb], 0);
+        const bool zero_mode = idx[0][0] == 0 && idx[1][0] == 0;      // then every orbit member is the (0, 0) column
+        Cd prev[2][2];
+        for (int bb = 0; bb < 2; ++bb) for (int aa = 0; aa < 2; ++aa) prev[bb][aa] = Cd{0.0, 0.0};
+        // ---- forward elimination (twiddled right-hand side in, partially eliminated ϕ out, in place)
+        for (int k = 0; k < Nz; ++k) {
+            Cd v[2][2];
+            for (int bb = 0; bb < 2; ++bb)
+                for (int aa = 0; aa < 2; ++aa) {
+                    if (aa < np[0] && bb < np[1]) { const Cplx<FT> e = spec[col[bb][aa] + plane * k]; v[bb][aa] = Cd{(double)e.x, (double)e.y}; }
+                    else v[bb][aa] = Cd{0.0, 0.0};
+                }
+            twiddle_fwd(v, idx);
+            const double a = k > 0 ? (double)rdzf[k] : 0.0;
+            for (int bb = 0; bb < np[1]; ++bb)
+                for (int aa = 0; aa < np[0]; ++aa) {
+                    const double r = (double)R[col[bb][aa] + plane * k];
+                    Cd e{(v[bb][aa].x - a * prev[bb][aa].x) * r, (v[bb][aa].y - a * prev[bb][aa].y) * r};
+                    prev[bb][aa] = e;
+                    spec[col[bb][aa] + plane * k] = Cplx<FT>{(FT)e.x, (FT)e.y};
+                }
+        }
+        // ---- back substitution; the finished level is scaled, pre-twiddled for the inverse transforms and stored.
+        // The singular column first stores the raw solution and its sum over k, then removes the mean in a second sweep.
+        Cd sum{0.0, 0.0};
+        for (int k = Nz - 1; k >= 0; --k) {
+            Cd v[2][2];
+            for (int bb = 0; bb < 2; ++bb) for (int aa = 0; aa < 2; ++aa) v[bb][aa] = Cd{0.0, 0.0};
+            for (int bb = 0; bb < np[1]; ++bb)
+                for (int aa = 0; aa < np[0]; ++aa) {
+                    Cd e;
+                    if (k == Nz - 1) e = prev[bb][aa];
+                    else {
+                        const Cplx<FT> s = spec[col[bb][aa] + plane * k];
+                        const double t = (double)T[col[bb][aa] + plane * (k + 1)];
+                        e = Cd{(double)s.x - t * prev[bb][aa].x, (double)s.y - t * prev[bb][aa].y};
+                    }
+                    prev[bb][aa] = e;
+                    v[bb][aa] = e;
+                }
+            if (zero_mode) {
+                sum = cadd(sum, v[0][0]);
+                for (int bb = 0; bb < np[1]; ++bb)
+                    for (int aa = 0; aa < np[0]; ++aa) spec[col[bb][aa] + plane * k] = Cplx<FT>{(FT)v[bb][aa].x, (FT)v[bb][aa].y};
+                continue;
+            }
+            for (int bb = 0; bb < 2; ++bb) for (int aa = 0; aa < 2; ++aa) { v[bb][aa].x *= norm; v[bb][aa].y *= norm; }
+            twiddle_inv(v, idx);
+            for (int bb = 0; bb < np[1]; ++bb)
+                for (int aa = 0; aa < np[0]; ++aa) spec[col[bb][aa] + plane * k] = Cplx<FT>{(FT)v[bb][aa].x, (FT)v[bb][aa].y};
+        }
+        if (!zero_mode) return;
+        const Cd mean{sum.x / Nz, sum.y / Nz};
+        for (int k = 0; k < Nz; ++k) {
+            const Cplx<FT> s = spec[col[0][0] + plane * k];
+            Cd v[2][2];
+            for (int bb = 0; bb < 2; ++bb)
+                for (int aa = 0; aa < 2; ++aa) v[bb][aa] = Cd{((double)s.x - mean.x) * norm, ((double)s.y - mean.y) * norm};
+            twiddle_inv(v, idx);
+            spec[col[0][0] + plane * k] = Cplx<FT>{(FT)v[0][0].x, (FT)v[0][0].y};
+        }
+    }
+};
+
 // ϕ at logical cell (i,j,k) from the transform buffer; i = -1 / N handled by the caller
 template <class FT>
 OC_HD FT phi_at(const SpectralLayout& L, const FT* buf, int i, int j, int k) {
@@ -304,7 +489,7 @@ struct ProjectionKernel {
         }
         if (!g.flat[2]) {
             FT pm = (k > 0) ? phi_at<FT>(L, buf, i, j, k - 1) : (g.bounded[2] ? p0 : phi_at<FT>(L, buf, i, j, g.N[2] - 1));
-            w[o] = w[o] - (p0 - pm) * g.rd[2];
+            w[o] = w[o] - (p0 - pm) * g.rdz_at(true, k);
         }
         pNHS[o] = (FT)((double)p0 / dt_plus);
     }
@@ -368,7 +553,7 @@ struct GradSubKernel {
         FT p0 = p[o];
         if (!g.flat[0]) u[o] = u[o] - (p0 - p[o - 1]) * g.rd[0];
         if (!g.flat[1]) v[o] = v[o] - (p0 - p[o - g.sy]) * g.rd[1];
-        if (!g.flat[2]) w[o] = w[o] - (p0 - p[o - g.sz]) * g.rd[2];
+        if (!g.flat[2]) w[o] = w[o] - (p0 - p[o - g.sz]) * g.rdz_at(true, k);
     }
 };
 template <class FT>

@@ -76,43 +76,47 @@ struct TendencyKernel {
 
     // viscous flux A_d · τ_{comp,d} at flux index o   (closure_kernel_operators.jl:22-41;
     // abstract_scalar_diffusivity_closure.jl:189-204; velocity_tracer_gradients.jl:25-42)
-    OC_HD FT viscous_flux(int o, int d) const {
+    // k = level of the flux point (stretched grids: Δz⁻¹ᶜ for Σ33 at ccc, Δz⁻¹ᶠ for ∂z u, ∂z v at fcf / cff; the area of an
+    // x- or y-face carries the Δz of the stepped field's own z-location)
+    OC_HD FT viscous_flux(int o, int d, int k) const {
         const Geom<FT>& g = a.g;
         FT sig;
         if (d == COMP) {
             const FT* u = a.U[d] + o;
-            sig = (u[g.st(d)] - u[0]) * g.rd[d];                                  // Σ_dd at ccc
+            sig = (u[g.st(d)] - u[0]) * (d == 2 ? g.rdz_at(false, k) : g.rd[d]);  // Σ_dd at ccc
         } else {
             int lo = d < COMP ? d : COMP, hi = d < COMP ? COMP : d;
             const FT* ul = a.U[lo] + o;
             const FT* uh = a.U[hi] + o;
-            FT dl = (ul[0] - ul[-g.st(hi)]) * g.rd[hi];                           // ∂_hi u_lo
+            FT dl = (ul[0] - ul[-g.st(hi)]) * (hi == 2 ? g.rdz_at(true, k) : g.rd[hi]);   // ∂_hi u_lo
             FT dh = (uh[0] - uh[-g.st(lo)]) * g.rd[lo];                           // ∂_lo u_hi
             sig = FT(0.5) * (dl + dh);
         }
+        const FT A = g.area_at(d, COMP == 2, k);
         FT flux = FT(0);
-        if (a.has_scalar) flux = g.A[d] * (FT(-2) * (a.nu * sig));
+        if (a.has_scalar) flux = A * (FT(-2) * (a.nu * sig));
         if (a.nu_e) {
             FT nu;
             if (d == COMP) nu = a.nu_e[o];
             else nu = nu_ff(o, d < COMP ? d : COMP, d < COMP ? COMP : d);
-            FT f2 = g.A[d] * (FT(-2) * (nu * sig));
+            FT f2 = A * (FT(-2) * (nu * sig));
             flux = a.has_scalar ? flux + f2 : f2;
         }
         return flux;
     }
 
     // diffusive tracer flux A_d · q_d at face index o   (:43-48, :240-242, κ at faces :327-330)
-    OC_HD FT diffusive_flux(int o, int d) const {
+    OC_HD FT diffusive_flux(int o, int d, int k) const {
         const Geom<FT>& g = a.g;
         int s = g.st(d);
         const FT* c = a.c + o;
-        FT grad = (c[0] - c[-s]) * g.rd[d];
+        FT grad = (c[0] - c[-s]) * (d == 2 ? g.rdz_at(true, k) : g.rd[d]);
+        const FT A = g.area_at(d, false, k);
         FT flux = FT(0);
-        if (a.has_scalar) flux = g.A[d] * (-(a.kappa * grad));
+        if (a.has_scalar) flux = A * (-(a.kappa * grad));
         if (a.kappa_e) {
             FT kap = FT(0.5) * (a.kappa_e[o - s] + a.kappa_e[o]);
-            FT f2 = g.A[d] * (-(kap * grad));
+            FT f2 = A * (-(kap * grad));
             flux = a.has_scalar ? flux + f2 : f2;
         }
         return flux;
@@ -127,7 +131,10 @@ struct TendencyKernel {
         int o = g.idx(i, j, k);
         int sd = g.st(d);
         int id = d == 0 ? i : (d == 1 ? j : k);
-        FT A = g.A[d];
+        // Centered: the area at the flux point (centered_advective_fluxes.jl:15-33); upwind schemes: the area of the advecting
+        // velocity's own point, inside the interpolation (upwind_biased_advective_fluxes.jl:23-121) — these differ only
+        // for the x / y fluxes of w on a stretched grid
+        FT A = g.area_at(d, COMP == 2 && ADV == 0, k);
         if (KIND == KIND_C) {
             FT u = a.U[d][o];
             const FT* c = a.c + o;
@@ -164,7 +171,10 @@ struct TendencyKernel {
                 } else {
                     OrderWindow wc = order_window(g.bounded[cc] != 0, false, g.N[cc]);
                     OrderWindow wd = order_window(g.bounded[d] != 0, false, g.N[d]);
-                    FT ut = g.flat[cc] ? A * adv[0] : weno5_symmetric<FT>(a.C, adv, sc, A, ic, wc);
+                    FT ut;
+                    if (g.flat[cc]) ut = A * adv[0];
+                    else if (cc == 2 && g.stretched()) ut = weno5_symmetric_z<FT>(a.C, adv, sc, g.d[d == 0 ? 1 : 0], g.dzc + k, ic, wc);
+                    else ut = weno5_symmetric<FT>(a.C, adv, sc, A, ic, wc);
                     FT pr = weno5_biased<FT>(a.C, psi, sd, ut > FT(0), id, wd);
                     return ut * pr;                                                // :31-93
                 }
@@ -177,7 +187,7 @@ struct TendencyKernel {
         if (a.has_scalar || a.nu_e || a.kappa_e) {
             if (!a.g.flat[d]) {
                 int o = a.g.idx(i, j, k);
-                F = F + (KIND == KIND_C ? diffusive_flux(o, d) : viscous_flux(o, d));
+                F = F + (KIND == KIND_C ? diffusive_flux(o, d, k) : viscous_flux(o, d, k));
             }
         }
         return F;
@@ -240,7 +250,7 @@ struct TendencyKernel {
                 FT dFx = fx[(kk * TY + jj) * (TX + 1) + ii + 1] - fx[(kk * TY + jj) * (TX + 1) + ii];
                 FT dFy = fy[(kk * (TY + 1) + jj + 1) * TX + ii] - fy[(kk * (TY + 1) + jj) * TX + ii];
                 FT dFz = fz[((kk + 1) * TY + jj) * TX + ii] - fz[(kk * TY + jj) * TX + ii];
-                FT G = -(g.rV * (dFx + dFy + dFz));
+                FT G = -(g.rV_at(COMP == 2, k) * (dFx + dFy + dFz));
                 if (KIND == KIND_W && a.buoyancy && !a.pHY && !g.flat[2]) {
                     // maybe_z_dot_g_bᶜᶜᶠ: only without the hydrostatic split (nonhydrostatic_tendency_kernel_functions.jl:168-170)
                     G = G + FT(0.5) * (buoyancy_at(o - g.sz) + buoyancy_at(o));
@@ -277,8 +287,9 @@ struct TendencyKernel {
                     // compute_flux_bcs.jl:126-163 — G[1] += J·A/V ; G[N] -= J·A/V
                     int ijk[3] = {i, j, k};
                     for (int d = 0; d < 3; ++d) {
-                        if (a.fbc.on[2 * d] && ijk[d] == 0) G = G + a.fbc.val[2 * d] * g.A[d] / g.V;
-                        if (a.fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) G = G - a.fbc.val[2 * d + 1] * g.A[d] / g.V;
+                        const FT A = g.area_at(d, COMP == 2, k), V = g.vol_at(COMP == 2, k);
+                        if (a.fbc.on[2 * d] && ijk[d] == 0) G = G + a.fbc.val[2 * d] * A / V;
+                        if (a.fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) G = G - a.fbc.val[2 * d + 1] * A / V;
                     }
                 }
                 a.Gn[o] = G;
@@ -337,6 +348,7 @@ struct FluxBCKernel {
     Geom<FT> g;
     FT* Gn;
     FluxBC<FT> fbc;
+    int zface;         // 1: the field is Face-located in z (w)
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
         int i = b.x * nt + tid, j = b.y, k = b.z;
@@ -346,8 +358,9 @@ struct FluxBCKernel {
         FT G = Gn[o];
         bool touched = false;
         for (int d = 0; d < 3; ++d) {
-            if (fbc.on[2 * d] && ijk[d] == 0) { G = G + fbc.val[2 * d] * g.A[d] / g.V; touched = true; }
-            if (fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) { G = G - fbc.val[2 * d + 1] * g.A[d] / g.V; touched = true; }
+            const FT A = g.area_at(d, zface != 0, k), V = g.vol_at(zface != 0, k);
+            if (fbc.on[2 * d] && ijk[d] == 0) { G = G + fbc.val[2 * d] * A / V; touched = true; }
+            if (fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) { G = G - fbc.val[2 * d + 1] * A / V; touched = true; }
         }
         if (touched) Gn[o] = G;
     }

@@ -286,18 +286,20 @@ def momentum_flux(ctx, scheme, U, comp, d, psi_f):
         return _zero_q(ctx)                                  # flat_advective_fluxes.jl:13-29
     adv = ctx.field(U[d])
     psi = ctx.field(psi_f)
-    A = g.A[d]
     if scheme.kind == "centered":
-        # centered_advective_fluxes.jl:15-27 :  A * sym(U) * sym(ψ)
+        # centered_advective_fluxes.jl:15-27 :  A * sym(U) * sym(ψ), A at the flux point (z-location of the stepped field)
+        A = ctx.area(d, "f" if comp == 2 else "c")
         if d == comp:
             ut = symmetric_center(ctx, scheme, adv, d)
             pt = symmetric_center(ctx, scheme, psi, d)
         else:
             ut = symmetric_face(ctx, scheme, adv, comp)      # interpolate advecting velocity along comp
             pt = symmetric_face(ctx, scheme, psi, d)         # interpolate advected along d
-        return lambda o: A * ut(o) * pt(o)
+        return lambda o: A(o) * ut(o) * pt(o)
     # upwind_biased_advective_fluxes.jl:23-93 :  ũ = sym(A*U) ; ψᴿ = biased(ψ; bias(ũ)) ; ũ*ψᴿ
-    aq = lambda o: A * adv(o)
+    # (Ax_qᶠᶜᶜ, Ay_qᶜᶠᶜ, Az_qᶜᶜᶠ: the area at the advecting velocity's own point, inside the interpolation)
+    A = ctx.area(d, "f" if d == 2 else "c")
+    aq = lambda o: A(o) * adv(o)
     if d == comp:
         ut = symmetric_center(ctx, scheme, aq, d)
         pt = biased_center(ctx, scheme, psi, d, lambda o: ut(o) > 0)
@@ -315,7 +317,7 @@ def div_momentum(ctx, scheme, U, comp):
         F = momentum_flux(ctx, scheme, U, comp, d, U[comp])
         term = (dF(ctx, F, d) if d == comp else dC(ctx, F, d))(O)
         total = term if total is None else total + term
-    return g.rV * total
+    return ctx.rvol("f" if comp == 2 else "c")(O) * total
 
 
 def tracer_flux(ctx, scheme, U, c_f, d):
@@ -325,12 +327,12 @@ def tracer_flux(ctx, scheme, U, c_f, d):
         return _zero_q(ctx)
     u = ctx.field(U[d])
     c = ctx.field(c_f)
-    A = g.A[d]
+    A = ctx.area(d, "f" if d == 2 else "c")                  # Axᶠᶜᶜ, Ayᶜᶠᶜ, Azᶜᶜᶠ
     if scheme.kind == "centered":
         ct = symmetric_face(ctx, scheme, c, d)
-        return lambda o: (A * u(o)) * ct(o)                  # Ax_q(U) * sym(c)  :31-33
+        return lambda o: (A(o) * u(o)) * ct(o)               # Ax_q(U) * sym(c)  :31-33
     ct = biased_face(ctx, scheme, c, d, lambda o: u(o) > 0)
-    return lambda o: A * u(o) * ct(o)                        # Ax * ũ * cᴿ  :99-121
+    return lambda o: A(o) * u(o) * ct(o)                     # Ax * ũ * cᴿ  :99-121
 
 
 def div_tracer(ctx, scheme, U, c_f):
@@ -340,4 +342,4 @@ def div_tracer(ctx, scheme, U, c_f):
     for d in range(3):
         term = dC(ctx, tracer_flux(ctx, scheme, U, c_f, d), d)(O)
         total = term if total is None else total + term
-    return g.rV * total
+    return ctx.rvol("c")(O) * total

@@ -83,11 +83,11 @@ def div_tau(ctx, closure_nu, U, comp):
             loc = "".join(l)
             sig = _strain_offdiag(ctx, U, comp, d)
         nu = _nu_at(ctx, closure_nu, loc)
-        A = g.A[d]
-        flux = (lambda nu, sig, A: (lambda o: A * (-two * (nu(o) * sig(o)))))(nu, sig, A)
+        A = ctx.area(d, loc[2])                  # Ax_qᶜᶜᶜ/Ay_qᶠᶠᶜ/Az_qᶠᶜᶠ … at the flux point (closure_kernel_operators.jl:22-41)
+        flux = (lambda nu, sig, A: (lambda o: A(o) * (-two * (nu(o) * sig(o)))))(nu, sig, A)
         term = (dF(ctx, flux, d) if d == comp else dC(ctx, flux, d))(O)
         total = term if total is None else total + term
-    return g.rV * total
+    return ctx.rvol("f" if comp == 2 else "c")(O) * total
 
 
 def div_q(ctx, kappa, c_f):
@@ -98,11 +98,11 @@ def div_q(ctx, kappa, c_f):
     for d in range(3):
         kap = _kappa_at(ctx, kappa, d)
         grad = ddF(ctx, c, d)
-        A = g.A[d]
-        flux = (lambda kap, grad, A: (lambda o: A * (-(kap(o) * grad(o)))))(kap, grad, A)
+        A = ctx.area(d, "f" if d == 2 else "c")
+        flux = (lambda kap, grad, A: (lambda o: A(o) * (-(kap(o) * grad(o)))))(kap, grad, A)
         term = dC(ctx, flux, d)(O)
         total = term if total is None else total + term
-    return g.rV * total
+    return ctx.rvol("c")(O) * total
 
 
 # ---------------------------------------------------------------------------------
@@ -121,24 +121,25 @@ class _AMD:
         g, FT = ctx.g, ctx.FT
         self.ctx = ctx
         u, v, w = (ctx.field(f) for f in U)
-        Dfx, Dfy, Dfz = FT(2) * g.dx, FT(2) * g.dy, FT(2) * g.dz      # Δᶠ = 2Δ (:224-226)
+        # Δᶠ = 2Δ (:224-226); every Δᶠz_{loc}(i,j,k) is 2·Δzᶜᶜᶜ(i,j,k) at the index of the evaluation point (:228-234)
+        Dfx, Dfy = FT(2) * g.dx, FT(2) * g.dy
+        _dzc = ctx.dz("c")
+        Dfz = lambda o: FT(2) * _dzc(o)
         self.Df = (Dfx, Dfy, Dfz)
         # normalised gradients (velocity_tracer_gradients.jl:126-154)
         self.dxu = ddC(ctx, u, 0)
         self.dyv = ddC(ctx, v, 1)
         self.dzw = ddC(ctx, w, 2)
         rxy, ryx = FT(Dfx / Dfy), FT(Dfy / Dfx)
-        rxz, rzx = FT(Dfx / Dfz), FT(Dfz / Dfx)
-        ryz, rzy = FT(Dfy / Dfz), FT(Dfz / Dfy)
         _dxv, _dyu = ddF(ctx, v, 0), ddF(ctx, u, 1)
         _dxw, _dzu = ddF(ctx, w, 0), ddF(ctx, u, 2)
         _dyw, _dzv = ddF(ctx, w, 1), ddF(ctx, v, 2)
         self.dxv = lambda o: rxy * _dxv(o)       # ffc
         self.dyu = lambda o: ryx * _dyu(o)       # ffc
-        self.dxw = lambda o: rxz * _dxw(o)       # fcf
-        self.dzu = lambda o: rzx * _dzu(o)       # fcf
-        self.dyw = lambda o: ryz * _dyw(o)       # cff
-        self.dzv = lambda o: rzy * _dzv(o)       # cff
+        self.dxw = lambda o: (Dfx / Dfz(o)) * _dxw(o)       # fcf
+        self.dzu = lambda o: (Dfz(o) / Dfx) * _dzu(o)       # fcf
+        self.dyw = lambda o: (Dfy / Dfz(o)) * _dyw(o)       # cff
+        self.dzv = lambda o: (Dfz(o) / Dfy) * _dzv(o)       # cff
         h = FT(0.5)
         self.S12 = lambda o: h * (self.dyu(o) + self.dxv(o))
         self.S13 = lambda o: h * (self.dzu(o) + self.dxw(o))
@@ -198,7 +199,7 @@ class _AMD:
     def delta2(self):
         FT = self.ctx.FT
         Dfx, Dfy, Dfz = self.Df
-        return FT(3) / (FT(1) / Dfx ** 2 + FT(1) / Dfy ** 2 + FT(1) / Dfz ** 2)
+        return FT(3) / (FT(1) / Dfx ** 2 + FT(1) / Dfy ** 2 + FT(1) / Dfz(O) ** 2)
 
     def tracer_terms(self, c_f):
         ctx = self.ctx
@@ -207,7 +208,7 @@ class _AMD:
         _cx, _cy, _cz = ddF(ctx, c, 0), ddF(ctx, c, 1), ddF(ctx, c, 2)
         cx = lambda o: Dfx * _cx(o)
         cy = lambda o: Dfy * _cy(o)
-        cz = lambda o: Dfz * _cz(o)
+        cz = lambda o: Dfz(o) * _cz(o)
         Ix = lambda q: iC(ctx, q, 0)
         Iy = lambda q: iC(ctx, q, 1)
         Iz = lambda q: iC(ctx, q, 2)
@@ -233,7 +234,7 @@ def compute_amd(ctx, closure, U, tracers, nu_e, kappa_e):
         q = amd.q_trace()
         r = amd.r_term()
         d2 = amd.delta2()
-        Cb_zeta = FT(0) / (FT(2) * g.dz)
+        Cb_zeta = FT(0) / amd.Df[2](O)
         nu = -FT(closure.Cnu) * d2 * (r - Cb_zeta) / q
         nu = np.where(q == 0, FT(0), nu)
         nu_e.interior[...] = np.maximum(FT(0), nu)

@@ -39,11 +39,21 @@ class Grid:
                 bounds[d] = (0.0, float(extent[n])) if d < 2 else (-float(extent[n]), 0.0)
         else:
             for d, b in enumerate((x, y, z)):
-                if b is not None:
+                if b is not None and isinstance(b, tuple) and len(b) == 2:
                     bounds[d] = (float(b[0]), float(b[1]))
         if halo is not None:
             halo = (halo,) if np.isscalar(halo) else tuple(halo)
         N, H, L, D, X0 = [1, 1, 1], [0, 0, 0], [1.0, 1.0, 1.0], [None] * 3, [0.0] * 3
+        # z = vector of Nz+1 faces or a function of the face index: vertically stretched grid
+        # (rectilinear_grid.jl:264-291 -> generate_coordinate(FT, topo, N, H, node_generator, …), grid_generation.jl:33-94)
+        self.z_faces = None
+        if z is not None and (callable(z) or not isinstance(z, tuple) or len(z) != 2):   # a 2-tuple is an interval (regular)
+            nz = int(size[nonflat.index(2)])
+            zf = [z(i) for i in range(1, nz + 2)] if callable(z) else list(z)
+            assert len(zf) == nz + 1, "z must list Nz+1 faces"
+            self.z_faces = np.asarray(zf, dtype=self.FT)
+            assert np.all(np.diff(self.z_faces) > 0), "The elements of z must be increasing!"
+            bounds[2] = (float(self.z_faces[0]), float(self.z_faces[-1]))
         for n, d in enumerate(nonflat):
             N[d] = int(size[n])
             H[d] = int(halo[n]) if halo is not None else min(3, N[d])
@@ -70,6 +80,50 @@ class Grid:
         self.rV = FTc(FTc(1) / self.V)
         self.rD = tuple(FTc(FTc(1) / dd) for dd in self.D)
         self.A = (self.Ax, self.Ay, self.Az)
+        self.stretched = self.z_faces is not None
+        if self.stretched:
+            assert self.topo[2] == BOUNDED, "only a Bounded z can be stretched (fourier_tridiagonal_poisson_solver.jl:86-90)"
+            self.L = (self.L[0], self.L[1], FTc(self.z_faces[-1] - self.z_faces[0]))
+            self.D = (self.D[0], self.D[1], None)
+            self.dz = None
+            # level-dependent metrics: use Ctx.dz / Ctx.area / Ctx.rvol / Ctx.rdelta (oracle/operators.py)
+            self.Ax = self.Ay = self.V = self.rV = None
+            self.A = (None, None, self.Az)
+            self.rD = (self.rD[0], self.rD[1], None)
+            self._generate_z()
+
+    def _generate_z(self):
+        """generate_coordinate for a Bounded, variably spaced coordinate (grid_generation.jl:33-94), in FT arithmetic.
+        Sets zF[k], zC[k], dzc[k] = Δzᵃᵃᶜ, dzf[k] = Δzᵃᵃᶠ as dicts-by-offset arrays: logical index k <-> array[k + Hz + 1]
+        for dzf (k = -Hz … Nz+Hz) and array[k + Hz - 1]-style accessors below."""
+        FT, N, H = self.FT, self.N[2], self.H[2]
+        Fi = self.z_faces
+        dlo = [FT(Fi[1] - Fi[0])] * H                       # lower_exterior_Δcoordᶠ(::BoundedTopology)
+        dhi = [FT(Fi[-1] - Fi[-2])] * H                     # reverse(upper_exterior_Δcoordᶠ)
+        def ssum(v):
+            s = FT(0)
+            for x in v:
+                s = FT(s + x)
+            return s
+        Flo = [FT(Fi[0] - ssum(dlo[i:H])) for i in range(H)]
+        Fhi = [FT(Fi[-1] + ssum(dhi[i:H])) for i in range(H)][::-1]
+        F = np.asarray(Flo + list(Fi) + Fhi, dtype=FT)      # N + 1 + 2H faces, logical index k <-> F[k + H - 1]
+        TC = N + 2 * H
+        C = np.asarray([FT(FT(F[i + 1] + F[i]) / FT(2)) for i in range(TC)], dtype=FT)
+        dF_raw = [FT(C[i] - C[i - 1]) for i in range(1, TC)]
+        dC_ = np.asarray([FT(F[i + 1] - F[i]) for i in range(len(F) - 1)], dtype=FT)   # Δᶜ, logical k <-> [k + H - 1]
+        dFp = [dF_raw[0]] + dF_raw + [dF_raw[-1]]
+        for i in range(len(dFp) - 1, 0, -1):
+            dFp[i] = dFp[i - 1]
+        dF_ = np.asarray(dFp, dtype=FT)                     # Δᶠ, OffsetArray(-H-1): logical k <-> [k + H]
+        self._zF, self._zC, self._dzc, self._dzf = F, C, dC_, dF_
+
+    def dz_at(self, zloc, k):
+        """Δzᵃᵃᶜ[k] / Δzᵃᵃᶠ[k] for 1-based logical (possibly array) index k"""
+        if not self.stretched:
+            return self.D[2]
+        k = np.asarray(k)
+        return self._dzc[k + self.H[2] - 1] if zloc == "c" else self._dzf[k + self.H[2]]
 
     def flat(self, d):
         return self.topo[d] == FLAT
@@ -83,11 +137,16 @@ class Grid:
         H = tuple(0 if self.flat(d) else int(halo[d]) for d in range(3))
         g.H = H
         g.Hx, g.Hy, g.Hz = H
+        if g.stretched:
+            g._generate_z()
         return g
 
     def nodes(self, d, loc):
         """Cell centres ('c') or faces ('f') along dimension d (interior)."""
         n = self.N[d] + (1 if (loc == "f" and self.bounded(d)) else 0)
+        if d == 2 and self.stretched:
+            H = self.H[2]
+            return (self._zC[H:H + n] if loc == "c" else self._zF[H:H + n]).astype(np.float64)
         i = np.arange(n, dtype=np.float64)
         off = 0.5 if loc == "c" else 0.0
         return self.x0[d] + (i + off) * float(self.D[d])
@@ -217,10 +276,11 @@ def fill_halo_regions(f, fill_open_bcs=True):
             f.data[tuple(sl_dst_w)] = f.data[tuple(sl_src_w)]
             f.data[tuple(sl_dst_e)] = f.data[tuple(sl_src_e)]
             continue
-        delta = g.D[d]
         for side, bc in ((0, left), (1, right)):
             if bc.kind is None:
                 continue
+            # Δ between the interior and the halo point, at the boundary face (fill_halo_regions_value_gradient.jl:44,60)
+            delta = g.dz_at("f", 1 if side == 0 else N + 1) if (d == 2 and g.stretched) else g.D[d]
             if bc.kind == "open":
                 # fill_halo_regions_open.jl:2-14 — sets the boundary face itself
                 if not fill_open_bcs:

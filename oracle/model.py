@@ -172,10 +172,11 @@ class OracleModel:
         bf = iF(ctx, b, 2)                                # z_dot_g_bᶜᶜᶠ = ℑzᵃᵃᶠ(b)   g_dot_b.jl:4
         p = ctx.field(self.pHY)
         tgt = lambda kk: self._target(self.pHY, Ctx(g, ir, jr, (kk, kk)))
-        tgt(Nz)[...] = -bf((0, 0, 1)) * g.dz
+        dzf = ctx.dz("f")                                 # Δzᶜᶜᶠ(k+1)
+        tgt(Nz)[...] = -bf((0, 0, 1)) * dzf((0, 0, 1))
         for k in range(Nz - 1, 0, -1):
             off = k - Nz
-            tgt(k)[...] = p((0, 0, off + 1)) - bf((0, 0, off + 1)) * g.dz
+            tgt(k)[...] = p((0, 0, off + 1)) - bf((0, 0, off + 1)) * dzf((0, 0, off + 1))
 
     # ------------------------------------------------------------------ tendencies
     def _closure_nu_kappa(self, ctx, c, name):
@@ -226,11 +227,14 @@ class OracleModel:
                     idx = 1 if side == 0 else g.N[d]
                     rng = [(1, g.N[e]) for e in range(3)]
                     rng[d] = (idx, idx)
-                    tgt = self._target(G, Ctx(g, *rng))
+                    cx = Ctx(g, *rng)
+                    tgt = self._target(G, cx)
                     val = bc.get(FT)
                     if not np.isscalar(val):
                         val = np.expand_dims(val, d)
-                    contrib = val * g.A[d] / g.V
+                    # A(…, flip(L_d)) / volume(…, LX, LY, LZ)   compute_flux_bcs.jl:116-161
+                    zl = f.loc[2]
+                    contrib = val * cx.area(d, zl)(O) / cx.vol(zl)(O)
                     if side == 0:
                         tgt[...] = tgt + contrib
                     else:
@@ -297,13 +301,76 @@ class OracleModel:
             phi = (phi * (1.0 / (2 * g.N[d]))).astype(CT)
         return phi.real.astype(FT)
 
+    def _tridiagonal_setup(self):
+        """FourierTridiagonalPoissonSolver(grid) for a z-stretched grid  fourier_tridiagonal_poisson_solver.jl:74-131,
+        compute_main_diagonal! (HomogeneousZFormulation) :172-185, compute_lower_diagonal! :198-202"""
+        g, FT = self.grid, self.FT
+        Nz = g.Nz
+        k = np.arange(1, Nz + 1)
+        dzc = g.dz_at("c", k)
+        one = FT(1)
+        lam = (self.lam[0][:, None] + self.lam[1][None, :])[:, :, None]          # Float64
+        D = np.empty((g.Nx, g.Ny, Nz), dtype=FT)
+        D[:, :, 0] = (-one / g.dz_at("f", 2) - dzc[0] * lam[:, :, 0]).astype(FT)
+        D[:, :, Nz - 1] = (-one / g.dz_at("f", Nz) - dzc[Nz - 1] * lam[:, :, 0]).astype(FT)
+        for kk in range(2, Nz):
+            D[:, :, kk - 1] = (-(one / g.dz_at("f", kk + 1) + one / g.dz_at("f", kk)) - dzc[kk - 1] * lam[:, :, 0]).astype(FT)
+        self._tri_D = D
+        self._tri_lower = np.asarray([one / g.dz_at("f", q + 1) for q in range(1, Nz)], dtype=FT)    # = upper diagonal
+        CT = np.complex128 if FT is np.float64 else np.complex64
+        self._tri_phi = np.zeros((g.Nx, g.Ny, Nz), dtype=CT)                     # solver.storage (persists between solves)
+        self._tri_t = np.zeros((g.Nx, g.Ny, Nz), dtype=FT)                       # scratch
+
+    def solve_poisson_tridiagonal(self, rhs):
+        """solve!(x, ::FourierTridiagonalPoissonSolver)  fourier_tridiagonal_poisson_solver.jl:204-231 with
+        solve_batched_tridiagonal_system_z!  batched_tridiagonal_solver.jl:220-243.
+        rhs: Δzᶜᶜᶜ·div (Nx,Ny,Nz) real FT (solve_for_pressure.jl:36-42,69-76)."""
+        g, FT = self.grid, self.FT
+        if not hasattr(self, "_tri_D"):
+            self._tridiagonal_setup()
+        CT = self._tri_phi.dtype.type
+        f = rhs.astype(CT)
+        bdims = [d for d in (0, 1) if g.bounded(d)]
+        pdims = [d for d in (0, 1) if g.topo[d] == "P"]
+        for d in bdims:
+            f = (sfft.dct(f.real, type=2, axis=d) + 1j * sfft.dct(f.imag, type=2, axis=d)).astype(CT)
+        if pdims:
+            f = sfft.fftn(f, axes=pdims).astype(CT)
+        a, b, c, t, phi = self._tri_lower, self._tri_D, self._tri_lower, self._tri_t, self._tri_phi
+        Nz = g.Nz
+        eps10 = 10 * np.finfo(FT).eps
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            beta = b[:, :, 0].copy()
+            phi[:, :, 0] = f[:, :, 0] / beta
+            for k in range(1, Nz):
+                t[:, :, k] = c[k - 1] / beta
+                beta = b[:, :, k] - a[k - 1] * t[:, :, k]
+                dominant = np.abs(beta) > eps10
+                star = (f[:, :, k] - a[k - 1] * phi[:, :, k - 1]) / beta
+                phi[:, :, k] = np.where(dominant, star, phi[:, :, k])
+            for k in range(Nz - 2, -1, -1):
+                phi[:, :, k] = phi[:, :, k] - t[:, :, k + 1] * phi[:, :, k + 1]
+        out = phi
+        if pdims:
+            out = sfft.ifftn(out, axes=pdims).astype(CT)
+        for d in bdims:
+            out = (sfft.dct(out.real, type=3, axis=d) + 1j * sfft.dct(out.imag, type=3, axis=d)).astype(CT)
+            out = (out * (1.0 / (2 * g.N[d]))).astype(CT)
+        out = (out - out.mean()).astype(CT)                      # ϕ .= ϕ .- mean(ϕ)
+        self._tri_phi[...] = out                                 # transforms and the mean removal act in place on storage
+        return out.real.astype(FT)
+
     def compute_pressure_correction(self, dt):
         """compute_pressure_correction!  pressure_correction.jl:8-20"""
         for f in self.U:
             fill_halo_regions(f)                                   # open BCs filled here
         ctx = self._ctx_full()
         rhs = div_ccc(ctx, self.u, self.v, self.w)                 # NOT divided by Δt (solve_for_pressure.jl:12-18)
-        self.pNHS.interior[...] = self.solve_poisson(rhs)
+        if self.grid.stretched:
+            # _fourier_tridiagonal_source_term!: Δzᶜᶜᶜ · div   (solve_for_pressure.jl:36-42)
+            self.pNHS.interior[...] = self.solve_poisson_tridiagonal(ctx.dz("c")(O) * rhs)
+        else:
+            self.pNHS.interior[...] = self.solve_poisson(rhs)
         fill_halo_regions(self.pNHS)
 
     def make_pressure_correction(self, dt):

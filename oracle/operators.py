@@ -55,6 +55,51 @@ class Ctx:
     def zeros(self):
         return np.zeros(self.shape, dtype=self.FT)
 
+    # ---- metrics as quantities (spacings_and_areas_and_volumes.jl:309-376, reciprocal_metric_operators.jl:7-13).
+    # x and y are regularly spaced; z may be stretched, in which case Δz depends on the level AND on the z-location
+    # ('c': Δzᵃᵃᶜ[k], 'f': Δzᵃᵃᶠ[k]) of the point where the metric is evaluated.
+    def dz(self, zloc):
+        g = self.g
+        if not g.stretched:
+            return lambda o: g.D[2]
+        return lambda o: g.dz_at(zloc, self.index(2, o))
+
+    def area(self, d, zloc):
+        """Ax = Δy·Δz, Ay = Δx·Δz, Az = Δx·Δy at a point whose z-location is zloc"""
+        g = self.g
+        if d == 2 or not g.stretched:
+            A = g.A[d]
+            return lambda o: A
+        other = g.D[1] if d == 0 else g.D[0]
+        dz = self.dz(zloc)
+        return lambda o: other * dz(o)
+
+    def rvol(self, zloc):
+        """V⁻¹ = 1 / (Az·Δz)"""
+        g = self.g
+        if not g.stretched:
+            return lambda o: g.rV
+        dz = self.dz(zloc)
+        one = self.FT(1)
+        return lambda o: one / (g.Az * dz(o))
+
+    def vol(self, zloc):
+        g = self.g
+        if not g.stretched:
+            return lambda o: g.V
+        dz = self.dz(zloc)
+        return lambda o: g.Az * dz(o)
+
+    def rdelta(self, d, loc):
+        """Δ⁻¹ along d at a point whose location along d is loc"""
+        g = self.g
+        if d != 2 or not g.stretched:
+            r = g.rD[d]
+            return lambda o: r
+        dz = self.dz(loc)
+        one = self.FT(1)
+        return lambda o: one / dz(o)
+
     def const(self, v):
         return lambda o: self.FT(v)
 
@@ -96,26 +141,25 @@ def iF(ctx, q, d):
 
 # derivative_operators.jl:20-22 : ∂ = δ * Δ⁻¹
 def ddC(ctx, q, d):
-    r = ctx.g.rD[d]
+    r = ctx.rdelta(d, "c")
     dq = dC(ctx, q, d)
-    return lambda o: dq(o) * r
+    return lambda o: dq(o) * r(o)
 
 
 def ddF(ctx, q, d):
-    r = ctx.g.rD[d]
+    r = ctx.rdelta(d, "f")
     dq = dF(ctx, q, d)
-    return lambda o: dq(o) * r
+    return lambda o: dq(o) * r(o)
 
 
 def scaled(q, a):
-    """a * q   (e.g. Ax_qᶠᶜᶜ = Ax * u)"""
-    return lambda o: a * q(o)
+    """a * q   (e.g. Ax_qᶠᶜᶜ = Ax * u); a is a metric quantity"""
+    return lambda o: a(o) * q(o)
 
 
 def div_ccc(ctx, u, v, w):
     """divᶜᶜᶜ  divergence_operators.jl:16-19"""
-    g = ctx.g
-    qx = dC(ctx, scaled(ctx.field(u), g.Ax), 0)
-    qy = dC(ctx, scaled(ctx.field(v), g.Ay), 1)
-    qz = dC(ctx, scaled(ctx.field(w), g.Az), 2)
-    return g.rV * (qx(O) + qy(O) + qz(O))
+    qx = dC(ctx, scaled(ctx.field(u), ctx.area(0, "c")), 0)
+    qy = dC(ctx, scaled(ctx.field(v), ctx.area(1, "c")), 1)
+    qz = dC(ctx, scaled(ctx.field(w), ctx.area(2, "f")), 2)
+    return ctx.rvol("c")(O) * (qx(O) + qy(O) + qz(O))

@@ -24,21 +24,29 @@ GOLDEN_CASES = {
     "ppf_weno_2d_f64": dict(N=(12, 10, 1), topo="PPF", scheme="weno", closure="none", buoy="none"),
     "ppb_weno_ab2_f64": dict(N=(12, 10, 8), topo="PPB", scheme="weno", ts="QuasiAdamsBashforth2"),
     "ppp_weno_ts_f32": dict(N=(12, 10, 8), topo="PPP", scheme="weno", FT=np.float32),
+    # vertically stretched grids (FourierTridiagonalPoissonSolver)
+    "stretched_ppb_weno_amd_fplane_bcs_f64": dict(N=(12, 10, 8), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, stretch="smooth"),
+    "stretched_bbb_centered_scalar_f64": dict(N=(12, 10, 8), topo="BBB", scheme="centered", stretch="facr"),
 }
 STEPS = (1, 3)
 
 
 
 
-def main():
+def main(only=None):
     import oracle
     from oracle import advection as adv, closures as clo
     import parity_harness as ph
     for name, kw in GOLDEN_CASES.items():
+        if only and name not in only:
+            continue
         om = ph.build_oracle(**kw)
         ic = ph.initial_conditions(om)
         om.set(**ic)
-        dt = 0.1 * float(min(om.grid.D[d] for d in range(3) if not om.grid.flat(d)))
+        dmin = [float(om.grid.D[d]) for d in range(3) if not om.grid.flat(d) and om.grid.D[d] is not None]
+        if om.grid.stretched:
+            dmin.append(float(np.min(om.grid.dz_at("c", np.arange(1, om.grid.Nz + 1)))))
+        dt = 0.1 * min(dmin)
         out = {"dt": np.float64(dt)}
         for n, a in ic.items():
             out["ic_" + n] = a
@@ -53,4 +61,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(only=sys.argv[1:])      # no arguments: regenerate every file

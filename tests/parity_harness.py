@@ -26,8 +26,33 @@ def _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent):
     return size, ext, tr
 
 
+def z_faces(Nz, Lz, kind):
+    """Vertically stretched face positions on [-Lz, 0]: 'smooth' refines towards the surface (the spacing of
+    examples/ocean_wind_mixing_and_convection.jl, in spirit); 'facr' is the irregular spacing of the reference's own
+    stretched-solver test (test/test_poisson_solvers_stretched_grids.jl:29-30: 1, 2, 4, 7, 11, 16, 22, 29, 37 …)."""
+    k = np.arange(Nz + 1, dtype=np.float64)
+    if kind == "facr":
+        f = 1.0 + k * (k + 1) / 2.0
+        return -Lz + Lz * (f - f[0]) / (f[-1] - f[0])
+    s = k / Nz
+    return -Lz + Lz * (s + 0.6 * np.sin(np.pi * s) / np.pi)
+
+
+def _grid_kwargs(N, topo, extent, stretch):
+    nonflat = [d for d in range(3) if topo[d] != "F"]
+    size = tuple(N[d] for d in nonflat)
+    if not stretch:
+        return dict(size=size, extent=tuple(extent[d] for d in nonflat))
+    kw = dict(size=size, z=[float(v) for v in z_faces(N[2], extent[2], stretch)])
+    if topo[0] != "F":
+        kw["x"] = (0.0, extent[0])
+    if topo[1] != "F":
+        kw["y"] = (0.0, extent[1])
+    return kw
+
+
 def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
-                 bcs=False, extent=EXTENT, **_):
+                 bcs=False, extent=EXTENT, stretch=None, **_):
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
     obo = clo.SeawaterBuoyancy() if buoy == "seawater" else (clo.BuoyancyTracer() if buoy == "tracer" else None)
     ocl = {"scalar": clo.ScalarDiffusivity(1e-3, 2e-3), "amd": clo.AnisotropicMinimumDissipation(), "none": None,
@@ -37,17 +62,18 @@ def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closur
         t0 = tr[0]
         bc_o = {"u": {"top": BC("flux", -2e-3)}, t0: {"top": BC("flux", 5e-3), "bottom": BC("gradient", 0.05)},
                 "v": {"bottom": BC("value", 0.1)}}
-    og = oracle.Grid(FT, size=size, extent=ext, topology=tuple(topo))
+    og = oracle.Grid(FT, topology=tuple(topo), **_grid_kwargs(N, topo, extent, stretch))
     oa = adv.Centered(FT, 2) if scheme == "centered" else adv.WENO(FT, 5)
     return oracle.OracleModel(og, advection=oa, tracers=tr, buoyancy=obo, closure=ocl, timestepper=ts, coriolis_f=f,
                               boundary_conditions=bc_o)
 
 
 def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
-                  bcs=False, library=None, extent=EXTENT, arch=None):
+                  bcs=False, library=None, extent=EXTENT, arch=None, stretch=None):
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
-    grid = ob.RectilinearGrid(arch if arch is not None else FT, FT, size=size, extent=ext, topology=tuple(TOPO[c] for c in topo)) \
-        if arch is not None else ob.RectilinearGrid(FT, size=size, extent=ext, topology=tuple(TOPO[c] for c in topo))
+    gkw = _grid_kwargs(N, topo, extent, stretch)
+    grid = ob.RectilinearGrid(arch if arch is not None else FT, FT, topology=tuple(TOPO[c] for c in topo), **gkw) \
+        if arch is not None else ob.RectilinearGrid(FT, topology=tuple(TOPO[c] for c in topo), **gkw)
     a = ob.Centered() if scheme == "centered" else ob.WENO()
     bo = ob.SeawaterBuoyancy() if buoy == "seawater" else (ob.BuoyancyTracer() if buoy == "tracer" else None)
     cl = {"scalar": ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), "amd": ob.AnisotropicMinimumDissipation(), "none": None,
@@ -101,7 +127,10 @@ def run_case(steps=(1, 10), dt=None, **kw):
     ob.set_(m, **ic)
     om.set(**ic)
     if dt is None:
-        dt = 0.1 * float(min(om.grid.D[d] for d in range(3) if not om.grid.flat(d)))
+        dmin = [float(om.grid.D[d]) for d in range(3) if not om.grid.flat(d) and om.grid.D[d] is not None]
+        if om.grid.stretched:
+            dmin.append(float(np.min(om.grid.dz_at("c", np.arange(1, om.grid.Nz + 1)))))
+        dt = 0.1 * min(dmin)
     out = {0: compare(m, om)}
     for s in range(1, max(steps) + 1):
         ob.time_step_(m, dt)
@@ -127,6 +156,19 @@ CASES = [
     ("PPB centered both closures bcs F32", dict(N=(16, 12, 8), topo="PPB", scheme="centered", closure="both", bcs=True, FT=np.float32)),
     ("odd sizes PPB", dict(N=(13, 9, 7), topo="PPB", scheme="weno")),
     ("tile-crossing 40x36x33 PPB", dict(N=(40, 36, 33), topo="PPB", scheme="weno")),
+]
+
+# vertically stretched grids: FourierTridiagonalPoissonSolver + level-dependent metrics
+STRETCHED_CASES = [
+    ("stretched PPB weno scalar TS", dict(N=(16, 12, 8), topo="PPB", scheme="weno", stretch="smooth")),
+    ("stretched PPB weno amd fplane bcs (LES)", dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, stretch="smooth")),
+    ("stretched PPB centered both closures bcs", dict(N=(16, 12, 8), topo="PPB", scheme="centered", closure="both", bcs=True, stretch="facr")),
+    ("stretched BBB weno amd", dict(N=(12, 10, 8), topo="BBB", scheme="weno", closure="amd", f=1e-2, stretch="facr")),
+    ("stretched PBB centered AB2", dict(N=(16, 12, 9), topo="PBB", scheme="centered", ts="QuasiAdamsBashforth2", stretch="smooth")),
+    ("stretched BPB weno F32", dict(N=(16, 12, 8), topo="BPB", scheme="weno", FT=np.float32, stretch="smooth")),
+    ("stretched PFB weno tracer-b fplane", dict(N=(16, 1, 12), topo="PFB", scheme="weno", buoy="tracer", f=0.2, stretch="smooth")),
+    ("stretched odd sizes PPB", dict(N=(13, 9, 7), topo="PPB", scheme="weno", stretch="facr")),
+    ("stretched tile-crossing 40x36x33 PPB", dict(N=(40, 36, 33), topo="PPB", scheme="weno", closure="amd", bcs=True, stretch="smooth")),
 ]
 
 

@@ -33,7 +33,7 @@ def test_cuda_library_loads_and_exports_every_symbol():
         assert hasattr(lib.dll, name), name
     cfg = _lib.oc_config()
     lib.oc_config_init(C.byref(cfg))     # pure host call; no compute without a GPU
-    assert cfg.abi_version == 1 and cfg.ab2_chi == 0.1 and abs(cfg.gravity - 9.80665) < 1e-15
+    assert cfg.abi_version == 2 and cfg.ab2_chi == 0.1 and abs(cfg.gravity - 9.80665) < 1e-15
 
 
 def test_missing_library_fails_loudly(tmp_path):
@@ -49,7 +49,12 @@ def test_out_of_scope_configurations_are_errors():
     with pytest.raises(NotImplementedError):
         ob.Centered(order=4)
     with pytest.raises(NotImplementedError):
-        ob.RectilinearGrid(np.float64, size=(4, 4, 4), x=(0, 1), y=(0, 1), z=[0, 0.1, 0.3, 0.6, 1.0])
+        ob.RectilinearGrid(np.float64, size=(4, 4, 4), x=[0, 0.1, 0.3, 0.6, 1.0], y=(0, 1), z=(0, 1))      # stretched x: out of scope
+    with pytest.raises(ValueError):
+        ob.RectilinearGrid(np.float64, size=(4, 4, 4), x=(0, 1), y=(0, 1), z=[0, 0.1, 0.3, 0.6, 1.0],
+                           topology=(ob.Periodic, ob.Periodic, ob.Periodic))                                # stretched z must be Bounded
+    gs = ob.RectilinearGrid(np.float64, size=(4, 4, 4), x=(0, 1), y=(0, 1), z=[0, 0.1, 0.3, 0.6, 1.0])
+    assert gs.z_faces is not None and gs.Lz == 1.0 and gs.dz is None
     with pytest.raises(ValueError):
         ob.RectilinearGrid(np.float64, size=(4, 4), extent=(1, 1, 1))
     g = ob.RectilinearGrid(np.float32, size=(4, 4, 4), extent=(1, 1, 1))

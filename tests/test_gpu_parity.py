@@ -24,6 +24,73 @@ def test_cuda_matches_oracle(ob, name, kw):
     ph.check_case(kw, library=None, steps=(1, 10))
 
 
+@pytest.mark.parametrize("name,kw", ph.STRETCHED_CASES, ids=[c[0] for c in ph.STRETCHED_CASES])
+def test_cuda_matches_oracle_on_stretched_grids(ob, name, kw):
+    """vertically stretched grids (FourierTridiagonalPoissonSolver, level-dependent metrics)"""
+    ph.check_case(kw, library=None, steps=(1, 10))
+
+
+def test_stretched_poisson_all_topologies(ob):
+    """solve!(ϕ, ::FourierTridiagonalPoissonSolver, b) with the faces / sizes of test/test_poisson_solvers_stretched_grids.jl:28-46"""
+    import oracle
+    rng = np.random.default_rng(11)
+    faces = {8: [1, 2, 4, 7, 11, 16, 22, 29, 37], 9: [1, 2, 4, 7, 11, 16, 22, 29, 37, 51], 4: [1, 2, 3, 4, 5]}
+    for FT, tol in ((np.float64, 1e-11), (np.float32, 1e-4)):
+        for topo in ["PPB", "PBB", "BPB", "BBB", "FBB", "FPB", "BFB", "PFB"]:
+            for N1, N2, Nz in [(8, 8, 8), (16, 8, 9), (8, 11, 8), (5, 8, 9), (7, 13, 8), (4, 5, 4)]:
+                kw, size = {}, []
+                if topo[0] != "F":
+                    kw["x"] = (0.0, 1.0); size.append(N1)
+                if topo[1] != "F":
+                    kw["y"] = (0.0, 1.0); size.append(N2)
+                size.append(Nz)
+                z = [float(f) for f in faces[Nz]]
+                grid = ob.RectilinearGrid(FT, size=tuple(size), z=z, topology=tuple(ph.TOPO[c] for c in topo), **kw)
+                m = ob.NonhydrostaticModel(grid=grid)
+                om = oracle.OracleModel(oracle.Grid(FT, size=tuple(size), z=z, topology=tuple(topo), **kw))
+                N = om.grid.N
+                dzc = om.grid.dz_at("c", np.arange(1, Nz + 1)).astype(np.float64)
+                rhs = rng.standard_normal(N)
+                rhs -= (rhs * dzc).sum() / (dzc.sum() * N[0] * N[1])
+                a = ob.solve_poisson(m, rhs)
+                b = om.solve_poisson_tridiagonal((rhs.astype(FT) * dzc.astype(FT)).astype(FT))
+                assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1.0), (FT, topo, N)
+
+
+def test_stretched_full_size_les_incompressible(ob):
+    """A C4-sized stretched LES (256×256×128 here; 512²×256 is the `c4s` bench workload): AMD, FPlane, flux BCs, WENO-5 on a
+    surface-refined grid.  Size-independent properties: ∇·U ≈ 0 after the FourierTridiagonal projection, the volume-weighted
+    tracer budget follows the boundary fluxes, fields stay finite."""
+    N = (256, 256, 128)
+    Lz = 128.0
+    zf = ph.z_faces(N[2], Lz, "smooth")
+    grid = ob.RectilinearGrid(np.float64, size=N, x=(0.0, 256.0), y=(0.0, 256.0), z=[float(v) for v in zf],
+                              topology=(ob.Periodic, ob.Periodic, ob.Bounded))
+    Q = 5e-5
+    bcs = {"T": ob.FieldBoundaryConditions(top=ob.FluxBoundaryCondition(Q))}
+    m = ob.NonhydrostaticModel(grid=grid, advection=ob.WENO(), tracers=("T", "S"), closure=ob.AnisotropicMinimumDissipation(),
+                               buoyancy=ob.SeawaterBuoyancy(equation_of_state=ob.LinearEquationOfState(thermal_expansion=2e-4, haline_contraction=8e-4)),
+                               coriolis=ob.FPlane(f=1e-4), boundary_conditions=bcs)
+    rng = np.random.default_rng(1234)
+    zc = 0.5 * (zf[1:] + zf[:-1])
+    dzc = np.diff(zf)
+    ic = {"u": 1e-2 * rng.standard_normal(N), "v": 1e-2 * rng.standard_normal(N),
+          "w": 1e-2 * rng.standard_normal((N[0], N[1], N[2] + 1)),
+          "T": 20 + 0.005 * zc[None, None, :] + 1e-4 * rng.standard_normal(N), "S": np.full(N, 35.0)}
+    ob.set_(m, **ic)
+    T0 = float((m.tracers.T.interior() * dzc).sum())
+    dt, steps = 0.5, 2
+    for _ in range(steps):
+        ob.time_step_(m, dt)
+    u, v, w = (m.velocities[n].interior().astype(np.float64) for n in "uvw")
+    div = (np.roll(u, -1, 0) - u) / 1.0 + (np.roll(v, -1, 1) - v) / 1.0 + (w[:, :, 1:] - w[:, :, :-1]) / dzc
+    assert np.abs(div).max() < 1e-10
+    T1 = float((m.tracers.T.interior() * dzc).sum())
+    # d/dt Σ T Δz = -Q per column (a positive top flux removes T): compute_flux_bcs.jl:116-161
+    assert abs((T1 - T0) + Q * dt * steps * N[0] * N[1]) <= 1e-11 * abs(T0)
+    assert np.isfinite(m.tracers.S.interior()).all()
+
+
 def test_poisson_all_topologies(ob):
     """divergence_free_poisson_solution: test/test_poisson_solvers.jl:58-98 through solve!"""
     import oracle

@@ -30,6 +30,39 @@ def test_hostsim_matches_oracle(hostsim, name, kw):
     ph.check_case(kw, library=hostsim, steps=(1, 3))
 
 
+@pytest.mark.parametrize("name,kw", ph.STRETCHED_CASES[:-1], ids=[c[0] for c in ph.STRETCHED_CASES[:-1]])
+def test_hostsim_matches_oracle_on_stretched_grids(hostsim, name, kw):
+    """vertically stretched grids — level-dependent metrics in every kernel + FourierTridiagonalPoissonSolver"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))
+
+
+def test_hostsim_stretched_poisson_all_topologies(hostsim):
+    """solve!(ϕ, ::FourierTridiagonalPoissonSolver, b): the sizes / faces of test/test_poisson_solvers_stretched_grids.jl:28-46"""
+    import oceananigans_b200 as ob
+    import oracle
+    rng = np.random.default_rng(11)
+    faces = {8: [1, 2, 4, 7, 11, 16, 22, 29, 37], 9: [1, 2, 4, 7, 11, 16, 22, 29, 37, 51], 4: [1, 2, 3, 4, 5]}
+    for topo in ["PPB", "PBB", "BPB", "BBB", "FBB", "FPB", "BFB", "PFB"]:
+        for N1, N2, Nz in [(8, 8, 8), (16, 8, 9), (8, 11, 8), (5, 8, 9), (7, 13, 8), (4, 5, 4)]:
+            kw, size = {}, []
+            if topo[0] != "F":
+                kw["x"] = (0.0, 1.0); size.append(N1)
+            if topo[1] != "F":
+                kw["y"] = (0.0, 1.0); size.append(N2)
+            size.append(Nz)
+            z = [float(f) for f in faces[Nz]]
+            grid = ob.RectilinearGrid(np.float64, size=tuple(size), z=z, topology=tuple(ph.TOPO[c] for c in topo), **kw)
+            m = ob.NonhydrostaticModel(grid=grid, library=hostsim)
+            om = oracle.OracleModel(oracle.Grid(np.float64, size=tuple(size), z=z, topology=tuple(topo), **kw))
+            N = om.grid.N
+            dzc = om.grid.dz_at("c", np.arange(1, Nz + 1))
+            rhs = rng.standard_normal(N)
+            rhs -= (rhs * dzc).sum() / (dzc.sum() * N[0] * N[1])          # compatible source: Σ Δz·b = 0
+            a = ob.solve_poisson(m, rhs)
+            b = om.solve_poisson_tridiagonal(rhs * dzc)
+            assert np.abs(a - b).max() <= 1e-11 * max(np.abs(b).max(), 1.0), (topo, N)
+
+
 def test_hostsim_poisson_all_topologies(hostsim):
     import oceananigans_b200 as ob
     import oracle

@@ -134,9 +134,10 @@ def _laplacian(g, phi_field):
     p = ctx.field(phi_field)
     tot = None
     for d in range(3):
-        t = dC(ctx, (lambda dd: (lambda o: g.A[dd] * ddF(ctx, p, dd)(o)))(d), d)(O)
+        A = ctx.area(d, "f" if d == 2 else "c")
+        t = dC(ctx, (lambda dd, A: (lambda o: A(o) * ddF(ctx, p, dd)(o)))(d, A), d)(O)
         tot = t if tot is None else tot + t
-    return g.rV * tot
+    return ctx.rvol("c")(O) * tot
 
 
 def _divergence_free_poisson_solution(g, seed=0):
@@ -182,6 +183,119 @@ def test_divergence_free_poisson_solution_float32():
     # :88-93
     assert _divergence_free_poisson_solution(Grid(np.float32, size=(16, 16, 16), extent=(1, 1, 1), topology=("P", "B", "B")))
     assert _divergence_free_poisson_solution(Grid(np.float32, size=(7, 11, 13), extent=(1, 1, 1), topology=("B", "B", "P")))
+
+
+# ----------------------------------------------------------------------------- stretched grids (§8f-1)
+def test_vertically_stretched_grid_spacings():
+    # test/test_grids.jl:440-485 (test_rectilinear_grid_correct_spacings, the z part) + halo continuation of
+    # generate_coordinate for a Bounded coordinate (src/Grids/grid_generation.jl:15-18,56-63)
+    for FT in (np.float32, np.float64):
+        N, S = 16, 3
+        zf = lambda k: np.tanh(S * (2 * (k - 1) / N - 1)) / np.tanh(S)
+        g = Grid(FT, size=(N, N, N), x=(0, N), y=(0, N), z=zf, topology=("P", "P", "B"))
+        k = np.arange(1, N + 1)
+        zc = (zf(k) + zf(k + 1)) / 2
+        assert g.stretched and g._dzc.dtype == FT and g._dzf.dtype == FT
+        assert np.allclose(g.nodes(2, "f"), zf(np.arange(1, N + 2)))
+        assert np.allclose(g.nodes(2, "c"), zc)
+        assert np.allclose(g.dz_at("c", k), zf(k + 1) - zf(k), rtol=1e-5 if FT is np.float32 else 1e-12)
+        assert np.allclose(g.dz_at("f", k[1:]), zc[1:] - zc[:-1], rtol=1e-5 if FT is np.float32 else 1e-12)
+        H = g.H[2]
+        assert len(g._dzf) == N + 2 * H + 1 and len(g._dzc) == N + 2 * H          # test_grids.jl:652-653
+        # halo cells continue with the first / last interior spacing; the wall face spacing equals the adjacent cell's
+        rt = 1e-4 if FT is np.float32 else 1e-12      # (face positions are rounded to FT before differencing)
+        assert np.allclose(g.dz_at("c", np.arange(1 - H, 1)), g.dz_at("c", 1), rtol=rt)
+        assert np.allclose(g.dz_at("c", np.arange(N + 1, N + H + 1)), g.dz_at("c", N), rtol=rt)
+        assert np.isclose(g.dz_at("f", 1), g.dz_at("c", 1), rtol=rt) and np.isclose(g.dz_at("f", N + 1), g.dz_at("c", N), rtol=rt)
+    with pytest.raises(AssertionError):
+        Grid(np.float64, size=(4, 4, 4), x=(0, 1), y=(0, 1), z=[0, 0.3, 0.2, 0.6, 1.0], topology=("P", "P", "B"))
+
+
+def test_regularly_spaced_faces_reproduce_the_regular_grid():
+    # test/test_grids.jl:638-663: a "stretched" grid built from regularly spaced faces has the regular grid's metrics;
+    # here additionally: the FourierTridiagonal and the FFT-based (DCT) solvers then give the same model trajectory
+    N = (8, 6, 8)
+    res = []
+    for z in ((-0.5, 0.0), [float(v) for v in np.linspace(-0.5, 0.0, 9)]):
+        g = Grid(np.float64, size=N, x=(0, 1), y=(0, 1), z=z, topology=("P", "P", "B"))
+        m = OracleModel(g, advection=adv.Centered(np.float64, 2), tracers=("T", "S"), buoyancy=clo.SeawaterBuoyancy(),
+                        closure=clo.ScalarDiffusivity(1e-3, 1e-3), coriolis_f=1e-2)
+        rng = np.random.default_rng(3)
+        ic = {n: rng.uniform(-1, 1, m.fields[n].interior.shape) for n in ("u", "v", "w")}
+        ic["T"] = 20 + 0.01 * rng.standard_normal(N)
+        ic["S"] = 35 + 0.01 * rng.standard_normal(N)
+        m.set(**ic)
+        for _ in range(3):
+            m.time_step(0.01)
+        res.append(m)
+    assert np.all(res[1].grid.dz_at("c", np.arange(1, 9)) == res[0].grid.dz)
+    for n in res[0].fields:
+        a, b = res[0].fields[n].interior, res[1].fields[n].interior
+        assert np.abs(a - b).max() <= 1e-12 * np.abs(a).max(), n
+    assert np.abs(res[0].pNHS.interior - res[1].pNHS.interior).max() <= 1e-11 * np.abs(res[0].pNHS.interior).max()
+
+
+FACES_EVEN = [1, 2, 4, 7, 11, 16, 22, 29, 37]
+FACES_ODD = [1, 2, 4, 7, 11, 16, 22, 29, 37, 51]
+VS_TOPOS = [("P", "P", "B"), ("P", "B", "B"), ("B", "P", "B"), ("B", "B", "B"), ("F", "B", "B"), ("F", "P", "B"),
+            ("B", "F", "B"), ("P", "F", "B")]
+
+
+def _stretched_poisson_solver_correct_answer(FT, topo, N1, N2, faces, seed=0):
+    # stretched_poisson_solver_correct_answer, test/dependencies_for_poisson_solvers.jl:231-256 (stretched_axis = 3):
+    # R = divergence of a random velocity; solve; ∇²ϕ ≈ R
+    kw = {}
+    size = []
+    if topo[0] != "F":
+        kw["x"] = (0, 1)
+        size.append(N1)
+    if topo[1] != "F":
+        kw["y"] = (0, 1)
+        size.append(N2)
+    size.append(len(faces) - 1)
+    g = Grid(FT, size=tuple(size), z=[float(f) for f in faces], topology=topo, **kw)
+    rng = np.random.default_rng(seed)
+    m = OracleModel(g)
+    for f in m.U:
+        f.set(rng.random(f.interior.shape))
+        fill_halo_regions(f)
+    R = m.divergence()
+    m.compute_pressure_correction(1.0)          # Δzᶜᶜᶜ·R -> FourierTridiagonalPoissonSolver -> pNHS (+ halos)
+    lap = _laplacian(g, m.pNHS)
+    tol = np.sqrt(np.finfo(g.FT).eps)
+    ok = np.linalg.norm((lap - R).ravel()) <= tol * max(np.linalg.norm(lap.ravel()), np.linalg.norm(R.ravel()))
+    return ok and abs(float(m.pNHS.interior.mean())) <= 100 * np.finfo(g.FT).eps * max(1.0, np.abs(m.pNHS.interior).max())
+
+
+@pytest.mark.parametrize("topo", VS_TOPOS)
+def test_stretched_poisson_solver_correct_answer(topo):
+    # test/test_poisson_solvers_stretched_grids.jl:12-52 with stretched_axis = 3 (the only stretched axis on this path)
+    assert _stretched_poisson_solver_correct_answer(np.float64, topo, 4, 5, range(1, 5))
+    assert _stretched_poisson_solver_correct_answer(np.float64, topo, 8, 8, range(1, 9))
+    assert _stretched_poisson_solver_correct_answer(np.float64, topo, 7, 7, range(1, 8))
+    assert _stretched_poisson_solver_correct_answer(np.float32, topo, 8, 8, range(1, 9))
+    for faces in (FACES_EVEN, FACES_ODD):
+        for N1, N2 in ((8, 8), (16, 8), (8, 16), (8, 11), (5, 8), (7, 13)):
+            assert _stretched_poisson_solver_correct_answer(np.float64, topo, N1, N2, faces), (N1, N2)
+
+
+def test_stretched_model_stays_incompressible_and_conserves_tracer():
+    # test/test_time_stepping.jl:124-199 on a vertically stretched grid (the FourierTridiagonal path of time_step!)
+    faces = [float(-0.5 + 0.5 * (f - 1) / 36.0) for f in FACES_EVEN]
+    g = Grid(np.float64, size=(8, 6, 8), x=(0, 1), y=(0, 1), z=faces, topology=("P", "B", "B"))
+    m = OracleModel(g, advection=adv.WENO(np.float64, 5), tracers=("T", "S"), buoyancy=clo.SeawaterBuoyancy(),
+                    closure=clo.AnisotropicMinimumDissipation())
+    rng = np.random.default_rng(5)
+    ic = {n: rng.uniform(-1, 1, m.fields[n].interior.shape) for n in ("u", "v", "w")}
+    ic["T"] = 20 + 0.01 * rng.standard_normal((8, 6, 8))
+    ic["S"] = 35 + 0.01 * rng.standard_normal((8, 6, 8))
+    m.set(**ic)
+    dzc = g.dz_at("c", np.arange(1, 9))
+    T0 = float((m.tracers["T"].interior * dzc).sum())
+    for _ in range(5):
+        m.time_step(0.005)
+    assert np.abs(m.divergence()).max() < 5e-8
+    assert abs(float((m.tracers["T"].interior * dzc).sum()) - T0) <= 1e-12 * abs(T0)      # volume-weighted: flux form conserves
 
 
 def _analytic_error(N, topo, mode):
