@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — cell-updates/s per full time step of the NonhydrostaticModel hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c3f32|c4|c1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c3f32|c4|c4s|c1] [--impl ours|reference]
 
 One "step" is one full `time_step!(model, Δt)` (RK3: three stages, each tendency+substep, halo fills, FFT
 pressure solve and projection) over one synthetic, seeded initial state.
@@ -50,7 +50,17 @@ WORKLOADS = {
                   F=5, b=1, a=0, label="C3 512^3 (P,P,P) WENO-5 T,S SeawaterBuoyancy ScalarDiffusivity F32"),
     "c4": dict(N=(512, 512, 256), topo="PPB", FT="f64", adv="weno", tracers=("T", "S"), buoy="seawater", closure="amd",
                F=5, b=1, a=1, label="C4 512^2x256 (P,P,B) WENO-5 AMD FPlane flux BCs F64"),
+    # the C4 physics on a vertically stretched (surface-refined) grid — FourierTridiagonalPoissonSolver
+    "c4s": dict(N=(512, 512, 256), topo="PPB", FT="f64", adv="weno", tracers=("T", "S"), buoy="seawater", closure="amd",
+                F=5, b=1, a=1, stretched=True,
+                label="C4s 512^2x256 (P,P,B) stretched z, FourierTridiagonal solver, WENO-5 AMD FPlane flux BCs F64"),
 }
+
+
+def stretched_faces(Nz, Lz):
+    """Surface-refined faces on [-Lz, 0] (spacing ratio 4:1 bottom:top), cf. examples/ocean_wind_mixing_and_convection.jl"""
+    s = np.arange(Nz + 1, dtype=np.float64) / Nz
+    return -Lz + Lz * (s + 0.6 * np.sin(np.pi * s) / np.pi)
 
 
 def reals_per_cell_step(w):
@@ -155,7 +165,11 @@ def build_model(w, device, rank=0, world=1):
     arch = ob.B200(device) if world == 1 else ob.Distributed(ob.B200(device), partition=ob.Partition(1, world), rank=rank, nranks=world)
     if world > 1:
         extent = tuple(gsize[d] / 512.0 for d in nonflat)          # same Δ as the single-GPU workload
-    grid = ob.RectilinearGrid(arch, FT, size=size, extent=extent, topology=tuple(topo[c] for c in w["topo"]))
+    if w.get("stretched"):
+        grid = ob.RectilinearGrid(arch, FT, size=size, x=(0.0, extent[0]), y=(0.0, extent[1]),
+                                  z=[float(v) for v in stretched_faces(w["N"][2], extent[2])], topology=tuple(topo[c] for c in w["topo"]))
+    else:
+        grid = ob.RectilinearGrid(arch, FT, size=size, extent=extent, topology=tuple(topo[c] for c in w["topo"]))
     adv = ob.WENO() if w["adv"] == "weno" else ob.Centered()
     kw = dict(grid=grid, advection=adv, tracers=w["tracers"])
     if w["buoy"] == "seawater":
@@ -369,7 +383,11 @@ def oracle_model(w, N):
     nonflat = [d for d in range(3) if w["topo"][d] != "F"]
     size = tuple(N[d] for d in nonflat)
     extent = tuple(float(N[d]) for d in nonflat) if w["closure"] == "amd" else tuple(1.0 for _ in nonflat)
-    og = oracle.Grid(FT, size=size, extent=extent, topology=tuple(w["topo"]))
+    if w.get("stretched"):
+        og = oracle.Grid(FT, size=size, x=(0.0, extent[0]), y=(0.0, extent[1]),
+                         z=[float(v) for v in stretched_faces(N[2], extent[2])], topology=tuple(w["topo"]))
+    else:
+        og = oracle.Grid(FT, size=size, extent=extent, topology=tuple(w["topo"]))
     kw = dict(advection=adv.WENO(FT, 5) if w["adv"] == "weno" else adv.Centered(FT, 2), tracers=w["tracers"])
     if w["buoy"] == "seawater":
         kw["buoyancy"] = clo.SeawaterBuoyancy()
@@ -382,7 +400,10 @@ def oracle_model(w, N):
                                      "S": {"top": BC("flux", 5e-8)}}
     om = oracle.OracleModel(og, **kw)
     rng = np.random.default_rng(1234)
-    ic = {n: rng.uniform(-1, 1, om.fields[n].interior.shape) for n in ("u", "v", "w")}
+    if w["closure"] == "amd":        # the LES workloads step with Δt = 1 s at Δ = 1 m: small velocities, like synthetic_ic
+        ic = {n: 1e-3 * rng.standard_normal(om.fields[n].interior.shape) for n in ("u", "v", "w")}
+    else:
+        ic = {n: rng.uniform(-1, 1, om.fields[n].interior.shape) for n in ("u", "v", "w")}
     for n in w["tracers"]:
         ic[n] = {"T": 20.0, "S": 35.0}.get(n, 0.0) + 0.01 * rng.standard_normal(om.fields[n].interior.shape)
     om.set(**ic)

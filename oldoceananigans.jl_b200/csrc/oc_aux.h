@@ -53,44 +53,50 @@ struct HydrostaticPressureKernel {
 // AMD.  One thread per cell; gradients are re-derived from u, v, w (stencil radius 1 around the cell).
 // The helper struct mirrors the reference's operator names so each term can be checked line by line.
 // ---------------------------------------------------------------------------------------------------------
-template <class FT>
+// STR = false: regular grid — the ratios with Δᶠz and the z-derivative metrics are constants (folded at compile time into the
+// same arithmetic as before); STR = true: vertically stretched grid — they depend on the level of the evaluation point:
+// every Δᶠz_{loc}(i,j,k′) is 2·Δzᶜᶜᶜ(k′) at the INDEX k′ of the point (:228-234), ∂z at fcf / cff uses Δz⁻¹ᶠ(k′), ∂z w at ccc Δz⁻¹ᶜ(k).
+// `up` = 0: the point is on the cell's level k, 1: on the level above.
+template <class FT, bool STR>
 struct AmdPoint {
     const Geom<FT>& g;
     const FT* u;
     const FT* v;
     const FT* w;
     FT rxy, ryx;                       // Δᶠa/Δᶠb with Δᶠ = 2Δ   (:224-226)
-    // ratios with Δᶠz and the z-derivative metrics at the cell's level [0] and the level above [1]: every Δᶠz_{loc}(i,j,k′) is
-    // 2·Δzᶜᶜᶜ(k′) at the INDEX k′ of the evaluation point (:228-234), ∂z at fcf / cff uses Δz⁻¹ᶠ(k′), ∂z w at ccc Δz⁻¹ᶜ(k)
-    FT rxz[2], rzx[2], ryz[2], rzy[2], rdzf[2], fz[2], rdzc;
+    FT rxz_[2], rzx_[2], ryz_[2], rzy_[2], rdzf_[2], fz_[2], rdzc_;
     // the filter-width ratios are loop invariants with divisions: on a regular grid formed once on the host (set_consts), same FT
     // arithmetic; on a stretched grid formed here from the level tables
     OC_HD AmdPoint(const Geom<FT>& g_, const FT* u_, const FT* v_, const FT* w_, const FT* r, int k) : g(g_), u(u_), v(v_), w(w_) {
         rxy = r[0]; ryx = r[1];
-        if (!g.stretched()) {
-            for (int n = 0; n < 2; ++n) { rxz[n] = r[2]; rzx[n] = r[3]; ryz[n] = r[4]; rzy[n] = r[5]; rdzf[n] = g.rd[2]; fz[n] = FT(2) * g.d[2]; }
-            rdzc = g.rd[2];
+        if (!STR) {
+            rxz_[0] = r[2]; rzx_[0] = r[3]; ryz_[0] = r[4]; rzy_[0] = r[5]; rdzf_[0] = g.rd[2]; fz_[0] = FT(2) * g.d[2]; rdzc_ = g.rd[2];
         } else {
             const FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1];
             for (int n = 0; n < 2; ++n) {
-                fz[n] = FT(2) * g.dzc[k + n];
-                rxz[n] = fx / fz[n]; rzx[n] = fz[n] / fx; ryz[n] = fy / fz[n]; rzy[n] = fz[n] / fy;
-                rdzf[n] = g.rdzf[k + n];
+                fz_[n] = FT(2) * g.dzc[k + n];
+                rxz_[n] = fx / fz_[n]; rzx_[n] = fz_[n] / fx; ryz_[n] = fy / fz_[n]; rzy_[n] = fz_[n] / fy;
+                rdzf_[n] = g.rdzf[k + n];
             }
-            rdzc = g.rdzc[k];
+            rdzc_ = g.rdzc[k];
         }
     }
-    // normalised gradients at their natural locations (velocity_tracer_gradients.jl:126-154); o = linear index,
-    // up = 0: the point is on the cell's level, 1: on the level above
+    OC_HD FT rxz(int up) const { return rxz_[STR ? up : 0]; }
+    OC_HD FT rzx(int up) const { return rzx_[STR ? up : 0]; }
+    OC_HD FT ryz(int up) const { return ryz_[STR ? up : 0]; }
+    OC_HD FT rzy(int up) const { return rzy_[STR ? up : 0]; }
+    OC_HD FT rdzf(int up) const { return rdzf_[STR ? up : 0]; }
+    OC_HD FT fz(int up) const { return fz_[STR ? up : 0]; }
+    // normalised gradients at their natural locations (velocity_tracer_gradients.jl:126-154); o = linear index
     OC_HD FT dxu(int o) const { return (u[o + 1] - u[o]) * g.rd[0]; }                       // ccc
     OC_HD FT dyv(int o) const { return (v[o + g.sy] - v[o]) * g.rd[1]; }                    // ccc
-    OC_HD FT dzw(int o) const { return (w[o + g.sz] - w[o]) * rdzc; }                       // ccc
+    OC_HD FT dzw(int o) const { return (w[o + g.sz] - w[o]) * rdzc_; }                      // ccc
     OC_HD FT dxv(int o) const { return rxy * ((v[o] - v[o - 1]) * g.rd[0]); }               // ffc
     OC_HD FT dyu(int o) const { return ryx * ((u[o] - u[o - g.sy]) * g.rd[1]); }            // ffc
-    OC_HD FT dxw(int o, int up) const { return rxz[up] * ((w[o] - w[o - 1]) * g.rd[0]); }       // fcf
-    OC_HD FT dzu(int o, int up) const { return rzx[up] * ((u[o] - u[o - g.sz]) * rdzf[up]); }   // fcf
-    OC_HD FT dyw(int o, int up) const { return ryz[up] * ((w[o] - w[o - g.sy]) * g.rd[1]); }    // cff
-    OC_HD FT dzv(int o, int up) const { return rzy[up] * ((v[o] - v[o - g.sz]) * rdzf[up]); }   // cff
+    OC_HD FT dxw(int o, int up) const { return rxz(up) * ((w[o] - w[o - 1]) * g.rd[0]); }       // fcf
+    OC_HD FT dzu(int o, int up) const { return rzx(up) * ((u[o] - u[o - g.sz]) * rdzf(up)); }   // fcf
+    OC_HD FT dyw(int o, int up) const { return ryz(up) * ((w[o] - w[o - g.sy]) * g.rd[1]); }    // cff
+    OC_HD FT dzv(int o, int up) const { return rzy(up) * ((v[o] - v[o - g.sz]) * rdzf(up)); }   // cff
 };
 
 // ℑ of a functor F(o) from (Face,Face) in dims (d1<d2) to centre: ℑ_{d2}ᶜ(ℑ_{d1}ᶜ F)   interpolation_operators.jl:45-56
@@ -107,7 +113,7 @@ OC_HD FT interp1c(const F& fn, int o, int s) {
 template <class FT>
 OC_HD FT interp4(const FT* f) { return FT(0.5) * (FT(0.5) * (f[0] + f[1]) + FT(0.5) * (f[2] + f[3])); }
 
-template <class FT>
+template <class FT, bool STR = false>
 struct AmdKernel {
     static constexpr int PHASES = 1;
     static constexpr int THREADS = 256;      // 32 (x) × 8 (y) cells per CTA: the 27-point neighbourhoods share L1 lines in x AND y
@@ -140,9 +146,9 @@ struct AmdKernel {
         if (i >= g.N[0] || j >= g.N[1]) return;
         const int o = g.idx(i, j, k);
         const int sx = 1, sy = g.sy, sz = g.sz;
-        AmdPoint<FT> P(g, u, v, w, ratios, k);
-        const FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = P.fz[0];
-        const FT d2 = g.stretched() ? FT(3) / (FT(1) / (fx * fx) + FT(1) / (fy * fy) + FT(1) / (fz * fz)) : delta2;   // δ² (:166,190)
+        AmdPoint<FT, STR> P(g, u, v, w, ratios, k);
+        const FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = P.fz(0);
+        const FT d2 = STR ? FT(3) / (FT(1) / (fx * fx) + FT(1) / (fy * fy) + FT(1) / (fz * fz)) : delta2;   // δ² (:166,190)
         auto sq = [](FT x) { return x * x; };
         const int cxy[4] = {o, o + sx, o + sy, o + sx + sy};
         const int cxz[4] = {o, o + sx, o + sz, o + sx + sz};
@@ -218,7 +224,7 @@ struct AmdKernel {
             const FT* cc = c[tr];
             auto cx = [&](int p) { return fx * ((cc[p] - cc[p - sx]) * g.rd[0]); };       // norm_∂x_c at fcc
             auto cy = [&](int p) { return fy * ((cc[p] - cc[p - sy]) * g.rd[1]); };
-            auto cz = [&](int p, int up) { return P.fz[up] * ((cc[p] - cc[p - sz]) * P.rdzf[up]); };   // norm_∂z_c at ccf
+            auto cz = [&](int p, int up) { return P.fz(up) * ((cc[p] - cc[p - sz]) * P.rdzf(up)); };   // norm_∂z_c at ccf
             const FT cx0 = cx(o), cx1 = cx(o + sx), cy0 = cy(o), cy1 = cy(o + sy), cz0 = cz(o, 0), cz1 = cz(o + sz, 1);
             FT Ix_cx2 = FT(0.5) * (sq(cx0) + sq(cx1));
             FT Iy_cy2 = FT(0.5) * (sq(cy0) + sq(cy1));

@@ -407,7 +407,7 @@ OC_HD FT t_weno5_symmetric_z(const A& a, int ii, int jj, int lev, FT h, const FT
 // One thread per y-face: THREADS = TX·(TY+1); the x-faces and z-faces map onto the same threads so that every
 // warp evaluates at most three fluxes per level (no tail warps in front of the barrier).
 // ---------------------------------------------------------------------------------------------------------
-template <class FT, int ADV, int KIND, int BND, int CLO, int TY_ = 8>
+template <class FT, int ADV, int KIND, int BND, int CLO, int TY_ = 8, int STR = 0>
 struct MarchKernel {
     static constexpr int TX = 32, TY = TY_;
     static constexpr int THREADS = TX * (TY + 1);
@@ -462,13 +462,15 @@ struct MarchKernel {
     OC_HD G3 r3(const Ctx& c) const { return G3{reinterpret_cast<FT*>(c.smem + OFF_R3), c.k, c.st.sk[3]}; }
     OC_HD Ctx raw(char* smem) const { return Ctx{smem, 0, MarchSlots{{0, 0, 0, 0}}}; }
 
-    // ---- metrics.  Only a Bounded z can be stretched, so the level tables exist only in kernels with wall logic in z;
-    // everywhere else these fold to the constants of the regular grid.  zf: the point is Face-located in z.
-    static constexpr bool ZS = WINV<2>;
-    OC_HD FT m_area(int D, bool zf, int lev) const { return ZS ? a.g.area_at(D, zf, lev) : a.g.A[D]; }
-    OC_HD FT m_rdz(bool zf, int lev) const { return ZS ? a.g.rdz_at(zf, lev) : a.g.rd[2]; }
-    OC_HD FT m_rV(bool zf, int lev) const { return ZS ? a.g.rV_at(zf, lev) : a.g.rV; }
-    OC_HD FT m_vol(bool zf, int lev) const { return ZS ? a.g.vol_at(zf, lev) : a.g.V; }
+    // ---- metrics.  STR = 1: vertically stretched grid (z Bounded, level tables in Geom); STR = 0: these fold to the constants
+    // of the regular grid, so the regular kernels carry no trace of the stretched path.  zf: the point is Face-located in z.
+    static constexpr bool ZS = STR != 0;
+    static_assert(!ZS || WINV<2>, "a stretched z is Bounded");
+    OC_HD FT m_dz(bool zf, int lev) const { return zf ? a.g.dzf[lev] : a.g.dzc[lev]; }
+    OC_HD FT m_area(int D, bool zf, int lev) const { return (ZS && D != 2) ? a.g.d[D == 0 ? 1 : 0] * m_dz(zf, lev) : a.g.A[D]; }
+    OC_HD FT m_rdz(bool zf, int lev) const { return ZS ? (zf ? a.g.rdzf[lev] : a.g.rdzc[lev]) : a.g.rd[2]; }
+    OC_HD FT m_rV(bool zf, int lev) const { return ZS ? (zf ? a.g.rVf[lev] : a.g.rVc[lev]) : a.g.rV; }
+    OC_HD FT m_vol(bool zf, int lev) const { return ZS ? a.g.A[2] * m_dz(zf, lev) : a.g.V; }
 
     // ---- loads -----------------------------------------------------------------------------------------------
     template <class G, class RS>
@@ -625,7 +627,7 @@ struct MarchKernel {
                     if (WINV<CC>) wc = order_window(g.bounded[CC] != 0, false, g.N[CC]);
                     if (WINV<D>) wd = order_window(g.bounded[D] != 0, false, g.N[D]);
                     FT ut;
-                    if (ZS && CC == 2 && g.stretched()) {
+                    if (ZS && CC == 2) {
                         const FT h = g.d[D == 0 ? 1 : 0];
                         if (D == SP::F1) ut = t_weno5_symmetric_z<WINV<CC>, FT>(r1(smem), ii, jj, lev, h, g.dzc + lev, ic, wc);
                         else ut = t_weno5_symmetric_z<WINV<CC>, FT>(r2(smem), ii, jj, lev, h, g.dzc + lev, ic, wc);

@@ -732,17 +732,20 @@ void Model<FT>::fill_halo_regions(const int* fields, int n, int fill_open) {
 template <class FT>
 void Model<FT>::aux() {
     if (has_amd_) {
-        AmdKernel<FT> k;
-        k.g = g_;
-        k.u = state_[0].p; k.v = state_[1].p; k.w = state_[2].p;
-        k.nu_e = nu_e_.p;
-        k.Cnu = (FT)cfg_.amd_Cnu;
-        k.ntr = cfg_.n_tracers;
-        for (int t = 0; t < cfg_.n_tracers; ++t) { k.c[t] = state_[3 + t].p; k.kappa_e[t] = kappa_e_[t].p; k.Ckappa[t] = (FT)cfg_.amd_Ckappa[t]; }
-        k.set_consts();
-        Dim3 ag;
-        ag.x = (g_.N[0] + 31) / 32; ag.y = (g_.N[1] + 7) / 8; ag.z = g_.N[2];
-        go(k, ag, 0, OC_TIMER_AUX);
+        auto run_amd = [&](auto k) {
+            k.g = g_;
+            k.u = state_[0].p; k.v = state_[1].p; k.w = state_[2].p;
+            k.nu_e = nu_e_.p;
+            k.Cnu = (FT)cfg_.amd_Cnu;
+            k.ntr = cfg_.n_tracers;
+            for (int t = 0; t < cfg_.n_tracers; ++t) { k.c[t] = state_[3 + t].p; k.kappa_e[t] = kappa_e_[t].p; k.Ckappa[t] = (FT)cfg_.amd_Ckappa[t]; }
+            k.set_consts();
+            Dim3 ag;
+            ag.x = (g_.N[0] + 31) / 32; ag.y = (g_.N[1] + 7) / 8; ag.z = g_.N[2];
+            go(k, ag, 0, OC_TIMER_AUX);
+        };
+        if (stretched_) run_amd(AmdKernel<FT, true>{});
+        else run_amd(AmdKernel<FT, false>{});
         std::vector<FieldRec*> list{&nu_e_};
         for (auto& f : kappa_e_) list.push_back(&f);
         halo(list, true);
@@ -883,7 +886,13 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
     auto pick = [&](auto adv) {
         constexpr int ADV = decltype(adv)::value;
         const bool zonly = !g_.bounded[0] && !g_.bounded[1] && g_.bounded[2];     // the LES topology (Periodic, Periodic, Bounded)
-        if (!bnd && !gen) run(MarchKernel<FT, ADV, KIND, 0, 0>{});
+        if (stretched_) {          // z Bounded and variably spaced: level tables instead of the constant z metrics
+            if (zonly && !gen) run(MarchKernel<FT, ADV, KIND, 4, 0, 8, 1>{});
+            else if (zonly) run(MarchKernel<FT, ADV, KIND, 4, 1, 8, 1>{});
+            else if (!gen) run(MarchKernel<FT, ADV, KIND, 7, 0, 8, 1>{});
+            else run(MarchKernel<FT, ADV, KIND, 7, 1, 8, 1>{});
+        }
+        else if (!bnd && !gen) run(MarchKernel<FT, ADV, KIND, 0, 0>{});
         else if (!bnd) run(MarchKernel<FT, ADV, KIND, 0, 1>{});
         else if (zonly && !gen) run(MarchKernel<FT, ADV, KIND, 4, 0>{});
         else if (zonly) run(MarchKernel<FT, ADV, KIND, 4, 1>{});
@@ -1052,6 +1061,17 @@ void Model<FT>::run_fft_solve() {
     if (!e.empty()) throw Error(OC_ERR_CUDA, e);
     if (stretched_) {
         // solve!(ϕ, ::BatchedTridiagonalSolver, rhs) + ϕ .-= mean(ϕ)   fourier_tridiagonal_poisson_solver.jl:213-226
+        if (!g_.bounded[0] && !g_.bounded[1]) {
+            TridiagSolvePPKernel<FT> k;
+            k.L = fft_.L;
+            k.spec = fftbuf_;
+            k.R = tri_R_; k.T = tri_T_; k.rdzf = g_.rdzf;
+            k.norm = 1.0 / ((double)g_.N[0] * g_.N[1]);
+            Dim3 grid;
+            const long long n2 = 2LL * fft_.L.nxc * g_.N[1];
+            grid.x = (int)((n2 + TridiagSolvePPKernel<FT>::THREADS - 1) / TridiagSolvePPKernel<FT>::THREADS);
+            go(k, grid, 0, OC_TIMER_POISSON_MID);
+        } else {
         TridiagSolveKernel<FT> k;
         k.L = fft_.L;
         k.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_);
@@ -1064,6 +1084,7 @@ void Model<FT>::run_fft_solve() {
         grid.x = (k.nrep[0] + TridiagSolveKernel<FT>::THREADS - 1) / TridiagSolveKernel<FT>::THREADS;
         grid.y = k.nrep[1];
         go(k, grid, 0, OC_TIMER_POISSON_MID);
+        }
     } else if (!g_.bounded[0] && !g_.bounded[1] && !g_.bounded[2]) {
         PoissonDivideKernel<FT> k;
         k.L = fft_.L;

@@ -450,6 +450,79 @@ struct TridiagSolveKernel {
     }
 };
 
+// The common LES topology (Periodic, Periodic, Bounded-stretched): no twiddles, and — the coefficients being real — the real and
+// imaginary parts of every column are two independent real systems.  One thread per (column, part): consecutive threads touch
+// consecutive reals (fully coalesced 8-byte accesses), twice the parallelism of a thread per complex column, and the loads of
+// the next PF levels are issued ahead of the serial recurrence.  Same arithmetic, in the same order, as TridiagSolveKernel.
+template <class FT>
+struct TridiagSolvePPKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int PF = 8;
+    SpectralLayout L;
+    FT* spec;                  // the spectral buffer viewed as reals: (re, im) interleaved
+    const FT* R;
+    const FT* T;
+    const FT* rdzf;
+    double norm;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const long long plane = (long long)L.nxc * L.N[1];
+        const long long n2 = 2 * plane;
+        const long long r = (long long)b.x * nt + tid;
+        if (r >= n2) return;
+        const int Nz = L.N[2];
+        FT* p = spec + r;
+        const FT* Rp = R + (r >> 1);
+        const FT* Tp = T + (r >> 1);
+        const bool zero_mode = (r >> 1) == 0;
+        FT vb[PF], cb[PF];
+        // ---- forward elimination
+        for (int q = 0; q < PF; ++q)
+            if (q < Nz) { vb[q] = p[n2 * q]; cb[q] = Rp[plane * q]; }
+        double prev = 0.0;
+        for (int k0 = 0; k0 < Nz; k0 += PF) {
+#pragma unroll
+            for (int q = 0; q < PF; ++q) {
+                const int k = k0 + q;
+                if (k < Nz) {
+                    const double v = (double)vb[q], rr = (double)cb[q];
+                    if (k + PF < Nz) { vb[q] = p[n2 * (k + PF)]; cb[q] = Rp[plane * (k + PF)]; }
+                    const double a = k > 0 ? (double)rdzf[k] : 0.0;
+                    const double e = (v - a * prev) * rr;
+                    prev = e;
+                    p[n2 * k] = (FT)e;
+                }
+            }
+        }
+        // ---- back substitution (descending levels; level Nz-1 is already final)
+        double sum = prev;
+        p[n2 * (Nz - 1)] = (FT)(zero_mode ? prev : prev * norm);
+        for (int q = 0; q < PF; ++q) {
+            const int k = Nz - 2 - q;
+            if (k >= 0) { vb[q] = p[n2 * k]; cb[q] = Tp[plane * (k + 1)]; }
+        }
+        for (int k0 = Nz - 2; k0 >= 0; k0 -= PF) {
+#pragma unroll
+            for (int q = 0; q < PF; ++q) {
+                const int k = k0 - q;
+                if (k >= 0) {
+                    const double sv = (double)vb[q], t = (double)cb[q];
+                    if (k - PF >= 0) { vb[q] = p[n2 * (k - PF)]; cb[q] = Tp[plane * (k - PF + 1)]; }
+                    const double e = sv - t * prev;
+                    prev = e;
+                    sum += e;
+                    p[n2 * k] = (FT)(zero_mode ? e : e * norm);
+                }
+            }
+        }
+        if (!zero_mode) return;
+        const double mean = sum / Nz;        // ϕ .-= mean(ϕ): the volume mean lives in the (0, 0) column
+        for (int k = 0; k < Nz; ++k) p[n2 * k] = (FT)(((double)p[n2 * k] - mean) * norm);
+    }
+};
+
 // ϕ at logical cell (i,j,k) from the transform buffer; i = -1 / N handled by the caller
 template <class FT>
 OC_HD FT phi_at(const SpectralLayout& L, const FT* buf, int i, int j, int k) {
