@@ -141,6 +141,12 @@ struct MarchStateT {
     MarchSlots sl;
     FT fz_prev;   // this thread's upper z-face flux of the previous level (= lower flux of the current one)
     FT dfz;       // δz of the z-face fluxes of the level whose divergence is formed next
+    // global-memory operands of the divergence phase, loaded one flux evaluation (~400 instructions) ahead of their use:
+    // measured (ncu source page, C4): their consumers carried most of the long-scoreboard stalls
+    FT gm;        // G⁻ of the cell being finished
+    FT ph0, ph1;  // pHY′ at the cell and at its lower x / y neighbour (u and v kernels)
+    int o;        // global offset of this thread's cell at the level being finished (advanced by one plane per iteration)
+    int cell;     // this thread owns a cell of the grid (row < TY, inside the domain): loop invariant
 };
 
 // Loads for iteration it + PF are issued in step<1>(it), after every thread has finished iteration it-1; they overwrite the
@@ -498,6 +504,13 @@ struct MarchKernel {
     OC_DEV void begin1(const Block& b, int tid, char* smem, State& stt) const {
         MarchSlots& st = stt.sl;
         stt.fz_prev = FT(0); stt.dfz = FT(0);
+        stt.gm = FT(0); stt.ph0 = FT(0); stt.ph1 = FT(0);
+        {
+            const int lane_ = tid & (TX - 1), row_ = tid / TX;
+            const int ci = b.x * TX + lane_, cj = b.y * TY + row_;
+            stt.cell = (row_ < TY && ci < a.g.N[0] && cj < a.g.N[1]) ? 1 : 0;
+            stt.o = a.g.idx(ci, cj, k_begin(b) - 2);        // iteration it finishes level k_begin - 2 + it
+        }
         {   // ring slots of the first level (kf = k_begin - 1)
             const int kf0 = k_begin(b) - 1;
             st.sk[0] = G0::slot_of(kf0); st.sk[1] = G1::slot_of(kf0); st.sk[2] = G2::slot_of(kf0); st.sk[3] = G3::slot_of(kf0);
@@ -536,8 +549,24 @@ struct MarchKernel {
         return FT(0.5) * (FT(0.5) * (n[-s1 - s2] + n[-s2]) + FT(0.5) * (n[-s1] + n[0]));
     }
 
+    // νₑ at the flux point of τ_{COMP,D} (ccc for D == COMP, else the edge that is Face in D and COMP), κₑ at the D-face
+    // (abstract_scalar_diffusivity_closure.jl:310-332).  Called BEFORE the advective flux is evaluated so that the global loads
+    // are in flight during the reconstruction.
     template <int D>
-    OC_HD FT viscous_flux(const Ctx& smem, int ii, int jj, int lev, int i, int j) const {
+    OC_HD FT eddy_coefficient(int i, int j, int lev) const {
+        const Geom<FT>& g = a.g;
+        const int o = g.idx(i, j, lev);
+        if (KIND == KIND_C) {
+            if (!a.kappa_e) return FT(0);
+            return FT(0.5) * (a.kappa_e[o - g.st(D)] + a.kappa_e[o]);
+        }
+        if (!a.nu_e) return FT(0);
+        if (D == COMP) return a.nu_e[o];
+        return nu_ff(o, D < COMP ? D : COMP, D < COMP ? COMP : D);
+    }
+
+    template <int D>
+    OC_HD FT viscous_flux(const Ctx& smem, int ii, int jj, int lev, FT nu) const {
         const Geom<FT>& g = a.g;
         FT sig;
         if (D == COMP) {
@@ -553,10 +582,6 @@ struct MarchKernel {
         FT flux = FT(0);
         if (a.has_scalar) flux = AD * (FT(-2) * (a.nu * sig));
         if (a.nu_e) {
-            const int o = g.idx(i, j, lev);
-            FT nu;
-            if (D == COMP) nu = a.nu_e[o];
-            else nu = nu_ff(o, D < COMP ? D : COMP, D < COMP ? COMP : D);
             FT f2 = AD * (FT(-2) * (nu * sig));
             flux = a.has_scalar ? flux + f2 : f2;
         }
@@ -564,7 +589,7 @@ struct MarchKernel {
     }
 
     template <int D>
-    OC_HD FT diffusive_flux(const Ctx& smem, int ii, int jj, int lev, int i, int j) const {
+    OC_HD FT diffusive_flux(const Ctx& smem, int ii, int jj, int lev, FT kap) const {
         const Geom<FT>& g = a.g;
         G0 c = r0(smem);
         FT grad = (rd<D, FT>(c, ii, jj, lev, 0) - rd<D, FT>(c, ii, jj, lev, -1)) * (D == 2 ? m_rdz(true, lev) : g.rd[D]);
@@ -573,9 +598,6 @@ struct MarchKernel {
         FT flux = FT(0);
         if (a.has_scalar) flux = AD * (-(a.kappa * grad));
         if (a.kappa_e) {
-            const int o = g.idx(i, j, lev);
-            int s = g.st(D);
-            FT kap = FT(0.5) * (a.kappa_e[o - s] + a.kappa_e[o]);
             FT f2 = AD * (-(kap * grad));
             flux = a.has_scalar ? flux + f2 : f2;
         }
@@ -645,6 +667,8 @@ struct MarchKernel {
     OC_HD FT total_flux(const Ctx& smem, int ii, int jj, int i, int j, int k) const {
         const int id = D == 0 ? i : (D == 1 ? j : k);
         const int ic = COMP == 0 ? i : (COMP == 1 ? j : k);
+        FT eddy = FT(0);
+        if (CLO != 0) eddy = eddy_coefficient<D>(i, j, k);
         FT F = advective_flux<D>(smem, ii, jj, k, id, ic);
         if (CLO == 0 && KIND == KIND_C) {
             // constant κ: F - (κ A / Δ)(c[0] - c[-1]) with the constant folded (one subtraction and one FMA)
@@ -653,8 +677,8 @@ struct MarchKernel {
             return fmaT(-(a.kappa * m_area(D, false, k) * (D == 2 ? m_rdz(true, k) : a.g.rd[D])), dc, F);
         }
         if (CLO == 0 || a.has_scalar || a.nu_e || a.kappa_e) {
-            if constexpr (KIND == KIND_C) F = F + diffusive_flux<D>(smem, ii, jj, k, i, j);
-            else F = F + viscous_flux<D>(smem, ii, jj, k, i, j);
+            if constexpr (KIND == KIND_C) F = F + diffusive_flux<D>(smem, ii, jj, k, eddy);
+            else F = F + viscous_flux<D>(smem, ii, jj, k, eddy);
         }
         return F;
     }
@@ -696,6 +720,15 @@ struct MarchKernel {
         uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
         const int lane = tid & (TX - 1), row = tid / TX;     // row = 0 … TY
         if (PHASE == 0) {
+            if (it >= 2 && stt.cell) {
+                // operands of step<1>(it), which finishes level k-1 for cell (lane, row) — also in the last iteration (it == nit)
+                const int op = stt.o;
+                if (a.mode == STEP_RK3 || (a.mode == STEP_AB2 && !a.ab2_euler)) stt.gm = a.Gm[op];
+                if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) {
+                    stt.ph0 = a.pHY[op];
+                    stt.ph1 = a.pHY[op - (KIND == KIND_U ? 1 : g.sy)];
+                }
+            }
             if (it >= nit) return;
             mbar_wait(bar + (it % MARCH_NBAR), (it / MARCH_NBAR) & 1);
             if (it == 0) return;
@@ -730,6 +763,8 @@ struct MarchKernel {
             stt.sl.sk[0] = G0::next_slot(stt.sl.sk[0]); stt.sl.sk[1] = G1::next_slot(stt.sl.sk[1]);
             stt.sl.sk[2] = G2::next_slot(stt.sl.sk[2]); stt.sl.sk[3] = G3::next_slot(stt.sl.sk[3]);
         } else {
+            const int o_cell = stt.o;
+            stt.o = o_cell + g.sz;
             if (tid == 0) {
                 const int lit = it + SP::PF;
                 if (lit < nit) {
@@ -738,14 +773,13 @@ struct MarchKernel {
                     issue_iteration(smem, i0, j0, k + SP::PF, bar + (lit % MARCH_NBAR));
                 }
             }
-            if (it < 2 || row >= TY) return;                 // levels start at iteration 1; their divergence is formed one iteration later
+            if (it < 2 || !stt.cell) return;                 // levels start at iteration 1; their divergence is formed one iteration later
             const int kc = k - 1;                            // the level being finished
             const FT* fx = reinterpret_cast<const FT*>(smem + OFF_FX) + ((it - 1) % NSYNC) * NFXP;
             const FT* fy = reinterpret_cast<const FT*>(smem + OFF_FY) + ((it - 1) % NSYNC) * NFYP;
             const int ii = lane, jj = row;
             const int i = i0 + ii, j = j0 + jj;
-            if (i >= g.N[0] || j >= g.N[1]) return;
-            const int o = g.idx(i, j, kc);
+            const int o = o_cell;
             const FT u0 = r0(cx)(ii, jj, kc);
             if (WIN && COMP >= 0) {
                 // exclude_periphery: the wall face of a wall-normal velocity is not stepped (kernel_launching.jl:145-146)
@@ -783,10 +817,7 @@ struct MarchKernel {
                     G = G - (a.f * val);
                 }
             }
-            if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) {
-                const int sp = KIND == KIND_U ? 1 : g.sy;
-                G = G - (a.pHY[o] - a.pHY[o - sp]) * g.rd[KIND == KIND_U ? 0 : 1];
-            }
+            if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) G = G - (stt.ph0 - stt.ph1) * g.rd[KIND == KIND_U ? 0 : 1];
             if (WIN && a.add_flux_bcs) {
                 const int ijk[3] = {i, j, kc};
                 for (int d = 0; d < 3; ++d) {
@@ -799,9 +830,9 @@ struct MarchKernel {
             if (a.mode == STEP_RK3_FIRST) {
                 a.Unew[o] = u0 + a.ca * G;
             } else if (a.mode == STEP_RK3) {
-                a.Unew[o] = u0 + a.dt * (a.ca * G + a.cb * a.Gm[o]);
+                a.Unew[o] = u0 + a.dt * (a.ca * G + a.cb * stt.gm);
             } else if (a.mode == STEP_AB2) {
-                FT Gu = a.ab2_euler ? a.ca * G : a.ca * G - a.cb * a.Gm[o];
+                FT Gu = a.ab2_euler ? a.ca * G : a.ca * G - a.cb * stt.gm;
                 a.Unew[o] = u0 + a.dt * Gu;
             }
         }
