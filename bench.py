@@ -35,8 +35,8 @@ if ROOT not in sys.path:
 METRIC = "cell-updates/sec per full RK3 step"
 # measured DRAM traffic per MarchKernel launch (bytes), from one `ncu --set full` capture per workload (profiles/)
 NCU_TRAFFIC = {"c3": 6.53e9}
-# FP64 instructions executed per cell per MarchKernel launch (ncu source page, profiles/r01d_ncu_march_c3_summary.txt)
-NCU_FP64_PER_CELL = {"c3": 196.0}
+# FP64 instructions executed per cell per MarchKernel launch (ncu source page, profiles/r01f_ncu_march_c3_summary.txt)
+NCU_FP64_PER_CELL = {"c3": 203.0}        # mean of u, v, w, T, S kernels (213, 213, 211, 189, 189): ncu source page, executed DFMA+DMUL+DADD+DSETP
 
 # name -> description of the BASELINE.json configuration
 WORKLOADS = {
@@ -347,7 +347,7 @@ def run_ours(args):
                    if cells >= 256 ** 3 else "working set may fit L2 (launch-latency configuration)"},
         "roofline": {"bound": "hbm", "kernel": "TendencyKernel (fused tendency + RK3 substep, one launch per prognostic field)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(args.workload if world == 1 else None),
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 5 first-stage launches in profiles/r01d_ncu_march_c3_summary.txt (ncu --set full)" if (world == 1 and args.workload in NCU_TRAFFIC) else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 5 first-stage launches in profiles/r01f_ncu_march_c3_summary.txt (ncu --set full)" if (world == 1 and args.workload in NCU_TRAFFIC) else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                      "avg_launch_ms": avg_launch_ms, "launches_per_step": launches_per_step,
                      "step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak,

@@ -53,66 +53,6 @@ struct HydrostaticPressureKernel {
 // AMD.  One thread per cell; gradients are re-derived from u, v, w (stencil radius 1 around the cell).
 // The helper struct mirrors the reference's operator names so each term can be checked line by line.
 // ---------------------------------------------------------------------------------------------------------
-// STR = false: regular grid — the ratios with Δᶠz and the z-derivative metrics are constants (folded at compile time into the
-// same arithmetic as before); STR = true: vertically stretched grid — they depend on the level of the evaluation point:
-// every Δᶠz_{loc}(i,j,k′) is 2·Δzᶜᶜᶜ(k′) at the INDEX k′ of the point (:228-234), ∂z at fcf / cff uses Δz⁻¹ᶠ(k′), ∂z w at ccc Δz⁻¹ᶜ(k).
-// `up` = 0: the point is on the cell's level k, 1: on the level above.
-template <class FT, bool STR>
-struct AmdPoint {
-    const Geom<FT>& g;
-    const FT* u;
-    const FT* v;
-    const FT* w;
-    FT rxy, ryx;                       // Δᶠa/Δᶠb with Δᶠ = 2Δ   (:224-226)
-    FT rxz_[2], rzx_[2], ryz_[2], rzy_[2], rdzf_[2], fz_[2], rdzc_;
-    // the filter-width ratios are loop invariants with divisions: on a regular grid formed once on the host (set_consts), same FT
-    // arithmetic; on a stretched grid formed here from the level tables
-    OC_HD AmdPoint(const Geom<FT>& g_, const FT* u_, const FT* v_, const FT* w_, const FT* r, int k) : g(g_), u(u_), v(v_), w(w_) {
-        rxy = r[0]; ryx = r[1];
-        if (!STR) {
-            rxz_[0] = r[2]; rzx_[0] = r[3]; ryz_[0] = r[4]; rzy_[0] = r[5]; rdzf_[0] = g.rd[2]; fz_[0] = FT(2) * g.d[2]; rdzc_ = g.rd[2];
-        } else {
-            const FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1];
-            for (int n = 0; n < 2; ++n) {
-                fz_[n] = FT(2) * g.dzc[k + n];
-                rxz_[n] = fx / fz_[n]; rzx_[n] = fz_[n] / fx; ryz_[n] = fy / fz_[n]; rzy_[n] = fz_[n] / fy;
-                rdzf_[n] = g.rdzf[k + n];
-            }
-            rdzc_ = g.rdzc[k];
-        }
-    }
-    OC_HD FT rxz(int up) const { return rxz_[STR ? up : 0]; }
-    OC_HD FT rzx(int up) const { return rzx_[STR ? up : 0]; }
-    OC_HD FT ryz(int up) const { return ryz_[STR ? up : 0]; }
-    OC_HD FT rzy(int up) const { return rzy_[STR ? up : 0]; }
-    OC_HD FT rdzf(int up) const { return rdzf_[STR ? up : 0]; }
-    OC_HD FT fz(int up) const { return fz_[STR ? up : 0]; }
-    // normalised gradients at their natural locations (velocity_tracer_gradients.jl:126-154); o = linear index
-    OC_HD FT dxu(int o) const { return (u[o + 1] - u[o]) * g.rd[0]; }                       // ccc
-    OC_HD FT dyv(int o) const { return (v[o + g.sy] - v[o]) * g.rd[1]; }                    // ccc
-    OC_HD FT dzw(int o) const { return (w[o + g.sz] - w[o]) * rdzc_; }                      // ccc
-    OC_HD FT dxv(int o) const { return rxy * ((v[o] - v[o - 1]) * g.rd[0]); }               // ffc
-    OC_HD FT dyu(int o) const { return ryx * ((u[o] - u[o - g.sy]) * g.rd[1]); }            // ffc
-    OC_HD FT dxw(int o, int up) const { return rxz(up) * ((w[o] - w[o - 1]) * g.rd[0]); }       // fcf
-    OC_HD FT dzu(int o, int up) const { return rzx(up) * ((u[o] - u[o - g.sz]) * rdzf(up)); }   // fcf
-    OC_HD FT dyw(int o, int up) const { return ryz(up) * ((w[o] - w[o - g.sy]) * g.rd[1]); }    // cff
-    OC_HD FT dzv(int o, int up) const { return rzy(up) * ((v[o] - v[o - g.sz]) * rdzf(up)); }   // cff
-};
-
-// ℑ of a functor F(o) from (Face,Face) in dims (d1<d2) to centre: ℑ_{d2}ᶜ(ℑ_{d1}ᶜ F)   interpolation_operators.jl:45-56
-template <class FT, class F>
-OC_HD FT interp2c(const F& fn, int o, int s1, int s2) {
-    return FT(0.5) * (FT(0.5) * (fn(o) + fn(o + s1)) + FT(0.5) * (fn(o + s2) + fn(o + s1 + s2)));
-}
-template <class FT, class F>
-OC_HD FT interp1c(const F& fn, int o, int s) {
-    return FT(0.5) * (fn(o) + fn(o + s));
-}
-
-// 4-point interpolation of values already evaluated at the corners {o, o+s1, o+s2, o+s1+s2} — the arithmetic of interp2c
-template <class FT>
-OC_HD FT interp4(const FT* f) { return FT(0.5) * (FT(0.5) * (f[0] + f[1]) + FT(0.5) * (f[2] + f[3])); }
-
 template <class FT, bool STR = false>
 struct AmdKernel {
     static constexpr int PHASES = 1;
@@ -130,15 +70,29 @@ struct AmdKernel {
     FT Ckappa[8];
     FT ratios[6];      // Δᶠa/Δᶠb   (:224-226)
     FT delta2;         // δ² = 3 / (1/Δᶠx² + 1/Δᶠy² + 1/Δᶠz²)   (:166,190)
+    // stretched grids: per-level tables of the constants that contain divisions by Δzᶜ[k], formed once on the host in the same
+    // FT arithmetic (Model::build_z_tables): kxw = (Δᶠx/Δᶠz)/Δx, kzu = (Δᶠz/Δᶠx)/Δzᶠ, kyw = (Δᶠy/Δᶠz)/Δy, kzv = (Δᶠz/Δᶠy)/Δzᶠ,
+    // kcz = Δᶠz/Δzᶠ, d2 = δ²; indexable like Geom::dzc
+    const FT* lv_kxw; const FT* lv_kzu; const FT* lv_kyw; const FT* lv_kzv; const FT* lv_kcz; const FT* lv_d2;
     void set_consts() {
         FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = FT(2) * g.d[2];
         ratios[0] = fx / fy; ratios[1] = fy / fx; ratios[2] = fx / fz; ratios[3] = fz / fx; ratios[4] = fy / fz; ratios[5] = fz / fy;
         delta2 = FT(3) / (FT(1) / (fx * fx) + FT(1) / (fy * fy) + FT(1) / (fz * fz));
     }
 
-    // Every normalised gradient is evaluated ONCE at the four corners its interpolations need (24 evaluations per cell);
-    // all 30 terms of AMD are then products of those — same operands, same order of operations as the reference's
-    // nested ℑ(…) calls (anisotropic_minimum_dissipation.jl:240-351).
+    // Every normalised gradient is evaluated ONCE at the four corners its interpolations need (24 evaluations per cell).
+    // The reference's nested ℑ(…) expressions (anisotropic_minimum_dissipation.jl:240-351) are then assembled from 15 corner
+    // sums instead of 30 separately interpolated products — an exact algebraic identity (ℑ of four corners = ¼ Σ; products with
+    // Σ₁₂ = ½(∂y u + ∂x v) expand into the sums of squares and one cross sum per plane):
+    //   A1 = Σ ∂x v, B1 = Σ ∂y u, A2 = Σ (∂x v)², B2 = Σ (∂y u)², AB = Σ ∂x v ∂y u over the xy corners; C·, D· (∂x w, ∂z u) over xz;
+    //   E·, F· (∂y w, ∂z v) over yz (all normalised gradients);
+    //   q = S11² + S22² + S33² + ¼ (A2 + B2 + C2 + D2 + E2 + F2)                                              (:285-306)
+    //   r = S11³ + S22³ + S33³ + ¼ [S11 (Sxy + Sxz) + S22 (Sxy + Syz) + S33 (Sxz + Syz)]
+    //       + (1/64) [A1 C1 (E1 + F1) + B1 E1 (C1 + D1) + D1 F1 (A1 + B1)],   Sxy = A2 + B2 + AB, …              (:240-279)
+    //   σ = ½ (X2 + Y2 + Z2),  θ = ½ (S11 X2 + S22 Y2 + S33 Z2) + (1/16) [X1 Y1 (A1 + B1) + X1 Z1 (C1 + D1) + Y1 Z1 (G1 + F1)]
+    //       with X1 = Σ ∂x c, X2 = Σ (∂x c)² over the two x-faces, …, and G1 = Σ ∂y w over the XZ corners (sic, :336)   (:322-351)
+    // Measured (ncu): the kernel is bound by the FP64 pipe (60 %); this form needs ≈ 300 FP64 instructions per cell instead of 456.
+    // Differences to the reference's order of operations are rounding-level (≈ 1e-16 relative per term).
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
         (void)nt;
@@ -146,98 +100,65 @@ struct AmdKernel {
         if (i >= g.N[0] || j >= g.N[1]) return;
         const int o = g.idx(i, j, k);
         const int sx = 1, sy = g.sy, sz = g.sz;
-        AmdPoint<FT, STR> P(g, u, v, w, ratios, k);
-        const FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = P.fz(0);
-        const FT d2 = STR ? FT(3) / (FT(1) / (fx * fx) + FT(1) / (fy * fy) + FT(1) / (fz * fz)) : delta2;   // δ² (:166,190)
-        auto sq = [](FT x) { return x * x; };
+        const FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1];
+        const FT d2 = STR ? lv_d2[k] : delta2;                                             // δ² (:166,190)
+        // combined constants: (filter-width ratio) × (reciprocal spacing); [0] on the cell's level, [1] on the level above
+        const FT kxv = ratios[0] * g.rd[0], kyu = ratios[1] * g.rd[1];
+        FT kxw[2], kzu[2], kyw[2], kzv[2], kcz[2];
+        for (int n = 0; n < 2; ++n) {
+            if (STR) { kxw[n] = lv_kxw[k + n]; kzu[n] = lv_kzu[k + n]; kyw[n] = lv_kyw[k + n]; kzv[n] = lv_kzv[k + n]; kcz[n] = lv_kcz[k + n]; }
+            else {
+                kxw[n] = ratios[2] * g.rd[0]; kzu[n] = ratios[3] * g.rd[2]; kyw[n] = ratios[4] * g.rd[1]; kzv[n] = ratios[5] * g.rd[2];
+                kcz[n] = (FT(2) * g.d[2]) * g.rd[2];
+            }
+        }
+        const FT rdzc = STR ? g.rdzc[k] : g.rd[2];
         const int cxy[4] = {o, o + sx, o + sy, o + sx + sy};
         const int cxz[4] = {o, o + sx, o + sz, o + sx + sz};
         const int cyz[4] = {o, o + sy, o + sz, o + sy + sz};
-        FT dxv[4], dyu[4], dxw[4], dzu[4], dyw[4], dzv[4], t[4];
+        FT A1 = FT(0), B1 = FT(0), A2 = FT(0), B2 = FT(0), AB = FT(0);
+        FT C1 = FT(0), D1 = FT(0), C2 = FT(0), D2 = FT(0), CD = FT(0);
+        FT E1 = FT(0), F1 = FT(0), E2 = FT(0), F2 = FT(0), EF = FT(0);
+        FT G1 = FT(0);
         for (int n = 0; n < 4; ++n) {
-            dxv[n] = P.dxv(cxy[n]); dyu[n] = P.dyu(cxy[n]);
-            dxw[n] = P.dxw(cxz[n], n >> 1); dzu[n] = P.dzu(cxz[n], n >> 1);     // corners 2, 3 are on the level above
-            dyw[n] = P.dyw(cyz[n], n >> 1); dzv[n] = P.dzv(cyz[n], n >> 1);
+            const int up = n >> 1;                      // corners 2, 3 of the xz / yz sets are on the level above
+            const int pxy = cxy[n], pxz = cxz[n], pyz = cyz[n];
+            const FT dxv = (v[pxy] - v[pxy - sx]) * kxv, dyu = (u[pxy] - u[pxy - sy]) * kyu;           // ffc
+            const FT dxw = (w[pxz] - w[pxz - sx]) * kxw[up], dzu = (u[pxz] - u[pxz - sz]) * kzu[up];   // fcf
+            const FT dyw = (w[pyz] - w[pyz - sy]) * kyw[up], dzv = (v[pyz] - v[pyz - sz]) * kzv[up];   // cff
+            A1 += dxv; B1 += dyu; A2 += dxv * dxv; B2 += dyu * dyu; AB += dxv * dyu;
+            C1 += dxw; D1 += dzu; C2 += dxw * dxw; D2 += dzu * dzu; CD += dxw * dzu;
+            E1 += dyw; F1 += dzv; E2 += dyw * dyw; F2 += dzv * dzv; EF += dyw * dzv;
+            if (ntr > 0) G1 += (w[pxz] - w[pxz - sy]) * kyw[up];                                       // ∂y w at the xz corners (:336)
         }
-        const FT dxu = P.dxu(o), dyv = P.dyv(o), dzw = P.dzw(o);
-        for (int n = 0; n < 4; ++n) t[n] = sq(dxv[n]);
-        const FT Ixy_dxv2 = interp4<FT>(t);
-        for (int n = 0; n < 4; ++n) t[n] = sq(dyu[n]);
-        const FT Ixy_dyu2 = interp4<FT>(t);
-        for (int n = 0; n < 4; ++n) t[n] = sq(dxw[n]);
-        const FT Ixz_dxw2 = interp4<FT>(t);
-        for (int n = 0; n < 4; ++n) t[n] = sq(dzu[n]);
-        const FT Ixz_dzu2 = interp4<FT>(t);
-        for (int n = 0; n < 4; ++n) t[n] = sq(dyw[n]);
-        const FT Iyz_dyw2 = interp4<FT>(t);
-        for (int n = 0; n < 4; ++n) t[n] = sq(dzv[n]);
-        const FT Iyz_dzv2 = interp4<FT>(t);
-        const FT Ixy_dxv = interp4<FT>(dxv), Ixy_dyu = interp4<FT>(dyu);
-        const FT Ixz_dxw = interp4<FT>(dxw), Ixz_dzu = interp4<FT>(dzu);
-        const FT Iyz_dyw = interp4<FT>(dyw), Iyz_dzv = interp4<FT>(dzv);
-        // norm_tr_∇uᶜᶜᶜ :285-306
-        FT q = sq(dxu) + sq(dyv) + sq(dzw) + Ixy_dxv2 + Ixy_dyu2 + Ixz_dxw2 + Ixz_dzu2 + Iyz_dyw2 + Iyz_dzv2;
+        const FT S11 = (u[o + sx] - u[o]) * g.rd[0], S22 = (v[o + sy] - v[o]) * g.rd[1], S33 = (w[o + sz] - w[o]) * rdzc;   // ccc
+        const FT q11 = S11 * S11, q22 = S22 * S22, q33 = S33 * S33;
+        const FT q = (q11 + q22 + q33) + FT(0.25) * (((A2 + B2) + (C2 + D2)) + (E2 + F2));
         FT nu = FT(0);
         if (q != FT(0)) {
-            // norm_uᵢₐ_uⱼₐ_Σᵢⱼᶜᶜᶜ :240-279
-            FT S12[4], S13[4], S23[4];
-            for (int n = 0; n < 4; ++n) {
-                S12[n] = FT(0.5) * (dyu[n] + dxv[n]);
-                S13[n] = FT(0.5) * (dzu[n] + dxw[n]);
-                S23[n] = FT(0.5) * (dzv[n] + dyw[n]);
-            }
-            const FT Ixy_S12 = interp4<FT>(S12), Ixz_S13 = interp4<FT>(S13), Iyz_S23 = interp4<FT>(S23);
-            for (int n = 0; n < 4; ++n) t[n] = dxv[n] * S12[n];
-            const FT Ixy_dxvS12 = interp4<FT>(t);
-            for (int n = 0; n < 4; ++n) t[n] = dxw[n] * S13[n];
-            const FT Ixz_dxwS13 = interp4<FT>(t);
-            for (int n = 0; n < 4; ++n) t[n] = dyu[n] * S12[n];
-            const FT Ixy_dyuS12 = interp4<FT>(t);
-            for (int n = 0; n < 4; ++n) t[n] = dyw[n] * S23[n];
-            const FT Iyz_dywS23 = interp4<FT>(t);
-            for (int n = 0; n < 4; ++n) t[n] = dzu[n] * S13[n];
-            const FT Ixz_dzuS13 = interp4<FT>(t);
-            for (int n = 0; n < 4; ++n) t[n] = dzv[n] * S23[n];
-            const FT Iyz_dzvS23 = interp4<FT>(t);
-            FT t1 = dxu * sq(dxu) + dyv * Ixy_dxv2 + dzw * Ixz_dxw2
-                  + FT(2) * dxu * Ixy_dxvS12
-                  + FT(2) * dxu * Ixz_dxwS13
-                  + FT(2) * Ixy_dxv * Ixz_dxw * Iyz_S23;
-            FT t2 = dxu * Ixy_dyu2 + dyv * sq(dyv) + dzw * Iyz_dyw2
-                  + FT(2) * dyv * Ixy_dyuS12
-                  + FT(2) * Ixy_dyu * Iyz_dyw * Ixz_S13
-                  + FT(2) * dyv * Iyz_dywS23;
-            FT t3 = dxu * Ixz_dzu2 + dyv * Iyz_dzv2 + dzw * sq(dzw)
-                  + FT(2) * Ixz_dzu * Iyz_dzv * Ixy_S12
-                  + FT(2) * dzw * Ixz_dzuS13
-                  + FT(2) * dzw * Iyz_dzvS23;
-            FT r = t1 + t2 + t3;
-            FT Cb_zeta = FT(0) / fz;                                                       // Cb = nothing :281
-            nu = -Cnu * d2 * (r - Cb_zeta) / q;                                            // :168
+            const FT Sxy = A2 + B2 + AB, Sxz = C2 + D2 + CD, Syz = E2 + F2 + EF;
+            const FT cubes = S11 * q11 + S22 * q22 + S33 * q33;
+            const FT mixed = S11 * (Sxy + Sxz) + S22 * (Sxy + Syz) + S33 * (Sxz + Syz);
+            const FT triple = A1 * C1 * (E1 + F1) + B1 * E1 * (C1 + D1) + D1 * F1 * (A1 + B1);
+            const FT r = cubes + FT(0.25) * mixed + FT(0.015625) * triple;
+            nu = -Cnu * d2 * r / q;                                                        // Cb = nothing: no buoyancy term (:168,281)
         }
         nu_e[o] = oc_max<FT>(FT(0), nu);
         if (ntr == 0) return;
-        // ℑxzᶜᵃᶜ(norm_∂y_w) — sic, :336 — needs ∂y w at the xz corners
-        for (int n = 0; n < 4; ++n) t[n] = P.dyw(cxz[n], n >> 1);
-        const FT Ixz_dyw = interp4<FT>(t);
+        const FT kcx = fx * g.rd[0], kcy = fy * g.rd[1];
         for (int tr = 0; tr < ntr; ++tr) {
             const FT* cc = c[tr];
-            auto cx = [&](int p) { return fx * ((cc[p] - cc[p - sx]) * g.rd[0]); };       // norm_∂x_c at fcc
-            auto cy = [&](int p) { return fy * ((cc[p] - cc[p - sy]) * g.rd[1]); };
-            auto cz = [&](int p, int up) { return P.fz(up) * ((cc[p] - cc[p - sz]) * P.rdzf(up)); };   // norm_∂z_c at ccf
-            const FT cx0 = cx(o), cx1 = cx(o + sx), cy0 = cy(o), cy1 = cy(o + sy), cz0 = cz(o, 0), cz1 = cz(o + sz, 1);
-            FT Ix_cx2 = FT(0.5) * (sq(cx0) + sq(cx1));
-            FT Iy_cy2 = FT(0.5) * (sq(cy0) + sq(cy1));
-            FT Iz_cz2 = FT(0.5) * (sq(cz0) + sq(cz1));
-            FT sigma = Ix_cx2 + Iy_cy2 + Iz_cz2;                                           // norm_θᵢ²ᶜᶜᶜ :349-351
+            const FT c0 = cc[o];
+            const FT cx0 = (c0 - cc[o - sx]) * kcx, cx1 = (cc[o + sx] - c0) * kcx;        // norm_∂x_c at the two x-faces (fcc)
+            const FT cy0 = (c0 - cc[o - sy]) * kcy, cy1 = (cc[o + sy] - c0) * kcy;
+            const FT cz0 = (c0 - cc[o - sz]) * kcz[0], cz1 = (cc[o + sz] - c0) * kcz[1];  // ccf: the upper face is on the level above
+            const FT X1 = cx0 + cx1, Y1 = cy0 + cy1, Z1 = cz0 + cz1;
+            const FT X2 = cx0 * cx0 + cx1 * cx1, Y2 = cy0 * cy0 + cy1 * cy1, Z2 = cz0 * cz0 + cz1 * cz1;
+            const FT sigma = FT(0.5) * (X2 + Y2 + Z2);                                     // norm_θᵢ²ᶜᶜᶜ :349-351
             FT kap = FT(0);
             if (sigma != FT(0)) {
-                FT Ix_cx = FT(0.5) * (cx0 + cx1), Iy_cy = FT(0.5) * (cy0 + cy1), Iz_cz = FT(0.5) * (cz0 + cz1);
-                // norm_uᵢⱼ_cⱼ_cᵢᶜᶜᶜ :322-347
-                FT a1 = dxu * Ix_cx2 + Ixy_dxv * Ix_cx * Iy_cy + Ixz_dxw * Ix_cx * Iz_cz;
-                FT a2 = Ixy_dyu * Iy_cy * Ix_cx + dyv * Iy_cy2 + Ixz_dyw * Iy_cy * Iz_cz;
-                FT a3 = Ixz_dzu * Iz_cz * Ix_cx + Iyz_dzv * Iz_cz * Iy_cy + dzw * Iz_cz2;
-                FT theta = a1 + a2 + a3;
+                const FT theta = FT(0.5) * (S11 * X2 + S22 * Y2 + S33 * Z2)
+                               + FT(0.0625) * (X1 * Y1 * (A1 + B1) + X1 * Z1 * (C1 + D1) + Y1 * Z1 * (G1 + F1));   // :322-347
                 kap = -Ckappa[tr] * d2 * theta / sigma;                                    // :191
             }
             kappa_e[tr][o] = oc_max<FT>(FT(0), kap);

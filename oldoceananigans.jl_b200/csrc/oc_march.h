@@ -546,7 +546,8 @@ struct MarchKernel {
         const Geom<FT>& g = a.g;
         int s1 = g.st(d1), s2 = g.st(d2);
         const FT* n = a.nu_e + o;
-        return FT(0.5) * (FT(0.5) * (n[-s1 - s2] + n[-s2]) + FT(0.5) * (n[-s1] + n[0]));
+        // = ½(½(a+b) + ½(c+d)) bit for bit (scaling by powers of two is exact)
+        return FT(0.25) * ((n[-s1 - s2] + n[-s2]) + (n[-s1] + n[0]));
     }
 
     // νₑ at the flux point of τ_{COMP,D} (ccc for D == COMP, else the edge that is Face in D and COMP), κₑ at the D-face
@@ -798,7 +799,7 @@ struct MarchKernel {
                 G1 q = r1(cx);
                 FT num, cnt = FT(1);
                 if (KIND == KIND_U) {
-                    num = FT(0.5) * (FT(0.5) * (q(ii - 1, jj, kc) + q(ii, jj, kc)) + FT(0.5) * (q(ii - 1, jj + 1, kc) + q(ii, jj + 1, kc)));
+                    num = FT(0.25) * ((q(ii - 1, jj, kc) + q(ii, jj, kc)) + (q(ii - 1, jj + 1, kc) + q(ii, jj + 1, kc)));
                     if (WIN) {
                         int ax0 = !(g.bounded[0] && (i - 1 < 0)), ax1 = 1;
                         int ay0 = !(g.bounded[1] && (j < 1)), ay1 = !(g.bounded[1] && (j + 1 > g.N[1] - 1));
@@ -807,7 +808,7 @@ struct MarchKernel {
                     FT val = cnt == FT(0) ? FT(0) : num / cnt;
                     G = G - (-a.f * val);
                 } else {
-                    num = FT(0.5) * (FT(0.5) * (q(ii, jj - 1, kc) + q(ii + 1, jj - 1, kc)) + FT(0.5) * (q(ii, jj, kc) + q(ii + 1, jj, kc)));
+                    num = FT(0.25) * ((q(ii, jj - 1, kc) + q(ii + 1, jj - 1, kc)) + (q(ii, jj, kc) + q(ii + 1, jj, kc)));
                     if (WIN) {
                         int ax0 = !(g.bounded[0] && (i < 1)), ax1 = !(g.bounded[0] && (i + 1 > g.N[0] - 1));
                         int ay0 = !(g.bounded[1] && (j - 1 < 0)), ay1 = 1;

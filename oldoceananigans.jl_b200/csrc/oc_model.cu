@@ -276,8 +276,10 @@ void Model<FT>::build_z_tables(const double* faces) {
     // one more face above so that the centre of the topmost level exists
     { FT shi = FT(0); for (int q = 0; q < H + 1; ++q) shi = shi + dhi; F[nt] = F[H + N] + shi; }
     for (int n = 0; n < nt; ++n) Cc[n] = (F[n + 1] + F[n]) / FT(2);
-    std::vector<FT> tab(6 * (size_t)nt);
+    std::vector<FT> tab(12 * (size_t)nt);
     FT* dzc = tab.data(); FT* dzf = dzc + nt; FT* rdzc = dzf + nt; FT* rdzf = rdzc + nt; FT* rVc = rdzf + nt; FT* rVf = rVc + nt;
+    FT* amd = rVf + nt;      // six AMD tables (AmdKernel::lv_*)
+    const FT fx = FT(2) * g_.d[0], fy = FT(2) * g_.d[1];
     for (int n = 0; n < nt; ++n) {
         dzc[n] = F[n + 1] - F[n];
         dzf[n] = n > 0 ? Cc[n] - Cc[n - 1] : Cc[1] - Cc[0];
@@ -285,6 +287,14 @@ void Model<FT>::build_z_tables(const double* faces) {
         rdzf[n] = FT(1) / dzf[n];
         rVc[n] = FT(1) / (g_.A[2] * dzc[n]);             // V = Az·Δz ; V⁻¹ = 1/V
         rVf[n] = FT(1) / (g_.A[2] * dzf[n]);
+        // AMD: Δᶠz = 2 Δzᶜ[k] at the index of the evaluation point (anisotropic_minimum_dissipation.jl:224-234)
+        const FT fz = FT(2) * dzc[n];
+        amd[0 * nt + n] = (fx / fz) * g_.rd[0];
+        amd[1 * nt + n] = (fz / fx) * rdzf[n];
+        amd[2 * nt + n] = (fy / fz) * g_.rd[1];
+        amd[3 * nt + n] = (fz / fy) * rdzf[n];
+        amd[4 * nt + n] = fz * rdzf[n];
+        amd[5 * nt + n] = FT(3) / (FT(1) / (fx * fx) + FT(1) / (fy * fy) + FT(1) / (fz * fz));
     }
     ztab_ = (FT*)dev_alloc(sizeof(FT) * tab.size());
     dev_upload(ztab_, tab.data(), sizeof(FT) * tab.size(), stream_);
@@ -740,6 +750,10 @@ void Model<FT>::aux() {
             k.ntr = cfg_.n_tracers;
             for (int t = 0; t < cfg_.n_tracers; ++t) { k.c[t] = state_[3 + t].p; k.kappa_e[t] = kappa_e_[t].p; k.Ckappa[t] = (FT)cfg_.amd_Ckappa[t]; }
             k.set_consts();
+            const size_t nt = (size_t)g_.N[2] + 2 * (g_.H[2] + 1) + 1;
+            const FT* at = stretched_ ? g_.rVf + nt : nullptr;         // the AMD tables follow the six metric tables (build_z_tables)
+            k.lv_kxw = at; k.lv_kzu = at ? at + nt : nullptr; k.lv_kyw = at ? at + 2 * nt : nullptr; k.lv_kzv = at ? at + 3 * nt : nullptr;
+            k.lv_kcz = at ? at + 4 * nt : nullptr; k.lv_d2 = at ? at + 5 * nt : nullptr;
             Dim3 ag;
             ag.x = (g_.N[0] + 31) / 32; ag.y = (g_.N[1] + 7) / 8; ag.z = g_.N[2];
             go(k, ag, 0, OC_TIMER_AUX);
