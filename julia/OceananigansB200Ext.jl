@@ -63,7 +63,9 @@ mutable struct OcConfig               # `oc_config`, same field order; NTuple fo
     tracer_T::Int32; tracer_S::Int32; tracer_b::Int32
     has_coriolis::Int32; coriolis_f::Float64
     bcs::NTuple{OC_MAX_FIELDS,NTuple{6,OcBC}}
-    device::Int32; reserved::NTuple{7,Int32}
+    device::Int32; dist_rank::Int32; dist_nranks::Int32
+    z_stretched::Int32; z_faces::Ptr{Float64}      # ABI v2: vertically stretched grid (Nz+1 faces, read during oc_model_create only)
+    reserved::NTuple{2,Int32}
     OcConfig() = new()
 end
 
@@ -109,9 +111,17 @@ function config(model::NonhydrostaticModel)
     TX, TY, TZ = topology(grid)
     cfg.topology = (topo_code(TX), topo_code(TY), topo_code(TZ))
     cfg.N = Int32.((grid.Nx, grid.Ny, grid.Nz)); cfg.H = Int32.(halo_size(grid))
-    grid.Δxᶜᵃᵃ isa Number && grid.Δyᵃᶜᵃ isa Number && grid.z.Δᵃᵃᶜ isa Number ||
-        throw(ArgumentError("B200: stretched grids are out of scope (FourierTridiagonalPoissonSolver path)"))
-    cfg.delta = Float64.((grid.Δxᶜᵃᵃ, grid.Δyᵃᶜᵃ, grid.z.Δᵃᵃᶜ)); cfg.extent = Float64.((grid.Lx, grid.Ly, grid.Lz))
+    grid.Δxᶜᵃᵃ isa Number && grid.Δyᵃᶜᵃ isa Number ||
+        throw(ArgumentError("B200: stretched x / y are out of scope (only z can be variably spaced)"))
+    zfaces = nothing
+    if grid.z.Δᵃᵃᶜ isa Number
+        cfg.delta = Float64.((grid.Δxᶜᵃᵃ, grid.Δyᵃᶜᵃ, grid.z.Δᵃᵃᶜ))
+    else    # vertically stretched: pass the Nz+1 interior faces; the library regenerates the halo spacings like generate_coordinate
+        TZ === Bounded || throw(ArgumentError("B200: a stretched z needs the Bounded topology"))
+        zfaces = Float64.(Array(grid.z.cᵃᵃᶠ[1:grid.Nz+1]))
+        cfg.delta = Float64.((grid.Δxᶜᵃᵃ, grid.Δyᵃᶜᵃ, 0.0)); cfg.z_stretched = 1
+    end
+    cfg.extent = Float64.((grid.Lx, grid.Ly, grid.Lz))
     adv = model.advection.momentum
     cfg.advection = adv isa Centered && Oceananigans.Advection.required_halo_size_x(adv) == 1 ? 0 :
                     adv isa WENO && Oceananigans.Advection.required_halo_size_x(adv) == 3 ? 1 :
@@ -157,10 +167,19 @@ function config(model::NonhydrostaticModel)
         map(bc_record, (bcs.west, bcs.east, bcs.south, bcs.north, bcs.bottom, bcs.top))
     end
     cfg.device = AC.architecture(grid).device
-    return cfg
+    return cfg, zfaces
 end
 
-twin(model) = get!(() -> DeviceModel(config(model)), TWINS, model)
+function twin(model)
+    get!(TWINS, model) do
+        cfg, zfaces = config(model)
+        zfaces === nothing && return DeviceModel(cfg)
+        GC.@preserve zfaces begin                      # oc_model_create copies the faces; the pointer is not kept
+            cfg.z_faces = pointer(zfaces)
+            DeviceModel(cfg)
+        end
+    end
+end
 
 prognostic(model) = (model.velocities..., model.tracers...)
 
