@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — cell-updates/s per full time step of the NonhydrostaticModel hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c3f32|c4|c4s|c1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c3f32|c4|c4s|c1|c3u5|c2c4] [--impl ours|reference]
 
 One "step" is one full `time_step!(model, Δt)` (RK3: three stages, each tendency+substep, halo fills, FFT
 pressure solve and projection) over one synthetic, seeded initial state.
@@ -50,6 +50,11 @@ WORKLOADS = {
                   F=5, b=1, a=0, label="C3 512^3 (P,P,P) WENO-5 T,S SeawaterBuoyancy ScalarDiffusivity F32"),
     "c4": dict(N=(512, 512, 256), topo="PPB", FT="f64", adv="weno", tracers=("T", "S"), buoy="seawater", closure="amd",
                F=5, b=1, a=1, label="C4 512^2x256 (P,P,B) WENO-5 AMD FPlane flux BCs F64"),
+    # the C3 physics with the linear fifth-order upwind scheme / C2 with Centered(4) — general tile kernel
+    "c3u5": dict(N=(512, 512, 512), topo="PPP", FT="f64", adv="upwind5", tracers=("T", "S"), buoy="seawater", closure="scalar",
+                 F=5, b=1, a=0, label="C3 physics with UpwindBiased(order=5): 512^3 (P,P,P) T,S SeawaterBuoyancy ScalarDiffusivity F64"),
+    "c2c4": dict(N=(256, 256, 256), topo="PPP", FT="f64", adv="centered4", tracers=(), buoy=None, closure=None, F=3, b=0, a=0,
+                 label="C2 physics with Centered(order=4): 256^3 (P,P,P) F64 no tracers"),
     # the C4 physics on a vertically stretched (surface-refined) grid — FourierTridiagonalPoissonSolver
     "c4s": dict(N=(512, 512, 256), topo="PPB", FT="f64", adv="weno", tracers=("T", "S"), buoy="seawater", closure="amd",
                 F=5, b=1, a=1, stretched=True,
@@ -170,7 +175,8 @@ def build_model(w, device, rank=0, world=1):
                                   z=[float(v) for v in stretched_faces(w["N"][2], extent[2])], topology=tuple(topo[c] for c in w["topo"]))
     else:
         grid = ob.RectilinearGrid(arch, FT, size=size, extent=extent, topology=tuple(topo[c] for c in w["topo"]))
-    adv = ob.WENO() if w["adv"] == "weno" else ob.Centered()
+    adv = {"weno": ob.WENO, "centered": ob.Centered, "upwind5": lambda: ob.UpwindBiased(order=5),
+           "centered4": lambda: ob.Centered(order=4)}[w["adv"]]()
     kw = dict(grid=grid, advection=adv, tracers=w["tracers"])
     if w["buoy"] == "seawater":
         if w["closure"] == "amd":
@@ -388,7 +394,9 @@ def oracle_model(w, N):
                          z=[float(v) for v in stretched_faces(N[2], extent[2])], topology=tuple(w["topo"]))
     else:
         og = oracle.Grid(FT, size=size, extent=extent, topology=tuple(w["topo"]))
-    kw = dict(advection=adv.WENO(FT, 5) if w["adv"] == "weno" else adv.Centered(FT, 2), tracers=w["tracers"])
+    kw = dict(advection={"weno": lambda: adv.WENO(FT, 5), "centered": lambda: adv.Centered(FT, 2),
+                         "upwind5": lambda: adv.UpwindBiased(FT, 5), "centered4": lambda: adv.Centered(FT, 4)}[w["adv"]](),
+              tracers=w["tracers"])
     if w["buoy"] == "seawater":
         kw["buoyancy"] = clo.SeawaterBuoyancy()
     if w["closure"] == "scalar":
@@ -432,7 +440,7 @@ def c_twin_model(w, n):
 def cpu_run(w, n_numpy, max_steps, budget_s, warmup=1):
     """Time the CPU restatement of the reference algorithm on a bounded sample of the workload: the multi-threaded C twin for the
     triply periodic workloads (Float64 arithmetic), the NumPy oracle otherwise.  Returns (cells/s, s/step, steps, cores, sample)."""
-    if w["topo"] == "PPP" and w["closure"] != "amd":
+    if w["topo"] == "PPP" and w["closure"] != "amd" and w["adv"] in ("weno", "centered"):
         n = 128
         model, N = c_twin_model(w, n)
         dt = 0.1 / n

@@ -36,7 +36,11 @@ typedef enum { OC_OK = 0, OC_ERR_INVALID = -1, OC_ERR_UNSUPPORTED = -2, OC_ERR_C
 
 typedef enum { OC_F64 = 0, OC_F32 = 1 } oc_float_type;
 typedef enum { OC_PERIODIC = 0, OC_BOUNDED = 1, OC_FLAT = 2 } oc_topology;          /* src/Grids/Grids.jl:68-104 */
-typedef enum { OC_CENTERED2 = 0, OC_WENO5 = 1 } oc_advection;                        /* Centered(order=2), WENO(order=5) */
+/* Centered(order=2), WENO(order=5): the BASELINE schemes (TMA-staged z-marching kernel); Centered(order=4),
+ * UpwindBiased(order=3|5|1), WENO(order=3), advection=nothing: the rest of the family up to order 5
+ * (src/Advection/{centered,upwind_biased,weno}_reconstruction.jl), in the general tile kernel */
+typedef enum { OC_CENTERED2 = 0, OC_WENO5 = 1, OC_CENTERED4 = 2, OC_UPWIND3 = 3, OC_UPWIND5 = 4, OC_WENO3 = 5, OC_UPWIND1 = 6,
+               OC_ADVECTION_NONE = 7 } oc_advection;
 typedef enum { OC_RK3 = 0, OC_AB2 = 1 } oc_timestepper;                              /* src/TimeSteppers */
 typedef enum { OC_BUOYANCY_NONE = 0, OC_BUOYANCY_TRACER = 1, OC_BUOYANCY_SEAWATER_LINEAR = 2 } oc_buoyancy;
 

@@ -15,7 +15,7 @@ OC_TIMER_NAMES = ("tendency", "halo", "poisson_rhs", "fft", "poisson_mid", "proj
 # enums
 OC_F64, OC_F32 = 0, 1
 OC_PERIODIC, OC_BOUNDED, OC_FLAT = 0, 1, 2
-OC_CENTERED2, OC_WENO5 = 0, 1
+OC_CENTERED2, OC_WENO5, OC_CENTERED4, OC_UPWIND3, OC_UPWIND5, OC_WENO3, OC_UPWIND1, OC_ADVECTION_NONE = range(8)
 OC_RK3, OC_AB2 = 0, 1
 OC_BUOYANCY_NONE, OC_BUOYANCY_TRACER, OC_BUOYANCY_SEAWATER_LINEAR = 0, 1, 2
 OC_BC_DEFAULT, OC_BC_PERIODIC, OC_BC_FLUX, OC_BC_VALUE, OC_BC_GRADIENT, OC_BC_OPEN, OC_BC_NONE = range(7)

@@ -24,7 +24,7 @@ from . import _lib as L
 
 __all__ = [
     "B200", "Distributed", "Partition", "Periodic", "Bounded", "Flat", "Center", "Face", "RectilinearGrid",
-    "Centered", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation",
+    "Centered", "UpwindBiased", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation",
     "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "FPlane",
     "FluxBoundaryCondition", "ValueBoundaryCondition", "GradientBoundaryCondition", "OpenBoundaryCondition",
     "FieldBoundaryConditions", "NonhydrostaticModel", "Field", "set_", "time_step_", "update_state_",
@@ -188,17 +188,40 @@ class RectilinearGrid:
 
 # ------------------------------------------------------------------------------------------ physics descriptors
 class Centered:
+    """Centered(order = 2 | 4)   src/Advection/centered_reconstruction.jl:5-55"""
+
     def __init__(self, FT=np.float64, order=2):
-        if order != 2:
-            raise NotImplementedError("Centered: only order=2 is implemented on B200 (other orders: SURVEY §8f)")
-        self.order, self.buffer, self.code = 2, 1, L.OC_CENTERED2
+        if order not in (2, 4):
+            raise NotImplementedError("Centered: orders 2 and 4 are implemented on B200 (higher orders: SURVEY §8f)")
+        self.order, self.buffer = order, order // 2
+        self.code = L.OC_CENTERED2 if order == 2 else L.OC_CENTERED4
+
+
+class UpwindBiased:
+    """UpwindBiased(order = 1 | 3 | 5)   src/Advection/upwind_biased_reconstruction.jl:57-86"""
+
+    def __init__(self, FT=np.float64, order=3):
+        if order % 2 == 0:
+            raise ValueError("UpwindBiased reconstruction scheme is defined only for odd orders")     # :59
+        if order not in (1, 3, 5):
+            raise NotImplementedError("UpwindBiased: orders 1, 3 and 5 are implemented on B200")
+        self.order, self.buffer = order, (order + 1) // 2
+        self.code = {1: L.OC_UPWIND1, 3: L.OC_UPWIND3, 5: L.OC_UPWIND5}[order]
 
 
 class WENO:
+    """WENO(order = 3 | 5)   src/Advection/weno_reconstruction.jl:7-93"""
+
     def __init__(self, FT=np.float64, order=5, bounds=None):
-        if order != 5 or bounds is not None:
-            raise NotImplementedError("WENO: only order=5 without bounds is implemented on B200")
-        self.order, self.buffer, self.code = 5, 3, L.OC_WENO5
+        if order not in (3, 5) or bounds is not None:
+            raise NotImplementedError("WENO: orders 3 and 5 without bounds are implemented on B200")
+        self.order, self.buffer = order, (order + 1) // 2
+        self.code = L.OC_WENO5 if order == 5 else L.OC_WENO3
+
+
+class _NoAdvection:
+    """advection = nothing: no advective fluxes (momentum_advection_operators.jl:86-95)"""
+    order, buffer, code = 0, 1, L.OC_ADVECTION_NONE
 
 
 class ScalarDiffusivity:
@@ -368,7 +391,7 @@ class _NT(dict):
 
 
 class NonhydrostaticModel:
-    def __init__(self, *, grid, advection=None, closure=None, tracers=(), buoyancy=None, coriolis=None,
+    def __init__(self, *, grid, advection="default", closure=None, tracers=(), buoyancy=None, coriolis=None,
                  timestepper="RungeKutta3", boundary_conditions=None, forcing=None, stokes_drift=None,
                  background_fields=None, biogeochemistry=None, particles=None, library=None):
         for name, val in (("forcing", forcing), ("stokes_drift", stokes_drift), ("background_fields", background_fields),
@@ -379,7 +402,11 @@ class NonhydrostaticModel:
         tracers = (tracers,) if isinstance(tracers, str) else tuple(tracers)
         if len(tracers) > L.OC_MAX_TRACERS:
             raise ValueError("too many tracers")
-        advection = advection if advection is not None else Centered()
+        # advection = Centered() by default (nonhydrostatic_model.jl:117); advection = nothing (None) switches advection off
+        if isinstance(advection, str) and advection == "default":
+            advection = Centered()
+        elif advection is None:
+            advection = _NoAdvection()
         closures = () if closure is None else (tuple(closure) if isinstance(closure, (tuple, list)) else (closure,))
         # inflate_grid_halo_size   nonhydrostatic_model.jl:184,248-262
         need = advection.buffer

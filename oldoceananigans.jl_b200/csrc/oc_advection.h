@@ -128,6 +128,55 @@ OC_HD FT weno5_symmetric(const AdvCoef<FT>& C, const FT* p, int s, FT a, int f, 
     if (f >= w.lo_hi && f <= w.hi_hi) return sym4<FT>(C, p, s, a);
     return sym2<FT>(p, s, a);
 }
+
+// ---- the other schemes of the reference's family up to order 5 -----------------------------------
+// _biased_interpolate with the boundary chain of topologically_conditional_interpolation.jl:46-52,99-120:
+//   UpwindBiased(5) -> UpwindBiased(3) -> UpwindBiased(1);  UpwindBiased(3) -> UpwindBiased(1);  WENO(3) -> UpwindBiased(1).
+// The hi / mid windows of OrderWindow are the required_halo_size = 3 / 2 conditions.
+template <int ADV, class FT>
+OC_HD FT biased_any(const AdvCoef<FT>& C, const FT* p, int s, bool left, int f, const OrderWindow& w) {
+    if (ADV == ADV_WENO5) return weno5_biased<FT>(C, p, s, left, f, w);
+    if (ADV == ADV_UPWIND5 && f >= w.lo_hi && f <= w.hi_hi) {
+        // upwind-ordered stencil: Left (ψ[i-3] … ψ[i+1]), Right (ψ[i+2] … ψ[i-2])
+        const int o0 = left ? -3 * s : 2 * s, ds = left ? s : -s;
+        const FT* c = left ? C.u5l : C.u5r;
+        FT r = c[0] * p[o0];
+        r = r + c[1] * p[o0 + ds];
+        r = r + c[2] * p[o0 + 2 * ds];
+        r = r + c[3] * p[o0 + 3 * ds];
+        r = r + c[4] * p[o0 + 4 * ds];
+        return r;
+    }
+    if ((ADV == ADV_UPWIND5 || ADV == ADV_UPWIND3) && f >= w.lo_mid && f <= w.hi_mid) {
+        const int o0 = left ? -2 * s : s, ds = left ? s : -s;
+        const FT* c = left ? C.u3l : C.u3r;
+        FT r = c[0] * p[o0];
+        r = r + c[1] * p[o0 + ds];
+        r = r + c[2] * p[o0 + 2 * ds];
+        return r;
+    }
+    if (ADV == ADV_WENO3 && f >= w.lo_mid && f <= w.hi_mid) {
+        const int o0 = left ? -2 * s : s, ds = left ? s : -s;
+        return weno3_value<FT>(C, p[o0], p[o0 + ds], p[o0 + 2 * ds]);
+    }
+    return left ? p[-s] : p[0];                                      // UpwindBiased(order=1)
+}
+
+// _symmetric_interpolate of a·q: Centered(4) inside the scheme's window, Centered(2) otherwise.
+//   WENO(5), UpwindBiased(5): advecting_velocity_scheme = Centered(4) in the hi window; Centered(4) itself: in the mid window
+//   (its required_halo_size is 2); every other scheme: Centered(2).
+template <int ADV, class FT>
+OC_HD FT symmetric_any(const AdvCoef<FT>& C, const FT* p, int s, FT a, int f, const OrderWindow& w) {
+    if ((ADV == ADV_WENO5 || ADV == ADV_UPWIND5) && f >= w.lo_hi && f <= w.hi_hi) return sym4<FT>(C, p, s, a);
+    if (ADV == ADV_CENTERED4 && f >= w.lo_mid && f <= w.hi_mid) return sym4<FT>(C, p, s, a);
+    return sym2<FT>(p, s, a);
+}
+template <int ADV, class FT>
+OC_HD FT symmetric_any_z(const AdvCoef<FT>& C, const FT* p, int s, FT h, const FT* dz, int f, const OrderWindow& w) {
+    if ((ADV == ADV_WENO5 || ADV == ADV_UPWIND5) && f >= w.lo_hi && f <= w.hi_hi) return sym4z<FT>(C, p, s, h, dz);
+    return sym2z<FT>(p, s, h, dz);
+}
+
 template <class FT>
 OC_HD FT weno5_symmetric_z(const AdvCoef<FT>& C, const FT* p, int s, FT h, const FT* dz, int f, const OrderWindow& w) {
     if (f >= w.lo_hi && f <= w.hi_hi) return sym4z<FT>(C, p, s, h, dz);

@@ -57,7 +57,15 @@ struct AdvCoef {
     FT w3p[2][2];    // WENO{2} coeff_p(r)
     FT w3c[2];       // C★ = 2/3, 1/3         :78-79
     FT eps;          // ϵ = 1f-8 widened      :71
+    // UpwindBiased(order = 5, 3): uniform_reconstruction_coefficients(FT, Val(:left / :right), buffer) re-ordered to the UPWIND-ordered
+    // stencil q0 … (Left: ψ[i-B] …, Right: ψ[i+B-1] …; calc_reconstruction_stencil, reconstruction_coefficients.jl:87-89,122-152)
+    FT u5l[5], u5r[5];
+    FT u3l[3], u3r[3];
 };
+
+// advection scheme codes (oc_advection in include/oceananigans_b200.h)
+enum { ADV_CENTERED2 = 0, ADV_WENO5 = 1, ADV_CENTERED4 = 2, ADV_UPWIND3 = 3, ADV_UPWIND5 = 4, ADV_WENO3 = 5, ADV_UPWIND1 = 6, ADV_NONE = 7 };
+OC_HD constexpr bool adv_is_centered(int adv) { return adv == ADV_CENTERED2 || adv == ADV_CENTERED4; }
 
 template <class FT>
 OC_HD FT oc_abs(FT x) { return x < FT(0) ? -x : x; }

@@ -58,6 +58,17 @@ static AdvCoef<FT> make_coefficients() {
     C.w5c[0] = (FT)(3.0L / 10.0L); C.w5c[1] = (FT)(3.0L / 5.0L); C.w5c[2] = (FT)(1.0L / 10.0L);
     C.w3c[0] = (FT)(2.0L / 3.0L); C.w3c[1] = (FT)(1.0L / 3.0L);
     C.eps = (FT)1e-8f;
+    // UpwindBiased: coeff_left = stencil_coefficients(r = buffer-2), coeff_right = (r = buffer-1), order = 2 buffer - 1
+    // (reconstruction_coefficients.jl:88-89).  calc_reconstruction_stencil (:122-152) gives the idx-th stencil point the coefficient
+    // coeff[order-idx+1]: Left idx = 1 … order is ψ[i-B] … ψ[i+B-2], Right is ψ[i-B+1] … ψ[i+B-1].  Upwind-ordered (q0 = the point
+    // farthest upwind): Left q_n = ψ[i-B+n] -> coeff_left[order-1-n]; Right q_n = ψ[i+B-1-n] -> coeff_right[n].
+    {
+        FT l5[5], r5[5], l3[3], r3[3];
+        stencil_coefficients<FT>(1, 5, l5); stencil_coefficients<FT>(2, 5, r5);
+        stencil_coefficients<FT>(0, 3, l3); stencil_coefficients<FT>(1, 3, r3);
+        for (int n = 0; n < 5; ++n) { C.u5l[n] = l5[4 - n]; C.u5r[n] = r5[n]; }
+        for (int n = 0; n < 3; ++n) { C.u3l[n] = l3[2 - n]; C.u3r[n] = r3[n]; }
+    }
     return C;
 }
 
@@ -66,7 +77,8 @@ template <class FT>
 Model<FT>::Model(const oc_config& c) : cfg_(c) {
     if (c.abi_version != OC_ABI_VERSION) throw Error(OC_ERR_INVALID, "oc_config.abi_version mismatch");
     if (c.n_tracers < 0 || c.n_tracers > OC_MAX_TRACERS) throw Error(OC_ERR_INVALID, "n_tracers out of range");
-    if (c.advection != OC_CENTERED2 && c.advection != OC_WENO5) throw Error(OC_ERR_UNSUPPORTED, "advection scheme: only Centered(order=2) and WENO(order=5)");
+    if (c.advection < OC_CENTERED2 || c.advection > OC_ADVECTION_NONE)
+        throw Error(OC_ERR_UNSUPPORTED, "advection scheme: Centered(order=2|4), UpwindBiased(order=1|3|5), WENO(order=3|5) or nothing");
     if (c.timestepper != OC_RK3 && c.timestepper != OC_AB2) throw Error(OC_ERR_UNSUPPORTED, "timestepper: only RungeKutta3 and QuasiAdamsBashforth2");
     F_ = 3 + c.n_tracers;
     stretched_ = c.z_stretched != 0;
@@ -79,7 +91,9 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
             if (!((FT)c.z_faces[k + 1] > (FT)c.z_faces[k])) throw Error(OC_ERR_INVALID, "The elements of z must be increasing!");
         if (c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "distributed models on vertically stretched grids (DistributedFourierTridiagonalPoissonSolver: next)");
     }
-    int need = c.advection == OC_WENO5 ? 3 : 1;
+    // required_halo_size of the scheme (its buffer)
+    int need = (c.advection == OC_WENO5 || c.advection == OC_UPWIND5) ? 3
+             : (c.advection == OC_CENTERED4 || c.advection == OC_UPWIND3 || c.advection == OC_WENO3) ? 2 : 1;
     if (c.has_amd) need = std::max(need, 2);
     for (int d = 0; d < 3; ++d) {
         const int t = c.topology[d];
@@ -122,7 +136,9 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     if (field_elems_ >= ((size_t)1 << 31)) throw Error(OC_ERR_UNSUPPORTED, "field larger than 2^31 elements");
     origin_off_ = pad + (long long)g_.H[1] * g_.sy + (long long)g_.H[2] * g_.sz;
     xpad_ = pad;
-    march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]);
+    // the z-marching TMA kernel: no Flat dimension, and the two schemes of the BASELINE configurations; the other schemes of the
+    // family run in the general tile kernel (oc_tendency.h)
+    march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) && (c.advection == OC_CENTERED2 || c.advection == OC_WENO5);
     g_.dzc = g_.dzf = g_.rdzc = g_.rdzf = g_.rVc = g_.rVf = nullptr;
     C_ = make_coefficients<FT>();
     {   // the compile-time table of oc_march.h must be the very same numbers
@@ -794,14 +810,19 @@ void Model<FT>::launch_tendency(int fidx, TendencyArgs<FT>& a) {
     grid.x = (g_.N[0] + TX - 1) / TX;
     grid.y = (g_.N[1] + TY - 1) / TY;
     grid.z = (g_.N[2] + TZ - 1) / TZ;
-    if (cfg_.advection == OC_WENO5) {
-        TendencyKernel<FT, 1, KIND, TX, TY, TZ> k;
+    auto run = [&](auto k) {
         k.a = a;
         go(k, grid, k.SMEM, OC_TIMER_TENDENCY);
-    } else {
-        TendencyKernel<FT, 0, KIND, TX, TY, TZ> k;
-        k.a = a;
-        go(k, grid, k.SMEM, OC_TIMER_TENDENCY);
+    };
+    switch (cfg_.advection) {
+        case OC_WENO5: run(TendencyKernel<FT, ADV_WENO5, KIND, TX, TY, TZ>{}); break;
+        case OC_CENTERED4: run(TendencyKernel<FT, ADV_CENTERED4, KIND, TX, TY, TZ>{}); break;
+        case OC_UPWIND3: run(TendencyKernel<FT, ADV_UPWIND3, KIND, TX, TY, TZ>{}); break;
+        case OC_UPWIND5: run(TendencyKernel<FT, ADV_UPWIND5, KIND, TX, TY, TZ>{}); break;
+        case OC_WENO3: run(TendencyKernel<FT, ADV_WENO3, KIND, TX, TY, TZ>{}); break;
+        case OC_UPWIND1: run(TendencyKernel<FT, ADV_UPWIND1, KIND, TX, TY, TZ>{}); break;
+        case OC_ADVECTION_NONE: run(TendencyKernel<FT, ADV_NONE, KIND, TX, TY, TZ>{}); break;
+        default: run(TendencyKernel<FT, ADV_CENTERED2, KIND, TX, TY, TZ>{}); break;
     }
 }
 

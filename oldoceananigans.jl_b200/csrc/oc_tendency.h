@@ -134,15 +134,19 @@ struct TendencyKernel {
         // Centered: the area at the flux point (centered_advective_fluxes.jl:15-33); upwind schemes: the area of the advecting
         // velocity's own point, inside the interpolation (upwind_biased_advective_fluxes.jl:23-121) — these differ only
         // for the x / y fluxes of w on a stretched grid
-        FT A = g.area_at(d, COMP == 2 && ADV == 0, k);
+        FT A = g.area_at(d, COMP == 2 && adv_is_centered(ADV), k);
+        if (ADV == ADV_NONE) return FT(0);                                        // advection = nothing
+        constexpr bool CEN = adv_is_centered(ADV);
         if (KIND == KIND_C) {
             FT u = a.U[d][o];
             const FT* c = a.c + o;
-            if (ADV == 0) {
+            OrderWindow w = order_window(g.bounded[d] != 0, false, g.N[d]);
+            if (ADV == ADV_CENTERED2) {
                 return (A * u) * (FT(0.5) * c[-sd] + FT(0.5) * c[0]);              // centered_advective_fluxes.jl:31-33
+            } else if (CEN) {
+                return (A * u) * symmetric_any<ADV, FT>(a.C, c, sd, FT(1), id, w);
             } else {
-                OrderWindow w = order_window(g.bounded[d] != 0, false, g.N[d]);
-                FT cr = weno5_biased<FT>(a.C, c, sd, u > FT(0), id, w);            // upwind_biased_advective_fluxes.jl:99-121
+                FT cr = biased_any<ADV, FT>(a.C, c, sd, u > FT(0), id, w);         // upwind_biased_advective_fluxes.jl:99-121
                 return A * u * cr;
             }
         } else {
@@ -150,32 +154,40 @@ struct TendencyKernel {
             const FT* adv = a.U[d] + o;
             if (d == COMP) {
                 // centre-type: evaluate the face-type stencils at face id+1
-                if (ADV == 0) {
+                OrderWindow w = order_window(g.bounded[d] != 0, true, g.N[d]);
+                if (ADV == ADV_CENTERED2) {
                     FT ut = FT(0.5) * adv[0] + FT(0.5) * adv[sd];
                     FT pt = FT(0.5) * psi[0] + FT(0.5) * psi[sd];
                     return A * ut * pt;                                            // centered_advective_fluxes.jl:15,22,27
+                } else if (CEN) {
+                    FT ut = symmetric_any<ADV, FT>(a.C, adv + sd, sd, FT(1), id + 1, w);
+                    FT pt = symmetric_any<ADV, FT>(a.C, psi + sd, sd, FT(1), id + 1, w);
+                    return A * ut * pt;
                 } else {
-                    OrderWindow w = order_window(g.bounded[d] != 0, true, g.N[d]);
-                    FT ut = weno5_symmetric<FT>(a.C, adv + sd, sd, A, id + 1, w);
-                    FT pr = weno5_biased<FT>(a.C, psi + sd, sd, ut > FT(0), id + 1, w);
+                    FT ut = symmetric_any<ADV, FT>(a.C, adv + sd, sd, A, id + 1, w);
+                    FT pr = biased_any<ADV, FT>(a.C, psi + sd, sd, ut > FT(0), id + 1, w);
                     return ut * pr;                                                // upwind_biased_advective_fluxes.jl:23-29
                 }
             } else {
                 int cc = COMP < 0 ? 0 : COMP;
                 int sc = g.st(cc);
                 int ic = cc == 0 ? i : (cc == 1 ? j : k);
-                if (ADV == 0) {
+                OrderWindow wc = order_window(g.bounded[cc] != 0, false, g.N[cc]);
+                OrderWindow wd = order_window(g.bounded[d] != 0, false, g.N[d]);
+                if (ADV == ADV_CENTERED2) {
                     FT ut = g.flat[cc] ? adv[0] : (FT(0.5) * adv[-sc] + FT(0.5) * adv[0]);
                     FT pt = FT(0.5) * psi[-sd] + FT(0.5) * psi[0];
                     return A * ut * pt;                                            // :16-26
+                } else if (CEN) {
+                    FT ut = g.flat[cc] ? adv[0] : symmetric_any<ADV, FT>(a.C, adv, sc, FT(1), ic, wc);
+                    FT pt = symmetric_any<ADV, FT>(a.C, psi, sd, FT(1), id, wd);
+                    return A * ut * pt;
                 } else {
-                    OrderWindow wc = order_window(g.bounded[cc] != 0, false, g.N[cc]);
-                    OrderWindow wd = order_window(g.bounded[d] != 0, false, g.N[d]);
                     FT ut;
                     if (g.flat[cc]) ut = A * adv[0];
-                    else if (cc == 2 && g.stretched()) ut = weno5_symmetric_z<FT>(a.C, adv, sc, g.d[d == 0 ? 1 : 0], g.dzc + k, ic, wc);
-                    else ut = weno5_symmetric<FT>(a.C, adv, sc, A, ic, wc);
-                    FT pr = weno5_biased<FT>(a.C, psi, sd, ut > FT(0), id, wd);
+                    else if (cc == 2 && g.stretched()) ut = symmetric_any_z<ADV, FT>(a.C, adv, sc, g.d[d == 0 ? 1 : 0], g.dzc + k, ic, wc);
+                    else ut = symmetric_any<ADV, FT>(a.C, adv, sc, A, ic, wc);
+                    FT pr = biased_any<ADV, FT>(a.C, psi, sd, ut > FT(0), id, wd);
                     return ut * pr;                                                // :31-93
                 }
             }

@@ -86,6 +86,53 @@ class UpwindBiased1:
         self.kind = "upwind1"
 
 
+class UpwindBiased:
+    """UpwindBiased(order = 1, 3, 5): buffer N = (order+1)/2, advecting_velocity_scheme = Centered(order-1) (Centered(2) for
+    order 1), buffer_scheme = UpwindBiased(order-2)   upwind_biased_reconstruction.jl:57-86.
+    coeff_left / coeff_right = uniform_reconstruction_coefficients(FT, Val(:left / :right), buffer)
+    (reconstruction_coefficients.jl:87-89)."""
+
+    def __init__(self, FT=np.float64, order=3):
+        assert order in (1, 3, 5)
+        self.FT = np.dtype(FT).type
+        self.order = order
+        self.buffer = (order + 1) // 2
+        self.kind = "upwind"
+        B = self.buffer
+        if B > 1:
+            self.advecting_velocity_scheme = Centered(FT, order - 1)
+            self.buffer_scheme = UpwindBiased(FT, order - 2)
+            self.coeff_left = stencil_coefficients(self.FT, B - 2, order)
+            self.coeff_right = stencil_coefficients(self.FT, B - 1, order)
+        else:
+            self.advecting_velocity_scheme = Centered(FT, 2)
+            self.buffer_scheme = None
+            self.coeff_left = self.coeff_right = (self.FT(1),)
+
+
+class NoAdvection:
+    """advection = nothing: every advective flux is zero(grid) (momentum_advection_operators.jl:86-95, tracer_advection_operators.jl)"""
+
+    def __init__(self, FT=np.float64):
+        self.FT = np.dtype(FT).type
+        self.buffer = 1
+        self.kind = "none"
+
+
+def _upwind_value(sch, S, left):
+    """biased_interpolate for UpwindBiased{B}: S = (ψ[i-B], …, ψ[i+B-1]); calc_reconstruction_stencil
+    (reconstruction_coefficients.jl:122-152): the idx-th point of the left stencil is ψ[i+idx-B-1], of the right stencil
+    ψ[i+idx-B], each with coefficient coeff[order-idx+1]; summed left to right."""
+    B, order = sch.buffer, sch.order
+    L = R = None
+    for idx in range(1, order + 1):
+        tl = sch.coeff_left[order - idx] * S[idx - 1]
+        tr = sch.coeff_right[order - idx] * S[idx]
+        L = tl if L is None else L + tl
+        R = tr if R is None else R + tr
+    return np.where(left, L, R)
+
+
 class WENO:
     """WENO{N,FT,Float32}: order 5 (buffer 3) or 3 (buffer 2).  weno_reconstruction.jl:77-93"""
 
@@ -245,8 +292,8 @@ def _biased(ctx, scheme, q, d, left_q, center_type):
             return _centered_value(sch, [q(sh(oo, d, n)) for n in range(-B, B)])
         B = sch.buffer
         S = [q(sh(oo, d, n)) for n in range(-B, B)]
-        val = _weno_value(sch, S, left)
-        if g.bounded(d):
+        val = _upwind_value(sch, S, left) if sch.kind == "upwind" else _weno_value(sch, S, left)
+        if g.bounded(d) and sch.buffer_scheme is not None:
             R, N = B, g.N[d]
             if center_type:   # outside_biased_haloᶜ
                 lo, hi = max(R, R - 1), min(N + 1 - (R - 1), N + 1 - R)
@@ -282,8 +329,8 @@ def momentum_flux(ctx, scheme, U, comp, d, psi_f):
     in direction ``d`` by U[d].  Returns a quantity.  Flux location: centre-type in d if d == comp
     (ccc), otherwise face-type in both d and comp."""
     g, FT = ctx.g, ctx.FT
-    if g.flat(d):
-        return _zero_q(ctx)                                  # flat_advective_fluxes.jl:13-29
+    if g.flat(d) or scheme.kind == "none":
+        return _zero_q(ctx)                                  # flat_advective_fluxes.jl:13-29 ; advection = nothing
     adv = ctx.field(U[d])
     psi = ctx.field(psi_f)
     if scheme.kind == "centered":
@@ -323,7 +370,7 @@ def div_momentum(ctx, scheme, U, comp):
 def tracer_flux(ctx, scheme, U, c_f, d):
     """advective_tracer_flux_{x,y,z}"""
     g = ctx.g
-    if g.flat(d):
+    if g.flat(d) or scheme.kind == "none":
         return _zero_q(ctx)
     u = ctx.field(U[d])
     c = ctx.field(c_f)

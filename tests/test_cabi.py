@@ -47,7 +47,9 @@ def test_out_of_scope_configurations_are_errors():
     with pytest.raises(NotImplementedError):
         ob.WENO(order=7)
     with pytest.raises(NotImplementedError):
-        ob.Centered(order=4)
+        ob.Centered(order=6)
+    with pytest.raises(NotImplementedError):
+        ob.UpwindBiased(order=7)
     with pytest.raises(NotImplementedError):
         ob.RectilinearGrid(np.float64, size=(4, 4, 4), x=[0, 0.1, 0.3, 0.6, 1.0], y=(0, 1), z=(0, 1))      # stretched x: out of scope
     with pytest.raises(ValueError):

@@ -30,6 +30,12 @@ def test_cuda_matches_oracle_on_stretched_grids(ob, name, kw):
     ph.check_case(kw, library=None, steps=(1, 10))
 
 
+@pytest.mark.parametrize("name,kw", ph.SCHEME_CASES, ids=[c[0] for c in ph.SCHEME_CASES])
+def test_cuda_matches_oracle_for_the_other_advection_schemes(ob, name, kw):
+    """Centered(4), UpwindBiased(1, 3, 5), WENO(3), advection = nothing (test/test_time_stepping.jl:261-267)"""
+    ph.check_case(kw, library=None, steps=(1, 10))
+
+
 def test_stretched_poisson_all_topologies(ob):
     """solve!(ϕ, ::FourierTridiagonalPoissonSolver, b) with the faces / sizes of test/test_poisson_solvers_stretched_grids.jl:28-46"""
     import oracle

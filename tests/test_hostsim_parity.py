@@ -36,6 +36,12 @@ def test_hostsim_matches_oracle_on_stretched_grids(hostsim, name, kw):
     ph.check_case(kw, library=hostsim, steps=(1, 3))
 
 
+@pytest.mark.parametrize("name,kw", ph.SCHEME_CASES, ids=[c[0] for c in ph.SCHEME_CASES])
+def test_hostsim_matches_oracle_for_the_other_advection_schemes(hostsim, name, kw):
+    """Centered(4), UpwindBiased(1, 3, 5), WENO(3), advection = nothing (test/test_time_stepping.jl:261-267)"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))
+
+
 def test_hostsim_stretched_poisson_all_topologies(hostsim):
     """solve!(ϕ, ::FourierTridiagonalPoissonSolver, b): the sizes / faces of test/test_poisson_solvers_stretched_grids.jl:28-46"""
     import oceananigans_b200 as ob

@@ -41,6 +41,74 @@ def test_centered4_and_weno5_coefficients():
     assert w.advecting_velocity_scheme.buffer == 2
 
 
+def test_upwind_biased_stencils_and_polynomial_reproduction():
+    # calc_reconstruction_stencil docstrings (src/Advection/reconstruction_coefficients.jl:103-120):
+    #   (Float64, 1, :left) = 1.0 ψ[i-1];  (Float32, 1, :right) = 1.0 ψ[i];
+    #   (Float32, 3, :left) = 0.0333333 ψ[i-3] - 0.21666667 ψ[i-2] + 0.78333336 ψ[i-1] + 0.45 ψ[i] - 0.05 ψ[i+1]
+    u1 = adv.UpwindBiased(np.float64, 1)
+    S = [np.array([3.0]), np.array([7.0])]                       # ψ[i-1], ψ[i]
+    assert adv._upwind_value(u1, S, np.array([True]))[0] == 3.0 and adv._upwind_value(u1, S, np.array([False]))[0] == 7.0
+    u5 = adv.UpwindBiased(np.float32, 5)
+    expect = np.array([0.0333333, -0.21666667, 0.78333336, 0.45, -0.05], dtype=np.float32)    # ψ[i-3] … ψ[i+1]
+    for n in range(5):
+        S = [np.zeros(1, np.float32) for _ in range(6)]          # ψ[i-3] … ψ[i+2]
+        S[n] = np.ones(1, np.float32)
+        assert adv._upwind_value(u5, S, np.array([True]))[0] == expect[n]
+    # the right-biased stencil is the mirror image (ψ[i+2] … ψ[i-2]) up to the rounding of "last = 1 - sum(others)"
+    for n in range(5):
+        S = [np.zeros(1, np.float32) for _ in range(6)]
+        S[5 - n] = np.ones(1, np.float32)
+        assert abs(adv._upwind_value(u5, S, np.array([False]))[0] - expect[n]) < 1e-7
+    # order of accuracy: cell averages of a polynomial of degree order-1 give its exact face value
+    for order in (3, 5):
+        sch = adv.UpwindBiased(np.float64, order)
+        B = sch.buffer
+        for deg in range(order):
+            avg = lambda m: ((m + 1.0) ** (deg + 1) - float(m) ** (deg + 1)) / (deg + 1)      # cell [m, m+1]
+            S = [np.array([avg(m)]) for m in range(-B, B)]       # ψ[i-B] … ψ[i+B-1]; the face is x = 0
+            exact = 1.0 if deg == 0 else 0.0
+            for left in (True, False):
+                assert abs(adv._upwind_value(sch, S, np.array([left]))[0] - exact) < 1e-12, (order, deg, left)
+    c4 = adv.Centered(np.float64, 4)
+    for deg in range(4):
+        avg = lambda m: ((m + 1.0) ** (deg + 1) - float(m) ** (deg + 1)) / (deg + 1)
+        S = [np.array([avg(m)]) for m in range(-2, 2)]
+        assert abs(adv._centered_value(c4, S)[0] - (1.0 if deg == 0 else 0.0)) < 1e-12
+    # buffer / fallback chains (upwind_biased_reconstruction.jl:57-74, centered_reconstruction.jl:24-45)
+    assert u5.buffer == 3 and u5.buffer_scheme.buffer == 2 and u5.buffer_scheme.buffer_scheme.buffer == 1
+    assert u5.advecting_velocity_scheme.buffer == 2 and u5.buffer_scheme.advecting_velocity_scheme.buffer == 1
+    assert c4.buffer_scheme.buffer == 1
+
+
+@pytest.mark.parametrize("name", ["upwind1", "centered", "upwind3", "centered4", "upwind5", "weno", "none"])
+def test_time_stepping_works_with_advection_scheme(name):
+    # test/test_time_stepping.jl:52-58,261-267 (+ incompressibility, which the reference checks separately)
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import parity_harness as ph
+    sch = ph.oracle_scheme(name, np.float64)
+    g = Grid(np.float64, size=(3, 3, 3), halo=(3, 3, 3), extent=(1, 2, 3), topology=("P", "P", "B"))
+    m = OracleModel(g, advection=sch)
+    rng = np.random.default_rng(0)
+    m.set(u=rng.uniform(-1, 1, (3, 3, 3)), v=rng.uniform(-1, 1, (3, 3, 3)), w=rng.uniform(-1, 1, (3, 3, 4)))
+    m.time_step(0.01)
+    assert np.isfinite(m.u.interior).all() and np.abs(m.divergence()).max() < 1e-12
+
+
+def test_halo_inflation_for_advection_schemes():
+    # test/test_nonhydrostatic_models.jl:44-67: halos >= 2 for Centered(4) / UpwindBiased(3), >= 3 for WENO() / UpwindBiased(5)
+    import oceananigans_b200 as ob
+    for sch, need in ((adv.Centered(np.float64, 4), 2), (adv.UpwindBiased(np.float64, 3), 2), (adv.WENO(np.float64, 5), 3),
+                      (adv.UpwindBiased(np.float64, 5), 3)):
+        g = Grid(np.float64, size=(4, 4, 4), halo=(1, 1, 1), extent=(1, 2, 3), topology=("P", "P", "B"))
+        assert OracleModel(g, advection=sch).grid.H == (need,) * 3
+        g = Grid(np.float64, size=(4, 4, 4), halo=(1, 3, 4), extent=(1, 2, 3), topology=("P", "P", "B"))
+        assert OracleModel(g, advection=sch).grid.H == (need, 3, 4)
+    assert ob.Centered(order=4).buffer == 2 and ob.UpwindBiased(order=3).buffer == 2 and ob.UpwindBiased(order=5).buffer == 3
+    with pytest.raises(ValueError):
+        ob.UpwindBiased(order=4)
+
+
 def test_weno_reproduces_polynomials():
     # WENO-5 is exact (to round-off of the non-linear weights) for smooth data: for a quadratic all candidate
     # stencils give the exact face value, so the result is exact regardless of the weights.
