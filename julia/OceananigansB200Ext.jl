@@ -123,9 +123,12 @@ function config(model::NonhydrostaticModel)
     end
     cfg.extent = Float64.((grid.Lx, grid.Ly, grid.Lz))
     adv = model.advection.momentum
-    cfg.advection = adv isa Centered && Oceananigans.Advection.required_halo_size_x(adv) == 1 ? 0 :
-                    adv isa WENO && Oceananigans.Advection.required_halo_size_x(adv) == 3 ? 1 :
-                    throw(ArgumentError("B200: advection must be Centered(order=2) or WENO(order=5)"))
+    hs = adv === nothing ? 0 : Oceananigans.Advection.required_halo_size_x(adv)
+    cfg.advection = adv === nothing ? 7 :
+                    adv isa Centered && hs == 1 ? 0 : adv isa Centered && hs == 2 ? 2 :
+                    adv isa WENO && hs == 3 ? 1 : adv isa WENO && hs == 2 ? 5 :
+                    adv isa UpwindBiased && hs == 1 ? 6 : adv isa UpwindBiased && hs == 2 ? 3 : adv isa UpwindBiased && hs == 3 ? 4 :
+                    throw(ArgumentError("B200: advection must be Centered(order<=4), UpwindBiased(order<=5), WENO(order<=5) or nothing"))
     cfg.timestepper = model.timestepper isa RungeKutta3TimeStepper ? 0 :
                       model.timestepper isa QuasiAdamsBashforth2TimeStepper ? 1 : throw(ArgumentError("B200: unsupported time stepper"))
     model.timestepper isa QuasiAdamsBashforth2TimeStepper && (cfg.ab2_chi = model.timestepper.χ)

@@ -356,9 +356,23 @@ OC_HD FT rd(const A& a, int ii, int jj, int lev, int n) {
     return a(ii, jj, lev + n);
 }
 
-// _biased_interpolate (WENO(order=5) chain) at face (ii,jj,lev) along DIR; f = global face index along DIR.
+// UpwindBiased(order=5) / (order=3) value from the upwind-ordered stencil: the exact rationals (1/30, -13/60, 47/60, 9/20, -1/20) and
+// (-1/6, 5/6, 1/3) of uniform_reconstruction_coefficients (reconstruction_coefficients.jl:87-89) with the common denominator pulled
+// out — integer constants, one multiplication by 1/60 (1/6)
+template <class FT>
+OC_HD FT upwind5_value_c(FT q0, FT q1, FT q2, FT q3, FT q4) {
+    return (FT(1) / FT(60)) * fmaT(FT(2), q0, fmaT(FT(-13), q1, fmaT(FT(47), q2, fmaT(FT(27), q3, FT(-3) * q4))));
+}
+template <class FT>
+OC_HD FT upwind3_value_c(FT q0, FT q1, FT q2) {
+    return (FT(1) / FT(6)) * fmaT(FT(-1), q0, fmaT(FT(5), q1, FT(2) * q2));
+}
+
+// _biased_interpolate at face (ii,jj,lev) along DIR; f = global face index along DIR.  LIN = false: the WENO(order=5) chain
+// (WENO5 -> WENO3 -> UpwindBiased1); LIN = true: the UpwindBiased(order=5) chain (UB5 -> UB3 -> UB1) — the same stencils and order
+// windows (topologically_conditional_interpolation.jl:46-52), linear weights.
 // WIN = false: the dimension is not Bounded — always the high-order branch, no window logic.
-template <int DIR, bool WIN, class FT, class A>
+template <int DIR, bool WIN, bool LIN, class FT, class A>
 OC_HD FT t_weno5_biased(const A& a, int ii, int jj, int lev, bool left, int f, const OrderWindow& w) {
     if (!WIN || (f >= w.lo_hi && f <= w.hi_hi)) {
         if (DIR < 2) {
@@ -367,14 +381,17 @@ OC_HD FT t_weno5_biased(const A& a, int ii, int jj, int lev, bool left, int f, c
             const FT* c = a.ptr(ii, jj, lev);
             const FT* ctr = left ? c - st : c;
             const int sg = left ? st : -st;
+            if (LIN) return upwind5_value_c<FT>(ctr[-2 * sg], ctr[-sg], ctr[0], ctr[sg], ctr[2 * sg]);
             return weno5_value_c<FT>(ctr[-2 * sg], ctr[-sg], ctr[0], ctr[sg], ctr[2 * sg]);
         }
         FT m3 = rd<DIR, FT>(a, ii, jj, lev, -3), m2 = rd<DIR, FT>(a, ii, jj, lev, -2), m1 = rd<DIR, FT>(a, ii, jj, lev, -1);
         FT p0 = rd<DIR, FT>(a, ii, jj, lev, 0), p1 = rd<DIR, FT>(a, ii, jj, lev, 1), p2 = rd<DIR, FT>(a, ii, jj, lev, 2);
+        if (LIN) return upwind5_value_c<FT>(left ? m3 : p2, left ? m2 : p1, left ? m1 : p0, left ? p0 : m1, left ? p1 : m2);
         return weno5_value_c<FT>(left ? m3 : p2, left ? m2 : p1, left ? m1 : p0, left ? p0 : m1, left ? p1 : m2);
     } else if (f >= w.lo_mid && f <= w.hi_mid) {
         FT m2 = rd<DIR, FT>(a, ii, jj, lev, -2), m1 = rd<DIR, FT>(a, ii, jj, lev, -1);
         FT p0 = rd<DIR, FT>(a, ii, jj, lev, 0), p1 = rd<DIR, FT>(a, ii, jj, lev, 1);
+        if (LIN) return upwind3_value_c<FT>(left ? m2 : p1, left ? m1 : p0, left ? p0 : m1);
         return weno3_value_c<FT>(left ? m2 : p1, left ? m1 : p0, left ? p0 : m1);
     }
     return left ? rd<DIR, FT>(a, ii, jj, lev, -1) : rd<DIR, FT>(a, ii, jj, lev, 0);
@@ -410,6 +427,8 @@ OC_HD FT t_weno5_symmetric_z(const A& a, int ii, int jj, int lev, FT h, const FT
 // ---------------------------------------------------------------------------------------------------------
 // the kernel.  BND = bit mask of possibly-Bounded dimensions: 0 (none: all wall logic compiled out), 4 (z only), 7 (generic).
 //              CLO = 0: constant ν, κ (possibly 0: no closure); 1: generic (AMD eddy fields, closure tuples).
+//              ADV = ADV_CENTERED2, ADV_WENO5 (the BASELINE schemes) or ADV_UPWIND5 (the WENO-5 stencils with linear weights: the same
+//              data movement with a tenth of the FP64 work — the measurement that separates the HBM bound from the FP64 bound).
 // One thread per y-face: THREADS = TX·(TY+1); the x-faces and z-faces map onto the same threads so that every
 // warp evaluates at most three fluxes per level (no tail warps in front of the barrier).
 // ---------------------------------------------------------------------------------------------------------
@@ -620,7 +639,7 @@ struct MarchKernel {
             } else {
                 OrderWindow w;
                 if (WINV<D>) w = order_window(g.bounded[D] != 0, false, g.N[D]);
-                FT cr = t_weno5_biased<D, WINV<D>, FT>(c, ii, jj, lev, u > FT(0), id, w);
+                FT cr = t_weno5_biased<D, WINV<D>, ADV == ADV_UPWIND5, FT>(c, ii, jj, lev, u > FT(0), id, w);
                 return A * u * cr;
             }
         } else {
@@ -636,7 +655,7 @@ struct MarchKernel {
                     if (WINV<D>) w = order_window(g.bounded[D] != 0, true, g.N[D]);
                     const int i1 = ii + (D == 0), j1 = jj + (D == 1), l1 = lev + (D == 2);
                     FT ut = t_weno5_symmetric<D, WINV<D>, FT>(psi, i1, j1, l1, A, id + 1, w);
-                    FT pr = t_weno5_biased<D, WINV<D>, FT>(psi, i1, j1, l1, ut > FT(0), id + 1, w);
+                    FT pr = t_weno5_biased<D, WINV<D>, ADV == ADV_UPWIND5, FT>(psi, i1, j1, l1, ut > FT(0), id + 1, w);
                     return ut * pr;
                 }
             } else {
@@ -656,7 +675,7 @@ struct MarchKernel {
                         else ut = t_weno5_symmetric_z<WINV<CC>, FT>(r2(smem), ii, jj, lev, h, g.dzc + lev, ic, wc);
                     } else if (D == SP::F1) ut = t_weno5_symmetric<CC, WINV<CC>, FT>(r1(smem), ii, jj, lev, A, ic, wc);
                     else ut = t_weno5_symmetric<CC, WINV<CC>, FT>(r2(smem), ii, jj, lev, A, ic, wc);
-                    FT pr = t_weno5_biased<D, WINV<D>, FT>(psi, ii, jj, lev, ut > FT(0), id, wd);
+                    FT pr = t_weno5_biased<D, WINV<D>, ADV == ADV_UPWIND5, FT>(psi, ii, jj, lev, ut > FT(0), id, wd);
                     return ut * pr;
                 }
             }

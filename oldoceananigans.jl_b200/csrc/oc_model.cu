@@ -138,7 +138,8 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     xpad_ = pad;
     // the z-marching TMA kernel: no Flat dimension, and the two schemes of the BASELINE configurations; the other schemes of the
     // family run in the general tile kernel (oc_tendency.h)
-    march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) && (c.advection == OC_CENTERED2 || c.advection == OC_WENO5);
+    march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) &&
+                (c.advection == OC_CENTERED2 || c.advection == OC_WENO5 || c.advection == OC_UPWIND5);
     g_.dzc = g_.dzf = g_.rdzc = g_.rdzf = g_.rVc = g_.rVf = nullptr;
     C_ = make_coefficients<FT>();
     {   // the compile-time table of oc_march.h must be the very same numbers
@@ -934,8 +935,9 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
         else if (!gen) run(MarchKernel<FT, ADV, KIND, 7, 0>{});
         else run(MarchKernel<FT, ADV, KIND, 7, 1>{});
     };
-    if (cfg_.advection == OC_WENO5) pick(std::integral_constant<int, 1>{});
-    else pick(std::integral_constant<int, 0>{});
+    if (cfg_.advection == OC_WENO5) pick(std::integral_constant<int, ADV_WENO5>{});
+    else if (cfg_.advection == OC_UPWIND5) pick(std::integral_constant<int, ADV_UPWIND5>{});
+    else pick(std::integral_constant<int, ADV_CENTERED2>{});
 }
 
 template <class FT>
