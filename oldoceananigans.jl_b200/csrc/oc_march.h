@@ -136,17 +136,17 @@ struct Ring {
 struct MarchSlots {
     int sk[4];    // ring slot of the current level, per ring
 };
-template <class FT>
+template <class FT, int CPT>
 struct MarchStateT {
     MarchSlots sl;
-    FT fz_prev;   // this thread's upper z-face flux of the previous level (= lower flux of the current one)
-    FT dfz;       // δz of the z-face fluxes of the level whose divergence is formed next
+    FT fz_prev[CPT];   // this thread's upper z-face flux of the previous level (= lower flux of the current one), per owned cell
+    FT dfz[CPT];       // δz of the z-face fluxes of the level whose divergence is formed next
     // global-memory operands of the divergence phase, loaded one flux evaluation (~400 instructions) ahead of their use:
     // measured (ncu source page, C4): their consumers carried most of the long-scoreboard stalls
-    FT gm;        // G⁻ of the cell being finished
-    FT ph0, ph1;  // pHY′ at the cell and at its lower x / y neighbour (u and v kernels)
-    int o;        // global offset of this thread's cell at the level being finished (advanced by one plane per iteration)
-    int cell;     // this thread owns a cell of the grid (row < TY, inside the domain): loop invariant
+    FT gm[CPT];        // G⁻ of the cell being finished
+    FT ph0[CPT], ph1[CPT];   // pHY′ at the cell and at its lower x / y neighbour (u and v kernels)
+    int o;        // global offset of this thread's FIRST cell at the level being finished (advanced by one plane per iteration)
+    int cell;     // bit h: this thread owns its h-th cell (thread row < TR, inside the domain): loop invariant
 };
 
 // Loads for iteration it + PF are issued in step<1>(it), after every thread has finished iteration it-1; they overwrite the
@@ -435,9 +435,17 @@ OC_HD FT t_weno5_symmetric_z(const A& a, int ii, int jj, int lev, FT h, const FT
 template <class FT, int ADV, int KIND, int BND, int CLO, int TY_ = 8, int STR = 0>
 struct MarchKernel {
     static constexpr int TX = 32, TY = TY_;
-    static constexpr int THREADS = TX * (TY + 1);
-    // 32×8 tiles: three 288-thread CTAs per SM (the w kernel needs PF = 1 for that: with PF = 2 its three 4-to-6-level rings
-    // fit only two, measured 3.5 vs 3.0 ms).  32×16 tiles: two 544-thread CTAs per SM, PF = 1, three flux stages.
+    // CPT cells per thread along y: thread row r (0 … TR-1) owns the cells of tile rows r + h·TR, h = 0 … CPT-1.  The per-level fixed
+    // costs of a thread (barrier wait / arrive and polling, ring-slot arithmetic, constant reloads, loop control) are paid once per
+    // CPT cells — the kernel is bound by instruction issue, and ≈ 40 % of its non-FP64 instructions are such per-level costs.
+    static constexpr int TR = 8;
+    static constexpr int CPT = TY_ / TR;
+    static_assert(CPT * TR == TY_ && (CPT == 1 || CPT == 2), "tile heights 8 (one cell per thread) and 16 (two)");
+    static constexpr int THREADS = TX * (TR + 1);
+    // 32×8 tiles, one cell per thread: three 288-thread CTAs per SM (the w kernel needs PF = 1 for that: with PF = 2 its three
+    // 4-to-6-level rings fit only two, measured 3.5 vs 3.0 ms).  32×16 tiles, two cells per thread: two 288-thread CTAs per SM (1024
+    // instead of 768 cells in flight per SM), PF = 1, three flux stages (≈ 100 KB of shared memory per CTA; the w kernel's deeper rings
+    // would leave room for one CTA only, so it stays on 32×8 tiles).
     static constexpr int MIN_BLOCKS = TY_ == 8 ? 3 : 2;
     static constexpr int PFK = TY_ == 8 ? (KIND == KIND_W ? 1 : 2) : 1;
     static constexpr int NSYNC = TY_ == 8 ? 4 : 3;
@@ -519,15 +527,17 @@ struct MarchKernel {
             mbar_fence_init();
         }
     }
-    typedef MarchStateT<FT> State;
+    typedef MarchStateT<FT, CPT> State;
     OC_DEV void begin1(const Block& b, int tid, char* smem, State& stt) const {
         MarchSlots& st = stt.sl;
-        stt.fz_prev = FT(0); stt.dfz = FT(0);
-        stt.gm = FT(0); stt.ph0 = FT(0); stt.ph1 = FT(0);
         {
             const int lane_ = tid & (TX - 1), row_ = tid / TX;
             const int ci = b.x * TX + lane_, cj = b.y * TY + row_;
-            stt.cell = (row_ < TY && ci < a.g.N[0] && cj < a.g.N[1]) ? 1 : 0;
+            stt.cell = 0;
+            for (int h = 0; h < CPT; ++h) {
+                stt.fz_prev[h] = FT(0); stt.dfz[h] = FT(0); stt.gm[h] = FT(0); stt.ph0[h] = FT(0); stt.ph1[h] = FT(0);
+                if (row_ < TR && ci < a.g.N[0] && cj + h * TR < a.g.N[1]) stt.cell |= 1 << h;
+            }
             stt.o = a.g.idx(ci, cj, k_begin(b) - 2);        // iteration it finishes level k_begin - 2 + it
         }
         {   // ring slots of the first level (kf = k_begin - 1)
@@ -738,15 +748,19 @@ struct MarchKernel {
         const Ctx cx{smem, k, stt.sl};
         constexpr int shx = COMP == 0 ? -1 : 0, shy = COMP == 1 ? -1 : 0, shz = COMP == 2 ? -1 : 0;
         uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-        const int lane = tid & (TX - 1), row = tid / TX;     // row = 0 … TY
+        const int lane = tid & (TX - 1), row = tid / TX;     // row = 0 … TR
         if (PHASE == 0) {
-            if (it >= 2 && stt.cell) {
-                // operands of step<1>(it), which finishes level k-1 for cell (lane, row) — also in the last iteration (it == nit)
-                const int op = stt.o;
-                if (a.mode == STEP_RK3 || (a.mode == STEP_AB2 && !a.ab2_euler)) stt.gm = a.Gm[op];
-                if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) {
-                    stt.ph0 = a.pHY[op];
-                    stt.ph1 = a.pHY[op - (KIND == KIND_U ? 1 : g.sy)];
+            if (it >= 2) {
+                // operands of step<1>(it), which finishes level k-1 for this thread's cells — also in the last iteration (it == nit)
+#pragma unroll
+                for (int h = 0; h < CPT; ++h) {
+                    if (!((stt.cell >> h) & 1)) continue;
+                    const int op = stt.o + h * TR * g.sy;
+                    if (a.mode == STEP_RK3 || (a.mode == STEP_AB2 && !a.ab2_euler)) stt.gm[h] = a.Gm[op];
+                    if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) {
+                        stt.ph0[h] = a.pHY[op];
+                        stt.ph1[h] = a.pHY[op - (KIND == KIND_U ? 1 : g.sy)];
+                    }
                 }
             }
             if (it >= nit) return;
@@ -754,16 +768,30 @@ struct MarchKernel {
             if (it == 0) return;
             FT* fx = reinterpret_cast<FT*>(smem + OFF_FX) + (it % NSYNC) * NFXP;
             FT* fy = reinterpret_cast<FT*>(smem + OFF_FY) + (it % NSYNC) * NFYP;
-            {   // y-face (lane, row).  CLO == 0: every operand is in shared memory, so out-of-range faces of partial
-                // tiles are evaluated too (on zero-filled / neighbouring data) and discarded — no divergent branch
-                const bool ok = i0 + lane < g.N[0] && j0 + row <= g.N[1];
+            // y-faces: thread row r takes the face rows r + h·(TR+1) ≤ TY.  CLO == 0: every operand is in shared memory, so
+            // out-of-range faces of partial tiles are evaluated too (on zero-filled / neighbouring data) and discarded — no
+            // divergent branch
+#pragma unroll
+            for (int h = 0; h < CPT; ++h) {
+                const int fr = row + h * (TR + 1);
+                if (h > 0 && fr > TY) continue;
+                const bool ok = i0 + lane < g.N[0] && j0 + fr <= g.N[1];
                 FT F = FT(0);
-                if (CLO == 0 || ok) F = total_flux<1>(cx, lane, row + shy, i0 + lane, j0 + row + shy, k);
-                fy[row * TX + lane] = (CLO == 0 || ok) ? F : FT(0);     // faces outside the grid are never consumed
+                if (CLO == 0 || ok) F = total_flux<1>(cx, lane, fr + shy, i0 + lane, j0 + fr + shy, k);
+                fy[fr * TX + lane] = (CLO == 0 || ok) ? F : FT(0);      // faces outside the grid are never consumed
             }
-            // x-faces: rows 0 … TY-1 take faces s = 0 … TX-1; the last warp takes the TY faces s = TX
-            const int s = row < TY ? lane : TX, jj = row < TY ? row : lane;
-            if (row < TY || lane < TY) {
+            // x-faces: thread rows 0 … TR-1 take the faces s = 0 … TX-1 of their tile rows; the last warp takes the TY faces s = TX
+            if (row < TR) {
+#pragma unroll
+                for (int h = 0; h < CPT; ++h) {
+                    const int s = lane, jj = row + h * TR;
+                    const bool ok = j0 + jj < g.N[1] && i0 + s <= g.N[0];
+                    FT F = FT(0);
+                    if (CLO == 0 || ok) F = total_flux<0>(cx, s + shx, jj, i0 + s + shx, j0 + jj, k);
+                    fx[jj * (TX + 1) + s] = (CLO == 0 || ok) ? F : FT(0);
+                }
+            } else if (lane < TY) {
+                const int s = TX, jj = lane;
                 const bool ok = j0 + jj < g.N[1] && i0 + s <= g.N[0];
                 FT F = FT(0);
                 if (CLO == 0 || ok) F = total_flux<0>(cx, s + shx, jj, i0 + s + shx, j0 + jj, k);
@@ -771,20 +799,24 @@ struct MarchKernel {
             }
         } else if (PHASE == 2) {
             if (it >= nit) return;
-            if (row < TY) {   // upper z-face of cell (lane, row)
-                const bool ok = i0 + lane < g.N[0] && j0 + row < g.N[1] && k + 1 <= g.N[2];
-                FT F = FT(0);
-                if (CLO == 0 || ok) F = total_flux<2>(cx, lane, row, i0 + lane, j0 + row, k + 1 + shz);
-                F = (CLO == 0 || ok) ? F : FT(0);
-                stt.dfz = F - stt.fz_prev;
-                stt.fz_prev = F;
+            if (row < TR) {   // upper z-faces of this thread's cells
+#pragma unroll
+                for (int h = 0; h < CPT; ++h) {
+                    const int jj = row + h * TR;
+                    const bool ok = i0 + lane < g.N[0] && j0 + jj < g.N[1] && k + 1 <= g.N[2];
+                    FT F = FT(0);
+                    if (CLO == 0 || ok) F = total_flux<2>(cx, lane, jj, i0 + lane, j0 + jj, k + 1 + shz);
+                    F = (CLO == 0 || ok) ? F : FT(0);
+                    stt.dfz[h] = F - stt.fz_prev[h];
+                    stt.fz_prev[h] = F;
+                }
             }
             // advance the ring slots to the next level
             stt.sl.sk[0] = G0::next_slot(stt.sl.sk[0]); stt.sl.sk[1] = G1::next_slot(stt.sl.sk[1]);
             stt.sl.sk[2] = G2::next_slot(stt.sl.sk[2]); stt.sl.sk[3] = G3::next_slot(stt.sl.sk[3]);
         } else {
-            const int o_cell = stt.o;
-            stt.o = o_cell + g.sz;
+            const int o_first = stt.o;
+            stt.o = o_first + g.sz;
             if (tid == 0) {
                 const int lit = it + SP::PF;
                 if (lit < nit) {
@@ -797,63 +829,67 @@ struct MarchKernel {
             const int kc = k - 1;                            // the level being finished
             const FT* fx = reinterpret_cast<const FT*>(smem + OFF_FX) + ((it - 1) % NSYNC) * NFXP;
             const FT* fy = reinterpret_cast<const FT*>(smem + OFF_FY) + ((it - 1) % NSYNC) * NFYP;
-            const int ii = lane, jj = row;
-            const int i = i0 + ii, j = j0 + jj;
-            const int o = o_cell;
-            const FT u0 = r0(cx)(ii, jj, kc);
-            if (WIN && COMP >= 0) {
-                // exclude_periphery: the wall face of a wall-normal velocity is not stepped (kernel_launching.jl:145-146)
-                const int ic = COMP == 0 ? i : (COMP == 1 ? j : kc);
-                if (g.bounded[COMP < 0 ? 0 : COMP] && ic == 0 && g.N[COMP < 0 ? 0 : COMP] > 1) {
-                    if (a.mode != STEP_NONE) a.Unew[o] = u0;
-                    return;
-                }
-            }
-            const FT dFx = fx[jj * (TX + 1) + ii + 1] - fx[jj * (TX + 1) + ii];
-            const FT dFy = fy[(jj + 1) * TX + ii] - fy[jj * TX + ii];
-            const FT dFz = stt.dfz;
-            FT G = -(m_rV(COMP == 2, kc) * (dFx + dFy + dFz));
-            if ((KIND == KIND_U || KIND == KIND_V) && a.has_coriolis) {
-                // FPlane (f_plane.jl:50-52); the other horizontal component is ring 1
-                G1 q = r1(cx);
-                FT num, cnt = FT(1);
-                if (KIND == KIND_U) {
-                    num = FT(0.25) * ((q(ii - 1, jj, kc) + q(ii, jj, kc)) + (q(ii - 1, jj + 1, kc) + q(ii, jj + 1, kc)));
-                    if (WIN) {
-                        int ax0 = !(g.bounded[0] && (i - 1 < 0)), ax1 = 1;
-                        int ay0 = !(g.bounded[1] && (j < 1)), ay1 = !(g.bounded[1] && (j + 1 > g.N[1] - 1));
-                        cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
+#pragma unroll
+            for (int h = 0; h < CPT; ++h) {
+                if (!((stt.cell >> h) & 1)) continue;
+                const int ii = lane, jj = row + h * TR;
+                const int i = i0 + ii, j = j0 + jj;
+                const int o = o_first + h * TR * g.sy;
+                const FT u0 = r0(cx)(ii, jj, kc);
+                if (WIN && COMP >= 0) {
+                    // exclude_periphery: the wall face of a wall-normal velocity is not stepped (kernel_launching.jl:145-146)
+                    const int ic = COMP == 0 ? i : (COMP == 1 ? j : kc);
+                    if (g.bounded[COMP < 0 ? 0 : COMP] && ic == 0 && g.N[COMP < 0 ? 0 : COMP] > 1) {
+                        if (a.mode != STEP_NONE) a.Unew[o] = u0;
+                        continue;
                     }
-                    FT val = cnt == FT(0) ? FT(0) : num / cnt;
-                    G = G - (-a.f * val);
-                } else {
-                    num = FT(0.25) * ((q(ii, jj - 1, kc) + q(ii + 1, jj - 1, kc)) + (q(ii, jj, kc) + q(ii + 1, jj, kc)));
-                    if (WIN) {
-                        int ax0 = !(g.bounded[0] && (i < 1)), ax1 = !(g.bounded[0] && (i + 1 > g.N[0] - 1));
-                        int ay0 = !(g.bounded[1] && (j - 1 < 0)), ay1 = 1;
-                        cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
+                }
+                const FT dFx = fx[jj * (TX + 1) + ii + 1] - fx[jj * (TX + 1) + ii];
+                const FT dFy = fy[(jj + 1) * TX + ii] - fy[jj * TX + ii];
+                const FT dFz = stt.dfz[h];
+                FT G = -(m_rV(COMP == 2, kc) * (dFx + dFy + dFz));
+                if ((KIND == KIND_U || KIND == KIND_V) && a.has_coriolis) {
+                    // FPlane (f_plane.jl:50-52); the other horizontal component is ring 1
+                    G1 q = r1(cx);
+                    FT num, cnt = FT(1);
+                    if (KIND == KIND_U) {
+                        num = FT(0.25) * ((q(ii - 1, jj, kc) + q(ii, jj, kc)) + (q(ii - 1, jj + 1, kc) + q(ii, jj + 1, kc)));
+                        if (WIN) {
+                            int ax0 = !(g.bounded[0] && (i - 1 < 0)), ax1 = 1;
+                            int ay0 = !(g.bounded[1] && (j < 1)), ay1 = !(g.bounded[1] && (j + 1 > g.N[1] - 1));
+                            cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
+                        }
+                        FT val = cnt == FT(0) ? FT(0) : num / cnt;
+                        G = G - (-a.f * val);
+                    } else {
+                        num = FT(0.25) * ((q(ii, jj - 1, kc) + q(ii + 1, jj - 1, kc)) + (q(ii, jj, kc) + q(ii + 1, jj, kc)));
+                        if (WIN) {
+                            int ax0 = !(g.bounded[0] && (i < 1)), ax1 = !(g.bounded[0] && (i + 1 > g.N[0] - 1));
+                            int ay0 = !(g.bounded[1] && (j - 1 < 0)), ay1 = 1;
+                            cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
+                        }
+                        FT val = cnt == FT(0) ? FT(0) : num / cnt;
+                        G = G - (a.f * val);
                     }
-                    FT val = cnt == FT(0) ? FT(0) : num / cnt;
-                    G = G - (a.f * val);
                 }
-            }
-            if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) G = G - (stt.ph0 - stt.ph1) * g.rd[KIND == KIND_U ? 0 : 1];
-            if (WIN && a.add_flux_bcs) {
-                const int ijk[3] = {i, j, kc};
-                for (int d = 0; d < 3; ++d) {
-                    const FT Ad = m_area(d, COMP == 2, kc), Vd = m_vol(COMP == 2, kc);
-                    if (a.fbc.on[2 * d] && ijk[d] == 0) G = G + a.fbc.val[2 * d] * Ad / Vd;
-                    if (a.fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) G = G - a.fbc.val[2 * d + 1] * Ad / Vd;
+                if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) G = G - (stt.ph0[h] - stt.ph1[h]) * g.rd[KIND == KIND_U ? 0 : 1];
+                if (WIN && a.add_flux_bcs) {
+                    const int ijk[3] = {i, j, kc};
+                    for (int d = 0; d < 3; ++d) {
+                        const FT Ad = m_area(d, COMP == 2, kc), Vd = m_vol(COMP == 2, kc);
+                        if (a.fbc.on[2 * d] && ijk[d] == 0) G = G + a.fbc.val[2 * d] * Ad / Vd;
+                        if (a.fbc.on[2 * d + 1] && ijk[d] == g.N[d] - 1) G = G - a.fbc.val[2 * d + 1] * Ad / Vd;
+                    }
                 }
-            }
-            a.Gn[o] = G;
-            if (a.mode == STEP_RK3_FIRST) {
-                a.Unew[o] = u0 + a.ca * G;
-            } else if (a.mode == STEP_RK3) {
-                a.Unew[o] = u0 + a.dt * (a.ca * G + a.cb * stt.gm);
-            } else if (a.mode == STEP_AB2) {
-                FT Gu = a.ab2_euler ? a.ca * G : a.ca * G - a.cb * stt.gm;
-                a.Unew[o] = u0 + a.dt * Gu;
+                a.Gn[o] = G;
+                if (a.mode == STEP_RK3_FIRST) {
+                    a.Unew[o] = u0 + a.ca * G;
+                } else if (a.mode == STEP_RK3) {
+                    a.Unew[o] = u0 + a.dt * (a.ca * G + a.cb * stt.gm[h]);
+                } else if (a.mode == STEP_AB2) {
+                    FT Gu = a.ab2_euler ? a.ca * G : a.ca * G - a.cb * stt.gm[h];
+                    a.Unew[o] = u0 + a.dt * Gu;
+                }
             }
         }
     }

@@ -917,6 +917,12 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
     };
     const bool bnd = g_.bounded[0] || g_.bounded[1] || g_.bounded[2];
     const bool gen = has_amd_;
+    // Two cells per thread (32×16 tiles) for the u, v and tracer kernels of the triply periodic fifth-order configurations (C3 / C5).
+    // Measured (profiles/r01g_two_cells_per_thread.txt): tendency time per step 42.1 -> 40.9 ms (C3 Float64), 31.6 -> 28.5 ms (C3
+    // Float32); but Centered(2) 1.89 -> 2.02 ms (C2) and the Bounded-z AMD kernels 31.7 -> 36.8 ms (C4, 83-92 registers, 18 instead of
+    // 27 warps per SM to hide their global loads) — so those stay on one cell per thread.  OC_MARCH_CPT=1 switches back (measurement).
+    static const char* cpt_env = getenv("OC_MARCH_CPT");
+    const bool two_cells = cpt_env ? atoi(cpt_env) == 2 : true;
     // (A 32×16-tile variant — MarchKernel<…, 16>: two 544-thread CTAs per SM, 34 warps, 50 registers — was measured slower,
     //  48.3 vs 45.4 ms per step at 512³: the kernel is bound by the FP64 pipe and dependent-issue latency, not by warp count.)
     auto pick = [&](auto adv) {
@@ -927,6 +933,10 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
             else if (zonly) run(MarchKernel<FT, ADV, KIND, 4, 1, 8, 1>{});
             else if (!gen) run(MarchKernel<FT, ADV, KIND, 7, 0, 8, 1>{});
             else run(MarchKernel<FT, ADV, KIND, 7, 1, 8, 1>{});
+        }
+        else if (two_cells && !bnd && !gen) {
+            if constexpr (KIND != KIND_W && ADV != ADV_CENTERED2) run(MarchKernel<FT, ADV, KIND, 0, 0, 16>{});
+            else run(MarchKernel<FT, ADV, KIND, 0, 0>{});
         }
         else if (!bnd && !gen) run(MarchKernel<FT, ADV, KIND, 0, 0>{});
         else if (!bnd) run(MarchKernel<FT, ADV, KIND, 0, 1>{});
