@@ -138,8 +138,12 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     xpad_ = pad;
     // the z-marching TMA kernel: no Flat dimension, and the two schemes of the BASELINE configurations; the other schemes of the
     // family run in the general tile kernel (oc_tendency.h)
-    march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) &&
-                (c.advection == OC_CENTERED2 || c.advection == OC_WENO5 || c.advection == OC_UPWIND5);
+    // (UpwindBiased(5): the triply periodic constant-viscosity variant only — the measurement configuration of §6)
+    {
+        const bool any_bounded = c.topology[0] == OC_BOUNDED || c.topology[1] == OC_BOUNDED || c.topology[2] == OC_BOUNDED;
+        march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) &&
+                    (c.advection == OC_CENTERED2 || c.advection == OC_WENO5 || (c.advection == OC_UPWIND5 && !any_bounded && !c.has_amd));
+    }
     g_.dzc = g_.dzf = g_.rdzc = g_.rdzf = g_.rVc = g_.rVf = nullptr;
     C_ = make_coefficients<FT>();
     {   // the compile-time table of oc_march.h must be the very same numbers
@@ -917,10 +921,11 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
     };
     const bool bnd = g_.bounded[0] || g_.bounded[1] || g_.bounded[2];
     const bool gen = has_amd_;
-    // Two cells per thread (32×16 tiles) for the u, v and tracer kernels of the triply periodic fifth-order configurations (C3 / C5).
+    // Two cells per thread (32×16 tiles) for the u, v and tracer kernels of the triply periodic WENO(5) configurations (C3 / C5).
     // Measured (profiles/r01g_two_cells_per_thread.txt): tendency time per step 42.1 -> 40.9 ms (C3 Float64), 31.6 -> 28.5 ms (C3
     // Float32); but Centered(2) 1.89 -> 2.02 ms (C2) and the Bounded-z AMD kernels 31.7 -> 36.8 ms (C4, 83-92 registers, 18 instead of
-    // 27 warps per SM to hide their global loads) — so those stay on one cell per thread.  OC_MARCH_CPT=1 switches back (measurement).
+    // 27 warps per SM to hide their global loads), UpwindBiased(5) 29.3 -> 32.5 ms — so those stay on one cell per thread: with little
+    // FP64 work per cell the kernels need the third CTA's warps more than the saved instructions.  OC_MARCH_CPT=1 switches back (measurement).
     static const char* cpt_env = getenv("OC_MARCH_CPT");
     const bool two_cells = cpt_env ? atoi(cpt_env) == 2 : true;
     // (A 32×16-tile variant — MarchKernel<…, 16>: two 544-thread CTAs per SM, 34 warps, 50 registers — was measured slower,
@@ -928,6 +933,9 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
     auto pick = [&](auto adv) {
         constexpr int ADV = decltype(adv)::value;
         const bool zonly = !g_.bounded[0] && !g_.bounded[1] && g_.bounded[2];     // the LES topology (Periodic, Periodic, Bounded)
+        if constexpr (ADV == ADV_UPWIND5) {
+            run(MarchKernel<FT, ADV, KIND, 0, 0>{});       // march_ok_ admits only the triply periodic constant-viscosity case
+        } else {
         if (stretched_) {          // z Bounded and variably spaced: level tables instead of the constant z metrics
             if (zonly && !gen) run(MarchKernel<FT, ADV, KIND, 4, 0, 8, 1>{});
             else if (zonly) run(MarchKernel<FT, ADV, KIND, 4, 1, 8, 1>{});
@@ -935,7 +943,7 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
             else run(MarchKernel<FT, ADV, KIND, 7, 1, 8, 1>{});
         }
         else if (two_cells && !bnd && !gen) {
-            if constexpr (KIND != KIND_W && ADV != ADV_CENTERED2) run(MarchKernel<FT, ADV, KIND, 0, 0, 16>{});
+            if constexpr (KIND != KIND_W && ADV == ADV_WENO5) run(MarchKernel<FT, ADV, KIND, 0, 0, 16>{});
             else run(MarchKernel<FT, ADV, KIND, 0, 0>{});
         }
         else if (!bnd && !gen) run(MarchKernel<FT, ADV, KIND, 0, 0>{});
@@ -944,6 +952,7 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
         else if (zonly) run(MarchKernel<FT, ADV, KIND, 4, 1>{});
         else if (!gen) run(MarchKernel<FT, ADV, KIND, 7, 0>{});
         else run(MarchKernel<FT, ADV, KIND, 7, 1>{});
+        }
     };
     if (cfg_.advection == OC_WENO5) pick(std::integral_constant<int, ADV_WENO5>{});
     else if (cfg_.advection == OC_UPWIND5) pick(std::integral_constant<int, ADV_UPWIND5>{});
