@@ -155,6 +155,11 @@ int  oc_time_step_rk3(oc_model* m, double dt);
 int  oc_time_step_ab2(oc_model* m, double dt, int euler);
 int  oc_get_clock(oc_model* m, oc_clock* clock);
 int  oc_set_clock(oc_model* m, const oc_clock* clock);                 /* Checkpointer pickup: checkpointer.jl:202-228 */
+/* Checkpointer pickup of the time stepper: set!(timestepper.G⁻, file) (src/OutputWriters/checkpointer.jl:230-262).  `field` is a
+ * prognostic index; the host buffer is the PARENT array of G⁻ as oc_download_parent(m, OC_FIELD_GM0 + field, …) returned it.  Call it
+ * after the state has been restored with oc_upload_parent: the next time step then uses this G⁻ (QuasiAdamsBashforth2 needs it; Gⁿ is
+ * always recomputed from the restored state, like the reference's update_state! after a pickup). */
+int  oc_restore_previous_tendency(oc_model* m, int field, const void* parent_host, size_t nbytes);
 
 /* ---- on-device step diagnostics (one reduction pass, a 40-byte device-to-host copy) ----
  * cell_advection_timescale(grid, velocities)  src/Advection/cell_advection_timescale.jl:13-34  (TimeStepWizard,

@@ -30,7 +30,7 @@ __all__ = [
     "FieldBoundaryConditions", "NonhydrostaticModel", "Field", "set_", "time_step_", "update_state_",
     "compute_tendencies_", "compute_flux_bc_tendencies_", "rk3_substep_", "ab2_step_", "cache_previous_tendencies_",
     "compute_pressure_correction_", "make_pressure_correction_", "fill_halo_regions_", "solve_poisson",
-    "interior", "parent", "Simulation", "run_", "Clock", "OceananigansB200Error",
+    "interior", "parent", "Simulation", "run_", "Clock", "Checkpointer", "OceananigansB200Error",
     "cell_advection_timescale", "hasnan", "step_diagnostics", "TimeStepWizard",
 ]
 
@@ -689,6 +689,49 @@ class TimeStepWizard:
 
 
 # ------------------------------------------------------------------------------------------ Simulation
+class Checkpointer:
+    """Checkpointer(model; …): the parent arrays of the prognostic fields, of the time stepper's G⁻ and the clock — what the
+    reference's Checkpointer writes and `set!(model, filepath)` picks up (src/OutputWriters/checkpointer.jl:161-262).  The container
+    here is an .npz file with the reference's property names ("u", "v", "w", tracers, "timestepper/G⁻/<name>", "clock/…"); a JLD2 file
+    holds the same arrays (x fastest, halos included), so the Julia extension can hand them over unchanged."""
+
+    def __init__(self, model, prefix="checkpoint"):
+        self.model, self.prefix = model, prefix
+
+    def state(self):
+        m = self.model
+        out = {}
+        for n, f in m.fields.items():
+            out[n] = f.parent()
+        for n, f in m.timestepper.Gm.items():
+            out["timestepper/G⁻/" + n] = f.parent()          # (brings the tendencies up to date first, like update_state!)
+        c = m.clock._get()
+        out["clock/time"], out["clock/iteration"], out["clock/stage"] = np.float64(c.time), np.int64(c.iteration), np.int32(c.stage)
+        out["clock/last_Δt"], out["clock/last_stage_Δt"] = np.float64(c.last_dt), np.float64(c.last_stage_dt)
+        return out
+
+    def write(self, path=None):
+        path = path or f"{self.prefix}_iteration{self.model.clock.iteration}.npz"
+        np.savez(path, **self.state())
+        return path
+
+    @staticmethod
+    def pickup(model, source):
+        """set!(model, filepath): restore fields, G⁻ and the clock (checkpointer.jl:202-262)."""
+        z = np.load(source) if isinstance(source, str) else source
+        lib, h = model._lib, model._h
+        for n, f in model.fields.items():
+            f.set_parent(z[n])
+        for fidx, n in enumerate(model.fields):
+            a = np.asfortranarray(np.asarray(z["timestepper/G⁻/" + n], dtype=model.grid.FT))
+            lib.check(lib.oc_restore_previous_tendency(h, fidx, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        c = L.oc_clock()
+        c.time, c.iteration, c.stage = float(z["clock/time"]), int(z["clock/iteration"]), int(z["clock/stage"])
+        c.last_dt, c.last_stage_dt = float(z["clock/last_Δt"]), float(z["clock/last_stage_Δt"])
+        lib.check(lib.oc_set_clock(h, C.byref(c)))
+        return model
+
+
 class Simulation:
     """Simulation(model; Δt, stop_iteration=Inf, stop_time=Inf)   src/Simulations/simulation.jl"""
 

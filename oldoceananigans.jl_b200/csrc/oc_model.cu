@@ -435,7 +435,9 @@ typename Model<FT>::FieldRec& Model<FT>::lookup(int field) {
 template <class FT>
 void Model<FT>::field_info(int field, oc_field_info* info) {
     if ((field == OC_FIELD_PHY || field == OC_FIELD_NU_E || (field >= OC_FIELD_KAPPA_E0 && field < OC_FIELD_GN0)) && !aux_valid_) aux();
-    if (field >= OC_FIELD_GN0 && field < OC_FIELD_GN0 + F_) compute_tendencies_if_stale();
+    // Gⁿ AND G⁻ are API-valid only after the evaluation the reference's update_state! performs at the end of every step: between
+    // steps the library keeps the last substep's tendencies in the Gⁿ slot (they become G⁻ by a pointer swap at the next stage)
+    if ((field >= OC_FIELD_GN0 && field < OC_FIELD_GN0 + F_) || (field >= OC_FIELD_GM0 && field < OC_FIELD_GM0 + F_)) compute_tendencies_if_stale();
     FieldRec& f = lookup(field);
     for (int d = 0; d < 3; ++d) {
         info->location[d] = f.face[d];
@@ -1286,6 +1288,26 @@ void Model<FT>::diagnostics(oc_diagnostics* out) {
     out->pad = 0;
 }
 
+// Checkpointer pickup of G⁻ (checkpointer.jl:230-262).  Between steps the library keeps the tendencies of the last substep in the
+// Gⁿ slot and marks them stale; the next stage turns them into G⁻ by a pointer swap (stage()).  A restored G⁻ therefore goes into
+// that slot, and the stale mark is (re)asserted so that no fresh evaluation is swapped over it.
+template <class FT>
+void Model<FT>::restore_previous_tendency(int field, const void* host, size_t nbytes) {
+    if (field < 0 || field >= F_) throw Error(OC_ERR_INVALID, "restore_previous_tendency: not a prognostic field index");
+    join_tracers();
+    FieldRec& f = Gn_[field];
+    int ext[3];
+    size_t n = 1;
+    for (int d = 0; d < 3; ++d) {
+        ext[d] = g_.N[d] + ((f.face[d] && g_.bounded[d]) ? 1 : 0) + 2 * Hcfg_[d];
+        n *= (size_t)ext[d];
+    }
+    if (n * sizeof(FT) != nbytes) throw Error(OC_ERR_INVALID, "host buffer size mismatch: expected " + std::to_string(n * sizeof(FT)) + " bytes");
+    FT* origin = f.p - Hcfg_[0] - (long long)Hcfg_[1] * g_.sy - (long long)Hcfg_[2] * g_.sz;
+    dev_copy_box(origin, sizeof(FT), g_.sy, g_.sz, const_cast<void*>(host), ext, true, stream_);
+    tend_valid_ = false;
+}
+
 template <class FT>
 void Model<FT>::poisson_solve(const void* rhs, void* phi, size_t nbytes) {
     size_t n = (size_t)g_.N[0] * g_.N[1] * g_.N[2];
@@ -1467,6 +1489,7 @@ int oc_time_step_rk3(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&]
 int oc_time_step_ab2(oc_model* m, double dt, int euler) { OC_REQUIRE(m); return guarded([&] { m->impl->time_step_ab2(dt, euler); }); }
 int oc_get_clock(oc_model* m, oc_clock* c) { OC_REQUIRE(m); *c = m->impl->clock; return OC_OK; }
 int oc_set_clock(oc_model* m, const oc_clock* c) { OC_REQUIRE(m); m->impl->clock = *c; return OC_OK; }
+int oc_restore_previous_tendency(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->restore_previous_tendency(field, host, nbytes); }); }
 int oc_compute_diagnostics(oc_model* m, oc_diagnostics* out) { OC_REQUIRE(m); return guarded([&] { m->impl->diagnostics(out); }); }
 int oc_dist_unique_id(void* id128) {
     if (!id128) { g_last_error = "null argument"; return OC_ERR_INVALID; }

@@ -98,6 +98,7 @@ struct ModelBase {
     virtual void time_step_rk3(double dt) = 0;
     virtual void time_step_ab2(double dt, int euler) = 0;
     virtual void diagnostics(oc_diagnostics* out) = 0;
+    virtual void restore_previous_tendency(int field, const void* host, size_t nbytes) = 0;
     virtual void dist_attach(Transport* t) = 0;
     virtual int dist_rank() const = 0;
     virtual int dist_nranks() const = 0;
@@ -133,6 +134,7 @@ public:
     void time_step_rk3(double dt) override;
     void time_step_ab2(double dt, int euler) override;
     void diagnostics(oc_diagnostics* out) override;
+    void restore_previous_tendency(int field, const void* host, size_t nbytes) override;
     void dist_attach(Transport* t) override;
     int dist_rank() const override { return rank_; }
     int dist_nranks() const override { return R_; }

@@ -189,3 +189,24 @@ def test_full_size_c3_tracer_conservation(ob):
     assert abs(m.tracers.T.interior().mean() - T0) < 1e-11 * 20
     assert abs(m.tracers.S.interior().mean() - S0) < 1e-11 * 35
     assert np.abs(_divergence(m)).max() < 1e-9 * 256
+
+
+@pytest.mark.parametrize("ts", ["QuasiAdamsBashforth2", "RungeKutta3"])
+def test_checkpoint_pickup_continues_bit_for_bit(ob, ts, tmp_path):
+    """Checkpointer + pickup through the CUDA library (src/OutputWriters/checkpointer.jl:161-262)"""
+    kw = dict(N=(24, 20, 16), topo="PPB", scheme="weno", closure="amd", bcs=True, f=1e-2, ts=ts)
+    m1, om = ph.build_pair(**kw)
+    ic = ph.initial_conditions(om)
+    ob.set_(m1, **ic)
+    dt = 0.002
+    for _ in range(2):
+        ob.time_step_(m1, dt)
+    path = ob.Checkpointer(m1, prefix=str(tmp_path / "ckpt")).write()
+    for _ in range(2):
+        ob.time_step_(m1, dt)
+    m2 = ph.build_product(**kw)
+    ob.Checkpointer.pickup(m2, path)
+    for _ in range(2):
+        ob.time_step_(m2, dt)
+    for n in m1.fields:
+        assert np.array_equal(m1.fields[n].parent(), m2.fields[n].parent()), n

@@ -123,3 +123,29 @@ def test_clock_matches_reference_semantics(hostsim):
     assert m.clock.iteration == om.clock.iteration == 3
     assert m.clock.time == om.clock.time
     assert m.clock.last_Δt == om.clock.last_dt and m.clock.last_stage_Δt == om.clock.last_stage_dt
+
+
+@pytest.mark.parametrize("ts", ["QuasiAdamsBashforth2", "RungeKutta3"])
+def test_checkpoint_pickup_continues_bit_for_bit(hostsim, ts, tmp_path):
+    """Checkpointer + set!(model, filepath) (src/OutputWriters/checkpointer.jl:161-262): a model picked up from the parent arrays,
+    G⁻ and the clock continues exactly like the one that kept running (AB2 needs the restored G⁻)."""
+    import oceananigans_b200 as ob
+    kw = dict(N=(12, 10, 8), topo="PPB", scheme="weno", closure="amd", bcs=True, f=1e-2, ts=ts, library=hostsim)
+    m1, om = ph.build_pair(**kw)
+    ic = ph.initial_conditions(om)
+    ob.set_(m1, **ic)
+    dt = 0.004
+    for _ in range(2):
+        ob.time_step_(m1, dt)
+    path = ob.Checkpointer(m1, prefix=str(tmp_path / "ckpt")).write()
+    for _ in range(2):
+        ob.time_step_(m1, dt)
+    m2 = ph.build_product(**kw)
+    ob.Checkpointer.pickup(m2, path)
+    assert m2.clock.iteration == 2 and m2.clock.time == 2 * dt
+    for _ in range(2):
+        ob.time_step_(m2, dt)
+    for n in m1.fields:
+        assert np.array_equal(m1.fields[n].parent(), m2.fields[n].parent()), n
+    assert np.array_equal(m1.pressures.pNHS.interior(), m2.pressures.pNHS.interior())
+    assert m1.clock.time == m2.clock.time and m1.clock.iteration == m2.clock.iteration == 4
