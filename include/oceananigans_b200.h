@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OC_ABI_VERSION 2
+#define OC_ABI_VERSION 3
 #define OC_MAX_TRACERS 8
 #define OC_MAX_FIELDS (3 + OC_MAX_TRACERS)
 
@@ -89,7 +89,14 @@ typedef struct {
      * (src/Solvers/fourier_tridiagonal_poisson_solver.jl:74-131; NonhydrostaticModels.jl:35-40). */
     int32_t z_stretched;
     const double* z_faces;
-    int32_t reserved[2];
+    /* Smagorinsky(coefficient = C, Pr)  (src/TurbulenceClosures/turbulence_closure_implementations/Smagorinskys/smagorinsky.jl:31-84):
+     * smagorinsky = 1; SmagorinskyLilly(C, Cb, Pr) = Smagorinsky(coefficient = LillyCoefficient(smagorinsky = C, reduction_factor = Cb))
+     * (Smagorinskys/lilly_coefficient.jl:47-112): smagorinsky = 2.  νₑ = ς (C Δᶠ)² √(2Σ²), κₑ = νₑ / Pr[tracer]; νₑ and κₑ are the fields
+     * OC_FIELD_NU_E / OC_FIELD_KAPPA_E0 + t, like AMD's.  DynamicCoefficient is not implemented (rejected). */
+    int32_t smagorinsky;          /* 0 = none, 1 = constant coefficient, 2 = LillyCoefficient */
+    int32_t reserved;
+    double  smag_C, smag_Cb;
+    double  smag_Pr[OC_MAX_TRACERS];
 } oc_config;
 
 typedef struct oc_model oc_model;

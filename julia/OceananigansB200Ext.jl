@@ -20,6 +20,7 @@ using Oceananigans.TimeSteppers: RungeKutta3TimeStepper, QuasiAdamsBashforth2Tim
 using Oceananigans.Models.NonhydrostaticModels: NonhydrostaticModel
 using Oceananigans.Advection: Centered, WENO
 using Oceananigans.TurbulenceClosures: ScalarDiffusivity, AnisotropicMinimumDissipation
+using Oceananigans.TurbulenceClosures.Smagorinskys: Smagorinsky, LillyCoefficient
 using Oceananigans.BuoyancyFormulations: SeawaterBuoyancy, BuoyancyTracer, LinearEquationOfState, BuoyancyForce
 using Oceananigans.Coriolis: FPlane
 using Oceananigans.BoundaryConditions: BoundaryCondition, Flux, Value, Gradient, Open, Periodic as PeriodicBC
@@ -65,7 +66,8 @@ mutable struct OcConfig               # `oc_config`, same field order; NTuple fo
     bcs::NTuple{OC_MAX_FIELDS,NTuple{6,OcBC}}
     device::Int32; dist_rank::Int32; dist_nranks::Int32
     z_stretched::Int32; z_faces::Ptr{Float64}      # ABI v2: vertically stretched grid (Nz+1 faces, read during oc_model_create only)
-    reserved::NTuple{2,Int32}
+    smagorinsky::Int32; reserved::Int32            # ABI v3: 0 none, 1 Smagorinsky(coefficient::Number), 2 LillyCoefficient
+    smag_C::Float64; smag_Cb::Float64; smag_Pr::NTuple{OC_MAX_TRACERS,Float64}
     OcConfig() = new()
 end
 
@@ -143,6 +145,14 @@ function config(model::NonhydrostaticModel)
             c.Cb === nothing || throw(ArgumentError("B200: AMD buoyancy modification is out of scope"))
             cfg.has_amd = 1; cfg.amd_Cnu = c.Cν
             cfg.amd_Ckappa = ntuple(t -> t <= length(names) ? Float64(c.Cκ[t]) : 0.0, OC_MAX_TRACERS)
+        elseif c isa Smagorinsky && (c.coefficient isa Number || c.coefficient isa LillyCoefficient)
+            # Smagorinsky(coefficient, Pr) / SmagorinskyLilly(C, Cb, Pr)  (Smagorinskys/smagorinsky.jl:31-84, lilly_coefficient.jl:47-112)
+            if c.coefficient isa LillyCoefficient
+                cfg.smagorinsky = 2; cfg.smag_C = c.coefficient.smagorinsky; cfg.smag_Cb = c.coefficient.reduction_factor
+            else
+                cfg.smagorinsky = 1; cfg.smag_C = c.coefficient
+            end
+            cfg.smag_Pr = ntuple(t -> t <= length(names) ? Float64(c.Pr[t]) : 1.0, OC_MAX_TRACERS)
         else
             throw(ArgumentError("B200: closure $(summary(c)) is out of scope"))
         end

@@ -7,7 +7,7 @@ C ABI of the host-simulation build (tests/hostsim) — the package itself never 
 import ctypes as C
 import os
 
-OC_ABI_VERSION = 2
+OC_ABI_VERSION = 3
 OC_MAX_TRACERS = 8
 OC_MAX_FIELDS = 3 + OC_MAX_TRACERS
 OC_TIMER_NAMES = ("tendency", "halo", "poisson_rhs", "fft", "poisson_mid", "projection", "aux", "substep", "comm")
@@ -41,7 +41,9 @@ class oc_config(C.Structure):
         ("has_coriolis", C.c_int32), ("coriolis_f", C.c_double),
         ("bcs", (oc_bc * 6) * OC_MAX_FIELDS),
         ("device", C.c_int32), ("dist_rank", C.c_int32), ("dist_nranks", C.c_int32),
-        ("z_stretched", C.c_int32), ("z_faces", C.POINTER(C.c_double)), ("reserved", C.c_int32 * 2),
+        ("z_stretched", C.c_int32), ("z_faces", C.POINTER(C.c_double)),
+        ("smagorinsky", C.c_int32), ("reserved", C.c_int32), ("smag_C", C.c_double), ("smag_Cb", C.c_double),
+        ("smag_Pr", C.c_double * OC_MAX_TRACERS),
     ]
 
 

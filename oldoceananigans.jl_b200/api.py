@@ -24,7 +24,7 @@ from . import _lib as L
 
 __all__ = [
     "B200", "Distributed", "Partition", "Periodic", "Bounded", "Flat", "Center", "Face", "RectilinearGrid",
-    "Centered", "UpwindBiased", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation",
+    "Centered", "UpwindBiased", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation", "Smagorinsky", "SmagorinskyLilly", "LillyCoefficient",
     "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "FPlane",
     "FluxBoundaryCondition", "ValueBoundaryCondition", "GradientBoundaryCondition", "OpenBoundaryCondition",
     "FieldBoundaryConditions", "NonhydrostaticModel", "Field", "set_", "time_step_", "update_state_",
@@ -240,6 +240,28 @@ class AnisotropicMinimumDissipation:
         self.Ckappa = C if Ckappa is None else Ckappa
 
 
+class LillyCoefficient:
+    """LillyCoefficient(smagorinsky=0.16, reduction_factor=1)  Smagorinskys/lilly_coefficient.jl:47-48"""
+
+    def __init__(self, FT=np.float64, smagorinsky=0.16, reduction_factor=1.0):
+        self.smagorinsky, self.reduction_factor = smagorinsky, reduction_factor
+
+
+class Smagorinsky:
+    """Smagorinsky(coefficient=0.16, Pr=1.0)  Smagorinskys/smagorinsky.jl:76-80; `coefficient` a number or a LillyCoefficient
+    (DynamicCoefficient is out of scope); `Pr` a number or a dict tracer -> number (tracer_diffusivities)."""
+
+    def __init__(self, FT=np.float64, coefficient=0.16, Pr=1.0):
+        if not isinstance(coefficient, (int, float, LillyCoefficient)):
+            raise NotImplementedError("Smagorinsky: coefficient must be a number or a LillyCoefficient (DynamicCoefficient is out of scope)")
+        self.coefficient, self.Pr = coefficient, Pr
+
+
+def SmagorinskyLilly(FT=np.float64, C=0.16, Cb=1.0, Pr=1.0):
+    """SmagorinskyLilly(C=0.16, Cb=1, Pr=1)  Smagorinskys/lilly_coefficient.jl:107-112"""
+    return Smagorinsky(FT, coefficient=LillyCoefficient(FT, smagorinsky=C, reduction_factor=Cb), Pr=Pr)
+
+
 class LinearEquationOfState:
     def __init__(self, FT=np.float64, thermal_expansion=1.67e-4, haline_contraction=7.8e-4):
         self.thermal_expansion, self.haline_contraction = thermal_expansion, haline_contraction
@@ -411,7 +433,7 @@ class NonhydrostaticModel:
         # inflate_grid_halo_size   nonhydrostatic_model.jl:184,248-262
         need = advection.buffer
         for c in closures:
-            need = max(need, 2 if isinstance(c, AnisotropicMinimumDissipation) else 1)
+            need = max(need, 2 if isinstance(c, (AnisotropicMinimumDissipation, Smagorinsky)) else 1)
         H = tuple(max(grid.H[d], need) if grid.topology[d] is not Flat else 0 for d in range(3))
         if H != grid.H:
             grid = grid.with_halo(H)
@@ -443,8 +465,10 @@ class NonhydrostaticModel:
         cfg.n_tracers = len(tracers)
         sd = [c for c in closures if isinstance(c, ScalarDiffusivity)]
         amd = [c for c in closures if isinstance(c, AnisotropicMinimumDissipation)]
-        if len(sd) > 1 or len(amd) > 1 or len(sd) + len(amd) != len(closures):
-            raise NotImplementedError("closure must be ScalarDiffusivity, AnisotropicMinimumDissipation or a 2-tuple of them")
+        smag = [c for c in closures if isinstance(c, Smagorinsky)]
+        if len(sd) > 1 or len(amd) + len(smag) > 1 or len(sd) + len(amd) + len(smag) != len(closures):
+            raise NotImplementedError("closure must be ScalarDiffusivity, AnisotropicMinimumDissipation, Smagorinsky or a tuple of a "
+                                      "ScalarDiffusivity and one of the eddy-viscosity closures")
         pick = lambda v, n: float(v[n]) if isinstance(v, dict) else float(v)
         if sd:
             cfg.has_scalar_diffusivity, cfg.nu = 1, float(sd[0].nu)
@@ -454,6 +478,14 @@ class NonhydrostaticModel:
             cfg.has_amd, cfg.amd_Cnu = 1, float(amd[0].Cnu)
             for t, n in enumerate(tracers):
                 cfg.amd_Ckappa[t] = pick(amd[0].Ckappa, n)
+        if smag:
+            co = smag[0].coefficient
+            if isinstance(co, LillyCoefficient):
+                cfg.smagorinsky, cfg.smag_C, cfg.smag_Cb = 2, float(co.smagorinsky), float(co.reduction_factor)
+            else:
+                cfg.smagorinsky, cfg.smag_C = 1, float(co)
+            for t, n in enumerate(tracers):
+                cfg.smag_Pr[t] = pick(smag[0].Pr, n)
         if buoyancy is not None:
             for n in buoyancy.required:
                 if n not in tracers:
@@ -498,7 +530,7 @@ class NonhydrostaticModel:
         self.pressures = _NT(pNHS=Field(self, L.OC_FIELD_PNHS, "pNHS"),
                              pHY=Field(self, L.OC_FIELD_PHY, "pHY′") if buoyancy is not None else None)
         self.diffusivity_fields = None
-        if amd:
+        if amd or smag:
             self.diffusivity_fields = _NT(nu_e=Field(self, L.OC_FIELD_NU_E, "νₑ"),
                                           kappa_e=_NT({n: Field(self, L.OC_FIELD_KAPPA_E0 + t, "κₑ." + n) for t, n in enumerate(tracers)}))
         self.fields = _NT({**self.velocities, **self.tracers})

@@ -1,4 +1,4 @@
-// oc_aux.h — auxiliary-field kernels of update_state!: hydrostatic pressure anomaly and AMD eddy
+// oc_aux.h — auxiliary-field kernels of update_state!: hydrostatic pressure anomaly, AMD and Smagorinsky(-Lilly) eddy
 // viscosity / diffusivities.
 //
 // Replaces _update_hydrostatic_pressure! (src/Models/NonhydrostaticModels/update_hydrostatic_pressure.jl:12-49)
@@ -163,6 +163,97 @@ struct AmdKernel {
             }
             kappa_e[tr][o] = oc_max<FT>(FT(0), kap);
         }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Smagorinsky / SmagorinskyLilly eddy viscosity.  Replaces _compute_smagorinsky_viscosity!
+// (src/TurbulenceClosures/turbulence_closure_implementations/Smagorinskys/smagorinsky.jl:92-108) with
+// ΣᵢⱼΣᵢⱼᶜᶜᶜ (Smagorinskys/scale_invariant_operators.jl:10-13; velocity_tracer_gradients.jl:25-46,78) and, for the
+// LillyCoefficient, square_smagorinsky_coefficient / stability (Smagorinskys/lilly_coefficient.jl:114-135) with ∂z_b
+// (buoyancy_tracer.jl:16, seawater_buoyancy.jl:219-224).  One thread per cell, the AmdKernel's CTA shape; the off-diagonal
+// strains are evaluated once at each of the four corners their interpolation needs.  κₑ[t] = νₑ / Pr[t] is stored per tracer
+// (the reference divides the interpolated νₑ, smagorinsky.jl:154-156: the same value up to one rounding), so that the tendency
+// kernels read eddy diffusivities exactly as they do for AMD.
+// ---------------------------------------------------------------------------------------------------------
+template <class FT, bool STR = false>
+struct SmagorinskyKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 3;
+    Geom<FT> g;
+    const FT* u;
+    const FT* v;
+    const FT* w;
+    FT* nu_e;
+    int ntr;
+    FT* kappa_e[8];
+    FT Pr[8];
+    FT cs2;              // C² (smagorinsky.jl:110; lilly_coefficient.jl:133)
+    int lilly;           // 1: multiply by ς(N², Σ², Cb)
+    FT Cb;
+    int buoyancy;        // 0 none (∂z_b = 0, no_buoyancy.jl:9), 1 tracer b, 2 seawater linear
+    const FT* bT;
+    const FT* bS;
+    FT grav, alpha, beta;
+    FT df2;              // Δᶠ² = cbrt(Δx Δy Δz)², regular grids
+    const FT* lv_df2;    // per level on a stretched grid (Model::build_z_tables), indexable like Geom::dzc
+
+    // ∂z_b at ccf, level k (face between cells k-1 and k); o = index of cell k
+    OC_HD FT dzb(int o, int k) const {
+        const FT r = STR ? g.rdzf[k] : g.rd[2];
+        if (buoyancy == 1) return (bT[o] - bT[o - g.sz]) * r;
+        return grav * (alpha * ((bT[o] - bT[o - g.sz]) * r) - beta * ((bS[o] - bS[o - g.sz]) * r));
+    }
+
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        (void)nt;
+        int i = b.x * 32 + (tid & 31), j = b.y * 8 + (tid >> 5), k = b.z;
+        if (i >= g.N[0] || j >= g.N[1]) return;
+        const int o = g.idx(i, j, k);
+        const int sx = 1, sy = g.sy, sz = g.sz;
+        const FT rdx = g.rd[0], rdy = g.rd[1];
+        FT rzf[2];                                      // Δz⁻¹ at the ccf / fcf / cff level of the cell and of the level above
+        rzf[0] = STR ? g.rdzf[k] : g.rd[2];
+        rzf[1] = STR ? g.rdzf[k + 1] : g.rd[2];
+        const FT rdzc = STR ? g.rdzc[k] : g.rd[2];
+        const int cxy[4] = {o, o + sx, o + sy, o + sx + sy};
+        const int cxz[4] = {o, o + sx, o + sz, o + sx + sz};
+        const int cyz[4] = {o, o + sy, o + sz, o + sy + sz};
+        FT q12[4], q13[4], q23[4];
+        for (int n = 0; n < 4; ++n) {
+            const int up = n >> 1;
+            const int pxy = cxy[n], pxz = cxz[n], pyz = cyz[n];
+            const FT S12 = FT(0.5) * ((u[pxy] - u[pxy - sy]) * rdy + (v[pxy] - v[pxy - sx]) * rdx);          // ffc: ½(∂y u + ∂x v)
+            const FT S13 = FT(0.5) * ((u[pxz] - u[pxz - sz]) * rzf[up] + (w[pxz] - w[pxz - sx]) * rdx);      // fcf: ½(∂z u + ∂x w)
+            const FT S23 = FT(0.5) * ((v[pyz] - v[pyz - sz]) * rzf[up] + (w[pyz] - w[pyz - sy]) * rdy);      // cff: ½(∂z v + ∂y w)
+            q12[n] = S12 * S12; q13[n] = S13 * S13; q23[n] = S23 * S23;
+        }
+        // ℑxyᶜᶜᵃ = ℑyᶜ(ℑxᶜ ·) and so on: the lower dimension is the inner operator (interpolation_operators.jl:45-56)
+        const FT I12 = FT(0.5) * (FT(0.5) * (q12[0] + q12[1]) + FT(0.5) * (q12[2] + q12[3]));
+        const FT I13 = FT(0.5) * (FT(0.5) * (q13[0] + q13[1]) + FT(0.5) * (q13[2] + q13[3]));
+        const FT I23 = FT(0.5) * (FT(0.5) * (q23[0] + q23[1]) + FT(0.5) * (q23[2] + q23[3]));
+        const FT S11 = (u[o + sx] - u[o]) * rdx, S22 = (v[o + sy] - v[o]) * rdy, S33 = (w[o + sz] - w[o]) * rdzc;
+        const FT tr = S11 * S11 + S22 * S22 + S33 * S33;
+        const FT S2 = tr + FT(2) * I12 + FT(2) * I13 + FT(2) * I23;
+        FT c2 = cs2;
+        if (lilly) {
+            FT N2 = FT(0);
+            if (buoyancy) N2 = FT(0.5) * (dzb(o, k) + dzb(o + sz, k + 1));                  // ℑzᵃᵃᶜ ∂z_b
+            const FT N2p = oc_max<FT>(FT(0), N2);
+            FT sig = FT(0);
+            if (S2 != FT(0)) {
+                FT ratio = Cb * N2p / S2;
+                if (!(ratio < FT(1))) ratio = FT(1);                                       // min(1, ·)
+                sig = oc_sqrt<FT>(FT(1) - ratio);
+            }
+            c2 = sig * cs2;
+        }
+        const FT d2 = STR ? lv_df2[k] : df2;
+        const FT nu = c2 * d2 * oc_sqrt<FT>(FT(2) * S2);
+        nu_e[o] = nu;
+        for (int t = 0; t < ntr; ++t) kappa_e[t][o] = nu / Pr[t];
     }
 };
 

@@ -73,6 +73,24 @@ OC_HD FT oc_abs(FT x) { return x < FT(0) ? -x : x; }
 template <class FT>
 OC_HD FT oc_max(FT a, FT b) { return a > b ? a : b; }
 
+// IEEE square root (sqrt.rn on the device; the kernels are compiled without fast-math)
+OC_HD double oc_sqrt_(double x) {
+#ifdef OC_HOSTSIM
+    return std::sqrt(x);
+#else
+    return sqrt(x);
+#endif
+}
+OC_HD float oc_sqrt_(float x) {
+#ifdef OC_HOSTSIM
+    return std::sqrt(x);
+#else
+    return sqrtf(x);
+#endif
+}
+template <class FT>
+OC_HD FT oc_sqrt(FT x) { return oc_sqrt_(x); }
+
 OC_HD double oc_fma(double a, double b, double c) {
 #ifdef OC_HOSTSIM
     return std::fma(a, b, c);

@@ -94,7 +94,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     // required_halo_size of the scheme (its buffer)
     int need = (c.advection == OC_WENO5 || c.advection == OC_UPWIND5) ? 3
              : (c.advection == OC_CENTERED4 || c.advection == OC_UPWIND3 || c.advection == OC_WENO3) ? 2 : 1;
-    if (c.has_amd) need = std::max(need, 2);
+    if (c.has_amd || c.smagorinsky) need = std::max(need, 2);      // AbstractScalarDiffusivity{…, 2}: anisotropic_minimum_dissipation.jl, smagorinsky.jl:31
     for (int d = 0; d < 3; ++d) {
         const int t = c.topology[d];
         if (t != OC_PERIODIC && t != OC_BOUNDED && t != OC_FLAT) throw Error(OC_ERR_INVALID, "bad topology");
@@ -116,6 +116,13 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         g_.rd[d] = FT(1) / g_.d[d];
     }
     if (c.has_amd && (g_.flat[0] || g_.flat[1] || g_.flat[2])) throw Error(OC_ERR_UNSUPPORTED, "AnisotropicMinimumDissipation on a grid with Flat dimensions");
+    if (c.smagorinsky) {
+        if (c.smagorinsky != 1 && c.smagorinsky != 2) throw Error(OC_ERR_UNSUPPORTED, "Smagorinsky: constant coefficient (1) or LillyCoefficient (2); DynamicCoefficient is not implemented");
+        if (c.has_amd) throw Error(OC_ERR_UNSUPPORTED, "AnisotropicMinimumDissipation and Smagorinsky in one closure tuple");
+        if (g_.flat[0] || g_.flat[1] || g_.flat[2]) throw Error(OC_ERR_UNSUPPORTED, "Smagorinsky on a grid with Flat dimensions");
+        for (int t = 0; t < c.n_tracers; ++t)
+            if (!(c.smag_Pr[t] > 0)) throw Error(OC_ERR_INVALID, "Smagorinsky: the turbulent Prandtl number of every tracer must be positive");
+    }
     if (c.buoyancy == OC_BUOYANCY_SEAWATER_LINEAR && (c.tracer_T < 0 || c.tracer_S < 0 || c.tracer_T >= c.n_tracers || c.tracer_S >= c.n_tracers))
         throw Error(OC_ERR_INVALID, "SeawaterBuoyancy needs tracers T and S");
     if (c.buoyancy == OC_BUOYANCY_TRACER && (c.tracer_b < 0 || c.tracer_b >= c.n_tracers)) throw Error(OC_ERR_INVALID, "BuoyancyTracer needs tracer b");
@@ -142,7 +149,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     {
         const bool any_bounded = c.topology[0] == OC_BOUNDED || c.topology[1] == OC_BOUNDED || c.topology[2] == OC_BOUNDED;
         march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) &&
-                    (c.advection == OC_CENTERED2 || c.advection == OC_WENO5 || (c.advection == OC_UPWIND5 && !any_bounded && !c.has_amd));
+                    (c.advection == OC_CENTERED2 || c.advection == OC_WENO5 || (c.advection == OC_UPWIND5 && !any_bounded && !c.has_amd && !c.smagorinsky));
     }
     g_.dzc = g_.dzf = g_.rdzc = g_.rdzf = g_.rVc = g_.rVf = nullptr;
     C_ = make_coefficients<FT>();
@@ -193,7 +200,9 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     has_pHY_ = c.buoyancy != OC_BUOYANCY_NONE;          // nonhydrostatic_model.jl:147-153
     if (has_pHY_) { pHY_ = alloc_field(locs[3]); resolve_bcs(pHY_, nullptr); }
     has_amd_ = c.has_amd != 0;
-    if (has_amd_) {
+    has_smag_ = c.smagorinsky != 0;
+    has_eddy_ = has_amd_ || has_smag_;
+    if (has_eddy_) {
         nu_e_ = alloc_field(locs[3]);
         resolve_bcs(nu_e_, nullptr);
         for (int t = 0; t < c.n_tracers; ++t) { kappa_e_.push_back(alloc_field(locs[3])); resolve_bcs(kappa_e_.back(), nullptr); }
@@ -297,7 +306,7 @@ void Model<FT>::build_z_tables(const double* faces) {
     // one more face above so that the centre of the topmost level exists
     { FT shi = FT(0); for (int q = 0; q < H + 1; ++q) shi = shi + dhi; F[nt] = F[H + N] + shi; }
     for (int n = 0; n < nt; ++n) Cc[n] = (F[n + 1] + F[n]) / FT(2);
-    std::vector<FT> tab(12 * (size_t)nt);
+    std::vector<FT> tab(13 * (size_t)nt);
     FT* dzc = tab.data(); FT* dzf = dzc + nt; FT* rdzc = dzf + nt; FT* rdzf = rdzc + nt; FT* rVc = rdzf + nt; FT* rVf = rVc + nt;
     FT* amd = rVf + nt;      // six AMD tables (AmdKernel::lv_*)
     const FT fx = FT(2) * g_.d[0], fy = FT(2) * g_.d[1];
@@ -316,6 +325,9 @@ void Model<FT>::build_z_tables(const double* faces) {
         amd[3 * nt + n] = (fz / fy) * rdzf[n];
         amd[4 * nt + n] = fz * rdzf[n];
         amd[5 * nt + n] = FT(3) / (FT(1) / (fx * fx) + FT(1) / (fy * fy) + FT(1) / (fz * fz));
+        // Smagorinsky: Δᶠ² with Δᶠ = cbrt(Δxᶜᶜᶜ Δyᶜᶜᶜ Δzᶜᶜᶜ)  (smagorinsky.jl:99-100)
+        const FT df = std::cbrt(g_.d[0] * g_.d[1] * dzc[n]);
+        amd[6 * nt + n] = df * df;
     }
     ztab_ = (FT*)dev_alloc(sizeof(FT) * tab.size());
     dev_upload(ztab_, tab.data(), sizeof(FT) * tab.size(), stream_);
@@ -425,7 +437,7 @@ typename Model<FT>::FieldRec& Model<FT>::lookup(int field) {
     if (field >= 0 && field < F_) return state_[field];
     if (field == OC_FIELD_PNHS) return pNHS_;
     if (field == OC_FIELD_PHY && has_pHY_) return pHY_;
-    if (field == OC_FIELD_NU_E && has_amd_) return nu_e_;
+    if (field == OC_FIELD_NU_E && has_eddy_) return nu_e_;
     if (field >= OC_FIELD_KAPPA_E0 && field < OC_FIELD_KAPPA_E0 + (int)kappa_e_.size()) return kappa_e_[field - OC_FIELD_KAPPA_E0];
     if (field >= OC_FIELD_GN0 && field < OC_FIELD_GN0 + F_) return Gn_[field - OC_FIELD_GN0];
     if (field >= OC_FIELD_GM0 && field < OC_FIELD_GM0 + F_) return Gm_[field - OC_FIELD_GM0];
@@ -787,6 +799,41 @@ void Model<FT>::aux() {
         for (auto& f : kappa_e_) list.push_back(&f);
         halo(list, true);
     }
+    if (has_smag_) {
+        auto run_smag = [&](auto k) {
+            k.g = g_;
+            k.u = state_[0].p; k.v = state_[1].p; k.w = state_[2].p;
+            k.nu_e = nu_e_.p;
+            k.ntr = cfg_.n_tracers;
+            for (int t = 0; t < cfg_.n_tracers; ++t) { k.kappa_e[t] = kappa_e_[t].p; k.Pr[t] = (FT)cfg_.smag_Pr[t]; }
+            const FT C = (FT)cfg_.smag_C;
+            k.cs2 = C * C;
+            k.lilly = cfg_.smagorinsky == 2;
+            k.Cb = (FT)cfg_.smag_Cb;
+            k.buoyancy = cfg_.buoyancy;
+            k.bT = k.bS = nullptr;
+            if (cfg_.buoyancy == OC_BUOYANCY_TRACER) k.bT = state_[3 + cfg_.tracer_b].p;
+            else if (cfg_.buoyancy == OC_BUOYANCY_SEAWATER_LINEAR) { k.bT = state_[3 + cfg_.tracer_T].p; k.bS = state_[3 + cfg_.tracer_S].p; }
+            k.grav = (FT)cfg_.gravity; k.alpha = (FT)cfg_.thermal_expansion; k.beta = (FT)cfg_.haline_contraction;
+            if (stretched_) {
+                const size_t nt = (size_t)g_.N[2] + 2 * (g_.H[2] + 1) + 1;
+                k.lv_df2 = g_.rVf + nt + 6 * nt;          // after the six metric tables and the six AMD tables (build_z_tables)
+                k.df2 = FT(0);
+            } else {
+                const FT df = std::cbrt(g_.d[0] * g_.d[1] * g_.d[2]);
+                k.df2 = df * df;
+                k.lv_df2 = nullptr;
+            }
+            Dim3 ag;
+            ag.x = (g_.N[0] + 31) / 32; ag.y = (g_.N[1] + 7) / 8; ag.z = g_.N[2];
+            go(k, ag, 0, OC_TIMER_AUX);
+        };
+        if (stretched_) run_smag(SmagorinskyKernel<FT, true>{});
+        else run_smag(SmagorinskyKernel<FT, false>{});
+        std::vector<FieldRec*> list{&nu_e_};
+        for (auto& f : kappa_e_) list.push_back(&f);
+        halo(list, true);
+    }
     if (has_pHY_ && !g_.flat[2]) {
         HydrostaticPressureKernel<FT> k;
         k.g = g_;
@@ -922,7 +969,7 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
         ++launches;
     };
     const bool bnd = g_.bounded[0] || g_.bounded[1] || g_.bounded[2];
-    const bool gen = has_amd_;
+    const bool gen = has_eddy_;
     // Two cells per thread (32×16 tiles) for the u, v and tracer kernels of the triply periodic WENO(5) configurations (C3 / C5).
     // Measured (profiles/r01g_two_cells_per_thread.txt): tendency time per step 42.1 -> 40.9 ms (C3 Float64), 31.6 -> 28.5 ms (C3
     // Float32); but Centered(2) 1.89 -> 2.02 ms (C2) and the Bounded-z AMD kernels 31.7 -> 36.8 ms (C4, 83-92 registers, 18 instead of
@@ -981,8 +1028,8 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
         a.pHY = (has_pHY_ && !g_.flat[2]) ? pHY_.p : nullptr;
         a.bT = a.bS = nullptr;
         a.buoyancy = 0;     // the w-equation gets no buoyancy term when pHY′ exists (always, when buoyancy != nothing)
-        a.nu_e = (has_amd_ && f < 3) ? nu_e_.p : nullptr;
-        a.kappa_e = (has_amd_ && f >= 3) ? kappa_e_[f - 3].p : nullptr;
+        a.nu_e = (has_eddy_ && f < 3) ? nu_e_.p : nullptr;
+        a.kappa_e = (has_eddy_ && f >= 3) ? kappa_e_[f - 3].p : nullptr;
         a.Gm = Gm_[f].p;
         a.Gn = Gn_[f].p;
         a.Ucur = state_[f].p;
@@ -1447,6 +1494,8 @@ void oc_config_init(oc_config* c) {
     c->thermal_expansion = 1.67e-4;       // LinearEquationOfState defaults   linear_equation_of_state.jl:39-40
     c->haline_contraction = 7.8e-4;
     c->tracer_T = c->tracer_S = c->tracer_b = -1;
+    c->smagorinsky = 0; c->smag_C = 0.16; c->smag_Cb = 1.0;          // smagorinsky.jl:77-78, lilly_coefficient.jl:47
+    for (int t = 0; t < OC_MAX_TRACERS; ++t) c->smag_Pr[t] = 1.0;
     c->amd_Cnu = 1.0 / 3.0;
     for (int t = 0; t < OC_MAX_TRACERS; ++t) c->amd_Ckappa[t] = 1.0 / 3.0;
     c->z_stretched = 0;

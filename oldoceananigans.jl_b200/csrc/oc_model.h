@@ -161,7 +161,7 @@ private:
     std::vector<FieldRec> state_, next_, Gn_, Gm_;
     FieldRec pNHS_, pHY_, nu_e_;
     std::vector<FieldRec> kappa_e_;
-    bool has_pHY_ = false, has_amd_ = false;
+    bool has_pHY_ = false, has_amd_ = false, has_smag_ = false, has_eddy_ = false;   // has_eddy_: νₑ / κₑ fields exist (AMD or Smagorinsky)
     bool tend_valid_ = false;     // Gⁿ == G(current state)
     bool aux_valid_ = false;      // pHY′, νₑ, κₑ computed from the current state
     struct HaloCache { HaloBox* boxes; int nboxes; int nblocks; };

@@ -1,4 +1,4 @@
-"""Oracle: turbulence closures (ScalarDiffusivity, AnisotropicMinimumDissipation), buoyancy, Coriolis.
+"""Oracle: turbulence closures (ScalarDiffusivity, AnisotropicMinimumDissipation, Smagorinsky / SmagorinskyLilly), buoyancy, Coriolis.
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  Restates
   src/TurbulenceClosures/closure_kernel_operators.jl:22-48
@@ -6,7 +6,9 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  Restates
   src/TurbulenceClosures/velocity_tracer_gradients.jl:6-46,126-250
   src/TurbulenceClosures/turbulence_closure_implementations/scalar_diffusivity.jl:195-198
   src/TurbulenceClosures/turbulence_closure_implementations/anisotropic_minimum_dissipation.jl:154-351
-  src/BuoyancyFormulations/linear_equation_of_state.jl:72-80, buoyancy_tracer.jl:12, g_dot_b.jl:2-4
+  src/TurbulenceClosures/turbulence_closure_implementations/Smagorinskys/smagorinsky.jl:31-158,
+      Smagorinskys/lilly_coefficient.jl:47-135, Smagorinskys/scale_invariant_operators.jl:10-13
+  src/BuoyancyFormulations/linear_equation_of_state.jl:72-80, buoyancy_tracer.jl:12-16, seawater_buoyancy.jl:219-224, g_dot_b.jl:2-4
   src/Coriolis/f_plane.jl:50-52, src/Operators/interpolation_operators.jl:119-131, src/Grids/inactive_node.jl
 """
 import numpy as np
@@ -31,6 +33,22 @@ class AnisotropicMinimumDissipation:
 
     def Ckappa_for(self, name):
         return self.Ckappa[name] if isinstance(self.Ckappa, dict) else self.Ckappa
+
+
+class Smagorinsky:
+    """Smagorinsky(coefficient=0.16, Pr=1.0)  smagorinsky.jl:31-84; with Cb given: SmagorinskyLilly(C, Cb, Pr), i.e.
+    Smagorinsky(coefficient=LillyCoefficient(smagorinsky=C, reduction_factor=Cb))  lilly_coefficient.jl:47-112"""
+
+    def __init__(self, coefficient=0.16, Pr=1.0, Cb=None):
+        self.C, self.Pr, self.Cb = coefficient, Pr, Cb
+        self.kind = "smagorinsky"
+
+    def Pr_for(self, name):
+        return self.Pr[name] if isinstance(self.Pr, dict) else self.Pr
+
+
+def SmagorinskyLilly(C=0.16, Cb=1.0, Pr=1.0):
+    return Smagorinsky(coefficient=C, Pr=Pr, Cb=Cb)
 
 
 # ---------------------------------------------------------------------------------
@@ -243,6 +261,61 @@ def compute_amd(ctx, closure, U, tracers, nu_e, kappa_e):
             kap = -FT(closure.Ckappa_for(name)) * d2 * theta / sigma
             kap = np.where(sigma == 0, FT(0), kap)
             kappa_e[name].interior[...] = np.maximum(FT(0), kap)
+
+
+# ---------------------------------------------------------------------------------
+# Smagorinsky / SmagorinskyLilly   Smagorinskys/smagorinsky.jl:92-125, lilly_coefficient.jl:114-135
+# ---------------------------------------------------------------------------------
+def strain_double_dot_ccc(ctx, U):
+    """ΣᵢⱼΣᵢⱼᶜᶜᶜ = tr_Σ² + 2 ℑxyᶜᶜᵃ Σ₁₂² + 2 ℑxzᶜᵃᶜ Σ₁₃² + 2 ℑyzᵃᶜᶜ Σ₂₃²   scale_invariant_operators.jl:10-13,
+    velocity_tracer_gradients.jl:25-46,78"""
+    FT = ctx.FT
+    u, v, w = (ctx.field(f) for f in U)
+    two = FT(2)
+    tr = ddC(ctx, u, 0)(O) ** 2 + ddC(ctx, v, 1)(O) ** 2 + ddC(ctx, w, 2)(O) ** 2
+    S12, S13, S23 = _strain_offdiag(ctx, U, 0, 1), _strain_offdiag(ctx, U, 0, 2), _strain_offdiag(ctx, U, 1, 2)
+    Ixy = iC(ctx, iC(ctx, _sq(S12), 0), 1)
+    Ixz = iC(ctx, iC(ctx, _sq(S13), 0), 2)
+    Iyz = iC(ctx, iC(ctx, _sq(S23), 1), 2)
+    return tr + two * Ixy(O) + two * Ixz(O) + two * Iyz(O)
+
+
+def dz_b_q(ctx, buoyancy, tracers):
+    """∂z_b at ccf: buoyancy_tracer.jl:16 ; seawater_buoyancy.jl:219-224 (LinearEquationOfState: α, β constants) ; no_buoyancy.jl:9"""
+    FT = ctx.FT
+    if buoyancy is None:
+        return lambda o: ctx.zeros()
+    if buoyancy.kind == "tracer":
+        return ddF(ctx, ctx.field(tracers["b"]), 2)
+    dT, dS = ddF(ctx, ctx.field(tracers["T"]), 2), ddF(ctx, ctx.field(tracers["S"]), 2)
+    gg, al, be = FT(buoyancy.g), FT(buoyancy.alpha), FT(buoyancy.beta)
+    return lambda o: gg * (al * dT(o) - be * dS(o))
+
+
+def lilly_stability(FT, N2, S2, cb):
+    """stability(N², Σ², cᵇ)  lilly_coefficient.jl:114-126"""
+    N2p = np.maximum(FT(0), N2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s2 = FT(1) - np.minimum(FT(1), cb * N2p / S2)
+        return np.where(S2 == 0, FT(0), np.sqrt(s2)).astype(FT)
+
+
+def compute_smagorinsky(ctx, closure, U, tracers, buoyancy, nu_e, kappa_e):
+    """_compute_smagorinsky_viscosity!  smagorinsky.jl:92-108 ; κₑ = νₑ / Pr  (:44,154-156: the face diffusivities are
+    ℑ(νₑ) / Pr — the oracle stores νₑ / Pr per tracer and interpolates that, identical up to one rounding)"""
+    g, FT = ctx.g, ctx.FT
+    S2 = strain_double_dot_ccc(ctx, U)
+    D3 = g.D[0] * g.D[1] * ctx.dz("c")(O)                     # Δxᶜᶜᶜ Δyᶜᶜᶜ Δzᶜᶜᶜ (Flat: 1)
+    Df = np.cbrt(np.asarray(D3, dtype=FT))
+    if closure.Cb is None:
+        cs2 = FT(closure.C) ** 2                             # square_smagorinsky_coefficient(::ConstantSmagorinsky) :110
+    else:
+        N2 = iC(ctx, dz_b_q(ctx, buoyancy, tracers), 2)(O)   # ℑzᵃᵃᶜ ∂z_b   lilly_coefficient.jl:130
+        cs2 = lilly_stability(FT, N2, S2, FT(closure.Cb)) * FT(closure.C) ** 2
+    nu = cs2 * Df ** 2 * np.sqrt(FT(2) * S2)
+    nu_e.interior[...] = nu
+    for name in tracers:
+        kappa_e[name].interior[...] = nu / FT(closure.Pr_for(name))
 
 
 # ---------------------------------------------------------------------------------

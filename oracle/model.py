@@ -65,7 +65,7 @@ class OracleModel:
         need = advection.buffer
         closures = () if closure is None else (tuple(closure) if isinstance(closure, (tuple, list)) else (closure,))
         for c in closures:
-            need = max(need, 2 if c.kind == "amd" else 1)
+            need = max(need, 2 if c.kind in ("amd", "smagorinsky") else 1)   # AbstractScalarDiffusivity{…, 2}: smagorinsky.jl:31
         H = tuple(max(grid.H[d], need) if not grid.flat(d) else 0 for d in range(3))
         if H != grid.H:
             grid = grid.with_halo(H)
@@ -88,7 +88,8 @@ class OracleModel:
         self.pHY = Field(grid, "ccc", None, "pHY") if buoyancy is not None else None
         self.nu_e = self.kappa_e = None
         for c in closures:
-            if c.kind == "amd":
+            if c.kind in ("amd", "smagorinsky"):
+                assert self.nu_e is None, "one eddy-viscosity closure per model"
                 self.nu_e = Field(grid, "ccc", None, "nu_e")
                 self.kappa_e = {n: Field(grid, "ccc", None, "kappa_e_" + n) for n in tracers}
         self.fields = {"u": self.u, "v": self.v, "w": self.w, **self.tracers}
@@ -157,6 +158,8 @@ class OracleModel:
         for c in self.closures:
             if c.kind == "amd":
                 clo.compute_amd(self._ctx_full(), c, self.U, self.tracers, self.nu_e, self.kappa_e)
+            elif c.kind == "smagorinsky":
+                clo.compute_smagorinsky(self._ctx_full(), c, self.U, self.tracers, self.buoyancy, self.nu_e, self.kappa_e)
         self.update_hydrostatic_pressure()
 
     def update_hydrostatic_pressure(self):

@@ -69,7 +69,10 @@ def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closur
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
     obo = clo.SeawaterBuoyancy() if buoy == "seawater" else (clo.BuoyancyTracer() if buoy == "tracer" else None)
     ocl = {"scalar": clo.ScalarDiffusivity(1e-3, 2e-3), "amd": clo.AnisotropicMinimumDissipation(), "none": None,
-           "both": (clo.ScalarDiffusivity(1e-3, 2e-3), clo.AnisotropicMinimumDissipation())}[closure]
+           "both": (clo.ScalarDiffusivity(1e-3, 2e-3), clo.AnisotropicMinimumDissipation()),
+           "smag": clo.Smagorinsky(0.16, Pr=1.0),
+           # the closure of test/test_nonhydrostatic_regression.jl:68 (C = 0.23, Cb = 1, Pr = 1 + molecular values), Pr varied per tracer
+           "lilly": (clo.SmagorinskyLilly(0.23, 1.0, {n: 1.0 + 0.5 * t for t, n in enumerate(tr)}), clo.ScalarDiffusivity(1.05e-6, 1.46e-7))}[closure]
     bc_o = None
     if bcs:
         t0 = tr[0]
@@ -90,7 +93,10 @@ def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closu
     a = product_scheme(scheme)
     bo = ob.SeawaterBuoyancy() if buoy == "seawater" else (ob.BuoyancyTracer() if buoy == "tracer" else None)
     cl = {"scalar": ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), "amd": ob.AnisotropicMinimumDissipation(), "none": None,
-          "both": (ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), ob.AnisotropicMinimumDissipation())}[closure]
+          "both": (ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), ob.AnisotropicMinimumDissipation()),
+          "smag": ob.Smagorinsky(coefficient=0.16, Pr=1.0),
+          "lilly": (ob.SmagorinskyLilly(C=0.23, Cb=1.0, Pr={n: 1.0 + 0.5 * t for t, n in enumerate(tr)}),
+                    ob.ScalarDiffusivity(nu=1.05e-6, kappa=1.46e-7))}[closure]
     bc_b = None
     if bcs:
         # the BC kinds of test/regression_tests/ocean_large_eddy_simulation_regression_test.jl:19-37
@@ -130,6 +136,10 @@ def compare(m, om, parent_too=True):
         if parent_too:
             worst[name + ".parent"] = rel_linf(m.fields[name].parent(), om.fields[name].data)
     worst["p"] = rel_linf(m.pressures.pNHS.interior(), om.pNHS.interior)
+    if any(c.kind == "smagorinsky" for c in om.closures):          # the eddy viscosity / diffusivities themselves
+        worst["nu_e"] = rel_linf(m.diffusivity_fields.nu_e.interior(), om.nu_e.interior)
+        for n in om.tracers:
+            worst["kappa_e." + n] = rel_linf(m.diffusivity_fields.kappa_e[n].interior(), om.kappa_e[n].interior)
     return worst
 
 
@@ -183,6 +193,18 @@ SCHEME_CASES = [
     ("PPF centered4 2D", dict(N=(16, 12, 1), topo="PPF", scheme="centered4", closure="none", buoy="none")),
     ("stretched PPB upwind5 amd bcs", dict(N=(16, 12, 10), topo="PPB", scheme="upwind5", closure="amd", bcs=True, stretch="smooth")),
     ("stretched BPB centered4", dict(N=(16, 12, 8), topo="BPB", scheme="centered4", stretch="facr")),
+]
+
+# Smagorinsky / SmagorinskyLilly eddy-viscosity closures (Smagorinskys/smagorinsky.jl, lilly_coefficient.jl)
+SMAGORINSKY_CASES = [
+    ("PPP weno smagorinsky TS", dict(N=(16, 12, 8), topo="PPP", scheme="weno", closure="smag")),
+    ("PPB weno smagorinsky-lilly fplane bcs (LES)", dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="lilly", f=1e-2, bcs=True)),
+    ("BBB centered smagorinsky-lilly tracer-b", dict(N=(12, 10, 8), topo="BBB", scheme="centered", closure="lilly", buoy="tracer")),
+    ("PPB upwind3 smagorinsky no buoyancy AB2", dict(N=(16, 12, 8), topo="PPB", scheme="upwind3", closure="smag", buoy="passive", ts="QuasiAdamsBashforth2")),
+    ("PPB weno smagorinsky-lilly F32", dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="lilly", FT=np.float32)),
+    ("stretched PPB weno smagorinsky-lilly bcs", dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="lilly", bcs=True, stretch="smooth")),
+    ("stretched BPB centered smagorinsky", dict(N=(16, 12, 8), topo="BPB", scheme="centered", closure="smag", stretch="facr")),
+    ("tile-crossing 40x36x33 PPB smagorinsky-lilly", dict(N=(40, 36, 33), topo="PPB", scheme="weno", closure="lilly", bcs=True)),
 ]
 
 # vertically stretched grids: FourierTridiagonalPoissonSolver + level-dependent metrics

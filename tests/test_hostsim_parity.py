@@ -149,3 +149,9 @@ def test_checkpoint_pickup_continues_bit_for_bit(hostsim, ts, tmp_path):
         assert np.array_equal(m1.fields[n].parent(), m2.fields[n].parent()), n
     assert np.array_equal(m1.pressures.pNHS.interior(), m2.pressures.pNHS.interior())
     assert m1.clock.time == m2.clock.time and m1.clock.iteration == m2.clock.iteration == 4
+
+
+@pytest.mark.parametrize("name,kw", ph.SMAGORINSKY_CASES[:-1], ids=[c[0] for c in ph.SMAGORINSKY_CASES[:-1]])
+def test_hostsim_matches_oracle_with_smagorinsky_closures(hostsim, name, kw):
+    """Smagorinsky / SmagorinskyLilly (Smagorinskys/smagorinsky.jl:92-108, lilly_coefficient.jl:114-135)"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))

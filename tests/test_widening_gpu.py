@@ -1,0 +1,24 @@
+"""GPU parity tests (`-m gpu`) of the SURVEY §8f item 3 widening added after the last GPU session of round 1: the Smagorinsky /
+SmagorinskyLilly closures.  Same harness and tolerances as tests/test_gpu_parity.py (through the C ABI, against the CPU oracle,
+1 and 10 steps, interior and parent arrays).  The kernel logic of these cases is also exercised on CPU by the host-simulation
+build (tests/test_hostsim_parity.py)."""
+import pytest
+
+import parity_harness as ph
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import oceananigans_b200 as ob_
+    from oceananigans_b200 import _lib
+    lib = _lib.load()                    # raises if the CUDA library is missing
+    assert lib.path.endswith("liboceananigans_b200.so")
+    return ob_
+
+
+@pytest.mark.parametrize("name,kw", ph.SMAGORINSKY_CASES, ids=[c[0] for c in ph.SMAGORINSKY_CASES])
+def test_cuda_matches_oracle_with_smagorinsky_closures(ob, name, kw):
+    """Smagorinsky(coefficient, Pr) and SmagorinskyLilly(C, Cb, Pr): Smagorinskys/smagorinsky.jl:92-108, lilly_coefficient.jl:114-135"""
+    ph.check_case(kw, library=None, steps=(1, 10))
