@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — cell-updates/s per full time step of the NonhydrostaticModel hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c3f32|c4|c4s|c1|c3u5|c2c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c3f32|c4|c4s|c4l|c1|c3u5|c2c4] [--impl ours|reference]
 
 One "step" is one full `time_step!(model, Δt)` (RK3: three stages, each tendency+substep, halo fills, FFT
 pressure solve and projection) over one synthetic, seeded initial state.
@@ -59,7 +59,12 @@ WORKLOADS = {
     "c4s": dict(N=(512, 512, 256), topo="PPB", FT="f64", adv="weno", tracers=("T", "S"), buoy="seawater", closure="amd",
                 F=5, b=1, a=1, stretched=True,
                 label="C4s 512^2x256 (P,P,B) stretched z, FourierTridiagonal solver, WENO-5 AMD FPlane flux BCs F64"),
+    # the C4 physics with the closure of test/test_nonhydrostatic_regression.jl:68 instead of AMD
+    "c4l": dict(N=(512, 512, 256), topo="PPB", FT="f64", adv="weno", tracers=("T", "S"), buoy="seawater", closure="lilly",
+                F=5, b=1, a=1,
+                label="C4 physics with (SmagorinskyLilly(C=0.23, Cb=1, Pr=1), ScalarDiffusivity): 512^2x256 (P,P,B) WENO-5 FPlane flux BCs F64"),
 }
+LES = ("amd", "lilly")       # the C4 family: Δ = 1 m, LES initial condition, Δt = 1 s, FPlane, surface flux BCs
 
 
 def stretched_faces(Nz, Lz):
@@ -161,7 +166,7 @@ def build_model(w, device, rank=0, world=1):
     nonflat = [d for d in range(3) if w["topo"][d] != "F"]
     gsize = global_size(w, world)
     size = tuple(gsize[d] for d in nonflat)
-    if w is WORKLOADS["c4"] or w.get("closure") == "amd":
+    if w.get("closure") in LES:
         extent = tuple(float(w["N"][d]) for d in nonflat)                      # Δ = 1 m
     elif w["topo"] == "PPF":
         extent = (2 * np.pi, 2 * np.pi)
@@ -179,14 +184,15 @@ def build_model(w, device, rank=0, world=1):
            "centered4": lambda: ob.Centered(order=4)}[w["adv"]]()
     kw = dict(grid=grid, advection=adv, tracers=w["tracers"])
     if w["buoy"] == "seawater":
-        if w["closure"] == "amd":
+        if w["closure"] in LES:
             kw["buoyancy"] = ob.SeawaterBuoyancy(equation_of_state=ob.LinearEquationOfState(thermal_expansion=2e-4, haline_contraction=8e-4))
         else:
             kw["buoyancy"] = ob.SeawaterBuoyancy()
     if w["closure"] == "scalar":
         kw["closure"] = ob.ScalarDiffusivity(nu=1e-5, kappa=1e-5)
-    elif w["closure"] == "amd":
-        kw["closure"] = ob.AnisotropicMinimumDissipation()
+    elif w["closure"] in LES:
+        kw["closure"] = ob.AnisotropicMinimumDissipation() if w["closure"] == "amd" else \
+            (ob.SmagorinskyLilly(C=0.23, Cb=1.0, Pr=1.0), ob.ScalarDiffusivity(nu=1.05e-6, kappa=1.46e-7))
         kw["coriolis"] = ob.FPlane(f=1e-4)
         kw["boundary_conditions"] = {      # test/regression_tests/ocean_large_eddy_simulation_regression_test.jl:19-37
             "u": ob.FieldBoundaryConditions(top=ob.FluxBoundaryCondition(-2e-5)),
@@ -204,7 +210,7 @@ def synthetic_ic(w, model, seed=1234):
     ic = {}
     for n in ("u", "v", "w"):
         shape = tuple(model.fields[n].info().interior_size)
-        if w["closure"] == "amd":
+        if w["closure"] in LES:
             ic[n] = (1e-3 * rng.standard_normal(shape, dtype=np.float32)).astype(FT)
         else:
             ic[n] = rng.uniform(-1, 1, shape).astype(FT) if FT is np.float64 else (2 * rng.random(shape, dtype=np.float32) - 1)
@@ -216,7 +222,7 @@ def synthetic_ic(w, model, seed=1234):
 
 
 def default_dt(w):
-    if w["closure"] == "amd":
+    if w["closure"] in LES:
         return 1.0
     if w["topo"] == "PPF":
         return 0.01
@@ -225,18 +231,18 @@ def default_dt(w):
 
 # ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
-    import torch
-    import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
-    torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1:            # torch is plumbing for the multi-rank runs only (rendezvous, NCCL id broadcast, max over ranks)
+        import torch
+        import torch.distributed as dist
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = WORKLOADS[args.workload]
     ob, model = build_model(w, local, rank, world)
@@ -388,7 +394,7 @@ def oracle_model(w, N):
     FT = np.float64 if w["FT"] == "f64" else np.float32
     nonflat = [d for d in range(3) if w["topo"][d] != "F"]
     size = tuple(N[d] for d in nonflat)
-    extent = tuple(float(N[d]) for d in nonflat) if w["closure"] == "amd" else tuple(1.0 for _ in nonflat)
+    extent = tuple(float(N[d]) for d in nonflat) if w["closure"] in LES else tuple(1.0 for _ in nonflat)
     if w.get("stretched"):
         og = oracle.Grid(FT, size=size, x=(0.0, extent[0]), y=(0.0, extent[1]),
                          z=[float(v) for v in stretched_faces(N[2], extent[2])], topology=tuple(w["topo"]))
@@ -401,14 +407,15 @@ def oracle_model(w, N):
         kw["buoyancy"] = clo.SeawaterBuoyancy()
     if w["closure"] == "scalar":
         kw["closure"] = clo.ScalarDiffusivity(1e-5, 1e-5)
-    elif w["closure"] == "amd":
-        kw["closure"] = clo.AnisotropicMinimumDissipation()
+    elif w["closure"] in LES:
+        kw["closure"] = clo.AnisotropicMinimumDissipation() if w["closure"] == "amd" else \
+            (clo.SmagorinskyLilly(0.23, 1.0, 1.0), clo.ScalarDiffusivity(1.05e-6, 1.46e-7))
         kw["coriolis_f"] = 1e-4
         kw["boundary_conditions"] = {"u": {"top": BC("flux", -2e-5)}, "T": {"top": BC("flux", 5e-5), "bottom": BC("gradient", 0.005)},
                                      "S": {"top": BC("flux", 5e-8)}}
     om = oracle.OracleModel(og, **kw)
     rng = np.random.default_rng(1234)
-    if w["closure"] == "amd":        # the LES workloads step with Δt = 1 s at Δ = 1 m: small velocities, like synthetic_ic
+    if w["closure"] in LES:          # the LES workloads step with Δt = 1 s at Δ = 1 m: small velocities, like synthetic_ic
         ic = {n: 1e-3 * rng.standard_normal(om.fields[n].interior.shape) for n in ("u", "v", "w")}
     else:
         ic = {n: rng.uniform(-1, 1, om.fields[n].interior.shape) for n in ("u", "v", "w")}
@@ -440,7 +447,7 @@ def c_twin_model(w, n):
 def cpu_run(w, n_numpy, max_steps, budget_s, warmup=1):
     """Time the CPU restatement of the reference algorithm on a bounded sample of the workload: the multi-threaded C twin for the
     triply periodic workloads (Float64 arithmetic), the NumPy oracle otherwise.  Returns (cells/s, s/step, steps, cores, sample)."""
-    if w["topo"] == "PPP" and w["closure"] != "amd" and w["adv"] in ("weno", "centered"):
+    if w["topo"] == "PPP" and w["closure"] not in LES and w["adv"] in ("weno", "centered"):
         n = 128
         model, N = c_twin_model(w, n)
         dt = 0.1 / n
@@ -449,7 +456,7 @@ def cpu_run(w, n_numpy, max_steps, budget_s, warmup=1):
     else:
         N = cpu_sample_size(w, n_numpy)
         model = oracle_model(w, N)
-        dt = default_dt(w) * w["N"][0] / N[0] if w["closure"] != "amd" else 1.0
+        dt = default_dt(w) * w["N"][0] / N[0] if w["closure"] not in LES else 1.0
         cores = 1
         what = "NumPy oracle, 1 thread"
     for _ in range(warmup):
