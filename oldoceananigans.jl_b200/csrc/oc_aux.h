@@ -188,7 +188,7 @@ struct SmagorinskyKernel {
     FT* nu_e;
     int ntr;
     FT* kappa_e[8];
-    FT Pr[8];
+    FT rPr[8];           // 1 / Pr[tracer]
     FT cs2;              // C² (smagorinsky.jl:110; lilly_coefficient.jl:133)
     int lilly;           // 1: multiply by ς(N², Σ², Cb)
     FT Cb;
@@ -237,23 +237,17 @@ struct SmagorinskyKernel {
         const FT S11 = (u[o + sx] - u[o]) * rdx, S22 = (v[o + sy] - v[o]) * rdy, S33 = (w[o + sz] - w[o]) * rdzc;
         const FT tr = S11 * S11 + S22 * S22 + S33 * S33;
         const FT S2 = tr + FT(2) * I12 + FT(2) * I13 + FT(2) * I23;
-        FT c2 = cs2;
-        if (lilly) {
-            FT N2 = FT(0);
-            if (buoyancy) N2 = FT(0.5) * (dzb(o, k) + dzb(o + sz, k + 1));                  // ℑzᵃᵃᶜ ∂z_b
-            const FT N2p = oc_max<FT>(FT(0), N2);
-            FT sig = FT(0);
-            if (S2 != FT(0)) {
-                FT ratio = Cb * N2p / S2;
-                if (!(ratio < FT(1))) ratio = FT(1);                                       // min(1, ·)
-                sig = oc_sqrt<FT>(FT(1) - ratio);
-            }
-            c2 = sig * cs2;
+        // νₑ = ς c² Δᶠ² √(2Σ²) with ς = √(1 − min(1, Cb N²⁺ / Σ²)) (0 when Σ² = 0)  ==  c² Δᶠ² √(2 max(0, Σ² − Cb N²⁺)):
+        // the same value with one square root and no division (both forms lose the same digits when Σ² ≈ Cb N²⁺)
+        FT arg = S2;
+        if (lilly && buoyancy) {
+            const FT N2 = FT(0.5) * (dzb(o, k) + dzb(o + sz, k + 1));                      // ℑzᵃᵃᶜ ∂z_b   lilly_coefficient.jl:130
+            arg = oc_max<FT>(FT(0), S2 - Cb * oc_max<FT>(FT(0), N2));
         }
         const FT d2 = STR ? lv_df2[k] : df2;
-        const FT nu = c2 * d2 * oc_sqrt<FT>(FT(2) * S2);
+        const FT nu = cs2 * d2 * oc_sqrt<FT>(FT(2) * arg);
         nu_e[o] = nu;
-        for (int t = 0; t < ntr; ++t) kappa_e[t][o] = nu / Pr[t];
+        for (int t = 0; t < ntr; ++t) kappa_e[t][o] = nu * rPr[t];                         // κₑ = νₑ / Pr; rPr = 1 / Pr formed on the host
     }
 };
 

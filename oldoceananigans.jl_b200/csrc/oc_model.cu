@@ -805,7 +805,7 @@ void Model<FT>::aux() {
             k.u = state_[0].p; k.v = state_[1].p; k.w = state_[2].p;
             k.nu_e = nu_e_.p;
             k.ntr = cfg_.n_tracers;
-            for (int t = 0; t < cfg_.n_tracers; ++t) { k.kappa_e[t] = kappa_e_[t].p; k.Pr[t] = (FT)cfg_.smag_Pr[t]; }
+            for (int t = 0; t < cfg_.n_tracers; ++t) { k.kappa_e[t] = kappa_e_[t].p; k.rPr[t] = FT(1) / (FT)cfg_.smag_Pr[t]; }
             const FT C = (FT)cfg_.smag_C;
             k.cs2 = C * C;
             k.lilly = cfg_.smagorinsky == 2;

@@ -112,15 +112,16 @@ def build_pair(library=None, **kw):
     return build_product(library=library, **kw), build_oracle(**kw)
 
 
-def initial_conditions(om, seed=1234, smooth=False):
-    """SURVEY §8d synthetic inputs: rng(1234); u,v,w ~ U(-1,1); T = 20 + 0.01 N(0,1); S = 35 + 0.01 N(0,1)."""
+def initial_conditions(om, seed=1234, smooth=False, tracer_noise=0.01):
+    """SURVEY §8d synthetic inputs: rng(1234); u,v,w ~ U(-1,1); T = 20 + 0.01 N(0,1); S = 35 + 0.01 N(0,1).
+    tracer_noise: amplitude of the tracer perturbation (large values make N² comparable to Σ²: the SmagorinskyLilly cut-off)."""
     rng = np.random.default_rng(seed)
     ic = {}
     for name in ("u", "v", "w"):
         ic[name] = rng.uniform(-1, 1, om.fields[name].interior.shape)
     base = {"T": 20.0, "S": 35.0, "b": 0.0, "c": 1.0}
     for n in om.tracers:
-        ic[n] = base.get(n, 0.0) + 0.01 * rng.standard_normal(om.fields[n].interior.shape)
+        ic[n] = base.get(n, 0.0) + tracer_noise * rng.standard_normal(om.fields[n].interior.shape)
     return ic
 
 
@@ -145,8 +146,9 @@ def compare(m, om, parent_too=True):
 
 def run_case(steps=(1, 10), dt=None, **kw):
     """returns {step: {field: rel error}}"""
+    tracer_noise = kw.pop("tracer_noise", 0.01)
     m, om = build_pair(**kw)
-    ic = initial_conditions(om)
+    ic = initial_conditions(om, tracer_noise=tracer_noise)
     ob.set_(m, **ic)
     om.set(**ic)
     if dt is None:
@@ -199,7 +201,8 @@ SCHEME_CASES = [
 SMAGORINSKY_CASES = [
     ("PPP weno smagorinsky TS", dict(N=(16, 12, 8), topo="PPP", scheme="weno", closure="smag")),
     ("PPB weno smagorinsky-lilly fplane bcs (LES)", dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="lilly", f=1e-2, bcs=True)),
-    ("BBB centered smagorinsky-lilly tracer-b", dict(N=(12, 10, 8), topo="BBB", scheme="centered", closure="lilly", buoy="tracer")),
+    # b = 30 N(0,1): N² is of the size of Σ², so that all three branches of the stability function are taken (checked below)
+    ("BBB centered smagorinsky-lilly tracer-b strong stratification", dict(N=(12, 10, 8), topo="BBB", scheme="centered", closure="lilly", buoy="tracer", tracer_noise=30.0)),
     ("PPB upwind3 smagorinsky no buoyancy AB2", dict(N=(16, 12, 8), topo="PPB", scheme="upwind3", closure="smag", buoy="passive", ts="QuasiAdamsBashforth2")),
     ("PPB weno smagorinsky-lilly F32", dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="lilly", FT=np.float32)),
     ("stretched PPB weno smagorinsky-lilly bcs", dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="lilly", bcs=True, stretch="smooth")),
@@ -225,7 +228,7 @@ def check_case(kw, library=None, steps=(1, 10)):
     FT = kw.get("FT", np.float64)
     if max(kw["N"]) > 32:
         steps = (1, 2)
-    out, m, om = run_case(steps=steps, library=library, **kw)
+    out, m, om = run_case(steps=steps, library=library, **dict(kw))
     tol = TOL[FT]
     for s, errs in out.items():
         for name, e in errs.items():
