@@ -174,6 +174,11 @@ int  oc_restore_previous_tendency(oc_model* m, int field, const void* parent_hos
  * Distributed models return the LOCAL values: reduce them across ranks as the reference does (all_reduce(min, …)). */
 typedef struct { double cell_advection_timescale; double max_abs_u, max_abs_v, max_abs_w; int32_t has_nan; int32_t pad; } oc_diagnostics;
 int  oc_compute_diagnostics(oc_model* m, oc_diagnostics* out);
+/* maximum(abs, interior(field)) of one field, reduced on the device (an 8-byte device-to-host copy); NaN if the field holds a NaN.
+ * What cell_diffusion_timescale(model) needs for the eddy-viscosity closures — maximum(νₑ), maximum(κₑ)
+ * (src/TurbulenceClosures/turbulence_closure_diagnostics.jl:57-69; the TimeStepWizard's diffusive_cfl,
+ * src/Simulations/time_step_wizard.jl:101-108) — and progress messages need for tracers.  Local value on distributed models. */
+int  oc_field_maximum_abs(oc_model* m, int field, double* out);
 
 /* ---- multi-GPU: one process per GPU, slab decomposition in y ----
  * Replaces Distributed(...) + fill_halo_regions! on distributed fields (src/DistributedComputations/halo_communication.jl:87-333)

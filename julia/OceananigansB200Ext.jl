@@ -253,4 +253,42 @@ end
 update_state!(model::B200Model, callbacks=[]; compute_tendencies=true) =
     check(ccall((:oc_update_state, LIB), Cint, (Ptr{Cvoid}, Cint), twin(model).handle, compute_tendencies))
 
+# ---- on-device step diagnostics (SURVEY §8f item 2): no full-field device-to-host copies for the TimeStepWizard / NaNChecker ----------
+struct OcDiagnostics
+    cell_advection_timescale::Float64; max_abs_u::Float64; max_abs_v::Float64; max_abs_w::Float64; has_nan::Int32; pad::Int32
+end
+function step_diagnostics(model::B200Model)
+    d = Ref{OcDiagnostics}()
+    check(ccall((:oc_compute_diagnostics, LIB), Cint, (Ptr{Cvoid}, Ref{OcDiagnostics}), twin(model).handle, d))
+    return d[]
+end
+# cell_advection_timescale(model)  src/Advection/cell_advection_timescale.jl:13-34 (TimeStepWizard: src/Simulations/time_step_wizard.jl:101-115)
+Oceananigans.Advection.cell_advection_timescale(model::B200Model) = step_diagnostics(model).cell_advection_timescale
+
+"maximum(abs, interior(field)) reduced on the device; `id` = field id of include/oceananigans_b200.h (νₑ = 34, κₑ = 40 + t)"
+function field_maximum_abs(model::B200Model, id)
+    out = Ref{Cdouble}(0)
+    check(ccall((:oc_field_maximum_abs, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Cdouble}), twin(model).handle, id, out))
+    return out[]
+end
+# cell_diffusion_timescale(model)  src/TurbulenceClosures/turbulence_closure_diagnostics.jl:23-25,57-69: the host method is kept for
+# ScalarDiffusivity (numbers); for the eddy-viscosity closures maximum(νₑ), maximum(κₑ) come from the device
+function Oceananigans.Diagnostics.cell_diffusion_timescale(model::B200Model)
+    closures = model.closure isa Tuple ? model.closure : (model.closure,)
+    Δ² = Oceananigans.TurbulenceClosures.min_Δxyz(model.grid, Oceananigans.TurbulenceClosures.ThreeDimensionalFormulation())^2
+    nt = length(model.tracers)
+    τ = Inf
+    for c in closures
+        if c isa ScalarDiffusivity
+            τ = min(τ, Δ² / c.ν, (Δ² / κ for κ in c.κ)...)
+        elseif c isa Smagorinsky
+            minPr = nt == 0 ? 1 : minimum(c.Pr)
+            τ = min(τ, Δ² / (field_maximum_abs(model, 34) * max(1, 1 / minPr)))
+        elseif c isa AnisotropicMinimumDissipation
+            τ = min(τ, Δ² / field_maximum_abs(model, 34), (Δ² / field_maximum_abs(model, 40 + t - 1) for t in 1:nt)...)
+        end
+    end
+    return τ
+end
+
 end # module

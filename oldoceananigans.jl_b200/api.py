@@ -31,7 +31,7 @@ __all__ = [
     "compute_tendencies_", "compute_flux_bc_tendencies_", "rk3_substep_", "ab2_step_", "cache_previous_tendencies_",
     "compute_pressure_correction_", "make_pressure_correction_", "fill_halo_regions_", "solve_poisson",
     "interior", "parent", "Simulation", "run_", "Clock", "Checkpointer", "OceananigansB200Error",
-    "cell_advection_timescale", "hasnan", "step_diagnostics", "TimeStepWizard",
+    "cell_advection_timescale", "cell_diffusion_timescale", "hasnan", "step_diagnostics", "TimeStepWizard",
 ]
 
 OceananigansB200Error = L.OceananigansB200Error
@@ -367,6 +367,12 @@ class Field:
     def interior(self):
         return self._download(False)
 
+    def maximum_abs(self):
+        """maximum(abs, interior(field)), reduced on the device (oc_field_maximum_abs): an 8-byte copy instead of the field"""
+        out = C.c_double()
+        self.model._lib.check(self.model._lib.oc_field_maximum_abs(self.model._h, self.id, C.byref(out)))
+        return out.value
+
     def parent(self):
         return self._download(True)
 
@@ -697,11 +703,39 @@ def hasnan(model):
     return step_diagnostics(model)["has_nan"]
 
 
-class TimeStepWizard:
-    """TimeStepWizard(cfl=0.2, max_change=1.1, min_change=0.5, max_Δt=Inf, min_Δt=0)   src/Simulations/time_step_wizard.jl:65-116
-    (advective CFL only: the diffusive timescale is out of scope)."""
+def cell_diffusion_timescale(model):
+    """cell_diffusion_timescale(model)   src/TurbulenceClosures/turbulence_closure_diagnostics.jl:23-25,41-46,57-69,83-84:
+    Δ² / max diffusivity with Δ = min(Δx, Δy, Δz) over the non-Flat dimensions (ThreeDimensionalFormulation); closure tuples take the
+    minimum; no closure: Inf.  The maxima of νₑ / κₑ are reduced on the device (oc_field_maximum_abs)."""
+    g = model.grid
+    spac = [g.D[d] for d in range(3) if g.topology[d] is not Flat and not (d == 2 and g.z_faces is not None)]
+    if g.z_faces is not None:
+        spac.append(float(np.min(np.diff(g.z_faces.astype(g.FT)))))
+    delta2 = min(spac) ** 2 if spac else math.inf
+    closures = model.closure if isinstance(model.closure, (tuple, list)) else (() if model.closure is None else (model.closure,))
+    div = lambda a, b: math.inf if b == 0 else a / b
+    pick = lambda v: max(v.values()) if isinstance(v, dict) else v
+    out = math.inf
+    for c in closures:
+        if isinstance(c, ScalarDiffusivity):
+            kap = [c.kappa[n] if isinstance(c.kappa, dict) else c.kappa for n in model.tracer_names] or [0.0]
+            out = min(out, div(delta2, float(c.nu)), div(delta2, float(max(kap))))
+        elif isinstance(c, Smagorinsky):
+            prs = [c.Pr[n] if isinstance(c.Pr, dict) else c.Pr for n in model.tracer_names] or [1.0]
+            out = min(out, div(delta2, model.diffusivity_fields.nu_e.maximum_abs() * max(1.0, 1.0 / min(prs))))
+        elif isinstance(c, AnisotropicMinimumDissipation):
+            out = min(out, div(delta2, model.diffusivity_fields.nu_e.maximum_abs()))
+            for f in model.diffusivity_fields.kappa_e.values():
+                out = min(out, div(delta2, f.maximum_abs()))
+    return out
 
-    def __init__(self, cfl=0.2, max_change=1.1, min_change=0.5, max_Δt=math.inf, min_Δt=0.0, max_dt=None, min_dt=None):
+
+class TimeStepWizard:
+    """TimeStepWizard(cfl=0.2, diffusive_cfl=Inf, max_change=1.1, min_change=0.5, max_Δt=Inf, min_Δt=0)
+    src/Simulations/time_step_wizard.jl:65-116"""
+
+    def __init__(self, cfl=0.2, diffusive_cfl=math.inf, max_change=1.1, min_change=0.5, max_Δt=math.inf, min_Δt=0.0, max_dt=None, min_dt=None):
+        self.diffusive_cfl = diffusive_cfl
         if min_change >= 1:
             raise ValueError(f"min_change must be < 1. You provided min_change = {min_change}.")
         if max_change <= 1:
@@ -712,6 +746,8 @@ class TimeStepWizard:
 
     def new_time_step(self, old_dt, model):
         new_dt = self.cfl * cell_advection_timescale(model)
+        if math.isfinite(self.diffusive_cfl):        # :77-79: the diffusion timescale is evaluated only when a diffusive CFL is given
+            new_dt = min(new_dt, self.diffusive_cfl * cell_diffusion_timescale(model))
         new_dt = min(self.max_change * old_dt, new_dt)
         new_dt = max(self.min_change * old_dt, new_dt)
         return min(max(new_dt, self.min_dt), self.max_dt)

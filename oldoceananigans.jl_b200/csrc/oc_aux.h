@@ -316,4 +316,48 @@ struct DiagnosticsKernel {
     }
 };
 
+// maximum(abs, interior(field)) of ONE field, on the device (8-byte result): what cell_diffusion_timescale needs for the eddy-viscosity
+// closures (maximum(νₑ), maximum(κₑ): src/TurbulenceClosures/turbulence_closure_diagnostics.jl:57-69) and progress messages need for
+// tracers.  |x| ≥ 0, so the bit patterns of the doubles order like unsigned integers; a NaN anywhere raises out[1].
+template <class FT>
+struct FieldMaxAbsKernel {
+    static constexpr int PHASES = 2;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr size_t SMEM = sizeof(double) * 2 * THREADS;
+    Geom<FT> g;
+    const FT* f;
+    int nx;                // interior extent along x (N, +1 for a Face-located field in a Bounded x)
+    unsigned long long* out;
+    OC_HD static unsigned long long bits(double x) { unsigned long long b; memcpy(&b, &x, 8); return b; }
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char* smem) const {
+        double* sh = reinterpret_cast<double*>(smem);
+        if (PHASE == 0) {
+            double mx = 0.0, nan = 0.0;
+            for (int i = tid; i < nx; i += nt) {
+                const FT x = f[g.idx(i, b.y, b.z)];
+                const double a = (double)oc_abs<FT>(x);
+                if (a > mx) mx = a;
+                if (x != x) nan = 1.0;
+            }
+            sh[tid] = mx; sh[nt + tid] = nan;
+        } else {
+            if (tid != 0) return;
+            double mx = 0.0, nan = 0.0;
+            for (int t = 0; t < nt; ++t) {
+                if (sh[t] > mx) mx = sh[t];
+                if (sh[nt + t] > nan) nan = sh[nt + t];
+            }
+#if defined(__CUDA_ARCH__)
+            atomicMax(out + 0, bits(mx));
+            if (nan > 0.0) atomicMax(out + 1, 1ull);
+#else
+            if (bits(mx) > out[0]) out[0] = bits(mx);
+            if (nan > 0.0) out[1] = 1ull;
+#endif
+        }
+    }
+};
+
 }  // namespace oc

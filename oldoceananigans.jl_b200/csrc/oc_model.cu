@@ -1335,6 +1335,31 @@ void Model<FT>::diagnostics(oc_diagnostics* out) {
     out->pad = 0;
 }
 
+// maximum(abs, interior(field)); NaN if the field holds a NaN (like Julia's maximum)
+template <class FT>
+double Model<FT>::field_maximum_abs(int field) {
+    join_tracers();
+    oc_field_info info;
+    field_info(field, &info);          // brings auxiliary fields / tendencies up to date exactly like a download would
+    FieldRec& f = lookup(field);
+    if (!diag_dev_) diag_dev_ = (unsigned long long*)dev_alloc(sizeof(unsigned long long) * 5);
+    unsigned long long init[2] = {0, 0};
+    dev_upload(diag_dev_, init, sizeof(init), stream_);
+    FieldMaxAbsKernel<FT> k;
+    k.g = g_;
+    k.f = f.p;
+    k.nx = info.interior_size[0];
+    k.out = diag_dev_;
+    Dim3 grid;
+    grid.x = 1; grid.y = info.interior_size[1]; grid.z = info.interior_size[2];
+    go(k, grid, FieldMaxAbsKernel<FT>::SMEM, OC_TIMER_AUX);
+    unsigned long long res[2];
+    dev_download(res, diag_dev_, sizeof(res), stream_);
+    double d;
+    memcpy(&d, &res[0], 8);
+    return res[1] ? (double)NAN : d;
+}
+
 // Checkpointer pickup of G⁻ (checkpointer.jl:230-262).  Between steps the library keeps the tendencies of the last substep in the
 // Gⁿ slot and marks them stale; the next stage turns them into G⁻ by a pointer swap (stage()).  A restored G⁻ therefore goes into
 // that slot, and the stale mark is (re)asserted so that no fresh evaluation is swapped over it.
@@ -1540,6 +1565,11 @@ int oc_get_clock(oc_model* m, oc_clock* c) { OC_REQUIRE(m); *c = m->impl->clock;
 int oc_set_clock(oc_model* m, const oc_clock* c) { OC_REQUIRE(m); m->impl->clock = *c; return OC_OK; }
 int oc_restore_previous_tendency(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->restore_previous_tendency(field, host, nbytes); }); }
 int oc_compute_diagnostics(oc_model* m, oc_diagnostics* out) { OC_REQUIRE(m); return guarded([&] { m->impl->diagnostics(out); }); }
+int oc_field_maximum_abs(oc_model* m, int field, double* out) {
+    OC_REQUIRE(m);
+    if (!out) { g_last_error = "null argument"; return OC_ERR_INVALID; }
+    return guarded([&] { *out = m->impl->field_maximum_abs(field); });
+}
 int oc_dist_unique_id(void* id128) {
     if (!id128) { g_last_error = "null argument"; return OC_ERR_INVALID; }
     return guarded([&] {

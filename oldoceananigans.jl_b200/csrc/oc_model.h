@@ -98,6 +98,7 @@ struct ModelBase {
     virtual void time_step_rk3(double dt) = 0;
     virtual void time_step_ab2(double dt, int euler) = 0;
     virtual void diagnostics(oc_diagnostics* out) = 0;
+    virtual double field_maximum_abs(int field) = 0;
     virtual void restore_previous_tendency(int field, const void* host, size_t nbytes) = 0;
     virtual void dist_attach(Transport* t) = 0;
     virtual int dist_rank() const = 0;
@@ -134,6 +135,7 @@ public:
     void time_step_rk3(double dt) override;
     void time_step_ab2(double dt, int euler) override;
     void diagnostics(oc_diagnostics* out) override;
+    double field_maximum_abs(int field) override;
     void restore_previous_tendency(int field, const void* host, size_t nbytes) override;
     void dist_attach(Transport* t) override;
     int dist_rank() const override { return rank_; }

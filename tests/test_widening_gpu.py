@@ -22,3 +22,11 @@ def ob():
 def test_cuda_matches_oracle_with_smagorinsky_closures(ob, name, kw):
     """Smagorinsky(coefficient, Pr) and SmagorinskyLilly(C, Cb, Pr): Smagorinskys/smagorinsky.jl:92-108, lilly_coefficient.jl:114-135"""
     ph.check_case(kw, library=None, steps=(1, 10))
+
+
+def test_wizard_known_answers_and_diffusion_timescale_cuda(ob):
+    """TimeStepWizard known answers of test/test_simulations.jl:14-76 (advective and diffusive CFL) and cell_diffusion_timescale of the
+    eddy-viscosity closures, with maximum(νₑ) / maximum(κₑ) reduced on the device (oc_field_maximum_abs)."""
+    import test_diagnostics as td
+    td._wizard_known_answers(None, 4)
+    td._diffusion_timescale_of_eddy_closures(None)
