@@ -427,7 +427,10 @@ class NonhydrostaticModel:
             if val:
                 raise NotImplementedError(f"{name} is out of scope of the B200 path (Julia closures / other subsystems)")
         self._lib = library if library is not None else L.load()
-        tracers = (tracers,) if isinstance(tracers, str) else tuple(tracers)
+        # tracers = :c, (:T, :S), () or nothing   (tracernames: src/Fields/field_tuples.jl)
+        tracers = () if tracers is None else ((tracers,) if isinstance(tracers, str) else tuple(tracers))
+        if boundary_conditions is not None and not isinstance(boundary_conditions, dict):
+            raise TypeError("boundary_conditions must be a NamedTuple-like mapping field name -> FieldBoundaryConditions")
         if len(tracers) > L.OC_MAX_TRACERS:
             raise ValueError("too many tracers")
         # advection = Centered() by default (nonhydrostatic_model.jl:117); advection = nothing (None) switches advection off

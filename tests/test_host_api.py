@@ -1,0 +1,117 @@
+"""Host API mirror (oceananigans_b200 = oldoceananigans.jl_b200/api.py) against the reference's own constructor / set! tests
+(test/test_nonhydrostatic_models.jl), through the C ABI: on CPU with the host-simulation build of the kernel sources, on the GPU
+(`-m gpu`, tests/test_widening_gpu.py) with the CUDA library.  Same names, argument meaning and error behaviour as the reference."""
+import os
+
+import numpy as np
+import pytest
+
+import oceananigans_b200 as ob
+
+
+def _hostsim():
+    from oceananigans_b200 import _lib
+    import __graft_entry__ as ge
+    if not os.path.exists(ge.HOSTSIM):
+        ge.build()
+    return _lib.Library(ge.HOSTSIM)
+
+
+def model_construction(library):
+    """test/test_nonhydrostatic_models.jl:22-38: NonhydrostaticModel(; grid) for the four topologies × float types at (16, 16, 2);
+    :101-112: a single tracer given as a name, and tracers = nothing"""
+    kw = {} if library is None else {"library": library}
+    for topo in ((ob.Periodic, ob.Periodic, ob.Periodic), (ob.Periodic, ob.Periodic, ob.Bounded),
+                 (ob.Periodic, ob.Bounded, ob.Bounded), (ob.Bounded, ob.Bounded, ob.Bounded)):
+        for FT in (np.float64, np.float32):
+            grid = ob.RectilinearGrid(FT, topology=topo, size=(16, 16, 2), extent=(1, 2, 3))
+            model = ob.NonhydrostaticModel(grid=grid, **kw)
+            assert isinstance(model, ob.NonhydrostaticModel) and model.grid.FT is FT
+            assert (model.grid.Hx, model.grid.Hy, model.grid.Hz) == (3, 3, 2)            # default halo min(3, N): input_validation.jl:71-77
+    grid = ob.RectilinearGrid(size=(1, 1, 1), extent=(1, 1, 1))
+    m = ob.NonhydrostaticModel(grid=grid, tracers="c", buoyancy=None, **kw)
+    assert tuple(m.tracers.keys()) == ("c",)
+    m = ob.NonhydrostaticModel(grid=grid, tracers=None, buoyancy=None, **kw)
+    assert len(m.tracers) == 0
+    # :14-16 wrong-typed keyword arguments are errors (TypeError in the reference)
+    for bad in (dict(boundary_conditions=1), dict(forcing=2), dict(background_fields=3)):
+        with pytest.raises((TypeError, NotImplementedError, AttributeError, ValueError)):
+            ob.NonhydrostaticModel(grid=grid, **bad, **kw)
+
+
+def halo_adjustment(library):
+    """test/test_nonhydrostatic_models.jl:40-69 (inflate_grid_halo_size) and :78-86 (adapt_advection_order: not implemented -> error)"""
+    kw = {} if library is None else {"library": library}
+    minimal = ob.RectilinearGrid(size=(4, 4, 4), extent=(1, 2, 3), halo=(1, 1, 1))
+    funny = ob.RectilinearGrid(size=(4, 4, 4), extent=(1, 2, 3), halo=(1, 3, 4))
+    H = lambda m: (m.grid.Hx, m.grid.Hy, m.grid.Hz)
+    assert H(ob.NonhydrostaticModel(grid=minimal, **kw)) == (1, 1, 1)
+    assert H(ob.NonhydrostaticModel(grid=funny, **kw)) == (1, 3, 4)
+    for scheme in (ob.Centered(order=4), ob.UpwindBiased(order=3)):
+        assert H(ob.NonhydrostaticModel(advection=scheme, grid=minimal, **kw)) == (2, 2, 2)
+        assert H(ob.NonhydrostaticModel(advection=scheme, grid=funny, **kw)) == (2, 3, 4)
+    for scheme in (ob.WENO(), ob.UpwindBiased(order=5)):
+        assert H(ob.NonhydrostaticModel(advection=scheme, grid=minimal, **kw)) == (3, 3, 3)
+        assert H(ob.NonhydrostaticModel(advection=scheme, grid=funny, **kw)) == (3, 3, 4)
+    for closure in (ob.AnisotropicMinimumDissipation(), ob.Smagorinsky()):             # required halo 2, like ScalarBiharmonicDiffusivity :72-76
+        assert H(ob.NonhydrostaticModel(closure=closure, grid=minimal, **kw)) == (2, 2, 2)
+        assert H(ob.NonhydrostaticModel(closure=closure, grid=funny, **kw)) == (2, 3, 4)
+    # the minimal grid itself is not modified (the model holds an inflated copy)
+    assert (minimal.Hx, minimal.Hy, minimal.Hz) == (1, 1, 1)
+    # :78-86 the reference lowers the order of WENO() to fit Ny = 2; this path does not implement that lowering: a loud error
+    small = ob.RectilinearGrid(size=(4, 2, 4), extent=(1, 2, 3), halo=(1, 1, 1))
+    with pytest.raises((ob.OceananigansB200Error, NotImplementedError, ValueError)):
+        ob.NonhydrostaticModel(grid=small, advection=ob.WENO(), **kw)
+
+
+def setting_model_fields(library, FT):
+    """test/test_nonhydrostatic_models.jl:114-195 on the RectilinearGrid: set! from arrays and from functions of (x, y, z), halo
+    regions filled by set! (periodicity, free slip), enforce_incompressibility"""
+    kw = {} if library is None else {"library": library}
+    N, Lxyz = (4, 4, 4), (2 * np.pi, 3 * np.pi, 5 * np.pi)
+    grid = ob.RectilinearGrid(FT, size=N, extent=Lxyz, topology=(ob.Periodic, ob.Bounded, ob.Bounded))
+    model = ob.NonhydrostaticModel(grid=grid, buoyancy=ob.SeawaterBuoyancy(), tracers=("T", "S"), **kw)
+    u, v, w = (model.velocities[n] for n in "uvw")
+    T, S = model.tracers["T"], model.tracers["S"]
+    T0 = np.random.default_rng(1).random(N).astype(FT)
+    ob.set_(model, enforce_incompressibility=False, T=T0)
+    assert np.array_equal(T.interior(), T0)
+    u0 = lambda x, y, z: 1 + x + y + z
+    v0 = lambda x, y, z: 2 + np.sin(x * y * z)
+    w0 = lambda x, y, z: 3 + y * z
+    T0f = lambda x, y, z: 4 + np.tanh(x + y - z)
+    S0f = lambda x, y, z: 5 + 0 * x
+    ob.set_(model, enforce_incompressibility=False, u=u0, v=v0, w=w0, T=T0f, S=S0f)
+    g = model.grid
+    xC, yC, zC = (g.nodes(d, ob.Center).reshape([-1 if e == d else 1 for e in range(3)]) for d in range(3))
+    xF, yF, zF = (g.nodes(d, ob.Face).reshape([-1 if e == d else 1 for e in range(3)]) for d in range(3))
+    Nx, Ny, Nz = N
+    tol = dict(rtol=8 * np.finfo(FT).eps, atol=0)
+    assert np.allclose(u.interior(), u0(xF, yC, zC), **tol)
+    assert np.allclose(v.interior()[:, 1:Ny, :], v0(xC, yF, zC)[:, 1:Ny, :], **tol)          # wall faces are overwritten by the BC
+    assert np.allclose(w.interior()[:, :, 1:Nz], w0(xC, yC, zF)[:, :, 1:Nz], **tol)
+    assert np.allclose(T.interior(), T0f(xC, yC, zC), **tol)
+    assert np.allclose(S.interior(), np.broadcast_to(S0f(xC, yC, zC), N), **tol)
+    # set! fills the halo regions: parent index = logical index + H - 1
+    up = u.parent()
+    Hx, Hy, Hz = g.Hx, g.Hy, g.Hz
+    P = lambda i, j, k: up[i + Hx - 1, j + Hy - 1, k + Hz - 1]
+    assert P(1, 1, 1) == P(Nx + 1, 1, 1)                                                       # x-periodicity
+    assert np.array_equal(up[Hx:Hx + Nx, Hy:Hy + Ny, Hz], up[Hx:Hx + Nx, Hy:Hy + Ny, Hz - 1])            # free slip at the bottom
+    assert np.array_equal(up[Hx:Hx + Nx, Hy:Hy + Ny, Hz + Nz - 1], up[Hx:Hx + Nx, Hy:Hy + Ny, Hz + Nz])  # and at the top
+    # enforce_incompressibility: a uniform w = 1 between two walls is projected out
+    ob.set_(model, u=0, v=0, w=1, T=0, S=0)
+    assert np.all(np.abs(w.interior()) < 10 * np.finfo(FT).eps)
+
+
+def test_model_construction_hostsim():
+    model_construction(_hostsim())
+
+
+def test_halo_adjustment_hostsim():
+    halo_adjustment(_hostsim())
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_setting_model_fields_hostsim(FT):
+    setting_model_fields(_hostsim(), FT)

@@ -677,3 +677,81 @@ def test_smagorinsky_model_steps_and_stays_incompressible():
         from oracle.operators import div_ccc
         assert np.abs(div_ccc(ctx, m.u, m.v, m.w)).max() < 1e-12
         assert abs(m.tracers["T"].interior.mean() - T0) < 1e-13 * 20
+
+
+# ----------------------------------------------------------------------------- operators (test/test_operators.jl)
+def _phi2_field(g, phi):
+    """a ccc field holding ϕ² in its interior (the point function f(i, j, k, grid, ϕ) = ϕ[i, j, k]^2 of the reference test)"""
+    f = Field(g, "ccc")
+    f.interior[...] = phi ** 2
+    return f
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_function_differences_derivatives_interpolations(FT):
+    # test/test_operators.jl:52-86 (test_function_differentiation: extent 3 => Δ = 1, ∂ == δ), :125-152 (test_function_interpolation),
+    # :8-50 (differences, on the non-immersed grid) — exact equality at (i, j, k) = (2, 2, 2)
+    from oracle.operators import dC, dF, ddC, iC, iF
+    g = Grid(FT, size=(3, 3, 3), extent=(3, 3, 3), topology=("P", "P", "B"))
+    phi = np.random.default_rng(5).random((3, 3, 3)).astype(FT)
+    p2 = phi ** 2
+    ctx = Ctx(g, (2, 2), (2, 2), (2, 2))
+    q = ctx.field(_phi2_field(g, phi))
+    at = lambda i, j, k: p2[i - 1, j - 1, k - 1]
+    for d in range(3):
+        lo, hi = [2, 2, 2], [2, 2, 2]
+        lo[d], hi[d] = 1, 3
+        assert dC(ctx, q, d)(O)[0, 0, 0] == at(*hi) - at(2, 2, 2)              # δᶜ: ϕ²[i+1] − ϕ²[i]
+        assert dF(ctx, q, d)(O)[0, 0, 0] == at(2, 2, 2) - at(*lo)              # δᶠ: ϕ²[i] − ϕ²[i−1]
+        assert ddC(ctx, q, d)(O)[0, 0, 0] == at(*hi) - at(2, 2, 2)             # ∂ᶜ with Δ = 1
+        assert ddF(ctx, q, d)(O)[0, 0, 0] == at(2, 2, 2) - at(*lo)
+        assert iC(ctx, q, d)(O)[0, 0, 0] == (at(*hi) + at(2, 2, 2)) / 2        # ℑᶜ
+        assert iF(ctx, q, d)(O)[0, 0, 0] == (at(2, 2, 2) + at(*lo)) / 2        # ℑᶠ
+
+
+def test_derivatives_on_a_stretched_z():
+    # test/test_operators.jl:88-123 (test_function_differentiation, stretched part), restricted to the z direction (the only one this
+    # path stretches): faces (0, 1, 3, 6) => Δzᶜ = (1, 2, 3), centres (0.5, 2, 4.5) => Δzᶠ(2) = 1.5;  ∂z = δz / Δz at (2, 2, 2)
+    from oracle.operators import ddC
+    FT = np.float64
+    g = Grid(FT, size=(3, 3, 3), x=(0, 3), y=(0, 3), z=[0.0, 1.0, 3.0, 6.0], topology=("B", "B", "B"))
+    phi = np.random.default_rng(6).random((3, 3, 3))
+    p2 = phi ** 2
+    ctx = Ctx(g, (2, 2), (2, 2), (2, 2))
+    q = ctx.field(_phi2_field(g, phi))
+    assert ddC(ctx, q, 2)(O)[0, 0, 0] == 1 / 2.0 * (p2[1, 1, 2] - p2[1, 1, 1])          # 1/dc(2) (ϕ²[k+1] − ϕ²[k]), dc(2) = 3 − 1
+    assert ddF(ctx, q, 2)(O)[0, 0, 0] == 1 / 1.5 * (p2[1, 1, 1] - p2[1, 1, 0])          # 1/df(2) (ϕ²[k] − ϕ²[k−1]), df(2) = 2 − 0.5
+    assert ddC(ctx, q, 0)(O)[0, 0, 0] == p2[2, 1, 1] - p2[1, 1, 1]                      # regular x, Δ = 1
+
+
+def test_grid_lengths_areas_volumes():
+    # test/test_operators.jl:154-222: RectilinearGrid(size=(1,1,1), extent=(π, 2π, 3π)): Δ = π, 2π, 3π; Ax = 6π², Ay = 3π², Az = 2π², V = 6π³
+    FT = np.float64
+    g = Grid(FT, size=(1, 1, 1), extent=(np.pi, 2 * np.pi, 3 * np.pi), topology=("P", "P", "B"))
+    pi = FT(np.pi)
+    assert g.D == (pi, FT(2 * np.pi), FT(3 * np.pi))
+    ctx = Ctx(g, (1, 1), (1, 1), (1, 1))
+    for zl in "cf":
+        assert ctx.area(0, zl)(O) == FT(2 * np.pi) * FT(3 * np.pi) and np.isclose(ctx.area(0, zl)(O), 6 * np.pi ** 2, rtol=4e-16)
+        assert ctx.area(1, zl)(O) == pi * FT(3 * np.pi) and np.isclose(ctx.area(1, zl)(O), 3 * np.pi ** 2, rtol=4e-16)
+        assert ctx.area(2, zl)(O) == pi * FT(2 * np.pi) and np.isclose(ctx.area(2, zl)(O), 2 * np.pi ** 2, rtol=4e-16)
+        assert np.isclose(ctx.vol(zl)(O), 6 * np.pi ** 3, rtol=4e-16)
+        assert ctx.dz(zl)(O) == FT(3 * np.pi)
+
+
+def test_flat_dimension_operators():
+    # test/test_operators.jl:262-304: on a grid with a Flat dimension, differences along it vanish and the other directions act as in 3-D
+    from oracle.operators import dC, dF, iC, iF
+    FT = np.float64
+    g = Grid(FT, size=(4, 5), extent=(1, 1), topology=("F", "P", "B"))
+    rng = np.random.default_rng(7)
+    f = Field(g, "ccc")
+    f.interior[...] = rng.random(f.interior.shape)
+    fill_halo_regions(f)
+    ctx = Ctx(g, (1, 1), (2, 3), (2, 4))
+    q = ctx.field(f)
+    assert np.all(dC(ctx, q, 0)(O) == 0) and np.all(dF(ctx, q, 0)(O) == 0)
+    assert np.all(iC(ctx, q, 0)(O) == q(O)) and np.all(iF(ctx, q, 0)(O) == q(O))         # Flat interpolation = identity
+    a = f.interior
+    assert np.array_equal(dC(ctx, q, 1)(O)[0], a[0, 2:4, 1:4] - a[0, 1:3, 1:4])
+    assert np.array_equal(dF(ctx, q, 2)(O)[0], a[0, 1:3, 1:4] - a[0, 1:3, 0:3])

@@ -30,3 +30,14 @@ def test_wizard_known_answers_and_diffusion_timescale_cuda(ob):
     import test_diagnostics as td
     td._wizard_known_answers(None, 4)
     td._diffusion_timescale_of_eddy_closures(None)
+
+
+@pytest.mark.parametrize("FT", ["f64", "f32"])
+def test_host_api_mirrors_the_reference_constructor_and_set(ob, FT):
+    """test/test_nonhydrostatic_models.jl:22-69,101-195 through the CUDA library (tests/test_host_api.py holds the checks)"""
+    import numpy as np
+    import test_host_api as th
+    if FT == "f64":
+        th.model_construction(None)
+        th.halo_adjustment(None)
+    th.setting_model_fields(None, np.float64 if FT == "f64" else np.float32)
