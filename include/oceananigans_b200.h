@@ -42,6 +42,7 @@ typedef enum { OC_PERIODIC = 0, OC_BOUNDED = 1, OC_FLAT = 2 } oc_topology;      
 typedef enum { OC_CENTERED2 = 0, OC_WENO5 = 1, OC_CENTERED4 = 2, OC_UPWIND3 = 3, OC_UPWIND5 = 4, OC_WENO3 = 5, OC_UPWIND1 = 6,
                OC_ADVECTION_NONE = 7 } oc_advection;
 typedef enum { OC_RK3 = 0, OC_AB2 = 1 } oc_timestepper;                              /* src/TimeSteppers */
+typedef enum { OC_CORIOLIS_NONE = 0, OC_CORIOLIS_FPLANE = 1, OC_CORIOLIS_BETAPLANE = 2, OC_CORIOLIS_CARTESIAN = 3 } oc_coriolis;   /* oc_config.has_coriolis */
 typedef enum { OC_BUOYANCY_NONE = 0, OC_BUOYANCY_TRACER = 1, OC_BUOYANCY_SEAWATER_LINEAR = 2 } oc_buoyancy;
 
 /* boundary_condition.jl:8,83-110.  OC_BC_DEFAULT resolves by topology and location
@@ -76,7 +77,7 @@ typedef struct {
     int32_t buoyancy;             /* oc_buoyancy */
     double  gravity, thermal_expansion, haline_contraction;                         /* SeawaterBuoyancy + LinearEquationOfState */
     int32_t tracer_T, tracer_S, tracer_b;  /* tracer indices used by the buoyancy model (-1 if unused) */
-    int32_t has_coriolis; double coriolis_f;                                        /* FPlane(f) */
+    int32_t has_coriolis; double coriolis_f;   /* oc_coriolis kind (0 = nothing); FPlane(f) / BetaPlane f₀ */
     oc_bc   bcs[OC_MAX_FIELDS][6];         /* per prognostic field × side */
     int32_t device;               /* CUDA device ordinal */
     /* Distributed(arch; partition = Partition(1, R)): slab decomposition in y (distributed_architectures.jl:242-302).
@@ -97,6 +98,11 @@ typedef struct {
     int32_t reserved;
     double  smag_C, smag_Cb;
     double  smag_Pr[OC_MAX_TRACERS];
+    /* The Coriolis family (ABI v3).  BetaPlane(f₀, β): f = f₀ + β y at the y-node of the velocity point (src/Coriolis/beta_plane.jl:56-72);
+     * origin_y = y of the south face of the GLOBAL domain (ynode = origin_y + (j − ½ | j − 1) Δy).  ConstantCartesianCoriolis(fx, fy, fz)
+     * (src/Coriolis/constant_cartesian_coriolis.jl:70-81): all three momentum equations.  Both run in the general tile kernel. */
+    double  coriolis_beta, origin_y;
+    double  coriolis_fxyz[3];
 } oc_config;
 
 typedef struct oc_model oc_model;

@@ -22,7 +22,7 @@ using Oceananigans.Advection: Centered, WENO
 using Oceananigans.TurbulenceClosures: ScalarDiffusivity, AnisotropicMinimumDissipation
 using Oceananigans.TurbulenceClosures.Smagorinskys: Smagorinsky, LillyCoefficient
 using Oceananigans.BuoyancyFormulations: SeawaterBuoyancy, BuoyancyTracer, LinearEquationOfState, BuoyancyForce
-using Oceananigans.Coriolis: FPlane
+using Oceananigans.Coriolis: FPlane, BetaPlane, ConstantCartesianCoriolis
 using Oceananigans.BoundaryConditions: BoundaryCondition, Flux, Value, Gradient, Open, Periodic as PeriodicBC
 
 import Oceananigans.Architectures as AC
@@ -68,6 +68,7 @@ mutable struct OcConfig               # `oc_config`, same field order; NTuple fo
     z_stretched::Int32; z_faces::Ptr{Float64}      # ABI v2: vertically stretched grid (Nz+1 faces, read during oc_model_create only)
     smagorinsky::Int32; reserved::Int32            # ABI v3: 0 none, 1 Smagorinsky(coefficient::Number), 2 LillyCoefficient
     smag_C::Float64; smag_Cb::Float64; smag_Pr::NTuple{OC_MAX_TRACERS,Float64}
+    coriolis_beta::Float64; origin_y::Float64; coriolis_fxyz::NTuple{3,Float64}   # ABI v3: BetaPlane, ConstantCartesianCoriolis
     OcConfig() = new()
 end
 
@@ -170,8 +171,13 @@ function config(model::NonhydrostaticModel)
     end
     if model.coriolis isa FPlane
         cfg.has_coriolis = 1; cfg.coriolis_f = model.coriolis.f
+    elseif model.coriolis isa BetaPlane            # f = f₀ + β ynode  (src/Coriolis/beta_plane.jl:56-72)
+        cfg.has_coriolis = 2; cfg.coriolis_f = model.coriolis.f₀; cfg.coriolis_beta = model.coriolis.β
+        cfg.origin_y = TY === Flat ? 0.0 : Float64(grid.yᵃᶠᵃ[1])
+    elseif model.coriolis isa ConstantCartesianCoriolis     # src/Coriolis/constant_cartesian_coriolis.jl:70-81
+        cfg.has_coriolis = 3; cfg.coriolis_fxyz = Float64.((model.coriolis.fx, model.coriolis.fy, model.coriolis.fz))
     elseif model.coriolis !== nothing
-        throw(ArgumentError("B200: only FPlane"))
+        throw(ArgumentError("B200: Coriolis must be FPlane, BetaPlane or ConstantCartesianCoriolis"))
     end
     fields = (model.velocities..., model.tracers...)
     cfg.bcs = ntuple(OC_MAX_FIELDS) do f

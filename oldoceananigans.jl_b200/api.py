@@ -25,7 +25,7 @@ from . import _lib as L
 __all__ = [
     "B200", "Distributed", "Partition", "Periodic", "Bounded", "Flat", "Center", "Face", "RectilinearGrid",
     "Centered", "UpwindBiased", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation", "Smagorinsky", "SmagorinskyLilly", "LillyCoefficient",
-    "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "FPlane",
+    "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "FPlane", "BetaPlane", "ConstantCartesianCoriolis",
     "FluxBoundaryCondition", "ValueBoundaryCondition", "GradientBoundaryCondition", "OpenBoundaryCondition",
     "FieldBoundaryConditions", "NonhydrostaticModel", "Field", "set_", "time_step_", "update_state_",
     "compute_tendencies_", "compute_flux_bc_tendencies_", "rk3_substep_", "ab2_step_", "cache_previous_tendencies_",
@@ -283,11 +283,76 @@ class BuoyancyTracer:
     required = ("b",)
 
 
+_OMEGA_EARTH = 7.292115e-5      # Oceananigans.defaults.planet_rotation_rate
+_R_EARTH = 6371.0e3             # Oceananigans.defaults.planet_radius
+
+
+def _sind(deg):
+    """Julia's sind / cosd are exact at multiples of 30° / 90°"""
+    exact = {0: 0.0, 30: 0.5, 90: 1.0, 150: 0.5, 180: 0.0}
+    d = deg % 360
+    if d in exact:
+        return exact[d]
+    if d - 180 in exact:
+        return -exact[d - 180]
+    return math.sin(math.radians(deg))
+
+
+def _cosd(deg):
+    return _sind(deg + 90)
+
+
 class FPlane:
-    def __init__(self, FT=np.float64, f=None):
-        if f is None:
-            raise ValueError("FPlane needs f")
+    """FPlane(f=…) or FPlane(rotation_rate=Ω_Earth, latitude=φ): f = 2Ω sind(φ)   src/Coriolis/f_plane.jl:9-44"""
+
+    def __init__(self, FT=np.float64, f=None, rotation_rate=None, latitude=None):
+        use_f, use_planet = f is not None, latitude is not None
+        if use_f == use_planet or (use_f and rotation_rate is not None):
+            raise ValueError("Either both keywords rotation_rate and latitude must be specified, *or* only f must be specified.")
+        if use_planet:
+            f = 2 * (_OMEGA_EARTH if rotation_rate is None else rotation_rate) * _sind(latitude)
         self.f = f
+
+
+class BetaPlane:
+    """BetaPlane(f₀=…, β=…) or BetaPlane(rotation_rate, latitude, radius): f = f₀ + β y   src/Coriolis/beta_plane.jl:1-47"""
+
+    def __init__(self, FT=np.float64, f0=None, beta=None, rotation_rate=None, latitude=None, radius=None, **kw):
+        f0, beta = kw.pop("f₀", f0), kw.pop("β", beta)
+        if kw:
+            raise TypeError(f"unexpected keyword arguments {sorted(kw)}")
+        use_fb, use_planet = f0 is not None and beta is not None, latitude is not None
+        if use_fb == use_planet or ((f0 is None) != (beta is None)):
+            raise ValueError("Either both keywords f₀ and β must be specified, *or* all of rotation_rate, latitude, and radius.")
+        if use_planet:
+            om = _OMEGA_EARTH if rotation_rate is None else rotation_rate
+            f0, beta = 2 * om * _sind(latitude), 2 * om * _cosd(latitude) / (_R_EARTH if radius is None else radius)
+        self.f0, self.beta = f0, beta
+
+
+class ConstantCartesianCoriolis:
+    """ConstantCartesianCoriolis(fx, fy, fz | f, rotation_axis | latitude, rotation_rate)   src/Coriolis/constant_cartesian_coriolis.jl:11-67"""
+
+    def __init__(self, FT=np.float64, fx=None, fy=None, fz=None, f=None, rotation_axis=None, latitude=None, rotation_rate=None):
+        comps = (fx, fy, fz)
+        if latitude is not None:
+            if any(c is not None for c in comps) or f is not None:
+                raise ValueError("Only `rotation_rate` can be specified when using `latitude`.")
+            om = _OMEGA_EARTH if rotation_rate is None else rotation_rate
+            fx, fy, fz = 0.0, 2 * om * _cosd(latitude), 2 * om * _sind(latitude)
+        elif f is not None:
+            if any(c is not None for c in comps):
+                raise ValueError("Only `rotation_axis` can be specified when using `f`.")
+            if rotation_axis is None:                                   # ZDirection()
+                fx, fy, fz = 0.0, 0.0, f
+            else:
+                ax = np.asarray(rotation_axis, dtype=np.float64)
+                if ax.shape != (3,) or not np.isclose(float(np.sqrt((ax ** 2).sum())), 1.0):      # validate_unit_vector
+                    raise ValueError("unit vector must be unitary")
+                fx, fy, fz = (f * float(a) for a in ax)
+        elif not all(c is not None for c in comps):
+            raise ValueError("Either (i) `latitude`, or (ii) `f`, or (iii) `fx`, `fy` and `fz` must be specified.")
+        self.fx, self.fy, self.fz = fx, fy, fz
 
 
 class _BC:
@@ -508,9 +573,17 @@ class NonhydrostaticModel:
             else:
                 raise NotImplementedError("unsupported buoyancy model")
         if coriolis is not None:
-            if not isinstance(coriolis, FPlane):
-                raise NotImplementedError("only FPlane Coriolis")
-            cfg.has_coriolis, cfg.coriolis_f = 1, float(coriolis.f)
+            if isinstance(coriolis, FPlane):
+                cfg.has_coriolis, cfg.coriolis_f = L.OC_CORIOLIS_FPLANE, float(coriolis.f)
+            elif isinstance(coriolis, BetaPlane):
+                cfg.has_coriolis, cfg.coriolis_f, cfg.coriolis_beta = L.OC_CORIOLIS_BETAPLANE, float(coriolis.f0), float(coriolis.beta)
+                cfg.origin_y = float(grid.x0[1])
+            elif isinstance(coriolis, ConstantCartesianCoriolis):
+                cfg.has_coriolis = L.OC_CORIOLIS_CARTESIAN
+                cfg.coriolis_fxyz[0], cfg.coriolis_fxyz[1], cfg.coriolis_fxyz[2] = float(coriolis.fx), float(coriolis.fy), float(coriolis.fz)
+            else:
+                raise NotImplementedError("Coriolis must be FPlane, BetaPlane or ConstantCartesianCoriolis "
+                                          "(NonTraditionalBetaPlane, HydrostaticSphericalCoriolis are out of scope)")
         names = ("u", "v", "w") + tracers
         bcs = boundary_conditions or {}
         for k in bcs:

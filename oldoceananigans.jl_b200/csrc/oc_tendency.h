@@ -44,13 +44,21 @@ struct TendencyArgs {
     FT nu, kappa;        // its ν and this tracer's κ
     int buoyancy;        // 0 none, 1 tracer b (bT), 2 seawater linear (bT = T, bS = S)
     FT grav, alpha, beta;
-    int has_coriolis;
+    int has_coriolis;    // oc_coriolis (1 FPlane; 2, 3: general tile kernel only, parameters in CoriolisExt)
     FT f;
     FluxBC<FT> fbc;      // flux boundary conditions of this field
     int add_flux_bcs;
     int mode;            // SubstepMode
     FT dt, ca, cb;       // RK3_FIRST: U + (dt·γ)·G with ca = dt·γ ; RK3: U + dt(ca·G + cb·G⁻) ; AB2: ca = 1.5+χ, cb = 0.5+χ
     int ab2_euler;
+};
+
+// BetaPlane / ConstantCartesianCoriolis parameters.  Kept OUT of TendencyArgs so that the parameter block — and with it the
+// generated code — of the z-marching kernel of the measured configurations (oc_march.h) stays exactly what was profiled.
+template <class FT>
+struct CoriolisExt {
+    FT beta, y0;         // BetaPlane: f = f₀ + β ynode; y0 = y of the south face of this rank's first row
+    FT cf[3];            // ConstantCartesianCoriolis fx, fy, fz
 };
 
 template <class FT, int ADV, int KIND, int TX_, int TY_, int TZ_>
@@ -64,6 +72,7 @@ struct TendencyKernel {
     static constexpr int COMP = KIND == KIND_C ? -1 : KIND;
 
     TendencyArgs<FT> a;
+    CoriolisExt<FT> cor;
 
     // ---- closure fluxes -------------------------------------------------------------------------------
     // ν at the location that is Face in dims (d1,d2) (d1 < d2): ℑ_{d2}ᶠ(ℑ_{d1}ᶠ νₑ)  interpolation_operators.jl:45-56
@@ -267,8 +276,28 @@ struct TendencyKernel {
                     // maybe_z_dot_g_bᶜᶜᶠ: only without the hydrostatic split (nonhydrostatic_tendency_kernel_functions.jl:168-170)
                     G = G + FT(0.5) * (buoyancy_at(o - g.sz) + buoyancy_at(o));
                 }
-                if ((KIND == KIND_U || KIND == KIND_V) && a.has_coriolis) {
+                if (KIND != KIND_C && a.has_coriolis == 3) {
+                    // ConstantCartesianCoriolis (constant_cartesian_coriolis.jl:70-81): x: ℑxᶠ(fy ℑzᶜ w − fz ℑyᶜ v), y: ℑyᶠ(fz ℑxᶜ u − fx ℑzᶜ w),
+                    // z: ℑzᶠ(fx ℑyᶜ v − fy ℑxᶜ u); no active-node weighting.  Flat dimensions are stored periodic with N = 1: ℑ = identity.
+                    const FT* u = a.U[0]; const FT* v = a.U[1]; const FT* w = a.U[2];
+                    const FT h = FT(0.5);
+                    const int sC = KIND == KIND_U ? 1 : (KIND == KIND_V ? g.sy : g.sz);
+                    FT acc[2];
+                    for (int n = 0; n < 2; ++n) {
+                        const int p = o - (1 - n) * sC;                    // the two ccc points either side of the velocity point
+                        FT hv;
+                        if (KIND == KIND_U) hv = cor.cf[1] * (h * (w[p] + w[p + g.sz])) - cor.cf[2] * (h * (v[p] + v[p + g.sy]));
+                        else if (KIND == KIND_V) hv = cor.cf[2] * (h * (u[p] + u[p + 1])) - cor.cf[0] * (h * (w[p] + w[p + g.sz]));
+                        else hv = cor.cf[0] * (h * (v[p] + v[p + g.sy])) - cor.cf[1] * (h * (u[p] + u[p + 1]));
+                        acc[n] = hv;
+                    }
+                    G = G - h * (acc[0] + acc[1]);
+                }
+                if ((KIND == KIND_U || KIND == KIND_V) && (a.has_coriolis == 1 || a.has_coriolis == 2)) {
                     // FPlane: x_f_cross_U = -f·ℑxyᶠᶜᶜ(v)/active ; y_f_cross_U = +f·ℑxyᶜᶠᶜ(u)/active   f_plane.jl:50-52
+                    // BetaPlane: the same with f = f₀ + β·ynode(fcc | cfc)   beta_plane.jl:56-72
+                    FT fj = a.f;
+                    if (a.has_coriolis == 2) fj = a.f + cor.beta * (cor.y0 + (FT(j) + (KIND == KIND_U ? FT(0.5) : FT(0))) * g.d[1]);
                     FT num, cnt;
                     if (KIND == KIND_U) {
                         const FT* v = a.U[1] + o;
@@ -278,7 +307,7 @@ struct TendencyKernel {
                         int ay0 = !(g.bounded[1] && (j < 1)), ay1 = !(g.bounded[1] && (j + 1 > g.N[1] - 1));
                         cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
                         FT val = cnt == FT(0) ? FT(0) : num / cnt;
-                        G = G - (-a.f * val);
+                        G = G - (-fj * val);
                     } else {
                         const FT* u = a.U[0] + o;
                         num = FT(0.5) * (FT(0.5) * (u[-g.sy] + u[-g.sy + 1]) + FT(0.5) * (u[0] + u[1]));
@@ -287,7 +316,7 @@ struct TendencyKernel {
                         int ay0 = !(g.bounded[1] && (j - 1 < 0)), ay1 = 1;
                         cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
                         FT val = cnt == FT(0) ? FT(0) : num / cnt;
-                        G = G - (a.f * val);
+                        G = G - (fj * val);
                     }
                 }
                 if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) {

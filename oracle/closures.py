@@ -367,6 +367,108 @@ def _peripheral(ctx, o, loc):
     return res
 
 
+class FPlane:
+    """FPlane(f) or FPlane(rotation_rate, latitude): f = 2Ω sind(φ)   src/Coriolis/f_plane.jl:9-44"""
+
+    def __init__(self, f=None, rotation_rate=None, latitude=None):
+        use_f = f is not None
+        use_planet = latitude is not None
+        if use_f == use_planet or (use_f and rotation_rate is not None):
+            raise ValueError("Either both keywords rotation_rate and latitude must be specified, *or* only f must be specified.")
+        if use_planet:
+            rotation_rate = 7.292115e-5 if rotation_rate is None else rotation_rate
+            f = 2 * rotation_rate * _sind(latitude)
+        self.f = f
+        self.kind = "fplane"
+
+
+class BetaPlane:
+    """BetaPlane(f₀, β) or BetaPlane(rotation_rate, latitude, radius): f = f₀ + β y   src/Coriolis/beta_plane.jl:1-47"""
+
+    def __init__(self, f0=None, beta=None, rotation_rate=None, latitude=None, radius=None):
+        use_fb = f0 is not None and beta is not None
+        use_planet = latitude is not None
+        if use_fb == use_planet or ((f0 is None) != (beta is None)):
+            raise ValueError("Either both keywords f₀ and β must be specified, *or* all of rotation_rate, latitude, and radius.")
+        if use_planet:
+            rotation_rate = 7.292115e-5 if rotation_rate is None else rotation_rate
+            radius = 6371.0e3 if radius is None else radius
+            f0 = 2 * rotation_rate * _sind(latitude)
+            beta = 2 * rotation_rate * _cosd(latitude) / radius
+        self.f0, self.beta = f0, beta
+        self.kind = "betaplane"
+
+
+class ConstantCartesianCoriolis:
+    """ConstantCartesianCoriolis(fx, fy, fz | f, rotation_axis | latitude, rotation_rate)   src/Coriolis/constant_cartesian_coriolis.jl:11-67"""
+
+    def __init__(self, fx=None, fy=None, fz=None, f=None, rotation_axis=None, latitude=None, rotation_rate=None):
+        comps = (fx, fy, fz)
+        if latitude is not None:
+            if any(c is not None for c in comps) or f is not None:
+                raise ValueError("Only `rotation_rate` can be specified when using `latitude`.")
+            rotation_rate = 7.292115e-5 if rotation_rate is None else rotation_rate
+            fx, fy, fz = 0.0, 2 * rotation_rate * _cosd(latitude), 2 * rotation_rate * _sind(latitude)
+        elif f is not None:
+            if any(c is not None for c in comps):
+                raise ValueError("Only `rotation_axis` can be specified when using `f`.")
+            if rotation_axis is None:
+                fx, fy, fz = 0.0, 0.0, f
+            else:
+                ax = np.asarray(rotation_axis, dtype=np.float64)
+                if ax.shape != (3,) or not np.isclose(np.sqrt((ax ** 2).sum()), 1.0):      # validate_unit_vector
+                    raise ValueError("unit vector must be unitary")
+                fx, fy, fz = (f * a for a in ax)
+        elif all(c is not None for c in comps):
+            pass
+        else:
+            raise ValueError("Either (i) `latitude`, or (ii) `f`, or (iii) `fx`, `fy` and `fz` must be specified.")
+        self.fx, self.fy, self.fz = fx, fy, fz
+        self.kind = "cartesian"
+
+
+def _sind(deg):
+    """sind / cosd of Julia are exact at multiples of 30° / 45° / 90°"""
+    exact = {0: 0.0, 30: 0.5, 90: 1.0, 150: 0.5, 180: 0.0}
+    d = deg % 360
+    if d in exact:
+        return exact[d]
+    if d - 180 in exact:
+        return -exact[d - 180]
+    return float(np.sin(np.deg2rad(deg)))
+
+
+def _cosd(deg):
+    return _sind(deg + 90)
+
+
+def coriolis_cross(ctx, cor, U, comp):
+    """x_f_cross_U / y_f_cross_U / z_f_cross_U at the location of velocity component comp, over the window of ctx.
+    FPlane f_plane.jl:50-52 ; BetaPlane beta_plane.jl:56-72 ; ConstantCartesianCoriolis constant_cartesian_coriolis.jl:70-81"""
+    FT, g = ctx.FT, ctx.g
+    if cor.kind == "fplane":
+        return fplane_x(ctx, cor.f, U) if comp == 0 else (fplane_y(ctx, cor.f, U) if comp == 1 else ctx.zeros())
+    if cor.kind == "betaplane":
+        if comp == 2:
+            return ctx.zeros()
+        # ynode(i, j, k, grid, Face, Center, Center) for u ; (Center, Face, Center) for v
+        off = 0.5 if comp == 0 else 0.0
+        y = FT(g.x0[1]) + (ctx.index(1, O).astype(np.float64) - 1 + off) * float(g.D[1]) if not g.flat(1) else np.zeros((1, 1, 1))
+        fy = FT(cor.f0) + FT(cor.beta) * y.astype(FT)
+        unit = fplane_x(ctx, 1.0, U) if comp == 0 else fplane_y(ctx, 1.0, U)          # ∓ active_weighted_ℑxy(·)
+        return fy * unit
+    fx, fy, fz = FT(cor.fx), FT(cor.fy), FT(cor.fz)
+    u, v, w = (ctx.field(f) for f in U)
+    if comp == 0:
+        a, b = iC(ctx, w, 2), iC(ctx, v, 1)
+        return iF(ctx, lambda o: fy * a(o) - fz * b(o), 0)(O)
+    if comp == 1:
+        a, b = iC(ctx, u, 0), iC(ctx, w, 2)
+        return iF(ctx, lambda o: fz * a(o) - fx * b(o), 1)(O)
+    a, b = iC(ctx, v, 1), iC(ctx, u, 0)
+    return iF(ctx, lambda o: fx * a(o) - fy * b(o), 2)(O)
+
+
 def fplane_x(ctx, f, U):
     """x_f_cross_U = -f * active_weighted_ℑxyᶠᶜᶜ(v)   f_plane.jl:50"""
     FT = ctx.FT

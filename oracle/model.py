@@ -56,9 +56,11 @@ class OracleModel:
     """NonhydrostaticModel(; grid, advection, closure, tracers, buoyancy, coriolis, timestepper, boundary_conditions)."""
 
     def __init__(self, grid, advection=None, closure=None, tracers=(), buoyancy=None, coriolis_f=None,
-                 timestepper="RungeKutta3", boundary_conditions=None, chi=0.1):
+                 timestepper="RungeKutta3", boundary_conditions=None, chi=0.1, coriolis=None):
         FT = grid.FT
-        tracers = tuple(tracers)
+        tracers = () if tracers is None else tuple(tracers)
+        if coriolis is None and coriolis_f is not None:
+            coriolis = clo.FPlane(f=coriolis_f)
         if advection is None:
             advection = adv.Centered(FT, 2)
         # inflate_grid_halo_size  nonhydrostatic_model.jl:184,248-262
@@ -73,7 +75,7 @@ class OracleModel:
             if not grid.flat(d):
                 assert grid.N[d] >= advection.buffer, "adapt_advection_order lowering is not restated"
         self.grid, self.FT = grid, FT
-        self.advection, self.closures, self.buoyancy, self.coriolis_f = advection, closures, buoyancy, coriolis_f
+        self.advection, self.closures, self.buoyancy, self.coriolis = advection, closures, buoyancy, coriolis
         bcs = boundary_conditions or {}
         self.u = Field(grid, "fcc", bcs.get("u"), "u")
         self.v = Field(grid, "cfc", bcs.get("v"), "v")
@@ -198,11 +200,9 @@ class OracleModel:
             # buoyancy: gravity = -ẑ  =>  x̂·g b = ŷ·g b = 0 ; ẑ·g b only when pHY′ is nothing (:168-170,222)
             if comp == 2 and self.buoyancy is not None and self.pHY is None:
                 G = G + iF(ctx, clo.buoyancy_q(ctx, self.buoyancy, self.tracers), 2)(O)
-            if self.coriolis_f is not None:
-                if comp == 0:
-                    G = G - clo.fplane_x(ctx, self.coriolis_f, self.U)
-                elif comp == 1:
-                    G = G - clo.fplane_y(ctx, self.coriolis_f, self.U)
+            if self.coriolis is not None:
+                if comp < 2 or self.coriolis.kind == "cartesian":       # z_f_cross_U = 0 for FPlane / BetaPlane
+                    G = G - clo.coriolis_cross(ctx, self.coriolis, self.U, comp)
             if self.pHY is not None and comp < 2:
                 G = G - ddF(ctx, ctx.field(self.pHY), comp)(O)      # hydrostatic_pressure_gradient_x/y
             for c in self.closures:

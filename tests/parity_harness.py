@@ -64,6 +64,17 @@ def product_scheme(scheme):
             "upwind5": lambda: ob.UpwindBiased(order=5), "weno3": lambda: ob.WENO(order=3), "none": lambda: None}[scheme]()
 
 
+def _coriolis(mod, f):
+    """f: None | number (FPlane) | ("beta", f₀, β) | ("cartesian", fx, fy, fz) — the same spelling in the oracle and the product"""
+    if not f:
+        return None
+    if isinstance(f, tuple):
+        if f[0] == "beta":
+            return mod.BetaPlane(f0=f[1], beta=f[2])
+        return mod.ConstantCartesianCoriolis(fx=f[1], fy=f[2], fz=f[3])
+    return mod.FPlane(f=f)
+
+
 def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
                  bcs=False, extent=EXTENT, stretch=None, **_):
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
@@ -80,7 +91,7 @@ def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closur
                 "v": {"bottom": BC("value", 0.1)}}
     og = oracle.Grid(FT, topology=tuple(topo), **_grid_kwargs(N, topo, extent, stretch))
     oa = oracle_scheme(scheme, FT)
-    return oracle.OracleModel(og, advection=oa, tracers=tr, buoyancy=obo, closure=ocl, timestepper=ts, coriolis_f=f,
+    return oracle.OracleModel(og, advection=oa, tracers=tr, buoyancy=obo, closure=ocl, timestepper=ts, coriolis=_coriolis(clo, f),
                               boundary_conditions=bc_o)
 
 
@@ -105,7 +116,7 @@ def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closu
                 t0: ob.FieldBoundaryConditions(top=ob.FluxBoundaryCondition(5e-3), bottom=ob.GradientBoundaryCondition(0.05)),
                 "v": ob.FieldBoundaryConditions(bottom=ob.ValueBoundaryCondition(0.1))}
     return ob.NonhydrostaticModel(grid=grid, advection=a, tracers=tr, buoyancy=bo, closure=cl, timestepper=ts,
-                                  coriolis=ob.FPlane(f=f) if f else None, boundary_conditions=bc_b, library=library)
+                                  coriolis=_coriolis(ob, f), boundary_conditions=bc_b, library=library)
 
 
 def build_pair(library=None, **kw):
@@ -208,6 +219,18 @@ SMAGORINSKY_CASES = [
     ("stretched PPB weno smagorinsky-lilly bcs", dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="lilly", bcs=True, stretch="smooth")),
     ("stretched BPB centered smagorinsky", dict(N=(16, 12, 8), topo="BPB", scheme="centered", closure="smag", stretch="facr")),
     ("tile-crossing 40x36x33 PPB smagorinsky-lilly", dict(N=(40, 36, 33), topo="PPB", scheme="weno", closure="lilly", bcs=True)),
+]
+
+# the Coriolis family: BetaPlane, ConstantCartesianCoriolis (general tile kernel)
+CORIOLIS_CASES = [
+    ("PPP weno betaplane TS", dict(N=(16, 12, 8), topo="PPP", scheme="weno", f=("beta", 0.3, 2.0))),
+    ("PPB weno amd betaplane bcs (LES)", dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="amd", f=("beta", 1e-2, 0.5), bcs=True)),
+    ("BBB centered betaplane AB2", dict(N=(12, 10, 8), topo="BBB", scheme="centered", f=("beta", 0.2, 1.0), ts="QuasiAdamsBashforth2")),
+    ("stretched PBB upwind3 betaplane", dict(N=(16, 12, 9), topo="PBB", scheme="upwind3", f=("beta", 0.2, 1.0), stretch="smooth")),
+    ("PPP weno cartesian coriolis TS", dict(N=(16, 12, 8), topo="PPP", scheme="weno", f=("cartesian", 0.3, -0.5, 0.7))),
+    ("BBB centered cartesian coriolis smagorinsky", dict(N=(12, 10, 8), topo="BBB", scheme="centered", closure="smag", f=("cartesian", 0.3, -0.5, 0.7))),
+    ("stretched PPB weno cartesian coriolis bcs F32", dict(N=(16, 12, 10), topo="PPB", scheme="weno", f=("cartesian", 0.0, 0.6, 0.8), bcs=True, stretch="smooth", FT=np.float32)),
+    ("PFB centered cartesian coriolis 2D", dict(N=(16, 1, 12), topo="PFB", scheme="centered", buoy="tracer", f=("cartesian", 0.3, -0.5, 0.7))),
 ]
 
 # vertically stretched grids: FourierTridiagonalPoissonSolver + level-dependent metrics

@@ -115,3 +115,36 @@ def test_halo_adjustment_hostsim():
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
 def test_setting_model_fields_hostsim(FT):
     setting_model_fields(_hostsim(), FT)
+
+
+def coriolis_constructors_and_inertial_oscillation(library, size=(2, 2, 2)):
+    """test/test_coriolis.jl:17-51,104-119 (constructors) and test/test_dynamics.jl:357-397 (inertial oscillations with the rotation
+    about x̂ and about ẑ: w_z == 0, u_x == 0, |U| ≈ 1, u_z ≈ v_x, v_z ≈ w_x), through the C ABI."""
+    from test_oracle_known_answers import _coriolis_constructor_checks
+    _coriolis_constructor_checks(ob, ValueError)
+    kw = {} if library is None else {"library": library}
+    f0, dt = 1.0, 1e-2
+    nsteps = int(round(np.pi / f0 / dt))
+    out = {}
+    for axis, cor, ic in (("x", ob.ConstantCartesianCoriolis(f=f0, rotation_axis=(1, 0, 0)), "v"), ("z", ob.FPlane(f=f0), "u")):
+        grid = ob.RectilinearGrid(np.float64, size=size, extent=(1, 1, 1), topology=(ob.Periodic, ob.Periodic, ob.Periodic))
+        m = ob.NonhydrostaticModel(grid=grid, coriolis=cor, buoyancy=None, tracers=None, closure=None, timestepper="RungeKutta3", **kw)
+        ob.set_(m, **{ic: 1.0})
+        sim = ob.Simulation(m, Δt=dt, stop_iteration=nsteps)
+        ob.run_(sim)
+        vals = []
+        for n in "uvw":
+            a = m.velocities[n].interior()
+            assert np.ptp(a) < 1e-14
+            vals.append(float(a[0, 0, 0]))
+        out[axis] = vals
+    (u_x, v_x, w_x), (u_z, v_z, w_z) = out["x"], out["z"]
+    assert w_z == 0 and u_x == 0
+    assert np.isclose(np.hypot(v_x, w_x), 1.0, rtol=1e-6) and np.isclose(np.hypot(u_z, v_z), 1.0, rtol=1e-6)
+    assert np.isclose(u_z, v_x, rtol=1e-12, atol=1e-12) and np.isclose(v_z, w_x, rtol=1e-12, atol=1e-12)
+    t = nsteps * dt
+    assert np.isclose(u_z, np.cos(f0 * t), atol=1e-6) and np.isclose(v_z, -np.sin(f0 * t), atol=1e-6)
+
+
+def test_coriolis_constructors_and_inertial_oscillation_hostsim():
+    coriolis_constructors_and_inertial_oscillation(_hostsim())

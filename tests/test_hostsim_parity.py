@@ -155,3 +155,9 @@ def test_checkpoint_pickup_continues_bit_for_bit(hostsim, ts, tmp_path):
 def test_hostsim_matches_oracle_with_smagorinsky_closures(hostsim, name, kw):
     """Smagorinsky / SmagorinskyLilly (Smagorinskys/smagorinsky.jl:92-108, lilly_coefficient.jl:114-135)"""
     ph.check_case(kw, library=hostsim, steps=(1, 3))
+
+
+@pytest.mark.parametrize("name,kw", ph.CORIOLIS_CASES, ids=[c[0] for c in ph.CORIOLIS_CASES])
+def test_hostsim_matches_oracle_for_the_coriolis_family(hostsim, name, kw):
+    """BetaPlane (beta_plane.jl:56-72), ConstantCartesianCoriolis (constant_cartesian_coriolis.jl:70-81)"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))

@@ -755,3 +755,77 @@ def test_flat_dimension_operators():
     a = f.interior
     assert np.array_equal(dC(ctx, q, 1)(O)[0], a[0, 2:4, 1:4] - a[0, 1:3, 1:4])
     assert np.array_equal(dF(ctx, q, 2)(O)[0], a[0, 1:3, 1:4] - a[0, 1:3, 0:3])
+
+
+# ----------------------------------------------------------------------------- Coriolis family (test/test_coriolis.jl, test/test_dynamics.jl)
+def _coriolis_constructor_checks(mod, exc):
+    """test/test_coriolis.jl:17-51 (values) and :104-119 (argument errors), for the oracle (mod = oracle.closures) or the product API"""
+    pi, e = np.pi, np.e
+    assert np.isclose(mod.FPlane(f=pi).f, pi)
+    assert np.isclose(mod.FPlane(rotation_rate=2, latitude=30).f, 2.0)
+    c = mod.ConstantCartesianCoriolis(f=1, rotation_axis=[0, np.cos(np.pi / 4), np.sin(np.pi / 4)])
+    assert np.isclose(c.fy, np.cos(np.pi / 4)) and np.isclose(c.fz, np.sin(np.pi / 4)) and c.fx == 0
+    c = mod.ConstantCartesianCoriolis(f=10, rotation_axis=[np.sqrt(1 / 3)] * 3)
+    assert np.allclose([c.fx, c.fy, c.fz], 10 * np.sqrt(1 / 3))
+    b = mod.BetaPlane(f0=pi, beta=2 * pi)
+    assert np.isclose(b.f0, pi) and np.isclose(b.beta, 2 * pi)
+    b = mod.BetaPlane(latitude=70, radius=2 * pi, rotation_rate=3 * pi)
+    assert np.isclose(b.f0, 6 * pi * np.sin(np.deg2rad(70))) and np.isclose(b.beta, 6 * pi * np.cos(np.deg2rad(70)) / (2 * pi))
+    for bad in (lambda: mod.FPlane(), lambda: mod.FPlane(rotation_rate=7e-5), lambda: mod.FPlane(f=1, latitude=40),
+                lambda: mod.FPlane(f=1, rotation_rate=7e-5, latitude=40),
+                lambda: mod.ConstantCartesianCoriolis(rotation_axis=[0, 1, 1]), lambda: mod.ConstantCartesianCoriolis(f=1, latitude=45),
+                lambda: mod.ConstantCartesianCoriolis(fx=1, latitude=45), lambda: mod.ConstantCartesianCoriolis(fx=1, f=1),
+                lambda: mod.ConstantCartesianCoriolis(f=1, rotation_axis=[0, 1, 1]),
+                lambda: mod.BetaPlane(), lambda: mod.BetaPlane(f0=1), lambda: mod.BetaPlane(beta=1),
+                lambda: mod.BetaPlane(f0=1e-4, beta=1e-11, latitude=70)):
+        with pytest.raises(exc):
+            bad()
+
+
+def test_coriolis_constructors():
+    _coriolis_constructor_checks(clo, ValueError)
+
+
+def test_inertial_oscillations_with_rotation_about_different_axes():
+    # test/test_dynamics.jl:357-397: a uniform flow under FPlane(f = 1) (u = 1) and under ConstantCartesianCoriolis(f = 1, axis = x̂) (v = 1)
+    # for half an inertial period: w_z == 0, u_x == 0, |U| ≈ 1, u_z ≈ v_x, v_z ≈ w_x.  (The reference uses a (Flat, Flat, Flat) grid and
+    # Δt = 1e-3; a 2×2×2 periodic box with uniform fields is the same ODE — every interpolation of a uniform field is the identity —
+    # and Δt = 1e-2 keeps the oracle fast: RK3 damps the amplitude by (fΔt)⁴/24 per step, 1.3e-7 in total.)
+    f0, dt = 1.0, 1e-2
+    nsteps = int(round(np.pi / f0 / dt))
+    out = {}
+    for axis, cor, ic in (("x", clo.ConstantCartesianCoriolis(f=f0, rotation_axis=(1, 0, 0)), "v"), ("z", clo.FPlane(f=f0), "u")):
+        g = Grid(np.float64, size=(2, 2, 2), extent=(1, 1, 1), topology=("P", "P", "P"))
+        m = OracleModel(g, coriolis=cor)
+        m.set(**{ic: np.ones(m.fields[ic].interior.shape)})
+        for _ in range(nsteps):
+            m.time_step(dt)
+        for n in "uvw":
+            a = m.fields[n].interior
+            assert np.ptp(a) < 1e-14                       # the flow stays uniform
+        out[axis] = tuple(float(m.fields[n].interior[0, 0, 0]) for n in "uvw")
+    (u_x, v_x, w_x), (u_z, v_z, w_z) = out["x"], out["z"]
+    assert w_z == 0 and u_x == 0
+    assert np.isclose(np.hypot(v_x, w_x), 1.0, rtol=1e-6) and np.isclose(np.hypot(u_z, v_z), 1.0, rtol=1e-6)
+    assert np.isclose(u_z, v_x, rtol=1e-12, atol=1e-12) and np.isclose(v_z, w_x, rtol=1e-12, atol=1e-12)
+    # half an inertial period reverses the flow: (u, v)(t) = (cos f t, −sin f t)
+    t = nsteps * dt
+    assert np.isclose(u_z, np.cos(f0 * t), atol=1e-6) and np.isclose(v_z, -np.sin(f0 * t), atol=1e-6)
+
+
+def test_beta_plane_reduces_to_f_plane_and_varies_linearly_in_y():
+    # beta_plane.jl:56-72: x_f_cross_U = −(f₀ + β y) ℑxy v with y = ynode(fcc).  With v = 1: −x_f_cross_U = f₀ + β y_c(j) exactly.
+    FT = np.float64
+    g = Grid(FT, size=(4, 6, 2), x=(0, 1), y=(-3.0, 3.0), z=(-1, 0), topology=("P", "P", "P"))
+    u, v, w = Field(g, "fcc"), Field(g, "cfc"), Field(g, "ccf")
+    v.data[...] = 1.0
+    u.data[...] = 2.0
+    ctx = Ctx(g, (1, 4), (1, 6), (1, 2))
+    bp = clo.BetaPlane(f0=0.5, beta=0.25)
+    yc, yf = g.nodes(1, "c"), g.nodes(1, "f")
+    x = clo.coriolis_cross(ctx, bp, (u, v, w), 0)
+    y = clo.coriolis_cross(ctx, bp, (u, v, w), 1)
+    assert np.allclose(-x[0, :, 0], 0.5 + 0.25 * yc, rtol=1e-15) and np.allclose(y[0, :, 0], 2.0 * (0.5 + 0.25 * yf), rtol=1e-15)
+    assert np.all(clo.coriolis_cross(ctx, bp, (u, v, w), 2) == 0)
+    fp = clo.coriolis_cross(ctx, clo.FPlane(f=0.5), (u, v, w), 0)
+    assert np.array_equal(clo.coriolis_cross(ctx, clo.BetaPlane(f0=0.5, beta=0.0), (u, v, w), 0), fp)

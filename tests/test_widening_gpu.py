@@ -41,3 +41,15 @@ def test_host_api_mirrors_the_reference_constructor_and_set(ob, FT):
         th.model_construction(None)
         th.halo_adjustment(None)
     th.setting_model_fields(None, np.float64 if FT == "f64" else np.float32)
+
+
+@pytest.mark.parametrize("name,kw", ph.CORIOLIS_CASES, ids=[c[0] for c in ph.CORIOLIS_CASES])
+def test_cuda_matches_oracle_for_the_coriolis_family(ob, name, kw):
+    """BetaPlane (beta_plane.jl:56-72) and ConstantCartesianCoriolis (constant_cartesian_coriolis.jl:70-81)"""
+    ph.check_case(kw, library=None, steps=(1, 10))
+
+
+def test_coriolis_constructors_and_inertial_oscillation_cuda(ob):
+    """test/test_coriolis.jl:17-51,104-119 and the inertial oscillations of test/test_dynamics.jl:357-397 through the CUDA library"""
+    import test_host_api as th
+    th.coriolis_constructors_and_inertial_oscillation(None, size=(16, 12, 8))
