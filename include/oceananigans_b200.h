@@ -103,6 +103,11 @@ typedef struct {
      * (src/Coriolis/constant_cartesian_coriolis.jl:70-81): all three momentum equations.  Both run in the general tile kernel. */
     double  coriolis_beta, origin_y;
     double  coriolis_fxyz[3];
+    /* BuoyancyForce(formulation; gravity_unit_vector = g̃)  (src/BuoyancyFormulations/buoyancy_force.jl:47-58, g_dot_b.jl:1-3):
+     * tilted_gravity = 1: ĝ = −g̃ multiplies ℑxᶠ b / ℑyᶠ b in the u / v equations and ℑzᶠ b in the pHY′ integral; general tile kernel. */
+    int32_t tilted_gravity;
+    int32_t reserved2;
+    double  gravity_unit_vector[3];
 } oc_config;
 
 typedef struct oc_model oc_model;

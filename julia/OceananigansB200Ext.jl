@@ -69,6 +69,7 @@ mutable struct OcConfig               # `oc_config`, same field order; NTuple fo
     smagorinsky::Int32; reserved::Int32            # ABI v3: 0 none, 1 Smagorinsky(coefficient::Number), 2 LillyCoefficient
     smag_C::Float64; smag_Cb::Float64; smag_Pr::NTuple{OC_MAX_TRACERS,Float64}
     coriolis_beta::Float64; origin_y::Float64; coriolis_fxyz::NTuple{3,Float64}   # ABI v3: BetaPlane, ConstantCartesianCoriolis
+    tilted_gravity::Int32; reserved2::Int32; gravity_unit_vector::NTuple{3,Float64} # ABI v3: BuoyancyForce(…; gravity_unit_vector)
     OcConfig() = new()
 end
 
@@ -159,6 +160,9 @@ function config(model::NonhydrostaticModel)
         end
     end
     b = model.buoyancy isa BuoyancyForce ? model.buoyancy.formulation : model.buoyancy
+    if model.buoyancy isa BuoyancyForce && !(model.buoyancy.gravity_unit_vector isa Oceananigans.Grids.NegativeZDirection)
+        cfg.tilted_gravity = 1; cfg.gravity_unit_vector = Float64.(Tuple(model.buoyancy.gravity_unit_vector))   # buoyancy_force.jl:47-58
+    end
     if b isa SeawaterBuoyancy
         eos = b.equation_of_state; eos isa LinearEquationOfState || throw(ArgumentError("B200: only LinearEquationOfState"))
         cfg.buoyancy = 2; cfg.gravity = b.gravitational_acceleration

@@ -46,6 +46,7 @@ class oc_config(C.Structure):
         ("smagorinsky", C.c_int32), ("reserved", C.c_int32), ("smag_C", C.c_double), ("smag_Cb", C.c_double),
         ("smag_Pr", C.c_double * OC_MAX_TRACERS),
         ("coriolis_beta", C.c_double), ("origin_y", C.c_double), ("coriolis_fxyz", C.c_double * 3),
+        ("tilted_gravity", C.c_int32), ("reserved2", C.c_int32), ("gravity_unit_vector", C.c_double * 3),
     ]
 
 

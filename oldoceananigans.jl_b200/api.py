@@ -25,7 +25,7 @@ from . import _lib as L
 __all__ = [
     "B200", "Distributed", "Partition", "Periodic", "Bounded", "Flat", "Center", "Face", "RectilinearGrid",
     "Centered", "UpwindBiased", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation", "Smagorinsky", "SmagorinskyLilly", "LillyCoefficient",
-    "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "FPlane", "BetaPlane", "ConstantCartesianCoriolis",
+    "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "BuoyancyForce", "FPlane", "BetaPlane", "ConstantCartesianCoriolis",
     "FluxBoundaryCondition", "ValueBoundaryCondition", "GradientBoundaryCondition", "OpenBoundaryCondition",
     "FieldBoundaryConditions", "NonhydrostaticModel", "Field", "set_", "time_step_", "update_state_",
     "compute_tendencies_", "compute_flux_bc_tendencies_", "rk3_substep_", "ab2_step_", "cache_previous_tendencies_",
@@ -281,6 +281,22 @@ class SeawaterBuoyancy:
 
 class BuoyancyTracer:
     required = ("b",)
+
+
+class BuoyancyForce:
+    """BuoyancyForce(formulation; gravity_unit_vector=NegativeZDirection())   src/BuoyancyFormulations/buoyancy_force.jl:47-58"""
+
+    def __init__(self, formulation, gravity_unit_vector=None):
+        if not isinstance(formulation, (SeawaterBuoyancy, BuoyancyTracer)):
+            raise NotImplementedError("BuoyancyForce: SeawaterBuoyancy (LinearEquationOfState) or BuoyancyTracer")
+        self.formulation = formulation
+        self.gravity_unit_vector = None
+        if gravity_unit_vector is not None:
+            v = tuple(float(x) for x in gravity_unit_vector)
+            if len(v) != 3 or not np.isclose(math.sqrt(sum(x * x for x in v)), 1.0):           # validate_unit_vector
+                raise ValueError("gravity_unit_vector must have three components and be unitary")
+            self.gravity_unit_vector = v
+        self.required = formulation.required
 
 
 _OMEGA_EARTH = 7.292115e-5      # Oceananigans.defaults.planet_rotation_rate
@@ -560,6 +576,12 @@ class NonhydrostaticModel:
                 cfg.smagorinsky, cfg.smag_C = 1, float(co)
             for t, n in enumerate(tracers):
                 cfg.smag_Pr[t] = pick(smag[0].Pr, n)
+        if isinstance(buoyancy, BuoyancyForce):
+            if buoyancy.gravity_unit_vector is not None:
+                cfg.tilted_gravity = 1
+                for d in range(3):
+                    cfg.gravity_unit_vector[d] = buoyancy.gravity_unit_vector[d]
+            buoyancy = buoyancy.formulation
         if buoyancy is not None:
             for n in buoyancy.required:
                 if n not in tracers:

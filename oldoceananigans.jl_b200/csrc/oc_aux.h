@@ -21,6 +21,8 @@ struct HydrostaticPressureKernel {
     const FT* bS;
     int buoyancy;          // 1 tracer, 2 seawater linear
     FT grav, alpha, beta;
+    int tilted;            // BuoyancyForce with a gravity_unit_vector: z_dot_g_b = ĝ_z ℑzᶠ b   g_dot_b.jl:3
+    FT gz;
     int ilo, ni, jlo, nj;  // column range: 0:N+1 (i.e. -1..N) unless Flat (p_kernel_parameters :41-49)
 
     OC_HD FT b_at(int o) const {
@@ -41,6 +43,7 @@ struct HydrostaticPressureKernel {
             o -= g.sz;
             FT bk = b_at(o);
             FT bf = FT(0.5) * (bk + bup);              // z_dot_g_bᶜᶜᶠ(k+1) = ℑzᵃᵃᶠ b   g_dot_b.jl:4
+            if (tilted) bf = gz * bf;
             const FT dzf = g.dz_at(true, k + 1);       // Δzᶜᶜᶠ of the face above cell k   update_hydrostatic_pressure.jl:15-19
             p = (k == Nz - 1) ? -bf * dzf : p - bf * dzf;
             pHY[o] = p;

@@ -124,6 +124,12 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
             if (!(c.smag_Pr[t] > 0)) throw Error(OC_ERR_INVALID, "Smagorinsky: the turbulent Prandtl number of every tracer must be positive");
     }
     if (c.has_coriolis < OC_CORIOLIS_NONE || c.has_coriolis > OC_CORIOLIS_CARTESIAN) throw Error(OC_ERR_UNSUPPORTED, "Coriolis: FPlane, BetaPlane or ConstantCartesianCoriolis");
+    if (c.tilted_gravity) {
+        const double* v = c.gravity_unit_vector;
+        const double nrm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (!(std::fabs(nrm - 1.0) < 1e-8)) throw Error(OC_ERR_INVALID, "gravity_unit_vector must be unitary (validate_unit_vector)");
+        if (c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "tilted gravity on distributed models");
+    }
     if (c.has_coriolis == OC_CORIOLIS_BETAPLANE && g_.flat[1]) throw Error(OC_ERR_UNSUPPORTED, "BetaPlane on a grid with a Flat y");
     if (c.has_coriolis == OC_CORIOLIS_CARTESIAN && c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "ConstantCartesianCoriolis on distributed models");
     if (c.buoyancy == OC_BUOYANCY_SEAWATER_LINEAR && (c.tracer_T < 0 || c.tracer_S < 0 || c.tracer_T >= c.n_tracers || c.tracer_S >= c.n_tracers))
@@ -153,7 +159,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         const bool any_bounded = c.topology[0] == OC_BOUNDED || c.topology[1] == OC_BOUNDED || c.topology[2] == OC_BOUNDED;
         // BetaPlane / ConstantCartesianCoriolis run in the general tile kernel: the z-marching kernel of the
         // measured BASELINE configurations keeps exactly the code (and register counts) it was profiled with
-        march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) && c.has_coriolis <= OC_CORIOLIS_FPLANE &&
+        march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) && c.has_coriolis <= OC_CORIOLIS_FPLANE && !c.tilted_gravity &&
                     (c.advection == OC_CENTERED2 || c.advection == OC_WENO5 || (c.advection == OC_UPWIND5 && !any_bounded && !c.has_amd && !c.smagorinsky));
     }
     g_.dzc = g_.dzf = g_.rdzc = g_.rdzf = g_.rVc = g_.rVf = nullptr;
@@ -847,6 +853,8 @@ void Model<FT>::aux() {
         if (cfg_.buoyancy == OC_BUOYANCY_TRACER) { k.bT = state_[3 + cfg_.tracer_b].p; k.bS = nullptr; }
         else { k.bT = state_[3 + cfg_.tracer_T].p; k.bS = state_[3 + cfg_.tracer_S].p; }
         k.grav = (FT)cfg_.gravity; k.alpha = (FT)cfg_.thermal_expansion; k.beta = (FT)cfg_.haline_contraction;
+        k.tilted = cfg_.tilted_gravity ? 1 : 0;
+        k.gz = -(FT)cfg_.gravity_unit_vector[2];
         k.ilo = g_.flat[0] ? 0 : -1; k.ni = g_.flat[0] ? g_.N[0] : g_.N[0] + 2;
         k.jlo = g_.flat[1] ? 0 : -1; k.nj = g_.flat[1] ? g_.N[1] : g_.N[1] + 2;
         Dim3 grid;
@@ -875,6 +883,12 @@ void Model<FT>::launch_tendency(int fidx, TendencyArgs<FT>& a) {
         // south face of this rank's first row (slab decomposition in y: rank r owns rows r·Ny … (r+1)·Ny − 1)
         k.cor.y0 = (FT)cfg_.origin_y + (FT)((dist_ ? rank_ : 0) * g_.N[1]) * g_.d[1];
         for (int d = 0; d < 3; ++d) k.cor.cf[d] = (FT)cfg_.coriolis_fxyz[d];
+        k.cor.tilted = (cfg_.tilted_gravity && cfg_.buoyancy != OC_BUOYANCY_NONE) ? 1 : 0;
+        for (int d = 0; d < 3; ++d) k.cor.gh[d] = -(FT)cfg_.gravity_unit_vector[d];
+        k.cor.tb_kind = cfg_.buoyancy;
+        k.cor.tbT = k.cor.tbS = nullptr;
+        if (cfg_.buoyancy == OC_BUOYANCY_TRACER) k.cor.tbT = state_[3 + cfg_.tracer_b].p;
+        else if (cfg_.buoyancy == OC_BUOYANCY_SEAWATER_LINEAR) { k.cor.tbT = state_[3 + cfg_.tracer_T].p; k.cor.tbS = state_[3 + cfg_.tracer_S].p; }
         go(k, grid, k.SMEM, OC_TIMER_TENDENCY);
     };
     switch (cfg_.advection) {
@@ -1528,6 +1542,7 @@ void oc_config_init(oc_config* c) {
     c->thermal_expansion = 1.67e-4;       // LinearEquationOfState defaults   linear_equation_of_state.jl:39-40
     c->haline_contraction = 7.8e-4;
     c->tracer_T = c->tracer_S = c->tracer_b = -1;
+    c->tilted_gravity = 0; c->reserved2 = 0; c->gravity_unit_vector[0] = c->gravity_unit_vector[1] = 0.0; c->gravity_unit_vector[2] = -1.0;
     c->coriolis_beta = 0.0; c->origin_y = 0.0; c->coriolis_fxyz[0] = c->coriolis_fxyz[1] = c->coriolis_fxyz[2] = 0.0;
     c->smagorinsky = 0; c->smag_C = 0.16; c->smag_Cb = 1.0;          // smagorinsky.jl:77-78, lilly_coefficient.jl:47
     for (int t = 0; t < OC_MAX_TRACERS; ++t) c->smag_Pr[t] = 1.0;

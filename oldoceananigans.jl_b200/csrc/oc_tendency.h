@@ -59,6 +59,11 @@ template <class FT>
 struct CoriolisExt {
     FT beta, y0;         // BetaPlane: f = f₀ + β ynode; y0 = y of the south face of this rank's first row
     FT cf[3];            // ConstantCartesianCoriolis fx, fy, fz
+    int tilted;          // BuoyancyForce(…; gravity_unit_vector): x_dot_g_bᶠᶜᶜ = ĝ_x ℑxᶠ b, y_dot_g_bᶜᶠᶜ = ĝ_y ℑyᶠ b   g_dot_b.jl:1-2
+    FT gh[3];            // ĝ = −gravity_unit_vector   buoyancy_force.jl:52-54
+    int tb_kind;         // buoyancy model of the tilted terms: 1 tracer b, 2 seawater linear (own copies: TendencyArgs::buoyancy
+    const FT* tbT;       // is 0 whenever pHY′ exists)
+    const FT* tbS;
 };
 
 template <class FT, int ADV, int KIND, int TX_, int TY_, int TZ_>
@@ -275,6 +280,16 @@ struct TendencyKernel {
                 if (KIND == KIND_W && a.buoyancy && !a.pHY && !g.flat[2]) {
                     // maybe_z_dot_g_bᶜᶜᶠ: only without the hydrostatic split (nonhydrostatic_tendency_kernel_functions.jl:168-170)
                     G = G + FT(0.5) * (buoyancy_at(o - g.sz) + buoyancy_at(o));
+                }
+                if ((KIND == KIND_U || KIND == KIND_V) && cor.tilted && !g.flat[KIND == KIND_U ? 0 : 1]) {
+                    const int s = KIND == KIND_U ? 1 : g.sy;
+                    FT b0, b1;
+                    if (cor.tb_kind == 1) { b0 = cor.tbT[o - s]; b1 = cor.tbT[o]; }
+                    else {
+                        b0 = a.grav * (a.alpha * cor.tbT[o - s] - a.beta * cor.tbS[o - s]);
+                        b1 = a.grav * (a.alpha * cor.tbT[o] - a.beta * cor.tbS[o]);
+                    }
+                    G = G + cor.gh[KIND == KIND_U ? 0 : 1] * (FT(0.5) * (b0 + b1));
                 }
                 if (KIND != KIND_C && a.has_coriolis == 3) {
                     // ConstantCartesianCoriolis (constant_cartesian_coriolis.jl:70-81): x: ℑxᶠ(fy ℑzᶜ w − fz ℑyᶜ v), y: ℑyᶠ(fz ℑxᶜ u − fx ℑzᶜ w),

@@ -321,19 +321,38 @@ def compute_smagorinsky(ctx, closure, U, tracers, buoyancy, nu_e, kappa_e):
 # ---------------------------------------------------------------------------------
 # Buoyancy
 # ---------------------------------------------------------------------------------
-class SeawaterBuoyancy:
-    """SeawaterBuoyancy with LinearEquationOfState: b = g (α T - β S)"""
+def _validate_unit_vector(v):
+    """validate_unit_vector  src/Grids/grid_utils.jl: three components, unit norm"""
+    v = tuple(float(x) for x in v)
+    if len(v) != 3 or not np.isclose(np.sqrt(sum(x * x for x in v)), 1.0):
+        raise ValueError("unit vector must have three components and be unitary")
+    return v
 
-    def __init__(self, g=9.80665, alpha=1.67e-4, beta=7.8e-4):
+
+class SeawaterBuoyancy:
+    """SeawaterBuoyancy with LinearEquationOfState: b = g (α T - β S).  gravity_unit_vector: BuoyancyForce(formulation;
+    gravity_unit_vector)  src/BuoyancyFormulations/buoyancy_force.jl:47-58 (None = NegativeZDirection())"""
+
+    def __init__(self, g=9.80665, alpha=1.67e-4, beta=7.8e-4, gravity_unit_vector=None):
         self.g, self.alpha, self.beta = g, alpha, beta
         self.kind = "seawater"
         self.required = ("T", "S")
+        self.gravity_unit_vector = None if gravity_unit_vector is None else _validate_unit_vector(gravity_unit_vector)
 
 
 class BuoyancyTracer:
-    def __init__(self):
+    def __init__(self, gravity_unit_vector=None):
         self.kind = "tracer"
         self.required = ("b",)
+        self.gravity_unit_vector = None if gravity_unit_vector is None else _validate_unit_vector(gravity_unit_vector)
+
+
+def g_hat(buoyancy, d):
+    """ĝ_x, ĝ_y, ĝ_z = −gravity_unit_vector (0, 0, 1 for NegativeZDirection)   buoyancy_force.jl:52-58"""
+    guv = getattr(buoyancy, "gravity_unit_vector", None)
+    if guv is None:
+        return (0.0, 0.0, 1.0)[d]
+    return -guv[d]
 
 
 def buoyancy_q(ctx, buoyancy, tracers):

@@ -174,7 +174,10 @@ class OracleModel:
         Nz = g.Nz
         ctx = Ctx(g, ir, jr, (Nz, Nz))
         b = clo.buoyancy_q(ctx, self.buoyancy, self.tracers)
-        bf = iF(ctx, b, 2)                                # z_dot_g_bᶜᶜᶠ = ℑzᵃᵃᶠ(b)   g_dot_b.jl:4
+        bf = iF(ctx, b, 2)                                # z_dot_g_bᶜᶜᶠ = ĝ_z ℑzᵃᵃᶠ(b)   g_dot_b.jl:3
+        if self.buoyancy.gravity_unit_vector is not None:
+            gz, bf0 = self.FT(clo.g_hat(self.buoyancy, 2)), bf
+            bf = lambda o: gz * bf0(o)
         p = ctx.field(self.pHY)
         tgt = lambda kk: self._target(self.pHY, Ctx(g, ir, jr, (kk, kk)))
         dzf = ctx.dz("f")                                 # Δzᶜᶜᶠ(k+1)
@@ -200,6 +203,9 @@ class OracleModel:
             # buoyancy: gravity = -ẑ  =>  x̂·g b = ŷ·g b = 0 ; ẑ·g b only when pHY′ is nothing (:168-170,222)
             if comp == 2 and self.buoyancy is not None and self.pHY is None:
                 G = G + iF(ctx, clo.buoyancy_q(ctx, self.buoyancy, self.tracers), 2)(O)
+            # tilted gravity: x_dot_g_bᶠᶜᶜ = ĝ_x ℑxᶠ b, y_dot_g_bᶜᶠᶜ = ĝ_y ℑyᶠ b   g_dot_b.jl:1-2 (:95,157)
+            if comp < 2 and self.buoyancy is not None and self.buoyancy.gravity_unit_vector is not None:
+                G = G + FT(clo.g_hat(self.buoyancy, comp)) * iF(ctx, clo.buoyancy_q(ctx, self.buoyancy, self.tracers), comp)(O)
             if self.coriolis is not None:
                 if comp < 2 or self.coriolis.kind == "cartesian":       # z_f_cross_U = 0 for FPlane / BetaPlane
                     G = G - clo.coriolis_cross(ctx, self.coriolis, self.U, comp)

@@ -76,9 +76,9 @@ def _coriolis(mod, f):
 
 
 def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
-                 bcs=False, extent=EXTENT, stretch=None, **_):
+                 bcs=False, extent=EXTENT, stretch=None, tilt=None, **_):
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
-    obo = clo.SeawaterBuoyancy() if buoy == "seawater" else (clo.BuoyancyTracer() if buoy == "tracer" else None)
+    obo = clo.SeawaterBuoyancy(gravity_unit_vector=tilt) if buoy == "seawater" else (clo.BuoyancyTracer(gravity_unit_vector=tilt) if buoy == "tracer" else None)
     ocl = {"scalar": clo.ScalarDiffusivity(1e-3, 2e-3), "amd": clo.AnisotropicMinimumDissipation(), "none": None,
            "both": (clo.ScalarDiffusivity(1e-3, 2e-3), clo.AnisotropicMinimumDissipation()),
            "smag": clo.Smagorinsky(0.16, Pr=1.0),
@@ -96,13 +96,15 @@ def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closur
 
 
 def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
-                  bcs=False, library=None, extent=EXTENT, arch=None, stretch=None):
+                  bcs=False, library=None, extent=EXTENT, arch=None, stretch=None, tilt=None):
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
     gkw = _grid_kwargs(N, topo, extent, stretch)
     grid = ob.RectilinearGrid(arch if arch is not None else FT, FT, topology=tuple(TOPO[c] for c in topo), **gkw) \
         if arch is not None else ob.RectilinearGrid(FT, topology=tuple(TOPO[c] for c in topo), **gkw)
     a = product_scheme(scheme)
     bo = ob.SeawaterBuoyancy() if buoy == "seawater" else (ob.BuoyancyTracer() if buoy == "tracer" else None)
+    if tilt is not None and bo is not None:
+        bo = ob.BuoyancyForce(bo, gravity_unit_vector=tilt)
     cl = {"scalar": ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), "amd": ob.AnisotropicMinimumDissipation(), "none": None,
           "both": (ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), ob.AnisotropicMinimumDissipation()),
           "smag": ob.Smagorinsky(coefficient=0.16, Pr=1.0),
@@ -231,6 +233,16 @@ CORIOLIS_CASES = [
     ("BBB centered cartesian coriolis smagorinsky", dict(N=(12, 10, 8), topo="BBB", scheme="centered", closure="smag", f=("cartesian", 0.3, -0.5, 0.7))),
     ("stretched PPB weno cartesian coriolis bcs F32", dict(N=(16, 12, 10), topo="PPB", scheme="weno", f=("cartesian", 0.0, 0.6, 0.8), bcs=True, stretch="smooth", FT=np.float32)),
     ("PFB centered cartesian coriolis 2D", dict(N=(16, 1, 12), topo="PFB", scheme="centered", buoy="tracer", f=("cartesian", 0.3, -0.5, 0.7))),
+]
+
+# tilted gravity: BuoyancyForce(formulation; gravity_unit_vector)  (buoyancy_force.jl:47-58, g_dot_b.jl:1-3)
+_T60 = (0.0, -float(np.sin(np.pi / 3)), -0.5)          # −(0, sind 60°, cosd 60°): the vector of test/test_dynamics.jl:267-268
+TILTED_CASES = [
+    ("PBB weno tilted gravity seawater", dict(N=(16, 12, 8), topo="PBB", scheme="weno", tilt=_T60)),
+    ("PPB centered tilted gravity tracer-b fplane bcs", dict(N=(16, 12, 8), topo="PPB", scheme="centered", buoy="tracer", f=1e-2, bcs=True, tilt=(0.6, 0.0, -0.8), tracer_noise=1.0)),
+    ("BBB weno amd tilted gravity cartesian coriolis", dict(N=(12, 10, 8), topo="BBB", scheme="weno", closure="amd", tilt=(0.48, -0.6, -0.64), f=("cartesian", 0.3, -0.5, 0.7), tracer_noise=1.0)),
+    ("stretched PPB upwind5 tilted gravity smagorinsky-lilly F32", dict(N=(16, 12, 10), topo="PPB", scheme="upwind5", closure="lilly", tilt=_T60, stretch="smooth", FT=np.float32)),
+    ("PFB weno tilted gravity tracer-b 2D", dict(N=(16, 1, 12), topo="PFB", scheme="weno", buoy="tracer", tilt=(0.6, 0.0, -0.8), tracer_noise=1.0)),
 ]
 
 # vertically stretched grids: FourierTridiagonalPoissonSolver + level-dependent metrics

@@ -148,3 +148,58 @@ def coriolis_constructors_and_inertial_oscillation(library, size=(2, 2, 2)):
 
 def test_coriolis_constructors_and_inertial_oscillation_hostsim():
     coriolis_constructors_and_inertial_oscillation(_hostsim())
+
+
+def stratified_fluid_remains_at_rest_with_tilted_gravity(make_model, N=16, L=2000.0, theta=60.0, N2=1e-5):
+    """test/test_dynamics.jl:263-353: a fluid stratified ALONG a tilted gravity vector stays at rest — after six 10-minute steps ∂y b
+    and ∂z b still equal N² g̃₂ and N² g̃₃ at every point (buoyancy-tracer and temperature variants).  make_model(kind, grid kwargs,
+    g̃, tracer BCs as {side: gradient}) builds the model in the oracle or in the product; returns nothing."""
+    gt = (0.0, float(np.sin(np.deg2rad(theta))), float(np.cos(np.deg2rad(theta))))
+    for kind in ("tracer", "seawater"):
+        if kind == "tracer":
+            guv, scale, name = tuple(-x for x in gt), N2, "b"                  # gravity_unit_vector = −g̃ (:268)
+        else:
+            guv, scale, name = gt, N2 / (9.80665 * 1.67e-4), "T"                # gravity_unit_vector = g̃, ∂T∂z = N² / (g₀ α) (:313-317)
+        grads = {"bottom": scale * gt[2], "top": scale * gt[2], "south": scale * gt[1], "north": scale * gt[1]}
+        set_, step_, field = make_model(kind, dict(size=(1, N, N), extent=(L, L, L)), guv, name, grads)
+        set_(name, lambda x, y, z: scale * (x * gt[0] + y * gt[1] + z * gt[2]))
+        for _ in range(6):
+            step_(600.0)
+        c = field(name)
+        d = L / N
+        dy = (c[:, 1:, :] - c[:, :-1, :]) / d
+        dz = (c[:, :, 1:] - c[:, :, :-1]) / d
+        assert np.allclose(dy, scale * gt[1], rtol=1e-7, atol=0) and np.allclose(dz, scale * gt[2], rtol=1e-7, atol=0)
+        for n in "uvw":
+            assert np.abs(field(n)).max() < 1e-10
+
+
+def _product_maker(library):
+    kw = {} if library is None else {"library": library}
+
+    def make(kind, gkw, guv, name, grads):
+        grid = ob.RectilinearGrid(np.float64, topology=(ob.Periodic, ob.Bounded, ob.Bounded), **gkw)
+        form = ob.BuoyancyTracer() if kind == "tracer" else ob.SeawaterBuoyancy()
+        bcs = {name: ob.FieldBoundaryConditions(**{s: ob.GradientBoundaryCondition(v) for s, v in grads.items()})}
+        m = ob.NonhydrostaticModel(grid=grid, buoyancy=ob.BuoyancyForce(form, gravity_unit_vector=guv),
+                                   tracers=("b",) if kind == "tracer" else ("T", "S"), closure=None, boundary_conditions=bcs, **kw)
+        return (lambda n, f: ob.set_(m, **{n: f})), (lambda dt: ob.time_step_(m, dt)), (lambda n: m.fields[n].interior())
+    return make
+
+
+def test_stratified_fluid_remains_at_rest_with_tilted_gravity_hostsim():
+    stratified_fluid_remains_at_rest_with_tilted_gravity(_product_maker(_hostsim()))
+
+
+def test_stratified_fluid_remains_at_rest_with_tilted_gravity_oracle():
+    import oracle
+    from oracle import closures as clo
+    from oracle.grid import BC
+
+    def make(kind, gkw, guv, name, grads):
+        g = oracle.Grid(np.float64, topology=("P", "B", "B"), **gkw)
+        form = clo.BuoyancyTracer(gravity_unit_vector=guv) if kind == "tracer" else clo.SeawaterBuoyancy(gravity_unit_vector=guv)
+        m = oracle.OracleModel(g, buoyancy=form, tracers=("b",) if kind == "tracer" else ("T", "S"),
+                               boundary_conditions={name: {s: BC("gradient", v) for s, v in grads.items()}})
+        return (lambda n, f: m.set(**{n: f})), (lambda dt: m.time_step(dt)), (lambda n: m.fields[n].interior)
+    stratified_fluid_remains_at_rest_with_tilted_gravity(make)

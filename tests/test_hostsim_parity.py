@@ -161,3 +161,9 @@ def test_hostsim_matches_oracle_with_smagorinsky_closures(hostsim, name, kw):
 def test_hostsim_matches_oracle_for_the_coriolis_family(hostsim, name, kw):
     """BetaPlane (beta_plane.jl:56-72), ConstantCartesianCoriolis (constant_cartesian_coriolis.jl:70-81)"""
     ph.check_case(kw, library=hostsim, steps=(1, 3))
+
+
+@pytest.mark.parametrize("name,kw", ph.TILTED_CASES, ids=[c[0] for c in ph.TILTED_CASES])
+def test_hostsim_matches_oracle_with_tilted_gravity(hostsim, name, kw):
+    """BuoyancyForce(formulation; gravity_unit_vector)  buoyancy_force.jl:47-58, g_dot_b.jl:1-3"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))

@@ -53,3 +53,15 @@ def test_coriolis_constructors_and_inertial_oscillation_cuda(ob):
     """test/test_coriolis.jl:17-51,104-119 and the inertial oscillations of test/test_dynamics.jl:357-397 through the CUDA library"""
     import test_host_api as th
     th.coriolis_constructors_and_inertial_oscillation(None, size=(16, 12, 8))
+
+
+@pytest.mark.parametrize("name,kw", ph.TILTED_CASES, ids=[c[0] for c in ph.TILTED_CASES])
+def test_cuda_matches_oracle_with_tilted_gravity(ob, name, kw):
+    """BuoyancyForce(formulation; gravity_unit_vector)  buoyancy_force.jl:47-58, g_dot_b.jl:1-3"""
+    ph.check_case(kw, library=None, steps=(1, 10))
+
+
+def test_stratified_fluid_remains_at_rest_with_tilted_gravity_cuda(ob):
+    """test/test_dynamics.jl:263-353 through the CUDA library"""
+    import test_host_api as th
+    th.stratified_fluid_remains_at_rest_with_tilted_gravity(th._product_maker(None))
