@@ -97,6 +97,7 @@ topo_code(::Type{Periodic}) = Int32(0); topo_code(::Type{Bounded}) = Int32(1); t
 
 bc_record(bc::BoundaryCondition{<:Flux, Nothing}) = OcBC(2, 0, 0.0)
 bc_record(bc::BoundaryCondition{<:Flux, <:Number}) = OcBC(2, 1, bc.condition)
+bc_record(bc::BoundaryCondition{<:Flux, <:AbstractArray}) = OcBC(2, 1, 0.0)      # values follow through oc_set_flux_bc_array (twin)
 bc_record(bc::BoundaryCondition{<:Value, <:Number}) = OcBC(3, 1, bc.condition)
 bc_record(bc::BoundaryCondition{<:Gradient, <:Number}) = OcBC(4, 1, bc.condition)
 bc_record(bc::BoundaryCondition{<:Open, Nothing}) = OcBC(5, 0, 0.0)
@@ -196,11 +197,25 @@ end
 function twin(model)
     get!(TWINS, model) do
         cfg, zfaces = config(model)
-        zfaces === nothing && return DeviceModel(cfg)
-        GC.@preserve zfaces begin                      # oc_model_create copies the faces; the pointer is not kept
-            cfg.z_faces = pointer(zfaces)
+        dm = if zfaces === nothing
             DeviceModel(cfg)
+        else
+            GC.@preserve zfaces begin                  # oc_model_create copies the faces; the pointer is not kept
+                cfg.z_faces = pointer(zfaces)
+                DeviceModel(cfg)
+            end
         end
+        # FluxBoundaryCondition(J::AbstractArray): upload the N₁×N₂ values (getbc(bc, i, j, …) = J[i, j])
+        for (f, field) in enumerate((model.velocities..., model.tracers...))
+            bcs = field.boundary_conditions
+            for (s, bc) in enumerate((bcs.west, bcs.east, bcs.south, bcs.north, bcs.bottom, bcs.top))
+                bc isa BoundaryCondition{<:Flux, <:AbstractArray} || continue
+                J = Array{eltype(model.grid)}(bc.condition)
+                GC.@preserve J check(ccall((:oc_set_flux_bc_array, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Csize_t),
+                                           dm.handle, f - 1, s - 1, J, sizeof(J)))
+            end
+        end
+        dm
     end
 end
 

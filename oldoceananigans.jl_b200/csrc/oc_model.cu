@@ -356,6 +356,8 @@ Model<FT>::~Model() {
     for (auto& f : next_) fr(f);
     for (auto& f : Gn_) fr(f);
     for (auto& f : Gm_) fr(f);
+    for (int f = 0; f < OC_MAX_FIELDS; ++f)
+        for (int s = 0; s < 6; ++s) if (flux_array_[f][s]) dev_free(flux_array_[f][s]);
     fr(pNHS_); fr(pHY_); fr(nu_e_);
     for (auto& f : kappa_e_) fr(f);
     dev_free(fftbuf_);
@@ -1066,7 +1068,7 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
         for (int s = 0; s < 6; ++s) {
             const SideBC& bc = state_[f].bc[s];
             const oc_bc& ub = cfg_.bcs[f][s];
-            a.fbc.on[s] = (bc.kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX && ub.has_value) ? 1 : 0;
+            a.fbc.on[s] = (bc.kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX && ub.has_value && !flux_array_[f][s]) ? 1 : 0;
             a.fbc.val[s] = (FT)bc.value;
         }
         a.add_flux_bcs = add_flux_bcs ? 1 : 0;
@@ -1085,6 +1087,10 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
         else if (f == 1) launch_tendency<KIND_V>(f, a);
         else if (f == 2) launch_tendency<KIND_W>(f, a);
         else launch_tendency<KIND_C>(f, a);
+        if (add_flux_bcs) {          // array-valued Flux BCs: boundary-plane pass on the same stream (FluxArrayKernel)
+            const FT coef = mode == STEP_RK3_FIRST ? a.ca : ((mode == STEP_RK3 || mode == STEP_AB2) ? a.dt * a.ca : FT(0));
+            apply_flux_arrays(f, a.Gn, mode == STEP_NONE ? nullptr : a.Unew, coef);
+        }
     }
     launch_stream_ = stream_;
     if (swap_state && mode != STEP_NONE)
@@ -1124,12 +1130,57 @@ void Model<FT>::compute_flux_bc_tendencies() {
         bool any = false;
         for (int s = 0; s < 6; ++s) {
             const oc_bc& ub = cfg_.bcs[f][s];
-            k.fbc.on[s] = (state_[f].bc[s].kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX && ub.has_value) ? 1 : 0;
+            k.fbc.on[s] = (state_[f].bc[s].kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX && ub.has_value && !flux_array_[f][s]) ? 1 : 0;
             k.fbc.val[s] = (FT)state_[f].bc[s].value;
             any = any || k.fbc.on[s];
         }
         if (any) go(k, grid_xyz(256), 0, OC_TIMER_SUBSTEP);
+        apply_flux_arrays(f, Gn_[f].p, nullptr, FT(0));
     }
+}
+
+// FluxBoundaryCondition(array): one boundary-plane launch per array-valued side of field f
+template <class FT>
+void Model<FT>::apply_flux_arrays(int f, FT* Gn, FT* Unew, FT coef) {
+    for (int s = 0; s < 6; ++s) {
+        if (!flux_array_[f][s]) continue;
+        FluxArrayKernel<FT> k;
+        k.g = g_;
+        k.Gn = Gn; k.Unew = Unew; k.coef = coef;
+        k.J = flux_array_[f][s];
+        k.d = s / 2; k.side = s % 2;
+        k.comp = f < 3 ? f : -1;
+        k.zface = f == 2 ? 1 : 0;
+        const int t1 = k.d == 0 ? 1 : 0, t2 = k.d == 2 ? 1 : 2;
+        k.n1 = g_.N[t1]; k.n2 = g_.N[t2];
+        Dim3 grid;
+        grid.x = (k.n1 + FluxArrayKernel<FT>::THREADS - 1) / FluxArrayKernel<FT>::THREADS; grid.y = k.n2; grid.z = 1;
+        go(k, grid, 0, OC_TIMER_SUBSTEP);
+    }
+}
+
+template <class FT>
+void Model<FT>::set_flux_bc_array(int field, int side, const void* host, size_t nbytes) {
+    if (field < 0 || field >= F_) throw Error(OC_ERR_INVALID, "set_flux_bc_array: not a prognostic field index");
+    if (side < 0 || side > 5) throw Error(OC_ERR_INVALID, "set_flux_bc_array: side must be 0 … 5 (west, east, south, north, bottom, top)");
+    if (dist_) throw Error(OC_ERR_UNSUPPORTED, "array-valued boundary conditions on distributed models");
+    const oc_bc& ub = cfg_.bcs[field][side];
+    if (!(state_[field].bc[side].kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX))
+        throw Error(OC_ERR_INVALID, "set_flux_bc_array: this side of the field must have been created with a Flux boundary condition");
+    const int d = side / 2, t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+    const size_t n = (size_t)g_.N[t1] * g_.N[t2];
+    if (n * sizeof(FT) != nbytes) throw Error(OC_ERR_INVALID, "host buffer size mismatch: expected " + std::to_string(n * sizeof(FT)) + " bytes");
+    join_tracers();
+    if (!flux_array_[field][side]) {
+        flux_array_[field][side] = (FT*)dev_alloc(n * sizeof(FT));
+        device_bytes += (int64_t)(n * sizeof(FT));
+    }
+    dev_upload(flux_array_[field][side], host, n * sizeof(FT), stream_);
+#ifndef OC_HOSTSIM
+    cuda_check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");     // the caller's buffer may go away
+#endif
+    cfg_.bcs[field][side].has_value = 1;
+    tend_valid_ = false;
 }
 
 template <class FT>
@@ -1590,6 +1641,11 @@ int oc_get_clock(oc_model* m, oc_clock* c) { OC_REQUIRE(m); *c = m->impl->clock;
 int oc_set_clock(oc_model* m, const oc_clock* c) { OC_REQUIRE(m); m->impl->clock = *c; return OC_OK; }
 int oc_restore_previous_tendency(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->restore_previous_tendency(field, host, nbytes); }); }
 int oc_compute_diagnostics(oc_model* m, oc_diagnostics* out) { OC_REQUIRE(m); return guarded([&] { m->impl->diagnostics(out); }); }
+int oc_set_flux_bc_array(oc_model* m, int field, int side, const void* host, size_t nbytes) {
+    OC_REQUIRE(m);
+    if (!host) { g_last_error = "null argument"; return OC_ERR_INVALID; }
+    return guarded([&] { m->impl->set_flux_bc_array(field, side, host, nbytes); });
+}
 int oc_field_maximum_abs(oc_model* m, int field, double* out) {
     OC_REQUIRE(m);
     if (!out) { g_last_error = "null argument"; return OC_ERR_INVALID; }

@@ -99,6 +99,7 @@ struct ModelBase {
     virtual void time_step_ab2(double dt, int euler) = 0;
     virtual void diagnostics(oc_diagnostics* out) = 0;
     virtual double field_maximum_abs(int field) = 0;
+    virtual void set_flux_bc_array(int field, int side, const void* host, size_t nbytes) = 0;
     virtual void restore_previous_tendency(int field, const void* host, size_t nbytes) = 0;
     virtual void dist_attach(Transport* t) = 0;
     virtual int dist_rank() const = 0;
@@ -136,6 +137,9 @@ public:
     void time_step_ab2(double dt, int euler) override;
     void diagnostics(oc_diagnostics* out) override;
     double field_maximum_abs(int field) override;
+    void set_flux_bc_array(int field, int side, const void* host, size_t nbytes) override;
+    void apply_flux_arrays(int f, FT* Gn, FT* Unew, FT coef);
+    FT* flux_array_[OC_MAX_FIELDS][6] = {};      // device arrays of array-valued Flux BCs (nullptr: scalar)
     void restore_previous_tendency(int field, const void* host, size_t nbytes) override;
     void dist_attach(Transport* t) override;
     int dist_rank() const override { return rank_; }

@@ -422,6 +422,44 @@ struct FluxBCKernel {
     }
 };
 
+// Array-valued flux boundary condition on ONE side of one field: FluxBoundaryCondition(J::AbstractArray) — getbc(bc, i, j, …) = J[i, j]
+// (src/BoundaryConditions/boundary_condition.jl getbc for arrays; compute_flux_bcs.jl:116-163: G[1] += J·A/V, G[N] −= J·A/V).
+// Runs after the fused tendency + substep launch of that field, on the boundary plane only: Gⁿ receives the flux term and, because the
+// substep is linear in Gⁿ, U* receives coef · (flux term) (coef = Δt γ for RK3, Δt (3/2 + χ) for AB2; 0 for the staged evaluation).
+// The scalar-valued sides stay fused in the tendency kernels.
+template <class FT>
+struct FluxArrayKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    FT* Gn;
+    FT* Unew;          // nullptr: tendencies only
+    FT coef;
+    const FT* J;       // n1 × n2 values, first tangential dimension fastest
+    int d;             // normal dimension, side 0 (low: +) / 1 (high: −)
+    int side;
+    int comp;          // velocity component of the field or −1
+    int zface;         // field is Face-located in z (w): area / volume metrics
+    int n1, n2;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const int i1 = b.x * nt + tid, i2 = b.y;
+        if (i1 >= n1 || i2 >= n2) return;
+        int ijk[3];
+        const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+        ijk[d] = side == 0 ? 0 : g.N[d] - 1;
+        ijk[t1] = i1; ijk[t2] = i2;
+        if (comp >= 0 && g.bounded[comp] && ijk[comp] == 0 && g.N[comp] > 1) return;          // wall faces are not stepped
+        const int k = ijk[2];
+        const FT A = g.area_at(d, zface != 0, k), V = g.vol_at(zface != 0, k);
+        const FT dG = J[i1 + (size_t)n1 * i2] * A / V;
+        const int o = g.idx(ijk[0], ijk[1], ijk[2]);
+        if (side == 0) { Gn[o] = Gn[o] + dG; if (Unew) Unew[o] = Unew[o] + coef * dG; }
+        else { Gn[o] = Gn[o] - dG; if (Unew) Unew[o] = Unew[o] - coef * dG; }
+    }
+};
+
 // Copy interior (cache_previous_tendencies! for the staged API)
 template <class FT>
 struct CopyKernel {

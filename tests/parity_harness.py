@@ -75,6 +75,28 @@ def _coriolis(mod, f):
     return mod.FPlane(f=f)
 
 
+def _array_bcs(N, topo, tr):
+    """array-valued FluxBoundaryConditions on every Bounded side that takes one: the first tracer on all of them, u at the top and
+    bottom (a wind-stress pattern), v on west / east — seeded, so the oracle and the product see the same numbers"""
+    rng = np.random.default_rng(99)
+    out = {tr[0]: {}, "u": {}, "v": {}}
+    dims = {0: (1, 2), 1: (0, 2), 2: (0, 1)}
+    names = {0: ("west", "east"), 1: ("south", "north"), 2: ("bottom", "top")}
+    for d in range(3):
+        if topo[d] != "B":
+            continue
+        shape = tuple(N[e] for e in dims[d])
+        for side in names[d]:
+            out[tr[0]][side] = 1e-2 * rng.standard_normal(shape)
+        if d == 2:
+            out["u"]["top"] = 1e-2 * rng.standard_normal(shape)
+            out["u"]["bottom"] = 1e-2 * rng.standard_normal(shape)
+        if d == 0:
+            out["v"]["west"] = 1e-2 * rng.standard_normal(shape)
+            out["v"]["east"] = 1e-2 * rng.standard_normal(shape)
+    return {n: v for n, v in out.items() if v}
+
+
 def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
                  bcs=False, extent=EXTENT, stretch=None, tilt=None, **_):
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
@@ -85,7 +107,9 @@ def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closur
            # the closure of test/test_nonhydrostatic_regression.jl:68 (C = 0.23, Cb = 1, Pr = 1 + molecular values), Pr varied per tracer
            "lilly": (clo.SmagorinskyLilly(0.23, 1.0, {n: 1.0 + 0.5 * t for t, n in enumerate(tr)}), clo.ScalarDiffusivity(1.05e-6, 1.46e-7))}[closure]
     bc_o = None
-    if bcs:
+    if bcs == "array":
+        bc_o = {n: {side: BC("flux", a) for side, a in sides.items()} for n, sides in _array_bcs(N, topo, tr).items()}
+    elif bcs:
         t0 = tr[0]
         bc_o = {"u": {"top": BC("flux", -2e-3)}, t0: {"top": BC("flux", 5e-3), "bottom": BC("gradient", 0.05)},
                 "v": {"bottom": BC("value", 0.1)}}
@@ -111,7 +135,10 @@ def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closu
           "lilly": (ob.SmagorinskyLilly(C=0.23, Cb=1.0, Pr={n: 1.0 + 0.5 * t for t, n in enumerate(tr)}),
                     ob.ScalarDiffusivity(nu=1.05e-6, kappa=1.46e-7))}[closure]
     bc_b = None
-    if bcs:
+    if bcs == "array":
+        bc_b = {n: ob.FieldBoundaryConditions(**{side: ob.FluxBoundaryCondition(a) for side, a in sides.items()})
+                for n, sides in _array_bcs(N, topo, tr).items()}
+    elif bcs:
         # the BC kinds of test/regression_tests/ocean_large_eddy_simulation_regression_test.jl:19-37
         t0 = tr[0]
         bc_b = {"u": ob.FieldBoundaryConditions(top=ob.FluxBoundaryCondition(-2e-3)),
@@ -233,6 +260,15 @@ CORIOLIS_CASES = [
     ("BBB centered cartesian coriolis smagorinsky", dict(N=(12, 10, 8), topo="BBB", scheme="centered", closure="smag", f=("cartesian", 0.3, -0.5, 0.7))),
     ("stretched PPB weno cartesian coriolis bcs F32", dict(N=(16, 12, 10), topo="PPB", scheme="weno", f=("cartesian", 0.0, 0.6, 0.8), bcs=True, stretch="smooth", FT=np.float32)),
     ("PFB centered cartesian coriolis 2D", dict(N=(16, 1, 12), topo="PFB", scheme="centered", buoy="tracer", f=("cartesian", 0.3, -0.5, 0.7))),
+]
+
+# array-valued flux boundary conditions: FluxBoundaryCondition(J::AbstractArray)  (oc_set_flux_bc_array; compute_flux_bcs.jl:116-163)
+ARRAY_BC_CASES = [
+    ("PPB weno array flux bcs (marching kernel)", dict(N=(16, 12, 8), topo="PPB", scheme="weno", bcs="array")),
+    ("BBB centered amd array flux bcs AB2", dict(N=(12, 10, 8), topo="BBB", scheme="centered", closure="amd", bcs="array", ts="QuasiAdamsBashforth2")),
+    ("PBB upwind3 array flux bcs (general kernel)", dict(N=(16, 12, 8), topo="PBB", scheme="upwind3", bcs="array")),
+    ("stretched PPB weno smagorinsky-lilly array flux bcs F32", dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="lilly", bcs="array", stretch="smooth", FT=np.float32)),
+    ("tile-crossing 40x36x33 BPB weno array flux bcs", dict(N=(40, 36, 33), topo="BPB", scheme="weno", bcs="array")),
 ]
 
 # tilted gravity: BuoyancyForce(formulation; gravity_unit_vector)  (buoyancy_force.jl:47-58, g_dot_b.jl:1-3)

@@ -167,3 +167,9 @@ def test_hostsim_matches_oracle_for_the_coriolis_family(hostsim, name, kw):
 def test_hostsim_matches_oracle_with_tilted_gravity(hostsim, name, kw):
     """BuoyancyForce(formulation; gravity_unit_vector)  buoyancy_force.jl:47-58, g_dot_b.jl:1-3"""
     ph.check_case(kw, library=hostsim, steps=(1, 3))
+
+
+@pytest.mark.parametrize("name,kw", ph.ARRAY_BC_CASES, ids=[c[0] for c in ph.ARRAY_BC_CASES])
+def test_hostsim_matches_oracle_with_array_valued_flux_bcs(hostsim, name, kw):
+    """FluxBoundaryCondition(J::AbstractArray) on every Bounded side (oc_set_flux_bc_array; compute_flux_bcs.jl:116-163)"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))
