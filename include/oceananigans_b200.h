@@ -186,6 +186,18 @@ int  oc_set_clock(oc_model* m, const oc_clock* clock);                 /* Checkp
  * always recomputed from the restored state, like the reference's update_state! after a pickup). */
 int  oc_restore_previous_tendency(oc_model* m, int field, const void* parent_host, size_t nbytes);
 
+/* ---- asynchronous output ----
+ * What an output writer needs from the device without stalling the step loop: `Array(interior(field))[i₁:i₂, j₁:j₂, k₁:k₂]` of
+ * JLD2Writer / NetCDFWriter (src/OutputWriters/jld2_writer.jl: fetch_and_convert_output → on_architecture(CPU(), ·)) as a
+ * two-stage copy.  oc_output_begin snapshots the box lo[d] … lo[d] + n[d] − 1 (0-based interior indices; may reach into the halos) into a
+ * device staging buffer IN STREAM ORDER with the time stepping (a device-to-device copy at HBM speed), then streams it to `host`
+ * (page-locked memory from oc_host_alloc for a truly asynchronous copy) on a separate copy stream; time steps issued afterwards overlap
+ * that transfer and do not disturb the snapshot.  oc_output_wait blocks until the host buffer is complete; oc_output_test polls.
+ * A ticket is valid until waited for; at most 64 may be in flight. */
+int  oc_output_begin(oc_model* m, int field, const int lo[3], const int n[3], void* host, size_t nbytes, int* ticket);
+int  oc_output_wait(oc_model* m, int ticket);
+int  oc_output_test(oc_model* m, int ticket, int* done);
+
 /* ---- on-device step diagnostics (one reduction pass, a 40-byte device-to-host copy) ----
  * cell_advection_timescale(grid, velocities)  src/Advection/cell_advection_timescale.jl:13-34  (TimeStepWizard,
  * src/Simulations/time_step_wizard.jl:101-115); maximum(abs, u|v|w) for progress messages; hasnan(u)  src/Diagnostics/nan_checker.jl.

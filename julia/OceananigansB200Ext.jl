@@ -278,6 +278,21 @@ end
 update_state!(model::B200Model, callbacks=[]; compute_tendencies=true) =
     check(ccall((:oc_update_state, LIB), Cint, (Ptr{Cvoid}, Cint), twin(model).handle, compute_tendencies))
 
+# ---- asynchronous output (SURVEY §8f item 4): what JLD2Writer's fetch_and_convert_output needs, without stalling the step loop --------
+"Start copying `interior(field)[i, j, k]` (unit-stride ranges) of the device field `id` to a page-locked host array; returns (ticket, array)."
+function begin_output(model::B200Model, id, i::UnitRange, j::UnitRange, k::UnitRange)
+    FT = eltype(model.grid)
+    n = Cint.((length(i), length(j), length(k))); lo = Cint.((first(i) - 1, first(j) - 1, first(k) - 1))
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:oc_host_alloc, LIB), Cint, (Ref{Ptr{Cvoid}}, Csize_t), p, prod(n) * sizeof(FT)))
+    a = unsafe_wrap(Array, Ptr{FT}(p[]), Int.(n))          # free with oc_host_free after use
+    t = Ref{Cint}(0)
+    check(ccall((:oc_output_begin, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{NTuple{3,Cint}}, Ref{NTuple{3,Cint}}, Ptr{Cvoid}, Csize_t, Ref{Cint}),
+                twin(model).handle, id, lo, n, p[], sizeof(a), t))
+    return t[], a
+end
+wait_output(model::B200Model, ticket) = check(ccall((:oc_output_wait, LIB), Cint, (Ptr{Cvoid}, Cint), twin(model).handle, ticket))
+
 # ---- on-device step diagnostics (SURVEY §8f item 2): no full-field device-to-host copies for the TimeStepWizard / NaNChecker ----------
 struct OcDiagnostics
     cell_advection_timescale::Float64; max_abs_u::Float64; max_abs_v::Float64; max_abs_w::Float64; has_nan::Int32; pad::Int32

@@ -27,7 +27,7 @@ __all__ = [
     "Centered", "UpwindBiased", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation", "Smagorinsky", "SmagorinskyLilly", "LillyCoefficient",
     "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "BuoyancyForce", "FPlane", "BetaPlane", "ConstantCartesianCoriolis",
     "FluxBoundaryCondition", "ValueBoundaryCondition", "GradientBoundaryCondition", "OpenBoundaryCondition",
-    "FieldBoundaryConditions", "NonhydrostaticModel", "Field", "set_", "time_step_", "update_state_",
+    "FieldBoundaryConditions", "NonhydrostaticModel", "Field", "OutputTicket", "set_", "time_step_", "update_state_",
     "compute_tendencies_", "compute_flux_bc_tendencies_", "rk3_substep_", "ab2_step_", "cache_previous_tendencies_",
     "compute_pressure_correction_", "make_pressure_correction_", "fill_halo_regions_", "solve_poisson",
     "interior", "parent", "Simulation", "run_", "Clock", "Checkpointer", "OceananigansB200Error",
@@ -430,6 +430,52 @@ class Clock:
     last_stage_Δt = property(lambda s: s._get().last_stage_dt)
 
 
+class OutputTicket:
+    """One asynchronous output in flight (oc_output_begin / oc_output_wait / oc_output_test)."""
+
+    def __init__(self, model, fid, lo, n):
+        lib = model._lib
+        self._lib, self._h, self.shape = lib, model._h, tuple(n)
+        FT = model.grid.FT
+        self.nbytes = int(np.prod(n)) * np.dtype(FT).itemsize
+        self._ptr = C.c_void_p()
+        lib.check(lib.oc_host_alloc(C.byref(self._ptr), max(self.nbytes, 1)))            # page-locked: the copy is truly asynchronous
+        ctype = C.c_double if FT is np.float64 else C.c_float
+        self._view = np.ctypeslib.as_array(C.cast(self._ptr, C.POINTER(ctype)), shape=(int(np.prod(n)),))
+        t = C.c_int()
+        try:
+            lib.check(lib.oc_output_begin(self._h, fid, (C.c_int * 3)(*lo), (C.c_int * 3)(*n), self._ptr, self.nbytes, C.byref(t)))
+        except Exception:
+            lib.oc_host_free(self._ptr)
+            self._ptr = None
+            raise
+        self._ticket, self._result = t.value, None
+
+    def done(self):
+        if self._result is not None:
+            return True
+        d = C.c_int()
+        self._lib.check(self._lib.oc_output_test(self._h, self._ticket, C.byref(d)))
+        return bool(d.value)
+
+    def wait(self):
+        """block until the host copy is complete; returns the array indexed [i, j, k]"""
+        if self._result is None:
+            self._lib.check(self._lib.oc_output_wait(self._h, self._ticket))
+            self._result = np.array(self._view, copy=True).reshape(self.shape, order="F")
+            self._lib.oc_host_free(self._ptr)
+            self._ptr = None
+        return self._result
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ptr", None) is not None and self._result is None:
+                self._lib.oc_output_wait(self._h, self._ticket)
+                self._lib.oc_host_free(self._ptr)
+        except Exception:
+            pass
+
+
 class Field:
     """A handle to a device field.  `interior(f)` / `parent(f)` return host copies (numpy, indexed [i, j, k])."""
 
@@ -455,6 +501,24 @@ class Field:
 
     def interior(self):
         return self._download(False)
+
+    def begin_output(self, indices=None):
+        """Asynchronous `Array(interior(field)[indices...])` for output writers (oc_output_begin): snapshots the index box now, in
+        stream order with the time stepping, and copies it to page-locked host memory on a separate stream.  `indices`: a 3-tuple of
+        slices / integers over the interior (0-based; None = the whole interior).  Returns an OutputTicket; `.wait()` gives the array."""
+        info = self.info()
+        size = tuple(info.interior_size)
+        idx = (slice(None),) * 3 if indices is None else tuple(indices)
+        lo, n = [], []
+        for d in range(3):
+            if isinstance(idx[d], slice):
+                a, b, st = idx[d].indices(size[d])
+                if st != 1:
+                    raise ValueError("output slices must have unit stride")
+                lo.append(a); n.append(b - a)
+            else:
+                lo.append(int(idx[d])); n.append(1)
+        return OutputTicket(self.model, self.id, lo, n)
 
     def maximum_abs(self):
         """maximum(abs, interior(field)), reduced on the device (oc_field_maximum_abs): an 8-byte copy instead of the field"""

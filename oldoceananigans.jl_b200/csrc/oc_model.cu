@@ -373,6 +373,12 @@ Model<FT>::~Model() {
     if (ev_fork_) { cudaEventDestroy((cudaEvent_t)ev_fork_); cudaEventDestroy((cudaEvent_t)ev_join_); }
     for (void* e : ev_a2a_) cudaEventDestroy((cudaEvent_t)e);
     for (void* e : ev_mid_) cudaEventDestroy((cudaEvent_t)e);
+    for (auto& s : out_slots_) {
+        if (s.ev_done) cudaEventSynchronize((cudaEvent_t)s.ev_done);
+        if (s.ev_snap) { cudaEventDestroy((cudaEvent_t)s.ev_snap); cudaEventDestroy((cudaEvent_t)s.ev_done); }
+        if (s.stage) cudaFree(s.stage);
+    }
+    if (out_stream_) cudaStreamDestroy(out_stream_);
     if (stream3_) cudaStreamDestroy(stream3_);
     if (stream2_) cudaStreamDestroy(stream2_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -1409,6 +1415,86 @@ void Model<FT>::diagnostics(oc_diagnostics* out) {
     out->pad = 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// asynchronous output: snapshot a box of a field in stream order (D2D into a staging buffer), then copy it to the host on a separate
+// stream while the time stepping continues
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+int Model<FT>::output_begin(int field, const int lo[3], const int n[3], void* host, size_t nbytes) {
+    join_tracers();
+    oc_field_info info;
+    field_info(field, &info);                // brings auxiliary fields / tendencies up to date like a download
+    FieldRec& f = lookup(field);
+    size_t cnt = 1;
+    for (int d = 0; d < 3; ++d) {
+        if (n[d] < 1 || lo[d] < -Hcfg_[d] || lo[d] + n[d] > info.interior_size[d] + Hcfg_[d])
+            throw Error(OC_ERR_INVALID, "output box outside the parent array of the field");
+        cnt *= (size_t)n[d];
+    }
+    if (cnt * sizeof(FT) != nbytes) throw Error(OC_ERR_INVALID, "host buffer size mismatch: expected " + std::to_string(cnt * sizeof(FT)) + " bytes");
+    int t = -1;
+    for (size_t i = 0; i < out_slots_.size(); ++i) if (!out_slots_[i].busy) { t = (int)i; break; }
+    if (t < 0) {
+        if (out_slots_.size() >= 64) throw Error(OC_ERR_STATE, "more than 64 outputs in flight: call oc_output_wait");
+        out_slots_.emplace_back();
+        t = (int)out_slots_.size() - 1;
+    }
+    OutputSlot& s = out_slots_[t];
+    FT* origin = f.p + lo[0] + (long long)lo[1] * g_.sy + (long long)lo[2] * g_.sz;
+#ifndef OC_HOSTSIM
+    if (!out_stream_) cuda_check(cudaStreamCreateWithFlags(&out_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!s.ev_snap) {
+        cudaEvent_t a, b;
+        cuda_check(cudaEventCreateWithFlags(&a, cudaEventDisableTiming), "cudaEventCreate");
+        cuda_check(cudaEventCreateWithFlags(&b, cudaEventDisableTiming), "cudaEventCreate");
+        s.ev_snap = a; s.ev_done = b;
+    }
+    if (s.cap < nbytes) {
+        if (s.stage) { cuda_check(cudaFree(s.stage), "cudaFree"); device_bytes -= (int64_t)s.cap; }
+        s.stage = nullptr; s.cap = 0;
+        void* p = nullptr;
+        cuda_check(cudaMalloc(&p, nbytes), "cudaMalloc(output staging)");
+        s.stage = (FT*)p; s.cap = nbytes;
+        device_bytes += (int64_t)nbytes;
+    }
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    p.srcPtr = make_cudaPitchedPtr(origin, (size_t)g_.sy * sizeof(FT), (size_t)g_.sy * sizeof(FT), (size_t)(g_.sz / g_.sy));
+    p.dstPtr = make_cudaPitchedPtr(s.stage, (size_t)n[0] * sizeof(FT), (size_t)n[0] * sizeof(FT), (size_t)n[1]);
+    p.extent = make_cudaExtent((size_t)n[0] * sizeof(FT), (size_t)n[1], (size_t)n[2]);
+    p.kind = cudaMemcpyDeviceToDevice;
+    cuda_check(cudaMemcpy3DAsync(&p, stream_), "cudaMemcpy3DAsync(snapshot)");
+    cuda_check(cudaEventRecord((cudaEvent_t)s.ev_snap, stream_), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(out_stream_, (cudaEvent_t)s.ev_snap, 0), "cudaStreamWaitEvent");
+    cuda_check(cudaMemcpyAsync(host, s.stage, nbytes, cudaMemcpyDeviceToHost, out_stream_), "cudaMemcpyAsync(output)");
+    cuda_check(cudaEventRecord((cudaEvent_t)s.ev_done, out_stream_), "cudaEventRecord");
+#else
+    dev_copy_box(origin, sizeof(FT), g_.sy, g_.sz, host, n, false, stream_);      // the host simulation snapshots synchronously
+#endif
+    s.busy = true;
+    return t;
+}
+
+template <class FT>
+void Model<FT>::output_wait(int ticket) {
+    if (ticket < 0 || ticket >= (int)out_slots_.size() || !out_slots_[ticket].busy) throw Error(OC_ERR_INVALID, "oc_output_wait: unknown or finished ticket");
+#ifndef OC_HOSTSIM
+    cuda_check(cudaEventSynchronize((cudaEvent_t)out_slots_[ticket].ev_done), "cudaEventSynchronize(output)");
+#endif
+    out_slots_[ticket].busy = false;
+}
+
+template <class FT>
+bool Model<FT>::output_test(int ticket) {
+    if (ticket < 0 || ticket >= (int)out_slots_.size() || !out_slots_[ticket].busy) throw Error(OC_ERR_INVALID, "oc_output_test: unknown or finished ticket");
+#ifndef OC_HOSTSIM
+    cudaError_t e = cudaEventQuery((cudaEvent_t)out_slots_[ticket].ev_done);
+    if (e == cudaErrorNotReady) return false;
+    cuda_check(e, "cudaEventQuery(output)");
+#endif
+    return true;
+}
+
 // maximum(abs, interior(field)); NaN if the field holds a NaN (like Julia's maximum)
 template <class FT>
 double Model<FT>::field_maximum_abs(int field) {
@@ -1645,6 +1731,17 @@ int oc_set_flux_bc_array(oc_model* m, int field, int side, const void* host, siz
     OC_REQUIRE(m);
     if (!host) { g_last_error = "null argument"; return OC_ERR_INVALID; }
     return guarded([&] { m->impl->set_flux_bc_array(field, side, host, nbytes); });
+}
+int oc_output_begin(oc_model* m, int field, const int lo[3], const int n[3], void* host, size_t nbytes, int* ticket) {
+    OC_REQUIRE(m);
+    if (!lo || !n || !host || !ticket) { g_last_error = "null argument"; return OC_ERR_INVALID; }
+    return guarded([&] { *ticket = m->impl->output_begin(field, lo, n, host, nbytes); });
+}
+int oc_output_wait(oc_model* m, int ticket) { OC_REQUIRE(m); return guarded([&] { m->impl->output_wait(ticket); }); }
+int oc_output_test(oc_model* m, int ticket, int* done) {
+    OC_REQUIRE(m);
+    if (!done) { g_last_error = "null argument"; return OC_ERR_INVALID; }
+    return guarded([&] { *done = m->impl->output_test(ticket) ? 1 : 0; });
 }
 int oc_field_maximum_abs(oc_model* m, int field, double* out) {
     OC_REQUIRE(m);

@@ -203,3 +203,48 @@ def test_stratified_fluid_remains_at_rest_with_tilted_gravity_oracle():
                                boundary_conditions={name: {s: BC("gradient", v) for s, v in grads.items()}})
         return (lambda n, f: m.set(**{n: f})), (lambda dt: m.time_step(dt)), (lambda n: m.fields[n].interior)
     stratified_fluid_remains_at_rest_with_tilted_gravity(make)
+
+
+def asynchronous_output(library):
+    """oc_output_begin snapshots a box of a field in stream order; time steps issued before oc_output_wait neither
+    wait for the host copy nor disturb it.  Checked: whole interiors, an x–y slice, a box reaching into the halos through the C ABI,
+    several tickets in flight, ticket reuse, and the error paths."""
+    import ctypes as C
+    import parity_harness as ph
+    m, om = ph.build_pair(N=(16, 12, 8), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, library=library)
+    ic = ph.initial_conditions(om)
+    ob.set_(m, **ic)
+    for _ in range(2):
+        ob.time_step_(m, 1e-3)
+    for rounds in range(2):                                   # the second round reuses the tickets' staging buffers
+        want_T = m.tracers["T"].interior()
+        want_u = m.velocities.u.interior()
+        want_nu = m.diffusivity_fields.nu_e.interior()
+        tickets = [m.tracers["T"].begin_output(), m.velocities.u.begin_output((slice(None), slice(None), 3)),
+                   m.velocities.u.begin_output((slice(2, 9), 5, slice(1, 8))), m.diffusivity_fields.nu_e.begin_output()]
+        for _ in range(3):                                    # the model moves on while the copies are in flight
+            ob.time_step_(m, 1e-3)
+        assert not np.array_equal(m.tracers["T"].interior(), want_T)
+        got = [t.wait() for t in tickets]
+        assert all(t.done() for t in tickets)
+        assert np.array_equal(got[0], want_T)
+        assert np.array_equal(got[1], want_u[:, :, 3:4]) and np.array_equal(got[2], want_u[2:9, 5:6, 1:8])
+        assert np.array_equal(got[3], want_nu)
+    # a box that reaches into the halos (parent coordinates) through the C ABI
+    lib, h = m._lib, m._h
+    Hx, Hy, Hz = m.grid.Hx, m.grid.Hy, m.grid.Hz
+    parent = m.tracers["T"].parent()
+    lo, n = (C.c_int * 3)(-Hx, -1, 0), (C.c_int * 3)(16 + 2 * Hx, 3, 2)
+    buf = np.empty((16 + 2 * Hx, 3, 2), dtype=np.float64, order="F")
+    t = C.c_int()
+    lib.check(lib.oc_output_begin(h, 3, lo, n, buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(t)))
+    lib.check(lib.oc_output_wait(h, t.value))
+    assert np.array_equal(buf, parent[:, Hy - 1:Hy + 2, Hz:Hz + 2])
+    assert lib.oc_output_wait(h, t.value) != 0                                           # a finished ticket is an error
+    bad = (C.c_int * 3)(0, 0, 7)
+    assert lib.oc_output_begin(h, 3, bad, n, buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(t)) != 0       # outside the parent array
+    assert lib.oc_output_begin(h, 3, lo, n, buf.ctypes.data_as(C.c_void_p), buf.nbytes - 8, C.byref(t)) != 0    # size mismatch
+
+
+def test_asynchronous_output_hostsim():
+    asynchronous_output(_hostsim())

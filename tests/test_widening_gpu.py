@@ -71,3 +71,9 @@ def test_stratified_fluid_remains_at_rest_with_tilted_gravity_cuda(ob):
 def test_cuda_matches_oracle_with_array_valued_flux_bcs(ob, name, kw):
     """FluxBoundaryCondition(J::AbstractArray) on every Bounded side (oc_set_flux_bc_array; compute_flux_bcs.jl:116-163)"""
     ph.check_case(kw, library=None, steps=(1, 10))
+
+
+def test_asynchronous_output_cuda(ob):
+    """snapshots taken by oc_output_begin are unaffected by the time steps issued before oc_output_wait"""
+    import test_host_api as th
+    th.asynchronous_output(None)
