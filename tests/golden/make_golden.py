@@ -28,6 +28,14 @@ GOLDEN_CASES = {
     "stretched_ppb_weno_amd_fplane_bcs_f64": dict(N=(12, 10, 8), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, stretch="smooth"),
     "stretched_bbb_centered_scalar_f64": dict(N=(12, 10, 8), topo="BBB", scheme="centered", stretch="facr"),
 }
+# the round-1 widening: Smagorinsky-Lilly, the Coriolis family, tilted gravity, array-valued flux BCs.  Kept in a
+# separate table because their GPU checks live in tests/test_widening_gpu.py (they run after the GPU-verified suites).
+GOLDEN_CASES_WIDENING = {
+    "ppb_weno_smagorinsky_lilly_fplane_bcs_f64": dict(N=(12, 10, 8), topo="PPB", scheme="weno", closure="lilly", f=1e-2, bcs=True),
+    "bbb_centered_cartesian_coriolis_tilted_gravity_f64": dict(N=(12, 10, 8), topo="BBB", scheme="centered", buoy="tracer",
+                                                               f=("cartesian", 0.3, -0.5, 0.7), tilt=(0.48, -0.6, -0.64)),
+    "ppb_weno_betaplane_array_bcs_f64": dict(N=(12, 10, 8), topo="PPB", scheme="weno", f=("beta", 0.3, 2.0), bcs="array"),
+}
 STEPS = (1, 3)
 
 
@@ -37,7 +45,7 @@ def main(only=None):
     import oracle
     from oracle import advection as adv, closures as clo
     import parity_harness as ph
-    for name, kw in GOLDEN_CASES.items():
+    for name, kw in {**GOLDEN_CASES, **GOLDEN_CASES_WIDENING}.items():
         if only and name not in only:
             continue
         om = ph.build_oracle(**kw)

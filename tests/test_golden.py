@@ -14,6 +14,8 @@ import make_golden as mg  # noqa: E402
 import parity_harness as ph  # noqa: E402
 
 CASES = sorted(mg.GOLDEN_CASES)
+WIDENING = sorted(mg.GOLDEN_CASES_WIDENING)          # CPU checks here; their GPU check is in tests/test_widening_gpu.py
+ALL = {**mg.GOLDEN_CASES, **mg.GOLDEN_CASES_WIDENING}
 
 
 def _load(name):
@@ -28,10 +30,10 @@ def _ic(z):
     return {k[3:]: z[k] for k in z.files if k.startswith("ic_")}
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + WIDENING)
 def test_oracle_reproduces_golden(name):
     z = _load(name)
-    kw = mg.GOLDEN_CASES[name]
+    kw = ALL[name]
     om = ph.build_oracle(**kw)
     om.set(**_ic(z))
     tol = 1e-13 if kw.get("FT", np.float64) is np.float64 else 1e-5
@@ -46,7 +48,7 @@ def test_oracle_reproduces_golden(name):
 def _product_vs_golden(name, library):
     import oceananigans_b200 as ob
     z = _load(name)
-    kw = mg.GOLDEN_CASES[name]
+    kw = ALL[name]
     FT = kw.get("FT", np.float64)
     m = ph.build_product(library=library, **kw)
     ob.set_(m, **_ic(z))
@@ -58,7 +60,7 @@ def _product_vs_golden(name, library):
                 assert ph.rel_linf(got, ref) <= ph.TOL[FT], (name, s, n)
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + WIDENING)
 def test_hostsim_matches_golden(name):
     from oceananigans_b200 import _lib
     import __graft_entry__ as ge

@@ -77,3 +77,18 @@ def test_asynchronous_output_cuda(ob):
     """snapshots taken by oc_output_begin are unaffected by the time steps issued before oc_output_wait"""
     import test_host_api as th
     th.asynchronous_output(None)
+
+
+def _widening_goldens():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as mg
+    return sorted(mg.GOLDEN_CASES_WIDENING)
+
+
+@pytest.mark.parametrize("name", _widening_goldens())
+def test_cuda_matches_widening_golden(ob, name):
+    """frozen vectors of the widening features (tests/golden/make_golden.py: GOLDEN_CASES_WIDENING)"""
+    import test_golden as tg
+    tg._product_vs_golden(name, None)
