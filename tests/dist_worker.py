@@ -53,6 +53,10 @@ def main():
     arch = ob.Distributed(ob.B200(rank if nccl else 0), partition=ob.Partition(1, R), rank=rank, nranks=R,
                           exchange=None if nccl else gloo_exchange)
     scheme = kw.get("scheme", "weno")
+    f = kw.get("f")
+    if isinstance(f, list):                      # ("beta", f₀, β): JSON turns the tuple into a list
+        f = tuple(f)
+    kw["f"] = f
     case = dict(N=N, topo=topo, scheme=scheme, FT=FT, f=kw.get("f"), closure=kw.get("closure", "scalar"), bcs=kw.get("bcs", False),
                 ts=kw.get("ts", "RungeKutta3"))
     model = ph.build_product(library=lib, arch=arch, **case)

@@ -47,6 +47,9 @@ def run_ranks(R, case, timeout=600, backend="gloo"):
     # the LES topology: Bounded z (DCT twiddles around the transposed stage), AMD, FPlane, flux / gradient / value BCs
     (2, dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, steps=2)),
     (2, dict(N=(12, 8, 6), topo="PPB", scheme="centered", steps=2, ts="QuasiAdamsBashforth2")),
+    # the round-1 widening on slabs: Smagorinsky(-Lilly) eddy viscosities need their own halo exchange; BetaPlane needs the rank's y offset
+    (2, dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="lilly", f=("beta", 0.3, 2.0), bcs=True, steps=2)),
+    (4, dict(N=(12, 16, 8), topo="PPP", scheme="upwind3", closure="smag", f=("beta", 0.3, 2.0), steps=1)),
 ])
 def test_slab_decomposition_matches_single_domain_oracle(R, case):
     res = run_ranks(R, dict(case))
