@@ -139,12 +139,13 @@ int  oc_download_interior(oc_model* m, int field, void* host, size_t nbytes);
 int  oc_upload_parent(oc_model* m, int field, const void* host, size_t nbytes);
 int  oc_download_parent(oc_model* m, int field, void* host, size_t nbytes);
 
-/* Array-valued flux boundary condition: FluxBoundaryCondition(J::AbstractArray) on one side of a prognostic field
- * (src/BoundaryConditions/boundary_condition.jl: getbc(bc, i, j, …) = bc.condition[i, j]; compute_flux_bcs.jl:116-163).  `host` holds
- * N₁×N₂ values of the model's float type over the two tangential interior dimensions (first one fastest: Nx×Ny for bottom / top,
- * Nx×Nz for south / north, Ny×Nz for west / east).  The side must have been created as OC_BC_FLUX in oc_config (its scalar is then
- * ignored).  May be called again to update the values (time-dependent forcing from the host).  Value / Gradient arrays: not implemented. */
-int  oc_set_flux_bc_array(oc_model* m, int field, int side, const void* host, size_t nbytes);
+/* Array-valued boundary condition — FluxBoundaryCondition(A::AbstractArray), ValueBoundaryCondition(A), GradientBoundaryCondition(A) —
+ * on one side of a prognostic field (src/BoundaryConditions/boundary_condition.jl: getbc(bc, i, j, …) = bc.condition[i, j];
+ * compute_flux_bcs.jl:116-163; fill_halo_regions_value_gradient.jl:7-119).  `host` holds N₁×N₂ values of the model's float type over
+ * the two tangential interior dimensions (first one fastest: Nx×Ny for bottom / top, Nx×Nz for south / north, Ny×Nz for west / east).
+ * The side must have been created with that kind (OC_BC_FLUX / OC_BC_VALUE / OC_BC_GRADIENT) in oc_config; its scalar is then ignored.
+ * May be called again to update the values (time-dependent forcing from the host). */
+int  oc_set_bc_array(oc_model* m, int field, int side, const void* host, size_t nbytes);
 
 /* ---- staged entry points (the methods time_step! calls; used by parity tests and mid-step callbacks) ---- */
 /* fill_halo_regions!(fields...; fill_open_bcs)  src/BoundaryConditions/fill_halo_regions.jl:25-36; `fields` lists field ids */

@@ -97,7 +97,9 @@ topo_code(::Type{Periodic}) = Int32(0); topo_code(::Type{Bounded}) = Int32(1); t
 
 bc_record(bc::BoundaryCondition{<:Flux, Nothing}) = OcBC(2, 0, 0.0)
 bc_record(bc::BoundaryCondition{<:Flux, <:Number}) = OcBC(2, 1, bc.condition)
-bc_record(bc::BoundaryCondition{<:Flux, <:AbstractArray}) = OcBC(2, 1, 0.0)      # values follow through oc_set_flux_bc_array (twin)
+bc_record(bc::BoundaryCondition{<:Flux, <:AbstractArray}) = OcBC(2, 1, 0.0)      # values follow through oc_set_bc_array (twin)
+bc_record(bc::BoundaryCondition{<:Value, <:AbstractArray}) = OcBC(3, 1, 0.0)
+bc_record(bc::BoundaryCondition{<:Gradient, <:AbstractArray}) = OcBC(4, 1, 0.0)
 bc_record(bc::BoundaryCondition{<:Value, <:Number}) = OcBC(3, 1, bc.condition)
 bc_record(bc::BoundaryCondition{<:Gradient, <:Number}) = OcBC(4, 1, bc.condition)
 bc_record(bc::BoundaryCondition{<:Open, Nothing}) = OcBC(5, 0, 0.0)
@@ -205,13 +207,13 @@ function twin(model)
                 DeviceModel(cfg)
             end
         end
-        # FluxBoundaryCondition(J::AbstractArray): upload the N₁×N₂ values (getbc(bc, i, j, …) = J[i, j])
+        # Flux / Value / GradientBoundaryCondition(A::AbstractArray): upload the N₁×N₂ values (getbc(bc, i, j, …) = A[i, j])
         for (f, field) in enumerate((model.velocities..., model.tracers...))
             bcs = field.boundary_conditions
             for (s, bc) in enumerate((bcs.west, bcs.east, bcs.south, bcs.north, bcs.bottom, bcs.top))
-                bc isa BoundaryCondition{<:Flux, <:AbstractArray} || continue
+                bc isa BoundaryCondition{<:Union{Flux, Value, Gradient}, <:AbstractArray} || continue
                 J = Array{eltype(model.grid)}(bc.condition)
-                GC.@preserve J check(ccall((:oc_set_flux_bc_array, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Csize_t),
+                GC.@preserve J check(ccall((:oc_set_bc_array, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Csize_t),
                                            dm.handle, f - 1, s - 1, J, sizeof(J)))
             end
         end

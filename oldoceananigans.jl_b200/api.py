@@ -377,8 +377,8 @@ class _BC:
         if callable(value):
             raise NotImplementedError("function-valued boundary conditions are out of scope (Julia closures cannot cross the C ABI)")
         if value is not None and not np.isscalar(value):
-            if kind != L.OC_BC_FLUX:
-                raise NotImplementedError("array-valued boundary conditions: FluxBoundaryCondition only (Value / Gradient arrays: next)")
+            if kind not in (L.OC_BC_FLUX, L.OC_BC_VALUE, L.OC_BC_GRADIENT):
+                raise NotImplementedError("array-valued boundary conditions: Flux, Value or Gradient")
             self.array = np.asarray(value)
             if self.array.ndim != 2:
                 raise ValueError("an array-valued boundary condition needs a 2-D array over the two tangential dimensions")
@@ -698,12 +698,12 @@ class NonhydrostaticModel:
         h = C.c_void_p()
         self._lib.check(self._lib.oc_model_create(C.byref(cfg), C.byref(h)))
         self._h = h
-        for f, n in enumerate(names):              # FluxBoundaryCondition(array)
+        for f, n in enumerate(names):              # FluxBoundaryCondition(array), ValueBoundaryCondition(array), GradientBoundaryCondition(array)
             fb = bcs.get(n)
             for s, side in enumerate(_SIDES):
                 bc = fb.sides.get(side) if fb is not None else None
                 if bc is not None and bc.array is not None:
-                    self.set_flux_boundary_condition_array(f, s, bc.array)
+                    self.set_boundary_condition_array(f, s, bc.array)
         if self.distributed:
             self._attach_transport(arch)
         self.tracer_names = tracers
@@ -722,8 +722,8 @@ class NonhydrostaticModel:
         # constructor tail: update_state!(model; compute_tendencies=false)   nonhydrostatic_model.jl:241
         self._lib.check(self._lib.oc_update_state(self._h, 0))
 
-    def set_flux_boundary_condition_array(self, field, side, array):
-        """(re)load the N₁×N₂ values of an array-valued FluxBoundaryCondition (oc_set_flux_bc_array); `array` is indexed [i₁, i₂]"""
+    def set_boundary_condition_array(self, field, side, array):
+        """(re)load the N₁×N₂ values of an array-valued Flux / Value / Gradient boundary condition (oc_set_bc_array); `array` is indexed [i₁, i₂]"""
         d = side // 2
         t1, t2 = (1 if d == 0 else 0), (1 if d == 2 else 2)
         shape = (self.grid.N[t1], self.grid.N[t2])
@@ -731,7 +731,7 @@ class NonhydrostaticModel:
         if a.shape != shape:
             raise ValueError(f"boundary-condition array of shape {a.shape}; expected {shape}")
         a = np.asfortranarray(a.astype(self.grid.FT))
-        self._lib.check(self._lib.oc_set_flux_bc_array(self._h, field, side, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        self._lib.check(self._lib.oc_set_bc_array(self._h, field, side, a.ctypes.data_as(C.c_void_p), a.nbytes))
 
     def _attach_transport(self, arch):
         if arch.exchange is not None:

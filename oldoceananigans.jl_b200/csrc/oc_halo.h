@@ -130,4 +130,45 @@ struct HaloKernel {
     }
 };
 
+// Array-valued Value / Gradient boundary condition on ONE side of one Center-located field: ValueBoundaryCondition(A::AbstractArray),
+// GradientBoundaryCondition(A) — getbc(bc, i, j, …) = A[i, j] in _fill_*_halo! (fill_halo_regions_value_gradient.jl:7-119).  Runs right
+// after HaloKernel (which filled these cells with the side's scalar) and rewrites exactly the cells HaloKernel writes for that side: the
+// first halo plane, over the interior range of Bounded tangential dimensions and the whole (wrapped) extent of periodic ones, so that
+// corners receive the periodic images of the BC halos (boundary_condition_ordering.jl:113-128).
+template <class FT>
+struct HaloArrayKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 128;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    FT* p;
+    const FT* A;       // n1 × n2 values over the tangential interior, first tangential dimension fastest
+    int d, side, kind; // normal dimension; 0 low / 1 high; 3 value, 4 gradient
+    int n1;
+    int lo1, m1, lo2, m2;   // index ranges of the two tangential dimensions covered by this launch
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const int a1 = b.x * nt + tid, a2 = b.y;
+        if (a1 >= m1 || a2 >= m2) return;
+        const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+        int P[3], Q[3];
+        P[t1] = lo1 + a1; P[t2] = lo2 + a2;
+        P[d] = side == 0 ? -1 : g.N[d];
+        Q[d] = side == 0 ? 0 : g.N[d] - 1;
+        for (int n = 0; n < 2; ++n) {
+            const int t = n == 0 ? t1 : t2;
+            int q = P[t];
+            if (!g.bounded[t]) { q %= g.N[t]; if (q < 0) q += g.N[t]; }      // periodic (and Flat, stored as periodic with N = 1)
+            Q[t] = q;
+        }
+        const FT val = A[Q[t1] + (size_t)n1 * Q[t2]];
+        const FT delta = d == 2 ? g.dz_at(true, side == 0 ? 0 : g.N[2]) : g.d[d];
+        FT cI = p[g.idx(Q[0], Q[1], Q[2])];
+        if (kind == 4) cI = cI + val * (side == 0 ? -delta : delta);                          // _value_gradient.jl:9-10
+        else if (side == 0) { const FT grad = (cI - val) / (delta / FT(2)); cI = cI + grad * (-delta); }   // :12-13
+        else { const FT grad = (val - cI) / (delta / FT(2)); cI = cI + grad * delta; }
+        p[g.idx(P[0], P[1], P[2])] = cI;
+    }
+};
+
 }  // namespace oc

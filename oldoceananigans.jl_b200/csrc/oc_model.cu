@@ -357,7 +357,7 @@ Model<FT>::~Model() {
     for (auto& f : Gn_) fr(f);
     for (auto& f : Gm_) fr(f);
     for (int f = 0; f < OC_MAX_FIELDS; ++f)
-        for (int s = 0; s < 6; ++s) if (flux_array_[f][s]) dev_free(flux_array_[f][s]);
+        for (int s = 0; s < 6; ++s) if (bc_array_[f][s]) dev_free(bc_array_[f][s]);
     fr(pNHS_); fr(pHY_); fr(nu_e_);
     for (auto& f : kappa_e_) fr(f);
     dev_free(fftbuf_);
@@ -661,6 +661,27 @@ void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open) {
     Dim3 grid;
     grid.x = it->second.nblocks;
     go(k, grid, 0, OC_TIMER_HALO);
+    // array-valued Value / Gradient BCs of prognostic fields: rewrite those sides' halo plane (HaloArrayKernel)
+    for (FieldRec* fr : fields) {
+        if (state_.empty() || fr < &state_[0] || fr >= &state_[0] + F_) continue;
+        const int f = (int)(fr - &state_[0]);
+        for (int s = 0; s < 6; ++s) {
+            if (!bc_array_[f][s] || (fr->bc[s].kind != OC_BC_VALUE && fr->bc[s].kind != OC_BC_GRADIENT)) continue;
+            HaloArrayKernel<FT> hk;
+            hk.g = g_;
+            hk.p = fr->p;
+            hk.A = bc_array_[f][s];
+            hk.d = s / 2; hk.side = s % 2; hk.kind = fr->bc[s].kind;
+            const int t1 = hk.d == 0 ? 1 : 0, t2 = hk.d == 2 ? 1 : 2;
+            hk.n1 = g_.N[t1];
+            // the cells HaloKernel writes for this side: interior range of Bounded tangential dimensions, whole extent of periodic ones
+            hk.lo1 = g_.bounded[t1] ? 0 : -g_.H[t1]; hk.m1 = g_.bounded[t1] ? g_.N[t1] : g_.N[t1] + 2 * g_.H[t1] + 1;
+            hk.lo2 = g_.bounded[t2] ? 0 : -g_.H[t2]; hk.m2 = g_.bounded[t2] ? g_.N[t2] : g_.N[t2] + 2 * g_.H[t2] + 1;
+            Dim3 hg;
+            hg.x = (hk.m1 + HaloArrayKernel<FT>::THREADS - 1) / HaloArrayKernel<FT>::THREADS; hg.y = hk.m2; hg.z = 1;
+            go(hk, hg, 0, OC_TIMER_HALO);
+        }
+    }
     if (dist_) exchange_y(fields);
 }
 
@@ -1074,7 +1095,7 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
         for (int s = 0; s < 6; ++s) {
             const SideBC& bc = state_[f].bc[s];
             const oc_bc& ub = cfg_.bcs[f][s];
-            a.fbc.on[s] = (bc.kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX && ub.has_value && !flux_array_[f][s]) ? 1 : 0;
+            a.fbc.on[s] = (bc.kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX && ub.has_value && !bc_array_[f][s]) ? 1 : 0;
             a.fbc.val[s] = (FT)bc.value;
         }
         a.add_flux_bcs = add_flux_bcs ? 1 : 0;
@@ -1136,7 +1157,7 @@ void Model<FT>::compute_flux_bc_tendencies() {
         bool any = false;
         for (int s = 0; s < 6; ++s) {
             const oc_bc& ub = cfg_.bcs[f][s];
-            k.fbc.on[s] = (state_[f].bc[s].kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX && ub.has_value && !flux_array_[f][s]) ? 1 : 0;
+            k.fbc.on[s] = (state_[f].bc[s].kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX && ub.has_value && !bc_array_[f][s]) ? 1 : 0;
             k.fbc.val[s] = (FT)state_[f].bc[s].value;
             any = any || k.fbc.on[s];
         }
@@ -1149,11 +1170,11 @@ void Model<FT>::compute_flux_bc_tendencies() {
 template <class FT>
 void Model<FT>::apply_flux_arrays(int f, FT* Gn, FT* Unew, FT coef) {
     for (int s = 0; s < 6; ++s) {
-        if (!flux_array_[f][s]) continue;
+        if (!bc_array_[f][s] || state_[f].bc[s].kind != OC_BC_FLUX) continue;
         FluxArrayKernel<FT> k;
         k.g = g_;
         k.Gn = Gn; k.Unew = Unew; k.coef = coef;
-        k.J = flux_array_[f][s];
+        k.J = bc_array_[f][s];
         k.d = s / 2; k.side = s % 2;
         k.comp = f < 3 ? f : -1;
         k.zface = f == 2 ? 1 : 0;
@@ -1166,27 +1187,32 @@ void Model<FT>::apply_flux_arrays(int f, FT* Gn, FT* Unew, FT coef) {
 }
 
 template <class FT>
-void Model<FT>::set_flux_bc_array(int field, int side, const void* host, size_t nbytes) {
-    if (field < 0 || field >= F_) throw Error(OC_ERR_INVALID, "set_flux_bc_array: not a prognostic field index");
-    if (side < 0 || side > 5) throw Error(OC_ERR_INVALID, "set_flux_bc_array: side must be 0 … 5 (west, east, south, north, bottom, top)");
+void Model<FT>::set_bc_array(int field, int side, const void* host, size_t nbytes) {
+    if (field < 0 || field >= F_) throw Error(OC_ERR_INVALID, "set_bc_array: not a prognostic field index");
+    if (side < 0 || side > 5) throw Error(OC_ERR_INVALID, "set_bc_array: side must be 0 … 5 (west, east, south, north, bottom, top)");
     if (dist_) throw Error(OC_ERR_UNSUPPORTED, "array-valued boundary conditions on distributed models");
     const oc_bc& ub = cfg_.bcs[field][side];
-    if (!(state_[field].bc[side].kind == OC_BC_FLUX && ub.kind == OC_BC_FLUX))
-        throw Error(OC_ERR_INVALID, "set_flux_bc_array: this side of the field must have been created with a Flux boundary condition");
+    const int kind = state_[field].bc[side].kind;
+    if (!(kind == ub.kind && (kind == OC_BC_FLUX || kind == OC_BC_VALUE || kind == OC_BC_GRADIENT)))
+        throw Error(OC_ERR_INVALID, "set_bc_array: this side of the field must have been created with a Flux, Value or Gradient boundary condition");
+    if (kind != OC_BC_FLUX && state_[field].face[side / 2])
+        throw Error(OC_ERR_INVALID, "set_bc_array: Value / Gradient conditions apply to fields located at Center in the wall-normal direction");
     const int d = side / 2, t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
     const size_t n = (size_t)g_.N[t1] * g_.N[t2];
     if (n * sizeof(FT) != nbytes) throw Error(OC_ERR_INVALID, "host buffer size mismatch: expected " + std::to_string(n * sizeof(FT)) + " bytes");
     join_tracers();
-    if (!flux_array_[field][side]) {
-        flux_array_[field][side] = (FT*)dev_alloc(n * sizeof(FT));
+    if (!bc_array_[field][side]) {
+        bc_array_[field][side] = (FT*)dev_alloc(n * sizeof(FT));
         device_bytes += (int64_t)(n * sizeof(FT));
     }
-    dev_upload(flux_array_[field][side], host, n * sizeof(FT), stream_);
+    dev_upload(bc_array_[field][side], host, n * sizeof(FT), stream_);
 #ifndef OC_HOSTSIM
     cuda_check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");     // the caller's buffer may go away
 #endif
     cfg_.bcs[field][side].has_value = 1;
     tend_valid_ = false;
+    aux_valid_ = false;
+    if (kind != OC_BC_FLUX) { std::vector<FieldRec*> one{&state_[field]}; halo(one, false); }      // the halo plane follows the new values
 }
 
 template <class FT>
@@ -1727,10 +1753,10 @@ int oc_get_clock(oc_model* m, oc_clock* c) { OC_REQUIRE(m); *c = m->impl->clock;
 int oc_set_clock(oc_model* m, const oc_clock* c) { OC_REQUIRE(m); m->impl->clock = *c; return OC_OK; }
 int oc_restore_previous_tendency(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->restore_previous_tendency(field, host, nbytes); }); }
 int oc_compute_diagnostics(oc_model* m, oc_diagnostics* out) { OC_REQUIRE(m); return guarded([&] { m->impl->diagnostics(out); }); }
-int oc_set_flux_bc_array(oc_model* m, int field, int side, const void* host, size_t nbytes) {
+int oc_set_bc_array(oc_model* m, int field, int side, const void* host, size_t nbytes) {
     OC_REQUIRE(m);
     if (!host) { g_last_error = "null argument"; return OC_ERR_INVALID; }
-    return guarded([&] { m->impl->set_flux_bc_array(field, side, host, nbytes); });
+    return guarded([&] { m->impl->set_bc_array(field, side, host, nbytes); });
 }
 int oc_output_begin(oc_model* m, int field, const int lo[3], const int n[3], void* host, size_t nbytes, int* ticket) {
     OC_REQUIRE(m);

@@ -102,7 +102,7 @@ struct ModelBase {
     virtual int output_begin(int field, const int lo[3], const int n[3], void* host, size_t nbytes) = 0;
     virtual void output_wait(int ticket) = 0;
     virtual bool output_test(int ticket) = 0;
-    virtual void set_flux_bc_array(int field, int side, const void* host, size_t nbytes) = 0;
+    virtual void set_bc_array(int field, int side, const void* host, size_t nbytes) = 0;
     virtual void restore_previous_tendency(int field, const void* host, size_t nbytes) = 0;
     virtual void dist_attach(Transport* t) = 0;
     virtual int dist_rank() const = 0;
@@ -146,9 +146,9 @@ public:
     struct OutputSlot { FT* stage = nullptr; size_t cap = 0; void* ev_snap = nullptr; void* ev_done = nullptr; bool busy = false; };
     std::vector<OutputSlot> out_slots_;
     Stream out_stream_ = 0;       // device-to-host copies of output snapshots, concurrent with the time stepping on stream_
-    void set_flux_bc_array(int field, int side, const void* host, size_t nbytes) override;
+    void set_bc_array(int field, int side, const void* host, size_t nbytes) override;
     void apply_flux_arrays(int f, FT* Gn, FT* Unew, FT coef);
-    FT* flux_array_[OC_MAX_FIELDS][6] = {};      // device arrays of array-valued Flux BCs (nullptr: scalar)
+    FT* bc_array_[OC_MAX_FIELDS][6] = {};      // device arrays of array-valued Flux BCs (nullptr: scalar)
     void restore_previous_tendency(int field, const void* host, size_t nbytes) override;
     void dist_attach(Transport* t) override;
     int dist_rank() const override { return rank_; }

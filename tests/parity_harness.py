@@ -76,24 +76,32 @@ def _coriolis(mod, f):
 
 
 def _array_bcs(N, topo, tr):
-    """array-valued FluxBoundaryConditions on every Bounded side that takes one: the first tracer on all of them, u at the top and
-    bottom (a wind-stress pattern), v on west / east — seeded, so the oracle and the product see the same numbers"""
+    """array-valued boundary conditions on every Bounded side that takes one — {field: {side: (kind, array)}}: the first tracer gets a
+    Gradient array on the low side and a Flux array on the high side, the second tracer Value arrays, u a Value array at the bottom (a
+    moving wall) and a Flux array at the top (a wind-stress pattern), v Flux arrays on west / east.  Seeded: the oracle and the product
+    see the same numbers."""
     rng = np.random.default_rng(99)
-    out = {tr[0]: {}, "u": {}, "v": {}}
+    out = {n: {} for n in tr[:2]}
+    out.update({"u": {}, "v": {}})
     dims = {0: (1, 2), 1: (0, 2), 2: (0, 1)}
     names = {0: ("west", "east"), 1: ("south", "north"), 2: ("bottom", "top")}
+    base = {"T": 20.0, "S": 35.0, "b": 0.0, "c": 1.0}
     for d in range(3):
         if topo[d] != "B":
             continue
         shape = tuple(N[e] for e in dims[d])
-        for side in names[d]:
-            out[tr[0]][side] = 1e-2 * rng.standard_normal(shape)
+        lo, hi = names[d]
+        out[tr[0]][lo] = ("gradient", 5e-2 * rng.standard_normal(shape))
+        out[tr[0]][hi] = ("flux", 1e-2 * rng.standard_normal(shape))
+        if len(tr) > 1:
+            out[tr[1]][lo] = ("value", base.get(tr[1], 0.0) + 1e-2 * rng.standard_normal(shape))
+            out[tr[1]][hi] = ("value", base.get(tr[1], 0.0) + 1e-2 * rng.standard_normal(shape))
         if d == 2:
-            out["u"]["top"] = 1e-2 * rng.standard_normal(shape)
-            out["u"]["bottom"] = 1e-2 * rng.standard_normal(shape)
+            out["u"]["top"] = ("flux", 1e-2 * rng.standard_normal(shape))
+            out["u"]["bottom"] = ("value", 0.1 * rng.standard_normal(shape))
         if d == 0:
-            out["v"]["west"] = 1e-2 * rng.standard_normal(shape)
-            out["v"]["east"] = 1e-2 * rng.standard_normal(shape)
+            out["v"]["west"] = ("flux", 1e-2 * rng.standard_normal(shape))
+            out["v"]["east"] = ("flux", 1e-2 * rng.standard_normal(shape))
     return {n: v for n, v in out.items() if v}
 
 
@@ -108,7 +116,7 @@ def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closur
            "lilly": (clo.SmagorinskyLilly(0.23, 1.0, {n: 1.0 + 0.5 * t for t, n in enumerate(tr)}), clo.ScalarDiffusivity(1.05e-6, 1.46e-7))}[closure]
     bc_o = None
     if bcs == "array":
-        bc_o = {n: {side: BC("flux", a) for side, a in sides.items()} for n, sides in _array_bcs(N, topo, tr).items()}
+        bc_o = {n: {side: BC(kind, a) for side, (kind, a) in sides.items()} for n, sides in _array_bcs(N, topo, tr).items()}
     elif bcs:
         t0 = tr[0]
         bc_o = {"u": {"top": BC("flux", -2e-3)}, t0: {"top": BC("flux", 5e-3), "bottom": BC("gradient", 0.05)},
@@ -136,7 +144,8 @@ def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closu
                     ob.ScalarDiffusivity(nu=1.05e-6, kappa=1.46e-7))}[closure]
     bc_b = None
     if bcs == "array":
-        bc_b = {n: ob.FieldBoundaryConditions(**{side: ob.FluxBoundaryCondition(a) for side, a in sides.items()})
+        mk = {"flux": ob.FluxBoundaryCondition, "value": ob.ValueBoundaryCondition, "gradient": ob.GradientBoundaryCondition}
+        bc_b = {n: ob.FieldBoundaryConditions(**{side: mk[kind](a) for side, (kind, a) in sides.items()})
                 for n, sides in _array_bcs(N, topo, tr).items()}
     elif bcs:
         # the BC kinds of test/regression_tests/ocean_large_eddy_simulation_regression_test.jl:19-37
@@ -262,7 +271,8 @@ CORIOLIS_CASES = [
     ("PFB centered cartesian coriolis 2D", dict(N=(16, 1, 12), topo="PFB", scheme="centered", buoy="tracer", f=("cartesian", 0.3, -0.5, 0.7))),
 ]
 
-# array-valued flux boundary conditions: FluxBoundaryCondition(J::AbstractArray)  (oc_set_flux_bc_array; compute_flux_bcs.jl:116-163)
+# array-valued boundary conditions: Flux / Value / Gradient BoundaryCondition(A::AbstractArray)  (oc_set_bc_array; compute_flux_bcs.jl:116-163,
+# fill_halo_regions_value_gradient.jl:7-119)
 ARRAY_BC_CASES = [
     ("PPB weno array flux bcs (marching kernel)", dict(N=(16, 12, 8), topo="PPB", scheme="weno", bcs="array")),
     ("BBB centered amd array flux bcs AB2", dict(N=(12, 10, 8), topo="BBB", scheme="centered", closure="amd", bcs="array", ts="QuasiAdamsBashforth2")),

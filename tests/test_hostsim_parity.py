@@ -171,5 +171,5 @@ def test_hostsim_matches_oracle_with_tilted_gravity(hostsim, name, kw):
 
 @pytest.mark.parametrize("name,kw", ph.ARRAY_BC_CASES, ids=[c[0] for c in ph.ARRAY_BC_CASES])
 def test_hostsim_matches_oracle_with_array_valued_flux_bcs(hostsim, name, kw):
-    """FluxBoundaryCondition(J::AbstractArray) on every Bounded side (oc_set_flux_bc_array; compute_flux_bcs.jl:116-163)"""
+    """FluxBoundaryCondition(J::AbstractArray) on every Bounded side (oc_set_bc_array; compute_flux_bcs.jl:116-163)"""
     ph.check_case(kw, library=hostsim, steps=(1, 3))

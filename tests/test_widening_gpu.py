@@ -69,7 +69,7 @@ def test_stratified_fluid_remains_at_rest_with_tilted_gravity_cuda(ob):
 
 @pytest.mark.parametrize("name,kw", ph.ARRAY_BC_CASES, ids=[c[0] for c in ph.ARRAY_BC_CASES])
 def test_cuda_matches_oracle_with_array_valued_flux_bcs(ob, name, kw):
-    """FluxBoundaryCondition(J::AbstractArray) on every Bounded side (oc_set_flux_bc_array; compute_flux_bcs.jl:116-163)"""
+    """FluxBoundaryCondition(J::AbstractArray) on every Bounded side (oc_set_bc_array; compute_flux_bcs.jl:116-163)"""
     ph.check_case(kw, library=None, steps=(1, 10))
 
 
