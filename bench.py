@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — cell-updates/s per full time step of the NonhydrostaticModel hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c3f32|c4|c4s|c4l|c1|c3u5|c2c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c3f32|c4|c4s|c4l|c4cb|c1|c3u5|c2c4] [--impl ours|reference]
 
 One "step" is one full `time_step!(model, Δt)` (RK3: three stages, each tendency+substep, halo fills, FFT
 pressure solve and projection) over one synthetic, seeded initial state.
@@ -63,8 +63,11 @@ WORKLOADS = {
     "c4l": dict(N=(512, 512, 256), topo="PPB", FT="f64", adv="weno", tracers=("T", "S"), buoy="seawater", closure="lilly",
                 F=5, b=1, a=1,
                 label="C4 physics with (SmagorinskyLilly(C=0.23, Cb=1, Pr=1), ScalarDiffusivity): 512^2x256 (P,P,B) WENO-5 FPlane flux BCs F64"),
+    # the C4 physics with AMD's buoyancy modification (AnisotropicMinimumDissipation(; Cb = 1), anisotropic_minimum_dissipation.jl:62-68)
+    "c4cb": dict(N=(512, 512, 256), topo="PPB", FT="f64", adv="weno", tracers=("T", "S"), buoy="seawater", closure="amdcb",
+                 F=5, b=1, a=1, label="C4 physics with AnisotropicMinimumDissipation(Cb=1): 512^2x256 (P,P,B) WENO-5 FPlane flux BCs F64"),
 }
-LES = ("amd", "lilly")       # the C4 family: Δ = 1 m, LES initial condition, Δt = 1 s, FPlane, surface flux BCs
+LES = ("amd", "lilly", "amdcb")       # the C4 family: Δ = 1 m, LES initial condition, Δt = 1 s, FPlane, surface flux BCs
 
 
 def stretched_faces(Nz, Lz):
@@ -192,6 +195,7 @@ def build_model(w, device, rank=0, world=1):
         kw["closure"] = ob.ScalarDiffusivity(nu=1e-5, kappa=1e-5)
     elif w["closure"] in LES:
         kw["closure"] = ob.AnisotropicMinimumDissipation() if w["closure"] == "amd" else \
+            ob.AnisotropicMinimumDissipation(Cb=1.0) if w["closure"] == "amdcb" else \
             (ob.SmagorinskyLilly(C=0.23, Cb=1.0, Pr=1.0), ob.ScalarDiffusivity(nu=1.05e-6, kappa=1.46e-7))
         kw["coriolis"] = ob.FPlane(f=1e-4)
         kw["boundary_conditions"] = {      # test/regression_tests/ocean_large_eddy_simulation_regression_test.jl:19-37
@@ -409,6 +413,7 @@ def oracle_model(w, N):
         kw["closure"] = clo.ScalarDiffusivity(1e-5, 1e-5)
     elif w["closure"] in LES:
         kw["closure"] = clo.AnisotropicMinimumDissipation() if w["closure"] == "amd" else \
+            clo.AnisotropicMinimumDissipation(Cb=1.0) if w["closure"] == "amdcb" else \
             (clo.SmagorinskyLilly(0.23, 1.0, 1.0), clo.ScalarDiffusivity(1.05e-6, 1.46e-7))
         kw["coriolis_f"] = 1e-4
         kw["boundary_conditions"] = {"u": {"top": BC("flux", -2e-5)}, "T": {"top": BC("flux", 5e-5), "bottom": BC("gradient", 0.005)},

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OC_ABI_VERSION 3
+#define OC_ABI_VERSION 4
 #define OC_MAX_TRACERS 8
 #define OC_MAX_FIELDS (3 + OC_MAX_TRACERS)
 
@@ -95,7 +95,7 @@ typedef struct {
      * (Smagorinskys/lilly_coefficient.jl:47-112): smagorinsky = 2.  νₑ = ς (C Δᶠ)² √(2Σ²), κₑ = νₑ / Pr[tracer]; νₑ and κₑ are the fields
      * OC_FIELD_NU_E / OC_FIELD_KAPPA_E0 + t, like AMD's.  DynamicCoefficient is not implemented (rejected). */
     int32_t smagorinsky;          /* 0 = none, 1 = constant coefficient, 2 = LillyCoefficient */
-    int32_t reserved;
+    int32_t amd_has_Cb;           /* ABI v4 (the slot was reserved in v3): 1 = AMD buoyancy modification on, see amd_Cb below */
     double  smag_C, smag_Cb;
     double  smag_Pr[OC_MAX_TRACERS];
     /* The Coriolis family (ABI v3).  BetaPlane(f₀, β): f = f₀ + β y at the y-node of the velocity point (src/Coriolis/beta_plane.jl:56-72);
@@ -108,6 +108,10 @@ typedef struct {
     int32_t tilted_gravity;
     int32_t reserved2;
     double  gravity_unit_vector[3];
+    /* ABI v4.  AnisotropicMinimumDissipation(; Cb): the buoyancy modification multiplier (anisotropic_minimum_dissipation.jl:62-68,
+     * 137; `Cb = nothing` = amd_has_Cb 0).  νₑ = max(0, −Cν δ² (r − Cb ζ) / q) with Cb ζ = Cb_norm_wᵢ_bᵢᶜᶜᶜ / Δᶠz (:168-172, :310-323),
+     * b = buoyancy_perturbationᶜᶜᶜ of the model's buoyancy formulation (0 without buoyancy). */
+    double  amd_Cb;
 } oc_config;
 
 typedef struct oc_model oc_model;

@@ -66,10 +66,11 @@ mutable struct OcConfig               # `oc_config`, same field order; NTuple fo
     bcs::NTuple{OC_MAX_FIELDS,NTuple{6,OcBC}}
     device::Int32; dist_rank::Int32; dist_nranks::Int32
     z_stretched::Int32; z_faces::Ptr{Float64}      # ABI v2: vertically stretched grid (Nz+1 faces, read during oc_model_create only)
-    smagorinsky::Int32; reserved::Int32            # ABI v3: 0 none, 1 Smagorinsky(coefficient::Number), 2 LillyCoefficient
+    smagorinsky::Int32; amd_has_Cb::Int32            # ABI v3: 0 none, 1 Smagorinsky(coefficient::Number), 2 LillyCoefficient
     smag_C::Float64; smag_Cb::Float64; smag_Pr::NTuple{OC_MAX_TRACERS,Float64}
     coriolis_beta::Float64; origin_y::Float64; coriolis_fxyz::NTuple{3,Float64}   # ABI v3: BetaPlane, ConstantCartesianCoriolis
     tilted_gravity::Int32; reserved2::Int32; gravity_unit_vector::NTuple{3,Float64} # ABI v3: BuoyancyForce(…; gravity_unit_vector)
+    amd_Cb::Float64                                 # ABI v4: AnisotropicMinimumDissipation(; Cb), with amd_has_Cb
     OcConfig() = new()
 end
 
@@ -147,8 +148,10 @@ function config(model::NonhydrostaticModel)
             cfg.has_scalar_diffusivity = 1; cfg.nu = c.ν
             cfg.kappa = ntuple(t -> t <= length(names) ? Float64(c.κ[t]) : 0.0, OC_MAX_TRACERS)
         elseif c isa AnisotropicMinimumDissipation
-            c.Cb === nothing || throw(ArgumentError("B200: AMD buoyancy modification is out of scope"))
             cfg.has_amd = 1; cfg.amd_Cnu = c.Cν
+            if c.Cb !== nothing      # buoyancy modification (anisotropic_minimum_dissipation.jl:62-68): ABI v4
+                cfg.amd_has_Cb = 1; cfg.amd_Cb = c.Cb
+            end
             cfg.amd_Ckappa = ntuple(t -> t <= length(names) ? Float64(c.Cκ[t]) : 0.0, OC_MAX_TRACERS)
         elseif c isa Smagorinsky && (c.coefficient isa Number || c.coefficient isa LillyCoefficient)
             # Smagorinsky(coefficient, Pr) / SmagorinskyLilly(C, Cb, Pr)  (Smagorinskys/smagorinsky.jl:31-84, lilly_coefficient.jl:47-112)

@@ -7,7 +7,7 @@ C ABI of the host-simulation build (tests/hostsim) — the package itself never 
 import ctypes as C
 import os
 
-OC_ABI_VERSION = 3
+OC_ABI_VERSION = 4
 OC_MAX_TRACERS = 8
 OC_MAX_FIELDS = 3 + OC_MAX_TRACERS
 OC_TIMER_NAMES = ("tendency", "halo", "poisson_rhs", "fft", "poisson_mid", "projection", "aux", "substep", "comm")
@@ -43,10 +43,11 @@ class oc_config(C.Structure):
         ("bcs", (oc_bc * 6) * OC_MAX_FIELDS),
         ("device", C.c_int32), ("dist_rank", C.c_int32), ("dist_nranks", C.c_int32),
         ("z_stretched", C.c_int32), ("z_faces", C.POINTER(C.c_double)),
-        ("smagorinsky", C.c_int32), ("reserved", C.c_int32), ("smag_C", C.c_double), ("smag_Cb", C.c_double),
+        ("smagorinsky", C.c_int32), ("amd_has_Cb", C.c_int32), ("smag_C", C.c_double), ("smag_Cb", C.c_double),
         ("smag_Pr", C.c_double * OC_MAX_TRACERS),
         ("coriolis_beta", C.c_double), ("origin_y", C.c_double), ("coriolis_fxyz", C.c_double * 3),
         ("tilted_gravity", C.c_int32), ("reserved2", C.c_int32), ("gravity_unit_vector", C.c_double * 3),
+        ("amd_Cb", C.c_double),
     ]
 
 

@@ -234,10 +234,11 @@ class ScalarDiffusivity:
 
 class AnisotropicMinimumDissipation:
     def __init__(self, FT=np.float64, C=1.0 / 3.0, Cnu=None, Ckappa=None, Cb=None):
-        if Cb is not None:
-            raise NotImplementedError("AMD buoyancy modification (Cb) is out of scope")
+        # Cb: buoyancy modification multiplier; None turns the term off (anisotropic_minimum_dissipation.jl:35,62-68; the reference
+        # warns that the modification is unvalidated, :137)
         self.Cnu = C if Cnu is None else Cnu
         self.Ckappa = C if Ckappa is None else Ckappa
+        self.Cb = Cb
 
 
 class LillyCoefficient:
@@ -638,6 +639,8 @@ class NonhydrostaticModel:
                 cfg.kappa[t] = pick(sd[0].kappa, n)
         if amd:
             cfg.has_amd, cfg.amd_Cnu = 1, float(amd[0].Cnu)
+            if amd[0].Cb is not None:
+                cfg.amd_has_Cb, cfg.amd_Cb = 1, float(amd[0].Cb)
             for t, n in enumerate(tracers):
                 cfg.amd_Ckappa[t] = pick(amd[0].Ckappa, n)
         if smag:

@@ -56,7 +56,7 @@ struct HydrostaticPressureKernel {
 // AMD.  One thread per cell; gradients are re-derived from u, v, w (stencil radius 1 around the cell).
 // The helper struct mirrors the reference's operator names so each term can be checked line by line.
 // ---------------------------------------------------------------------------------------------------------
-template <class FT, bool STR = false>
+template <class FT, bool STR = false, bool CB = false>
 struct AmdKernel {
     static constexpr int PHASES = 1;
     static constexpr int THREADS = 256;      // 32 (x) × 8 (y) cells per CTA: the 27-point neighbourhoods share L1 lines in x AND y
@@ -77,6 +77,16 @@ struct AmdKernel {
     // FT arithmetic (Model::build_z_tables): kxw = (Δᶠx/Δᶠz)/Δx, kzu = (Δᶠz/Δᶠx)/Δzᶠ, kyw = (Δᶠy/Δᶠz)/Δy, kzv = (Δᶠz/Δᶠy)/Δzᶠ,
     // kcz = Δᶠz/Δzᶠ, d2 = δ²; indexable like Geom::dzc
     const FT* lv_kxw; const FT* lv_kzu; const FT* lv_kyw; const FT* lv_kzv; const FT* lv_kcz; const FT* lv_d2;
+    // CB variant only — the buoyancy modification (Cb ≠ nothing, :62-68): b = buoyancy_perturbationᶜᶜᶜ from the tracers
+    FT Cb;
+    int buoyancy;        // 1 tracer b, 2 seawater linear (CB is never instantiated without buoyancy: the term is zero)
+    const FT* bT;
+    const FT* bS;
+    FT grav, alpha, beta;
+    OC_HD FT b_at(int p) const {                                                          // buoyancy_tracer.jl:12 ; seawater_buoyancy.jl:203-207
+        if (buoyancy == 1) return bT[p];
+        return grav * (alpha * bT[p] - beta * bS[p]);
+    }
     void set_consts() {
         FT fx = FT(2) * g.d[0], fy = FT(2) * g.d[1], fz = FT(2) * g.d[2];
         ratios[0] = fx / fy; ratios[1] = fy / fx; ratios[2] = fx / fz; ratios[3] = fz / fx; ratios[4] = fy / fz; ratios[5] = fz / fy;
@@ -144,6 +154,17 @@ struct AmdKernel {
             const FT mixed = S11 * (Sxy + Sxz) + S22 * (Sxy + Syz) + S33 * (Sxz + Syz);
             const FT triple = A1 * C1 * (E1 + F1) + B1 * E1 * (C1 + D1) + D1 * F1 * (A1 + B1);
             const FT r = cubes + FT(0.25) * mixed + FT(0.015625) * triple;
+            if (CB) {
+                // Cb ζ = Cb (ℑxz norm_∂x_w · Δᶠx ℑx ∂x b + ℑyz norm_∂y_w · Δᶠy ℑy ∂y b + ∂z w · Δᶠz ℑz ∂z b) / Δᶠz        (:168, :310-323)
+                const FT b0 = b_at(o);
+                const FT bx = FT(0.5) * ((b0 - b_at(o - sx)) * g.rd[0] + (b_at(o + sx) - b0) * g.rd[0]);
+                const FT by = FT(0.5) * ((b0 - b_at(o - sy)) * g.rd[1] + (b_at(o + sy) - b0) * g.rd[1]);
+                const FT rzf0 = STR ? g.rdzf[k] : g.rd[2], rzf1 = STR ? g.rdzf[k + 1] : g.rd[2];
+                const FT bz = FT(0.5) * ((b0 - b_at(o - sz)) * rzf0 + (b_at(o + sz) - b0) * rzf1);
+                const FT fz = FT(2) * (STR ? g.dzc[k] : g.d[2]);
+                const FT wb = (FT(0.25) * C1) * fx * bx + (FT(0.25) * E1) * fy * by + S33 * fz * bz;
+                nu = -Cnu * d2 * (r - Cb * wb / fz) / q;
+            } else
             nu = -Cnu * d2 * r / q;                                                        // Cb = nothing: no buoyancy term (:168,281)
         }
         nu_e[o] = oc_max<FT>(FT(0), nu);

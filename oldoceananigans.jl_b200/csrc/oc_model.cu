@@ -829,11 +829,20 @@ void Model<FT>::aux() {
             const FT* at = stretched_ ? g_.rVf + nt : nullptr;         // the AMD tables follow the six metric tables (build_z_tables)
             k.lv_kxw = at; k.lv_kzu = at ? at + nt : nullptr; k.lv_kyw = at ? at + 2 * nt : nullptr; k.lv_kzv = at ? at + 3 * nt : nullptr;
             k.lv_kcz = at ? at + 4 * nt : nullptr; k.lv_d2 = at ? at + 5 * nt : nullptr;
+            k.Cb = (FT)cfg_.amd_Cb;
+            k.buoyancy = cfg_.buoyancy;
+            k.bT = k.bS = nullptr;
+            if (cfg_.buoyancy == OC_BUOYANCY_TRACER) k.bT = state_[3 + cfg_.tracer_b].p;
+            else if (cfg_.buoyancy == OC_BUOYANCY_SEAWATER_LINEAR) { k.bT = state_[3 + cfg_.tracer_T].p; k.bS = state_[3 + cfg_.tracer_S].p; }
+            k.grav = (FT)cfg_.gravity; k.alpha = (FT)cfg_.thermal_expansion; k.beta = (FT)cfg_.haline_contraction;
             Dim3 ag;
             ag.x = (g_.N[0] + 31) / 32; ag.y = (g_.N[1] + 7) / 8; ag.z = g_.N[2];
             go(k, ag, 0, OC_TIMER_AUX);
         };
-        if (stretched_) run_amd(AmdKernel<FT, true>{});
+        // the buoyancy modification (amd_has_Cb) is a separate instantiation: without buoyancy ∂b = 0 and the plain kernel is exact
+        const bool cb = cfg_.amd_has_Cb && cfg_.buoyancy != OC_BUOYANCY_NONE;
+        if (cb) { if (stretched_) run_amd(AmdKernel<FT, true, true>{}); else run_amd(AmdKernel<FT, false, true>{}); }
+        else if (stretched_) run_amd(AmdKernel<FT, true>{});
         else run_amd(AmdKernel<FT, false>{});
         std::vector<FieldRec*> list{&nu_e_};
         for (auto& f : kappa_e_) list.push_back(&f);
@@ -1705,6 +1714,7 @@ void oc_config_init(oc_config* c) {
     c->thermal_expansion = 1.67e-4;       // LinearEquationOfState defaults   linear_equation_of_state.jl:39-40
     c->haline_contraction = 7.8e-4;
     c->tracer_T = c->tracer_S = c->tracer_b = -1;
+    c->amd_has_Cb = 0; c->amd_Cb = 0.0;
     c->tilted_gravity = 0; c->reserved2 = 0; c->gravity_unit_vector[0] = c->gravity_unit_vector[1] = 0.0; c->gravity_unit_vector[2] = -1.0;
     c->coriolis_beta = 0.0; c->origin_y = 0.0; c->coriolis_fxyz[0] = c->coriolis_fxyz[1] = c->coriolis_fxyz[2] = 0.0;
     c->smagorinsky = 0; c->smag_C = 0.16; c->smag_Cb = 1.0;          // smagorinsky.jl:77-78, lilly_coefficient.jl:47

@@ -26,9 +26,10 @@ class ScalarDiffusivity:
 
 
 class AnisotropicMinimumDissipation:
-    def __init__(self, C=1.0 / 3.0, Cnu=None, Ckappa=None):
+    def __init__(self, C=1.0 / 3.0, Cnu=None, Ckappa=None, Cb=None):
         self.Cnu = C if Cnu is None else Cnu
         self.Ckappa = C if Ckappa is None else Ckappa
+        self.Cb = Cb          # buoyancy modification multiplier; None turns the term off  (anisotropic_minimum_dissipation.jl:62-68)
         self.kind = "amd"
 
     def Ckappa_for(self, name):
@@ -214,6 +215,20 @@ class _AMD:
         t3 = t3 + two * self.dzw(O) * Iyz(_mul(self.dzv, self.S23))(O)
         return t1 + t2 + t3
 
+    def Cb_wi_bi(self, Cb, b):
+        """Cb_norm_wᵢ_bᵢᶜᶜᶜ  :308-323 ; b = buoyancy_perturbationᶜᶜᶜ as a quantity (None without buoyancy: ∂b = 0)"""
+        ctx, FT = self.ctx, self.ctx.FT
+        if Cb is None or b is None:
+            return FT(0)
+        Dfx, Dfy, Dfz = self.Df
+        bx = iC(ctx, ddF(ctx, b, 0), 0)(O)          # ℑxᶜᵃᵃ ∂xᶠᶜᶜ b
+        by = iC(ctx, ddF(ctx, b, 1), 1)(O)          # ℑyᵃᶜᵃ ∂yᶜᶠᶜ b
+        bz = iC(ctx, ddF(ctx, b, 2), 2)(O)          # ℑzᵃᵃᶜ ∂zᶜᶜᶠ b
+        wx_bx = self.Ixz(self.dxw)(O) * Dfx * bx
+        wy_by = self.Iyz(self.dyw)(O) * Dfy * by
+        wz_bz = self.dzw(O) * Dfz(O) * bz            # norm_∂z_w = ∂z_w: the diagonal terms carry no width ratio (velocity_tracer_gradients.jl:126-128)
+        return FT(Cb) * (wx_bx + wy_by + wz_bz)
+
     def delta2(self):
         FT = self.ctx.FT
         Dfx, Dfy, Dfz = self.Df
@@ -244,7 +259,7 @@ class _AMD:
         return sigma, a + b + cc
 
 
-def compute_amd(ctx, closure, U, tracers, nu_e, kappa_e):
+def compute_amd(ctx, closure, U, tracers, nu_e, kappa_e, buoyancy=None):
     """_compute_AMD_viscosity! / _compute_AMD_diffusivity!  :154-197 over the window of ctx (interior)."""
     g, FT = ctx.g, ctx.FT
     amd = _AMD(ctx, U)
@@ -252,7 +267,8 @@ def compute_amd(ctx, closure, U, tracers, nu_e, kappa_e):
         q = amd.q_trace()
         r = amd.r_term()
         d2 = amd.delta2()
-        Cb_zeta = FT(0) / amd.Df[2](O)
+        b = buoyancy_q(ctx, buoyancy, tracers) if (buoyancy is not None and getattr(closure, "Cb", None) is not None) else None
+        Cb_zeta = amd.Cb_wi_bi(getattr(closure, "Cb", None), b) / amd.Df[2](O)
         nu = -FT(closure.Cnu) * d2 * (r - Cb_zeta) / q
         nu = np.where(q == 0, FT(0), nu)
         nu_e.interior[...] = np.maximum(FT(0), nu)

@@ -159,7 +159,7 @@ class OracleModel:
         """compute_auxiliaries!  :58-69 — diffusivities then hydrostatic pressure"""
         for c in self.closures:
             if c.kind == "amd":
-                clo.compute_amd(self._ctx_full(), c, self.U, self.tracers, self.nu_e, self.kappa_e)
+                clo.compute_amd(self._ctx_full(), c, self.U, self.tracers, self.nu_e, self.kappa_e, self.buoyancy)
             elif c.kind == "smagorinsky":
                 clo.compute_smagorinsky(self._ctx_full(), c, self.U, self.tracers, self.buoyancy, self.nu_e, self.kappa_e)
         self.update_hydrostatic_pressure()

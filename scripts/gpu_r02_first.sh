@@ -2,6 +2,8 @@
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash scripts/gpu_r02_first.sh'
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_widening_gpu.py -q -m gpu 2>&1 | tail -15 > gpurun_out/r02a_pytest_widening.log; cat gpurun_out/r02a_pytest_widening.log
+# AMD buoyancy modification (AmdKernel<FT, STR, CB = true>): the C4 physics with Cb = 1 next to plain C4
+timeout 120 python bench.py --workload c4cb --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02a_bench_c4cb.json 2> gpurun_out/r02a_bench_c4cb.err; echo "c4cb rc=$?"
 # the C4 physics with (SmagorinskyLilly, ScalarDiffusivity): the division-free SmagorinskyKernel has no timing yet
 timeout 120 python bench.py --workload c4l --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02a_bench_c4l.json 2> gpurun_out/r02a_bench_c4l.err; echo "c4l rc=$?"
 # launch list of one c4l step (per-kernel share) and one full capture of the SmagorinskyKernel

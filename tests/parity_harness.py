@@ -110,6 +110,7 @@ def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closur
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
     obo = clo.SeawaterBuoyancy(gravity_unit_vector=tilt) if buoy == "seawater" else (clo.BuoyancyTracer(gravity_unit_vector=tilt) if buoy == "tracer" else None)
     ocl = {"scalar": clo.ScalarDiffusivity(1e-3, 2e-3), "amd": clo.AnisotropicMinimumDissipation(), "none": None,
+           "amdcb": clo.AnisotropicMinimumDissipation(Cb=1.0),       # Cb = 1: the value of Abkar et al. (2016), :62-63
            "both": (clo.ScalarDiffusivity(1e-3, 2e-3), clo.AnisotropicMinimumDissipation()),
            "smag": clo.Smagorinsky(0.16, Pr=1.0),
            # the closure of test/test_nonhydrostatic_regression.jl:68 (C = 0.23, Cb = 1, Pr = 1 + molecular values), Pr varied per tracer
@@ -138,6 +139,7 @@ def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closu
     if tilt is not None and bo is not None:
         bo = ob.BuoyancyForce(bo, gravity_unit_vector=tilt)
     cl = {"scalar": ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), "amd": ob.AnisotropicMinimumDissipation(), "none": None,
+          "amdcb": ob.AnisotropicMinimumDissipation(Cb=1.0),
           "both": (ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), ob.AnisotropicMinimumDissipation()),
           "smag": ob.Smagorinsky(coefficient=0.16, Pr=1.0),
           "lilly": (ob.SmagorinskyLilly(C=0.23, Cb=1.0, Pr={n: 1.0 + 0.5 * t for t, n in enumerate(tr)}),
@@ -257,6 +259,19 @@ SMAGORINSKY_CASES = [
     ("stretched PPB weno smagorinsky-lilly bcs", dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="lilly", bcs=True, stretch="smooth")),
     ("stretched BPB centered smagorinsky", dict(N=(16, 12, 8), topo="BPB", scheme="centered", closure="smag", stretch="facr")),
     ("tile-crossing 40x36x33 PPB smagorinsky-lilly", dict(N=(40, 36, 33), topo="PPB", scheme="weno", closure="lilly", bcs=True)),
+]
+
+# AMD's buoyancy modification (AnisotropicMinimumDissipation(; Cb), anisotropic_minimum_dissipation.jl:62-68, 168-172, 310-323).
+# tracer_noise makes Cb ζ comparable to r so that the term moves νₑ through the max(0, ·) clip both ways (checked in the tests)
+AMD_CB_CASES = [
+    ("PPB weno amd Cb=1 fplane bcs (LES)", dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="amdcb", f=1e-2, bcs=True)),
+    ("BBB centered amd Cb=1 tracer-b strong stratification", dict(N=(12, 10, 8), topo="BBB", scheme="centered", closure="amdcb", buoy="tracer", tracer_noise=30.0)),
+    ("PPP weno amd Cb=1 AB2", dict(N=(16, 12, 8), topo="PPP", scheme="weno", closure="amdcb", ts="QuasiAdamsBashforth2")),
+    ("PPB weno amd Cb=1 F32", dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="amdcb", FT=np.float32)),
+    ("PPB upwind3 amd Cb=1 no buoyancy", dict(N=(16, 12, 8), topo="PPB", scheme="upwind3", closure="amdcb", buoy="passive")),
+    ("stretched PPB weno amd Cb=1 bcs", dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="amdcb", bcs=True, stretch="smooth")),
+    ("stretched BPB centered amd Cb=1 tracer-b", dict(N=(16, 12, 8), topo="BPB", scheme="centered", closure="amdcb", buoy="tracer", stretch="facr")),
+    ("tile-crossing 40x36x33 PPB amd Cb=1", dict(N=(40, 36, 33), topo="PPB", scheme="weno", closure="amdcb", bcs=True)),
 ]
 
 # the Coriolis family: BetaPlane, ConstantCartesianCoriolis (general tile kernel)

@@ -157,6 +157,25 @@ def test_hostsim_matches_oracle_with_smagorinsky_closures(hostsim, name, kw):
     ph.check_case(kw, library=hostsim, steps=(1, 3))
 
 
+@pytest.mark.parametrize("name,kw", ph.AMD_CB_CASES[:-1], ids=[c[0] for c in ph.AMD_CB_CASES[:-1]])
+def test_hostsim_matches_oracle_with_amd_buoyancy_modification(hostsim, name, kw):
+    """AnisotropicMinimumDissipation(; Cb = 1): anisotropic_minimum_dissipation.jl:62-68, 168-172, 310-323 (AmdKernel<FT, STR, CB = true>)"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))
+
+
+def test_hostsim_amd_buoyancy_modification_changes_the_eddy_viscosity(hostsim):
+    """The Cb term is active in the parity cases: νₑ differs from the Cb = nothing model in both directions of the max(0, ·) clip."""
+    kw = dict(N=(12, 10, 8), topo="BBB", scheme="centered", buoy="tracer")
+    nus = []
+    for closure in ("amd", "amdcb"):
+        m, om = ph.build_pair(library=hostsim, closure=closure, **kw)
+        ic = ph.initial_conditions(om, tracer_noise=30.0)
+        ph.ob.set_(m, **ic)
+        nus.append(np.array(m.diffusivity_fields.nu_e.interior()))
+    plain, cb = nus
+    assert np.any((plain == 0) & (cb > 0)) and np.any((plain > 0) & (cb == 0)) and np.any((plain > 0) & (cb > 0) & (plain != cb))
+
+
 @pytest.mark.parametrize("name,kw", ph.CORIOLIS_CASES, ids=[c[0] for c in ph.CORIOLIS_CASES])
 def test_hostsim_matches_oracle_for_the_coriolis_family(hostsim, name, kw):
     """BetaPlane (beta_plane.jl:56-72), ConstantCartesianCoriolis (constant_cartesian_coriolis.jl:70-81)"""

@@ -639,6 +639,49 @@ def test_smagorinsky_uniform_strain_closed_forms(FT):
     assert np.all(nu.interior == 0)
 
 
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_amd_buoyancy_modification_closed_forms(FT):
+    """AnisotropicMinimumDissipation(; Cb)  anisotropic_minimum_dissipation.jl:62-68: νₑ = max(0, −Cν δ² (r − Cb ζ) / q) with
+    Cb ζ = Cb_norm_wᵢ_bᵢᶜᶜᶜ / Δᶠz (:168-172, :310-323).  The reference has no numbers for the (unvalidated, :137) modification; the
+    restatement is pinned by closed forms for uniform gradients:
+      w = a x, b = s x:  q = (Δᶠx/Δᶠz)² a², r = 0, ζ = a s Δᶠx²/Δᶠz²   ->  νₑ = Cν δ² Cb s / a      (same with y)
+      w = a z, b = N² z:  q = a², r = a³, ζ = a N²                       ->  νₑ = −Cν δ² (a − Cb N² / a)"""
+    g = Grid(FT, size=(6, 5, 4), extent=(3.0, 2.0, 1.0), topology=("B", "B", "B"), halo=(2, 2, 2))
+    Cnu, a, s = 1.0 / 3.0, 0.4, 0.7
+    Df = [2 * float(g.D[d]) for d in range(3)]
+    d2 = 3.0 / sum(1.0 / x ** 2 for x in Df)
+    ctx = Ctx(g, (1, g.Nx), (1, g.Ny), (1, g.Nz))
+    nu, kap = Field(g, "ccc"), {"b": Field(g, "ccc")}
+    tol = 100 * np.finfo(FT).eps
+    bt = clo.BuoyancyTracer()
+    for wfun, bfun in ((lambda x, y, z: a * x + 0 * y + 0 * z, lambda x, y, z: s * x + 0 * y + 0 * z),
+                       (lambda x, y, z: a * y + 0 * x + 0 * z, lambda x, y, z: s * y + 0 * x + 0 * z)):
+        U, b = _smag_fields(g, wfun=wfun, bfun=bfun)
+        for Cb in (1.0, 2.5):
+            clo.compute_amd(ctx, clo.AnisotropicMinimumDissipation(Cb=Cb), U, {"b": b}, nu, kap, bt)
+            assert np.allclose(nu.interior, Cnu * d2 * Cb * s / a, rtol=tol, atol=0), Cb
+        # an unstable alignment (Cb ζ < 0) is clipped; Cb = nothing and "no buoyancy" leave r = 0 -> νₑ = 0
+        clo.compute_amd(ctx, clo.AnisotropicMinimumDissipation(Cb=-1.0), U, {"b": b}, nu, kap, bt)
+        assert np.all(nu.interior == 0)
+        clo.compute_amd(ctx, clo.AnisotropicMinimumDissipation(), U, {"b": b}, nu, kap, bt)
+        assert np.all(nu.interior == 0)
+        clo.compute_amd(ctx, clo.AnisotropicMinimumDissipation(Cb=1.0), U, {"b": b}, nu, kap, None)
+        assert np.all(nu.interior == 0)
+    for aa, N2, Cb in ((-0.4, 0.05, 1.0), (-0.4, 0.05, 0.0), (-0.4, -0.2, 1.0), (0.4, 0.3, 1.0), (0.4, 0.05, 1.0)):
+        U, b = _smag_fields(g, wfun=lambda x, y, z: aa * z + 0 * x + 0 * y, bfun=lambda x, y, z: N2 * z + 0 * x + 0 * y)
+        clo.compute_amd(ctx, clo.AnisotropicMinimumDissipation(Cb=Cb), U, {"b": b}, nu, kap, bt)
+        want = max(0.0, -Cnu * d2 * (aa - Cb * N2 / aa))
+        assert np.allclose(nu.interior, want, rtol=tol, atol=10 * np.finfo(FT).eps * Cnu * d2), (aa, N2, Cb)
+    # SeawaterBuoyancy: b = g (α T − β S)  (seawater_buoyancy.jl:203-207, linear_equation_of_state.jl:72-80)
+    sw = clo.SeawaterBuoyancy()
+    U, T = _smag_fields(g, wfun=lambda x, y, z: a * x + 0 * y + 0 * z, bfun=lambda x, y, z: s * x + 0 * y + 0 * z)
+    _, S = _smag_fields(g, bfun=lambda x, y, z: -2 * s * x + 0 * y + 0 * z)
+    kap2 = {"T": Field(g, "ccc"), "S": Field(g, "ccc")}
+    clo.compute_amd(ctx, clo.AnisotropicMinimumDissipation(Cb=1.0), U, {"T": T, "S": S}, nu, kap2, sw)
+    sb = float(sw.g) * (float(sw.alpha) * s + float(sw.beta) * 2 * s)
+    assert np.allclose(nu.interior, Cnu * d2 * sb / a, rtol=tol, atol=0)
+
+
 def test_smagorinsky_lilly_stability_function():
     FT = np.float64
     g = Grid(FT, size=(4, 4, 6), extent=(2.0, 2.0, 3.0), topology=("B", "B", "B"), halo=(2, 2, 2))

@@ -24,6 +24,12 @@ def test_cuda_matches_oracle_with_smagorinsky_closures(ob, name, kw):
     ph.check_case(kw, library=None, steps=(1, 10))
 
 
+@pytest.mark.parametrize("name,kw", ph.AMD_CB_CASES, ids=[c[0] for c in ph.AMD_CB_CASES])
+def test_cuda_matches_oracle_with_amd_buoyancy_modification(ob, name, kw):
+    """AnisotropicMinimumDissipation(; Cb = 1): anisotropic_minimum_dissipation.jl:62-68, 168-172, 310-323 (AmdKernel<FT, STR, CB = true>)"""
+    ph.check_case(kw, library=None, steps=(1, 10))
+
+
 def test_wizard_known_answers_and_diffusion_timescale_cuda(ob):
     """TimeStepWizard known answers of test/test_simulations.jl:14-76 (advective and diffusive CFL) and cell_diffusion_timescale of the
     eddy-viscosity closures, with maximum(νₑ) / maximum(κₑ) reduced on the device (oc_field_maximum_abs)."""
