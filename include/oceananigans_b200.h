@@ -42,7 +42,8 @@ typedef enum { OC_PERIODIC = 0, OC_BOUNDED = 1, OC_FLAT = 2 } oc_topology;      
 typedef enum { OC_CENTERED2 = 0, OC_WENO5 = 1, OC_CENTERED4 = 2, OC_UPWIND3 = 3, OC_UPWIND5 = 4, OC_WENO3 = 5, OC_UPWIND1 = 6,
                OC_ADVECTION_NONE = 7 } oc_advection;
 typedef enum { OC_RK3 = 0, OC_AB2 = 1 } oc_timestepper;                              /* src/TimeSteppers */
-typedef enum { OC_CORIOLIS_NONE = 0, OC_CORIOLIS_FPLANE = 1, OC_CORIOLIS_BETAPLANE = 2, OC_CORIOLIS_CARTESIAN = 3 } oc_coriolis;   /* oc_config.has_coriolis */
+typedef enum { OC_CORIOLIS_NONE = 0, OC_CORIOLIS_FPLANE = 1, OC_CORIOLIS_BETAPLANE = 2, OC_CORIOLIS_CARTESIAN = 3,
+               OC_CORIOLIS_NONTRADITIONAL_BETAPLANE = 4 } oc_coriolis;   /* oc_config.has_coriolis */
 typedef enum { OC_BUOYANCY_NONE = 0, OC_BUOYANCY_TRACER = 1, OC_BUOYANCY_SEAWATER_LINEAR = 2 } oc_buoyancy;
 
 /* boundary_condition.jl:8,83-110.  OC_BC_DEFAULT resolves by topology and location
@@ -112,6 +113,11 @@ typedef struct {
      * 137; `Cb = nothing` = amd_has_Cb 0).  νₑ = max(0, −Cν δ² (r − Cb ζ) / q) with Cb ζ = Cb_norm_wᵢ_bᵢᶜᶜᶜ / Δᶠz (:168-172, :310-323),
      * b = buoyancy_perturbationᶜᶜᶜ of the model's buoyancy formulation (0 without buoyancy). */
     double  amd_Cb;
+    /* ABI v4.  NonTraditionalBetaPlane(fz, fy, β, γ, R)  (src/Coriolis/non_traditional_beta_plane.jl:16-77): has_coriolis = 4 with
+     * fy = coriolis_fxyz[1], fz = coriolis_fxyz[2], β = coriolis_beta, γ = coriolis_gamma, R = coriolis_radius;
+     * 2Ωʸ = fy (1 − z/R) + γ y, 2Ωᶻ = fz (1 + 2z/R) + β y at the y- and z-nodes of the evaluation points (:79-96); origin_y as for
+     * BetaPlane, origin_z = z of the bottom face of the domain.  Regular z spacing only; general tile kernel; serial models. */
+    double  coriolis_gamma, coriolis_radius, origin_z;
 } oc_config;
 
 typedef struct oc_model oc_model;

@@ -22,7 +22,7 @@ using Oceananigans.Advection: Centered, WENO
 using Oceananigans.TurbulenceClosures: ScalarDiffusivity, AnisotropicMinimumDissipation
 using Oceananigans.TurbulenceClosures.Smagorinskys: Smagorinsky, LillyCoefficient
 using Oceananigans.BuoyancyFormulations: SeawaterBuoyancy, BuoyancyTracer, LinearEquationOfState, BuoyancyForce
-using Oceananigans.Coriolis: FPlane, BetaPlane, ConstantCartesianCoriolis
+using Oceananigans.Coriolis: FPlane, BetaPlane, ConstantCartesianCoriolis, NonTraditionalBetaPlane
 using Oceananigans.BoundaryConditions: BoundaryCondition, Flux, Value, Gradient, Open, Periodic as PeriodicBC
 
 import Oceananigans.Architectures as AC
@@ -71,6 +71,7 @@ mutable struct OcConfig               # `oc_config`, same field order; NTuple fo
     coriolis_beta::Float64; origin_y::Float64; coriolis_fxyz::NTuple{3,Float64}   # ABI v3: BetaPlane, ConstantCartesianCoriolis
     tilted_gravity::Int32; reserved2::Int32; gravity_unit_vector::NTuple{3,Float64} # ABI v3: BuoyancyForce(…; gravity_unit_vector)
     amd_Cb::Float64                                 # ABI v4: AnisotropicMinimumDissipation(; Cb), with amd_has_Cb
+    coriolis_gamma::Float64; coriolis_radius::Float64; origin_z::Float64  # ABI v4: NonTraditionalBetaPlane (has_coriolis = 4)
     OcConfig() = new()
 end
 
@@ -186,8 +187,13 @@ function config(model::NonhydrostaticModel)
         cfg.origin_y = TY === Flat ? 0.0 : Float64(grid.yᵃᶠᵃ[1])
     elseif model.coriolis isa ConstantCartesianCoriolis     # src/Coriolis/constant_cartesian_coriolis.jl:70-81
         cfg.has_coriolis = 3; cfg.coriolis_fxyz = Float64.((model.coriolis.fx, model.coriolis.fy, model.coriolis.fz))
+    elseif model.coriolis isa NonTraditionalBetaPlane       # src/Coriolis/non_traditional_beta_plane.jl:79-96 (ABI v4; regular z only)
+        c = model.coriolis
+        cfg.has_coriolis = 4; cfg.coriolis_fxyz = (0.0, Float64(c.fy), Float64(c.fz))
+        cfg.coriolis_beta = c.β; cfg.coriolis_gamma = c.γ; cfg.coriolis_radius = c.R
+        cfg.origin_y = Float64(grid.yᵃᶠᵃ[1]); cfg.origin_z = Float64(grid.z.cᵃᵃᶠ[1])
     elseif model.coriolis !== nothing
-        throw(ArgumentError("B200: Coriolis must be FPlane, BetaPlane or ConstantCartesianCoriolis"))
+        throw(ArgumentError("B200: Coriolis must be FPlane, BetaPlane, ConstantCartesianCoriolis or NonTraditionalBetaPlane"))
     end
     fields = (model.velocities..., model.tracers...)
     cfg.bcs = ntuple(OC_MAX_FIELDS) do f

@@ -17,7 +17,7 @@ OC_F64, OC_F32 = 0, 1
 OC_PERIODIC, OC_BOUNDED, OC_FLAT = 0, 1, 2
 OC_CENTERED2, OC_WENO5, OC_CENTERED4, OC_UPWIND3, OC_UPWIND5, OC_WENO3, OC_UPWIND1, OC_ADVECTION_NONE = range(8)
 OC_RK3, OC_AB2 = 0, 1
-OC_CORIOLIS_NONE, OC_CORIOLIS_FPLANE, OC_CORIOLIS_BETAPLANE, OC_CORIOLIS_CARTESIAN = 0, 1, 2, 3
+OC_CORIOLIS_NONE, OC_CORIOLIS_FPLANE, OC_CORIOLIS_BETAPLANE, OC_CORIOLIS_CARTESIAN, OC_CORIOLIS_NONTRADITIONAL_BETAPLANE = 0, 1, 2, 3, 4
 OC_BUOYANCY_NONE, OC_BUOYANCY_TRACER, OC_BUOYANCY_SEAWATER_LINEAR = 0, 1, 2
 OC_BC_DEFAULT, OC_BC_PERIODIC, OC_BC_FLUX, OC_BC_VALUE, OC_BC_GRADIENT, OC_BC_OPEN, OC_BC_NONE = range(7)
 OC_FIELD_U, OC_FIELD_V, OC_FIELD_W, OC_FIELD_TRACER0 = 0, 1, 2, 3
@@ -48,6 +48,7 @@ class oc_config(C.Structure):
         ("coriolis_beta", C.c_double), ("origin_y", C.c_double), ("coriolis_fxyz", C.c_double * 3),
         ("tilted_gravity", C.c_int32), ("reserved2", C.c_int32), ("gravity_unit_vector", C.c_double * 3),
         ("amd_Cb", C.c_double),
+        ("coriolis_gamma", C.c_double), ("coriolis_radius", C.c_double), ("origin_z", C.c_double),
     ]
 
 

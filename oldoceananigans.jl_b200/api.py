@@ -25,7 +25,7 @@ from . import _lib as L
 __all__ = [
     "B200", "Distributed", "Partition", "Periodic", "Bounded", "Flat", "Center", "Face", "RectilinearGrid",
     "Centered", "UpwindBiased", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation", "Smagorinsky", "SmagorinskyLilly", "LillyCoefficient",
-    "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "BuoyancyForce", "FPlane", "BetaPlane", "ConstantCartesianCoriolis",
+    "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "BuoyancyForce", "FPlane", "BetaPlane", "ConstantCartesianCoriolis", "NonTraditionalBetaPlane",
     "FluxBoundaryCondition", "ValueBoundaryCondition", "GradientBoundaryCondition", "OpenBoundaryCondition",
     "FieldBoundaryConditions", "NonhydrostaticModel", "Field", "OutputTicket", "set_", "time_step_", "update_state_",
     "compute_tendencies_", "compute_flux_bc_tendencies_", "rk3_substep_", "ab2_step_", "cache_previous_tendencies_",
@@ -345,6 +345,28 @@ class BetaPlane:
             om = _OMEGA_EARTH if rotation_rate is None else rotation_rate
             f0, beta = 2 * om * _sind(latitude), 2 * om * _cosd(latitude) / (_R_EARTH if radius is None else radius)
         self.f0, self.beta = f0, beta
+
+
+class NonTraditionalBetaPlane:
+    """NonTraditionalBetaPlane(fz, fy, β, γ, radius | rotation_rate, latitude, radius)   src/Coriolis/non_traditional_beta_plane.jl:16-77"""
+
+    def __init__(self, FT=np.float64, fz=None, fy=None, beta=None, gamma=None, rotation_rate=None, latitude=None, radius=None, **kw):
+        beta, gamma = kw.pop("β", beta), kw.pop("γ", gamma)
+        if kw:
+            raise TypeError(f"unexpected keyword arguments {sorted(kw)}")
+        fs = (fz, fy, beta, gamma)
+        use_f = (not all(c is None for c in fs)) and latitude is None
+        use_planet = latitude is not None and all(c is None for c in fs)
+        if use_f == use_planet:
+            raise ValueError("Either the keywords fz, fy, β, γ, and radius must be specified, *or* all of rotation_rate, latitude, and radius.")
+        radius = _R_EARTH if radius is None else radius
+        if use_planet:
+            om = _OMEGA_EARTH if rotation_rate is None else rotation_rate
+            fz, fy = 2 * om * _sind(latitude), 2 * om * _cosd(latitude)
+            beta, gamma = 2 * om * _cosd(latitude) / radius, -4 * om * _sind(latitude) / radius
+        if any(c is None for c in (fz, fy, beta, gamma)):
+            raise ValueError("NonTraditionalBetaPlane: fz, fy, β and γ must all be given")      # the reference would fail converting nothing to FT
+        self.fz, self.fy, self.beta, self.gamma, self.R = fz, fy, beta, gamma, radius
 
 
 class ConstantCartesianCoriolis:
@@ -678,9 +700,14 @@ class NonhydrostaticModel:
             elif isinstance(coriolis, ConstantCartesianCoriolis):
                 cfg.has_coriolis = L.OC_CORIOLIS_CARTESIAN
                 cfg.coriolis_fxyz[0], cfg.coriolis_fxyz[1], cfg.coriolis_fxyz[2] = float(coriolis.fx), float(coriolis.fy), float(coriolis.fz)
+            elif isinstance(coriolis, NonTraditionalBetaPlane):
+                cfg.has_coriolis = L.OC_CORIOLIS_NONTRADITIONAL_BETAPLANE
+                cfg.coriolis_fxyz[1], cfg.coriolis_fxyz[2] = float(coriolis.fy), float(coriolis.fz)
+                cfg.coriolis_beta, cfg.coriolis_gamma, cfg.coriolis_radius = float(coriolis.beta), float(coriolis.gamma), float(coriolis.R)
+                cfg.origin_y, cfg.origin_z = float(grid.x0[1]), float(grid.x0[2])
             else:
-                raise NotImplementedError("Coriolis must be FPlane, BetaPlane or ConstantCartesianCoriolis "
-                                          "(NonTraditionalBetaPlane, HydrostaticSphericalCoriolis are out of scope)")
+                raise NotImplementedError("Coriolis must be FPlane, BetaPlane, ConstantCartesianCoriolis or NonTraditionalBetaPlane "
+                                          "(HydrostaticSphericalCoriolis is out of scope)")
         names = ("u", "v", "w") + tracers
         bcs = boundary_conditions or {}
         for k in bcs:

@@ -123,7 +123,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         for (int t = 0; t < c.n_tracers; ++t)
             if (!(c.smag_Pr[t] > 0)) throw Error(OC_ERR_INVALID, "Smagorinsky: the turbulent Prandtl number of every tracer must be positive");
     }
-    if (c.has_coriolis < OC_CORIOLIS_NONE || c.has_coriolis > OC_CORIOLIS_CARTESIAN) throw Error(OC_ERR_UNSUPPORTED, "Coriolis: FPlane, BetaPlane or ConstantCartesianCoriolis");
+    if (c.has_coriolis < OC_CORIOLIS_NONE || c.has_coriolis > OC_CORIOLIS_NONTRADITIONAL_BETAPLANE) throw Error(OC_ERR_UNSUPPORTED, "Coriolis: FPlane, BetaPlane, ConstantCartesianCoriolis or NonTraditionalBetaPlane");
     if (c.tilted_gravity) {
         const double* v = c.gravity_unit_vector;
         const double nrm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
@@ -131,6 +131,12 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         if (c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "tilted gravity on distributed models");
     }
     if (c.has_coriolis == OC_CORIOLIS_BETAPLANE && g_.flat[1]) throw Error(OC_ERR_UNSUPPORTED, "BetaPlane on a grid with a Flat y");
+    if (c.has_coriolis == OC_CORIOLIS_NONTRADITIONAL_BETAPLANE) {
+        if (c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "NonTraditionalBetaPlane on distributed models");
+        if (g_.flat[1] || g_.flat[2]) throw Error(OC_ERR_UNSUPPORTED, "NonTraditionalBetaPlane on a grid with a Flat y or z");
+        if (c.z_stretched) throw Error(OC_ERR_UNSUPPORTED, "NonTraditionalBetaPlane on a vertically stretched grid");
+        if (!(c.coriolis_radius != 0.0)) throw Error(OC_ERR_INVALID, "NonTraditionalBetaPlane: radius must be non-zero");
+    }
     if (c.has_coriolis == OC_CORIOLIS_CARTESIAN && c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "ConstantCartesianCoriolis on distributed models");
     if (c.buoyancy == OC_BUOYANCY_SEAWATER_LINEAR && (c.tracer_T < 0 || c.tracer_S < 0 || c.tracer_T >= c.n_tracers || c.tracer_S >= c.n_tracers))
         throw Error(OC_ERR_INVALID, "SeawaterBuoyancy needs tracers T and S");
@@ -921,6 +927,7 @@ void Model<FT>::launch_tendency(int fidx, TendencyArgs<FT>& a) {
         // south face of this rank's first row (slab decomposition in y: rank r owns rows r·Ny … (r+1)·Ny − 1)
         k.cor.y0 = (FT)cfg_.origin_y + (FT)((dist_ ? rank_ : 0) * g_.N[1]) * g_.d[1];
         for (int d = 0; d < 3; ++d) k.cor.cf[d] = (FT)cfg_.coriolis_fxyz[d];
+        k.cor.gamma = (FT)cfg_.coriolis_gamma; k.cor.R = (FT)cfg_.coriolis_radius; k.cor.z0 = (FT)cfg_.origin_z;
         k.cor.tilted = (cfg_.tilted_gravity && cfg_.buoyancy != OC_BUOYANCY_NONE) ? 1 : 0;
         for (int d = 0; d < 3; ++d) k.cor.gh[d] = -(FT)cfg_.gravity_unit_vector[d];
         k.cor.tb_kind = cfg_.buoyancy;
@@ -1715,6 +1722,7 @@ void oc_config_init(oc_config* c) {
     c->haline_contraction = 7.8e-4;
     c->tracer_T = c->tracer_S = c->tracer_b = -1;
     c->amd_has_Cb = 0; c->amd_Cb = 0.0;
+    c->coriolis_gamma = 0.0; c->coriolis_radius = 6371.0e3; c->origin_z = 0.0;      // Oceananigans.defaults.planet_radius
     c->tilted_gravity = 0; c->reserved2 = 0; c->gravity_unit_vector[0] = c->gravity_unit_vector[1] = 0.0; c->gravity_unit_vector[2] = -1.0;
     c->coriolis_beta = 0.0; c->origin_y = 0.0; c->coriolis_fxyz[0] = c->coriolis_fxyz[1] = c->coriolis_fxyz[2] = 0.0;
     c->smagorinsky = 0; c->smag_C = 0.16; c->smag_Cb = 1.0;          // smagorinsky.jl:77-78, lilly_coefficient.jl:47

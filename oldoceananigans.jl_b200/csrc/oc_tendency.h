@@ -58,7 +58,8 @@ struct TendencyArgs {
 template <class FT>
 struct CoriolisExt {
     FT beta, y0;         // BetaPlane: f = f₀ + β ynode; y0 = y of the south face of this rank's first row
-    FT cf[3];            // ConstantCartesianCoriolis fx, fy, fz
+    FT cf[3];            // ConstantCartesianCoriolis fx, fy, fz; NonTraditionalBetaPlane: cf[1] = fy, cf[2] = fz
+    FT gamma, R, z0;     // NonTraditionalBetaPlane γ, R; z0 = z of the bottom face (regular z only)
     int tilted;          // BuoyancyForce(…; gravity_unit_vector): x_dot_g_bᶠᶜᶜ = ĝ_x ℑxᶠ b, y_dot_g_bᶜᶠᶜ = ĝ_y ℑyᶠ b   g_dot_b.jl:1-2
     FT gh[3];            // ĝ = −gravity_unit_vector   buoyancy_force.jl:52-54
     int tb_kind;         // buoyancy model of the tilted terms: 1 tracer b, 2 seawater linear (own copies: TendencyArgs::buoyancy
@@ -307,6 +308,28 @@ struct TendencyKernel {
                         acc[n] = hv;
                     }
                     G = G - h * (acc[0] + acc[1]);
+                }
+                if (KIND != KIND_C && a.has_coriolis == 4) {
+                    // NonTraditionalBetaPlane (non_traditional_beta_plane.jl:79-96): 2Ωʸ = fy (1 − z/R) + γ y, 2Ωᶻ = fz (1 + 2z/R) + β y
+                    //   x: ℑxᶠ(2Ωʸ ℑzᶜ w − 2Ωᶻ ℑyᶜ v) with y, z at ccc;  y: 2Ωᶻ(cfc) ℑxyᶜᶠ u;  z: −2Ωʸ(ccf) ℑxzᶜᶠ u;  no active-node weighting
+                    const FT* u = a.U[0]; const FT* v = a.U[1]; const FT* w = a.U[2];
+                    const FT h = FT(0.5);
+                    const FT y = cor.y0 + (FT(j) + (KIND == KIND_V ? FT(0) : FT(0.5))) * g.d[1];
+                    const FT z = cor.z0 + (FT(k) + (KIND == KIND_W ? FT(0) : FT(0.5))) * g.d[2];
+                    const FT Oy = cor.cf[1] * (FT(1) - z / cor.R) + cor.gamma * y;
+                    const FT Oz = cor.cf[2] * (FT(1) + FT(2) * z / cor.R) + cor.beta * y;
+                    if (KIND == KIND_U) {
+                        FT acc[2];
+                        for (int n = 0; n < 2; ++n) {
+                            const int p = o - (1 - n);
+                            acc[n] = Oy * (h * (w[p] + w[p + g.sz])) - Oz * (h * (v[p] + v[p + g.sy]));
+                        }
+                        G = G - h * (acc[0] + acc[1]);
+                    } else if (KIND == KIND_V) {
+                        G = G - Oz * (h * (h * (u[o - g.sy] + u[o - g.sy + 1]) + h * (u[o] + u[o + 1])));
+                    } else {
+                        G = G + Oy * (h * (h * (u[o - g.sz] + u[o - g.sz + 1]) + h * (u[o] + u[o + 1])));
+                    }
                 }
                 if ((KIND == KIND_U || KIND == KIND_V) && (a.has_coriolis == 1 || a.has_coriolis == 2)) {
                     // FPlane: x_f_cross_U = -f·ℑxyᶠᶜᶜ(v)/active ; y_f_cross_U = +f·ℑxyᶜᶠᶜ(u)/active   f_plane.jl:50-52

@@ -434,6 +434,24 @@ class BetaPlane:
         self.kind = "betaplane"
 
 
+class NonTraditionalBetaPlane:
+    """NonTraditionalBetaPlane(fz, fy, β, γ, radius | rotation_rate, latitude, radius)   src/Coriolis/non_traditional_beta_plane.jl:16-77"""
+
+    def __init__(self, fz=None, fy=None, beta=None, gamma=None, rotation_rate=None, latitude=None, radius=None):
+        fs = (fz, fy, beta, gamma)
+        use_f = (not all(c is None for c in fs)) and latitude is None
+        use_planet = latitude is not None and all(c is None for c in fs)
+        if use_f == use_planet:                                                                        # !xor(...)  :64-67
+            raise ValueError("Either the keywords fz, fy, β, γ, and radius must be specified, *or* all of rotation_rate, latitude, and radius.")
+        radius = 6371.0e3 if radius is None else radius
+        if use_planet:
+            om = 7.292115e-5 if rotation_rate is None else rotation_rate
+            fz, fy = 2 * om * _sind(latitude), 2 * om * _cosd(latitude)
+            beta, gamma = 2 * om * _cosd(latitude) / radius, -4 * om * _sind(latitude) / radius
+        self.fz, self.fy, self.beta, self.gamma, self.R = fz, fy, beta, gamma, radius
+        self.kind = "ntbetaplane"
+
+
 class ConstantCartesianCoriolis:
     """ConstantCartesianCoriolis(fx, fy, fz | f, rotation_axis | latitude, rotation_rate)   src/Coriolis/constant_cartesian_coriolis.jl:11-67"""
 
@@ -492,6 +510,28 @@ def coriolis_cross(ctx, cor, U, comp):
         fy = FT(cor.f0) + FT(cor.beta) * y.astype(FT)
         unit = fplane_x(ctx, 1.0, U) if comp == 0 else fplane_y(ctx, 1.0, U)          # ∓ active_weighted_ℑxy(·)
         return fy * unit
+    if cor.kind == "ntbetaplane":
+        # two_Ωʸ = fy (1 − z/R) + γ y ; two_Ωᶻ = fz (1 + 2z/R) + β y at ynode / znode of the evaluation point   non_traditional_beta_plane.jl:79-96
+        u, v, w = (ctx.field(f) for f in U)
+        fzz, fyy, be, ga, R = FT(cor.fz), FT(cor.fy), FT(cor.beta), FT(cor.gamma), FT(cor.R)
+
+        def node(d, off):
+            return lambda o: (FT(g.x0[d]) + ((ctx.index(d, o).astype(np.float64) - 1 + off) * float(g.D[d])).astype(FT)).astype(FT)
+
+        def Oy(y, z):
+            return lambda o: fyy * (FT(1) - z(o) / R) + ga * y(o)
+
+        def Oz(y, z):
+            return lambda o: fzz * (FT(1) + FT(2) * z(o) / R) + be * y(o)
+
+        yc, yf, zc, zf = node(1, 0.5), node(1, 0.0), node(2, 0.5), node(2, 0.0)
+        if comp == 0:
+            a, b = iC(ctx, w, 2), iC(ctx, v, 1)
+            oy, oz = Oy(yc, zc), Oz(yc, zc)
+            return iF(ctx, lambda o: oy(o) * a(o) - oz(o) * b(o), 0)(O)
+        if comp == 1:
+            return Oz(yf, zc)(O) * iF(ctx, iC(ctx, u, 0), 1)(O)                    # ℑxyᶜᶠᵃ = ℑyᶠ(ℑxᶜ u)
+        return -Oy(yc, zf)(O) * iF(ctx, iC(ctx, u, 0), 2)(O)                       # ℑxzᶜᵃᶠ = ℑzᶠ(ℑxᶜ u)
     fx, fy, fz = FT(cor.fx), FT(cor.fy), FT(cor.fz)
     u, v, w = (ctx.field(f) for f in U)
     if comp == 0:

@@ -207,7 +207,7 @@ class OracleModel:
             if comp < 2 and self.buoyancy is not None and self.buoyancy.gravity_unit_vector is not None:
                 G = G + FT(clo.g_hat(self.buoyancy, comp)) * iF(ctx, clo.buoyancy_q(ctx, self.buoyancy, self.tracers), comp)(O)
             if self.coriolis is not None:
-                if comp < 2 or self.coriolis.kind == "cartesian":       # z_f_cross_U = 0 for FPlane / BetaPlane
+                if comp < 2 or self.coriolis.kind in ("cartesian", "ntbetaplane"):       # z_f_cross_U = 0 for FPlane / BetaPlane
                     G = G - clo.coriolis_cross(ctx, self.coriolis, self.U, comp)
             if self.pHY is not None and comp < 2:
                 G = G - ddF(ctx, ctx.field(self.pHY), comp)(O)      # hydrostatic_pressure_gradient_x/y

@@ -71,6 +71,8 @@ def _coriolis(mod, f):
     if isinstance(f, tuple):
         if f[0] == "beta":
             return mod.BetaPlane(f0=f[1], beta=f[2])
+        if f[0] == "ntbeta":
+            return mod.NonTraditionalBetaPlane(fz=f[1], fy=f[2], beta=f[3], gamma=f[4], radius=f[5])
         return mod.ConstantCartesianCoriolis(fx=f[1], fy=f[2], fz=f[3])
     return mod.FPlane(f=f)
 
@@ -283,6 +285,10 @@ CORIOLIS_CASES = [
     ("PPP weno cartesian coriolis TS", dict(N=(16, 12, 8), topo="PPP", scheme="weno", f=("cartesian", 0.3, -0.5, 0.7))),
     ("BBB centered cartesian coriolis smagorinsky", dict(N=(12, 10, 8), topo="BBB", scheme="centered", closure="smag", f=("cartesian", 0.3, -0.5, 0.7))),
     ("stretched PPB weno cartesian coriolis bcs F32", dict(N=(16, 12, 10), topo="PPB", scheme="weno", f=("cartesian", 0.0, 0.6, 0.8), bcs=True, stretch="smooth", FT=np.float32)),
+    # NonTraditionalBetaPlane(fz, fy, β, γ, R) (non_traditional_beta_plane.jl:79-96); R of the size of the domain so that the z/R factors matter
+    ("PPP weno nontraditional betaplane TS", dict(N=(16, 12, 8), topo="PPP", scheme="weno", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0))),
+    ("BBB centered nontraditional betaplane AB2", dict(N=(12, 10, 8), topo="BBB", scheme="centered", f=("ntbeta", 0.7, 0.5, 1.0, -0.8, 5.0), ts="QuasiAdamsBashforth2")),
+    ("PPB weno amd nontraditional betaplane bcs F32", dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="amd", f=("ntbeta", 0.1, 0.2, 0.5, -0.3, 4.0), bcs=True, FT=np.float32)),
     ("PFB centered cartesian coriolis 2D", dict(N=(16, 1, 12), topo="PFB", scheme="centered", buoy="tracer", f=("cartesian", 0.3, -0.5, 0.7))),
 ]
 

@@ -182,6 +182,17 @@ def test_hostsim_matches_oracle_for_the_coriolis_family(hostsim, name, kw):
     ph.check_case(kw, library=hostsim, steps=(1, 3))
 
 
+def test_hostsim_nontraditional_beta_plane_rejects_what_it_does_not_cover(hostsim):
+    """NonTraditionalBetaPlane needs y- and z-nodes: Flat y / z and vertically stretched grids are loud errors (regular z only)."""
+    ob = ph.ob
+    cor = ob.NonTraditionalBetaPlane(fz=0.7, fy=0.5, beta=1.0, gamma=-0.8, radius=5.0)
+    flat = ob.RectilinearGrid(size=(8, 8), extent=(1, 1), topology=(ob.Periodic, ob.Flat, ob.Bounded))
+    stretched = ob.RectilinearGrid(size=(8, 8, 4), x=(0, 1), y=(0, 1), z=[-1.0, -0.6, -0.3, -0.1, 0.0], topology=(ob.Periodic, ob.Periodic, ob.Bounded))
+    for grid in (flat, stretched):
+        with pytest.raises((ob.OceananigansB200Error, NotImplementedError, ValueError)):
+            ob.NonhydrostaticModel(grid=grid, coriolis=cor, library=hostsim)
+
+
 @pytest.mark.parametrize("name,kw", ph.TILTED_CASES, ids=[c[0] for c in ph.TILTED_CASES])
 def test_hostsim_matches_oracle_with_tilted_gravity(hostsim, name, kw):
     """BuoyancyForce(formulation; gravity_unit_vector)  buoyancy_force.jl:47-58, g_dot_b.jl:1-3"""

@@ -814,6 +814,19 @@ def _coriolis_constructor_checks(mod, exc):
     assert np.isclose(b.f0, pi) and np.isclose(b.beta, 2 * pi)
     b = mod.BetaPlane(latitude=70, radius=2 * pi, rotation_rate=3 * pi)
     assert np.isclose(b.f0, 6 * pi * np.sin(np.deg2rad(70))) and np.isclose(b.beta, 6 * pi * np.cos(np.deg2rad(70)) / (2 * pi))
+    # test/test_coriolis.jl:53-68 (values) and :121-133 (argument errors)
+    n = mod.NonTraditionalBetaPlane(fz=pi, fy=e, beta=1 / 7, gamma=5)
+    assert np.isclose(n.fz, pi) and np.isclose(n.fy, e) and np.isclose(n.beta, 1 / 7) and np.isclose(n.gamma, 5)
+    n = mod.NonTraditionalBetaPlane(rotation_rate=pi, latitude=17, radius=e)
+    s17, c17 = np.sin(np.deg2rad(17)), np.cos(np.deg2rad(17))
+    assert np.isclose(n.fz, 2 * pi * s17) and np.isclose(n.fy, 2 * pi * c17)
+    assert np.isclose(n.beta, 2 * pi * c17 / e) and np.isclose(n.gamma, -4 * pi * s17 / e) and n.R == e
+    for kwargs in ({}, dict(rotation_rate=7e-5), dict(fz=1, latitude=40), dict(fz=1, rotation_rate=7e-5, latitude=40), dict(fy=1, latitude=40),
+                   dict(fy=1, rotation_rate=7e-5, latitude=40), dict(fz=1, fy=2, latitude=40), dict(fz=1, fy=2, rotation_rate=7e-5, latitude=40),
+                   dict(fz=1, fy=2, beta=3, latitude=40), dict(fz=1, fy=2, beta=3, rotation_rate=7e-5, latitude=40),
+                   dict(fz=1, fy=2, beta=3, gamma=4, latitude=40), dict(fz=1, fy=2, beta=3, gamma=4, rotation_rate=7e-5, latitude=40)):
+        with pytest.raises(exc):
+            mod.NonTraditionalBetaPlane(**kwargs)
     for bad in (lambda: mod.FPlane(), lambda: mod.FPlane(rotation_rate=7e-5), lambda: mod.FPlane(f=1, latitude=40),
                 lambda: mod.FPlane(f=1, rotation_rate=7e-5, latitude=40),
                 lambda: mod.ConstantCartesianCoriolis(rotation_axis=[0, 1, 1]), lambda: mod.ConstantCartesianCoriolis(f=1, latitude=45),
@@ -827,6 +840,34 @@ def _coriolis_constructor_checks(mod, exc):
 
 def test_coriolis_constructors():
     _coriolis_constructor_checks(clo, ValueError)
+
+
+def test_nontraditional_beta_plane_terms_for_uniform_flows():
+    """non_traditional_beta_plane.jl:79-96 evaluated for uniform flows (interpolations of constants are exact): with
+    2Ωʸ = fy (1 − z/R) + γ y and 2Ωᶻ = fz (1 + 2z/R) + β y,
+      u = 1:  y_f_cross_U = 2Ωᶻ(y_f, z_c),  z_f_cross_U = −2Ωʸ(y_c, z_f),  x_f_cross_U = 0
+      v = 1:  x_f_cross_U = −2Ωᶻ(y_c, z_c);   w = 1:  x_f_cross_U = +2Ωʸ(y_c, z_c)"""
+    FT = np.float64
+    g = Grid(FT, size=(6, 5, 4), extent=(3.0, 2.0, 2.0), topology=("P", "P", "P"), halo=(2, 2, 2))
+    cor = clo.NonTraditionalBetaPlane(fz=0.7, fy=-0.5, beta=2.0, gamma=1.5, radius=3.0)
+    ctx = Ctx(g, (1, g.Nx), (1, g.Ny), (1, g.Nz))
+    yc, yf = g.nodes(1, "c")[None, :, None], g.nodes(1, "f")[None, :g.Ny, None]
+    zc, zf = g.nodes(2, "c")[None, None, :], g.nodes(2, "f")[None, None, :g.Nz]
+    Oy = lambda y, z: cor.fy * (1 - z / cor.R) + cor.gamma * y
+    Oz = lambda y, z: cor.fz * (1 + 2 * z / cor.R) + cor.beta * y
+    def fields(which):
+        U = (Field(g, "fcc"), Field(g, "cfc"), Field(g, "ccf"))
+        U[which].data[...] = 1.0
+        return U
+    one = np.ones((g.Nx, 1, 1))
+    U = fields(0)
+    assert np.allclose(clo.coriolis_cross(ctx, cor, U, 1), one * Oz(yf, zc), rtol=1e-14, atol=0)
+    assert np.allclose(clo.coriolis_cross(ctx, cor, U, 2), -one * Oy(yc, zf), rtol=1e-14, atol=0)
+    assert np.all(clo.coriolis_cross(ctx, cor, U, 0) == 0)
+    assert np.allclose(clo.coriolis_cross(ctx, cor, fields(1), 0), -one * Oz(yc, zc), rtol=1e-14, atol=0)
+    assert np.allclose(clo.coriolis_cross(ctx, cor, fields(2), 0), one * Oy(yc, zc), rtol=1e-14, atol=0)
+    # the coefficients vary over the domain (the z/R and β y, γ y factors are active)
+    assert np.ptp(Oz(yf, zc)) > 0.5 and np.ptp(Oy(yc, zf)) > 0.5
 
 
 def test_inertial_oscillations_with_rotation_about_different_axes():
