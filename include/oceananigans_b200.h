@@ -116,7 +116,8 @@ typedef struct {
     /* ABI v4.  NonTraditionalBetaPlane(fz, fy, β, γ, R)  (src/Coriolis/non_traditional_beta_plane.jl:16-77): has_coriolis = 4 with
      * fy = coriolis_fxyz[1], fz = coriolis_fxyz[2], β = coriolis_beta, γ = coriolis_gamma, R = coriolis_radius;
      * 2Ωʸ = fy (1 − z/R) + γ y, 2Ωᶻ = fz (1 + 2z/R) + β y at the y- and z-nodes of the evaluation points (:79-96); origin_y as for
-     * BetaPlane, origin_z = z of the bottom face of the domain.  Regular z spacing only; general tile kernel; serial models. */
+     * BetaPlane, origin_z = z of the bottom face of the domain (regular z; a stretched grid takes its z-nodes from z_faces).
+     * General tile kernel; serial models; no Flat y / z. */
     double  coriolis_gamma, coriolis_radius, origin_z;
 } oc_config;
 

@@ -187,7 +187,7 @@ function config(model::NonhydrostaticModel)
         cfg.origin_y = TY === Flat ? 0.0 : Float64(grid.yᵃᶠᵃ[1])
     elseif model.coriolis isa ConstantCartesianCoriolis     # src/Coriolis/constant_cartesian_coriolis.jl:70-81
         cfg.has_coriolis = 3; cfg.coriolis_fxyz = Float64.((model.coriolis.fx, model.coriolis.fy, model.coriolis.fz))
-    elseif model.coriolis isa NonTraditionalBetaPlane       # src/Coriolis/non_traditional_beta_plane.jl:79-96 (ABI v4; regular z only)
+    elseif model.coriolis isa NonTraditionalBetaPlane       # src/Coriolis/non_traditional_beta_plane.jl:79-96 (ABI v4)
         c = model.coriolis
         cfg.has_coriolis = 4; cfg.coriolis_fxyz = (0.0, Float64(c.fy), Float64(c.fz))
         cfg.coriolis_beta = c.β; cfg.coriolis_gamma = c.γ; cfg.coriolis_radius = c.R

@@ -134,7 +134,6 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     if (c.has_coriolis == OC_CORIOLIS_NONTRADITIONAL_BETAPLANE) {
         if (c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "NonTraditionalBetaPlane on distributed models");
         if (g_.flat[1] || g_.flat[2]) throw Error(OC_ERR_UNSUPPORTED, "NonTraditionalBetaPlane on a grid with a Flat y or z");
-        if (c.z_stretched) throw Error(OC_ERR_UNSUPPORTED, "NonTraditionalBetaPlane on a vertically stretched grid");
         if (!(c.coriolis_radius != 0.0)) throw Error(OC_ERR_INVALID, "NonTraditionalBetaPlane: radius must be non-zero");
     }
     if (c.has_coriolis == OC_CORIOLIS_CARTESIAN && c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "ConstantCartesianCoriolis on distributed models");
@@ -323,7 +322,7 @@ void Model<FT>::build_z_tables(const double* faces) {
     // one more face above so that the centre of the topmost level exists
     { FT shi = FT(0); for (int q = 0; q < H + 1; ++q) shi = shi + dhi; F[nt] = F[H + N] + shi; }
     for (int n = 0; n < nt; ++n) Cc[n] = (F[n + 1] + F[n]) / FT(2);
-    std::vector<FT> tab(13 * (size_t)nt);
+    std::vector<FT> tab(15 * (size_t)nt);
     FT* dzc = tab.data(); FT* dzf = dzc + nt; FT* rdzc = dzf + nt; FT* rdzf = rdzc + nt; FT* rVc = rdzf + nt; FT* rVf = rVc + nt;
     FT* amd = rVf + nt;      // six AMD tables (AmdKernel::lv_*)
     const FT fx = FT(2) * g_.d[0], fy = FT(2) * g_.d[1];
@@ -345,6 +344,9 @@ void Model<FT>::build_z_tables(const double* faces) {
         // Smagorinsky: Δᶠ² with Δᶠ = cbrt(Δxᶜᶜᶜ Δyᶜᶜᶜ Δzᶜᶜᶜ)  (smagorinsky.jl:99-100)
         const FT df = std::cbrt(g_.d[0] * g_.d[1] * dzc[n]);
         amd[6 * nt + n] = df * df;
+        // NonTraditionalBetaPlane: znode at Center / Face levels (grid.z.cᵃᵃᶜ, grid.z.cᵃᵃᶠ)
+        amd[7 * nt + n] = Cc[n];
+        amd[8 * nt + n] = F[n];
     }
     ztab_ = (FT*)dev_alloc(sizeof(FT) * tab.size());
     dev_upload(ztab_, tab.data(), sizeof(FT) * tab.size(), stream_);
@@ -928,6 +930,11 @@ void Model<FT>::launch_tendency(int fidx, TendencyArgs<FT>& a) {
         k.cor.y0 = (FT)cfg_.origin_y + (FT)((dist_ ? rank_ : 0) * g_.N[1]) * g_.d[1];
         for (int d = 0; d < 3; ++d) k.cor.cf[d] = (FT)cfg_.coriolis_fxyz[d];
         k.cor.gamma = (FT)cfg_.coriolis_gamma; k.cor.R = (FT)cfg_.coriolis_radius; k.cor.z0 = (FT)cfg_.origin_z;
+        {
+            const size_t nt = (size_t)g_.N[2] + 2 * (g_.H[2] + 1) + 1;
+            k.cor.zc = stretched_ ? g_.rVf + nt + 7 * nt : nullptr;       // after the metric, AMD and Smagorinsky tables (build_z_tables)
+            k.cor.zf = stretched_ ? g_.rVf + nt + 8 * nt : nullptr;
+        }
         k.cor.tilted = (cfg_.tilted_gravity && cfg_.buoyancy != OC_BUOYANCY_NONE) ? 1 : 0;
         for (int d = 0; d < 3; ++d) k.cor.gh[d] = -(FT)cfg_.gravity_unit_vector[d];
         k.cor.tb_kind = cfg_.buoyancy;

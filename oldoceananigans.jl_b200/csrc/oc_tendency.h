@@ -59,7 +59,9 @@ template <class FT>
 struct CoriolisExt {
     FT beta, y0;         // BetaPlane: f = f₀ + β ynode; y0 = y of the south face of this rank's first row
     FT cf[3];            // ConstantCartesianCoriolis fx, fy, fz; NonTraditionalBetaPlane: cf[1] = fy, cf[2] = fz
-    FT gamma, R, z0;     // NonTraditionalBetaPlane γ, R; z0 = z of the bottom face (regular z only)
+    FT gamma, R, z0;     // NonTraditionalBetaPlane γ, R; z0 = z of the bottom face (regular z)
+    const FT* zc;        // stretched z: znode tables at Center / Face levels, indexable like Geom::dzc (nullptr on regular grids)
+    const FT* zf;
     int tilted;          // BuoyancyForce(…; gravity_unit_vector): x_dot_g_bᶠᶜᶜ = ĝ_x ℑxᶠ b, y_dot_g_bᶜᶠᶜ = ĝ_y ℑyᶠ b   g_dot_b.jl:1-2
     FT gh[3];            // ĝ = −gravity_unit_vector   buoyancy_force.jl:52-54
     int tb_kind;         // buoyancy model of the tilted terms: 1 tracer b, 2 seawater linear (own copies: TendencyArgs::buoyancy
@@ -315,7 +317,8 @@ struct TendencyKernel {
                     const FT* u = a.U[0]; const FT* v = a.U[1]; const FT* w = a.U[2];
                     const FT h = FT(0.5);
                     const FT y = cor.y0 + (FT(j) + (KIND == KIND_V ? FT(0) : FT(0.5))) * g.d[1];
-                    const FT z = cor.z0 + (FT(k) + (KIND == KIND_W ? FT(0) : FT(0.5))) * g.d[2];
+                    const FT z = cor.zc ? (KIND == KIND_W ? cor.zf[k] : cor.zc[k])
+                                        : cor.z0 + (FT(k) + (KIND == KIND_W ? FT(0) : FT(0.5))) * g.d[2];
                     const FT Oy = cor.cf[1] * (FT(1) - z / cor.R) + cor.gamma * y;
                     const FT Oz = cor.cf[2] * (FT(1) + FT(2) * z / cor.R) + cor.beta * y;
                     if (KIND == KIND_U) {

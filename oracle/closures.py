@@ -516,6 +516,9 @@ def coriolis_cross(ctx, cor, U, comp):
         fzz, fyy, be, ga, R = FT(cor.fz), FT(cor.fy), FT(cor.beta), FT(cor.gamma), FT(cor.R)
 
         def node(d, off):
+            if d == 2 and g.stretched:                 # grid.z.cᵃᵃᶜ[k] / grid.z.cᵃᵃᶠ[k]  (grid_generation.jl:33-94)
+                tab = g._zC if off else g._zF
+                return lambda o: tab[ctx.index(2, o) - 1 + g.H[2]].astype(FT)
             return lambda o: (FT(g.x0[d]) + ((ctx.index(d, o).astype(np.float64) - 1 + off) * float(g.D[d])).astype(FT)).astype(FT)
 
         def Oy(y, z):

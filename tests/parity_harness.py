@@ -289,6 +289,7 @@ CORIOLIS_CASES = [
     ("PPP weno nontraditional betaplane TS", dict(N=(16, 12, 8), topo="PPP", scheme="weno", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0))),
     ("BBB centered nontraditional betaplane AB2", dict(N=(12, 10, 8), topo="BBB", scheme="centered", f=("ntbeta", 0.7, 0.5, 1.0, -0.8, 5.0), ts="QuasiAdamsBashforth2")),
     ("PPB weno amd nontraditional betaplane bcs F32", dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="amd", f=("ntbeta", 0.1, 0.2, 0.5, -0.3, 4.0), bcs=True, FT=np.float32)),
+    ("stretched PBB upwind3 nontraditional betaplane", dict(N=(16, 12, 9), topo="PBB", scheme="upwind3", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0), stretch="smooth")),
     ("PFB centered cartesian coriolis 2D", dict(N=(16, 1, 12), topo="PFB", scheme="centered", buoy="tracer", f=("cartesian", 0.3, -0.5, 0.7))),
 ]
 
