@@ -35,6 +35,9 @@ GOLDEN_CASES_WIDENING = {
     "bbb_centered_cartesian_coriolis_tilted_gravity_f64": dict(N=(12, 10, 8), topo="BBB", scheme="centered", buoy="tracer",
                                                                f=("cartesian", 0.3, -0.5, 0.7), tilt=(0.48, -0.6, -0.64)),
     "ppb_weno_betaplane_array_bcs_f64": dict(N=(12, 10, 8), topo="PPB", scheme="weno", f=("beta", 0.3, 2.0), bcs="array"),
+    # AMD with the buoyancy modification (Cb = 1) under a NonTraditionalBetaPlane, on a stretched grid (ABI v4 features)
+    "stretched_ppb_weno_amd_cb_nontraditional_betaplane_bcs_f64": dict(N=(12, 10, 8), topo="PPB", scheme="weno", closure="amdcb", bcs=True,
+                                                                       f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0), stretch="smooth"),
 }
 STEPS = (1, 3)
 
