@@ -117,7 +117,7 @@ typedef struct {
      * fy = coriolis_fxyz[1], fz = coriolis_fxyz[2], β = coriolis_beta, γ = coriolis_gamma, R = coriolis_radius;
      * 2Ωʸ = fy (1 − z/R) + γ y, 2Ωᶻ = fz (1 + 2z/R) + β y at the y- and z-nodes of the evaluation points (:79-96); origin_y as for
      * BetaPlane, origin_z = z of the bottom face of the domain (regular z; a stretched grid takes its z-nodes from z_faces).
-     * General tile kernel; serial models; no Flat y / z. */
+     * General tile kernel; serial and slab-decomposed models; no Flat y / z. */
     double  coriolis_gamma, coriolis_radius, origin_z;
 } oc_config;
 

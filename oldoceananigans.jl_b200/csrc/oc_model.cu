@@ -132,11 +132,9 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     }
     if (c.has_coriolis == OC_CORIOLIS_BETAPLANE && g_.flat[1]) throw Error(OC_ERR_UNSUPPORTED, "BetaPlane on a grid with a Flat y");
     if (c.has_coriolis == OC_CORIOLIS_NONTRADITIONAL_BETAPLANE) {
-        if (c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "NonTraditionalBetaPlane on distributed models");
         if (g_.flat[1] || g_.flat[2]) throw Error(OC_ERR_UNSUPPORTED, "NonTraditionalBetaPlane on a grid with a Flat y or z");
         if (!(c.coriolis_radius != 0.0)) throw Error(OC_ERR_INVALID, "NonTraditionalBetaPlane: radius must be non-zero");
     }
-    if (c.has_coriolis == OC_CORIOLIS_CARTESIAN && c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "ConstantCartesianCoriolis on distributed models");
     if (c.buoyancy == OC_BUOYANCY_SEAWATER_LINEAR && (c.tracer_T < 0 || c.tracer_S < 0 || c.tracer_T >= c.n_tracers || c.tracer_S >= c.n_tracers))
         throw Error(OC_ERR_INVALID, "SeawaterBuoyancy needs tracers T and S");
     if (c.buoyancy == OC_BUOYANCY_TRACER && (c.tracer_b < 0 || c.tracer_b >= c.n_tracers)) throw Error(OC_ERR_INVALID, "BuoyancyTracer needs tracer b");

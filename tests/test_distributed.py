@@ -50,6 +50,10 @@ def run_ranks(R, case, timeout=600, backend="gloo"):
     # the round-1 widening on slabs: Smagorinsky(-Lilly) eddy viscosities need their own halo exchange; BetaPlane needs the rank's y offset
     (2, dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="lilly", f=("beta", 0.3, 2.0), bcs=True, steps=2)),
     (4, dict(N=(12, 16, 8), topo="PPP", scheme="upwind3", closure="smag", f=("beta", 0.3, 2.0), steps=1)),
+    # the three-component Coriolis forms on slabs: w and v halos across the slab boundary; NonTraditionalBetaPlane needs the rank's y offset
+    (2, dict(N=(16, 12, 8), topo="PPB", scheme="weno", f=("cartesian", 0.3, -0.5, 0.7), bcs=True, steps=2)),
+    (2, dict(N=(16, 12, 8), topo="PPP", scheme="centered", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0), steps=2)),
+    (4, dict(N=(12, 16, 8), topo="PPB", scheme="weno", closure="amd", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0), steps=1)),
 ])
 def test_slab_decomposition_matches_single_domain_oracle(R, case):
     res = run_ranks(R, dict(case))
