@@ -158,6 +158,13 @@ int  oc_download_parent(oc_model* m, int field, void* host, size_t nbytes);
  * May be called again to update the values (time-dependent forcing from the host). */
 int  oc_set_bc_array(oc_model* m, int field, int side, const void* host, size_t nbytes);
 
+/* Boundary condition of a DIFFUSIVITY field — `boundary_conditions = (κₑ = (b = FieldBoundaryConditions(bottom = ValueBoundaryCondition(κ₀)),),)`
+ * (build_diffusivity_fields, anisotropic_minimum_dissipation.jl:358-372; test/test_boundary_conditions_integration.jl:54-103): `field` is
+ * OC_FIELD_NU_E or OC_FIELD_KAPPA_E0 + t of a model with an eddy-viscosity closure, `side` 0 … 5 (west, east, south, north, bottom, top) of a
+ * Bounded dimension, `kind` OC_BC_FLUX (the default: no flux, halo = interior), OC_BC_VALUE or OC_BC_GRADIENT with the scalar `value`.
+ * The halo fill of the diffusivities (compute_diffusivities! -> fill_halo_regions!) applies it from the next update_state! on. */
+int  oc_set_diffusivity_bc(oc_model* m, int field, int side, int kind, double value);
+
 /* ---- staged entry points (the methods time_step! calls; used by parity tests and mid-step callbacks) ---- */
 /* fill_halo_regions!(fields...; fill_open_bcs)  src/BoundaryConditions/fill_halo_regions.jl:25-36; `fields` lists field ids */
 int  oc_fill_halo_regions(oc_model* m, const int* fields, int nfields, int fill_open_bcs);

@@ -106,6 +106,7 @@ SYMBOLS = {
     "oc_compute_diagnostics": (C.c_int, [_M, C.POINTER(oc_diagnostics)]),
     "oc_field_maximum_abs": (C.c_int, [_M, C.c_int, C.POINTER(C.c_double)]),
     "oc_set_bc_array": (C.c_int, [_M, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "oc_set_diffusivity_bc": (C.c_int, [_M, C.c_int, C.c_int, C.c_int, C.c_double]),
     "oc_dist_unique_id": (C.c_int, [C.c_void_p]),
     "oc_dist_attach_nccl": (C.c_int, [_M, C.c_void_p]),
     "oc_dist_attach_host": (C.c_int, [_M, C.c_void_p, C.c_void_p]),

@@ -710,6 +710,11 @@ class NonhydrostaticModel:
                                           "(HydrostaticSphericalCoriolis is out of scope)")
         names = ("u", "v", "w") + tracers
         bcs = boundary_conditions or {}
+        # (νₑ = …, κₑ = (tracer = …,)): boundary conditions of the diffusivity fields (build_diffusivity_fields), applied after creation
+        diff_bcs = {k: bcs[k] for k in ("νₑ", "nu_e", "κₑ", "kappa_e") if k in bcs}
+        bcs = {k: v for k, v in bcs.items() if k not in diff_bcs}
+        if diff_bcs and not (amd or smag):
+            raise ValueError("boundary conditions for νₑ / κₑ need a closure with diffusivity fields (AnisotropicMinimumDissipation, Smagorinsky)")
         for k in bcs:
             if k not in names:
                 raise ValueError(f"boundary_conditions given for unknown field {k}")
@@ -734,6 +739,17 @@ class NonhydrostaticModel:
                 bc = fb.sides.get(side) if fb is not None else None
                 if bc is not None and bc.array is not None:
                     self.set_boundary_condition_array(f, s, bc.array)
+        for key, fb in diff_bcs.items():
+            per_field = {L.OC_FIELD_NU_E: fb} if key in ("νₑ", "nu_e") else \
+                {L.OC_FIELD_KAPPA_E0 + tracers.index(n): b for n, b in (fb.items() if isinstance(fb, dict) else vars(fb).items())}
+            for fid, b in per_field.items():
+                for s, side in enumerate(_SIDES):
+                    bc = b.sides.get(side)
+                    if bc is None:
+                        continue
+                    if bc.array is not None:
+                        raise NotImplementedError("array-valued boundary conditions on diffusivity fields")
+                    self._lib.check(self._lib.oc_set_diffusivity_bc(self._h, fid, s, bc.kind, 0.0 if bc.value is None else float(bc.value)))
         if self.distributed:
             self._attach_transport(arch)
         self.tracer_names = tracers

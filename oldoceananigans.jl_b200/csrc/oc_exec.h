@@ -41,6 +41,7 @@ struct Dim3 {
 
 #ifndef OC_HOSTSIM
 typedef cudaStream_t Stream;
+enum { OC_MAX_DEVICES = 64 };
 
 template <class K>
 __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) kernel_entry(const __grid_constant__ K k) {
@@ -65,11 +66,17 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) kernel_entry(const 
 template <class K>
 inline cudaError_t launch(const K& k, Dim3 grid, size_t smem_bytes, Stream stream) {
     if (grid.x <= 0 || grid.y <= 0 || grid.z <= 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured && smem_bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: cache what was configured per device
+    static size_t configured[OC_MAX_DEVICES] = {};
+    if (smem_bytes > 48 * 1024) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev < 0 || dev >= OC_MAX_DEVICES || configured[dev] < smem_bytes) {
+            e = cudaFuncSetAttribute(kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < OC_MAX_DEVICES) configured[dev] = smem_bytes;
+        }
     }
     kernel_entry<K><<<dim3(grid.x, grid.y, grid.z), K::THREADS, smem_bytes, stream>>>(k);
     return cudaGetLastError();
@@ -105,11 +112,16 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) march_entry(const _
 template <class K>
 inline cudaError_t launch_march(const K& k, Dim3 grid, size_t smem_bytes, Stream stream) {
     if (grid.x <= 0 || grid.y <= 0 || grid.z <= 0) return cudaSuccess;
-    static size_t configured = 0;
-    if (configured < smem_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(march_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    static size_t configured[OC_MAX_DEVICES] = {};
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        configured = smem_bytes;
+        if (dev < 0 || dev >= OC_MAX_DEVICES || configured[dev] < smem_bytes) {
+            e = cudaFuncSetAttribute(march_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < OC_MAX_DEVICES) configured[dev] = smem_bytes;
+        }
     }
     march_entry<K><<<dim3(grid.x, grid.y, grid.z), K::THREADS, smem_bytes, stream>>>(k);
     return cudaGetLastError();

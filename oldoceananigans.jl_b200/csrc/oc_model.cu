@@ -181,6 +181,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     zeta_[0] = FT(0); zeta_[1] = (FT)(-17.0L / 60.0L); zeta_[2] = (FT)(-5.0L / 12.0L);
 #ifndef OC_HOSTSIM
     cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    device = c.device;
     {
         int lo = 0, hi = 0;
         cuda_check(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
@@ -453,6 +454,23 @@ void Model<FT>::join_tracers() {
 #ifndef OC_HOSTSIM
     cuda_check(cudaEventRecord((cudaEvent_t)ev_join_, stream2_), "cudaEventRecord");
     cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_join_, 0), "cudaStreamWaitEvent");
+#endif
+    tracers_in_flight_ = false;
+}
+
+// An exception that crosses an entry point may leave launch_stream_ on a side stream (fork_tracers, the sub-chunked y stage of the
+// distributed solve) with work in flight there: go back to the main stream and make it wait for the side streams, so that later
+// calls on the (still usable) handle are ordered instead of racing.
+template <class FT>
+void Model<FT>::recover() {
+#ifndef OC_HOSTSIM
+    launch_stream_ = stream_;
+    cudaEvent_t ev = (cudaEvent_t)ev_join_;
+    if (ev) {
+        if (stream2_ && cudaEventRecord(ev, stream2_) == cudaSuccess) cudaStreamWaitEvent(stream_, ev, 0);
+        if (stream3_ && cudaEventRecord(ev, stream3_) == cudaSuccess) cudaStreamWaitEvent(stream_, ev, 0);
+    }
+    cudaGetLastError();
 #endif
     tracers_in_flight_ = false;
 }
@@ -1145,16 +1163,25 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
         for (int f = 0; f < F_; ++f) std::swap(state_[f].p, next_[f].p), std::swap(state_[f].base, next_[f].base);
 }
 
+// cache_previous_tendencies! by pointer swap (quasi_adams_bashforth_2.jl:116-120, runge_kutta_3.jl:131,147): the fused stage leaves its
+// evaluation in the Gⁿ slot (gn_pending_); whoever evaluates next — a fused stage, update_state!(compute_tendencies = true), a read of
+// Gⁿ / G⁻ — first rotates it into the G⁻ slot.  Exactly one rotation per consumed evaluation, whatever the caller interleaves.
+template <class FT>
+void Model<FT>::rotate_pending_tendencies() {
+    if (!gn_pending_) return;
+    for (int f = 0; f < F_; ++f) std::swap(Gn_[f].p, Gm_[f].p), std::swap(Gn_[f].base, Gm_[f].base);
+    gn_pending_ = false;
+}
+
 template <class FT>
 void Model<FT>::compute_tendencies_if_stale() {
-    if (tend_valid_) return;
-    for (int f = 0; f < F_; ++f) std::swap(Gn_[f].p, Gm_[f].p), std::swap(Gn_[f].base, Gm_[f].base);   // cache, then recompute
-    tendencies(STEP_NONE, 0.0, 1, 0.0, false, false, false);
-    tend_valid_ = true;
+    if (tend_valid_ && !gn_pending_) return;
+    compute_tendencies();
 }
 
 template <class FT>
 void Model<FT>::compute_tendencies() {
+    rotate_pending_tendencies();
     tendencies(STEP_NONE, 0.0, 1, 0.0, false, false, false);
     tend_valid_ = true;
 }
@@ -1234,6 +1261,22 @@ void Model<FT>::set_bc_array(int field, int side, const void* host, size_t nbyte
     tend_valid_ = false;
     aux_valid_ = false;
     if (kind != OC_BC_FLUX) { std::vector<FieldRec*> one{&state_[field]}; halo(one, false); }      // the halo plane follows the new values
+}
+
+// boundary conditions of νₑ / κₑ (build_diffusivity_fields: anisotropic_minimum_dissipation.jl:358-372, smagorinsky.jl:163-176)
+template <class FT>
+void Model<FT>::set_diffusivity_bc(int field, int side, int kind, double value) {
+    const bool is_nu = field == OC_FIELD_NU_E, is_kappa = field >= OC_FIELD_KAPPA_E0 && field < OC_FIELD_KAPPA_E0 + (int)kappa_e_.size();
+    if (!has_eddy_ || !(is_nu || is_kappa)) throw Error(OC_ERR_INVALID, "set_diffusivity_bc: OC_FIELD_NU_E or OC_FIELD_KAPPA_E0 + tracer of a model with an eddy-viscosity closure");
+    if (side < 0 || side > 5) throw Error(OC_ERR_INVALID, "set_diffusivity_bc: side must be 0 … 5 (west, east, south, north, bottom, top)");
+    if (cfg_.topology[side / 2] != OC_BOUNDED) throw Error(OC_ERR_INVALID, "set_diffusivity_bc: non-periodic boundary condition in a dimension that is not Bounded");
+    if (kind != OC_BC_FLUX && kind != OC_BC_VALUE && kind != OC_BC_GRADIENT) throw Error(OC_ERR_INVALID, "set_diffusivity_bc: Flux (no flux), Value or Gradient");
+    join_tracers();
+    FieldRec& f = lookup(field);
+    f.bc[side].kind = kind;
+    f.bc[side].value = kind == OC_BC_FLUX ? 0.0 : value;
+    aux_valid_ = false;
+    tend_valid_ = false;
 }
 
 template <class FT>
@@ -1584,6 +1627,7 @@ void Model<FT>::restore_previous_tendency(int field, const void* host, size_t nb
     if (n * sizeof(FT) != nbytes) throw Error(OC_ERR_INVALID, "host buffer size mismatch: expected " + std::to_string(n * sizeof(FT)) + " bytes");
     FT* origin = f.p - Hcfg_[0] - (long long)Hcfg_[1] * g_.sy - (long long)Hcfg_[2] * g_.sz;
     dev_copy_box(origin, sizeof(FT), g_.sy, g_.sz, const_cast<void*>(host), ext, true, stream_);
+    gn_pending_ = true;
     tend_valid_ = false;
 }
 
@@ -1631,9 +1675,9 @@ void Model<FT>::set_finalize(int enforce) {
 // One fused stage: [aux] -> tendency+substep per field -> halo(U, open) -> Poisson -> projection -> halo(all)
 template <class FT>
 void Model<FT>::stage(int mode, double dt, int stage_no, double stage_dt, double chi, bool euler) {
-    if (!tend_valid_)                                    // Gⁿ holds the previous evaluation: it becomes G⁻ (cache by swap)
-        for (int f = 0; f < F_; ++f) std::swap(Gn_[f].p, Gm_[f].p), std::swap(Gn_[f].base, Gm_[f].base);
+    rotate_pending_tendencies();                         // the previous stage's evaluation becomes G⁻ (cache by swap)
     tendencies(mode, dt, stage_no, chi, euler, true, true, /*defer_tracer_join=*/true);
+    gn_pending_ = true;
     tend_valid_ = false;
     aux_valid_ = false;
     std::vector<FieldRec*> vel{&state_[0], &state_[1], &state_[2]};
@@ -1694,20 +1738,41 @@ struct oc_model {
 
 static thread_local std::string g_last_error;
 
+// Every entry point runs with the model's device current and restores the caller's (torch, another model on another GPU) on return.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+#ifndef OC_HOSTSIM
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+#else
+        (void)dev;
+#endif
+    }
+    ~DeviceGuard() {
+#ifndef OC_HOSTSIM
+        if (prev >= 0) cudaSetDevice(prev);
+#endif
+    }
+};
+
 template <class Fn>
-static int guarded(Fn&& fn) {
+static int guarded(Fn&& fn, oc::ModelBase* model = nullptr) {
     try {
         fn();
         return OC_OK;
     } catch (const oc::Error& e) {
         g_last_error = e.what();
+        if (model) model->recover();
         return e.code;
     } catch (const std::exception& e) {
         g_last_error = e.what();
+        if (model) model->recover();
         return OC_ERR_INVALID;
     }
 }
-#define OC_REQUIRE(m) if (!(m) || !(m)->impl) { g_last_error = "null model handle"; return OC_ERR_INVALID; }
+#define OC_REQUIRE(m) if (!(m) || !(m)->impl) { g_last_error = "null model handle"; return OC_ERR_INVALID; } \
+    DeviceGuard oc_device_guard_((m)->impl->device); oc::ModelBase* oc_model_ = (m)->impl.get(); (void)oc_model_;
 
 extern "C" {
 
@@ -1751,42 +1816,44 @@ int oc_model_create(const oc_config* cfg, oc_model** out) {
 }
 int oc_model_destroy(oc_model* m) {
     if (!m) return OC_OK;
+    DeviceGuard dg(m->impl ? m->impl->device : 0);
     return guarded([&] { delete m; });
 }
-int oc_sync(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->sync(); }); }
-int oc_field_info_get(oc_model* m, int field, oc_field_info* info) { OC_REQUIRE(m); return guarded([&] { m->impl->field_info(field, info); }); }
-int oc_upload_interior(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, const_cast<void*>(host), nbytes, false, true); }); }
-int oc_download_interior(oc_model* m, int field, void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, host, nbytes, false, false); }); }
-int oc_upload_parent(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, const_cast<void*>(host), nbytes, true, true); }); }
-int oc_download_parent(oc_model* m, int field, void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, host, nbytes, true, false); }); }
-int oc_fill_halo_regions(oc_model* m, const int* fields, int nfields, int fill_open_bcs) { OC_REQUIRE(m); return guarded([&] { m->impl->fill_halo_regions(fields, nfields, fill_open_bcs); }); }
-int oc_update_state(oc_model* m, int compute_tendencies) { OC_REQUIRE(m); return guarded([&] { m->impl->update_state(compute_tendencies); }); }
-int oc_compute_tendencies(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->compute_tendencies(); }); }
-int oc_compute_flux_bc_tendencies(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->compute_flux_bc_tendencies(); }); }
-int oc_rk3_substep(oc_model* m, double dt, int stage) { OC_REQUIRE(m); return guarded([&] { m->impl->rk3_substep(dt, stage); }); }
-int oc_ab2_step(oc_model* m, double dt, double chi) { OC_REQUIRE(m); return guarded([&] { m->impl->ab2_step(dt, chi); }); }
-int oc_cache_previous_tendencies(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->cache_previous_tendencies(); }); }
-int oc_compute_pressure_correction(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&] { m->impl->compute_pressure_correction(dt); }); }
-int oc_make_pressure_correction(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&] { m->impl->make_pressure_correction(dt); }); }
-int oc_poisson_solve(oc_model* m, const void* rhs, void* phi, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->poisson_solve(rhs, phi, nbytes); }); }
-int oc_set_finalize(oc_model* m, int enforce) { OC_REQUIRE(m); return guarded([&] { m->impl->set_finalize(enforce); }); }
-int oc_time_step_rk3(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&] { m->impl->time_step_rk3(dt); }); }
-int oc_time_step_ab2(oc_model* m, double dt, int euler) { OC_REQUIRE(m); return guarded([&] { m->impl->time_step_ab2(dt, euler); }); }
+int oc_sync(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->sync(); }, oc_model_); }
+int oc_field_info_get(oc_model* m, int field, oc_field_info* info) { OC_REQUIRE(m); return guarded([&] { m->impl->field_info(field, info); }, oc_model_); }
+int oc_upload_interior(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, const_cast<void*>(host), nbytes, false, true); }, oc_model_); }
+int oc_download_interior(oc_model* m, int field, void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, host, nbytes, false, false); }, oc_model_); }
+int oc_upload_parent(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, const_cast<void*>(host), nbytes, true, true); }, oc_model_); }
+int oc_download_parent(oc_model* m, int field, void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->transfer(field, host, nbytes, true, false); }, oc_model_); }
+int oc_fill_halo_regions(oc_model* m, const int* fields, int nfields, int fill_open_bcs) { OC_REQUIRE(m); return guarded([&] { m->impl->fill_halo_regions(fields, nfields, fill_open_bcs); }, oc_model_); }
+int oc_update_state(oc_model* m, int compute_tendencies) { OC_REQUIRE(m); return guarded([&] { m->impl->update_state(compute_tendencies); }, oc_model_); }
+int oc_compute_tendencies(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->compute_tendencies(); }, oc_model_); }
+int oc_compute_flux_bc_tendencies(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->compute_flux_bc_tendencies(); }, oc_model_); }
+int oc_rk3_substep(oc_model* m, double dt, int stage) { OC_REQUIRE(m); return guarded([&] { m->impl->rk3_substep(dt, stage); }, oc_model_); }
+int oc_ab2_step(oc_model* m, double dt, double chi) { OC_REQUIRE(m); return guarded([&] { m->impl->ab2_step(dt, chi); }, oc_model_); }
+int oc_cache_previous_tendencies(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->cache_previous_tendencies(); }, oc_model_); }
+int oc_compute_pressure_correction(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&] { m->impl->compute_pressure_correction(dt); }, oc_model_); }
+int oc_make_pressure_correction(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&] { m->impl->make_pressure_correction(dt); }, oc_model_); }
+int oc_poisson_solve(oc_model* m, const void* rhs, void* phi, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->poisson_solve(rhs, phi, nbytes); }, oc_model_); }
+int oc_set_finalize(oc_model* m, int enforce) { OC_REQUIRE(m); return guarded([&] { m->impl->set_finalize(enforce); }, oc_model_); }
+int oc_time_step_rk3(oc_model* m, double dt) { OC_REQUIRE(m); return guarded([&] { m->impl->time_step_rk3(dt); }, oc_model_); }
+int oc_time_step_ab2(oc_model* m, double dt, int euler) { OC_REQUIRE(m); return guarded([&] { m->impl->time_step_ab2(dt, euler); }, oc_model_); }
 int oc_get_clock(oc_model* m, oc_clock* c) { OC_REQUIRE(m); *c = m->impl->clock; return OC_OK; }
 int oc_set_clock(oc_model* m, const oc_clock* c) { OC_REQUIRE(m); m->impl->clock = *c; return OC_OK; }
-int oc_restore_previous_tendency(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->restore_previous_tendency(field, host, nbytes); }); }
-int oc_compute_diagnostics(oc_model* m, oc_diagnostics* out) { OC_REQUIRE(m); return guarded([&] { m->impl->diagnostics(out); }); }
+int oc_restore_previous_tendency(oc_model* m, int field, const void* host, size_t nbytes) { OC_REQUIRE(m); return guarded([&] { m->impl->restore_previous_tendency(field, host, nbytes); }, oc_model_); }
+int oc_compute_diagnostics(oc_model* m, oc_diagnostics* out) { OC_REQUIRE(m); return guarded([&] { m->impl->diagnostics(out); }, oc_model_); }
 int oc_set_bc_array(oc_model* m, int field, int side, const void* host, size_t nbytes) {
     OC_REQUIRE(m);
     if (!host) { g_last_error = "null argument"; return OC_ERR_INVALID; }
     return guarded([&] { m->impl->set_bc_array(field, side, host, nbytes); });
 }
+int oc_set_diffusivity_bc(oc_model* m, int field, int side, int kind, double value) { OC_REQUIRE(m); return guarded([&] { m->impl->set_diffusivity_bc(field, side, kind, value); }, oc_model_); }
 int oc_output_begin(oc_model* m, int field, const int lo[3], const int n[3], void* host, size_t nbytes, int* ticket) {
     OC_REQUIRE(m);
     if (!lo || !n || !host || !ticket) { g_last_error = "null argument"; return OC_ERR_INVALID; }
     return guarded([&] { *ticket = m->impl->output_begin(field, lo, n, host, nbytes); });
 }
-int oc_output_wait(oc_model* m, int ticket) { OC_REQUIRE(m); return guarded([&] { m->impl->output_wait(ticket); }); }
+int oc_output_wait(oc_model* m, int ticket) { OC_REQUIRE(m); return guarded([&] { m->impl->output_wait(ticket); }, oc_model_); }
 int oc_output_test(oc_model* m, int ticket, int* done) {
     OC_REQUIRE(m);
     if (!done) { g_last_error = "null argument"; return OC_ERR_INVALID; }
@@ -1839,11 +1906,11 @@ int oc_dist_attach_host(oc_model* m, oc_exchange_fn fn, void* user) {
 #endif
     });
 }
-int oc_timers_enable(oc_model* m, int enable) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_enable(enable); }); }
-int oc_timers_reset(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_reset(); }); }
-int oc_timers_get(oc_model* m, double* ms, int64_t* n) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_get(ms, n); }); }
-int oc_stopwatch_start(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->stopwatch_start(); }); }
-int oc_stopwatch_stop(oc_model* m, double* ms) { OC_REQUIRE(m); return guarded([&] { *ms = m->impl->stopwatch_stop(); }); }
+int oc_timers_enable(oc_model* m, int enable) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_enable(enable); }, oc_model_); }
+int oc_timers_reset(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_reset(); }, oc_model_); }
+int oc_timers_get(oc_model* m, double* ms, int64_t* n) { OC_REQUIRE(m); return guarded([&] { m->impl->timers_get(ms, n); }, oc_model_); }
+int oc_stopwatch_start(oc_model* m) { OC_REQUIRE(m); return guarded([&] { m->impl->stopwatch_start(); }, oc_model_); }
+int oc_stopwatch_stop(oc_model* m, double* ms) { OC_REQUIRE(m); return guarded([&] { *ms = m->impl->stopwatch_stop(); }, oc_model_); }
 int oc_host_alloc(void** ptr, size_t nbytes) {
     return guarded([&] {
 #ifndef OC_HOSTSIM

@@ -104,6 +104,7 @@ struct ModelBase {
     virtual bool output_test(int ticket) = 0;
     virtual void set_bc_array(int field, int side, const void* host, size_t nbytes) = 0;
     virtual void restore_previous_tendency(int field, const void* host, size_t nbytes) = 0;
+    virtual void set_diffusivity_bc(int field, int side, int kind, double value) = 0;
     virtual void dist_attach(Transport* t) = 0;
     virtual int dist_rank() const = 0;
     virtual int dist_nranks() const = 0;
@@ -112,7 +113,9 @@ struct ModelBase {
     virtual void timers_get(double* ms, int64_t* n) = 0;
     virtual void stopwatch_start() = 0;
     virtual double stopwatch_stop() = 0;
+    virtual void recover() = 0;             // after an exception crossed an entry point: back to the main stream, side streams joined
     oc_clock clock{0.0, 0, 1, INFINITY, INFINITY};
+    int device = 0;                         // the CUDA device every entry point makes current for its duration (DeviceGuard)
     int64_t launches = 0;
     int64_t device_bytes = 0;
 };
@@ -150,6 +153,8 @@ public:
     void apply_flux_arrays(int f, FT* Gn, FT* Unew, FT coef);
     FT* bc_array_[OC_MAX_FIELDS][6] = {};      // device arrays of array-valued Flux BCs (nullptr: scalar)
     void restore_previous_tendency(int field, const void* host, size_t nbytes) override;
+    void set_diffusivity_bc(int field, int side, int kind, double value) override;
+    void recover() override;
     void dist_attach(Transport* t) override;
     int dist_rank() const override { return rank_; }
     int dist_nranks() const override { return R_; }
@@ -178,6 +183,7 @@ private:
     std::vector<FieldRec> kappa_e_;
     bool has_pHY_ = false, has_amd_ = false, has_smag_ = false, has_eddy_ = false;   // has_eddy_: νₑ / κₑ fields exist (AMD or Smagorinsky)
     bool tend_valid_ = false;     // Gⁿ == G(current state)
+    bool gn_pending_ = false;     // the Gⁿ slot holds the evaluation the last fused stage consumed: it becomes G⁻ (pointer swap) before the next evaluation
     bool aux_valid_ = false;      // pHY′, νₑ, κₑ computed from the current state
     struct HaloCache { HaloBox* boxes; int nboxes; int nblocks; };
     std::map<std::string, HaloCache> halo_cache_;
@@ -212,6 +218,7 @@ private:
     void halo(const std::vector<FieldRec*>& fields, bool fill_open);
     void aux();
     void compute_tendencies_if_stale();
+    void rotate_pending_tendencies();
     void tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state, bool defer_tracer_join = false);
     template <int KIND> void launch_tendency(int fidx, TendencyArgs<FT>& a);
     template <int KIND> void launch_march_tendency(int fidx, TendencyArgs<FT>& a);

@@ -92,8 +92,10 @@ class OracleModel:
         for c in closures:
             if c.kind in ("amd", "smagorinsky"):
                 assert self.nu_e is None, "one eddy-viscosity closure per model"
-                self.nu_e = Field(grid, "ccc", None, "nu_e")
-                self.kappa_e = {n: Field(grid, "ccc", None, "kappa_e_" + n) for n in tracers}
+                # boundary conditions of the diffusivity fields: (νₑ = …, κₑ = (tracer = …,)) in the reference's model_bcs
+                # (test/test_boundary_conditions_integration.jl:62-65; build_diffusivity_fields, anisotropic_minimum_dissipation.jl:364-384)
+                self.nu_e = Field(grid, "ccc", bcs.get("nu_e"), "nu_e")
+                self.kappa_e = {n: Field(grid, "ccc", (bcs.get("kappa_e") or {}).get(n), "kappa_e_" + n) for n in tracers}
         self.fields = {"u": self.u, "v": self.v, "w": self.w, **self.tracers}
         self.Gn = {n: f.like("Gn_" + n) for n, f in self.fields.items()}
         self.Gm = {n: f.like("Gm_" + n) for n, f in self.fields.items()}

@@ -236,6 +236,16 @@ CASES = [
     ("tile-crossing 40x36x33 PPB", dict(N=(40, 36, 33), topo="PPB", scheme="weno")),
 ]
 
+# The kernel instances the BENCHMARK runs (C3 / C5: MarchKernel<…, BND = 0, CLO = 0, TY = 16> for u, v and tracers, TY = 8 for w; C2: the
+# Centered(2) instances), driven across several 32×16 tiles and — 36 levels > 2 chunks of 16 — several z-chunks, partial tiles included
+BENCH_INSTANCE_CASES = [
+    ("multi-tile 72x40x36 PPP weno TS F64", dict(N=(72, 40, 36), topo="PPP", scheme="weno")),
+    ("multi-tile 72x40x36 PPP weno TS F32", dict(N=(72, 40, 36), topo="PPP", scheme="weno", FT=np.float32)),
+    ("multi-tile 72x40x36 PPP centered F64", dict(N=(72, 40, 36), topo="PPP", scheme="centered", closure="none", buoy="none")),
+    ("multi-tile 70x35x33 PPP weno TS AB2 (odd, partial tiles)", dict(N=(70, 35, 33), topo="PPP", scheme="weno", ts="QuasiAdamsBashforth2")),
+    ("multi-tile 72x40x36 PPP upwind5 TS F64", dict(N=(72, 40, 36), topo="PPP", scheme="upwind5")),
+]
+
 # the other advection schemes of the family up to order 5 (the list of test/test_time_stepping.jl:261-267)
 SCHEME_CASES = [
     ("PPB centered4 scalar TS", dict(N=(16, 12, 8), topo="PPB", scheme="centered4")),

@@ -24,6 +24,46 @@ def test_cuda_matches_oracle(ob, name, kw):
     ph.check_case(kw, library=None, steps=(1, 10))
 
 
+@pytest.mark.parametrize("name,kw", ph.BENCH_INSTANCE_CASES, ids=[c[0] for c in ph.BENCH_INSTANCE_CASES])
+def test_cuda_benchmark_kernel_instances_match_oracle_across_tiles(ob, name, kw):
+    """The instances bench.py measures (triply periodic: 32×16 tiles, two cells per thread) on grids that span several tiles and
+    z-chunks, against the NumPy oracle after 1 and 2 steps (check_case shortens runs of grids wider than 32)."""
+    ph.check_case(kw, library=None)
+
+
+@pytest.mark.parametrize("scheme,FT,steps", [("weno", np.float64, 10), ("centered", np.float64, 10), ("weno", np.float32, 4)],
+                         ids=["C3 physics F64", "C2 physics F64", "C3 physics F32"])
+def test_cuda_matches_c_twin_at_128_cubed(ob, scheme, FT, steps):
+    """The BASELINE physics (C3: WENO-5, T, S, SeawaterBuoyancy, ScalarDiffusivity; C2: Centered-2, no tracers) at 128³ — 4 × 8 tiles
+    of 32 × 16 cells, 8 z-chunks — against the C99 twin of the oracle (oracle/nhm_step.c, cross-checked against the NumPy oracle in
+    tests/test_oracle_c.py) after 1 and `steps` RK3 steps: relative L∞ ≤ 1e-11 (Float64) / 1e-4 (Float32) for u, v, w, p, T, S."""
+    from oracle.c_twin import CTwin
+    N = (128, 128, 128)
+    tracers = scheme == "weno"
+    kw = dict(N=N, topo="PPP", scheme=scheme, FT=FT) if tracers else dict(N=N, topo="PPP", scheme=scheme, closure="none", buoy="none", FT=FT)
+    m = ph.build_product(**kw)
+    ct = CTwin(N, ph.EXTENT, weno=tracers, tracers=tracers, nu=1e-3 if tracers else 0.0, kappa=2e-3 if tracers else 0.0)
+    rng = np.random.default_rng(1234)
+    ic = {n: rng.uniform(-1, 1, N) for n in ("u", "v", "w")}
+    if tracers:
+        ic["T"] = 20.0 + 0.01 * rng.standard_normal(N)
+        ic["S"] = 35.0 + 0.01 * rng.standard_normal(N)
+    ic = {n: a.astype(FT).astype(np.float64) for n, a in ic.items()}      # the same representable numbers on both sides
+    ob.set_(m, **ic)
+    ct.set(**ic)
+    dt = 0.1 * min(ph.EXTENT[d] / N[d] for d in range(3))
+    tol = ph.TOL[FT]
+    for s in range(1, steps + 1):
+        ob.time_step_(m, dt)
+        ct.time_step(dt)
+        if s in (1, steps):
+            for n in ic:
+                e = ph.rel_linf(m.fields[n].interior(), ct.get(n))
+                assert e <= tol, f"step {s} field {n}: rel L-inf {e:.3e} > {tol:g}"
+            e = ph.rel_linf(m.pressures.pNHS.interior(), ct.get("p"))
+            assert e <= tol * (10 if FT == np.float64 else 1), f"step {s} p: rel L-inf {e:.3e}"
+
+
 @pytest.mark.parametrize("name,kw", ph.STRETCHED_CASES, ids=[c[0] for c in ph.STRETCHED_CASES])
 def test_cuda_matches_oracle_on_stretched_grids(ob, name, kw):
     """vertically stretched grids (FourierTridiagonalPoissonSolver, level-dependent metrics)"""

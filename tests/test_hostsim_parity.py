@@ -30,6 +30,12 @@ def test_hostsim_matches_oracle(hostsim, name, kw):
     ph.check_case(kw, library=hostsim, steps=(1, 3))
 
 
+@pytest.mark.parametrize("name,kw", [ph.BENCH_INSTANCE_CASES[0], ph.BENCH_INSTANCE_CASES[3]], ids=["72x40x36 weno F64", "70x35x33 weno AB2"])
+def test_hostsim_benchmark_kernel_instances_across_tiles(hostsim, name, kw):
+    """the triply periodic 32×16-tile (two cells per thread) instances bench.py measures, across several tiles and z-chunks"""
+    ph.check_case(kw, library=hostsim)
+
+
 @pytest.mark.parametrize("name,kw", ph.STRETCHED_CASES[:-1], ids=[c[0] for c in ph.STRETCHED_CASES[:-1]])
 def test_hostsim_matches_oracle_on_stretched_grids(hostsim, name, kw):
     """vertically stretched grids — level-dependent metrics in every kernel + FourierTridiagonalPoissonSolver"""
@@ -149,6 +155,46 @@ def test_checkpoint_pickup_continues_bit_for_bit(hostsim, ts, tmp_path):
         assert np.array_equal(m1.fields[n].parent(), m2.fields[n].parent()), n
     assert np.array_equal(m1.pressures.pNHS.interior(), m2.pressures.pNHS.interior())
     assert m1.clock.time == m2.clock.time and m1.clock.iteration == m2.clock.iteration == 4
+
+
+@pytest.mark.parametrize("ts", ["QuasiAdamsBashforth2", "RungeKutta3"])
+def test_previous_tendency_survives_interleaved_state_updates(hostsim, ts, tmp_path):
+    """G⁻ is cached by a pointer swap; update_state!(compute_tendencies=true), reads of Gⁿ / G⁻ and a pickup followed by
+    update_state! (the reference's run!(pickup=true) -> initialize! -> update_state! sequence) between fused steps must not
+    disturb it: in the reference they are harmless because cache_previous_tendencies! copies
+    (quasi_adams_bashforth_2.jl:116-120).  Every variant must continue bit for bit like the plain run."""
+    import oceananigans_b200 as ob
+    kw = dict(N=(8, 8, 8), topo="PPB", scheme="centered", closure="scalar", ts=ts, library=hostsim)
+    dt = 0.01
+
+    def run(between, pickup_after=None):
+        m = ph.build_product(**kw)
+        om = ph.build_oracle(**{k: v for k, v in kw.items() if k != "library"})
+        ob.set_(m, **ph.initial_conditions(om))
+        for s in range(4):
+            ob.time_step_(m, dt)
+            between(m)
+            if pickup_after == s:
+                path = ob.Checkpointer(m, prefix=str(tmp_path / f"ck{s}")).write()
+                m = ph.build_product(**kw)
+                ob.Checkpointer.pickup(m, path)
+                ob.update_state_(m, True)
+        return m
+
+    ref = run(lambda m: None)
+    variants = {
+        "update_state(compute_tendencies=true)": run(lambda m: ob.update_state_(m, True)),
+        "update_state twice": run(lambda m: (ob.update_state_(m, True), ob.update_state_(m, True))),
+        "compute_tendencies": run(lambda m: ob.compute_tendencies_(m)),
+        "read Gn": run(lambda m: m.timestepper.Gn["u"].interior()),
+        "read Gn, update_state": run(lambda m: (m.timestepper.Gm["v"].interior(), ob.update_state_(m, True))),
+        "pickup + update_state": run(lambda m: None, pickup_after=1),
+        "update_state, pickup + update_state": run(lambda m: ob.update_state_(m, True), pickup_after=2),
+    }
+    for what, m in variants.items():
+        for n in ref.fields:
+            assert np.array_equal(ref.fields[n].parent(), m.fields[n].parent()), (what, n)
+        assert np.array_equal(ref.pressures.pNHS.interior(), m.pressures.pNHS.interior()), what
 
 
 @pytest.mark.parametrize("name,kw", ph.SMAGORINSKY_CASES[:-1], ids=[c[0] for c in ph.SMAGORINSKY_CASES[:-1]])

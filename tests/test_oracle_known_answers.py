@@ -913,3 +913,90 @@ def test_beta_plane_reduces_to_f_plane_and_varies_linearly_in_y():
     assert np.all(clo.coriolis_cross(ctx, bp, (u, v, w), 2) == 0)
     fp = clo.coriolis_cross(ctx, clo.FPlane(f=0.5), (u, v, w), 0)
     assert np.array_equal(clo.coriolis_cross(ctx, clo.BetaPlane(f0=0.5, beta=0.0), (u, v, w), 0), fp)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Reference-held pins restated in round 2 (VERDICT r01 "missing" item 3)
+# ---------------------------------------------------------------------------------------------------------------------
+def gaussian_advection_setup(N=128):
+    """passive_tracer_advection_test  test/test_dynamics.jl:177-208 — the numbers of the reference test"""
+    Ld, U, V = 1.0, 0.5, 0.8
+    delta, x0, y0 = Ld / 15, Ld / 2, Ld / 2
+    dt = 0.05 * Ld / N / np.sqrt(U ** 2 + V ** 2)
+    T = lambda x, y, z, t: np.exp(-((x - U * t - x0) ** 2 + (y - V * t - y0) ** 2) / (2 * delta ** 2))
+    return Ld, U, V, dt, T
+
+
+def gaussian_relative_error(T_num, nodes, T, time):
+    """relative_error(u_num, u, time)  test/test_dynamics.jl:10-15 : mean((num - exact)²) / mean(exact²)"""
+    X, Y, Z = np.meshgrid(*nodes, indexing="ij")
+    ans = T(X, Y, Z, time)
+    return float(np.mean((T_num - ans) ** 2) / np.mean(ans ** 2))
+
+
+@pytest.mark.parametrize("ts", ["QuasiAdamsBashforth2"])          # the reference runs AB2 only (test_dynamics.jl:628)
+def test_passive_tracer_advection(ts):
+    """A Gaussian advected diagonally by a uniform flow for 100 steps on the reference's 128 × 128 × 2 grid with its defaults
+    (Centered(2), (Periodic, Periodic, Bounded), κ = ν = 1e-12, SeawaterBuoyancy, T and S): relative error < 1e-4."""
+    N, Nt = 128, 100
+    Ld, U, V, dt, T = gaussian_advection_setup(N)
+    g = Grid(np.float64, size=(N, N, 2), extent=(Ld, Ld, Ld), topology=("P", "P", "B"))
+    m = OracleModel(g, closure=clo.ScalarDiffusivity(nu=1e-12, kappa=1e-12), buoyancy=clo.SeawaterBuoyancy(), tracers=("T", "S"),
+                    timestepper=ts)
+    m.set(u=lambda x, y, z: U + 0 * x, v=lambda x, y, z: V + 0 * x, T=lambda x, y, z: T(x, y, z, 0.0))
+    for _ in range(Nt):
+        m.time_step(dt)
+    nodes = [g.nodes(0, "c"), g.nodes(1, "c"), g.nodes(2, "c")]
+    err = gaussian_relative_error(m.tracers["T"].interior, nodes, T, m.clock.time)
+    assert err < 1e-4, err
+    assert np.abs(m.tracers["S"].interior).max() == 0.0                       # S was never set
+
+
+# (topology, extents) and the (field, side, L) list of test/test_boundary_conditions_integration.jl:309-360
+FLUX_BUDGET_MATRIX = []
+for _topo, _names, _sides in ((("P", "B", "B"), ("u", "c"), (("north", 0.4), ("south", 0.4), ("top", 0.5), ("bottom", 0.5))),
+                              (("B", "P", "B"), ("v", "c"), (("east", 0.3), ("west", 0.3), ("top", 0.5), ("bottom", 0.5))),
+                              (("B", "B", "P"), ("w", "c"), (("east", 0.3), ("west", 0.3), ("north", 0.4), ("south", 0.4)))):
+    for _n in _names:
+        for _s, _L in _sides:
+            FLUX_BUDGET_MATRIX.append((_topo, _n, _s, _L))
+
+
+@pytest.mark.parametrize("topo,name,side,Lside", FLUX_BUDGET_MATRIX, ids=["".join(t) + f"-{n}-{s}" for t, n, s, _ in FLUX_BUDGET_MATRIX])
+def test_nonhydrostatic_flux_budget_matrix(topo, name, side, Lside):
+    """test_nonhydrostatic_flux_budget (test/test_boundary_conditions_integration.jl:28-52): every field × side of the reference's
+    matrix on its 2 × 2 × 2 grid, flux = ±π, one time step of Δt = 1: mean(ϕ) ≈ flux t / L."""
+    g = Grid(np.float64, size=(2, 2, 2), x=(0, 0.3), y=(0, 0.4), z=(0, 0.5), topology=topo)
+    flux = np.pi
+    direction = 1 if side in ("west", "south", "bottom") else -1
+    m = OracleModel(g, tracers=("c",), boundary_conditions={name: {side: BC("flux", flux * direction)}})
+    m.fields[name].set(0)
+    m.time_step(1.0)
+    mean = float(m.fields[name].interior.mean())
+    if name in ("u", "v", "w") and topo["uvw".index(name)] == "B":
+        pytest.skip("not in the reference matrix")       # (the matrix only lists tangential velocities; kept for safety)
+    assert np.isclose(mean, flux * m.clock.time / Lside, rtol=1e-8), (mean, flux * m.clock.time / Lside)
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_fluxes_with_diffusivity_boundary_conditions_are_correct(FT):
+    """test/test_boundary_conditions_integration.jl:54-103: AMD with a Value boundary condition κ₀ on κₑ at the bottom and a Gradient
+    condition bz on b there: the bottom diffusive flux is −κ₀ bz whatever the closure computes inside, so the mean of b changes by
+    flux · t / Lz  (the reference's own numbers: −3.14159265e-5 after 10 steps; atol 1e-6)."""
+    Lz = 1.0
+    k0 = FT(np.exp(-3))
+    bz = FT(np.pi)
+    flux = -k0 * bz
+    g = Grid(FT, size=(16, 16, 16), extent=(1, 1, Lz), topology=("P", "P", "B"))
+    bcs = {"b": {"bottom": BC("gradient", bz)}, "kappa_e": {"b": {"bottom": BC("value", k0)}}}
+    m = OracleModel(g, timestepper="QuasiAdamsBashforth2", tracers=("b",), buoyancy=clo.BuoyancyTracer(),
+                    closure=clo.AnisotropicMinimumDissipation(), boundary_conditions=bcs)
+    m.set(b=lambda x, y, z: z * float(bz))
+    mean0 = float(m.tracers["b"].interior.astype(np.float64).mean())
+    dt = 1e-6 * Lz ** 2 / float(k0)
+    for n in range(10):
+        m.time_step(dt, euler=(n == 0))
+    mean1 = float(m.tracers["b"].interior.astype(np.float64).mean())
+    assert abs((mean1 - mean0) - float(flux) * m.clock.time / Lz) <= 1e-6
+    if FT == np.float64:
+        assert np.isclose(mean1 - mean0, -3.141592656086267e-5, rtol=1e-6)      # the Float64 value quoted in the reference test
