@@ -22,6 +22,11 @@
 #include <cuda.h>
 #endif
 
+// prefetch distance of the velocity rings (MarchSpec::PFV) for tile height TY, kernel kind and ring-0 distance PF
+#ifndef OC_MARCH_PFV
+#define OC_MARCH_PFV(TY, KIND, PF) ((TY) == 16 ? (PF) + 1 : (PF))
+#endif
+
 namespace oc {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -147,55 +152,61 @@ struct MarchStateT {
     FT ph0[CPT], ph1[CPT];   // pHY′ at the cell and at its lower x / y neighbour (u and v kernels)
     int o;        // global offset of this thread's FIRST cell at the level being finished (advanced by one plane per iteration)
     int cell;     // bit h: this thread owns its h-th cell (thread row < TR, inside the domain): loop invariant
+    int nit;      // iterations of this block (k_end - k_begin + 1): loop invariant, kept here so that no phase recomputes it
 };
 
 // Loads for iteration it + PF are issued in step<1>(it), after every thread has finished iteration it-1; they overwrite the
 // slot of level k + PF + HI - D, which must lie below everything iteration it still reads: D >= LIVE + PF, and one more for a
 // ring whose level k-1 is read by the divergence phase of iteration it (the Coriolis operand of the u / v kernels).
-enum { MARCH_NBAR = 4 };     // data barriers; the prefetch distance PF and the number of flux stages NSYNC are per kernel
+enum { MARCH_NBAR = 4 };     // data barriers per ring group (velocity rings, ring 0); the prefetch distances and the number of flux stages NSYNC are per kernel
 
 // Which planes each kernel stages.  `FIELD` names the global field: -1 = the stepped field itself (ψ or c), 0/1/2 = u/v/w.
 // E = elements per 16 bytes; box x-origins are kept multiples of E (16-byte aligned box rows).
 // PF = prefetch distance in levels; ring depth D = LIVE + PF (one more for a ring whose level k-1 is read by the divergence phase).
-template <int KIND, int TX, int TY, int E, int PF_>
+// Two prefetch distances: PF for ring 0 (the stepped field — its newest plane, level k+3, is first read by the z-face flux at the END
+// of the iteration, so its barrier is waited for there) and PFV for the velocity rings 1 … 3 (their newest plane is read by the in-plane
+// fluxes at the START of the iteration; the planes are small — no halo rows — so a deeper prefetch is cheap).  Measured reason
+// (profiles/r02b_ncu_march_c3_by_line.txt): with one distance of 1 the warps polled the data barrier 12 times per level — the planes
+// the iteration starts with arrived late.
+template <int KIND, int TX, int TY, int E, int PF_, int PFV_>
 struct MarchSpec;
-template <int TX, int TY, int E, int PF_>
-struct MarchSpec<KIND_C, TX, TY, E, PF_> {
-    static constexpr int PF = PF_;
+template <int TX, int TY, int E, int PF_, int PFV_>
+struct MarchSpec<KIND_C, TX, TY, E, PF_, PFV_> {
+    static constexpr int PF = PF_, PFV = PFV_;
     static constexpr int NR = 4;
     using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 6 + PF>;   // c: WENO-5 radius in x, y, z
-    using R1 = RingSpec<0, TX + 4, 0, TY, 0, 0, 1 + PF>;          // u at the x-faces of level k
-    using R2 = RingSpec<0, TX, 0, TY + 1, 0, 0, 1 + PF>;          // v at the y-faces
-    using R3 = RingSpec<0, TX, 0, TY, 1, 1, 1 + PF>;              // w at the upper z-face (level k+1)
+    using R1 = RingSpec<0, TX + 4, 0, TY, 0, 0, 1 + PFV>;         // u at the x-faces of level k
+    using R2 = RingSpec<0, TX, 0, TY + 1, 0, 0, 1 + PFV>;         // v at the y-faces
+    using R3 = RingSpec<0, TX, 0, TY, 1, 1, 1 + PFV>;             // w at the upper z-face (level k+1)
     static constexpr int F1 = 0, F2 = 1, F3 = 2;
 };
-template <int TX, int TY, int E, int PF_>
-struct MarchSpec<KIND_U, TX, TY, E, PF_> {
-    static constexpr int PF = PF_;
+template <int TX, int TY, int E, int PF_, int PFV_>
+struct MarchSpec<KIND_U, TX, TY, E, PF_, PFV_> {
+    static constexpr int PF = PF_, PFV = PFV_;
     static constexpr int NR = 3;
     using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 6 + PF>;       // u
-    using R1 = RingSpec<-E, TX + 2 * E, 0, TY + 1, 0, 0, 2 + PF>;     // v[i-2..i+1, j0..j0+TY] (Centered-4 along x, Coriolis, τ12); +1: level k-1 is read by the divergence phase
-    using R2 = RingSpec<-E, TX + 2 * E, 0, TY, 1, 1, 1 + PF>;         // w[i-2..i+1] at level k+1
+    using R1 = RingSpec<-E, TX + 2 * E, 0, TY + 1, 0, 0, 2 + PFV>;    // v[i-2..i+1, j0..j0+TY] (Centered-4 along x, Coriolis, τ12); +1: level k-1 is read by the divergence phase
+    using R2 = RingSpec<-E, TX + 2 * E, 0, TY, 1, 1, 1 + PFV>;        // w[i-2..i+1] at level k+1
     using R3 = RingSpec<0, 4, 0, 1, 0, 0, 1>;
     static constexpr int F1 = 1, F2 = 2, F3 = -2;
 };
-template <int TX, int TY, int E, int PF_>
-struct MarchSpec<KIND_V, TX, TY, E, PF_> {
-    static constexpr int PF = PF_;
+template <int TX, int TY, int E, int PF_, int PFV_>
+struct MarchSpec<KIND_V, TX, TY, E, PF_, PFV_> {
+    static constexpr int PF = PF_, PFV = PFV_;
     static constexpr int NR = 3;
     using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 6 + PF>;   // v
-    using R1 = RingSpec<0, TX + 4, -2, TY + 3, 0, 0, 2 + PF>;     // u[i0..i0+TX, j-2..j+1]; +1: also read by the divergence phase (Coriolis)
-    using R2 = RingSpec<0, TX, -2, TY + 3, 1, 1, 1 + PF>;         // w[j-2..j+1] at level k+1
+    using R1 = RingSpec<0, TX + 4, -2, TY + 3, 0, 0, 2 + PFV>;    // u[i0..i0+TX, j-2..j+1]; +1: also read by the divergence phase (Coriolis)
+    using R2 = RingSpec<0, TX, -2, TY + 3, 1, 1, 1 + PFV>;        // w[j-2..j+1] at level k+1
     using R3 = RingSpec<0, 4, 0, 1, 0, 0, 1>;
     static constexpr int F1 = 0, F2 = 2, F3 = -2;
 };
-template <int TX, int TY, int E, int PF_>
-struct MarchSpec<KIND_W, TX, TY, E, PF_> {
-    static constexpr int PF = PF_;
+template <int TX, int TY, int E, int PF_, int PFV_>
+struct MarchSpec<KIND_W, TX, TY, E, PF_, PFV_> {
+    static constexpr int PF = PF_, PFV = PFV_;
     static constexpr int NR = 3;
     using R0 = RingSpec<-4, TX + 8, -3, TY + 6, -2, 3, 6 + PF>;   // w
-    using R1 = RingSpec<0, TX + 4, 0, TY, -2, 1, 4 + PF>;         // u[k-2..k+1] at the x-faces (Centered-4 along z)
-    using R2 = RingSpec<0, TX, 0, TY + 1, -2, 1, 4 + PF>;         // v[k-2..k+1] at the y-faces
+    using R1 = RingSpec<0, TX + 4, 0, TY, -2, 1, 4 + PFV>;        // u[k-2..k+1] at the x-faces (Centered-4 along z)
+    using R2 = RingSpec<0, TX, 0, TY + 1, -2, 1, 4 + PFV>;        // v[k-2..k+1] at the y-faces
     using R3 = RingSpec<0, 4, 0, 1, 0, 0, 1>;
     static constexpr int F1 = 0, F2 = 1, F3 = -2;
 };
@@ -295,11 +306,12 @@ OC_HD float rcp_den(float x) { return rcp_fast(x); }
 // Algebraically the reference's formula, arranged to minimise FP64 instructions:
 //   β_r = ψ1(C1ψ1+C2ψ2+C3ψ3)+ψ2(C4ψ2+C5ψ3)+C6ψ3² = 13/4 (second difference)² + 3/4 (one-sided first difference)²;
 //   everything is carried divided by 3/4 (ε too), which leaves τ/(β+ε) unchanged;
-//   Σ ω_r p_r = q2 + Σ C★_r w_r (p_r - q2) / Σ C★_r w_r  with  w_r = 1 + (τ/(β_r+ε))²  (the coeff_p(r) sum to 1);
-//   numerator and denominator both carry a factor 60, which makes every constant a small integer
-//   (C★ = 3/10, 3/5, 1/10; C★_r (p_r - q2) = (12 e3 - 3 e4, 6 e2 + 12 e3, 5 e2 - 2 e1) / 60).
+//   Σ ω_r p_r with w_r = 1 + (τ/(β_r+ε))², ω_r = C★_r w_r / Σ C★ w (the coeff_p(r) sum to 1, so do the ω): written around the middle
+//   candidate, q2 + (p_1 - q2) + ω_0 (p_0 - p_1) + ω_2 (p_2 - p_1), the differences of the candidates are third differences of q
+//   with small-integer factors (see the body).
 // Float64: the three weights are formed without divisions, w_r ∝ (b_r² + τ²)·(b_s b_t)² (one common factor
 // (b0 b1 b2)² cancels in the ratio), leaving ONE reciprocal per face.  Float32 keeps newton_div (a single MUFU.RCP).
+// 47 FP64 instructions (51 before round 2's rearrangement of the weights and of the final sum).
 template <class FT>
 OC_HD FT weno5_value_c(FT q0, FT q1, FT q2, FT q3, FT q4) {
     using K = AdvConst<FT>;
@@ -314,20 +326,26 @@ OC_HD FT weno5_value_c(FT q0, FT q1, FT q2, FT q3, FT q4) {
     const FT tau = b0 - b2;                                  // only τ² is used
     FT w0, w1, w2;
     if (sizeof(FT) == 8) {
-        const FT t2 = tau * tau;
-        const FT m01 = b0 * b1, m02 = b0 * b2, m12 = b1 * b2;
-        w0 = fmaT(b0, b0, t2) * (m12 * m12);
-        w1 = fmaT(b1, b1, t2) * (m02 * m02);
-        w2 = fmaT(b2, b2, t2) * (m01 * m01);
+        // w_r ∝ (b_r² + τ²) b_s² b_t² = P + τ² b_s² b_t²  with  P = b_0² b_1² b_2²
+        const FT T2 = tau * tau;
+        const FT B0 = b0 * b0, B1 = b1 * b1, B2 = b2 * b2;
+        const FT m12 = B1 * B2, m02 = B0 * B2, m01 = B0 * B1;
+        const FT P = B0 * m12;
+        w0 = fmaT(T2, m12, P); w1 = fmaT(T2, m02, P); w2 = fmaT(T2, m01, P);
     } else {
         const FT at = absT(tau);
         const FT r0 = newton_div_fast(at, b0), r1 = newton_div_fast(at, b1), r2 = newton_div_fast(at, b2);
         w0 = fmaT(r0, r0, FT(1)); w1 = fmaT(r1, r1, FT(1)); w2 = fmaT(r2, r2, FT(1));
     }
-    const FT den = fmaT(FT(6), w2, fmaT(FT(36), w1, FT(18) * w0));
-    const FT t0 = fmaT(FT(-3), e4, FT(12) * e3), t1 = fmaT(FT(12), e3, FT(6) * e2), t2n = fmaT(FT(-2), e1, FT(5) * e2);
-    const FT num = fmaT(w2, t2n, fmaT(w1, t1, w0 * t0));
-    return fmaT(num, rcp_den(den), q2);
+    // Σ ω_r p_r = q2 + (p_1 - q2) + ω_0 (p_0 - p_1) + ω_2 (p_2 - p_1),  ω_r = C★_r w_r / Σ C★ w  (the ω sum to 1):
+    //   p_1 - q2 = (e2 + 2 e3)/6,  p_0 - p_1 = -(d0 - d1)/6,  p_2 - p_1 = -2 (d1 - d2)/6,  C★ = (3, 6, 1)/10
+    //   = q2 + [ (e2 + 2 e3) - (3 w0 (d0 - d1) + 2 w2 (d1 - d2)) / (3 w0 + 6 w1 + w2) ] / 6
+    const FT x = d0 - d1, y = d1 - d2;
+    const FT lin = fmaT(FT(2), e3, e2);
+    const FT w03 = FT(3) * w0;
+    const FT den = fmaT(FT(6), w1, w03 + w2);
+    const FT num = fmaT(w2, y + y, w03 * x);
+    return fmaT(fmaT(-num, rcp_den(den), lin), FT(1) / FT(6), q2);
 }
 
 template <class FT>
@@ -447,13 +465,17 @@ struct MarchKernel {
     // instead of 768 cells in flight per SM), PF = 1, three flux stages (≈ 100 KB of shared memory per CTA; the w kernel's deeper rings
     // would leave room for one CTA only, so it stays on 32×8 tiles).
     static constexpr int MIN_BLOCKS = TY_ == 8 ? 3 : 2;
-    static constexpr int PFK = TY_ == 8 ? (KIND == KIND_W ? 1 : 2) : 1;
+    static constexpr int PFK = sizeof(FT) == 4 ? 2 : (TY_ == 8 ? (KIND == KIND_W ? 1 : 2) : 1);      // Float32 planes are half the size: room for 2
+    // velocity rings one level deeper where the CTAs per SM still fit: the 32×16-tile kernels (Float64 tracer kernel: 98.9 -> 111.6 KB of
+    // the 113 KB two CTAs per SM may use; checked by the static_assert below).  The 32×8-tile w kernel (75.3 KB of 75 KB for three CTAs) cannot.
+    static constexpr int PFVK = OC_MARCH_PFV(TY_, KIND, PFK);
     static constexpr int NSYNC = TY_ == 8 ? 4 : 3;
     static constexpr int COMP = KIND == KIND_C ? -1 : KIND;
     static constexpr bool WIN = BND != 0;                 // any wall logic at all
     // BND is a bit mask of the dimensions that MAY be Bounded (7 = generic): order-reduction windows exist only there
     template <int D> static constexpr bool WINV = ((BND >> D) & 1) != 0;
-    using SP = MarchSpec<KIND, TX, TY, 16 / (int)sizeof(FT), PFK>;
+    using SP = MarchSpec<KIND, TX, TY, 16 / (int)sizeof(FT), PFK, PFVK>;
+    static_assert(SP::PF < MARCH_NBAR && SP::PFV < MARCH_NBAR, "one barrier per iteration in flight");
     using G0 = Ring<FT, typename SP::R0>;
     using G1 = Ring<FT, typename SP::R1>;
     using G2 = Ring<FT, typename SP::R2>;
@@ -470,9 +492,13 @@ struct MarchKernel {
     static constexpr size_t OFF_FX = OFF_R3 + (NR > 3 ? G3::BYTES : 0);
     static constexpr size_t OFF_FY = OFF_FX + sizeof(FT) * NSYNC * NFXP;
     static constexpr size_t SMEM = OFF_FY + sizeof(FT) * NSYNC * NFYP;
-    static constexpr int LEVEL_BYTES = G0::BOX_BYTES + G1::BOX_BYTES + G2::BOX_BYTES + (NR > 3 ? G3::BOX_BYTES : 0);
-    static constexpr int FIRST_BYTES = G0::BOX_BYTES * SP::R0::LIVE + G1::BOX_BYTES * SP::R1::LIVE + G2::BOX_BYTES * SP::R2::LIVE +
-                                       (NR > 3 ? G3::BOX_BYTES * SP::R3::LIVE : 0);
+    // 228 KB of shared memory per SM, 1 KB reserved per resident CTA
+    static_assert(SMEM <= (233472 - MIN_BLOCKS * 1024) / MIN_BLOCKS, "the kernel's shared memory must allow MIN_BLOCKS CTAs per SM");
+    // bytes per iteration / of the first iteration, per ring group (C: ring 0, V: rings 1 … 3)
+    static constexpr int LEVEL_BYTES_C = G0::BOX_BYTES;
+    static constexpr int LEVEL_BYTES_V = G1::BOX_BYTES + G2::BOX_BYTES + (NR > 3 ? G3::BOX_BYTES : 0);
+    static constexpr int FIRST_BYTES_C = G0::BOX_BYTES * SP::R0::LIVE;
+    static constexpr int FIRST_BYTES_V = G1::BOX_BYTES * SP::R1::LIVE + G2::BOX_BYTES * SP::R2::LIVE + (NR > 3 ? G3::BOX_BYTES * SP::R3::LIVE : 0);
 
     TendencyArgs<FT> a;
     TileSrc<FT> src[4];   // staged fields, ring order
@@ -510,10 +536,15 @@ struct MarchKernel {
     OC_DEV void issue_level(const G& ring, const TileSrc<FT>* s, int i0, int j0, int lev, uint64_t* bar) const {
         tile_issue<FT>(ring.slot(lev), s, i0 + RS::XO + xpad, j0 + RS::YO + a.g.H[1], lev + a.g.H[2], bar, RS::BX, RS::BY);
     }
-    // the new level every ring needs for the iteration at level k
-    OC_DEV void issue_iteration(char* smem, int i0, int j0, int k, uint64_t* bar) const {
+    // the new level every ring of a group needs for the iteration at level k
+    OC_HD uint64_t* bar_c(char* smem, int it) const { return reinterpret_cast<uint64_t*>(smem + OFF_BAR) + (it % MARCH_NBAR); }
+    OC_HD uint64_t* bar_v(char* smem, int it) const { return reinterpret_cast<uint64_t*>(smem + OFF_BAR) + MARCH_NBAR + (it % MARCH_NBAR); }
+    OC_DEV void issue_iteration_c(char* smem, int i0, int j0, int k, uint64_t* bar) const {
         const Ctx c = raw(smem);
         issue_level<G0, typename SP::R0>(r0(c), &src[0], i0, j0, k + SP::R0::HI, bar);
+    }
+    OC_DEV void issue_iteration_v(char* smem, int i0, int j0, int k, uint64_t* bar) const {
+        const Ctx c = raw(smem);
         issue_level<G1, typename SP::R1>(r1(c), &src[1], i0, j0, k + SP::R1::HI, bar);
         issue_level<G2, typename SP::R2>(r2(c), &src[2], i0, j0, k + SP::R2::HI, bar);
         if (NR > 3) issue_level<G3, typename SP::R3>(r3(c), &src[3], i0, j0, k + SP::R3::HI, bar);
@@ -522,8 +553,8 @@ struct MarchKernel {
     OC_DEV void begin0(const Block&, int tid, char* smem) const {
         if (tid == 0) {
             uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-            for (int n = 0; n < MARCH_NBAR; ++n) mbar_init(bar + n, 1);
-            for (int n = 0; n < NSYNC; ++n) mbar_init(bar + MARCH_NBAR + n, THREADS / 32);   // one arrival per warp
+            for (int n = 0; n < 2 * MARCH_NBAR; ++n) mbar_init(bar + n, 1);
+            for (int n = 0; n < NSYNC; ++n) mbar_init(bar + 2 * MARCH_NBAR + n, THREADS / 32);   // one arrival per warp
             mbar_fence_init();
         }
     }
@@ -539,26 +570,34 @@ struct MarchKernel {
                 if (row_ < TR && ci < a.g.N[0] && cj + h * TR < a.g.N[1]) stt.cell |= 1 << h;
             }
             stt.o = a.g.idx(ci, cj, k_begin(b) - 2);        // iteration it finishes level k_begin - 2 + it
+            stt.nit = iterations(b);
         }
         {   // ring slots of the first level (kf = k_begin - 1)
             const int kf0 = k_begin(b) - 1;
             st.sk[0] = G0::slot_of(kf0); st.sk[1] = G1::slot_of(kf0); st.sk[2] = G2::slot_of(kf0); st.sk[3] = G3::slot_of(kf0);
         }
         if (tid != 0) return;
-        uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
         const int i0 = b.x * TX, j0 = b.y * TY, kf = k_begin(b) - 1, n = iterations(b);
         // iteration 0 (level kf): every live level of every ring
-        mbar_expect(bar, FIRST_BYTES);
         const Ctx c = raw(smem);
-        for (int l = SP::R0::LO; l < SP::R0::HI; ++l) issue_level<G0, typename SP::R0>(r0(c), &src[0], i0, j0, kf + l, bar);
-        for (int l = SP::R1::LO; l < SP::R1::HI; ++l) issue_level<G1, typename SP::R1>(r1(c), &src[1], i0, j0, kf + l, bar);
-        for (int l = SP::R2::LO; l < SP::R2::HI; ++l) issue_level<G2, typename SP::R2>(r2(c), &src[2], i0, j0, kf + l, bar);
+        uint64_t* bv = bar_v(smem, 0);
+        mbar_expect(bv, FIRST_BYTES_V);
+        for (int l = SP::R1::LO; l < SP::R1::HI; ++l) issue_level<G1, typename SP::R1>(r1(c), &src[1], i0, j0, kf + l, bv);
+        for (int l = SP::R2::LO; l < SP::R2::HI; ++l) issue_level<G2, typename SP::R2>(r2(c), &src[2], i0, j0, kf + l, bv);
         if (NR > 3)
-            for (int l = SP::R3::LO; l < SP::R3::HI; ++l) issue_level<G3, typename SP::R3>(r3(c), &src[3], i0, j0, kf + l, bar);
-        issue_iteration(smem, i0, j0, kf, bar);
+            for (int l = SP::R3::LO; l < SP::R3::HI; ++l) issue_level<G3, typename SP::R3>(r3(c), &src[3], i0, j0, kf + l, bv);
+        issue_iteration_v(smem, i0, j0, kf, bv);
+        uint64_t* bc = bar_c(smem, 0);
+        mbar_expect(bc, FIRST_BYTES_C);
+        for (int l = SP::R0::LO; l < SP::R0::HI; ++l) issue_level<G0, typename SP::R0>(r0(c), &src[0], i0, j0, kf + l, bc);
+        issue_iteration_c(smem, i0, j0, kf, bc);
+        for (int it = 1; it < SP::PFV && it < n; ++it) {
+            mbar_expect(bar_v(smem, it), LEVEL_BYTES_V);
+            issue_iteration_v(smem, i0, j0, kf + it, bar_v(smem, it));
+        }
         for (int it = 1; it < SP::PF && it < n; ++it) {
-            mbar_expect(bar + (it % MARCH_NBAR), LEVEL_BYTES);
-            issue_iteration(smem, i0, j0, kf + it, bar + (it % MARCH_NBAR));
+            mbar_expect(bar_c(smem, it), LEVEL_BYTES_C);
+            issue_iteration_c(smem, i0, j0, kf + it, bar_c(smem, it));
         }
     }
 
@@ -724,7 +763,7 @@ struct MarchKernel {
     // step<0>(it+4), which is only reached after the wait for iteration it+2, i.e. after every thread finished
     // step<1>(it+1) (the last reader).  Ring slots: the loads issued in step<1>(it) overwrite levels that were last read in
     // iteration it-1 (see MarchSpec), whose arrivals have all been observed.
-    OC_HD uint64_t* sync_bar(char* smem, int it) const { return reinterpret_cast<uint64_t*>(smem + OFF_BAR) + MARCH_NBAR + (it % NSYNC); }
+    OC_HD uint64_t* sync_bar(char* smem, int it) const { return reinterpret_cast<uint64_t*>(smem + OFF_BAR) + 2 * MARCH_NBAR + (it % NSYNC); }
     OC_HD static int sync_parity(int it) { return (it / NSYNC) & 1; }
 
     OC_DEV void sync_wait(char* smem, int it) const { mbar_wait(sync_bar(smem, it), sync_parity(it)); }
@@ -743,11 +782,10 @@ struct MarchKernel {
     OC_DEV void step(const Block& b, int tid, char* smem, int it, State& stt) const {
         const Geom<FT>& g = a.g;
         const int i0 = b.x * TX, j0 = b.y * TY;
-        const int nit = iterations(b);
+        const int nit = stt.nit;
         const int k = k_begin(b) - 1 + it;                   // level of this iteration (it = 0: z-flux only)
         const Ctx cx{smem, k, stt.sl};
         constexpr int shx = COMP == 0 ? -1 : 0, shy = COMP == 1 ? -1 : 0, shz = COMP == 2 ? -1 : 0;
-        uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
         const int lane = tid & (TX - 1), row = tid / TX;     // row = 0 … TR
         if (PHASE == 0) {
             if (it >= 2) {
@@ -764,7 +802,7 @@ struct MarchKernel {
                 }
             }
             if (it >= nit) return;
-            mbar_wait(bar + (it % MARCH_NBAR), (it / MARCH_NBAR) & 1);
+            mbar_wait(bar_v(smem, it), (it / MARCH_NBAR) & 1);       // the velocity planes of this level
             if (it == 0) return;
             FT* fx = reinterpret_cast<FT*>(smem + OFF_FX) + (it % NSYNC) * NFXP;
             FT* fy = reinterpret_cast<FT*>(smem + OFF_FY) + (it % NSYNC) * NFYP;
@@ -799,6 +837,7 @@ struct MarchKernel {
             }
         } else if (PHASE == 2) {
             if (it >= nit) return;
+            mbar_wait(bar_c(smem, it), (it / MARCH_NBAR) & 1);       // ring 0's newest plane (level k+3): first read here
             if (row < TR) {   // upper z-faces of this thread's cells
 #pragma unroll
                 for (int h = 0; h < CPT; ++h) {
@@ -818,11 +857,15 @@ struct MarchKernel {
             const int o_first = stt.o;
             stt.o = o_first + g.sz;
             if (tid == 0) {
-                const int lit = it + SP::PF;
+                const int lit = it + SP::PF, litv = it + SP::PFV;
+                if (lit < nit || litv < nit) proxy_fence_async();
+                if (litv < nit) {
+                    mbar_expect(bar_v(smem, litv), LEVEL_BYTES_V);
+                    issue_iteration_v(smem, i0, j0, k + SP::PFV, bar_v(smem, litv));
+                }
                 if (lit < nit) {
-                    proxy_fence_async();
-                    mbar_expect(bar + (lit % MARCH_NBAR), LEVEL_BYTES);
-                    issue_iteration(smem, i0, j0, k + SP::PF, bar + (lit % MARCH_NBAR));
+                    mbar_expect(bar_c(smem, lit), LEVEL_BYTES_C);
+                    issue_iteration_c(smem, i0, j0, k + SP::PF, bar_c(smem, lit));
                 }
             }
             if (it < 2 || !stt.cell) return;                 // levels start at iteration 1; their divergence is formed one iteration later

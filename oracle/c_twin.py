@@ -11,14 +11,16 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "nhm_step.c")
 LIB = os.path.join(HERE, "_build", "libnhm_step.so")
+LIB_EXTENDED = os.path.join(HERE, "_build", "libnhm_step_ld.so")      # the same formulas in x87 extended precision (-DNHC_LONG_DOUBLE)
 
 
-def build(force=False):
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
-        os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.run(["gcc", "-O3", "-fopenmp", "-ffp-contract=off", "-std=gnu99", "-shared", "-fPIC", SRC, "-o", LIB, "-lm"],
-                       check=True)
-    return LIB
+def build(force=False, extended=False):
+    lib = LIB_EXTENDED if extended else LIB
+    if force or not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(SRC):
+        os.makedirs(os.path.dirname(lib), exist_ok=True)
+        subprocess.run(["gcc", "-O3", "-fopenmp", "-ffp-contract=off", "-std=gnu99", "-shared", "-fPIC"] +
+                       (["-DNHC_LONG_DOUBLE"] if extended else []) + [SRC, "-o", lib, "-lm"], check=True)
+    return lib
 
 
 class CTwin:
@@ -26,8 +28,8 @@ class CTwin:
     ScalarDiffusivity(ν, κ), RungeKutta3."""
     NAMES = ("u", "v", "w", "T", "S", "p")
 
-    def __init__(self, size, extent, weno=True, tracers=True, nu=0.0, kappa=0.0, g=9.80665, alpha=1.67e-4, beta=7.8e-4):
-        self.lib = C.CDLL(build())
+    def __init__(self, size, extent, weno=True, tracers=True, nu=0.0, kappa=0.0, g=9.80665, alpha=1.67e-4, beta=7.8e-4, extended=False, beta_difference_form=False):
+        self.lib = C.CDLL(build(extended=extended))
         self.lib.nhc_create.restype = C.c_void_p
         self.lib.nhc_create.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 2 + [C.c_double] * 5
         for fn in (self.lib.nhc_set, self.lib.nhc_get):
@@ -38,6 +40,10 @@ class CTwin:
         self.N = tuple(int(n) for n in size)
         self.ntr = 2 if tracers else 0
         self.h = self.lib.nhc_create(*self.N, *[float(x) for x in extent], int(weno), self.ntr, nu, kappa, g, alpha, beta)
+        # the WENO smoothness indicators in difference form (exact identity, well conditioned) instead of the reference's expanded form:
+        # tests use it to attribute T / S differences to the reference's own Float64 round-off (see nhm_step.c: weno5)
+        self.lib.nhc_set_beta_difference_form.argtypes = [C.c_void_p, C.c_int]
+        self.lib.nhc_set_beta_difference_form(self.h, int(beta_difference_form))
 
     def set(self, **fields):
         for n, a in fields.items():

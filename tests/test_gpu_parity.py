@@ -36,13 +36,22 @@ def test_cuda_benchmark_kernel_instances_match_oracle_across_tiles(ob, name, kw)
 def test_cuda_matches_c_twin_at_128_cubed(ob, scheme, FT, steps):
     """The BASELINE physics (C3: WENO-5, T, S, SeawaterBuoyancy, ScalarDiffusivity; C2: Centered-2, no tracers) at 128³ — 4 × 8 tiles
     of 32 × 16 cells, 8 z-chunks — against the C99 twin of the oracle (oracle/nhm_step.c, cross-checked against the NumPy oracle in
-    tests/test_oracle_c.py) after 1 and `steps` RK3 steps: relative L∞ ≤ 1e-11 (Float64) / 1e-4 (Float32) for u, v, w, p, T, S."""
+    tests/test_oracle_c.py) after 1 and `steps` RK3 steps: relative L∞ ≤ 1e-11 (Float64) / 1e-4 (Float32) for u, v, w, p, T, S.
+
+    Float64 WENO, T and S: the reference evaluates the smoothness indicators in expanded form, which cancels catastrophically for fields
+    with a large mean (S = 35 ± 0.01: ~1e-8 relative round-off on a small β), and the worst cell of 2·10⁶ after 10 steps carries ~1e-8 of
+    it — the REFERENCE's own Float64 noise, shown against x87 extended precision in tests/test_oracle_c.py.  The kernel evaluates the
+    same polynomials in difference form.  So T and S are held to 1e-11 against the twin run with the difference form (every other
+    operation in the reference's order), and to 1e-7 against the twin in the reference's order; u, v, w, p to 1e-11 against both."""
     from oracle.c_twin import CTwin
     N = (128, 128, 128)
     tracers = scheme == "weno"
     kw = dict(N=N, topo="PPP", scheme=scheme, FT=FT) if tracers else dict(N=N, topo="PPP", scheme=scheme, closure="none", buoy="none", FT=FT)
     m = ph.build_product(**kw)
-    ct = CTwin(N, ph.EXTENT, weno=tracers, tracers=tracers, nu=1e-3 if tracers else 0.0, kappa=2e-3 if tracers else 0.0)
+    tw = dict(weno=tracers, tracers=tracers, nu=1e-3 if tracers else 0.0, kappa=2e-3 if tracers else 0.0)
+    twins = {"reference order": CTwin(N, ph.EXTENT, **tw)}
+    if tracers and FT == np.float64:
+        twins["difference-form β"] = CTwin(N, ph.EXTENT, beta_difference_form=True, **tw)
     rng = np.random.default_rng(1234)
     ic = {n: rng.uniform(-1, 1, N) for n in ("u", "v", "w")}
     if tracers:
@@ -50,18 +59,25 @@ def test_cuda_matches_c_twin_at_128_cubed(ob, scheme, FT, steps):
         ic["S"] = 35.0 + 0.01 * rng.standard_normal(N)
     ic = {n: a.astype(FT).astype(np.float64) for n, a in ic.items()}      # the same representable numbers on both sides
     ob.set_(m, **ic)
-    ct.set(**ic)
+    for ct in twins.values():
+        ct.set(**ic)
     dt = 0.1 * min(ph.EXTENT[d] / N[d] for d in range(3))
     tol = ph.TOL[FT]
+    report = {}
     for s in range(1, steps + 1):
         ob.time_step_(m, dt)
-        ct.time_step(dt)
+        for ct in twins.values():
+            ct.time_step(dt)
         if s in (1, steps):
-            for n in ic:
-                e = ph.rel_linf(m.fields[n].interior(), ct.get(n))
-                assert e <= tol, f"step {s} field {n}: rel L-inf {e:.3e} > {tol:g}"
-            e = ph.rel_linf(m.pressures.pNHS.interior(), ct.get("p"))
-            assert e <= tol * (10 if FT == np.float64 else 1), f"step {s} p: rel L-inf {e:.3e}"
+            for which, ct in twins.items():
+                noisy = which == "reference order" and len(twins) > 1
+                for n in list(ic) + ["p"]:
+                    a = m.pressures.pNHS.interior() if n == "p" else m.fields[n].interior()
+                    e = ph.rel_linf(a, ct.get(n))
+                    report[(s, which, n)] = e
+                    bound = 1e-7 if (noisy and n in ("T", "S")) else tol
+                    assert e <= bound, f"step {s} field {n} vs twin ({which}): rel L-inf {e:.3e} > {bound:g}\n{report}"
+    print("\n128^3 parity report (step, twin, field) -> rel L-inf:", {k: f"{v:.2e}" for k, v in report.items()})
 
 
 @pytest.mark.parametrize("name,kw", ph.STRETCHED_CASES, ids=[c[0] for c in ph.STRETCHED_CASES])
