@@ -233,6 +233,105 @@ def default_dt(w):
     return 0.1 / w["N"][0]
 
 
+# ----------------------------------------------------------------------------------------------- correctness next to the number
+def parity_check(w, local, rank, world, steps=2, library=None):
+    """Before anything is timed: the benchmark's physics on a small global grid, 64 x (16 N) x 64, decomposed over the N ranks exactly like
+    the timed problem (slab-y, NCCL halo exchange, transposed distributed FFT), against the single-domain CPU restatement of the reference
+    (oracle/nhm_step.c — the checker, never the thing measured) after `steps` RK3 steps.  Relative L-inf over u, v, w, p, T, S (normalised
+    by the global maximum), max over ranks.  `worst` is against the twin in the reference's order of operations; `worst_difference_form`
+    against the twin with the WENO smoothness indicators in the well-conditioned difference form the kernel uses (the reference's expanded
+    form carries its own ~1e-12 … 1e-8 round-off on T, S: tests/test_oracle_c.py).  Triply periodic workloads only (the twin's scope)."""
+    if w["topo"] != "PPP" or w["adv"] not in ("weno", "centered") or w["closure"] in LES:
+        return None
+    import oceananigans_b200 as ob
+    from oracle.c_twin import CTwin
+    FT = np.float64 if w["FT"] == "f64" else np.float32
+    N = (64, 16 * world, 64)
+    extent = tuple(n / 64.0 for n in N)
+    arch = ob.B200(local) if world == 1 else ob.Distributed(ob.B200(local), partition=ob.Partition(1, world), rank=rank, nranks=world)
+    grid = ob.RectilinearGrid(arch, FT, size=N, extent=extent, topology=(ob.Periodic, ob.Periodic, ob.Periodic))
+    kw = dict(grid=grid, advection=ob.WENO() if w["adv"] == "weno" else ob.Centered(), tracers=w["tracers"])
+    if w["buoy"] == "seawater":
+        kw["buoyancy"] = ob.SeawaterBuoyancy()
+    nu = 1e-5 if w["closure"] == "scalar" else 0.0
+    if w["closure"] == "scalar":
+        kw["closure"] = ob.ScalarDiffusivity(nu=nu, kappa=nu)
+    if library is not None:          # tests/test_bench_contract.py: the host simulation of the kernel sources (CPU-only test of this function)
+        kw["library"] = library
+    model = ob.NonhydrostaticModel(**kw)
+    rng = np.random.default_rng(4321)
+    ic = {n: rng.uniform(-1, 1, N) for n in ("u", "v", "w")}
+    for n in w["tracers"]:
+        ic[n] = {"T": 20.0, "S": 35.0}.get(n, 0.0) + 0.01 * rng.standard_normal(N)
+    ic = {n: a.astype(FT).astype(np.float64) for n, a in ic.items()}
+    nyl = N[1] // world
+    sl = slice(rank * nyl, (rank + 1) * nyl)
+    ob.set_(model, **{n: a[:, sl, :] for n, a in ic.items()})
+    twins = {"worst": CTwin(N, extent, weno=w["adv"] == "weno", tracers=bool(w["tracers"]), nu=nu, kappa=nu)}
+    if w["adv"] == "weno" and w["tracers"]:
+        twins["worst_difference_form"] = CTwin(N, extent, weno=True, tracers=True, nu=nu, kappa=nu, beta_difference_form=True)
+    dt = 0.1 / 64
+    for ct in twins.values():
+        ct.set(**ic)
+    for _ in range(steps):
+        ob.time_step_(model, dt)
+        for ct in twins.values():
+            ct.time_step(dt)
+    out = {}
+    for key, ct in twins.items():
+        worst = 0.0
+        for n in tuple(ic) + ("p",):
+            ref = ct.get(n)
+            got = (model.pressures.pNHS if n == "p" else model.fields[n]).interior().astype(np.float64)
+            worst = max(worst, float(np.abs(got - ref[:, sl, :]).max() / np.abs(ref).max()))
+        out[key] = worst
+    del model
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([out.get("worst", 0.0), out.get("worst_difference_form", 0.0)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out = {k: float(t[i].item()) for i, k in enumerate(("worst", "worst_difference_form")) if k in out}
+    tol = 1e-11 if FT is np.float64 else 1e-4
+    out.update({"tol": tol, "ok": bool(out["worst"] <= tol), "grid": list(N), "steps": steps, "ranks": world,
+                "against": "oracle/nhm_step.c (C99 restatement of the reference algorithm) on the undecomposed grid, u, v, w, p and tracers"})
+    return out
+
+
+def time_workload(name, local, steps=5, warmup=3):
+    """One more BASELINE configuration, timed on the device like the main line (state resident in HBM, CUDA events on the library's
+    stream), so that the driver's record carries configs 2-4 too."""
+    w = WORKLOADS[name]
+    ob, model = build_model(w, local)
+    lib, h = model._lib, model._h
+    ob.set_(model, **synthetic_ic(w, model))
+    dt = default_dt(w)
+    for _ in range(warmup):
+        ob.time_step_(model, dt)
+    model.sync()
+    model.timers(enable=True)
+    model.timers(reset=True)
+    ms = C.c_double()
+    lib.check(lib.oc_stopwatch_start(h))
+    for _ in range(steps):
+        ob.time_step_(model, dt)
+    lib.check(lib.oc_stopwatch_stop(h, C.byref(ms)))
+    timers = model.timers()
+    if not np.isfinite(float(np.abs(model.velocities.u.interior()).max())):
+        raise SystemExit(f"{name}: state became non-finite")
+    cells = int(np.prod(w["N"]))
+    itemsize = 8 if w["FT"] == "f64" else 4
+    ms_per_step = ms.value / steps
+    peak, _ = peaks()
+    step_gbs = cells * reals_per_cell_step(w) * itemsize / (ms_per_step * 1e-3) / 1e9
+    del model
+    return {"workload": w["label"], "dtype": w["FT"], "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "value": cells / (ms_per_step * 1e-3), "unit": "cell-updates/s",
+            "step_roofline": {"achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+                              "reals_per_cell_step": reals_per_cell_step(w)},
+            "kernel_ms_per_step": {k: v[0] / steps for k, v in timers.items() if v[1]}}
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -249,6 +348,7 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = WORKLOADS[args.workload]
+    parity = None if args.no_parity_check else parity_check(w, local, rank, world)
     ob, model = build_model(w, local, rank, world)
     lib, h = model._lib, model._h
     ic = synthetic_ic(w, model, seed=1234 + rank)
@@ -339,10 +439,17 @@ def run_ours(args):
         for n in bufs:
             lib.oc_host_free(bufs[n][0])
 
+    device_bytes = model.device_bytes()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # the other single-GPU BASELINE configurations, device-timed like the main line (sequentially, after the main model is gone)
+    others = None
+    if world == 1 and not args.no_other_workloads and args.workload == "c3":
+        del model
+        others = {n: time_workload(n, local) for n in ("c2", "c3f32", "c4", "c1")}
 
     peak, peak_src = peaks()
     tend_ms, tend_n = timers["tendency"]
@@ -381,7 +488,9 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": e2e,
-        "device_bytes": model.device_bytes(),
+        "device_bytes": device_bytes,
+        "parity_check": parity,
+        "other_workloads": others,
     }
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(w, args.cpu_size)
@@ -491,10 +600,10 @@ def run_reference(args):
         return
     os.environ.pop("OMP_NUM_THREADS", None)          # torchrun pins it to 1: the reference arm may use every core
     w = WORKLOADS[args.workload]
-    v, s, steps, cores, sample, N = cpu_run(w, args.cpu_size, max_steps=max(1, args.steps), budget_s=60.0, warmup=min(args.warmup, 1))
+    v, s, steps, cores, sample, N = cpu_run(w, args.cpu_size, max_steps=max(1, args.steps), budget_s=60.0, warmup=args.warmup)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (seeded rng 1234)", "config": {"workload": w["label"], "sample_grid": list(N)},
         "cpu_baseline": {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -511,6 +620,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true")
     ap.add_argument("--cpu-size", type=int, default=48, help="edge of the bounded CPU sample")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write banners to file descriptor 1 behind Python's back ("NCCL version …" at

@@ -8,6 +8,8 @@
 #   reference             python bench.py --impl reference                         -> <tag>_bench_reference.json
 #   list:<wl>             ncu launch list (gpu__time_duration) of one step         -> <tag>_launches_<wl>.csv
 #   ncu:<wl>:<regex>:<skip>:<count>   ncu --set full --import-source on            -> <tag>_ncu_<wl>_<n>.ncu-rep
+#   disttests             NCCL parity tests on the box's GPUs (gpurun --gpus N)
+#   scale:<N>[:steps]     torchrun bench.py --gpus N                                -> <tag>_bench_n<N>.json
 #   memcheck | racecheck  compute-sanitizer on smoke()                             -> <tag>_<tool>.log
 #   py:<script>           python <script> (free-form experiments under scripts/)
 set -u
@@ -21,21 +23,21 @@ for task in "$@"; do
     tests)
       timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/${TAG}_pytest_gpu.log ;;
     bench)
-      timeout 600 python bench.py --workload $a --steps ${b:-5} --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_bench_$a.json 2> gpurun_out/${TAG}_bench_$a.err
+      timeout 600 python bench.py --workload $a --steps ${b:-5} --warmup 3 --no-e2e --no-cpu-baseline --no-parity-check --no-other-workloads > gpurun_out/${TAG}_bench_$a.json 2> gpurun_out/${TAG}_bench_$a.err
       echo "bench $a rc=$?"; cat gpurun_out/${TAG}_bench_$a.json; tail -3 gpurun_out/${TAG}_bench_$a.err ;;
     default)
       timeout 900 python bench.py > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err; echo "default rc=$?"; cat gpurun_out/${TAG}_bench_default.json; tail -3 gpurun_out/${TAG}_bench_default.err ;;
     reference)
       timeout 900 python bench.py --impl reference > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; echo "reference rc=$?"; cat gpurun_out/${TAG}_bench_reference.json ;;
     list)
-      timeout 300 python bench.py --workload $a --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_plain_$a.log 2>&1 &&
+      timeout 300 python bench.py --workload $a --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-parity-check --no-other-workloads > gpurun_out/${TAG}_plain_$a.log 2>&1 &&
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_$a.csv \
-          python bench.py --workload $a --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_list_$a.log 2>&1; echo "list $a rc=$?" ;;
+          python bench.py --workload $a --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-parity-check --no-other-workloads > gpurun_out/${TAG}_ncu_list_$a.log 2>&1; echo "list $a rc=$?" ;;
     ncu)
       n=$((n+1))
-      timeout 300 python bench.py --workload $a --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_plain_$a.log 2>&1 &&
+      timeout 300 python bench.py --workload $a --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-parity-check --no-other-workloads > gpurun_out/${TAG}_plain_$a.log 2>&1 &&
       timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$b" -s ${c:-0} -c ${d:-3} -f \
-          -o gpurun_out/${TAG}_ncu_${a}_$n python bench.py --workload $a --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_${a}_$n.log 2>&1
+          -o gpurun_out/${TAG}_ncu_${a}_$n python bench.py --workload $a --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-parity-check --no-other-workloads > gpurun_out/${TAG}_ncu_${a}_$n.log 2>&1
       echo "ncu $a /$b/ rc=$?"; tail -3 gpurun_out/${TAG}_ncu_${a}_$n.log
       # the .ncu-rep with imported source is ~10 MB per launch and gpurun_out/ is capped at 64 MiB: export the pages here, drop the report
       rep=gpurun_out/${TAG}_ncu_${a}_$n.ncu-rep
@@ -46,6 +48,11 @@ for task in "$@"; do
         done
         [ "${KEEP_REP:-0}" = 1 ] || rm -f $rep
       fi ;;
+    disttests)       # NCCL parity (tests/test_distributed.py -m gpu): needs gpurun --gpus N
+      timeout 1500 python -m pytest tests/test_distributed.py -m gpu -q -rs > gpurun_out/${TAG}_pytest_dist.log 2>&1; echo "disttests rc=$?"; tail -8 gpurun_out/${TAG}_pytest_dist.log ;;
+    scale)           # bench.py under torchrun on $a GPUs, as the driver launches it
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $a --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $a --steps ${b:-5} --warmup 3 \
+          > gpurun_out/${TAG}_bench_n$a.json 2> gpurun_out/${TAG}_bench_n$a.err; echo "scale $a rc=$?"; cat gpurun_out/${TAG}_bench_n$a.json; tail -3 gpurun_out/${TAG}_bench_n$a.err ;;
     memcheck|racecheck)
       timeout 1200 compute-sanitizer --tool $kind --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_$kind.log 2>&1; echo "$kind rc=$?"; tail -6 gpurun_out/${TAG}_$kind.log ;;
     py)

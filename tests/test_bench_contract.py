@@ -30,3 +30,15 @@ def test_workload_byte_model_matches_baseline_table():
     assert bench.reals_per_cell_step(bench.WORKLOADS["c3"]) == 119
     assert bench.reals_per_cell_step(bench.WORKLOADS["c4"]) == 152
     assert bench.reals_per_cell_step(bench.WORKLOADS["c1"]) == 66
+
+
+def test_parity_check_of_the_bench_line_on_the_host_simulation():
+    """bench.py's `parity_check` (the correctness figure next to every throughput number) run on CPU: the host simulation of the kernel
+    sources stands in for the CUDA library, one rank."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from test_host_api import _hostsim
+    for name in ("c3", "c2"):
+        r = bench.parity_check(bench.WORKLOADS[name], 0, 0, 1, steps=1, library=_hostsim())
+        assert r["ok"] and r["worst"] <= 1e-11 and r["grid"] == [64, 16, 64], r
+    assert bench.parity_check(bench.WORKLOADS["c4"], 0, 0, 1) is None        # outside the C twin's scope: no figure rather than a wrong one

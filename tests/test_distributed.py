@@ -82,10 +82,17 @@ def _gpu_count():
     (2, dict(N=(64, 48, 32), topo="PPP", scheme="weno", steps=2)),
     (2, dict(N=(40, 24, 16), topo="PPP", scheme="centered", f=1e-2, steps=3)),
     (2, dict(N=(48, 32, 16), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, steps=2)),
+    # R >= 3: the two neighbours are different peers (R = 2 is the degenerate case), every rank sends R - 1 transposed-FFT chunks
+    (4, dict(N=(64, 48, 32), topo="PPP", scheme="weno", steps=2)),
+    (4, dict(N=(48, 32, 16), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, steps=2)),
+    (4, dict(N=(40, 24, 16), topo="PPP", scheme="centered", f=1e-2, steps=3, ts="QuasiAdamsBashforth2")),
+    (8, dict(N=(64, 48, 32), topo="PPP", scheme="weno", steps=2)),
+    (8, dict(N=(48, 32, 16), topo="PPB", scheme="weno", closure="lilly", f=("beta", 0.3, 2.0), bcs=True, steps=2)),
+    (8, dict(N=(40, 24, 16), topo="PPP", scheme="weno", steps=2, f32=True)),
 ])
 def test_nccl_slab_decomposition_matches_oracle(R, case):
     """The CUDA library on R GPUs of one box (NCCL halo exchange + transposed distributed FFT) against the oracle."""
     if _gpu_count() < R:
         pytest.skip(f"needs {R} GPUs")
     res = run_ranks(R, dict(case), backend="nccl")
-    assert res["ranks"] == R and res["worst"] <= 1e-11, res
+    assert res["ranks"] == R and res["worst"] <= (1e-4 if case.get("f32") else 1e-11), res
