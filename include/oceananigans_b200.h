@@ -214,6 +214,13 @@ int  oc_restore_previous_tendency(oc_model* m, int field, const void* parent_hos
  * that transfer and do not disturb the snapshot.  oc_output_wait blocks until the host buffer is complete; oc_output_test polls.
  * A ticket is valid until waited for; at most 64 may be in flight. */
 int  oc_output_begin(oc_model* m, int field, const int lo[3], const int n[3], void* host, size_t nbytes, int* ticket);
+/* The mirror image for input: `set!(field, host_array)` (src/Fields/set!.jl:101-121) without stalling the step loop.  The interior of a
+ * prognostic field is streamed from `host` (page-locked) into a device staging buffer on a separate copy stream, and copied into the
+ * field IN STREAM ORDER with the time stepping once it has arrived — time steps issued before the call are not disturbed, entry points
+ * called afterwards see the new values.  The ticket (same space, same oc_output_wait / oc_output_test) completes when the field has been
+ * written: `host` and the staging buffer may be reused then.  Like oc_upload_interior it does not fill halos or project: call
+ * oc_set_finalize afterwards.  With two tickets per field in flight the transfer of step n+1's inputs overlaps step n. */
+int  oc_upload_begin(oc_model* m, int field, const void* host, size_t nbytes, int* ticket);
 int  oc_output_wait(oc_model* m, int ticket);
 int  oc_output_test(oc_model* m, int ticket, int* done);
 

@@ -101,6 +101,7 @@ SYMBOLS = {
     "oc_set_clock": (C.c_int, [_M, C.POINTER(oc_clock)]),
     "oc_restore_previous_tendency": (C.c_int, [_M, C.c_int, C.c_void_p, C.c_size_t]),
     "oc_output_begin": (C.c_int, [_M, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
+    "oc_upload_begin": (C.c_int, [_M, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "oc_output_wait": (C.c_int, [_M, C.c_int]),
     "oc_output_test": (C.c_int, [_M, C.c_int, C.POINTER(C.c_int)]),
     "oc_compute_diagnostics": (C.c_int, [_M, C.POINTER(oc_diagnostics)]),

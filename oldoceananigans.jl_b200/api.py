@@ -453,6 +453,48 @@ class Clock:
     last_stage_Δt = property(lambda s: s._get().last_stage_dt)
 
 
+class UploadTicket:
+    """One asynchronous `set!(field, array)` in flight (oc_upload_begin): the values travel from a page-locked copy of `array` to the device
+    on a separate stream and land in the field in stream order with the time stepping.  `.wait()` returns once the field holds them."""
+
+    def __init__(self, model, fid, array):
+        lib = model._lib
+        self._lib, self._h = lib, model._h
+        FT = model.grid.FT
+        a = np.asfortranarray(np.asarray(array, dtype=FT))
+        self.nbytes = a.nbytes
+        self._ptr = C.c_void_p()
+        lib.check(lib.oc_host_alloc(C.byref(self._ptr), max(self.nbytes, 1)))
+        C.memmove(self._ptr, a.ctypes.data, self.nbytes)
+        t = C.c_int()
+        try:
+            lib.check(lib.oc_upload_begin(self._h, fid, self._ptr, self.nbytes, C.byref(t)))
+        except Exception:
+            lib.oc_host_free(self._ptr)
+            self._ptr = None
+            raise
+        self._ticket = t.value
+
+    def done(self):
+        if self._ptr is None:
+            return True
+        d = C.c_int()
+        self._lib.check(self._lib.oc_output_test(self._h, self._ticket, C.byref(d)))
+        return bool(d.value)
+
+    def wait(self):
+        if self._ptr is not None:
+            self._lib.check(self._lib.oc_output_wait(self._h, self._ticket))
+            self._lib.oc_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.wait()
+        except Exception:
+            pass
+
+
 class OutputTicket:
     """One asynchronous output in flight (oc_output_begin / oc_output_wait / oc_output_test)."""
 
@@ -542,6 +584,17 @@ class Field:
             else:
                 lo.append(int(idx[d])); n.append(1)
         return OutputTicket(self.model, self.id, lo, n)
+
+    def begin_set(self, array):
+        """Asynchronous `set!(field, array)` (oc_upload_begin): returns an UploadTicket at once; the interior values are in place — in
+        stream order — for every entry point called afterwards.  Like `set_parent` / oc_upload_interior it neither fills halos nor
+        projects: follow it with `oc_set_finalize` (set_(model) does both synchronously)."""
+        info = self.info()
+        shape = tuple(info.interior_size)
+        a = np.asarray(array)
+        if a.shape != shape:
+            a = a.reshape(shape)
+        return UploadTicket(self.model, self.id, a)
 
     def maximum_abs(self):
         """maximum(abs, interior(field)), reduced on the device (oc_field_maximum_abs): an 8-byte copy instead of the field"""

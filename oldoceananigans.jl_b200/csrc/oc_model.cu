@@ -378,6 +378,7 @@ Model<FT>::~Model() {
     for (auto& r : timer_recs_) { cudaEventDestroy((cudaEvent_t)r.e0); cudaEventDestroy((cudaEvent_t)r.e1); }
     if (sw0_) { cudaEventDestroy((cudaEvent_t)sw0_); cudaEventDestroy((cudaEvent_t)sw1_); }
     if (ev_fork_) { cudaEventDestroy((cudaEvent_t)ev_fork_); cudaEventDestroy((cudaEvent_t)ev_join_); }
+    if (ev_phy_) cudaEventDestroy((cudaEvent_t)ev_phy_);
     for (void* e : ev_a2a_) cudaEventDestroy((cudaEvent_t)e);
     for (void* e : ev_mid_) cudaEventDestroy((cudaEvent_t)e);
     for (auto& s : out_slots_) {
@@ -386,6 +387,7 @@ Model<FT>::~Model() {
         if (s.stage) cudaFree(s.stage);
     }
     if (out_stream_) cudaStreamDestroy(out_stream_);
+    if (in_stream_) cudaStreamDestroy(in_stream_);
     if (stream3_) cudaStreamDestroy(stream3_);
     if (stream2_) cudaStreamDestroy(stream2_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -907,6 +909,13 @@ void Model<FT>::aux() {
         for (auto& f : kappa_e_) list.push_back(&f);
         halo(list, true);
     }
+    hydrostatic_pressure();
+    aux_valid_ = true;
+}
+
+// update_hydrostatic_pressure!  (update_hydrostatic_pressure.jl:12-49): one column scan, launched on launch_stream_
+template <class FT>
+void Model<FT>::hydrostatic_pressure() {
     if (has_pHY_ && !g_.flat[2]) {
         HydrostaticPressureKernel<FT> k;
         k.g = g_;
@@ -924,7 +933,6 @@ void Model<FT>::aux() {
         grid.y = k.nj;
         go(k, grid, 0, OC_TIMER_AUX);
     }
-    aux_valid_ = true;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1102,14 +1110,45 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
 template <class FT>
 void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state, bool defer_tracer_join) {
     join_tracers();
+    // The hydrostatic-pressure scan (HBM-bound, needed by the u and v kernels only) runs on the second stream beside the w and tracer
+    // tendency kernels (bound by the FP64 pipe / instruction issue, two ~100 KB CTAs per SM: its small register-only CTAs fit into what
+    // they leave free); u and v are launched last and wait for it.  OC_PHY_ASYNC=0 switches back (measurement).
+    static const char* phy_env = getenv("OC_PHY_ASYNC");
+    bool phy_async = false;
+#ifndef OC_HOSTSIM
+    phy_async = !aux_valid_ && has_pHY_ && !g_.flat[2] && !has_eddy_ && march_ok_ && F_ > 3 && (phy_env ? atoi(phy_env) != 0 : true);
+    if (phy_async) {
+        if (!ev_phy_) { cudaEvent_t e; cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate"); ev_phy_ = e; }
+        cuda_check(cudaEventRecord((cudaEvent_t)ev_fork_, stream_), "cudaEventRecord");
+        cuda_check(cudaStreamWaitEvent(stream2_, (cudaEvent_t)ev_fork_, 0), "cudaStreamWaitEvent");
+        launch_stream_ = stream2_;
+        hydrostatic_pressure();
+        launch_stream_ = stream_;
+        cuda_check(cudaEventRecord((cudaEvent_t)ev_phy_, stream2_), "cudaEventRecord");
+        aux_valid_ = true;
+    }
+#else
+    (void)phy_env;
+#endif
     if (!aux_valid_) aux();
     // Measured (profiles/): on one GPU the co-residency costs the tracer kernels more than the overlap wins (69.4 vs 67.5 ms);
     // across GPUs it hides part of the NCCL transposes (77.1 vs 79.4 ms at 2 GPUs) — so it is on for distributed models only.
     static const char* ov_env = getenv("OC_OVERLAP");
     const bool want = ov_env ? atoi(ov_env) != 0 : dist_;
     const bool overlap = defer_tracer_join && F_ > 3 && march_ok_ && want;
-    for (int f = 0; f < F_; ++f) {
+    bool phy_pending = phy_async;
+    for (int n = 0; n < F_; ++n) {
+        // launch order when the pHY′ scan is in flight: the kernels that do not read it first — w and the tracers, then u and v; with the
+        // distributed overlap (tracers beside the pressure solve, after the velocities) only w: w, u, v, tracers
+        const int f = !phy_async ? n : (overlap ? (n == 0 ? 2 : (n < 3 ? n - 1 : n)) : (n < F_ - 2 ? n + 2 : n - (F_ - 2)));
         if (f == 3 && overlap) fork_tracers();
+        if (f < 2 && phy_pending) {
+#ifndef OC_HOSTSIM
+            if (launch_stream_ != stream_) launch_stream_ = stream_;          // (u, v always run on the main stream)
+            cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_phy_, 0), "cudaStreamWaitEvent");
+#endif
+            phy_pending = false;
+        }
         TendencyArgs<FT> a;
         memset(&a, 0, sizeof(a));
         a.g = g_;
@@ -1509,6 +1548,77 @@ void Model<FT>::diagnostics(oc_diagnostics* out) {
 // asynchronous output: snapshot a box of a field in stream order (D2D into a staging buffer), then copy it to the host on a separate
 // stream while the time stepping continues
 // ---------------------------------------------------------------------------------------------------------
+// a free ticket slot with its events and a device staging buffer of at least nbytes
+template <class FT>
+int Model<FT>::acquire_slot(size_t nbytes) {
+    int t = -1;
+    // prefer a free slot whose staging buffer is already large enough (steady-state loops then never reallocate)
+    for (size_t i = 0; i < out_slots_.size(); ++i) if (!out_slots_[i].busy && out_slots_[i].cap >= nbytes) { t = (int)i; break; }
+    if (t < 0) for (size_t i = 0; i < out_slots_.size(); ++i) if (!out_slots_[i].busy) { t = (int)i; break; }
+    if (t < 0) {
+        if (out_slots_.size() >= 64) throw Error(OC_ERR_STATE, "more than 64 transfers in flight: call oc_output_wait");
+        out_slots_.emplace_back();
+        t = (int)out_slots_.size() - 1;
+    }
+    OutputSlot& s = out_slots_[t];
+#ifndef OC_HOSTSIM
+    if (!s.ev_snap) {
+        cudaEvent_t a, b;
+        cuda_check(cudaEventCreateWithFlags(&a, cudaEventDisableTiming), "cudaEventCreate");
+        cuda_check(cudaEventCreateWithFlags(&b, cudaEventDisableTiming), "cudaEventCreate");
+        s.ev_snap = a; s.ev_done = b;
+    }
+    if (s.cap < nbytes) {
+        if (s.stage) { cuda_check(cudaFree(s.stage), "cudaFree"); device_bytes -= (int64_t)s.cap; }
+        s.stage = nullptr; s.cap = 0;
+        void* p = nullptr;
+        cuda_check(cudaMalloc(&p, nbytes), "cudaMalloc(transfer staging)");
+        s.stage = (FT*)p; s.cap = nbytes;
+        device_bytes += (int64_t)nbytes;
+    }
+#else
+    (void)nbytes;
+#endif
+    return t;
+}
+
+// set!(field, host_array) in stream order without a host-side wait: H2D into staging on in_stream_, D2D into the field on stream_
+template <class FT>
+int Model<FT>::upload_begin(int field, const void* host, size_t nbytes) {
+    if (field < 0 || field >= F_) throw Error(OC_ERR_INVALID, "oc_upload_begin: not a prognostic field index");
+    join_tracers();
+    oc_field_info info;
+    field_info(field, &info);
+    FieldRec& f = lookup(field);
+    size_t cnt = 1;
+    int n[3];
+    for (int d = 0; d < 3; ++d) { n[d] = info.interior_size[d]; cnt *= (size_t)n[d]; }
+    if (cnt * sizeof(FT) != nbytes) throw Error(OC_ERR_INVALID, "host buffer size mismatch: expected " + std::to_string(cnt * sizeof(FT)) + " bytes");
+    const int t = acquire_slot(nbytes);
+    OutputSlot& s = out_slots_[t];
+#ifndef OC_HOSTSIM
+    if (!in_stream_) cuda_check(cudaStreamCreateWithFlags(&in_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    cuda_check(cudaMemcpyAsync(s.stage, host, nbytes, cudaMemcpyHostToDevice, in_stream_), "cudaMemcpyAsync(upload)");
+    cuda_check(cudaEventRecord((cudaEvent_t)s.ev_snap, in_stream_), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)s.ev_snap, 0), "cudaStreamWaitEvent");
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    p.srcPtr = make_cudaPitchedPtr(s.stage, (size_t)n[0] * sizeof(FT), (size_t)n[0] * sizeof(FT), (size_t)n[1]);
+    p.dstPtr = make_cudaPitchedPtr(f.p, (size_t)g_.sy * sizeof(FT), (size_t)g_.sy * sizeof(FT), (size_t)(g_.sz / g_.sy));
+    p.extent = make_cudaExtent((size_t)n[0] * sizeof(FT), (size_t)n[1], (size_t)n[2]);
+    p.kind = cudaMemcpyDeviceToDevice;
+    cuda_check(cudaMemcpy3DAsync(&p, stream_), "cudaMemcpy3DAsync(upload)");
+    cuda_check(cudaEventRecord((cudaEvent_t)s.ev_done, stream_), "cudaEventRecord");
+#else
+    dev_copy_box(f.p, sizeof(FT), g_.sy, g_.sz, const_cast<void*>(host), n, true, stream_);
+#endif
+    if (g_.flat[0] || g_.flat[1] || g_.flat[2]) { std::vector<FieldRec*> one{&f}; halo(one, false); }     // like transfer(): Flat dimensions are stored as periodic N = 1
+    tend_valid_ = false;
+    aux_valid_ = false;
+    s.busy = true;
+    return t;
+}
+
 template <class FT>
 int Model<FT>::output_begin(int field, const int lo[3], const int n[3], void* host, size_t nbytes) {
     join_tracers();
@@ -1522,31 +1632,11 @@ int Model<FT>::output_begin(int field, const int lo[3], const int n[3], void* ho
         cnt *= (size_t)n[d];
     }
     if (cnt * sizeof(FT) != nbytes) throw Error(OC_ERR_INVALID, "host buffer size mismatch: expected " + std::to_string(cnt * sizeof(FT)) + " bytes");
-    int t = -1;
-    for (size_t i = 0; i < out_slots_.size(); ++i) if (!out_slots_[i].busy) { t = (int)i; break; }
-    if (t < 0) {
-        if (out_slots_.size() >= 64) throw Error(OC_ERR_STATE, "more than 64 outputs in flight: call oc_output_wait");
-        out_slots_.emplace_back();
-        t = (int)out_slots_.size() - 1;
-    }
+    const int t = acquire_slot(nbytes);
     OutputSlot& s = out_slots_[t];
     FT* origin = f.p + lo[0] + (long long)lo[1] * g_.sy + (long long)lo[2] * g_.sz;
 #ifndef OC_HOSTSIM
     if (!out_stream_) cuda_check(cudaStreamCreateWithFlags(&out_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
-    if (!s.ev_snap) {
-        cudaEvent_t a, b;
-        cuda_check(cudaEventCreateWithFlags(&a, cudaEventDisableTiming), "cudaEventCreate");
-        cuda_check(cudaEventCreateWithFlags(&b, cudaEventDisableTiming), "cudaEventCreate");
-        s.ev_snap = a; s.ev_done = b;
-    }
-    if (s.cap < nbytes) {
-        if (s.stage) { cuda_check(cudaFree(s.stage), "cudaFree"); device_bytes -= (int64_t)s.cap; }
-        s.stage = nullptr; s.cap = 0;
-        void* p = nullptr;
-        cuda_check(cudaMalloc(&p, nbytes), "cudaMalloc(output staging)");
-        s.stage = (FT*)p; s.cap = nbytes;
-        device_bytes += (int64_t)nbytes;
-    }
     cudaMemcpy3DParms p;
     memset(&p, 0, sizeof(p));
     p.srcPtr = make_cudaPitchedPtr(origin, (size_t)g_.sy * sizeof(FT), (size_t)g_.sy * sizeof(FT), (size_t)(g_.sz / g_.sy));
@@ -1852,6 +1942,11 @@ int oc_output_begin(oc_model* m, int field, const int lo[3], const int n[3], voi
     OC_REQUIRE(m);
     if (!lo || !n || !host || !ticket) { g_last_error = "null argument"; return OC_ERR_INVALID; }
     return guarded([&] { *ticket = m->impl->output_begin(field, lo, n, host, nbytes); });
+}
+int oc_upload_begin(oc_model* m, int field, const void* host, size_t nbytes, int* ticket) {
+    OC_REQUIRE(m);
+    if (!host || !ticket) { g_last_error = "null argument"; return OC_ERR_INVALID; }
+    return guarded([&] { *ticket = m->impl->upload_begin(field, host, nbytes); }, oc_model_);
 }
 int oc_output_wait(oc_model* m, int ticket) { OC_REQUIRE(m); return guarded([&] { m->impl->output_wait(ticket); }, oc_model_); }
 int oc_output_test(oc_model* m, int ticket, int* done) {

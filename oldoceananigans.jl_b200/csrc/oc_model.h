@@ -100,6 +100,7 @@ struct ModelBase {
     virtual void diagnostics(oc_diagnostics* out) = 0;
     virtual double field_maximum_abs(int field) = 0;
     virtual int output_begin(int field, const int lo[3], const int n[3], void* host, size_t nbytes) = 0;
+    virtual int upload_begin(int field, const void* host, size_t nbytes) = 0;
     virtual void output_wait(int ticket) = 0;
     virtual bool output_test(int ticket) = 0;
     virtual void set_bc_array(int field, int side, const void* host, size_t nbytes) = 0;
@@ -144,11 +145,14 @@ public:
     void diagnostics(oc_diagnostics* out) override;
     double field_maximum_abs(int field) override;
     int output_begin(int field, const int lo[3], const int n[3], void* host, size_t nbytes) override;
+    int upload_begin(int field, const void* host, size_t nbytes) override;
     void output_wait(int ticket) override;
     bool output_test(int ticket) override;
     struct OutputSlot { FT* stage = nullptr; size_t cap = 0; void* ev_snap = nullptr; void* ev_done = nullptr; bool busy = false; };
     std::vector<OutputSlot> out_slots_;
     Stream out_stream_ = 0;       // device-to-host copies of output snapshots, concurrent with the time stepping on stream_
+    Stream in_stream_ = 0;        // host-to-device copies of oc_upload_begin
+    int acquire_slot(size_t nbytes);
     void set_bc_array(int field, int side, const void* host, size_t nbytes) override;
     void apply_flux_arrays(int f, FT* Gn, FT* Unew, FT coef);
     FT* bc_array_[OC_MAX_FIELDS][6] = {};      // device arrays of array-valued Flux BCs (nullptr: scalar)
@@ -198,6 +202,7 @@ private:
     Stream launch_stream_ = 0;    // the stream kernel launches and timer events currently go to
     void* ev_fork_ = nullptr;
     void* ev_join_ = nullptr;
+    void* ev_phy_ = nullptr;      // the pHY′ scan on stream2_ has finished (tendencies())
     bool tracers_in_flight_ = false;
     void fork_tracers();
     void join_tracers();
@@ -217,6 +222,7 @@ private:
     void resolve_bcs(FieldRec& f, const oc_bc* user);
     void halo(const std::vector<FieldRec*>& fields, bool fill_open);
     void aux();
+    void hydrostatic_pressure();
     void compute_tendencies_if_stale();
     void rotate_pending_tendencies();
     void tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state, bool defer_tracer_join = false);

@@ -248,3 +248,46 @@ def asynchronous_output(library):
 
 def test_asynchronous_output_hostsim():
     asynchronous_output(_hostsim())
+
+
+def asynchronous_upload(library):
+    """oc_upload_begin: set!(field, array) in stream order without a host-side wait.  A model fed through it must step exactly like one
+    fed through the synchronous path; uploads issued while steps are in flight land after them; error paths."""
+    kw = {} if library is None else {"library": library}
+    grid = ob.RectilinearGrid(np.float64, size=(12, 10, 8), extent=(1, 1, 1))
+    mk = lambda: ob.NonhydrostaticModel(grid=grid, advection=ob.WENO(), tracers=("T", "S"), buoyancy=ob.SeawaterBuoyancy(),
+                                        closure=ob.ScalarDiffusivity(nu=1e-3, kappa=1e-3), **kw)
+    a, b = mk(), mk()
+    rng = np.random.default_rng(5)
+    ics = []
+    for _ in range(3):
+        ic = {n: rng.uniform(-1, 1, a.fields[n].interior().shape) for n in ("u", "v", "w")}
+        ic["T"] = 20 + 0.01 * rng.standard_normal((12, 10, 8)); ic["S"] = 35 + 0.01 * rng.standard_normal((12, 10, 8))
+        ics.append(ic)
+    pending = []
+    for ic in ics:                       # every "step": new inputs from the host, set! without projection, one time step
+        for n, v in ic.items():
+            a.fields[n].set(v)
+        a._lib.check(a._lib.oc_set_finalize(a._h, 0))
+        ob.time_step_(a, 1e-3)
+        tickets = [b.fields[n].begin_set(v) for n, v in ic.items()]          # not waited for before the step is issued
+        b._lib.check(b._lib.oc_set_finalize(b._h, 0))
+        ob.time_step_(b, 1e-3)
+        pending.append(tickets)
+    for tickets in pending:
+        for t in tickets:
+            t.wait()
+            assert t.done()
+    for n in a.fields:
+        assert np.array_equal(a.fields[n].parent(), b.fields[n].parent()), n
+    assert np.array_equal(a.pressures.pNHS.interior(), b.pressures.pNHS.interior())
+    from oceananigans_b200 import _lib as L
+    import ctypes as C
+    t = C.c_int()
+    buf = np.zeros(7)
+    assert b._lib.oc_upload_begin(b._h, 0, buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(t)) != 0          # wrong size
+    assert b._lib.oc_upload_begin(b._h, L.OC_FIELD_PNHS, buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(t)) != 0   # not prognostic
+
+
+def test_asynchronous_upload_hostsim():
+    asynchronous_upload(_hostsim())
