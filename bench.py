@@ -476,7 +476,7 @@ def run_ours(args):
             return sec
 
         pipelined(2)                                        # allocates the staging buffers (not part of any step)
-        pipe_steps = max(e2e_steps, 6)                      # the pipeline's fill and drain are inside the timed region: amortise them
+        pipe_steps = max(e2e_steps, 20)                     # the pipeline's fill and drain are inside the timed region: amortise them
         e2e_s = timed(pipelined, pipe_steps)
         serial_s = timed(serial, e2e_steps)
         e2e = {"value": world * cells / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

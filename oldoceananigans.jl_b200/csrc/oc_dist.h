@@ -36,6 +36,13 @@ typedef int (*HostExchangeFn)(void*, int, const int*, const int*, const int*, vo
 struct Transport {
     virtual ~Transport() {}
     virtual std::string exchange(const std::vector<Msg>& msgs, Stream stream) = 0;
+    // Peer memory (NVLink / NVSwitch): map every rank's allocation `local` (a cudaMalloc base, the same call on every rank, in the same
+    // order) into this process; peers[r] is rank r's buffer (peers[rank] = local).  Returns "" on success; transports without peer
+    // memory return a reason and the caller keeps the send / receive path.
+    virtual std::string map_peers(void* local, std::vector<void*>& peers, Stream stream) { (void)local; (void)peers; (void)stream; return "no peer memory in this transport"; }
+    // every rank's work enqueued before the barrier is complete (and its peer writes visible) before any rank's work enqueued after it starts
+    virtual std::string barrier(Stream stream) { (void)stream; return "no barrier in this transport"; }
+    virtual int agree(bool failed, Stream stream) { (void)stream; return failed ? 1 : 0; }
 };
 
 struct HostTransport : Transport {
@@ -65,6 +72,7 @@ struct NcclApi {
     int (*CommDestroy)(comm_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -79,6 +87,7 @@ struct NcclApi {
         OC_NCCL_SYM(CommDestroy, "ncclCommDestroy")
         OC_NCCL_SYM(Send, "ncclSend")
         OC_NCCL_SYM(Recv, "ncclRecv")
+        OC_NCCL_SYM(AllReduce, "ncclAllReduce")
         OC_NCCL_SYM(GroupStart, "ncclGroupStart")
         OC_NCCL_SYM(GroupEnd, "ncclGroupEnd")
         OC_NCCL_SYM(GetErrorString, "ncclGetErrorString")
@@ -90,16 +99,77 @@ inline NcclApi& nccl_api() { static NcclApi api; return api; }
 
 struct NcclTransport : Transport {
     NcclApi::comm_t comm = nullptr;
+    int rank_ = 0, nranks_ = 1;
+    int* flag_ = nullptr;                  // device word of the barrier's all-reduce
+    std::vector<void*> mapped_;            // peer allocations opened with cudaIpcOpenMemHandle
     std::string init(int rank, int nranks, const void* id128) {
         std::string e = nccl_api().load();
         if (!e.empty()) return e;
         NcclApi::UniqueId id;
         memcpy(id.internal, id128, 128);
+        rank_ = rank; nranks_ = nranks;
         int rc = nccl_api().CommInitRank(&comm, nranks, id, rank);
         if (rc != 0) return std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(rc);
+        if (cudaMalloc((void**)&flag_, 2 * sizeof(int)) != cudaSuccess || cudaMemset(flag_, 0, 2 * sizeof(int)) != cudaSuccess) return "cudaMalloc(barrier word) failed";
         return "";
     }
-    ~NcclTransport() override { if (comm) nccl_api().CommDestroy(comm); }
+    ~NcclTransport() override {
+        for (void* p : mapped_) cudaIpcCloseMemHandle(p);
+        if (flag_) cudaFree(flag_);
+        if (comm) nccl_api().CommDestroy(comm);
+    }
+    // CUDA IPC: one process per GPU, so a peer's cudaMalloc'ed buffer is reached through its IPC handle; the 64-byte handles travel
+    // over the communicator (grouped send / receive through a small device buffer)
+    // (Collective: a rank whose own steps fail still takes part in the exchange, so that nobody hangs; agree() then settles the outcome.)
+    std::string map_peers(void* local, std::vector<void*>& peers, Stream stream) override {
+        peers.assign(nranks_, nullptr);
+        std::string err;
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof(mine));
+        if (cudaIpcGetMemHandle(&mine, local) != cudaSuccess) { cudaGetLastError(); err = "cudaIpcGetMemHandle failed"; }
+        const size_t hb = sizeof(cudaIpcMemHandle_t);
+        char* dbuf = nullptr;
+        if (cudaMalloc((void**)&dbuf, hb * nranks_) != cudaSuccess) return "cudaMalloc(IPC handles) failed";
+        std::vector<cudaIpcMemHandle_t> all(nranks_);
+        if (cudaMemcpyAsync(dbuf + hb * rank_, &mine, hb, cudaMemcpyHostToDevice, stream) != cudaSuccess && err.empty()) err = "cudaMemcpy(IPC handle) failed";
+        {
+            std::vector<Msg> msgs;
+            for (int d = 1; d < nranks_; ++d) {
+                const int to = (rank_ + d) % nranks_, from = (rank_ + nranks_ - d) % nranks_;
+                msgs.push_back(Msg{to, from, 900 + d, dbuf + hb * rank_, hb, dbuf + hb * from, hb});
+            }
+            std::string e = exchange(msgs, stream);
+            if (err.empty()) err = e;
+        }
+        if ((cudaMemcpyAsync(all.data(), dbuf, hb * nranks_, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+             cudaStreamSynchronize(stream) != cudaSuccess) && err.empty()) err = "cudaMemcpy(IPC handles) failed";
+        cudaFree(dbuf);
+        if (!err.empty()) return err;
+        for (int r = 0; r < nranks_; ++r) {
+            if (r == rank_) { peers[r] = local; continue; }
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                return "cudaIpcOpenMemHandle(rank " + std::to_string(r) + ") failed";
+            }
+            mapped_.push_back(p);
+            peers[r] = p;
+        }
+        return "";
+    }
+    // number of ranks that report a failure (collective; synchronises the stream)
+    int agree(bool failed, Stream stream) override {
+        int v[2] = {failed ? 1 : 0, 0};
+        if (cudaMemcpyAsync(flag_, v, sizeof(int), cudaMemcpyHostToDevice, stream) != cudaSuccess) return nranks_;
+        if (nccl_api().AllReduce(flag_, flag_ + 1, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, comm, stream) != 0) return nranks_;
+        if (cudaMemcpyAsync(&v[1], flag_ + 1, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) return nranks_;
+        cudaMemsetAsync(flag_, 0, 2 * sizeof(int), stream);
+        return v[1];
+    }
+    std::string barrier(Stream stream) override {
+        int rc = nccl_api().AllReduce(flag_, flag_ + 1, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, comm, stream);
+        return rc == 0 ? "" : std::string("NCCL all-reduce (barrier): ") + nccl_api().GetErrorString(rc);
+    }
     std::string exchange(const std::vector<Msg>& msgs, Stream stream) override {
         NcclApi& n = nccl_api();
         int rc = n.GroupStart();
@@ -185,6 +255,66 @@ struct TransposeKernel {
                 if (x < nxc && y < ny) {
                     Cplx<FT>* p = T + (((long long)zl * nxc + x) * ny + y);
                     if (to_T) *p = tile[tx * 33 + r]; else tile[tx * 33 + r] = *p;
+                }
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// The transposes of the distributed solve as ONE kernel each over peer memory (NVLink / NVSwitch), replacing pack -> all-to-all ->
+// unpack (distributed_transpose.jl:25-191: pack_buffer!, Alltoallv, unpack_buffer!): every CTA reads a 32×32 tile of the local
+// buffer through shared memory and stores it — transposed — straight into the buffer of the rank that owns it.  The transfer IS the
+// transpose: no staging buffer, no separate transpose pass, and the stores of all CTAs keep all NVLink lanes busy.
+//   forward : local spectral [z][yl][x] (x fastest)  ->  T of rank d = z / nzl :  [zl][x][y], y = rank·nyl + yl   (y fastest)
+//   backward: local T [zl][x][y]                      ->  spectral of rank s = y / nyl : [z = rank·nzl + zl][yl][x]  (x fastest)
+// Ordering between ranks is the caller's (a barrier before and after each launch, run_fft_solve_dist).
+// ---------------------------------------------------------------------------------------------------------
+enum { DIST_MAX_RANKS = 16 };
+template <class FT>
+struct TransposePutKernel {
+    static constexpr int PHASES = 2;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr size_t SMEM = sizeof(Cplx<FT>) * 32 * 33;
+    int nxc, nyl, nzl, R, rank;
+    int forward;
+    Cplx<FT>* spec[DIST_MAX_RANKS];     // every rank's spectral buffer (spec[rank]: the local one)
+    Cplx<FT>* T[DIST_MAX_RANKS];        // every rank's transposed buffer
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char* smem) const {
+        Cplx<FT>* tile = reinterpret_cast<Cplx<FT>*>(smem);
+        const int ny = nyl * R;
+        const int tx = tid & 31, ty = tid >> 5;        // 32 × 8
+        const int x0 = b.x * 32;
+        if (forward) {
+            const int yl0 = b.y * 32, z = b.z, d = z / nzl, zl = z - d * nzl;
+            if (PHASE == 0) {                          // local read, x contiguous
+                for (int r = ty; r < 32; r += 8) {
+                    const int x = x0 + tx, yl = yl0 + r;
+                    if (x < nxc && yl < nyl) tile[r * 33 + tx] = spec[rank][((long long)z * nyl + yl) * nxc + x];
+                }
+            } else {                                   // peer write, y contiguous
+                Cplx<FT>* dst = T[d];
+                for (int r = ty; r < 32; r += 8) {
+                    const int x = x0 + r, yl = yl0 + tx;
+                    if (x < nxc && yl < nyl) dst[((long long)zl * nxc + x) * ny + rank * nyl + yl] = tile[tx * 33 + r];
+                }
+            }
+        } else {
+            const int y0 = b.y * 32, zl = b.z;
+            if (PHASE == 0) {                          // local read, y contiguous
+                for (int r = ty; r < 32; r += 8) {
+                    const int x = x0 + r, y = y0 + tx;
+                    if (x < nxc && y < ny) tile[tx * 33 + r] = T[rank][((long long)zl * nxc + x) * ny + y];
+                }
+            } else {                                   // peer write, x contiguous
+                for (int r = ty; r < 32; r += 8) {
+                    const int x = x0 + tx, y = y0 + r;
+                    if (x < nxc && y < ny) {
+                        const int s = y / nyl, yl = y - s * nyl;
+                        spec[s][((long long)(rank * nzl + zl) * nyl + yl) * nxc + x] = tile[r * 33 + tx];
+                    }
                 }
             }
         }
@@ -307,6 +437,7 @@ public:
     }
 
 #ifndef OC_HOSTSIM
+    void set_y_stream(Stream s) { cufftSetStream(y_, s); }
     std::string zx(void* buf, bool fwd) {
         cufftResult r;
         if (sizeof(FT) == 8) r = fwd ? cufftExecD2Z(fwd_, (cufftDoubleReal*)buf, (cufftDoubleComplex*)buf) : cufftExecZ2D(inv_, (cufftDoubleComplex*)buf, (cufftDoubleReal*)buf);

@@ -718,6 +718,68 @@ template <class FT>
 void Model<FT>::dist_attach(Transport* t) {
     if (!dist_) { delete t; throw Error(OC_ERR_STATE, "the model was not created with dist_nranks > 1"); }
     transport_.reset(t);
+    // Peer memory for the transposed FFT (OC_DIST_P2P=0 keeps the all-to-all path: measurement / machines without P2P)
+    static const char* p2p_env = getenv("OC_DIST_P2P");
+    p2p_ = false;
+    if (R_ <= DIST_MAX_RANKS && (p2p_env ? atoi(p2p_env) != 0 : true)) {
+        std::string e1 = transport_->map_peers(fftbuf_, peer_spec_, stream_);
+        std::string e2 = transport_->map_peers(distT_, peer_T_, stream_);
+        if (e2.empty()) e2 = e1;
+        p2p_ = transport_->agree(!e2.empty(), stream_) == 0;          // every rank or none
+#ifndef OC_HOSTSIM
+        if (!p2p_ && getenv("OC_VERBOSE")) fprintf(stderr, "oceananigans_b200: peer-memory transposes unavailable (%s): NCCL all-to-all path\n", e2.c_str());
+        if (p2p_) dfft_.set_y_stream(stream_);
+#endif
+    }
+}
+
+// FFT(z,x) local -> transposed put into the owners' buffers -> FFT(y) -> divide -> FFT⁻¹(y) -> transposed put back -> FFT⁻¹(z,x)
+// over peer memory: the all-to-all and the transpose are one kernel (TransposePutKernel).  Three barriers order the ranks: nobody
+// writes a peer's T before that peer has left its previous y stage, nobody reads T before every put has landed, nobody reads the
+// spectral buffer before every put back has landed.
+template <class FT>
+void Model<FT>::run_fft_solve_p2p() {
+    auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
+    auto barrier = [&]() { begin_timer(OC_TIMER_COMM); std::string e = transport_->barrier(stream_); end_timer(); chk(e); };
+    begin_timer(OC_TIMER_FFT); std::string e = dfft_.zx(fftbuf_, true); end_timer(); chk(e);
+    ZTwiddleKernel<FT> zt;
+    Dim3 zg;
+    if (g_.bounded[2]) {
+        zt.plane = dfft_.nxc * g_.N[1]; zt.Nz = g_.N[2]; zt.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_); zt.twz = tw_[2];
+        zg.x = (zt.plane + 255) / 256; zg.y = g_.N[2] / 2 + 1;
+        zt.inverse = 0;
+        go(zt, zg, 0, OC_TIMER_POISSON_MID);
+    }
+    TransposePutKernel<FT> t;
+    t.nxc = dfft_.nxc; t.nyl = g_.N[1]; t.nzl = dfft_.Nzl; t.R = R_; t.rank = rank_;
+    for (int r = 0; r < R_; ++r) { t.spec[r] = reinterpret_cast<Cplx<FT>*>(peer_spec_[r]); t.T[r] = reinterpret_cast<Cplx<FT>*>(peer_T_[r]); }
+    Dim3 tg;
+    barrier();
+    t.forward = 1;
+    tg.x = (dfft_.nxc + 31) / 32; tg.y = (g_.N[1] + 31) / 32; tg.z = g_.N[2];
+    go(t, tg, TransposePutKernel<FT>::SMEM, OC_TIMER_COMM);
+    barrier();
+    const int C = dfft_.C, nz = dfft_.Nzl / C;
+    for (int c = 0; c < C; ++c) { begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, true, c); end_timer(); chk(e); }
+    PoissonDivideTKernel<FT> k;
+    k.nxc = dfft_.nxc; k.ny = dfft_.Ny; k.nzl = dfft_.Nzl; k.kz0 = rank_ * dfft_.Nzl; k.zl0 = 0;
+    k.T = reinterpret_cast<Cplx<FT>*>(distT_);
+    for (int d = 0; d < 3; ++d) k.lam[d] = lam_[d];
+    k.norm = 1.0 / ((double)g_.N[0] * dfft_.Ny * g_.N[2]);
+    Dim3 grid;
+    grid.x = (dfft_.Ny + 255) / 256; grid.y = dfft_.nxc; grid.z = dfft_.Nzl;
+    go(k, grid, 0, OC_TIMER_POISSON_MID);
+    for (int c = 0; c < C; ++c) { begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, false, c); end_timer(); chk(e); }
+    (void)nz;
+    t.forward = 0;
+    tg.x = (dfft_.nxc + 31) / 32; tg.y = (dfft_.Ny + 31) / 32; tg.z = dfft_.Nzl;
+    go(t, tg, TransposePutKernel<FT>::SMEM, OC_TIMER_COMM);
+    barrier();
+    if (g_.bounded[2]) {
+        zt.inverse = 1;
+        go(zt, zg, 0, OC_TIMER_POISSON_MID);
+    }
+    begin_timer(OC_TIMER_FFT); e = dfft_.zx(fftbuf_, false); end_timer(); chk(e);
 }
 
 template <class FT>
@@ -775,6 +837,7 @@ void Model<FT>::all_to_all(FT* send, FT* recv, int c, int C) {
 // and the way back starts as soon as a sub-chunk is finished.  (The reference does not overlap transposes with FFTs.)
 template <class FT>
 void Model<FT>::run_fft_solve_dist() {
+    if (p2p_) { run_fft_solve_p2p(); return; }
     auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
     const int C = dfft_.C, nz = dfft_.Nzl / C;
     begin_timer(OC_TIMER_FFT); std::string e = dfft_.zx(fftbuf_, true); end_timer(); chk(e);

@@ -236,6 +236,9 @@ private:
     DistFft<FT> dfft_;
     FT* distT_ = nullptr;          // transposed spectral buffer (y fastest)
     FT* diststage_ = nullptr;      // all-to-all staging
+    bool p2p_ = false;             // the transposes go through peer memory (TransposePutKernel) instead of NCCL all-to-alls
+    std::vector<void*> peer_spec_, peer_T_;     // every rank's fftbuf_ / distT_ (CUDA IPC mappings)
+    void run_fft_solve_p2p();
     FT* halo_send_ = nullptr;
     FT* halo_recv_ = nullptr;
     size_t halo_buf_elems_ = 0;
