@@ -31,11 +31,17 @@ struct HaloField {
     SideBC bc[6];
 };
 
+// A halo slab of one field.  Blocks tile it in (x, y) with 2^tshift × (256 >> tshift) threads — 32 × 8 for slabs that are long in x
+// (coalesced rows), 4 × 64 for the west / east slabs that are only H cells wide — and one level of z per block, so that a thread's
+// cell follows from shifts and ONE block-uniform division (the first version decoded a linear cell index with two divisions and
+// three modulo operations per thread: ~60 % of the kernel's instructions, profiles/r02b_ncu_other_c3_summary.txt).
 struct HaloBox {
     int field;
     int lo[3];
     int n[3];
     int first_block;   // prefix sum of blocks
+    int tshift;        // log2 of the tile width in x
+    int nbx, nby;      // tiles in x and y
 };
 
 template <class FT>
@@ -56,15 +62,17 @@ struct HaloKernel {
         int bi = nboxes - 1;
         while (bi > 0 && boxes[bi].first_block > b.x) --bi;
         const HaloBox bx = boxes[bi];
-        // boxes are halo slabs: far fewer than 2^31 cells each (checked on the host), so 32-bit index arithmetic
-        const unsigned cell = (unsigned)(b.x - bx.first_block) * (unsigned)nt + (unsigned)tid;
-        const unsigned ncell = (unsigned)bx.n[0] * (unsigned)bx.n[1] * (unsigned)bx.n[2];
-        if (cell >= ncell) return;
+        (void)nt;
+        const unsigned lb = (unsigned)(b.x - bx.first_block);
+        const unsigned per_plane = (unsigned)bx.nbx * (unsigned)bx.nby;
+        const unsigned pl = lb / per_plane, rem = lb - pl * per_plane;
+        const unsigned by = rem / (unsigned)bx.nbx, bxi = rem - by * (unsigned)bx.nbx;
+        const int tx = tid & ((1 << bx.tshift) - 1), ty = tid >> bx.tshift;
+        const int c0 = (int)(bxi << bx.tshift) + tx, c1 = (int)by * (THREADS >> bx.tshift) + ty;
+        if (c0 >= bx.n[0] || c1 >= bx.n[1]) return;
         int P[3];
-        const unsigned row = cell / (unsigned)bx.n[0];
-        P[0] = bx.lo[0] + (int)(cell - row * (unsigned)bx.n[0]);
-        const unsigned pl = row / (unsigned)bx.n[1];
-        P[1] = bx.lo[1] + (int)(row - pl * (unsigned)bx.n[1]);
+        P[0] = bx.lo[0] + c0;
+        P[1] = bx.lo[1] + c1;
         P[2] = bx.lo[2] + (int)pl;
         const HaloField<FT>& fld = f[bx.field];
 
@@ -77,8 +85,8 @@ struct HaloKernel {
             int idx = P[d], N = g.N[d];
             if (!g.bounded[d]) {                       // Periodic (and Flat stored as periodic)
                 if (skip[d] && (idx < 0 || idx >= N)) return;
-                int q = idx % N;
-                if (q < 0) q += N;
+                int q = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);          // one wrap is enough when N >= H …
+                if ((unsigned)q >= (unsigned)N) { q %= N; if (q < 0) q += N; }    // … tiny grids (N < internal halo) wrap repeatedly
                 if (q != idx) moved = true;
                 Q[d] = q;
             } else if (fld.face[d]) {                  // wall-normal velocity: interior points 0..N

@@ -627,6 +627,7 @@ void Model<FT>::go(const K& k, Dim3 grid, size_t smem, int cls) {
 // ---------------------------------------------------------------------------------------------------------
 template <class FT>
 void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open) {
+    NvtxRange nvtx_("fill_halo_regions!");
     if (fields.empty()) return;
     if ((int)fields.size() > HALO_MAX_FIELDS) throw Error(OC_ERR_INVALID, "too many fields in one halo fill");
     std::string key;
@@ -642,9 +643,13 @@ void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open) {
             b.lo[0] = lo0; b.lo[1] = lo1; b.lo[2] = lo2;
             b.n[0] = n0; b.n[1] = n1; b.n[2] = n2;
             b.first_block = nb;
-            long long cells = (long long)n0 * n1 * n2;
-            if (cells >= (1LL << 31)) throw Error(OC_ERR_UNSUPPORTED, "halo slab with 2^31 or more cells");
-            nb += (int)((cells + HaloKernel<FT>::THREADS - 1) / HaloKernel<FT>::THREADS);
+            b.tshift = n0 <= 4 ? 2 : (n0 <= 8 ? 3 : 5);                  // 4 × 64, 8 × 32 or 32 × 8 threads per tile
+            const int tw = 1 << b.tshift, th = HaloKernel<FT>::THREADS >> b.tshift;
+            b.nbx = (n0 + tw - 1) / tw;
+            b.nby = (n1 + th - 1) / th;
+            const long long blocks = (long long)b.nbx * b.nby * n2;
+            if ((long long)nb + blocks >= (1LL << 31)) throw Error(OC_ERR_UNSUPPORTED, "halo slabs with 2^31 or more blocks");
+            nb += (int)blocks;
             boxes.push_back(b);
         };
         const int* N = g_.N;
@@ -739,6 +744,7 @@ void Model<FT>::dist_attach(Transport* t) {
 // spectral buffer before every put back has landed.
 template <class FT>
 void Model<FT>::run_fft_solve_p2p() {
+    NvtxRange nvtx_("distributed FFT solve (peer memory)");
     auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
     auto barrier = [&]() { begin_timer(OC_TIMER_COMM); std::string e = transport_->barrier(stream_); end_timer(); chk(e); };
     begin_timer(OC_TIMER_FFT); std::string e = dfft_.zx(fftbuf_, true); end_timer(); chk(e);
@@ -784,6 +790,7 @@ void Model<FT>::run_fft_solve_p2p() {
 
 template <class FT>
 void Model<FT>::exchange_y(const std::vector<FieldRec*>& fields) {
+    NvtxRange nvtx_("halo exchange (y)");
     if (!transport_) throw Error(OC_ERR_STATE, "distributed model without a transport: call oc_dist_attach_nccl first");
     const int nf = (int)fields.size();
     if (nf > F_) throw Error(OC_ERR_INVALID, "halo exchange of more fields than the exchange buffers hold");
@@ -905,6 +912,7 @@ void Model<FT>::fill_halo_regions(const int* fields, int n, int fill_open) {
 // ---------------------------------------------------------------------------------------------------------
 template <class FT>
 void Model<FT>::aux() {
+    NvtxRange nvtx_("compute_auxiliaries!");
     if (has_amd_) {
         auto run_amd = [&](auto k) {
             k.g = g_;
@@ -1172,6 +1180,7 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
 
 template <class FT>
 void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state, bool defer_tracer_join) {
+    NvtxRange nvtx_("compute_tendencies! + substep");
     join_tracers();
     // The hydrostatic-pressure scan (HBM-bound, needed by the u and v kernels only) runs on the second stream beside the w and tracer
     // tendency kernels (bound by the FP64 pipe / instruction issue, two ~100 KB CTAs per SM: its small register-only CTAs fit into what
@@ -1431,6 +1440,7 @@ void Model<FT>::cache_previous_tendencies() {
 // ---------------------------------------------------------------------------------------------------------
 template <class FT>
 void Model<FT>::run_fft_solve() {
+    NvtxRange nvtx_("solve! (FFTBasedPoissonSolver)");
     if (dist_) { run_fft_solve_dist(); return; }
     begin_timer(OC_TIMER_FFT);
     std::string e = fft_.forward(fftbuf_);
@@ -1507,6 +1517,7 @@ void Model<FT>::run_fft_solve() {
 
 template <class FT>
 void Model<FT>::pressure_solve_from_state() {
+    NvtxRange nvtx_("compute_pressure_correction!");
     PoissonRhsKernel<FT> k;
     k.g = g_;
     k.L = fft_.L;
@@ -1518,6 +1529,7 @@ void Model<FT>::pressure_solve_from_state() {
 
 template <class FT>
 void Model<FT>::projection(double dt) {
+    NvtxRange nvtx_("make_pressure_correction!");
     const FT* prev_row = nullptr;
     if (dist_) {
         // the pressure gradient at the first local row needs the y-neighbour's last row of ϕ: one dense (Nx, Nz) message
@@ -1648,6 +1660,7 @@ int Model<FT>::acquire_slot(size_t nbytes) {
 // set!(field, host_array) in stream order without a host-side wait: H2D into staging on in_stream_, D2D into the field on stream_
 template <class FT>
 int Model<FT>::upload_begin(int field, const void* host, size_t nbytes) {
+    NvtxRange nvtx_("upload_begin");
     if (field < 0 || field >= F_) throw Error(OC_ERR_INVALID, "oc_upload_begin: not a prognostic field index");
     join_tracers();
     oc_field_info info;
@@ -1684,6 +1697,7 @@ int Model<FT>::upload_begin(int field, const void* host, size_t nbytes) {
 
 template <class FT>
 int Model<FT>::output_begin(int field, const int lo[3], const int n[3], void* host, size_t nbytes) {
+    NvtxRange nvtx_("output_begin");
     join_tracers();
     oc_field_info info;
     field_info(field, &info);                // brings auxiliary fields / tendencies up to date like a download
@@ -1813,6 +1827,7 @@ void Model<FT>::poisson_solve(const void* rhs, void* phi, size_t nbytes) {
 // ---------------------------------------------------------------------------------------------------------
 template <class FT>
 void Model<FT>::set_finalize(int enforce) {
+    NvtxRange nvtx_("set!(model)");
     std::vector<FieldRec*> all;
     for (auto& f : state_) all.push_back(&f);
     halo(all, true);                                     // set!: fill_halo_regions!(ϕ) per field (open BCs included)
@@ -1828,6 +1843,7 @@ void Model<FT>::set_finalize(int enforce) {
 // One fused stage: [aux] -> tendency+substep per field -> halo(U, open) -> Poisson -> projection -> halo(all)
 template <class FT>
 void Model<FT>::stage(int mode, double dt, int stage_no, double stage_dt, double chi, bool euler) {
+    NvtxRange nvtx_("time-stepper stage");
     rotate_pending_tendencies();                         // the previous stage's evaluation becomes G⁻ (cache by swap)
     tendencies(mode, dt, stage_no, chi, euler, true, true, /*defer_tracer_join=*/true);
     gn_pending_ = true;
@@ -1845,6 +1861,7 @@ void Model<FT>::stage(int mode, double dt, int stage_no, double stage_dt, double
 
 template <class FT>
 void Model<FT>::time_step_rk3(double dt) {
+    NvtxRange nvtx_("time_step! (RungeKutta3)");
     if (cfg_.timestepper != OC_RK3) throw Error(OC_ERR_STATE, "model was created with another time stepper");
     // stage_Δt(Δt, γ, ζ) = Δt (γ + ζ) with γ, ζ in FT   runge_kutta_3.jl:107-109,176-177
     const double dt1 = dt * (double)gamma_[0];
@@ -1866,6 +1883,7 @@ void Model<FT>::time_step_rk3(double dt) {
 
 template <class FT>
 void Model<FT>::time_step_ab2(double dt, int euler_in) {
+    NvtxRange nvtx_("time_step! (QuasiAdamsBashforth2)");
     if (cfg_.timestepper != OC_AB2) throw Error(OC_ERR_STATE, "model was created with another time stepper");
     const bool euler = euler_in || (dt != clock.last_dt);            // quasi_adams_bashforth_2.jl:88
     const double chi = euler ? -0.5 : cfg_.ab2_chi;

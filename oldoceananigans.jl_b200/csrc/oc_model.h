@@ -13,6 +13,9 @@
 #include <stdexcept>
 
 #include "../../include/oceananigans_b200.h"
+#ifndef OC_HOSTSIM
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges cost nothing without an attached tool
+#endif
 #include "oc_aux.h"
 #include "oc_dist.h"
 #include "oc_fft.h"
@@ -78,6 +81,17 @@ inline void dev_copy_box(void* dev_origin, size_t elem, long long sy, long long 
         }
 }
 #endif
+
+// One NVTX range per phase of the step (time_step! / stage / tendencies / halo / pressure solve / projection / output): Nsight
+// Systems / Compute timelines show the reference's phase names (the reference has no tracing of its own beyond @info logs).
+struct NvtxRange {
+#ifndef OC_HOSTSIM
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+#else
+    explicit NvtxRange(const char*) {}
+#endif
+};
 
 struct ModelBase {
     virtual ~ModelBase() {}
