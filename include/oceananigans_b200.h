@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OC_ABI_VERSION 4
+#define OC_ABI_VERSION 5
 #define OC_MAX_TRACERS 8
 #define OC_MAX_FIELDS (3 + OC_MAX_TRACERS)
 
@@ -119,6 +119,13 @@ typedef struct {
      * BetaPlane, origin_z = z of the bottom face of the domain (regular z; a stretched grid takes its z-nodes from z_faces).
      * General tile kernel; serial and slab-decomposed models; no Flat y / z. */
     double  coriolis_gamma, coriolis_radius, origin_z;
+    /* ABI v5.  adapt_advection_order (src/Advection/adapt_advection_order.jl:18-96): on a grid with fewer points than the scheme's buffer
+     * in some direction the reference lowers the scheme THERE (Centered(2N), UpwindBiased(2N-1), WENO(2N-1); WENO(1) = UpwindBiased(1))
+     * and steps with FluxFormAdvection(x, y, z).  has_advection_dir = 1: advection_dir[d] is the oc_advection code of the scheme that
+     * computes the fluxes through the faces normal to d (`advection` stays the user's scheme); H[d] >= that scheme's buffer and
+     * N[d] >= H[d] are then required per direction.  General tile kernel. */
+    int32_t has_advection_dir;
+    int32_t advection_dir[3];
 } oc_config;
 
 typedef struct oc_model oc_model;

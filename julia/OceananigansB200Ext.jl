@@ -72,6 +72,7 @@ mutable struct OcConfig               # `oc_config`, same field order; NTuple fo
     tilted_gravity::Int32; reserved2::Int32; gravity_unit_vector::NTuple{3,Float64} # ABI v3: BuoyancyForce(…; gravity_unit_vector)
     amd_Cb::Float64                                 # ABI v4: AnisotropicMinimumDissipation(; Cb), with amd_has_Cb
     coriolis_gamma::Float64; coriolis_radius::Float64; origin_z::Float64  # ABI v4: NonTraditionalBetaPlane (has_coriolis = 4)
+    has_advection_dir::Int32; advection_dir::NTuple{3,Int32}            # ABI v5: FluxFormAdvection(x, y, z) from adapt_advection_order
     OcConfig() = new()
 end
 

@@ -24,7 +24,7 @@ from . import _lib as L
 
 __all__ = [
     "B200", "Distributed", "Partition", "Periodic", "Bounded", "Flat", "Center", "Face", "RectilinearGrid",
-    "Centered", "UpwindBiased", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation", "Smagorinsky", "SmagorinskyLilly", "LillyCoefficient",
+    "Centered", "FluxFormAdvection", "adapt_advection_order", "required_halo_size", "UpwindBiased", "WENO", "ScalarDiffusivity", "AnisotropicMinimumDissipation", "Smagorinsky", "SmagorinskyLilly", "LillyCoefficient",
     "SeawaterBuoyancy", "LinearEquationOfState", "BuoyancyTracer", "BuoyancyForce", "FPlane", "BetaPlane", "ConstantCartesianCoriolis", "NonTraditionalBetaPlane",
     "FluxBoundaryCondition", "ValueBoundaryCondition", "GradientBoundaryCondition", "OpenBoundaryCondition",
     "FieldBoundaryConditions", "NonhydrostaticModel", "Field", "OutputTicket", "set_", "time_step_", "update_state_",
@@ -222,6 +222,45 @@ class WENO:
 class _NoAdvection:
     """advection = nothing: no advective fluxes (momentum_advection_operators.jl:86-95)"""
     order, buffer, code = 0, 1, L.OC_ADVECTION_NONE
+
+
+class FluxFormAdvection:
+    """FluxFormAdvection(x, y, z): one scheme per flux direction (src/Advection/flux_form_advection.jl) — what adapt_advection_order
+    returns when it had to lower the scheme in some direction."""
+
+    def __init__(self, x, y, z):
+        self.x, self.y, self.z = x, y, z
+        self.dirs = (x, y, z)
+        self.buffer = max(s.buffer for s in self.dirs)
+        self.code = max(self.dirs, key=lambda s: s.buffer).code
+
+
+def required_halo_size(advection, d):
+    """required_halo_size_x / _y / _z(advection)"""
+    return advection.dirs[d].buffer if isinstance(advection, FluxFormAdvection) else advection.buffer
+
+
+def adapt_advection_order(advection, grid):
+    """adapt_advection_order(advection, grid)  (src/Advection/adapt_advection_order.jl:18-96): where the grid has fewer points than the
+    scheme's buffer the scheme is lowered in that direction — Centered(order = 2N), UpwindBiased(order = 2N − 1), WENO(order = 2N − 1)
+    (WENO(order = 1) is UpwindBiased(order = 1): weno_reconstruction.jl:83-85); Flat directions are left alone.  Returns the scheme
+    itself when nothing changed, a FluxFormAdvection otherwise."""
+    if isinstance(advection, _NoAdvection):
+        return advection
+    dirs = list(advection.dirs) if isinstance(advection, FluxFormAdvection) else [advection] * 3
+    changed = False
+    for d in range(3):
+        sch, N = dirs[d], grid.N[d]
+        if grid.topology[d] is Flat or isinstance(sch, _NoAdvection) or N >= sch.buffer:
+            continue
+        if isinstance(sch, Centered):
+            new = Centered(order=2 * N)
+        elif isinstance(sch, UpwindBiased):
+            new = UpwindBiased(order=2 * N - 1)
+        else:
+            new = WENO(order=2 * N - 1) if 2 * N - 1 >= 3 else UpwindBiased(order=1)
+        dirs[d], changed = new, True
+    return FluxFormAdvection(*dirs) if changed else advection
 
 
 class ScalarDiffusivity:
@@ -668,11 +707,24 @@ class NonhydrostaticModel:
         elif advection is None:
             advection = _NoAdvection()
         closures = () if closure is None else (tuple(closure) if isinstance(closure, (tuple, list)) else (closure,))
-        # inflate_grid_halo_size   nonhydrostatic_model.jl:184,248-262
-        need = advection.buffer
+        # adapt_advection_order, then inflate_grid_halo_size — per direction   nonhydrostatic_model.jl:175-184,248-262
+        advection = adapt_advection_order(advection, grid)
+        cneed = 1
         for c in closures:
-            need = max(need, 2 if isinstance(c, (AnisotropicMinimumDissipation, Smagorinsky)) else 1)
-        H = tuple(max(grid.H[d], need) if grid.topology[d] is not Flat else 0 for d in range(3))
+            cneed = max(cneed, 2 if isinstance(c, (AnisotropicMinimumDissipation, Smagorinsky)) else 1)
+        H = tuple(max(grid.H[d], required_halo_size(advection, d), cneed) if grid.topology[d] is not Flat else 0 for d in range(3))
+        if isinstance(advection, FluxFormAdvection):
+            # The scheme of flux direction d interpolates the advecting velocity ALONG every other direction c (`_advective_momentum_flux_Uv
+            # (…, scheme.x, …)`: ℑy of U with the x scheme, upwind_biased_advective_fluxes.jl:47-53) — Centered(4), two points deep, for
+            # the fifth-order schemes and Centered(4).  The adapted scheme only gives c the halo of ITS lowered scheme: with H[c] = 1 the
+            # reference reads outside the halo (unspecified values).  Nothing to be bit-compatible with: refused.
+            for d in range(3):
+                deep = 2 if isinstance(advection.dirs[d], (WENO, UpwindBiased)) and advection.dirs[d].order == 5 or \
+                    isinstance(advection.dirs[d], Centered) and advection.dirs[d].order == 4 else 1
+                for c in range(3):
+                    if c != d and grid.topology[c] is not Flat and grid.topology[d] is not Flat and H[c] < deep:
+                        raise NotImplementedError(f"adapt_advection_order: the {'xyz'[d]}-scheme interpolates velocities two points deep along "
+                                                  f"{'xyz'[c]}, where the adapted grid has a halo of {H[c]} (the reference reads outside the halo)")
         if H != grid.H:
             grid = grid.with_halo(H)
         self.grid, self.advection, self.closure, self.buoyancy, self.coriolis = grid, advection, closure, buoyancy, coriolis
@@ -699,6 +751,10 @@ class NonhydrostaticModel:
             cfg.N[1] = grid.N[1] // arch.nranks
             cfg.dist_rank, cfg.dist_nranks = arch.rank, arch.nranks
         cfg.advection = advection.code
+        if isinstance(advection, FluxFormAdvection):
+            cfg.has_advection_dir = 1
+            for d in range(3):
+                cfg.advection_dir[d] = advection.dirs[d].code
         cfg.timestepper = L.OC_RK3 if timestepper == "RungeKutta3" else L.OC_AB2
         cfg.n_tracers = len(tracers)
         sd = [c for c in closures if isinstance(c, ScalarDiffusivity)]

@@ -64,7 +64,8 @@ struct AdvCoef {
 };
 
 // advection scheme codes (oc_advection in include/oceananigans_b200.h)
-enum { ADV_CENTERED2 = 0, ADV_WENO5 = 1, ADV_CENTERED4 = 2, ADV_UPWIND3 = 3, ADV_UPWIND5 = 4, ADV_WENO3 = 5, ADV_UPWIND1 = 6, ADV_NONE = 7 };
+enum { ADV_CENTERED2 = 0, ADV_WENO5 = 1, ADV_CENTERED4 = 2, ADV_UPWIND3 = 3, ADV_UPWIND5 = 4, ADV_WENO3 = 5, ADV_UPWIND1 = 6, ADV_NONE = 7,
+       ADV_MIXED = 8 /* FluxFormAdvection(x, y, z): the scheme of each flux direction is a run-time code (TendencyArgs::adv_dir) */ };
 OC_HD constexpr bool adv_is_centered(int adv) { return adv == ADV_CENTERED2 || adv == ADV_CENTERED4; }
 
 template <class FT>

@@ -91,11 +91,14 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
             if (!((FT)c.z_faces[k + 1] > (FT)c.z_faces[k])) throw Error(OC_ERR_INVALID, "The elements of z must be increasing!");
         if (c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "distributed models on vertically stretched grids (DistributedFourierTridiagonalPoissonSolver: next)");
     }
-    // required_halo_size of the scheme (its buffer)
-    int need = (c.advection == OC_WENO5 || c.advection == OC_UPWIND5) ? 3
-             : (c.advection == OC_CENTERED4 || c.advection == OC_UPWIND3 || c.advection == OC_WENO3) ? 2 : 1;
-    if (c.has_amd || c.smagorinsky) need = std::max(need, 2);      // AbstractScalarDiffusivity{…, 2}: anisotropic_minimum_dissipation.jl, smagorinsky.jl:31
+    // required_halo_size of the scheme (its buffer) — per direction for FluxFormAdvection (adapt_advection_order.jl:18-96)
+    auto buffer_of = [](int adv) { return (adv == OC_WENO5 || adv == OC_UPWIND5) ? 3 : (adv == OC_CENTERED4 || adv == OC_UPWIND3 || adv == OC_WENO3) ? 2 : 1; };
+    if (c.has_advection_dir)
+        for (int d = 0; d < 3; ++d)
+            if (c.advection_dir[d] < OC_CENTERED2 || c.advection_dir[d] > OC_ADVECTION_NONE) throw Error(OC_ERR_INVALID, "advection_dir: unknown advection scheme code");
     for (int d = 0; d < 3; ++d) {
+        int need = buffer_of(c.has_advection_dir ? c.advection_dir[d] : c.advection);
+        if (c.has_amd || c.smagorinsky) need = std::max(need, 2);      // AbstractScalarDiffusivity{…, 2}: anisotropic_minimum_dissipation.jl, smagorinsky.jl:31
         const int t = c.topology[d];
         if (t != OC_PERIODIC && t != OC_BOUNDED && t != OC_FLAT) throw Error(OC_ERR_INVALID, "bad topology");
         if (c.N[d] < 1) throw Error(OC_ERR_INVALID, "grid size must be >= 1");
@@ -104,7 +107,8 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         } else {
             if (c.H[d] < need) throw Error(OC_ERR_INVALID, "halo too small for the advection scheme / closure (inflate_grid_halo_size)");
             if (c.H[d] > 8) throw Error(OC_ERR_UNSUPPORTED, "halo larger than 8");
-            if (c.N[d] < c.H[d]) throw Error(OC_ERR_UNSUPPORTED, "N < H in a non-Flat dimension (adapt_advection_order lowering is not implemented)");
+            if (c.N[d] < c.H[d]) throw Error(OC_ERR_INVALID, "halo must be <= size in every non-Flat dimension (validate_halo, input_validation.jl:86-92); "
+                                                                   "lower the advection scheme there with has_advection_dir (adapt_advection_order)");
             if (!(stretched_ && d == 2) && !(c.delta[d] > 0)) throw Error(OC_ERR_INVALID, "grid spacing must be positive");
         }
         Hcfg_[d] = c.H[d];
@@ -114,6 +118,17 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         g_.flat[d] = t == OC_FLAT;
         g_.d[d] = t == OC_FLAT ? FT(1) : (FT)c.delta[d];
         g_.rd[d] = FT(1) / g_.d[d];
+    }
+    if (c.has_advection_dir) {
+        // the scheme of flux direction d interpolates the advecting velocity along every other direction with Centered(4) (fifth-order
+        // schemes, Centered(4)) or Centered(2): where the adapted halo is smaller the reference reads outside the halo — refused
+        for (int d = 0; d < 3; ++d) {
+            const int a = c.advection_dir[d];
+            const int deep = (a == OC_WENO5 || a == OC_UPWIND5 || a == OC_CENTERED4) ? 2 : 1;
+            for (int e = 0; e < 3; ++e)
+                if (e != d && c.topology[e] != OC_FLAT && c.topology[d] != OC_FLAT && a != OC_ADVECTION_NONE && c.H[e] < deep)
+                    throw Error(OC_ERR_UNSUPPORTED, "advection_dir: a scheme interpolates velocities two points deep along a direction whose halo is 1 (the reference reads outside the halo there)");
+        }
     }
     if (c.has_amd && (g_.flat[0] || g_.flat[1] || g_.flat[2])) throw Error(OC_ERR_UNSUPPORTED, "AnisotropicMinimumDissipation on a grid with Flat dimensions");
     if (c.smagorinsky) {
@@ -162,7 +177,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         const bool any_bounded = c.topology[0] == OC_BOUNDED || c.topology[1] == OC_BOUNDED || c.topology[2] == OC_BOUNDED;
         // BetaPlane / ConstantCartesianCoriolis run in the general tile kernel: the z-marching kernel of the
         // measured BASELINE configurations keeps exactly the code (and register counts) it was profiled with
-        march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) && c.has_coriolis <= OC_CORIOLIS_FPLANE && !c.tilted_gravity &&
+        march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) && c.has_coriolis <= OC_CORIOLIS_FPLANE && !c.tilted_gravity && !c.has_advection_dir &&
                     (c.advection == OC_CENTERED2 || c.advection == OC_WENO5 || (c.advection == OC_UPWIND5 && !any_bounded && !c.has_amd && !c.smagorinsky));
     }
     g_.dzc = g_.dzf = g_.rdzc = g_.rdzf = g_.rVc = g_.rVf = nullptr;
@@ -1038,6 +1053,7 @@ void Model<FT>::launch_tendency(int fidx, TendencyArgs<FT>& a) {
         else if (cfg_.buoyancy == OC_BUOYANCY_SEAWATER_LINEAR) { k.cor.tbT = state_[3 + cfg_.tracer_T].p; k.cor.tbS = state_[3 + cfg_.tracer_S].p; }
         go(k, grid, k.SMEM, OC_TIMER_TENDENCY);
     };
+    if (cfg_.has_advection_dir) { run(TendencyKernel<FT, ADV_MIXED, KIND, TX, TY, TZ>{}); return; }
     switch (cfg_.advection) {
         case OC_WENO5: run(TendencyKernel<FT, ADV_WENO5, KIND, TX, TY, TZ>{}); break;
         case OC_CENTERED4: run(TendencyKernel<FT, ADV_CENTERED4, KIND, TX, TY, TZ>{}); break;
@@ -1249,6 +1265,7 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
             a.fbc.val[s] = (FT)bc.value;
         }
         a.add_flux_bcs = add_flux_bcs ? 1 : 0;
+        for (int d = 0; d < 3; ++d) a.adv_dir[d] = cfg_.has_advection_dir ? cfg_.advection_dir[d] : cfg_.advection;
         a.mode = mode;
         a.dt = (FT)dt;
         a.ab2_euler = euler ? 1 : 0;
@@ -1972,6 +1989,8 @@ void oc_config_init(oc_config* c) {
     for (int t = 0; t < OC_MAX_TRACERS; ++t) c->amd_Ckappa[t] = 1.0 / 3.0;
     c->z_stretched = 0;
     c->z_faces = nullptr;
+    c->has_advection_dir = 0;
+    c->advection_dir[0] = c->advection_dir[1] = c->advection_dir[2] = OC_CENTERED2;
 }
 
 int oc_model_create(const oc_config* cfg, oc_model** out) {

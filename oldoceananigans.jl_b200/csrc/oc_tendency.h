@@ -48,6 +48,7 @@ struct TendencyArgs {
     FT f;
     FluxBC<FT> fbc;      // flux boundary conditions of this field
     int add_flux_bcs;
+    int adv_dir[3];      // ADV_MIXED kernels: scheme code of the fluxes through the faces normal to d (adapt_advection_order.jl:18-96)
     int mode;            // SubstepMode
     FT dt, ca, cb;       // RK3_FIRST: U + (dt·γ)·G with ca = dt·γ ; RK3: U + dt(ca·G + cb·G⁻) ; AB2: ca = 1.5+χ, cb = 0.5+χ
     int ab2_euler;
@@ -142,7 +143,26 @@ struct TendencyKernel {
     // ---- advective fluxes -----------------------------------------------------------------------------
     // Flux of this field through the faces normal to d, at flux index (i,j,k): for momentum component
     // COMP the flux is centre-type in d when d == COMP (located at ccc) and face-type otherwise.
+    // FluxFormAdvection(x, y, z): every flux direction has its own scheme — `_advective_momentum_flux_Uu(…, advection::FluxFormAdvection, …)
+    // = _advective_momentum_flux_Uu(…, advection.x, …)` etc. (src/Advection/flux_form_advection.jl): the scheme of direction d does BOTH
+    // interpolations of the flux through the d-faces
     OC_HD FT advective_flux(int i, int j, int k, int d) const {
+        if constexpr (ADV != ADV_MIXED) return advective_flux_t<ADV>(i, j, k, d);
+        else {
+            switch (a.adv_dir[d]) {
+                case ADV_WENO5: return advective_flux_t<ADV_WENO5>(i, j, k, d);
+                case ADV_CENTERED4: return advective_flux_t<ADV_CENTERED4>(i, j, k, d);
+                case ADV_UPWIND3: return advective_flux_t<ADV_UPWIND3>(i, j, k, d);
+                case ADV_UPWIND5: return advective_flux_t<ADV_UPWIND5>(i, j, k, d);
+                case ADV_WENO3: return advective_flux_t<ADV_WENO3>(i, j, k, d);
+                case ADV_UPWIND1: return advective_flux_t<ADV_UPWIND1>(i, j, k, d);
+                case ADV_NONE: return FT(0);
+                default: return advective_flux_t<ADV_CENTERED2>(i, j, k, d);
+            }
+        }
+    }
+    template <int ADVD>
+    OC_HD FT advective_flux_t(int i, int j, int k, int d) const {
         const Geom<FT>& g = a.g;
         if (g.flat[d]) return FT(0);                                               // flat_advective_fluxes.jl:13-29
         int o = g.idx(i, j, k);
@@ -151,19 +171,19 @@ struct TendencyKernel {
         // Centered: the area at the flux point (centered_advective_fluxes.jl:15-33); upwind schemes: the area of the advecting
         // velocity's own point, inside the interpolation (upwind_biased_advective_fluxes.jl:23-121) — these differ only
         // for the x / y fluxes of w on a stretched grid
-        FT A = g.area_at(d, COMP == 2 && adv_is_centered(ADV), k);
-        if (ADV == ADV_NONE) return FT(0);                                        // advection = nothing
-        constexpr bool CEN = adv_is_centered(ADV);
+        FT A = g.area_at(d, COMP == 2 && adv_is_centered(ADVD), k);
+        if (ADVD == ADV_NONE) return FT(0);                                        // advection = nothing
+        constexpr bool CEN = adv_is_centered(ADVD);
         if (KIND == KIND_C) {
             FT u = a.U[d][o];
             const FT* c = a.c + o;
             OrderWindow w = order_window(g.bounded[d] != 0, false, g.N[d]);
-            if (ADV == ADV_CENTERED2) {
+            if (ADVD == ADV_CENTERED2) {
                 return (A * u) * (FT(0.5) * c[-sd] + FT(0.5) * c[0]);              // centered_advective_fluxes.jl:31-33
             } else if (CEN) {
-                return (A * u) * symmetric_any<ADV, FT>(a.C, c, sd, FT(1), id, w);
+                return (A * u) * symmetric_any<ADVD, FT>(a.C, c, sd, FT(1), id, w);
             } else {
-                FT cr = biased_any<ADV, FT>(a.C, c, sd, u > FT(0), id, w);         // upwind_biased_advective_fluxes.jl:99-121
+                FT cr = biased_any<ADVD, FT>(a.C, c, sd, u > FT(0), id, w);         // upwind_biased_advective_fluxes.jl:99-121
                 return A * u * cr;
             }
         } else {
@@ -172,17 +192,17 @@ struct TendencyKernel {
             if (d == COMP) {
                 // centre-type: evaluate the face-type stencils at face id+1
                 OrderWindow w = order_window(g.bounded[d] != 0, true, g.N[d]);
-                if (ADV == ADV_CENTERED2) {
+                if (ADVD == ADV_CENTERED2) {
                     FT ut = FT(0.5) * adv[0] + FT(0.5) * adv[sd];
                     FT pt = FT(0.5) * psi[0] + FT(0.5) * psi[sd];
                     return A * ut * pt;                                            // centered_advective_fluxes.jl:15,22,27
                 } else if (CEN) {
-                    FT ut = symmetric_any<ADV, FT>(a.C, adv + sd, sd, FT(1), id + 1, w);
-                    FT pt = symmetric_any<ADV, FT>(a.C, psi + sd, sd, FT(1), id + 1, w);
+                    FT ut = symmetric_any<ADVD, FT>(a.C, adv + sd, sd, FT(1), id + 1, w);
+                    FT pt = symmetric_any<ADVD, FT>(a.C, psi + sd, sd, FT(1), id + 1, w);
                     return A * ut * pt;
                 } else {
-                    FT ut = symmetric_any<ADV, FT>(a.C, adv + sd, sd, A, id + 1, w);
-                    FT pr = biased_any<ADV, FT>(a.C, psi + sd, sd, ut > FT(0), id + 1, w);
+                    FT ut = symmetric_any<ADVD, FT>(a.C, adv + sd, sd, A, id + 1, w);
+                    FT pr = biased_any<ADVD, FT>(a.C, psi + sd, sd, ut > FT(0), id + 1, w);
                     return ut * pr;                                                // upwind_biased_advective_fluxes.jl:23-29
                 }
             } else {
@@ -191,20 +211,20 @@ struct TendencyKernel {
                 int ic = cc == 0 ? i : (cc == 1 ? j : k);
                 OrderWindow wc = order_window(g.bounded[cc] != 0, false, g.N[cc]);
                 OrderWindow wd = order_window(g.bounded[d] != 0, false, g.N[d]);
-                if (ADV == ADV_CENTERED2) {
+                if (ADVD == ADV_CENTERED2) {
                     FT ut = g.flat[cc] ? adv[0] : (FT(0.5) * adv[-sc] + FT(0.5) * adv[0]);
                     FT pt = FT(0.5) * psi[-sd] + FT(0.5) * psi[0];
                     return A * ut * pt;                                            // :16-26
                 } else if (CEN) {
-                    FT ut = g.flat[cc] ? adv[0] : symmetric_any<ADV, FT>(a.C, adv, sc, FT(1), ic, wc);
-                    FT pt = symmetric_any<ADV, FT>(a.C, psi, sd, FT(1), id, wd);
+                    FT ut = g.flat[cc] ? adv[0] : symmetric_any<ADVD, FT>(a.C, adv, sc, FT(1), ic, wc);
+                    FT pt = symmetric_any<ADVD, FT>(a.C, psi, sd, FT(1), id, wd);
                     return A * ut * pt;
                 } else {
                     FT ut;
                     if (g.flat[cc]) ut = A * adv[0];
-                    else if (cc == 2 && g.stretched()) ut = symmetric_any_z<ADV, FT>(a.C, adv, sc, g.d[d == 0 ? 1 : 0], g.dzc + k, ic, wc);
-                    else ut = symmetric_any<ADV, FT>(a.C, adv, sc, A, ic, wc);
-                    FT pr = biased_any<ADV, FT>(a.C, psi, sd, ut > FT(0), id, wd);
+                    else if (cc == 2 && g.stretched()) ut = symmetric_any_z<ADVD, FT>(a.C, adv, sc, g.d[d == 0 ? 1 : 0], g.dzc + k, ic, wc);
+                    else ut = symmetric_any<ADVD, FT>(a.C, adv, sc, A, ic, wc);
+                    FT pr = biased_any<ADVD, FT>(a.C, psi, sd, ut > FT(0), id, wd);
                     return ut * pr;                                                // :31-93
                 }
             }

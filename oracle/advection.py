@@ -119,6 +119,44 @@ class NoAdvection:
         self.kind = "none"
 
 
+class FluxFormAdvection:
+    """FluxFormAdvection(x, y, z) (src/Advection/flux_form_advection.jl): the scheme of direction d computes the whole flux through
+    the d-faces — `_advective_momentum_flux_Uu(i, j, k, grid, advection::FluxFormAdvection, U, u) = _advective_momentum_flux_Uu(i, j, k,
+    grid, advection.x, U, u)` and likewise for every component and direction."""
+
+    def __init__(self, x, y, z):
+        self.dirs = (x, y, z)
+        self.FT = x.FT
+        self.buffer = max(s.buffer for s in self.dirs)
+        self.kind = "fluxform"
+
+
+def scheme_of(scheme, d):
+    return scheme.dirs[d] if getattr(scheme, "kind", None) == "fluxform" else scheme
+
+
+def adapt_advection_order(advection, grid):
+    """adapt_advection_order(advection, grid)  src/Advection/adapt_advection_order.jl:18-96 — Centered(2N), UpwindBiased(2N-1),
+    WENO(2N-1) in the directions with N < buffer (WENO(1) = UpwindBiased(1): weno_reconstruction.jl:83-85); Flat directions untouched."""
+    if advection.kind == "none":
+        return advection
+    FT = advection.FT
+    dirs = [scheme_of(advection, d) for d in range(3)]
+    changed = False
+    for d in range(3):
+        sch, N = dirs[d], grid.N[d]
+        if grid.flat(d) or N >= sch.buffer:
+            continue
+        if sch.kind == "centered":
+            new = Centered(FT, 2 * N)
+        elif sch.kind in ("upwind", "upwind1"):
+            new = UpwindBiased(FT, 2 * N - 1)
+        else:
+            new = WENO(FT, 2 * N - 1) if 2 * N - 1 >= 3 else UpwindBiased(FT, 1)
+        dirs[d], changed = new, True
+    return FluxFormAdvection(*dirs) if changed else advection
+
+
 def _upwind_value(sch, S, left):
     """biased_interpolate for UpwindBiased{B}: S = (ψ[i-B], …, ψ[i+B-1]); calc_reconstruction_stencil
     (reconstruction_coefficients.jl:122-152): the idx-th point of the left stencil is ψ[i+idx-B-1], of the right stencil
@@ -329,6 +367,7 @@ def momentum_flux(ctx, scheme, U, comp, d, psi_f):
     in direction ``d`` by U[d].  Returns a quantity.  Flux location: centre-type in d if d == comp
     (ccc), otherwise face-type in both d and comp."""
     g, FT = ctx.g, ctx.FT
+    scheme = scheme_of(scheme, d)
     if g.flat(d) or scheme.kind == "none":
         return _zero_q(ctx)                                  # flat_advective_fluxes.jl:13-29 ; advection = nothing
     adv = ctx.field(U[d])
@@ -370,6 +409,7 @@ def div_momentum(ctx, scheme, U, comp):
 def tracer_flux(ctx, scheme, U, c_f, d):
     """advective_tracer_flux_{x,y,z}"""
     g = ctx.g
+    scheme = scheme_of(scheme, d)
     if g.flat(d) or scheme.kind == "none":
         return _zero_q(ctx)
     u = ctx.field(U[d])

@@ -63,17 +63,24 @@ class OracleModel:
             coriolis = clo.FPlane(f=coriolis_f)
         if advection is None:
             advection = adv.Centered(FT, 2)
-        # inflate_grid_halo_size  nonhydrostatic_model.jl:184,248-262
-        need = advection.buffer
+        # adapt_advection_order, then inflate_grid_halo_size (per direction)  nonhydrostatic_model.jl:175-184,248-262
+        advection = adv.adapt_advection_order(advection, grid)
         closures = () if closure is None else (tuple(closure) if isinstance(closure, (tuple, list)) else (closure,))
+        cneed = 1
         for c in closures:
-            need = max(need, 2 if c.kind in ("amd", "smagorinsky") else 1)   # AbstractScalarDiffusivity{…, 2}: smagorinsky.jl:31
-        H = tuple(max(grid.H[d], need) if not grid.flat(d) else 0 for d in range(3))
+            cneed = max(cneed, 2 if c.kind in ("amd", "smagorinsky") else 1)   # AbstractScalarDiffusivity{…, 2}: smagorinsky.jl:31
+        H = tuple(max(grid.H[d], adv.scheme_of(advection, d).buffer, cneed) if not grid.flat(d) else 0 for d in range(3))
         if H != grid.H:
             grid = grid.with_halo(H)
         for d in range(3):
             if not grid.flat(d):
-                assert grid.N[d] >= advection.buffer, "adapt_advection_order lowering is not restated"
+                assert grid.N[d] >= grid.H[d], "halo must be <= size (validate_halo)"
+                # the d-scheme interpolates velocities along every other direction c with its advecting_velocity_scheme: where the
+                # adapted grid's halo H[c] is smaller than that stencil the reference reads outside the halo — not restated
+                sd = adv.scheme_of(advection, d)
+                deep = 2 if (sd.kind in ("weno", "upwind") and sd.buffer == 3) or (sd.kind == "centered" and sd.buffer == 2) else 1
+                for c in range(3):
+                    assert c == d or grid.flat(c) or grid.H[c] >= deep, "adapted scheme reads outside the halo in the reference"
         self.grid, self.FT = grid, FT
         self.advection, self.closures, self.buoyancy, self.coriolis = advection, closures, buoyancy, coriolis
         bcs = boundary_conditions or {}

@@ -246,6 +246,17 @@ BENCH_INSTANCE_CASES = [
     ("multi-tile 72x40x36 PPP upwind5 TS F64", dict(N=(72, 40, 36), topo="PPP", scheme="upwind5")),
 ]
 
+# adapt_advection_order (src/Advection/adapt_advection_order.jl:18-96): grids with fewer points than the scheme's buffer in some direction
+# — the scheme is lowered THERE and the model steps with FluxFormAdvection(x, y, z) (general tile kernel, run-time scheme per direction)
+ADAPT_CASES = [
+    ("4x2x4 PPB weno -> WENO(3) in y (the reference's small_grid)", dict(N=(4, 2, 4), topo="PPB", scheme="weno")),
+    ("8x1x8 PPB weno3 -> UpwindBiased(1) in y", dict(N=(8, 1, 8), topo="PPB", scheme="weno3")),
+    ("2x8x6 PPP upwind5 -> UpwindBiased(3) in x", dict(N=(2, 8, 6), topo="PPP", scheme="upwind5")),
+    ("8x6x1 PPB upwind3 -> UpwindBiased(1) in z, AB2", dict(N=(8, 6, 1), topo="PPB", scheme="upwind3", ts="QuasiAdamsBashforth2")),
+    ("2x2x8 BBB weno amd fplane F32", dict(N=(2, 2, 8), topo="BBB", scheme="weno", closure="amd", f=1e-2, FT=np.float32)),
+    ("1x8x8 PPB upwind3 -> UpwindBiased(1) in x, bcs", dict(N=(1, 8, 8), topo="PPB", scheme="upwind3", bcs=True)),
+]
+
 # the other advection schemes of the family up to order 5 (the list of test/test_time_stepping.jl:261-267)
 SCHEME_CASES = [
     ("PPB centered4 scalar TS", dict(N=(16, 12, 8), topo="PPB", scheme="centered4")),

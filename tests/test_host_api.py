@@ -40,7 +40,7 @@ def model_construction(library):
 
 
 def halo_adjustment(library):
-    """test/test_nonhydrostatic_models.jl:40-69 (inflate_grid_halo_size) and :78-86 (adapt_advection_order: not implemented -> error)"""
+    """test/test_nonhydrostatic_models.jl:40-69 (inflate_grid_halo_size)"""
     kw = {} if library is None else {"library": library}
     minimal = ob.RectilinearGrid(size=(4, 4, 4), extent=(1, 2, 3), halo=(1, 1, 1))
     funny = ob.RectilinearGrid(size=(4, 4, 4), extent=(1, 2, 3), halo=(1, 3, 4))
@@ -58,10 +58,7 @@ def halo_adjustment(library):
         assert H(ob.NonhydrostaticModel(closure=closure, grid=funny, **kw)) == (2, 3, 4)
     # the minimal grid itself is not modified (the model holds an inflated copy)
     assert (minimal.Hx, minimal.Hy, minimal.Hz) == (1, 1, 1)
-    # :78-86 the reference lowers the order of WENO() to fit Ny = 2; this path does not implement that lowering: a loud error
-    small = ob.RectilinearGrid(size=(4, 2, 4), extent=(1, 2, 3), halo=(1, 1, 1))
-    with pytest.raises((ob.OceananigansB200Error, NotImplementedError, ValueError)):
-        ob.NonhydrostaticModel(grid=small, advection=ob.WENO(), **kw)
+    # :78-86 adapt_advection_order: adjustment_of_advection_schemes() below
 
 
 def setting_model_fields(library, FT):
@@ -291,3 +288,39 @@ def asynchronous_upload(library):
 
 def test_asynchronous_upload_hostsim():
     asynchronous_upload(_hostsim())
+
+
+def adjustment_of_advection_schemes(library):
+    """test/test_nonhydrostatic_models.jl:78-98 "Testing adjustment of advection schemes in NonhydrostaticModel constructor": on
+    small_grid = (4, 2, 4) with halo (1, 1, 1) WENO() becomes a FluxFormAdvection with required halos (3, 2, 3), and the grid's halos
+    follow.  (The reference's UpwindBiased(order = 9) / Centered(order = 10) rows need schemes above order 5: rejected here.)"""
+    kw = {} if library is None else {"library": library}
+    small_grid = ob.RectilinearGrid(np.float64, size=(4, 2, 4), extent=(1, 2, 3), halo=(1, 1, 1))
+    model = ob.NonhydrostaticModel(grid=small_grid, advection=ob.WENO(), **kw)
+    assert isinstance(model.advection, ob.FluxFormAdvection)
+    assert [ob.required_halo_size(model.advection, d) for d in range(3)] == [3, 2, 3]
+    assert (model.grid.Hx, model.grid.Hy, model.grid.Hz) == (3, 2, 3)
+    assert isinstance(model.advection.y, ob.WENO) and model.advection.y.order == 3
+    model = ob.NonhydrostaticModel(grid=small_grid, advection=ob.UpwindBiased(order=5), **kw)
+    assert isinstance(model.advection.y, ob.UpwindBiased) and model.advection.y.order == 3
+    model = ob.NonhydrostaticModel(grid=small_grid, advection=ob.Centered(order=4), **kw)
+    assert not isinstance(model.advection, ob.FluxFormAdvection)               # N = 2 >= buffer 2: nothing to adapt
+    one = ob.RectilinearGrid(np.float64, size=(4, 1, 4), extent=(1, 2, 3), halo=(1, 1, 1))
+    adapted = ob.adapt_advection_order(ob.WENO(), one)
+    assert isinstance(adapted.y, ob.UpwindBiased) and adapted.y.order == 1       # WENO(order = 1) is UpwindBiased(order = 1)
+    # … but stepping it is refused: the x and z schemes (WENO(5)) interpolate the advecting velocity ALONG y with Centered(4), two points
+    # deep, while the adapted scheme gives y a halo of one — the reference reads outside the halo there (undefined values)
+    with pytest.raises(NotImplementedError):
+        ob.NonhydrostaticModel(grid=one, advection=ob.WENO(), **kw)
+    model = ob.NonhydrostaticModel(grid=one, advection=ob.WENO(order=3), **kw)           # WENO(3): Centered(2) for the velocities — fits
+    assert isinstance(model.advection.y, ob.UpwindBiased) and model.advection.y.order == 1
+    assert (model.grid.Hx, model.grid.Hy, model.grid.Hz) == (2, 1, 2)
+    ob.time_step_(model, 1e-3)
+    flat = ob.RectilinearGrid(np.float64, size=(4, 4), extent=(1, 3), topology=(ob.Periodic, ob.Flat, ob.Bounded))
+    model = ob.NonhydrostaticModel(grid=flat, advection=ob.WENO(), **kw)       # Flat directions are not adapted
+    assert not isinstance(model.advection, ob.FluxFormAdvection)
+    ob.time_step_(model, 1e-3)
+
+
+def test_adjustment_of_advection_schemes_hostsim():
+    adjustment_of_advection_schemes(_hostsim())

@@ -98,3 +98,9 @@ def test_cuda_matches_widening_golden(ob, name):
     """frozen vectors of the widening features (tests/golden/make_golden.py: GOLDEN_CASES_WIDENING)"""
     import test_golden as tg
     tg._product_vs_golden(name, None)
+
+
+@pytest.mark.parametrize("name,kw", ph.ADAPT_CASES, ids=[c[0] for c in ph.ADAPT_CASES])
+def test_cuda_matches_oracle_with_adapted_advection_order(ob, name, kw):
+    """adapt_advection_order (src/Advection/adapt_advection_order.jl:18-96): the scheme lowered per direction where N < buffer"""
+    ph.check_case(kw, library=None, steps=(1, 10))
