@@ -658,11 +658,11 @@ void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open) {
             b.lo[0] = lo0; b.lo[1] = lo1; b.lo[2] = lo2;
             b.n[0] = n0; b.n[1] = n1; b.n[2] = n2;
             b.first_block = nb;
-            b.tshift = n0 <= 4 ? 2 : (n0 <= 8 ? 3 : 5);                  // 4 × 64, 8 × 32 or 32 × 8 threads per tile
+            b.tshift = n0 <= 4 ? 2 : (n0 <= 8 ? 3 : (n1 <= 4 ? 6 : 5));     // 4 × 64, 8 × 32, 64 × 4 (slabs a few rows high) or 32 × 8 threads per tile
             const int tw = 1 << b.tshift, th = HaloKernel<FT>::THREADS >> b.tshift;
             b.nbx = (n0 + tw - 1) / tw;
             b.nby = (n1 + th - 1) / th;
-            const long long blocks = (long long)b.nbx * b.nby * n2;
+            const long long blocks = (long long)b.nbx * b.nby * ((n2 + HaloKernel<FT>::ZPT - 1) / HaloKernel<FT>::ZPT);
             if ((long long)nb + blocks >= (1LL << 31)) throw Error(OC_ERR_UNSUPPORTED, "halo slabs with 2^31 or more blocks");
             nb += (int)blocks;
             boxes.push_back(b);
