@@ -373,6 +373,7 @@ void Model<FT>::build_z_tables(const double* faces) {
 
 template <class FT>
 Model<FT>::~Model() {
+    graphs_clear();
     auto fr = [](FieldRec& f) { dev_free(f.base); };
     for (auto& f : state_) fr(f);
     for (auto& f : next_) fr(f);
@@ -627,7 +628,7 @@ template <class FT>
 template <class K>
 void Model<FT>::go(const K& k, Dim3 grid, size_t smem, int cls) {
     begin_timer(cls);
-    cudaError_t e = launch(k, grid, smem, launch_stream_);
+    cudaError_t e = replay_ ? cudaSuccess : launch(k, grid, smem, launch_stream_);
     end_timer();
 #ifndef OC_HOSTSIM
     cuda_check(e, "kernel launch");
@@ -741,7 +742,10 @@ void Model<FT>::dist_attach(Transport* t) {
     // Peer memory for the transposed FFT (OC_DIST_P2P=0 keeps the all-to-all path: measurement / machines without P2P)
     static const char* p2p_env = getenv("OC_DIST_P2P");
     p2p_ = false;
-    if (R_ <= DIST_MAX_RANKS && (p2p_env ? atoi(p2p_env) != 0 : true)) {
+    // Measured (profiles/r02f…r02j): 2 GPUs 70.7 vs 72.7 ms per step, 4 GPUs 71.8 vs 72.5 with / without peer-memory transposes; at 8 GPUs
+    // the first version (every rank writing to rank 0 first: incast) lost, 88.9 vs 77.4, and the round-robin version has not been timed
+    // there — so the default is peer memory up to 4 ranks and the sub-chunked all-to-all beyond; OC_DIST_P2P=1 forces it.
+    if (R_ <= DIST_MAX_RANKS && (p2p_env ? atoi(p2p_env) != 0 : R_ <= 4)) {
         std::string e1 = transport_->map_peers(fftbuf_, peer_spec_, stream_);
         std::string e2 = transport_->map_peers(distT_, peer_T_, stream_);
         if (e2.empty()) e2 = e1;
@@ -1145,7 +1149,7 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
         // asking for more shared memory than they use — so that the FFT passes and the NCCL kernels can be co-resident.
         size_t smem = K::SMEM;
         if (launch_stream_ != stream_ && smem < 80 * 1024) smem = 80 * 1024;
-        cudaError_t e = launch_march(k, grid, smem, launch_stream_);
+        cudaError_t e = replay_ ? cudaSuccess : launch_march(k, grid, smem, launch_stream_);
         end_timer();
 #ifndef OC_HOSTSIM
         cuda_check(e, "march kernel launch");
@@ -1207,12 +1211,14 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
     phy_async = !aux_valid_ && has_pHY_ && !g_.flat[2] && !has_eddy_ && march_ok_ && F_ > 3 && (phy_env ? atoi(phy_env) != 0 : true);
     if (phy_async) {
         if (!ev_phy_) { cudaEvent_t e; cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate"); ev_phy_ = e; }
-        cuda_check(cudaEventRecord((cudaEvent_t)ev_fork_, stream_), "cudaEventRecord");
-        cuda_check(cudaStreamWaitEvent(stream2_, (cudaEvent_t)ev_fork_, 0), "cudaStreamWaitEvent");
+        if (!replay_) {
+            cuda_check(cudaEventRecord((cudaEvent_t)ev_fork_, stream_), "cudaEventRecord");
+            cuda_check(cudaStreamWaitEvent(stream2_, (cudaEvent_t)ev_fork_, 0), "cudaStreamWaitEvent");
+        }
         launch_stream_ = stream2_;
         hydrostatic_pressure();
         launch_stream_ = stream_;
-        cuda_check(cudaEventRecord((cudaEvent_t)ev_phy_, stream2_), "cudaEventRecord");
+        if (!replay_) cuda_check(cudaEventRecord((cudaEvent_t)ev_phy_, stream2_), "cudaEventRecord");
         aux_valid_ = true;
     }
 #else
@@ -1233,7 +1239,7 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
         if (f < 2 && phy_pending) {
 #ifndef OC_HOSTSIM
             if (launch_stream_ != stream_) launch_stream_ = stream_;          // (u, v always run on the main stream)
-            cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_phy_, 0), "cudaStreamWaitEvent");
+            if (!replay_) cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_phy_, 0), "cudaStreamWaitEvent");
 #endif
             phy_pending = false;
         }
@@ -1386,6 +1392,7 @@ void Model<FT>::set_bc_array(int field, int side, const void* host, size_t nbyte
     cuda_check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");     // the caller's buffer may go away
 #endif
     cfg_.bcs[field][side].has_value = 1;
+    graphs_clear();                                       // (a first upload allocates the array: new kernel arguments)
     tend_valid_ = false;
     aux_valid_ = false;
     if (kind != OC_BC_FLUX) { std::vector<FieldRec*> one{&state_[field]}; halo(one, false); }      // the halo plane follows the new values
@@ -1403,6 +1410,7 @@ void Model<FT>::set_diffusivity_bc(int field, int side, int kind, double value) 
     FieldRec& f = lookup(field);
     f.bc[side].kind = kind;
     f.bc[side].value = kind == OC_BC_FLUX ? 0.0 : value;
+    graphs_clear();                                       // kernel arguments are baked into captured graphs
     aux_valid_ = false;
     tend_valid_ = false;
 }
@@ -1460,7 +1468,7 @@ void Model<FT>::run_fft_solve() {
     NvtxRange nvtx_("solve! (FFTBasedPoissonSolver)");
     if (dist_) { run_fft_solve_dist(); return; }
     begin_timer(OC_TIMER_FFT);
-    std::string e = fft_.forward(fftbuf_);
+    std::string e = replay_ ? std::string() : fft_.forward(fftbuf_);
     end_timer();
     if (!e.empty()) throw Error(OC_ERR_CUDA, e);
     if (stretched_) {
@@ -1527,7 +1535,7 @@ void Model<FT>::run_fft_solve() {
     go(k, grid, 0, OC_TIMER_POISSON_MID);
     }
     begin_timer(OC_TIMER_FFT);
-    e = fft_.inverse(fftbuf_);
+    e = replay_ ? std::string() : fft_.inverse(fftbuf_);
     end_timer();
     if (!e.empty()) throw Error(OC_ERR_CUDA, e);
 }
@@ -1840,6 +1848,70 @@ void Model<FT>::poisson_solve(const void* rhs, void* phi, size_t nbytes) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// CUDA Graphs for launch-bound grids
+// ---------------------------------------------------------------------------------------------------------
+template <class FT>
+bool Model<FT>::graph_eligible() const {
+#ifndef OC_HOSTSIM
+    static const char* env = getenv("OC_GRAPHS");
+    if (env && atoi(env) == 0) return false;
+    const long long cells = (long long)g_.N[0] * g_.N[1] * g_.N[2];
+    return !timing_ && !dist_ && !tracers_in_flight_ && cells <= (env && atoi(env) > 1 ? (1LL << 40) : (1LL << 20));     // OC_GRAPHS=2: any size (measurement)
+#else
+    return false;
+#endif
+}
+
+template <class FT>
+void Model<FT>::graphs_clear() {
+#ifndef OC_HOSTSIM
+    for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy((cudaGraphExec_t)kv.second.exec);
+#endif
+    graphs_.clear();
+}
+
+// body() enqueues one time step AND does its host-side bookkeeping.  First use of a key: eager (lazy initialisations — halo box tables,
+// function attributes — happen outside any capture).  Second use: captured into a graph, instantiated, launched.  From then on: body()
+// runs with replay_ set (bookkeeping only) and the graph is launched.
+template <class FT>
+template <class Body>
+void Model<FT>::run_graphed(const std::string& key, Body&& body) {
+#ifndef OC_HOSTSIM
+    if (!graph_eligible()) { body(); return; }
+    if (graphs_.size() > 16) graphs_clear();
+    GraphEntry& e = graphs_[key];
+    if (e.exec) {
+        replay_ = true;
+        try { body(); } catch (...) { replay_ = false; throw; }
+        replay_ = false;
+        cuda_check(cudaGraphLaunch((cudaGraphExec_t)e.exec, stream_), "cudaGraphLaunch");
+        return;
+    }
+    if (e.seen++ == 0) { body(); return; }
+    cuda_check(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+    cudaGraph_t graph = nullptr;
+    try {
+        body();
+    } catch (...) {
+        cudaStreamEndCapture(stream_, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        throw;
+    }
+    cuda_check(cudaStreamEndCapture(stream_, &graph), "cudaStreamEndCapture");
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    cuda_check(err, "cudaGraphInstantiate");
+    e.exec = exec;
+    cuda_check(cudaGraphLaunch(exec, stream_), "cudaGraphLaunch");
+#else
+    (void)key;
+    body();
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // hot path
 // ---------------------------------------------------------------------------------------------------------
 template <class FT>
@@ -1885,11 +1957,16 @@ void Model<FT>::time_step_rk3(double dt) {
     const double dt2 = dt * (double)(FT)(gamma_[1] + zeta_[1]);
     const double dt3 = dt * (double)(FT)(gamma_[2] + zeta_[2]);
     const double tn1 = clock.time + dt;
-    stage(STEP_RK3_FIRST, dt, 1, dt1, 0.0, false);
+    join_tracers();
+    char key[160];
+    snprintf(key, sizeof(key), "rk3 %p %p %d %d %a", (void*)state_[0].p, (void*)Gn_[0].p, (int)gn_pending_, (int)aux_valid_, dt);
+    run_graphed(key, [&] {
+        stage(STEP_RK3_FIRST, dt, 1, dt1, 0.0, false);
+        stage(STEP_RK3, dt, 2, dt2, 0.0, false);
+        stage(STEP_RK3, dt, 3, dt3, 0.0, false);
+    });
     clock.time += dt1; clock.stage += 1; clock.last_stage_dt = dt1;
-    stage(STEP_RK3, dt, 2, dt2, 0.0, false);
     clock.time += dt2; clock.stage += 1; clock.last_stage_dt = dt2;
-    stage(STEP_RK3, dt, 3, dt3, 0.0, false);
     const double corrected = tn1 - clock.time;           // :148-161
     clock.time += dt3;
     clock.iteration += 1;
@@ -1904,7 +1981,10 @@ void Model<FT>::time_step_ab2(double dt, int euler_in) {
     if (cfg_.timestepper != OC_AB2) throw Error(OC_ERR_STATE, "model was created with another time stepper");
     const bool euler = euler_in || (dt != clock.last_dt);            // quasi_adams_bashforth_2.jl:88
     const double chi = euler ? -0.5 : cfg_.ab2_chi;
-    stage(STEP_AB2, dt, 1, dt, chi, euler);
+    join_tracers();
+    char key[160];
+    snprintf(key, sizeof(key), "ab2 %p %p %d %d %a %d", (void*)state_[0].p, (void*)Gn_[0].p, (int)gn_pending_, (int)aux_valid_, dt, (int)euler);
+    run_graphed(key, [&] { stage(STEP_AB2, dt, 1, dt, chi, euler); });
     clock.time += dt;
     clock.iteration += 1;
     clock.stage = 1;

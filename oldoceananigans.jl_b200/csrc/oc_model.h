@@ -201,6 +201,15 @@ private:
     std::vector<FieldRec> kappa_e_;
     bool has_pHY_ = false, has_amd_ = false, has_smag_ = false, has_eddy_ = false;   // has_eddy_: νₑ / κₑ fields exist (AMD or Smagorinsky)
     bool tend_valid_ = false;     // Gⁿ == G(current state)
+    // CUDA Graphs for launch-bound (small) grids: one whole time step — ~40 launches, each shorter than its launch overhead below ~10⁶ cells
+    // — is captured once per buffer parity and replayed with ONE launch.  The host-side bookkeeping of the step (pointer swaps of the
+    // double-buffered state and of Gⁿ / G⁻, validity flags, the clock) runs every time; in replay mode only the enqueues are skipped.
+    struct GraphEntry { void* exec = nullptr; int seen = 0; };
+    std::map<std::string, GraphEntry> graphs_;
+    bool replay_ = false;
+    bool graph_eligible() const;
+    void graphs_clear();
+    template <class Body> void run_graphed(const std::string& key, Body&& body);
     bool gn_pending_ = false;     // the Gⁿ slot holds the evaluation the last fused stage consumed: it becomes G⁻ (pointer swap) before the next evaluation
     bool aux_valid_ = false;      // pHY′, νₑ, κₑ computed from the current state
     struct HaloCache { HaloBox* boxes; int nboxes; int nblocks; };
