@@ -33,10 +33,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "cell-updates/sec per full RK3 step"
-# measured DRAM traffic per MarchKernel launch (bytes), from one `ncu --set full` capture per workload (profiles/)
-NCU_TRAFFIC = {"c3": 6.53e9}
-# FP64 instructions executed per cell per MarchKernel launch (ncu source page, profiles/r01f_ncu_march_c3_summary.txt)
-NCU_FP64_PER_CELL = {"c3": 203.0}        # mean of u, v, w, T, S kernels (213, 213, 211, 189, 189): ncu source page, executed DFMA+DMUL+DADD+DSETP
+# measured DRAM traffic per MarchKernel launch (bytes) and FP64 instructions executed per cell: derived from the ncu capture of the SHIPPED
+# kernels by the session that made the capture (profiles/ncu_march_traffic.json names the capture files) — not constants of this file
+def _ncu_facts():
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_march_traffic.json")))
+    except Exception:
+        return {}, {}, {}
+    return ({k: v["dram_bytes_per_launch_mean"] for k, v in d.items()}, {k: v["fp64_instr_per_cell"]["mean"] for k, v in d.items()},
+            {k: v["source"] for k, v in d.items()})
+
+
+NCU_TRAFFIC, NCU_FP64_PER_CELL, NCU_SOURCE = _ncu_facts()
 
 # name -> description of the BASELINE.json configuration
 WORKLOADS = {
@@ -531,7 +539,7 @@ def run_ours(args):
                    if cells >= 256 ** 3 else "working set may fit L2 (launch-latency configuration)"},
         "roofline": {"bound": "hbm", "kernel": "TendencyKernel (fused tendency + RK3 substep, one launch per prognostic field)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(args.workload if world == 1 else None),
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 5 first-stage launches in profiles/r01f_ncu_march_c3_summary.txt (ncu --set full)" if (world == 1 and args.workload in NCU_TRAFFIC) else None,
+                     "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 5 launches of one stage: " + NCU_SOURCE[args.workload]) if (world == 1 and args.workload in NCU_TRAFFIC) else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                      "avg_launch_ms": avg_launch_ms, "launches_per_step": launches_per_step,
                      "step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
@@ -542,7 +550,7 @@ def run_ours(args):
                        "achieved_lane_ops_per_s": NCU_FP64_PER_CELL[args.workload] * cells / (avg_launch_ms * 1e-3),
                        "peak_lane_ops_per_s": 64 * 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6,
                        "frac": NCU_FP64_PER_CELL[args.workload] * cells / (avg_launch_ms * 1e-3) / (64 * 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
-                       "source": "instruction count from the ncu source page; time from this run's CUDA events"}
+                       "source": "instruction count from the ncu source page (profiles/ncu_march_traffic.json); time from this run's CUDA events"}
                       if (world == 1 and args.workload in NCU_FP64_PER_CELL and tend_n) else None),
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()},
         "kernel_launches_per_step": {k: v[1] / args.steps for k, v in timers.items()},
