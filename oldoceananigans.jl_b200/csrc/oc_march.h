@@ -504,6 +504,7 @@ struct MarchKernel {
     TileSrc<FT> src[4];   // staged fields, ring order
     int xpad;             // TMA coordinate of interior index i = 0 (j = 0 ↔ H[1], k = 0 ↔ H[2])
     int KC;               // z-levels per chunk (grid.z chunks)
+    int by0;              // first tile row of this launch (interior / boundary-strip split of distributed models: oc_model.cu tendencies())
 
     OC_HD int k_begin(const Block& b) const { return b.z * KC; }
     OC_HD int k_end(const Block& b) const { int e = (b.z + 1) * KC; return e < a.g.N[2] ? e : a.g.N[2]; }
@@ -563,7 +564,7 @@ struct MarchKernel {
         MarchSlots& st = stt.sl;
         {
             const int lane_ = tid & (TX - 1), row_ = tid / TX;
-            const int ci = b.x * TX + lane_, cj = b.y * TY + row_;
+            const int ci = b.x * TX + lane_, cj = (b.y + by0) * TY + row_;
             stt.cell = 0;
             for (int h = 0; h < CPT; ++h) {
                 stt.fz_prev[h] = FT(0); stt.dfz[h] = FT(0); stt.gm[h] = FT(0); stt.ph0[h] = FT(0); stt.ph1[h] = FT(0);
@@ -577,7 +578,7 @@ struct MarchKernel {
             st.sk[0] = G0::slot_of(kf0); st.sk[1] = G1::slot_of(kf0); st.sk[2] = G2::slot_of(kf0); st.sk[3] = G3::slot_of(kf0);
         }
         if (tid != 0) return;
-        const int i0 = b.x * TX, j0 = b.y * TY, kf = k_begin(b) - 1, n = iterations(b);
+        const int i0 = b.x * TX, j0 = (b.y + by0) * TY, kf = k_begin(b) - 1, n = iterations(b);
         // iteration 0 (level kf): every live level of every ring
         const Ctx c = raw(smem);
         uint64_t* bv = bar_v(smem, 0);
@@ -781,7 +782,7 @@ struct MarchKernel {
     template <int PHASE>
     OC_DEV void step(const Block& b, int tid, char* smem, int it, State& stt) const {
         const Geom<FT>& g = a.g;
-        const int i0 = b.x * TX, j0 = b.y * TY;
+        const int i0 = b.x * TX, j0 = (b.y + by0) * TY;
         const int nit = stt.nit;
         const int k = k_begin(b) - 1 + it;                   // level of this iteration (it = 0: z-flux only)
         const Ctx cx{smem, k, stt.sl};
@@ -892,7 +893,10 @@ struct MarchKernel {
                 const FT dFz = stt.dfz[h];
                 FT G = -(m_rV(COMP == 2, kc) * (dFx + dFy + dFz));
                 if ((KIND == KIND_U || KIND == KIND_V) && a.has_coriolis) {
-                    // FPlane (f_plane.jl:50-52); the other horizontal component is ring 1
+                    // FPlane (f_plane.jl:50-52) and BetaPlane (beta_plane.jl:56-72: the same with f = f₀ + β·ynode of the velocity point,
+                    // one more FMA); the other horizontal component is ring 1
+                    FT fj = a.f;
+                    if (a.has_coriolis == 2) fj = a.f + a.cor_beta * (a.cor_y0 + (FT(j) + (KIND == KIND_U ? FT(0.5) : FT(0))) * g.d[1]);
                     G1 q = r1(cx);
                     FT num, cnt = FT(1);
                     if (KIND == KIND_U) {
@@ -903,7 +907,7 @@ struct MarchKernel {
                             cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
                         }
                         FT val = cnt == FT(0) ? FT(0) : num / cnt;
-                        G = G - (-a.f * val);
+                        G = G - (-fj * val);
                     } else {
                         num = FT(0.25) * ((q(ii, jj - 1, kc) + q(ii + 1, jj - 1, kc)) + (q(ii, jj, kc) + q(ii + 1, jj, kc)));
                         if (WIN) {
@@ -912,7 +916,7 @@ struct MarchKernel {
                             cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
                         }
                         FT val = cnt == FT(0) ? FT(0) : num / cnt;
-                        G = G - (a.f * val);
+                        G = G - (fj * val);
                     }
                 }
                 if ((KIND == KIND_U || KIND == KIND_V) && a.pHY) G = G - (stt.ph0[h] - stt.ph1[h]) * g.rd[KIND == KIND_U ? 0 : 1];

@@ -177,7 +177,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         const bool any_bounded = c.topology[0] == OC_BOUNDED || c.topology[1] == OC_BOUNDED || c.topology[2] == OC_BOUNDED;
         // BetaPlane / ConstantCartesianCoriolis run in the general tile kernel: the z-marching kernel of the
         // measured BASELINE configurations keeps exactly the code (and register counts) it was profiled with
-        march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) && c.has_coriolis <= OC_CORIOLIS_FPLANE && !c.tilted_gravity && !c.has_advection_dir &&
+        march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) && (c.has_coriolis <= OC_CORIOLIS_FPLANE || c.has_coriolis == OC_CORIOLIS_BETAPLANE) && !c.tilted_gravity && !c.has_advection_dir &&
                     (c.advection == OC_CENTERED2 || c.advection == OC_WENO5 || (c.advection == OC_UPWIND5 && !any_bounded && !c.has_amd && !c.smagorinsky));
     }
     g_.dzc = g_.dzf = g_.rdzc = g_.rdzf = g_.rVc = g_.rVf = nullptr;
@@ -395,6 +395,7 @@ Model<FT>::~Model() {
     if (sw0_) { cudaEventDestroy((cudaEvent_t)sw0_); cudaEventDestroy((cudaEvent_t)sw1_); }
     if (ev_fork_) { cudaEventDestroy((cudaEvent_t)ev_fork_); cudaEventDestroy((cudaEvent_t)ev_join_); }
     if (ev_phy_) cudaEventDestroy((cudaEvent_t)ev_phy_);
+    if (ev_xchg_) cudaEventDestroy((cudaEvent_t)ev_xchg_);
     for (void* e : ev_a2a_) cudaEventDestroy((cudaEvent_t)e);
     for (void* e : ev_mid_) cudaEventDestroy((cudaEvent_t)e);
     for (auto& s : out_slots_) {
@@ -450,6 +451,7 @@ template <class FT>
 void Model<FT>::sync() {
 #ifndef OC_HOSTSIM
     join_tracers();
+    join_exchange();
     cuda_check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");
 #endif
 }
@@ -491,6 +493,7 @@ void Model<FT>::recover() {
     cudaGetLastError();
 #endif
     tracers_in_flight_ = false;
+    xchg_pending_ = false;           // (stream3_ was joined above)
 }
 
 template <class FT>
@@ -642,7 +645,7 @@ void Model<FT>::go(const K& k, Dim3 grid, size_t smem, int cls) {
 // halo fill: one launch for any list of fields
 // ---------------------------------------------------------------------------------------------------------
 template <class FT>
-void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open) {
+void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open, bool defer_exchange) {
     NvtxRange nvtx_("fill_halo_regions!");
     if (fields.empty()) return;
     if ((int)fields.size() > HALO_MAX_FIELDS) throw Error(OC_ERR_INVALID, "too many fields in one halo fill");
@@ -729,7 +732,36 @@ void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open) {
             go(hk, hg, 0, OC_TIMER_HALO);
         }
     }
-    if (dist_) exchange_y(fields);
+    if (!dist_) return;
+#ifndef OC_HOSTSIM
+    if (defer_exchange && stream3_) {
+        // The exchange runs on the communication stream while the NEXT stage's interior tendency kernels — which read no y-halo row —
+        // run on the main stream (interleave_communication_and_computation.jl:29-67); tendencies() waits for ev_xchg_ before the two
+        // boundary strips.  No other NCCL call is enqueued anywhere until that wait, so the communicator sees one stream at a time.
+        if (!ev_xchg_) { cudaEvent_t e; cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate"); ev_xchg_ = e; }
+        cuda_check(cudaEventRecord((cudaEvent_t)ev_fork_, stream_), "cudaEventRecord");
+        cuda_check(cudaStreamWaitEvent(stream3_, (cudaEvent_t)ev_fork_, 0), "cudaStreamWaitEvent");
+        launch_stream_ = stream3_;
+        try { exchange_y(fields); } catch (...) { launch_stream_ = stream_; throw; }
+        launch_stream_ = stream_;
+        cuda_check(cudaEventRecord((cudaEvent_t)ev_xchg_, stream3_), "cudaEventRecord");
+        xchg_pending_ = true;
+        return;
+    }
+#else
+    (void)defer_exchange;
+#endif
+    exchange_y(fields);
+}
+
+// the main stream waits for a deferred y-halo exchange (every consumer of halo rows other than the split tendencies() calls this)
+template <class FT>
+void Model<FT>::join_exchange() {
+    if (!xchg_pending_) return;
+#ifndef OC_HOSTSIM
+    cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_xchg_, 0), "cudaStreamWaitEvent");
+#endif
+    xchg_pending_ = false;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -830,7 +862,7 @@ void Model<FT>::exchange_y(const std::vector<FieldRec*>& fields) {
     msgs.push_back(Msg{prev, next, 0, halo_send_, per_side * sizeof(FT), halo_recv_ + per_side, per_side * sizeof(FT)});
     msgs.push_back(Msg{next, prev, 1, halo_send_ + per_side, per_side * sizeof(FT), halo_recv_, per_side * sizeof(FT)});
     begin_timer(OC_TIMER_COMM);
-    std::string e = transport_->exchange(msgs, stream_);
+    std::string e = transport_->exchange(msgs, launch_stream_);
     end_timer();
     if (!e.empty()) throw Error(OC_ERR_CUDA, e);
     k.unpack = 1; k.buf = halo_recv_;
@@ -1006,6 +1038,13 @@ void Model<FT>::aux() {
 // update_hydrostatic_pressure!  (update_hydrostatic_pressure.jl:12-49): one column scan, launched on launch_stream_
 template <class FT>
 void Model<FT>::hydrostatic_pressure() {
+    hydrostatic_pressure_rows(g_.flat[1] ? 0 : -1, g_.flat[1] ? g_.N[1] : g_.N[1] + 2);
+}
+
+// … for the rows jlo … jlo + nj - 1 (the reference's range is -1 … Ny, p_kernel_parameters :41-49; the distributed split computes the
+// two halo rows after the exchange that fills T and S there)
+template <class FT>
+void Model<FT>::hydrostatic_pressure_rows(int jlo, int nj) {
     if (has_pHY_ && !g_.flat[2]) {
         HydrostaticPressureKernel<FT> k;
         k.g = g_;
@@ -1017,7 +1056,7 @@ void Model<FT>::hydrostatic_pressure() {
         k.tilted = cfg_.tilted_gravity ? 1 : 0;
         k.gz = -(FT)cfg_.gravity_unit_vector[2];
         k.ilo = g_.flat[0] ? 0 : -1; k.ni = g_.flat[0] ? g_.N[0] : g_.N[0] + 2;
-        k.jlo = g_.flat[1] ? 0 : -1; k.nj = g_.flat[1] ? g_.N[1] : g_.N[1] + 2;
+        k.jlo = jlo; k.nj = nj;
         Dim3 grid;
         grid.x = (k.ni + HydrostaticPressureKernel<FT>::THREADS - 1) / HydrostaticPressureKernel<FT>::THREADS;
         grid.y = k.nj;
@@ -1121,7 +1160,7 @@ TileSrc<FT> Model<FT>::tile_src(const FT* base, int bx, int by) {
 
 template <class FT>
 template <int KIND>
-void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
+void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a, int part) {
     auto run = [&](auto k) {
         using K = decltype(k);
         using SP = typename K::SP;
@@ -1144,19 +1183,30 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a) {
         zch = std::max(1, std::min(zch, (g_.N[2] + 15) / 16));
         k.KC = (g_.N[2] + zch - 1) / zch;
         grid.z = (g_.N[2] + k.KC - 1) / k.KC;
-        begin_timer(OC_TIMER_TENDENCY);
         // Kernels that overlap the pressure solve (stream2) leave a third of every SM free — two CTAs per SM instead of three, by
         // asking for more shared memory than they use — so that the FFT passes and the NCCL kernels can be co-resident.
         size_t smem = K::SMEM;
         if (launch_stream_ != stream_ && smem < 80 * 1024) smem = 80 * 1024;
-        cudaError_t e = replay_ ? cudaSuccess : launch_march(k, grid, smem, launch_stream_);
-        end_timer();
+        // tile rows of this launch: everything, the interior (no stencil of tile rows 1 … NBY-2 reaches a y-halo row: TY >= 8 > 3),
+        // or the two boundary strips.  With fewer than three tile rows there is no interior: the strips are everything.
+        const int NBY = grid.y;
+        int rows[2][2] = {{0, NBY}, {0, 0}};
+        if (part == PART_INTERIOR) { rows[0][0] = 1; rows[0][1] = NBY >= 3 ? NBY - 2 : 0; }
+        else if (part == PART_STRIPS && NBY >= 3) { rows[0][0] = 0; rows[0][1] = 1; rows[1][0] = NBY - 1; rows[1][1] = 1; }
+        for (int r = 0; r < 2; ++r) {
+            if (rows[r][1] <= 0) continue;
+            k.by0 = rows[r][0];
+            grid.y = rows[r][1];
+            begin_timer(OC_TIMER_TENDENCY);
+            cudaError_t e = replay_ ? cudaSuccess : launch_march(k, grid, smem, launch_stream_);
+            end_timer();
 #ifndef OC_HOSTSIM
-        cuda_check(e, "march kernel launch");
+            cuda_check(e, "march kernel launch");
 #else
-        (void)e;
+            (void)e;
 #endif
-        ++launches;
+            ++launches;
+        }
     };
     const bool bnd = g_.bounded[0] || g_.bounded[1] || g_.bounded[2];
     const bool gen = has_eddy_;
@@ -1207,6 +1257,13 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
     // they leave free); u and v are launched last and wait for it.  OC_PHY_ASYNC=0 switches back (measurement).
     static const char* phy_env = getenv("OC_PHY_ASYNC");
     bool phy_async = false;
+    // Distributed models: the previous stage's y-halo exchange may still be in flight on the communication stream (halo(): defer_exchange).
+    // Then every field's INTERIOR tile rows are launched first — none of their stencils reaches a y-halo row —, the main stream (and the
+    // tracer stream) wait for the exchange, and the two boundary strips follow (interleave_communication_and_computation.jl:29-67,
+    // compute_nonhydrostatic_buffer_tendencies.jl:10-84).  pHY′: rows 0 … Ny-1 now, the two halo rows after the exchange.  Closures with
+    // eddy-viscosity fields read halo rows in aux(): no split for them.
+    const bool split = xchg_pending_ && march_ok_ && !has_eddy_;
+    if (xchg_pending_ && !split) join_exchange();
 #ifndef OC_HOSTSIM
     phy_async = !aux_valid_ && has_pHY_ && !g_.flat[2] && !has_eddy_ && march_ok_ && F_ > 3 && (phy_env ? atoi(phy_env) != 0 : true);
     if (phy_async) {
@@ -1216,7 +1273,7 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
             cuda_check(cudaStreamWaitEvent(stream2_, (cudaEvent_t)ev_fork_, 0), "cudaStreamWaitEvent");
         }
         launch_stream_ = stream2_;
-        hydrostatic_pressure();
+        if (split) hydrostatic_pressure_rows(0, g_.N[1]); else hydrostatic_pressure();
         launch_stream_ = stream_;
         if (!replay_) cuda_check(cudaEventRecord((cudaEvent_t)ev_phy_, stream2_), "cudaEventRecord");
         aux_valid_ = true;
@@ -1224,25 +1281,15 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
 #else
     (void)phy_env;
 #endif
+    if (split && has_pHY_ && !g_.flat[2] && !aux_valid_) { hydrostatic_pressure_rows(0, g_.N[1]); aux_valid_ = true; }
+    const bool do_split = split && xchg_pending_;
     if (!aux_valid_) aux();
     // Measured (profiles/): on one GPU the co-residency costs the tracer kernels more than the overlap wins (69.4 vs 67.5 ms);
     // across GPUs it hides part of the NCCL transposes (77.1 vs 79.4 ms at 2 GPUs) — so it is on for distributed models only.
     static const char* ov_env = getenv("OC_OVERLAP");
     const bool want = ov_env ? atoi(ov_env) != 0 : dist_;
     const bool overlap = defer_tracer_join && F_ > 3 && march_ok_ && want;
-    bool phy_pending = phy_async;
-    for (int n = 0; n < F_; ++n) {
-        // launch order when the pHY′ scan is in flight: the kernels that do not read it first — w and the tracers, then u and v; with the
-        // distributed overlap (tracers beside the pressure solve, after the velocities) only w: w, u, v, tracers
-        const int f = !phy_async ? n : (overlap ? (n == 0 ? 2 : (n < 3 ? n - 1 : n)) : (n < F_ - 2 ? n + 2 : n - (F_ - 2)));
-        if (f == 3 && overlap) fork_tracers();
-        if (f < 2 && phy_pending) {
-#ifndef OC_HOSTSIM
-            if (launch_stream_ != stream_) launch_stream_ = stream_;          // (u, v always run on the main stream)
-            if (!replay_) cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_phy_, 0), "cudaStreamWaitEvent");
-#endif
-            phy_pending = false;
-        }
+    auto make_args = [&](int f) {
         TendencyArgs<FT> a;
         memset(&a, 0, sizeof(a));
         a.g = g_;
@@ -1264,6 +1311,8 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
         a.grav = (FT)cfg_.gravity; a.alpha = (FT)cfg_.thermal_expansion; a.beta = (FT)cfg_.haline_contraction;
         a.has_coriolis = cfg_.has_coriolis;
         a.f = (FT)cfg_.coriolis_f;
+        a.cor_beta = (FT)cfg_.coriolis_beta;
+        a.cor_y0 = (FT)cfg_.origin_y + (FT)((dist_ ? rank_ : 0) * g_.N[1]) * g_.d[1];
         for (int s = 0; s < 6; ++s) {
             const SideBC& bc = state_[f].bc[s];
             const oc_bc& ub = cfg_.bcs[f][s];
@@ -1278,19 +1327,56 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
         if (mode == STEP_RK3_FIRST) { a.ca = (FT)dt * gamma_[0]; a.cb = FT(0); }
         else if (mode == STEP_RK3) { a.ca = gamma_[stage - 1]; a.cb = zeta_[stage - 1]; }
         else if (mode == STEP_AB2) { a.ca = FT(1.5) + (FT)chi; a.cb = FT(0.5) + (FT)chi; }
-        if (march_ok_) {
-            if (f == 0) launch_march_tendency<KIND_U>(f, a);
-            else if (f == 1) launch_march_tendency<KIND_V>(f, a);
-            else if (f == 2) launch_march_tendency<KIND_W>(f, a);
-            else launch_march_tendency<KIND_C>(f, a);
-        } else if (f == 0) launch_tendency<KIND_U>(f, a);
-        else if (f == 1) launch_tendency<KIND_V>(f, a);
-        else if (f == 2) launch_tendency<KIND_W>(f, a);
-        else launch_tendency<KIND_C>(f, a);
-        if (add_flux_bcs) {          // array-valued Flux BCs: boundary-plane pass on the same stream (FluxArrayKernel)
-            const FT coef = mode == STEP_RK3_FIRST ? a.ca : ((mode == STEP_RK3 || mode == STEP_AB2) ? a.dt * a.ca : FT(0));
-            apply_flux_arrays(f, a.Gn, mode == STEP_NONE ? nullptr : a.Unew, coef);
+        return a;
+    };
+    // launch order when the pHY′ scan is in flight: the kernels that do not read it first — w and the tracers, then u and v; with the
+    // distributed overlap (tracers beside the pressure solve, after the velocities) only w: w, u, v, tracers
+    auto field_of = [&](int n) { return !phy_async ? n : (overlap ? (n == 0 ? 2 : (n < 3 ? n - 1 : n)) : (n < F_ - 2 ? n + 2 : n - (F_ - 2))); };
+    bool phy_pending = phy_async;
+    auto launch_pass = [&](int part) {
+        for (int n = 0; n < F_; ++n) {
+            const int f = field_of(n);
+            if (f >= 3 && overlap) { if (!tracers_in_flight_) fork_tracers(); }
+#ifndef OC_HOSTSIM
+            if (overlap) launch_stream_ = f >= 3 ? stream2_ : stream_;
+#endif
+            if (f < 2 && phy_pending) {
+#ifndef OC_HOSTSIM
+                if (!replay_) cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_phy_, 0), "cudaStreamWaitEvent");
+#endif
+                phy_pending = false;
+            }
+            TendencyArgs<FT> a = make_args(f);
+            if (march_ok_) {
+                if (f == 0) launch_march_tendency<KIND_U>(f, a, part);
+                else if (f == 1) launch_march_tendency<KIND_V>(f, a, part);
+                else if (f == 2) launch_march_tendency<KIND_W>(f, a, part);
+                else launch_march_tendency<KIND_C>(f, a, part);
+            } else if (f == 0) launch_tendency<KIND_U>(f, a);
+            else if (f == 1) launch_tendency<KIND_V>(f, a);
+            else if (f == 2) launch_tendency<KIND_W>(f, a);
+            else launch_tendency<KIND_C>(f, a);
+            if (add_flux_bcs && part != PART_INTERIOR) {          // array-valued Flux BCs: boundary-plane pass on the same stream (FluxArrayKernel)
+                const FT coef = mode == STEP_RK3_FIRST ? a.ca : ((mode == STEP_RK3 || mode == STEP_AB2) ? a.dt * a.ca : FT(0));
+                apply_flux_arrays(f, a.Gn, mode == STEP_NONE ? nullptr : a.Unew, coef);
+            }
         }
+    };
+    if (!do_split) {
+        launch_pass(PART_ALL);
+    } else {
+        launch_pass(PART_INTERIOR);
+#ifndef OC_HOSTSIM
+        launch_stream_ = stream_;
+        cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_xchg_, 0), "cudaStreamWaitEvent");
+        if (tracers_in_flight_) cuda_check(cudaStreamWaitEvent(stream2_, (cudaEvent_t)ev_xchg_, 0), "cudaStreamWaitEvent");
+#endif
+        xchg_pending_ = false;
+        if (has_pHY_ && !g_.flat[2]) {           // the two halo rows of pHY′ (T, S are there now); the v strip at j = 0 reads row -1
+            hydrostatic_pressure_rows(-1, 1);
+            hydrostatic_pressure_rows(g_.N[1], 1);
+        }
+        launch_pass(PART_STRIPS);
     }
     launch_stream_ = stream_;
     if (swap_state && mode != STEP_NONE)
@@ -1945,7 +2031,11 @@ void Model<FT>::stage(int mode, double dt, int stage_no, double stage_dt, double
     join_tracers();                                      // the tracer substeps (stream2) before their halos are filled
     std::vector<FieldRec*> all;
     for (auto& f : state_) all.push_back(&f);
-    halo(all, false);
+    // stages 1 and 2 of an RK3 step are followed by another stage of the same call: their y-halo exchange is overlapped with that stage's
+    // interior tendency kernels (tendencies()); the last stage's exchange completes before time_step! returns.  OC_XCHG_OVERLAP=0: off.
+    static const char* xo_env = getenv("OC_XCHG_OVERLAP");
+    const bool defer = dist_ && march_ok_ && !has_eddy_ && mode != STEP_AB2 && stage_no < 3 && (xo_env ? atoi(xo_env) != 0 : true);
+    halo(all, false, defer);
 }
 
 template <class FT>

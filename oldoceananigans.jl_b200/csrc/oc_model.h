@@ -225,6 +225,10 @@ private:
     Stream launch_stream_ = 0;    // the stream kernel launches and timer events currently go to
     void* ev_fork_ = nullptr;
     void* ev_join_ = nullptr;
+    void* ev_xchg_ = nullptr;     // the deferred end-of-stage y-halo exchange on stream3_ has finished
+    bool xchg_pending_ = false;   // … and the next tendencies() has not consumed it yet
+    void join_exchange();
+    void hydrostatic_pressure_rows(int jlo, int nj);
     void* ev_phy_ = nullptr;      // the pHY′ scan on stream2_ has finished (tendencies())
     bool tracers_in_flight_ = false;
     void fork_tracers();
@@ -243,14 +247,15 @@ private:
     FieldRec alloc_field(const int face[3]);
     FieldRec& lookup(int field);
     void resolve_bcs(FieldRec& f, const oc_bc* user);
-    void halo(const std::vector<FieldRec*>& fields, bool fill_open);
+    void halo(const std::vector<FieldRec*>& fields, bool fill_open, bool defer_exchange = false);
     void aux();
     void hydrostatic_pressure();
     void compute_tendencies_if_stale();
     void rotate_pending_tendencies();
     void tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state, bool defer_tracer_join = false);
     template <int KIND> void launch_tendency(int fidx, TendencyArgs<FT>& a);
-    template <int KIND> void launch_march_tendency(int fidx, TendencyArgs<FT>& a);
+    enum { PART_ALL = 0, PART_INTERIOR = 1, PART_STRIPS = 2 };
+    template <int KIND> void launch_march_tendency(int fidx, TendencyArgs<FT>& a, int part = PART_ALL);
     TileSrc<FT> tile_src(const FT* base, int bx, int by);
     // slab decomposition in y (oc_dist.h)
     bool dist_ = false;

@@ -48,6 +48,7 @@ struct TendencyArgs {
     FT f;
     FluxBC<FT> fbc;      // flux boundary conditions of this field
     int add_flux_bcs;
+    FT cor_beta, cor_y0; // BetaPlane in the z-marching kernel: f = f₀ + β ynode (beta_plane.jl:56-72); y0 = south face of this rank's first row
     int adv_dir[3];      // ADV_MIXED kernels: scheme code of the fluxes through the faces normal to d (adapt_advection_order.jl:18-96)
     int mode;            // SubstepMode
     FT dt, ca, cb;       // RK3_FIRST: U + (dt·γ)·G with ca = dt·γ ; RK3: U + dt(ca·G + cb·G⁻) ; AB2: ca = 1.5+χ, cb = 0.5+χ

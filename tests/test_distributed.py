@@ -82,6 +82,10 @@ def _gpu_count():
     (2, dict(N=(64, 48, 32), topo="PPP", scheme="weno", steps=2)),
     (2, dict(N=(40, 24, 16), topo="PPP", scheme="centered", f=1e-2, steps=3)),
     (2, dict(N=(48, 32, 16), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, steps=2)),
+    # slabs tall enough (64 rows) for the interior / boundary-strip split: the end-of-stage exchange of stages 1 and 2 overlaps the next
+    # stage's interior tile rows (interleave_communication_and_computation.jl:29-67)
+    (2, dict(N=(40, 128, 16), topo="PPP", scheme="weno", steps=2)),
+    (2, dict(N=(40, 96, 16), topo="PPB", scheme="centered", f=1e-2, bcs=True, steps=2)),
     # R >= 3: the two neighbours are different peers (R = 2 is the degenerate case), every rank sends R - 1 transposed-FFT chunks
     (4, dict(N=(64, 48, 32), topo="PPP", scheme="weno", steps=2)),
     (4, dict(N=(48, 32, 16), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, steps=2)),
