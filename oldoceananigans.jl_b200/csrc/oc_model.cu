@@ -180,6 +180,12 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) && (c.has_coriolis <= OC_CORIOLIS_FPLANE || c.has_coriolis == OC_CORIOLIS_BETAPLANE) && !c.tilted_gravity && !c.has_advection_dir &&
                     (c.advection == OC_CENTERED2 || c.advection == OC_WENO5 || (c.advection == OC_UPWIND5 && !any_bounded && !c.has_amd && !c.smagorinsky));
     }
+    {
+        static const char* uvw_env = getenv("OC_UVW");
+        const bool any_bounded = c.topology[0] == OC_BOUNDED || c.topology[1] == OC_BOUNDED || c.topology[2] == OC_BOUNDED;
+        uvw_ok_ = march_ok_ && c.advection == OC_CENTERED2 && !any_bounded && !c.has_amd && !c.smagorinsky && c.dist_nranks <= 1 &&
+                  (uvw_env ? atoi(uvw_env) != 0 : true);
+    }
     g_.dzc = g_.dzf = g_.rdzc = g_.rdzf = g_.rVc = g_.rVf = nullptr;
     C_ = make_coefficients<FT>();
     {   // the compile-time table of oc_march.h must be the very same numbers
@@ -1248,6 +1254,40 @@ void Model<FT>::launch_march_tendency(int fidx, TendencyArgs<FT>& a, int part) {
     else pick(std::integral_constant<int, ADV_CENTERED2>{});
 }
 
+// one launch for u, v and w (oc_uvw.h): Centered(2), no Bounded dimension, constant ν
+template <class FT>
+void Model<FT>::launch_uvw(const TendencyArgs<FT>& au, const TendencyArgs<FT>& av, const TendencyArgs<FT>& aw) {
+    typedef UvwCenteredKernel<FT> K;
+    K k;
+    k.a.g = g_;
+    k.a.pHY = au.pHY;
+    const TendencyArgs<FT>* as[3] = {&au, &av, &aw};
+    for (int c = 0; c < 3; ++c) { k.a.Gm[c] = as[c]->Gm; k.a.Gn[c] = as[c]->Gn; k.a.Unew[c] = as[c]->Unew; }
+    k.a.nu = au.has_scalar ? au.nu : FT(0);
+    k.a.has_coriolis = au.has_coriolis; k.a.f = au.f; k.a.cor_beta = au.cor_beta; k.a.cor_y0 = au.cor_y0;
+    k.a.mode = au.mode; k.a.dt = au.dt; k.a.ca = au.ca; k.a.cb = au.cb; k.a.ab2_euler = au.ab2_euler;
+    for (int c = 0; c < 3; ++c) k.src[c] = tile_src(state_[c].base, K::RS::BX, K::RS::BY);
+    k.xpad = xpad_;
+    k.by0 = 0;
+    Dim3 grid;
+    grid.x = (g_.N[0] + K::TX - 1) / K::TX;
+    grid.y = (g_.N[1] + K::TY - 1) / K::TY;
+    const int tiles = grid.x * grid.y;
+    int zch = (148 * 8 + tiles - 1) / tiles;
+    zch = std::max(1, std::min(zch, (g_.N[2] + 15) / 16));
+    k.KC = (g_.N[2] + zch - 1) / zch;
+    grid.z = (g_.N[2] + k.KC - 1) / k.KC;
+    begin_timer(OC_TIMER_TENDENCY);
+    cudaError_t e = replay_ ? cudaSuccess : launch_march(k, grid, K::SMEM, launch_stream_);
+    end_timer();
+#ifndef OC_HOSTSIM
+    cuda_check(e, "uvw kernel launch");
+#else
+    (void)e;
+#endif
+    ++launches;
+}
+
 template <class FT>
 void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state, bool defer_tracer_join) {
     NvtxRange nvtx_("compute_tendencies! + substep");
@@ -1334,8 +1374,21 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
     auto field_of = [&](int n) { return !phy_async ? n : (overlap ? (n == 0 ? 2 : (n < 3 ? n - 1 : n)) : (n < F_ - 2 ? n + 2 : n - (F_ - 2))); };
     bool phy_pending = phy_async;
     auto launch_pass = [&](int part) {
+        int momentum_seen = 0;
         for (int n = 0; n < F_; ++n) {
             const int f = field_of(n);
+            if (uvw_ok_ && f < 3) {            // u, v, w in ONE launch, issued where the last of the three would have been
+                if (++momentum_seen < 3) continue;
+                if (phy_pending) {
+#ifndef OC_HOSTSIM
+                    if (!replay_) cuda_check(cudaStreamWaitEvent(stream_, (cudaEvent_t)ev_phy_, 0), "cudaStreamWaitEvent");
+#endif
+                    phy_pending = false;
+                }
+                TendencyArgs<FT> au = make_args(0), av = make_args(1), aw = make_args(2);
+                launch_uvw(au, av, aw);
+                continue;
+            }
             if (f >= 3 && overlap) { if (!tracers_in_flight_) fork_tracers(); }
 #ifndef OC_HOSTSIM
             if (overlap) launch_stream_ = f >= 3 ? stream2_ : stream_;

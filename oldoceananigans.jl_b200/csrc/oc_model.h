@@ -21,6 +21,7 @@
 #include "oc_fft.h"
 #include "oc_halo.h"
 #include "oc_march.h"
+#include "oc_uvw.h"
 #include "oc_tendency.h"
 
 namespace oc {
@@ -254,6 +255,8 @@ private:
     void rotate_pending_tendencies();
     void tendencies(int mode, double dt, int stage, double chi, bool euler, bool add_flux_bcs, bool swap_state, bool defer_tracer_join = false);
     template <int KIND> void launch_tendency(int fidx, TendencyArgs<FT>& a);
+    void launch_uvw(const TendencyArgs<FT>& au, const TendencyArgs<FT>& av, const TendencyArgs<FT>& aw);
+    bool uvw_ok_ = false;         // Centered(2) without Bounded dimensions, eddy closures or slabs: one launch for u, v and w (oc_uvw.h)
     enum { PART_ALL = 0, PART_INTERIOR = 1, PART_STRIPS = 2 };
     template <int KIND> void launch_march_tendency(int fidx, TendencyArgs<FT>& a, int part = PART_ALL);
     TileSrc<FT> tile_src(const FT* base, int bx, int by);

@@ -246,6 +246,15 @@ BENCH_INSTANCE_CASES = [
     ("multi-tile 72x40x36 PPP upwind5 TS F64", dict(N=(72, 40, 36), topo="PPP", scheme="upwind5")),
 ]
 
+# UvwCenteredKernel (oc_uvw.h): ONE launch for u, v and w of Centered(2) models without Bounded dimensions — tiles, z-chunks, partial
+# tiles, the Coriolis and pHY′ terms, both time steppers, both float types
+UVW_CASES = [
+    ("uvw 40x36x33 PPP centered TS fplane", dict(N=(40, 36, 33), topo="PPP", scheme="centered", f=1e-2)),
+    ("uvw 40x36x33 PPP centered TS betaplane AB2", dict(N=(40, 36, 33), topo="PPP", scheme="centered", f=("beta", 0.3, 2.0), ts="QuasiAdamsBashforth2")),
+    ("uvw 16x12x8 PPP centered TS fplane F32", dict(N=(16, 12, 8), topo="PPP", scheme="centered", FT=np.float32, f=1e-2)),
+    ("uvw 33x17x9 PPP centered no closure tracer-b", dict(N=(33, 17, 9), topo="PPP", scheme="centered", closure="none", buoy="tracer")),
+]
+
 # adapt_advection_order (src/Advection/adapt_advection_order.jl:18-96): grids with fewer points than the scheme's buffer in some direction
 # — the scheme is lowered THERE and the model steps with FluxFormAdvection(x, y, z) (general tile kernel, run-time scheme per direction)
 ADAPT_CASES = [

@@ -83,6 +83,12 @@ def test_cuda_matches_c_twin_at_128_cubed(ob, scheme, FT, steps):
     print("\n128^3 parity report (step, twin, field) -> rel L-inf:", text)
 
 
+@pytest.mark.parametrize("name,kw", ph.UVW_CASES, ids=[c[0] for c in ph.UVW_CASES])
+def test_cuda_fused_momentum_kernel_matches_oracle(ob, name, kw):
+    """UvwCenteredKernel (oc_uvw.h): one launch for the three momentum tendencies of Centered(2) models without Bounded dimensions"""
+    ph.check_case(kw, library=None)
+
+
 @pytest.mark.parametrize("name,kw", ph.STRETCHED_CASES, ids=[c[0] for c in ph.STRETCHED_CASES])
 def test_cuda_matches_oracle_on_stretched_grids(ob, name, kw):
     """vertically stretched grids (FourierTridiagonalPoissonSolver, level-dependent metrics)"""

@@ -36,6 +36,12 @@ def test_hostsim_benchmark_kernel_instances_across_tiles(hostsim, name, kw):
     ph.check_case(kw, library=hostsim)
 
 
+@pytest.mark.parametrize("name,kw", ph.UVW_CASES, ids=[c[0] for c in ph.UVW_CASES])
+def test_hostsim_fused_momentum_kernel_matches_oracle(hostsim, name, kw):
+    """UvwCenteredKernel: u, v and w tendencies + substep of Centered(2) models in one launch"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))
+
+
 @pytest.mark.parametrize("name,kw", ph.ADAPT_CASES, ids=[c[0] for c in ph.ADAPT_CASES])
 def test_hostsim_matches_oracle_with_adapted_advection_order(hostsim, name, kw):
     """adapt_advection_order: FluxFormAdvection with the scheme lowered where N < buffer (adapt_advection_order.jl:18-96)"""
