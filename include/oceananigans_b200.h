@@ -126,6 +126,13 @@ typedef struct {
      * N[d] >= H[d] are then required per direction.  General tile kernel. */
     int32_t has_advection_dir;
     int32_t advection_dir[3];
+    /* ABI v5.  ScalarDiffusivity(ν = A, κ = (T = B, …)) with AbstractArray / Field coefficients located at (Center, Center, Center)
+     * (abstract_scalar_diffusivity_closure.jl:323-332: νᶜᶜᶜ = ν[i, j, k], νᶠᶠᶜ = ℑxy ν, κᶠᶜᶜ = ℑx κ, … — the interpolations the eddy-viscosity
+     * closures use).  array_diffusivity = 1: the model owns the fields OC_FIELD_NU_E and OC_FIELD_KAPPA_E0 + t, never computes them, and
+     * the caller fills them with oc_upload_interior / _parent (+ oc_fill_halo_regions, like fill_halo_regions!(ν) in the reference);
+     * fields never uploaded are zero.  May be combined with a constant ScalarDiffusivity (a closure tuple), not with AMD / Smagorinsky. */
+    int32_t array_diffusivity;
+    int32_t reserved3;
 } oc_config;
 
 typedef struct oc_model oc_model;

@@ -73,6 +73,7 @@ mutable struct OcConfig               # `oc_config`, same field order; NTuple fo
     amd_Cb::Float64                                 # ABI v4: AnisotropicMinimumDissipation(; Cb), with amd_has_Cb
     coriolis_gamma::Float64; coriolis_radius::Float64; origin_z::Float64  # ABI v4: NonTraditionalBetaPlane (has_coriolis = 4)
     has_advection_dir::Int32; advection_dir::NTuple{3,Int32}            # ABI v5: FluxFormAdvection(x, y, z) from adapt_advection_order
+    array_diffusivity::Int32; reserved3::Int32                          # ABI v5: ScalarDiffusivity with array-valued ν / κ
     OcConfig() = new()
 end
 

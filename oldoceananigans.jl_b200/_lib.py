@@ -50,6 +50,7 @@ class oc_config(C.Structure):
         ("amd_Cb", C.c_double),
         ("coriolis_gamma", C.c_double), ("coriolis_radius", C.c_double), ("origin_z", C.c_double),
         ("has_advection_dir", C.c_int32), ("advection_dir", C.c_int32 * 3),
+        ("array_diffusivity", C.c_int32), ("reserved3", C.c_int32),
     ]
 
 

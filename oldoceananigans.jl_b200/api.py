@@ -264,11 +264,17 @@ def adapt_advection_order(advection, grid):
 
 
 class ScalarDiffusivity:
+    """ScalarDiffusivity(ν, κ): numbers — or arrays of the grid's size, located at (Center, Center, Center), for ν and / or for κ (one array,
+    or a dict tracer -> array | number): the reference interpolates array coefficients to the flux points exactly like eddy viscosities
+    (abstract_scalar_diffusivity_closure.jl:323-332).  Halos follow the default boundary conditions of a Center field (periodic / no flux)."""
+
     def __init__(self, FT=np.float64, nu=0.0, kappa=0.0, **kw):
         self.nu = kw.get("ν", nu)
         self.kappa = kw.get("κ", kappa)
-        if callable(self.nu) or callable(self.kappa):
+        vals = [self.nu] + (list(self.kappa.values()) if isinstance(self.kappa, dict) else [self.kappa])
+        if any(callable(v) for v in vals):
             raise NotImplementedError("function-valued diffusivities are out of scope")
+        self.is_array = any(isinstance(v, np.ndarray) for v in vals)
 
 
 class AnisotropicMinimumDissipation:
@@ -760,9 +766,13 @@ class NonhydrostaticModel:
         sd = [c for c in closures if isinstance(c, ScalarDiffusivity)]
         amd = [c for c in closures if isinstance(c, AnisotropicMinimumDissipation)]
         smag = [c for c in closures if isinstance(c, Smagorinsky)]
-        if len(sd) > 1 or len(amd) + len(smag) > 1 or len(sd) + len(amd) + len(smag) != len(closures):
-            raise NotImplementedError("closure must be ScalarDiffusivity, AnisotropicMinimumDissipation, Smagorinsky or a tuple of a "
-                                      "ScalarDiffusivity and one of the eddy-viscosity closures")
+        sda = [c for c in sd if c.is_array]              # array-valued coefficients: they live in the diffusivity fields (νₑ, κₑ)
+        sd = [c for c in sd if not c.is_array]
+        if len(sd) > 1 or len(sda) > 1 or len(amd) + len(smag) + len(sda) > 1 or len(sd) + len(sda) + len(amd) + len(smag) != len(closures):
+            raise NotImplementedError("closure must be ScalarDiffusivity, AnisotropicMinimumDissipation, Smagorinsky or a tuple of a constant "
+                                      "ScalarDiffusivity and one of: an eddy-viscosity closure, an array-valued ScalarDiffusivity")
+        if sda:
+            cfg.array_diffusivity = 1
         pick = lambda v, n: float(v[n]) if isinstance(v, dict) else float(v)
         if sd:
             cfg.has_scalar_diffusivity, cfg.nu = 1, float(sd[0].nu)
@@ -867,13 +877,24 @@ class NonhydrostaticModel:
         self.pressures = _NT(pNHS=Field(self, L.OC_FIELD_PNHS, "pNHS"),
                              pHY=Field(self, L.OC_FIELD_PHY, "pHY′") if buoyancy is not None else None)
         self.diffusivity_fields = None
-        if amd or smag:
+        if amd or smag or sda:
             self.diffusivity_fields = _NT(nu_e=Field(self, L.OC_FIELD_NU_E, "νₑ"),
                                           kappa_e=_NT({n: Field(self, L.OC_FIELD_KAPPA_E0 + t, "κₑ." + n) for t, n in enumerate(tracers)}))
         self.fields = _NT({**self.velocities, **self.tracers})
         self.timestepper = _NT(Gn=_NT({n: Field(self, L.OC_FIELD_GN0 + f, "Gⁿ." + n) for f, n in enumerate(names)}),
                                Gm=_NT({n: Field(self, L.OC_FIELD_GM0 + f, "G⁻." + n) for f, n in enumerate(names)}))
         self.clock = Clock(self)
+        if sda:
+            # the array coefficients: interior values, then halos like fill_halo_regions!(ν) on a Center field with default BCs
+            shape = tuple(self.grid.N)
+            full = lambda v: np.asarray(v, dtype=self.grid.FT) if isinstance(v, np.ndarray) else np.full(shape, float(v), dtype=self.grid.FT)
+            self.diffusivity_fields.nu_e.set(full(sda[0].nu))
+            ids = [L.OC_FIELD_NU_E]
+            for t, n in enumerate(tracers):
+                k = sda[0].kappa
+                self.diffusivity_fields.kappa_e[n].set(full(k[n] if isinstance(k, dict) else k))
+                ids.append(L.OC_FIELD_KAPPA_E0 + t)
+            self._lib.check(self._lib.oc_fill_halo_regions(self._h, (C.c_int * len(ids))(*ids), len(ids), 1))
         # constructor tail: update_state!(model; compute_tendencies=false)   nonhydrostatic_model.jl:241
         self._lib.check(self._lib.oc_update_state(self._h, 0))
 

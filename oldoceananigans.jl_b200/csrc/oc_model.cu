@@ -183,7 +183,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     {
         static const char* uvw_env = getenv("OC_UVW");
         const bool any_bounded = c.topology[0] == OC_BOUNDED || c.topology[1] == OC_BOUNDED || c.topology[2] == OC_BOUNDED;
-        uvw_ok_ = march_ok_ && c.advection == OC_CENTERED2 && !any_bounded && !c.has_amd && !c.smagorinsky && c.dist_nranks <= 1 &&
+        uvw_ok_ = march_ok_ && c.advection == OC_CENTERED2 && !any_bounded && !c.has_amd && !c.smagorinsky && !c.array_diffusivity && c.dist_nranks <= 1 &&
                   (uvw_env ? atoi(uvw_env) != 0 : true);
     }
     g_.dzc = g_.dzf = g_.rdzc = g_.rdzf = g_.rVc = g_.rVf = nullptr;
@@ -237,7 +237,9 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     if (has_pHY_) { pHY_ = alloc_field(locs[3]); resolve_bcs(pHY_, nullptr); }
     has_amd_ = c.has_amd != 0;
     has_smag_ = c.smagorinsky != 0;
-    has_eddy_ = has_amd_ || has_smag_;
+    array_diff_ = c.array_diffusivity != 0;
+    if (array_diff_ && (has_amd_ || has_smag_)) throw Error(OC_ERR_UNSUPPORTED, "array-valued ScalarDiffusivity together with AnisotropicMinimumDissipation / Smagorinsky (they share the diffusivity fields)");
+    has_eddy_ = has_amd_ || has_smag_ || array_diff_;
     if (has_eddy_) {
         nu_e_ = alloc_field(locs[3]);
         resolve_bcs(nu_e_, nullptr);
@@ -550,6 +552,7 @@ void Model<FT>::transfer(int field, void* host, size_t nbytes, bool parent, bool
         // Flat dimensions are stored as periodic N=1: refresh their (internal) halo copies
         if (g_.flat[0] || g_.flat[1] || g_.flat[2]) { std::vector<FieldRec*> one{&f}; halo(one, false); }
         if (field < F_) { tend_valid_ = false; aux_valid_ = false; }
+        if (array_diff_ && (field == OC_FIELD_NU_E || (field >= OC_FIELD_KAPPA_E0 && field < OC_FIELD_GN0))) tend_valid_ = false;
     }
 }
 
@@ -2213,6 +2216,7 @@ void oc_config_init(oc_config* c) {
     c->z_stretched = 0;
     c->z_faces = nullptr;
     c->has_advection_dir = 0;
+    c->array_diffusivity = 0; c->reserved3 = 0;
     c->advection_dir[0] = c->advection_dir[1] = c->advection_dir[2] = OC_CENTERED2;
 }
 

@@ -200,7 +200,8 @@ private:
     std::vector<FieldRec> state_, next_, Gn_, Gm_;
     FieldRec pNHS_, pHY_, nu_e_;
     std::vector<FieldRec> kappa_e_;
-    bool has_pHY_ = false, has_amd_ = false, has_smag_ = false, has_eddy_ = false;   // has_eddy_: νₑ / κₑ fields exist (AMD or Smagorinsky)
+    bool has_pHY_ = false, has_amd_ = false, has_smag_ = false, has_eddy_ = false;   // has_eddy_: νₑ / κₑ fields exist (AMD, Smagorinsky, or array-valued ν / κ)
+    bool array_diff_ = false;     // ScalarDiffusivity with array-valued coefficients: the caller owns the contents of νₑ / κₑ
     bool tend_valid_ = false;     // Gⁿ == G(current state)
     // CUDA Graphs for launch-bound (small) grids: one whole time step — ~40 launches, each shorter than its launch overhead below ~10⁶ cells
     // — is captured once per buffer parity and replayed with ONE launch.  The host-side bookkeeping of the step (pointer swaps of the

@@ -17,9 +17,16 @@ from .operators import O, dC, dF, ddC, ddF, iC, iF, sh
 
 
 class ScalarDiffusivity:
+    """ScalarDiffusivity(ν, κ): numbers, or arrays at (Center, Center, Center) — `νᶜᶜᶜ(…, ν::AbstractArray, …) = ν[i, j, k]`, `νᶠᶠᶜ = ℑxy ν`,
+    `κᶠᶜᶜ = ℑx κ` … (abstract_scalar_diffusivity_closure.jl:323-332): the model turns array coefficients into Center fields whose halos
+    follow the default boundary conditions, and the flux operators interpolate them like eddy viscosities."""
+
     def __init__(self, nu=0.0, kappa=0.0):
-        self.nu, self.kappa = nu, kappa       # kappa: number or dict tracer->number
+        self.nu, self.kappa = nu, kappa       # kappa: number | array, or dict tracer -> number | array
         self.kind = "scalar"
+        vals = [nu] + (list(kappa.values()) if isinstance(kappa, dict) else [kappa])
+        self.is_array = any(isinstance(v, np.ndarray) for v in vals)
+        self.nu_field, self.kappa_fields = None, {}
 
     def kappa_for(self, name):
         return self.kappa[name] if isinstance(self.kappa, dict) else self.kappa

@@ -103,6 +103,15 @@ class OracleModel:
                 # (test/test_boundary_conditions_integration.jl:62-65; build_diffusivity_fields, anisotropic_minimum_dissipation.jl:364-384)
                 self.nu_e = Field(grid, "ccc", bcs.get("nu_e"), "nu_e")
                 self.kappa_e = {n: Field(grid, "ccc", (bcs.get("kappa_e") or {}).get(n), "kappa_e_" + n) for n in tracers}
+        for c in closures:
+            if c.kind == "scalar" and getattr(c, "is_array", False):
+                def center_field(v, label):
+                    f = Field(grid, "ccc", None, label)
+                    f.set(v if isinstance(v, np.ndarray) else float(v))
+                    fill_halo_regions(f)
+                    return f
+                c.nu_field = center_field(c.nu, "nu")
+                c.kappa_fields = {n: center_field(c.kappa_for(n), "kappa_" + n) for n in tracers}
         self.fields = {"u": self.u, "v": self.v, "w": self.w, **self.tracers}
         self.Gn = {n: f.like("Gn_" + n) for n, f in self.fields.items()}
         self.Gm = {n: f.like("Gm_" + n) for n, f in self.fields.items()}
@@ -197,6 +206,8 @@ class OracleModel:
 
     # ------------------------------------------------------------------ tendencies
     def _closure_nu_kappa(self, ctx, c, name):
+        if c.kind == "scalar" and getattr(c, "is_array", False):
+            return ctx.field(c.nu_field), (ctx.field(c.kappa_fields[name]) if name is not None else None)
         if c.kind == "scalar":
             return c.nu, (c.kappa_for(name) if name is not None else None)
         return ctx.field(self.nu_e), (ctx.field(self.kappa_e[name]) if name is not None else None)

@@ -107,6 +107,15 @@ def _array_bcs(N, topo, tr):
     return {n: v for n, v in out.items() if v}
 
 
+def _array_coefficients(N, topo, tr):
+    """array-valued ν and κ (ScalarDiffusivity(ν = A, κ = (T = B, S = number))) on the grid's cells, positive, seeded"""
+    rng = np.random.default_rng(77)
+    shape = tuple(N)
+    nu = 1e-3 * (1.0 + 0.5 * rng.random(shape))
+    kap = {n: (2e-3 * (1.0 + 0.5 * rng.random(shape)) if t == 0 else 1.5e-3) for t, n in enumerate(tr)}
+    return nu, kap
+
+
 def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
                  bcs=False, extent=EXTENT, stretch=None, tilt=None, **_):
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
@@ -116,7 +125,13 @@ def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closur
            "both": (clo.ScalarDiffusivity(1e-3, 2e-3), clo.AnisotropicMinimumDissipation()),
            "smag": clo.Smagorinsky(0.16, Pr=1.0),
            # the closure of test/test_nonhydrostatic_regression.jl:68 (C = 0.23, Cb = 1, Pr = 1 + molecular values), Pr varied per tracer
-           "lilly": (clo.SmagorinskyLilly(0.23, 1.0, {n: 1.0 + 0.5 * t for t, n in enumerate(tr)}), clo.ScalarDiffusivity(1.05e-6, 1.46e-7))}[closure]
+           "lilly": (clo.SmagorinskyLilly(0.23, 1.0, {n: 1.0 + 0.5 * t for t, n in enumerate(tr)}), clo.ScalarDiffusivity(1.05e-6, 1.46e-7)),
+           "arrays": None, "arrays+const": None}[closure]
+    if closure in ("arrays", "arrays+const"):
+        nu, kap = _array_coefficients(N, topo, tr)
+        ocl = clo.ScalarDiffusivity(nu, kap)
+        if closure == "arrays+const":
+            ocl = (clo.ScalarDiffusivity(1e-3, 2e-3), ocl)
     bc_o = None
     if bcs == "array":
         bc_o = {n: {side: BC(kind, a) for side, (kind, a) in sides.items()} for n, sides in _array_bcs(N, topo, tr).items()}
@@ -145,7 +160,13 @@ def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closu
           "both": (ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), ob.AnisotropicMinimumDissipation()),
           "smag": ob.Smagorinsky(coefficient=0.16, Pr=1.0),
           "lilly": (ob.SmagorinskyLilly(C=0.23, Cb=1.0, Pr={n: 1.0 + 0.5 * t for t, n in enumerate(tr)}),
-                    ob.ScalarDiffusivity(nu=1.05e-6, kappa=1.46e-7))}[closure]
+                    ob.ScalarDiffusivity(nu=1.05e-6, kappa=1.46e-7)),
+          "arrays": None, "arrays+const": None}[closure]
+    if closure in ("arrays", "arrays+const"):
+        nu, kap = _array_coefficients(N, topo, tr)
+        cl = ob.ScalarDiffusivity(nu=nu, kappa=kap)
+        if closure == "arrays+const":
+            cl = (ob.ScalarDiffusivity(nu=1e-3, kappa=2e-3), cl)
     bc_b = None
     if bcs == "array":
         mk = {"flux": ob.FluxBoundaryCondition, "value": ob.ValueBoundaryCondition, "gradient": ob.GradientBoundaryCondition}
@@ -253,6 +274,15 @@ UVW_CASES = [
     ("uvw 40x36x33 PPP centered TS betaplane AB2", dict(N=(40, 36, 33), topo="PPP", scheme="centered", f=("beta", 0.3, 2.0), ts="QuasiAdamsBashforth2")),
     ("uvw 16x12x8 PPP centered TS fplane F32", dict(N=(16, 12, 8), topo="PPP", scheme="centered", FT=np.float32, f=1e-2)),
     ("uvw 33x17x9 PPP centered no closure tracer-b", dict(N=(33, 17, 9), topo="PPP", scheme="centered", closure="none", buoy="tracer")),
+]
+
+# ScalarDiffusivity with array-valued ν / κ (abstract_scalar_diffusivity_closure.jl:323-332): the coefficients live in the model's
+# diffusivity fields and are interpolated to the flux points like eddy viscosities (the kernels' generic-closure instances)
+ARRAY_DIFFUSIVITY_CASES = [
+    ("PPP weno array nu kappa TS", dict(N=(16, 12, 8), topo="PPP", scheme="weno", closure="arrays")),
+    ("PPB centered array + constant diffusivity bcs AB2", dict(N=(16, 12, 8), topo="PPB", scheme="centered", closure="arrays+const", bcs=True, ts="QuasiAdamsBashforth2")),
+    ("BBB upwind3 array diffusivity fplane F32", dict(N=(12, 10, 8), topo="BBB", scheme="upwind3", closure="arrays", f=1e-2, FT=np.float32)),
+    ("stretched PPB weno array diffusivity", dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="arrays", stretch="smooth")),
 ]
 
 # adapt_advection_order (src/Advection/adapt_advection_order.jl:18-96): grids with fewer points than the scheme's buffer in some direction

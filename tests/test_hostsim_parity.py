@@ -42,6 +42,12 @@ def test_hostsim_fused_momentum_kernel_matches_oracle(hostsim, name, kw):
     ph.check_case(kw, library=hostsim, steps=(1, 3))
 
 
+@pytest.mark.parametrize("name,kw", ph.ARRAY_DIFFUSIVITY_CASES, ids=[c[0] for c in ph.ARRAY_DIFFUSIVITY_CASES])
+def test_hostsim_matches_oracle_with_array_valued_diffusivities(hostsim, name, kw):
+    """ScalarDiffusivity(ν = array, κ = (T = array, S = number))  abstract_scalar_diffusivity_closure.jl:323-332"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))
+
+
 @pytest.mark.parametrize("name,kw", ph.ADAPT_CASES, ids=[c[0] for c in ph.ADAPT_CASES])
 def test_hostsim_matches_oracle_with_adapted_advection_order(hostsim, name, kw):
     """adapt_advection_order: FluxFormAdvection with the scheme lowered where N < buffer (adapt_advection_order.jl:18-96)"""

@@ -104,3 +104,9 @@ def test_cuda_matches_widening_golden(ob, name):
 def test_cuda_matches_oracle_with_adapted_advection_order(ob, name, kw):
     """adapt_advection_order (src/Advection/adapt_advection_order.jl:18-96): the scheme lowered per direction where N < buffer"""
     ph.check_case(kw, library=None, steps=(1, 10))
+
+
+@pytest.mark.parametrize("name,kw", ph.ARRAY_DIFFUSIVITY_CASES, ids=[c[0] for c in ph.ARRAY_DIFFUSIVITY_CASES])
+def test_cuda_matches_oracle_with_array_valued_diffusivities(ob, name, kw):
+    """ScalarDiffusivity(ν = array, κ = (T = array, S = number)): abstract_scalar_diffusivity_closure.jl:323-332"""
+    ph.check_case(kw, library=None, steps=(1, 10))
