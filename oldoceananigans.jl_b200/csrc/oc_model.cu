@@ -784,8 +784,8 @@ void Model<FT>::dist_attach(Transport* t) {
     static const char* p2p_env = getenv("OC_DIST_P2P");
     p2p_ = false;
     // Measured (profiles/r02f…r02j): 2 GPUs 70.7 vs 72.7 ms per step, 4 GPUs 71.8 vs 72.5 with / without peer-memory transposes; at 8 GPUs
-    // the first version (every rank writing to rank 0 first: incast) lost, 88.9 vs 77.4, and the round-robin version has not been timed
-    // there — so the default is peer memory up to 4 ranks and the sub-chunked all-to-all beyond; OC_DIST_P2P=1 forces it.
+    // the first version (every rank writing to rank 0 first: incast) lost, 88.9 vs 77.4; the round-robin version: 77.2 vs 76.3 (r02o) — the
+    // sub-chunked all-to-all still wins there.  So the default is peer memory up to 4 ranks and the all-to-all beyond; OC_DIST_P2P=1 forces it.
     if (R_ <= DIST_MAX_RANKS && (p2p_env ? atoi(p2p_env) != 0 : R_ <= 4)) {
         std::string e1 = transport_->map_peers(fftbuf_, peer_spec_, stream_);
         std::string e2 = transport_->map_peers(distT_, peer_T_, stream_);
