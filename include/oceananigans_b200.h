@@ -40,7 +40,7 @@ typedef enum { OC_PERIODIC = 0, OC_BOUNDED = 1, OC_FLAT = 2 } oc_topology;      
  * UpwindBiased(order=3|5|1), WENO(order=3), advection=nothing: the rest of the family up to order 5
  * (src/Advection/{centered,upwind_biased,weno}_reconstruction.jl), in the general tile kernel */
 typedef enum { OC_CENTERED2 = 0, OC_WENO5 = 1, OC_CENTERED4 = 2, OC_UPWIND3 = 3, OC_UPWIND5 = 4, OC_WENO3 = 5, OC_UPWIND1 = 6,
-               OC_ADVECTION_NONE = 7 } oc_advection;
+               OC_ADVECTION_NONE = 7, OC_WENO7 = 9, OC_WENO9 = 10 /* 8 is internal (FluxFormAdvection dispatch) */ } oc_advection;
 typedef enum { OC_RK3 = 0, OC_AB2 = 1 } oc_timestepper;                              /* src/TimeSteppers */
 typedef enum { OC_CORIOLIS_NONE = 0, OC_CORIOLIS_FPLANE = 1, OC_CORIOLIS_BETAPLANE = 2, OC_CORIOLIS_CARTESIAN = 3,
                OC_CORIOLIS_NONTRADITIONAL_BETAPLANE = 4 } oc_coriolis;   /* oc_config.has_coriolis */

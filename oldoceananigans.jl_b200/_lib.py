@@ -16,6 +16,7 @@ OC_TIMER_NAMES = ("tendency", "halo", "poisson_rhs", "fft", "poisson_mid", "proj
 OC_F64, OC_F32 = 0, 1
 OC_PERIODIC, OC_BOUNDED, OC_FLAT = 0, 1, 2
 OC_CENTERED2, OC_WENO5, OC_CENTERED4, OC_UPWIND3, OC_UPWIND5, OC_WENO3, OC_UPWIND1, OC_ADVECTION_NONE = range(8)
+OC_WENO7, OC_WENO9 = 9, 10
 OC_RK3, OC_AB2 = 0, 1
 OC_CORIOLIS_NONE, OC_CORIOLIS_FPLANE, OC_CORIOLIS_BETAPLANE, OC_CORIOLIS_CARTESIAN, OC_CORIOLIS_NONTRADITIONAL_BETAPLANE = 0, 1, 2, 3, 4
 OC_BUOYANCY_NONE, OC_BUOYANCY_TRACER, OC_BUOYANCY_SEAWATER_LINEAR = 0, 1, 2

@@ -213,10 +213,12 @@ class WENO:
     """WENO(order = 3 | 5)   src/Advection/weno_reconstruction.jl:7-93"""
 
     def __init__(self, FT=np.float64, order=5, bounds=None):
-        if order not in (3, 5) or bounds is not None:
-            raise NotImplementedError("WENO: orders 3 and 5 without bounds are implemented on B200")
+        if order % 2 == 0:
+            raise ValueError("WENO reconstruction scheme is defined only for odd orders")         # weno_reconstruction.jl:81
+        if order not in (3, 5, 7, 9) or bounds is not None:
+            raise NotImplementedError("WENO: orders 3, 5, 7 and 9 without bounds are implemented on B200")
         self.order, self.buffer = order, (order + 1) // 2
-        self.code = L.OC_WENO5 if order == 5 else L.OC_WENO3
+        self.code = {3: L.OC_WENO3, 5: L.OC_WENO5, 7: L.OC_WENO7, 9: L.OC_WENO9}[order]
 
 
 class _NoAdvection:
@@ -725,8 +727,8 @@ class NonhydrostaticModel:
             # the fifth-order schemes and Centered(4).  The adapted scheme only gives c the halo of ITS lowered scheme: with H[c] = 1 the
             # reference reads outside the halo (unspecified values).  Nothing to be bit-compatible with: refused.
             for d in range(3):
-                deep = 2 if isinstance(advection.dirs[d], (WENO, UpwindBiased)) and advection.dirs[d].order == 5 or \
-                    isinstance(advection.dirs[d], Centered) and advection.dirs[d].order == 4 else 1
+                sd = advection.dirs[d]        # its advecting_velocity_scheme is Centered(order - 1) (Centered: itself): buffer (order - 1) / 2
+                deep = 1 if isinstance(sd, _NoAdvection) else (sd.order // 2 if isinstance(sd, Centered) else max(1, (sd.order - 1) // 2))
                 for c in range(3):
                     if c != d and grid.topology[c] is not Flat and grid.topology[d] is not Flat and H[c] < deep:
                         raise NotImplementedError(f"adapt_advection_order: the {'xyz'[d]}-scheme interpolates velocities two points deep along "

@@ -129,6 +129,99 @@ OC_HD FT weno5_symmetric(const AdvCoef<FT>& C, const FT* p, int s, FT a, int f, 
     return sym2<FT>(p, s, a);
 }
 
+template <class FT>
+OC_HD FT weno5_symmetric_z(const AdvCoef<FT>& C, const FT* p, int s, FT h, const FT* dz, int f, const OrderWindow& w) {
+    if (f >= w.lo_hi && f <= w.hi_hi) return sym4z<FT>(C, p, s, h, dz);
+    return sym2z<FT>(p, s, h, dz);
+}
+
+
+// ---- WENO(order = 7 | 9): buffer B = 4 | 5 ------------------------------------------------------
+// The reference's generic machinery (weno_interpolants.jl): sub-stencil r = 0 … B-1 of the upwind-ordered stencil q0 … q(2B-2) is
+// S_r = (q[B-1-r] … q[2B-2-r]) (:409-437); β_r by the metaprogrammed quadratic form (:204-266) with the tabulated coefficients
+// (:175-185); τ = |β₀ + 3β₁ − 3β₂ − β₃| (B = 4), |β₀ + 2β₁ − 6β₂ + 2β₃ + β₄| (B = 5) (:303-307); α_r = C★_r (1 + (τ / (β_r + ϵ))²) with
+// newton_div (:290-297); Σ (α_r / Σα) p_r with p_r = Σ coeff_p(r) · S_r (:136-137, :332-338, :500).
+template <int B, class FT>
+OC_HD FT weno_hi_value(const AdvCoef<FT>& C, const FT* q) {
+    constexpr int NS = B * (B + 1) / 2;
+    const FT* S = C.hi + (B == 4 ? HiOrderTab::S7 : HiOrderTab::S9);
+    const FT* P = C.hi + (B == 4 ? HiOrderTab::P7 : HiOrderTab::P9);
+    const FT* CS = C.hi + (B == 4 ? HiOrderTab::C7 : HiOrderTab::C9);
+    FT beta[B], pr[B];
+#ifndef OC_HOSTSIM
+#pragma unroll
+#endif
+    for (int r = 0; r < B; ++r) {
+        const FT* psi = q + (B - 1 - r);
+        const FT* c = S + r * NS;
+        FT b = FT(0);
+        int ci = 0;
+        for (int s0 = 0; s0 < B - 1; ++s0) {
+            FT inner = c[ci] * psi[s0];
+            for (int i = s0 + 1; i < B; ++i) inner = inner + c[ci + i - s0] * psi[i];
+            ci += B - s0;
+            const FT term = psi[s0] * inner;
+            b = s0 == 0 ? term : b + term;
+        }
+        beta[r] = b + psi[B - 1] * psi[B - 1] * c[ci];
+        FT p = P[r * B] * psi[0];
+        for (int j = 1; j < B; ++j) p = p + P[r * B + j] * psi[j];
+        pr[r] = p;
+    }
+    FT tau;
+    if (B == 4) tau = oc_abs<FT>(beta[0] + FT(3) * beta[1] - FT(3) * beta[2] - beta[3]);
+    else tau = oc_abs<FT>(beta[0] + FT(2) * beta[1] - FT(6) * beta[2] + FT(2) * beta[3] + beta[B - 1]);
+    FT alpha[B];
+    FT sum = FT(0);
+    for (int r = 0; r < B; ++r) {
+        const FT t = newton_div(tau, beta[r] + C.eps);
+        alpha[r] = CS[r] * (FT(1) + t * t);
+        sum = r == 0 ? alpha[0] : sum + alpha[r];
+    }
+    const FT rs = FT(1) / sum;
+    FT out = (alpha[0] * rs) * pr[0];
+    for (int r = 1; r < B; ++r) out = out + (alpha[r] * rs) * pr[r];
+    return out;
+}
+
+// order windows of buffer b in terms of the 0-based face index f: face-type b <= f <= N - b, centre-type (evaluated at face c + 1)
+// b <= f <= N + 1 - b (topologically_conditional_interpolation.jl:46-52 with required_halo_size = b)
+// — from the OrderWindow of buffer 3 (hi_hi = N - 3 face-type, N - 2 centre-type; lo_hi < 0: the dimension is not Bounded)
+OC_HD bool in_order_window(int b, int f, const OrderWindow& w) {
+    return w.lo_hi < 0 || (f >= b && f <= w.hi_hi + 3 - b);
+}
+
+// _biased_interpolate of WENO(2B-1), B = 4 | 5: the scheme inside its window, else its buffer_scheme (WENO(2B-3) …) — the chain ends in
+// weno5_biased (WENO(5) -> WENO(3) -> UpwindBiased(1))
+template <int B, class FT>
+OC_HD FT weno_hi_biased(const AdvCoef<FT>& C, const FT* p, int s, bool left, int f, const OrderWindow& w) {
+    if (in_order_window(B, f, w)) {
+        FT q[2 * B - 1];
+        const int o0 = left ? -B * s : (B - 1) * s, ds = left ? s : -s;
+        for (int n = 0; n < 2 * B - 1; ++n) q[n] = p[o0 + n * ds];
+        return weno_hi_value<B, FT>(C, q);
+    }
+    if constexpr (B == 5) return weno_hi_biased<4, FT>(C, p, s, left, f, w);
+    else return weno5_biased<FT>(C, p, s, left, f, w);
+}
+
+// Centered(6) / Centered(8) of a·q in stencil order ψ[i-B'] … ψ[i+B'-1], summed left to right; `dz` != nullptr: the stretched-z form with
+// the area inside the interpolation, a_n = a·Δzᶜ[k+n] (sym4z)
+template <int BC, class FT>
+OC_HD FT sym_hi(const AdvCoef<FT>& C, const FT* p, int s, FT a, const FT* dz) {
+    const FT* c = C.hi + (BC == 3 ? HiOrderTab::CEN6 : HiOrderTab::CEN8);
+    FT r = c[0] * ((dz ? a * dz[-BC] : a) * p[-BC * s]);
+    for (int n = 1; n < 2 * BC; ++n) r = r + c[n] * ((dz ? a * dz[n - BC] : a) * p[(n - BC) * s]);
+    return r;
+}
+// _symmetric_interpolate of WENO(2B-1): advecting_velocity_scheme = Centered(2B-2) inside the window of B, else the buffer scheme's
+template <int B, class FT>
+OC_HD FT weno_hi_symmetric(const AdvCoef<FT>& C, const FT* p, int s, FT a, const FT* dz, int f, const OrderWindow& w) {
+    if (in_order_window(B, f, w)) return sym_hi<B - 1, FT>(C, p, s, a, dz);
+    if constexpr (B == 5) return weno_hi_symmetric<4, FT>(C, p, s, a, dz, f, w);
+    else return dz ? weno5_symmetric_z<FT>(C, p, s, a, dz, f, w) : weno5_symmetric<FT>(C, p, s, a, f, w);
+}
+
 // ---- the other schemes of the reference's family up to order 5 -----------------------------------
 // _biased_interpolate with the boundary chain of topologically_conditional_interpolation.jl:46-52,99-120:
 //   UpwindBiased(5) -> UpwindBiased(3) -> UpwindBiased(1);  UpwindBiased(3) -> UpwindBiased(1);  WENO(3) -> UpwindBiased(1).
@@ -136,6 +229,8 @@ OC_HD FT weno5_symmetric(const AdvCoef<FT>& C, const FT* p, int s, FT a, int f, 
 template <int ADV, class FT>
 OC_HD FT biased_any(const AdvCoef<FT>& C, const FT* p, int s, bool left, int f, const OrderWindow& w) {
     if (ADV == ADV_WENO5) return weno5_biased<FT>(C, p, s, left, f, w);
+    if (ADV == ADV_WENO7) return weno_hi_biased<4, FT>(C, p, s, left, f, w);
+    if (ADV == ADV_WENO9) return weno_hi_biased<5, FT>(C, p, s, left, f, w);
     if (ADV == ADV_UPWIND5 && f >= w.lo_hi && f <= w.hi_hi) {
         // upwind-ordered stencil: Left (ψ[i-3] … ψ[i+1]), Right (ψ[i+2] … ψ[i-2])
         const int o0 = left ? -3 * s : 2 * s, ds = left ? s : -s;
@@ -167,19 +262,17 @@ OC_HD FT biased_any(const AdvCoef<FT>& C, const FT* p, int s, bool left, int f, 
 //   (its required_halo_size is 2); every other scheme: Centered(2).
 template <int ADV, class FT>
 OC_HD FT symmetric_any(const AdvCoef<FT>& C, const FT* p, int s, FT a, int f, const OrderWindow& w) {
+    if (ADV == ADV_WENO7) return weno_hi_symmetric<4, FT>(C, p, s, a, nullptr, f, w);
+    if (ADV == ADV_WENO9) return weno_hi_symmetric<5, FT>(C, p, s, a, nullptr, f, w);
     if ((ADV == ADV_WENO5 || ADV == ADV_UPWIND5) && f >= w.lo_hi && f <= w.hi_hi) return sym4<FT>(C, p, s, a);
     if (ADV == ADV_CENTERED4 && f >= w.lo_mid && f <= w.hi_mid) return sym4<FT>(C, p, s, a);
     return sym2<FT>(p, s, a);
 }
 template <int ADV, class FT>
 OC_HD FT symmetric_any_z(const AdvCoef<FT>& C, const FT* p, int s, FT h, const FT* dz, int f, const OrderWindow& w) {
+    if (ADV == ADV_WENO7) return weno_hi_symmetric<4, FT>(C, p, s, h, dz, f, w);
+    if (ADV == ADV_WENO9) return weno_hi_symmetric<5, FT>(C, p, s, h, dz, f, w);
     if ((ADV == ADV_WENO5 || ADV == ADV_UPWIND5) && f >= w.lo_hi && f <= w.hi_hi) return sym4z<FT>(C, p, s, h, dz);
-    return sym2z<FT>(p, s, h, dz);
-}
-
-template <class FT>
-OC_HD FT weno5_symmetric_z(const AdvCoef<FT>& C, const FT* p, int s, FT h, const FT* dz, int f, const OrderWindow& w) {
-    if (f >= w.lo_hi && f <= w.hi_hi) return sym4z<FT>(C, p, s, h, dz);
     return sym2z<FT>(p, s, h, dz);
 }
 

@@ -61,11 +61,21 @@ struct AdvCoef {
     // stencil q0 … (Left: ψ[i-B] …, Right: ψ[i+B-1] …; calc_reconstruction_stencil, reconstruction_coefficients.jl:87-89,122-152)
     FT u5l[5], u5r[5];
     FT u3l[3], u3r[3];
+    // WENO(order = 7 | 9) and their Centered(6) / Centered(8) advecting-velocity schemes: one device table (HiOrderTab layout below),
+    // nullptr unless the model uses them — the kernel parameter block of every other scheme stays what it was
+    const FT* hi;
+};
+
+// layout of AdvCoef::hi (FT values): smoothness coefficients, coeff_p, C★ of WENO{4} and WENO{5}
+// (weno_interpolants.jl:81-90,175-185, :117-118), Centered(6) and Centered(8) in stencil order
+struct HiOrderTab {
+    enum { S7 = 0, P7 = S7 + 4 * 10, C7 = P7 + 4 * 4, S9 = C7 + 4, P9 = S9 + 5 * 15, C9 = P9 + 5 * 5, CEN6 = C9 + 5, CEN8 = CEN6 + 6, SIZE = CEN8 + 8 };
 };
 
 // advection scheme codes (oc_advection in include/oceananigans_b200.h)
 enum { ADV_CENTERED2 = 0, ADV_WENO5 = 1, ADV_CENTERED4 = 2, ADV_UPWIND3 = 3, ADV_UPWIND5 = 4, ADV_WENO3 = 5, ADV_UPWIND1 = 6, ADV_NONE = 7,
-       ADV_MIXED = 8 /* FluxFormAdvection(x, y, z): the scheme of each flux direction is a run-time code (TendencyArgs::adv_dir) */ };
+       ADV_MIXED = 8 /* FluxFormAdvection(x, y, z): the scheme of each flux direction is a run-time code (TendencyArgs::adv_dir) */,
+       ADV_WENO7 = 9, ADV_WENO9 = 10 };
 OC_HD constexpr bool adv_is_centered(int adv) { return adv == ADV_CENTERED2 || adv == ADV_CENTERED4; }
 
 template <class FT>

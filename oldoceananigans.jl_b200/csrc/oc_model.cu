@@ -69,7 +69,42 @@ static AdvCoef<FT> make_coefficients() {
         for (int n = 0; n < 5; ++n) { C.u5l[n] = l5[4 - n]; C.u5r[n] = r5[n]; }
         for (int n = 0; n < 3; ++n) { C.u3l[n] = l3[2 - n]; C.u3r[n] = r3[n]; }
     }
+    C.hi = nullptr;
     return C;
+}
+
+// the table behind AdvCoef::hi (HiOrderTab): WENO{4}, WENO{5} and their Centered(6), Centered(8) advecting-velocity schemes
+// (weno_interpolants.jl:81-90 C★, :117-118 coeff_p, :175-185 smoothness coefficients; centered_reconstruction.jl / reconstruction_coefficients.jl:87)
+template <class FT>
+static std::vector<FT> make_hi_order_table() {
+    std::vector<FT> t(HiOrderTab::SIZE, FT(0));
+    static const double s7[4][10] = {{2.107, -9.402, 7.042, -1.854, 11.003, -17.246, 4.642, 7.043, -3.882, 0.547},
+                                     {0.547, -2.522, 1.922, -0.494, 3.443, -5.966, 1.602, 2.843, -1.642, 0.267},
+                                     {0.267, -1.642, 1.602, -0.494, 2.843, -5.966, 1.922, 3.443, -2.522, 0.547},
+                                     {0.547, -3.882, 4.642, -1.854, 7.043, -17.246, 7.042, 11.003, -9.402, 2.107}};
+    static const double s9[5][15] = {
+        {1.07918, -6.49501, 7.58823, -4.11487, 0.86329, 10.20563, -24.62076, 13.58458, -2.88007, 15.21393, -17.04396, 3.64863, 4.82963, -2.08501, 0.22658},
+        {0.22658, -1.40251, 1.65153, -0.88297, 0.18079, 2.42723, -6.11976, 3.37018, -0.70237, 4.06293, -4.64976, 0.99213, 1.38563, -0.60871, 0.06908},
+        {0.06908, -0.51001, 0.67923, -0.38947, 0.08209, 1.04963, -2.99076, 1.79098, -0.38947, 2.31153, -2.99076, 0.67923, 1.04963, -0.51001, 0.06908},
+        {0.06908, -0.60871, 0.99213, -0.70237, 0.18079, 1.38563, -4.64976, 3.37018, -0.88297, 4.06293, -6.11976, 1.65153, 2.42723, -1.40251, 0.22658},
+        {0.22658, -2.08501, 3.64863, -2.88007, 0.86329, 4.82963, -17.04396, 13.58458, -4.11487, 15.21393, -24.62076, 7.58823, 10.20563, -6.49501, 1.07918}};
+    for (int r = 0; r < 4; ++r) for (int n = 0; n < 10; ++n) t[HiOrderTab::S7 + r * 10 + n] = (FT)s7[r][n];
+    for (int r = 0; r < 5; ++r) for (int n = 0; n < 15; ++n) t[HiOrderTab::S9 + r * 15 + n] = (FT)s9[r][n];
+    for (int r = 0; r < 4; ++r) stencil_coefficients<FT>(r, 4, &t[HiOrderTab::P7 + r * 4]);
+    for (int r = 0; r < 5; ++r) stencil_coefficients<FT>(r, 5, &t[HiOrderTab::P9 + r * 5]);
+    // FT(4//35) …: the rational rounded once to Float64 (IEEE division of two exact integers), then to FT
+    const double c7[4] = {4.0 / 35.0, 18.0 / 35.0, 12.0 / 35.0, 1.0 / 35.0};
+    const double c9[5] = {5.0 / 126.0, 20.0 / 63.0, 10.0 / 21.0, 10.0 / 63.0, 1.0 / 126.0};
+    for (int r = 0; r < 4; ++r) t[HiOrderTab::C7 + r] = (FT)c7[r];
+    for (int r = 0; r < 5; ++r) t[HiOrderTab::C9 + r] = (FT)c9[r];
+    // Centered(order): coefficients of the symmetric stencil ψ[i-B] … ψ[i+B-1] = stencil_coefficients(r = B-1, order) reversed
+    // (calc_reconstruction_stencil gives the idx-th point the coefficient coeff[order-idx+1], like Centered(4) above)
+    FT c6[6], c8[8];
+    stencil_coefficients<FT>(2, 6, c6);
+    stencil_coefficients<FT>(3, 8, c8);
+    for (int idx = 1; idx <= 6; ++idx) t[HiOrderTab::CEN6 + idx - 1] = c6[6 - idx];
+    for (int idx = 1; idx <= 8; ++idx) t[HiOrderTab::CEN8 + idx - 1] = c8[8 - idx];
+    return t;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -77,8 +112,9 @@ template <class FT>
 Model<FT>::Model(const oc_config& c) : cfg_(c) {
     if (c.abi_version != OC_ABI_VERSION) throw Error(OC_ERR_INVALID, "oc_config.abi_version mismatch");
     if (c.n_tracers < 0 || c.n_tracers > OC_MAX_TRACERS) throw Error(OC_ERR_INVALID, "n_tracers out of range");
-    if (c.advection < OC_CENTERED2 || c.advection > OC_ADVECTION_NONE)
-        throw Error(OC_ERR_UNSUPPORTED, "advection scheme: Centered(order=2|4), UpwindBiased(order=1|3|5), WENO(order=3|5) or nothing");
+    auto known_scheme = [](int a) { return (a >= OC_CENTERED2 && a <= OC_ADVECTION_NONE) || a == OC_WENO7 || a == OC_WENO9; };
+    if (!known_scheme(c.advection))
+        throw Error(OC_ERR_UNSUPPORTED, "advection scheme: Centered(order=2|4), UpwindBiased(order=1|3|5), WENO(order=3|5|7|9) or nothing");
     if (c.timestepper != OC_RK3 && c.timestepper != OC_AB2) throw Error(OC_ERR_UNSUPPORTED, "timestepper: only RungeKutta3 and QuasiAdamsBashforth2");
     F_ = 3 + c.n_tracers;
     stretched_ = c.z_stretched != 0;
@@ -92,10 +128,10 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         if (c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "distributed models on vertically stretched grids (DistributedFourierTridiagonalPoissonSolver: next)");
     }
     // required_halo_size of the scheme (its buffer) — per direction for FluxFormAdvection (adapt_advection_order.jl:18-96)
-    auto buffer_of = [](int adv) { return (adv == OC_WENO5 || adv == OC_UPWIND5) ? 3 : (adv == OC_CENTERED4 || adv == OC_UPWIND3 || adv == OC_WENO3) ? 2 : 1; };
+    auto buffer_of = [](int adv) { return adv == OC_WENO9 ? 5 : adv == OC_WENO7 ? 4 : (adv == OC_WENO5 || adv == OC_UPWIND5) ? 3 : (adv == OC_CENTERED4 || adv == OC_UPWIND3 || adv == OC_WENO3) ? 2 : 1; };
     if (c.has_advection_dir)
         for (int d = 0; d < 3; ++d)
-            if (c.advection_dir[d] < OC_CENTERED2 || c.advection_dir[d] > OC_ADVECTION_NONE) throw Error(OC_ERR_INVALID, "advection_dir: unknown advection scheme code");
+            if (!known_scheme(c.advection_dir[d])) throw Error(OC_ERR_INVALID, "advection_dir: unknown advection scheme code");
     for (int d = 0; d < 3; ++d) {
         int need = buffer_of(c.has_advection_dir ? c.advection_dir[d] : c.advection);
         if (c.has_amd || c.smagorinsky) need = std::max(need, 2);      // AbstractScalarDiffusivity{…, 2}: anisotropic_minimum_dissipation.jl, smagorinsky.jl:31
@@ -124,7 +160,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         // schemes, Centered(4)) or Centered(2): where the adapted halo is smaller the reference reads outside the halo — refused
         for (int d = 0; d < 3; ++d) {
             const int a = c.advection_dir[d];
-            const int deep = (a == OC_WENO5 || a == OC_UPWIND5 || a == OC_CENTERED4) ? 2 : 1;
+            const int deep = a == OC_WENO9 ? 4 : a == OC_WENO7 ? 3 : (a == OC_WENO5 || a == OC_UPWIND5 || a == OC_CENTERED4) ? 2 : 1;
             for (int e = 0; e < 3; ++e)
                 if (e != d && c.topology[e] != OC_FLAT && c.topology[d] != OC_FLAT && a != OC_ADVECTION_NONE && c.H[e] < deep)
                     throw Error(OC_ERR_UNSUPPORTED, "advection_dir: a scheme interpolates velocities two points deep along a direction whose halo is 1 (the reference reads outside the halo there)");
@@ -188,6 +224,8 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     }
     g_.dzc = g_.dzf = g_.rdzc = g_.rdzf = g_.rVc = g_.rVf = nullptr;
     C_ = make_coefficients<FT>();
+    hi_adv_ = c.advection == OC_WENO7 || c.advection == OC_WENO9;
+    if (c.has_advection_dir) for (int d = 0; d < 3; ++d) hi_adv_ = hi_adv_ || c.advection_dir[d] == OC_WENO7 || c.advection_dir[d] == OC_WENO9;
     {   // the compile-time table of oc_march.h must be the very same numbers
         using K = AdvConst<FT>;
         const FT tab[] = {K::p00, K::p01, K::p02, K::p10, K::p11, K::p12, K::p20, K::p21, K::p22, K::c50, K::c51, K::c52,
@@ -217,6 +255,16 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     }
     launch_stream_ = stream_;
 #endif
+    if (hi_adv_) {
+        std::vector<FT> tab = make_hi_order_table<FT>();
+        hi_tab_ = (FT*)dev_alloc(sizeof(FT) * tab.size());
+        dev_upload(hi_tab_, tab.data(), sizeof(FT) * tab.size(), stream_);
+#ifndef OC_HOSTSIM
+        cuda_check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");     // `tab` is a local staging buffer
+#endif
+        C_.hi = hi_tab_;
+        device_bytes += (int64_t)(sizeof(FT) * tab.size());
+    }
     const int locs[4][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
     for (int f = 0; f < F_; ++f) {
         const int* loc = locs[f < 3 ? f : 3];
@@ -392,7 +440,7 @@ Model<FT>::~Model() {
     fr(pNHS_); fr(pHY_); fr(nu_e_);
     for (auto& f : kappa_e_) fr(f);
     dev_free(fftbuf_);
-    dev_free(ztab_); dev_free(tri_R_); dev_free(tri_T_);
+    dev_free(ztab_); dev_free(tri_R_); dev_free(tri_T_); dev_free(hi_tab_);
     dev_free(diag_dev_);
     dev_free(distT_); dev_free(diststage_); dev_free(halo_send_); dev_free(halo_recv_);
     for (int d = 0; d < 3; ++d) { dev_free(lam_[d]); dev_free(tw_[d]); }
@@ -1113,6 +1161,8 @@ void Model<FT>::launch_tendency(int fidx, TendencyArgs<FT>& a) {
         case OC_UPWIND5: run(TendencyKernel<FT, ADV_UPWIND5, KIND, TX, TY, TZ>{}); break;
         case OC_WENO3: run(TendencyKernel<FT, ADV_WENO3, KIND, TX, TY, TZ>{}); break;
         case OC_UPWIND1: run(TendencyKernel<FT, ADV_UPWIND1, KIND, TX, TY, TZ>{}); break;
+        case OC_WENO7: run(TendencyKernel<FT, ADV_WENO7, KIND, TX, TY, TZ>{}); break;
+        case OC_WENO9: run(TendencyKernel<FT, ADV_WENO9, KIND, TX, TY, TZ>{}); break;
         case OC_ADVECTION_NONE: run(TendencyKernel<FT, ADV_NONE, KIND, TX, TY, TZ>{}); break;
         default: run(TendencyKernel<FT, ADV_CENTERED2, KIND, TX, TY, TZ>{}); break;
     }

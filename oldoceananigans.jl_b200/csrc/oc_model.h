@@ -201,6 +201,8 @@ private:
     FieldRec pNHS_, pHY_, nu_e_;
     std::vector<FieldRec> kappa_e_;
     bool has_pHY_ = false, has_amd_ = false, has_smag_ = false, has_eddy_ = false;   // has_eddy_: νₑ / κₑ fields exist (AMD, Smagorinsky, or array-valued ν / κ)
+    bool hi_adv_ = false;         // WENO(7) / WENO(9) somewhere: AdvCoef::hi points to hi_tab_
+    FT* hi_tab_ = nullptr;
     bool array_diff_ = false;     // ScalarDiffusivity with array-valued coefficients: the caller owns the contents of νₑ / κₑ
     bool tend_valid_ = false;     // Gⁿ == G(current state)
     // CUDA Graphs for launch-bound (small) grids: one whole time step — ~40 launches, each shorter than its launch overhead below ~10⁶ cells

@@ -157,6 +157,8 @@ struct TendencyKernel {
                 case ADV_UPWIND5: return advective_flux_t<ADV_UPWIND5>(i, j, k, d);
                 case ADV_WENO3: return advective_flux_t<ADV_WENO3>(i, j, k, d);
                 case ADV_UPWIND1: return advective_flux_t<ADV_UPWIND1>(i, j, k, d);
+                case ADV_WENO7: return advective_flux_t<ADV_WENO7>(i, j, k, d);
+                case ADV_WENO9: return advective_flux_t<ADV_WENO9>(i, j, k, d);
                 case ADV_NONE: return FT(0);
                 default: return advective_flux_t<ADV_CENTERED2>(i, j, k, d);
             }

@@ -67,7 +67,7 @@ def centered_coefficients(FT, buffer):
 
 class Centered:
     def __init__(self, FT=np.float64, order=2):
-        assert order in (2, 4)
+        assert order in (2, 4, 6, 8)
         self.FT = np.dtype(FT).type
         self.buffer = order // 2
         self.coeffs = centered_coefficients(self.FT, self.buffer)
@@ -176,12 +176,26 @@ class WENO:
 
     # smoothness_coefficients weno_interpolants.jl:169-174
     SMOOTH = {2: ((1, -2, 1), (1, -2, 1)),
-              3: ((10, -31, 11, 25, -19, 4), (4, -13, 5, 13, -13, 4), (4, -19, 11, 25, -31, 10))}
+              3: ((10, -31, 11, 25, -19, 4), (4, -13, 5, 13, -13, 4), (4, -19, 11, 25, -31, 10)),
+              # weno_interpolants.jl:175-185 (Float64 decimal literals converted to FT)
+              4: ((2.107, -9.402, 7.042, -1.854, 11.003, -17.246, 4.642, 7.043, -3.882, 0.547),
+                  (0.547, -2.522, 1.922, -0.494, 3.443, -5.966, 1.602, 2.843, -1.642, 0.267),
+                  (0.267, -1.642, 1.602, -0.494, 2.843, -5.966, 1.922, 3.443, -2.522, 0.547),
+                  (0.547, -3.882, 4.642, -1.854, 7.043, -17.246, 7.042, 11.003, -9.402, 2.107)),
+              5: ((1.07918, -6.49501, 7.58823, -4.11487, 0.86329, 10.20563, -24.62076, 13.58458, -2.88007, 15.21393, -17.04396, 3.64863, 4.82963, -2.08501, 0.22658),
+                  (0.22658, -1.40251, 1.65153, -0.88297, 0.18079, 2.42723, -6.11976, 3.37018, -0.70237, 4.06293, -4.64976, 0.99213, 1.38563, -0.60871, 0.06908),
+                  (0.06908, -0.51001, 0.67923, -0.38947, 0.08209, 1.04963, -2.99076, 1.79098, -0.38947, 2.31153, -2.99076, 0.67923, 1.04963, -0.51001, 0.06908),
+                  (0.06908, -0.60871, 0.99213, -0.70237, 0.18079, 1.38563, -4.64976, 3.37018, -0.88297, 4.06293, -6.11976, 1.65153, 2.42723, -1.40251, 0.22658),
+                  (0.22658, -2.08501, 3.64863, -2.88007, 0.86329, 4.82963, -17.04396, 13.58458, -4.11487, 15.21393, -24.62076, 7.58823, 10.20563, -6.49501, 1.07918))}
     CSTAR = {2: (Fraction(2, 3), Fraction(1, 3)),
-             3: (Fraction(3, 10), Fraction(3, 5), Fraction(1, 10))}
+             3: (Fraction(3, 10), Fraction(3, 5), Fraction(1, 10)),
+             4: (Fraction(4, 35), Fraction(18, 35), Fraction(12, 35), Fraction(1, 35)),
+             5: (Fraction(5, 126), Fraction(20, 63), Fraction(10, 21), Fraction(10, 63), Fraction(1, 126))}
+    # global_smoothness_indicator  weno_interpolants.jl:303-307: τ = |Σ TAU[r] β_r|, summed left to right
+    TAU = {2: (1, -1), 3: (1, 0, -1), 4: (1, 3, -3, -1), 5: (1, 2, -6, 2, 1)}
 
     def __init__(self, FT=np.float64, order=5):
-        assert order in (3, 5)
+        assert order in (3, 5, 7, 9)
         self.FT = np.dtype(FT).type
         self.buffer = (order + 1) // 2
         self.kind = "weno"
@@ -230,7 +244,13 @@ def _weno_value(sch, S, left):
             beta = term if beta is None else beta + term
         beta = beta + psi[B - 1] * psi[B - 1] * C[c]
         betas.append(beta)
-    tau = np.abs(betas[0] - betas[B - 1])
+    acc = None                                           # global_smoothness_indicator :303-307 (β[1] + 3β[2] - 3β[3] - β[4] …)
+    for r, t in enumerate(sch.TAU[B]):
+        if t == 0:
+            continue
+        term = betas[r] if abs(t) == 1 else FT(abs(t)) * betas[r]
+        acc = term if acc is None else (acc + term if t > 0 else acc - term)
+    tau = np.abs(acc)
     alphas = []
     for r in range(B):
         q = newton_div(FT, tau, betas[r] + sch.eps)

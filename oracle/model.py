@@ -78,7 +78,7 @@ class OracleModel:
                 # the d-scheme interpolates velocities along every other direction c with its advecting_velocity_scheme: where the
                 # adapted grid's halo H[c] is smaller than that stencil the reference reads outside the halo — not restated
                 sd = adv.scheme_of(advection, d)
-                deep = 2 if (sd.kind in ("weno", "upwind") and sd.buffer == 3) or (sd.kind == "centered" and sd.buffer == 2) else 1
+                deep = sd.buffer if sd.kind == "centered" else (sd.advecting_velocity_scheme.buffer if hasattr(sd, "advecting_velocity_scheme") else 1)
                 for c in range(3):
                     assert c == d or grid.flat(c) or grid.H[c] >= deep, "adapted scheme reads outside the halo in the reference"
         self.grid, self.FT = grid, FT

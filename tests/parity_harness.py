@@ -55,13 +55,15 @@ def _grid_kwargs(N, topo, extent, stretch):
 def oracle_scheme(scheme, FT):
     return {"centered": lambda: adv.Centered(FT, 2), "weno": lambda: adv.WENO(FT, 5), "centered4": lambda: adv.Centered(FT, 4),
             "upwind1": lambda: adv.UpwindBiased(FT, 1), "upwind3": lambda: adv.UpwindBiased(FT, 3),
-            "upwind5": lambda: adv.UpwindBiased(FT, 5), "weno3": lambda: adv.WENO(FT, 3), "none": lambda: adv.NoAdvection(FT)}[scheme]()
+            "upwind5": lambda: adv.UpwindBiased(FT, 5), "weno3": lambda: adv.WENO(FT, 3), "none": lambda: adv.NoAdvection(FT),
+            "weno7": lambda: adv.WENO(FT, 7), "weno9": lambda: adv.WENO(FT, 9)}[scheme]()
 
 
 def product_scheme(scheme):
     return {"centered": ob.Centered, "weno": ob.WENO, "centered4": lambda: ob.Centered(order=4),
             "upwind1": lambda: ob.UpwindBiased(order=1), "upwind3": lambda: ob.UpwindBiased(order=3),
-            "upwind5": lambda: ob.UpwindBiased(order=5), "weno3": lambda: ob.WENO(order=3), "none": lambda: None}[scheme]()
+            "upwind5": lambda: ob.UpwindBiased(order=5), "weno3": lambda: ob.WENO(order=3), "none": lambda: None,
+            "weno7": lambda: ob.WENO(order=7), "weno9": lambda: ob.WENO(order=9)}[scheme]()
 
 
 def _coriolis(mod, f):
@@ -283,6 +285,23 @@ ARRAY_DIFFUSIVITY_CASES = [
     ("PPB centered array + constant diffusivity bcs AB2", dict(N=(16, 12, 8), topo="PPB", scheme="centered", closure="arrays+const", bcs=True, ts="QuasiAdamsBashforth2")),
     ("BBB upwind3 array diffusivity fplane F32", dict(N=(12, 10, 8), topo="BBB", scheme="upwind3", closure="arrays", f=1e-2, FT=np.float32)),
     ("stretched PPB weno array diffusivity", dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="arrays", stretch="smooth")),
+]
+
+# WENO(order = 7) and WENO(order = 9) (weno_interpolants.jl:81-90,175-185,303-307): general tile kernel, halos of 4 / 5, the order-reduction
+# chains WENO(9) -> (7) -> (5) -> (3) -> UpwindBiased(1) and Centered(8) -> (6) -> (4) -> (2) near walls
+WENO_HI_CASES = [
+    ("PPP weno7 TS", dict(N=(16, 12, 8), topo="PPP", scheme="weno7")),
+    ("PPB weno7 amd fplane bcs", dict(N=(16, 12, 10), topo="PPB", scheme="weno7", closure="amd", f=1e-2, bcs=True)),
+    ("BBB weno9 tracer-b AB2", dict(N=(14, 12, 11), topo="BBB", scheme="weno9", buoy="tracer", ts="QuasiAdamsBashforth2")),
+    ("stretched PPB weno7 bcs", dict(N=(16, 12, 10), topo="PPB", scheme="weno7", bcs=True, stretch="smooth")),
+    ("6x6x6 BBB weno9 (adapted to WENO(5) nowhere: N >= 5; every face in a reduced window)", dict(N=(6, 6, 6), topo="BBB", scheme="weno9")),
+]
+
+# Float32 (host simulation only: the Float32 pressure of this case sits at 5e-5 of the 1e-4 tolerance, too close to hand to another FFT).
+# Tracer b about zero: in Float32 the reference's expanded smoothness indicators are pure round-off for T = 20 ± 0.01, S = 35 ± 0.01.
+WENO_HI_F32_CASES = [
+    ("PPP weno9 tracer-b F32", dict(N=(16, 12, 10), topo="PPP", scheme="weno9", buoy="tracer", FT=np.float32)),
+    ("PPB weno7 tracer-b F32", dict(N=(16, 12, 10), topo="PPB", scheme="weno7", buoy="tracer", FT=np.float32)),
 ]
 
 # adapt_advection_order (src/Advection/adapt_advection_order.jl:18-96): grids with fewer points than the scheme's buffer in some direction

@@ -48,6 +48,12 @@ def test_hostsim_matches_oracle_with_array_valued_diffusivities(hostsim, name, k
     ph.check_case(kw, library=hostsim, steps=(1, 3))
 
 
+@pytest.mark.parametrize("name,kw", ph.WENO_HI_CASES + ph.WENO_HI_F32_CASES, ids=[c[0] for c in ph.WENO_HI_CASES + ph.WENO_HI_F32_CASES])
+def test_hostsim_matches_oracle_for_weno7_and_weno9(hostsim, name, kw):
+    """WENO(order = 7 | 9): weno_interpolants.jl:81-90,175-185,303-307 (general tile kernel, AdvCoef::hi tables)"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))
+
+
 @pytest.mark.parametrize("name,kw", ph.ADAPT_CASES, ids=[c[0] for c in ph.ADAPT_CASES])
 def test_hostsim_matches_oracle_with_adapted_advection_order(hostsim, name, kw):
     """adapt_advection_order: FluxFormAdvection with the scheme lowered where N < buffer (adapt_advection_order.jl:18-96)"""

@@ -1000,3 +1000,49 @@ def test_fluxes_with_diffusivity_boundary_conditions_are_correct(FT):
     assert abs((mean1 - mean0) - float(flux) * m.clock.time / Lz) <= 1e-6
     if FT == np.float64:
         assert np.isclose(mean1 - mean0, -3.141592656086267e-5, rtol=1e-6)      # the Float64 value quoted in the reference test
+
+
+@pytest.mark.parametrize("order", [5, 7, 9])
+def test_weno_high_order_tables(order):
+    """WENO(order = 5 | 7 | 9) tables restated from weno_interpolants.jl:81-90 (C★), :117-118 (coeff_p), :175-185 (smoothness coefficients):
+    (i) the C★-weighted candidates ARE the UpwindBiased(order) reconstruction (what "optimal weights" means: Balsara & Shu), which pins
+    C★ and the ordering of coeff_p against the independently restated stencil coefficients; (ii) the smoothness forms of mirrored
+    sub-stencils are mirror images (a typo in one of the 115 decimals breaks it) and vanish on constants; (iii) smooth data: every
+    candidate reproduces polynomials of degree < buffer exactly, so the result does whatever the weights are."""
+    FT = np.float64
+    w = adv.WENO(FT, order)
+    B = w.buffer
+    # (i) Σ_r C★_r p_r = UpwindBiased(order) left reconstruction
+    comb = np.zeros(2 * B - 1)
+    for r in range(B):
+        for j in range(B):
+            comb[B - 1 - r + j] += float(w.cstar[r]) * float(w.coeff_p[r][j])        # S_r = (q[B-1-r] … q[2B-2-r])
+    left = adv.stencil_coefficients(FT, B - 2, order)
+    up = np.array([float(left[order - 1 - n]) for n in range(order)])                # q_n = ψ[i-B+n] -> coeff_left[order-1-n]
+    assert np.allclose(comb, up, atol=1e-14)
+    assert abs(sum(float(c) for c in w.cstar) - 1) < 1e-15
+    # (ii) mirror symmetry and constants
+    def quad(C):
+        Q, c = np.zeros((B, B)), 0
+        for s_ in range(B):
+            for i in range(s_, B):
+                Q[s_, i] += C[c + i - s_]
+            c += B - s_
+        return Q
+    for r in range(B):
+        Q, Qm = quad([float(x) for x in w.smooth[r]]), quad([float(x) for x in w.smooth[B - 1 - r]])
+        S, Sm = Q + Q.T, Qm + Qm.T
+        assert np.allclose(S, Sm[::-1, ::-1], atol=1e-12)
+        assert abs(S.sum()) < 1e-9                                                   # β of a constant field is zero
+    # (iii) polynomial of degree B - 1 through the conditional interpolation
+    g = Grid(FT, size=(24, 4, 4), extent=(24, 4, 4), topology=("P", "P", "P"), halo=(B, B, B))
+    f = Field(g, "ccc")
+    x = np.arange(-B, 24 + B) + 0.5
+    deg = B - 1
+    # cell averages of x^deg over unit cells: ((x+½)^(deg+1) − (x−½)^(deg+1)) / (deg+1)
+    f.data[...] = (((x + 0.5) ** (deg + 1) - (x - 0.5) ** (deg + 1)) / (deg + 1))[:, None, None]
+    ctx = Ctx(g, (8, 16), (1, 4), (1, 4))
+    for left_bias in (True, False):
+        val = adv.biased_face(ctx, w, ctx.field(f), 0, lambda o: np.full(ctx.shape, left_bias))(O)
+        xf = np.arange(8, 17) - 1.0
+        assert np.allclose(val[:, 0, 0], xf ** deg, rtol=1e-10, atol=1e-8)

@@ -110,3 +110,9 @@ def test_cuda_matches_oracle_with_adapted_advection_order(ob, name, kw):
 def test_cuda_matches_oracle_with_array_valued_diffusivities(ob, name, kw):
     """ScalarDiffusivity(ν = array, κ = (T = array, S = number)): abstract_scalar_diffusivity_closure.jl:323-332"""
     ph.check_case(kw, library=None, steps=(1, 10))
+
+
+@pytest.mark.parametrize("name,kw", ph.WENO_HI_CASES, ids=[c[0] for c in ph.WENO_HI_CASES])
+def test_cuda_matches_oracle_for_weno7_and_weno9(ob, name, kw):
+    """WENO(order = 7 | 9): weno_interpolants.jl:81-90,175-185,303-307 — general tile kernel, halos of 4 / 5, order-reduction chains near walls"""
+    ph.check_case(kw, library=None, steps=(1, 10))
