@@ -44,8 +44,11 @@ def test_missing_library_fails_loudly(tmp_path):
 
 def test_out_of_scope_configurations_are_errors():
     import oceananigans_b200 as ob
+    assert ob.WENO(order=7).buffer == 4 and ob.WENO(order=9).buffer == 5          # in scope since round 2
     with pytest.raises(NotImplementedError):
-        ob.WENO(order=7)
+        ob.WENO(order=11)
+    with pytest.raises(ValueError):
+        ob.WENO(order=6)                                                             # "defined only for odd orders"
     with pytest.raises(NotImplementedError):
         ob.Centered(order=6)
     with pytest.raises(NotImplementedError):
