@@ -18,7 +18,7 @@ using Oceananigans.Grids: RectilinearGrid, Periodic, Bounded, Flat, topology, ha
 using Oceananigans.Fields: interior
 using Oceananigans.TimeSteppers: RungeKutta3TimeStepper, QuasiAdamsBashforth2TimeStepper
 using Oceananigans.Models.NonhydrostaticModels: NonhydrostaticModel
-using Oceananigans.Advection: Centered, WENO
+using Oceananigans.Advection: Centered, WENO, UpwindBiased, required_halo_size_x
 using Oceananigans.TurbulenceClosures: ScalarDiffusivity, AnisotropicMinimumDissipation
 using Oceananigans.TurbulenceClosures.Smagorinskys: Smagorinsky, LillyCoefficient
 using Oceananigans.BuoyancyFormulations: SeawaterBuoyancy, BuoyancyTracer, LinearEquationOfState, BuoyancyForce
@@ -133,13 +133,21 @@ function config(model::NonhydrostaticModel)
         cfg.delta = Float64.((grid.Δxᶜᵃᵃ, grid.Δyᵃᶜᵃ, 0.0)); cfg.z_stretched = 1
     end
     cfg.extent = Float64.((grid.Lx, grid.Ly, grid.Lz))
+    # oc_advection code of one scheme (by its buffer = required halo)
+    scheme_code(a) = a === nothing ? Int32(7) :
+                     a isa Centered && required_halo_size_x(a) == 1 ? Int32(0) : a isa Centered && required_halo_size_x(a) == 2 ? Int32(2) :
+                     a isa WENO ? Int32((0, 5, 1, 9, 10)[required_halo_size_x(a)]) :                      # WENO(3), (5), (7), (9); WENO(1) is UpwindBiased(1)
+                     a isa UpwindBiased ? Int32((6, 3, 4)[required_halo_size_x(a)]) :
+                     throw(ArgumentError("B200: advection must be Centered(order<=4), UpwindBiased(order<=5), WENO(order<=9) or nothing"))
     adv = model.advection.momentum
-    hs = adv === nothing ? 0 : Oceananigans.Advection.required_halo_size_x(adv)
-    cfg.advection = adv === nothing ? 7 :
-                    adv isa Centered && hs == 1 ? 0 : adv isa Centered && hs == 2 ? 2 :
-                    adv isa WENO && hs == 3 ? 1 : adv isa WENO && hs == 2 ? 5 :
-                    adv isa UpwindBiased && hs == 1 ? 6 : adv isa UpwindBiased && hs == 2 ? 3 : adv isa UpwindBiased && hs == 3 ? 4 :
-                    throw(ArgumentError("B200: advection must be Centered(order<=4), UpwindBiased(order<=5), WENO(order<=5) or nothing"))
+    if adv isa Oceananigans.Advection.FluxFormAdvection          # adapt_advection_order lowered the scheme in some direction (ABI v5)
+        cfg.has_advection_dir = 1
+        cfg.advection_dir = (scheme_code(adv.x), scheme_code(adv.y), scheme_code(adv.z))
+        cfg.advection = maximum(cfg.advection_dir)              # informational; the per-direction codes are what the kernels use
+    else
+        cfg.has_advection_dir = 0
+        cfg.advection = scheme_code(adv)
+    end
     cfg.timestepper = model.timestepper isa RungeKutta3TimeStepper ? 0 :
                       model.timestepper isa QuasiAdamsBashforth2TimeStepper ? 1 : throw(ArgumentError("B200: unsupported time stepper"))
     model.timestepper isa QuasiAdamsBashforth2TimeStepper && (cfg.ab2_chi = model.timestepper.χ)

@@ -1138,6 +1138,8 @@ class Checkpointer:
             out[n] = f.parent()
         for n, f in m.timestepper.Gm.items():
             out["timestepper/G⁻/" + n] = f.parent()          # (brings the tendencies up to date first, like update_state!)
+        for n, f in m.timestepper.Gn.items():                 # the reference's checkpoints hold Gⁿ too (checkpointer.jl:161-200); a pickup
+            out["timestepper/Gⁿ/" + n] = f.parent()          # recomputes it from the restored state, so it is written for layout parity only
         c = m.clock._get()
         out["clock/time"], out["clock/iteration"], out["clock/stage"] = np.float64(c.time), np.int64(c.iteration), np.int32(c.stage)
         out["clock/last_Δt"], out["clock/last_stage_Δt"] = np.float64(c.last_dt), np.float64(c.last_stage_dt)
