@@ -504,7 +504,7 @@ struct MarchKernel {
     TileSrc<FT> src[4];   // staged fields, ring order
     int xpad;             // TMA coordinate of interior index i = 0 (j = 0 ↔ H[1], k = 0 ↔ H[2])
     int KC;               // z-levels per chunk (grid.z chunks)
-    int by0;              // first tile row of this launch (interior / boundary-strip split of distributed models: oc_model.cu tendencies())
+    int by0;              // first tile row of this launch (interior / boundary-strip split of distributed models: oc_model_impl.h tendencies())
 
     OC_HD int k_begin(const Block& b) const { return b.z * KC; }
     OC_HD int k_end(const Block& b) const { int e = (b.z + 1) * KC; return e < a.g.N[2] ? e : a.g.N[2]; }

@@ -16,12 +16,8 @@ HOSTSIM = os.path.join(ROOT, "tests", "hostsim", "liboc_hostsim.so")
 
 @pytest.fixture(scope="module")
 def hostsim():
-    src = os.path.join(ROOT, "oldoceananigans.jl_b200", "csrc", "oc_model.cu")
-    csrc = os.path.dirname(src)
-    newest = max(os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc))
-    if not os.path.exists(HOSTSIM) or os.path.getmtime(HOSTSIM) < newest:
-        subprocess.run(["g++", "-x", "c++", "-DOC_HOSTSIM", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
-                        src, "-o", HOSTSIM], check=True)
+    import __graft_entry__ as ge
+    ge.build()                       # rebuilds tests/hostsim/liboc_hostsim.so (and the product library) only when a source is newer
     return _lib.Library(HOSTSIM)
 
 
