@@ -82,7 +82,10 @@ typedef struct {
     oc_bc   bcs[OC_MAX_FIELDS][6];         /* per prognostic field × side */
     int32_t device;               /* CUDA device ordinal */
     /* Distributed(arch; partition = Partition(1, R)): slab decomposition in y (distributed_architectures.jl:242-302).
-     * N[1] is the LOCAL size, extent[1] the GLOBAL extent; dist_nranks <= 1 means a serial model. */
+     * N[1] is the LOCAL size, extent[1] the GLOBAL extent; dist_nranks <= 1 means a serial model.  topology[] and bcs[] describe the
+     * GLOBAL domain: with a Bounded y only rank 0 has the south wall and only rank R-1 the north one (the RightConnected /
+     * FullyConnected / LeftConnected local grids of distributed_grids.jl:75-126) — the other sides' entries are ignored there, and
+     * rank R-1 owns the wall face of y-Face fields (interior_size[1] = N[1] + 1). */
     int32_t dist_rank, dist_nranks;
     /* Vertically stretched grid: RectilinearGrid(…; z = faces::AbstractVector)  (rectilinear_grid.jl:264-291,
      * grid_generation.jl:33-94).  z_stretched = 1: z_faces points to N[2]+1 increasing face positions (FT values widened to
@@ -250,7 +253,7 @@ int  oc_compute_diagnostics(oc_model* m, oc_diagnostics* out);
  * src/Simulations/time_step_wizard.jl:101-108) — and progress messages need for tracers.  Local value on distributed models. */
 int  oc_field_maximum_abs(oc_model* m, int field, double* out);
 
-/* ---- multi-GPU: one process per GPU, slab decomposition in y ----
+/* ---- multi-GPU: one process per GPU, slab decomposition in y (x, y, z each Periodic or Bounded) ----
  * Replaces Distributed(...) + fill_halo_regions! on distributed fields (src/DistributedComputations/halo_communication.jl:87-333)
  * and DistributedFFTBasedPoissonSolver (distributed_fft_based_poisson_solver.jl:92-188).  Create the model with
  * cfg.dist_rank / cfg.dist_nranks set, then attach a transport before the first halo fill:

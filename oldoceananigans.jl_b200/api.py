@@ -46,7 +46,7 @@ class B200:
 
 class Partition:
     """Partition(x, y, z): ranks per dimension (src/DistributedComputations/distributed_architectures.jl:14-18).
-    The B200 path implements the slab decomposition Partition(1, R)."""
+    The B200 path implements the slab decomposition Partition(1, R), for Periodic and Bounded x, y and z."""
 
     def __init__(self, x=1, y=1, z=1):
         if x != 1 or z != 1:
@@ -661,8 +661,10 @@ class Field:
             locs = [Face if x else Center for x in info.location]
             nodes = [g.nodes(d, locs[d]) if g.topology[d] is not Flat else np.zeros(1) for d in range(3)]
             if self.model.distributed:      # this rank's rows
-                nyl, r = info.interior_size[1], g.architecture.rank
-                nodes[1] = nodes[1][r * nyl:(r + 1) * nyl]
+                # (the last slab of a Bounded y also owns the wall face of a y-Face field: interior_size[1] = Ny_l + 1)
+                r = g.architecture.rank
+                j0 = r * (g.N[1] // g.architecture.nranks)
+                nodes[1] = nodes[1][j0:j0 + info.interior_size[1]]
             X = np.meshgrid(*nodes, indexing="ij")
             args = [A for d, A in enumerate(X) if g.topology[d] is not Flat]
             value = np.broadcast_to(np.asarray(value(*args), dtype=np.float64), X[0].shape)
@@ -1029,10 +1031,16 @@ def fill_halo_regions_(fields, fill_open_bcs=True):
 
 
 def solve_poisson(model, rhs):
-    """solve!(ϕ, model.pressure_solver, rhs) for a host right-hand side of shape (Nx, Ny, Nz)"""
+    """solve!(ϕ, model.pressure_solver, rhs) for a host right-hand side of shape (Nx, Ny, Nz); on a distributed model every rank
+    passes (and receives) its own slab of rows, (Nx, Ny / R, Nz) — a collective call, like the reference's solve! on a
+    DistributedFFTBasedPoissonSolver (distributed_fft_based_poisson_solver.jl:141-178)"""
     g = model.grid
-    a = np.asfortranarray(np.asarray(rhs).reshape(g.N).astype(g.FT))
-    out = np.empty(g.N, dtype=g.FT, order="F")
+    shape = list(g.N)
+    if getattr(model, "distributed", False):
+        shape[1] //= g.architecture.nranks
+    shape = tuple(shape)
+    a = np.asfortranarray(np.asarray(rhs).reshape(shape).astype(g.FT))
+    out = np.empty(shape, dtype=g.FT, order="F")
     model._lib.check(model._lib.oc_poisson_solve(model._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), a.nbytes))
     return out
 

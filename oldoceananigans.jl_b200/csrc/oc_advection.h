@@ -97,14 +97,16 @@ OC_HD FT weno3_value(const AdvCoef<FT>& C, FT q0, FT q1, FT q2) {
 struct OrderWindow {
     int lo_hi = 0, hi_hi = 0, lo_mid = 0, hi_mid = 0;
 };
-OC_HD OrderWindow order_window(bool bounded, bool centre_type, int N) {
+// wlo / whi: a wall on the low / high side (a connected side of a slab never lowers the order: RightConnected / LeftConnected,
+// topologically_conditional_interpolation.jl:55-69)
+OC_HD OrderWindow order_window(bool wlo, bool whi, bool centre_type, int N) {
     OrderWindow w;
-    if (!bounded) {
-        w.lo_hi = -(1 << 30); w.hi_hi = (1 << 30); w.lo_mid = w.lo_hi; w.hi_mid = w.hi_hi;
-    } else if (centre_type) {
-        w.lo_hi = 3; w.hi_hi = N - 2; w.lo_mid = 2; w.hi_mid = N - 1;
-    } else {
-        w.lo_hi = 3; w.hi_hi = N - 3; w.lo_mid = 2; w.hi_mid = N - 2;
+    w.lo_hi = w.lo_mid = -(1 << 30);
+    w.hi_hi = w.hi_mid = (1 << 30);
+    if (wlo) { w.lo_hi = 3; w.lo_mid = 2; }
+    if (whi) {
+        if (centre_type) { w.hi_hi = N - 2; w.hi_mid = N - 1; }
+        else { w.hi_hi = N - 3; w.hi_mid = N - 2; }
     }
     return w;
 }

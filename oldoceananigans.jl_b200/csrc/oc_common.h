@@ -16,6 +16,10 @@ struct Geom {
     int N[3];        // interior size
     int H[3];        // internal halo size
     int bounded[3];  // 1 = Bounded topology
+    // a wall on the low / high side of THIS domain: both equal `bounded` on one GPU; on a slab of a distributed Bounded dimension only
+    // the first rank has the low wall and the last rank the high one (RightConnected / LeftConnected / FullyConnected local grids,
+    // distributed_grids.jl:75-126) — every wall-aware kernel tests these, never `bounded`
+    int wlo[3], whi[3];
     int flat[3];     // 1 = Flat (stored as periodic N=1)
     int sy, sz;      // strides in elements (sx = 1)
     FT d[3];         // Δx, Δy, Δz

@@ -48,7 +48,39 @@ struct Transport {
 struct HostTransport : Transport {
     HostExchangeFn fn;
     void* user;
-    HostTransport(HostExchangeFn f, void* u) : fn(f), user(u) {}
+    int rank, nranks;
+    // TEST-ONLY (host simulation, OC_HOSTSIM_THREADS=1): the ranks are threads of ONE process, so a peer's buffer is simply its pointer
+    // and the peer-memory transposes (TransposePutKernel) can be exercised without a GPU; the collectives go through the callback
+    bool same_process;
+    HostTransport(HostExchangeFn f, void* u, int r, int n, bool threads) : fn(f), user(u), rank(r), nranks(n), same_process(threads) {}
+    std::string all_gather(const void* mine, void* all, size_t bytes, int tag) {
+        memcpy((char*)all + bytes * rank, mine, bytes);
+        std::vector<Msg> msgs;
+        for (int d = 1; d < nranks; ++d) {
+            const int to = (rank + d) % nranks, from = (rank + nranks - d) % nranks;
+            msgs.push_back(Msg{to, from, tag + d, (char*)all + bytes * rank, bytes, (char*)all + bytes * from, bytes});
+        }
+        return exchange(msgs, Stream());
+    }
+    std::string map_peers(void* local, std::vector<void*>& peers, Stream) override {
+        if (!same_process) return "no peer memory in this transport";
+        peers.assign(nranks, nullptr);
+        return all_gather(&local, peers.data(), sizeof(void*), 900);
+    }
+    std::string barrier(Stream) override {
+        if (!same_process) return "no barrier in this transport";
+        char mine = 0;
+        std::vector<char> all(nranks, 0);
+        return all_gather(&mine, all.data(), 1, 940);
+    }
+    int agree(bool failed, Stream) override {
+        if (!same_process) return failed ? 1 : 0;
+        int mine = failed ? 1 : 0, sum = 0;
+        std::vector<int> all(nranks, 0);
+        if (!all_gather(&mine, all.data(), sizeof(int), 980).empty()) return nranks;
+        for (int v : all) sum += v;
+        return sum;
+    }
     std::string exchange(const std::vector<Msg>& msgs, Stream) override {
         std::vector<int> sp, rp, tg;
         std::vector<void*> sptr, rptr;
@@ -209,6 +241,7 @@ struct HaloPackKernel {
         const int row = (int)(r % rows); r /= rows;
         const int pl = (int)(r % planes);
         const int f = (int)(r / planes);
+        if (unpack && (side == 0 ? g.wlo[1] : g.whi[1])) return;       // a wall side (Bounded y, outer rank): nothing was received
         // allocation row index of interior row j is j + H[1]
         int jrow;
         if (!unpack) jrow = side == 0 ? g.H[1] + row : g.H[1] + g.N[1] - rows + row;          // low edge / high edge interior rows
@@ -230,6 +263,7 @@ struct TransposeKernel {
     int nxc, nyl, nzl, R;
     int zl0;                   // first local z-level of this launch (grid.z levels from there): sub-chunk pipelining
     int to_T;                  // 1: stage -> T ; 0: T -> stage
+    int yperm;                 // Bounded y: T holds the Makhoul-permuted line (v[n] = x[2n], v[N-1-n] = x[2n+1]) the DCT's FFT runs on
     Cplx<FT>* stage;
     Cplx<FT>* T;
     template <int PHASE>
@@ -253,7 +287,7 @@ struct TransposeKernel {
             for (int r = ty; r < 32; r += 8) {
                 const int x = x0 + r, y = y0 + tx;
                 if (x < nxc && y < ny) {
-                    Cplx<FT>* p = T + (((long long)zl * nxc + x) * ny + y);
+                    Cplx<FT>* p = T + (((long long)zl * nxc + x) * ny + makhoul(y, ny, yperm));
                     if (to_T) *p = tile[tx * 33 + r]; else tile[tx * 33 + r] = *p;
                 }
             }
@@ -279,6 +313,7 @@ struct TransposePutKernel {
     static constexpr size_t SMEM = sizeof(Cplx<FT>) * 32 * 33;
     int nxc, nyl, nzl, R, rank;
     int forward;
+    int yperm;                          // Bounded y: Makhoul-permuted positions in T (see TransposeKernel)
     Cplx<FT>* spec[DIST_MAX_RANKS];     // every rank's spectral buffer (spec[rank]: the local one)
     Cplx<FT>* T[DIST_MAX_RANKS];        // every rank's transposed buffer
     template <int PHASE>
@@ -302,7 +337,7 @@ struct TransposePutKernel {
                 Cplx<FT>* dst = T[d];
                 for (int r = ty; r < 32; r += 8) {
                     const int x = x0 + r, yl = yl0 + tx;
-                    if (x < nxc && yl < nyl) dst[((long long)zl * nxc + x) * ny + rank * nyl + yl] = tile[tx * 33 + r];
+                    if (x < nxc && yl < nyl) dst[((long long)zl * nxc + x) * ny + makhoul(rank * nyl + yl, ny, yperm)] = tile[tx * 33 + r];
                 }
             }
         } else {
@@ -312,7 +347,7 @@ struct TransposePutKernel {
             if (PHASE == 0) {                          // local read, y contiguous
                 for (int r = ty; r < 32; r += 8) {
                     const int x = x0 + r, y = y0 + tx;
-                    if (x < nxc && y < ny) tile[tx * 33 + r] = T[rank][((long long)zl * nxc + x) * ny + y];
+                    if (x < nxc && y < ny) tile[tx * 33 + r] = T[rank][((long long)zl * nxc + x) * ny + makhoul(y, ny, yperm)];
                 }
             } else {                                   // peer write, x contiguous
                 for (int r = ty; r < 32; r += 8) {
@@ -327,30 +362,37 @@ struct TransposePutKernel {
     }
 };
 
-// Bounded z in a slab (y) decomposition: z is local in the first stage, so the Makhoul twiddles of the DCT are applied on the
-// local layout (complex (nxc, Ny_l, Nz), x fastest) right after the forward (z, x) FFT / right before the inverse one — the
+// Bounded x or z in a slab (y) decomposition: both are local in the first stage, so the Makhoul twiddles of their DCTs are applied on
+// the local layout (complex (nxc, Ny_l, Nz), x fastest) right after the forward (z, x) FFT / right before the inverse one — the
 // forward and inverse halves of PoissonMidZKernel, separated by the transposed y stage.
 //   forward : X[k] = ω_k V[k] + conj(ω_k) V[N-k]                 (DCT-II, FFTW REDFT10 scaling)
 //   inverse : W[k] = ½ conj(ω_k) (Φ[k] - i Φ[N-k]),  Φ[N] := 0   (DCT-III with its 1/2N folded in)
+// One thread per line and reflection orbit {k, N-k}.  Line n starts at (n % inner) + (n / inner)·souter and its wavenumbers are sk
+// elements apart: z lines — sk = inner = the (x, y) plane; x lines — sk = 1, inner = 1, souter = the row length (threads then run
+// along k: kfast).
 template <class FT>
-struct ZTwiddleKernel {
+struct TwiddleKernel {
     static constexpr int PHASES = 1;
     static constexpr int THREADS = 256;
     static constexpr int MIN_BLOCKS = 1;
-    int plane, Nz;             // plane = nxc · Ny_l
+    long long sk, souter, count;
+    int inner, N, kfast;
     int inverse;
     Cplx<FT>* spec;
-    const Cd* twz;
+    const Cd* tw;
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
-        const int n = b.x * nt + tid;
-        if (n >= plane) return;
-        const int k0 = b.y, k1 = (Nz - k0) % Nz;
-        Cplx<FT>* p0 = spec + (long long)plane * k0 + n;
-        Cplx<FT>* p1 = spec + (long long)plane * k1 + n;
+        const int nk = N / 2 + 1;
+        const long long t = (long long)b.x * nt + tid;
+        if (t >= count * nk) return;
+        const long long n = kfast ? t / nk : t % count;
+        const int k0 = (int)(kfast ? t % nk : t / count), k1 = (N - k0) % N;
+        Cplx<FT>* line = spec + (n % inner) + (n / inner) * souter;
+        Cplx<FT>* p0 = line + sk * k0;
+        Cplx<FT>* p1 = line + sk * k1;
         const Cplx<FT> s0 = *p0, s1 = *p1;
         const Cd a0{(double)s0.x, (double)s0.y}, a1{(double)s1.x, (double)s1.y};
-        const Cd w0 = twz[k0], w1 = twz[k1];
+        const Cd w0 = tw[k0], w1 = tw[k1];
         Cd e0, e1;
         if (!inverse) {
             e0 = cadd(cmul(w0, a0), cmul(cconj(w0), a1));
@@ -368,7 +410,8 @@ struct ZTwiddleKernel {
     }
 };
 
-// spectral divide in the transposed layout T = [zl][x][y]: global kz = rank·nzl + zl
+// spectral divide in the transposed layout T = [zl][x][y]: global kz = rank·nzl + zl.  Bounded y (tw != nullptr): y is whole here, so
+// the twiddles of its DCT wrap the divide — one thread per reflection orbit {y, Ny-y}, like PoissonMidZKernel does for z.
 template <class FT>
 struct PoissonDivideTKernel {
     static constexpr int PHASES = 1;
@@ -378,18 +421,39 @@ struct PoissonDivideTKernel {
     int zl0;
     Cplx<FT>* T;
     const double* lam[3];      // λx[nxc…], λy[ny] (GLOBAL y), λz[Nz] (global z)
+    const Cd* tw;              // ω_k = exp(-iπk/2Ny) of a Bounded y, else nullptr
     double norm;
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
         const int y = b.x * nt + tid, x = b.y, zl = zl0 + b.z;
-        if (y >= ny) return;
         const int kz = kz0 + zl;
-        const double l = lam[0][x] + lam[1][y] + lam[2][kz];
-        Cplx<FT>* p = T + (((long long)zl * nxc + x) * ny + y);
-        Cplx<FT> e = *p;
-        double s = -norm / l;
-        if (x == 0 && y == 0 && kz == 0) s = 0.0;
-        *p = Cplx<FT>{(FT)((double)e.x * s), (FT)((double)e.y * s)};
+        Cplx<FT>* row = T + ((long long)zl * nxc + x) * ny;
+        if (!tw) {
+            if (y >= ny) return;
+            const double l = lam[0][x] + lam[1][y] + lam[2][kz];
+            Cplx<FT> e = row[y];
+            double s = -norm / l;
+            if (x == 0 && y == 0 && kz == 0) s = 0.0;
+            row[y] = Cplx<FT>{(FT)((double)e.x * s), (FT)((double)e.y * s)};
+            return;
+        }
+        if (y > ny / 2) return;
+        const int y1 = (ny - y) % ny;
+        const Cplx<FT> s0 = row[y], s1 = row[y1];
+        const Cd a0{(double)s0.x, (double)s0.y}, a1{(double)s1.x, (double)s1.y};
+        const Cd w0 = tw[y], w1 = tw[y1];
+        Cd X0 = cadd(cmul(w0, a0), cmul(cconj(w0), a1));
+        Cd X1 = cadd(cmul(w1, a1), cmul(cconj(w1), a0));
+        double c0 = -norm / (lam[0][x] + lam[1][y] + lam[2][kz]), c1 = -norm / (lam[0][x] + lam[1][y1] + lam[2][kz]);
+        if (x == 0 && kz == 0) { if (y == 0) c0 = 0.0; if (y1 == 0) c1 = 0.0; }
+        X0 = Cd{X0.x * c0, X0.y * c0};
+        X1 = Cd{X1.x * c1, X1.y * c1};
+        const Cd r0 = y == 0 ? Cd{0.0, 0.0} : X1;
+        const Cd r1 = y1 == 0 ? Cd{0.0, 0.0} : X0;
+        const Cd t0{X0.x + r0.y, X0.y - r0.x}, t1{X1.x + r1.y, X1.y - r1.x};
+        const Cd h0 = cmul(cconj(w0), t0), h1 = cmul(cconj(w1), t1);
+        row[y] = Cplx<FT>{(FT)(0.5 * h0.x), (FT)(0.5 * h0.y)};
+        row[y1] = Cplx<FT>{(FT)(0.5 * h1.x), (FT)(0.5 * h1.y)};
     }
 };
 
@@ -403,9 +467,12 @@ public:
     size_t work_bytes = 0;
 
     int C = 1;                 // the y stage runs in C sub-chunks of Nzl / C levels (pipelined against the all-to-alls)
-    std::string init(int nx, int nyl, int nz, int r, Stream stream, Stream ystream) {
+    bool c2c = false;          // Bounded x: the (z, x) stage is complex-to-complex over whole rows (the permuted line of the DCT), like
+                               // Fft3 on one GPU (plan_transforms.jl:16-136); otherwise real-to-complex, Nx/2+1 coefficients per row
+    std::string init(int nx, int nyl, int nz, int r, bool x_bounded, Stream stream, Stream ystream) {
         Nx = nx; Nyl = nyl; Nz = nz; R = r;
-        nxc = Nx / 2 + 1; nxr = 2 * nxc; Ny = Nyl * R; Nzl = Nz / R;
+        c2c = x_bounded;
+        nxc = c2c ? Nx : Nx / 2 + 1; nxr = 2 * nxc; Ny = Nyl * R; Nzl = Nz / R;
         C = Nzl % 4 == 0 ? 4 : (Nzl % 2 == 0 ? 2 : 1);
 #ifndef OC_HOSTSIM
         const bool dbl = sizeof(FT) == 8;
@@ -416,10 +483,15 @@ public:
         }
         int n2[2] = {Nz, Nx};
         int rembed[2] = {Nz, nxr * Nyl}, cembed[2] = {Nz, nxc * Nyl};
+        if (c2c) {
+            if (cufftMakePlanMany(fwd_, 2, n2, cembed, 1, nxc, cembed, 1, nxc, dbl ? CUFFT_Z2Z : CUFFT_C2C, Nyl, &w[0]) != CUFFT_SUCCESS)
+                return "cufftMakePlanMany(zx complex) failed";
+        } else {
         if (cufftMakePlanMany(fwd_, 2, n2, rembed, 1, nxr, cembed, 1, nxc, dbl ? CUFFT_D2Z : CUFFT_R2C, Nyl, &w[0]) != CUFFT_SUCCESS)
             return "cufftMakePlanMany(zx forward) failed";
         if (cufftMakePlanMany(inv_, 2, n2, cembed, 1, nxc, rembed, 1, nxr, dbl ? CUFFT_Z2D : CUFFT_C2R, Nyl, &w[1]) != CUFFT_SUCCESS)
             return "cufftMakePlanMany(zx inverse) failed";
+        }
         int n1[1] = {Ny};
         if (cufftMakePlanMany(y_, 1, n1, nullptr, 1, Ny, nullptr, 1, Ny, dbl ? CUFFT_Z2Z : CUFFT_C2C, nxc * (Nzl / C), &w[2]) != CUFFT_SUCCESS)
             return "cufftMakePlanMany(y) failed";
@@ -446,7 +518,11 @@ public:
     void set_y_stream(Stream s) { cufftSetStream(y_, s); }
     std::string zx(void* buf, bool fwd) {
         cufftResult r;
-        if (sizeof(FT) == 8) r = fwd ? cufftExecD2Z(fwd_, (cufftDoubleReal*)buf, (cufftDoubleComplex*)buf) : cufftExecZ2D(inv_, (cufftDoubleComplex*)buf, (cufftDoubleReal*)buf);
+        if (c2c) {
+            if (sizeof(FT) == 8) r = cufftExecZ2Z(fwd_, (cufftDoubleComplex*)buf, (cufftDoubleComplex*)buf, fwd ? CUFFT_FORWARD : CUFFT_INVERSE);
+            else r = cufftExecC2C(fwd_, (cufftComplex*)buf, (cufftComplex*)buf, fwd ? CUFFT_FORWARD : CUFFT_INVERSE);
+        }
+        else if (sizeof(FT) == 8) r = fwd ? cufftExecD2Z(fwd_, (cufftDoubleReal*)buf, (cufftDoubleComplex*)buf) : cufftExecZ2D(inv_, (cufftDoubleComplex*)buf, (cufftDoubleReal*)buf);
         else r = fwd ? cufftExecR2C(fwd_, (cufftReal*)buf, (cufftComplex*)buf) : cufftExecC2R(inv_, (cufftComplex*)buf, (cufftReal*)buf);
         return r == CUFFT_SUCCESS ? "" : "cuFFT zx exec failed with code " + std::to_string((int)r);
     }
@@ -479,7 +555,9 @@ public:
         for (int j = 0; j < Nyl; ++j) {
             std::vector<Cd> full((size_t)Nx * Nz);
             auto at = [&](int i, int k) -> Cd& { return full[(size_t)i + (size_t)Nx * k]; };
-            if (fwd) {
+            if (c2c) {
+                for (int k = 0; k < Nz; ++k) for (int i = 0; i < Nx; ++i) { long long c = i + (long long)nxc * (j + (long long)Nyl * k); at(i, k) = Cd{(double)buf[2 * c], (double)buf[2 * c + 1]}; }
+            } else if (fwd) {
                 for (int k = 0; k < Nz; ++k) for (int i = 0; i < Nx; ++i) at(i, k) = Cd{(double)buf[i + (long long)nxr * (j + (long long)Nyl * k)], 0.0};
             } else {
                 for (int k = 0; k < Nz; ++k) for (int i = 0; i < Nx; ++i) {
@@ -489,7 +567,7 @@ public:
             }
             for (int k = 0; k < Nz; ++k) { std::vector<Cd> l(Nx); for (int i = 0; i < Nx; ++i) l[i] = at(i, k); dft(l, fwd); for (int i = 0; i < Nx; ++i) at(i, k) = l[i]; }
             for (int i = 0; i < Nx; ++i) { std::vector<Cd> l(Nz); for (int k = 0; k < Nz; ++k) l[k] = at(i, k); dft(l, fwd); for (int k = 0; k < Nz; ++k) at(i, k) = l[k]; }
-            if (fwd) {
+            if (fwd || c2c) {
                 for (int k = 0; k < Nz; ++k) for (int i = 0; i < nxc; ++i) { long long c = i + (long long)nxc * (j + (long long)Nyl * k); buf[2 * c] = (FT)at(i, k).x; buf[2 * c + 1] = (FT)at(i, k).y; }
             } else {
                 for (int k = 0; k < Nz; ++k) for (int i = 0; i < Nx; ++i) buf[i + (long long)nxr * (j + (long long)Nyl * k)] = (FT)at(i, k).x;

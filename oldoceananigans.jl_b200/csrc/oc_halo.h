@@ -79,16 +79,17 @@ struct HaloKernel {
                 Q[d] = q;
             } else if (fld.face[d]) {                  // wall-normal velocity: interior points 0..N
                 if (idx < 0 || idx > N) return r;      // never filled (field_boundary_conditions.jl:15-25: Open only)
+                if (idx == N && !g.whi[d]) return r;   // connected side of a slab: the neighbour's first face, by exchange
                 Q[d] = idx;
-                if (idx == 0 || idx == N) {
+                if ((idx == 0 && g.wlo[d]) || (idx == N && g.whi[d])) {
                     const SideBC& s = fld.bc[2 * d + (idx == 0 ? 0 : 1)];
                     if (s.kind == 5 && fill_open) { wall = true; wall_value = FT(s.value); }
                 }
             } else {                                   // Center-located in a Bounded dimension
                 if (idx >= 0 && idx < N) Q[d] = idx;
-                else if (idx == -1) { Q[d] = 0; bc_dim = d; bc_side = 0; ++nbc; }
-                else if (idx == N) { Q[d] = N - 1; bc_dim = d; bc_side = 1; ++nbc; }
-                else return r;                         // halo planes 2..H are never written
+                else if (idx == -1 && g.wlo[d]) { Q[d] = 0; bc_dim = d; bc_side = 0; ++nbc; }
+                else if (idx == N && g.whi[d]) { Q[d] = N - 1; bc_dim = d; bc_side = 1; ++nbc; }
+                else return r;                         // halo planes 2..H are never written; connected sides of a slab: by exchange
             }
         }
         if (nbc > 1) return r;                         // Bounded×Bounded corners are never written

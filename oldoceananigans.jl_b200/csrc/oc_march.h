@@ -688,7 +688,7 @@ struct MarchKernel {
                 return (A * u) * (FT(0.5) * rd<D, FT>(c, ii, jj, lev, -1) + FT(0.5) * rd<D, FT>(c, ii, jj, lev, 0));
             } else {
                 OrderWindow w;
-                if (WINV<D>) w = order_window(g.bounded[D] != 0, false, g.N[D]);
+                if (WINV<D>) w = order_window(g.wlo[D] != 0, g.whi[D] != 0, false, g.N[D]);
                 FT cr = t_weno5_biased<D, WINV<D>, ADV == ADV_UPWIND5, FT>(c, ii, jj, lev, u > FT(0), id, w);
                 return A * u * cr;
             }
@@ -702,7 +702,7 @@ struct MarchKernel {
                     return A * ut * ut;
                 } else {
                     OrderWindow w;
-                    if (WINV<D>) w = order_window(g.bounded[D] != 0, true, g.N[D]);
+                    if (WINV<D>) w = order_window(g.wlo[D] != 0, g.whi[D] != 0, true, g.N[D]);
                     const int i1 = ii + (D == 0), j1 = jj + (D == 1), l1 = lev + (D == 2);
                     FT ut = t_weno5_symmetric<D, WINV<D>, FT>(psi, i1, j1, l1, A, id + 1, w);
                     FT pr = t_weno5_biased<D, WINV<D>, ADV == ADV_UPWIND5, FT>(psi, i1, j1, l1, ut > FT(0), id + 1, w);
@@ -716,8 +716,8 @@ struct MarchKernel {
                     return A * ut * pt;
                 } else {
                     OrderWindow wc, wd;
-                    if (WINV<CC>) wc = order_window(g.bounded[CC] != 0, false, g.N[CC]);
-                    if (WINV<D>) wd = order_window(g.bounded[D] != 0, false, g.N[D]);
+                    if (WINV<CC>) wc = order_window(g.wlo[CC] != 0, g.whi[CC] != 0, false, g.N[CC]);
+                    if (WINV<D>) wd = order_window(g.wlo[D] != 0, g.whi[D] != 0, false, g.N[D]);
                     FT ut;
                     if (ZS && CC == 2) {
                         const FT h = g.d[D == 0 ? 1 : 0];
@@ -883,7 +883,7 @@ struct MarchKernel {
                 if (WIN && COMP >= 0) {
                     // exclude_periphery: the wall face of a wall-normal velocity is not stepped (kernel_launching.jl:145-146)
                     const int ic = COMP == 0 ? i : (COMP == 1 ? j : kc);
-                    if (g.bounded[COMP < 0 ? 0 : COMP] && ic == 0 && g.N[COMP < 0 ? 0 : COMP] > 1) {
+                    if (g.wlo[COMP < 0 ? 0 : COMP] && ic == 0 && g.N[COMP < 0 ? 0 : COMP] > 1) {
                         if (a.mode != STEP_NONE) a.Unew[o] = u0;
                         continue;
                     }
@@ -902,8 +902,8 @@ struct MarchKernel {
                     if (KIND == KIND_U) {
                         num = FT(0.25) * ((q(ii - 1, jj, kc) + q(ii, jj, kc)) + (q(ii - 1, jj + 1, kc) + q(ii, jj + 1, kc)));
                         if (WIN) {
-                            int ax0 = !(g.bounded[0] && (i - 1 < 0)), ax1 = 1;
-                            int ay0 = !(g.bounded[1] && (j < 1)), ay1 = !(g.bounded[1] && (j + 1 > g.N[1] - 1));
+                            int ax0 = !(g.wlo[0] && (i - 1 < 0)), ax1 = 1;
+                            int ay0 = !(g.wlo[1] && (j < 1)), ay1 = !(g.whi[1] && (j + 1 > g.N[1] - 1));
                             cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
                         }
                         FT val = cnt == FT(0) ? FT(0) : num / cnt;
@@ -911,8 +911,8 @@ struct MarchKernel {
                     } else {
                         num = FT(0.25) * ((q(ii, jj - 1, kc) + q(ii + 1, jj - 1, kc)) + (q(ii, jj, kc) + q(ii + 1, jj, kc)));
                         if (WIN) {
-                            int ax0 = !(g.bounded[0] && (i < 1)), ax1 = !(g.bounded[0] && (i + 1 > g.N[0] - 1));
-                            int ay0 = !(g.bounded[1] && (j - 1 < 0)), ay1 = 1;
+                            int ax0 = !(g.wlo[0] && (i < 1)), ax1 = !(g.whi[0] && (i + 1 > g.N[0] - 1));
+                            int ay0 = !(g.wlo[1] && (j - 1 < 0)), ay1 = 1;
                             cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
                         }
                         FT val = cnt == FT(0) ? FT(0) : num / cnt;

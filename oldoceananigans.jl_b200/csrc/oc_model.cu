@@ -186,7 +186,8 @@ int oc_dist_attach_host(oc_model* m, oc_exchange_fn fn, void* user) {
     return guarded([&] {
 #ifdef OC_HOSTSIM
         if (!fn) throw oc::Error(OC_ERR_INVALID, "null exchange callback");
-        m->impl->dist_attach(new oc::HostTransport(fn, user));
+        const char* threads = getenv("OC_HOSTSIM_THREADS");
+        m->impl->dist_attach(new oc::HostTransport(fn, user, m->impl->dist_rank(), m->impl->dist_nranks(), threads && atoi(threads) != 0));
 #else
         (void)fn; (void)user;
         throw oc::Error(OC_ERR_UNSUPPORTED, "the host-callback transport is a test facility of the host simulation build; use oc_dist_attach_nccl");

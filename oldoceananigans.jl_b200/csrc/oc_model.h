@@ -273,6 +273,7 @@ private:
     bool p2p_ = false;             // the transposes go through peer memory (TransposePutKernel) instead of NCCL all-to-alls
     std::vector<void*> peer_spec_, peer_T_;     // every rank's fftbuf_ / distT_ (CUDA IPC mappings)
     void run_fft_solve_p2p();
+    void local_twiddles(bool inverse);
     FT* halo_send_ = nullptr;
     FT* halo_recv_ = nullptr;
     size_t halo_buf_elems_ = 0;

@@ -153,6 +153,11 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         g_.N[d] = c.N[d];
         g_.H[d] = t == OC_FLAT ? 3 : std::max(3, c.H[d]);   // internal halo >= 3 (TMA boxes); the API halo is Hcfg_
         g_.bounded[d] = t == OC_BOUNDED;
+        g_.wlo[d] = g_.whi[d] = g_.bounded[d];
+        if (d == 1 && c.dist_nranks > 1 && g_.bounded[d]) {      // slab of a Bounded y: only the outer ranks have a wall (distributed_grids.jl:75-126)
+            g_.wlo[d] = c.dist_rank == 0;
+            g_.whi[d] = c.dist_rank == c.dist_nranks - 1;
+        }
         g_.flat[d] = t == OC_FLAT;
         g_.d[d] = t == OC_FLAT ? FT(1) : (FT)c.delta[d];
         g_.rd[d] = FT(1) / g_.d[d];
@@ -300,15 +305,17 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     if (dist_) {
         rank_ = c.dist_rank; R_ = c.dist_nranks;
         if (rank_ < 0 || rank_ >= R_) throw Error(OC_ERR_INVALID, "dist_rank out of range");
-        if (c.topology[0] != OC_PERIODIC || c.topology[1] != OC_PERIODIC || c.topology[2] == OC_FLAT)
-            throw Error(OC_ERR_UNSUPPORTED, "distributed models: (Periodic, Periodic, Periodic | Bounded) grids (Bounded x / y and Flat dimensions: next)");
+        if (c.topology[0] == OC_FLAT || c.topology[1] == OC_FLAT || c.topology[2] == OC_FLAT)
+            throw Error(OC_ERR_UNSUPPORTED, "distributed models: Periodic or Bounded x, y and z (Flat dimensions: next)");
         if (g_.N[2] % R_ != 0) throw Error(OC_ERR_INVALID, "distributed FFT: Nz must be divisible by the number of ranks (distributed_fft_based_poisson_solver.jl:211-229)");
         if (g_.N[1] < g_.H[1]) throw Error(OC_ERR_INVALID, "distributed models: local Ny smaller than the halo");
     }
     if (stretched_) build_z_tables(c.z_faces);
     cfg_.z_faces = nullptr;                              // borrowed host pointer: not kept
     // pressure solver
-    std::string err = fft_.init(g_.N, g_.bounded, stream_, !dist_, stretched_);
+    // slab decomposition: y is transformed in the transposed layout, where it is whole — the local buffer carries no y permutation
+    const int local_bounded[3] = {g_.bounded[0], dist_ ? 0 : g_.bounded[1], g_.bounded[2]};
+    std::string err = fft_.init(g_.N, local_bounded, stream_, !dist_, stretched_);
     if (!err.empty()) throw Error(OC_ERR_CUDA, err);
     fftbuf_ = (FT*)dev_alloc(fft_.buffer_bytes);
     device_bytes += (int64_t)fft_.buffer_bytes + (int64_t)fft_.work_bytes;
@@ -316,7 +323,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
 #ifndef OC_HOSTSIM
         cuda_check(cudaStreamCreateWithFlags(&stream3_, cudaStreamNonBlocking), "cudaStreamCreate");
 #endif
-        err = dfft_.init(g_.N[0], g_.N[1], g_.N[2], R_, stream_, stream3_);
+        err = dfft_.init(g_.N[0], g_.N[1], g_.N[2], R_, g_.bounded[0] != 0, stream_, stream3_);
 #ifndef OC_HOSTSIM
         for (int c = 0; c < dfft_.C; ++c) {
             cudaEvent_t a, b;
@@ -494,6 +501,13 @@ void Model<FT>::resolve_bcs(FieldRec& f, const oc_bc* user) {
             } else if (t == OC_FLAT) {
                 r.kind = OC_BC_NONE;
             } else {
+                if (!(s == 0 ? g_.wlo[d] : g_.whi[d])) {
+                    // a connected side of a slab: the neighbour's rows arrive by halo exchange, whatever the user declared for the
+                    // global boundary (inject_halo_communication_boundary_conditions, halo_communication_bcs.jl:14-51)
+                    r.kind = OC_BC_NONE;
+                    f.bc[2 * d + s] = r;
+                    continue;
+                }
                 if (kind == OC_BC_DEFAULT) kind = f.face[d] ? OC_BC_OPEN : OC_BC_FLUX;
                 if (kind == OC_BC_PERIODIC) throw Error(OC_ERR_INVALID, "periodic boundary condition in a Bounded dimension");
                 if (f.face[d] && kind != OC_BC_OPEN) throw Error(OC_ERR_UNSUPPORTED, "wall-normal velocity supports only Open (impenetrable) boundary conditions");
@@ -575,7 +589,7 @@ void Model<FT>::field_info(int field, oc_field_info* info) {
     FieldRec& f = lookup(field);
     for (int d = 0; d < 3; ++d) {
         info->location[d] = f.face[d];
-        info->interior_size[d] = g_.N[d] + ((f.face[d] && g_.bounded[d]) ? 1 : 0);
+        info->interior_size[d] = g_.N[d] + ((f.face[d] && g_.whi[d]) ? 1 : 0);
         info->parent_size[d] = info->interior_size[d] + 2 * Hcfg_[d];
     }
     info->device_ptr = f.p;
@@ -831,7 +845,7 @@ void Model<FT>::dist_attach(Transport* t) {
     if (!dist_) { delete t; throw Error(OC_ERR_STATE, "the model was not created with dist_nranks > 1"); }
     transport_.reset(t);
     // Peer memory for the transposed FFT (OC_DIST_P2P=0 keeps the all-to-all path: measurement / machines without P2P)
-    static const char* p2p_env = getenv("OC_DIST_P2P");
+    const char* p2p_env = getenv("OC_DIST_P2P");
     p2p_ = false;
     // Measured (profiles/r02f…r02j): 2 GPUs 70.7 vs 72.7 ms per step, 4 GPUs 71.8 vs 72.5 with / without peer-memory transposes; at 8 GPUs
     // the first version (every rank writing to rank 0 first: incast) lost, 88.9 vs 77.4; the round-robin version: 77.2 vs 76.3 (r02o) — the
@@ -846,6 +860,7 @@ void Model<FT>::dist_attach(Transport* t) {
         if (p2p_) dfft_.set_y_stream(stream_);
 #endif
     }
+    if (getenv("OC_VERBOSE")) fprintf(stderr, "oceananigans_b200: rank %d of %d: distributed FFT transposes over %s\n", rank_, R_, p2p_ ? "peer memory" : "send/receive all-to-all");
 }
 
 // FFT(z,x) local -> transposed put into the owners' buffers -> FFT(y) -> divide -> FFT⁻¹(y) -> transposed put back -> FFT⁻¹(z,x)
@@ -858,16 +873,9 @@ void Model<FT>::run_fft_solve_p2p() {
     auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
     auto barrier = [&]() { begin_timer(OC_TIMER_COMM); std::string e = transport_->barrier(stream_); end_timer(); chk(e); };
     begin_timer(OC_TIMER_FFT); std::string e = dfft_.zx(fftbuf_, true); end_timer(); chk(e);
-    ZTwiddleKernel<FT> zt;
-    Dim3 zg;
-    if (g_.bounded[2]) {
-        zt.plane = dfft_.nxc * g_.N[1]; zt.Nz = g_.N[2]; zt.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_); zt.twz = tw_[2];
-        zg.x = (zt.plane + 255) / 256; zg.y = g_.N[2] / 2 + 1;
-        zt.inverse = 0;
-        go(zt, zg, 0, OC_TIMER_POISSON_MID);
-    }
+    local_twiddles(false);
     TransposePutKernel<FT> t;
-    t.nxc = dfft_.nxc; t.nyl = g_.N[1]; t.nzl = dfft_.Nzl; t.R = R_; t.rank = rank_;
+    t.nxc = dfft_.nxc; t.nyl = g_.N[1]; t.nzl = dfft_.Nzl; t.R = R_; t.rank = rank_; t.yperm = g_.bounded[1];
     for (int r = 0; r < R_; ++r) { t.spec[r] = reinterpret_cast<Cplx<FT>*>(peer_spec_[r]); t.T[r] = reinterpret_cast<Cplx<FT>*>(peer_T_[r]); }
     Dim3 tg;
     barrier();
@@ -881,6 +889,7 @@ void Model<FT>::run_fft_solve_p2p() {
     k.nxc = dfft_.nxc; k.ny = dfft_.Ny; k.nzl = dfft_.Nzl; k.kz0 = rank_ * dfft_.Nzl; k.zl0 = 0;
     k.T = reinterpret_cast<Cplx<FT>*>(distT_);
     for (int d = 0; d < 3; ++d) k.lam[d] = lam_[d];
+    k.tw = g_.bounded[1] ? tw_[1] : nullptr;
     k.norm = 1.0 / ((double)g_.N[0] * dfft_.Ny * g_.N[2]);
     Dim3 grid;
     grid.x = (dfft_.Ny + 255) / 256; grid.y = dfft_.nxc; grid.z = dfft_.Nzl;
@@ -891,11 +900,24 @@ void Model<FT>::run_fft_solve_p2p() {
     tg.x = (dfft_.nxc + 31) / 32; tg.y = (dfft_.Ny + 31) / 32; tg.z = dfft_.Nzl;
     go(t, tg, TransposePutKernel<FT>::SMEM, OC_TIMER_COMM);
     barrier();
-    if (g_.bounded[2]) {
-        zt.inverse = 1;
-        go(zt, zg, 0, OC_TIMER_POISSON_MID);
-    }
+    local_twiddles(true);
     begin_timer(OC_TIMER_FFT); e = dfft_.zx(fftbuf_, false); end_timer(); chk(e);
+}
+
+// the DCT twiddles of the dimensions that are whole in the slab layout — x and z — on the local spectral buffer (TwiddleKernel)
+template <class FT>
+void Model<FT>::local_twiddles(bool inverse) {
+    for (int d = 0; d < 3; d += 2) {
+        if (!g_.bounded[d]) continue;
+        TwiddleKernel<FT> k;
+        const long long plane = (long long)dfft_.nxc * g_.N[1];
+        k.N = g_.N[d]; k.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_); k.tw = tw_[d]; k.inverse = inverse ? 1 : 0;
+        if (d == 2) { k.sk = plane; k.inner = (int)plane; k.souter = 0; k.count = plane; k.kfast = 0; }
+        else { k.sk = 1; k.inner = 1; k.souter = dfft_.nxc; k.count = (long long)g_.N[1] * g_.N[2]; k.kfast = 1; }
+        Dim3 grid;
+        grid.x = (int)((k.count * (k.N / 2 + 1) + 255) / 256);
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+    }
 }
 
 template <class FT>
@@ -916,10 +938,12 @@ void Model<FT>::exchange_y(const std::vector<FieldRec*>& fields) {
     go(k, grid, 0, OC_TIMER_COMM);
     const int prev = (rank_ + R_ - 1) % R_, next = (rank_ + 1) % R_;
     // low-edge rows go to prev (they are its high halo); high-edge rows go to next (its low halo).  Posting order: for R = 2 the
-    // peer's first send (its low edge) must meet my first receive (my high halo).
+    // peer's first send (its low edge) must meet my first receive (my high halo).  A wall side (Bounded y) has no partner: the chain
+    // of slabs is open, and that half of the message is empty.
+    const size_t to_prev = g_.wlo[1] ? 0 : per_side * sizeof(FT), to_next = g_.whi[1] ? 0 : per_side * sizeof(FT);
     std::vector<Msg> msgs;
-    msgs.push_back(Msg{prev, next, 0, halo_send_, per_side * sizeof(FT), halo_recv_ + per_side, per_side * sizeof(FT)});
-    msgs.push_back(Msg{next, prev, 1, halo_send_ + per_side, per_side * sizeof(FT), halo_recv_, per_side * sizeof(FT)});
+    msgs.push_back(Msg{prev, next, 0, halo_send_, to_prev, halo_recv_ + per_side, to_next});
+    msgs.push_back(Msg{next, prev, 1, halo_send_ + per_side, to_next, halo_recv_, to_prev});
     begin_timer(OC_TIMER_COMM);
     std::string e = transport_->exchange(msgs, launch_stream_);
     end_timer();
@@ -958,14 +982,7 @@ void Model<FT>::run_fft_solve_dist() {
     auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
     const int C = dfft_.C, nz = dfft_.Nzl / C;
     begin_timer(OC_TIMER_FFT); std::string e = dfft_.zx(fftbuf_, true); end_timer(); chk(e);
-    ZTwiddleKernel<FT> zt;
-    Dim3 zg;
-    if (g_.bounded[2]) {      // DCT-II post-twiddle while z is still local
-        zt.plane = dfft_.nxc * g_.N[1]; zt.Nz = g_.N[2]; zt.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_); zt.twz = tw_[2];
-        zg.x = (zt.plane + 255) / 256; zg.y = g_.N[2] / 2 + 1;
-        zt.inverse = 0;
-        go(zt, zg, 0, OC_TIMER_POISSON_MID);
-    }
+    local_twiddles(false);    // DCT-II post-twiddles while x and z are still local
     for (int c = 0; c < C; ++c) {
         all_to_all(fftbuf_, diststage_, c, C);
 #ifndef OC_HOSTSIM
@@ -978,7 +995,7 @@ void Model<FT>::run_fft_solve_dist() {
         launch_stream_ = stream3_;
 #endif
         TransposeKernel<FT> t;
-        t.nxc = dfft_.nxc; t.nyl = g_.N[1]; t.nzl = dfft_.Nzl; t.R = R_; t.zl0 = c * nz;
+        t.nxc = dfft_.nxc; t.nyl = g_.N[1]; t.nzl = dfft_.Nzl; t.R = R_; t.zl0 = c * nz; t.yperm = g_.bounded[1];
         t.stage = reinterpret_cast<Cplx<FT>*>(diststage_); t.T = reinterpret_cast<Cplx<FT>*>(distT_);
         Dim3 tg;
         tg.x = (dfft_.nxc + 31) / 32; tg.y = (dfft_.Ny + 31) / 32; tg.z = nz;
@@ -989,6 +1006,7 @@ void Model<FT>::run_fft_solve_dist() {
         k.nxc = dfft_.nxc; k.ny = dfft_.Ny; k.nzl = dfft_.Nzl; k.kz0 = rank_ * dfft_.Nzl; k.zl0 = c * nz;
         k.T = reinterpret_cast<Cplx<FT>*>(distT_);
         for (int d = 0; d < 3; ++d) k.lam[d] = lam_[d];
+        k.tw = g_.bounded[1] ? tw_[1] : nullptr;
         k.norm = 1.0 / ((double)g_.N[0] * dfft_.Ny * g_.N[2]);
         Dim3 grid;
         grid.x = (dfft_.Ny + 255) / 256; grid.y = dfft_.nxc; grid.z = nz;
@@ -1003,10 +1021,7 @@ void Model<FT>::run_fft_solve_dist() {
 #endif
         all_to_all(diststage_, fftbuf_, c, C);
     }
-    if (g_.bounded[2]) {      // DCT-III pre-twiddle, z local again
-        zt.inverse = 1;
-        go(zt, zg, 0, OC_TIMER_POISSON_MID);
-    }
+    local_twiddles(true);     // DCT-III pre-twiddles, x and z local again
     begin_timer(OC_TIMER_FFT); e = dfft_.zx(fftbuf_, false); end_timer(); chk(e);
 }
 
@@ -1761,12 +1776,12 @@ void Model<FT>::projection(double dt) {
         rg.x = (g_.N[0] + 255) / 256; rg.y = g_.N[2];
         go(r, rg, 0, OC_TIMER_COMM);
         const int prev = (rank_ + R_ - 1) % R_, next = (rank_ + 1) % R_;
-        std::vector<Msg> msgs{Msg{next, prev, 1, halo_send_, n * sizeof(FT), halo_recv_, n * sizeof(FT)}};
+        std::vector<Msg> msgs{Msg{next, prev, 1, halo_send_, g_.whi[1] ? 0 : n * sizeof(FT), halo_recv_, g_.wlo[1] ? 0 : n * sizeof(FT)}};
         begin_timer(OC_TIMER_COMM);
         std::string e = transport_ ? transport_->exchange(msgs, stream_) : std::string("distributed model without a transport");
         end_timer();
         if (!e.empty()) throw Error(OC_ERR_CUDA, e);
-        prev_row = halo_recv_;
+        prev_row = g_.wlo[1] ? nullptr : halo_recv_;          // first slab of a Bounded y: the wall face is not corrected
     }
     ProjectionKernel<FT> k;
     k.g = g_;
@@ -2007,7 +2022,7 @@ void Model<FT>::restore_previous_tendency(int field, const void* host, size_t nb
     int ext[3];
     size_t n = 1;
     for (int d = 0; d < 3; ++d) {
-        ext[d] = g_.N[d] + ((f.face[d] && g_.bounded[d]) ? 1 : 0) + 2 * Hcfg_[d];
+        ext[d] = g_.N[d] + ((f.face[d] && g_.whi[d]) ? 1 : 0) + 2 * Hcfg_[d];
         n *= (size_t)ext[d];
     }
     if (n * sizeof(FT) != nbytes) throw Error(OC_ERR_INVALID, "host buffer size mismatch: expected " + std::to_string(n * sizeof(FT)) + " bytes");

@@ -552,16 +552,16 @@ struct ProjectionKernel {
         int o = g.idx(i, j, k);
         FT p0 = phi_at<FT>(L, buf, i, j, k);
         if (!g.flat[0]) {
-            FT pm = (i > 0) ? phi_at<FT>(L, buf, i - 1, j, k) : (g.bounded[0] ? p0 : phi_at<FT>(L, buf, g.N[0] - 1, j, k));
+            FT pm = (i > 0) ? phi_at<FT>(L, buf, i - 1, j, k) : (g.wlo[0] ? p0 : phi_at<FT>(L, buf, g.N[0] - 1, j, k));
             u[o] = u[o] - (p0 - pm) * g.rd[0];
         }
         if (!g.flat[1]) {
             FT pm = (j > 0) ? phi_at<FT>(L, buf, i, j - 1, k)
-                            : (prev_row ? prev_row[i + (long long)g.N[0] * k] : (g.bounded[1] ? p0 : phi_at<FT>(L, buf, i, g.N[1] - 1, k)));
+                            : (prev_row ? prev_row[i + (long long)g.N[0] * k] : (g.wlo[1] ? p0 : phi_at<FT>(L, buf, i, g.N[1] - 1, k)));
             v[o] = v[o] - (p0 - pm) * g.rd[1];
         }
         if (!g.flat[2]) {
-            FT pm = (k > 0) ? phi_at<FT>(L, buf, i, j, k - 1) : (g.bounded[2] ? p0 : phi_at<FT>(L, buf, i, j, g.N[2] - 1));
+            FT pm = (k > 0) ? phi_at<FT>(L, buf, i, j, k - 1) : (g.wlo[2] ? p0 : phi_at<FT>(L, buf, i, j, g.N[2] - 1));
             w[o] = w[o] - (p0 - pm) * g.rdz_at(true, k);
         }
         pNHS[o] = (FT)((double)p0 / dt_plus);

@@ -180,7 +180,7 @@ struct TendencyKernel {
         if (KIND == KIND_C) {
             FT u = a.U[d][o];
             const FT* c = a.c + o;
-            OrderWindow w = order_window(g.bounded[d] != 0, false, g.N[d]);
+            OrderWindow w = order_window(g.wlo[d] != 0, g.whi[d] != 0, false, g.N[d]);
             if (ADVD == ADV_CENTERED2) {
                 return (A * u) * (FT(0.5) * c[-sd] + FT(0.5) * c[0]);              // centered_advective_fluxes.jl:31-33
             } else if (CEN) {
@@ -194,7 +194,7 @@ struct TendencyKernel {
             const FT* adv = a.U[d] + o;
             if (d == COMP) {
                 // centre-type: evaluate the face-type stencils at face id+1
-                OrderWindow w = order_window(g.bounded[d] != 0, true, g.N[d]);
+                OrderWindow w = order_window(g.wlo[d] != 0, g.whi[d] != 0, true, g.N[d]);
                 if (ADVD == ADV_CENTERED2) {
                     FT ut = FT(0.5) * adv[0] + FT(0.5) * adv[sd];
                     FT pt = FT(0.5) * psi[0] + FT(0.5) * psi[sd];
@@ -212,8 +212,8 @@ struct TendencyKernel {
                 int cc = COMP < 0 ? 0 : COMP;
                 int sc = g.st(cc);
                 int ic = cc == 0 ? i : (cc == 1 ? j : k);
-                OrderWindow wc = order_window(g.bounded[cc] != 0, false, g.N[cc]);
-                OrderWindow wd = order_window(g.bounded[d] != 0, false, g.N[d]);
+                OrderWindow wc = order_window(g.wlo[cc] != 0, g.whi[cc] != 0, false, g.N[cc]);
+                OrderWindow wd = order_window(g.wlo[d] != 0, g.whi[d] != 0, false, g.N[d]);
                 if (ADVD == ADV_CENTERED2) {
                     FT ut = g.flat[cc] ? adv[0] : (FT(0.5) * adv[-sc] + FT(0.5) * adv[0]);
                     FT pt = FT(0.5) * psi[-sd] + FT(0.5) * psi[0];
@@ -293,7 +293,7 @@ struct TendencyKernel {
                 bool wall = false;
                 if (COMP >= 0) {
                     int ic = COMP == 0 ? i : (COMP == 1 ? j : k);
-                    wall = g.bounded[COMP] && ic == 0 && g.N[COMP] > 1;
+                    wall = g.wlo[COMP] && ic == 0 && g.N[COMP] > 1;
                 }
                 if (wall) {
                     if (a.mode != STEP_NONE) a.Unew[o] = u0;
@@ -367,8 +367,8 @@ struct TendencyKernel {
                         const FT* v = a.U[1] + o;
                         num = FT(0.5) * (FT(0.5) * (v[-1] + v[0]) + FT(0.5) * (v[g.sy - 1] + v[g.sy]));
                         // v-nodes (i-1,j),(i,j),(i-1,j+1),(i,j+1): active iff not on/outside a wall (inactive_node.jl:152-158)
-                        int ax0 = !(g.bounded[0] && (i - 1 < 0)), ax1 = 1;
-                        int ay0 = !(g.bounded[1] && (j < 1)), ay1 = !(g.bounded[1] && (j + 1 > g.N[1] - 1));
+                        int ax0 = !(g.wlo[0] && (i - 1 < 0)), ax1 = 1;
+                        int ay0 = !(g.wlo[1] && (j < 1)), ay1 = !(g.whi[1] && (j + 1 > g.N[1] - 1));
                         cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
                         FT val = cnt == FT(0) ? FT(0) : num / cnt;
                         G = G - (-fj * val);
@@ -376,8 +376,8 @@ struct TendencyKernel {
                         const FT* u = a.U[0] + o;
                         num = FT(0.5) * (FT(0.5) * (u[-g.sy] + u[-g.sy + 1]) + FT(0.5) * (u[0] + u[1]));
                         // u-nodes (i,j-1),(i+1,j-1),(i,j),(i+1,j)
-                        int ax0 = !(g.bounded[0] && (i < 1)), ax1 = !(g.bounded[0] && (i + 1 > g.N[0] - 1));
-                        int ay0 = !(g.bounded[1] && (j - 1 < 0)), ay1 = 1;
+                        int ax0 = !(g.wlo[0] && (i < 1)), ax1 = !(g.whi[0] && (i + 1 > g.N[0] - 1));
+                        int ay0 = !(g.wlo[1] && (j - 1 < 0)), ay1 = 1;
                         cnt = FT(0.5) * (FT(0.5) * FT(ax0 * ay0 + ax1 * ay0) + FT(0.5) * FT(ax0 * ay1 + ax1 * ay1));
                         FT val = cnt == FT(0) ? FT(0) : num / cnt;
                         G = G - (fj * val);
@@ -431,7 +431,7 @@ struct SubstepKernel {
         if (i >= g.N[0]) return;
         if (comp >= 0) {
             int ic = comp == 0 ? i : (comp == 1 ? j : k);
-            if (g.bounded[comp] && ic == 0 && g.N[comp] > 1) return;
+            if (g.wlo[comp] && ic == 0 && g.N[comp] > 1) return;
         }
         int o = g.idx(i, j, k);
         FT G = Gn[o];
@@ -499,7 +499,7 @@ struct FluxArrayKernel {
         const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
         ijk[d] = side == 0 ? 0 : g.N[d] - 1;
         ijk[t1] = i1; ijk[t2] = i2;
-        if (comp >= 0 && g.bounded[comp] && ijk[comp] == 0 && g.N[comp] > 1) return;          // wall faces are not stepped
+        if (comp >= 0 && g.wlo[comp] && ijk[comp] == 0 && g.N[comp] > 1) return;          // wall faces are not stepped
         const int k = ijk[2];
         const FT A = g.area_at(d, zface != 0, k), V = g.vol_at(zface != 0, k);
         const FT dG = J[i1 + (size_t)n1 * i2] * A / V;

@@ -118,6 +118,32 @@ def _array_coefficients(N, topo, tr):
     return nu, kap
 
 
+def _wall_bcs(topo, tr):
+    """bcs="walls": non-default boundary conditions on EVERY Bounded side, lateral ones included (no-slip / moving walls, heated and
+    cooled side walls) — the sides a slab decomposition of a Bounded y keeps on its outer ranks only.
+    {field: {side: (kind, value)}}"""
+    t0 = tr[0] if tr else None
+    out = {"u": {}, "v": {}, "w": {}}
+    if t0:
+        out[t0] = {}
+    if topo[2] == "B":
+        out["u"]["top"] = ("flux", -2e-3)
+        out["v"]["bottom"] = ("value", 0.1)
+        if t0:
+            out[t0].update(top=("flux", 5e-3), bottom=("gradient", 0.05))
+    if topo[1] == "B":
+        out["u"].update(south=("value", 0.3), north=("flux", 1e-3))
+        out["w"].update(south=("gradient", -0.2), north=("value", -0.1))
+        if t0:
+            out[t0].update(south=("value", 20.5), north=("flux", -4e-3))
+    if topo[0] == "B":
+        out["v"].update(west=("value", -0.2), east=("gradient", 0.1))
+        out["w"]["east"] = ("flux", 2e-3)
+        if t0:
+            out[t0]["west"] = ("gradient", -0.03)
+    return {n: sides for n, sides in out.items() if sides}
+
+
 def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
                  bcs=False, extent=EXTENT, stretch=None, tilt=None, **_):
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
@@ -137,6 +163,8 @@ def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closur
     bc_o = None
     if bcs == "array":
         bc_o = {n: {side: BC(kind, a) for side, (kind, a) in sides.items()} for n, sides in _array_bcs(N, topo, tr).items()}
+    elif bcs == "walls":
+        bc_o = {n: {side: BC(kind, v) for side, (kind, v) in sides.items()} for n, sides in _wall_bcs(topo, tr).items()}
     elif bcs:
         t0 = tr[0]
         bc_o = {"u": {"top": BC("flux", -2e-3)}, t0: {"top": BC("flux", 5e-3), "bottom": BC("gradient", 0.05)},
@@ -174,6 +202,10 @@ def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closu
         mk = {"flux": ob.FluxBoundaryCondition, "value": ob.ValueBoundaryCondition, "gradient": ob.GradientBoundaryCondition}
         bc_b = {n: ob.FieldBoundaryConditions(**{side: mk[kind](a) for side, (kind, a) in sides.items()})
                 for n, sides in _array_bcs(N, topo, tr).items()}
+    elif bcs == "walls":
+        mk = {"flux": ob.FluxBoundaryCondition, "value": ob.ValueBoundaryCondition, "gradient": ob.GradientBoundaryCondition}
+        bc_b = {n: ob.FieldBoundaryConditions(**{side: mk[kind](v) for side, (kind, v) in sides.items()})
+                for n, sides in _wall_bcs(topo, tr).items()}
     elif bcs:
         # the BC kinds of test/regression_tests/ocean_large_eddy_simulation_regression_test.jl:19-37
         t0 = tr[0]
@@ -380,6 +412,16 @@ ARRAY_BC_CASES = [
     ("PBB upwind3 array flux bcs (general kernel)", dict(N=(16, 12, 8), topo="PBB", scheme="upwind3", bcs="array")),
     ("stretched PPB weno smagorinsky-lilly array flux bcs F32", dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="lilly", bcs="array", stretch="smooth", FT=np.float32)),
     ("tile-crossing 40x36x33 BPB weno array flux bcs", dict(N=(40, 36, 33), topo="BPB", scheme="weno", bcs="array")),
+]
+
+# scalar Value / Gradient / Flux boundary conditions on the LATERAL walls too (bcs="walls": every Bounded side of u, v, w and the first
+# tracer) — no-slip and moving side walls, heated / cooled side walls: fill_halo_regions_value_gradient.jl:7-119 west / east / south /
+# north, compute_flux_bcs.jl:116-163 x and y fluxes
+WALL_BC_CASES = [
+    ("BBB weno amd fplane wall bcs", dict(N=(16, 12, 8), topo="BBB", scheme="weno", closure="amd", f=1e-2, bcs="walls")),
+    ("PBB centered smagorinsky-lilly wall bcs AB2", dict(N=(16, 12, 8), topo="PBB", scheme="centered", closure="lilly", bcs="walls", ts="QuasiAdamsBashforth2")),
+    ("BPB upwind3 wall bcs F32 (general kernel)", dict(N=(16, 12, 8), topo="BPB", scheme="upwind3", bcs="walls", FT=np.float32)),
+    ("tile-crossing 40x36x33 BBB weno wall bcs", dict(N=(40, 36, 33), topo="BBB", scheme="weno", bcs="walls")),
 ]
 
 # tilted gravity: BuoyancyForce(formulation; gravity_unit_vector)  (buoyancy_force.jl:47-58, g_dot_b.jl:1-3)

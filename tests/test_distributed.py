@@ -54,11 +54,31 @@ def run_ranks(R, case, timeout=600, backend="gloo"):
     (2, dict(N=(16, 12, 8), topo="PPB", scheme="weno", f=("cartesian", 0.3, -0.5, 0.7), bcs=True, steps=2)),
     (2, dict(N=(16, 12, 8), topo="PPP", scheme="centered", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0), steps=2)),
     (4, dict(N=(12, 16, 8), topo="PPB", scheme="weno", closure="amd", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0), steps=1)),
+    # Bounded x (whole on every slab: a complex (z, x) stage with the DCT's twiddles) and Bounded y (walls on the outer ranks only — the
+    # RightConnected / LeftConnected local grids of distributed_grids.jl:75-126 — an open chain of halo messages, the y DCT in the
+    # transposed layout), with non-default boundary conditions on every wall; 3 and 4 ranks have fully connected slabs in between
+    (2, dict(N=(16, 12, 8), topo="BPB", scheme="weno", bcs="walls", steps=2)),
+    (2, dict(N=(16, 12, 8), topo="PBB", scheme="weno", closure="amd", f=1e-2, bcs="walls", steps=2)),
+    (2, dict(N=(16, 12, 8), topo="BBB", scheme="weno", closure="lilly", f=("beta", 0.3, 2.0), bcs="walls", steps=2)),
+    (3, dict(N=(12, 18, 9), topo="BBB", scheme="weno", bcs="walls", steps=2)),
+    (4, dict(N=(12, 16, 8), topo="BBB", scheme="centered", closure="amd", f=("cartesian", 0.3, -0.5, 0.7), bcs="walls", steps=2, ts="QuasiAdamsBashforth2")),
+    (4, dict(N=(12, 16, 8), topo="PBB", scheme="upwind3", closure="smag", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0), bcs="walls", steps=1)),
+    (2, dict(N=(16, 12, 8), topo="PBP", scheme="weno", bcs="walls", f=1e-2, steps=2)),
+    (2, dict(N=(16, 12, 8), topo="BPB", scheme="weno", bcs="walls", steps=2, f32=True)),
 ])
 def test_slab_decomposition_matches_single_domain_oracle(R, case):
     res = run_ranks(R, dict(case))
     tol = 1e-4 if case.get("f32") else 1e-11
     assert res["ranks"] == R and res["worst"] <= tol, res
+
+
+@pytest.mark.parametrize("R,N", [(2, (16, 12, 8)), (4, (10, 16, 12)), (3, (9, 15, 6))])
+@pytest.mark.parametrize("topo", ["PPP", "PPB", "PBB", "BBB", "BPP", "PBP"])
+def test_distributed_poisson_solver_matches_single_domain_solve(R, N, topo):
+    """The distributed solver alone on every mix of Periodic and Bounded dimensions, even and odd sizes, 2 / 3 / 4 ranks
+    (test/test_distributed_poisson_solvers.jl:70-89,128-148 runs (4,1,1), (1,4,1), (2,2,1) partitions x 4 topologies)"""
+    res = run_ranks(R, dict(N=N, topo=topo, poisson=True))
+    assert res["ranks"] == R and res["worst"] <= 1e-13, res
 
 
 def test_distributed_rejects_unsupported_configurations():
@@ -93,6 +113,15 @@ def _gpu_count():
     (8, dict(N=(64, 48, 32), topo="PPP", scheme="weno", steps=2)),
     (8, dict(N=(48, 32, 16), topo="PPB", scheme="weno", closure="lilly", f=("beta", 0.3, 2.0), bcs=True, steps=2)),
     (8, dict(N=(40, 24, 16), topo="PPP", scheme="weno", steps=2, f32=True)),
+    # Bounded x and y on slabs (walls on the outer ranks; DCTs in x on the slab and in y in the transposed layout)
+    (2, dict(N=(48, 64, 16), topo="PBB", scheme="weno", closure="amd", f=1e-2, bcs="walls", steps=2)),
+    (2, dict(N=(40, 24, 16), topo="BPB", scheme="weno", bcs="walls", steps=2)),
+    (4, dict(N=(48, 64, 16), topo="BBB", scheme="weno", closure="lilly", f=("beta", 0.3, 2.0), bcs="walls", steps=2)),
+    (4, dict(N=(40, 32, 16), topo="PBP", scheme="centered", bcs="walls", steps=2, ts="QuasiAdamsBashforth2")),
+    (8, dict(N=(48, 64, 16), topo="BBB", scheme="weno", bcs="walls", steps=2)),
+    (2, dict(N=(36, 40, 20), topo="BBB", poisson=True)),
+    (4, dict(N=(36, 40, 20), topo="PBB", poisson=True)),
+    (8, dict(N=(30, 48, 24), topo="BBB", poisson=True)),
 ])
 def test_nccl_slab_decomposition_matches_oracle(R, case):
     """The CUDA library on R GPUs of one box (NCCL halo exchange + transposed distributed FFT) against the oracle."""

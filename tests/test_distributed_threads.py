@@ -1,0 +1,102 @@
+"""The peer-memory path of the distributed pressure solve on CPU.
+
+On a GPU box with up to four ranks the transposes of the distributed FFT are ONE kernel each over CUDA-IPC peer memory (TransposePutKernel,
+csrc/oc_dist.h) instead of pack -> all-to-all -> unpack; the gloo multi-process tests (tests/test_distributed.py) cannot reach that kernel
+because separate processes share no address space.  Here the ranks are THREADS of one process running the host simulation: a peer's buffer
+is simply its pointer (HostTransport with OC_HOSTSIM_THREADS=1), the collectives (pointer exchange, barriers, halo messages) go through an
+in-process mailbox, and every slab is compared with the single-domain oracle exactly like the multi-process tests do."""
+import ctypes as C
+import os
+import queue
+import sys
+import threading
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+class Mailbox:
+    """FIFO per (source, destination, tag): messages between one pair of ranks are matched in posting order"""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.queues = {}
+
+    def of(self, key):
+        with self.lock:
+            return self.queues.setdefault(key, queue.Queue())
+
+    def exchange_for(self, rank):
+        def exchange(msgs):
+            for sp, rp, tag, sptr, sb, rptr, rb in msgs:
+                if sb:
+                    self.of((rank, sp, tag)).put(C.string_at(sptr, sb))
+            for sp, rp, tag, sptr, sb, rptr, rb in msgs:
+                if rb:
+                    C.memmove(rptr, self.of((rp, rank, tag)).get(timeout=300), rb)
+            return 0
+        return exchange
+
+
+def run_threads(R, case, p2p=True):
+    import __graft_entry__ as ge
+    import oceananigans_b200 as ob
+    from oceananigans_b200 import _lib
+    import dist_worker
+    ge.build()
+    os.environ["OC_HOSTSIM_THREADS"] = "1"
+    os.environ["OC_DIST_P2P"] = "1" if p2p else "0"
+    try:
+        lib = _lib.Library(ge.HOSTSIM)
+        box = Mailbox()
+        out, errs = [None] * R, []
+
+        def body(rank):
+            try:
+                arch = ob.Distributed(ob.B200(0), partition=ob.Partition(1, R), rank=rank, nranks=R, exchange=box.exchange_for(rank))
+                out[rank] = dist_worker.run_rank(case, rank, R, arch, lib)
+            except BaseException as e:       # noqa: BLE001 — reported by the main thread
+                errs.append((rank, repr(e)))
+
+        threads = [threading.Thread(target=body, args=(r,)) for r in range(R)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=900)
+        assert not errs, errs
+        assert all(o is not None for o in out), "a rank did not finish"
+        return max(out)
+    finally:
+        os.environ.pop("OC_HOSTSIM_THREADS", None)
+        os.environ.pop("OC_DIST_P2P", None)
+
+
+@pytest.mark.parametrize("R,case", [
+    (2, dict(N=(16, 12, 8), topo="PPP", scheme="weno", steps=2)),
+    (4, dict(N=(12, 16, 8), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, steps=1)),
+    # Bounded y: the Makhoul permutation of the y line happens inside the transposed put
+    (2, dict(N=(16, 12, 8), topo="PBB", scheme="weno", bcs="walls", steps=2)),
+    (3, dict(N=(12, 18, 9), topo="BBB", scheme="centered", bcs="walls", steps=1)),
+    (4, dict(N=(10, 16, 12), topo="BBB", poisson=True)),
+    (4, dict(N=(10, 16, 12), topo="PBP", poisson=True)),
+    (3, dict(N=(9, 15, 6), topo="BPB", poisson=True)),
+])
+def test_peer_memory_transposes_match_single_domain_oracle(R, case):
+    worst = run_threads(R, case)
+    assert worst <= 1e-11, worst
+
+
+def test_thread_ranks_with_all_to_all_agree_with_peer_memory(capfd, monkeypatch):
+    """the same case through the send / receive transposes (what more than four ranks use) and through peer memory: both against the
+    oracle, and the library says which path it took"""
+    monkeypatch.setenv("OC_VERBOSE", "1")
+    case = dict(N=(12, 16, 8), topo="PBB", scheme="weno", steps=1)
+    assert run_threads(4, case, p2p=False) <= 1e-11
+    err = capfd.readouterr().err
+    assert err.count("transposes over send/receive all-to-all") == 4 and "peer memory" not in err
+    assert run_threads(4, case, p2p=True) <= 1e-11
+    err = capfd.readouterr().err
+    assert err.count("transposes over peer memory") == 4 and "all-to-all" not in err

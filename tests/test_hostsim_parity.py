@@ -265,6 +265,12 @@ def test_hostsim_matches_oracle_with_tilted_gravity(hostsim, name, kw):
     ph.check_case(kw, library=hostsim, steps=(1, 3))
 
 
+@pytest.mark.parametrize("name,kw", ph.WALL_BC_CASES[:-1], ids=[c[0] for c in ph.WALL_BC_CASES[:-1]])
+def test_hostsim_matches_oracle_with_lateral_wall_bcs(hostsim, name, kw):
+    """Value / Gradient / Flux boundary conditions on west / east / south / north walls"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))
+
+
 @pytest.mark.parametrize("name,kw", ph.ARRAY_BC_CASES, ids=[c[0] for c in ph.ARRAY_BC_CASES])
 def test_hostsim_matches_oracle_with_array_valued_flux_bcs(hostsim, name, kw):
     """FluxBoundaryCondition(J::AbstractArray) on every Bounded side (oc_set_bc_array; compute_flux_bcs.jl:116-163)"""

@@ -73,6 +73,12 @@ def test_stratified_fluid_remains_at_rest_with_tilted_gravity_cuda(ob):
     th.stratified_fluid_remains_at_rest_with_tilted_gravity(th._product_maker(None))
 
 
+@pytest.mark.parametrize("name,kw", ph.WALL_BC_CASES, ids=[c[0] for c in ph.WALL_BC_CASES])
+def test_cuda_matches_oracle_with_lateral_wall_bcs(ob, name, kw):
+    """Value / Gradient / Flux boundary conditions on west / east / south / north walls"""
+    ph.check_case(kw, library=None, steps=(1, 10))
+
+
 @pytest.mark.parametrize("name,kw", ph.ARRAY_BC_CASES, ids=[c[0] for c in ph.ARRAY_BC_CASES])
 def test_cuda_matches_oracle_with_array_valued_flux_bcs(ob, name, kw):
     """FluxBoundaryCondition(J::AbstractArray) on every Bounded side (oc_set_bc_array; compute_flux_bcs.jl:116-163)"""
