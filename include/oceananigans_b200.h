@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OC_ABI_VERSION 5
+#define OC_ABI_VERSION 6
 #define OC_MAX_TRACERS 8
 #define OC_MAX_FIELDS (3 + OC_MAX_TRACERS)
 
@@ -135,7 +135,10 @@ typedef struct {
      * the caller fills them with oc_upload_interior / _parent (+ oc_fill_halo_regions, like fill_halo_regions!(ν) in the reference);
      * fields never uploaded are zero.  May be combined with a constant ScalarDiffusivity (a closure tuple), not with AMD / Smagorinsky. */
     int32_t array_diffusivity;
-    int32_t reserved3;
+    /* ABI v6.  Partition(Rx, Ry): ranks along x (distributed_architectures.jl:14-18,242-302); 0 or 1 = the slab decomposition in y.
+     * dist_nranks = Rx·Ry, dist_rank = rx·Ry + ry (x-major, rank2index :354-362); N[0] and N[1] are LOCAL sizes, extent[] global.
+     * The distributed solver needs Nz % Ry == 0 and (N[1]·Ry) % Rx == 0 (distributed_fft_based_poisson_solver.jl:211-229). */
+    int32_t dist_ranks_x;
 } oc_config;
 
 typedef struct oc_model oc_model;

@@ -73,7 +73,8 @@ mutable struct OcConfig               # `oc_config`, same field order; NTuple fo
     amd_Cb::Float64                                 # ABI v4: AnisotropicMinimumDissipation(; Cb), with amd_has_Cb
     coriolis_gamma::Float64; coriolis_radius::Float64; origin_z::Float64  # ABI v4: NonTraditionalBetaPlane (has_coriolis = 4)
     has_advection_dir::Int32; advection_dir::NTuple{3,Int32}            # ABI v5: FluxFormAdvection(x, y, z) from adapt_advection_order
-    array_diffusivity::Int32; reserved3::Int32                          # ABI v5: ScalarDiffusivity with array-valued ν / κ
+    array_diffusivity::Int32                                            # ABI v5: ScalarDiffusivity with array-valued ν / κ
+    dist_ranks_x::Int32                                                 # ABI v6: Partition(Rx, Ry); 0 / 1 = slabs in y
     OcConfig() = new()
 end
 
@@ -133,6 +134,21 @@ function config(model::NonhydrostaticModel)
         cfg.delta = Float64.((grid.Δxᶜᵃᵃ, grid.Δyᵃᶜᵃ, 0.0)); cfg.z_stretched = 1
     end
     cfg.extent = Float64.((grid.Lx, grid.Ly, grid.Lz))
+    arch = architecture(grid)
+    if arch isa Oceananigans.DistributedComputations.Distributed
+        # Distributed(B200(); partition = Partition(Rx, Ry)): the local grid's sizes are already this rank's (distributed_grids.jl:75-126),
+        # its extents are local too — the library wants the global ones, and the GLOBAL topology (the local LeftConnected /
+        # RightConnected / FullyConnected come from a Bounded or Periodic global dimension, :75-126): both from
+        # reconstruct_global_grid (distributed_grids.jl:192-233).  Ranks are x-major on both sides (rank2index,
+        # distributed_architectures.jl:354-362).
+        Rx, Ry, Rz = arch.ranks
+        Rz == 1 || throw(ArgumentError("B200: z is never partitioned"))
+        gg = Oceananigans.DistributedComputations.reconstruct_global_grid(grid)
+        GX, GY, GZ = topology(gg)
+        cfg.dist_rank = arch.local_rank; cfg.dist_nranks = Rx * Ry; cfg.dist_ranks_x = Rx
+        cfg.extent = Float64.((gg.Lx, gg.Ly, gg.Lz))
+        cfg.topology = (topo_code(GX), topo_code(GY), topo_code(GZ))
+    end
     # oc_advection code of one scheme (by its buffer = required halo)
     scheme_code(a) = a === nothing ? Int32(7) :
                      a isa Centered && required_halo_size_x(a) == 1 ? Int32(0) : a isa Centered && required_halo_size_x(a) == 2 ? Int32(2) :

@@ -7,7 +7,7 @@ C ABI of the host-simulation build (tests/hostsim) — the package itself never 
 import ctypes as C
 import os
 
-OC_ABI_VERSION = 5
+OC_ABI_VERSION = 6
 OC_MAX_TRACERS = 8
 OC_MAX_FIELDS = 3 + OC_MAX_TRACERS
 OC_TIMER_NAMES = ("tendency", "halo", "poisson_rhs", "fft", "poisson_mid", "projection", "aux", "substep", "comm")
@@ -51,7 +51,7 @@ class oc_config(C.Structure):
         ("amd_Cb", C.c_double),
         ("coriolis_gamma", C.c_double), ("coriolis_radius", C.c_double), ("origin_z", C.c_double),
         ("has_advection_dir", C.c_int32), ("advection_dir", C.c_int32 * 3),
-        ("array_diffusivity", C.c_int32), ("reserved3", C.c_int32),
+        ("array_diffusivity", C.c_int32), ("dist_ranks_x", C.c_int32),
     ]
 
 

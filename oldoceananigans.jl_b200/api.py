@@ -46,12 +46,14 @@ class B200:
 
 class Partition:
     """Partition(x, y, z): ranks per dimension (src/DistributedComputations/distributed_architectures.jl:14-18).
-    The B200 path implements the slab decomposition Partition(1, R), for Periodic and Bounded x, y and z."""
+    The B200 path implements slabs, Partition(1, R) and Partition(R, 1), and pencils, Partition(Rx, Ry), for Periodic and Bounded
+    x, y and z; z is never partitioned (the reference's solver cannot either, distributed_fft_based_poisson_solver.jl:211-229)."""
 
     def __init__(self, x=1, y=1, z=1):
-        if x != 1 or z != 1:
-            raise NotImplementedError("only slab decompositions in y, Partition(1, R), are implemented (z is never partitioned in "
-                                      "the reference either; pencil decompositions: next)")
+        if z != 1:
+            raise NotImplementedError("z is never partitioned (distributed_fft_based_poisson_solver.jl:211-229)")
+        if int(x) < 1 or int(y) < 1:
+            raise ValueError("ranks per dimension must be positive")
         self.x, self.y, self.z = int(x), int(y), int(z)
 
 
@@ -71,9 +73,21 @@ class Distributed:
             rank, nranks = dist.get_rank(), dist.get_world_size()
         self.rank, self.nranks = int(rank), int(nranks)
         self.partition = partition or Partition(1, self.nranks)
-        if self.partition.y != self.nranks:
+        if self.partition.x * self.partition.y != self.nranks:
             raise ValueError("partition does not match the number of ranks")
+        # rank -> (index along x, index along y): x-major, rank2index (distributed_architectures.jl:354-362)
+        self.rx, self.ry = self.rank // self.partition.y, self.rank % self.partition.y
         self.exchange = exchange
+
+    def local_range(self, d, n_global):
+        """first index and length of this rank's share of a dimension of n_global cells"""
+        if d == 0:
+            n = n_global // self.partition.x
+            return self.rx * n, n
+        if d == 1:
+            n = n_global // self.partition.y
+            return self.ry * n, n
+        return 0, n_global
 
 
 class _Topo:
@@ -661,10 +675,10 @@ class Field:
             locs = [Face if x else Center for x in info.location]
             nodes = [g.nodes(d, locs[d]) if g.topology[d] is not Flat else np.zeros(1) for d in range(3)]
             if self.model.distributed:      # this rank's rows
-                # (the last slab of a Bounded y also owns the wall face of a y-Face field: interior_size[1] = Ny_l + 1)
-                r = g.architecture.rank
-                j0 = r * (g.N[1] // g.architecture.nranks)
-                nodes[1] = nodes[1][j0:j0 + info.interior_size[1]]
+                # (the last rank of a Bounded partitioned dimension also owns the wall face of a Face field there: interior_size = N_l + 1)
+                for d in (0, 1):
+                    j0, _ = g.architecture.local_range(d, g.N[d])
+                    nodes[d] = nodes[d][j0:j0 + info.interior_size[d]]
             X = np.meshgrid(*nodes, indexing="ij")
             args = [A for d, A in enumerate(X) if g.topology[d] is not Flat]
             value = np.broadcast_to(np.asarray(value(*args), dtype=np.float64), X[0].shape)
@@ -756,10 +770,11 @@ class NonhydrostaticModel:
         self.distributed = isinstance(arch, Distributed) and arch.nranks > 1
         if self.distributed:
             # local grid of this rank: Ny / R rows (distributed_grids.jl:75-126); the spacing and the global extent stay
-            if grid.N[1] % arch.nranks != 0:
-                raise ValueError("Ny must be divisible by the number of ranks")
-            cfg.N[1] = grid.N[1] // arch.nranks
-            cfg.dist_rank, cfg.dist_nranks = arch.rank, arch.nranks
+            part = arch.partition
+            if grid.N[0] % part.x != 0 or grid.N[1] % part.y != 0:
+                raise ValueError("Nx and Ny must be divisible by the number of ranks along x and y")
+            cfg.N[0], cfg.N[1] = grid.N[0] // part.x, grid.N[1] // part.y
+            cfg.dist_rank, cfg.dist_nranks, cfg.dist_ranks_x = arch.rank, arch.nranks, part.x
         cfg.advection = advection.code
         if isinstance(advection, FluxFormAdvection):
             cfg.has_advection_dir = 1
@@ -1037,7 +1052,8 @@ def solve_poisson(model, rhs):
     g = model.grid
     shape = list(g.N)
     if getattr(model, "distributed", False):
-        shape[1] //= g.architecture.nranks
+        shape[0] //= g.architecture.partition.x
+        shape[1] //= g.architecture.partition.y
     shape = tuple(shape)
     a = np.asfortranarray(np.asarray(rhs).reshape(shape).astype(g.FT))
     out = np.empty(shape, dtype=g.FT, order="F")

@@ -251,6 +251,39 @@ struct HaloPackKernel {
     }
 };
 
+// x-halo pack / unpack (pencil decompositions): H columns of EVERY row of the parent array — wall-side boundary-condition halos
+// included — and every plane.  buffer layout: [side][field][plane][row][column]
+template <class FT>
+struct HaloPackXKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    Geom<FT> g;
+    int nfields, planes, rows, cols;   // rows = rows of the allocation (sz / sy); cols = halo width exchanged
+    int unpack;                        // 0: interior edge columns -> buffer ; 1: buffer -> halo columns
+    FT* base[HALO_MAX_FIELDS];         // allocation bases
+    int x0[HALO_MAX_FIELDS];           // offset of interior column 0 within a row
+    FT* buf;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const long long per_side = (long long)nfields * planes * rows * cols;
+        long long n = (long long)b.x * nt + tid;
+        if (n >= 2 * per_side) return;
+        const int side = (int)(n / per_side);
+        long long r = n - side * per_side;
+        const int c = (int)(r % cols); r /= cols;
+        const int row = (int)(r % rows); r /= rows;
+        const int pl = (int)(r % planes);
+        const int f = (int)(r / planes);
+        if (unpack && (side == 0 ? g.wlo[0] : g.whi[0])) return;       // a wall side: nothing was received
+        int col;
+        if (!unpack) col = side == 0 ? c : g.N[0] - cols + c;          // low edge / high edge interior columns
+        else col = side == 0 ? c - cols : g.N[0] + c;                  // low halo / high halo columns
+        FT* p = base[f] + (long long)pl * g.sz + (long long)row * g.sy + x0[f] + col;
+        if (!unpack) buf[n] = *p; else *p = buf[n];
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // transposes between stage = [s][zl][yl][x] (x fastest) and T = [zl][x][y] (y fastest), y = s·Ny_l + yl.  32×32 tiles.
 // ---------------------------------------------------------------------------------------------------------
@@ -410,6 +443,59 @@ struct TwiddleKernel {
     }
 };
 
+// Pencil decompositions: the second transpose, y <-> x among the Rx ranks of a row.  T1 = [zl][xl][y] (y whole, fastest) is cut into Rx
+// chunks of nyx = Ny / Rx rows; the exchange buffer B = [r][zl][yl2][xl] holds one chunk per peer r; T2 = [zl][yl2][x] has x whole and
+// fastest, x = r·Nx_l + xl, stored at its Makhoul-permuted position when x is Bounded (the line the DCT's FFT runs on).
+//   mode 0: B <- T1 (pack for the forward exchange)     mode 1: T2 <- B (unpack)
+//   mode 2: B <- T2 (pack for the way back)             mode 3: T1 <- B (unpack)
+template <class FT>
+struct PencilXKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    int nxl, nyx, nzl, Rx, xperm, mode;
+    Cplx<FT>* B;
+    Cplx<FT>* T;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const long long n = (long long)b.x * nt + tid, total = (long long)nxl * nyx * nzl * Rx;
+        if (n >= total) return;
+        long long q = n;
+        const int xl = (int)(q % nxl); q /= nxl;
+        const int yl2 = (int)(q % nyx); q /= nyx;
+        const int zl = (int)(q % nzl);
+        const int r = (int)(q / nzl);
+        const int Ny = nyx * Rx, Nx = nxl * Rx;
+        Cplx<FT>* t;
+        if (mode == 0 || mode == 3) t = T + ((long long)zl * nxl + xl) * Ny + r * nyx + yl2;
+        else t = T + ((long long)zl * nyx + yl2) * Nx + makhoul(r * nxl + xl, Nx, xperm);
+        if (mode == 0 || mode == 2) B[n] = *t; else *t = B[n];
+    }
+};
+
+// the divide in the pencil layout T2 = [zl][yl2][x]: global y = y0 + yl2, kz = kz0 + zl
+template <class FT>
+struct PoissonDividePencilKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    int Nx, nyx, nzl, y0, kz0;
+    Cplx<FT>* T;
+    const double* lam[3];
+    double norm;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        const int x = b.x * nt + tid, yl2 = b.y, zl = b.z;
+        if (x >= Nx) return;
+        const int y = y0 + yl2, kz = kz0 + zl;
+        Cplx<FT>* p = T + ((long long)zl * nyx + yl2) * Nx + x;
+        const Cplx<FT> e = *p;
+        double s = -norm / (lam[0][x] + lam[1][y] + lam[2][kz]);
+        if (x == 0 && y == 0 && kz == 0) s = 0.0;
+        *p = Cplx<FT>{(FT)((double)e.x * s), (FT)((double)e.y * s)};
+    }
+};
+
 // spectral divide in the transposed layout T = [zl][x][y]: global kz = rank·nzl + zl.  Bounded y (tw != nullptr): y is whole here, so
 // the twiddles of its DCT wrap the divide — one thread per reflection orbit {y, Ny-y}, like PoissonMidZKernel does for z.
 template <class FT>
@@ -469,9 +555,10 @@ public:
     int C = 1;                 // the y stage runs in C sub-chunks of Nzl / C levels (pipelined against the all-to-alls)
     bool c2c = false;          // Bounded x: the (z, x) stage is complex-to-complex over whole rows (the permuted line of the DCT), like
                                // Fft3 on one GPU (plan_transforms.jl:16-136); otherwise real-to-complex, Nx/2+1 coefficients per row
-    std::string init(int nx, int nyl, int nz, int r, bool x_bounded, Stream stream, Stream ystream) {
-        Nx = nx; Nyl = nyl; Nz = nz; R = r;
-        c2c = x_bounded;
+    int Rx = 1;                // pencils: ranks along x — x is not local: z alone is transformed first (z()), x last (x()), all complex
+    std::string init(int nx, int nyl, int nz, int r, bool x_bounded, Stream stream, Stream ystream, int rx = 1) {
+        Nx = nx; Nyl = nyl; Nz = nz; R = r; Rx = rx;
+        c2c = x_bounded || Rx > 1;
         nxc = c2c ? Nx : Nx / 2 + 1; nxr = 2 * nxc; Ny = Nyl * R; Nzl = Nz / R;
         C = Nzl % 4 == 0 ? 4 : (Nzl % 2 == 0 ? 2 : 1);
 #ifndef OC_HOSTSIM
@@ -483,7 +570,17 @@ public:
         }
         int n2[2] = {Nz, Nx};
         int rembed[2] = {Nz, nxr * Nyl}, cembed[2] = {Nz, nxc * Nyl};
-        if (c2c) {
+        if (Rx > 1) {
+            // z lines of the local (Nx_l, Ny_l, Nz) buffer: stride = the (x, y) plane, one line per element of the plane
+            int nzv[1] = {Nz}, emb[1] = {Nz};
+            const int plane = nxc * Nyl;
+            if (cufftMakePlanMany(fwd_, 1, nzv, emb, plane, 1, emb, plane, 1, dbl ? CUFFT_Z2Z : CUFFT_C2C, plane, &w[0]) != CUFFT_SUCCESS)
+                return "cufftMakePlanMany(z lines) failed";
+            // x lines of T2 = [zl][yl2][x]: contiguous, Nx·Rx long
+            int nxv[1] = {Nx * Rx};
+            if (cufftMakePlanMany(inv_, 1, nxv, nullptr, 1, Nx * Rx, nullptr, 1, Nx * Rx, dbl ? CUFFT_Z2Z : CUFFT_C2C, (Nz / R) * (Nyl * R / Rx), &w[1]) != CUFFT_SUCCESS)
+                return "cufftMakePlanMany(x lines) failed";
+        } else if (c2c) {
             if (cufftMakePlanMany(fwd_, 2, n2, cembed, 1, nxc, cembed, 1, nxc, dbl ? CUFFT_Z2Z : CUFFT_C2C, Nyl, &w[0]) != CUFFT_SUCCESS)
                 return "cufftMakePlanMany(zx complex) failed";
         } else {
@@ -516,6 +613,15 @@ public:
 
 #ifndef OC_HOSTSIM
     void set_y_stream(Stream s) { cufftSetStream(y_, s); }
+    // pencils: the z lines of the local buffer (plan fwd_) and the x lines of T2 (plan inv_), complex, in place
+    std::string lines(cufftHandle h, void* buf, bool fwd) {
+        cufftResult r;
+        if (sizeof(FT) == 8) r = cufftExecZ2Z(h, (cufftDoubleComplex*)buf, (cufftDoubleComplex*)buf, fwd ? CUFFT_FORWARD : CUFFT_INVERSE);
+        else r = cufftExecC2C(h, (cufftComplex*)buf, (cufftComplex*)buf, fwd ? CUFFT_FORWARD : CUFFT_INVERSE);
+        return r == CUFFT_SUCCESS ? "" : "cuFFT line transform failed with code " + std::to_string((int)r);
+    }
+    std::string z(void* buf, bool fwd) { return lines(fwd_, buf, fwd); }
+    std::string x(void* buf, bool fwd) { return lines(inv_, buf, fwd); }
     std::string zx(void* buf, bool fwd) {
         cufftResult r;
         if (c2c) {
@@ -572,6 +678,29 @@ public:
             } else {
                 for (int k = 0; k < Nz; ++k) for (int i = 0; i < Nx; ++i) buf[i + (long long)nxr * (j + (long long)Nyl * k)] = (FT)at(i, k).x;
             }
+        }
+        return "";
+    }
+    // pencils (test-only naive DFTs): z lines of the local buffer, x lines of T2
+    std::string z(void* bufv, bool fwd) {
+        FT* buf = (FT*)bufv;
+        const long long plane = (long long)nxc * Nyl;
+        for (long long n = 0; n < plane; ++n) {
+            std::vector<Cd> l(Nz);
+            for (int k = 0; k < Nz; ++k) l[k] = Cd{(double)buf[2 * (n + plane * k)], (double)buf[2 * (n + plane * k) + 1]};
+            dft(l, fwd);
+            for (int k = 0; k < Nz; ++k) { buf[2 * (n + plane * k)] = (FT)l[k].x; buf[2 * (n + plane * k) + 1] = (FT)l[k].y; }
+        }
+        return "";
+    }
+    std::string x(void* Tv, bool fwd) {
+        FT* T = (FT*)Tv;
+        const int n = Nx * Rx;
+        for (long long b = 0; b < (long long)Nzl * (Ny / Rx); ++b) {
+            std::vector<Cd> l(n);
+            for (int i = 0; i < n; ++i) l[i] = Cd{(double)T[2 * (b * n + i)], (double)T[2 * (b * n + i) + 1]};
+            dft(l, fwd);
+            for (int i = 0; i < n; ++i) { T[2 * (b * n + i)] = (FT)l[i].x; T[2 * (b * n + i) + 1] = (FT)l[i].y; }
         }
         return "";
     }

@@ -23,11 +23,12 @@ public:
 
     // zbatch: z is not transformed (FourierTridiagonalPoissonSolver on a stretched grid: plan_transforms(grid, storage,
     // planner_flag, tridiagonal_dim), fourier_tridiagonal_poisson_solver.jl:107) — batched (y, x) transforms, one per level
-    std::string init(const int N[3], const int bounded[3], Stream stream, bool plan = true, bool zbatch = false) {
+    // force_c2c: a full complex buffer even though x is not Bounded (pencil decompositions: x is not local, every stage is complex)
+    std::string init(const int N[3], const int bounded[3], Stream stream, bool plan = true, bool zbatch = false, bool force_c2c = false) {
         for (int d = 0; d < 3; ++d) { L.N[d] = N[d]; L.bounded[d] = bounded[d]; }
         zbatch_ = zbatch;
         if (zbatch) L.bounded[2] = 0;                 // no Makhoul permutation, no twiddles along z
-        L.r2c = (!bounded[0] && N[0] > 1) ? 1 : 0;
+        L.r2c = (!bounded[0] && N[0] > 1 && !force_c2c) ? 1 : 0;
         L.nxc = L.r2c ? N[0] / 2 + 1 : N[0];
         L.nxr = 2 * L.nxc;
         buffer_bytes = sizeof(FT) * 2 * (size_t)L.nxc * N[1] * N[2];

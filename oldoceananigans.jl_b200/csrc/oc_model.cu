@@ -81,7 +81,7 @@ void oc_config_init(oc_config* c) {
     c->z_stretched = 0;
     c->z_faces = nullptr;
     c->has_advection_dir = 0;
-    c->array_diffusivity = 0; c->reserved3 = 0;
+    c->array_diffusivity = 0; c->dist_ranks_x = 0;
     c->advection_dir[0] = c->advection_dir[1] = c->advection_dir[2] = OC_CENTERED2;
 }
 

@@ -175,8 +175,8 @@ public:
     void set_diffusivity_bc(int field, int side, int kind, double value) override;
     void recover() override;
     void dist_attach(Transport* t) override;
-    int dist_rank() const override { return rank_; }
-    int dist_nranks() const override { return R_; }
+    int dist_rank() const override { return grank(rx_, rank_); }
+    int dist_nranks() const override { return R_ * Rx_; }
     void timers_enable(int on) override { timing_ = on != 0; }
     void timers_reset() override;
     void timers_get(double* ms, int64_t* n) override;
@@ -263,9 +263,15 @@ private:
     enum { PART_ALL = 0, PART_INTERIOR = 1, PART_STRIPS = 2 };
     template <int KIND> void launch_march_tendency(int fidx, TendencyArgs<FT>& a, int part = PART_ALL);
     TileSrc<FT> tile_src(const FT* base, int bx, int by);
-    // slab decomposition in y (oc_dist.h)
+    // domain decomposition (oc_dist.h): slabs in y, Partition(1, R), or pencils, Partition(Rx, Ry).  rank_ / R_ are this rank's index
+    // and the number of ranks ALONG Y (the whole job for slabs); rx_ / Rx_ along x; messages name their peers by global rank
     bool dist_ = false;
     int rank_ = 0, R_ = 1;
+    int rx_ = 0, Rx_ = 1;
+    int grank(int rx, int ry) const { return rx * R_ + ry; }      // x-major, like rank2index (distributed_architectures.jl:354-362)
+    void exchange_x(const std::vector<FieldRec*>& fields);
+    void all_to_all_x(FT* send, FT* recv);
+    void run_fft_solve_pencil();
     std::unique_ptr<Transport> transport_;
     DistFft<FT> dfft_;
     FT* distT_ = nullptr;          // transposed spectral buffer (y fastest)

@@ -154,9 +154,10 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         g_.H[d] = t == OC_FLAT ? 3 : std::max(3, c.H[d]);   // internal halo >= 3 (TMA boxes); the API halo is Hcfg_
         g_.bounded[d] = t == OC_BOUNDED;
         g_.wlo[d] = g_.whi[d] = g_.bounded[d];
-        if (d == 1 && c.dist_nranks > 1 && g_.bounded[d]) {      // slab of a Bounded y: only the outer ranks have a wall (distributed_grids.jl:75-126)
-            g_.wlo[d] = c.dist_rank == 0;
-            g_.whi[d] = c.dist_rank == c.dist_nranks - 1;
+        if (d < 2 && c.dist_nranks > 1 && g_.bounded[d]) {       // a Bounded partitioned dimension: only the outer ranks have a wall (distributed_grids.jl:75-126)
+            const int Rx = std::max(1, c.dist_ranks_x), Ry = c.dist_nranks / Rx;
+            const int r = d == 0 ? c.dist_rank / std::max(1, Ry) : c.dist_rank % std::max(1, Ry), n = d == 0 ? Rx : Ry;
+            if (n > 1) { g_.wlo[d] = r == 0; g_.whi[d] = r == n - 1; }
         }
         g_.flat[d] = t == OC_FLAT;
         g_.d[d] = t == OC_FLAT ? FT(1) : (FT)c.delta[d];
@@ -303,19 +304,24 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
     // slab decomposition in y (Distributed(arch; partition = Partition(1, R)))
     dist_ = c.dist_nranks > 1;
     if (dist_) {
-        rank_ = c.dist_rank; R_ = c.dist_nranks;
-        if (rank_ < 0 || rank_ >= R_) throw Error(OC_ERR_INVALID, "dist_rank out of range");
+        Rx_ = std::max(1, c.dist_ranks_x);
+        if (c.dist_nranks % Rx_ != 0) throw Error(OC_ERR_INVALID, "dist_nranks is not a multiple of dist_ranks_x");
+        R_ = c.dist_nranks / Rx_;
+        if (c.dist_rank < 0 || c.dist_rank >= c.dist_nranks) throw Error(OC_ERR_INVALID, "dist_rank out of range");
+        rx_ = c.dist_rank / R_; rank_ = c.dist_rank % R_;
         if (c.topology[0] == OC_FLAT || c.topology[1] == OC_FLAT || c.topology[2] == OC_FLAT)
             throw Error(OC_ERR_UNSUPPORTED, "distributed models: Periodic or Bounded x, y and z (Flat dimensions: next)");
-        if (g_.N[2] % R_ != 0) throw Error(OC_ERR_INVALID, "distributed FFT: Nz must be divisible by the number of ranks (distributed_fft_based_poisson_solver.jl:211-229)");
-        if (g_.N[1] < g_.H[1]) throw Error(OC_ERR_INVALID, "distributed models: local Ny smaller than the halo");
+        if (g_.N[2] % R_ != 0) throw Error(OC_ERR_INVALID, "distributed FFT: Nz must be divisible by the number of ranks along y (distributed_fft_based_poisson_solver.jl:211-229)");
+        if (((long long)g_.N[1] * R_) % Rx_ != 0) throw Error(OC_ERR_INVALID, "distributed FFT: Ny must be divisible by the number of ranks along x (distributed_fft_based_poisson_solver.jl:211-229)");
+        if (g_.N[1] < g_.H[1] || g_.N[0] < g_.H[0]) throw Error(OC_ERR_INVALID, "distributed models: local size smaller than the halo");
     }
     if (stretched_) build_z_tables(c.z_faces);
     cfg_.z_faces = nullptr;                              // borrowed host pointer: not kept
     // pressure solver
     // slab decomposition: y is transformed in the transposed layout, where it is whole — the local buffer carries no y permutation
-    const int local_bounded[3] = {g_.bounded[0], dist_ ? 0 : g_.bounded[1], g_.bounded[2]};
-    std::string err = fft_.init(g_.N, local_bounded, stream_, !dist_, stretched_);
+    // (pencils: neither is x — a full complex local buffer, no permutation in x or y)
+    const int local_bounded[3] = {Rx_ > 1 ? 0 : g_.bounded[0], dist_ ? 0 : g_.bounded[1], g_.bounded[2]};
+    std::string err = fft_.init(g_.N, local_bounded, stream_, !dist_, stretched_, Rx_ > 1);
     if (!err.empty()) throw Error(OC_ERR_CUDA, err);
     fftbuf_ = (FT*)dev_alloc(fft_.buffer_bytes);
     device_bytes += (int64_t)fft_.buffer_bytes + (int64_t)fft_.work_bytes;
@@ -323,7 +329,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
 #ifndef OC_HOSTSIM
         cuda_check(cudaStreamCreateWithFlags(&stream3_, cudaStreamNonBlocking), "cudaStreamCreate");
 #endif
-        err = dfft_.init(g_.N[0], g_.N[1], g_.N[2], R_, g_.bounded[0] != 0, stream_, stream3_);
+        err = dfft_.init(g_.N[0], g_.N[1], g_.N[2], R_, g_.bounded[0] != 0, stream_, stream3_, Rx_);
 #ifndef OC_HOSTSIM
         for (int c = 0; c < dfft_.C; ++c) {
             cudaEvent_t a, b;
@@ -337,12 +343,13 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         diststage_ = (FT*)dev_alloc(fft_.buffer_bytes);
         const int planes = (int)(field_elems_ / (size_t)g_.sz);
         halo_buf_elems_ = (size_t)2 * F_ * planes * g_.H[1] * g_.sy;
+        if (Rx_ > 1) halo_buf_elems_ = std::max(halo_buf_elems_, (size_t)2 * F_ * planes * (size_t)(g_.sz / g_.sy) * g_.H[0]);      // x slabs: H columns of every row
         halo_send_ = (FT*)dev_alloc(sizeof(FT) * halo_buf_elems_);
         halo_recv_ = (FT*)dev_alloc(sizeof(FT) * halo_buf_elems_);
         device_bytes += (int64_t)(2 * fft_.buffer_bytes + dfft_.work_bytes + 2 * sizeof(FT) * halo_buf_elems_);
     }
     for (int d = 0; d < 3; ++d) {
-        const int N = (d == 1 && dist_) ? g_.N[d] * R_ : g_.N[d];       // eigenvalues are global arrays (distributed_fft_based_poisson_solver.jl:106-112)
+        const int N = (d == 1 && dist_) ? g_.N[d] * R_ : ((d == 0 && dist_) ? g_.N[d] * Rx_ : g_.N[d]);       // eigenvalues are global arrays (distributed_fft_based_poisson_solver.jl:106-112)
         std::vector<double> lam(N, 0.0);
         const double L = c.topology[d] == OC_FLAT ? 1.0 : c.extent[d];
         for (int i = 0; i < N; ++i) {                    // poisson_eigenvalues.jl:8-31 (Float64)
@@ -774,7 +781,7 @@ void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open, bool 
     k.nfields = (int)fields.size();
     k.nboxes = it->second.nboxes;
     k.fill_open = fill_open ? 1 : 0;
-    k.skip[0] = 0; k.skip[1] = dist_ ? 1 : 0; k.skip[2] = 0;
+    k.skip[0] = Rx_ > 1 ? 1 : 0; k.skip[1] = (dist_ && R_ > 1) ? 1 : 0; k.skip[2] = 0;
     k.boxes = it->second.boxes;
     for (int fi = 0; fi < (int)fields.size(); ++fi) {
         k.f[fi].p = fields[fi]->p;
@@ -806,6 +813,11 @@ void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open, bool 
         }
     }
     if (!dist_) return;
+    // pencils: x first, over every row of the parent array (wall-side boundary-condition halos included; the y-halo rows it carries are
+    // overwritten next), then y over whole padded rows — the corners arrive through the two hops, where the reference sends separate
+    // corner messages (halo_communication.jl:217-333)
+    if (Rx_ > 1) exchange_x(fields);
+    if (R_ <= 1) return;
 #ifndef OC_HOSTSIM
     if (defer_exchange && stream3_) {
         // The exchange runs on the communication stream while the NEXT stage's interior tendency kernels — which read no y-halo row —
@@ -850,7 +862,7 @@ void Model<FT>::dist_attach(Transport* t) {
     // Measured (profiles/r02f…r02j): 2 GPUs 70.7 vs 72.7 ms per step, 4 GPUs 71.8 vs 72.5 with / without peer-memory transposes; at 8 GPUs
     // the first version (every rank writing to rank 0 first: incast) lost, 88.9 vs 77.4; the round-robin version: 77.2 vs 76.3 (r02o) — the
     // sub-chunked all-to-all still wins there.  So the default is peer memory up to 4 ranks and the all-to-all beyond; OC_DIST_P2P=1 forces it.
-    if (R_ <= DIST_MAX_RANKS && (p2p_env ? atoi(p2p_env) != 0 : R_ <= 4)) {
+    if (Rx_ == 1 && R_ <= DIST_MAX_RANKS && (p2p_env ? atoi(p2p_env) != 0 : R_ <= 4)) {
         std::string e1 = transport_->map_peers(fftbuf_, peer_spec_, stream_);
         std::string e2 = transport_->map_peers(distT_, peer_T_, stream_);
         if (e2.empty()) e2 = e1;
@@ -908,7 +920,7 @@ void Model<FT>::run_fft_solve_p2p() {
 template <class FT>
 void Model<FT>::local_twiddles(bool inverse) {
     for (int d = 0; d < 3; d += 2) {
-        if (!g_.bounded[d]) continue;
+        if (!g_.bounded[d] || (d == 0 && Rx_ > 1)) continue;
         TwiddleKernel<FT> k;
         const long long plane = (long long)dfft_.nxc * g_.N[1];
         k.N = g_.N[d]; k.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_); k.tw = tw_[d]; k.inverse = inverse ? 1 : 0;
@@ -918,6 +930,133 @@ void Model<FT>::local_twiddles(bool inverse) {
         grid.x = (int)((k.count * (k.N / 2 + 1) + 255) / 256);
         go(k, grid, 0, OC_TIMER_POISSON_MID);
     }
+}
+
+// pencils: the x-halo exchange with the two neighbours along x — H columns of every row of the parent array
+template <class FT>
+void Model<FT>::exchange_x(const std::vector<FieldRec*>& fields) {
+    NvtxRange nvtx_("halo exchange (x)");
+    if (!transport_) throw Error(OC_ERR_STATE, "distributed model without a transport: call oc_dist_attach_nccl first");
+    const int nf = (int)fields.size();
+    if (nf > F_) throw Error(OC_ERR_INVALID, "halo exchange of more fields than the exchange buffers hold");
+    const int planes = (int)(field_elems_ / (size_t)g_.sz), rows = g_.sz / g_.sy;
+    HaloPackXKernel<FT> k;
+    k.g = g_;
+    k.nfields = nf; k.planes = planes; k.rows = rows; k.cols = g_.H[0];
+    for (int f = 0; f < nf; ++f) { k.base[f] = fields[f]->base; k.x0[f] = (int)((fields[f]->p - fields[f]->base) % g_.sy); }
+    const size_t per_side = (size_t)nf * planes * rows * g_.H[0];
+    if (2 * per_side > halo_buf_elems_) throw Error(OC_ERR_STATE, "internal: exchange buffer too small for the x slabs");
+    Dim3 grid;
+    grid.x = (int)((2 * per_side + 255) / 256);
+    k.unpack = 0; k.buf = halo_send_;
+    go(k, grid, 0, OC_TIMER_COMM);
+    const int prev = grank((rx_ + Rx_ - 1) % Rx_, rank_), next = grank((rx_ + 1) % Rx_, rank_);
+    const size_t to_prev = g_.wlo[0] ? 0 : per_side * sizeof(FT), to_next = g_.whi[0] ? 0 : per_side * sizeof(FT);
+    std::vector<Msg> msgs;
+    msgs.push_back(Msg{prev, next, 4, halo_send_, to_prev, halo_recv_ + per_side, to_next});
+    msgs.push_back(Msg{next, prev, 5, halo_send_ + per_side, to_next, halo_recv_, to_prev});
+    begin_timer(OC_TIMER_COMM);
+    std::string e = transport_->exchange(msgs, launch_stream_);
+    end_timer();
+    if (!e.empty()) throw Error(OC_ERR_CUDA, e);
+    k.unpack = 1; k.buf = halo_recv_;
+    go(k, grid, 0, OC_TIMER_COMM);
+}
+
+// all-to-all of the Rx equal chunks of a spectral buffer among the ranks of this rank's row (same y index)
+template <class FT>
+void Model<FT>::all_to_all_x(FT* send, FT* recv) {
+    const size_t chunk = fft_.buffer_bytes / Rx_;
+    std::vector<Msg> msgs;
+    for (int d = 1; d < Rx_; ++d) {
+        const int to = (rx_ + d) % Rx_, from = (rx_ + Rx_ - d) % Rx_;
+        msgs.push_back(Msg{grank(to, rank_), grank(from, rank_), 600 + d, (char*)send + chunk * to, chunk, (char*)recv + chunk * from, chunk});
+    }
+    begin_timer(OC_TIMER_COMM);
+#ifndef OC_HOSTSIM
+    cuda_check(cudaMemcpyAsync((char*)recv + chunk * rx_, (char*)send + chunk * rx_, chunk, cudaMemcpyDeviceToDevice, stream_), "cudaMemcpyAsync D2D");
+#else
+    memcpy((char*)recv + chunk * rx_, (char*)send + chunk * rx_, chunk);
+#endif
+    std::string e = transport_ ? transport_->exchange(msgs, stream_) : std::string("distributed model without a transport");
+    end_timer();
+    if (!e.empty()) throw Error(OC_ERR_CUDA, e);
+}
+
+// Pencils, Partition(Rx, Ry) (distributed_fft_based_poisson_solver.jl:141-178, the two-transpose branch):
+//   local (Nx_l, Ny_l, Nz)  FFT z  ->  transpose z <-> y among the Ry ranks of this column (the slab machinery, with Nx_l for the row
+//   length)  ->  T1 = [zl][xl][y]  FFT y  ->  transpose y <-> x among the Rx ranks of this row  ->  T2 = [zl][yl2][x]  FFT x  ->  divide
+//   -> and back.  Every stage is complex-to-complex; Bounded dimensions carry their DCT as a Makhoul permutation applied where the
+//   line becomes whole (z: by the right-hand-side kernel; y, x: inside the transposes) and twiddles after / before the FFTs.
+template <class FT>
+void Model<FT>::run_fft_solve_pencil() {
+    NvtxRange nvtx_("distributed FFT solve (pencils)");
+    auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
+    const int nxl = g_.N[0], nyl = g_.N[1], Ny = dfft_.Ny, Nx = nxl * Rx_, nzl = dfft_.Nzl, nyx = Ny / Rx_;
+    const int C = dfft_.C;
+    Cplx<FT>* spec = reinterpret_cast<Cplx<FT>*>(fftbuf_);
+    Cplx<FT>* stage = reinterpret_cast<Cplx<FT>*>(diststage_);
+    Cplx<FT>* T = reinterpret_cast<Cplx<FT>*>(distT_);
+    auto twiddle_lines = [&](Cplx<FT>* base, int n, long long count, const Cd* tw, bool inverse) {
+        TwiddleKernel<FT> k;
+        k.N = n; k.spec = base; k.tw = tw; k.inverse = inverse ? 1 : 0;
+        k.sk = 1; k.inner = 1; k.souter = n; k.count = count; k.kfast = 1;
+        Dim3 grid;
+        grid.x = (int)((count * (n / 2 + 1) + 255) / 256);
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+    };
+    auto transpose_y = [&](bool to_T) {
+        TransposeKernel<FT> t;
+        t.nxc = nxl; t.nyl = nyl; t.nzl = nzl; t.R = R_; t.zl0 = 0; t.yperm = g_.bounded[1];
+        t.stage = stage; t.T = T; t.to_T = to_T ? 1 : 0;
+        Dim3 tg;
+        tg.x = (nxl + 31) / 32; tg.y = (Ny + 31) / 32; tg.z = nzl;
+        go(t, tg, TransposeKernel<FT>::SMEM, OC_TIMER_POISSON_MID);
+    };
+    auto pencil_x = [&](int mode, Cplx<FT>* B, Cplx<FT>* Tb) {
+        PencilXKernel<FT> k;
+        k.nxl = nxl; k.nyx = nyx; k.nzl = nzl; k.Rx = Rx_; k.xperm = g_.bounded[0]; k.mode = mode; k.B = B; k.T = Tb;
+        Dim3 grid;
+        grid.x = (int)(((long long)nxl * nyx * nzl * Rx_ + 255) / 256);
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+    };
+    // z
+    begin_timer(OC_TIMER_FFT); std::string e = dfft_.z(fftbuf_, true); end_timer(); chk(e);
+    local_twiddles(false);
+    // z <-> y
+    for (int c = 0; c < C; ++c) all_to_all(fftbuf_, diststage_, c, C);
+    transpose_y(true);
+    for (int c = 0; c < C; ++c) { begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, true, c); end_timer(); chk(e); }
+    if (g_.bounded[1]) twiddle_lines(T, Ny, (long long)nzl * nxl, tw_[1], false);
+    // y <-> x
+    pencil_x(0, spec, T);
+    all_to_all_x(fftbuf_, diststage_);
+    pencil_x(1, stage, T);
+    begin_timer(OC_TIMER_FFT); e = dfft_.x(distT_, true); end_timer(); chk(e);
+    if (g_.bounded[0]) twiddle_lines(T, Nx, (long long)nzl * nyx, tw_[0], false);
+    {
+        PoissonDividePencilKernel<FT> k;
+        k.Nx = Nx; k.nyx = nyx; k.nzl = nzl; k.y0 = rx_ * nyx; k.kz0 = rank_ * nzl;
+        k.T = T;
+        for (int d = 0; d < 3; ++d) k.lam[d] = lam_[d];
+        k.norm = 1.0 / ((double)Nx * Ny * g_.N[2]);
+        Dim3 grid;
+        grid.x = (Nx + 255) / 256; grid.y = nyx; grid.z = nzl;
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+    }
+    if (g_.bounded[0]) twiddle_lines(T, Nx, (long long)nzl * nyx, tw_[0], true);
+    begin_timer(OC_TIMER_FFT); e = dfft_.x(distT_, false); end_timer(); chk(e);
+    // x <-> y
+    pencil_x(2, stage, T);
+    all_to_all_x(diststage_, fftbuf_);
+    pencil_x(3, spec, T);
+    if (g_.bounded[1]) twiddle_lines(T, Ny, (long long)nzl * nxl, tw_[1], true);
+    for (int c = 0; c < C; ++c) { begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, false, c); end_timer(); chk(e); }
+    // y <-> z
+    transpose_y(false);
+    for (int c = 0; c < C; ++c) all_to_all(diststage_, fftbuf_, c, C);
+    local_twiddles(true);
+    begin_timer(OC_TIMER_FFT); e = dfft_.z(fftbuf_, false); end_timer(); chk(e);
 }
 
 template <class FT>
@@ -936,7 +1075,7 @@ void Model<FT>::exchange_y(const std::vector<FieldRec*>& fields) {
     grid.x = (int)((2 * per_side + 255) / 256);
     k.unpack = 0; k.buf = halo_send_;
     go(k, grid, 0, OC_TIMER_COMM);
-    const int prev = (rank_ + R_ - 1) % R_, next = (rank_ + 1) % R_;
+    const int prev = grank(rx_, (rank_ + R_ - 1) % R_), next = grank(rx_, (rank_ + 1) % R_);
     // low-edge rows go to prev (they are its high halo); high-edge rows go to next (its low halo).  Posting order: for R = 2 the
     // peer's first send (its low edge) must meet my first receive (my high halo).  A wall side (Bounded y) has no partner: the chain
     // of slabs is open, and that half of the message is empty.
@@ -959,7 +1098,7 @@ void Model<FT>::all_to_all(FT* send, FT* recv, int c, int C) {
     std::vector<Msg> msgs;
     for (int d = 1; d < R_; ++d) {
         const int to = (rank_ + d) % R_, from = (rank_ + R_ - d) % R_;
-        msgs.push_back(Msg{to, from, 2 + d + 16 * c, (char*)send + chunk * to + off, sub, (char*)recv + chunk * from + off, sub});
+        msgs.push_back(Msg{grank(rx_, to), grank(rx_, from), 2 + d + 16 * c, (char*)send + chunk * to + off, sub, (char*)recv + chunk * from + off, sub});
     }
     begin_timer(OC_TIMER_COMM);
 #ifndef OC_HOSTSIM
@@ -978,6 +1117,7 @@ void Model<FT>::all_to_all(FT* send, FT* recv, int c, int C) {
 // and the way back starts as soon as a sub-chunk is finished.  (The reference does not overlap transposes with FFTs.)
 template <class FT>
 void Model<FT>::run_fft_solve_dist() {
+    if (Rx_ > 1) { run_fft_solve_pencil(); return; }
     if (p2p_) { run_fft_solve_p2p(); return; }
     auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
     const int C = dfft_.C, nz = dfft_.Nzl / C;
@@ -1372,7 +1512,7 @@ void Model<FT>::tendencies(int mode, double dt, int stage, double chi, bool eule
     // tracer stream) wait for the exchange, and the two boundary strips follow (interleave_communication_and_computation.jl:29-67,
     // compute_nonhydrostatic_buffer_tendencies.jl:10-84).  pHY′: rows 0 … Ny-1 now, the two halo rows after the exchange.  Closures with
     // eddy-viscosity fields read halo rows in aux(): no split for them.
-    const bool split = xchg_pending_ && march_ok_ && !has_eddy_;
+    const bool split = xchg_pending_ && march_ok_ && !has_eddy_ && Rx_ == 1;
     if (xchg_pending_ && !split) join_exchange();
 #ifndef OC_HOSTSIM
     phy_async = !aux_valid_ && has_pHY_ && !g_.flat[2] && !has_eddy_ && march_ok_ && F_ > 3 && (phy_env ? atoi(phy_env) != 0 : true);
@@ -1765,6 +1905,7 @@ template <class FT>
 void Model<FT>::projection(double dt) {
     NvtxRange nvtx_("make_pressure_correction!");
     const FT* prev_row = nullptr;
+    const FT* prev_col = nullptr;
     if (dist_) {
         // the pressure gradient at the first local row needs the y-neighbour's last row of ϕ: one dense (Nx, Nz) message
         // (the reference fills all of pNHS's halos, halo_communication.jl:87-187; only this row is ever read)
@@ -1775,13 +1916,29 @@ void Model<FT>::projection(double dt) {
         Dim3 rg;
         rg.x = (g_.N[0] + 255) / 256; rg.y = g_.N[2];
         go(r, rg, 0, OC_TIMER_COMM);
-        const int prev = (rank_ + R_ - 1) % R_, next = (rank_ + 1) % R_;
-        std::vector<Msg> msgs{Msg{next, prev, 1, halo_send_, g_.whi[1] ? 0 : n * sizeof(FT), halo_recv_, g_.wlo[1] ? 0 : n * sizeof(FT)}};
+        std::vector<Msg> msgs;
+        if (R_ > 1) {
+            const int prev = grank(rx_, (rank_ + R_ - 1) % R_), next = grank(rx_, (rank_ + 1) % R_);
+            msgs.push_back(Msg{next, prev, 1, halo_send_, g_.whi[1] ? 0 : n * sizeof(FT), halo_recv_, g_.wlo[1] ? 0 : n * sizeof(FT)});
+        }
+        const size_t m = (size_t)g_.N[1] * g_.N[2];
+        if (Rx_ > 1) {
+            // pencils: likewise the x-neighbour's last column, dense (Ny, Nz)
+            if (2 * (n + m) > halo_buf_elems_) throw Error(OC_ERR_STATE, "internal: exchange buffer too small for the ϕ column");
+            PhiColKernel<FT> c;
+            c.L = fft_.L; c.buf = fftbuf_; c.col = halo_send_ + n;
+            Dim3 cg;
+            cg.x = (g_.N[1] + 255) / 256; cg.y = g_.N[2];
+            go(c, cg, 0, OC_TIMER_COMM);
+            const int prev = grank((rx_ + Rx_ - 1) % Rx_, rank_), next = grank((rx_ + 1) % Rx_, rank_);
+            msgs.push_back(Msg{next, prev, 2, halo_send_ + n, g_.whi[0] ? 0 : m * sizeof(FT), halo_recv_ + n, g_.wlo[0] ? 0 : m * sizeof(FT)});
+        }
         begin_timer(OC_TIMER_COMM);
         std::string e = transport_ ? transport_->exchange(msgs, stream_) : std::string("distributed model without a transport");
         end_timer();
         if (!e.empty()) throw Error(OC_ERR_CUDA, e);
-        prev_row = g_.wlo[1] ? nullptr : halo_recv_;          // first slab of a Bounded y: the wall face is not corrected
+        prev_row = (g_.wlo[1] || R_ <= 1) ? nullptr : halo_recv_;          // first slab of a Bounded y: the wall face is not corrected
+        prev_col = (g_.wlo[0] || Rx_ <= 1) ? nullptr : halo_recv_ + n;
     }
     ProjectionKernel<FT> k;
     k.g = g_;
@@ -1790,6 +1947,7 @@ void Model<FT>::projection(double dt) {
     k.u = state_[0].p; k.v = state_[1].p; k.w = state_[2].p;
     k.pNHS = pNHS_.p;
     k.prev_row = prev_row;
+    k.prev_col = prev_col;
     k.dt_plus = std::max((double)std::numeric_limits<FT>::epsilon(), dt);
     go(k, grid_xyz(256), 0, OC_TIMER_PROJECTION);
 }
@@ -2157,7 +2315,7 @@ void Model<FT>::stage(int mode, double dt, int stage_no, double stage_dt, double
     // stages 1 and 2 of an RK3 step are followed by another stage of the same call: their y-halo exchange is overlapped with that stage's
     // interior tendency kernels (tendencies()); the last stage's exchange completes before time_step! returns.  OC_XCHG_OVERLAP=0: off.
     static const char* xo_env = getenv("OC_XCHG_OVERLAP");
-    const bool defer = dist_ && march_ok_ && !has_eddy_ && mode != STEP_AB2 && stage_no < 3 && (xo_env ? atoi(xo_env) != 0 : true);
+    const bool defer = dist_ && Rx_ == 1 && R_ > 1 && march_ok_ && !has_eddy_ && mode != STEP_AB2 && stage_no < 3 && (xo_env ? atoi(xo_env) != 0 : true);
     halo(all, false, defer);
 }
 

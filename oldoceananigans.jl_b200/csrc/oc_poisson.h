@@ -545,6 +545,7 @@ struct ProjectionKernel {
     FT* pNHS;
     double dt_plus;       // max(eps(FT), Δt)
     const FT* prev_row;   // slab decomposition: ϕ of the y-neighbour's last row, dense (Nx, Nz); nullptr on one GPU
+    const FT* prev_col;   // pencils: ϕ of the x-neighbour's last column, dense (Ny, Nz); else nullptr
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
         int i = b.x * nt + tid, j = b.y, k = b.z;
@@ -552,7 +553,8 @@ struct ProjectionKernel {
         int o = g.idx(i, j, k);
         FT p0 = phi_at<FT>(L, buf, i, j, k);
         if (!g.flat[0]) {
-            FT pm = (i > 0) ? phi_at<FT>(L, buf, i - 1, j, k) : (g.wlo[0] ? p0 : phi_at<FT>(L, buf, g.N[0] - 1, j, k));
+            FT pm = (i > 0) ? phi_at<FT>(L, buf, i - 1, j, k)
+                            : (prev_col ? prev_col[j + (long long)g.N[1] * k] : (g.wlo[0] ? p0 : phi_at<FT>(L, buf, g.N[0] - 1, j, k)));
             u[o] = u[o] - (p0 - pm) * g.rd[0];
         }
         if (!g.flat[1]) {
@@ -582,6 +584,23 @@ struct PhiRowKernel {
         int i = b.x * nt + tid, k = b.y;
         if (i >= L.N[0]) return;
         row[i + (long long)L.N[0] * k] = phi_at<FT>(L, buf, i, L.N[1] - 1, k);
+    }
+};
+
+// pencils: the last local column of ϕ, dense (Ny, Nz), for the x-neighbour's pressure gradient at its first column
+template <class FT>
+struct PhiColKernel {
+    static constexpr int PHASES = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    SpectralLayout L;
+    const FT* buf;
+    FT* col;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char*) const {
+        int j = b.x * nt + tid, k = b.y;
+        if (j >= L.N[1]) return;
+        col[j + (long long)L.N[1] * k] = phi_at<FT>(L, buf, L.N[0] - 1, j, k);
     }
 };
 

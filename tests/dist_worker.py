@@ -55,8 +55,10 @@ def run_rank(kw, rank, R, arch, lib, nccl=False):
     model = ph.build_product(library=lib, arch=arch, **case)
     om = ph.build_oracle(**case)
     ic = ph.initial_conditions(om)
-    nyl = N[1] // R
-    rows = slice(rank * nyl, (rank + 1) * nyl)
+    part = arch.partition
+    nxl, nyl = N[0] // part.x, N[1] // part.y
+    cols = slice(arch.rx * nxl, (arch.rx + 1) * nxl)
+    rows = slice(arch.ry * nyl, (arch.ry + 1) * nyl)
     if kw.get("poisson"):
         # the distributed solver on its own (test/test_distributed_poisson_solvers.jl:70-89,128-148): a seeded zero-mean right-hand side,
         # every rank solving for its rows, against the single-domain solve
@@ -66,17 +68,21 @@ def run_rank(kw, rank, R, arch, lib, nccl=False):
             rhs = rng.standard_normal(N).astype(FT)
             rhs -= rhs.mean()
             want = om.solve_poisson(rhs)
-            got = ob.solve_poisson(model, rhs[:, rows, :])
-            worst = max(worst, float(np.abs(got - want[:, rows, :]).max() / np.abs(want).max()))
+            got = ob.solve_poisson(model, rhs[cols, rows, :])
+            worst = max(worst, float(np.abs(got - want[cols, rows, :]).max() / np.abs(want).max()))
         return worst
 
     def sl_of(n):
-        # this rank's rows of field n; the last slab of a Bounded y also owns v's wall face (LeftConnected: Ny_l + 1 faces, grid_utils.jl:43)
-        if n == "v" and topo[1] == "B" and rank == R - 1:
-            return slice(rank * nyl, (rank + 1) * nyl + 1)
-        return rows
+        # this rank's share of field n; the last rank of a Bounded partitioned dimension also owns the wall face of the velocity normal to
+        # it (LeftConnected: N_l + 1 faces, grid_utils.jl:43)
+        cs, rs = cols, rows
+        if n == "u" and topo[0] == "B" and arch.rx == part.x - 1:
+            cs = slice(cols.start, cols.stop + 1)
+        if n == "v" and topo[1] == "B" and arch.ry == part.y - 1:
+            rs = slice(rows.start, rows.stop + 1)
+        return cs, rs, slice(None)
 
-    ob.set_(model, **{n: a[:, sl_of(n), :] for n, a in ic.items()})
+    ob.set_(model, **{n: a[sl_of(n)] for n, a in ic.items()})
     om.set(**ic)
     dt = 0.1 * float(min(om.grid.D))
     worst = 0.0
@@ -86,13 +92,16 @@ def run_rank(kw, rank, R, arch, lib, nccl=False):
             om.time_step(dt)
         for n in om.fields:
             sl = sl_of(n)
-            worst = max(worst, ph.rel_linf(model.fields[n].interior(), om.fields[n].interior[:, sl, :]) * (np.abs(om.fields[n].interior[:, sl, :]).max() / np.abs(om.fields[n].interior).max()))
-        worst = max(worst, float(np.abs(model.pressures.pNHS.interior() - om.pNHS.interior[:, rows, :]).max() / np.abs(om.pNHS.interior).max()))
+            worst = max(worst, ph.rel_linf(model.fields[n].interior(), om.fields[n].interior[sl]) * (np.abs(om.fields[n].interior[sl]).max() / np.abs(om.fields[n].interior).max()))
+        worst = max(worst, float(np.abs(model.pressures.pNHS.interior() - om.pNHS.interior[cols, rows, :]).max() / np.abs(om.pNHS.interior).max()))
     return worst
 
 
 def main():
-    kw = json.loads(sys.argv[1])
+    cases = json.loads(sys.argv[1])              # one case, or a list of cases run one after the other on the same process group
+    many = isinstance(cases, list)
+    if not many:
+        cases = [cases]
     nccl = os.environ.get("OC_DIST_BACKEND", "gloo") == "nccl"      # -m gpu variant: the CUDA library, NCCL over NVLink
     if nccl:
         torch.cuda.set_device(int(os.environ["RANK"]))
@@ -104,13 +113,17 @@ def main():
     from oceananigans_b200 import _lib
     import __graft_entry__ as ge
     lib = None if nccl else _lib.Library(ge.HOSTSIM)
-    arch = ob.Distributed(ob.B200(rank if nccl else 0), partition=ob.Partition(1, R), rank=rank, nranks=R,
-                          exchange=None if nccl else gloo_exchange)
-    worst = run_rank(kw, rank, R, arch, lib, nccl)
-    t = torch.tensor([worst], dtype=torch.float64, device="cuda" if nccl else "cpu")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = []
+    for kw in cases:
+        px = int(kw.get("px", 1))                   # Partition(px, R / px): ranks along x
+        arch = ob.Distributed(ob.B200(rank if nccl else 0), partition=ob.Partition(px, R // px), rank=rank, nranks=R,
+                              exchange=None if nccl else gloo_exchange)
+        worst = run_rank(kw, rank, R, arch, lib, nccl)
+        t = torch.tensor([worst], dtype=torch.float64, device="cuda" if nccl else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out.append({"worst": float(t.item()), "ranks": R, "steps": kw.get("steps", 2)})
     if rank == 0:
-        print(json.dumps({"worst": float(t.item()), "ranks": R, "steps": kw.get("steps", 2)}))
+        print(json.dumps(out if many else out[0]))
     dist.destroy_process_group()
 
 

@@ -33,7 +33,7 @@ def test_cuda_library_loads_and_exports_every_symbol():
         assert hasattr(lib.dll, name), name
     cfg = _lib.oc_config()
     lib.oc_config_init(C.byref(cfg))     # pure host call; no compute without a GPU
-    assert cfg.abi_version == _lib.OC_ABI_VERSION == 5 and cfg.amd_has_Cb == 0 and cfg.ab2_chi == 0.1 and abs(cfg.gravity - 9.80665) < 1e-15
+    assert cfg.abi_version == _lib.OC_ABI_VERSION == 6 and cfg.amd_has_Cb == 0 and cfg.ab2_chi == 0.1 and abs(cfg.gravity - 9.80665) < 1e-15
 
 
 def test_missing_library_fails_loudly(tmp_path):

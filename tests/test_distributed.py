@@ -39,7 +39,7 @@ def run_ranks(R, case, timeout=600, backend="gloo"):
     return json.loads(outs[0][0].strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("R,case", [
+CPU_MODEL_CASES = [
     (2, dict(N=(16, 12, 8), topo="PPP", scheme="weno", steps=2)),
     (2, dict(N=(16, 12, 8), topo="PPP", scheme="centered", f=1e-2, steps=2)),
     (4, dict(N=(12, 16, 8), topo="PPP", scheme="weno", steps=1)),
@@ -65,26 +65,65 @@ def run_ranks(R, case, timeout=600, backend="gloo"):
     (4, dict(N=(12, 16, 8), topo="PBB", scheme="upwind3", closure="smag", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0), bcs="walls", steps=1)),
     (2, dict(N=(16, 12, 8), topo="PBP", scheme="weno", bcs="walls", f=1e-2, steps=2)),
     (2, dict(N=(16, 12, 8), topo="BPB", scheme="weno", bcs="walls", steps=2, f32=True)),
-])
+    # pencils, Partition(px, R / px) (distributed_architectures.jl:242-302): halo exchange along x then y (corners through the two hops),
+    # the two-transpose solve (z <-> y among a column of ranks, y <-> x among a row), ϕ's neighbour row AND column in the projection;
+    # px = R is the slab decomposition in x
+    (4, dict(N=(16, 12, 8), topo="PPP", scheme="weno", steps=2, px=2)),
+    (4, dict(N=(16, 12, 8), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, steps=2, px=2)),
+    (4, dict(N=(16, 12, 8), topo="BBB", scheme="weno", closure="lilly", f=("beta", 0.3, 2.0), bcs="walls", steps=2, px=2)),
+    (2, dict(N=(16, 12, 8), topo="BPB", scheme="weno", bcs="walls", steps=2, px=2)),
+    (6, dict(N=(18, 12, 6), topo="PBB", scheme="centered", closure="amd", f=("cartesian", 0.3, -0.5, 0.7), bcs="walls", steps=2, ts="QuasiAdamsBashforth2", px=3)),
+    (6, dict(N=(12, 18, 9), topo="BBB", scheme="upwind3", closure="smag", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0), bcs="walls", steps=1, px=2)),
+    (4, dict(N=(16, 12, 8), topo="BPP", scheme="weno", steps=2, px=2, f32=True)),
+]
+
+POISSON_CASES = [(R, dict(N=N, topo=topo, poisson=True)) for R, N in ((2, (16, 12, 8)), (4, (10, 16, 12)), (3, (9, 15, 6)))
+                 for topo in ("PPP", "PPB", "PBB", "BBB", "BPP", "PBP")]
+PENCIL_POISSON_CASES = [(R, dict(N=N, topo=topo, poisson=True, px=px))
+                        for R, px, N in ((4, 2, (16, 12, 8)), (2, 2, (16, 12, 8)), (6, 3, (12, 12, 6)), (6, 2, (12, 18, 9)))
+                        for topo in ("PPP", "PBB", "BBB", "BPP")]
+
+_BATCH = {}
+
+
+def cpu_result(R, case):
+    """Every CPU case with the same number of ranks shares ONE launch of R gloo processes (starting the processes and importing torch
+    costs more than the cases themselves): the first request for a rank count runs them all."""
+    if R not in _BATCH:
+        todo = [c for r, c in CPU_MODEL_CASES + POISSON_CASES + PENCIL_POISSON_CASES if r == R]
+        res = run_ranks(R, todo, timeout=1800)
+        _BATCH[R] = {json.dumps(c, sort_keys=True): x for c, x in zip(todo, res)}
+    return _BATCH[R][json.dumps(case, sort_keys=True)]
+
+
+@pytest.mark.parametrize("R,case", CPU_MODEL_CASES)
 def test_slab_decomposition_matches_single_domain_oracle(R, case):
-    res = run_ranks(R, dict(case))
+    res = cpu_result(R, case)
     tol = 1e-4 if case.get("f32") else 1e-11
     assert res["ranks"] == R and res["worst"] <= tol, res
 
 
-@pytest.mark.parametrize("R,N", [(2, (16, 12, 8)), (4, (10, 16, 12)), (3, (9, 15, 6))])
-@pytest.mark.parametrize("topo", ["PPP", "PPB", "PBB", "BBB", "BPP", "PBP"])
-def test_distributed_poisson_solver_matches_single_domain_solve(R, N, topo):
+@pytest.mark.parametrize("R,case", POISSON_CASES, ids=[f"{r}-{c['topo']}" for r, c in POISSON_CASES])
+def test_distributed_poisson_solver_matches_single_domain_solve(R, case):
     """The distributed solver alone on every mix of Periodic and Bounded dimensions, even and odd sizes, 2 / 3 / 4 ranks
     (test/test_distributed_poisson_solvers.jl:70-89,128-148 runs (4,1,1), (1,4,1), (2,2,1) partitions x 4 topologies)"""
-    res = run_ranks(R, dict(N=N, topo=topo, poisson=True))
+    res = cpu_result(R, case)
+    assert res["ranks"] == R and res["worst"] <= 1e-13, res
+
+
+@pytest.mark.parametrize("R,case", PENCIL_POISSON_CASES, ids=[f"{r}-px{c['px']}-{c['topo']}" for r, c in PENCIL_POISSON_CASES])
+def test_pencil_poisson_solver_matches_single_domain_solve(R, case):
+    """Partition(px, R / px): (2,2), (2,1), (3,2) and (2,3) process grids (test/test_distributed_poisson_solvers.jl:70-89,128-148)"""
+    res = cpu_result(R, case)
     assert res["ranks"] == R and res["worst"] <= 1e-13, res
 
 
 def test_distributed_rejects_unsupported_configurations():
     import oceananigans_b200 as ob
     with pytest.raises(NotImplementedError):
-        ob.Partition(2, 2)
+        ob.Partition(2, 2, 2)              # z is never partitioned
+    with pytest.raises(ValueError):
+        ob.Distributed(ob.B200(0), partition=ob.Partition(2, 2), rank=0, nranks=6)
     with pytest.raises(ValueError):
         ob.Distributed(ob.B200(0), partition=ob.Partition(1, 3), rank=0, nranks=2)
 
@@ -97,8 +136,7 @@ def _gpu_count():
         return 0
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("R,case", [
+NCCL_CASES = [
     (2, dict(N=(64, 48, 32), topo="PPP", scheme="weno", steps=2)),
     (2, dict(N=(40, 24, 16), topo="PPP", scheme="centered", f=1e-2, steps=3)),
     (2, dict(N=(48, 32, 16), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, steps=2)),
@@ -122,10 +160,33 @@ def _gpu_count():
     (2, dict(N=(36, 40, 20), topo="BBB", poisson=True)),
     (4, dict(N=(36, 40, 20), topo="PBB", poisson=True)),
     (8, dict(N=(30, 48, 24), topo="BBB", poisson=True)),
-])
+    # pencils
+    (4, dict(N=(64, 48, 32), topo="PPP", scheme="weno", steps=2, px=2)),
+    (4, dict(N=(48, 64, 16), topo="BBB", scheme="weno", closure="amd", f=1e-2, bcs="walls", steps=2, px=2)),
+    (2, dict(N=(48, 32, 16), topo="PPB", scheme="weno", bcs=True, steps=2, px=2)),
+    (8, dict(N=(64, 48, 32), topo="PPB", scheme="weno", closure="lilly", f=("beta", 0.3, 2.0), bcs=True, steps=2, px=2)),
+    (8, dict(N=(64, 48, 32), topo="PBB", scheme="centered", bcs="walls", steps=2, px=4, ts="QuasiAdamsBashforth2")),
+    (4, dict(N=(36, 40, 20), topo="BBB", poisson=True, px=2)),
+    (8, dict(N=(32, 48, 24), topo="PBP", poisson=True, px=4)),
+]
+
+_NCCL_BATCH = {}
+
+
+def nccl_result(R, case):
+    """like cpu_result: one launch of R NCCL processes for every case with that rank count"""
+    if R not in _NCCL_BATCH:
+        todo = [c for r, c in NCCL_CASES if r == R]
+        res = run_ranks(R, todo, timeout=1800, backend="nccl")
+        _NCCL_BATCH[R] = {json.dumps(c, sort_keys=True): x for c, x in zip(todo, res)}
+    return _NCCL_BATCH[R][json.dumps(case, sort_keys=True)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,case", NCCL_CASES)
 def test_nccl_slab_decomposition_matches_oracle(R, case):
     """The CUDA library on R GPUs of one box (NCCL halo exchange + transposed distributed FFT) against the oracle."""
     if _gpu_count() < R:
         pytest.skip(f"needs {R} GPUs")
-    res = run_ranks(R, dict(case), backend="nccl")
+    res = nccl_result(R, case)
     assert res["ranks"] == R and res["worst"] <= (1e-4 if case.get("f32") else 1e-11), res

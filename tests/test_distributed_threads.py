@@ -56,7 +56,8 @@ def run_threads(R, case, p2p=True):
 
         def body(rank):
             try:
-                arch = ob.Distributed(ob.B200(0), partition=ob.Partition(1, R), rank=rank, nranks=R, exchange=box.exchange_for(rank))
+                px = int(case.get("px", 1))
+                arch = ob.Distributed(ob.B200(0), partition=ob.Partition(px, R // px), rank=rank, nranks=R, exchange=box.exchange_for(rank))
                 out[rank] = dist_worker.run_rank(case, rank, R, arch, lib)
             except BaseException as e:       # noqa: BLE001 — reported by the main thread
                 errs.append((rank, repr(e)))
@@ -83,6 +84,8 @@ def run_threads(R, case, p2p=True):
     (4, dict(N=(10, 16, 12), topo="BBB", poisson=True)),
     (4, dict(N=(10, 16, 12), topo="PBP", poisson=True)),
     (3, dict(N=(9, 15, 6), topo="BPB", poisson=True)),
+    # pencils with thread ranks (send / receive transposes: the peer-memory kernel is the slab path's)
+    (4, dict(N=(16, 12, 8), topo="PBB", scheme="weno", bcs="walls", steps=1, px=2)),
 ])
 def test_peer_memory_transposes_match_single_domain_oracle(R, case):
     worst = run_threads(R, case)
