@@ -3,6 +3,7 @@
 #   gpurun --timeout 900 -- 'bash scripts/gpu.sh <tag> <task> [<task> ...]'
 # tasks:
 #   tests                 python -m pytest tests -m gpu
+#   smoke                 __graft_entry__.smoke()
 #   bench:<wl>[:steps]    python bench.py --workload <wl> (no e2e / cpu baseline)  -> <tag>_bench_<wl>.json
 #   default               python bench.py exactly as the driver runs it            -> <tag>_bench_default.json
 #   reference             python bench.py --impl reference                         -> <tag>_bench_reference.json
@@ -20,8 +21,10 @@ for task in "$@"; do
   IFS=: read -r kind a b c d <<< "$task"
   echo "=== $task"
   case $kind in
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -4 gpurun_out/${TAG}_smoke.log ;;
     tests)
-      timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/${TAG}_pytest_gpu.log ;;
+      timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/${TAG}_pytest_gpu.log ;;
     bench)
       timeout 600 python bench.py --workload $a --steps ${b:-5} --warmup 3 --no-e2e --no-cpu-baseline --no-parity-check --no-other-workloads > gpurun_out/${TAG}_bench_$a.json 2> gpurun_out/${TAG}_bench_$a.err
       echo "bench $a rc=$?"; cat gpurun_out/${TAG}_bench_$a.json; tail -3 gpurun_out/${TAG}_bench_$a.err ;;
