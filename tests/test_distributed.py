@@ -170,23 +170,11 @@ NCCL_CASES = [
     (8, dict(N=(32, 48, 24), topo="PBP", poisson=True, px=4)),
 ]
 
-_NCCL_BATCH = {}
-
-
-def nccl_result(R, case):
-    """like cpu_result: one launch of R NCCL processes for every case with that rank count"""
-    if R not in _NCCL_BATCH:
-        todo = [c for r, c in NCCL_CASES if r == R]
-        res = run_ranks(R, todo, timeout=1800, backend="nccl")
-        _NCCL_BATCH[R] = {json.dumps(c, sort_keys=True): x for c, x in zip(todo, res)}
-    return _NCCL_BATCH[R][json.dumps(case, sort_keys=True)]
-
-
 @pytest.mark.gpu
 @pytest.mark.parametrize("R,case", NCCL_CASES)
 def test_nccl_slab_decomposition_matches_oracle(R, case):
     """The CUDA library on R GPUs of one box (NCCL halo exchange + transposed distributed FFT) against the oracle."""
     if _gpu_count() < R:
         pytest.skip(f"needs {R} GPUs")
-    res = nccl_result(R, case)
+    res = run_ranks(R, dict(case), timeout=300, backend="nccl")      # one launch per case: one model and one communicator per process
     assert res["ranks"] == R and res["worst"] <= (1e-4 if case.get("f32") else 1e-11), res
