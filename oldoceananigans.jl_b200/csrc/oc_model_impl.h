@@ -339,6 +339,9 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         }
 #endif
         if (!err.empty()) throw Error(OC_ERR_CUDA, err);
+#ifndef OC_HOSTSIM
+        if (Rx_ > 1) dfft_.set_y_stream(stream_);      // the pencil solve is one stream: no sub-chunk pipelining on stream3_ (yet)
+#endif
         distT_ = (FT*)dev_alloc(fft_.buffer_bytes);
         diststage_ = (FT*)dev_alloc(fft_.buffer_bytes);
         const int planes = (int)(field_elems_ / (size_t)g_.sz);

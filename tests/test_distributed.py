@@ -83,6 +83,13 @@ PENCIL_POISSON_CASES = [(R, dict(N=N, topo=topo, poisson=True, px=px))
                         for R, px, N in ((4, 2, (16, 12, 8)), (2, 2, (16, 12, 8)), (6, 3, (12, 12, 6)), (6, 2, (12, 18, 9)))
                         for topo in ("PPP", "PBB", "BBB", "BPP")]
 
+# the reference's own matrix (test/test_distributed_poisson_solvers.jl:128-148): sizes x process grids (4,1,1), (1,4,1), (2,2,1) x four
+# topologies, 3-D
+REFERENCE_POISSON_MATRIX = [(4, dict(N=N, topo=topo, poisson=True, px=px))
+                            for topo in ("PPP", "PPB", "PBB", "BBB")
+                            for px, N in ((4, (44, 44, 8)), (4, (16, 44, 8)), (1, (44, 44, 8)), (1, (44, 16, 8)), (1, (16, 44, 8)),
+                                          (2, (22, 44, 8)), (2, (44, 22, 8)))]
+
 _BATCH = {}
 
 
@@ -90,7 +97,7 @@ def cpu_result(R, case):
     """Every CPU case with the same number of ranks shares ONE launch of R gloo processes (starting the processes and importing torch
     costs more than the cases themselves): the first request for a rank count runs them all."""
     if R not in _BATCH:
-        todo = [c for r, c in CPU_MODEL_CASES + POISSON_CASES + PENCIL_POISSON_CASES if r == R]
+        todo = [c for r, c in CPU_MODEL_CASES + POISSON_CASES + PENCIL_POISSON_CASES + REFERENCE_POISSON_MATRIX if r == R]
         res = run_ranks(R, todo, timeout=1800)
         _BATCH[R] = {json.dumps(c, sort_keys=True): x for c, x in zip(todo, res)}
     return _BATCH[R][json.dumps(case, sort_keys=True)]
@@ -114,6 +121,13 @@ def test_distributed_poisson_solver_matches_single_domain_solve(R, case):
 @pytest.mark.parametrize("R,case", PENCIL_POISSON_CASES, ids=[f"{r}-px{c['px']}-{c['topo']}" for r, c in PENCIL_POISSON_CASES])
 def test_pencil_poisson_solver_matches_single_domain_solve(R, case):
     """Partition(px, R / px): (2,2), (2,1), (3,2) and (2,3) process grids (test/test_distributed_poisson_solvers.jl:70-89,128-148)"""
+    res = cpu_result(R, case)
+    assert res["ranks"] == R and res["worst"] <= 1e-13, res
+
+
+@pytest.mark.parametrize("R,case", REFERENCE_POISSON_MATRIX, ids=[f"{c['topo']}-px{c['px']}-{'x'.join(map(str, c['N']))}" for r, c in REFERENCE_POISSON_MATRIX])
+def test_distributed_poisson_solver_on_the_reference_test_matrix(R, case):
+    """sizes, process grids and topologies of the reference's 3-D distributed solver tests (test/test_distributed_poisson_solvers.jl:128-148)"""
     res = cpu_result(R, case)
     assert res["ranks"] == R and res["worst"] <= 1e-13, res
 
