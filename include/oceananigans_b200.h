@@ -175,7 +175,9 @@ int  oc_download_parent(oc_model* m, int field, void* host, size_t nbytes);
  * compute_flux_bcs.jl:116-163; fill_halo_regions_value_gradient.jl:7-119).  `host` holds N₁×N₂ values of the model's float type over
  * the two tangential interior dimensions (first one fastest: Nx×Ny for bottom / top, Nx×Nz for south / north, Ny×Nz for west / east).
  * The side must have been created with that kind (OC_BC_FLUX / OC_BC_VALUE / OC_BC_GRADIENT) in oc_config; its scalar is then ignored.
- * May be called again to update the values (time-dependent forcing from the host). */
+ * May be called again to update the values (time-dependent forcing from the host).  Distributed models: the LOCAL N₁×N₂ share; a
+ * collective call (Value / Gradient arrays refresh halos), made by every rank after the transport is attached — ranks on which the side
+ * is connected to a neighbour ignore the values. */
 int  oc_set_bc_array(oc_model* m, int field, int side, const void* host, size_t nbytes);
 
 /* Boundary condition of a DIFFUSIVITY field — `boundary_conditions = (κₑ = (b = FieldBoundaryConditions(bottom = ValueBoundaryCondition(κ₀)),),)`

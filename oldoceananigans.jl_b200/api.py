@@ -871,6 +871,8 @@ class NonhydrostaticModel:
         h = C.c_void_p()
         self._lib.check(self._lib.oc_model_create(C.byref(cfg), C.byref(h)))
         self._h = h
+        if self.distributed:
+            self._attach_transport(arch)           # before anything that fills halos (array-valued boundary conditions do)
         for f, n in enumerate(names):              # FluxBoundaryCondition(array), ValueBoundaryCondition(array), GradientBoundaryCondition(array)
             fb = bcs.get(n)
             for s, side in enumerate(_SIDES):
@@ -888,8 +890,6 @@ class NonhydrostaticModel:
                     if bc.array is not None:
                         raise NotImplementedError("array-valued boundary conditions on diffusivity fields")
                     self._lib.check(self._lib.oc_set_diffusivity_bc(self._h, fid, s, bc.kind, 0.0 if bc.value is None else float(bc.value)))
-        if self.distributed:
-            self._attach_transport(arch)
         self.tracer_names = tracers
         self.velocities = _NT(u=Field(self, 0, "u"), v=Field(self, 1, "v"), w=Field(self, 2, "w"))
         self.tracers = _NT({n: Field(self, 3 + t, n) for t, n in enumerate(tracers)})
@@ -906,7 +906,11 @@ class NonhydrostaticModel:
         if sda:
             # the array coefficients: interior values, then halos like fill_halo_regions!(ν) on a Center field with default BCs
             shape = tuple(self.grid.N)
-            full = lambda v: np.asarray(v, dtype=self.grid.FT) if isinstance(v, np.ndarray) else np.full(shape, float(v), dtype=self.grid.FT)
+            local = (slice(None),) * 3
+            if self.distributed:                   # coefficient arrays cover the global grid: this rank's share
+                (i0, ni), (j0, nj) = arch.local_range(0, shape[0]), arch.local_range(1, shape[1])
+                local = (slice(i0, i0 + ni), slice(j0, j0 + nj), slice(None))
+            full = lambda v: (np.asarray(v, dtype=self.grid.FT) if isinstance(v, np.ndarray) else np.full(shape, float(v), dtype=self.grid.FT))[local]
             self.diffusivity_fields.nu_e.set(full(sda[0].nu))
             ids = [L.OC_FIELD_NU_E]
             for t, n in enumerate(tracers):
@@ -925,6 +929,10 @@ class NonhydrostaticModel:
         a = np.asarray(array)
         if a.shape != shape:
             raise ValueError(f"boundary-condition array of shape {a.shape}; expected {shape}")
+        if self.distributed:                       # this rank's share of the side (a collective call: every rank makes it)
+            arch = self.grid.architecture
+            (i0, n1), (j0, n2) = arch.local_range(t1, shape[0]), arch.local_range(t2, shape[1])
+            a = a[i0:i0 + n1, j0:j0 + n2]
         a = np.asfortranarray(a.astype(self.grid.FT))
         self._lib.check(self._lib.oc_set_bc_array(self._h, field, side, a.ctypes.data_as(C.c_void_p), a.nbytes))
 

@@ -188,9 +188,10 @@ OC_HD FT weno_hi_value(const AdvCoef<FT>& C, const FT* q) {
 
 // order windows of buffer b in terms of the 0-based face index f: face-type b <= f <= N - b, centre-type (evaluated at face c + 1)
 // b <= f <= N + 1 - b (topologically_conditional_interpolation.jl:46-52 with required_halo_size = b)
-// — from the OrderWindow of buffer 3 (hi_hi = N - 3 face-type, N - 2 centre-type; lo_hi < 0: the dimension is not Bounded)
+// — from the OrderWindow of buffer 3 (hi_hi = N - 3 face-type, N - 2 centre-type; lo_hi < 0: no wall on the low side; hi_hi = 2^30: none
+// on the high side — each side on its own: the outer slabs of a distributed Bounded dimension have one wall only)
 OC_HD bool in_order_window(int b, int f, const OrderWindow& w) {
-    return w.lo_hi < 0 || (f >= b && f <= w.hi_hi + 3 - b);
+    return (w.lo_hi < 0 || f >= b) && f <= w.hi_hi + 3 - b;
 }
 
 // _biased_interpolate of WENO(2B-1), B = 4 | 5: the scheme inside its window, else its buffer_scheme (WENO(2B-3) …) — the chain ends in

@@ -187,7 +187,6 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         const double* v = c.gravity_unit_vector;
         const double nrm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
         if (!(std::fabs(nrm - 1.0) < 1e-8)) throw Error(OC_ERR_INVALID, "gravity_unit_vector must be unitary (validate_unit_vector)");
-        if (c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "tilted gravity on distributed models");
     }
     if (c.has_coriolis == OC_CORIOLIS_BETAPLANE && g_.flat[1]) throw Error(OC_ERR_UNSUPPORTED, "BetaPlane on a grid with a Flat y");
     if (c.has_coriolis == OC_CORIOLIS_NONTRADITIONAL_BETAPLANE) {
@@ -808,8 +807,11 @@ void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open, bool 
             const int t1 = hk.d == 0 ? 1 : 0, t2 = hk.d == 2 ? 1 : 2;
             hk.n1 = g_.N[t1];
             // the cells HaloKernel writes for this side: interior range of Bounded tangential dimensions, whole extent of periodic ones
-            hk.lo1 = g_.bounded[t1] ? 0 : -g_.H[t1]; hk.m1 = g_.bounded[t1] ? g_.N[t1] : g_.N[t1] + 2 * g_.H[t1] + 1;
-            hk.lo2 = g_.bounded[t2] ? 0 : -g_.H[t2]; hk.m2 = g_.bounded[t2] ? g_.N[t2] : g_.N[t2] + 2 * g_.H[t2] + 1;
+            // (a partitioned periodic dimension: interior only — its halo cells arrive with the exchange that follows)
+            const bool in1 = g_.bounded[t1] || (t1 == 0 && Rx_ > 1) || (t1 == 1 && dist_ && R_ > 1);
+            const bool in2 = g_.bounded[t2] || (t2 == 0 && Rx_ > 1) || (t2 == 1 && dist_ && R_ > 1);
+            hk.lo1 = in1 ? 0 : -g_.H[t1]; hk.m1 = in1 ? g_.N[t1] : g_.N[t1] + 2 * g_.H[t1] + 1;
+            hk.lo2 = in2 ? 0 : -g_.H[t2]; hk.m2 = in2 ? g_.N[t2] : g_.N[t2] + 2 * g_.H[t2] + 1;
             Dim3 hg;
             hg.x = (hk.m1 + HaloArrayKernel<FT>::THREADS - 1) / HaloArrayKernel<FT>::THREADS; hg.y = hk.m2; hg.z = 1;
             go(hk, hg, 0, OC_TIMER_HALO);
@@ -1724,8 +1726,17 @@ template <class FT>
 void Model<FT>::set_bc_array(int field, int side, const void* host, size_t nbytes) {
     if (field < 0 || field >= F_) throw Error(OC_ERR_INVALID, "set_bc_array: not a prognostic field index");
     if (side < 0 || side > 5) throw Error(OC_ERR_INVALID, "set_bc_array: side must be 0 … 5 (west, east, south, north, bottom, top)");
-    if (dist_) throw Error(OC_ERR_UNSUPPORTED, "array-valued boundary conditions on distributed models");
     const oc_bc& ub = cfg_.bcs[field][side];
+    {
+        // distributed models: the array is this rank's share of the side (N₁ × N₂ LOCAL values).  On a rank where the side is connected to
+        // a neighbour instead of a wall the condition does not apply — but the call is collective (the refreshed halo plane travels
+        // to the neighbours), so such a rank still takes part in the exchange
+        const int d = side / 2;
+        if (dist_ && g_.bounded[d] && !(side % 2 == 0 ? g_.wlo[d] : g_.whi[d])) {
+            if (ub.kind == OC_BC_VALUE || ub.kind == OC_BC_GRADIENT) { join_tracers(); std::vector<FieldRec*> one{&state_[field]}; halo(one, false); }
+            return;
+        }
+    }
     const int kind = state_[field].bc[side].kind;
     if (!(kind == ub.kind && (kind == OC_BC_FLUX || kind == OC_BC_VALUE || kind == OC_BC_GRADIENT)))
         throw Error(OC_ERR_INVALID, "set_bc_array: this side of the field must have been created with a Flux, Value or Gradient boundary condition");

@@ -37,6 +37,34 @@ def gloo_exchange(msgs):
     return 0
 
 
+def halo_fill(kw, rank, arch, lib, FT):
+    """test/test_distributed_models.jl:334-407: every field filled with the local rank; after fill_halo_regions! the halos of the
+    partitioned directions hold the neighbour's rank (the process grid wraps: triply periodic), the others the local rank, and — on a
+    (2, 2) process grid — the corners hold the diagonal neighbour's.  Returns the number of mismatching halo cells."""
+    import oceananigans_b200 as ob
+    H = int(kw["halo_fill"])
+    part = arch.partition
+    grid = ob.RectilinearGrid(arch, FT, size=tuple(kw["N"]), extent=(1, 2, 3), halo=(H, H, H), topology=(ob.Periodic,) * 3)
+    model = ob.NonhydrostaticModel(grid=grid, advection=ob.Centered() if H < 3 else ob.WENO(), tracers=("c",), closure=None, library=lib)
+    rank_of = lambda i, j: (i % part.x) * part.y + (j % part.y)            # index2rank, distributed_architectures.jl:354
+    i, j = arch.rx, arch.ry
+    bad = 0
+    for f in list(model.fields.values()) + [model.pressures.pNHS]:
+        f.set(float(rank))
+        ob.fill_halo_regions_(f)
+        p = f.parent()
+        inner = (slice(H, -H),) * 3
+        want = np.full(p.shape, float(rank))
+        lo, hi = slice(0, H), slice(-H, None)
+        mid = slice(H, -H)
+        for sx, di in ((lo, -1), (mid, 0), (hi, +1)):
+            for sy, dj in ((lo, -1), (mid, 0), (hi, +1)):
+                want[sx, sy, :] = rank_of(i + di, j + dj)
+        assert np.all(p[inner] == rank)
+        bad += int(np.count_nonzero(p != want))
+    return float(bad)
+
+
 def run_rank(kw, rank, R, arch, lib, nccl=False):
     """Build this rank's model, run the case, return the worst relative error of its slab against the single-domain oracle."""
     import oceananigans_b200 as ob
@@ -51,10 +79,12 @@ def run_rank(kw, rank, R, arch, lib, nccl=False):
         f = tuple(f)
     kw["f"] = f
     case = dict(N=N, topo=topo, scheme=scheme, FT=FT, f=kw.get("f"), closure=kw.get("closure", "scalar"), bcs=kw.get("bcs", False),
-                ts=kw.get("ts", "RungeKutta3"))
+                ts=kw.get("ts", "RungeKutta3"), buoy=kw.get("buoy", "seawater"), tilt=tuple(kw["tilt"]) if kw.get("tilt") else None)
+    if kw.get("halo_fill"):
+        return halo_fill(kw, rank, arch, lib, FT)
     model = ph.build_product(library=lib, arch=arch, **case)
     om = ph.build_oracle(**case)
-    ic = ph.initial_conditions(om)
+    ic = ph.initial_conditions(om, tracer_noise=kw.get("tracer_noise", 0.01))
     part = arch.partition
     nxl, nyl = N[0] // part.x, N[1] // part.y
     cols = slice(arch.rx * nxl, (arch.rx + 1) * nxl)

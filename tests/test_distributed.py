@@ -75,6 +75,25 @@ CPU_MODEL_CASES = [
     (6, dict(N=(18, 12, 6), topo="PBB", scheme="centered", closure="amd", f=("cartesian", 0.3, -0.5, 0.7), bcs="walls", steps=2, ts="QuasiAdamsBashforth2", px=3)),
     (6, dict(N=(12, 18, 9), topo="BBB", scheme="upwind3", closure="smag", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0), bcs="walls", steps=1, px=2)),
     (4, dict(N=(16, 12, 8), topo="BPP", scheme="weno", steps=2, px=2, f32=True)),
+    # tilted gravity (BuoyancyForce(…; gravity_unit_vector)) on slabs and pencils
+    (2, dict(N=(16, 12, 8), topo="PPB", scheme="centered", buoy="tracer", f=1e-2, bcs=True, tilt=(0.6, 0.0, -0.8), tracer_noise=1.0, steps=2)),
+    (4, dict(N=(16, 12, 8), topo="PPB", scheme="weno", tilt=(0.0, -0.8660254037844386, -0.5), steps=2, px=2)),
+    (2, dict(N=(16, 12, 8), topo="BBB", scheme="weno", buoy="tracer", closure="amd", tilt=(0.6, 0.0, -0.8), tracer_noise=1.0, bcs="walls", steps=2)),
+    # array-valued Flux / Value / Gradient boundary conditions: every rank loads its share of each wall (a collective call)
+    (2, dict(N=(16, 12, 8), topo="PPB", scheme="weno", bcs="array", steps=2)),
+    (2, dict(N=(12, 10, 8), topo="BBB", scheme="centered", closure="amd", bcs="array", ts="QuasiAdamsBashforth2", steps=2)),
+    (4, dict(N=(16, 12, 8), topo="PBB", scheme="upwind3", bcs="array", steps=2, px=2)),
+    (4, dict(N=(16, 16, 8), topo="BPB", scheme="weno", bcs="array", steps=2)),
+    # array-valued ν / κ
+    (2, dict(N=(16, 12, 8), topo="PPB", scheme="centered", closure="arrays+const", bcs=True, ts="QuasiAdamsBashforth2", steps=2)),
+    (4, dict(N=(16, 12, 8), topo="PBB", scheme="weno", closure="arrays", steps=2, px=2)),
+    # the rest of the advection family next to one-sided walls (an outer slab of a Bounded dimension lowers the order on ONE side only)
+    (2, dict(N=(16, 12, 10), topo="PPB", scheme="weno7", closure="amd", f=1e-2, bcs=True, steps=1)),
+    (4, dict(N=(16, 20, 10), topo="BBB", scheme="weno9", steps=1, px=2)),
+    (3, dict(N=(16, 24, 9), topo="PBB", scheme="weno7", closure="amd", bcs="walls", steps=1)),
+    (2, dict(N=(16, 12, 8), topo="PBB", scheme="upwind5", steps=2)),
+    (2, dict(N=(16, 12, 8), topo="BBP", scheme="centered4", steps=2, px=2)),
+    (2, dict(N=(16, 12, 8), topo="PBB", scheme="weno3", steps=2)),
 ]
 
 POISSON_CASES = [(R, dict(N=N, topo=topo, poisson=True)) for R, N in ((2, (16, 12, 8)), (4, (10, 16, 12)), (3, (9, 15, 6)))
@@ -90,6 +109,10 @@ REFERENCE_POISSON_MATRIX = [(4, dict(N=N, topo=topo, poisson=True, px=px))
                             for px, N in ((4, (44, 44, 8)), (4, (16, 44, 8)), (1, (44, 44, 8)), (1, (44, 16, 8)), (1, (16, 44, 8)),
                                           (2, (22, 44, 8)), (2, (44, 22, 8)))]
 
+# test/test_distributed_models.jl:334-407 (H in 1:3; (4,1,1), (1,4,1), (2,2,1) process grids; here 16 x 16 x 8 so that every local size
+# holds the library's internal halo of 3)
+HALO_FILL_CASES = [(4, dict(N=(16, 16, 8), topo="PPP", halo_fill=H, px=px)) for H in (1, 2, 3) for px in (4, 1, 2)]
+
 _BATCH = {}
 
 
@@ -97,7 +120,7 @@ def cpu_result(R, case):
     """Every CPU case with the same number of ranks shares ONE launch of R gloo processes (starting the processes and importing torch
     costs more than the cases themselves): the first request for a rank count runs them all."""
     if R not in _BATCH:
-        todo = [c for r, c in CPU_MODEL_CASES + POISSON_CASES + PENCIL_POISSON_CASES + REFERENCE_POISSON_MATRIX if r == R]
+        todo = [c for r, c in CPU_MODEL_CASES + POISSON_CASES + PENCIL_POISSON_CASES + REFERENCE_POISSON_MATRIX + HALO_FILL_CASES if r == R]
         res = run_ranks(R, todo, timeout=1800)
         _BATCH[R] = {json.dumps(c, sort_keys=True): x for c, x in zip(todo, res)}
     return _BATCH[R][json.dumps(case, sort_keys=True)]
@@ -130,6 +153,13 @@ def test_distributed_poisson_solver_on_the_reference_test_matrix(R, case):
     """sizes, process grids and topologies of the reference's 3-D distributed solver tests (test/test_distributed_poisson_solvers.jl:128-148)"""
     res = cpu_result(R, case)
     assert res["ranks"] == R and res["worst"] <= 1e-13, res
+
+
+@pytest.mark.parametrize("R,case", HALO_FILL_CASES, ids=[f"H{c['halo_fill']}-px{c['px']}" for r, c in HALO_FILL_CASES])
+def test_halo_communication_fills_halos_with_the_neighbours_rank(R, case):
+    """every field = local rank; the halos (corners included) must then hold the neighbouring ranks (test_distributed_models.jl:334-407)"""
+    res = cpu_result(R, case)
+    assert res["ranks"] == R and res["worst"] == 0, res
 
 
 def test_distributed_rejects_unsupported_configurations():
