@@ -448,6 +448,12 @@ void Model<FT>::build_z_tables(const double* faces) {
 template <class FT>
 Model<FT>::~Model() {
     graphs_clear();
+#ifndef OC_HOSTSIM
+    for (Stream st : {stream_, stream2_, stream3_}) if (st) cudaStreamSynchronize(st);
+#endif
+    // first the imports (peer buffers mapped through CUDA IPC) and the communicator, then the buffers this rank exported: no rank ever
+    // waits, inside a free, for a peer that is itself waiting
+    transport_.reset();
     auto fr = [](FieldRec& f) { dev_free(f.base); };
     for (auto& f : state_) fr(f);
     for (auto& f : next_) fr(f);
