@@ -845,7 +845,9 @@ void Model<FT>::halo(const std::vector<FieldRec*>& fields, bool fill_open, bool 
         return;
     }
 #else
-    (void)defer_exchange;
+    // host simulation: the exchange itself is synchronous, but the NEXT tendencies() still takes the split path (interior tile rows,
+    // then the two boundary strips) — so that the partitioning of the launches is exercised by the CPU tests
+    if (defer_exchange) { exchange_y(fields); xchg_pending_ = true; return; }
 #endif
     exchange_y(fields);
 }
@@ -2334,7 +2336,7 @@ void Model<FT>::stage(int mode, double dt, int stage_no, double stage_dt, double
     for (auto& f : state_) all.push_back(&f);
     // stages 1 and 2 of an RK3 step are followed by another stage of the same call: their y-halo exchange is overlapped with that stage's
     // interior tendency kernels (tendencies()); the last stage's exchange completes before time_step! returns.  OC_XCHG_OVERLAP=0: off.
-    static const char* xo_env = getenv("OC_XCHG_OVERLAP");
+    const char* xo_env = getenv("OC_XCHG_OVERLAP");
     const bool defer = dist_ && Rx_ == 1 && R_ > 1 && march_ok_ && !has_eddy_ && mode != STEP_AB2 && stage_no < 3 && (xo_env ? atoi(xo_env) != 0 : true);
     halo(all, false, defer);
 }

@@ -75,6 +75,10 @@ CPU_MODEL_CASES = [
     (6, dict(N=(18, 12, 6), topo="PBB", scheme="centered", closure="amd", f=("cartesian", 0.3, -0.5, 0.7), bcs="walls", steps=2, ts="QuasiAdamsBashforth2", px=3)),
     (6, dict(N=(12, 18, 9), topo="BBB", scheme="upwind3", closure="smag", f=("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0), bcs="walls", steps=1, px=2)),
     (4, dict(N=(16, 12, 8), topo="BPP", scheme="weno", steps=2, px=2, f32=True)),
+    # slabs tall enough for the interior / boundary-strip split of the tendency launches (three or more tile rows of 8 or 16): on the host
+    # simulation the deferred exchange is synchronous but the launches are partitioned exactly as on the GPU
+    (2, dict(N=(16, 64, 8), topo="PBB", scheme="weno", bcs="walls", steps=2)),
+    (2, dict(N=(16, 96, 8), topo="PPP", scheme="weno", steps=2)),
     # tilted gravity (BuoyancyForce(…; gravity_unit_vector)) on slabs and pencils
     (2, dict(N=(16, 12, 8), topo="PPB", scheme="centered", buoy="tracer", f=1e-2, bcs=True, tilt=(0.6, 0.0, -0.8), tracer_noise=1.0, steps=2)),
     (4, dict(N=(16, 12, 8), topo="PPB", scheme="weno", tilt=(0.0, -0.8660254037844386, -0.5), steps=2, px=2)),

@@ -103,3 +103,37 @@ def test_thread_ranks_with_all_to_all_agree_with_peer_memory(capfd, monkeypatch)
     assert run_threads(4, case, p2p=True) <= 1e-11
     err = capfd.readouterr().err
     assert err.count("transposes over peer memory") == 4 and "all-to-all" not in err
+
+
+def test_tall_slabs_split_their_tendency_launches(monkeypatch):
+    """interleave_communication_and_computation.jl:29-67: after a deferred end-of-stage exchange the next stage launches every field's
+    interior tile rows first and the two boundary strips afterwards — more launches, the same numbers (parity: tests/test_distributed.py)"""
+    import __graft_entry__ as ge
+    import oceananigans_b200 as ob
+    from oceananigans_b200 import _lib
+    import parity_harness as ph
+    ge.build()
+    monkeypatch.setenv("OC_HOSTSIM_THREADS", "1")
+    lib = _lib.Library(ge.HOSTSIM)
+
+    def launches(split):
+        monkeypatch.setenv("OC_XCHG_OVERLAP", "1" if split else "0")
+        box, R, out = Mailbox(), 2, [None, None]
+
+        def body(rank):
+            arch = ob.Distributed(ob.B200(0), partition=ob.Partition(1, R), rank=rank, nranks=R, exchange=box.exchange_for(rank))
+            m = ph.build_product(library=lib, arch=arch, N=(16, 64, 8), topo="PBB", scheme="weno", bcs="walls")
+            n0 = m.launch_count()
+            ob.time_step_(m, 1e-3)
+            out[rank] = (m.launch_count() - n0, m.fields["T"].interior().copy())
+        ts = [threading.Thread(target=body, args=(r,)) for r in range(R)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=600)
+        return out
+
+    a, b = launches(True), launches(False)
+    assert a[0][0] > b[0][0] and a[1][0] > b[1][0], (a[0][0], b[0][0])
+    for r in range(2):
+        assert (a[r][1] == b[r][1]).all()           # bit for bit: the same kernels on the same cells, in two or three launches
