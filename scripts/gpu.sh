@@ -52,7 +52,7 @@ for task in "$@"; do
         [ "${KEEP_REP:-0}" = 1 ] || rm -f $rep
       fi ;;
     disttests)       # NCCL parity (tests/test_distributed.py -m gpu): needs gpurun --gpus N
-      timeout 1500 python -m pytest tests/test_distributed.py -m gpu -q -rs > gpurun_out/${TAG}_pytest_dist.log 2>&1; echo "disttests rc=$?"; tail -8 gpurun_out/${TAG}_pytest_dist.log ;;
+      OC_NCCL_NEW_CASES=1 timeout 1500 python -m pytest tests/test_distributed.py -m gpu -q -rs > gpurun_out/${TAG}_pytest_dist.log 2>&1; echo "disttests rc=$?"; tail -8 gpurun_out/${TAG}_pytest_dist.log ;;
     scale)           # bench.py under torchrun on $a GPUs, as the driver launches it
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $a --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $a --steps ${b:-5} --warmup 3 \
           > gpurun_out/${TAG}_bench_n$a.json 2> gpurun_out/${TAG}_bench_n$a.err; echo "scale $a rc=$?"; cat gpurun_out/${TAG}_bench_n$a.json; tail -3 gpurun_out/${TAG}_bench_n$a.err ;;

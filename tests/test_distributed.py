@@ -199,6 +199,12 @@ NCCL_CASES = [
     (8, dict(N=(64, 48, 32), topo="PPP", scheme="weno", steps=2)),
     (8, dict(N=(48, 32, 16), topo="PPB", scheme="weno", closure="lilly", f=("beta", 0.3, 2.0), bcs=True, steps=2)),
     (8, dict(N=(40, 24, 16), topo="PPP", scheme="weno", steps=2, f32=True)),
+]
+
+# Added after the round's last multi-GPU run: verified on the host simulation (gloo and thread ranks) but NOT yet on GPUs — the single 2-GPU
+# call made for them ran into the end of the GPU budget without a result (profiles/README.md).  They run when OC_NCCL_NEW_CASES=1
+# (scripts/gpu.sh disttests sets it), so that an unvalidated multi-GPU case cannot stop a `pytest -m gpu -x` run of the validated suite.
+NCCL_NEW_CASES = [
     # Bounded x and y on slabs (walls on the outer ranks; DCTs in x on the slab and in y in the transposed layout)
     (2, dict(N=(48, 64, 16), topo="PBB", scheme="weno", closure="amd", f=1e-2, bcs="walls", steps=2)),
     (2, dict(N=(40, 24, 16), topo="BPB", scheme="weno", bcs="walls", steps=2)),
@@ -218,11 +224,23 @@ NCCL_CASES = [
     (8, dict(N=(32, 48, 24), topo="PBP", poisson=True, px=4)),
 ]
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("R,case", NCCL_CASES)
-def test_nccl_slab_decomposition_matches_oracle(R, case):
-    """The CUDA library on R GPUs of one box (NCCL halo exchange + transposed distributed FFT) against the oracle."""
+def _nccl_case(R, case):
     if _gpu_count() < R:
         pytest.skip(f"needs {R} GPUs")
     res = run_ranks(R, dict(case), timeout=300, backend="nccl")      # one launch per case: one model and one communicator per process
     assert res["ranks"] == R and res["worst"] <= (1e-4 if case.get("f32") else 1e-11), res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,case", NCCL_CASES)
+def test_nccl_slab_decomposition_matches_oracle(R, case):
+    """The CUDA library on R GPUs of one box (NCCL halo exchange + transposed distributed FFT) against the oracle."""
+    _nccl_case(R, case)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("OC_NCCL_NEW_CASES") != "1", reason="not yet validated on GPUs: set OC_NCCL_NEW_CASES=1 (scripts/gpu.sh disttests)")
+@pytest.mark.parametrize("R,case", NCCL_NEW_CASES)
+def test_nccl_bounded_and_pencil_decompositions_match_oracle(R, case):
+    """Distributed Bounded x / y and pencil partitions on R GPUs against the oracle."""
+    _nccl_case(R, case)
