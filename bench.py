@@ -161,6 +161,9 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- model construction
+PX = 1      # --px: ranks along x (Partition(PX, world / PX)); 1 = slabs in y, what the driver's scaling run uses
+
+
 def global_size(w, world):
     """Weak scaling: 2^27 cells per GPU for the 512^3 workloads; 8 GPUs = BASELINE's 1024^3 (slab-decomposed in y)."""
     if world == 1:
@@ -183,7 +186,7 @@ def build_model(w, device, rank=0, world=1):
         extent = (2 * np.pi, 2 * np.pi)
     else:
         extent = tuple(1.0 for _ in nonflat)
-    arch = ob.B200(device) if world == 1 else ob.Distributed(ob.B200(device), partition=ob.Partition(1, world), rank=rank, nranks=world)
+    arch = ob.B200(device) if world == 1 else ob.Distributed(ob.B200(device), partition=ob.Partition(PX, world // PX), rank=rank, nranks=world)
     if world > 1:
         extent = tuple(gsize[d] / 512.0 for d in nonflat)          # same Δ as the single-GPU workload
     if w.get("stretched"):
@@ -256,7 +259,7 @@ def parity_check(w, local, rank, world, steps=2, library=None):
     FT = np.float64 if w["FT"] == "f64" else np.float32
     N = (64, 16 * world, 64)
     extent = tuple(n / 64.0 for n in N)
-    arch = ob.B200(local) if world == 1 else ob.Distributed(ob.B200(local), partition=ob.Partition(1, world), rank=rank, nranks=world)
+    arch = ob.B200(local) if world == 1 else ob.Distributed(ob.B200(local), partition=ob.Partition(PX, world // PX), rank=rank, nranks=world)
     grid = ob.RectilinearGrid(arch, FT, size=N, extent=extent, topology=(ob.Periodic, ob.Periodic, ob.Periodic))
     kw = dict(grid=grid, advection=ob.WENO() if w["adv"] == "weno" else ob.Centered(), tracers=w["tracers"])
     if w["buoy"] == "seawater":
@@ -272,9 +275,12 @@ def parity_check(w, local, rank, world, steps=2, library=None):
     for n in w["tracers"]:
         ic[n] = {"T": 20.0, "S": 35.0}.get(n, 0.0) + 0.01 * rng.standard_normal(N)
     ic = {n: a.astype(FT).astype(np.float64) for n, a in ic.items()}
-    nyl = N[1] // world
-    sl = slice(rank * nyl, (rank + 1) * nyl)
-    ob.set_(model, **{n: a[:, sl, :] for n, a in ic.items()})
+    if world > 1:
+        (i0, ni), (j0, nj) = arch.local_range(0, N[0]), arch.local_range(1, N[1])
+    else:
+        (i0, ni), (j0, nj) = (0, N[0]), (0, N[1])
+    sl = (slice(i0, i0 + ni), slice(j0, j0 + nj), slice(None))
+    ob.set_(model, **{n: a[sl] for n, a in ic.items()})
     twins = {"worst": CTwin(N, extent, weno=w["adv"] == "weno", tracers=bool(w["tracers"]), nu=nu, kappa=nu)}
     if w["adv"] == "weno" and w["tracers"]:
         twins["worst_difference_form"] = CTwin(N, extent, weno=True, tracers=True, nu=nu, kappa=nu, beta_difference_form=True)
@@ -291,7 +297,7 @@ def parity_check(w, local, rank, world, steps=2, library=None):
         for n in tuple(ic) + ("p",):
             ref = ct.get(n)
             got = (model.pressures.pNHS if n == "p" else model.fields[n]).interior().astype(np.float64)
-            worst = max(worst, float(np.abs(got - ref[:, sl, :]).max() / np.abs(ref).max()))
+            worst = max(worst, float(np.abs(got - ref[sl]).max() / np.abs(ref).max()))
         out[key] = worst
     del model
     if world > 1:
@@ -533,7 +539,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": w["FT"], "data": "synthetic (seeded rng 1234, SURVEY.md 8d)",
-        "config": {"workload": w["label"] if world == 1 else w["label"].replace("512^3", "x".join(map(str, gsz)) + " (slab-y over %d GPUs)" % world),
+        "config": {"workload": w["label"] if world == 1 else w["label"].replace("512^3", "x".join(map(str, gsz)) + (" (slab-y over %d GPUs)" % world if PX == 1 else " (%d x %d pencils)" % (PX, world // PX))),
                    "grid": list(gsz), "topology": w["topo"], "timestepper": "RungeKutta3", "dt": dt,
                    "cells_per_gpu": cells, "l2_policy": "working set (>25 GB at 512^3) far exceeds the 126 MB L2; no flush needed"
                    if cells >= 256 ** 3 else "working set may fit L2 (launch-latency configuration)"},
@@ -682,6 +688,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--px", type=int, default=1, help="ranks along x: Partition(px, gpus / px); default 1 = slabs in y")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
@@ -693,6 +700,10 @@ def main():
     ap.add_argument("--no-other-workloads", action="store_true")
     ap.add_argument("--cpu-size", type=int, default=48, help="edge of the bounded CPU sample")
     args = ap.parse_args()
+    global PX
+    PX = max(1, args.px)
+    if args.gpus % PX != 0:
+        raise SystemExit("--px must divide --gpus")
     # The contract is ONE JSON line on stdout.  Libraries write banners to file descriptor 1 behind Python's back ("NCCL version …" at
     # communicator creation), so everything but the result line is routed to stderr: fd 1 points to fd 2 while the benchmark runs,
     # and print() is given the real stdout for the JSON line only.

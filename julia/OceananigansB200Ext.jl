@@ -242,6 +242,15 @@ function twin(model)
                 DeviceModel(cfg)
             end
         end
+        arch = architecture(model.grid)
+        if arch isa Oceananigans.DistributedComputations.Distributed
+            # one process per GPU: rank 0 makes the 128-byte NCCL id, MPI carries it, every rank joins the communicator inside the library
+            # (replaces the MPI halo / transpose machinery of src/DistributedComputations; must precede anything that fills halos)
+            id = zeros(UInt8, 128)
+            arch.local_rank == 0 && check(ccall((:oc_dist_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+            Oceananigans.DistributedComputations.MPI.Bcast!(id, 0, arch.communicator)
+            check(ccall((:oc_dist_attach_nccl, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), dm.handle, id))
+        end
         # Flux / Value / GradientBoundaryCondition(A::AbstractArray): upload the N₁×N₂ values (getbc(bc, i, j, …) = A[i, j])
         for (f, field) in enumerate((model.velocities..., model.tracers...))
             bcs = field.boundary_conditions
