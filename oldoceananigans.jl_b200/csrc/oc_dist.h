@@ -553,12 +553,13 @@ public:
     size_t work_bytes = 0;
 
     int C = 1;                 // the y stage runs in C sub-chunks of Nzl / C levels (pipelined against the all-to-alls)
+    bool zlines = false;       // the first stage transforms z alone (pencils, Flat x)
     bool c2c = false;          // Bounded x: the (z, x) stage is complex-to-complex over whole rows (the permuted line of the DCT), like
                                // Fft3 on one GPU (plan_transforms.jl:16-136); otherwise real-to-complex, Nx/2+1 coefficients per row
     int Rx = 1;                // pencils: ranks along x — x is not local: z alone is transformed first (z()), x last (x()), all complex
     std::string init(int nx, int nyl, int nz, int r, bool x_bounded, Stream stream, Stream ystream, int rx = 1) {
         Nx = nx; Nyl = nyl; Nz = nz; R = r; Rx = rx;
-        c2c = x_bounded || Rx > 1;
+        c2c = x_bounded || Rx > 1 || Nx == 1;      // (a Flat x: one complex number per row)
         nxc = c2c ? Nx : Nx / 2 + 1; nxr = 2 * nxc; Ny = Nyl * R; Nzl = Nz / R;
         C = Nzl % 4 == 0 ? 4 : (Nzl % 2 == 0 ? 2 : 1);
 #ifndef OC_HOSTSIM
@@ -570,16 +571,22 @@ public:
         }
         int n2[2] = {Nz, Nx};
         int rembed[2] = {Nz, nxr * Nyl}, cembed[2] = {Nz, nxc * Nyl};
-        if (Rx > 1) {
-            // z lines of the local (Nx_l, Ny_l, Nz) buffer: stride = the (x, y) plane, one line per element of the plane
+        zlines = Rx > 1 || Nx == 1;
+        if (zlines) {
+            // z lines of the local (Nx_l, Ny_l, Nz) buffer: stride = the (x, y) plane, one line per element of the plane (pencils; a Flat x
+            // on slabs, where the (z, x) stage has nothing to do along x).  A Flat z (Nz = 1) needs no transform at all.
             int nzv[1] = {Nz}, emb[1] = {Nz};
             const int plane = nxc * Nyl;
-            if (cufftMakePlanMany(fwd_, 1, nzv, emb, plane, 1, emb, plane, 1, dbl ? CUFFT_Z2Z : CUFFT_C2C, plane, &w[0]) != CUFFT_SUCCESS)
+            if (Nz > 1 && cufftMakePlanMany(fwd_, 1, nzv, emb, plane, 1, emb, plane, 1, dbl ? CUFFT_Z2Z : CUFFT_C2C, plane, &w[0]) != CUFFT_SUCCESS)
                 return "cufftMakePlanMany(z lines) failed";
+        }
+        if (Rx > 1) {
             // x lines of T2 = [zl][yl2][x]: contiguous, Nx·Rx long
             int nxv[1] = {Nx * Rx};
             if (cufftMakePlanMany(inv_, 1, nxv, nullptr, 1, Nx * Rx, nullptr, 1, Nx * Rx, dbl ? CUFFT_Z2Z : CUFFT_C2C, (Nz / R) * (Nyl * R / Rx), &w[1]) != CUFFT_SUCCESS)
                 return "cufftMakePlanMany(x lines) failed";
+        } else if (zlines) {
+            // (Flat x on slabs: the z lines above are the whole first stage)
         } else if (c2c) {
             if (cufftMakePlanMany(fwd_, 2, n2, cembed, 1, nxc, cembed, 1, nxc, dbl ? CUFFT_Z2Z : CUFFT_C2C, Nyl, &w[0]) != CUFFT_SUCCESS)
                 return "cufftMakePlanMany(zx complex) failed";
@@ -620,9 +627,10 @@ public:
         else r = cufftExecC2C(h, (cufftComplex*)buf, (cufftComplex*)buf, fwd ? CUFFT_FORWARD : CUFFT_INVERSE);
         return r == CUFFT_SUCCESS ? "" : "cuFFT line transform failed with code " + std::to_string((int)r);
     }
-    std::string z(void* buf, bool fwd) { return lines(fwd_, buf, fwd); }
+    std::string z(void* buf, bool fwd) { return Nz > 1 ? lines(fwd_, buf, fwd) : std::string(); }
     std::string x(void* buf, bool fwd) { return lines(inv_, buf, fwd); }
     std::string zx(void* buf, bool fwd) {
+        if (zlines) return z(buf, fwd);
         cufftResult r;
         if (c2c) {
             if (sizeof(FT) == 8) r = cufftExecZ2Z(fwd_, (cufftDoubleComplex*)buf, (cufftDoubleComplex*)buf, fwd ? CUFFT_FORWARD : CUFFT_INVERSE);

@@ -308,11 +308,14 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         R_ = c.dist_nranks / Rx_;
         if (c.dist_rank < 0 || c.dist_rank >= c.dist_nranks) throw Error(OC_ERR_INVALID, "dist_rank out of range");
         rx_ = c.dist_rank / R_; rank_ = c.dist_rank % R_;
-        if (c.topology[0] == OC_FLAT || c.topology[1] == OC_FLAT || c.topology[2] == OC_FLAT)
-            throw Error(OC_ERR_UNSUPPORTED, "distributed models: Periodic or Bounded x, y and z (Flat dimensions: next)");
+        // two-dimensional models: a Flat dimension cannot be partitioned — x-y models take slabs in x, Partition(R, 1); y-z models slabs
+        // in y, Partition(1, R); a Flat y would leave nothing to transpose x against (the reference's solver has the same constraint,
+        // Ny % Rx = 0, distributed_fft_based_poisson_solver.jl:211-229)
+        if (c.topology[1] == OC_FLAT || (c.topology[0] == OC_FLAT && Rx_ > 1) || (c.topology[2] == OC_FLAT && R_ > 1))
+            throw Error(OC_ERR_UNSUPPORTED, "distributed models with a Flat dimension: (x, y) models as Partition(R, 1), (y, z) models as Partition(1, R)");
         if (g_.N[2] % R_ != 0) throw Error(OC_ERR_INVALID, "distributed FFT: Nz must be divisible by the number of ranks along y (distributed_fft_based_poisson_solver.jl:211-229)");
         if (((long long)g_.N[1] * R_) % Rx_ != 0) throw Error(OC_ERR_INVALID, "distributed FFT: Ny must be divisible by the number of ranks along x (distributed_fft_based_poisson_solver.jl:211-229)");
-        if (g_.N[1] < g_.H[1] || g_.N[0] < g_.H[0]) throw Error(OC_ERR_INVALID, "distributed models: local size smaller than the halo");
+        if ((R_ > 1 && g_.N[1] < g_.H[1]) || (Rx_ > 1 && g_.N[0] < g_.H[0])) throw Error(OC_ERR_INVALID, "distributed models: local size smaller than the halo");
     }
     if (stretched_) build_z_tables(c.z_faces);
     cfg_.z_faces = nullptr;                              // borrowed host pointer: not kept

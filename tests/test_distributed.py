@@ -79,6 +79,11 @@ CPU_MODEL_CASES = [
     # simulation the deferred exchange is synchronous but the launches are partitioned exactly as on the GPU
     (2, dict(N=(16, 64, 8), topo="PBB", scheme="weno", bcs="walls", steps=2)),
     (2, dict(N=(16, 96, 8), topo="PPP", scheme="weno", steps=2)),
+    # two-dimensional models: (x, y) on slabs in x, (y, z) on slabs in y (a Flat dimension cannot be partitioned)
+    (2, dict(N=(16, 12, 1), topo="PPF", scheme="weno", closure="none", buoy="none", steps=2, px=2)),
+    (4, dict(N=(16, 12, 1), topo="BPF", scheme="centered", closure="scalar", buoy="none", steps=2, px=4)),
+    (2, dict(N=(1, 12, 8), topo="FPB", scheme="weno", buoy="tracer", f=0.2, steps=2)),
+    (4, dict(N=(1, 16, 8), topo="FBB", scheme="upwind3", buoy="tracer", steps=2)),
     # tilted gravity (BuoyancyForce(…; gravity_unit_vector)) on slabs and pencils
     (2, dict(N=(16, 12, 8), topo="PPB", scheme="centered", buoy="tracer", f=1e-2, bcs=True, tilt=(0.6, 0.0, -0.8), tracer_noise=1.0, steps=2)),
     (4, dict(N=(16, 12, 8), topo="PPB", scheme="weno", tilt=(0.0, -0.8660254037844386, -0.5), steps=2, px=2)),

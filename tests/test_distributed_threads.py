@@ -86,6 +86,8 @@ def run_threads(R, case, p2p=True):
     (3, dict(N=(9, 15, 6), topo="BPB", poisson=True)),
     # pencils with thread ranks (send / receive transposes: the peer-memory kernel is the slab path's)
     (4, dict(N=(16, 12, 8), topo="PBB", scheme="weno", bcs="walls", steps=1, px=2)),
+    # a (y, z) model on slabs: the first stage of the peer-memory solve transforms z alone
+    (2, dict(N=(1, 12, 8), topo="FPB", scheme="weno", buoy="tracer", f=0.2, steps=2)),
 ])
 def test_peer_memory_transposes_match_single_domain_oracle(R, case):
     worst = run_threads(R, case)
