@@ -221,7 +221,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         // BetaPlane / ConstantCartesianCoriolis run in the general tile kernel: the z-marching kernel of the
         // measured BASELINE configurations keeps exactly the code (and register counts) it was profiled with
         march_ok_ = !(g_.flat[0] || g_.flat[1] || g_.flat[2]) && (c.has_coriolis <= OC_CORIOLIS_FPLANE || c.has_coriolis == OC_CORIOLIS_BETAPLANE) && !c.tilted_gravity && !c.has_advection_dir &&
-                    (c.advection == OC_CENTERED2 || c.advection == OC_WENO5 || (c.advection == OC_UPWIND5 && !any_bounded && !c.has_amd && !c.smagorinsky));
+                    (c.advection == OC_CENTERED2 || c.advection == OC_WENO5 || (c.advection == OC_UPWIND5 && !any_bounded && !c.has_amd && !c.smagorinsky && !c.array_diffusivity));
     }
     {
         static const char* uvw_env = getenv("OC_UVW");

@@ -1,0 +1,182 @@
+"""Randomised differential test of the kernels against the oracle (CPU only: the host simulation of the kernel sources).
+
+Samples model configurations — topology, sizes, advection scheme, closure, buoyancy, Coriolis form, boundary conditions, time stepper,
+float type, stretched z, tilted gravity, and a domain decomposition (none, slabs in y, slabs in x, pencils; the ranks are threads of this
+process, tests/test_distributed_threads.py) — builds the product on the host simulation and the oracle with the same arguments, steps
+both twice and compares every prognostic field and the pressure.  Configurations either side refuses (the library's loud rejections, the
+reference's own argument errors restated by the oracle) are counted and skipped; a disagreement above the tolerance is a failure.
+
+    python scripts/fuzz_parity.py --seed 1 --cases 200 [--dist-only | --single-only]
+
+The rare-combination bugs this found are pinned as explicit cases in tests/parity_harness.py / tests/test_distributed.py."""
+import argparse
+import os
+import sys
+import threading
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SCHEMES = ["centered", "weno", "centered4", "upwind1", "upwind3", "upwind5", "weno3", "weno7", "weno9", "none"]
+CLOSURES = ["none", "scalar", "amd", "amdcb", "both", "smag", "lilly", "arrays", "arrays+const"]
+
+
+def sample(rng, dist):
+    topo = "".join(rng.choice(["P", "B"], p=[0.5, 0.5]) for _ in range(3))
+    if rng.random() < 0.12:                       # a two-dimensional model
+        d = int(rng.integers(0, 3))
+        topo = topo[:d] + "F" + topo[d + 1:]
+    scheme = str(rng.choice(SCHEMES))
+    need = {"weno7": 4, "weno9": 5}.get(scheme, 3)
+    part = (1, 1)
+    if dist:
+        part = [(1, 2), (2, 1), (1, 3), (2, 2), (1, 4), (4, 1), (3, 1), (2, 3), (3, 2)][int(rng.integers(0, 9))]
+    N = []
+    for d in range(3):
+        if topo[d] == "F":
+            N.append(1)
+            continue
+        r = part[d] if d < 2 else 1
+        local = int(rng.integers(max(need, 3), 9))
+        N.append(local * r)
+    if dist:
+        # the distributed solver's constraints (distributed_fft_based_poisson_solver.jl:211-229): Nz % Ry = 0, Ny % Rx = 0
+        if topo[2] != "F":
+            N[2] = max(need, 3, part[1]) if N[2] % part[1] else N[2]
+            N[2] = ((N[2] + part[1] - 1) // part[1]) * part[1]
+        if topo[1] != "F":
+            m = part[0] * part[1]
+            N[1] = ((N[1] + m - 1) // m) * m
+    kw = dict(N=tuple(N), topo=topo, scheme=scheme)
+    kw["closure"] = str(rng.choice(CLOSURES))
+    kw["buoy"] = str(rng.choice(["seawater", "tracer", "none", "passive"], p=[0.4, 0.3, 0.2, 0.1]))
+    u = rng.random()
+    if u < 0.2:
+        kw["f"] = float(rng.choice([1e-2, 0.3]))
+    elif u < 0.35:
+        kw["f"] = ("beta", 0.3, 2.0)
+    elif u < 0.5:
+        kw["f"] = ("cartesian", 0.3, -0.5, 0.7)
+    elif u < 0.6:
+        kw["f"] = ("ntbeta", 0.7, -0.5, 2.0, 1.5, 3.0)
+    u = rng.random()
+    has_tracer = kw["buoy"] != "none"
+    if u < 0.25 and topo[2] == "B" and has_tracer:
+        kw["bcs"] = True
+    elif u < 0.5 and has_tracer:
+        kw["bcs"] = "walls"
+    elif u < 0.65 and has_tracer:
+        kw["bcs"] = "array"
+    if rng.random() < 0.3:
+        kw["ts"] = "QuasiAdamsBashforth2"
+    if rng.random() < 0.15:
+        kw["FT"] = np.float32
+    if not dist and topo[2] == "B" and rng.random() < 0.2:
+        kw["stretch"] = str(rng.choice(["smooth", "facr"]))
+    if kw["buoy"] in ("seawater", "tracer") and rng.random() < 0.15:
+        kw["tilt"] = (0.6, 0.0, -0.8) if rng.random() < 0.5 else (0.0, -0.8660254037844386, -0.5)
+        kw["tracer_noise"] = 1.0
+    return kw, part
+
+
+class Skip(Exception):
+    pass
+
+
+def single(kw, lib):
+    import parity_harness as ph
+    kw = dict(kw)
+    try:
+        out, m, om = ph.run_case(steps=(1, 2), library=lib, **kw)
+    except Exception as e:          # noqa: BLE001
+        msg = repr(e)
+        if "OceananigansB200Error" in msg or isinstance(e, (NotImplementedError, ValueError, AssertionError, KeyError, IndexError)):
+            raise Skip(msg[:200])
+        raise
+    worst = 0.0
+    for s, errs in out.items():
+        for name, e in errs.items():
+            if name == "p" and kw.get("scheme") == "none":
+                continue
+            worst = max(worst, e)
+    return worst
+
+
+def distributed(kw, part, lib):
+    import oceananigans_b200 as ob
+    import dist_worker
+    from test_distributed_threads import Mailbox
+    R = part[0] * part[1]
+    case = dict(kw, px=part[0], steps=2)
+    if "FT" in case:
+        case["f32"] = case.pop("FT") is np.float32
+    box = Mailbox()
+    out, errs = [None] * R, []
+
+    def body(rank):
+        try:
+            arch = ob.Distributed(ob.B200(0), partition=ob.Partition(part[0], part[1]), rank=rank, nranks=R, exchange=box.exchange_for(rank))
+            out[rank] = dist_worker.run_rank(case, rank, R, arch, lib)
+        except BaseException as e:       # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(R)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    if errs:
+        msg = repr(errs[0])
+        if len(errs) == R and ("OceananigansB200Error" in msg or isinstance(errs[0], (NotImplementedError, ValueError, AssertionError, KeyError, IndexError))):
+            raise Skip(msg[:200])         # every rank refused the configuration
+        raise RuntimeError(f"{len(errs)} of {R} ranks failed: {msg}")
+    if any(o is None for o in out):
+        raise RuntimeError("a rank did not finish")
+    return max(out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cases", type=int, default=100)
+    ap.add_argument("--dist-only", action="store_true")
+    ap.add_argument("--single-only", action="store_true")
+    args = ap.parse_args()
+    os.environ["OC_HOSTSIM_THREADS"] = "1"
+    import __graft_entry__ as ge
+    from oceananigans_b200 import _lib
+    lib = _lib.Library(ge.HOSTSIM)
+    rng = np.random.default_rng(args.seed)
+    ran = skipped = 0
+    failures = []
+    for n in range(args.cases):
+        dist = (rng.random() < 0.5 or args.dist_only) and not args.single_only
+        kw, part = sample(rng, dist)
+        tol = 1e-4 if kw.get("FT") is np.float32 else 1e-10
+        try:
+            worst = distributed(kw, part, lib) if dist else single(kw, lib)
+        except Skip as e:
+            skipped += 1
+            print(f"[{n}] skip  {part} {kw}: {e}", flush=True)
+            continue
+        except Exception:      # noqa: BLE001
+            failures.append((n, part, kw, traceback.format_exc()[-600:]))
+            print(f"[{n}] ERROR {part} {kw}\n{failures[-1][3]}", flush=True)
+            continue
+        ran += 1
+        ok = worst <= tol
+        print(f"[{n}] {'ok   ' if ok else 'FAIL '} {worst:.2e} {part} {kw}", flush=True)
+        if not ok:
+            failures.append((n, part, kw, f"worst {worst:.3e} > {tol:g}"))
+    print(f"\n{ran} compared, {skipped} refused, {len(failures)} failures")
+    for f in failures:
+        print("FAILURE", f)
+    return 1 if failures else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -317,6 +317,8 @@ ARRAY_DIFFUSIVITY_CASES = [
     ("PPB centered array + constant diffusivity bcs AB2", dict(N=(16, 12, 8), topo="PPB", scheme="centered", closure="arrays+const", bcs=True, ts="QuasiAdamsBashforth2")),
     ("BBB upwind3 array diffusivity fplane F32", dict(N=(12, 10, 8), topo="BBB", scheme="upwind3", closure="arrays", f=1e-2, FT=np.float32)),
     ("stretched PPB weno array diffusivity", dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="arrays", stretch="smooth")),
+    # found by scripts/fuzz_parity.py: the triply periodic UpwindBiased(5) variant of the z-marching kernel is a constant-viscosity instance
+    ("PPP upwind5 array + constant diffusivity (general kernel)", dict(N=(8, 6, 3), topo="PPP", scheme="upwind5", closure="arrays+const", buoy="none")),
 ]
 
 # WENO(order = 7) and WENO(order = 9) (weno_interpolants.jl:81-90,175-185,303-307): general tile kernel, halos of 4 / 5, the order-reduction
