@@ -42,6 +42,11 @@ def sample(rng, dist):
             continue
         r = part[d] if d < 2 else 1
         local = int(rng.integers(max(need, 3), 9))
+        u = rng.random()
+        if u < 0.12:
+            local = int(rng.integers(33, 45))          # crosses the 32-wide tiles / 8- and 16-row tiles / 16-level z chunks of the kernels
+        elif u < 0.2 and not dist:
+            local = int(rng.integers(1, 3))            # smaller than the scheme's buffer: adapt_advection_order lowers it there
         N.append(local * r)
     if dist:
         # the distributed solver's constraints (distributed_fft_based_poisson_solver.jl:211-229): Nz % Ry = 0, Ny % Rx = 0
