@@ -557,8 +557,10 @@ public:
     bool c2c = false;          // Bounded x: the (z, x) stage is complex-to-complex over whole rows (the permuted line of the DCT), like
                                // Fft3 on one GPU (plan_transforms.jl:16-136); otherwise real-to-complex, Nx/2+1 coefficients per row
     int Rx = 1;                // pencils: ranks along x — x is not local: z alone is transformed first (z()), x last (x()), all complex
-    std::string init(int nx, int nyl, int nz, int r, bool x_bounded, Stream stream, Stream ystream, int rx = 1) {
-        Nx = nx; Nyl = nyl; Nz = nz; R = r; Rx = rx;
+    bool xonly = false;        // vertically stretched grid on slabs: z is not transformed — the first stage is the x rows alone
+    bool noz = false;          // vertically stretched grid (slabs or pencils): z() does nothing
+    std::string init(int nx, int nyl, int nz, int r, bool x_bounded, Stream stream, Stream ystream, int rx = 1, bool zbatch = false) {
+        Nx = nx; Nyl = nyl; Nz = nz; R = r; Rx = rx; xonly = zbatch && Rx == 1; noz = zbatch;
         c2c = x_bounded || Rx > 1 || Nx == 1;      // (a Flat x: one complex number per row)
         nxc = c2c ? Nx : Nx / 2 + 1; nxr = 2 * nxc; Ny = Nyl * R; Nzl = Nz / R;
         C = Nzl % 4 == 0 ? 4 : (Nzl % 2 == 0 ? 2 : 1);
@@ -571,16 +573,32 @@ public:
         }
         int n2[2] = {Nz, Nx};
         int rembed[2] = {Nz, nxr * Nyl}, cembed[2] = {Nz, nxc * Nyl};
-        zlines = Rx > 1 || Nx == 1;
-        if (zlines) {
+        zlines = (Rx > 1 || Nx == 1) && !xonly;
+        if (xonly) {
+            // rows of Nx reals -> Nx/2+1 coefficients (or Nx complex numbers, Bounded x), one per (y, z): contiguous
+            int nxv[1] = {Nx};
+            const int rows = Nyl * Nz;
+            if (c2c) {
+                if (cufftMakePlanMany(fwd_, 1, nxv, nullptr, 1, nxc, nullptr, 1, nxc, dbl ? CUFFT_Z2Z : CUFFT_C2C, rows, &w[0]) != CUFFT_SUCCESS)
+                    return "cufftMakePlanMany(x rows, complex) failed";
+            } else {
+                int remb[1] = {nxr}, cemb[1] = {nxc};
+                if (cufftMakePlanMany(fwd_, 1, nxv, remb, 1, nxr, cemb, 1, nxc, dbl ? CUFFT_D2Z : CUFFT_R2C, rows, &w[0]) != CUFFT_SUCCESS)
+                    return "cufftMakePlanMany(x rows forward) failed";
+                if (cufftMakePlanMany(inv_, 1, nxv, cemb, 1, nxc, remb, 1, nxr, dbl ? CUFFT_Z2D : CUFFT_C2R, rows, &w[1]) != CUFFT_SUCCESS)
+                    return "cufftMakePlanMany(x rows inverse) failed";
+            }
+        } else if (zlines) {
             // z lines of the local (Nx_l, Ny_l, Nz) buffer: stride = the (x, y) plane, one line per element of the plane (pencils; a Flat x
             // on slabs, where the (z, x) stage has nothing to do along x).  A Flat z (Nz = 1) needs no transform at all.
             int nzv[1] = {Nz}, emb[1] = {Nz};
             const int plane = nxc * Nyl;
-            if (Nz > 1 && cufftMakePlanMany(fwd_, 1, nzv, emb, plane, 1, emb, plane, 1, dbl ? CUFFT_Z2Z : CUFFT_C2C, plane, &w[0]) != CUFFT_SUCCESS)
+            if (Nz > 1 && !noz && cufftMakePlanMany(fwd_, 1, nzv, emb, plane, 1, emb, plane, 1, dbl ? CUFFT_Z2Z : CUFFT_C2C, plane, &w[0]) != CUFFT_SUCCESS)
                 return "cufftMakePlanMany(z lines) failed";
         }
-        if (Rx > 1) {
+        if (xonly) {
+            // (nothing else: the y plan follows)
+        } else if (Rx > 1) {
             // x lines of T2 = [zl][yl2][x]: contiguous, Nx·Rx long
             int nxv[1] = {Nx * Rx};
             if (cufftMakePlanMany(inv_, 1, nxv, nullptr, 1, Nx * Rx, nullptr, 1, Nx * Rx, dbl ? CUFFT_Z2Z : CUFFT_C2C, (Nz / R) * (Nyl * R / Rx), &w[1]) != CUFFT_SUCCESS)
@@ -627,7 +645,7 @@ public:
         else r = cufftExecC2C(h, (cufftComplex*)buf, (cufftComplex*)buf, fwd ? CUFFT_FORWARD : CUFFT_INVERSE);
         return r == CUFFT_SUCCESS ? "" : "cuFFT line transform failed with code " + std::to_string((int)r);
     }
-    std::string z(void* buf, bool fwd) { return Nz > 1 ? lines(fwd_, buf, fwd) : std::string(); }
+    std::string z(void* buf, bool fwd) { return (Nz > 1 && !noz) ? lines(fwd_, buf, fwd) : std::string(); }
     std::string x(void* buf, bool fwd) { return lines(inv_, buf, fwd); }
     std::string zx(void* buf, bool fwd) {
         if (zlines) return z(buf, fwd);
@@ -676,11 +694,11 @@ public:
             } else {
                 for (int k = 0; k < Nz; ++k) for (int i = 0; i < Nx; ++i) {
                     if (i < nxc) { long long c = i + (long long)nxc * (j + (long long)Nyl * k); at(i, k) = Cd{(double)buf[2 * c], (double)buf[2 * c + 1]}; }
-                    else { long long c = (Nx - i) + (long long)nxc * (j + (long long)Nyl * ((Nz - k) % Nz)); at(i, k) = Cd{(double)buf[2 * c], -(double)buf[2 * c + 1]}; }
+                    else { long long c = (Nx - i) + (long long)nxc * (j + (long long)Nyl * (xonly ? k : (Nz - k) % Nz)); at(i, k) = Cd{(double)buf[2 * c], -(double)buf[2 * c + 1]}; }
                 }
             }
             for (int k = 0; k < Nz; ++k) { std::vector<Cd> l(Nx); for (int i = 0; i < Nx; ++i) l[i] = at(i, k); dft(l, fwd); for (int i = 0; i < Nx; ++i) at(i, k) = l[i]; }
-            for (int i = 0; i < Nx; ++i) { std::vector<Cd> l(Nz); for (int k = 0; k < Nz; ++k) l[k] = at(i, k); dft(l, fwd); for (int k = 0; k < Nz; ++k) at(i, k) = l[k]; }
+            if (!xonly) for (int i = 0; i < Nx; ++i) { std::vector<Cd> l(Nz); for (int k = 0; k < Nz; ++k) l[k] = at(i, k); dft(l, fwd); for (int k = 0; k < Nz; ++k) at(i, k) = l[k]; }
             if (fwd || c2c) {
                 for (int k = 0; k < Nz; ++k) for (int i = 0; i < nxc; ++i) { long long c = i + (long long)nxc * (j + (long long)Nyl * k); buf[2 * c] = (FT)at(i, k).x; buf[2 * c + 1] = (FT)at(i, k).y; }
             } else {
@@ -691,6 +709,7 @@ public:
     }
     // pencils (test-only naive DFTs): z lines of the local buffer, x lines of T2
     std::string z(void* bufv, bool fwd) {
+        if (noz) return "";
         FT* buf = (FT*)bufv;
         const long long plane = (long long)nxc * Nyl;
         for (long long n = 0; n < plane; ++n) {

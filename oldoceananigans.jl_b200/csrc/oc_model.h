@@ -272,6 +272,7 @@ private:
     void exchange_x(const std::vector<FieldRec*>& fields);
     void all_to_all_x(FT* send, FT* recv);
     void run_fft_solve_pencil();
+    void run_fft_solve_dist_tridiagonal();
     std::unique_ptr<Transport> transport_;
     DistFft<FT> dfft_;
     FT* distT_ = nullptr;          // transposed spectral buffer (y fastest)

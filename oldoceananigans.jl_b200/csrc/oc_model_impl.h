@@ -127,7 +127,6 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         if (c.N[2] < 2) throw Error(OC_ERR_UNSUPPORTED, "stretched z with fewer than 2 levels");
         for (int k = 0; k < c.N[2]; ++k)
             if (!((FT)c.z_faces[k + 1] > (FT)c.z_faces[k])) throw Error(OC_ERR_INVALID, "The elements of z must be increasing!");
-        if (c.dist_nranks > 1) throw Error(OC_ERR_UNSUPPORTED, "distributed models on vertically stretched grids (DistributedFourierTridiagonalPoissonSolver: next)");
     }
     // required_halo_size of the scheme (its buffer) — per direction for FluxFormAdvection (adapt_advection_order.jl:18-96)
     auto buffer_of = [](int adv) { return adv == OC_WENO9 ? 5 : adv == OC_WENO7 ? 4 : (adv == OC_WENO5 || adv == OC_UPWIND5) ? 3 : (adv == OC_CENTERED4 || adv == OC_UPWIND3 || adv == OC_WENO3) ? 2 : 1; };
@@ -331,7 +330,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
 #ifndef OC_HOSTSIM
         cuda_check(cudaStreamCreateWithFlags(&stream3_, cudaStreamNonBlocking), "cudaStreamCreate");
 #endif
-        err = dfft_.init(g_.N[0], g_.N[1], g_.N[2], R_, g_.bounded[0] != 0, stream_, stream3_, Rx_);
+        err = dfft_.init(g_.N[0], g_.N[1], g_.N[2], R_, g_.bounded[0] != 0, stream_, stream3_, Rx_, stretched_);
 #ifndef OC_HOSTSIM
         for (int c = 0; c < dfft_.C; ++c) {
             cudaEvent_t a, b;
@@ -342,7 +341,7 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
 #endif
         if (!err.empty()) throw Error(OC_ERR_CUDA, err);
 #ifndef OC_HOSTSIM
-        if (Rx_ > 1) dfft_.set_y_stream(stream_);      // the pencil solve is one stream: no sub-chunk pipelining on stream3_ (yet)
+        if (Rx_ > 1 || stretched_) dfft_.set_y_stream(stream_);      // the pencil and the tridiagonal solves are one stream: no sub-chunk pipelining on stream3_ (yet)
 #endif
         distT_ = (FT*)dev_alloc(fft_.buffer_bytes);
         diststage_ = (FT*)dev_alloc(fft_.buffer_bytes);
@@ -380,7 +379,10 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
         device_bytes += (int64_t)(2 * sizeof(FT) * n);
         TridiagSetupKernel<FT> k;
         k.L = fft_.L;
-        k.lam[0] = lam_[0]; k.lam[1] = lam_[1];
+        // (slabs: the local rows hold the y-wavenumbers rank·Ny_l … of the global eigenvalue array, and only the first rank owns the
+        //  singular (0, 0) column)
+        k.lam[0] = lam_[0] + (Rx_ > 1 ? (size_t)rx_ * g_.N[0] : 0); k.lam[1] = lam_[1] + (dist_ ? (size_t)rank_ * g_.N[1] : 0);
+        k.zero_col = (!dist_ || (rank_ == 0 && rx_ == 0)) ? 1 : 0;
         k.dzc = g_.dzc; k.rdzf = g_.rdzf;
         k.R = tri_R_; k.T = tri_T_;
         k.eps10 = 10.0 * (double)std::numeric_limits<FT>::epsilon();
@@ -936,7 +938,7 @@ void Model<FT>::run_fft_solve_p2p() {
 template <class FT>
 void Model<FT>::local_twiddles(bool inverse) {
     for (int d = 0; d < 3; d += 2) {
-        if (!g_.bounded[d] || (d == 0 && Rx_ > 1)) continue;
+        if (!g_.bounded[d] || (d == 0 && Rx_ > 1) || (d == 2 && stretched_)) continue;      // (a stretched z is not transformed)
         TwiddleKernel<FT> k;
         const long long plane = (long long)dfft_.nxc * g_.N[1];
         k.N = g_.N[d]; k.spec = reinterpret_cast<Cplx<FT>*>(fftbuf_); k.tw = tw_[d]; k.inverse = inverse ? 1 : 0;
@@ -946,6 +948,68 @@ void Model<FT>::local_twiddles(bool inverse) {
         grid.x = (int)((k.count * (k.N / 2 + 1) + 255) / 256);
         go(k, grid, 0, OC_TIMER_POISSON_MID);
     }
+}
+
+// DistributedFourierTridiagonalPoissonSolver for a vertically stretched grid on slabs (distributed_fft_tridiagonal_solver.jl:262-293):
+// transforms along x (local rows) and y (in the transposed layout), the transposed layout brought BACK so that every rank holds whole
+// z-columns of its share of the (kx, ky) plane, the tridiagonal solves there (TridiagSolvePPKernel — the twiddles of Bounded x / y are
+// separate passes here, so the real-coefficient kernel serves every topology), and the same way out.  Twice the transposes of the
+// regular-grid solve, like the reference.  The middle pair of transposes carries no Makhoul permutation: the spectral coefficients keep
+// their natural order, local row yl = wavenumber rank·Ny_l + yl.  (The reference's distributed solver leaves the mean of ϕ wherever the
+// singular column's pivot puts it; this one removes it like the single-GPU solver, fourier_tridiagonal_poisson_solver.jl:222-226 — a
+// constant that no gradient sees.)
+template <class FT>
+void Model<FT>::run_fft_solve_dist_tridiagonal() {
+    NvtxRange nvtx_("distributed Fourier-tridiagonal solve");
+    auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
+    const int nxc = dfft_.nxc, nyl = g_.N[1], Ny = dfft_.Ny, nzl = dfft_.Nzl, C = dfft_.C;
+    Cplx<FT>* T = reinterpret_cast<Cplx<FT>*>(distT_);
+    auto transpose_y = [&](bool to_T, int yperm) {
+        TransposeKernel<FT> t;
+        t.nxc = nxc; t.nyl = nyl; t.nzl = nzl; t.R = R_; t.zl0 = 0; t.yperm = yperm;
+        t.stage = reinterpret_cast<Cplx<FT>*>(diststage_); t.T = T; t.to_T = to_T ? 1 : 0;
+        Dim3 tg;
+        tg.x = (nxc + 31) / 32; tg.y = (Ny + 31) / 32; tg.z = nzl;
+        go(t, tg, TransposeKernel<FT>::SMEM, OC_TIMER_POISSON_MID);
+    };
+    auto y_twiddles = [&](bool inverse) {
+        if (!g_.bounded[1]) return;
+        TwiddleKernel<FT> k;
+        k.N = Ny; k.spec = T; k.tw = tw_[1]; k.inverse = inverse ? 1 : 0;
+        k.sk = 1; k.inner = 1; k.souter = Ny; k.count = (long long)nzl * nxc; k.kfast = 1;
+        Dim3 grid;
+        grid.x = (int)((k.count * (Ny / 2 + 1) + 255) / 256);
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+    };
+    auto y_ffts = [&](bool fwd) {
+        for (int c = 0; c < C; ++c) { begin_timer(OC_TIMER_FFT); std::string e = dfft_.y(distT_, fwd, c); end_timer(); chk(e); }
+    };
+    auto to_T = [&](int yperm) { for (int c = 0; c < C; ++c) all_to_all(fftbuf_, diststage_, c, C); transpose_y(true, yperm); };
+    auto from_T = [&](int yperm) { transpose_y(false, yperm); for (int c = 0; c < C; ++c) all_to_all(diststage_, fftbuf_, c, C); };
+    begin_timer(OC_TIMER_FFT); std::string e = dfft_.zx(fftbuf_, true); end_timer(); chk(e);        // x rows only (DistFft::xonly)
+    local_twiddles(false);
+    to_T(g_.bounded[1]);
+    y_ffts(true);
+    y_twiddles(false);
+    from_T(0);
+    {
+        TridiagSolvePPKernel<FT> k;
+        k.L = fft_.L;
+        k.spec = fftbuf_;
+        k.R = tri_R_; k.T = tri_T_; k.rdzf = g_.rdzf;
+        k.norm = 1.0 / ((double)g_.N[0] * Ny);
+        k.zero_col = rank_ == 0 ? 1 : 0;
+        Dim3 grid;
+        const long long n2 = 2LL * fft_.L.nxc * g_.N[1];
+        grid.x = (int)((n2 + TridiagSolvePPKernel<FT>::THREADS - 1) / TridiagSolvePPKernel<FT>::THREADS);
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+    }
+    to_T(0);
+    y_twiddles(true);
+    y_ffts(false);
+    from_T(g_.bounded[1]);
+    local_twiddles(true);
+    begin_timer(OC_TIMER_FFT); e = dfft_.zx(fftbuf_, false); end_timer(); chk(e);
 }
 
 // pencils: the x-halo exchange with the two neighbours along x — H columns of every row of the parent array
@@ -1021,35 +1085,65 @@ void Model<FT>::run_fft_solve_pencil() {
         grid.x = (int)((count * (n / 2 + 1) + 255) / 256);
         go(k, grid, 0, OC_TIMER_POISSON_MID);
     };
-    auto transpose_y = [&](bool to_T) {
+    auto transpose_y = [&](bool to_T, int yperm) {
         TransposeKernel<FT> t;
-        t.nxc = nxl; t.nyl = nyl; t.nzl = nzl; t.R = R_; t.zl0 = 0; t.yperm = g_.bounded[1];
+        t.nxc = nxl; t.nyl = nyl; t.nzl = nzl; t.R = R_; t.zl0 = 0; t.yperm = yperm;
         t.stage = stage; t.T = T; t.to_T = to_T ? 1 : 0;
         Dim3 tg;
         tg.x = (nxl + 31) / 32; tg.y = (Ny + 31) / 32; tg.z = nzl;
         go(t, tg, TransposeKernel<FT>::SMEM, OC_TIMER_POISSON_MID);
     };
-    auto pencil_x = [&](int mode, Cplx<FT>* B, Cplx<FT>* Tb) {
+    auto pencil_x = [&](int mode, Cplx<FT>* B, Cplx<FT>* Tb, int xperm) {
         PencilXKernel<FT> k;
-        k.nxl = nxl; k.nyx = nyx; k.nzl = nzl; k.Rx = Rx_; k.xperm = g_.bounded[0]; k.mode = mode; k.B = B; k.T = Tb;
+        k.nxl = nxl; k.nyx = nyx; k.nzl = nzl; k.Rx = Rx_; k.xperm = xperm; k.mode = mode; k.B = B; k.T = Tb;
         Dim3 grid;
         grid.x = (int)(((long long)nxl * nyx * nzl * Rx_ + 255) / 256);
         go(k, grid, 0, OC_TIMER_POISSON_MID);
     };
-    // z
-    begin_timer(OC_TIMER_FFT); std::string e = dfft_.z(fftbuf_, true); end_timer(); chk(e);
-    local_twiddles(false);
-    // z <-> y
-    for (int c = 0; c < C; ++c) all_to_all(fftbuf_, diststage_, c, C);
-    transpose_y(true);
-    for (int c = 0; c < C; ++c) { begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, true, c); end_timer(); chk(e); }
-    if (g_.bounded[1]) twiddle_lines(T, Ny, (long long)nzl * nxl, tw_[1], false);
-    // y <-> x
-    pencil_x(0, spec, T);
-    all_to_all_x(fftbuf_, diststage_);
-    pencil_x(1, stage, T);
-    begin_timer(OC_TIMER_FFT); e = dfft_.x(distT_, true); end_timer(); chk(e);
-    if (g_.bounded[0]) twiddle_lines(T, Nx, (long long)nzl * nyx, tw_[0], false);
+    // the four moves between the three layouts; `perm`: the Makhoul permutation of a Bounded dimension is applied / undone by this move
+    auto z_to_y = [&](int perm) { for (int c = 0; c < C; ++c) all_to_all(fftbuf_, diststage_, c, C); transpose_y(true, perm); };
+    auto y_to_z = [&](int perm) { transpose_y(false, perm); for (int c = 0; c < C; ++c) all_to_all(diststage_, fftbuf_, c, C); };
+    auto y_to_x = [&](int perm) { pencil_x(0, spec, T, 0); all_to_all_x(fftbuf_, diststage_); pencil_x(1, stage, T, perm); };
+    auto x_to_y = [&](int perm) { pencil_x(2, stage, T, perm); all_to_all_x(diststage_, fftbuf_); pencil_x(3, spec, T, 0); };
+    auto fft_y = [&](bool fwd) {
+        if (!fwd && g_.bounded[1]) twiddle_lines(T, Ny, (long long)nzl * nxl, tw_[1], true);
+        for (int c = 0; c < C; ++c) { begin_timer(OC_TIMER_FFT); std::string e = dfft_.y(distT_, fwd, c); end_timer(); chk(e); }
+        if (fwd && g_.bounded[1]) twiddle_lines(T, Ny, (long long)nzl * nxl, tw_[1], false);
+    };
+    auto fft_x = [&](bool fwd) {
+        if (!fwd && g_.bounded[0]) twiddle_lines(T, Nx, (long long)nzl * nyx, tw_[0], true);
+        begin_timer(OC_TIMER_FFT); std::string e = dfft_.x(distT_, fwd); end_timer(); chk(e);
+        if (fwd && g_.bounded[0]) twiddle_lines(T, Nx, (long long)nzl * nyx, tw_[0], false);
+    };
+    auto fft_z = [&](bool fwd) {
+        if (!fwd) local_twiddles(true);
+        begin_timer(OC_TIMER_FFT); std::string e = dfft_.z(fftbuf_, fwd); end_timer(); chk(e);
+        if (fwd) local_twiddles(false);
+    };
+    const int py = g_.bounded[1], px = g_.bounded[0];
+    if (stretched_) {
+        // vertically stretched grid (distributed_fft_tridiagonal_solver.jl:262-293): y and x transforms, all the way back to whole
+        // z-columns of this rank's share of the (kx, ky) plane (natural order: the moves in between carry no permutation), the tridiagonal
+        // solves, and the same way out
+        z_to_y(py); fft_y(true); y_to_x(px); fft_x(true);
+        x_to_y(0); y_to_z(0);
+        TridiagSolvePPKernel<FT> k;
+        k.L = fft_.L;
+        k.spec = fftbuf_;
+        k.R = tri_R_; k.T = tri_T_; k.rdzf = g_.rdzf;
+        k.norm = 1.0 / ((double)Nx * Ny);
+        k.zero_col = (rank_ == 0 && rx_ == 0) ? 1 : 0;
+        Dim3 grid;
+        const long long n2 = 2LL * fft_.L.nxc * g_.N[1];
+        grid.x = (int)((n2 + TridiagSolvePPKernel<FT>::THREADS - 1) / TridiagSolvePPKernel<FT>::THREADS);
+        go(k, grid, 0, OC_TIMER_POISSON_MID);
+        z_to_y(0); y_to_x(0);
+        fft_x(false); x_to_y(px); fft_y(false); y_to_z(py);
+        return;
+    }
+    fft_z(true);
+    z_to_y(py); fft_y(true);
+    y_to_x(px); fft_x(true);
     {
         PoissonDividePencilKernel<FT> k;
         k.Nx = Nx; k.nyx = nyx; k.nzl = nzl; k.y0 = rx_ * nyx; k.kz0 = rank_ * nzl;
@@ -1060,19 +1154,9 @@ void Model<FT>::run_fft_solve_pencil() {
         grid.x = (Nx + 255) / 256; grid.y = nyx; grid.z = nzl;
         go(k, grid, 0, OC_TIMER_POISSON_MID);
     }
-    if (g_.bounded[0]) twiddle_lines(T, Nx, (long long)nzl * nyx, tw_[0], true);
-    begin_timer(OC_TIMER_FFT); e = dfft_.x(distT_, false); end_timer(); chk(e);
-    // x <-> y
-    pencil_x(2, stage, T);
-    all_to_all_x(diststage_, fftbuf_);
-    pencil_x(3, spec, T);
-    if (g_.bounded[1]) twiddle_lines(T, Ny, (long long)nzl * nxl, tw_[1], true);
-    for (int c = 0; c < C; ++c) { begin_timer(OC_TIMER_FFT); e = dfft_.y(distT_, false, c); end_timer(); chk(e); }
-    // y <-> z
-    transpose_y(false);
-    for (int c = 0; c < C; ++c) all_to_all(diststage_, fftbuf_, c, C);
-    local_twiddles(true);
-    begin_timer(OC_TIMER_FFT); e = dfft_.z(fftbuf_, false); end_timer(); chk(e);
+    fft_x(false); x_to_y(px);
+    fft_y(false); y_to_z(py);
+    fft_z(false);
 }
 
 template <class FT>
@@ -1134,6 +1218,7 @@ void Model<FT>::all_to_all(FT* send, FT* recv, int c, int C) {
 template <class FT>
 void Model<FT>::run_fft_solve_dist() {
     if (Rx_ > 1) { run_fft_solve_pencil(); return; }
+    if (stretched_) { run_fft_solve_dist_tridiagonal(); return; }
     if (p2p_) { run_fft_solve_p2p(); return; }
     auto chk = [](const std::string& e) { if (!e.empty()) throw Error(OC_ERR_CUDA, e); };
     const int C = dfft_.C, nz = dfft_.Nzl / C;
@@ -1853,6 +1938,7 @@ void Model<FT>::run_fft_solve() {
             k.spec = fftbuf_;
             k.R = tri_R_; k.T = tri_T_; k.rdzf = g_.rdzf;
             k.norm = 1.0 / ((double)g_.N[0] * g_.N[1]);
+            k.zero_col = 1;
             Dim3 grid;
             const long long n2 = 2LL * fft_.L.nxc * g_.N[1];
             grid.x = (int)((n2 + TridiagSolvePPKernel<FT>::THREADS - 1) / TridiagSolvePPKernel<FT>::THREADS);

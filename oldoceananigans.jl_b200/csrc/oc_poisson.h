@@ -293,6 +293,7 @@ struct TridiagSetupKernel {
     FT* R;
     FT* T;
     double eps10;
+    int zero_col;       // the local column (0, 0) is the (kx, ky) = (0, 0) column (always on one GPU; on slabs: the first rank only)
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
         const int i = b.x * nt + tid, j = b.y;
@@ -318,7 +319,7 @@ struct TridiagSetupKernel {
                 beta = D;
             }
             double r = (beta > eps10 || beta < -eps10) ? 1.0 / beta : 0.0;
-            if (i == 0 && j == 0 && k == Nz - 1) r = 0.0;
+            if (zero_col && i == 0 && j == 0 && k == Nz - 1) r = 0.0;
             R[c] = (FT)r;
             T[c] = (FT)t;
         }
@@ -466,6 +467,7 @@ struct TridiagSolvePPKernel {
     const FT* T;
     const FT* rdzf;
     double norm;
+    int zero_col;       // see TridiagSetupKernel
     template <int PHASE>
     OC_HD void run(const Block& b, int tid, int nt, char*) const {
         const long long plane = (long long)L.nxc * L.N[1];
@@ -476,7 +478,7 @@ struct TridiagSolvePPKernel {
         FT* p = spec + r;
         const FT* Rp = R + (r >> 1);
         const FT* Tp = T + (r >> 1);
-        const bool zero_mode = (r >> 1) == 0;
+        const bool zero_mode = zero_col && (r >> 1) == 0;
         FT vb[PF], cb[PF];
         // ---- forward elimination
         for (int q = 0; q < PF; ++q)

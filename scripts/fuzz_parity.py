@@ -80,7 +80,7 @@ def sample(rng, dist):
         kw["ts"] = "QuasiAdamsBashforth2"
     if rng.random() < 0.15:
         kw["FT"] = np.float32
-    if not dist and topo[2] == "B" and rng.random() < 0.2:
+    if topo[2] == "B" and rng.random() < 0.2:
         kw["stretch"] = str(rng.choice(["smooth", "facr"]))
     if kw["buoy"] in ("seawater", "tracer") and rng.random() < 0.15:
         kw["tilt"] = (0.6, 0.0, -0.8) if rng.random() < 0.5 else (0.0, -0.8660254037844386, -0.5)

@@ -79,7 +79,8 @@ def run_rank(kw, rank, R, arch, lib, nccl=False):
         f = tuple(f)
     kw["f"] = f
     case = dict(N=N, topo=topo, scheme=scheme, FT=FT, f=kw.get("f"), closure=kw.get("closure", "scalar"), bcs=kw.get("bcs", False),
-                ts=kw.get("ts", "RungeKutta3"), buoy=kw.get("buoy", "seawater"), tilt=tuple(kw["tilt"]) if kw.get("tilt") else None)
+                ts=kw.get("ts", "RungeKutta3"), buoy=kw.get("buoy", "seawater"), tilt=tuple(kw["tilt"]) if kw.get("tilt") else None,
+                stretch=kw.get("stretch"))
     if kw.get("halo_fill"):
         return halo_fill(kw, rank, arch, lib, FT)
     model = ph.build_product(library=lib, arch=arch, **case)
@@ -97,7 +98,12 @@ def run_rank(kw, rank, R, arch, lib, nccl=False):
         for _ in range(2):
             rhs = rng.standard_normal(N).astype(FT)
             rhs -= rhs.mean()
-            want = om.solve_poisson(rhs)
+            if kw.get("stretch"):          # solve!(ϕ, FourierTridiagonalPoissonSolver, rhs): the source term is Δzᶜ · rhs (:239-246)
+                dzc = om.grid.dz_at("c", np.arange(1, N[2] + 1))
+                rhs -= (rhs * dzc).sum() / (dzc.sum() * N[0] * N[1])          # compatible source: Σ Δz·b = 0
+                want = om.solve_poisson_tridiagonal(rhs * dzc)
+            else:
+                want = om.solve_poisson(rhs)
             got = ob.solve_poisson(model, rhs[cols, rows, :])
             worst = max(worst, float(np.abs(got - want[cols, rows, :]).max() / np.abs(want).max()))
         return worst
@@ -114,7 +120,10 @@ def run_rank(kw, rank, R, arch, lib, nccl=False):
 
     ob.set_(model, **{n: a[sl_of(n)] for n, a in ic.items()})
     om.set(**ic)
-    dt = 0.1 * float(min(om.grid.D))
+    dmin = [float(om.grid.D[d]) for d in range(3) if not om.grid.flat(d) and om.grid.D[d] is not None]
+    if om.grid.stretched:
+        dmin.append(float(np.min(om.grid.dz_at("c", np.arange(1, om.grid.Nz + 1)))))
+    dt = 0.1 * min(dmin)
     worst = 0.0
     for s in range(steps + 1):
         if s:

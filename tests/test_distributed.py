@@ -84,6 +84,11 @@ CPU_MODEL_CASES = [
     (4, dict(N=(16, 12, 1), topo="BPF", scheme="centered", closure="scalar", buoy="none", steps=2, px=4)),
     (2, dict(N=(1, 12, 8), topo="FPB", scheme="weno", buoy="tracer", f=0.2, steps=2)),
     (4, dict(N=(1, 16, 8), topo="FBB", scheme="upwind3", buoy="tracer", steps=2)),
+    # vertically stretched grids: the distributed Fourier-tridiagonal solve (distributed_fft_tridiagonal_solver.jl:262-293) on slabs and pencils
+    (2, dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, stretch="smooth", steps=2)),
+    (4, dict(N=(12, 16, 8), topo="BBB", scheme="centered", closure="both", bcs="walls", stretch="facr", steps=2)),
+    (2, dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="lilly", bcs=True, stretch="smooth", steps=2, ts="QuasiAdamsBashforth2")),
+    (4, dict(N=(16, 12, 10), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, stretch="smooth", steps=2, px=2)),
     # tilted gravity (BuoyancyForce(…; gravity_unit_vector)) on slabs and pencils
     (2, dict(N=(16, 12, 8), topo="PPB", scheme="centered", buoy="tracer", f=1e-2, bcs=True, tilt=(0.6, 0.0, -0.8), tracer_noise=1.0, steps=2)),
     (4, dict(N=(16, 12, 8), topo="PPB", scheme="weno", tilt=(0.0, -0.8660254037844386, -0.5), steps=2, px=2)),
@@ -107,6 +112,18 @@ CPU_MODEL_CASES = [
 
 POISSON_CASES = [(R, dict(N=N, topo=topo, poisson=True)) for R, N in ((2, (16, 12, 8)), (4, (10, 16, 12)), (3, (9, 15, 6)))
                  for topo in ("PPP", "PPB", "PBB", "BBB", "BPP", "PBP")]
+STRETCHED_POISSON_CASES = [
+    (2, dict(N=(16, 12, 8), topo="PPB", poisson=True, stretch="smooth")),
+    (4, dict(N=(10, 16, 12), topo="BBB", poisson=True, stretch="facr")),
+    (3, dict(N=(9, 15, 6), topo="PBB", poisson=True, stretch="smooth")),
+    (4, dict(N=(16, 12, 8), topo="PPB", poisson=True, stretch="smooth", px=2)),
+    (6, dict(N=(12, 12, 6), topo="BBB", poisson=True, stretch="facr", px=3)),
+    (2, dict(N=(16, 12, 8), topo="PBB", poisson=True, stretch="smooth", px=2)),
+]
+# the reference's stretched matrix (test/test_distributed_poisson_solvers.jl:150-163: (Bounded, Bounded, Bounded), z given by its faces),
+# minus the sizes whose local extent is below this library's internal halo of 3 ((4, 44, 8) on (4,1,1), (44, 4, 8) on (1,4,1))
+STRETCHED_POISSON_CASES += [(4, dict(N=N, topo="BBB", poisson=True, stretch="smooth", px=px))
+                            for px, N in ((4, (44, 44, 8)), (4, (16, 44, 8)), (1, (44, 44, 8)), (1, (16, 44, 8)), (2, (22, 8, 8)), (2, (8, 22, 8)))]
 PENCIL_POISSON_CASES = [(R, dict(N=N, topo=topo, poisson=True, px=px))
                         for R, px, N in ((4, 2, (16, 12, 8)), (2, 2, (16, 12, 8)), (6, 3, (12, 12, 6)), (6, 2, (12, 18, 9)))
                         for topo in ("PPP", "PBB", "BBB", "BPP")]
@@ -129,7 +146,7 @@ def cpu_result(R, case):
     """Every CPU case with the same number of ranks shares ONE launch of R gloo processes (starting the processes and importing torch
     costs more than the cases themselves): the first request for a rank count runs them all."""
     if R not in _BATCH:
-        todo = [c for r, c in CPU_MODEL_CASES + POISSON_CASES + PENCIL_POISSON_CASES + REFERENCE_POISSON_MATRIX + HALO_FILL_CASES if r == R]
+        todo = [c for r, c in CPU_MODEL_CASES + POISSON_CASES + PENCIL_POISSON_CASES + STRETCHED_POISSON_CASES + REFERENCE_POISSON_MATRIX + HALO_FILL_CASES if r == R]
         res = run_ranks(R, todo, timeout=1800)
         _BATCH[R] = {json.dumps(c, sort_keys=True): x for c, x in zip(todo, res)}
     return _BATCH[R][json.dumps(case, sort_keys=True)]
@@ -146,6 +163,14 @@ def test_slab_decomposition_matches_single_domain_oracle(R, case):
 def test_distributed_poisson_solver_matches_single_domain_solve(R, case):
     """The distributed solver alone on every mix of Periodic and Bounded dimensions, even and odd sizes, 2 / 3 / 4 ranks
     (test/test_distributed_poisson_solvers.jl:70-89,128-148 runs (4,1,1), (1,4,1), (2,2,1) partitions x 4 topologies)"""
+    res = cpu_result(R, case)
+    assert res["ranks"] == R and res["worst"] <= 1e-13, res
+
+
+@pytest.mark.parametrize("R,case", STRETCHED_POISSON_CASES, ids=[f"{r}-px{c.get('px', 1)}-{c['topo']}-{c['stretch']}-{'x'.join(map(str, c['N']))}" for r, c in STRETCHED_POISSON_CASES])
+def test_distributed_fourier_tridiagonal_solver_matches_single_domain_solve(R, case):
+    """DistributedFourierTridiagonalPoissonSolver (vertically stretched grids) on slabs and pencils against the oracle's
+    FourierTridiagonalPoissonSolver (test/test_distributed_poisson_solvers.jl:150-170 runs (4,1,1), (1,4,1), (2,2,1) x stretched z)"""
     res = cpu_result(R, case)
     assert res["ranks"] == R and res["worst"] <= 1e-13, res
 
@@ -227,6 +252,10 @@ NCCL_NEW_CASES = [
     (8, dict(N=(64, 48, 32), topo="PBB", scheme="centered", bcs="walls", steps=2, px=4, ts="QuasiAdamsBashforth2")),
     (4, dict(N=(36, 40, 20), topo="BBB", poisson=True, px=2)),
     (8, dict(N=(32, 48, 24), topo="PBP", poisson=True, px=4)),
+    # vertically stretched grids
+    (2, dict(N=(48, 32, 16), topo="PPB", scheme="weno", closure="amd", f=1e-2, bcs=True, stretch="smooth", steps=2)),
+    (4, dict(N=(48, 32, 16), topo="PPB", scheme="weno", closure="lilly", bcs=True, stretch="smooth", steps=2, px=2)),
+    (4, dict(N=(36, 40, 20), topo="BBB", poisson=True, stretch="facr")),
 ]
 
 def _nccl_case(R, case):
