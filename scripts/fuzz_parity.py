@@ -150,11 +150,14 @@ def main():
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--dist-only", action="store_true")
     ap.add_argument("--single-only", action="store_true")
+    ap.add_argument("--cuda", action="store_true", help="the CUDA library on cuda:0 instead of the host simulation (single-domain cases only)")
     args = ap.parse_args()
     os.environ["OC_HOSTSIM_THREADS"] = "1"
     import __graft_entry__ as ge
     from oceananigans_b200 import _lib
-    lib = _lib.Library(ge.HOSTSIM)
+    lib = None if args.cuda else _lib.Library(ge.HOSTSIM)          # None: the package's loader opens the CUDA library (and fails loudly without it)
+    if args.cuda:
+        args.single_only = True
     rng = np.random.default_rng(args.seed)
     ran = skipped = 0
     failures = []

@@ -4,6 +4,7 @@
 # tasks:
 #   tests                 python -m pytest tests -m gpu
 #   smoke                 __graft_entry__.smoke()
+#   fuzz:<seed>:<cases>   scripts/fuzz_parity.py --cuda (random configurations, CUDA library vs oracle)   -> <tag>_fuzz_cuda.log
 #   bench:<wl>[:steps]    python bench.py --workload <wl> (no e2e / cpu baseline)  -> <tag>_bench_<wl>.json
 #   default               python bench.py exactly as the driver runs it            -> <tag>_bench_default.json
 #   reference             python bench.py --impl reference                         -> <tag>_bench_reference.json
@@ -21,6 +22,8 @@ for task in "$@"; do
   IFS=: read -r kind a b c d <<< "$task"
   echo "=== $task"
   case $kind in
+    fuzz)            # the configuration fuzzer on the CUDA library: fuzz:<seed>:<cases>
+      timeout 1500 python scripts/fuzz_parity.py --cuda --seed ${a:-7} --cases ${b:-60} > gpurun_out/${TAG}_fuzz_cuda.log 2>&1; echo "fuzz rc=$?"; tail -6 gpurun_out/${TAG}_fuzz_cuda.log ;;
     smoke)
       timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -4 gpurun_out/${TAG}_smoke.log ;;
     tests)
