@@ -173,11 +173,9 @@ Model<FT>::Model(const oc_config& c) : cfg_(c) {
                     throw Error(OC_ERR_UNSUPPORTED, "advection_dir: a scheme interpolates velocities two points deep along a direction whose halo is 1 (the reference reads outside the halo there)");
         }
     }
-    if (c.has_amd && (g_.flat[0] || g_.flat[1] || g_.flat[2])) throw Error(OC_ERR_UNSUPPORTED, "AnisotropicMinimumDissipation on a grid with Flat dimensions");
     if (c.smagorinsky) {
         if (c.smagorinsky != 1 && c.smagorinsky != 2) throw Error(OC_ERR_UNSUPPORTED, "Smagorinsky: constant coefficient (1) or LillyCoefficient (2); DynamicCoefficient is not implemented");
         if (c.has_amd) throw Error(OC_ERR_UNSUPPORTED, "AnisotropicMinimumDissipation and Smagorinsky in one closure tuple");
-        if (g_.flat[0] || g_.flat[1] || g_.flat[2]) throw Error(OC_ERR_UNSUPPORTED, "Smagorinsky on a grid with Flat dimensions");
         for (int t = 0; t < c.n_tracers; ++t)
             if (!(c.smag_Pr[t] > 0)) throw Error(OC_ERR_INVALID, "Smagorinsky: the turbulent Prandtl number of every tracer must be positive");
     }

@@ -416,6 +416,15 @@ ARRAY_BC_CASES = [
     ("tile-crossing 40x36x33 BPB weno array flux bcs", dict(N=(40, 36, 33), topo="BPB", scheme="weno", bcs="array")),
 ]
 
+# eddy-viscosity closures on two-dimensional grids (Flat dimensions are stored as periodic with N = 1, so every difference along them
+# vanishes and the closures' own filter widths see Δ = 1 there, like the reference's spacing operators on Flat dimensions)
+FLAT_CLOSURE_CASES = [
+    ("PPF weno smagorinsky-lilly (2-D turbulence)", dict(N=(16, 12, 1), topo="PPF", scheme="weno", closure="lilly", buoy="passive")),
+    ("PFB weno amd tracer-b fplane bcs", dict(N=(16, 1, 12), topo="PFB", scheme="weno", closure="amd", buoy="tracer", f=0.2, bcs=True)),
+    ("FPB centered amd Cb=1 tracer-b", dict(N=(1, 12, 8), topo="FPB", scheme="centered", closure="amdcb", buoy="tracer")),
+    ("BBF upwind3 smagorinsky wall bcs AB2", dict(N=(12, 10, 1), topo="BBF", scheme="upwind3", closure="smag", buoy="passive", bcs="walls", ts="QuasiAdamsBashforth2")),
+]
+
 # scalar Value / Gradient / Flux boundary conditions on the LATERAL walls too (bcs="walls": every Bounded side of u, v, w and the first
 # tracer) — no-slip and moving side walls, heated / cooled side walls: fill_halo_regions_value_gradient.jl:7-119 west / east / south /
 # north, compute_flux_bcs.jl:116-163 x and y fluxes

@@ -265,6 +265,12 @@ def test_hostsim_matches_oracle_with_tilted_gravity(hostsim, name, kw):
     ph.check_case(kw, library=hostsim, steps=(1, 3))
 
 
+@pytest.mark.parametrize("name,kw", ph.FLAT_CLOSURE_CASES, ids=[c[0] for c in ph.FLAT_CLOSURE_CASES])
+def test_hostsim_matches_oracle_with_eddy_closures_on_two_dimensional_grids(hostsim, name, kw):
+    """AnisotropicMinimumDissipation / Smagorinsky(-Lilly) with a Flat dimension"""
+    ph.check_case(kw, library=hostsim, steps=(1, 3))
+
+
 @pytest.mark.parametrize("name,kw", ph.WALL_BC_CASES[:-1], ids=[c[0] for c in ph.WALL_BC_CASES[:-1]])
 def test_hostsim_matches_oracle_with_lateral_wall_bcs(hostsim, name, kw):
     """Value / Gradient / Flux boundary conditions on west / east / south / north walls"""
