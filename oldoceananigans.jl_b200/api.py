@@ -1178,7 +1178,10 @@ class Checkpointer:
         return out
 
     def write(self, path=None):
-        path = path or f"{self.prefix}_iteration{self.model.clock.iteration}.npz"
+        prefix = self.prefix
+        if getattr(self.model, "distributed", False):      # one file per rank: prefix *= "_rank$rank" (output_writer_utils.jl:240-241)
+            prefix += f"_rank{self.model.grid.architecture.rank}"
+        path = path or f"{prefix}_iteration{self.model.clock.iteration}.npz"
         np.savez(path, **self.state())
         return path
 
