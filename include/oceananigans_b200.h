@@ -265,7 +265,11 @@ int  oc_field_maximum_abs(oc_model* m, int field, double* out);
  *   oc_dist_unique_id   rank 0 makes the 128-byte NCCL id; the host layer broadcasts it (MPI.bcast / torch.distributed)
  *   oc_dist_attach_nccl ncclCommInitRank inside the library; halo exchange and FFT transposes are grouped ncclSend/ncclRecv
  *   oc_dist_attach_host TEST-ONLY (host simulation build): transfers go through a host callback so that the decomposition logic
- *                       can be exercised by world_size-2 gloo tests on CPU; the CUDA library returns OC_ERR_UNSUPPORTED. */
+ *                       can be exercised by world_size-2 gloo tests on CPU; the CUDA library returns OC_ERR_UNSUPPORTED.
+ * Collective calls — every rank makes them, in the same order, like fill_halo_regions! / solve! on distributed fields in the reference:
+ * everything that fills halos or solves for the pressure (oc_set_finalize, oc_update_state, oc_fill_halo_regions, oc_time_step_*, the
+ * staged entry points, oc_poisson_solve, oc_set_bc_array) and, on grids with a Flat dimension, oc_upload_interior / _parent (they
+ * refresh the internal copies of the Flat direction).  Downloads, clocks, timers and diagnostics are local. */
 typedef int (*oc_exchange_fn)(void* user, int nmsg, const int* send_peers, const int* recv_peers, const int* tags,
                               void* const* send_ptrs, const size_t* send_bytes, void* const* recv_ptrs, const size_t* recv_bytes);
 int  oc_dist_unique_id(void* id128);
