@@ -473,6 +473,46 @@ struct PencilXKernel {
     }
 };
 
+// Modes 0 and 3 of PencilXKernel transpose x against y: through a 32 × 33 shared-memory tile both sides are read and written in
+// contiguous runs (the plain kernel strides one of them by Ny).  pack = 1: B <- T1 (mode 0); pack = 0: T1 <- B (mode 3).
+template <class FT>
+struct PencilYXKernel {
+    static constexpr int PHASES = 2;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr size_t SMEM = sizeof(Cplx<FT>) * 32 * 33;
+    int nxl, nyx, nzl, Rx, pack;
+    Cplx<FT>* B;
+    Cplx<FT>* T;
+    template <int PHASE>
+    OC_HD void run(const Block& b, int tid, int nt, char* smem) const {
+        Cplx<FT>* tile = reinterpret_cast<Cplx<FT>*>(smem);
+        (void)nt;
+        const int tx = tid & 31, ty = tid >> 5;        // 32 × 8
+        const int x0 = b.x * 32, y0 = b.y * 32, zl = b.z % nzl, r = b.z / nzl;
+        const long long Ny = (long long)nyx * Rx;
+        if ((PHASE == 0) == (pack != 0)) {
+            // the T1 side (y contiguous): read in phase 0 when packing, written in phase 1 when unpacking
+            for (int rr = ty; rr < 32; rr += 8) {
+                const int xl = x0 + rr, yl2 = y0 + tx;
+                if (xl < nxl && yl2 < nyx) {
+                    Cplx<FT>* p = T + ((long long)zl * nxl + xl) * Ny + (long long)r * nyx + yl2;
+                    if (pack) tile[rr * 33 + tx] = *p; else *p = tile[rr * 33 + tx];
+                }
+            }
+        } else {
+            // the exchange-buffer side (x contiguous)
+            for (int rr = ty; rr < 32; rr += 8) {
+                const int xl = x0 + tx, yl2 = y0 + rr;
+                if (xl < nxl && yl2 < nyx) {
+                    Cplx<FT>* p = B + (((long long)r * nzl + zl) * nyx + yl2) * nxl + xl;
+                    if (pack) *p = tile[tx * 33 + rr]; else tile[tx * 33 + rr] = *p;
+                }
+            }
+        }
+    }
+};
+
 // the divide in the pencil layout T2 = [zl][yl2][x]: global y = y0 + yl2, kz = kz0 + zl
 template <class FT>
 struct PoissonDividePencilKernel {

@@ -1101,8 +1101,15 @@ void Model<FT>::run_fft_solve_pencil() {
     // the four moves between the three layouts; `perm`: the Makhoul permutation of a Bounded dimension is applied / undone by this move
     auto z_to_y = [&](int perm) { for (int c = 0; c < C; ++c) all_to_all(fftbuf_, diststage_, c, C); transpose_y(true, perm); };
     auto y_to_z = [&](int perm) { transpose_y(false, perm); for (int c = 0; c < C; ++c) all_to_all(diststage_, fftbuf_, c, C); };
-    auto y_to_x = [&](int perm) { pencil_x(0, spec, T, 0); all_to_all_x(fftbuf_, diststage_); pencil_x(1, stage, T, perm); };
-    auto x_to_y = [&](int perm) { pencil_x(2, stage, T, perm); all_to_all_x(diststage_, fftbuf_); pencil_x(3, spec, T, 0); };
+    auto pencil_yx = [&](bool pack, Cplx<FT>* B, Cplx<FT>* Tb) {        // modes 0 / 3 through a shared-memory tile
+        PencilYXKernel<FT> k;
+        k.nxl = nxl; k.nyx = nyx; k.nzl = nzl; k.Rx = Rx_; k.pack = pack ? 1 : 0; k.B = B; k.T = Tb;
+        Dim3 grid;
+        grid.x = (nxl + 31) / 32; grid.y = (nyx + 31) / 32; grid.z = nzl * Rx_;
+        go(k, grid, PencilYXKernel<FT>::SMEM, OC_TIMER_POISSON_MID);
+    };
+    auto y_to_x = [&](int perm) { pencil_yx(true, spec, T); all_to_all_x(fftbuf_, diststage_); pencil_x(1, stage, T, perm); };
+    auto x_to_y = [&](int perm) { pencil_x(2, stage, T, perm); all_to_all_x(diststage_, fftbuf_); pencil_yx(false, spec, T); };
     auto fft_y = [&](bool fwd) {
         if (!fwd && g_.bounded[1]) twiddle_lines(T, Ny, (long long)nzl * nxl, tw_[1], true);
         for (int c = 0; c < C; ++c) { begin_timer(OC_TIMER_FFT); std::string e = dfft_.y(distT_, fwd, c); end_timer(); chk(e); }

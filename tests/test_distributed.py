@@ -127,6 +127,8 @@ STRETCHED_POISSON_CASES += [(4, dict(N=N, topo="BBB", poisson=True, stretch="smo
 PENCIL_POISSON_CASES = [(R, dict(N=N, topo=topo, poisson=True, px=px))
                         for R, px, N in ((4, 2, (16, 12, 8)), (2, 2, (16, 12, 8)), (6, 3, (12, 12, 6)), (6, 2, (12, 18, 9)))
                         for topo in ("PPP", "PBB", "BBB", "BPP")]
+# local extents beyond one 32 x 32 tile of the transposition kernels (TransposeKernel, PencilYXKernel), partial tiles included
+PENCIL_POISSON_CASES += [(4, dict(N=(80, 72, 4), topo=topo, poisson=True, px=2)) for topo in ("PPP", "BBB")]
 
 # the reference's own matrix (test/test_distributed_poisson_solvers.jl:128-148): sizes x process grids (4,1,1), (1,4,1), (2,2,1) x four
 # topologies, 3-D
