@@ -122,3 +122,10 @@ def test_cuda_matches_oracle_with_array_valued_diffusivities(ob, name, kw):
 def test_cuda_matches_oracle_for_weno7_and_weno9(ob, name, kw):
     """WENO(order = 7 | 9): weno_interpolants.jl:81-90,175-185,303-307 — general tile kernel, halos of 4 / 5, order-reduction chains near walls"""
     ph.check_case(kw, library=None, steps=(1, 10))
+
+
+# (kept last in the last GPU test file: added after the round's final GPU run — verified on the host simulation only so far)
+@pytest.mark.parametrize("name,kw", ph.FLAT_CLOSURE_CASES, ids=[c[0] for c in ph.FLAT_CLOSURE_CASES])
+def test_cuda_matches_oracle_with_eddy_closures_on_two_dimensional_grids(ob, name, kw):
+    """AnisotropicMinimumDissipation / Smagorinsky(-Lilly) with a Flat dimension"""
+    ph.check_case(kw, library=None, steps=(1, 10))
