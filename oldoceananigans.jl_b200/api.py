@@ -60,6 +60,8 @@ class Partition:
 class Distributed:
     """Distributed(B200(device); partition=Partition(1, R)): one process per GPU
     (src/DistributedComputations/distributed_architectures.jl:242-302).  rank / nranks default to torch.distributed's.
+    Without `partition` the ranks form slabs in y, Partition(1, R) — the decomposition this library is tuned for (peer-memory transposes,
+    overlapped exchanges); the reference's default is Partition(R), slabs in x (:257-261), which is available by asking for it.
     `exchange` is the TEST-ONLY host transport of the host simulation (a Python callable, see tests/dist_worker.py); the
     CUDA library communicates with NCCL over NVLink."""
 
