@@ -111,6 +111,48 @@ def single(kw, lib):
     return worst
 
 
+def staged(kw, lib):
+    """time_step! assembled from the staged C entry points (the reference's own sequence, runge_kutta_3.jl:93-170) against the fused
+    oc_time_step_rk3 on the same random configuration: two steps, every field and the pressure"""
+    import oceananigans_b200 as ob
+    import parity_harness as ph
+    kw = dict(kw, ts="RungeKutta3")
+    noise = kw.pop("tracer_noise", 0.01)
+    try:
+        m1, om = ph.build_pair(library=lib, **kw)
+        m2 = ph.build_product(library=lib, **kw)
+    except Exception as e:          # noqa: BLE001
+        msg = repr(e)
+        if "OceananigansB200Error" in msg or isinstance(e, (NotImplementedError, ValueError, AssertionError, KeyError, IndexError)):
+            raise Skip(msg[:200])
+        raise
+    ic = ph.initial_conditions(om, tracer_noise=noise)
+    ob.set_(m1, **ic)
+    ob.set_(m2, **ic)
+    dmin = [float(om.grid.D[d]) for d in range(3) if not om.grid.flat(d) and om.grid.D[d] is not None]
+    if om.grid.stretched:
+        dmin.append(float(np.min(om.grid.dz_at("c", np.arange(1, om.grid.Nz + 1)))))
+    dt = 0.1 * min(dmin)
+    g, z = [8 / 15, 5 / 12, 3 / 4], [0.0, -17 / 60, -5 / 12]
+    FT = kw.get("FT", np.float64)
+    worst = 0.0
+    for _ in range(2):
+        ob.time_step_(m1, dt)
+        ob.update_state_(m2, True)
+        for st in (1, 2, 3):
+            ob.compute_flux_bc_tendencies_(m2)
+            ob.rk3_substep_(m2, dt, st)
+            sdt = dt * float(FT(FT(g[st - 1]) + FT(z[st - 1])))
+            ob.compute_pressure_correction_(m2, sdt)
+            ob.make_pressure_correction_(m2, sdt)
+            if st < 3:
+                ob.cache_previous_tendencies_(m2)
+            ob.update_state_(m2, True)
+        for n in m1.fields:
+            worst = max(worst, ph.rel_linf(m1.fields[n].interior(), m2.fields[n].interior()))
+    return worst
+
+
 def distributed(kw, part, lib):
     import oceananigans_b200 as ob
     import dist_worker
@@ -150,13 +192,14 @@ def main():
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--dist-only", action="store_true")
     ap.add_argument("--single-only", action="store_true")
+    ap.add_argument("--staged", action="store_true", help="compare the staged entry points with the fused step instead of product with oracle")
     ap.add_argument("--cuda", action="store_true", help="the CUDA library on cuda:0 instead of the host simulation (single-domain cases only)")
     args = ap.parse_args()
     os.environ["OC_HOSTSIM_THREADS"] = "1"
     import __graft_entry__ as ge
     from oceananigans_b200 import _lib
     lib = None if args.cuda else _lib.Library(ge.HOSTSIM)          # None: the package's loader opens the CUDA library (and fails loudly without it)
-    if args.cuda:
+    if args.cuda or args.staged:
         args.single_only = True
     rng = np.random.default_rng(args.seed)
     ran = skipped = 0
@@ -166,7 +209,7 @@ def main():
         kw, part = sample(rng, dist)
         tol = 1e-4 if kw.get("FT") is np.float32 else 1e-10
         try:
-            worst = distributed(kw, part, lib) if dist else single(kw, lib)
+            worst = staged(kw, lib) if args.staged else (distributed(kw, part, lib) if dist else single(kw, lib))
         except Skip as e:
             skipped += 1
             print(f"[{n}] skip  {part} {kw}: {e}", flush=True)
