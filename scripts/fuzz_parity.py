@@ -153,6 +153,44 @@ def staged(kw, lib):
     return worst
 
 
+def checkpointed(kw, lib):
+    """Checkpointer + set!(model, filepath) (checkpointer.jl:161-262) on a random configuration: a model picked up from the parent arrays,
+    G⁻ and the clock after two steps continues bit for bit like the one that kept running.  Returns 0.0 or the largest difference."""
+    import io
+    import oceananigans_b200 as ob
+    import parity_harness as ph
+    kw = dict(kw)
+    noise = kw.pop("tracer_noise", 0.01)
+    try:
+        m1, om = ph.build_pair(library=lib, **kw)
+        m2 = ph.build_product(library=lib, **kw)
+    except Exception as e:          # noqa: BLE001
+        msg = repr(e)
+        if "OceananigansB200Error" in msg or isinstance(e, (NotImplementedError, ValueError, AssertionError, KeyError, IndexError)):
+            raise Skip(msg[:200])
+        raise
+    ob.set_(m1, **ph.initial_conditions(om, tracer_noise=noise))
+    dmin = [float(om.grid.D[d]) for d in range(3) if not om.grid.flat(d) and om.grid.D[d] is not None]
+    if om.grid.stretched:
+        dmin.append(float(np.min(om.grid.dz_at("c", np.arange(1, om.grid.Nz + 1)))))
+    dt = 0.1 * min(dmin)
+    for _ in range(2):
+        ob.time_step_(m1, dt)
+    state = ob.Checkpointer(m1).state()
+    for _ in range(2):
+        ob.time_step_(m1, dt)
+    ob.Checkpointer.pickup(m2, state)
+    for _ in range(2):
+        ob.time_step_(m2, dt)
+    worst = 0.0
+    for n in m1.fields:
+        worst = max(worst, float(np.abs(m1.fields[n].parent() - m2.fields[n].parent()).max()))
+    worst = max(worst, float(np.abs(m1.pressures.pNHS.interior() - m2.pressures.pNHS.interior()).max()))
+    if not (m1.clock.time == m2.clock.time and m1.clock.iteration == m2.clock.iteration == 4):
+        return float("inf")
+    return worst
+
+
 def distributed(kw, part, lib):
     import oceananigans_b200 as ob
     import dist_worker
@@ -193,13 +231,14 @@ def main():
     ap.add_argument("--dist-only", action="store_true")
     ap.add_argument("--single-only", action="store_true")
     ap.add_argument("--staged", action="store_true", help="compare the staged entry points with the fused step instead of product with oracle")
+    ap.add_argument("--checkpoint", action="store_true", help="a picked-up model must continue bit for bit like the one that kept running")
     ap.add_argument("--cuda", action="store_true", help="the CUDA library on cuda:0 instead of the host simulation (single-domain cases only)")
     args = ap.parse_args()
     os.environ["OC_HOSTSIM_THREADS"] = "1"
     import __graft_entry__ as ge
     from oceananigans_b200 import _lib
     lib = None if args.cuda else _lib.Library(ge.HOSTSIM)          # None: the package's loader opens the CUDA library (and fails loudly without it)
-    if args.cuda or args.staged:
+    if args.cuda or args.staged or args.checkpoint:
         args.single_only = True
     rng = np.random.default_rng(args.seed)
     ran = skipped = 0
@@ -207,9 +246,9 @@ def main():
     for n in range(args.cases):
         dist = (rng.random() < 0.5 or args.dist_only) and not args.single_only
         kw, part = sample(rng, dist)
-        tol = 1e-4 if kw.get("FT") is np.float32 else 1e-10
+        tol = 0.0 if args.checkpoint else (1e-4 if kw.get("FT") is np.float32 else 1e-10)
         try:
-            worst = staged(kw, lib) if args.staged else (distributed(kw, part, lib) if dist else single(kw, lib))
+            worst = staged(kw, lib) if args.staged else checkpointed(kw, lib) if args.checkpoint else (distributed(kw, part, lib) if dist else single(kw, lib))
         except Skip as e:
             skipped += 1
             print(f"[{n}] skip  {part} {kw}: {e}", flush=True)

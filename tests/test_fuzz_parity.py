@@ -12,8 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("flags", [["--single-only", "--seed", "5", "--cases", "16"], ["--dist-only", "--seed", "6", "--cases", "10"],
-                                   ["--staged", "--seed", "7", "--cases", "10"]],
-                         ids=["single-domain", "thread-rank decompositions", "staged entry points vs fused step"])
+                                   ["--staged", "--seed", "7", "--cases", "10"], ["--checkpoint", "--seed", "8", "--cases", "8"]],
+                         ids=["single-domain", "thread-rank decompositions", "staged entry points vs fused step", "checkpoint pickup bit for bit"])
 def test_seeded_fuzz_run_agrees_with_the_oracle(flags):
     import __graft_entry__ as ge
     ge.build()
