@@ -204,6 +204,19 @@ def test_distributed_rejects_unsupported_configurations():
         ob.Partition(2, 2, 2)              # z is never partitioned
     with pytest.raises(ValueError):
         ob.Distributed(ob.B200(0), partition=ob.Partition(2, 2), rank=0, nranks=6)
+    # a Flat dimension cannot be partitioned: an (x, y) model on slabs in y is refused by the library, loudly
+    import __graft_entry__ as ge
+    from oceananigans_b200 import _lib
+    ge.build()
+    lib = _lib.Library(ge.HOSTSIM)
+    arch = ob.Distributed(ob.B200(0), partition=ob.Partition(1, 2), rank=0, nranks=2, exchange=lambda msgs: 0)
+    grid = ob.RectilinearGrid(arch, np.float64, size=(8, 8), extent=(1, 1), topology=(ob.Periodic, ob.Periodic, ob.Flat))
+    with pytest.raises(_lib.OceananigansB200Error, match="Flat"):
+        ob.NonhydrostaticModel(grid=grid, advection=ob.Centered(), library=lib)
+    # the distributed solver's divisibility constraints (distributed_fft_based_poisson_solver.jl:211-229)
+    grid = ob.RectilinearGrid(arch, np.float64, size=(8, 8, 5), extent=(1, 1, 1), topology=(ob.Periodic, ob.Periodic, ob.Bounded))
+    with pytest.raises(_lib.OceananigansB200Error, match="divisible"):
+        ob.NonhydrostaticModel(grid=grid, advection=ob.Centered(), library=lib)
     with pytest.raises(ValueError):
         ob.Distributed(ob.B200(0), partition=ob.Partition(1, 3), rank=0, nranks=2)
 
