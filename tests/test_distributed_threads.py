@@ -19,7 +19,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 class Mailbox:
-    """FIFO per (source, destination, tag): messages between one pair of ranks are matched in posting order"""
+    """One FIFO per (source, destination): like ncclSend / ncclRecv, messages between a pair of ranks carry NO tag and are matched
+    purely in posting order, and the two sides must agree on the size — so an exchange whose correctness leaned on the tags of the
+    host-callback interface (which gloo honours) fails here, as it would on NCCL."""
 
     def __init__(self):
         self.lock = threading.Lock()
@@ -33,10 +35,13 @@ class Mailbox:
         def exchange(msgs):
             for sp, rp, tag, sptr, sb, rptr, rb in msgs:
                 if sb:
-                    self.of((rank, sp, tag)).put(C.string_at(sptr, sb))
+                    self.of((rank, sp)).put(C.string_at(sptr, sb))
             for sp, rp, tag, sptr, sb, rptr, rb in msgs:
                 if rb:
-                    C.memmove(rptr, self.of((rp, rank, tag)).get(timeout=300), rb)
+                    data = self.of((rp, rank)).get(timeout=300)
+                    if len(data) != rb:
+                        raise RuntimeError(f"rank {rank}: a {rb}-byte receive from rank {rp} met a {len(data)}-byte send (tag {tag})")
+                    C.memmove(rptr, data, rb)
             return 0
         return exchange
 
