@@ -91,6 +91,10 @@ def run_threads(R, case, p2p=True):
     (3, dict(N=(9, 15, 6), topo="BPB", poisson=True)),
     # pencils with thread ranks (send / receive transposes: the peer-memory kernel is the slab path's)
     (4, dict(N=(16, 12, 8), topo="PBB", scheme="weno", bcs="walls", steps=1, px=2)),
+    # eight ranks, as in the driver's scaling run (C5 is 8 slabs): slabs through peer memory, 2 x 4 pencils, a stretched grid
+    (8, dict(N=(16, 32, 8), topo="PPP", scheme="weno", steps=1)),
+    (8, dict(N=(16, 32, 8), topo="PPB", scheme="weno", steps=1, px=2)),
+    (8, dict(N=(16, 32, 16), topo="PPB", scheme="weno", closure="lilly", bcs=True, stretch="smooth", steps=1)),
     # a (y, z) model on slabs: the first stage of the peer-memory solve transforms z alone
     (2, dict(N=(1, 12, 8), topo="FPB", scheme="weno", buoy="tracer", f=0.2, steps=2)),
 ])
