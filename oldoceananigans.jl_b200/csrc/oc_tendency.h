@@ -307,7 +307,8 @@ struct TendencyKernel {
                     // maybe_z_dot_g_bᶜᶜᶠ: only without the hydrostatic split (nonhydrostatic_tendency_kernel_functions.jl:168-170)
                     G = G + FT(0.5) * (buoyancy_at(o - g.sz) + buoyancy_at(o));
                 }
-                if ((KIND == KIND_U || KIND == KIND_V) && cor.tilted && !g.flat[KIND == KIND_U ? 0 : 1]) {
+                // (along a Flat dimension too: ℑ is the identity there, the term is ĝ·b — all planes of the Flat direction hold the same b)
+                if ((KIND == KIND_U || KIND == KIND_V) && cor.tilted) {
                     const int s = KIND == KIND_U ? 1 : g.sy;
                     FT b0, b1;
                     if (cor.tb_kind == 1) { b0 = cor.tbT[o - s]; b1 = cor.tbT[o]; }

@@ -423,6 +423,12 @@ FLAT_CLOSURE_CASES = [
     ("PFB weno amd tracer-b fplane bcs", dict(N=(16, 1, 12), topo="PFB", scheme="weno", closure="amd", buoy="tracer", f=0.2, bcs=True)),
     ("FPB centered amd Cb=1 tracer-b", dict(N=(1, 12, 8), topo="FPB", scheme="centered", closure="amdcb", buoy="tracer")),
     ("BBF upwind3 smagorinsky wall bcs AB2", dict(N=(12, 10, 1), topo="BBF", scheme="upwind3", closure="smag", buoy="passive", bcs="walls", ts="QuasiAdamsBashforth2")),
+    # found by scripts/fuzz_parity.py: gravity tilted TOWARDS the Flat direction — ℑy is the identity there, y_dot_g_b = ĝ_y b (g_dot_b.jl:1-3),
+    # which the kernel used to drop
+    ("PFB centered tilted gravity along the Flat y", dict(N=(16, 1, 12), topo="PFB", scheme="centered", closure="scalar", buoy="tracer", bcs=True, f=0.2,
+                                                          tilt=(0.0, -0.8660254037844386, -0.5), tracer_noise=1.0)),
+    ("PFP weno7 smagorinsky seawater tilted gravity along the Flat y", dict(N=(8, 1, 4), topo="PFP", scheme="weno7", closure="smag", buoy="seawater", bcs="walls",
+                                                                            tilt=(0.0, -0.8660254037844386, -0.5), tracer_noise=1.0)),
 ]
 
 # scalar Value / Gradient / Flux boundary conditions on the LATERAL walls too (bcs="walls": every Bounded side of u, v, w and the first
