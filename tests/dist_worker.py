@@ -74,13 +74,16 @@ def run_rank(kw, rank, R, arch, lib, nccl=False):
     FT = np.float32 if kw.pop("f32", False) else np.float64
     N, topo = tuple(kw["N"]), kw["topo"]
     scheme = kw.get("scheme", "weno")
+    if isinstance(scheme, list):                 # JSON: a tuple of per-direction schemes arrives as a list
+        scheme = tuple(scheme)
     f = kw.get("f")
     if isinstance(f, list):                      # ("beta", f₀, β): JSON turns the tuple into a list
         f = tuple(f)
     kw["f"] = f
     case = dict(N=N, topo=topo, scheme=scheme, FT=FT, f=kw.get("f"), closure=kw.get("closure", "scalar"), bcs=kw.get("bcs", False),
                 ts=kw.get("ts", "RungeKutta3"), buoy=kw.get("buoy", "seawater"), tilt=tuple(kw["tilt"]) if kw.get("tilt") else None,
-                stretch=kw.get("stretch"))
+                stretch=kw.get("stretch"), halo=tuple(kw["halo"]) if kw.get("halo") else None,
+                extent=tuple(kw["extent"]) if kw.get("extent") else ph.EXTENT)
     if kw.get("halo_fill"):
         return halo_fill(kw, rank, arch, lib, FT)
     model = ph.build_product(library=lib, arch=arch, **case)

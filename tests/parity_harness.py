@@ -38,12 +38,13 @@ def z_faces(Nz, Lz, kind):
     return -Lz + Lz * (s + 0.6 * np.sin(np.pi * s) / np.pi)
 
 
-def _grid_kwargs(N, topo, extent, stretch):
+def _grid_kwargs(N, topo, extent, stretch, halo=None):
     nonflat = [d for d in range(3) if topo[d] != "F"]
     size = tuple(N[d] for d in nonflat)
+    hk = {} if halo is None else dict(halo=tuple(halo[d] for d in nonflat))
     if not stretch:
-        return dict(size=size, extent=tuple(extent[d] for d in nonflat))
-    kw = dict(size=size, z=[float(v) for v in z_faces(N[2], extent[2], stretch)])
+        return dict(size=size, extent=tuple(extent[d] for d in nonflat), **hk)
+    kw = dict(size=size, z=[float(v) for v in z_faces(N[2], extent[2], stretch)], **hk)
     if topo[0] != "F":
         kw["x"] = (0.0, extent[0])
     if topo[1] != "F":
@@ -53,6 +54,8 @@ def _grid_kwargs(N, topo, extent, stretch):
 
 # advection schemes: name -> (oracle, product)
 def oracle_scheme(scheme, FT):
+    if isinstance(scheme, (tuple, list)):        # ("weno", "centered", "upwind3"): FluxFormAdvection(x, y, z), one scheme per flux direction
+        return adv.FluxFormAdvection(*[oracle_scheme(s, FT) for s in scheme])
     return {"centered": lambda: adv.Centered(FT, 2), "weno": lambda: adv.WENO(FT, 5), "centered4": lambda: adv.Centered(FT, 4),
             "upwind1": lambda: adv.UpwindBiased(FT, 1), "upwind3": lambda: adv.UpwindBiased(FT, 3),
             "upwind5": lambda: adv.UpwindBiased(FT, 5), "weno3": lambda: adv.WENO(FT, 3), "none": lambda: adv.NoAdvection(FT),
@@ -60,6 +63,8 @@ def oracle_scheme(scheme, FT):
 
 
 def product_scheme(scheme):
+    if isinstance(scheme, (tuple, list)):
+        return ob.FluxFormAdvection(*[product_scheme(s) for s in scheme])
     return {"centered": ob.Centered, "weno": ob.WENO, "centered4": lambda: ob.Centered(order=4),
             "upwind1": lambda: ob.UpwindBiased(order=1), "upwind3": lambda: ob.UpwindBiased(order=3),
             "upwind5": lambda: ob.UpwindBiased(order=5), "weno3": lambda: ob.WENO(order=3), "none": lambda: None,
@@ -145,7 +150,7 @@ def _wall_bcs(topo, tr):
 
 
 def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
-                 bcs=False, extent=EXTENT, stretch=None, tilt=None, **_):
+                 bcs=False, extent=EXTENT, stretch=None, tilt=None, halo=None, **_):
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
     obo = clo.SeawaterBuoyancy(gravity_unit_vector=tilt) if buoy == "seawater" else (clo.BuoyancyTracer(gravity_unit_vector=tilt) if buoy == "tracer" else None)
     ocl = {"scalar": clo.ScalarDiffusivity(1e-3, 2e-3), "amd": clo.AnisotropicMinimumDissipation(), "none": None,
@@ -169,16 +174,16 @@ def build_oracle(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closur
         t0 = tr[0]
         bc_o = {"u": {"top": BC("flux", -2e-3)}, t0: {"top": BC("flux", 5e-3), "bottom": BC("gradient", 0.05)},
                 "v": {"bottom": BC("value", 0.1)}}
-    og = oracle.Grid(FT, topology=tuple(topo), **_grid_kwargs(N, topo, extent, stretch))
+    og = oracle.Grid(FT, topology=tuple(topo), **_grid_kwargs(N, topo, extent, stretch, halo))
     oa = oracle_scheme(scheme, FT)
     return oracle.OracleModel(og, advection=oa, tracers=tr, buoyancy=obo, closure=ocl, timestepper=ts, coriolis=_coriolis(clo, f),
                               boundary_conditions=bc_o)
 
 
 def build_product(N, topo, scheme="weno", FT=np.float64, ts="RungeKutta3", closure="scalar", buoy="seawater", f=None,
-                  bcs=False, library=None, extent=EXTENT, arch=None, stretch=None, tilt=None):
+                  bcs=False, library=None, extent=EXTENT, arch=None, stretch=None, tilt=None, halo=None):
     size, ext, tr = _spec(N, topo, scheme, FT, ts, closure, buoy, f, bcs, extent)
-    gkw = _grid_kwargs(N, topo, extent, stretch)
+    gkw = _grid_kwargs(N, topo, extent, stretch, halo)
     grid = ob.RectilinearGrid(arch if arch is not None else FT, FT, topology=tuple(TOPO[c] for c in topo), **gkw) \
         if arch is not None else ob.RectilinearGrid(FT, topology=tuple(TOPO[c] for c in topo), **gkw)
     a = product_scheme(scheme)
