@@ -137,6 +137,8 @@ def run_rank(kw, rank, R, arch, lib, nccl=False):
             worst = max(worst, ph.rel_linf(model.fields[n].interior(), om.fields[n].interior[sl]) * (np.abs(om.fields[n].interior[sl]).max() / np.abs(om.fields[n].interior).max()))
         if scheme != "none":      # without advection the pressure correction is round-off sized: its RELATIVE error is meaningless
             worst = max(worst, float(np.abs(model.pressures.pNHS.interior() - om.pNHS.interior[cols, rows, :]).max() / np.abs(om.pNHS.interior).max()))
+    if max(float(np.abs(om.fields[n].interior).max()) for n in ("u", "v", "w")) > 1e3:
+        return float("nan")       # the harness's time step is unstable for this configuration (the fuzzer skips it)
     return worst
 
 
