@@ -148,3 +148,66 @@ def test_tall_slabs_split_their_tendency_launches(monkeypatch):
     assert a[0][0] > b[0][0] and a[1][0] > b[1][0], (a[0][0], b[0][0])
     for r in range(2):
         assert (a[r][1] == b[r][1]).all()           # bit for bit: the same kernels on the same cells, in two or three launches
+
+
+@pytest.mark.parametrize("R,px,kw", [
+    (2, 1, dict(N=(12, 12, 8), topo="PPB", scheme="weno", closure="amd", bcs=True, f=1e-2)),
+    (4, 2, dict(N=(12, 12, 8), topo="BBB", scheme="weno", closure="lilly", bcs="walls")),
+    (3, 1, dict(N=(12, 12, 9), topo="PBB", scheme="centered", bcs="array", stretch="smooth")),
+], ids=["slabs", "pencils", "stretched slabs with array BCs"])
+def test_staged_entry_points_match_fused_step_on_distributed_models(R, px, kw, monkeypatch):
+    """time_step! assembled from the staged C entry points (runge_kutta_3.jl:93-170) — every one of them collective on a distributed model —
+    against the fused oc_time_step_rk3: two models per rank (each with its own mailbox), two steps, every field"""
+    import numpy as np
+    import __graft_entry__ as ge
+    import oceananigans_b200 as ob
+    from oceananigans_b200 import _lib
+    import parity_harness as ph
+    ge.build()
+    monkeypatch.setenv("OC_HOSTSIM_THREADS", "1")
+    lib = _lib.Library(ge.HOSTSIM)
+    boxes = (Mailbox(), Mailbox())
+    out, errs = [None] * R, []
+    om = ph.build_oracle(**kw)
+    ic = ph.initial_conditions(om)
+    N, topo, py = kw["N"], kw["topo"], R // px
+    nxl, nyl = N[0] // px, N[1] // py
+
+    def body(rank):
+        try:
+            models = []
+            for box in boxes:
+                arch = ob.Distributed(ob.B200(0), partition=ob.Partition(px, py), rank=rank, nranks=R, exchange=box.exchange_for(rank))
+                m = ph.build_product(library=lib, arch=arch, **kw)
+                cs = lambda n: slice(arch.rx * nxl, (arch.rx + 1) * nxl + (1 if n == "u" and topo[0] == "B" and arch.rx == px - 1 else 0))
+                rs = lambda n: slice(arch.ry * nyl, (arch.ry + 1) * nyl + (1 if n == "v" and topo[1] == "B" and arch.ry == py - 1 else 0))
+                ob.set_(m, **{n: a[cs(n), rs(n), :] for n, a in ic.items()})
+                models.append(m)
+            m1, m2 = models
+            dt, g, z = 0.02, [8 / 15, 5 / 12, 3 / 4], [0.0, -17 / 60, -5 / 12]
+            worst = 0.0
+            for _ in range(2):
+                ob.time_step_(m1, dt)
+                ob.update_state_(m2, True)
+                for st in (1, 2, 3):
+                    ob.compute_flux_bc_tendencies_(m2)
+                    ob.rk3_substep_(m2, dt, st)
+                    sdt = dt * (g[st - 1] + z[st - 1])
+                    ob.compute_pressure_correction_(m2, sdt)
+                    ob.make_pressure_correction_(m2, sdt)
+                    if st < 3:
+                        ob.cache_previous_tendencies_(m2)
+                    ob.update_state_(m2, True)
+                for n in m1.fields:
+                    worst = max(worst, ph.rel_linf(m1.fields[n].interior(), m2.fields[n].interior()))
+            out[rank] = worst
+        except BaseException as e:       # noqa: BLE001
+            errs.append((rank, repr(e)))
+
+    ts = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(R)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=600)
+    assert not errs, errs
+    assert all(o is not None and np.isfinite(o) for o in out) and max(out) <= 1e-13, out
