@@ -285,6 +285,11 @@ def main():
             kw64 = {k: v for k, v in kw.items() if k != "FT"}
             try:
                 w64 = distributed(kw64, part, lib) if dist else single(kw64, lib)
+            except Skip as e:      # (the Float64 run shows the configuration is unstable with the harness's time step)
+                ran -= 1
+                skipped += 1
+                print(f"[{n}] skip  {part} {kw}: {e}", flush=True)
+                continue
             except Exception:      # noqa: BLE001
                 w64 = float("inf")
             ok = w64 <= (1e-9 if "extent" in kw else 1e-10)      # (anisotropic cells: the pressure's own conditioning, see single())
