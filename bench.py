@@ -37,7 +37,8 @@ METRIC = "cell-updates/sec per full RK3 step"
 # kernels by the session that made the capture (profiles/ncu_march_traffic.json names the capture files) — not constants of this file
 def _ncu_facts():
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_march_traffic.json")))
+        with open(os.path.join(ROOT, "profiles", "ncu_march_traffic.json")) as fh:
+            d = json.load(fh)
     except Exception:
         return {}, {}, {}
     return ({k: v["dram_bytes_per_launch_mean"] for k, v in d.items()}, {k: v["fp64_instr_per_cell"]["mean"] for k, v in d.items()},
